@@ -1,0 +1,55 @@
+"""PRN replica generation, host side (integer LFSR work).
+
+Product-side counterpart of the reference's ``generateCAcode.m`` /
+``makeCaTable.m`` (GPS/GPS_L1CA/include/generateCAcode.m:42-90,
+makeCaTable.m:43-67).  Written as a Galois-free bit-LFSR on 0/1 bits (the
+reference multiplies ±1 values); the C++ library carries its own copy of the same
+generator (csrc/codes.cpp) for the device tables — this module serves the
+synthetic-record generator and the host mirror.
+"""
+from __future__ import annotations
+
+from functools import lru_cache
+
+import numpy as np
+
+# G2 output delay (chips) per PRN, IS-GPS-200 Table 3-Ia; PRN 33..51 are the
+# SBAS entries the reference lists (true_PRN = PRN + 87).
+G2_DELAY = (5, 6, 7, 8, 17, 18, 139, 140, 141, 251, 252, 254, 255, 256, 257, 258,
+            469, 470, 471, 472, 473, 474, 509, 512, 513, 514, 515, 516, 859, 860, 861, 862,
+            145, 175, 52, 21, 237, 235, 886, 657, 634, 762, 355, 1012, 176, 603, 130, 359,
+            595, 68, 386)
+
+
+def _lfsr(taps) -> np.ndarray:
+    """1023-chip maximal sequence of a 10-stage register, all-ones start, output = stage 10."""
+    reg = [1] * 10
+    out = np.empty(1023, dtype=np.int8)
+    for i in range(1023):
+        out[i] = reg[9]
+        fb = 0
+        for t in taps:
+            fb ^= reg[t - 1]
+        reg = [fb] + reg[:9]
+    return out
+
+
+@lru_cache(maxsize=None)
+def ca_code(prn: int) -> np.ndarray:
+    """±1 C/A chips (int8, length 1023); bit 1 -> -1... sign convention of the reference:
+    chip = +1 where G1 xor G2 == 1 (generateCAcode.m:90, ``-(g1.*g2)`` on ±1 registers
+    loaded with -1)."""
+    g1 = _lfsr((3, 10))
+    g2 = _lfsr((2, 3, 6, 8, 9, 10))
+    g2 = np.roll(g2, G2_DELAY[prn - 1])
+    x = g1 ^ g2                      # 0/1, IS-GPS-200 logic levels
+    return (2 * x.astype(np.int8) - 1)
+
+
+def ca_first10_octal(prn: int) -> str:
+    """First 10 chips as the octal word IS-GPS-200 tabulates (known-answer test)."""
+    x = (ca_code(prn)[:10] > 0).astype(int)
+    v = 0
+    for b in x:
+        v = (v << 1) | int(b)
+    return format(v, "o")

@@ -1,0 +1,122 @@
+"""Seeded synthetic GPS L1 C/A IF records (8-bit complex, I,Q interleaved ``schar``).
+
+The reference ships no sample data (README.md:10-11 points at an unreachable drive), so
+every test and the benchmark run on records made here.  Signal model per satellite:
+``A * D(t) * c((f_code*t + tau0) mod 1023) * exp(i*(2*pi*(IF+fd)*t + phi0))`` with
+carrier-coherent code Doppler, 50 bps data bits aligned to code periods, plus complex
+white Gaussian noise of ``sigma`` LSB per component, rounded and clipped to int8.
+
+Two generators with the same model: :func:`make_record` (NumPy, CPU, for tests) and
+:func:`make_record_torch` (any torch device, chunked, for the 60 s benchmark record).
+The code generator used here is the package's own (:mod:`codes`), not the oracle's.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .codes import ca_code
+
+L1 = 1575.42e6
+
+
+@dataclass
+class Sat:
+    prn: int
+    doppler: float          # Hz
+    code_phase: float       # chips at t=0 (signal code phase; receiver sees code start at (1023-cp) chips)
+    cn0: float              # dB-Hz
+    phi0: float = 0.0       # rad
+    bit_seed: int = 0
+    bit_offset: int = 0     # code periods (0..19) to the first bit edge
+
+
+@dataclass
+class Scene:
+    fs: float = 16.368e6
+    IF: float = 20e3
+    sigma: float = 20.0
+    seed: int = 20260101
+    sats: list = field(default_factory=list)
+
+
+def default_scene(fs: float = 16.368e6, IF: float = 20e3, nsat: int = 8, seed: int = 20260101) -> Scene:
+    rng = np.random.default_rng(seed)
+    prns = rng.choice(np.arange(1, 33), size=nsat, replace=False)
+    sats = []
+    for i, p in enumerate(prns):
+        sats.append(Sat(prn=int(p), doppler=float(rng.uniform(-5000, 5000)),
+                        code_phase=float(rng.uniform(0, 1023)), cn0=float(rng.uniform(38, 50)),
+                        phi0=float(rng.uniform(0, 2 * np.pi)), bit_seed=int(rng.integers(1 << 30)),
+                        bit_offset=int(rng.integers(0, 20))))
+    return Scene(fs=fs, IF=IF, seed=seed, sats=sats)
+
+
+def _amp(cn0_db: float, sigma: float, fs: float) -> float:
+    # complex noise power 2*sigma^2 over bandwidth fs  ->  N0 = 2*sigma^2/fs ; C = A^2
+    return float(np.sqrt(10 ** (cn0_db / 10) * 2 * sigma * sigma / fs))
+
+
+def nav_bits(sat: Sat, nbits: int) -> np.ndarray:
+    return np.random.default_rng(sat.bit_seed).integers(0, 2, size=nbits).astype(np.float64) * 2 - 1
+
+
+def make_record(scene: Scene, nsamples: int, start: int = 0) -> np.ndarray:
+    """int8 array of length 2*nsamples (I0,Q0,I1,Q1,...), samples start..start+nsamples-1."""
+    n = np.arange(start, start + nsamples, dtype=np.float64)
+    t = n / scene.fs
+    sig = np.zeros(nsamples, dtype=np.complex128)
+    for s in scene.sats:
+        fcode = 1.023e6 * (1 + s.doppler / L1)
+        chips = fcode * t + s.code_phase
+        period = np.floor(chips / 1023.0).astype(np.int64)
+        idx = np.floor(chips - period * 1023.0).astype(np.int64) % 1023
+        code = ca_code(s.prn).astype(np.float64)[idx]
+        bits = nav_bits(s, int(period.max() // 20) + 3)
+        d = bits[(period + s.bit_offset) // 20]
+        ph = 2 * np.pi * ((scene.IF + s.doppler) * t % 1.0) + s.phi0
+        sig += _amp(s.cn0, scene.sigma, scene.fs) * d * code * np.exp(1j * ph)
+    # noise is a function of (seed, absolute chunk) so records can be made piecewise
+    rng = np.random.default_rng([scene.seed, start])
+    sig += scene.sigma * (rng.standard_normal(nsamples) + 1j * rng.standard_normal(nsamples))
+    out = np.empty(2 * nsamples, dtype=np.int8)
+    out[0::2] = np.clip(np.rint(sig.real), -127, 127).astype(np.int8)
+    out[1::2] = np.clip(np.rint(sig.imag), -127, 127).astype(np.int8)
+    return out
+
+
+def make_record_torch(scene: Scene, nsamples: int, device="cuda", chunk: int = 1 << 24):
+    """Same model on a torch device, generated in chunks; returns an int8 tensor (2*nsamples).
+
+    Noise comes from torch's generator (seeded), so the bytes differ from
+    :func:`make_record`; parity tests always feed the *same bytes* to both sides."""
+    import torch
+
+    out = torch.empty(2 * nsamples, dtype=torch.int8, device=device)
+    g = torch.Generator(device=device)
+    g.manual_seed(scene.seed)
+    codes = {s.prn: torch.tensor(ca_code(s.prn).astype(np.float32), device=device) for s in scene.sats}
+    bits = {s.prn: torch.tensor(nav_bits(s, int(nsamples / scene.fs * 50) + 5).astype(np.float32), device=device)
+            for s in scene.sats}
+    for c0 in range(0, nsamples, chunk):
+        m = min(chunk, nsamples - c0)
+        n = torch.arange(c0, c0 + m, dtype=torch.float64, device=device)
+        t = n / scene.fs
+        re = torch.zeros(m, dtype=torch.float32, device=device)
+        im = torch.zeros(m, dtype=torch.float32, device=device)
+        for s in scene.sats:
+            fcode = 1.023e6 * (1 + s.doppler / L1)
+            chips = fcode * t + s.code_phase
+            period = torch.floor(chips / 1023.0)
+            idx = torch.floor(chips - period * 1023.0).to(torch.int64) % 1023
+            d = bits[s.prn][((period.to(torch.int64) + s.bit_offset) // 20)]
+            a = _amp(s.cn0, scene.sigma, scene.fs) * d * codes[s.prn][idx]
+            ph = (2 * np.pi) * torch.frac((scene.IF + s.doppler) * t) + s.phi0
+            re += a * torch.cos(ph).to(torch.float32)
+            im += a * torch.sin(ph).to(torch.float32)
+        re += scene.sigma * torch.randn(m, device=device, generator=g)
+        im += scene.sigma * torch.randn(m, device=device, generator=g)
+        out[2 * c0: 2 * (c0 + m): 2] = torch.clamp(torch.round(re), -127, 127).to(torch.int8)
+        out[2 * c0 + 1: 2 * (c0 + m): 2] = torch.clamp(torch.round(im), -127, 127).to(torch.int8)
+    return out

@@ -1,0 +1,447 @@
+/*
+ * gnss_oracle.c — plain-C float64 restatement of the reference's GPS L1 C/A hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this library; the product
+ * (libgnsscorr.so) never links or calls it.
+ *
+ * PARITY UNPINNED: the reference is 100 % MATLAB with no tests/golden vectors and
+ * cannot be executed in this image (no MATLAB/Octave).  This file is an independent
+ * second restatement (the first is oracle/np_oracle.py); the two must agree, and both
+ * are pinned against the IS-GPS-200 C/A first-chip octals and closed-loop KATs.
+ *
+ * Every function cites the reference file:line it follows (paths relative to
+ * /root/reference/GPS/GPS_L1CA/).
+ *
+ * Build: gcc -O2 -fopenmp -fPIC -shared -o oracle/_build/libgnss_oracle.so oracle/gnss_oracle.c -lm
+ *        (-ffp-contract=off so a*b+c is never fused: MATLAB rounds each op)
+ */
+#include <complex.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef double complex cplx;
+
+typedef struct {
+    double samplingFreq, IF, codeFreqBasis, codeLength;            /* initSettings.m:71-76 */
+    double acqSearchBand, acqSearchStep, acqThreshold;             /* :86,:92,:90 */
+    int    acqNonCohTime;                                          /* :88 */
+    int    skipNumberOfBytes;                                      /* :56 */
+    double dllDampingRatio, dllNoiseBandwidth, dllCorrelatorSpacing; /* :100-102 */
+    double pllDampingRatio, pllNoiseBandwidth, intTime;            /* :105-108 */
+    double CNo_accTime; int CNo_VSMinterval;                       /* :133-135 */
+} orc_settings;
+
+/* ---------------------------------------------------------------- helpers */
+static double m_round(double x) { return x >= 0 ? floor(x + 0.5) : -floor(-x + 0.5); }
+
+int orc_samples_per_code(const orc_settings* s)                    /* acquisition.m:116-117 */
+{
+    return (int)m_round(s->samplingFreq / (s->codeFreqBasis / s->codeLength));
+}
+
+/* generateCAcode.m:42-90 — ±1 chips */
+static const int G2S[51] = {5, 6, 7, 8, 17, 18, 139, 140, 141, 251, 252, 254, 255, 256, 257, 258, 469, 470, 471, 472,
+                            473, 474, 509, 512, 513, 514, 515, 516, 859, 860, 861, 862,
+                            145, 175, 52, 21, 237, 235, 886, 657, 634, 762, 355, 1012, 176, 603, 130, 359, 595, 68, 386};
+
+void orc_generateCAcode(int PRN, double* CAcode /*1023*/)
+{
+    double g1[1023], g2[1023], reg[10];
+    int g2shift = G2S[PRN - 1];
+    for (int i = 0; i < 10; i++) reg[i] = -1;
+    for (int i = 0; i < 1023; i++) {
+        g1[i] = reg[9];
+        double saveBit = reg[2] * reg[9];
+        for (int j = 9; j >= 1; j--) reg[j] = reg[j - 1];
+        reg[0] = saveBit;
+    }
+    for (int i = 0; i < 10; i++) reg[i] = -1;
+    for (int i = 0; i < 1023; i++) {
+        g2[i] = reg[9];
+        double saveBit = reg[1] * reg[2] * reg[5] * reg[7] * reg[8] * reg[9];
+        for (int j = 9; j >= 1; j--) reg[j] = reg[j - 1];
+        reg[0] = saveBit;
+    }
+    /* g2 = [g2(1023-g2shift+1 : 1023), g2(1 : 1023-g2shift)] */
+    for (int i = 0; i < 1023; i++) {
+        int src = (i < g2shift) ? (1023 - g2shift + i) : (i - g2shift);
+        CAcode[i] = -(g1[i] * g2[src]);
+    }
+}
+
+/* makeCaTable.m:43-67 */
+void orc_makeCaTable(int PRN, const orc_settings* s, double* table /*N*/)
+{
+    int N = orc_samples_per_code(s);
+    double ts = 1 / s->samplingFreq, tc = 1 / s->codeFreqBasis;
+    double ca[1023];
+    orc_generateCAcode(PRN, ca);
+    for (int n = 1; n <= N; n++) {
+        int idx = (int)ceil((ts * (double)n) / tc);
+        if (n == N) idx = 1023;
+        table[n - 1] = ca[idx - 1];
+    }
+}
+
+/* ------------------------------------------------- mixed-radix FFT (f64)
+ * Stands in for MATLAB's fft/ifft built-ins (closed FFTW/MKL inside MATLAB; call sites
+ * acquisition.m:164,183,188).  Stockham autosort, generic radix butterfly; any length
+ * whose prime factors are small. */
+typedef struct { int n, nf, fac[40]; cplx* tw; } fftplan;
+
+static void plan_make(fftplan* p, int n)
+{
+    p->n = n; p->nf = 0;
+    int m = n;
+    while (m % 4 == 0) { p->fac[p->nf++] = 4; m /= 4; }
+    for (int f = 2; m > 1; f++) while (m % f == 0) { p->fac[p->nf++] = f; m /= f; }
+    p->tw = (cplx*)malloc(sizeof(cplx) * (size_t)n);
+    for (int k = 0; k < n; k++) {
+        /* octant-exact table */
+        long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)n;
+        p->tw[k] = (double)cosl(a) + I * (double)sinl(a);
+    }
+}
+static void plan_free(fftplan* p) { free(p->tw); }
+
+/* out-of-place ping-pong; result returned in x; sign=-1 forward, +1 inverse (unscaled) */
+static void fft_exec(const fftplan* p, cplx* x, cplx* y, int sign)
+{
+    int N = p->n, n = N, s = 1;
+    cplx *src = x, *dst = y;
+    for (int f = 0; f < p->nf; f++) {
+        int r = p->fac[f], m = n / r, tstep = N / n, rstep = N / r;
+        for (int pp = 0; pp < m; pp++) {
+            for (int q = 0; q < s; q++) {
+                cplx a[64];
+                for (int i = 0; i < r; i++) a[i] = src[q + s * (pp + i * m)];
+                for (int j = 0; j < r; j++) {
+                    cplx acc = a[0];
+                    for (int i = 1; i < r; i++) {
+                        cplx w = p->tw[((long)i * j % r) * rstep];
+                        if (sign > 0) w = conj(w);
+                        acc += a[i] * w;
+                    }
+                    cplx w = p->tw[((long)pp * j * tstep) % N];
+                    if (sign > 0) w = conj(w);
+                    dst[q + s * (r * pp + j)] = acc * w;
+                }
+            }
+        }
+        n = m; s *= r;
+        cplx* t = src; src = dst; dst = t;
+    }
+    if (src != x) memcpy(x, src, sizeof(cplx) * (size_t)N);
+}
+
+/* exported for the unit tests: dir=-1 fft, +1 ifft (scaled 1/n like MATLAB) */
+int orc_fft(double* reim /*interleaved, n*/, int n, int dir)
+{
+    fftplan p; plan_make(&p, n);
+    for (int i = 0; i < p.nf; i++) if (p.fac[i] > 64) { plan_free(&p); return -1; }
+    cplx* x = (cplx*)malloc(sizeof(cplx) * n), *y = (cplx*)malloc(sizeof(cplx) * n);
+    for (int i = 0; i < n; i++) x[i] = reim[2 * i] + I * reim[2 * i + 1];
+    fft_exec(&p, x, y, dir);
+    double sc = dir > 0 ? 1.0 / n : 1.0;
+    for (int i = 0; i < n; i++) { reim[2 * i] = creal(x[i]) * sc; reim[2 * i + 1] = cimag(x[i]) * sc; }
+    free(x); free(y); plan_free(&p);
+    return 0;
+}
+
+/* --------------------------------------------------------------- acquisition
+ * acquisition.m:113-292 (resampling branch :50-111 not restated, resamplingflag==0).
+ * iq: int8 interleaved I,Q record bytes AFTER the fseek of postProcessing.m:74; the first
+ * max(42,nonCoh+2) code periods are longSignal (postProcessing.m:83-96).
+ * Outputs indexed by PRN-1 (length 32): carrFreq, codePhase, peakMetric (acquisition.m:130-134)
+ * plus coarseBin/coarseCodePhase (1-based) for every searched PRN. */
+int orc_acquisition(const int8_t* iq, size_t nSamplesAvail, const orc_settings* s,
+                    const int* prnList, int nPrn,
+                    double* carrFreq, double* codePhaseOut, double* peakMetric,
+                    int* coarseBin, int* coarseCodePhase, double* sigPowerOut)
+{
+    const int N = orc_samples_per_code(s);
+    const int L2 = 2 * N;
+    const int codeLen = (42 > s->acqNonCohTime + 2) ? 42 : s->acqNonCohTime + 2;
+    if (nSamplesAvail < (size_t)codeLen * N) return -1;
+    const double ts = 1 / s->samplingFreq;                                       /* :119 */
+    const int nBins = (int)m_round(s->acqSearchBand * 2 / s->acqSearchStep) + 1; /* :124 */
+    const double fineSearchStep = 25;                                            /* :138 */
+    const int nFine = (int)m_round(s->acqSearchStep / fineSearchStep) + 1;       /* :140 */
+    const int nonCoh = s->acqNonCohTime;
+    for (int i = 0; i < 32; i++) { carrFreq[i] = codePhaseOut[i] = peakMetric[i] = 0; coarseBin[i] = coarseCodePhase[i] = 0; }
+
+    size_t Ltot = (size_t)codeLen * N;
+    cplx* sig = (cplx*)malloc(sizeof(cplx) * Ltot);
+    for (size_t i = 0; i < Ltot; i++) sig[i] = (double)iq[2 * i] + I * (double)iq[2 * i + 1];
+    double* phasePoints = (double*)malloc(sizeof(double) * L2);
+    for (int n = 0; n < L2; n++) phasePoints[n] = (double)n * 2 * M_PI * ts;     /* :122 */
+
+    /* :151 sigPower = sqrt(var(x(1:N))*N), var of complex with N-1 */
+    cplx mean = 0; for (int i = 0; i < N; i++) mean += sig[i]; mean /= N;
+    double v = 0; for (int i = 0; i < N; i++) { cplx d = sig[i] - mean; v += creal(d) * creal(d) + cimag(d) * cimag(d); }
+    double sigPower = sqrt(v / (N - 1) * N);
+    if (sigPowerOut) *sigPowerOut = sigPower;
+
+    fftplan plan; plan_make(&plan, L2);
+    for (int i = 0; i < plan.nf; i++) if (plan.fac[i] > 64) { plan_free(&plan); free(sig); free(phasePoints); return -2; }
+
+    int rc = 0;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int ip = 0; ip < nPrn; ip++) {
+        int PRN = prnList[ip];
+        double* table = (double*)malloc(sizeof(double) * N);
+        cplx* codeF = (cplx*)malloc(sizeof(cplx) * L2);
+        cplx* buf = (cplx*)malloc(sizeof(cplx) * L2);
+        cplx* tmp = (cplx*)malloc(sizeof(cplx) * L2);
+        cplx* carr = (cplx*)malloc(sizeof(cplx) * L2);
+        double* results = (double*)calloc((size_t)nBins * L2, sizeof(double));   /* :162 */
+        double* coarseFreqBin = (double*)malloc(sizeof(double) * nBins);
+        orc_makeCaTable(PRN, s, table);                                          /* :158 */
+        for (int n = 0; n < L2; n++) codeF[n] = n < N ? table[n] : 0.0;          /* :160 */
+        fft_exec(&plan, codeF, tmp, -1);
+        for (int n = 0; n < L2; n++) codeF[n] = conj(codeF[n]);                  /* :164 */
+        for (int k = 1; k <= nBins; k++) {                                       /* :167 */
+            coarseFreqBin[k - 1] = s->IF + s->acqSearchBand - s->acqSearchStep * (k - 1);   /* :169 */
+            for (int n = 0; n < L2; n++) {
+                double a = coarseFreqBin[k - 1] * phasePoints[n];
+                carr[n] = cos(a) - I * sin(a);                                   /* :172 */
+            }
+            for (int m = 1; m <= nonCoh; m++) {                                  /* :175 */
+                const cplx* w = sig + (size_t)(m - 1) * N;                       /* :177 */
+                for (int n = 0; n < L2; n++) buf[n] = carr[n] * w[n];            /* :180-181 */
+                fft_exec(&plan, buf, tmp, -1);                                   /* :183 */
+                for (int n = 0; n < L2; n++) buf[n] *= codeF[n];                 /* :186 */
+                fft_exec(&plan, buf, tmp, +1);
+                double* row = results + (size_t)(k - 1) * L2;
+                for (int n = 0; n < L2; n++) row[n] += cabs(buf[n]) / L2;        /* :188-190 */
+            }
+        }
+        /* :196  [~,bin] = max(max(results,[],2))   — first maximal row */
+        int bin = 1; double best = -1;
+        for (int k = 0; k < nBins; k++) {
+            double rm = results[(size_t)k * L2];
+            for (int n = 1; n < L2; n++) if (results[(size_t)k * L2 + n] > rm) rm = results[(size_t)k * L2 + n];
+            if (rm > best) { best = rm; bin = k + 1; }
+        }
+        /* :198  [peak,codePhase] = max(max(results)) — column max then first maximal column */
+        int cp = 1; double peak = -1;
+        for (int n = 0; n < L2; n++) {
+            double cm = results[n];
+            for (int k = 1; k < nBins; k++) if (results[(size_t)k * L2 + n] > cm) cm = results[(size_t)k * L2 + n];
+            if (cm > peak) { peak = cm; cp = n + 1; }
+        }
+        peakMetric[PRN - 1] = peak / sigPower / nonCoh;                          /* :200 */
+        coarseBin[PRN - 1] = bin; coarseCodePhase[PRN - 1] = cp;
+        if (peakMetric[PRN - 1] > s->acqThreshold) {                             /* :206 */
+            double ca[1023]; orc_generateCAcode(PRN, ca);                        /* :213 */
+            double bestFine = -1; int bestJ = 1; double bestFreq = 0;
+            for (int j = 1; j <= nFine; j++) {                                   /* :224 */
+                double f = coarseFreqBin[bin - 1] + s->acqSearchStep / 2 - fineSearchStep * (j - 1);  /* :227 */
+                cplx sumPerCode[40];
+                for (int c = 0; c < 40; c++) {
+                    cplx acc = 0;
+                    for (int n = 0; n < N; n++) {
+                        long gi = (long)c * N + n;
+                        long idx = (long)floor((ts * (double)gi) / (1 / s->codeFreqBasis));      /* :215 */
+                        double chip = ca[idx % (long)s->codeLength];                           /* :218 */
+                        double a = f * ((double)gi * 2 * M_PI * ts);                           /* :148,:230 */
+                        cplx cw = cos(a) - I * sin(a);
+                        acc += (sig[(size_t)(cp - 1) + gi] * chip) * cw;                       /* :221,:232,:236 */
+                    }
+                    sumPerCode[c] = acc;
+                }
+                double maxPower = 0;
+                for (int c = 0; c < 20; c++) {                                   /* :243 */
+                    cplx t = 0; for (int q = c; q < c + 20; q++) t += sumPerCode[q];
+                    double pw = cabs(t);                                         /* :245 */
+                    if (pw > maxPower) maxPower = pw;                            /* :247 */
+                }
+                if (maxPower > bestFine) { bestFine = maxPower; bestJ = j; bestFreq = f; }       /* :253 */
+            }
+            (void)bestJ;
+            carrFreq[PRN - 1] = bestFreq;                                        /* :254 */
+            codePhaseOut[PRN - 1] = cp;                                          /* :256 */
+            if (carrFreq[PRN - 1] == 0) carrFreq[PRN - 1] = 1;                   /* :258 */
+        }
+        free(table); free(codeF); free(buf); free(tmp); free(carr); free(results); free(coarseFreqBin);
+    }
+    plan_free(&plan); free(sig); free(phasePoints);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ tracking */
+/* Common/calcLoopCoef.m:41-45 */
+static void calcLoopCoef(double LBW, double zeta, double k, double* tau1, double* tau2)
+{
+    double Wn = LBW * 8 * zeta / (4 * zeta * zeta + 1);
+    *tau1 = k / (Wn * Wn);
+    *tau2 = 2.0 * zeta / Wn;
+}
+
+/* Common/CNoVSM.m:38-47 */
+double orc_CNoVSM(const double* Ip, const double* Qp, int n, double T)
+{
+    double Zm = 0; double Z[4096];
+    for (int i = 0; i < n; i++) { Z[i] = Ip[i] * Ip[i] + Qp[i] * Qp[i]; Zm += Z[i]; }
+    Zm /= n;
+    double Zv = 0; for (int i = 0; i < n; i++) Zv += (Z[i] - Zm) * (Z[i] - Zm); Zv /= (n - 1);
+    cplx Pav = csqrt((cplx)(Zm * Zm - Zv));
+    cplx Nv = 0.5 * (Zm - Pav);
+    return 10 * log10(cabs((1 / T) * Pav / (2 * Nv)));
+}
+
+/* element idx (0-based) of MATLAB's a:d:b with n+1 elements, last element c (colonop) */
+static inline double colon_elem(double a, double d, double c, int n, int idx)
+{
+    if (2 * idx < n) return a + (double)idx * d;
+    if (2 * idx > n) return c - (double)(n - idx) * d;
+    /* 2*idx == n: middle element of an odd-length vector */
+    return (a + c) / 2;
+}
+/* n (count-1) and c (last element) of MATLAB's a:d:b for non-integer a/d (colonop) */
+static void colon_setup(double a, double d, double b, int* n_out, double* c_out)
+{
+    double tol = 2.0 * 2.220446049250313e-16 * fmax(fabs(a), fabs(b));
+    int n;
+    if (a == floor(a) && d == 1) n = (int)(floor(b) - a);
+    else if (a == floor(a) && d == floor(d)) n = (int)trunc((b - a) / d);
+    else {
+        n = (int)m_round((b - a) / d);
+        if ((a + n * d - b) > tol) n -= 1;
+    }
+    double c = a + n * d;
+    if ((c - b) > -tol) c = b;
+    *n_out = n; *c_out = c;
+}
+
+#define ORC_NFIELDS 15
+/* field order of out[ch][field][epoch]: absoluteSample, codeFreq, carrFreq, I_P, I_E, I_L, Q_E, Q_P, Q_L,
+ * dllDiscr, dllDiscrFilt, pllDiscr, pllDiscrFilt, remCodePhase, remCarrPhase (tracking.m:48-77) */
+
+/* tracking.m:88-368 for fileType 2 / schar.  iq = whole file bytes (int8 I,Q interleaved), nBytes its size.
+ * Returns 0; epochsDone[ch] = completed epochs; a short read stops the WHOLE call (tracking.m:241-245). */
+int orc_tracking(const int8_t* iq, size_t nBytes, const orc_settings* s, int nCh,
+                 const int* PRN, const double* acquiredFreq, const double* codePhase,
+                 int nEpochs, double* out /* nCh*15*nEpochs */, double* vsmValue, double* vsmIndex /* nCh*floor(nE/VSMint) */,
+                 int* epochsDone, int parallel)
+{
+    const double earlyLateSpc = s->dllCorrelatorSpacing;                         /* :94 */
+    const double PDIcode = s->intTime, PDIcarr = s->intTime;                     /* :97,:106 */
+    double tau1code, tau2code, tau1carr, tau2carr;
+    calcLoopCoef(s->dllNoiseBandwidth, s->dllDampingRatio, 1.0, &tau1code, &tau2code);   /* :100 */
+    calcLoopCoef(s->pllNoiseBandwidth, s->pllDampingRatio, 0.25, &tau1carr, &tau2carr);  /* :109 */
+    const int L = (int)s->codeLength;
+    const int nV = nEpochs / s->CNo_VSMinterval;
+    /* result init (tracking.m:48-83): zeros for absoluteSample and I/Q, inf elsewhere */
+    for (int ch = 0; ch < nCh; ch++) {
+        double* o = out + (size_t)ch * ORC_NFIELDS * nEpochs;
+        for (int f = 0; f < ORC_NFIELDS; f++) {
+            double fill = (f == 0 || (f >= 3 && f <= 8)) ? 0.0 : INFINITY;
+            for (int e = 0; e < nEpochs; e++) o[(size_t)f * nEpochs + e] = fill;
+        }
+        for (int i = 0; i < nV; i++) { vsmValue[(size_t)ch * nV + i] = 0; vsmIndex[(size_t)ch * nV + i] = 0; }
+        epochsDone[ch] = 0;
+    }
+    volatile int abortAll = 0;
+#pragma omp parallel for schedule(dynamic, 1) if (parallel)
+    for (int ch = 0; ch < nCh; ch++) {                                           /* :133 */
+        if (PRN[ch] == 0) continue;                                              /* :136 */
+        if (!parallel && abortAll) continue;   /* sequential semantics: return ends all later channels */
+        double* o = out + (size_t)ch * ORC_NFIELDS * nEpochs;
+#define F(i) (o + (size_t)(i) * nEpochs)
+        size_t pos = (size_t)(2 * ((long)s->skipNumberOfBytes + (long)codePhase[ch] - 1));   /* :150 */
+        double ca[1023], caCode[1025];
+        orc_generateCAcode(PRN[ch], ca);                                         /* :156 */
+        caCode[0] = ca[L - 1]; memcpy(caCode + 1, ca, sizeof(double) * L); caCode[L + 1] = ca[0];   /* :158 */
+        double codeFreq = s->codeFreqBasis, remCodePhase = 0.0;                  /* :163-165 */
+        double carrFreq = acquiredFreq[ch], carrFreqBasis = acquiredFreq[ch], remCarrPhase = 0.0;   /* :167-170 */
+        double oldCodeNco = 0, oldCodeError = 0, oldCarrNco = 0, oldCarrError = 0;           /* :173-178 */
+        int vsmCnt = 0;
+        for (int loopCnt = 1; loopCnt <= nEpochs; loopCnt++) {                   /* :184 */
+            F(0)[loopCnt - 1] = (double)pos / 2;                                 /* :215 */
+            double codePhaseStep = codeFreq / s->samplingFreq;                   /* :219 */
+            int blksize = (int)ceil((s->codeLength - remCodePhase) / codePhaseStep);         /* :222 */
+            if (pos + 2 * (size_t)blksize > nBytes) { abortAll = 1; break; }     /* :241-245 */
+            const int8_t* raw = iq + pos; pos += 2 * (size_t)blksize;            /* :226 */
+            F(13)[loopCnt - 1] = remCodePhase;                                   /* :249 */
+            double aE = remCodePhase - earlyLateSpc, bE = (blksize - 1) * codePhaseStep + remCodePhase - earlyLateSpc;   /* :252 */
+            double aL = remCodePhase + earlyLateSpc, bL = (blksize - 1) * codePhaseStep + remCodePhase + earlyLateSpc;   /* :259 */
+            double aP = remCodePhase, bP = (blksize - 1) * codePhaseStep + remCodePhase;                                 /* :266 */
+            int nE_, nL_, nP_; double cE, cL, cP;
+            colon_setup(aE, codePhaseStep, bE, &nE_, &cE);
+            colon_setup(aL, codePhaseStep, bL, &nL_, &cL);
+            colon_setup(aP, codePhaseStep, bP, &nP_, &cP);
+            F(14)[loopCnt - 1] = remCarrPhase;                                   /* :277 */
+            double w = carrFreq * 2.0 * M_PI;                                    /* :281 */
+            double I_E = 0, Q_E = 0, I_P = 0, Q_P = 0, I_L = 0, Q_L = 0;
+            for (int n = 0; n < blksize; n++) {
+                double e = caCode[(int)ceil(colon_elem(aE, codePhaseStep, cE, nE_, n))];     /* :255-256 */
+                double l = caCode[(int)ceil(colon_elem(aL, codePhaseStep, cL, nL_, n))];     /* :262-263 */
+                double p = caCode[(int)ceil(colon_elem(aP, codePhaseStep, cP, nP_, n))];     /* :269-270 */
+                double trig = (w * ((double)n / s->samplingFreq)) + remCarrPhase;            /* :280-281 */
+                double c = cos(trig), sn = sin(trig);                            /* :287 exp(-1i*trig) = c - i*sn */
+                double xr = raw[2 * n], xi = raw[2 * n + 1];                     /* :233-235 */
+                double iBB = c * xr + sn * xi, qBB = c * xi - sn * xr;           /* :291-292 */
+                I_E += e * iBB; Q_E += e * qBB; I_P += p * iBB; Q_P += p * qBB; I_L += l * iBB; Q_L += l * qBB;   /* :295-300 */
+            }
+            remCodePhase = (colon_elem(aP, codePhaseStep, cP, nP_, blksize - 1) + codePhaseStep) - s->codeLength;  /* :273 */
+            double trigEnd = (w * ((double)blksize / s->samplingFreq)) + remCarrPhase;
+            remCarrPhase = fmod(trigEnd, 2 * M_PI);                              /* :283 */
+            double carrError = atan(Q_P / I_P) / (2.0 * M_PI);                   /* :305 */
+            double carrNco = oldCarrNco + (tau2carr / tau1carr) * (carrError - oldCarrError) + carrError * (PDIcarr / tau1carr);   /* :308 */
+            oldCarrNco = carrNco; oldCarrError = carrError;
+            F(2)[loopCnt - 1] = carrFreq;                                        /* :314 */
+            carrFreq = carrFreqBasis + carrNco;                                  /* :317 */
+            double sE = sqrt(I_E * I_E + Q_E * Q_E), sL = sqrt(I_L * I_L + Q_L * Q_L);
+            double codeError = (sE - sL) / (sE + sL);                            /* :322 */
+            double codeNco = oldCodeNco + (tau2code / tau1code) * (codeError - oldCodeError) + codeError * (PDIcode / tau1code);   /* :326 */
+            oldCodeNco = codeNco; oldCodeError = codeError;
+            F(1)[loopCnt - 1] = codeFreq;                                        /* :332 */
+            codeFreq = s->codeFreqBasis - codeNco;                               /* :335 */
+            F(9)[loopCnt - 1] = codeError; F(10)[loopCnt - 1] = codeNco;         /* :338-341 */
+            F(11)[loopCnt - 1] = carrError; F(12)[loopCnt - 1] = carrNco;
+            F(4)[loopCnt - 1] = I_E; F(3)[loopCnt - 1] = I_P; F(5)[loopCnt - 1] = I_L;       /* :343-348 */
+            F(6)[loopCnt - 1] = Q_E; F(7)[loopCnt - 1] = Q_P; F(8)[loopCnt - 1] = Q_L;
+            if (loopCnt % s->CNo_VSMinterval == 0) {                             /* :351 */
+                vsmCnt++;
+                int lo = loopCnt - s->CNo_VSMinterval;
+                vsmValue[(size_t)ch * nV + vsmCnt - 1] = orc_CNoVSM(F(3) + lo, F(7) + lo, s->CNo_VSMinterval, s->CNo_accTime);   /* :353 */
+                vsmIndex[(size_t)ch * nV + vsmCnt - 1] = loopCnt;                /* :356 */
+            }
+            epochsDone[ch] = loopCnt;
+        }
+#undef F
+    }
+    /* MATLAB `return` on a short read ends the whole function: channels after the first one that
+     * stopped early stay untouched (init fills).  Restore that when channels ran concurrently. */
+    if (parallel) {
+        int failed = -1;
+        for (int ch = 0; ch < nCh && failed < 0; ch++)
+            if (PRN[ch] != 0 && epochsDone[ch] < nEpochs) failed = ch;
+        for (int ch = failed + 1; failed >= 0 && ch < nCh; ch++) {
+            double* o = out + (size_t)ch * ORC_NFIELDS * nEpochs;
+            for (int f = 0; f < ORC_NFIELDS; f++) {
+                double fill = (f == 0 || (f >= 3 && f <= 8)) ? 0.0 : INFINITY;
+                for (int e = 0; e < nEpochs; e++) o[(size_t)f * nEpochs + e] = fill;
+            }
+            for (int i = 0; i < nV; i++) { vsmValue[(size_t)ch * nV + i] = 0; vsmIndex[(size_t)ch * nV + i] = 0; }
+            epochsDone[ch] = 0;
+        }
+    }
+    return 0;
+}
+
+int orc_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

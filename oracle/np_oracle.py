@@ -1,0 +1,412 @@
+"""NumPy float64 restatement of the reference's GPS L1 C/A hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product package may import this
+module; it is the checker for ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py``.
+
+PARITY UNPINNED: the reference (gnsscusdr/CU-SDR-Collection) is 100 % MATLAB,
+ships no tests, golden vectors or sample data, and neither MATLAB nor Octave is
+available in this image, so it cannot be executed.  This file restates the
+reference loops line by line (file:line cited per function, paths relative to
+``/root/reference``) and is pinned only by (1) ICD known answers the code
+embeds (IS-GPS-200 first-10-chip octals of the C/A codes), (2) an independent
+C restatement (``oracle/gnss_oracle.c``) that must agree with it, and (3)
+closed-loop known-answer tests on synthetic IF.
+
+MATLAB semantics reproduced here (each is a parity hazard):
+1-based indices in every returned index; ``max`` returns the first maximal
+index; ``var`` on complex uses N-1; ``round`` is half-away-from-zero; ``rem``
+keeps the sign of the dividend (``fmod``); ``atan`` (two quadrant); ``fft``
+unscaled / ``ifft`` scaled by 1/len; the floating-point colon operator builds
+its vector symmetrically from both ends (Cleve Moler's ``colonop``).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+try:  # scipy's pocketfft handles arbitrary lengths and is multi-threaded
+    import scipy.fft as _fft
+
+    def _FFT(x, workers=1):
+        return _fft.fft(x, axis=-1, workers=workers)
+
+    def _IFFT(x, workers=1):
+        return _fft.ifft(x, axis=-1, workers=workers)
+except Exception:  # pragma: no cover
+    def _FFT(x, workers=1):
+        return np.fft.fft(x, axis=-1)
+
+    def _IFFT(x, workers=1):
+        return np.fft.ifft(x, axis=-1)
+
+
+# ---------------------------------------------------------------------------
+# settings (GPS/GPS_L1CA/initSettings.m:44-136, hot-path fields only)
+# ---------------------------------------------------------------------------
+@dataclass
+class Settings:
+    msToProcess: int = 60000            # initSettings.m:47
+    numberOfChannels: int = 12          # :50
+    skipNumberOfBytes: int = 0          # :56
+    fileName: str = ""                  # :61
+    dataType: str = "schar"             # :63
+    fileType: int = 2                   # :68
+    IF: float = 20e3                    # :71
+    samplingFreq: float = 18e6          # :72
+    codeFreqBasis: float = 1.023e6      # :73
+    codeLength: float = 1023.0          # :76
+    skipAcquisition: int = 0            # :80
+    acqSatelliteList: list = field(default_factory=lambda: list(range(1, 33)))  # :83
+    acqSearchBand: float = 7000.0       # :86
+    acqNonCohTime: int = 20             # :88
+    acqThreshold: float = 3.5           # :90
+    acqSearchStep: float = 500.0        # :92
+    resamplingThreshold: float = 8e6    # :94
+    resamplingflag: int = 0             # :96
+    dllDampingRatio: float = 0.7        # :100
+    dllNoiseBandwidth: float = 1.5      # :101
+    dllCorrelatorSpacing: float = 0.5   # :102
+    pllDampingRatio: float = 0.7        # :105
+    pllNoiseBandwidth: float = 20.0     # :106
+    intTime: float = 0.001              # :108
+    CNo_accTime: float = 0.001          # :133
+    CNo_VSMinterval: int = 40           # :135
+
+
+def matlab_round(x: float) -> float:
+    """MATLAB ``round``: half away from zero."""
+    return math.floor(x + 0.5) if x >= 0 else -math.floor(-x + 0.5)
+
+
+def colonop(a: float, d: float, b: float) -> np.ndarray:
+    """MATLAB floating-point ``a:d:b`` (Cleve Moler, 'colonop').
+
+    The vector is built from both ends towards the middle so that the last
+    element is ``b`` (when ``a+n*d`` is within tolerance of it).  Used by
+    tracking.m:252-268 for the three ``tcode`` vectors; ``tcode(blksize)``
+    feeds ``remCodePhase`` (tracking.m:273).
+    """
+    if d == 0 or (a < b and d < 0) or (b < a and d > 0):
+        return np.zeros(0)
+    tol = 2.0 * np.finfo(float).eps * max(abs(a), abs(b))
+    sig = 1.0 if d > 0 else -1.0
+    if a == math.floor(a) and d == 1:
+        n = int(math.floor(b) - a)
+    elif a == math.floor(a) and d == math.floor(d):
+        n = int(math.trunc((b - a) / d))
+    else:
+        n = int(matlab_round((b - a) / d))
+        if sig * (a + n * d - b) > tol:
+            n -= 1
+    c = a + n * d
+    if sig * (c - b) > -tol:
+        c = b
+    out = np.empty(n + 1)
+    k = np.arange(0, n // 2 + 1, dtype=np.float64)
+    out[: n // 2 + 1] = a + k * d
+    out[n - np.arange(0, n // 2 + 1)] = c - k * d
+    if n % 2 == 0:
+        out[n // 2] = (a + c) / 2
+    return out
+
+
+# ---------------------------------------------------------------------------
+# code generation
+# ---------------------------------------------------------------------------
+_G2S = [5, 6, 7, 8, 17, 18, 139, 140, 141, 251,
+        252, 254, 255, 256, 257, 258, 469, 470, 471, 472,
+        473, 474, 509, 512, 513, 514, 515, 516, 859, 860,
+        861, 862,
+        145, 175, 52, 21, 237, 235, 886, 657,
+        634, 762, 355, 1012, 176, 603, 130, 359, 595, 68,
+        386]
+
+
+def generateCAcode(PRN: int) -> np.ndarray:
+    """GPS/GPS_L1CA/include/generateCAcode.m:42-90 — ±1 C/A chips (1023)."""
+    g2shift = _G2S[PRN - 1]
+    g1 = np.zeros(1023)
+    reg = -np.ones(10)
+    for i in range(1023):
+        g1[i] = reg[9]
+        saveBit = reg[2] * reg[9]
+        reg[1:10] = reg[0:9].copy()
+        reg[0] = saveBit
+    g2 = np.zeros(1023)
+    reg = -np.ones(10)
+    for i in range(1023):
+        g2[i] = reg[9]
+        saveBit = reg[1] * reg[2] * reg[5] * reg[7] * reg[8] * reg[9]
+        reg[1:10] = reg[0:9].copy()
+        reg[0] = saveBit
+    g2 = np.concatenate([g2[1023 - g2shift:], g2[:1023 - g2shift]])
+    return -(g1 * g2)
+
+
+def samples_per_code(s: Settings) -> int:
+    """acquisition.m:116-117 / makeCaTable.m:43-44."""
+    return int(matlab_round(s.samplingFreq / (s.codeFreqBasis / s.codeLength)))
+
+
+def makeCaTable(PRN: int, s: Settings) -> np.ndarray:
+    """GPS/GPS_L1CA/include/makeCaTable.m:43-67 — C/A code resampled to fs."""
+    N = samples_per_code(s)
+    ts = 1 / s.samplingFreq
+    tc = 1 / s.codeFreqBasis
+    caCode = generateCAcode(PRN)
+    codeValueIndex = np.ceil((ts * np.arange(1, N + 1, dtype=np.float64)) / tc).astype(np.int64)
+    codeValueIndex[-1] = 1023
+    return caCode[codeValueIndex - 1]
+
+
+# ---------------------------------------------------------------------------
+# read path (postProcessing.m:59-96)
+# ---------------------------------------------------------------------------
+def read_acq_signal(raw: np.ndarray, s: Settings) -> np.ndarray:
+    """postProcessing.m:83-96 — first max(42, nonCoh+2) code periods as a
+    complex-double row vector (``raw`` = int8 file bytes, I,Q interleaved for
+    fileType 2)."""
+    N = samples_per_code(s)
+    coef = 1 if s.fileType == 1 else 2
+    codeLen = max(42, s.acqNonCohTime + 2)
+    off = coef * s.skipNumberOfBytes
+    data = raw[off: off + coef * codeLen * N].astype(np.float64)
+    if coef == 2:
+        data = data[0::2] + 1j * data[1::2]
+    return data
+
+
+# ---------------------------------------------------------------------------
+# acquisition (GPS/GPS_L1CA/include/acquisition.m:113-292)
+# ---------------------------------------------------------------------------
+def acquisition(longSignal: np.ndarray, s: Settings, workers: int = 1, want_grid: bool = False):
+    """Line-by-line restatement of acquisition.m:113-292 (resampling branch
+    :50-111 not restated: resamplingflag is 0 in every initSettings.m).
+
+    Returns dict with 1x32 ``carrFreq``, ``codePhase``, ``peakMetric`` plus the
+    intermediate ``coarseBin`` (1-based, for every searched PRN) and
+    ``coarseCodePhase`` used by the parity tests.
+    """
+    N = samples_per_code(s)                                        # :116
+    ts = 1 / s.samplingFreq                                        # :119
+    phasePoints = np.arange(0, 2 * N, dtype=np.float64) * 2 * np.pi * ts   # :122
+    nBins = int(matlab_round(s.acqSearchBand * 2 / s.acqSearchStep)) + 1   # :124
+    coarseFreqBin = np.zeros(nBins)
+    res = dict(carrFreq=np.zeros(32), codePhase=np.zeros(32), peakMetric=np.zeros(32),
+               coarseBin=np.zeros(32, dtype=np.int64), coarseCodePhase=np.zeros(32, dtype=np.int64))
+    fineSearchStep = 25                                            # :138
+    numOfFineBins = int(matlab_round(s.acqSearchStep / fineSearchStep)) + 1  # :140
+    finePhasePoints = np.arange(0, 40 * N, dtype=np.float64) * 2 * np.pi * ts  # :148
+    x = longSignal[:N]
+    sigPower = math.sqrt(np.sum(np.abs(x - np.mean(x)) ** 2) / (N - 1) * N)    # :151
+    res["sigPower"] = sigPower
+    grids = {}
+    for PRN in s.acqSatelliteList:                                 # :155
+        caCodesTable = makeCaTable(PRN, s)                         # :158
+        caCodes2ms = np.concatenate([caCodesTable, np.zeros(N)])   # :160
+        results = np.zeros((nBins, 2 * N))                         # :162
+        caCodeFreqDom = np.conj(_FFT(caCodes2ms))                  # :164
+        for k in range(1, nBins + 1):                              # :167
+            coarseFreqBin[k - 1] = s.IF + s.acqSearchBand - s.acqSearchStep * (k - 1)  # :169
+            sigCarr = np.exp(-1j * coarseFreqBin[k - 1] * phasePoints)                  # :172
+            # :175-191, batched over the non-coherent blocks
+            win = np.stack([longSignal[(m - 1) * N: (m + 1) * N]
+                            for m in range(1, s.acqNonCohTime + 1)])
+            IQfreqDom = _FFT(sigCarr[None, :] * win, workers)      # :180-183
+            coh = np.abs(_IFFT(IQfreqDom * caCodeFreqDom[None, :], workers))  # :186-188
+            for m in range(coh.shape[0]):                          # :190 (sequential adds)
+                results[k - 1, :] += coh[m]
+        rowmax = results.max(axis=1)
+        acqCoarseBin = int(np.argmax(rowmax)) + 1                  # :196
+        colmax = results.max(axis=0)
+        codePhase = int(np.argmax(colmax)) + 1                     # :198
+        peakSize = colmax[codePhase - 1]
+        res["peakMetric"][PRN - 1] = peakSize / sigPower / s.acqNonCohTime   # :200
+        res["coarseBin"][PRN - 1] = acqCoarseBin
+        res["coarseCodePhase"][PRN - 1] = codePhase
+        if want_grid:
+            grids[PRN] = results
+        if res["peakMetric"][PRN - 1] > s.acqThreshold:            # :206
+            caCode = generateCAcode(PRN)                           # :213
+            codeValueIndex = np.floor((ts * np.arange(0, 40 * N, dtype=np.float64))
+                                      / (1 / s.codeFreqBasis)).astype(np.int64)   # :215
+            caCode40ms = caCode[np.fmod(codeValueIndex, int(s.codeLength))]        # :218
+            sig40 = longSignal[codePhase - 1: codePhase - 1 + 40 * N]              # :221
+            fineFreqBins = np.zeros(numOfFineBins)
+            fineResult = np.zeros(numOfFineBins)
+            for j in range(1, numOfFineBins + 1):                  # :224
+                fineFreqBins[j - 1] = coarseFreqBin[acqCoarseBin - 1] + \
+                    s.acqSearchStep / 2 - fineSearchStep * (j - 1)  # :227
+                sigCarr40 = np.exp(-1j * fineFreqBins[j - 1] * finePhasePoints)    # :230
+                basebandSig = sig40 * caCode40ms * sigCarr40       # :232
+                sumPerCode = basebandSig.reshape(40, N).sum(axis=1)  # :235-238
+                maxPower = 0.0
+                for c in range(1, 21):                             # :243
+                    comPower = abs(np.sum(sumPerCode[c - 1: c + 19]))  # :245
+                    maxPower = max(maxPower, comPower)             # :247
+                fineResult[j - 1] = maxPower                       # :249
+            maxFinBin = int(np.argmax(fineResult)) + 1             # :253
+            res["carrFreq"][PRN - 1] = fineFreqBins[maxFinBin - 1]  # :254
+            res["codePhase"][PRN - 1] = codePhase                  # :256
+            if res["carrFreq"][PRN - 1] == 0:                      # :258
+                res["carrFreq"][PRN - 1] = 1
+            res.setdefault("fineResult", {})[PRN] = fineResult
+    if want_grid:
+        res["grids"] = grids
+    return res
+
+
+# ---------------------------------------------------------------------------
+# preRun (GPS/GPS_L1CA/include/preRun.m:44-72)
+# ---------------------------------------------------------------------------
+def preRun(acq: dict, s: Settings):
+    """preRun.m:60-72 — strongest peaks first, up to numberOfChannels."""
+    chans = [dict(PRN=0, acquiredFreq=0.0, codePhase=0, status="-")
+             for _ in range(s.numberOfChannels)]
+    # MATLAB sort(...,'descend') is stable: ties keep ascending index order
+    order = np.argsort(-acq["peakMetric"], kind="stable")
+    n = min(s.numberOfChannels, int(np.sum(acq["carrFreq"] != 0)))
+    for ii in range(n):
+        p = int(order[ii])
+        chans[ii] = dict(PRN=p + 1, acquiredFreq=float(acq["carrFreq"][p]),
+                         codePhase=int(acq["codePhase"][p]), status="T")
+    return chans
+
+
+# ---------------------------------------------------------------------------
+# loop coefficients / C/N0
+# ---------------------------------------------------------------------------
+def calcLoopCoef(LBW: float, zeta: float, k: float):
+    """GPS/GPS_L1CA/Common/calcLoopCoef.m:41-45."""
+    Wn = LBW * 8 * zeta / (4 * zeta ** 2 + 1)
+    tau1 = k / (Wn * Wn)
+    tau2 = 2.0 * zeta / Wn
+    return tau1, tau2
+
+
+def CNoVSM(I: np.ndarray, Q: np.ndarray, T: float) -> float:
+    """GPS/GPS_L1CA/Common/CNoVSM.m:38-47."""
+    Z = I ** 2 + Q ** 2
+    Zm = np.mean(Z)
+    Zv = np.var(Z, ddof=1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        Pav = np.sqrt(np.complex128(Zm ** 2 - Zv))   # MATLAB sqrt of negative -> complex
+        Nv = 0.5 * (Zm - Pav)
+        return float(10 * np.log10(np.abs((1 / T) * Pav / (2 * Nv))))
+
+
+TRACK_FIELDS = ["absoluteSample", "codeFreq", "carrFreq", "I_P", "I_E", "I_L",
+                "Q_E", "Q_P", "Q_L", "dllDiscr", "dllDiscrFilt", "pllDiscr",
+                "pllDiscrFilt", "remCodePhase", "remCarrPhase"]
+
+
+# ---------------------------------------------------------------------------
+# tracking (GPS/GPS_L1CA/include/tracking.m:45-371)
+# ---------------------------------------------------------------------------
+def tracking(raw: np.ndarray, channel: list, s: Settings):
+    """Line-by-line restatement of tracking.m:45-371 for fileType 2 /
+    dataType schar.  ``raw`` plays the role of the open file (int8 bytes);
+    fseek/ftell/fread are restated as a byte cursor.  A short read ends the
+    whole call with partially filled results and status left '-'
+    (tracking.m:241-245)."""
+    nE = s.msToProcess
+    out = []
+    for _ in range(s.numberOfChannels):                            # :48-86
+        tr = dict(status="-", PRN=0)
+        tr["absoluteSample"] = np.zeros(nE)
+        for f in ("codeFreq", "carrFreq", "dllDiscr", "dllDiscrFilt", "pllDiscr",
+                  "pllDiscrFilt", "remCodePhase", "remCarrPhase"):
+            tr[f] = np.full(nE, np.inf)
+        for f in ("I_P", "I_E", "I_L", "Q_E", "Q_P", "Q_L"):
+            tr[f] = np.zeros(nE)
+        tr["VSMValue"] = np.zeros(nE // s.CNo_VSMinterval)
+        tr["VSMIndex"] = np.zeros(nE // s.CNo_VSMinterval)
+        out.append(tr)
+    earlyLateSpc = s.dllCorrelatorSpacing                          # :94
+    PDIcode = s.intTime                                            # :97
+    tau1code, tau2code = calcLoopCoef(s.dllNoiseBandwidth, s.dllDampingRatio, 1.0)   # :100
+    PDIcarr = s.intTime                                            # :106
+    tau1carr, tau2carr = calcLoopCoef(s.pllNoiseBandwidth, s.pllDampingRatio, 0.25)  # :109
+    coef = 1 if s.fileType == 1 else 2                             # :126-130
+    assert coef == 2 and s.dataType == "schar"
+    L = int(s.codeLength)
+    for ch in range(s.numberOfChannels):                           # :133
+        if channel[ch]["PRN"] == 0:                                # :136
+            continue
+        tr = out[ch]
+        tr["PRN"] = channel[ch]["PRN"]                             # :138
+        pos = coef * (s.skipNumberOfBytes + channel[ch]["codePhase"] - 1)   # :150 (byte cursor)
+        caCode = generateCAcode(channel[ch]["PRN"])                # :156
+        caCode = np.concatenate([[caCode[L - 1]], caCode, [caCode[0]]])     # :158
+        codeFreq = s.codeFreqBasis                                 # :163
+        remCodePhase = 0.0                                         # :165
+        carrFreq = channel[ch]["acquiredFreq"]                     # :167
+        carrFreqBasis = channel[ch]["acquiredFreq"]                # :168
+        remCarrPhase = 0.0                                         # :170
+        oldCodeNco = oldCodeError = 0.0                            # :173-174
+        oldCarrNco = oldCarrError = 0.0                            # :177-178
+        vsmCnt = 0                                                 # :181
+        for loopCnt in range(1, nE + 1):                           # :184
+            tr["absoluteSample"][loopCnt - 1] = pos / coef         # :215
+            codePhaseStep = codeFreq / s.samplingFreq              # :219
+            blksize = int(math.ceil((s.codeLength - remCodePhase) / codePhaseStep))   # :222
+            nbytes = coef * blksize
+            chunk = raw[pos: pos + nbytes]                         # :226
+            samplesRead = chunk.size
+            pos += samplesRead
+            if samplesRead != nbytes:                              # :241-245
+                return out
+            rawSignal = chunk[0::2].astype(np.float64) + 1j * chunk[1::2].astype(np.float64)  # :233-235
+            tr["remCodePhase"][loopCnt - 1] = remCodePhase         # :249
+            tcode = colonop(remCodePhase - earlyLateSpc, codePhaseStep,
+                            (blksize - 1) * codePhaseStep + remCodePhase - earlyLateSpc)   # :252
+            earlyCode = caCode[np.ceil(tcode).astype(np.int64)]    # :255-256 (+1, 1-based)
+            tcode = colonop(remCodePhase + earlyLateSpc, codePhaseStep,
+                            (blksize - 1) * codePhaseStep + remCodePhase + earlyLateSpc)   # :259
+            lateCode = caCode[np.ceil(tcode).astype(np.int64)]     # :262-263
+            tcode = colonop(remCodePhase, codePhaseStep,
+                            (blksize - 1) * codePhaseStep + remCodePhase)                  # :266
+            promptCode = caCode[np.ceil(tcode).astype(np.int64)]   # :269-270
+            remCodePhase = (tcode[blksize - 1] + codePhaseStep) - s.codeLength             # :273
+            tr["remCarrPhase"][loopCnt - 1] = remCarrPhase         # :277
+            time = np.arange(0, blksize + 1, dtype=np.float64) / s.samplingFreq            # :280
+            trigarg = ((carrFreq * 2.0 * np.pi) * time) + remCarrPhase                     # :281
+            remCarrPhase = math.fmod(trigarg[blksize], 2 * np.pi)  # :283
+            carrsig = np.exp(-1j * trigarg[:blksize])              # :287
+            bb = carrsig * rawSignal                               # :291-292
+            iBB, qBB = bb.real, bb.imag
+            I_E = float(np.sum(earlyCode * iBB)); Q_E = float(np.sum(earlyCode * qBB))     # :295-296
+            I_P = float(np.sum(promptCode * iBB)); Q_P = float(np.sum(promptCode * qBB))   # :297-298
+            I_L = float(np.sum(lateCode * iBB)); Q_L = float(np.sum(lateCode * qBB))       # :299-300
+            with np.errstate(divide="ignore", invalid="ignore"):
+                carrError = float(np.arctan(np.float64(Q_P) / np.float64(I_P)) / (2.0 * np.pi))   # :305
+            carrNco = oldCarrNco + (tau2carr / tau1carr) * (carrError - oldCarrError) \
+                + carrError * (PDIcarr / tau1carr)                 # :308
+            oldCarrNco = carrNco; oldCarrError = carrError         # :310-311
+            tr["carrFreq"][loopCnt - 1] = carrFreq                 # :314
+            carrFreq = carrFreqBasis + carrNco                     # :317
+            sE = math.sqrt(I_E * I_E + Q_E * Q_E); sL = math.sqrt(I_L * I_L + Q_L * Q_L)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                codeError = float((np.float64(sE) - sL) / (np.float64(sE) + sL))           # :322
+            codeNco = oldCodeNco + (tau2code / tau1code) * (codeError - oldCodeError) \
+                + codeError * (PDIcode / tau1code)                 # :326
+            oldCodeNco = codeNco; oldCodeError = codeError         # :328-329
+            tr["codeFreq"][loopCnt - 1] = codeFreq                 # :332
+            codeFreq = s.codeFreqBasis - codeNco                   # :335
+            tr["dllDiscr"][loopCnt - 1] = codeError                # :338-341
+            tr["dllDiscrFilt"][loopCnt - 1] = codeNco
+            tr["pllDiscr"][loopCnt - 1] = carrError
+            tr["pllDiscrFilt"][loopCnt - 1] = carrNco
+            tr["I_E"][loopCnt - 1] = I_E; tr["I_P"][loopCnt - 1] = I_P; tr["I_L"][loopCnt - 1] = I_L   # :343-348
+            tr["Q_E"][loopCnt - 1] = Q_E; tr["Q_P"][loopCnt - 1] = Q_P; tr["Q_L"][loopCnt - 1] = Q_L
+            if loopCnt % s.CNo_VSMinterval == 0:                   # :351
+                vsmCnt += 1
+                lo = loopCnt - s.CNo_VSMinterval
+                tr["VSMValue"][vsmCnt - 1] = CNoVSM(tr["I_P"][lo:loopCnt], tr["Q_P"][lo:loopCnt],
+                                                    s.CNo_accTime)   # :353
+                tr["VSMIndex"][vsmCnt - 1] = loopCnt               # :356
+        tr["status"] = channel[ch]["status"]                       # :365
+    return out
