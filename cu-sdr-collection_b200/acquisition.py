@@ -1,0 +1,47 @@
+"""``acqResults = acquisition(longSignal, settings)`` — host mirror of
+GPS/GPS_L1CA/include/acquisition.m (signature :1, result fields :130-134, console line
+:154,209,286,292).  The search itself runs on the GPU through ``gc_acquire_host``."""
+from __future__ import annotations
+
+import sys
+
+import numpy as np
+
+from .engine import Engine, GnssCorrError
+from .settings import Settings
+
+
+def _to_int8_iq(longSignal: np.ndarray) -> np.ndarray:
+    x = np.asarray(longSignal)
+    if not np.iscomplexobj(x):
+        raise GnssCorrError("real-valued longSignal (fileType 1) is not implemented")
+    re, im = x.real, x.imag
+    if not (np.all(re == np.rint(re)) and np.all(im == np.rint(im)) and
+            np.max(np.abs(re)) <= 128 and np.max(np.abs(im)) <= 128):
+        raise GnssCorrError("longSignal is not 8-bit integer valued; the accelerated path needs the raw 'schar' samples")
+    iq = np.empty(2 * x.size, dtype=np.int8)
+    iq[0::2] = re.astype(np.int8)
+    iq[1::2] = im.astype(np.int8)
+    return iq
+
+
+def acquisition(longSignal, settings: Settings, engine: Engine | None = None, verbose: bool = True) -> dict:
+    """Same contract as the reference function: ``longSignal`` is the complex row vector
+    postProcessing.m:88-96 builds from the first max(42, acqNonCohTime+2) code periods (an int8
+    I,Q-interleaved array is accepted too); returns ``acqResults`` with 1x32 ``carrFreq``,
+    ``codePhase`` and ``peakMetric`` (``carrFreq == 0`` means not acquired)."""
+    own = engine is None
+    eng = engine or Engine(settings)
+    try:
+        x = np.asarray(longSignal)
+        iq = x if x.dtype == np.int8 else _to_int8_iq(x)
+        r = eng.acquire(settings.acqSatelliteList, host_iq=iq)
+    finally:
+        if own:
+            eng.close()
+    if verbose:                                   # acquisition.m:154,209,286,292
+        sys.stdout.write("(")
+        for prn in settings.acqSatelliteList:
+            sys.stdout.write("%02d " % prn if r["carrFreq"][prn - 1] != 0 else ". ")
+        sys.stdout.write(")\n")
+    return r

@@ -1,0 +1,98 @@
+// Host/device interface of the acquisition kernels (internal to libgnsscorr).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gc {
+
+// ---- fused 33 x (32 x 31) path, FFT length 32736 -------------------------------------------
+constexpr int kFusedC = 33;
+constexpr int kFusedR = 992;
+constexpr int kFusedL = kFusedC * kFusedR;
+
+struct FwdColsParams {
+    const int8_t* rec;        // resident record (int8 I,Q)
+    long long winStart;       // sample index of longSignal(1) in the record
+    int N;                    // samplesPerCode
+    int nonCoh;
+    const uint64_t* dphi;     // [nBins] carrier phase increment per sample (turns, 0.64 fixed point)
+    const int8_t* codeTab;    // [nPrn][N] +-1 resampled replicas (code mode)
+    float2* out;              // [nRows][33][992]
+    const float2* twL;        // [33][992]  w_L^(j1*x), forward sign
+};
+
+struct RowsParams {
+    float2* X;                // forward: rows transformed in place; inverse: spectra [nBins*nonCoh][33][992]
+    const float2* Cc;         // [nPrnSlots][33][992] conj(FFT(code))/L
+    float2* W;                // inverse output [nPrnChunk][nBins][nonCoh][33][992]
+    const float2* twR;        // [32][31]  w_992^(b1*a2), forward sign
+    const float2* twL;        // [33][992]
+    long long nRows;          // forward only
+    int nonCoh, nBins;
+    int prnPerCta, mPerCta;   // warps of an inverse CTA = prnPerCta x mPerCta (same row j1, same bin)
+    int nPrnChunk, prnSlot0;  // list slots [prnSlot0, prnSlot0 + nPrnChunk) are processed by this launch
+    const int* prnList;       // [nSv] PRN-1 per list slot (index into Cc)
+};
+
+struct InvColsParams {
+    const float2* W;
+    int nBins, nonCoh, nPrnChunk, prnSlot0;
+    float* partMax;           // [nPrnSlots][nBins][parts]
+    int* partIdx;
+};
+
+int fused_row_smem_bytes();
+int fused_col_parts();
+cudaError_t launch_fwd_cols(const FwdColsParams& p, int nRows, bool codeMode, cudaStream_t s);
+cudaError_t launch_fwd_rows(const RowsParams& p, cudaStream_t s);
+cudaError_t launch_inv_rows(const RowsParams& p, cudaStream_t s);
+cudaError_t launch_finish_replica(float2* Cc, size_t n, cudaStream_t s);
+cudaError_t launch_inv_cols(const InvColsParams& p, cudaStream_t s);
+
+// ---- generic mixed-radix path (any length whose prime factors are <= 64) --------------------
+struct GenericPlan {
+    int L;                    // FFT length
+    int nf;
+    int fac[32];
+    const float2* tw;         // [L] w_L^t forward sign
+};
+// one Stockham pass over `batch` transforms: src -> dst
+cudaError_t launch_generic_stage(const GenericPlan& pl, int stage, int n, int s, bool inverse,
+                                 const float2* src, float2* dst, long long batch, cudaStream_t st);
+cudaError_t launch_generic_wipe(const int8_t* rec, long long winStart, int N, int nonCoh, int nBins,
+                                const uint64_t* dphi, float2* out, int L, cudaStream_t st);
+cudaError_t launch_generic_code(const int8_t* codeTab, int N, int nPrn, float2* out, int L, cudaStream_t st);
+cudaError_t launch_generic_mul(const float2* X, const float2* Cc, float2* out, int L, long long nKm, cudaStream_t st);
+cudaError_t launch_generic_absacc(const float2* W, int L, int nBins, int nonCoh, int parts,
+                                  float* partMax, int* partIdx, size_t outBase, cudaStream_t st);
+cudaError_t launch_generic_conj_scale(float2* Cc, size_t n, float scale, cudaStream_t st);
+
+// ---- shared by both paths -------------------------------------------------------------------
+struct PeakOut {              // one per PRN slot
+    double peak;              // max(max(results))                      acquisition.m:198
+    int bin;                  // acqCoarseBin, 1-based                  :196
+    int codePhase;            // 1-based                                :198
+};
+cudaError_t launch_sig_power(const int8_t* rec, long long winStart, int N, double* out, cudaStream_t s);
+cudaError_t launch_peak_select(const float* partMax, const int* partIdx, int nPrnSlots, int nBins, int parts,
+                               PeakOut* out, cudaStream_t s);
+
+struct FineParams {
+    const int8_t* rec;
+    long long winStart;
+    int N;                    // samplesPerCode
+    int nPeriods;             // 40   (acquisition.m:146-148)
+    int nFine;                // numOfFineBins (:140)
+    int codeLen;              // 1023
+    double ts, tc;            // 1/fs, 1/codeFreqBasis  (:215)
+    const int8_t* chips;      // [nAcq][codeLen] +-1 chips of the acquired PRNs
+    const int* codePhase;     // [nAcq] 1-based coarse code phase (:221)
+    const uint64_t* dphi;     // [nAcq][nFine] fine-bin phase increments
+    short2* prod;             // [nAcq][nPeriods*N] scratch: sig40cm .* caCode40ms (:232)
+    double* sums;             // [nAcq][nFine][nPeriods][2]  sumPerCode (:235-238)
+    int* best;                // [nAcq] arg-max fine bin, 0-based (:253)
+    double* fineResult;       // [nAcq][nFine]
+};
+cudaError_t launch_fine(const FineParams& p, int nAcq, cudaStream_t s);
+
+}  // namespace gc

@@ -1,0 +1,189 @@
+// Acquisition kernels shared by the fused and the generic path: input power, 2-D peak pick,
+// fine-frequency search.  GPS/GPS_L1CA/include/acquisition.m:151, :196-200, :206-260.
+#include "acq.h"
+#include "common.cuh"
+
+namespace gc {
+
+namespace {
+
+// sigPower = sqrt(var(longSignal(1:N)) * N), var of a complex vector with N-1 (acquisition.m:151).
+// The samples are small integers, so the three sums are exact in 64-bit integers.
+__global__ void __launch_bounds__(1024)
+sig_power_kernel(const int8_t* rec, long long winStart, int N, double* out)
+{
+    long long sI = 0, sQ = 0, s2 = 0;
+    const char2* x = reinterpret_cast<const char2*>(rec) + winStart;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const char2 v = x[i];
+        sI += v.x; sQ += v.y; s2 += (int)v.x * v.x + (int)v.y * v.y;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sI += __shfl_down_sync(0xffffffffu, sI, o);
+        sQ += __shfl_down_sync(0xffffffffu, sQ, o);
+        s2 += __shfl_down_sync(0xffffffffu, s2, o);
+    }
+    __shared__ long long sh[3][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sh[0][warp] = sI; sh[1][warp] = sQ; sh[2][warp] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sI = sQ = s2 = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { sI += sh[0][w]; sQ += sh[1][w]; s2 += sh[2][w]; }
+        const double n = (double)N;
+        const double var = ((double)s2 - ((double)sI * (double)sI + (double)sQ * (double)sQ) / n) / (n - 1.0);
+        *out = sqrt(var * n);
+    }
+}
+
+// [~,bin] = max(max(results,[],2)); [peak,codePhase] = max(max(results))  (acquisition.m:196-198)
+// from the per-(bin, column-tile) partial maxima.  MATLAB's max returns the first maximal index:
+// bin = first row holding the global maximum, codePhase = first column holding it.
+__global__ void __launch_bounds__(32)
+peak_select_kernel(const float* partMax, const int* partIdx, int nBins, int parts, PeakOut* out)
+{
+    const int slot = blockIdx.x, lane = threadIdx.x;
+    float best = -1.f;      // global max value
+    int bbin = 0x7fffffff;  // first row with it
+    int bcol = 0x7fffffff;  // first column with it
+    for (int k = lane; k < nBins; k += 32) {
+        float rmax = -1.f; int ridx = 0x7fffffff;
+        for (int q = 0; q < parts; ++q) {
+            const size_t o = ((size_t)slot * nBins + k) * parts + q;
+            const float v = partMax[o]; const int i = partIdx[o];
+            if (v > rmax || (v == rmax && i < ridx)) { rmax = v; ridx = i; }
+        }
+        if (rmax > best) { best = rmax; bbin = k; bcol = ridx; }
+        else if (rmax == best) { bbin = min(bbin, k); bcol = min(bcol, ridx); }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_down_sync(0xffffffffu, best, o);
+        const int obin = __shfl_down_sync(0xffffffffu, bbin, o);
+        const int ocol = __shfl_down_sync(0xffffffffu, bcol, o);
+        if (ob > best) { best = ob; bbin = obin; bcol = ocol; }
+        else if (ob == best) { bbin = min(bbin, obin); bcol = min(bcol, ocol); }
+    }
+    if (lane == 0) {
+        out[slot].peak = (double)best;
+        out[slot].bin = bbin + 1;
+        out[slot].codePhase = bcol + 1;
+    }
+}
+
+// ---- fine frequency search (acquisition.m:211-250) -----------------------------------------
+// prep: sig40cm .* caCode40ms for one acquired PRN, stored as int16 pairs.
+__global__ void fine_prep_kernel(FineParams p)
+{
+    short2* prod = p.prod;
+    const int a = blockIdx.y;
+    const long long total = (long long)p.nPeriods * p.N;
+    const char2* x = reinterpret_cast<const char2*>(p.rec) + p.winStart + (p.codePhase[a] - 1);   // :221
+    const int8_t* chips = p.chips + (size_t)a * p.codeLen;
+    for (long long gi = blockIdx.x * (long long)blockDim.x + threadIdx.x; gi < total; gi += (long long)gridDim.x * blockDim.x) {
+        // codeValueIndex = floor((ts*(0:40N-1)) / (1/codeFreqBasis))   :215
+        const long long idx = (long long)floor(__ddiv_rn(__dmul_rn(p.ts, (double)gi), p.tc));
+        const int c = chips[idx % p.codeLen];                                                      // :218
+        const char2 v = x[gi];
+        prod[(size_t)a * total + gi] = make_short2((short)(v.x * c), (short)(v.y * c));
+    }
+}
+
+constexpr int kFineBins = 8;   // fine bins handled per thread
+// grid (nPeriods, nAcq, ceil(nFine/8)), block 256: sumPerCode(index) for 8 fine bins (:232-238)
+__global__ void __launch_bounds__(256)
+fine_sum_kernel(FineParams p)
+{
+    const short2* prod = p.prod;
+    const int c = blockIdx.x, a = blockIdx.y, j0 = blockIdx.z * kFineBins;
+    const long long total = (long long)p.nPeriods * p.N;
+    const short2* x = prod + (size_t)a * total + (size_t)c * p.N;
+    uint64_t dphi[kFineBins];
+#pragma unroll
+    for (int j = 0; j < kFineBins; ++j) dphi[j] = (j0 + j < p.nFine) ? p.dphi[a * p.nFine + j0 + j] : 0;
+    float ar[kFineBins], ai[kFineBins];
+#pragma unroll
+    for (int j = 0; j < kFineBins; ++j) ar[j] = ai[j] = 0.f;
+    for (int n = threadIdx.x; n < p.N; n += 256) {
+        const short2 v = x[n];
+        const float I = (float)v.x, Q = (float)v.y;
+        const uint64_t gi = (uint64_t)c * p.N + n;     // finePhasePoints index (:148)
+#pragma unroll
+        for (int j = 0; j < kFineBins; ++j) {
+            float sn, cs;
+            fix_sincos(dphi[j] * gi, &sn, &cs);        // exp(-1i*f*finePhasePoints), :230
+            ar[j] += fmaf(cs, I, sn * Q);
+            ai[j] += fmaf(cs, Q, -sn * I);
+        }
+    }
+    __shared__ double sh[8][kFineBins][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < kFineBins; ++j) {
+        double r = ar[j], i = ai[j];
+        for (int o = 16; o > 0; o >>= 1) {
+            r += __shfl_down_sync(0xffffffffu, r, o);
+            i += __shfl_down_sync(0xffffffffu, i, o);
+        }
+        if (lane == 0) { sh[warp][j][0] = r; sh[warp][j][1] = i; }
+    }
+    __syncthreads();
+    if (threadIdx.x < kFineBins && j0 + threadIdx.x < p.nFine) {
+        double r = 0, i = 0;
+        for (int w = 0; w < 8; ++w) { r += sh[w][threadIdx.x][0]; i += sh[w][threadIdx.x][1]; }
+        double* o = p.sums + (((size_t)a * p.nFine + j0 + threadIdx.x) * p.nPeriods + c) * 2;
+        o[0] = r; o[1] = i;
+    }
+}
+
+// nav-bit-edge search and arg-max over the fine bins (acquisition.m:240-253): for each bin the
+// maximum over the 20 start offsets of |sum of 20 consecutive per-code sums|.
+__global__ void fine_select_kernel(FineParams p)
+{
+    const int a = blockIdx.x;
+    const int half = p.nPeriods / 2;
+    for (int j = threadIdx.x; j < p.nFine; j += blockDim.x) {
+        const double* s = p.sums + ((size_t)a * p.nFine + j) * p.nPeriods * 2;
+        double maxPower = 0;
+        for (int c = 0; c < half; ++c) {
+            double r = 0, i = 0;
+            for (int q = c; q < c + half; ++q) { r += s[2 * q]; i += s[2 * q + 1]; }
+            const double pw = sqrt(r * r + i * i);
+            if (pw > maxPower) maxPower = pw;
+        }
+        p.fineResult[a * p.nFine + j] = maxPower;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int best = 0; double bv = p.fineResult[a * p.nFine];
+        for (int j = 1; j < p.nFine; ++j)
+            if (p.fineResult[a * p.nFine + j] > bv) { bv = p.fineResult[a * p.nFine + j]; best = j; }
+        p.best[a] = best;
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_sig_power(const int8_t* rec, long long winStart, int N, double* out, cudaStream_t s)
+{
+    sig_power_kernel<<<1, 1024, 0, s>>>(rec, winStart, N, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_peak_select(const float* partMax, const int* partIdx, int nPrnSlots, int nBins, int parts,
+                               PeakOut* out, cudaStream_t s)
+{
+    peak_select_kernel<<<nPrnSlots, 32, 0, s>>>(partMax, partIdx, nBins, parts, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fine(const FineParams& p, int nAcq, cudaStream_t s)
+{
+    dim3 g1(148 * 2, nAcq);
+    fine_prep_kernel<<<g1, 256, 0, s>>>(p);
+    dim3 g2(p.nPeriods, nAcq, (p.nFine + kFineBins - 1) / kFineBins);
+    fine_sum_kernel<<<g2, 256, 0, s>>>(p);
+    fine_select_kernel<<<nAcq, 64, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace gc

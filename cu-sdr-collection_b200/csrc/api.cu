@@ -1,0 +1,632 @@
+// C ABI of libgnsscorr.so: handle management and host-side orchestration of the acquisition and
+// tracking kernels.  Declared in include/gnsscorr.h, which cites the reference interface each
+// entry point replaces.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/gnsscorr.h"
+#include "acq.h"
+#include "codes.h"
+#include "common.cuh"
+#include "track.h"
+
+using namespace gc;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+double m_round(double x) { return x >= 0 ? std::floor(x + 0.5) : -std::floor(-x + 0.5); }
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;   // elements
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+constexpr int kMaxSv = 32;
+constexpr int kEvents = 160;
+
+}  // namespace
+
+struct gc_handle {
+    gc_config cfg{};
+    std::string err;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[kEvents]{};
+    gc_stats stats{};
+
+    // derived (acquisition.m:116-124,138-140)
+    int N = 0, L = 0, nBins = 0, nFine = 0, nonCoh = 0;
+    double ts = 0;
+    bool fused = false;
+
+    // resident record
+    const int8_t* rec = nullptr;
+    size_t recBytes = 0;
+    DevBuf<int8_t> recOwned;
+
+    // acquisition
+    DevBuf<float2> twL, twR, twGen, X, T1, T2, Cc, W;
+    DevBuf<uint64_t> dphi, fdphi;
+    DevBuf<int8_t> codeTab, chips;
+    DevBuf<int> prnList, partIdx, fineCodePhase, fineBest;
+    DevBuf<float> partMax;
+    DevBuf<PeakOut> peaks;
+    DevBuf<double> sigPower, fineSums, fineResult;
+    DevBuf<short2> fineProd;
+    GenericPlan plan{};
+    bool replicasReady = false;
+    int parts = 0;
+
+    // tracking
+    DevBuf<TrackChan> chans;
+    DevBuf<int8_t> trackCodes;
+    DevBuf<double> trackOut;
+    DevBuf<int32_t> epochsDone;
+    double tau1code = 0, tau2code = 0, tau1carr = 0, tau2carr = 0;
+};
+
+namespace {
+
+int fail(gc_handle* h, int code, const std::string& msg)
+{
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define GC_CUDA(h, expr)                                                                         \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess)                                                                   \
+            return fail(h, GC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
+    } while (0)
+
+template <class T>
+cudaError_t upload(DevBuf<T>& b, const std::vector<T>& v, cudaStream_t s)
+{
+    cudaError_t e = b.reserve(v.size());
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+}
+
+// w_L^(r*c) = exp(-2*pi*i*r*c/L) tables in float, computed in long double
+std::vector<float2> tw_table_2d(int rows, int cols, int L)   // [r][c] -> w_L^(r*c)
+{
+    std::vector<float2> t((size_t)rows * cols);
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c) {
+            const long long k = ((long long)r * c) % L;
+            const long double a = -two_pi * (long double)k / (long double)L;
+            t[(size_t)r * cols + c] = make_float2((float)cosl(a), (float)sinl(a));
+        }
+    return t;
+}
+
+void calcLoopCoef(double LBW, double zeta, double k, double* tau1, double* tau2)
+{   // Common/calcLoopCoef.m:41-45
+    const double Wn = LBW * 8 * zeta / (4 * zeta * zeta + 1);
+    *tau1 = k / (Wn * Wn);
+    *tau2 = 2.0 * zeta / Wn;
+}
+
+// Replica spectra conj(fft([makeCaTable(PRN) zeros(1,N)]))/L for all PRNs (acquisition.m:158-164)
+int build_replicas(gc_handle* h)
+{
+    const int N = h->N, L = h->L;
+    std::vector<int8_t> tab((size_t)kMaxSv * N);
+    for (int prn = 1; prn <= kMaxSv; ++prn)
+        make_ca_table(prn, h->cfg.sampling_freq, h->cfg.code_freq_basis, h->cfg.code_length, N, tab.data() + (size_t)(prn - 1) * N);
+    GC_CUDA(h, upload(h->codeTab, tab, h->stream));
+    GC_CUDA(h, h->Cc.reserve((size_t)kMaxSv * L));
+    if (h->fused) {
+        FwdColsParams fp{};
+        fp.N = N; fp.codeTab = h->codeTab.p; fp.out = h->Cc.p; fp.twL = h->twL.p;
+        GC_CUDA(h, launch_fwd_cols(fp, kMaxSv, true, h->stream));
+        RowsParams rp{};
+        rp.X = h->Cc.p; rp.twR = h->twR.p; rp.twL = h->twL.p; rp.nRows = (long long)kMaxSv * kFusedC;
+        GC_CUDA(h, launch_fwd_rows(rp, h->stream));
+        GC_CUDA(h, launch_finish_replica(h->Cc.p, (size_t)kMaxSv * L, h->stream));
+    } else {
+        GC_CUDA(h, h->T1.reserve((size_t)std::max(kMaxSv, h->nBins * h->nonCoh) * L));
+        GC_CUDA(h, h->T2.reserve((size_t)std::max(kMaxSv, h->nBins * h->nonCoh) * L));
+        GC_CUDA(h, launch_generic_code(h->codeTab.p, N, kMaxSv, h->T1.p, L, h->stream));
+        float2 *src = h->T1.p, *dst = h->T2.p;
+        int n = L, s = 1;
+        for (int f = 0; f < h->plan.nf; ++f) {
+            GC_CUDA(h, launch_generic_stage(h->plan, f, n, s, false, src, dst, kMaxSv, h->stream));
+            n /= h->plan.fac[f]; s *= h->plan.fac[f];
+            std::swap(src, dst);
+        }
+        GC_CUDA(h, cudaMemcpyAsync(h->Cc.p, src, (size_t)kMaxSv * L * sizeof(float2), cudaMemcpyDeviceToDevice, h->stream));
+        GC_CUDA(h, launch_generic_conj_scale(h->Cc.p, (size_t)kMaxSv * L, 1.0f / (float)L, h->stream));
+    }
+    h->replicasReady = true;
+    return GC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gc_abi_version(void) { return GC_ABI_VERSION; }
+const char* gc_build_arch(void) { return "sm_100a"; }
+int gc_acq_result_len(int32_t signal) { return signal == GC_SIG_GPS_L1CA ? 32 : 0; }
+
+const char* gc_last_error(const gc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int gc_create(gc_handle** out, const gc_config* cfg)
+{
+    if (!out || !cfg) return fail(nullptr, GC_ERR_ARG, "gc_create: null argument");
+    *out = nullptr;
+    if (cfg->abi_version != GC_ABI_VERSION) return fail(nullptr, GC_ERR_ARG, "gc_create: abi_version mismatch");
+    if (cfg->signal != GC_SIG_GPS_L1CA) return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: only GC_SIG_GPS_L1CA is implemented");
+    if (cfg->file_type != 2 || cfg->sample_bytes != 1)
+        return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: only fileType 2 (I/Q) with dataType 'schar' is implemented");
+    if (!(cfg->sampling_freq > 0) || !(cfg->code_freq_basis > 0) || cfg->code_length != 1023 || cfg->acq_noncoh_time < 1 ||
+        !(cfg->acq_search_step > 0) || cfg->cno_vsm_interval < 2)
+        return fail(nullptr, GC_ERR_ARG, "gc_create: invalid settings");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(nullptr, GC_ERR_CUDA, std::string("gc_create: no CUDA device (") + cudaGetErrorString(ce) + ") - this engine has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, GC_ERR_ARG, "gc_create: bad device ordinal");
+    cudaDeviceProp prop{};
+    cudaGetDeviceProperties(&prop, cfg->device);
+    if (prop.major != 10)
+        return fail(nullptr, GC_ERR_CUDA, "gc_create: kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+
+    gc_handle* h = new gc_handle();
+    h->cfg = *cfg;
+    auto bail = [&](int rc) { g_create_error = h->err; gc_destroy(h); return rc; };
+    if (cudaSetDevice(cfg->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(GC_ERR_CUDA); }
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(GC_ERR_CUDA); }
+    for (auto& e : h->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) { h->err = "cudaEventCreate failed"; return bail(GC_ERR_CUDA); }
+
+    // acquisition.m:116-124,138-140
+    h->N = (int)m_round(cfg->sampling_freq / (cfg->code_freq_basis / (double)cfg->code_length));
+    h->L = 2 * h->N;
+    h->ts = 1 / cfg->sampling_freq;
+    h->nBins = (int)m_round(cfg->acq_search_band * 2 / cfg->acq_search_step) + 1;
+    h->nFine = (int)m_round(cfg->acq_search_step / 25.0) + 1;
+    h->nonCoh = cfg->acq_noncoh_time;
+    h->fused = (h->L == kFusedL) && !getenv("GC_FORCE_GENERIC");
+    h->stats.fft_len = h->L;
+    h->stats.acq_path = h->fused ? 1 : 0;
+
+    auto setup = [&]() -> int {
+        if (h->fused) {
+            GC_CUDA(h, upload(h->twL, tw_table_2d(kFusedC, kFusedR, kFusedL), h->stream));
+            GC_CUDA(h, upload(h->twR, tw_table_2d(32, 31, kFusedR), h->stream));
+            h->parts = fused_col_parts();
+        } else {
+            h->plan.L = h->L; h->plan.nf = 0;
+            int m = h->L;
+            while (m % 4 == 0) { h->plan.fac[h->plan.nf++] = 4; m /= 4; }
+            for (int f = 2; m > 1; ++f)
+                while (m % f == 0) {
+                    if (f > 64 || h->plan.nf >= 32) return fail(h, GC_ERR_UNSUPPORTED, "FFT length 2*samplesPerCode has a prime factor > 64");
+                    h->plan.fac[h->plan.nf++] = f; m /= f;
+                }
+            GC_CUDA(h, upload(h->twGen, tw_table_2d(2, h->L, h->L), h->stream));
+            h->plan.tw = h->twGen.p + h->L;   // row 1 of the [2][L] table = w_L^t
+            h->parts = 8;
+        }
+        calcLoopCoef(cfg->dll_noise_bandwidth, cfg->dll_damping_ratio, 1.0, &h->tau1code, &h->tau2code);    // tracking.m:100
+        calcLoopCoef(cfg->pll_noise_bandwidth, cfg->pll_damping_ratio, 0.25, &h->tau1carr, &h->tau2carr);   // tracking.m:109
+        int rc = build_replicas(h);
+        if (rc != GC_OK) return rc;
+        GC_CUDA(h, cudaStreamSynchronize(h->stream));
+        return GC_OK;
+    };
+    int rc = setup();
+    if (rc != GC_OK) return bail(rc);
+    *out = h;
+    return GC_OK;
+}
+
+void gc_destroy(gc_handle* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    h->recOwned.release();
+    h->twL.release(); h->twR.release(); h->twGen.release(); h->X.release(); h->T1.release(); h->T2.release();
+    h->Cc.release(); h->W.release(); h->dphi.release(); h->fdphi.release(); h->codeTab.release(); h->chips.release();
+    h->prnList.release(); h->partIdx.release(); h->fineCodePhase.release(); h->fineBest.release(); h->partMax.release();
+    h->peaks.release(); h->sigPower.release(); h->fineSums.release(); h->fineResult.release(); h->fineProd.release();
+    h->chans.release(); h->trackCodes.release(); h->trackOut.release(); h->epochsDone.release();
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int gc_set_record_host(gc_handle* h, const void* bytes, size_t nbytes)
+{
+    if (!h || !bytes || nbytes == 0) return fail(h, GC_ERR_ARG, "gc_set_record_host: bad argument");
+    cudaSetDevice(h->cfg.device);
+    const size_t cap = ((nbytes + 15) & ~(size_t)15) + 256;
+    GC_CUDA(h, h->recOwned.reserve(cap));
+    GC_CUDA(h, cudaMemcpyAsync(h->recOwned.p, bytes, nbytes, cudaMemcpyHostToDevice, h->stream));
+    GC_CUDA(h, cudaMemsetAsync(h->recOwned.p + nbytes, 0, cap - nbytes, h->stream));
+    GC_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->rec = h->recOwned.p;
+    h->recBytes = nbytes;
+    return GC_OK;
+}
+
+int gc_set_record_device(gc_handle* h, const void* dptr, size_t nbytes)
+{
+    if (!h || !dptr || nbytes == 0) return fail(h, GC_ERR_ARG, "gc_set_record_device: bad argument");
+    if (((uintptr_t)dptr & 15) != 0) return fail(h, GC_ERR_ARG, "gc_set_record_device: pointer must be 16-byte aligned");
+    h->rec = static_cast<const int8_t*>(dptr);
+    h->recBytes = nbytes;
+    return GC_OK;
+}
+
+static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int32_t* svList,
+                        double* carrFreq, double* codePhase, double* peakMetric,
+                        int32_t* coarseBin, int32_t* coarseCodePhase)
+{
+    const gc_config& c = h->cfg;
+    const int N = h->N, L = h->L, nBins = h->nBins, nonCoh = h->nonCoh, nKm = nBins * nonCoh;
+    if (!h->rec) return fail(h, GC_ERR_NO_RECORD, "gc_acquire: no record resident");
+    if (nSv < 1 || nSv > kMaxSv || !svList || !carrFreq || !codePhase || !peakMetric)
+        return fail(h, GC_ERR_ARG, "gc_acquire: bad argument");
+    for (int i = 0; i < nSv; ++i)
+        if (svList[i] < 1 || svList[i] > kMaxSv) return fail(h, GC_ERR_ARG, "gc_acquire: PRN out of range 1..32");
+    const int codeLen = std::max(42, nonCoh + 2);                                    // postProcessing.m:86
+    const long long recSamples = (long long)(h->recBytes / 2);
+    if (winStart < 0 || winStart + (long long)codeLen * N > recSamples)
+        return fail(h, GC_ERR_SHORT_RECORD, "gc_acquire: record shorter than max(42, acqNonCohTime+2) code periods");
+    cudaSetDevice(c.device);
+    cudaStream_t st = h->stream;
+    int launches = 0, evn = 0;
+    auto mark = [&]() { cudaEventRecord(h->ev[evn], st); return evn++; };
+
+    for (int i = 0; i < kMaxSv; ++i) {
+        carrFreq[i] = codePhase[i] = peakMetric[i] = 0;                              // acquisition.m:130-134
+        if (coarseBin) coarseBin[i] = 0;
+        if (coarseCodePhase) coarseCodePhase[i] = 0;
+    }
+    // coarse bin frequencies (:169) and their per-sample phase increments
+    std::vector<double> coarseFreq(nBins);
+    std::vector<uint64_t> dphi(nBins);
+    for (int k = 0; k < nBins; ++k) {
+        coarseFreq[k] = c.IF + c.acq_search_band - c.acq_search_step * k;
+        dphi[k] = turns_to_fix(coarseFreq[k] * h->ts);
+    }
+    GC_CUDA(h, upload(h->dphi, dphi, st));
+    std::vector<int> prnIdx(nSv);
+    for (int i = 0; i < nSv; ++i) prnIdx[i] = svList[i] - 1;
+    GC_CUDA(h, upload(h->prnList, prnIdx, st));
+    GC_CUDA(h, h->partMax.reserve((size_t)nSv * nBins * h->parts));
+    GC_CUDA(h, h->partIdx.reserve((size_t)nSv * nBins * h->parts));
+    GC_CUDA(h, h->peaks.reserve(nSv));
+    GC_CUDA(h, h->sigPower.reserve(1));
+    GC_CUDA(h, h->X.reserve((size_t)nKm * L));
+
+    const int e0 = mark();
+    GC_CUDA(h, launch_sig_power(h->rec, winStart, N, h->sigPower.p, st)); ++launches;   // :151
+    float rowsMs = 0, colsMs = 0;
+    std::vector<std::pair<int, int>> rowEv, colEv;
+    int e1;
+    if (h->fused) {
+        FwdColsParams fp{};
+        fp.rec = h->rec; fp.winStart = winStart; fp.N = N; fp.nonCoh = nonCoh; fp.dphi = h->dphi.p;
+        fp.out = h->X.p; fp.twL = h->twL.p;
+        GC_CUDA(h, launch_fwd_cols(fp, nKm, false, st)); ++launches;
+        RowsParams rp{};
+        rp.X = h->X.p; rp.twR = h->twR.p; rp.twL = h->twL.p; rp.nRows = (long long)nKm * kFusedC;
+        GC_CUDA(h, launch_fwd_rows(rp, st)); ++launches;
+        e1 = mark();
+        // PRN chunks sized so the inverse work buffer stays below ~2.5 GB
+        int chunk = (int)std::max<long long>(1, (long long)(2.5e9 / ((double)nKm * L * sizeof(float2))));
+        if (const char* e = getenv("GC_ACQ_CHUNK_PRNS")) chunk = std::max(1, atoi(e));
+        chunk = std::min(chunk, nSv);
+        GC_CUDA(h, h->W.reserve((size_t)chunk * nKm * L));
+        for (int s0 = 0; s0 < nSv; s0 += chunk) {
+            const int nc = std::min(chunk, nSv - s0);
+            RowsParams ip{};
+            ip.X = h->X.p; ip.Cc = h->Cc.p; ip.W = h->W.p; ip.twR = h->twR.p; ip.twL = h->twL.p;
+            ip.nonCoh = nonCoh; ip.nBins = nBins; ip.prnPerCta = 2; ip.mPerCta = 4;
+            ip.nPrnChunk = nc; ip.prnSlot0 = s0; ip.prnList = h->prnList.p;
+            const int a = mark();
+            GC_CUDA(h, launch_inv_rows(ip, st)); ++launches;
+            const int b = mark();
+            InvColsParams cp{};
+            cp.W = h->W.p; cp.nBins = nBins; cp.nonCoh = nonCoh; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
+            cp.partMax = h->partMax.p; cp.partIdx = h->partIdx.p;
+            GC_CUDA(h, launch_inv_cols(cp, st)); ++launches;
+            const int d = mark();
+            rowEv.push_back({a, b}); colEv.push_back({b, d});
+            if (evn > kEvents - 8) { GC_CUDA(h, cudaStreamSynchronize(st)); }
+        }
+    } else {
+        GC_CUDA(h, h->T1.reserve((size_t)std::max(kMaxSv, nKm) * L));
+        GC_CUDA(h, h->T2.reserve((size_t)std::max(kMaxSv, nKm) * L));
+        GC_CUDA(h, launch_generic_wipe(h->rec, winStart, N, nonCoh, nBins, h->dphi.p, h->T1.p, L, st)); ++launches;
+        float2 *src = h->T1.p, *dst = h->T2.p;
+        int n = L, s = 1;
+        for (int f = 0; f < h->plan.nf; ++f) {
+            GC_CUDA(h, launch_generic_stage(h->plan, f, n, s, false, src, dst, nKm, st)); ++launches;
+            n /= h->plan.fac[f]; s *= h->plan.fac[f];
+            std::swap(src, dst);
+        }
+        GC_CUDA(h, cudaMemcpyAsync(h->X.p, src, (size_t)nKm * L * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+        e1 = mark();
+        for (int i = 0; i < nSv; ++i) {
+            const int a = mark();
+            GC_CUDA(h, launch_generic_mul(h->X.p, h->Cc.p + (size_t)prnIdx[i] * L, h->T1.p, L, nKm, st)); ++launches;
+            src = h->T1.p; dst = h->T2.p; n = L; s = 1;
+            for (int f = 0; f < h->plan.nf; ++f) {
+                GC_CUDA(h, launch_generic_stage(h->plan, f, n, s, true, src, dst, nKm, st)); ++launches;
+                n /= h->plan.fac[f]; s *= h->plan.fac[f];
+                std::swap(src, dst);
+            }
+            const int b = mark();
+            GC_CUDA(h, launch_generic_absacc(src, L, nBins, nonCoh, h->parts, h->partMax.p, h->partIdx.p,
+                                             (size_t)i * nBins * h->parts, st)); ++launches;
+            const int d = mark();
+            rowEv.push_back({a, b}); colEv.push_back({b, d});
+            if (evn > kEvents - 8) {
+                GC_CUDA(h, cudaStreamSynchronize(st));
+                for (auto& pr : rowEv) { float ms; cudaEventElapsedTime(&ms, h->ev[pr.first], h->ev[pr.second]); rowsMs += ms; }
+                for (auto& pr : colEv) { float ms; cudaEventElapsedTime(&ms, h->ev[pr.first], h->ev[pr.second]); colsMs += ms; }
+                rowEv.clear(); colEv.clear();
+                evn = 3;   // keep e0, e1 (indices 0,1) and one spare
+            }
+        }
+    }
+    GC_CUDA(h, launch_peak_select(h->partMax.p, h->partIdx.p, nSv, nBins, h->parts, h->peaks.p, st)); ++launches;
+    const int e2 = mark();
+    std::vector<PeakOut> peaks(nSv);
+    double sigPower = 0;
+    GC_CUDA(h, cudaMemcpyAsync(peaks.data(), h->peaks.p, nSv * sizeof(PeakOut), cudaMemcpyDeviceToHost, st));
+    GC_CUDA(h, cudaMemcpyAsync(&sigPower, h->sigPower.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    GC_CUDA(h, cudaStreamSynchronize(st));
+
+    // threshold (:200-206) and fine search for the PRNs above it
+    std::vector<int> acq;   // indices into svList
+    for (int i = 0; i < nSv; ++i) {
+        const int prn = svList[i];
+        peakMetric[prn - 1] = peaks[i].peak / sigPower / nonCoh;                     // :200
+        if (coarseBin) coarseBin[prn - 1] = peaks[i].bin;
+        if (coarseCodePhase) coarseCodePhase[prn - 1] = peaks[i].codePhase;
+        if (peakMetric[prn - 1] > c.acq_threshold) acq.push_back(i);                 // :206
+    }
+    const int nAcq = (int)acq.size();
+    h->stats.n_acquired = nAcq;
+    const int e3a = mark();
+    if (nAcq > 0) {
+        const int nPeriods = 40;                                                     // :146-148
+        std::vector<int8_t> chips((size_t)nAcq * 1023);
+        std::vector<int> cps(nAcq);
+        std::vector<uint64_t> fd((size_t)nAcq * h->nFine);
+        std::vector<double> fineFreq((size_t)nAcq * h->nFine);
+        for (int a = 0; a < nAcq; ++a) {
+            const int i = acq[a];
+            ca_code(svList[i], chips.data() + (size_t)a * 1023);                     // :213
+            cps[a] = peaks[i].codePhase;
+            for (int j = 0; j < h->nFine; ++j) {
+                fineFreq[(size_t)a * h->nFine + j] = coarseFreq[peaks[i].bin - 1] + c.acq_search_step / 2 - 25.0 * j;   // :227
+                fd[(size_t)a * h->nFine + j] = turns_to_fix(fineFreq[(size_t)a * h->nFine + j] * h->ts);
+            }
+        }
+        GC_CUDA(h, upload(h->chips, chips, st));
+        GC_CUDA(h, upload(h->fineCodePhase, cps, st));
+        GC_CUDA(h, upload(h->fdphi, fd, st));
+        GC_CUDA(h, h->fineProd.reserve((size_t)nAcq * nPeriods * N));
+        GC_CUDA(h, h->fineSums.reserve((size_t)nAcq * h->nFine * nPeriods * 2));
+        GC_CUDA(h, h->fineResult.reserve((size_t)nAcq * h->nFine));
+        GC_CUDA(h, h->fineBest.reserve(nAcq));
+        FineParams fp{};
+        fp.rec = h->rec; fp.winStart = winStart; fp.N = N; fp.nPeriods = nPeriods; fp.nFine = h->nFine; fp.codeLen = 1023;
+        fp.ts = h->ts; fp.tc = 1 / c.code_freq_basis;
+        fp.chips = h->chips.p; fp.codePhase = h->fineCodePhase.p; fp.dphi = h->fdphi.p; fp.prod = h->fineProd.p;
+        fp.sums = h->fineSums.p; fp.best = h->fineBest.p; fp.fineResult = h->fineResult.p;
+        GC_CUDA(h, launch_fine(fp, nAcq, st)); launches += 3;
+        std::vector<int> best(nAcq);
+        GC_CUDA(h, cudaMemcpyAsync(best.data(), h->fineBest.p, nAcq * sizeof(int), cudaMemcpyDeviceToHost, st));
+        const int e3b = mark(); (void)e3b;
+        GC_CUDA(h, cudaStreamSynchronize(st));
+        for (int a = 0; a < nAcq; ++a) {
+            const int prn = svList[acq[a]];
+            carrFreq[prn - 1] = fineFreq[(size_t)a * h->nFine + best[a]];            // :254
+            codePhase[prn - 1] = peaks[acq[a]].codePhase;                            // :256
+            if (carrFreq[prn - 1] == 0) carrFreq[prn - 1] = 1;                       // :258
+        }
+    } else {
+        mark();
+        GC_CUDA(h, cudaStreamSynchronize(st));
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[e0], h->ev[e1]); h->stats.acq_fwd_ms = ms;
+    cudaEventElapsedTime(&ms, h->ev[e1], h->ev[e2]); h->stats.acq_corr_ms = ms;
+    cudaEventElapsedTime(&ms, h->ev[e3a], h->ev[e3a + 1]); h->stats.acq_fine_ms = ms;
+    h->stats.acq_total_ms = h->stats.acq_fwd_ms + h->stats.acq_corr_ms + h->stats.acq_fine_ms;
+    for (auto& pr : rowEv) { cudaEventElapsedTime(&ms, h->ev[pr.first], h->ev[pr.second]); rowsMs += ms; }
+    for (auto& pr : colEv) { cudaEventElapsedTime(&ms, h->ev[pr.first], h->ev[pr.second]); colsMs += ms; }
+    h->stats.corr_rows_ms = rowsMs;
+    h->stats.corr_cols_ms = colsMs;
+    h->stats.acq_launches = launches;
+    return GC_OK;
+}
+
+int gc_acquire(gc_handle* h, int32_t nSv, const int32_t* svList,
+               double* carrFreq, double* codePhase, double* peakMetric,
+               int32_t* coarseBin, int32_t* coarseCodePhase)
+{
+    if (!h) return GC_ERR_ARG;
+    // fseek(fid, dataAdaptCoeff*skipNumberOfBytes) (postProcessing.m:74): skip counts complex samples
+    return acquire_impl(h, (long long)h->cfg.skip_number_of_bytes, nSv, svList, carrFreq, codePhase, peakMetric,
+                        coarseBin, coarseCodePhase);
+}
+
+int gc_acquire_host(gc_handle* h, const int8_t* iq, size_t nSamples, int32_t nSv, const int32_t* svList,
+                    double* carrFreq, double* codePhase, double* peakMetric,
+                    int32_t* coarseBin, int32_t* coarseCodePhase)
+{
+    if (!h || !iq) return fail(h, GC_ERR_ARG, "gc_acquire_host: bad argument");
+    int rc = gc_set_record_host(h, iq, nSamples * 2);
+    if (rc != GC_OK) return rc;
+    return acquire_impl(h, 0, nSv, svList, carrFreq, codePhase, peakMetric, coarseBin, coarseCodePhase);
+}
+
+// Common/CNoVSM.m:38-47 on the host (40 values every 40 epochs — scalar work)
+static double cno_vsm(const double* I, const double* Q, int n, double T)
+{
+    std::vector<double> Z(n);
+    double Zm = 0;
+    for (int i = 0; i < n; ++i) { Z[i] = I[i] * I[i] + Q[i] * Q[i]; Zm += Z[i]; }
+    Zm /= n;
+    double Zv = 0;
+    for (int i = 0; i < n; ++i) Zv += (Z[i] - Zm) * (Z[i] - Zm);
+    Zv /= (n - 1);
+    // MATLAB sqrt of a negative number is complex: Pav = sqrt(Zm^2 - Zv)
+    const double d = Zm * Zm - Zv;
+    double pr, pi;
+    if (d >= 0) { pr = std::sqrt(d); pi = 0; } else { pr = 0; pi = std::sqrt(-d); }
+    // Nv = 0.5*(Zm - Pav);  CNo = 10*log10(abs((1/T)*Pav/(2*Nv)))
+    const double nr = 0.5 * (Zm - pr), ni = 0.5 * (-pi);
+    const double num = std::hypot(pr, pi) * (1 / T), den = 2 * std::hypot(nr, ni);
+    return 10 * std::log10(num / den);
+}
+
+int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq, const double* codePhase,
+             int32_t nEpochs, double* out, double* vsmValue, double* vsmIndex, int32_t* epochsDone)
+{
+    if (!h) return GC_ERR_ARG;
+    const gc_config& c = h->cfg;
+    if (!h->rec) return fail(h, GC_ERR_NO_RECORD, "gc_track: no record resident");
+    if (nCh < 1 || nEpochs < 1 || !sv || !acqFreq || !codePhase || !out || !epochsDone)
+        return fail(h, GC_ERR_ARG, "gc_track: bad argument");
+    cudaSetDevice(c.device);
+    cudaStream_t st = h->stream;
+    const int codeLen = c.code_length;
+    const int stride = (codeLen + 2 + 15) & ~15;
+    std::vector<TrackChan> chans(nCh);
+    std::vector<int8_t> tabs((size_t)nCh * stride, 0);
+    for (int ch = 0; ch < nCh; ++ch) {
+        chans[ch].prn = sv[ch]; chans[ch].pad = 0;
+        chans[ch].acqFreq = acqFreq[ch];
+        // fseek(fid, dataAdaptCoeff*(skipNumberOfBytes + codePhase-1)) (tracking.m:150)
+        chans[ch].startSample = (long long)c.skip_number_of_bytes + (long long)codePhase[ch] - 1;
+        if (sv[ch] != 0) {
+            if (sv[ch] < 1 || sv[ch] > kMaxSv) return fail(h, GC_ERR_ARG, "gc_track: PRN out of range 1..32");
+            if (chans[ch].startSample < 0) return fail(h, GC_ERR_ARG, "gc_track: codePhase must be >= 1");
+            int8_t* t = tabs.data() + (size_t)ch * stride;
+            ca_code(sv[ch], t + 1);                        // tracking.m:156
+            t[0] = t[codeLen]; t[codeLen + 1] = t[1];      // [c(L) c c(1)]  :158
+        }
+    }
+    TrackParams p{};
+    p.rec = h->rec;
+    p.recSamples = (long long)(h->recBytes / 2);
+    p.fs = c.sampling_freq; p.codeFreqBasis = c.code_freq_basis; p.codeLength = (double)codeLen;
+    p.spc = c.dll_correlator_spacing;
+    p.cA = h->tau2code / h->tau1code; p.cB = c.int_time / h->tau1code;     // tracking.m:326
+    p.pA = h->tau2carr / h->tau1carr; p.pB = c.int_time / h->tau1carr;     // tracking.m:308
+    p.nEpochs = nEpochs;
+    p.bufBytes = ((2 * (h->N + 64) + 16) + 15) & ~15;
+    p.codeLen = codeLen; p.codeStride = stride;
+    if (track_smem_bytes(p.bufBytes, codeLen) > 227 * 1024)
+        return fail(h, GC_ERR_UNSUPPORTED, "gc_track: one code period of samples does not fit in shared memory");
+    GC_CUDA(h, upload(h->chans, chans, st));
+    GC_CUDA(h, upload(h->trackCodes, tabs, st));
+    const size_t nOut = (size_t)nCh * GC_TRACK_NFIELDS * nEpochs;
+    GC_CUDA(h, h->trackOut.reserve(nOut));
+    GC_CUDA(h, h->epochsDone.reserve(nCh));
+    p.codeTables = h->trackCodes.p; p.chans = h->chans.p; p.out = h->trackOut.p; p.epochsDone = h->epochsDone.p;
+    GC_CUDA(h, launch_track_fill(h->trackOut.p, nCh, nEpochs, st));
+    cudaEventRecord(h->ev[0], st);
+    GC_CUDA(h, launch_track(p, nCh, st));
+    cudaEventRecord(h->ev[1], st);
+    GC_CUDA(h, cudaMemcpyAsync(out, h->trackOut.p, nOut * sizeof(double), cudaMemcpyDeviceToHost, st));
+    GC_CUDA(h, cudaMemcpyAsync(epochsDone, h->epochsDone.p, nCh * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    GC_CUDA(h, cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+    h->stats.track_kernel_ms = ms;
+    h->stats.track_launches = 2;
+
+    // A short read makes the reference `return` from tracking() (tracking.m:241-245): channels
+    // after the first one that ran out of data stay as initialised.
+    int failed = -1;
+    for (int ch = 0; ch < nCh && failed < 0; ++ch)
+        if (sv[ch] != 0 && epochsDone[ch] < nEpochs) failed = ch;
+    const double inf = std::numeric_limits<double>::infinity();
+    for (int ch = failed + 1; failed >= 0 && ch < nCh; ++ch) {
+        double* o = out + (size_t)ch * GC_TRACK_NFIELDS * nEpochs;
+        for (int f = 0; f < GC_TRACK_NFIELDS; ++f) {
+            const double fill = (f == GC_F_ABSOLUTE_SAMPLE || (f >= GC_F_I_P && f <= GC_F_Q_L)) ? 0.0 : inf;
+            std::fill(o + (size_t)f * nEpochs, o + (size_t)(f + 1) * nEpochs, fill);
+        }
+        epochsDone[ch] = 0;
+    }
+    // C/N0 every VSMinterval epochs over the last VSMinterval prompt values (tracking.m:351-358)
+    const int vint = c.cno_vsm_interval, nV = nEpochs / vint;
+    if (vsmValue && vsmIndex) {
+        std::fill(vsmValue, vsmValue + (size_t)nCh * nV, 0.0);
+        std::fill(vsmIndex, vsmIndex + (size_t)nCh * nV, 0.0);
+        for (int ch = 0; ch < nCh; ++ch) {
+            if (sv[ch] == 0) continue;
+            const double* o = out + (size_t)ch * GC_TRACK_NFIELDS * nEpochs;
+            for (int v = 1; v <= nV && v * vint <= epochsDone[ch]; ++v) {
+                const int lo = v * vint - vint;
+                vsmValue[(size_t)ch * nV + v - 1] = cno_vsm(o + (size_t)GC_F_I_P * nEpochs + lo, o + (size_t)GC_F_Q_P * nEpochs + lo, vint, c.cno_acc_time);
+                vsmIndex[(size_t)ch * nV + v - 1] = v * vint;
+            }
+        }
+    }
+    return GC_OK;
+}
+
+int gc_track_file(gc_handle* h, const char* path, int32_t nCh, const int32_t* sv, const double* acqFreq,
+                  const double* codePhase, int32_t nEpochs, double* out, double* vsmValue, double* vsmIndex,
+                  int32_t* epochsDone)
+{
+    if (!h || !path) return fail(h, GC_ERR_ARG, "gc_track_file: bad argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(h, GC_ERR_IO, std::string("gc_track_file: unable to read file ") + path);   // postProcessing.m:155-158
+    fseek(f, 0, SEEK_END);
+    const long long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    if (sz <= 0) { fclose(f); return fail(h, GC_ERR_IO, "gc_track_file: empty file"); }
+    void* pinned = nullptr;
+    cudaSetDevice(h->cfg.device);
+    if (cudaHostAlloc(&pinned, (size_t)sz, cudaHostAllocDefault) != cudaSuccess) { fclose(f); return fail(h, GC_ERR_CUDA, "gc_track_file: cudaHostAlloc failed"); }
+    const size_t got = fread(pinned, 1, (size_t)sz, f);
+    fclose(f);
+    int rc = (got == (size_t)sz) ? gc_set_record_host(h, pinned, (size_t)sz) : fail(h, GC_ERR_IO, "gc_track_file: short read");
+    cudaFreeHost(pinned);
+    if (rc != GC_OK) return rc;
+    return gc_track(h, nCh, sv, acqFreq, codePhase, nEpochs, out, vsmValue, vsmIndex, epochsDone);
+}
+
+int gc_get_stats(const gc_handle* h, gc_stats* out)
+{
+    if (!h || !out) return GC_ERR_ARG;
+    *out = h->stats;
+    return GC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,38 @@
+// Host/device interface of the tracking kernels (internal to libgnsscorr).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/gnsscorr.h"
+
+#define GC_TRACK_ROWS GC_TRACK_NFIELDS
+
+namespace gc {
+
+struct TrackChan {
+    int32_t prn;             // 0 = channel off
+    int32_t pad;
+    double acqFreq;          // channel.acquiredFreq
+    long long startSample;   // skipNumberOfBytes + codePhase - 1   (tracking.m:150)
+};
+
+struct TrackParams {
+    const int8_t* rec;       // resident IF record, int8 I,Q interleaved, 16-byte aligned
+    long long recSamples;    // complex samples in the record
+    double fs, codeFreqBasis, codeLength, spc;
+    double cA, cB;           // tau2code/tau1code, PDIcode/tau1code  (tracking.m:326)
+    double pA, pB;           // tau2carr/tau1carr, PDIcarr/tau1carr  (tracking.m:308)
+    int nEpochs;
+    int bufBytes;            // bytes staged per epoch (multiple of 16)
+    int codeLen;             // chips per code period
+    int codeStride;          // bytes between channels in codeTables
+    const int8_t* codeTables;   // [nCh][codeStride]: wrapped +-1 table [c(L) c(1..L) c(1)]
+    const TrackChan* chans;
+    double* out;             // [nCh][15][nEpochs]
+    int32_t* epochsDone;
+};
+
+size_t track_smem_bytes(int bufBytes, int codeLen);
+cudaError_t launch_track(const TrackParams& p, int nCh, cudaStream_t stream);
+cudaError_t launch_track_fill(double* out, int nCh, int nEpochs, cudaStream_t stream);
+
+}  // namespace gc

@@ -1,0 +1,187 @@
+"""ctypes binding of ``libgnsscorr.so`` (the C ABI in ``include/gnsscorr.h``) and the ``Engine``
+object the MATLAB-mirroring functions sit on."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .settings import Settings
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+GC_TRACK_NFIELDS = 15
+
+
+class GnssCorrError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libgnsscorr.so")
+
+
+class gc_config(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("signal", C.c_int32),
+                ("file_type", C.c_int32), ("sample_bytes", C.c_int32), ("code_length", C.c_int32),
+                ("acq_noncoh_time", C.c_int32), ("cno_vsm_interval", C.c_int32),
+                ("skip_number_of_bytes", C.c_int64),
+                ("sampling_freq", C.c_double), ("IF", C.c_double), ("code_freq_basis", C.c_double),
+                ("acq_search_band", C.c_double), ("acq_search_step", C.c_double), ("acq_threshold", C.c_double),
+                ("dll_damping_ratio", C.c_double), ("dll_noise_bandwidth", C.c_double),
+                ("dll_correlator_spacing", C.c_double), ("pll_damping_ratio", C.c_double),
+                ("pll_noise_bandwidth", C.c_double), ("int_time", C.c_double), ("cno_acc_time", C.c_double)]
+
+
+class gc_stats(C.Structure):
+    _fields_ = [("acq_total_ms", C.c_float), ("acq_fwd_ms", C.c_float), ("acq_corr_ms", C.c_float),
+                ("acq_fine_ms", C.c_float), ("track_kernel_ms", C.c_float),
+                ("acq_launches", C.c_int32), ("track_launches", C.c_int32), ("fft_len", C.c_int32),
+                ("acq_path", C.c_int32), ("n_acquired", C.c_int32),
+                ("corr_rows_ms", C.c_float), ("corr_cols_ms", C.c_float)]
+
+
+EXPORTS = ["gc_abi_version", "gc_build_arch", "gc_acq_result_len", "gc_create", "gc_destroy",
+           "gc_last_error", "gc_set_record_host", "gc_set_record_device", "gc_acquire",
+           "gc_acquire_host", "gc_track", "gc_track_file", "gc_get_stats"]
+
+_lib = None
+
+
+def load_lib():
+    """Load the CUDA library; there is no fallback, so a missing build is a hard error."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise GnssCorrError(f"{p} is missing - build it with __graft_entry__.build() "
+                            "(make -C cu-sdr-collection_b200/csrc); there is no CPU fallback")
+    lib = C.CDLL(p)
+    vp, i32p, dp = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    lib.gc_abi_version.restype = C.c_int
+    lib.gc_build_arch.restype = C.c_char_p
+    lib.gc_acq_result_len.argtypes = [C.c_int32]
+    lib.gc_create.argtypes = [C.POINTER(vp), C.POINTER(gc_config)]
+    lib.gc_destroy.argtypes = [vp]
+    lib.gc_destroy.restype = None
+    lib.gc_last_error.argtypes = [vp]
+    lib.gc_last_error.restype = C.c_char_p
+    lib.gc_set_record_host.argtypes = [vp, vp, C.c_size_t]
+    lib.gc_set_record_device.argtypes = [vp, vp, C.c_size_t]
+    lib.gc_acquire.argtypes = [vp, C.c_int32, i32p, dp, dp, dp, i32p, i32p]
+    lib.gc_acquire_host.argtypes = [vp, vp, C.c_size_t, C.c_int32, i32p, dp, dp, dp, i32p, i32p]
+    lib.gc_track.argtypes = [vp, C.c_int32, i32p, dp, dp, C.c_int32, dp, dp, dp, i32p]
+    lib.gc_track_file.argtypes = [vp, C.c_char_p, C.c_int32, i32p, dp, dp, C.c_int32, dp, dp, dp, i32p]
+    lib.gc_get_stats.argtypes = [vp, C.POINTER(gc_stats)]
+    _lib = lib
+    return lib
+
+
+def config_from_settings(s: Settings, device: int = 0) -> gc_config:
+    if s.resamplingflag != 0:
+        raise GnssCorrError("resamplingflag == 1 is outside the accelerated path "
+                            "(acquisition.m:50-111); run the reference for that case")
+    if s.fileType != 2 or s.dataType != "schar":
+        raise GnssCorrError("only fileType 2 with dataType 'schar' is implemented")
+    return gc_config(abi_version=1, device=device, signal=0, file_type=s.fileType, sample_bytes=1,
+                     code_length=int(s.codeLength), acq_noncoh_time=int(s.acqNonCohTime),
+                     cno_vsm_interval=int(s.CNo_VSMinterval), skip_number_of_bytes=int(s.skipNumberOfBytes),
+                     sampling_freq=s.samplingFreq, IF=s.IF, code_freq_basis=s.codeFreqBasis,
+                     acq_search_band=s.acqSearchBand, acq_search_step=s.acqSearchStep,
+                     acq_threshold=s.acqThreshold, dll_damping_ratio=s.dllDampingRatio,
+                     dll_noise_bandwidth=s.dllNoiseBandwidth, dll_correlator_spacing=s.dllCorrelatorSpacing,
+                     pll_damping_ratio=s.pllDampingRatio, pll_noise_bandwidth=s.pllNoiseBandwidth,
+                     int_time=s.intTime, cno_acc_time=s.CNo_accTime)
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class Engine:
+    """One engine = one GPU: owns the FFT plan, replica spectra and the resident IF record."""
+
+    def __init__(self, settings: Settings, device: int = 0):
+        self.lib = load_lib()
+        self.settings = settings
+        self._h = C.c_void_p()
+        cfg = config_from_settings(settings, device)
+        rc = self.lib.gc_create(C.byref(self._h), C.byref(cfg))
+        if rc != 0:
+            raise GnssCorrError(f"gc_create failed ({rc}): {self.lib.gc_last_error(None).decode()}")
+        self._keep = None
+
+    def close(self):
+        if self._h:
+            self.lib.gc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise GnssCorrError(f"{what} failed ({rc}): {self.lib.gc_last_error(self._h).decode()}")
+
+    # ---- record -------------------------------------------------------------------------
+    def set_record(self, data):
+        """Make an IF record resident.  ``data``: int8 numpy array (copied host->device) or an
+        int8 CUDA torch tensor (adopted without a copy; kept alive by the engine)."""
+        if isinstance(data, np.ndarray):
+            a = np.ascontiguousarray(data, dtype=np.int8)
+            self._check(self.lib.gc_set_record_host(self._h, a.ctypes.data, a.size), "gc_set_record_host")
+            self._keep = None
+        else:  # torch tensor on the GPU
+            assert data.is_cuda and data.element_size() == 1 and data.is_contiguous()
+            self._check(self.lib.gc_set_record_device(self._h, data.data_ptr(), data.numel()), "gc_set_record_device")
+            self._keep = data
+
+    # ---- acquisition --------------------------------------------------------------------
+    def acquire(self, sv_list=None, host_iq=None):
+        s = self.settings
+        sv = np.asarray(list(sv_list if sv_list is not None else s.acqSatelliteList), dtype=np.int32)
+        n = self.lib.gc_acq_result_len(0)
+        carr, cph, pm = np.zeros(n), np.zeros(n), np.zeros(n)
+        cbin, ccp = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        if host_iq is not None:
+            a = np.ascontiguousarray(host_iq, dtype=np.int8)
+            rc = self.lib.gc_acquire_host(self._h, a.ctypes.data, a.size // 2, sv.size, _ip(sv),
+                                          _dp(carr), _dp(cph), _dp(pm), _ip(cbin), _ip(ccp))
+            self._check(rc, "gc_acquire_host")
+        else:
+            rc = self.lib.gc_acquire(self._h, sv.size, _ip(sv), _dp(carr), _dp(cph), _dp(pm), _ip(cbin), _ip(ccp))
+            self._check(rc, "gc_acquire")
+        return dict(carrFreq=carr, codePhase=cph, peakMetric=pm, coarseBin=cbin, coarseCodePhase=ccp)
+
+    # ---- tracking -----------------------------------------------------------------------
+    def track(self, prn, acq_freq, code_phase, n_epochs, path=None):
+        prn = np.asarray(prn, dtype=np.int32)
+        af = np.asarray(acq_freq, dtype=np.float64)
+        cp = np.asarray(code_phase, dtype=np.float64)
+        nch = prn.size
+        nv = n_epochs // int(self.settings.CNo_VSMinterval)
+        out = np.empty((nch, GC_TRACK_NFIELDS, n_epochs))
+        vv, vi = np.zeros((nch, nv)), np.zeros((nch, nv))
+        done = np.zeros(nch, dtype=np.int32)
+        if path is not None:
+            rc = self.lib.gc_track_file(self._h, os.fsencode(path), nch, _ip(prn), _dp(af), _dp(cp), n_epochs,
+                                        _dp(out), _dp(vv), _dp(vi), _ip(done))
+            self._check(rc, "gc_track_file")
+        else:
+            rc = self.lib.gc_track(self._h, nch, _ip(prn), _dp(af), _dp(cp), n_epochs,
+                                   _dp(out), _dp(vv), _dp(vi), _ip(done))
+            self._check(rc, "gc_track")
+        return out, vv, vi, done
+
+    def stats(self) -> dict:
+        st = gc_stats()
+        self._check(self.lib.gc_get_stats(self._h, C.byref(st)), "gc_get_stats")
+        return {k: getattr(st, k) for k, _ in gc_stats._fields_}

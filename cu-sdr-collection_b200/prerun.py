@@ -1,0 +1,20 @@
+"""``channel = preRun(acqResults, settings)`` — GPS/GPS_L1CA/include/preRun.m:44-72.
+Caller glue between the two hot functions (host side, scalar)."""
+from __future__ import annotations
+
+import numpy as np
+
+from .settings import Settings
+
+
+def preRun(acqResults: dict, settings: Settings) -> list:
+    channel = [dict(PRN=0, acquiredFreq=0.0, codePhase=0, status="-")
+               for _ in range(settings.numberOfChannels)]                       # preRun.m:44-57
+    # [junk, PRNindexes] = sort(peakMetric, 2, 'descend')  — stable, first index wins ties (:60)
+    order = np.argsort(-np.asarray(acqResults["peakMetric"]), kind="stable")
+    n = min(settings.numberOfChannels, int(np.sum(np.asarray(acqResults["carrFreq"]) != 0)))   # :65
+    for ii in range(n):
+        p = int(order[ii])
+        channel[ii] = dict(PRN=p + 1, acquiredFreq=float(acqResults["carrFreq"][p]),
+                           codePhase=int(acqResults["codePhase"][p]), status="T")              # :66-71
+    return channel

@@ -1,0 +1,173 @@
+/*
+ * gnsscorr.h — C ABI of the B200 GNSS correlator engine (libgnsscorr.so).
+ *
+ * This is the drop-in boundary for the two hot functions of every per-signal folder of
+ * gnsscusdr/CU-SDR-Collection.  The reference has no FFI of its own; the interfaces replaced are
+ * two MATLAB function signatures, each called once from postProcessing.m:
+ *
+ *   acqResults              = acquisition(longSignal, settings)   GPS/GPS_L1CA/include/acquisition.m:1
+ *                                                                 (called at include/postProcessing.m:100)
+ *   [trackResults, channel] = tracking(fid, channel, settings)    GPS/GPS_L1CA/include/tracking.m:1
+ *                                                                 (called at include/postProcessing.m:124)
+ *
+ * A thin MEX gateway (matlab/gnsscorr_mex.c) marshals mxArray <-> these POD arguments; the same
+ * entry points are bound from Python with ctypes for all testing.
+ *
+ * Conventions: plain pointers and sizes only; the caller allocates every output; the library owns
+ * all device memory behind the handle; integer return codes (0 = ok, <0 = error, text via
+ * gc_last_error), never exceptions across the ABI; one handle = one GPU = one host thread.
+ * All indices in results are 1-based exactly as the MATLAB code returns them.
+ */
+#ifndef GNSSCORR_H
+#define GNSSCORR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GC_ABI_VERSION 1
+
+/* signal ids (one per reference folder); only GC_SIG_GPS_L1CA is implemented in this round */
+enum { GC_SIG_GPS_L1CA = 0 };
+
+/* error codes */
+enum {
+    GC_OK = 0,
+    GC_ERR_ARG = -1,          /* bad argument / unsupported configuration                          */
+    GC_ERR_CUDA = -2,         /* CUDA runtime failure (text in gc_last_error)                      */
+    GC_ERR_NO_RECORD = -3,    /* no IF record resident                                             */
+    GC_ERR_SHORT_RECORD = -4, /* record shorter than max(42, nonCoh+2) code periods (acquisition)  */
+    GC_ERR_UNSUPPORTED = -5,  /* e.g. resamplingflag==1, FFT length with a prime factor > 64       */
+    GC_ERR_IO = -6            /* gc_track_file: open/read failure (postProcessing.m:155-158)       */
+};
+
+/* POD image of the hot-path fields of the reference's `settings` struct
+ * (GPS/GPS_L1CA/initSettings.m:44-136).  Filled by the MATLAB wrapper / Python mirror. */
+typedef struct gc_config {
+    int32_t abi_version;         /* GC_ABI_VERSION                                                  */
+    int32_t device;              /* CUDA device ordinal                                             */
+    int32_t signal;              /* GC_SIG_*                                                        */
+    int32_t file_type;           /* settings.fileType: 1 = real, 2 = I/Q interleaved (:68)          */
+    int32_t sample_bytes;        /* settings.dataType: 1 = 'schar', 2 = 'int16' (:63)               */
+    int32_t code_length;         /* settings.codeLength (:76)                                       */
+    int32_t acq_noncoh_time;     /* settings.acqNonCohTime (:88)                                    */
+    int32_t cno_vsm_interval;    /* settings.CNo.VSMinterval (:135)                                 */
+    int64_t skip_number_of_bytes;/* settings.skipNumberOfBytes (:56) (the reference multiplies it
+                                    by dataAdaptCoeff, i.e. it counts samples)                      */
+    double sampling_freq;        /* settings.samplingFreq (:72)                                     */
+    double IF;                   /* settings.IF (:71)                                               */
+    double code_freq_basis;      /* settings.codeFreqBasis (:73)                                    */
+    double acq_search_band;      /* settings.acqSearchBand (:86)                                    */
+    double acq_search_step;      /* settings.acqSearchStep (:92)                                    */
+    double acq_threshold;        /* settings.acqThreshold (:90)                                     */
+    double dll_damping_ratio;    /* settings.dllDampingRatio (:100)                                 */
+    double dll_noise_bandwidth;  /* settings.dllNoiseBandwidth (:101)                               */
+    double dll_correlator_spacing;/* settings.dllCorrelatorSpacing (:102)                           */
+    double pll_damping_ratio;    /* settings.pllDampingRatio (:105)                                 */
+    double pll_noise_bandwidth;  /* settings.pllNoiseBandwidth (:106)                               */
+    double int_time;             /* settings.intTime (:108)                                         */
+    double cno_acc_time;         /* settings.CNo.accTime (:133)                                     */
+} gc_config;
+
+typedef struct gc_handle gc_handle;
+
+/* Number of per-epoch result rows gc_track writes per channel and their order
+ * (trackResults fields, GPS/GPS_L1CA/include/tracking.m:48-77). */
+#define GC_TRACK_NFIELDS 15
+enum {
+    GC_F_ABSOLUTE_SAMPLE = 0, GC_F_CODE_FREQ, GC_F_CARR_FREQ, GC_F_I_P, GC_F_I_E, GC_F_I_L,
+    GC_F_Q_E, GC_F_Q_P, GC_F_Q_L, GC_F_DLL_DISCR, GC_F_DLL_DISCR_FILT, GC_F_PLL_DISCR,
+    GC_F_PLL_DISCR_FILT, GC_F_REM_CODE_PHASE, GC_F_REM_CARR_PHASE
+};
+
+/* Length of the acqResults vectors for a signal (32 for GPS L1CA, acquisition.m:130-134). */
+int gc_acq_result_len(int32_t signal);
+
+/* Create / destroy an engine bound to one GPU.  Builds the FFT plan and twiddle tables for
+ * 2*samplesPerCode (acquisition.m:116-122) and the loop coefficients (tracking.m:100-110). */
+int  gc_create(gc_handle** out, const gc_config* cfg);
+void gc_destroy(gc_handle* h);
+/* Text of the last error on this handle (or of the last failed gc_create when h == NULL). */
+const char* gc_last_error(const gc_handle* h);
+
+/* Make an IF record resident in HBM.  `bytes` is the raw file image from byte 0
+ * (what fopen/fread see, postProcessing.m:59-96): int8 I,Q interleaved for fileType 2.
+ * _host copies host->device (pinned or pageable memory); _device adopts a device pointer without
+ * copying (must be 16-byte aligned with its capacity rounded up to a multiple of 16 bytes, which
+ * every cudaMalloc/torch allocation satisfies) — the caller keeps it alive. */
+int gc_set_record_host(gc_handle* h, const void* bytes, size_t nbytes);
+int gc_set_record_device(gc_handle* h, const void* dptr, size_t nbytes);
+
+/* acquisition(longSignal, settings) on the resident record — replaces
+ * GPS/GPS_L1CA/include/acquisition.m:113-292 (resamplingflag must be 0).
+ * longSignal = the max(42, nonCoh+2) code periods starting at skip_number_of_bytes
+ * (postProcessing.m:74,83-96).  svList = settings.acqSatelliteList (PRNs, 1-based).
+ * Outputs (length gc_acq_result_len, indexed PRN-1, zero for PRNs not searched):
+ *   carrFreq, codePhase, peakMetric  = acqResults fields (acquisition.m:130-134,200,254-260)
+ *   coarseBin, coarseCodePhase       = acqCoarseBin / codePhase of :196-198 for every searched
+ *                                      PRN (1-based; diagnostic, may be NULL). */
+int gc_acquire(gc_handle* h, int32_t nSv, const int32_t* svList,
+               double* carrFreq, double* codePhase, double* peakMetric,
+               int32_t* coarseBin, int32_t* coarseCodePhase);
+
+/* Same, but with longSignal supplied from HOST memory as int8 I,Q pairs (what the MEX gateway
+ * passes after checking the complex-double longSignal is integer valued): copies it to the GPU,
+ * runs gc_acquire on it (skip ignored — longSignal already starts at the skip point), copies the
+ * results back.  This is the reference-facing call and the one bench.py times as `e2e`. */
+int gc_acquire_host(gc_handle* h, const int8_t* iq, size_t nSamples,
+                    int32_t nSv, const int32_t* svList,
+                    double* carrFreq, double* codePhase, double* peakMetric,
+                    int32_t* coarseBin, int32_t* coarseCodePhase);
+
+/* tracking(fid, channel, settings) on the resident record — replaces
+ * GPS/GPS_L1CA/include/tracking.m:88-368.
+ *   sv[ch]        channel(ch).PRN (0 = channel off, tracking.m:136)
+ *   acqFreq[ch]   channel(ch).acquiredFreq        codePhase[ch]  channel(ch).codePhase (1-based)
+ *   nEpochs       settings.msToProcess (code periods)
+ *   out           [nCh][GC_TRACK_NFIELDS][nEpochs] doubles; rows pre-filled like tracking.m:51-77
+ *                 (zeros for absoluteSample and I/Q, +inf for the rest)
+ *   vsmValue/vsmIndex  [nCh][nEpochs / cno_vsm_interval]  (trackResults.CNo, tracking.m:80-83,351-358)
+ *   epochsDone    [nCh] completed epochs; < nEpochs means the record ran out (tracking.m:241-245):
+ *                 as in the reference the whole call stops there and later channels stay untouched,
+ *                 and `status` must be left '-' for every channel with epochsDone < nEpochs. */
+int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq,
+             const double* codePhase, int32_t nEpochs,
+             double* out, double* vsmValue, double* vsmIndex, int32_t* epochsDone);
+
+/* Convenience for the MATLAB wrapper: tracking() receives an open fid, which a MEX cannot use;
+ * the wrapper recovers the path with fopen(fid) and calls this.  Reads the file (from byte 0)
+ * into pinned memory, makes it resident, then gc_track. */
+int gc_track_file(gc_handle* h, const char* path,
+                  int32_t nCh, const int32_t* sv, const double* acqFreq,
+                  const double* codePhase, int32_t nEpochs,
+                  double* out, double* vsmValue, double* vsmIndex, int32_t* epochsDone);
+
+/* Device-side timing of the most recent gc_acquire / gc_track, measured with CUDA events on the
+ * engine's own stream (the stream the kernels are launched on). */
+typedef struct gc_stats {
+    float acq_total_ms;        /* all acquisition kernels of the last gc_acquire                    */
+    float acq_fwd_ms;          /* wipe-off + forward FFTs (PRN independent)                         */
+    float acq_corr_ms;         /* spectrum multiply + inverse FFT + |.| + non-coherent sum + argmax */
+    float acq_fine_ms;         /* fine-frequency search                                             */
+    float track_kernel_ms;     /* correlate-and-dump + loop closure kernel of the last gc_track     */
+    int32_t acq_launches;      /* kernels launched by the last gc_acquire                           */
+    int32_t track_launches;    /* kernels launched by the last gc_track                             */
+    int32_t fft_len;           /* 2*samplesPerCode                                                  */
+    int32_t acq_path;          /* 0 = generic mixed-radix path, 1 = fused 33x32x31 path (len 32736) */
+    int32_t n_acquired;        /* PRNs above threshold in the last gc_acquire                       */
+    float corr_rows_ms;        /* dominant kernel: spectrum multiply + inverse row FFT              */
+    float corr_cols_ms;        /* inverse column DFT + |.| + non-coherent sum + row max             */
+} gc_stats;
+int gc_get_stats(const gc_handle* h, gc_stats* out);
+
+/* Library-level: ABI version and the GPU architecture the kernels were compiled for ("sm_100a"). */
+int gc_abi_version(void);
+const char* gc_build_arch(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNSSCORR_H */

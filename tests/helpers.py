@@ -1,0 +1,108 @@
+"""Shared test plumbing: the oracle bindings (checker only), seeded scenes, comparisons."""
+import ctypes as C
+import os
+
+import numpy as np
+
+import np_oracle as O                                   # oracle/ (test infrastructure)
+from cu_sdr_collection_b200 import synth
+from cu_sdr_collection_b200.settings import Settings
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TRACK_FIELDS = O.TRACK_FIELDS
+
+
+class OrcSettings(C.Structure):
+    _fields_ = ([(n, C.c_double) for n in ["samplingFreq", "IF", "codeFreqBasis", "codeLength",
+                                           "acqSearchBand", "acqSearchStep", "acqThreshold"]] +
+                [("acqNonCohTime", C.c_int), ("skipNumberOfBytes", C.c_int)] +
+                [(n, C.c_double) for n in ["dllDampingRatio", "dllNoiseBandwidth", "dllCorrelatorSpacing",
+                                           "pllDampingRatio", "pllNoiseBandwidth", "intTime", "CNo_accTime"]] +
+                [("CNo_VSMinterval", C.c_int)])
+
+
+_orc = None
+
+
+def orc():
+    global _orc
+    if _orc is None:
+        _orc = C.CDLL(os.path.join(ROOT, "oracle", "_build", "libgnss_oracle.so"))
+        _orc.orc_CNoVSM.restype = C.c_double
+    return _orc
+
+
+def orc_settings(s) -> OrcSettings:
+    return OrcSettings(s.samplingFreq, s.IF, s.codeFreqBasis, s.codeLength, s.acqSearchBand, s.acqSearchStep,
+                       s.acqThreshold, s.acqNonCohTime, s.skipNumberOfBytes, s.dllDampingRatio,
+                       s.dllNoiseBandwidth, s.dllCorrelatorSpacing, s.pllDampingRatio, s.pllNoiseBandwidth,
+                       s.intTime, s.CNo_accTime, s.CNo_VSMinterval)
+
+
+def to_oracle_settings(s: Settings) -> "O.Settings":
+    o = O.Settings()
+    for k in vars(o):
+        if hasattr(s, k):
+            setattr(o, k, getattr(s, k))
+    return o
+
+
+def P(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def c_acquisition(raw: np.ndarray, s, prns):
+    """C oracle acquisition; raw starts at the skip point."""
+    cs = orc_settings(s)
+    prn = np.asarray(prns, dtype=np.int32)
+    cf, cp, pm = np.zeros(32), np.zeros(32), np.zeros(32)
+    cb, ccp = np.zeros(32, dtype=np.int32), np.zeros(32, dtype=np.int32)
+    sp = C.c_double()
+    rc = orc().orc_acquisition(P(raw), C.c_size_t(raw.size // 2), C.byref(cs), P(prn), int(prn.size),
+                               P(cf), P(cp), P(pm), P(cb), P(ccp), C.byref(sp))
+    assert rc == 0, rc
+    return dict(carrFreq=cf, codePhase=cp, peakMetric=pm, coarseBin=cb, coarseCodePhase=ccp, sigPower=sp.value)
+
+
+def c_tracking(raw: np.ndarray, s, prn, acq_freq, code_phase, n_epochs, parallel=1):
+    cs = orc_settings(s)
+    prn = np.asarray(prn, dtype=np.int32)
+    af = np.asarray(acq_freq, dtype=np.float64)
+    cp = np.asarray(code_phase, dtype=np.float64)
+    nch = prn.size
+    nv = n_epochs // s.CNo_VSMinterval
+    out = np.zeros((nch, 15, n_epochs))
+    vv, vi = np.zeros((nch, nv)), np.zeros((nch, nv))
+    done = np.zeros(nch, dtype=np.int32)
+    orc().orc_tracking(P(raw), C.c_size_t(raw.size), C.byref(cs), nch, P(prn), P(af), P(cp), n_epochs,
+                       P(out), P(vv), P(vi), P(done), parallel)
+    return out, vv, vi, done
+
+
+def scene(fs, nsat=4, seed=7, cn0=None, IF=20e3):
+    sc = synth.default_scene(fs=fs, IF=IF, nsat=nsat, seed=seed)
+    if cn0 is not None:
+        for s in sc.sats:
+            s.cn0 = cn0
+    return sc
+
+
+def iq_scale(out):
+    """|I_P + i*Q_P| per epoch: the scale the 1e-6 relative tolerance on I/Q sums refers to."""
+    return np.hypot(out[:, 3, :], out[:, 7, :])
+
+
+def track_rel_err(got, ref):
+    """max over epochs of |got-ref| / scale per field; scale = |P| for the six I/Q rows,
+    |ref| (floored) for the others."""
+    errs = {}
+    sc = iq_scale(ref)
+    for i, f in enumerate(TRACK_FIELDS):
+        d = np.abs(got[:, i, :] - ref[:, i, :])
+        if 3 <= i <= 8:
+            e = d / np.maximum(sc, 1e-30)
+        else:
+            e = d / np.maximum(np.abs(ref[:, i, :]), 1e-12)
+        e = np.where(d == 0, 0.0, e)
+        errs[f] = float(np.nanmax(e))
+    return errs

@@ -1,0 +1,202 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against
+the oracle on the same seeded bytes.  Bars: indices (acquired PRN set, code phase, Doppler bin,
+carrFreq grid value, absoluteSample) bit-exact; I/Q correlator sums within 1e-6 of |I_P + iQ_P|;
+peakMetric within 1e-6 relative."""
+import os
+
+import numpy as np
+import pytest
+
+import np_oracle as O
+from cu_sdr_collection_b200 import Engine, acquisition, init_settings, preRun, synth, tracking
+from helpers import ROOT, c_acquisition, c_tracking, scene, to_oracle_settings, track_rel_err
+
+pytestmark = pytest.mark.gpu
+
+IQ_TOL = 1e-6        # north_star: floating-point I_P/Q_P within 1e-6 relative
+METRIC_TOL = 1e-6
+
+
+def _acq_case(fs, nsat, seed, sv_extra, nonCoh=20, cn0=None, band=7000.0):
+    sc = scene(fs, nsat=nsat, seed=seed, cn0=cn0)
+    sv = sorted({x.prn for x in sc.sats} | set(sv_extra))
+    s = init_settings(samplingFreq=fs, IF=20e3, acqNonCohTime=nonCoh, acqSearchBand=band, acqSatelliteList=sv)
+    N = O.samples_per_code(to_oracle_settings(s))
+    raw = synth.make_record(sc, N * max(42, nonCoh + 2) + 64)
+    return sc, s, N, raw
+
+
+def _check_acq(got, ref, sv):
+    idx = np.array(sv) - 1
+    assert np.array_equal(got["carrFreq"] != 0, ref["carrFreq"] != 0), "acquired PRN set differs"
+    assert np.array_equal(got["coarseBin"][idx], ref["coarseBin"][idx]), "Doppler bin index differs"
+    acq = ref["carrFreq"] != 0
+    assert np.array_equal(got["coarseCodePhase"][acq], ref["coarseCodePhase"][acq]), "code phase differs"
+    assert np.array_equal(got["codePhase"], ref["codePhase"])
+    assert np.array_equal(got["carrFreq"], ref["carrFreq"]), "fine carrier frequency differs"
+    rel = np.abs(got["peakMetric"][idx] - ref["peakMetric"][idx]) / ref["peakMetric"][idx]
+    assert rel.max() < METRIC_TOL, rel.max()
+    return rel.max()
+
+
+def test_acquisition_fused_32736_vs_oracle():
+    """BASELINE config 2 geometry (16.368 Msps, 2N = 32736, 29 bins, 20 blocks), PRN subset."""
+    sc, s, N, raw = _acq_case(16.368e6, nsat=5, seed=20260101, sv_extra=[1, 2, 3])
+    eng = Engine(s)
+    got = eng.acquire(s.acqSatelliteList, host_iq=raw)
+    st = eng.stats()
+    assert st["acq_path"] == 1 and st["fft_len"] == 32736
+    ref = c_acquisition(raw, s, s.acqSatelliteList)
+    _check_acq(got, ref, s.acqSatelliteList)
+    for sat in sc.sats:                                   # closed loop: injected signals come back
+        assert got["carrFreq"][sat.prn - 1] != 0
+        assert abs(got["carrFreq"][sat.prn - 1] - (s.IF + sat.doppler)) <= 25
+    eng.close()
+
+
+def test_acquisition_fused_matches_numpy_oracle_too():
+    sc, s, N, raw = _acq_case(16.368e6, nsat=2, seed=5, sv_extra=[9], nonCoh=3)
+    so = to_oracle_settings(s)
+    ref = O.acquisition(O.read_acq_signal(raw, so), so)
+    got = acquisition(raw, s, verbose=False)
+    _check_acq(got, ref, s.acqSatelliteList)
+
+
+@pytest.mark.parametrize("fs,nonCoh", [(2.046e6, 4), (18e6, 2), (4.092e6, 20)])
+def test_acquisition_generic_lengths(fs, nonCoh):
+    """Other FFT lengths go through the generic mixed-radix path: 4092, 36000 (reference default
+    18 Msps), 8184."""
+    sc, s, N, raw = _acq_case(fs, nsat=3, seed=13, sv_extra=[4], nonCoh=nonCoh, cn0=47, band=6000.0)
+    eng = Engine(s)
+    got = eng.acquire(s.acqSatelliteList, host_iq=raw)
+    assert eng.stats()["acq_path"] == 0
+    ref = c_acquisition(raw, s, s.acqSatelliteList)
+    _check_acq(got, ref, s.acqSatelliteList)
+    eng.close()
+
+
+def test_acquisition_noise_only_and_short_record():
+    fs = 16.368e6
+    sc = scene(fs, nsat=0, seed=3)
+    s = init_settings(samplingFreq=fs, acqSatelliteList=[3, 17], acqNonCohTime=2)
+    N = 16368
+    raw = synth.make_record(sc, N * 42)
+    eng = Engine(s)
+    got = eng.acquire(s.acqSatelliteList, host_iq=raw)
+    assert np.all(got["carrFreq"] == 0) and np.all(got["codePhase"] == 0)
+    ref = c_acquisition(raw, s, s.acqSatelliteList)
+    assert np.allclose(got["peakMetric"], ref["peakMetric"], rtol=METRIC_TOL)
+    with pytest.raises(Exception, match="shorter"):
+        eng.acquire(s.acqSatelliteList, host_iq=raw[: 2 * N * 30])
+    eng.close()
+
+
+def _track_case(fs, nEpochs, nsat=3, seed=21, cn0=46):
+    sc = scene(fs, nsat=nsat, seed=seed, cn0=cn0)
+    s = init_settings(samplingFreq=fs, IF=20e3, msToProcess=nEpochs, numberOfChannels=nsat + 1)
+    N = O.samples_per_code(to_oracle_settings(s))
+    raw = synth.make_record(sc, N * (nEpochs + 6))
+    # channel hand-off values as acquisition would give them (exact Doppler grid / code start)
+    prn, af, cp = [], [], []
+    for sat in sc.sats:
+        prn.append(sat.prn)
+        af.append(round((s.IF + sat.doppler) / 25.0) * 25.0)
+        start = (1023 - sat.code_phase) * (fs / 1.023e6)
+        cp.append(float(int(round(start)) % N + 1))
+    prn.append(0); af.append(0.0); cp.append(0.0)       # an unused channel (PRN 0, tracking.m:136)
+    return sc, s, N, raw, prn, af, cp
+
+
+@pytest.mark.parametrize("fs,nEpochs", [(16.368e6, 400), (2.046e6, 1500), (18e6, 100)])
+def test_tracking_vs_oracle(fs, nEpochs):
+    sc, s, N, raw, prn, af, cp = _track_case(fs, nEpochs)
+    eng = Engine(s)
+    eng.set_record(raw)
+    out, vv, vi, done = eng.track(prn, af, cp, nEpochs)
+    ref, rvv, rvi, rdone = c_tracking(raw, s, prn, af, cp, nEpochs)
+    assert np.array_equal(done, rdone) and np.all(done[:-1] == nEpochs) and done[-1] == 0
+    live = np.array(prn) != 0
+    assert np.array_equal(out[live][:, 0], ref[live][:, 0]), "absoluteSample (block boundaries) differ"
+    errs = track_rel_err(out[live], ref[live])
+    for f in ("I_P", "Q_P", "I_E", "Q_E", "I_L", "Q_L"):
+        assert errs[f] < IQ_TOL, (f, errs[f])
+    for f in ("codeFreq", "carrFreq"):
+        assert errs[f] < 1e-6, (f, errs[f])
+    # quantities that pass through zero: absolute agreement (chips, rad, cycles)
+    for i, f in ((13, "remCodePhase"), (14, "remCarrPhase"), (11, "pllDiscr"), (9, "dllDiscr")):
+        d = np.abs(out[live][:, i] - ref[live][:, i])
+        d = np.minimum(d, np.abs(d - 2 * np.pi)) if f == "remCarrPhase" else d
+        assert d.max() < 2e-6, (f, d.max())
+    assert np.allclose(vv[live], rvv[live], rtol=1e-5) and np.array_equal(vi, rvi)
+    # untouched channel keeps the reference's initial fill (tracking.m:51-77)
+    assert np.all(out[-1, 0] == 0) and np.all(out[-1, 3:9] == 0) and np.all(np.isinf(out[-1, 1]))
+    # lock on every injected satellite
+    for c in range(len(sc.sats)):
+        assert np.mean(np.abs(out[c, 3, 50:])) > 3 * np.mean(np.abs(out[c, 7, 50:]))
+    eng.close()
+
+
+def test_tracking_short_record_semantics():
+    sc, s, N, raw, prn, af, cp = _track_case(16.368e6, 120)
+    short = raw[: 2 * N * 70]
+    eng = Engine(s)
+    eng.set_record(short)
+    out, vv, vi, done = eng.track(prn, af, cp, 120)
+    ref, rvv, rvi, rdone = c_tracking(short, s, prn, af, cp, 120)
+    assert np.array_equal(done, rdone) and 0 < done[0] < 120 and np.all(done[1:] == 0)
+    assert np.all(np.isinf(out[1:, 2])) and np.all(out[1:, 3] == 0)
+    n0 = done[0]
+    assert track_rel_err(out[:1, :, :n0], ref[:1, :, :n0])["I_P"] < IQ_TOL
+    assert np.all(np.isinf(out[0, 2, n0:]))
+    eng.close()
+
+
+def test_reference_facing_wrappers_roundtrip(tmp_path):
+    """acquisition() -> preRun() -> tracking(fid, ...) exactly as postProcessing.m:100-124 chains them."""
+    fs = 16.368e6
+    sc = scene(fs, nsat=3, seed=99, cn0=47)
+    s = init_settings(samplingFreq=fs, msToProcess=200, numberOfChannels=4,
+                      acqSatelliteList=sorted({x.prn for x in sc.sats} | {6}), acqNonCohTime=5)
+    N = 16368
+    raw = synth.make_record(sc, N * 260)
+    path = tmp_path / "if.bin"
+    raw.tofile(path)
+    so = to_oracle_settings(s)
+    longSignal = O.read_acq_signal(raw, so)               # complex double row vector, as MATLAB passes it
+    acq = acquisition(longSignal, s, verbose=True)
+    ch = preRun(acq, s)
+    assert sorted(c["PRN"] for c in ch if c["PRN"]) == sorted(x.prn for x in sc.sats)
+    with open(path, "rb") as fid:
+        tr, ch2 = tracking(fid, ch, s)
+    ref_acq = O.acquisition(longSignal, so)
+    ref_ch = O.preRun(ref_acq, so)
+    assert [c["PRN"] for c in ch] == [c["PRN"] for c in ref_ch]
+    ref_tr = O.tracking(raw, ref_ch, so)
+    for i, c in enumerate(ch):
+        if c["PRN"] == 0:
+            assert tr[i]["status"] == "-"
+            continue
+        assert tr[i]["status"] == "T" and tr[i]["PRN"] == c["PRN"]
+        sc_ = np.hypot(ref_tr[i]["I_P"], ref_tr[i]["Q_P"])
+        assert np.max(np.abs(tr[i]["I_P"] - ref_tr[i]["I_P"]) / sc_) < IQ_TOL
+        assert np.max(np.abs(tr[i]["Q_P"] - ref_tr[i]["Q_P"]) / sc_) < IQ_TOL
+        assert np.array_equal(tr[i]["absoluteSample"], ref_tr[i]["absoluteSample"])
+        assert np.allclose(tr[i]["CNo"]["VSMValue"], ref_tr[i]["VSMValue"], rtol=1e-5)
+
+
+def test_golden_fixture_through_cuda():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "l1ca_small.npz"))
+    s = init_settings(samplingFreq=float(g["fs"]), IF=float(g["IF"]), acqNonCohTime=int(g["nonCoh"]),
+                      acqSearchBand=float(g["band"]), msToProcess=int(g["nEpochs"]), numberOfChannels=int(g["nCh"]),
+                      acqSatelliteList=[int(p) for p in g["svList"]])
+    eng = Engine(s)
+    got = eng.acquire(s.acqSatelliteList, host_iq=g["raw"])
+    assert np.array_equal(got["carrFreq"], g["carrFreq"]) and np.array_equal(got["codePhase"], g["codePhase"])
+    idx = g["svList"] - 1
+    assert np.allclose(got["peakMetric"][idx], g["peakMetric"][idx], rtol=METRIC_TOL)
+    eng.set_record(g["raw"])
+    out, vv, vi, done = eng.track(g["chPRN"], g["chFreq"], g["chCodePhase"], s.msToProcess)
+    live = g["chPRN"] != 0
+    errs = track_rel_err(out[live], g["track"][live])
+    assert errs["I_P"] < IQ_TOL and errs["Q_P"] < IQ_TOL and errs["absoluteSample"] == 0
+    eng.close()

@@ -1,0 +1,150 @@
+"""CPU tests: the oracle against ICD known answers, its two restatements against each other,
+MATLAB-semantics helpers, and the committed golden vectors."""
+import os
+
+import numpy as np
+import pytest
+
+import np_oracle as O
+from cu_sdr_collection_b200 import codes, synth
+from helpers import ROOT, c_acquisition, c_tracking, orc, scene, P
+import ctypes as C
+
+# IS-GPS-200 Table 3-Ia, "first 10 chips octal" for PRN 1..32
+ICD_FIRST10 = ["1440", "1620", "1710", "1744", "1133", "1455", "1131", "1454", "1626", "1504", "1642", "1750",
+               "1764", "1772", "1775", "1776", "1156", "1467", "1633", "1715", "1746", "1763", "1063", "1706",
+               "1743", "1761", "1770", "1774", "1127", "1453", "1625", "1712"]
+
+
+def test_ca_code_icd_known_answers():
+    for prn in range(1, 33):
+        c = O.generateCAcode(prn)
+        assert set(np.unique(c)) == {-1.0, 1.0} and c.size == 1023
+        v = 0
+        for b in (c[:10] > 0):
+            v = (v << 1) | int(b)
+        assert format(v, "o") == ICD_FIRST10[prn - 1], prn
+        # product-side generator and the C oracle agree chip for chip
+        assert np.array_equal(c.astype(np.int8), codes.ca_code(prn))
+        cc = np.zeros(1023)
+        orc().orc_generateCAcode(prn, P(cc))
+        assert np.array_equal(cc, c)
+        assert abs(int(c.sum())) == 1          # balanced Gold code
+
+
+def test_ca_autocorrelation_three_valued():
+    c = O.generateCAcode(7)
+    r = np.array([np.dot(c, np.roll(c, k)) for k in range(1, 1023)])
+    assert set(np.unique(r)) <= {-65.0, -1.0, 63.0}
+
+
+def test_matlab_colon_and_round():
+    assert O.matlab_round(2.5) == 3 and O.matlab_round(-2.5) == -3 and O.matlab_round(0.49999) == 0
+    v = O.colonop(0.0, 0.0625, 1022.9375)
+    assert v.size == 16368 and v[0] == 0 and v[-1] == 1022.9375
+    a, d = 0.0123, 1.023e6 / 16.368e6 * (1 + 1e-7)
+    blk = int(np.ceil((1023 - a) / d))
+    v = O.colonop(a, d, (blk - 1) * d + a)
+    assert v.size == blk and v[-1] == (blk - 1) * d + a
+    assert np.all(np.diff(v) > 0)
+    assert np.max(np.abs(v - (a + np.arange(blk) * d))) < 1e-12
+
+
+def test_c_fft_matches_numpy():
+    rng = np.random.default_rng(3)
+    for n in (4092, 32736, 36000, 2 * 3 * 5 * 7 * 11):
+        x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        buf = np.empty(2 * n)
+        buf[0::2], buf[1::2] = x.real, x.imag
+        assert orc().orc_fft(P(buf), n, -1) == 0
+        y = buf[0::2] + 1j * buf[1::2]
+        ref = np.fft.fft(x)
+        assert np.max(np.abs(y - ref)) / np.max(np.abs(ref)) < 1e-12
+        assert orc().orc_fft(P(buf), n, +1) == 0
+        assert np.max(np.abs(buf[0::2] + 1j * buf[1::2] - x)) < 1e-11
+
+
+def _small_case():
+    fs = 2.046e6
+    sc = scene(fs, nsat=4, seed=7, cn0=48)
+    s = O.Settings(samplingFreq=fs, IF=20e3, acqNonCohTime=4, acqSearchBand=6000, msToProcess=120, numberOfChannels=5,
+                   acqSatelliteList=sorted({x.prn for x in sc.sats} | {1, 2}))
+    N = O.samples_per_code(s)
+    raw = synth.make_record(sc, N * 170)
+    return sc, s, N, raw
+
+
+def test_oracles_agree_and_find_injected_signals():
+    sc, s, N, raw = _small_case()
+    a = O.acquisition(O.read_acq_signal(raw, s), s)
+    c = c_acquisition(raw, s, s.acqSatelliteList)
+    for k in ("carrFreq", "codePhase"):
+        assert np.array_equal(a[k], c[k]), k
+    assert np.array_equal(a["coarseBin"], c["coarseBin"]) and np.array_equal(a["coarseCodePhase"], c["coarseCodePhase"])
+    assert np.allclose(a["peakMetric"], c["peakMetric"], rtol=1e-12, atol=0)
+    # closed-loop KAT: every injected satellite is found at its Doppler and code phase
+    for sat in sc.sats:
+        assert a["carrFreq"][sat.prn - 1] != 0, sat.prn
+        assert abs(a["carrFreq"][sat.prn - 1] - (s.IF + sat.doppler)) <= 25
+        start = (1023 - sat.code_phase) * (s.samplingFreq / 1.023e6)       # code start in samples
+        cp = (a["codePhase"][sat.prn - 1] - 1) % N
+        assert min(abs(cp - start), N - abs(cp - start)) <= 2.0
+    absent = [p for p in s.acqSatelliteList if p not in {x.prn for x in sc.sats}]
+    assert all(a["carrFreq"][p - 1] == 0 for p in absent)
+
+    ch = O.preRun(a, s)
+    tr = O.tracking(raw, ch, s)
+    prn = [c_["PRN"] for c_ in ch]
+    out, vv, vi, done = c_tracking(raw, s, prn, [c_["acquiredFreq"] for c_ in ch], [c_["codePhase"] for c_ in ch], s.msToProcess)
+    for i, c_ in enumerate(ch):
+        if c_["PRN"] == 0:
+            assert tr[i]["status"] == "-" and done[i] == 0
+            continue
+        assert done[i] == s.msToProcess and tr[i]["status"] == "T"
+        P_ = np.hypot(tr[i]["I_P"], tr[i]["Q_P"])
+        for f, fname in enumerate(O.TRACK_FIELDS):
+            d = np.abs(out[i, f] - tr[i][fname])
+            scale = P_ if 3 <= f <= 8 else np.maximum(np.abs(tr[i][fname]), 1e-9)
+            assert np.max(d / scale) < 1e-8, (fname, np.max(d / scale))
+        assert np.allclose(vv[i], tr[i]["VSMValue"], rtol=1e-9)
+        assert np.array_equal(vi[i], tr[i]["VSMIndex"])
+        # lock: prompt power dominates, data bits recovered up to a sign
+        assert np.mean(np.abs(tr[i]["I_P"][40:])) > 4 * np.mean(np.abs(tr[i]["Q_P"][40:]))
+
+
+def test_tracking_short_record_stops_whole_call():
+    """tracking.m:241-245: a short fread prints and returns; later channels stay untouched."""
+    sc, s, N, raw = _small_case()
+    a = O.acquisition(O.read_acq_signal(raw, s), s)
+    ch = O.preRun(a, s)
+    short = raw[: 2 * N * 60]
+    tr = O.tracking(short, ch, s)
+    assert tr[0]["status"] == "-" and np.isinf(tr[0]["carrFreq"][-1]) and np.isfinite(tr[0]["carrFreq"][0])
+    assert all(np.all(tr[i]["I_P"] == 0) and np.all(np.isinf(tr[i]["codeFreq"])) for i in range(1, len(ch)))
+    prn = [c_["PRN"] for c_ in ch]
+    for par in (0, 1):
+        out, vv, vi, done = c_tracking(short, s, prn, [c_["acquiredFreq"] for c_ in ch], [c_["codePhase"] for c_ in ch],
+                                       s.msToProcess, parallel=par)
+        assert 0 < done[0] < s.msToProcess and np.all(done[1:] == 0)
+        assert np.all(out[1:, 3] == 0) and np.all(np.isinf(out[1:, 1]))
+        n0 = done[0]
+        assert np.allclose(out[0, 3, :n0], tr[0]["I_P"][:n0], rtol=1e-8)
+
+
+def test_golden_vectors():
+    """Committed fixtures (made by tests/golden/make_golden.py from the NumPy oracle — the
+    reference itself ships none and cannot run here) guard both oracles against drift."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "l1ca_small.npz"))
+    raw = g["raw"]
+    s = O.Settings(samplingFreq=float(g["fs"]), IF=float(g["IF"]), acqNonCohTime=int(g["nonCoh"]),
+                   acqSearchBand=float(g["band"]), msToProcess=int(g["nEpochs"]),
+                   numberOfChannels=int(g["nCh"]), acqSatelliteList=[int(p) for p in g["svList"]])
+    c = c_acquisition(raw, s, s.acqSatelliteList)
+    assert np.array_equal(c["carrFreq"], g["carrFreq"]) and np.array_equal(c["codePhase"], g["codePhase"])
+    assert np.allclose(c["peakMetric"], g["peakMetric"], rtol=1e-10)
+    out, vv, vi, done = c_tracking(raw, s, g["chPRN"], g["chFreq"], g["chCodePhase"], s.msToProcess)
+    ref = g["track"]
+    sc_ = np.hypot(ref[:, 3], ref[:, 7])[:, None, :]
+    live = g["chPRN"] != 0
+    assert np.max(np.abs(out[live][:, 3:9] - ref[live][:, 3:9]) / sc_[live]) < 1e-8
+    assert np.array_equal(out[live][:, 0], ref[live][:, 0])          # absoluteSample exact
