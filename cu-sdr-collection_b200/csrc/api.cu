@@ -327,6 +327,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
     const int e0 = mark();
     GC_CUDA(h, launch_sig_power(h->rec, winStart, N, h->sigPower.p, st)); ++launches;   // :151
     float rowsMs = 0, colsMs = 0;
+    int nRowLaunches = 0;
     std::vector<std::pair<int, int>> rowEv, colEv;
     int e1;
     if (h->fused) {
@@ -357,7 +358,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
             cp.partMax = h->partMax.p; cp.partIdx = h->partIdx.p;
             GC_CUDA(h, launch_inv_cols(cp, st)); ++launches;
             const int d = mark();
-            rowEv.push_back({a, b}); colEv.push_back({b, d});
+            rowEv.push_back({a, b}); colEv.push_back({b, d}); ++nRowLaunches;
             if (evn > kEvents - 8) { GC_CUDA(h, cudaStreamSynchronize(st)); }
         }
     } else {
@@ -386,7 +387,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
             GC_CUDA(h, launch_generic_absacc(src, L, nBins, nonCoh, h->parts, h->partMax.p, h->partIdx.p,
                                              (size_t)i * nBins * h->parts, st)); ++launches;
             const int d = mark();
-            rowEv.push_back({a, b}); colEv.push_back({b, d});
+            rowEv.push_back({a, b}); colEv.push_back({b, d}); ++nRowLaunches;
             if (evn > kEvents - 8) {
                 GC_CUDA(h, cudaStreamSynchronize(st));
                 for (auto& pr : rowEv) { float ms; cudaEventElapsedTime(&ms, h->ev[pr.first], h->ev[pr.second]); rowsMs += ms; }
@@ -467,6 +468,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
     for (auto& pr : colEv) { cudaEventElapsedTime(&ms, h->ev[pr.first], h->ev[pr.second]); colsMs += ms; }
     h->stats.corr_rows_ms = rowsMs;
     h->stats.corr_cols_ms = colsMs;
+    h->stats.corr_row_launches = nRowLaunches;
     h->stats.acq_launches = launches;
     return GC_OK;
 }
@@ -621,6 +623,8 @@ int gc_track_file(gc_handle* h, const char* path, int32_t nCh, const int32_t* sv
     if (rc != GC_OK) return rc;
     return gc_track(h, nCh, sv, acqFreq, codePhase, nEpochs, out, vsmValue, vsmIndex, epochsDone);
 }
+
+void* gc_get_stream(const gc_handle* h) { return h ? (void*)h->stream : nullptr; }
 
 int gc_get_stats(const gc_handle* h, gc_stats* out)
 {

@@ -38,12 +38,12 @@ class gc_stats(C.Structure):
                 ("acq_fine_ms", C.c_float), ("track_kernel_ms", C.c_float),
                 ("acq_launches", C.c_int32), ("track_launches", C.c_int32), ("fft_len", C.c_int32),
                 ("acq_path", C.c_int32), ("n_acquired", C.c_int32),
-                ("corr_rows_ms", C.c_float), ("corr_cols_ms", C.c_float)]
+                ("corr_rows_ms", C.c_float), ("corr_cols_ms", C.c_float), ("corr_row_launches", C.c_int32)]
 
 
 EXPORTS = ["gc_abi_version", "gc_build_arch", "gc_acq_result_len", "gc_create", "gc_destroy",
            "gc_last_error", "gc_set_record_host", "gc_set_record_device", "gc_acquire",
-           "gc_acquire_host", "gc_track", "gc_track_file", "gc_get_stats"]
+           "gc_acquire_host", "gc_track", "gc_track_file", "gc_get_stats", "gc_get_stream"]
 
 _lib = None
 
@@ -74,6 +74,8 @@ def load_lib():
     lib.gc_track.argtypes = [vp, C.c_int32, i32p, dp, dp, C.c_int32, dp, dp, dp, i32p]
     lib.gc_track_file.argtypes = [vp, C.c_char_p, C.c_int32, i32p, dp, dp, C.c_int32, dp, dp, dp, i32p]
     lib.gc_get_stats.argtypes = [vp, C.POINTER(gc_stats)]
+    lib.gc_get_stream.argtypes = [vp]
+    lib.gc_get_stream.restype = C.c_void_p
     _lib = lib
     return lib
 
@@ -180,6 +182,16 @@ class Engine:
                                    _dp(out), _dp(vv), _dp(vi), _ip(done))
             self._check(rc, "gc_track")
         return out, vv, vi, done
+
+    @property
+    def stream_ptr(self) -> int:
+        """cudaStream_t the engine launches on (wrap with torch.cuda.ExternalStream to time it)."""
+        return int(self.lib.gc_get_stream(self._h) or 0)
+
+    def set_record_host_ptr(self, ptr: int, nbytes: int):
+        """Host pointer variant (e.g. a pinned torch tensor's data_ptr): copies host->device."""
+        self._check(self.lib.gc_set_record_host(self._h, ptr, nbytes), "gc_set_record_host")
+        self._keep = None
 
     def stats(self) -> dict:
         st = gc_stats()

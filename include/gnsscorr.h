@@ -160,8 +160,13 @@ typedef struct gc_stats {
     int32_t n_acquired;        /* PRNs above threshold in the last gc_acquire                       */
     float corr_rows_ms;        /* dominant kernel: spectrum multiply + inverse row FFT              */
     float corr_cols_ms;        /* inverse column DFT + |.| + non-coherent sum + row max             */
+    int32_t corr_row_launches; /* launches of the dominant (inverse row FFT) kernel in the last gc_acquire */
 } gc_stats;
 int gc_get_stats(const gc_handle* h, gc_stats* out);
+
+/* The CUDA stream (cudaStream_t) every kernel of this handle is launched on, for callers that want
+ * to bracket work with their own events. */
+void* gc_get_stream(const gc_handle* h);
 
 /* Library-level: ABI version and the GPU architecture the kernels were compiled for ("sm_100a"). */
 int gc_abi_version(void);
