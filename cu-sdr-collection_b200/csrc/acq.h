@@ -17,16 +17,13 @@ struct FwdColsParams {
     int nonCoh;
     const uint64_t* dphi;     // [nBins] carrier phase increment per sample (turns, 0.64 fixed point)
     const int8_t* codeTab;    // [nPrn][N] +-1 resampled replicas (code mode)
-    float2* out;              // [nRows][33][992]
-    const float2* twL;        // [33][992]  w_L^(j1*x), forward sign
+    float2* out;              // [nRows][33][992]  (k1, n2*31 + n3)
 };
 
 struct RowsParams {
     float2* X;                // forward: rows transformed in place; inverse: spectra [nBins*nonCoh][33][992]
     const float2* Cc;         // [nPrnSlots][33][992] conj(FFT(code))/L
     float2* W;                // inverse output [nPrnChunk][nBins][nonCoh][33][992]
-    const float2* twR;        // [32][31]  w_992^(b1*a2), forward sign
-    const float2* twL;        // [33][992]
     long long nRows;          // forward only
     int nonCoh, nBins;
     int prnPerCta, mPerCta;   // warps of an inverse CTA = prnPerCta x mPerCta (same row j1, same bin)
@@ -41,7 +38,6 @@ struct InvColsParams {
     int* partIdx;
 };
 
-int fused_row_smem_bytes();
 int fused_col_parts();
 cudaError_t launch_fwd_cols(const FwdColsParams& p, int nRows, bool codeMode, cudaStream_t s);
 cudaError_t launch_fwd_rows(const RowsParams& p, cudaStream_t s);

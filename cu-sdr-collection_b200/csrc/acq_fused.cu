@@ -5,19 +5,22 @@
 // MATLAB's fft/ifft are computed exactly at that length (no power-of-two padding, so the
 // code-phase index space 1..2N is the reference's own) as a four-step transform
 //
-//      L = C x R,  C = 33 (= 3 x 11, prime-factor codelet),  R = 992 = 32 x 31
+//      L = 33 x 32 x 31, pairwise coprime  ->  Good-Thomas prime-factor algorithm: with the time /
+//      lag index n = (992*n1 + 1023*n2 + 1056*n3) mod L and the frequency index addressed by its
+//      residues (j mod 33, j mod 32, j mod 31) the transform is a plain 3-D DFT, no twiddles.
 //
 //   forward  (wipe-off + FFT, PRN independent, acquisition.m:169-183):
-//      fwd_cols : one thread per column n2: 33 strided int8 I/Q samples, carrier wipe-off with a
-//                 64-bit fixed-point phase, 33-point DFT in registers, twiddle w_L^(j1*n2)
-//      fwd_rows : one warp per row j1: 992-point FFT as 32-point DFTs (31 lanes), twiddle,
-//                 shared-memory transpose, 31-point DFTs (32 lanes)
-//      spectrum layout X[j1][j2], frequency index j = j1 + 33*j2 (no transpose ever materialised)
+//      fwd_cols : one thread per (n2, n3): 33 gathered int8 I/Q samples, carrier wipe-off with a
+//                 64-bit fixed-point phase, 33-point DFT in registers (3 x 11 codelet)
+//      fwd_rows : one warp per row k1: 32-point DFTs (31 lanes), shared-memory transpose,
+//                 31-point DFTs (32 lanes)
+//      spectrum layout X[k1][k3][k2]; the replica spectra use the same layout, so no index map
+//      is ever applied in the frequency domain.
 //   inverse  (acquisition.m:186-190):
-//      inv_rows : one warp per row: load X*conj(FFT(code))/L, inverse 992-point FFT, twiddle
-//      inv_cols : one thread per column tau2: for each non-coherent block 33-point inverse DFT,
+//      inv_rows : one warp per row: load X*conj(FFT(code))/L, 31-point then 32-point inverse DFTs
+//      inv_cols : one thread per (t2, t3): for each non-coherent block 33-point inverse DFT,
 //                 |.|, accumulate in registers; after the last block the running maximum /
-//                 first arg-max of the thread's 33 code phases tau = tau2 + 992*tau1.
+//                 first arg-max over the thread's 33 code phases (992*t1 + 1023*t2 + 1056*t3) mod L.
 //   `results(freqBin, :)` (acquisition.m:162,190) is therefore never written to memory.
 #include "acq.h"
 #include "common.cuh"
@@ -31,18 +34,28 @@ constexpr int C = kFusedC;       // 33
 constexpr int R = kFusedR;       // 992
 constexpr int RA = 32, RB = 31;  // R = RA * RB
 constexpr int L = C * R;         // 32736
-constexpr int kPitch = RA + 1;   // smem row pitch (float2) for the 31 x 32 exchange
+constexpr int kPitchF = RA + 1;  // smem pitch (float2) of the forward 31 x 32 exchange
+constexpr int kPitchI = RB;      // smem pitch of the inverse 32 x 31 exchange
 constexpr int kRowWarps = 8;     // warps (= rows in flight) per CTA in the row kernels
+// Good-Thomas index maps (33, 32, 31 pairwise coprime): time / lag index
+//   n = (992*n1 + 1023*n2 + 1056*n3) mod 32736,   992 = L/33, 1023 = L/32, 1056 = L/31
+// while the frequency index j is addressed by its residues (j mod 33, j mod 32, j mod 31).
+// With these maps the 32736-point DFT is a plain 33 x 32 x 31 three-dimensional DFT: no twiddle
+// factors between the passes.
+constexpr int kM1 = R, kM2 = L / RA, kM3 = L / RB;
 
 // ------------------------------------------------------------------ column pass (forward)
-// grid (ceil(R/128), nRows), block 128.  MODE 0: IF samples with carrier wipe-off; MODE 1: code table.
+// grid (ceil(R/128), nRows), block 128; thread = (n2, n3) = p / 31, p % 31.
+// MODE 0: IF samples with carrier wipe-off; MODE 1: code table.
 template <int MODE>
 __global__ void __launch_bounds__(128)
 fwd_cols_kernel(FwdColsParams p)
 {
-    const int n2 = blockIdx.x * 128 + threadIdx.x;
-    if (n2 >= R) return;
+    const int pp = blockIdx.x * 128 + threadIdx.x;
+    if (pp >= R) return;
+    const int n2 = pp / RB, n3 = pp % RB;
     const int row = blockIdx.y;               // MODE 0: km = k*nonCoh + m ; MODE 1: prn slot
+    const int base = (kM2 * n2 + kM3 * n3) % L;
     float2 x[C];
     if (MODE == 0) {
         const int k = row / p.nonCoh, m = row % p.nonCoh;
@@ -50,7 +63,8 @@ fwd_cols_kernel(FwdColsParams p)
         const int8_t* src = p.rec + 2 * ((size_t)p.winStart + (size_t)m * p.N);   // window x((m-1)N+1 : (m+1)N)
 #pragma unroll
         for (int n1 = 0; n1 < C; ++n1) {
-            const int n = n1 * R + n2;
+            int n = base + kM1 * n1;
+            n -= (n >= L) ? L : 0;
             const char2 s = *reinterpret_cast<const char2*>(src + 2 * (size_t)n);
             float sn, cs;
             fix_sincos(dphi * (uint64_t)n, &sn, &cs);          // exp(-1i*f*phasePoints(n)), :172
@@ -61,83 +75,75 @@ fwd_cols_kernel(FwdColsParams p)
         const int8_t* code = p.codeTab + (size_t)row * p.N;    // caCodesTable, zero padded to 2N (:160)
 #pragma unroll
         for (int n1 = 0; n1 < C; ++n1) {
-            const int n = n1 * R + n2;
+            int n = base + kM1 * n1;
+            n -= (n >= L) ? L : 0;
             x[n1] = make_float2(n < p.N ? (float)code[n] : 0.f, 0.f);
         }
     }
-    float2* dst = p.out + (size_t)row * L + n2;
-    const float2* tw = p.twL + n2;
-    codelet::dft33_fwd(x, [&](int j1, float re, float im) {
-        const float2 w = __ldg(tw + (size_t)j1 * R);           // w_L^(j1*n2)
-        dst[(size_t)j1 * R] = cmul(make_float2(re, im), w);
-    });
+    float2* dst = p.out + (size_t)row * L + pp;
+    codelet::dft33_fwd(x, [&](int k1, float re, float im) { dst[(size_t)k1 * R] = make_float2(re, im); });
 }
 
-// ------------------------------------------------------------------ row pass (both directions)
-// One warp per 992-point row.  INV=false: plain forward FFT in place (spectrum rows).
-// INV=true : load X*Cc, inverse FFT, multiply by conj(w_L^(j1*tau2)), store to the work buffer.
-template <bool INV>
+// ------------------------------------------------------------------ row pass, forward
+// One warp per row (fixed k1): 32 x 31 two-dimensional DFT over (n2, n3) in place.
+// in : element (n2, n3) at n2*31 + n3       out: element (k2, k3) at k3*32 + k2
 __global__ void __launch_bounds__(kRowWarps * 32)
-rows_kernel(RowsParams p)
+fwd_rows_kernel(RowsParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* s_tw = reinterpret_cast<float2*>(smem_raw);                 // [RA][RB] w_R^(b1*a2)
-    float2* s_x = s_tw + RA * RB + (threadIdx.x >> 5) * (RB * kPitch);  // per-warp [RB][kPitch]
-    for (int i = threadIdx.x; i < RA * RB; i += blockDim.x) s_tw[i] = p.twR[i];
-    __syncthreads();
-
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // row decode
-    const float2 *src, *mul = nullptr, *otw = nullptr;
-    float2* dst;
-    if (!INV) {
-        const long long row = (long long)blockIdx.x * kRowWarps + warp;
-        if (row >= p.nRows) return;
-        src = p.X + row * R;
-        dst = p.X + row * R;
-    } else {
-        // blockIdx.x = j1, blockIdx.y = k, blockIdx.z = (prn group, m group); warp -> (prn, m)
-        const int j1 = blockIdx.x, k = blockIdx.y;
-        const int mGroups = (p.nonCoh + p.mPerCta - 1) / p.mPerCta;
-        const int pg = blockIdx.z / mGroups, mg = blockIdx.z % mGroups;
-        const int pi = pg * p.prnPerCta + warp / p.mPerCta;     // prn slot within this launch's chunk
-        const int m = mg * p.mPerCta + warp % p.mPerCta;
-        if (pi >= p.nPrnChunk || m >= p.nonCoh) return;
-        src = p.X + ((size_t)(k * p.nonCoh + m) * C + j1) * R;
-        mul = p.Cc + ((size_t)p.prnList[p.prnSlot0 + pi] * C + j1) * R;
-        otw = p.twL + (size_t)j1 * R;
-        dst = p.W + (((size_t)(pi * p.nBins + k) * p.nonCoh + m) * C + j1) * R;
-    }
-
-    // stage 1: lane = a2 (< 31), elements a1*31 + a2, 32-point DFT over a1
-    if (lane < RB) {
+    float2* s_x = reinterpret_cast<float2*>(smem_raw) + warp * (RB * kPitchF);
+    const long long row = (long long)blockIdx.x * kRowWarps + warp;
+    if (row >= p.nRows) return;
+    float2* io = p.X + row * R;
+    if (lane < RB) {                                             // lane = n3: DFT-32 over n2
         float2 v[RA];
 #pragma unroll
-        for (int a1 = 0; a1 < RA; ++a1) {
-            float2 t = src[a1 * RB + lane];
-            if (INV) t = cmul(t, __ldg(mul + a1 * RB + lane));  // IQfreqDom .* caCodeFreqDom (:186)
-            v[a1] = t;
-        }
-        auto put = [&](int b1, float re, float im) {
-            const float2 w = s_tw[b1 * RB + lane];
-            const float2 t = make_float2(re, im);
-            s_x[lane * kPitch + b1] = INV ? cmul_conj(t, w) : cmul(t, w);
-        };
-        if (INV) codelet::dft32_inv(v, put); else codelet::dft32_fwd(v, put);
+        for (int n2 = 0; n2 < RA; ++n2) v[n2] = io[n2 * RB + lane];
+        codelet::dft32_fwd(v, [&](int k2, float re, float im) { s_x[lane * kPitchF + k2] = make_float2(re, im); });
     }
     __syncwarp();
-    // stage 2: lane = b1 (all 32), 31-point DFT over a2, output index b1 + 32*c2
-    {
+    {                                                            // lane = k2: DFT-31 over n3
         float2 u[RB];
 #pragma unroll
-        for (int a2 = 0; a2 < RB; ++a2) u[a2] = s_x[a2 * kPitch + lane];
-        auto put = [&](int c2, float re, float im) {
-            const int o = lane + RA * c2;
-            float2 t = make_float2(re, im);
-            if (INV) t = cmul_conj(t, __ldg(otw + o));          // conj(w_L^(j1*tau2))
-            dst[o] = t;
-        };
-        if (INV) codelet::dft31_inv(u, put); else codelet::dft31_fwd(u, put);
+        for (int n3 = 0; n3 < RB; ++n3) u[n3] = s_x[n3 * kPitchF + lane];
+        codelet::dft31_fwd(u, [&](int k3, float re, float im) { io[k3 * RA + lane] = make_float2(re, im); });
+    }
+}
+
+// ------------------------------------------------------------------ row pass, inverse (dominant kernel)
+// One warp per row of one (PRN, bin, block): X .* Cc, inverse 31 x 32 DFT over (k3, k2) -> (t3, t2).
+// in : element (k2, k3) at k3*32 + k2       out: element (t2, t3) at t2*31 + t3
+// grid: x = k1 (33 rows), y = PRN group, z = bin * mGroups + block group, so that CTAs scheduled
+// together share one X slice (L1/L2 hits) while the replica spectra stay L2 resident.
+__global__ void __launch_bounds__(kRowWarps * 32)
+inv_rows_kernel(RowsParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2* s_x = reinterpret_cast<float2*>(smem_raw) + warp * (RA * kPitchI);
+    const int k1 = blockIdx.x, pg = blockIdx.y;
+    const int mGroups = (p.nonCoh + p.mPerCta - 1) / p.mPerCta;
+    const int k = blockIdx.z / mGroups, mg = blockIdx.z % mGroups;
+    const int pi = pg * p.prnPerCta + warp / p.mPerCta;         // list slot within this launch's chunk
+    const int m = mg * p.mPerCta + warp % p.mPerCta;
+    if (pi >= p.nPrnChunk || m >= p.nonCoh) return;
+    const float2* src = p.X + ((size_t)(k * p.nonCoh + m) * C + k1) * R;
+    const float2* mul = p.Cc + ((size_t)p.prnList[p.prnSlot0 + pi] * C + k1) * R;
+    float2* dst = p.W + (((size_t)(pi * p.nBins + k) * p.nonCoh + m) * C + k1) * R;
+    {                                                            // lane = k2: DFT-31 over k3
+        float2 u[RB];
+#pragma unroll
+        for (int k3 = 0; k3 < RB; ++k3)                          // IQfreqDom .* caCodeFreqDom (:186)
+            u[k3] = cmul(src[k3 * RA + lane], __ldg(mul + k3 * RA + lane));
+        codelet::dft31_inv(u, [&](int t3, float re, float im) { s_x[lane * kPitchI + t3] = make_float2(re, im); });
+    }
+    __syncwarp();
+    if (lane < RB) {                                             // lane = t3: DFT-32 over k2
+        float2 v[RA];
+#pragma unroll
+        for (int k2 = 0; k2 < RA; ++k2) v[k2] = s_x[k2 * kPitchI + lane];
+        codelet::dft32_inv(v, [&](int t2, float re, float im) { __stcs(dst + t2 * RB + lane, make_float2(re, im)); });
     }
 }
 
@@ -152,21 +158,21 @@ __global__ void finish_replica_kernel(float2* Cc, size_t n, float scale)
 }
 
 // ------------------------------------------------------------------ column pass (inverse) + |.| + sum + max
-// grid (ceil(R/128), nBins, nPrnChunk), block 128: thread = code-phase column tau2 of one (PRN, bin).
+// grid (ceil(R/128), nBins, nPrnChunk), block 128: thread = (t2, t3) column of one (PRN, bin).
 __global__ void __launch_bounds__(128)
 inv_cols_kernel(InvColsParams p)
 {
-    const int tau2 = blockIdx.x * 128 + threadIdx.x;
+    const int pp = blockIdx.x * 128 + threadIdx.x;
     const int k = blockIdx.y, pi = blockIdx.z;
     float acc[C];
 #pragma unroll
     for (int i = 0; i < C; ++i) acc[i] = 0.f;
-    if (tau2 < R) {
-        const float2* base = p.W + ((size_t)(pi * p.nBins + k) * p.nonCoh) * L + tau2;
+    if (pp < R) {
+        const float2* base = p.W + ((size_t)(pi * p.nBins + k) * p.nonCoh) * L + pp;
         for (int m = 0; m < p.nonCoh; ++m) {                    // acquisition.m:175
             float2 x[C];
 #pragma unroll
-            for (int j1 = 0; j1 < C; ++j1) x[j1] = __ldcs(base + (size_t)m * L + (size_t)j1 * R);
+            for (int k1 = 0; k1 < C; ++k1) x[k1] = __ldcs(base + (size_t)m * L + (size_t)k1 * R);
             codelet::dft33_inv(x, [&](int t1, float re, float im) {
                 acc[t1] += sqrtf(fmaf(re, re, im * im));        // abs(ifft(.)) summed over blocks (:188-190)
             });
@@ -175,10 +181,12 @@ inv_cols_kernel(InvColsParams p)
     // running maximum with MATLAB first-index tie breaking (smaller code phase wins)
     float best = -1.f;
     int bidx = 0x7fffffff;
-    if (tau2 < R) {
+    if (pp < R) {
+        const int rest = (kM2 * (pp / RB) + kM3 * (pp % RB)) % L;
 #pragma unroll
         for (int t1 = 0; t1 < C; ++t1) {
-            const int idx = tau2 + R * t1;
+            int idx = rest + kM1 * t1;                          // lag = (992*t1 + 1023*t2 + 1056*t3) mod L
+            idx -= (idx >= L) ? L : 0;
             if (acc[t1] > best || (acc[t1] == best && idx < bidx)) { best = acc[t1]; bidx = idx; }
         }
     }
@@ -203,7 +211,6 @@ inv_cols_kernel(InvColsParams p)
 
 }  // namespace
 
-int fused_row_smem_bytes() { return (int)(sizeof(float2) * (RA * RB + kRowWarps * RB * kPitch)); }
 int fused_col_parts() { return (R + 127) / 128; }
 
 cudaError_t launch_fwd_cols(const FwdColsParams& p, int nRows, bool codeMode, cudaStream_t s)
@@ -216,23 +223,23 @@ cudaError_t launch_fwd_cols(const FwdColsParams& p, int nRows, bool codeMode, cu
 
 cudaError_t launch_fwd_rows(const RowsParams& p, cudaStream_t s)
 {
-    const int smem = fused_row_smem_bytes();
-    cudaError_t e = cudaFuncSetAttribute(rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int smem = (int)(sizeof(float2) * kRowWarps * RB * kPitchF);
+    cudaError_t e = cudaFuncSetAttribute(fwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)((p.nRows + kRowWarps - 1) / kRowWarps);
-    rows_kernel<false><<<grid, kRowWarps * 32, smem, s>>>(p);
+    fwd_rows_kernel<<<grid, kRowWarps * 32, smem, s>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_inv_rows(const RowsParams& p, cudaStream_t s)
 {
-    const int smem = fused_row_smem_bytes();
-    cudaError_t e = cudaFuncSetAttribute(rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int smem = (int)(sizeof(float2) * kRowWarps * RA * kPitchI);
+    cudaError_t e = cudaFuncSetAttribute(inv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const int mGroups = (p.nonCoh + p.mPerCta - 1) / p.mPerCta;
     const int pGroups = (p.nPrnChunk + p.prnPerCta - 1) / p.prnPerCta;
-    dim3 grid(C, p.nBins, pGroups * mGroups);
-    rows_kernel<true><<<grid, kRowWarps * 32, smem, s>>>(p);
+    dim3 grid(C, pGroups, p.nBins * mGroups);
+    inv_rows_kernel<<<grid, kRowWarps * 32, smem, s>>>(p);
     return cudaGetLastError();
 }
 

@@ -63,7 +63,7 @@ struct gc_handle {
     DevBuf<int8_t> recOwned;
 
     // acquisition
-    DevBuf<float2> twL, twR, twGen, X, T1, T2, Cc, W;
+    DevBuf<float2> twGen, X, T1, T2, Cc, W;
     DevBuf<uint64_t> dphi, fdphi;
     DevBuf<int8_t> codeTab, chips;
     DevBuf<int> prnList, partIdx, fineCodePhase, fineBest;
@@ -138,10 +138,10 @@ int build_replicas(gc_handle* h)
     GC_CUDA(h, h->Cc.reserve((size_t)kMaxSv * L));
     if (h->fused) {
         FwdColsParams fp{};
-        fp.N = N; fp.codeTab = h->codeTab.p; fp.out = h->Cc.p; fp.twL = h->twL.p;
+        fp.N = N; fp.codeTab = h->codeTab.p; fp.out = h->Cc.p;
         GC_CUDA(h, launch_fwd_cols(fp, kMaxSv, true, h->stream));
         RowsParams rp{};
-        rp.X = h->Cc.p; rp.twR = h->twR.p; rp.twL = h->twL.p; rp.nRows = (long long)kMaxSv * kFusedC;
+        rp.X = h->Cc.p; rp.nRows = (long long)kMaxSv * kFusedC;
         GC_CUDA(h, launch_fwd_rows(rp, h->stream));
         GC_CUDA(h, launch_finish_replica(h->Cc.p, (size_t)kMaxSv * L, h->stream));
     } else {
@@ -214,8 +214,6 @@ int gc_create(gc_handle** out, const gc_config* cfg)
 
     auto setup = [&]() -> int {
         if (h->fused) {
-            GC_CUDA(h, upload(h->twL, tw_table_2d(kFusedC, kFusedR, kFusedL), h->stream));
-            GC_CUDA(h, upload(h->twR, tw_table_2d(32, 31, kFusedR), h->stream));
             h->parts = fused_col_parts();
         } else {
             h->plan.L = h->L; h->plan.nf = 0;
@@ -249,7 +247,7 @@ void gc_destroy(gc_handle* h)
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->recOwned.release();
-    h->twL.release(); h->twR.release(); h->twGen.release(); h->X.release(); h->T1.release(); h->T2.release();
+    h->twGen.release(); h->X.release(); h->T1.release(); h->T2.release();
     h->Cc.release(); h->W.release(); h->dphi.release(); h->fdphi.release(); h->codeTab.release(); h->chips.release();
     h->prnList.release(); h->partIdx.release(); h->fineCodePhase.release(); h->fineBest.release(); h->partMax.release();
     h->peaks.release(); h->sigPower.release(); h->fineSums.release(); h->fineResult.release(); h->fineProd.release();
@@ -333,10 +331,10 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
     if (h->fused) {
         FwdColsParams fp{};
         fp.rec = h->rec; fp.winStart = winStart; fp.N = N; fp.nonCoh = nonCoh; fp.dphi = h->dphi.p;
-        fp.out = h->X.p; fp.twL = h->twL.p;
+        fp.out = h->X.p;
         GC_CUDA(h, launch_fwd_cols(fp, nKm, false, st)); ++launches;
         RowsParams rp{};
-        rp.X = h->X.p; rp.twR = h->twR.p; rp.twL = h->twL.p; rp.nRows = (long long)nKm * kFusedC;
+        rp.X = h->X.p; rp.nRows = (long long)nKm * kFusedC;
         GC_CUDA(h, launch_fwd_rows(rp, st)); ++launches;
         e1 = mark();
         // PRN chunks sized so the inverse work buffer stays below ~2.5 GB
@@ -347,7 +345,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         for (int s0 = 0; s0 < nSv; s0 += chunk) {
             const int nc = std::min(chunk, nSv - s0);
             RowsParams ip{};
-            ip.X = h->X.p; ip.Cc = h->Cc.p; ip.W = h->W.p; ip.twR = h->twR.p; ip.twL = h->twL.p;
+            ip.X = h->X.p; ip.Cc = h->Cc.p; ip.W = h->W.p; 
             ip.nonCoh = nonCoh; ip.nBins = nBins; ip.prnPerCta = 2; ip.mPerCta = 4;
             ip.nPrnChunk = nc; ip.prnSlot0 = s0; ip.prnList = h->prnList.p;
             const int a = mark();

@@ -1,0 +1,127 @@
+/*
+ * gnsscorr_mex.c — thin MEX gateway: marshals mxArray <-> the POD arguments of the C ABI in
+ * include/gnsscorr.h and nothing else.  Build (MATLAB R2018a+, interleaved complex):
+ *
+ *     mex -R2018a -I../include gnsscorr_mex.c -L../cu-sdr-collection_b200 -lgnsscorr
+ *
+ * Called by the drop-in wrappers matlab/acquisition.m and matlab/tracking.m, which keep the
+ * reference signatures (GPS/GPS_L1CA/include/acquisition.m:1, tracking.m:1).
+ *
+ *   r = gnsscorr_mex('acquire', cfg, iq_int8, svList)
+ *         cfg     : struct with the gc_config field names (doubles)
+ *         iq_int8 : int8 vector, I,Q interleaved (longSignal as stored in the file)
+ *         svList  : double vector of PRNs
+ *         r       : struct carrFreq, codePhase, peakMetric (1x32 double)
+ *   r = gnsscorr_mex('track', cfg, path, prn, acqFreq, codePhase, nEpochs)
+ *         r       : struct out (nEpochs x 15 x nCh double, MATLAB column-major view of the
+ *                   C [nCh][15][nEpochs] block), vsmValue, vsmIndex, epochsDone
+ *
+ * This file cannot be exercised in the build image (no MATLAB); it is compile-checked against
+ * matlab/stub/mex.h and the same C entry points are exercised from Python (ctypes).
+ */
+#include <string.h>
+#include "mex.h"
+#include "gnsscorr.h"
+
+static double field(const mxArray* s, const char* name)
+{
+    const mxArray* f = mxGetField(s, 0, name);
+    if (!f) mexErrMsgIdAndTxt("gnsscorr:cfg", "settings field %s is missing", name);
+    return mxGetScalar(f);
+}
+
+static void fill_config(const mxArray* s, gc_config* c)
+{
+    memset(c, 0, sizeof(*c));
+    c->abi_version = GC_ABI_VERSION;
+    c->device = (int32_t)field(s, "device");
+    c->signal = GC_SIG_GPS_L1CA;
+    c->file_type = (int32_t)field(s, "file_type");
+    c->sample_bytes = (int32_t)field(s, "sample_bytes");
+    c->code_length = (int32_t)field(s, "code_length");
+    c->acq_noncoh_time = (int32_t)field(s, "acq_noncoh_time");
+    c->cno_vsm_interval = (int32_t)field(s, "cno_vsm_interval");
+    c->skip_number_of_bytes = (int64_t)field(s, "skip_number_of_bytes");
+    c->sampling_freq = field(s, "sampling_freq");
+    c->IF = field(s, "IF");
+    c->code_freq_basis = field(s, "code_freq_basis");
+    c->acq_search_band = field(s, "acq_search_band");
+    c->acq_search_step = field(s, "acq_search_step");
+    c->acq_threshold = field(s, "acq_threshold");
+    c->dll_damping_ratio = field(s, "dll_damping_ratio");
+    c->dll_noise_bandwidth = field(s, "dll_noise_bandwidth");
+    c->dll_correlator_spacing = field(s, "dll_correlator_spacing");
+    c->pll_damping_ratio = field(s, "pll_damping_ratio");
+    c->pll_noise_bandwidth = field(s, "pll_noise_bandwidth");
+    c->int_time = field(s, "int_time");
+    c->cno_acc_time = field(s, "cno_acc_time");
+}
+
+static void check(gc_handle* h, int rc, const char* what)
+{
+    if (rc != GC_OK) {
+        char msg[512];
+        strncpy(msg, gc_last_error(h), sizeof(msg) - 1);
+        msg[sizeof(msg) - 1] = 0;
+        if (h) gc_destroy(h);
+        mexErrMsgIdAndTxt("gnsscorr:fail", "%s failed (%d): %s", what, rc, msg);
+    }
+}
+
+void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
+{
+    char cmd[16];
+    gc_config cfg;
+    gc_handle* h = NULL;
+    (void)nlhs;
+    if (nrhs < 2 || mxGetString(prhs[0], cmd, sizeof(cmd))) mexErrMsgIdAndTxt("gnsscorr:args", "usage: gnsscorr_mex(cmd, cfg, ...)");
+    fill_config(prhs[1], &cfg);
+    check(NULL, gc_create(&h, &cfg), "gc_create");
+
+    if (!strcmp(cmd, "acquire")) {
+        const char* names[] = {"carrFreq", "codePhase", "peakMetric"};
+        const int n = gc_acq_result_len(cfg.signal);
+        const mwSize nSv = mxGetNumberOfElements(prhs[3]);
+        const double* svd = mxGetDoubles(prhs[3]);
+        int32_t sv[64];
+        mwSize i;
+        if (nrhs != 4 || !mxIsInt8(prhs[2]) || nSv > 64) { gc_destroy(h); mexErrMsgIdAndTxt("gnsscorr:args", "acquire: bad arguments"); }
+        for (i = 0; i < nSv; ++i) sv[i] = (int32_t)svd[i];
+        plhs[0] = mxCreateStructMatrix(1, 1, 3, names);
+        for (i = 0; i < 3; ++i) mxSetField(plhs[0], 0, names[i], mxCreateDoubleMatrix(1, n, mxREAL));
+        check(h, gc_acquire_host(h, (const int8_t*)mxGetInt8s(prhs[2]), mxGetNumberOfElements(prhs[2]) / 2, (int32_t)nSv, sv,
+                                 mxGetDoubles(mxGetField(plhs[0], 0, "carrFreq")), mxGetDoubles(mxGetField(plhs[0], 0, "codePhase")),
+                                 mxGetDoubles(mxGetField(plhs[0], 0, "peakMetric")), NULL, NULL),
+              "gc_acquire_host");
+    } else if (!strcmp(cmd, "track")) {
+        const char* names[] = {"out", "vsmValue", "vsmIndex", "epochsDone"};
+        char path[4096];
+        const mwSize nCh = mxGetNumberOfElements(prhs[3]);
+        const int32_t nEpochs = (int32_t)mxGetScalar(prhs[6]);
+        const mwSize nV = nEpochs / cfg.cno_vsm_interval;
+        const double* prnd = mxGetDoubles(prhs[3]);
+        mwSize dims[3];
+        int32_t prn[256];
+        mxArray *out, *vv, *vi, *done;
+        mwSize i;
+        if (nrhs != 7 || mxGetString(prhs[2], path, sizeof(path)) || nCh > 256) { gc_destroy(h); mexErrMsgIdAndTxt("gnsscorr:args", "track: bad arguments"); }
+        for (i = 0; i < nCh; ++i) prn[i] = (int32_t)prnd[i];
+        dims[0] = nEpochs; dims[1] = GC_TRACK_NFIELDS; dims[2] = nCh;
+        out = mxCreateNumericArray(3, dims, mxDOUBLE_CLASS, mxREAL);
+        vv = mxCreateDoubleMatrix(nV, nCh, mxREAL);
+        vi = mxCreateDoubleMatrix(nV, nCh, mxREAL);
+        done = mxCreateNumericMatrix(1, nCh, mxINT32_CLASS, mxREAL);
+        check(h, gc_track_file(h, path, (int32_t)nCh, prn, mxGetDoubles(prhs[4]), mxGetDoubles(prhs[5]), nEpochs,
+                               mxGetDoubles(out), mxGetDoubles(vv), mxGetDoubles(vi), (int32_t*)mxGetInt32s(done)),
+              "gc_track_file");
+        plhs[0] = mxCreateStructMatrix(1, 1, 4, names);
+        mxSetField(plhs[0], 0, "out", out);
+        mxSetField(plhs[0], 0, "vsmValue", vv);
+        mxSetField(plhs[0], 0, "vsmIndex", vi);
+        mxSetField(plhs[0], 0, "epochsDone", done);
+    } else {
+        gc_destroy(h);
+        mexErrMsgIdAndTxt("gnsscorr:args", "unknown command %s", cmd);
+    }
+    gc_destroy(h);
+}

@@ -1,0 +1,141 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, the
+MEX gateway type-checks against the header, the MATLAB-mirroring host logic, and the
+world_size-2 sharding/gather path over gloo."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import cu_sdr_collection_b200 as pkg
+from cu_sdr_collection_b200 import engine, shard
+from cu_sdr_collection_b200.settings import Settings, init_settings, samples_per_code
+from helpers import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "gnsscorr.h")).read()
+    declared = set(re.findall(r"\b(gc_[a-z_]+)\s*\(", hdr))
+    assert {"gc_create", "gc_destroy", "gc_acquire", "gc_acquire_host", "gc_track", "gc_track_file",
+            "gc_set_record_host", "gc_set_record_device", "gc_get_stats", "gc_last_error"} <= declared
+    lib = engine.load_lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert set(engine.EXPORTS) == declared
+    assert lib.gc_abi_version() == 1 and lib.gc_build_arch() == b"sm_100a"
+    assert lib.gc_acq_result_len(0) == 32
+
+
+def test_config_struct_layout_matches_header():
+    hdr = open(os.path.join(ROOT, "include", "gnsscorr.h")).read()
+    body = re.search(r"typedef struct gc_config \{(.*?)\} gc_config;", hdr, re.S).group(1)
+    names = re.findall(r"^\s*(?:int32_t|int64_t|double)\s+([A-Za-z_]+);", body, re.M)
+    assert names == [f for f, _ in engine.gc_config._fields_]
+    body = re.search(r"typedef struct gc_stats \{(.*?)\} gc_stats;", hdr, re.S).group(1)
+    names = re.findall(r"^\s*(?:int32_t|float)\s+([A-Za-z_]+);", body, re.M)
+    assert names == [f for f, _ in engine.gc_stats._fields_]
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(engine.GnssCorrError, match="no CPU fallback"):
+        pkg.Engine(init_settings(samplingFreq=16.368e6))
+
+
+def test_product_never_imports_the_oracle():
+    pkgdir = os.path.join(ROOT, "cu-sdr-collection_b200")
+    for dirpath, _, files in os.walk(pkgdir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "np_oracle" not in src and "gnss_oracle" not in src and "oracle/" not in src, f
+
+
+def test_mex_gateway_typechecks_against_header():
+    subprocess.check_call(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "matlab", "stub"),
+                           "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "matlab", "gnsscorr_mex.c")])
+
+
+def test_settings_defaults_match_reference_initsettings():
+    s = Settings()
+    assert (s.msToProcess, s.numberOfChannels, s.samplingFreq, s.IF) == (60000, 12, 18e6, 20e3)
+    assert (s.acqSearchBand, s.acqSearchStep, s.acqNonCohTime, s.acqThreshold) == (7000, 500, 20, 3.5)
+    assert s.acqSatelliteList == list(range(1, 33))
+    assert samples_per_code(s) == 18000
+    assert samples_per_code(init_settings(samplingFreq=16.368e6)) == 16368
+    with pytest.raises(AttributeError):
+        init_settings(noSuchField=1)
+    with pytest.raises(engine.GnssCorrError):
+        engine.config_from_settings(init_settings(resamplingflag=1))
+
+
+def test_prerun_orders_by_peak_metric():
+    acq = dict(peakMetric=np.zeros(32), carrFreq=np.zeros(32), codePhase=np.zeros(32))
+    for prn, pm in ((3, 5.0), (9, 9.0), (20, 7.0), (31, 2.0)):
+        acq["peakMetric"][prn - 1] = pm
+    for prn in (3, 9, 20):
+        acq["carrFreq"][prn - 1] = 20e3 + prn
+        acq["codePhase"][prn - 1] = 100 * prn
+    ch = pkg.preRun(acq, init_settings(numberOfChannels=4))
+    assert [c["PRN"] for c in ch] == [9, 20, 3, 0]
+    assert ch[0]["acquiredFreq"] == 20009 and ch[0]["codePhase"] == 900 and ch[3]["status"] == "-"
+    ch = pkg.preRun(acq, init_settings(numberOfChannels=2))
+    assert [c["PRN"] for c in ch] == [9, 20]
+
+
+def test_acquisition_rejects_non_integer_signal():
+    from cu_sdr_collection_b200.acquisition import _to_int8_iq
+    x = (np.arange(8) - 4) + 1j * (np.arange(8) - 3)
+    iq = _to_int8_iq(x.astype(np.complex128))
+    assert iq.dtype == np.int8 and list(iq[:4]) == [-4, -3, -3, -2]
+    with pytest.raises(engine.GnssCorrError):
+        _to_int8_iq(x + 0.5)
+    with pytest.raises(engine.GnssCorrError):
+        _to_int8_iq(np.arange(8, dtype=np.float64))
+
+
+def test_shard_units_partition():
+    sv = list(range(1, 33))
+    parts = [shard.shard_units(sv, r, 4) for r in range(4)]
+    assert sorted(sum(parts, [])) == sv and all(len(p) == 8 for p in parts)
+    assert shard.shard_units(sv, 0, 1) == sv
+    assert [len(shard.shard_units(list(range(14)), r, 4)) for r in range(4)] == [4, 4, 3, 3]   # GLONASS K list
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch.distributed as dist
+from cu_sdr_collection_b200 import shard
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+sv = shard.shard_units(list(range(1, 33)), rank, 2)
+local = dict(peakMetric=np.zeros(32), codePhase=np.zeros(32), carrFreq=np.zeros(32), coarseBin=np.zeros(32, dtype=np.int32))
+for p in sv:                                    # stand-in for the per-rank GPU search
+    local["peakMetric"][p - 1] = 1.0 + p
+    local["codePhase"][p - 1] = 10 * p
+    local["carrFreq"][p - 1] = 20e3 + p if p % 3 == 0 else 0.0
+    local["coarseBin"][p - 1] = p % 29 + 1
+m = shard.gather_acq_results(local, sv)
+assert np.array_equal(m["peakMetric"], 1.0 + np.arange(1, 33)), m["peakMetric"]
+assert np.array_equal(m["codePhase"], 10.0 * np.arange(1, 33))
+assert np.array_equal(m["carrFreq"] != 0, np.arange(1, 33) % 3 == 0)
+assert np.array_equal(m["coarseBin"], np.arange(1, 33) % 29 + 1)
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_two_rank_gloo_gather(tmp_path):
+    """world_size 2 over gloo: PRNs sharded round-robin, one all-gather rebuilds acqResults."""
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER.format(root=ROOT, port=29000 + os.getpid() % 2000))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)
