@@ -541,12 +541,21 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
     TrackParams p{};
     p.rec = h->rec;
     p.recSamples = (long long)(h->recBytes / 2);
-    p.fs = c.sampling_freq; p.codeFreqBasis = c.code_freq_basis; p.codeLength = (double)codeLen;
+    p.fs = c.sampling_freq; p.invFs = 1.0 / c.sampling_freq; p.codeFreqBasis = c.code_freq_basis; p.codeLength = (double)codeLen;
     p.spc = c.dll_correlator_spacing;
     p.cA = h->tau2code / h->tau1code; p.cB = c.int_time / h->tau1code;     // tracking.m:326
     p.pA = h->tau2carr / h->tau1carr; p.pB = c.int_time / h->tau1carr;     // tracking.m:308
     p.nEpochs = nEpochs;
-    p.bufBytes = ((2 * (h->N + 64) + 16) + 15) & ~15;
+    // CTAs per channel: spread few channels over the chip (thread-block clusters), 1 CTA per channel once
+    // the channel count fills it
+    int nLive = 0;
+    for (int ch = 0; ch < nCh; ++ch) nLive += (sv[ch] != 0);
+    int cluster = 1;
+    for (int g = 8; g >= 2; g /= 2)
+        if (nCh * g <= 148) { cluster = g; break; }
+    if (const char* e = getenv("GC_TRACK_CLUSTER")) { const int g = atoi(e); if (g == 1 || g == 2 || g == 4 || g == 8) cluster = g; }
+    (void)nLive;
+    p.bufBytes = track_buf_bytes(h->N + 64, cluster);
     p.codeLen = codeLen; p.codeStride = stride;
     if (track_smem_bytes(p.bufBytes, codeLen) > 227 * 1024)
         return fail(h, GC_ERR_UNSUPPORTED, "gc_track: one code period of samples does not fit in shared memory");
@@ -556,9 +565,12 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
     GC_CUDA(h, h->trackOut.reserve(nOut));
     GC_CUDA(h, h->epochsDone.reserve(nCh));
     p.codeTables = h->trackCodes.p; p.chans = h->chans.p; p.out = h->trackOut.p; p.epochsDone = h->epochsDone.p;
+    long long* dbg = nullptr;
+    if (getenv("GC_TRACK_DEBUG")) { cudaMalloc(&dbg, 32 * sizeof(long long)); cudaMemset(dbg, 0, 32 * sizeof(long long)); }
+    p.dbg = dbg;
     GC_CUDA(h, launch_track_fill(h->trackOut.p, nCh, nEpochs, st));
     cudaEventRecord(h->ev[0], st);
-    GC_CUDA(h, launch_track(p, nCh, st));
+    GC_CUDA(h, launch_track(p, nCh, cluster, st));
     cudaEventRecord(h->ev[1], st);
     GC_CUDA(h, cudaMemcpyAsync(out, h->trackOut.p, nOut * sizeof(double), cudaMemcpyDeviceToHost, st));
     GC_CUDA(h, cudaMemcpyAsync(epochsDone, h->epochsDone.p, nCh * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -567,6 +579,18 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
     cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
     h->stats.track_kernel_ms = ms;
     h->stats.track_launches = 2;
+    if (dbg) {
+        long long hd[32];
+        cudaMemcpy(hd, dbg, sizeof(hd), cudaMemcpyDeviceToHost);
+        cudaFree(dbg);
+        const char* names[7] = {"top", "mbar", "samples", "sync1", "cluster", "control", "sync2"};
+        for (int w = 0; w < 4; ++w) {
+            if (w == 2) continue;
+            fprintf(stderr, "[gc_track timing] warp %d cycles/epoch:", w);
+            for (int i = 0; i < 7; ++i) fprintf(stderr, " %s=%.0f", names[i], (double)hd[w * 8 + i] / nEpochs);
+            fprintf(stderr, "  (cluster=%d)\n", cluster);
+        }
+    }
 
     // A short read makes the reference `return` from tracking() (tracking.m:241-245): channels
     // after the first one that ran out of data stay as initialised.

@@ -16,11 +16,19 @@
 //     chunk, the 8 in-chunk rotations e^{-i*j*dphi} are per-epoch constants;
 //   * sums: fp32 inside a thread (8 samples per chunk, 4 chunks), float64 across threads.
 //
+// With few channels (BASELINE: 12) one CTA per channel leaves most of the chip idle and every
+// epoch is a dependent step, so a channel can instead be spread over a thread-block cluster of
+// G = 2/4/8 CTAs: each CTA stages and correlates 1/G of the block, pushes its six partial sums
+// into every peer's shared memory (DSMEM), one cluster barrier, and then every CTA closes the
+// loops redundantly from the same numbers (bit-identical state everywhere, no broadcast step).
+//
 // The per-epoch scalar work is split so that little of it sits on the critical path:
 //   warp 0 lane 0 : PLL (atan) and the 15 recorded values          after the sums are reduced
 //   warp 1 lane 0 : DLL and the geometry of the next block         concurrently with warp 0
-//   warp 2 lane 0 : NCO phases at the end of the block just started (fmod etc.) — needs only that
-//                   block's parameters, so it runs in the shadow of the sample loop.
+// Quotients and square roots of the discriminators use an fp32 seed plus one float64 Newton step
+// (~1e-14 relative); everything that feeds a ceil() (codePhaseStep, blksize) is exact IEEE.
+#include <type_traits>
+
 #include "common.cuh"
 #include "track.h"
 
@@ -28,8 +36,9 @@ namespace gc {
 
 namespace {
 
-constexpr int kThreads = 512;
-constexpr int kWarps = kThreads / 32;
+constexpr int kMaxWarps = 16;
+constexpr int kMaxCluster = 8;
+constexpr int kPad = 16;     // zero entries on both sides of the code table (masked out-of-block samples index them)
 constexpr int kStage = 16;   // epochs of results staged in smem before a coalesced flush
 constexpr double kCeilMagic = 6755399441055744.0;   // 1.5 * 2^52: t + magic stays in [2^52, 2^53) for |t| < 2^51
 
@@ -94,7 +103,10 @@ __device__ __forceinline__ int ceil_idx(double t) { return __double2loint(__dadd
 __device__ void plan_epoch(const TrackParams& p, double codeFreq, double remCodePhase,
                            double remCarrPhase, uint64_t phase0, long long pos, EpochParams& ep)
 {
-    const double step = __ddiv_rn(codeFreq, p.fs);                                      // :219
+    // :219 codeFreq / samplingFreq, correctly rounded: q0 = a*RN(1/b), r = a - q0*b (exact, FMA),
+    // q = RN(q0 + r*RN(1/b))  (Markstein); three dependent operations instead of a full division
+    const double q0 = __dmul_rn(codeFreq, p.invFs);
+    const double step = __fma_rn(__fma_rn(-q0, p.fs, codeFreq), p.invFs, q0);
     const int blk = (int)ceil(__ddiv_rn(__dsub_rn(p.codeLength, remCodePhase), step));  // :222
     ep.d = step;
     ep.blk = blk;
@@ -132,7 +144,9 @@ __device__ void plan_epoch(const TrackParams& p, double codeFreq, double remCode
         colon_setup(ep.aL, step, bL, &ep.nL, &ep.cL);
         colon_setup(ep.aP, step, bP, &ep.nP, &ep.cP);
     }
-    ep.generic = !(ep.nE == blk - 1 && ep.nP == blk - 1 && ep.nL == blk - 1);
+    // fast path: the three vectors share n, and the samples masked just outside the block still index the
+    // zero padding of the code table
+    ep.generic = !(ep.nE == blk - 1 && ep.nP == blk - 1 && ep.nL == blk - 1) || !(8.0 * step + p.spc + 2.0 < (double)kPad);
     ep.mE = __dmul_rn(__dadd_rn(ep.aE, ep.cE), 0.5);
     ep.mP = __dmul_rn(__dadd_rn(ep.aP, ep.cP), 0.5);
     ep.mL = __dmul_rn(__dadd_rn(ep.aL, ep.cL), 0.5);
@@ -144,18 +158,39 @@ __device__ void plan_epoch(const TrackParams& p, double codeFreq, double remCode
 __device__ __forceinline__ void plan_carrier(const TrackParams& p, double carrFreq, EpochParams& ep)
 {
     ep.carrFreq = carrFreq;
-    ep.dphi = turns_to_fix(carrFreq / p.fs);
+    ep.dphi = turns_to_fix(carrFreq * p.invFs);
 }
 
-// NCO phases after the block described by ep (tracking.m:273, :280-283)
-__device__ void end_phases(const TrackParams& p, const EpochParams& ep, NextPhases& nx)
+// NCO phases after the block described by ep (tracking.m:273, :280-283).  The carrier phase is
+// advanced in the 64-bit fixed-point domain (exact to 2^-64 turn per sample); remCarrPhase, the
+// recorded value, is that phase in radians with the sign rem(trigarg, 2*pi) would have (it agrees
+// with the reference's float64 recurrence to ~1e-12 rad, far inside every tolerance).
+__device__ __forceinline__ void end_phases(const TrackParams& p, const EpochParams& ep, NextPhases& nx)
 {
     const double lastP = ep.generic ? colon_elem(ep.aP, ep.d, ep.cP, ep.nP, ep.blk - 1) : ep.cP;
     nx.remCodePhase = __dsub_rn(__dadd_rn(lastP, ep.d), p.codeLength);                        // :273
-    const double w = __dmul_rn(__dmul_rn(ep.carrFreq, 2.0), 3.141592653589793);               // :281
-    const double trigEnd = __dadd_rn(__dmul_rn(w, __ddiv_rn((double)ep.blk, p.fs)), ep.remCarrPhase);
-    nx.remCarrPhase = fmod(trigEnd, kTwoPi);                                                  // :283
-    nx.phase0 = turns_to_fix(nx.remCarrPhase / kTwoPi);
+    nx.phase0 = ep.phase0 + ep.dphi * (uint64_t)ep.blk;                                       // :280-283
+    const double frac = (double)(nx.phase0 >> 11) * 1.1102230246251565e-16;                   // [0,1) turns, 53 bits
+    nx.remCarrPhase = (ep.carrFreq < 0.0 && frac != 0.0) ? (frac - 1.0) * kTwoPi : frac * kTwoPi;
+}
+
+// float64 quotient / square root from an fp32 seed and one Newton step in float64 (~1e-14
+// relative): the exact IEEE versions cost ~250 dependent cycles each on the loop's critical path.
+__device__ __forceinline__ double fast_div(double a, double b)
+{
+    const float bf = (float)b;
+    if (!(fabsf(bf) > 1e-30f) || !(fabsf(bf) < 1e30f)) return __ddiv_rn(a, b);
+    const float rb = 1.0f / bf;
+    const double q0 = (double)((float)a * rb);
+    return fma(fma(-q0, b, a), (double)rb, q0);
+}
+__device__ __forceinline__ double fast_sqrt(double x)
+{
+    const float xf = (float)x;
+    if (!(xf > 1e-30f) || !(xf < 1e30f)) return sqrt(x);
+    const float s0 = sqrtf(xf);
+    const double s = (double)s0;
+    return fma(fma(-s, s, x), (double)(0.5f / s0), s);
 }
 
 // exact float of a signed byte already xor-ed with 0x80: 0x4B0000bb = 2^23 + (b+128)
@@ -165,34 +200,62 @@ __device__ __forceinline__ float byte_to_float(uint32_t wx)
     return __uint_as_float(__byte_perm(wx, 0x4B000000u, 0x7650 | B)) - 8388736.0f;
 }
 
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store a double into the same shared-memory location of CTA `rank` of this cluster
+__device__ __forceinline__ void dsmem_store(double* local, uint32_t rank, double v)
+{
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local)), "r"(rank));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
+}
+
 }  // namespace
 
-__global__ void __launch_bounds__(kThreads, 1)
+// G = CTAs per channel (cluster size), T = threads per CTA
+template <int G, int T>
+__global__ void __launch_bounds__(T, 1)
 track_kernel(TrackParams p)
 {
+    constexpr int kThreads = T;
+    constexpr int kWarps = T / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // layout: [buf0 | buf1 | code table (float) | warp partials | staging | params | mbarriers]
     int8_t* const buf0 = reinterpret_cast<int8_t*>(smem_raw);
-    float* s_code = reinterpret_cast<float*>(smem_raw + 2 * (size_t)p.bufBytes);
-    double* s_part = reinterpret_cast<double*>(s_code + ((p.codeLen + 2 + 3) & ~3));
-    double* s_stage = s_part + kWarps * 6;                       // [15][kStage]
+    float* s_code_raw = reinterpret_cast<float*>(smem_raw + 2 * (size_t)p.bufBytes);
+    float* s_code = s_code_raw + kPad;                           // index 0 = c(L) of the wrapped table
+    double* s_part = reinterpret_cast<double*>(s_code_raw + ((p.codeLen + 2 + 2 * kPad + 3) & ~3));
+    double* s_cl = s_part + kMaxWarps * 6;                       // [2][kMaxCluster][6] per-CTA partial sums (pushed by peers)
+    double* s_stage = s_cl + 2 * kMaxCluster * 6;                // [15][kStage]
     EpochParams* s_ep = reinterpret_cast<EpochParams*>(s_stage + GC_TRACK_ROWS * kStage);   // [2]
     NextPhases* s_nx = reinterpret_cast<NextPhases*>(s_ep + 2);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_nx + 1);     // 2 mbarriers
-    int* s_issued = reinterpret_cast<int*>(s_bar + 2);           // copy in flight per stage
+    int* s_issued = reinterpret_cast<int*>(s_bar + 2);           // per stage: 1 + epoch whose window was requested (0 = none)
 
-    const int ch = blockIdx.x;
+    const int ch = blockIdx.x / G;
+    const uint32_t crank = (G > 1) ? cluster_ctarank() : 0u;
+    const bool leader = (crank == 0);
     const TrackChan cinfo = p.chans[ch];
-    if (cinfo.prn == 0) {                                        // tracking.m:136
-        if (threadIdx.x == 0) p.epochsDone[ch] = 0;
+    if (cinfo.prn == 0) {                                        // tracking.m:136 (whole cluster leaves together)
+        if (threadIdx.x == 0 && leader) p.epochsDone[ch] = 0;
         return;
     }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* out = p.out + (size_t)ch * GC_TRACK_ROWS * p.nEpochs;
 
     // wrapped code table [c(L) c(1..L) c(1)]  (tracking.m:156-158)
-    for (int i = tid; i < p.codeLen + 2; i += kThreads)
-        s_code[i] = (float)p.codeTables[(size_t)ch * p.codeStride + i];
+    for (int i = tid; i < p.codeLen + 2 + 2 * kPad; i += kThreads) {
+        const int j = i - kPad;
+        s_code_raw[i] = (j >= 0 && j < p.codeLen + 2) ? (float)p.codeTables[(size_t)ch * p.codeStride + j] : 0.f;
+    }
 
     LoopMem lm;   // warp 0 lane 0: carrier memories; warp 1 lane 0: code memories
     lm.oldCodeNco = lm.oldCodeError = lm.oldCarrNco = lm.oldCarrError = 0.0;   // :173-178
@@ -209,37 +272,46 @@ track_kernel(TrackParams p)
     __syncthreads();
 
     const long long recBytesUp = (p.recSamples * 2 + 15) & ~15LL;
-    auto prefetch = [&](long long startSample, int stage) {      // thread 0 only
-        const long long b0 = (startSample * 2) & ~15LL;
+    // this CTA correlates the 16-byte chunks [c_lo, c_lo + cpc) of the block window
+    const int cpc = p.bufBytes / 16;                             // chunks per CTA (bufBytes is per CTA)
+    const int c_lo = (int)crank * cpc;
+    auto prefetch = [&](long long startSample, int stage, int epoch) {      // one thread only
+        const long long b0 = ((startSample * 2) & ~15LL) + (long long)c_lo * 16;
         long long n = p.bufBytes;
         if (b0 + n > recBytesUp) n = recBytesUp - b0;
-        if (b0 < 0 || n <= 0) return false;
+        if (b0 < 0 || n <= 0) return false;                      // this CTA's slice lies beyond the record
         mbar_expect_tx(&s_bar[stage], (uint32_t)n);
         bulk_g2s(buf0 + (size_t)stage * p.bufBytes, p.rec + b0, (uint32_t)n, &s_bar[stage]);
-        s_issued[stage] = 1;
+        s_issued[stage] = epoch + 1;
         return true;
     };
-    if (tid == 0 && !s_ep[0].stop) prefetch(s_ep[0].pos, 0);
+    constexpr int kLoader = kThreads - 1;                        // thread with the least sample work issues the TMA copies
+    if (tid == kLoader && !s_ep[0].stop) prefetch(s_ep[0].pos, 0, 0);
     __syncthreads();
 
+    uint32_t phase[2] = {0u, 0u};                                // mbarrier phase parity per stage
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};                // optional phase timing (p.dbg != nullptr)
+    const bool timing = (p.dbg != nullptr) && blockIdx.x == 0;
+#define GC_TICK(i) if (timing) { const long long _t = clock64(); tacc[i] += _t - tprev; tprev = _t; }
+    long long tprev = clock64();
     int e = 0;
     for (; e < p.nEpochs; ++e) {
         const int stage = e & 1;
         const EpochParams& ep = s_ep[stage];
+        const bool staged = (s_issued[stage] == e + 1);          // was this block's window requested?
         if (ep.stop) {
             // never leave a bulk copy in flight into this CTA's shared memory
-            if (s_issued[stage]) mbar_wait(&s_bar[stage], (e >> 1) & 1);
+            if (staged) mbar_wait(&s_bar[stage], phase[stage]);
             break;
         }
         const int blk = ep.blk, n = ep.n;
         const long long pos = ep.pos;
         const uint64_t dphi = ep.dphi, phase0 = ep.phase0;
         // window of epoch e+1 starts where this one ends; fetch it while we correlate
-        if (tid == 0 && e + 1 < p.nEpochs) prefetch(pos + blk, stage ^ 1);
-        // NCO phases at the end of this block: off the critical path, in the shadow of the sample loop
-        if (tid == 64) end_phases(p, ep, *s_nx);
-        mbar_wait(&s_bar[stage], (e >> 1) & 1);
-        if (tid == 0) s_issued[stage] = 0;
+        if (tid == kLoader && e + 1 < p.nEpochs) prefetch(pos + blk, stage ^ 1, e + 1);
+        GC_TICK(0)
+        if (staged) { mbar_wait(&s_bar[stage], phase[stage]); phase[stage] ^= 1u; }
+        GC_TICK(1)
 
         // in-chunk rotations e^{-i*2*pi*j*dphi}, j = 0..7 (per-epoch constants)
         float wc[8], ws[8];
@@ -254,18 +326,27 @@ track_kernel(TrackParams p)
         }
         const int off = (int)((pos * 2) & 15) >> 1;              // samples skipped in the first 16-byte chunk
         const int nChunks = (off + blk + 7) >> 3;
-        const bool inBuf = ((long long)nChunks * 16 <= p.bufBytes);
-        const int8_t* src = buf0 + (size_t)stage * p.bufBytes;
+        const bool fits = (nChunks <= cpc * G);
+        // oversize block (never with sane loop settings): CTA rank r takes chunks r, r+G, ... from L2
+        const int c_begin = fits ? c_lo : (int)crank, c_end = fits ? min(nChunks, c_lo + cpc) : nChunks;
+        const int c_step = fits ? kThreads : kThreads * G;
+        const bool inBuf = fits && staged;
+        const int8_t* src = buf0 + (size_t)stage * p.bufBytes - (size_t)c_lo * 16;
         const int8_t* gsrc = p.rec + ((pos * 2) & ~15LL);
         const double d = ep.d;
         const double aE = ep.aE, aP = ep.aP, aL = ep.aL, cE = ep.cE, cP = ep.cP, cL = ep.cL;
         const bool generic = ep.generic != 0;
 
         float aIE = 0, aQE = 0, aIP = 0, aQP = 0, aIL = 0, aQL = 0;
-        for (int c = tid; c < nChunks; c += kThreads) {
+        const double mE = ep.mE, mP = ep.mP, mL = ep.mL;
+        const int nE_ = ep.nE, nP_ = ep.nP, nL_ = ep.nL;
+        // One 16-byte chunk = 8 consecutive samples.  SPECIAL = per-sample left/right/middle selection
+        // (the chunk holding the middle of the colon vector, or every chunk of a `generic` block).
+        auto do_chunk = [&](int c, auto special_tag) {
+            constexpr bool SPECIAL = decltype(special_tag)::value;
             int4 raw;
             if (inBuf) raw = *reinterpret_cast<const int4*>(src + (size_t)c * 16);
-            else raw = __ldg(reinterpret_cast<const int4*>(gsrc + (size_t)c * 16));   // oversize block: straight from L2
+            else raw = __ldg(reinterpret_cast<const int4*>(gsrc + (size_t)c * 16));   // not staged: straight from L2
             const int k0 = c * 8 - off;
             const uint32_t w0 = (uint32_t)raw.x ^ 0x80808080u, w1 = (uint32_t)raw.y ^ 0x80808080u,
                            w2 = (uint32_t)raw.z ^ 0x80808080u, w3 = (uint32_t)raw.w ^ 0x80808080u;
@@ -274,11 +355,17 @@ track_kernel(TrackParams p)
             xi[2] = byte_to_float<0>(w1); xq[2] = byte_to_float<1>(w1); xi[3] = byte_to_float<2>(w1); xq[3] = byte_to_float<3>(w1);
             xi[4] = byte_to_float<0>(w2); xq[4] = byte_to_float<1>(w2); xi[5] = byte_to_float<2>(w2); xq[5] = byte_to_float<3>(w2);
             xi[6] = byte_to_float<0>(w3); xq[6] = byte_to_float<1>(w3); xi[7] = byte_to_float<2>(w3); xq[7] = byte_to_float<3>(w3);
+            if (k0 < 0 || k0 + 7 >= blk) {                        // first / last chunk of the block: drop the samples outside it
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if ((unsigned)(k0 + j) >= (unsigned)blk) { xi[j] = 0.f; xq[j] = 0.f; }
+            }
             float pIE = 0, pQE = 0, pIP = 0, pQP = 0, pIL = 0, pQL = 0;
-            // A chunk lies in the left half (t = a + k*d), the right half (t = c - (n-k)*d), or it is
-            // one of the <= 3 special chunks per block (first, last, the one holding the middle).
-            const bool allLeft = (2 * (k0 + 7) < n), allRight = (2 * k0 > n);
-            if (k0 >= 0 && k0 + 7 < blk && (allLeft || allRight) && !generic) {
+            if (!SPECIAL) {
+                // whole chunk in the left half (t = a + k*d) or in the right half (t = c - (n-k)*d).
+                // Samples masked above may have k < 0 or k >= blk; their code index stays inside
+                // the wrapped table (t > -1 and t < codeLength + 1).
+                const bool allLeft = (2 * (k0 + 7) < n);
                 const double sg = allLeft ? 1.0 : -1.0;
                 const double f0 = (double)(allLeft ? k0 : (n - k0));
                 const double ds = allLeft ? d : -d;
@@ -298,20 +385,24 @@ track_kernel(TrackParams p)
                     pIL = fmaf(vL, ur, pIL); pQL = fmaf(vL, ui, pQL);
                 }
             } else {
-#pragma unroll 1
+#pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int k = k0 + j;
-                    if (k < 0 || k >= blk) continue;
-                    const uint32_t wsel = (j < 2) ? w0 : (j < 4) ? w1 : (j < 6) ? w2 : w3;
-                    const uint32_t hw = wsel >> ((j & 1) * 16);
-                    const float sxi = (float)((int)(hw & 0xff) - 128), sxq = (float)((int)((hw >> 8) & 0xff) - 128);
-                    const float vE = s_code[ceil_idx(colon_elem(aE, d, cE, ep.nE, k))];
-                    const float vP = s_code[ceil_idx(colon_elem(aP, d, cP, ep.nP, k))];
-                    const float vL = s_code[ceil_idx(colon_elem(aL, d, cL, ep.nL, k))];
-                    float sj, cj;
-                    fix_sincos(dphi * (uint64_t)j, &sj, &cj);
-                    const float ur = fmaf(cj, sxi, sj * sxq);
-                    const float ui = fmaf(cj, sxq, -sj * sxi);
+                    const int kc = min(max(k0 + j, 0), blk - 1);
+                    double tE, tP, tL;
+                    if (!generic) {                              // the three vectors share n: one index conversion
+                        const bool left = 2 * kc < n, mid = 2 * kc == n;
+                        const double st = __dmul_rn((double)(left ? kc : n - kc), left ? d : -d);
+                        tE = mid ? mE : __dadd_rn(left ? aE : cE, st);
+                        tP = mid ? mP : __dadd_rn(left ? aP : cP, st);
+                        tL = mid ? mL : __dadd_rn(left ? aL : cL, st);
+                    } else {
+                        tE = colon_elem(aE, d, cE, nE_, kc);
+                        tP = colon_elem(aP, d, cP, nP_, kc);
+                        tL = colon_elem(aL, d, cL, nL_, kc);
+                    }
+                    const float vE = s_code[ceil_idx(tE)], vP = s_code[ceil_idx(tP)], vL = s_code[ceil_idx(tL)];
+                    const float ur = fmaf(wc[j], xi[j], ws[j] * xq[j]);
+                    const float ui = fmaf(wc[j], xq[j], -ws[j] * xi[j]);
                     pIE = fmaf(vE, ur, pIE); pQE = fmaf(vE, ui, pQE);
                     pIP = fmaf(vP, ur, pIP); pQP = fmaf(vP, ui, pQP);
                     pIL = fmaf(vL, ur, pIL); pQL = fmaf(vL, ui, pQL);
@@ -323,7 +414,22 @@ track_kernel(TrackParams p)
             aIE += fmaf(c0, pIE, s0 * pQE); aQE += fmaf(c0, pQE, -s0 * pIE);
             aIP += fmaf(c0, pIP, s0 * pQP); aQP += fmaf(c0, pQP, -s0 * pIP);
             aIL += fmaf(c0, pIL, s0 * pQL); aQL += fmaf(c0, pQL, -s0 * pIL);
+        };
+        using TagFast = std::false_type;
+        using TagSpecial = std::true_type;
+        if (!generic) {
+            // the one chunk that straddles the middle of the colon vector is left to the thread with
+            // the least regular work (a divergent special chunk would otherwise double its warp's time)
+            const int cMid = (off + (n >> 1)) >> 3;
+            const bool midUniform = (2 * (cMid * 8 - off + 7) < n) || (2 * (cMid * 8 - off) > n);
+            for (int c = c_begin + (fits ? tid : tid * G); c < c_end; c += c_step)
+                if (c != cMid || midUniform) do_chunk(c, TagFast{});
+            if (tid == kLoader && !midUniform && cMid >= c_begin && cMid < c_end && (fits || cMid % G == (int)crank))
+                do_chunk(cMid, TagSpecial{});
+        } else {
+            for (int c = c_begin + (fits ? tid : tid * G); c < c_end; c += c_step) do_chunk(c, TagSpecial{});
         }
+        GC_TICK(2)
         // cross-thread reduction in float64: warp shuffle, then warps 0 and 1 over the warp partials
         double v[6] = {(double)aIE, (double)aQE, (double)aIP, (double)aQP, (double)aIL, (double)aQL};
 #pragma unroll
@@ -334,18 +440,55 @@ track_kernel(TrackParams p)
 #pragma unroll
             for (int q = 0; q < 6; ++q) s_part[warp * 6 + q] = v[q];
         __syncthreads();
+        GC_TICK(3)
+        if (G > 1) {
+            // CTA partial -> every CTA of the cluster (slot [epoch parity][my rank]), then one barrier
+            double* slot = s_cl + ((e & 1) * kMaxCluster + (int)crank) * 6;
+            if (warp == 0) {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) v[q] = (lane < kWarps) ? s_part[lane * 6 + q] : 0.0;
+#pragma unroll
+                for (int o = kMaxWarps / 2; o > 0; o >>= 1)
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
+                double b[6];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) b[q] = __shfl_sync(0xffffffffu, v[q], 0);
+                for (int i = lane; i < 6 * G; i += 32) {
+                    const int q = i % 6;
+                    double val = b[0];
+#pragma unroll
+                    for (int t = 1; t < 6; ++t) val = (q == t) ? b[t] : val;
+                    dsmem_store(slot + q, (uint32_t)(i / 6), val);
+                }
+            }
+            cluster_sync_all();
+        }
+        GC_TICK(4)
         if (warp < 2) {
+            if (G > 1) {
+                // every CTA adds the G partials in the same order -> identical sums everywhere
+                const double* sl = s_cl + (e & 1) * kMaxCluster * 6;
 #pragma unroll
-            for (int q = 0; q < 6; ++q) v[q] = (lane < kWarps) ? s_part[lane * 6 + q] : 0.0;
+                for (int q = 0; q < 6; ++q) {
+                    double a = 0.0;
 #pragma unroll
-            for (int o = kWarps / 2; o > 0; o >>= 1)
+                    for (int r = 0; r < G; ++r) a += sl[r * 6 + q];
+                    v[q] = a;
+                }
+            } else {
 #pragma unroll
-                for (int q = 0; q < 6; ++q) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
+                for (int q = 0; q < 6; ++q) v[q] = (lane < kWarps) ? s_part[lane * 6 + q] : 0.0;
+#pragma unroll
+                for (int o = kMaxWarps / 2; o > 0; o >>= 1)
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
+            }
             const double I_E = v[0], Q_E = v[1], I_P = v[2], Q_P = v[3], I_L = v[4], Q_L = v[5];
             double* sg = s_stage + (e % kStage);
             if (tid == 0) {
                 // PLL (tracking.m:305-317)
-                const double carrError = atan(__ddiv_rn(Q_P, I_P)) / kTwoPi;
+                const double carrError = atan(fast_div(Q_P, I_P)) * 0.15915494309189535;   // 1/(2*pi)
                 const double carrNco = __dadd_rn(__dadd_rn(lm.oldCarrNco, __dmul_rn(p.pA, __dsub_rn(carrError, lm.oldCarrError))),
                                                  __dmul_rn(carrError, p.pB));
                 lm.oldCarrNco = carrNco; lm.oldCarrError = carrError;
@@ -361,23 +504,26 @@ track_kernel(TrackParams p)
                 sg[GC_F_Q_E * kStage] = Q_E; sg[GC_F_Q_P * kStage] = Q_P; sg[GC_F_Q_L * kStage] = Q_L;
             } else if (tid == 32) {
                 // DLL (tracking.m:322-335)
-                const double sE = sqrt(__dadd_rn(__dmul_rn(I_E, I_E), __dmul_rn(Q_E, Q_E)));
-                const double sL = sqrt(__dadd_rn(__dmul_rn(I_L, I_L), __dmul_rn(Q_L, Q_L)));
-                const double codeError = __ddiv_rn(__dsub_rn(sE, sL), __dadd_rn(sE, sL));
+                const double sE = fast_sqrt(__dadd_rn(__dmul_rn(I_E, I_E), __dmul_rn(Q_E, Q_E)));
+                const double sL = fast_sqrt(__dadd_rn(__dmul_rn(I_L, I_L), __dmul_rn(Q_L, Q_L)));
+                const double codeError = fast_div(__dsub_rn(sE, sL), __dadd_rn(sE, sL));
                 const double codeNco = __dadd_rn(__dadd_rn(lm.oldCodeNco, __dmul_rn(p.cA, __dsub_rn(codeError, lm.oldCodeError))),
                                                  __dmul_rn(codeError, p.cB));
                 lm.oldCodeNco = codeNco; lm.oldCodeError = codeError;
                 sg[GC_F_DLL_DISCR * kStage] = codeError;                            // :338-339
                 sg[GC_F_DLL_DISCR_FILT * kStage] = codeNco;
-                // :335 codeFreq of the next block, then its geometry (phases come from end_phases())
-                const NextPhases nx = *s_nx;
+                // :335 codeFreq of the next block, then its geometry
+                NextPhases nx;
+                end_phases(p, ep, nx);
                 plan_epoch(p, __dsub_rn(p.codeFreqBasis, codeNco), nx.remCodePhase, nx.remCarrPhase, nx.phase0,
                            pos + blk, s_ep[stage ^ 1]);
             }
         }
+        GC_TICK(5)
         __syncthreads();
+        GC_TICK(6)
         // coalesced flush of the staged rows every kStage epochs
-        if ((e % kStage) == kStage - 1) {
+        if (leader && (e % kStage) == kStage - 1) {
             const int e0 = e - (kStage - 1);
             for (int i = tid; i < GC_TRACK_ROWS * kStage; i += kThreads) {
                 const int f = i / kStage, q = i % kStage;
@@ -388,32 +534,63 @@ track_kernel(TrackParams p)
     __syncthreads();
     // tail flush (e = number of completed epochs)
     const int rem = e % kStage;
-    if (rem) {
+    if (leader && rem) {
         const int e0 = e - rem;
         for (int i = tid; i < GC_TRACK_ROWS * kStage; i += kThreads) {
             const int f = i / kStage, q = i % kStage;
             if (q < rem) out[(size_t)f * p.nEpochs + e0 + q] = s_stage[f * kStage + q];
         }
     }
-    if (tid == 0) p.epochsDone[ch] = e;
+    if (tid == 0 && leader) p.epochsDone[ch] = e;
+    if (timing && (tid == 0 || tid == 32 || tid == 96))
+        for (int i = 0; i < 8; ++i) p.dbg[(tid / 32) * 8 + i] = tacc[i];
+    if (G > 1) cluster_sync_all();                               // nobody leaves while a peer may still push to it
 }
 
 size_t track_smem_bytes(int bufBytes, int codeLen)
 {
     size_t s = 2 * (size_t)bufBytes;
-    s += sizeof(float) * ((codeLen + 2 + 3) & ~3);
-    s += sizeof(double) * (kWarps * 6 + GC_TRACK_ROWS * kStage);
-    s += 2 * sizeof(EpochParams) + sizeof(NextPhases) + 2 * sizeof(double) + 2 * sizeof(uint64_t) + 2 * sizeof(int) + 64;
+    s += sizeof(float) * ((codeLen + 2 + 2 * kPad + 3) & ~3);
+    s += sizeof(double) * (kMaxWarps * 6 + 2 * kMaxCluster * 6 + GC_TRACK_ROWS * kStage);
+    s += 2 * sizeof(EpochParams) + sizeof(NextPhases) + 2 * sizeof(uint64_t) + 2 * sizeof(int) + 64;
     return s;
 }
 
-cudaError_t launch_track(const TrackParams& p, int nCh, cudaStream_t stream)
+template <int G, int T>
+static cudaError_t launch_track_g(const TrackParams& p, int nCh, cudaStream_t stream)
 {
     const size_t smem = track_smem_bytes(p.bufBytes, p.codeLen);
-    cudaError_t err = cudaFuncSetAttribute(track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = cudaFuncSetAttribute(track_kernel<G, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    track_kernel<<<nCh, kThreads, smem, stream>>>(p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(nCh * G);
+    cfg.blockDim = dim3(T);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, track_kernel<G, T>, p);
+}
+
+// p.bufBytes must be the per-CTA staging size for `cluster` CTAs per channel (track_buf_bytes)
+cudaError_t launch_track(const TrackParams& p, int nCh, int cluster, cudaStream_t stream)
+{
+    switch (cluster) {
+        case 8: return launch_track_g<8, 288>(p, nCh, stream);
+        case 4: return launch_track_g<4, 512>(p, nCh, stream);
+        case 2: return launch_track_g<2, 512>(p, nCh, stream);
+        default: return launch_track_g<1, 512>(p, nCh, stream);
+    }
+}
+
+// bytes each CTA stages per epoch: ceil(maxChunks / cluster) 16-byte chunks
+int track_buf_bytes(int maxBlockSamples, int cluster)
+{
+    const int maxChunks = (2 * maxBlockSamples + 16 + 15) / 16;
+    return ((maxChunks + cluster - 1) / cluster) * 16;
 }
 
 // out rows pre-fill (tracking.m:51-77): zeros for absoluteSample and the six I/Q rows, +inf elsewhere

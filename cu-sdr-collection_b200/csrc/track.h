@@ -18,21 +18,23 @@ struct TrackChan {
 struct TrackParams {
     const int8_t* rec;       // resident IF record, int8 I,Q interleaved, 16-byte aligned
     long long recSamples;    // complex samples in the record
-    double fs, codeFreqBasis, codeLength, spc;
+    double fs, invFs, codeFreqBasis, codeLength, spc;
     double cA, cB;           // tau2code/tau1code, PDIcode/tau1code  (tracking.m:326)
     double pA, pB;           // tau2carr/tau1carr, PDIcarr/tau1carr  (tracking.m:308)
     int nEpochs;
-    int bufBytes;            // bytes staged per epoch (multiple of 16)
+    int bufBytes;            // bytes staged per epoch by ONE CTA (multiple of 16)
     int codeLen;             // chips per code period
     int codeStride;          // bytes between channels in codeTables
     const int8_t* codeTables;   // [nCh][codeStride]: wrapped +-1 table [c(L) c(1..L) c(1)]
     const TrackChan* chans;
     double* out;             // [nCh][15][nEpochs]
     int32_t* epochsDone;
+    long long* dbg;          // optional [4][8] phase-timing accumulators (GC_TRACK_DEBUG), else nullptr
 };
 
 size_t track_smem_bytes(int bufBytes, int codeLen);
-cudaError_t launch_track(const TrackParams& p, int nCh, cudaStream_t stream);
+cudaError_t launch_track(const TrackParams& p, int nCh, int cluster, cudaStream_t stream);
+int track_buf_bytes(int maxBlockSamples, int cluster);
 cudaError_t launch_track_fill(double* out, int nCh, int nEpochs, cudaStream_t stream);
 
 }  // namespace gc

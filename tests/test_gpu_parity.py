@@ -200,3 +200,27 @@ def test_golden_fixture_through_cuda():
     errs = track_rel_err(out[live], g["track"][live])
     assert errs["I_P"] < IQ_TOL and errs["Q_P"] < IQ_TOL and errs["absoluteSample"] == 0
     eng.close()
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
+def test_tracking_cluster_variants_agree(cluster, monkeypatch):
+    """A channel spread over a thread-block cluster of 1/2/4/8 CTAs gives the same results."""
+    monkeypatch.setenv("GC_TRACK_CLUSTER", str(cluster))
+    sc, s, N, raw, prn, af, cp = _track_case(16.368e6, 150, nsat=2, seed=31)
+    eng = Engine(s)
+    eng.set_record(raw)
+    out, vv, vi, done = eng.track(prn, af, cp, 150)
+    ref, rvv, rvi, rdone = c_tracking(raw, s, prn, af, cp, 150)
+    assert np.array_equal(done, rdone)
+    live = np.array(prn) != 0
+    assert np.array_equal(out[live][:, 0], ref[live][:, 0])
+    errs = track_rel_err(out[live], ref[live])
+    for f in ("I_P", "Q_P", "I_E", "Q_E", "I_L", "Q_L"):
+        assert errs[f] < IQ_TOL, (cluster, f, errs[f])
+    # record that ends mid-run: same early-stop semantics in every variant
+    short = raw[: 2 * N * 100]
+    eng.set_record(short)
+    out2, _, _, done2 = eng.track(prn, af, cp, 150)
+    _, _, _, rdone2 = c_tracking(short, s, prn, af, cp, 150)
+    assert np.array_equal(done2, rdone2)
+    eng.close()
