@@ -546,6 +546,7 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
     p.cA = h->tau2code / h->tau1code; p.cB = c.int_time / h->tau1code;     // tracking.m:326
     p.pA = h->tau2carr / h->tau1carr; p.pB = c.int_time / h->tau1carr;     // tracking.m:308
     p.nEpochs = nEpochs;
+    p.exactDisc = getenv("GC_TRACK_EXACT_DISC") ? 1 : 0;
     // CTAs per channel: spread few channels over the chip (thread-block clusters), 1 CTA per channel once
     // the channel count fills it
     int nLive = 0;
@@ -566,7 +567,7 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
     GC_CUDA(h, h->epochsDone.reserve(nCh));
     p.codeTables = h->trackCodes.p; p.chans = h->chans.p; p.out = h->trackOut.p; p.epochsDone = h->epochsDone.p;
     long long* dbg = nullptr;
-    if (getenv("GC_TRACK_DEBUG")) { cudaMalloc(&dbg, 32 * sizeof(long long)); cudaMemset(dbg, 0, 32 * sizeof(long long)); }
+    if (getenv("GC_TRACK_DEBUG")) { cudaMalloc(&dbg, 96 * sizeof(long long)); cudaMemset(dbg, 0, 96 * sizeof(long long)); }
     p.dbg = dbg;
     GC_CUDA(h, launch_track_fill(h->trackOut.p, nCh, nEpochs, st));
     cudaEventRecord(h->ev[0], st);
@@ -580,7 +581,7 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
     h->stats.track_kernel_ms = ms;
     h->stats.track_launches = 2;
     if (dbg) {
-        long long hd[32];
+        long long hd[96];
         cudaMemcpy(hd, dbg, sizeof(hd), cudaMemcpyDeviceToHost);
         cudaFree(dbg);
         const char* names[7] = {"top", "mbar", "samples", "sync1", "cluster", "control", "sync2"};
@@ -589,6 +590,11 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
             fprintf(stderr, "[gc_track timing] warp %d cycles/epoch:", w);
             for (int i = 0; i < 7; ++i) fprintf(stderr, " %s=%.0f", names[i], (double)hd[w * 8 + i] / nEpochs);
             fprintf(stderr, "  (cluster=%d)\n", cluster);
+        }
+        for (int r = 0; r < cluster && cluster > 1; ++r) {
+            fprintf(stderr, "[gc_track timing] rank %d warp0 cycles/epoch:", r);
+            for (int i = 0; i < 7; ++i) fprintf(stderr, " %s=%.0f", names[i], (double)hd[32 + r * 8 + i] / nEpochs);
+            fprintf(stderr, "\n");
         }
     }
 

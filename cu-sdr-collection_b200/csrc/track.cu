@@ -101,13 +101,23 @@ __device__ __forceinline__ int ceil_idx(double t) { return __double2loint(__dadd
 
 // Geometry of a block from the NCO state (tracking.m:219-222, 252-268).
 __device__ void plan_epoch(const TrackParams& p, double codeFreq, double remCodePhase,
-                           double remCarrPhase, uint64_t phase0, long long pos, EpochParams& ep)
+                           double remCarrPhase, uint64_t phase0, long long pos, EpochParams& ep, double& invStep)
 {
     // :219 codeFreq / samplingFreq, correctly rounded: q0 = a*RN(1/b), r = a - q0*b (exact, FMA),
     // q = RN(q0 + r*RN(1/b))  (Markstein); three dependent operations instead of a full division
     const double q0 = __dmul_rn(codeFreq, p.invFs);
     const double step = __fma_rn(__fma_rn(-q0, p.fs, codeFreq), p.invFs, q0);
-    const int blk = (int)ceil(__ddiv_rn(__dsub_rn(p.codeLength, remCodePhase), step));  // :222
+    // :222 blksize = ceil((codeLength - remCodePhase) / codePhaseStep).  The quotient is formed with a
+    // reciprocal carried from the previous block and refreshed by a Newton step (the step moves by
+    // < 1e-6 relative per epoch, so the refreshed value is good to ~1e-12); if the quotient is within 1e-6
+    // of an integer the exact IEEE division decides, so the result always equals the reference's.
+    const double x = __dsub_rn(p.codeLength, remCodePhase);
+    double y = (invStep != 0.0) ? invStep : __ddiv_rn(1.0, step);
+    y = fma(y, fma(-step, y, 1.0), y);
+    invStep = y;
+    double q = x * y;
+    if (!(fabs(q - rint(q)) > 1e-6)) q = __ddiv_rn(x, step);
+    const int blk = (int)ceil(q);
     ep.d = step;
     ep.blk = blk;
     ep.n = blk - 1;
@@ -174,25 +184,6 @@ __device__ __forceinline__ void end_phases(const TrackParams& p, const EpochPara
     nx.remCarrPhase = (ep.carrFreq < 0.0 && frac != 0.0) ? (frac - 1.0) * kTwoPi : frac * kTwoPi;
 }
 
-// float64 quotient / square root from an fp32 seed and one Newton step in float64 (~1e-14
-// relative): the exact IEEE versions cost ~250 dependent cycles each on the loop's critical path.
-__device__ __forceinline__ double fast_div(double a, double b)
-{
-    const float bf = (float)b;
-    if (!(fabsf(bf) > 1e-30f) || !(fabsf(bf) < 1e30f)) return __ddiv_rn(a, b);
-    const float rb = 1.0f / bf;
-    const double q0 = (double)((float)a * rb);
-    return fma(fma(-q0, b, a), (double)rb, q0);
-}
-__device__ __forceinline__ double fast_sqrt(double x)
-{
-    const float xf = (float)x;
-    if (!(xf > 1e-30f) || !(xf < 1e30f)) return sqrt(x);
-    const float s0 = sqrtf(xf);
-    const double s = (double)s0;
-    return fma(fma(-s, s, x), (double)(0.5f / s0), s);
-}
-
 // exact float of a signed byte already xor-ed with 0x80: 0x4B0000bb = 2^23 + (b+128)
 template <int B>
 __device__ __forceinline__ float byte_to_float(uint32_t wx)
@@ -210,12 +201,16 @@ __device__ __forceinline__ void cluster_sync_all()
 {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// store a double into the same shared-memory location of CTA `rank` of this cluster
-__device__ __forceinline__ void dsmem_store(double* local, uint32_t rank, double v)
+// store a double into the same shared-memory location of CTA `rank` of this cluster and credit 8
+// bytes to that CTA's mbarrier `bar` (same offset): data and signal travel together, so the
+// consumer needs no cluster-wide barrier, only a wait on its own mbarrier.
+__device__ __forceinline__ void dsmem_push(double* local, uint64_t* bar, uint32_t rank, double v)
 {
-    uint32_t remote;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local)), "r"(rank));
-    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
+    uint32_t raddr, rbar;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(local)), "r"(rank));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                 ::"r"(raddr), "l"(__double_as_longlong(v)), "r"(rbar) : "memory");
 }
 
 }  // namespace
@@ -227,6 +222,12 @@ track_kernel(TrackParams p)
 {
     constexpr int kThreads = T;
     constexpr int kWarps = T / 32;
+    // Role threads.  The 8-CTA variant carries three spare warps so that the TMA issue, the one
+    // non-uniform chunk and the loop closure never serialise with a warp full of regular chunks.
+    constexpr int kSpecialTid = (G == 8) ? 9 * 32 : T - 1;      // chunk holding the middle of the colon vector
+    constexpr int kLoader = (G == 8) ? 10 * 32 : T - 1;         // issues the bulk copies
+    constexpr int kPllTid = (G == 8) ? 10 * 32 : 0;             // carrier loop
+    constexpr int kDllTid = (G == 8) ? 9 * 32 : 32;             // code loop + geometry of the next block
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // layout: [buf0 | buf1 | code table (float) | warp partials | staging | params | mbarriers]
     int8_t* const buf0 = reinterpret_cast<int8_t*>(smem_raw);
@@ -237,8 +238,9 @@ track_kernel(TrackParams p)
     double* s_stage = s_cl + 2 * kMaxCluster * 6;                // [15][kStage]
     EpochParams* s_ep = reinterpret_cast<EpochParams*>(s_stage + GC_TRACK_ROWS * kStage);   // [2]
     NextPhases* s_nx = reinterpret_cast<NextPhases*>(s_ep + 2);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_nx + 1);     // 2 mbarriers
-    int* s_issued = reinterpret_cast<int*>(s_bar + 2);           // per stage: 1 + epoch whose window was requested (0 = none)
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_nx + 1);     // 2 mbarriers (TMA stages) + 2 (partial-sum exchange)
+    uint64_t* s_xbar = s_bar + 2;
+    int* s_issued = reinterpret_cast<int*>(s_bar + 4);           // per stage: 1 + epoch whose window was requested (0 = none)
 
     const int ch = blockIdx.x / G;
     const uint32_t crank = (G > 1) ? cluster_ctarank() : 0u;
@@ -260,13 +262,17 @@ track_kernel(TrackParams p)
     LoopMem lm;   // warp 0 lane 0: carrier memories; warp 1 lane 0: code memories
     lm.oldCodeNco = lm.oldCodeError = lm.oldCarrNco = lm.oldCarrError = 0.0;   // :173-178
     lm.carrFreqBasis = cinfo.acqFreq;                                          // :168
+    double invStep = 0.0;                                        // DLL thread: 1/codePhaseStep of the previous block
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
+        mbar_init(&s_xbar[0], 1);
+        mbar_init(&s_xbar[1], 1);
         mbar_fence_init();
         s_issued[0] = s_issued[1] = 0;
         // :163-170 codeFreq = codeFreqBasis, remCodePhase = 0, carrFreq = acquiredFreq, remCarrPhase = 0; :150 fseek
-        plan_epoch(p, p.codeFreqBasis, 0.0, 0.0, 0ull, cinfo.startSample, s_ep[0]);
+        double inv0 = 0.0;
+        plan_epoch(p, p.codeFreqBasis, 0.0, 0.0, 0ull, cinfo.startSample, s_ep[0], inv0);
         plan_carrier(p, cinfo.acqFreq, s_ep[0]);
     }
     __syncthreads();
@@ -285,13 +291,14 @@ track_kernel(TrackParams p)
         s_issued[stage] = epoch + 1;
         return true;
     };
-    constexpr int kLoader = kThreads - 1;                        // thread with the least sample work issues the TMA copies
     if (tid == kLoader && !s_ep[0].stop) prefetch(s_ep[0].pos, 0, 0);
     __syncthreads();
+    if (G > 1) cluster_sync_all();                               // every peer's exchange barriers are initialised
+    uint32_t xphase[2] = {0u, 0u};
 
     uint32_t phase[2] = {0u, 0u};                                // mbarrier phase parity per stage
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};                // optional phase timing (p.dbg != nullptr)
-    const bool timing = (p.dbg != nullptr) && blockIdx.x == 0;
+    const bool timing = (p.dbg != nullptr) && blockIdx.x < G;
 #define GC_TICK(i) if (timing) { const long long _t = clock64(); tacc[i] += _t - tprev; tprev = _t; }
     long long tprev = clock64();
     int e = 0;
@@ -309,6 +316,7 @@ track_kernel(TrackParams p)
         const uint64_t dphi = ep.dphi, phase0 = ep.phase0;
         // window of epoch e+1 starts where this one ends; fetch it while we correlate
         if (tid == kLoader && e + 1 < p.nEpochs) prefetch(pos + blk, stage ^ 1, e + 1);
+        if (G > 1 && tid == kPllTid) mbar_expect_tx(&s_xbar[e & 1], 48u * G);   // G CTAs x 6 doubles will arrive
         GC_TICK(0)
         if (staged) { mbar_wait(&s_bar[stage], phase[stage]); phase[stage] ^= 1u; }
         GC_TICK(1)
@@ -424,18 +432,21 @@ track_kernel(TrackParams p)
             const bool midUniform = (2 * (cMid * 8 - off + 7) < n) || (2 * (cMid * 8 - off) > n);
             for (int c = c_begin + (fits ? tid : tid * G); c < c_end; c += c_step)
                 if (c != cMid || midUniform) do_chunk(c, TagFast{});
-            if (tid == kLoader && !midUniform && cMid >= c_begin && cMid < c_end && (fits || cMid % G == (int)crank))
+            if (tid == kSpecialTid && !midUniform && cMid >= c_begin && cMid < c_end && (fits || cMid % G == (int)crank))
                 do_chunk(cMid, TagSpecial{});
         } else {
             for (int c = c_begin + (fits ? tid : tid * G); c < c_end; c += c_step) do_chunk(c, TagSpecial{});
         }
         GC_TICK(2)
         // cross-thread reduction in float64: warp shuffle, then warps 0 and 1 over the warp partials
-        double v[6] = {(double)aIE, (double)aQE, (double)aIP, (double)aQP, (double)aIL, (double)aQL};
+        // (the 32 lane partials of a warp are combined in fp32 - they are fp32 sums of <= 32 samples each -
+        //  and everything from the warp partials on is float64)
+        float vf[6] = {aIE, aQE, aIP, aQP, aIL, aQL};
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-            for (int q = 0; q < 6; ++q) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
+            for (int q = 0; q < 6; ++q) vf[q] += __shfl_down_sync(0xffffffffu, vf[q], o);
+        double v[6] = {(double)vf[0], (double)vf[1], (double)vf[2], (double)vf[3], (double)vf[4], (double)vf[5]};
         if (lane == 0)
 #pragma unroll
             for (int q = 0; q < 6; ++q) s_part[warp * 6 + q] = v[q];
@@ -459,22 +470,27 @@ track_kernel(TrackParams p)
                     double val = b[0];
 #pragma unroll
                     for (int t = 1; t < 6; ++t) val = (q == t) ? b[t] : val;
-                    dsmem_store(slot + q, (uint32_t)(i / 6), val);
+                    dsmem_push(slot + q, &s_xbar[e & 1], (uint32_t)(i / 6), val);
                 }
             }
-            cluster_sync_all();
         }
         GC_TICK(4)
-        if (warp < 2) {
+        if (warp == kPllTid / 32 || warp == kDllTid / 32) {
             if (G > 1) {
-                // every CTA adds the G partials in the same order -> identical sums everywhere
+                mbar_wait(&s_xbar[e & 1], xphase[e & 1]);       // all G partial sets have landed here
+                xphase[e & 1] ^= 1u;
+                // every CTA adds the G partials in the same (pairwise) order -> identical sums everywhere
                 const double* sl = s_cl + (e & 1) * kMaxCluster * 6;
 #pragma unroll
                 for (int q = 0; q < 6; ++q) {
-                    double a = 0.0;
+                    double t[G];
 #pragma unroll
-                    for (int r = 0; r < G; ++r) a += sl[r * 6 + q];
-                    v[q] = a;
+                    for (int r = 0; r < G; ++r) t[r] = sl[r * 6 + q];
+#pragma unroll
+                    for (int w = G / 2; w > 0; w >>= 1)
+#pragma unroll
+                        for (int r = 0; r < w; ++r) t[r] += t[r + w];
+                    v[q] = t[0];
                 }
             } else {
 #pragma unroll
@@ -486,9 +502,12 @@ track_kernel(TrackParams p)
             }
             const double I_E = v[0], Q_E = v[1], I_P = v[2], Q_P = v[3], I_L = v[4], Q_L = v[5];
             double* sg = s_stage + (e % kStage);
-            if (tid == 0) {
+            if (tid == kPllTid) {
                 // PLL (tracking.m:305-317)
-                const double carrError = atan(fast_div(Q_P, I_P)) * 0.15915494309189535;   // 1/(2*pi)
+                // The discriminator is evaluated in fp32: its inputs are sums of fp32 products, so float64
+                // would not make it more accurate, and a float64 atan is ~1000 dependent cycles per epoch.
+                const double carrError = p.exactDisc ? atan(__ddiv_rn(Q_P, I_P)) / kTwoPi
+                                                     : (double)atanf((float)Q_P / (float)I_P) * 0.15915494309189535;
                 const double carrNco = __dadd_rn(__dadd_rn(lm.oldCarrNco, __dmul_rn(p.pA, __dsub_rn(carrError, lm.oldCarrError))),
                                                  __dmul_rn(carrError, p.pB));
                 lm.oldCarrNco = carrNco; lm.oldCarrError = carrError;
@@ -502,11 +521,18 @@ track_kernel(TrackParams p)
                 sg[GC_F_PLL_DISCR_FILT * kStage] = carrNco;
                 sg[GC_F_I_E * kStage] = I_E; sg[GC_F_I_P * kStage] = I_P; sg[GC_F_I_L * kStage] = I_L;   // :343-348
                 sg[GC_F_Q_E * kStage] = Q_E; sg[GC_F_Q_P * kStage] = Q_P; sg[GC_F_Q_L * kStage] = Q_L;
-            } else if (tid == 32) {
+            } else if (tid == kDllTid) {
                 // DLL (tracking.m:322-335)
-                const double sE = fast_sqrt(__dadd_rn(__dmul_rn(I_E, I_E), __dmul_rn(Q_E, Q_E)));
-                const double sL = fast_sqrt(__dadd_rn(__dmul_rn(I_L, I_L), __dmul_rn(Q_L, Q_L)));
-                const double codeError = fast_div(__dsub_rn(sE, sL), __dadd_rn(sE, sL));
+                const double pE = __dadd_rn(__dmul_rn(I_E, I_E), __dmul_rn(Q_E, Q_E));
+                const double pL = __dadd_rn(__dmul_rn(I_L, I_L), __dmul_rn(Q_L, Q_L));
+                double codeError;
+                if (p.exactDisc) {
+                    const double sE = sqrt(pE), sL = sqrt(pL);
+                    codeError = __ddiv_rn(__dsub_rn(sE, sL), __dadd_rn(sE, sL));
+                } else {
+                    const float sE = sqrtf((float)pE), sL = sqrtf((float)pL);
+                    codeError = (double)((sE - sL) / (sE + sL));
+                }
                 const double codeNco = __dadd_rn(__dadd_rn(lm.oldCodeNco, __dmul_rn(p.cA, __dsub_rn(codeError, lm.oldCodeError))),
                                                  __dmul_rn(codeError, p.cB));
                 lm.oldCodeNco = codeNco; lm.oldCodeError = codeError;
@@ -516,7 +542,7 @@ track_kernel(TrackParams p)
                 NextPhases nx;
                 end_phases(p, ep, nx);
                 plan_epoch(p, __dsub_rn(p.codeFreqBasis, codeNco), nx.remCodePhase, nx.remCarrPhase, nx.phase0,
-                           pos + blk, s_ep[stage ^ 1]);
+                           pos + blk, s_ep[stage ^ 1], invStep);
             }
         }
         GC_TICK(5)
@@ -542,8 +568,10 @@ track_kernel(TrackParams p)
         }
     }
     if (tid == 0 && leader) p.epochsDone[ch] = e;
-    if (timing && (tid == 0 || tid == 32 || tid == 96))
-        for (int i = 0; i < 8; ++i) p.dbg[(tid / 32) * 8 + i] = tacc[i];
+    if (timing && blockIdx.x == 0 && (tid == kPllTid || tid == kDllTid || tid == 96))
+        for (int i = 0; i < 8; ++i) p.dbg[(tid == kPllTid ? 0 : tid == kDllTid ? 1 : 3) * 8 + i] = tacc[i];
+    if (timing && tid == 0)                                      // per-rank view of regular warp 0
+        for (int i = 0; i < 8; ++i) p.dbg[32 + blockIdx.x * 8 + i] = tacc[i];
     if (G > 1) cluster_sync_all();                               // nobody leaves while a peer may still push to it
 }
 
@@ -552,7 +580,7 @@ size_t track_smem_bytes(int bufBytes, int codeLen)
     size_t s = 2 * (size_t)bufBytes;
     s += sizeof(float) * ((codeLen + 2 + 2 * kPad + 3) & ~3);
     s += sizeof(double) * (kMaxWarps * 6 + 2 * kMaxCluster * 6 + GC_TRACK_ROWS * kStage);
-    s += 2 * sizeof(EpochParams) + sizeof(NextPhases) + 2 * sizeof(uint64_t) + 2 * sizeof(int) + 64;
+    s += 2 * sizeof(EpochParams) + sizeof(NextPhases) + 4 * sizeof(uint64_t) + 2 * sizeof(int) + 64;
     return s;
 }
 
@@ -579,7 +607,7 @@ static cudaError_t launch_track_g(const TrackParams& p, int nCh, cudaStream_t st
 cudaError_t launch_track(const TrackParams& p, int nCh, int cluster, cudaStream_t stream)
 {
     switch (cluster) {
-        case 8: return launch_track_g<8, 288>(p, nCh, stream);
+        case 8: return launch_track_g<8, 352>(p, nCh, stream);
         case 4: return launch_track_g<4, 512>(p, nCh, stream);
         case 2: return launch_track_g<2, 512>(p, nCh, stream);
         default: return launch_track_g<1, 512>(p, nCh, stream);

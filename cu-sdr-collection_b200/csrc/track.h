@@ -22,6 +22,7 @@ struct TrackParams {
     double cA, cB;           // tau2code/tau1code, PDIcode/tau1code  (tracking.m:326)
     double pA, pB;           // tau2carr/tau1carr, PDIcarr/tau1carr  (tracking.m:308)
     int nEpochs;
+    int exactDisc;           // 1: float64 atan/sqrt/divide in the discriminators (GC_TRACK_EXACT_DISC), 0: fp32-seeded
     int bufBytes;            // bytes staged per epoch by ONE CTA (multiple of 16)
     int codeLen;             // chips per code period
     int codeStride;          // bytes between channels in codeTables
