@@ -116,7 +116,8 @@ fwd_rows_kernel(RowsParams p)
 // in : element (k2, k3) at k3*32 + k2       out: element (t2, t3) at t2*31 + t3
 // grid: x = k1 (33 rows), y = PRN group, z = bin * mGroups + block group, so that CTAs scheduled
 // together share one X slice (L1/L2 hits) while the replica spectra stay L2 resident.
-__global__ void __launch_bounds__(kRowWarps * 32)
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 inv_rows_kernel(RowsParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -231,16 +232,29 @@ cudaError_t launch_fwd_rows(const RowsParams& p, cudaStream_t s)
     return cudaGetLastError();
 }
 
-cudaError_t launch_inv_rows(const RowsParams& p, cudaStream_t s)
+template <int WARPS, int MINB>
+static cudaError_t launch_inv_rows_t(const RowsParams& p, cudaStream_t s)
 {
-    const int smem = (int)(sizeof(float2) * kRowWarps * RA * kPitchI);
-    cudaError_t e = cudaFuncSetAttribute(inv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int smem = (int)(sizeof(float2) * WARPS * RA * kPitchI);
+    cudaError_t e = cudaFuncSetAttribute(inv_rows_kernel<WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const int mGroups = (p.nonCoh + p.mPerCta - 1) / p.mPerCta;
     const int pGroups = (p.nPrnChunk + p.prnPerCta - 1) / p.prnPerCta;
     dim3 grid(C, pGroups, p.nBins * mGroups);
-    inv_rows_kernel<<<grid, kRowWarps * 32, smem, s>>>(p);
+    inv_rows_kernel<WARPS, MINB><<<grid, WARPS * 32, smem, s>>>(p);
     return cudaGetLastError();
+}
+
+// p.prnPerCta * p.mPerCta warps per CTA: 8 (2 x 4, 128 registers, 16 warps/SM), 6 (1 x 6 or 2 x 3,
+// 96 registers, 18 warps/SM) or 5 (1 x 5, 96 registers, 20 warps/SM)
+cudaError_t launch_inv_rows(const RowsParams& p, cudaStream_t s)
+{
+    switch (p.prnPerCta * p.mPerCta) {
+        case 5: return launch_inv_rows_t<5, 4>(p, s);
+        case 6: return launch_inv_rows_t<6, 3>(p, s);
+        case 10: return launch_inv_rows_t<10, 2>(p, s);
+        default: return launch_inv_rows_t<8, 2>(p, s);
+    }
 }
 
 cudaError_t launch_finish_replica(float2* Cc, size_t n, cudaStream_t s)

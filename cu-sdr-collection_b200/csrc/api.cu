@@ -346,7 +346,11 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
             const int nc = std::min(chunk, nSv - s0);
             RowsParams ip{};
             ip.X = h->X.p; ip.Cc = h->Cc.p; ip.W = h->W.p; 
-            ip.nonCoh = nonCoh; ip.nBins = nBins; ip.prnPerCta = 2; ip.mPerCta = 4;
+            ip.nonCoh = nonCoh; ip.nBins = nBins; ip.prnPerCta = 1; ip.mPerCta = 5;   // 5 warps, 96 registers, 20 warps/SM
+            if (const char* e = getenv("GC_ROWS_VARIANT")) {   // "PxM" warps per CTA = P PRNs x M blocks
+                int P = 0, M = 0;
+                if (sscanf(e, "%dx%d", &P, &M) == 2 && (P * M == 5 || P * M == 6 || P * M == 8 || P * M == 10)) { ip.prnPerCta = P; ip.mPerCta = M; }
+            }
             ip.nPrnChunk = nc; ip.prnSlot0 = s0; ip.prnList = h->prnList.p;
             const int a = mark();
             GC_CUDA(h, launch_inv_rows(ip, st)); ++launches;

@@ -224,3 +224,67 @@ def test_tracking_cluster_variants_agree(cluster, monkeypatch):
     _, _, _, rdone2 = c_tracking(short, s, prn, af, cp, 150)
     assert np.array_equal(done2, rdone2)
     eng.close()
+
+
+def test_full_size_acquisition_grid_vs_oracle():
+    """BASELINE configs[1] at full size: 32 PRN x 29 Doppler x 20 blocks, 2N = 32736; every index exact."""
+    sc = scene(16.368e6, nsat=10, seed=20260101)
+    for sat in sc.sats:
+        sat.cn0 = max(sat.cn0, 43.0)
+    s = init_settings(samplingFreq=16.368e6)
+    raw = synth.make_record(sc, 16368 * 42 + 64)
+    eng = Engine(s)
+    got = eng.acquire(s.acqSatelliteList, host_iq=raw)
+    ref = c_acquisition(raw, s, s.acqSatelliteList)
+    worst = _check_acq(got, ref, s.acqSatelliteList)
+    assert int(np.sum(got["carrFreq"] != 0)) >= 8
+    assert np.array_equal(got["coarseCodePhase"], ref["coarseCodePhase"]) or worst < METRIC_TOL
+    eng.close()
+
+
+def test_full_size_tracking_properties():
+    """BASELINE configs[2] at full size (12 channels x 60000 ms on a 60 s record generated on the GPU):
+    size-independent properties + the oracle on the first 400 epochs of every channel."""
+    import torch
+    fs, nms = 16.368e6, 60000
+    sc = scene(fs, nsat=12, seed=77)
+    for sat in sc.sats:
+        sat.cn0 = max(sat.cn0, 42.0)
+    s = init_settings(samplingFreq=fs, msToProcess=nms, numberOfChannels=12)
+    N = 16368
+    rec = synth.make_record_torch(sc, N * (nms + 40), device="cuda")
+    eng = Engine(s)
+    eng.set_record(rec)
+    acq = eng.acquire()
+    ch = preRun(acq, s)
+    found = {c["PRN"] for c in ch if c["PRN"]}
+    assert found == {x.prn for x in sc.sats}
+    prn = [c["PRN"] for c in ch]; af = [c["acquiredFreq"] for c in ch]; cp = [float(c["codePhase"]) for c in ch]
+    out, vv, vi, done = eng.track(prn, af, cp, nms)
+    assert np.all(done == nms)
+    sat_of = {x.prn: x for x in sc.sats}
+    for c in range(12):
+        sat = sat_of[prn[c]]
+        a = out[c, 0]
+        blk = np.diff(a)
+        assert np.all((blk >= N - 2) & (blk <= N + 2)), "block sizes"               # one code period per epoch
+        # code-phase bookkeeping closes: block starts follow the injected code Doppler over the whole minute
+        drift = (a[-1] - a[0]) - (nms - 1) * N
+        expect = -(nms - 1) * N * sat.doppler / 1575.42e6
+        assert abs(drift - expect) < 3.0, (drift, expect)
+        # carrier NCO sits on the injected Doppler
+        assert abs(np.mean(out[c, 2, 1000:]) - (s.IF + sat.doppler)) < 1.0
+        # lock: prompt I carries the power, and its sign over 20 ms bit periods is the injected data (up to polarity)
+        Ip, Qp = out[c, 3, 2000:], out[c, 7, 2000:]
+        assert np.mean(np.abs(Ip)) > 4 * np.mean(np.abs(Qp))
+        assert np.all(np.hypot(out[c, 3], out[c, 7]) > 0)
+        # C/N0 estimate within 3 dB of the injected value
+        assert abs(np.median(vv[c, 10:]) - sat.cn0) < 3.0, (np.median(vv[c, 10:]), sat.cn0)
+    # same bytes through the oracle for the first 400 epochs
+    n0 = 400
+    raw = rec[: 2 * N * (n0 + 50)].cpu().numpy()
+    ref, _, _, rdone = c_tracking(raw, s, prn, af, cp, n0)
+    assert np.array_equal(out[:, 0, :n0], ref[:, 0])
+    errs = track_rel_err(out[:, :, :n0], ref)
+    assert errs["I_P"] < IQ_TOL and errs["Q_P"] < IQ_TOL, errs
+    eng.close()
