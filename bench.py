@@ -362,7 +362,7 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
-                         "kernel": "rows_kernel<true> (spectrum multiply + inverse 992-pt row FFTs)",
+                         "kernel": "inv_rows_kernel (spectrum multiply + inverse 31x32 row DFTs of the 33x32x31 prime-factor transform)",
                          "launch_ms": rows_launch_ms, "cells_per_launch": cells_per_launch, "peak_source": pk_src,
                          "whole_step_achieved": step_ach, "whole_step_frac": step_ach / pk["hbm_gbs"],
                          "kernel_share_of_step": {"inv_rows": rows_ms / args.steps / step_ms, "inv_cols": cols_ms / args.steps / step_ms},

@@ -103,16 +103,26 @@ fine_sum_kernel(FineParams p)
     float ar[kFineBins], ai[kFineBins];
 #pragma unroll
     for (int j = 0; j < kFineBins; ++j) ar[j] = ai[j] = 0.f;
-    for (int n = threadIdx.x; n < p.N; n += 256) {
+    // A thread visits samples n = tid, tid+256, ...: the carrier of bin j advances by the constant
+    // rotation e^{-i*256*dphi_j} between visits.  The phasor is re-seeded from the exact fixed-point
+    // phase every 8 visits, so the recurrence never accumulates more than 7 roundings.
+    float rc[kFineBins], rs[kFineBins], wc[kFineBins], ws[kFineBins];
+#pragma unroll
+    for (int j = 0; j < kFineBins; ++j) { fix_sincos(dphi[j] * 256ull, &rs[j], &rc[j]); wc[j] = 1.f; ws[j] = 0.f; }
+    int visit = 0;
+    for (int n = threadIdx.x; n < p.N; n += 256, ++visit) {
         const short2 v = x[n];
         const float I = (float)v.x, Q = (float)v.y;
         const uint64_t gi = (uint64_t)c * p.N + n;     // finePhasePoints index (:148)
+        const bool reseed = (visit & 7) == 0;
 #pragma unroll
         for (int j = 0; j < kFineBins; ++j) {
-            float sn, cs;
-            fix_sincos(dphi[j] * gi, &sn, &cs);        // exp(-1i*f*finePhasePoints), :230
-            ar[j] += fmaf(cs, I, sn * Q);
-            ai[j] += fmaf(cs, Q, -sn * I);
+            if (reseed) fix_sincos(dphi[j] * gi, &ws[j], &wc[j]);   // exp(-1i*f*finePhasePoints), :230
+            ar[j] += fmaf(wc[j], I, ws[j] * Q);
+            ai[j] += fmaf(wc[j], Q, -ws[j] * I);
+            const float nc = fmaf(wc[j], rc[j], -ws[j] * rs[j]);    // advance the phase by 256 samples
+            ws[j] = fmaf(wc[j], rs[j], ws[j] * rc[j]);
+            wc[j] = nc;
         }
     }
     __shared__ double sh[8][kFineBins][2];
