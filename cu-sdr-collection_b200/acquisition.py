@@ -11,7 +11,9 @@ from .engine import Engine, GnssCorrError
 from .settings import Settings
 
 
-def _to_int8_iq(longSignal: np.ndarray) -> np.ndarray:
+def _to_int8_iq(longSignal: np.ndarray, swapped: bool = False) -> np.ndarray:
+    """Complex longSignal -> the file's int8 I,Q byte order.  ``swapped``: the GLONASS read path
+    builds ``data2 + 1i*data1`` (GLO_GL1/include/postProcessing.m:94), so real/imag are Q/I."""
     x = np.asarray(longSignal)
     if not np.iscomplexobj(x):
         raise GnssCorrError("real-valued longSignal (fileType 1) is not implemented")
@@ -20,8 +22,8 @@ def _to_int8_iq(longSignal: np.ndarray) -> np.ndarray:
             np.max(np.abs(re)) <= 128 and np.max(np.abs(im)) <= 128):
         raise GnssCorrError("longSignal is not 8-bit integer valued; the accelerated path needs the raw 'schar' samples")
     iq = np.empty(2 * x.size, dtype=np.int8)
-    iq[0::2] = re.astype(np.int8)
-    iq[1::2] = im.astype(np.int8)
+    iq[0::2] = (im if swapped else re).astype(np.int8)
+    iq[1::2] = (re if swapped else im).astype(np.int8)
     return iq
 
 
@@ -29,19 +31,22 @@ def acquisition(longSignal, settings: Settings, engine: Engine | None = None, ve
     """Same contract as the reference function: ``longSignal`` is the complex row vector
     postProcessing.m:88-96 builds from the first max(42, acqNonCohTime+2) code periods (an int8
     I,Q-interleaved array is accepted too); returns ``acqResults`` with 1x32 ``carrFreq``,
-    ``codePhase`` and ``peakMetric`` (``carrFreq == 0`` means not acquired)."""
+    ``codePhase`` and ``peakMetric`` (``carrFreq == 0`` means not acquired).  GLONASS
+    (GLO_GL1/include/acquisition.m): ``acqSatelliteList`` holds frequency numbers K, the vectors are
+    1x21 and indexed K+8 (K+7 here, 0-based)."""
     own = engine is None
     eng = engine or Engine(settings)
     try:
         x = np.asarray(longSignal)
-        iq = x if x.dtype == np.int8 else _to_int8_iq(x)
+        iq = x if x.dtype == np.int8 else _to_int8_iq(x, swapped=settings.is_glonass)
         r = eng.acquire(settings.acqSatelliteList, host_iq=iq)
     finally:
         if own:
             eng.close()
     if verbose:                                   # acquisition.m:154,209,286,292
         sys.stdout.write("(")
-        for prn in settings.acqSatelliteList:
-            sys.stdout.write("%02d " % prn if r["carrFreq"][prn - 1] != 0 else ". ")
+        off = 7 if settings.is_glonass else -1
+        for sv in settings.acqSatelliteList:
+            sys.stdout.write("%02d " % sv if r["carrFreq"][sv + off] != 0 else ". ")
         sys.stdout.write(")\n")
     return r

@@ -53,3 +53,16 @@ def ca_first10_octal(prn: int) -> str:
     for b in x:
         v = (v << 1) | int(b)
     return format(v, "o")
+
+
+@lru_cache(maxsize=None)
+def glo_code() -> np.ndarray:
+    """+-1 GLONASS ST code (511 chips): 9-stage register, feedback from stages 5 and 9, output of
+    stage 7, all-ones start (GLO/GLO_GL1/include/generateCAcode.m:95-108; bit 1 <-> -1)."""
+    reg = [1] * 9
+    out = np.empty(511, dtype=np.int8)
+    for i in range(511):
+        out[i] = -1 if reg[6] else 1
+        fb = reg[4] ^ reg[8]
+        reg = [fb] + reg[:8]
+    return out

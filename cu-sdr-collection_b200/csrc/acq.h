@@ -15,6 +15,7 @@ struct FwdColsParams {
     long long winStart;       // sample index of longSignal(1) in the record
     int N;                    // samplesPerCode
     int nonCoh;
+    int swapIQ;               // GLONASS: rawSignal = Q + 1i*I (GLO_GL1/include/postProcessing.m:94)
     const uint64_t* dphi;     // [nBins] carrier phase increment per sample (turns, 0.64 fixed point)
     const int8_t* codeTab;    // [nPrn][N] +-1 resampled replicas (code mode)
     float2* out;              // [nRows][33][992]  (k1, n2*31 + n3)
@@ -55,7 +56,7 @@ struct GenericPlan {
 // one Stockham pass over `batch` transforms: src -> dst
 cudaError_t launch_generic_stage(const GenericPlan& pl, int stage, int n, int s, bool inverse,
                                  const float2* src, float2* dst, long long batch, cudaStream_t st);
-cudaError_t launch_generic_wipe(const int8_t* rec, long long winStart, int N, int nonCoh, int nBins,
+cudaError_t launch_generic_wipe(const int8_t* rec, long long winStart, int N, int nonCoh, int nBins, int swapIQ,
                                 const uint64_t* dphi, float2* out, int L, cudaStream_t st);
 cudaError_t launch_generic_code(const int8_t* codeTab, int N, int nPrn, float2* out, int L, cudaStream_t st);
 cudaError_t launch_generic_mul(const float2* X, const float2* Cc, float2* out, int L, long long nKm, cudaStream_t st);
@@ -79,8 +80,10 @@ struct FineParams {
     int N;                    // samplesPerCode
     int nPeriods;             // 40   (acquisition.m:146-148)
     int nFine;                // numOfFineBins (:140)
-    int codeLen;              // 1023
-    double ts, tc;            // 1/fs, 1/codeFreqBasis  (:215)
+    int codeLen;              // 1023 (511 GLONASS)
+    int swapIQ;               // GLONASS I/Q swap
+    int splitHalves;          // 0: |sum of 20 codes| (acquisition.m:245); 1: |sum of 10 - sum of next 10| (GLO :246-252)
+    const int16_t* chipIdx;   // [nPeriods*N] sample -> chip index of the 40 ms replica (host table, :215-218)
     const int8_t* chips;      // [nAcq][codeLen] +-1 chips of the acquired PRNs
     const int* codePhase;     // [nAcq] 1-based coarse code phase (:221)
     const uint64_t* dphi;     // [nAcq][nFine] fine-bin phase increments

@@ -80,10 +80,9 @@ __global__ void fine_prep_kernel(FineParams p)
     const char2* x = reinterpret_cast<const char2*>(p.rec) + p.winStart + (p.codePhase[a] - 1);   // :221
     const int8_t* chips = p.chips + (size_t)a * p.codeLen;
     for (long long gi = blockIdx.x * (long long)blockDim.x + threadIdx.x; gi < total; gi += (long long)gridDim.x * blockDim.x) {
-        // codeValueIndex = floor((ts*(0:40N-1)) / (1/codeFreqBasis))   :215
-        const long long idx = (long long)floor(__ddiv_rn(__dmul_rn(p.ts, (double)gi), p.tc));
-        const int c = chips[idx % p.codeLen];                                                      // :218
-        const char2 v = x[gi];
+        const int c = chips[p.chipIdx[gi]];                      // caCode40ms (:215-218; GLO generateCAcode.m:110-116)
+        char2 v = x[gi];
+        if (p.swapIQ) v = make_char2(v.y, v.x);
         prod[(size_t)a * total + gi] = make_short2((short)(v.x * c), (short)(v.y * c));
     }
 }
@@ -156,7 +155,12 @@ __global__ void fine_select_kernel(FineParams p)
         double maxPower = 0;
         for (int c = 0; c < half; ++c) {
             double r = 0, i = 0;
-            for (int q = c; q < c + half; ++q) { r += s[2 * q]; i += s[2 * q + 1]; }
+            if (!p.splitHalves) {
+                for (int q = c; q < c + half; ++q) { r += s[2 * q]; i += s[2 * q + 1]; }
+            } else {                                             // 10 ms meander halves of opposite sign (GLO :246-252)
+                for (int q = c; q < c + half / 2; ++q) { r += s[2 * q]; i += s[2 * q + 1]; }
+                for (int q = c + half / 2; q < c + half; ++q) { r -= s[2 * q]; i -= s[2 * q + 1]; }
+            }
             const double pw = sqrt(r * r + i * i);
             if (pw > maxPower) maxPower = pw;
         }

@@ -68,7 +68,7 @@ fwd_cols_kernel(FwdColsParams p)
             const char2 s = *reinterpret_cast<const char2*>(src + 2 * (size_t)n);
             float sn, cs;
             fix_sincos(dphi * (uint64_t)n, &sn, &cs);          // exp(-1i*f*phasePoints(n)), :172
-            const float I = (float)s.x, Q = (float)s.y;
+            const float I = p.swapIQ ? (float)s.y : (float)s.x, Q = p.swapIQ ? (float)s.x : (float)s.y;
             x[n1] = make_float2(fmaf(cs, I, sn * Q), fmaf(cs, Q, -sn * I));   // :180-181
         }
     } else {

@@ -12,7 +12,7 @@ namespace gc {
 namespace {
 
 // out[(k*nonCoh+m)][n] = longSignal(m*N + n) * exp(-1i*f_k*phasePoints(n))   (acquisition.m:172-181)
-__global__ void wipe_kernel(const int8_t* rec, long long winStart, int N, int nonCoh,
+__global__ void wipe_kernel(const int8_t* rec, long long winStart, int N, int nonCoh, int swapIQ,
                             const uint64_t* dphi, float2* out, int L)
 {
     const int km = blockIdx.y, k = km / nonCoh, m = km % nonCoh;
@@ -22,7 +22,7 @@ __global__ void wipe_kernel(const int8_t* rec, long long winStart, int N, int no
         const char2 s = x[n];
         float sn, cs;
         fix_sincos(d * (uint64_t)n, &sn, &cs);
-        const float I = (float)s.x, Q = (float)s.y;
+        const float I = swapIQ ? (float)s.y : (float)s.x, Q = swapIQ ? (float)s.x : (float)s.y;
         out[(size_t)km * L + n] = make_float2(fmaf(cs, I, sn * Q), fmaf(cs, Q, -sn * I));
     }
 }
@@ -141,11 +141,11 @@ cudaError_t launch_generic_stage(const GenericPlan& pl, int stage, int n, int s,
     return cudaGetLastError();
 }
 
-cudaError_t launch_generic_wipe(const int8_t* rec, long long winStart, int N, int nonCoh, int nBins,
+cudaError_t launch_generic_wipe(const int8_t* rec, long long winStart, int N, int nonCoh, int nBins, int swapIQ,
                                 const uint64_t* dphi, float2* out, int L, cudaStream_t st)
 {
     dim3 grid((L + 255) / 256, nBins * nonCoh);
-    wipe_kernel<<<grid, 256, 0, st>>>(rec, winStart, N, nonCoh, dphi, out, L);
+    wipe_kernel<<<grid, 256, 0, st>>>(rec, winStart, N, nonCoh, swapIQ, dphi, out, L);
     return cudaGetLastError();
 }
 

@@ -40,7 +40,7 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-constexpr int kMaxSv = 32;
+constexpr int kMaxSv = 32;            // most SVs a list can hold / replica slots
 constexpr int kEvents = 160;
 
 }  // namespace
@@ -51,6 +51,12 @@ struct gc_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[kEvents]{};
     gc_stats stats{};
+
+    // per-signal description
+    bool glo = false;            // GLONASS: FDMA channels K, one shared code, I/Q swapped, 3-coefficient carrier filter
+    int nReplicas = 32;          // replica spectra held (32 GPS PRNs; 1 GLONASS)
+    int resultLen = 32;          // length of the acqResults vectors
+    DevBuf<int16_t> chipIdx;     // sample -> chip index of the 40-period fine-search replica
 
     // derived (acquisition.m:116-124,138-140)
     int N = 0, L = 0, nBins = 0, nFine = 0, nonCoh = 0;
@@ -127,36 +133,61 @@ void calcLoopCoef(double LBW, double zeta, double k, double* tau1, double* tau2)
     *tau2 = 2.0 * zeta / Wn;
 }
 
-// Replica spectra conj(fft([makeCaTable(PRN) zeros(1,N)]))/L for all PRNs (acquisition.m:158-164)
+// SV id -> (valid, result index, replica slot, carrier offset)
+bool sv_ok(const gc_handle* h, int sv) { return h->glo ? (sv >= -7 && sv <= 13) : (sv >= 1 && sv <= kMaxSv); }
+int sv_result_index(const gc_handle* h, int sv) { return h->glo ? sv + 7 : sv - 1; }       // MATLAB K+8 / PRN, 0-based
+int sv_replica(const gc_handle* h, int sv) { return h->glo ? 0 : sv - 1; }
+double sv_freq_offset(const gc_handle* h, int sv) { return h->glo ? -h->cfg.freq_spacing * (double)sv : 0.0; }
+
+// +-1 chips of one code period for an SV (tracking / fine-search replica)
+void sv_chips(const gc_handle* h, int sv, int8_t* out)
+{
+    if (h->glo) glo_code(out); else ca_code(sv, out);
+}
+
+// Replica spectra conj(fft([code zeros(1,N)]))/L (acquisition.m:158-164; GLO acquisition.m:145-149) and
+// the sample -> chip map of the 40-period fine-search replica (acquisition.m:215-218; GLO :164).
 int build_replicas(gc_handle* h)
 {
-    const int N = h->N, L = h->L;
-    std::vector<int8_t> tab((size_t)kMaxSv * N);
-    for (int prn = 1; prn <= kMaxSv; ++prn)
-        make_ca_table(prn, h->cfg.sampling_freq, h->cfg.code_freq_basis, h->cfg.code_length, N, tab.data() + (size_t)(prn - 1) * N);
+    const int N = h->N, L = h->L, nRep = h->nReplicas, codeLen = h->cfg.code_length;
+    std::vector<int8_t> tab((size_t)nRep * N);
+    std::vector<int16_t> idx40((size_t)40 * N);
+    if (h->glo) {
+        int8_t chips[511];
+        glo_code(chips);
+        std::vector<int16_t> idx(N);
+        glo_sample_index(h->cfg.code_freq_basis, h->cfg.sampling_freq, codeLen, N, idx.data());   // generateCAcode(0, fs, N)
+        for (int n = 0; n < N; ++n) tab[n] = chips[idx[n]];
+        glo_sample_index(h->cfg.code_freq_basis, h->cfg.sampling_freq, codeLen, 40LL * N, idx40.data());
+    } else {
+        for (int prn = 1; prn <= nRep; ++prn)
+            make_ca_table(prn, h->cfg.sampling_freq, h->cfg.code_freq_basis, codeLen, N, tab.data() + (size_t)(prn - 1) * N);
+        gps_fine_index(h->cfg.sampling_freq, h->cfg.code_freq_basis, codeLen, 40LL * N, idx40.data());
+    }
     GC_CUDA(h, upload(h->codeTab, tab, h->stream));
-    GC_CUDA(h, h->Cc.reserve((size_t)kMaxSv * L));
+    GC_CUDA(h, upload(h->chipIdx, idx40, h->stream));
+    GC_CUDA(h, h->Cc.reserve((size_t)nRep * L));
     if (h->fused) {
         FwdColsParams fp{};
         fp.N = N; fp.codeTab = h->codeTab.p; fp.out = h->Cc.p;
-        GC_CUDA(h, launch_fwd_cols(fp, kMaxSv, true, h->stream));
+        GC_CUDA(h, launch_fwd_cols(fp, nRep, true, h->stream));
         RowsParams rp{};
-        rp.X = h->Cc.p; rp.nRows = (long long)kMaxSv * kFusedC;
+        rp.X = h->Cc.p; rp.nRows = (long long)nRep * kFusedC;
         GC_CUDA(h, launch_fwd_rows(rp, h->stream));
-        GC_CUDA(h, launch_finish_replica(h->Cc.p, (size_t)kMaxSv * L, h->stream));
+        GC_CUDA(h, launch_finish_replica(h->Cc.p, (size_t)nRep * L, h->stream));
     } else {
-        GC_CUDA(h, h->T1.reserve((size_t)std::max(kMaxSv, h->nBins * h->nonCoh) * L));
-        GC_CUDA(h, h->T2.reserve((size_t)std::max(kMaxSv, h->nBins * h->nonCoh) * L));
-        GC_CUDA(h, launch_generic_code(h->codeTab.p, N, kMaxSv, h->T1.p, L, h->stream));
+        GC_CUDA(h, h->T1.reserve((size_t)std::max(nRep, h->nBins * h->nonCoh) * L));
+        GC_CUDA(h, h->T2.reserve((size_t)std::max(nRep, h->nBins * h->nonCoh) * L));
+        GC_CUDA(h, launch_generic_code(h->codeTab.p, N, nRep, h->T1.p, L, h->stream));
         float2 *src = h->T1.p, *dst = h->T2.p;
         int n = L, s = 1;
         for (int f = 0; f < h->plan.nf; ++f) {
-            GC_CUDA(h, launch_generic_stage(h->plan, f, n, s, false, src, dst, kMaxSv, h->stream));
+            GC_CUDA(h, launch_generic_stage(h->plan, f, n, s, false, src, dst, nRep, h->stream));
             n /= h->plan.fac[f]; s *= h->plan.fac[f];
             std::swap(src, dst);
         }
-        GC_CUDA(h, cudaMemcpyAsync(h->Cc.p, src, (size_t)kMaxSv * L * sizeof(float2), cudaMemcpyDeviceToDevice, h->stream));
-        GC_CUDA(h, launch_generic_conj_scale(h->Cc.p, (size_t)kMaxSv * L, 1.0f / (float)L, h->stream));
+        GC_CUDA(h, cudaMemcpyAsync(h->Cc.p, src, (size_t)nRep * L * sizeof(float2), cudaMemcpyDeviceToDevice, h->stream));
+        GC_CUDA(h, launch_generic_conj_scale(h->Cc.p, (size_t)nRep * L, 1.0f / (float)L, h->stream));
     }
     h->replicasReady = true;
     return GC_OK;
@@ -168,7 +199,7 @@ extern "C" {
 
 int gc_abi_version(void) { return GC_ABI_VERSION; }
 const char* gc_build_arch(void) { return "sm_100a"; }
-int gc_acq_result_len(int32_t signal) { return signal == GC_SIG_GPS_L1CA ? 32 : 0; }
+int gc_acq_result_len(int32_t signal) { return signal == GC_SIG_GPS_L1CA ? 32 : signal == GC_SIG_GLO_G1G2 ? 21 : 0; }
 
 const char* gc_last_error(const gc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -177,10 +208,12 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     if (!out || !cfg) return fail(nullptr, GC_ERR_ARG, "gc_create: null argument");
     *out = nullptr;
     if (cfg->abi_version != GC_ABI_VERSION) return fail(nullptr, GC_ERR_ARG, "gc_create: abi_version mismatch");
-    if (cfg->signal != GC_SIG_GPS_L1CA) return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: only GC_SIG_GPS_L1CA is implemented");
+    if (cfg->signal != GC_SIG_GPS_L1CA && cfg->signal != GC_SIG_GLO_G1G2)
+        return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: only GC_SIG_GPS_L1CA and GC_SIG_GLO_G1G2 are implemented");
     if (cfg->file_type != 2 || cfg->sample_bytes != 1)
         return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: only fileType 2 (I/Q) with dataType 'schar' is implemented");
-    if (!(cfg->sampling_freq > 0) || !(cfg->code_freq_basis > 0) || cfg->code_length != 1023 || cfg->acq_noncoh_time < 1 ||
+    if (!(cfg->sampling_freq > 0) || !(cfg->code_freq_basis > 0) ||
+        cfg->code_length != (cfg->signal == GC_SIG_GLO_G1G2 ? 511 : 1023) || cfg->acq_noncoh_time < 1 ||
         !(cfg->acq_search_step > 0) || cfg->cno_vsm_interval < 2)
         return fail(nullptr, GC_ERR_ARG, "gc_create: invalid settings");
     int ndev = 0;
@@ -195,6 +228,9 @@ int gc_create(gc_handle** out, const gc_config* cfg)
 
     gc_handle* h = new gc_handle();
     h->cfg = *cfg;
+    h->glo = (cfg->signal == GC_SIG_GLO_G1G2);
+    h->nReplicas = h->glo ? 1 : kMaxSv;
+    h->resultLen = gc_acq_result_len(cfg->signal);
     auto bail = [&](int rc) { g_create_error = h->err; gc_destroy(h); return rc; };
     if (cudaSetDevice(cfg->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(GC_ERR_CUDA); }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(GC_ERR_CUDA); }
@@ -248,6 +284,7 @@ void gc_destroy(gc_handle* h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->recOwned.release();
     h->twGen.release(); h->X.release(); h->T1.release(); h->T2.release();
+    h->chipIdx.release();
     h->Cc.release(); h->W.release(); h->dphi.release(); h->fdphi.release(); h->codeTab.release(); h->chips.release();
     h->prnList.release(); h->partIdx.release(); h->fineCodePhase.release(); h->fineBest.release(); h->partMax.release();
     h->peaks.release(); h->sigPower.release(); h->fineSums.release(); h->fineResult.release(); h->fineProd.release();
@@ -286,151 +323,172 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
 {
     const gc_config& c = h->cfg;
     const int N = h->N, L = h->L, nBins = h->nBins, nonCoh = h->nonCoh, nKm = nBins * nonCoh;
+    const int codeLen = c.code_length;
     if (!h->rec) return fail(h, GC_ERR_NO_RECORD, "gc_acquire: no record resident");
     if (nSv < 1 || nSv > kMaxSv || !svList || !carrFreq || !codePhase || !peakMetric)
         return fail(h, GC_ERR_ARG, "gc_acquire: bad argument");
     for (int i = 0; i < nSv; ++i)
-        if (svList[i] < 1 || svList[i] > kMaxSv) return fail(h, GC_ERR_ARG, "gc_acquire: PRN out of range 1..32");
-    const int codeLen = std::max(42, nonCoh + 2);                                    // postProcessing.m:86
+        if (!sv_ok(h, svList[i])) return fail(h, GC_ERR_ARG, h->glo ? "gc_acquire: frequency number out of range -7..13" : "gc_acquire: PRN out of range 1..32");
+    const int nPeriodsAcq = std::max(42, nonCoh + 2);                                // postProcessing.m:86
     const long long recSamples = (long long)(h->recBytes / 2);
-    if (winStart < 0 || winStart + (long long)codeLen * N > recSamples)
+    if (winStart < 0 || winStart + (long long)nPeriodsAcq * N > recSamples)
         return fail(h, GC_ERR_SHORT_RECORD, "gc_acquire: record shorter than max(42, acqNonCohTime+2) code periods");
     cudaSetDevice(c.device);
     cudaStream_t st = h->stream;
-    int launches = 0, evn = 0;
+    int launches = 0, evn = 0, nRowLaunches = 0;
+    float rowsMs = 0, colsMs = 0, fwdMs = 0;
     auto mark = [&]() { cudaEventRecord(h->ev[evn], st); return evn++; };
+    std::vector<std::pair<int, int>> rowEv, colEv, fwdEv;
+    auto drain_events = [&]() {
+        cudaStreamSynchronize(st);
+        float ms;
+        for (auto& pr : rowEv) { cudaEventElapsedTime(&ms, h->ev[pr.first], h->ev[pr.second]); rowsMs += ms; }
+        for (auto& pr : colEv) { cudaEventElapsedTime(&ms, h->ev[pr.first], h->ev[pr.second]); colsMs += ms; }
+        for (auto& pr : fwdEv) { cudaEventElapsedTime(&ms, h->ev[pr.first], h->ev[pr.second]); fwdMs += ms; }
+        rowEv.clear(); colEv.clear(); fwdEv.clear();
+        evn = 2;                                      // events 0 and 1 bracket the whole coarse search
+    };
 
-    for (int i = 0; i < kMaxSv; ++i) {
+    for (int i = 0; i < h->resultLen; ++i) {
         carrFreq[i] = codePhase[i] = peakMetric[i] = 0;                              // acquisition.m:130-134
         if (coarseBin) coarseBin[i] = 0;
         if (coarseCodePhase) coarseCodePhase[i] = 0;
     }
-    // coarse bin frequencies (:169) and their per-sample phase increments
-    std::vector<double> coarseFreq(nBins);
-    std::vector<uint64_t> dphi(nBins);
-    for (int k = 0; k < nBins; ++k) {
-        coarseFreq[k] = c.IF + c.acq_search_band - c.acq_search_step * k;
-        dphi[k] = turns_to_fix(coarseFreq[k] * h->ts);
-    }
-    GC_CUDA(h, upload(h->dphi, dphi, st));
-    std::vector<int> prnIdx(nSv);
-    for (int i = 0; i < nSv; ++i) prnIdx[i] = svList[i] - 1;
-    GC_CUDA(h, upload(h->prnList, prnIdx, st));
+    // SVs that share a carrier grid share the wiped-off spectra: GPS = one group of all PRNs,
+    // GLONASS = one group per frequency number (grid shifted by -freqSpacing*K, GLO acquisition.m:181-182).
+    std::vector<int> order(nSv);
+    for (int i = 0; i < nSv; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return sv_freq_offset(h, svList[a]) < sv_freq_offset(h, svList[b]); });
+    std::vector<int> slotReplica(nSv);                // device list slot -> replica spectrum
+    for (int s = 0; s < nSv; ++s) slotReplica[s] = sv_replica(h, svList[order[s]]);
+    GC_CUDA(h, upload(h->prnList, slotReplica, st));
     GC_CUDA(h, h->partMax.reserve((size_t)nSv * nBins * h->parts));
     GC_CUDA(h, h->partIdx.reserve((size_t)nSv * nBins * h->parts));
     GC_CUDA(h, h->peaks.reserve(nSv));
     GC_CUDA(h, h->sigPower.reserve(1));
     GC_CUDA(h, h->X.reserve((size_t)nKm * L));
+    GC_CUDA(h, h->dphi.reserve(nBins));
+    std::vector<std::vector<double>> coarseFreqOf(nSv);   // per list slot: the bin frequencies it was searched on
 
     const int e0 = mark();
     GC_CUDA(h, launch_sig_power(h->rec, winStart, N, h->sigPower.p, st)); ++launches;   // :151
-    float rowsMs = 0, colsMs = 0;
-    int nRowLaunches = 0;
-    std::vector<std::pair<int, int>> rowEv, colEv;
-    int e1;
-    if (h->fused) {
-        FwdColsParams fp{};
-        fp.rec = h->rec; fp.winStart = winStart; fp.N = N; fp.nonCoh = nonCoh; fp.dphi = h->dphi.p;
-        fp.out = h->X.p;
-        GC_CUDA(h, launch_fwd_cols(fp, nKm, false, st)); ++launches;
-        RowsParams rp{};
-        rp.X = h->X.p; rp.nRows = (long long)nKm * kFusedC;
-        GC_CUDA(h, launch_fwd_rows(rp, st)); ++launches;
-        e1 = mark();
-        // PRN chunks sized so the inverse work buffer stays below ~2.5 GB
-        int chunk = (int)std::max<long long>(1, (long long)(2.5e9 / ((double)nKm * L * sizeof(float2))));
-        if (const char* e = getenv("GC_ACQ_CHUNK_PRNS")) chunk = std::max(1, atoi(e));
-        chunk = std::min(chunk, nSv);
-        GC_CUDA(h, h->W.reserve((size_t)chunk * nKm * L));
-        for (int s0 = 0; s0 < nSv; s0 += chunk) {
-            const int nc = std::min(chunk, nSv - s0);
-            RowsParams ip{};
-            ip.X = h->X.p; ip.Cc = h->Cc.p; ip.W = h->W.p; 
-            ip.nonCoh = nonCoh; ip.nBins = nBins; ip.prnPerCta = 1; ip.mPerCta = 5;   // 5 warps, 96 registers, 20 warps/SM
-            if (const char* e = getenv("GC_ROWS_VARIANT")) {   // "PxM" warps per CTA = P PRNs x M blocks
-                int P = 0, M = 0;
-                if (sscanf(e, "%dx%d", &P, &M) == 2 && (P * M == 5 || P * M == 6 || P * M == 8 || P * M == 10)) { ip.prnPerCta = P; ip.mPerCta = M; }
+    mark();                                           // event 1 (re-recorded at the end of the coarse search)
+    for (int g0 = 0; g0 < nSv;) {
+        int g1 = g0 + 1;
+        const double off = sv_freq_offset(h, svList[order[g0]]);
+        while (g1 < nSv && sv_freq_offset(h, svList[order[g1]]) == off) ++g1;
+        // coarse bin frequencies (:169) and their per-sample phase increments
+        std::vector<double> coarseFreq(nBins);
+        std::vector<uint64_t> dphi(nBins);
+        for (int k = 0; k < nBins; ++k) {
+            coarseFreq[k] = (c.IF + off) + c.acq_search_band - c.acq_search_step * k;
+            dphi[k] = turns_to_fix(coarseFreq[k] * h->ts);
+        }
+        for (int s = g0; s < g1; ++s) coarseFreqOf[s] = coarseFreq;
+        if (evn > kEvents - 12) drain_events();
+        GC_CUDA(h, cudaMemcpyAsync(h->dphi.p, dphi.data(), nBins * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        const int f0 = mark();
+        if (h->fused) {
+            FwdColsParams fp{};
+            fp.rec = h->rec; fp.winStart = winStart; fp.N = N; fp.nonCoh = nonCoh; fp.swapIQ = h->glo ? 1 : 0;
+            fp.dphi = h->dphi.p; fp.out = h->X.p;
+            GC_CUDA(h, launch_fwd_cols(fp, nKm, false, st)); ++launches;
+            RowsParams rp{};
+            rp.X = h->X.p; rp.nRows = (long long)nKm * kFusedC;
+            GC_CUDA(h, launch_fwd_rows(rp, st)); ++launches;
+            fwdEv.push_back({f0, mark()});
+            // PRN chunks sized so the inverse work buffer stays below ~2.5 GB
+            int chunk = (int)std::max<long long>(1, (long long)(2.5e9 / ((double)nKm * L * sizeof(float2))));
+            if (const char* e = getenv("GC_ACQ_CHUNK_PRNS")) chunk = std::max(1, atoi(e));
+            chunk = std::min(chunk, g1 - g0);
+            GC_CUDA(h, h->W.reserve((size_t)chunk * nKm * L));
+            for (int s0 = g0; s0 < g1; s0 += chunk) {
+                const int nc = std::min(chunk, g1 - s0);
+                RowsParams ip{};
+                ip.X = h->X.p; ip.Cc = h->Cc.p; ip.W = h->W.p;
+                ip.nonCoh = nonCoh; ip.nBins = nBins; ip.prnPerCta = 1; ip.mPerCta = 5;   // 5 warps, 96 registers, 20 warps/SM
+                if (const char* e = getenv("GC_ROWS_VARIANT")) {   // "PxM" warps per CTA = P PRNs x M blocks
+                    int P = 0, M = 0;
+                    if (sscanf(e, "%dx%d", &P, &M) == 2 && (P * M == 5 || P * M == 6 || P * M == 8 || P * M == 10)) { ip.prnPerCta = P; ip.mPerCta = M; }
+                }
+                ip.nPrnChunk = nc; ip.prnSlot0 = s0; ip.prnList = h->prnList.p;
+                if (evn > kEvents - 12) drain_events();
+                const int a = mark();
+                GC_CUDA(h, launch_inv_rows(ip, st)); ++launches;
+                const int b = mark();
+                InvColsParams cp{};
+                cp.W = h->W.p; cp.nBins = nBins; cp.nonCoh = nonCoh; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
+                cp.partMax = h->partMax.p; cp.partIdx = h->partIdx.p;
+                GC_CUDA(h, launch_inv_cols(cp, st)); ++launches;
+                const int d = mark();
+                rowEv.push_back({a, b}); colEv.push_back({b, d}); ++nRowLaunches;
             }
-            ip.nPrnChunk = nc; ip.prnSlot0 = s0; ip.prnList = h->prnList.p;
-            const int a = mark();
-            GC_CUDA(h, launch_inv_rows(ip, st)); ++launches;
-            const int b = mark();
-            InvColsParams cp{};
-            cp.W = h->W.p; cp.nBins = nBins; cp.nonCoh = nonCoh; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
-            cp.partMax = h->partMax.p; cp.partIdx = h->partIdx.p;
-            GC_CUDA(h, launch_inv_cols(cp, st)); ++launches;
-            const int d = mark();
-            rowEv.push_back({a, b}); colEv.push_back({b, d}); ++nRowLaunches;
-            if (evn > kEvents - 8) { GC_CUDA(h, cudaStreamSynchronize(st)); }
-        }
-    } else {
-        GC_CUDA(h, h->T1.reserve((size_t)std::max(kMaxSv, nKm) * L));
-        GC_CUDA(h, h->T2.reserve((size_t)std::max(kMaxSv, nKm) * L));
-        GC_CUDA(h, launch_generic_wipe(h->rec, winStart, N, nonCoh, nBins, h->dphi.p, h->T1.p, L, st)); ++launches;
-        float2 *src = h->T1.p, *dst = h->T2.p;
-        int n = L, s = 1;
-        for (int f = 0; f < h->plan.nf; ++f) {
-            GC_CUDA(h, launch_generic_stage(h->plan, f, n, s, false, src, dst, nKm, st)); ++launches;
-            n /= h->plan.fac[f]; s *= h->plan.fac[f];
-            std::swap(src, dst);
-        }
-        GC_CUDA(h, cudaMemcpyAsync(h->X.p, src, (size_t)nKm * L * sizeof(float2), cudaMemcpyDeviceToDevice, st));
-        e1 = mark();
-        for (int i = 0; i < nSv; ++i) {
-            const int a = mark();
-            GC_CUDA(h, launch_generic_mul(h->X.p, h->Cc.p + (size_t)prnIdx[i] * L, h->T1.p, L, nKm, st)); ++launches;
-            src = h->T1.p; dst = h->T2.p; n = L; s = 1;
+        } else {
+            GC_CUDA(h, h->T1.reserve((size_t)std::max(h->nReplicas, nKm) * L));
+            GC_CUDA(h, h->T2.reserve((size_t)std::max(h->nReplicas, nKm) * L));
+            GC_CUDA(h, launch_generic_wipe(h->rec, winStart, N, nonCoh, nBins, h->glo ? 1 : 0, h->dphi.p, h->T1.p, L, st)); ++launches;
+            float2 *src = h->T1.p, *dst = h->T2.p;
+            int n = L, s = 1;
             for (int f = 0; f < h->plan.nf; ++f) {
-                GC_CUDA(h, launch_generic_stage(h->plan, f, n, s, true, src, dst, nKm, st)); ++launches;
+                GC_CUDA(h, launch_generic_stage(h->plan, f, n, s, false, src, dst, nKm, st)); ++launches;
                 n /= h->plan.fac[f]; s *= h->plan.fac[f];
                 std::swap(src, dst);
             }
-            const int b = mark();
-            GC_CUDA(h, launch_generic_absacc(src, L, nBins, nonCoh, h->parts, h->partMax.p, h->partIdx.p,
-                                             (size_t)i * nBins * h->parts, st)); ++launches;
-            const int d = mark();
-            rowEv.push_back({a, b}); colEv.push_back({b, d}); ++nRowLaunches;
-            if (evn > kEvents - 8) {
-                GC_CUDA(h, cudaStreamSynchronize(st));
-                for (auto& pr : rowEv) { float ms; cudaEventElapsedTime(&ms, h->ev[pr.first], h->ev[pr.second]); rowsMs += ms; }
-                for (auto& pr : colEv) { float ms; cudaEventElapsedTime(&ms, h->ev[pr.first], h->ev[pr.second]); colsMs += ms; }
-                rowEv.clear(); colEv.clear();
-                evn = 3;   // keep e0, e1 (indices 0,1) and one spare
+            GC_CUDA(h, cudaMemcpyAsync(h->X.p, src, (size_t)nKm * L * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+            fwdEv.push_back({f0, mark()});
+            for (int sl = g0; sl < g1; ++sl) {
+                if (evn > kEvents - 12) drain_events();
+                const int a = mark();
+                GC_CUDA(h, launch_generic_mul(h->X.p, h->Cc.p + (size_t)slotReplica[sl] * L, h->T1.p, L, nKm, st)); ++launches;
+                src = h->T1.p; dst = h->T2.p; n = L; s = 1;
+                for (int f = 0; f < h->plan.nf; ++f) {
+                    GC_CUDA(h, launch_generic_stage(h->plan, f, n, s, true, src, dst, nKm, st)); ++launches;
+                    n /= h->plan.fac[f]; s *= h->plan.fac[f];
+                    std::swap(src, dst);
+                }
+                const int b = mark();
+                GC_CUDA(h, launch_generic_absacc(src, L, nBins, nonCoh, h->parts, h->partMax.p, h->partIdx.p,
+                                                 (size_t)sl * nBins * h->parts, st)); ++launches;
+                const int d = mark();
+                rowEv.push_back({a, b}); colEv.push_back({b, d}); ++nRowLaunches;
             }
         }
+        g0 = g1;
     }
     GC_CUDA(h, launch_peak_select(h->partMax.p, h->partIdx.p, nSv, nBins, h->parts, h->peaks.p, st)); ++launches;
-    const int e2 = mark();
+    cudaEventRecord(h->ev[1], st);
     std::vector<PeakOut> peaks(nSv);
     double sigPower = 0;
     GC_CUDA(h, cudaMemcpyAsync(peaks.data(), h->peaks.p, nSv * sizeof(PeakOut), cudaMemcpyDeviceToHost, st));
     GC_CUDA(h, cudaMemcpyAsync(&sigPower, h->sigPower.p, sizeof(double), cudaMemcpyDeviceToHost, st));
-    GC_CUDA(h, cudaStreamSynchronize(st));
+    drain_events();
+    float coarseMs = 0;
+    cudaEventElapsedTime(&coarseMs, h->ev[e0], h->ev[1]);
 
-    // threshold (:200-206) and fine search for the PRNs above it
-    std::vector<int> acq;   // indices into svList
-    for (int i = 0; i < nSv; ++i) {
-        const int prn = svList[i];
-        peakMetric[prn - 1] = peaks[i].peak / sigPower / nonCoh;                     // :200
-        if (coarseBin) coarseBin[prn - 1] = peaks[i].bin;
-        if (coarseCodePhase) coarseCodePhase[prn - 1] = peaks[i].codePhase;
-        if (peakMetric[prn - 1] > c.acq_threshold) acq.push_back(i);                 // :206
+    // threshold (:200-206) and fine search for the SVs above it
+    std::vector<int> acq;   // device list slots
+    for (int s = 0; s < nSv; ++s) {
+        const int ri = sv_result_index(h, svList[order[s]]);
+        peakMetric[ri] = peaks[s].peak / sigPower / nonCoh;                          // :200
+        if (coarseBin) coarseBin[ri] = peaks[s].bin;
+        if (coarseCodePhase) coarseCodePhase[ri] = peaks[s].codePhase;
+        if (peakMetric[ri] > c.acq_threshold) acq.push_back(s);                      // :206
     }
     const int nAcq = (int)acq.size();
     h->stats.n_acquired = nAcq;
-    const int e3a = mark();
+    float fineMs = 0;
     if (nAcq > 0) {
         const int nPeriods = 40;                                                     // :146-148
-        std::vector<int8_t> chips((size_t)nAcq * 1023);
+        std::vector<int8_t> chips((size_t)nAcq * codeLen);
         std::vector<int> cps(nAcq);
         std::vector<uint64_t> fd((size_t)nAcq * h->nFine);
         std::vector<double> fineFreq((size_t)nAcq * h->nFine);
         for (int a = 0; a < nAcq; ++a) {
-            const int i = acq[a];
-            ca_code(svList[i], chips.data() + (size_t)a * 1023);                     // :213
-            cps[a] = peaks[i].codePhase;
+            const int s = acq[a];
+            sv_chips(h, svList[order[s]], chips.data() + (size_t)a * codeLen);       // :213
+            cps[a] = peaks[s].codePhase;
             for (int j = 0; j < h->nFine; ++j) {
-                fineFreq[(size_t)a * h->nFine + j] = coarseFreq[peaks[i].bin - 1] + c.acq_search_step / 2 - 25.0 * j;   // :227
+                fineFreq[(size_t)a * h->nFine + j] = coarseFreqOf[s][peaks[s].bin - 1] + c.acq_search_step / 2 - 25.0 * j;   // :227
                 fd[(size_t)a * h->nFine + j] = turns_to_fix(fineFreq[(size_t)a * h->nFine + j] * h->ts);
             }
         }
@@ -442,32 +500,28 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         GC_CUDA(h, h->fineResult.reserve((size_t)nAcq * h->nFine));
         GC_CUDA(h, h->fineBest.reserve(nAcq));
         FineParams fp{};
-        fp.rec = h->rec; fp.winStart = winStart; fp.N = N; fp.nPeriods = nPeriods; fp.nFine = h->nFine; fp.codeLen = 1023;
-        fp.ts = h->ts; fp.tc = 1 / c.code_freq_basis;
+        fp.rec = h->rec; fp.winStart = winStart; fp.N = N; fp.nPeriods = nPeriods; fp.nFine = h->nFine; fp.codeLen = codeLen;
+        fp.swapIQ = h->glo ? 1 : 0; fp.splitHalves = h->glo ? 1 : 0; fp.chipIdx = h->chipIdx.p;
         fp.chips = h->chips.p; fp.codePhase = h->fineCodePhase.p; fp.dphi = h->fdphi.p; fp.prod = h->fineProd.p;
         fp.sums = h->fineSums.p; fp.best = h->fineBest.p; fp.fineResult = h->fineResult.p;
+        const int fa = mark();
         GC_CUDA(h, launch_fine(fp, nAcq, st)); launches += 3;
         std::vector<int> best(nAcq);
         GC_CUDA(h, cudaMemcpyAsync(best.data(), h->fineBest.p, nAcq * sizeof(int), cudaMemcpyDeviceToHost, st));
-        const int e3b = mark(); (void)e3b;
+        const int fb = mark();
         GC_CUDA(h, cudaStreamSynchronize(st));
+        cudaEventElapsedTime(&fineMs, h->ev[fa], h->ev[fb]);
         for (int a = 0; a < nAcq; ++a) {
-            const int prn = svList[acq[a]];
-            carrFreq[prn - 1] = fineFreq[(size_t)a * h->nFine + best[a]];            // :254
-            codePhase[prn - 1] = peaks[acq[a]].codePhase;                            // :256
-            if (carrFreq[prn - 1] == 0) carrFreq[prn - 1] = 1;                       // :258
+            const int ri = sv_result_index(h, svList[order[acq[a]]]);
+            carrFreq[ri] = fineFreq[(size_t)a * h->nFine + best[a]];                 // :254
+            codePhase[ri] = peaks[acq[a]].codePhase;                                 // :256
+            if (carrFreq[ri] == 0) carrFreq[ri] = 1;                                 // :258
         }
-    } else {
-        mark();
-        GC_CUDA(h, cudaStreamSynchronize(st));
     }
-    float ms = 0;
-    cudaEventElapsedTime(&ms, h->ev[e0], h->ev[e1]); h->stats.acq_fwd_ms = ms;
-    cudaEventElapsedTime(&ms, h->ev[e1], h->ev[e2]); h->stats.acq_corr_ms = ms;
-    cudaEventElapsedTime(&ms, h->ev[e3a], h->ev[e3a + 1]); h->stats.acq_fine_ms = ms;
-    h->stats.acq_total_ms = h->stats.acq_fwd_ms + h->stats.acq_corr_ms + h->stats.acq_fine_ms;
-    for (auto& pr : rowEv) { cudaEventElapsedTime(&ms, h->ev[pr.first], h->ev[pr.second]); rowsMs += ms; }
-    for (auto& pr : colEv) { cudaEventElapsedTime(&ms, h->ev[pr.first], h->ev[pr.second]); colsMs += ms; }
+    h->stats.acq_fwd_ms = fwdMs;
+    h->stats.acq_corr_ms = coarseMs - fwdMs;
+    h->stats.acq_fine_ms = fineMs;
+    h->stats.acq_total_ms = coarseMs + fineMs;
     h->stats.corr_rows_ms = rowsMs;
     h->stats.corr_cols_ms = colsMs;
     h->stats.corr_row_launches = nRowLaunches;
@@ -529,16 +583,19 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
     const int stride = (codeLen + 2 + 15) & ~15;
     std::vector<TrackChan> chans(nCh);
     std::vector<int8_t> tabs((size_t)nCh * stride, 0);
+    std::vector<char> live(nCh, 0);
     for (int ch = 0; ch < nCh; ++ch) {
-        chans[ch].prn = sv[ch]; chans[ch].pad = 0;
+        const bool active = h->glo ? (sv[ch] != GC_SV_NONE) : (sv[ch] != 0);   // tracking.m:136; GLO tracking.m:137
+        live[ch] = active;
+        chans[ch].prn = sv[ch]; chans[ch].pad = active ? 1 : 0;
         chans[ch].acqFreq = acqFreq[ch];
         // fseek(fid, dataAdaptCoeff*(skipNumberOfBytes + codePhase-1)) (tracking.m:150)
         chans[ch].startSample = (long long)c.skip_number_of_bytes + (long long)codePhase[ch] - 1;
-        if (sv[ch] != 0) {
-            if (sv[ch] < 1 || sv[ch] > kMaxSv) return fail(h, GC_ERR_ARG, "gc_track: PRN out of range 1..32");
+        if (active) {
+            if (!sv_ok(h, sv[ch])) return fail(h, GC_ERR_ARG, "gc_track: SV id out of range");
             if (chans[ch].startSample < 0) return fail(h, GC_ERR_ARG, "gc_track: codePhase must be >= 1");
             int8_t* t = tabs.data() + (size_t)ch * stride;
-            ca_code(sv[ch], t + 1);                        // tracking.m:156
+            sv_chips(h, sv[ch], t + 1);                    // tracking.m:156 (GLO tracking.m:88)
             t[0] = t[codeLen]; t[codeLen + 1] = t[1];      // [c(L) c c(1)]  :158
         }
     }
@@ -549,6 +606,14 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
     p.spc = c.dll_correlator_spacing;
     p.cA = h->tau2code / h->tau1code; p.cB = c.int_time / h->tau1code;     // tracking.m:326
     p.pA = h->tau2carr / h->tau1carr; p.pB = c.int_time / h->tau1carr;     // tracking.m:308
+    {   // Common/calcLoopCoefCarr.m:41-56 (GLONASS carrier filter)
+        const double Wn = 1.2 * c.pll_noise_bandwidth;
+        p.pf3 = std::pow(Wn, 3) * std::pow(c.int_time, 2);
+        p.pf2 = 2 * std::pow(Wn, 2) * c.int_time;
+        p.pf1 = 2 * Wn;
+    }
+    p.loopType = h->glo ? 1 : 0;
+    p.swapIQ = h->glo ? 1 : 0;
     p.nEpochs = nEpochs;
     p.exactDisc = getenv("GC_TRACK_EXACT_DISC") ? 1 : 0;
     // CTAs per channel: spread few channels over the chip (thread-block clusters), 1 CTA per channel once
@@ -606,7 +671,7 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
     // after the first one that ran out of data stay as initialised.
     int failed = -1;
     for (int ch = 0; ch < nCh && failed < 0; ++ch)
-        if (sv[ch] != 0 && epochsDone[ch] < nEpochs) failed = ch;
+        if (live[ch] && epochsDone[ch] < nEpochs) failed = ch;
     const double inf = std::numeric_limits<double>::infinity();
     for (int ch = failed + 1; failed >= 0 && ch < nCh; ++ch) {
         double* o = out + (size_t)ch * GC_TRACK_NFIELDS * nEpochs;
@@ -622,7 +687,7 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
         std::fill(vsmValue, vsmValue + (size_t)nCh * nV, 0.0);
         std::fill(vsmIndex, vsmIndex + (size_t)nCh * nV, 0.0);
         for (int ch = 0; ch < nCh; ++ch) {
-            if (sv[ch] == 0) continue;
+            if (!live[ch]) continue;
             const double* o = out + (size_t)ch * GC_TRACK_NFIELDS * nEpochs;
             for (int v = 1; v <= nV && v * vint <= epochsDone[ch]; ++v) {
                 const int lo = v * vint - vint;

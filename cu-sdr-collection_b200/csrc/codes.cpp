@@ -50,4 +50,49 @@ void make_ca_table(int prn, double fs, double codeFreqBasis, int codeLength, int
     }
 }
 
+void glo_code(int8_t* out)
+{
+    // the reference multiplies +-1 registers loaded with -1; with bits (1 <-> -1) the product is an xor
+    unsigned reg = 0x1ff;                                   // nine stages, all ones
+    for (int i = 0; i < 511; ++i) {
+        const unsigned o = (reg >> 6) & 1u;                 // stage 7
+        out[i] = o ? -1 : 1;
+        const unsigned fb = ((reg >> 4) ^ (reg >> 8)) & 1u; // stages 5 and 9
+        reg = ((reg << 1) | fb) & 0x1ff;
+    }
+}
+
+// MATLAB a:d:b with a = 0 (Cleve Moler's colonop): n+1 elements built from both ends
+void glo_sample_index(double codeRate, double fs, int codeLength, long long numSamples, int16_t* idx)
+{
+    const double d = codeRate / fs;                         // stepSize
+    const double b = ((double)numSamples * d) - d;
+    const double tol = 2.0 * 2.220446049250313e-16 * std::fmax(0.0, std::fabs(b));
+    long long n;
+    if (d == 1.0) n = (long long)std::floor(b);
+    else if (d == std::floor(d)) n = (long long)std::trunc(b / d);
+    else {
+        const double q = b / d;
+        n = (long long)(q >= 0 ? std::floor(q + 0.5) : -std::floor(-q + 0.5));
+        if ((0.0 + (double)n * d - b) > tol) n -= 1;
+    }
+    double c = 0.0 + (double)n * d;
+    if ((c - b) > -tol) c = b;
+    for (long long k = 0; k <= n && k < numSamples; ++k) {
+        double v;
+        if (2 * k < n) v = 0.0 + (double)k * d;
+        else if (2 * k > n) v = c - (double)(n - k) * d;
+        else v = (0.0 + c) / 2;
+        idx[k] = (int16_t)std::fmod(std::floor(v), (double)codeLength);
+    }
+    for (long long k = n + 1; k < numSamples; ++k) idx[k] = 0;   // (never happens: n == numSamples-1)
+}
+
+void gps_fine_index(double fs, double codeFreqBasis, int codeLength, long long numSamples, int16_t* idx)
+{
+    const double ts = 1 / fs, tc = 1 / codeFreqBasis;
+    for (long long k = 0; k < numSamples; ++k)
+        idx[k] = (int16_t)((long long)std::floor((ts * (double)k) / tc) % codeLength);
+}
+
 }  // namespace gc

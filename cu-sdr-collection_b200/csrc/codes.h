@@ -11,4 +11,16 @@ void ca_code(int prn, int8_t* out);
 // GPS/GPS_L1CA/include/makeCaTable.m:43-67 (index = ceil(ts*n/tc), last index forced to 1023).
 void make_ca_table(int prn, double fs, double codeFreqBasis, int codeLength, int N, int8_t* out);
 
+// +-1 GLONASS ST-code chips (511, 9-stage register, taps 5 and 9, output of stage 7).
+// GLO/GLO_GL1/include/generateCAcode.m:95-108.
+void glo_code(int8_t* out);
+
+// MATLAB colon vector 0:step:(num*step)-step floored and wrapped to the code length: the sample ->
+// chip index map of GLO/GLO_GL1/include/generateCAcode.m:110-116 (0-based chip indices).
+void glo_sample_index(double codeRate, double fs, int codeLength, long long numSamples, int16_t* idx);
+
+// codeValueIndex of the GPS fine search: floor((ts*(0:num-1)) / (1/codeFreqBasis)) mod codeLength
+// (GPS/GPS_L1CA/include/acquisition.m:215-218), 0-based.
+void gps_fine_index(double fs, double codeFreqBasis, int codeLength, long long numSamples, int16_t* idx);
+
 }  // namespace gc

@@ -65,6 +65,7 @@ struct NextPhases {           // NCO phases at the end of the block being correl
 
 struct LoopMem {              // loop-filter memories
     double oldCodeNco, oldCodeError, oldCarrNco, oldCarrError, carrFreqBasis;
+    double d2CarrError, dCarrError;   // loopType 1 (GLO tracking.m:171-172)
 };
 
 // MATLAB colon vector a:d:b for non-integer a (Cleve Moler's colonop): element count n+1 and
@@ -185,10 +186,9 @@ __device__ __forceinline__ void end_phases(const TrackParams& p, const EpochPara
 }
 
 // exact float of a signed byte already xor-ed with 0x80: 0x4B0000bb = 2^23 + (b+128)
-template <int B>
-__device__ __forceinline__ float byte_to_float(uint32_t wx)
+__device__ __forceinline__ float byte_to_float(uint32_t wx, uint32_t sel)
 {
-    return __uint_as_float(__byte_perm(wx, 0x4B000000u, 0x7650 | B)) - 8388736.0f;
+    return __uint_as_float(__byte_perm(wx, 0x4B000000u, sel)) - 8388736.0f;
 }
 
 __device__ __forceinline__ uint32_t cluster_ctarank()
@@ -246,7 +246,7 @@ track_kernel(TrackParams p)
     const uint32_t crank = (G > 1) ? cluster_ctarank() : 0u;
     const bool leader = (crank == 0);
     const TrackChan cinfo = p.chans[ch];
-    if (cinfo.prn == 0) {                                        // tracking.m:136 (whole cluster leaves together)
+    if (cinfo.pad == 0) {                                        // channel off (tracking.m:136; GLO tracking.m:137)
         if (threadIdx.x == 0 && leader) p.epochsDone[ch] = 0;
         return;
     }
@@ -259,9 +259,13 @@ track_kernel(TrackParams p)
         s_code_raw[i] = (j >= 0 && j < p.codeLen + 2) ? (float)p.codeTables[(size_t)ch * p.codeStride + j] : 0.f;
     }
 
-    LoopMem lm;   // warp 0 lane 0: carrier memories; warp 1 lane 0: code memories
+    // byte selectors: sample bytes are I,Q,I,Q; GLONASS takes rawSignal = Q + 1i*I (GLO tracking.m:227)
+    const uint32_t selI0 = p.swapIQ ? 0x7651u : 0x7650u, selQ0 = p.swapIQ ? 0x7650u : 0x7651u;
+    const uint32_t selI1 = p.swapIQ ? 0x7653u : 0x7652u, selQ1 = p.swapIQ ? 0x7652u : 0x7653u;
+    LoopMem lm;   // PLL thread: carrier memories; DLL thread: code memories
     lm.oldCodeNco = lm.oldCodeError = lm.oldCarrNco = lm.oldCarrError = 0.0;   // :173-178
     lm.carrFreqBasis = cinfo.acqFreq;                                          // :168
+    lm.d2CarrError = lm.dCarrError = 0.0;
     double invStep = 0.0;                                        // DLL thread: 1/codePhaseStep of the previous block
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
@@ -359,10 +363,10 @@ track_kernel(TrackParams p)
             const uint32_t w0 = (uint32_t)raw.x ^ 0x80808080u, w1 = (uint32_t)raw.y ^ 0x80808080u,
                            w2 = (uint32_t)raw.z ^ 0x80808080u, w3 = (uint32_t)raw.w ^ 0x80808080u;
             float xi[8], xq[8];                                   // tracking.m:233-235
-            xi[0] = byte_to_float<0>(w0); xq[0] = byte_to_float<1>(w0); xi[1] = byte_to_float<2>(w0); xq[1] = byte_to_float<3>(w0);
-            xi[2] = byte_to_float<0>(w1); xq[2] = byte_to_float<1>(w1); xi[3] = byte_to_float<2>(w1); xq[3] = byte_to_float<3>(w1);
-            xi[4] = byte_to_float<0>(w2); xq[4] = byte_to_float<1>(w2); xi[5] = byte_to_float<2>(w2); xq[5] = byte_to_float<3>(w2);
-            xi[6] = byte_to_float<0>(w3); xq[6] = byte_to_float<1>(w3); xi[7] = byte_to_float<2>(w3); xq[7] = byte_to_float<3>(w3);
+            xi[0] = byte_to_float(w0, selI0); xq[0] = byte_to_float(w0, selQ0); xi[1] = byte_to_float(w0, selI1); xq[1] = byte_to_float(w0, selQ1);
+            xi[2] = byte_to_float(w1, selI0); xq[2] = byte_to_float(w1, selQ0); xi[3] = byte_to_float(w1, selI1); xq[3] = byte_to_float(w1, selQ1);
+            xi[4] = byte_to_float(w2, selI0); xq[4] = byte_to_float(w2, selQ0); xi[5] = byte_to_float(w2, selI1); xq[5] = byte_to_float(w2, selQ1);
+            xi[6] = byte_to_float(w3, selI0); xq[6] = byte_to_float(w3, selQ0); xi[7] = byte_to_float(w3, selI1); xq[7] = byte_to_float(w3, selQ1);
             if (k0 < 0 || k0 + 7 >= blk) {                        // first / last chunk of the block: drop the samples outside it
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
@@ -508,9 +512,16 @@ track_kernel(TrackParams p)
                 // would not make it more accurate, and a float64 atan is ~1000 dependent cycles per epoch.
                 const double carrError = p.exactDisc ? atan(__ddiv_rn(Q_P, I_P)) / kTwoPi
                                                      : (double)atanf((float)Q_P / (float)I_P) * 0.15915494309189535;
-                const double carrNco = __dadd_rn(__dadd_rn(lm.oldCarrNco, __dmul_rn(p.pA, __dsub_rn(carrError, lm.oldCarrError))),
-                                                 __dmul_rn(carrError, p.pB));
-                lm.oldCarrNco = carrNco; lm.oldCarrError = carrError;
+                double carrNco;
+                if (p.loopType == 0) {
+                    carrNco = __dadd_rn(__dadd_rn(lm.oldCarrNco, __dmul_rn(p.pA, __dsub_rn(carrError, lm.oldCarrError))),
+                                        __dmul_rn(carrError, p.pB));
+                    lm.oldCarrNco = carrNco; lm.oldCarrError = carrError;
+                } else {                                         // GLO_GL1/include/tracking.m:281-285
+                    lm.d2CarrError = __dadd_rn(lm.d2CarrError, __dmul_rn(carrError, p.pf3));
+                    lm.dCarrError = __dadd_rn(__dadd_rn(lm.d2CarrError, __dmul_rn(carrError, p.pf2)), lm.dCarrError);
+                    carrNco = __dadd_rn(lm.dCarrError, __dmul_rn(carrError, p.pf1));
+                }
                 plan_carrier(p, __dadd_rn(lm.carrFreqBasis, carrNco), s_ep[stage ^ 1]);   // :317 carrFreq of the next block
                 sg[GC_F_ABSOLUTE_SAMPLE * kStage] = (double)pos;                    // :215 ftell/2
                 sg[GC_F_REM_CODE_PHASE * kStage] = ep.remCodePhase;                 // :249

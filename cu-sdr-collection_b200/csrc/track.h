@@ -9,8 +9,8 @@
 namespace gc {
 
 struct TrackChan {
-    int32_t prn;             // 0 = channel off
-    int32_t pad;
+    int32_t prn;             // PRN (GPS) or frequency number K (GLONASS)
+    int32_t pad;             // 1 = channel active, 0 = channel off
     double acqFreq;          // channel.acquiredFreq
     long long startSample;   // skipNumberOfBytes + codePhase - 1   (tracking.m:150)
 };
@@ -21,6 +21,9 @@ struct TrackParams {
     double fs, invFs, codeFreqBasis, codeLength, spc;
     double cA, cB;           // tau2code/tau1code, PDIcode/tau1code  (tracking.m:326)
     double pA, pB;           // tau2carr/tau1carr, PDIcarr/tau1carr  (tracking.m:308)
+    double pf1, pf2, pf3;    // carrier filter of Common/calcLoopCoefCarr.m (loopType 1)
+    int loopType;            // 0: GPS L1CA second-order form (tracking.m:308); 1: pf3/pf2/pf1 form (GLO tracking.m:281-285)
+    int swapIQ;              // GLONASS: rawSignal = Q + 1i*I (GLO tracking.m:227)
     int nEpochs;
     int exactDisc;           // 1: float64 atan/sqrt/divide in the discriminators (GC_TRACK_EXACT_DISC), 0: fp32-seeded
     int bufBytes;            // bytes staged per epoch by ONE CTA (multiple of 16)

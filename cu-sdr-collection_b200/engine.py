@@ -30,7 +30,12 @@ class gc_config(C.Structure):
                 ("acq_search_band", C.c_double), ("acq_search_step", C.c_double), ("acq_threshold", C.c_double),
                 ("dll_damping_ratio", C.c_double), ("dll_noise_bandwidth", C.c_double),
                 ("dll_correlator_spacing", C.c_double), ("pll_damping_ratio", C.c_double),
-                ("pll_noise_bandwidth", C.c_double), ("int_time", C.c_double), ("cno_acc_time", C.c_double)]
+                ("pll_noise_bandwidth", C.c_double), ("int_time", C.c_double), ("cno_acc_time", C.c_double),
+                ("freq_spacing", C.c_double)]
+
+
+GC_SIG_GPS_L1CA, GC_SIG_GLO_G1G2 = 0, 1
+GC_SV_NONE = -2147483648
 
 
 class gc_stats(C.Structure):
@@ -86,7 +91,9 @@ def config_from_settings(s: Settings, device: int = 0) -> gc_config:
                             "(acquisition.m:50-111); run the reference for that case")
     if s.fileType != 2 or s.dataType != "schar":
         raise GnssCorrError("only fileType 2 with dataType 'schar' is implemented")
-    return gc_config(abi_version=1, device=device, signal=0, file_type=s.fileType, sample_bytes=1,
+    sig = GC_SIG_GLO_G1G2 if s.is_glonass else GC_SIG_GPS_L1CA
+    return gc_config(abi_version=2, device=device, signal=sig, freq_spacing=float(s.freqSpacing),
+                     file_type=s.fileType, sample_bytes=1,
                      code_length=int(s.codeLength), acq_noncoh_time=int(s.acqNonCohTime),
                      cno_vsm_interval=int(s.CNo_VSMinterval), skip_number_of_bytes=int(s.skipNumberOfBytes),
                      sampling_freq=s.samplingFreq, IF=s.IF, code_freq_basis=s.codeFreqBasis,
@@ -150,7 +157,7 @@ class Engine:
     def acquire(self, sv_list=None, host_iq=None):
         s = self.settings
         sv = np.asarray(list(sv_list if sv_list is not None else s.acqSatelliteList), dtype=np.int32)
-        n = self.lib.gc_acq_result_len(0)
+        n = self.lib.gc_acq_result_len(GC_SIG_GLO_G1G2 if s.is_glonass else GC_SIG_GPS_L1CA)
         carr, cph, pm = np.zeros(n), np.zeros(n), np.zeros(n)
         cbin, ccp = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
         if host_iq is not None:

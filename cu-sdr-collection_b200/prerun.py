@@ -8,6 +8,15 @@ from .settings import Settings
 
 
 def preRun(acqResults: dict, settings: Settings) -> list:
+    if settings.is_glonass:                                                     # GLO_GL1/include/preRun.m:44-72
+        channel = [dict(K=0, acquiredFreq=0.0, codePhase=0, status="-") for _ in range(settings.numberOfChannels)]
+        order = np.argsort(-np.asarray(acqResults["peakMetric"]), kind="stable")
+        n = min(settings.numberOfChannels, int(np.sum(np.asarray(acqResults["carrFreq"]) != 0)))
+        for ii in range(n):
+            p = int(order[ii])
+            channel[ii] = dict(K=p + 1 - 8, acquiredFreq=float(acqResults["carrFreq"][p]),     # Kindexes(ii)-8
+                               codePhase=int(acqResults["codePhase"][p]), status="T")
+        return channel
     channel = [dict(PRN=0, acquiredFreq=0.0, codePhase=0, status="-")
                for _ in range(settings.numberOfChannels)]                       # preRun.m:44-57
     # [junk, PRNindexes] = sort(peakMetric, 2, 'descend')  — stable, first index wins ties (:60)

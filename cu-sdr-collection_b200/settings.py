@@ -10,6 +10,7 @@ from dataclasses import dataclass, field
 
 @dataclass
 class Settings:
+    signal: str = "GPS_L1CA"            # which reference folder these settings belong to
     msToProcess: int = 60000            # initSettings.m:47
     numberOfChannels: int = 12          # :50
     skipNumberOfBytes: int = 0          # :56
@@ -36,12 +37,35 @@ class Settings:
     intTime: float = 0.001              # :108
     CNo_accTime: float = 0.001          # :133
     CNo_VSMinterval: int = 40           # :135
+    freqSpacing: float = 0.0            # GLONASS only: FDMA channel spacing (GLO_GL1/initSettings.m:72)
+
+    @property
+    def is_glonass(self) -> bool:
+        return self.signal in ("GLO_GL1", "GLO_GL2")
 
 
-def init_settings(**overrides) -> Settings:
-    """``settings = initSettings()`` (GPS/GPS_L1CA/init.m:56) with optional field overrides."""
-    s = Settings()
+# GLO/GLO_GL1/initSettings.m:44-146 (GLO_GL2 differs in freqSpacing and fileName only).  The GLONASS
+# folders call the record offset `skipNumberOfSamples`; it is the same quantity as skipNumberOfBytes.
+_GLO_DEFAULTS = dict(fileName="../../../GL1_IF0KHz_FS12MHz.bin", IF=0.0, samplingFreq=12e6, codeFreqBasis=0.511e6,
+                     codeLength=511.0, acqSatelliteList=list(range(-7, 7)), acqSearchBand=5000.0, acqThreshold=2.0,
+                     dllNoiseBandwidth=2.0, pllNoiseBandwidth=25.0, freqSpacing=562.5e3)
+
+
+def init_settings(signal: str = "GPS_L1CA", **overrides) -> Settings:
+    """``settings = initSettings()`` of the given signal folder (GPS/GPS_L1CA/init.m:56,
+    GLO/GLO_GL1, GLO/GLO_GL2) with optional field overrides."""
+    s = Settings(signal=signal)
+    if signal in ("GLO_GL1", "GLO_GL2"):
+        for k, v in _GLO_DEFAULTS.items():
+            setattr(s, k, list(v) if isinstance(v, list) else v)
+        if signal == "GLO_GL2":
+            s.freqSpacing = 437.5e3
+            s.fileName = "../../../GL2_IF0KHz_FS12MHz.bin"
+    elif signal != "GPS_L1CA":
+        raise ValueError(f"signal {signal!r} is not implemented")
     for k, v in overrides.items():
+        if k == "skipNumberOfSamples":
+            k = "skipNumberOfBytes"
         if not hasattr(s, k):
             raise AttributeError(f"settings has no field {k!r}")
         setattr(s, k, v)

@@ -16,7 +16,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from .codes import ca_code
+from .codes import ca_code, glo_code
 
 L1 = 1575.42e6
 
@@ -39,6 +39,11 @@ class Scene:
     sigma: float = 20.0
     seed: int = 20260101
     sats: list = field(default_factory=list)
+    # GLONASS scenes: Sat.prn holds the frequency number K; every satellite uses the same 511-chip code
+    # on carrier IF - freqSpacing*K (+ Doppler) as seen AFTER the reference's I/Q swap, data symbols are
+    # 10 ms meander halves (+b, -b) of 20 ms bits.
+    glonass: bool = False
+    freqSpacing: float = 562.5e3
 
 
 def default_scene(fs: float = 16.368e6, IF: float = 20e3, nsat: int = 8, seed: int = 20260101) -> Scene:
@@ -62,27 +67,47 @@ def nav_bits(sat: Sat, nbits: int) -> np.ndarray:
     return np.random.default_rng(sat.bit_seed).integers(0, 2, size=nbits).astype(np.float64) * 2 - 1
 
 
+def default_scene_glo(fs: float = 12e6, IF: float = 0.0, nsat: int = 5, seed: int = 20260101, freqSpacing: float = 562.5e3) -> Scene:
+    rng = np.random.default_rng(seed)
+    ks = rng.choice(np.arange(-7, 7), size=nsat, replace=False)
+    sats = [Sat(prn=int(k), doppler=float(rng.uniform(-4000, 4000)), code_phase=float(rng.uniform(0, 511)),
+                cn0=float(rng.uniform(40, 50)), phi0=float(rng.uniform(0, 2 * np.pi)), bit_seed=int(rng.integers(1 << 30)),
+                bit_offset=int(rng.integers(0, 20))) for k in ks]
+    return Scene(fs=fs, IF=IF, seed=seed, sats=sats, glonass=True, freqSpacing=freqSpacing)
+
+
 def make_record(scene: Scene, nsamples: int, start: int = 0) -> np.ndarray:
     """int8 array of length 2*nsamples (I0,Q0,I1,Q1,...), samples start..start+nsamples-1."""
     n = np.arange(start, start + nsamples, dtype=np.float64)
     t = n / scene.fs
     sig = np.zeros(nsamples, dtype=np.complex128)
     for s in scene.sats:
-        fcode = 1.023e6 * (1 + s.doppler / L1)
+        if scene.glonass:
+            clen, crate, carrier = 511, 511e3, 1602e6
+            fc = scene.IF - scene.freqSpacing * s.prn + s.doppler
+            chipseq = glo_code().astype(np.float64)
+        else:
+            clen, crate, carrier = 1023, 1.023e6, L1
+            fc = scene.IF + s.doppler
+            chipseq = ca_code(s.prn).astype(np.float64)
+        fcode = crate * (1 + s.doppler / carrier)
         chips = fcode * t + s.code_phase
-        period = np.floor(chips / 1023.0).astype(np.int64)
-        idx = np.floor(chips - period * 1023.0).astype(np.int64) % 1023
-        code = ca_code(s.prn).astype(np.float64)[idx]
+        period = np.floor(chips / clen).astype(np.int64)
+        idx = np.floor(chips - period * float(clen)).astype(np.int64) % clen
+        code = chipseq[idx]
         bits = nav_bits(s, int(period.max() // 20) + 3)
         d = bits[(period + s.bit_offset) // 20]
-        ph = 2 * np.pi * ((scene.IF + s.doppler) * t % 1.0) + s.phi0
+        if scene.glonass:                       # meander: second 10 ms of every bit is inverted
+            d = d * np.where(((period + s.bit_offset) % 20) < 10, 1.0, -1.0)
+        ph = 2 * np.pi * (fc * t % 1.0) + s.phi0
         sig += _amp(s.cn0, scene.sigma, scene.fs) * d * code * np.exp(1j * ph)
     # noise is a function of (seed, absolute chunk) so records can be made piecewise
     rng = np.random.default_rng([scene.seed, start])
     sig += scene.sigma * (rng.standard_normal(nsamples) + 1j * rng.standard_normal(nsamples))
     out = np.empty(2 * nsamples, dtype=np.int8)
-    out[0::2] = np.clip(np.rint(sig.real), -127, 127).astype(np.int8)
-    out[1::2] = np.clip(np.rint(sig.imag), -127, 127).astype(np.int8)
+    re, im = (sig.imag, sig.real) if scene.glonass else (sig.real, sig.imag)   # GLONASS files are read as Q + 1i*I
+    out[0::2] = np.clip(np.rint(re), -127, 127).astype(np.int8)
+    out[1::2] = np.clip(np.rint(im), -127, 127).astype(np.int8)
     return out
 
 

@@ -5,7 +5,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .engine import Engine
+from .engine import GC_SV_NONE, Engine
 from .settings import Settings
 
 # row order of the C ABI's output block == GC_F_* in include/gnsscorr.h
@@ -24,7 +24,10 @@ def tracking(fid, channel: list, settings: Settings, engine: Engine | None = Non
     try:
         n = settings.msToProcess                                            # tracking.m:90
         nch = settings.numberOfChannels
-        prn = [int(c["PRN"]) for c in channel[:nch]]
+        if settings.is_glonass:     # a GLONASS channel is live when status ~= '-' and is identified by K (GLO tracking.m:137-141)
+            prn = [int(c["K"]) if c["status"] != "-" else GC_SV_NONE for c in channel[:nch]]
+        else:
+            prn = [int(c["PRN"]) for c in channel[:nch]]
         af = [float(c["acquiredFreq"]) for c in channel[:nch]]
         cp = [float(c["codePhase"]) for c in channel[:nch]]
         path = fid.name if fid is not None else None
@@ -38,12 +41,13 @@ def tracking(fid, channel: list, settings: Settings, engine: Engine | None = Non
         for i, f in enumerate(TRACK_FIELDS):
             tr[f] = out[ch, i]
         tr["CNo"] = {"VSMValue": vv[ch], "VSMIndex": vi[ch]}
-        if prn[ch] != 0:
-            tr["PRN"] = prn[ch]                                            # :138
-        if prn[ch] != 0 and done[ch] == n:
+        live = prn[ch] != (GC_SV_NONE if settings.is_glonass else 0)
+        if live:
+            tr["PRN"] = prn[ch]                                            # :138 (GLONASS stores K here)
+        if live and done[ch] == n:
             tr["status"] = channel[ch]["status"]                           # :365
         tr["epochsDone"] = int(done[ch])
         results.append(tr)
-    if any(prn[ch] != 0 and done[ch] < n for ch in range(nch)):
+    if any(prn[ch] != (GC_SV_NONE if settings.is_glonass else 0) and done[ch] < n for ch in range(nch)):
         print("Not able to read the specified number of samples  for tracking, exiting!")   # :242
     return results, channel

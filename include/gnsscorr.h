@@ -28,10 +28,16 @@
 extern "C" {
 #endif
 
-#define GC_ABI_VERSION 1
+#define GC_ABI_VERSION 2
 
-/* signal ids (one per reference folder); only GC_SIG_GPS_L1CA is implemented in this round */
-enum { GC_SIG_GPS_L1CA = 0 };
+/* signal ids (reference folders).  Implemented: GPS/GPS_L1CA and GLO/GLO_GL1 + GLO/GLO_GL2 (the two
+ * GLONASS folders differ only in settings.freqSpacing and the file name). */
+enum { GC_SIG_GPS_L1CA = 0, GC_SIG_GLO_G1G2 = 1 };
+
+/* "no satellite on this channel" for gc_track: GPS uses PRN 0 (tracking.m:136); a GLONASS channel is
+ * identified by its frequency number K, for which 0 is valid, so unused channels carry GC_SV_NONE
+ * (GLO_GL1/include/tracking.m:137 tests channel.status ~= '-'). */
+#define GC_SV_NONE (-2147483647 - 1)
 
 /* error codes */
 enum {
@@ -70,6 +76,8 @@ typedef struct gc_config {
     double pll_noise_bandwidth;  /* settings.pllNoiseBandwidth (:106)                               */
     double int_time;             /* settings.intTime (:108)                                         */
     double cno_acc_time;         /* settings.CNo.accTime (:133)                                     */
+    double freq_spacing;         /* GLONASS only: settings.freqSpacing, FDMA channel spacing in Hz
+                                    (GLO/GLO_GL1/initSettings.m: 562.5e3, GLO_GL2: 437.5e3)         */
 } gc_config;
 
 typedef struct gc_handle gc_handle;
@@ -83,7 +91,8 @@ enum {
     GC_F_PLL_DISCR_FILT, GC_F_REM_CODE_PHASE, GC_F_REM_CARR_PHASE
 };
 
-/* Length of the acqResults vectors for a signal (32 for GPS L1CA, acquisition.m:130-134). */
+/* Length of the acqResults vectors for a signal: 32 for GPS L1CA indexed PRN-1 (acquisition.m:130-134),
+ * 21 for GLONASS indexed K+7, i.e. MATLAB's K+8 (GLO_GL1/include/acquisition.m:138-142,212). */
 int gc_acq_result_len(int32_t signal);
 
 /* Create / destroy an engine bound to one GPU.  Builds the FFT plan and twiddle tables for
@@ -104,8 +113,10 @@ int gc_set_record_device(gc_handle* h, const void* dptr, size_t nbytes);
 /* acquisition(longSignal, settings) on the resident record — replaces
  * GPS/GPS_L1CA/include/acquisition.m:113-292 (resamplingflag must be 0).
  * longSignal = the max(42, nonCoh+2) code periods starting at skip_number_of_bytes
- * (postProcessing.m:74,83-96).  svList = settings.acqSatelliteList (PRNs, 1-based).
- * Outputs (length gc_acq_result_len, indexed PRN-1, zero for PRNs not searched):
+ * (postProcessing.m:74,83-96).  svList = settings.acqSatelliteList (GPS: PRNs 1..32; GLONASS: frequency
+ * numbers K = -7..13, GLO_GL1/include/acquisition.m:172-183 — one shared 511-chip replica, carrier grid
+ * shifted by -freqSpacing*K per channel, I/Q swapped on input).
+ * Outputs (length gc_acq_result_len, indexed PRN-1 / K+7, zero for SVs not searched):
  *   carrFreq, codePhase, peakMetric  = acqResults fields (acquisition.m:130-134,200,254-260)
  *   coarseBin, coarseCodePhase       = acqCoarseBin / codePhase of :196-198 for every searched
  *                                      PRN (1-based; diagnostic, may be NULL). */
@@ -124,7 +135,9 @@ int gc_acquire_host(gc_handle* h, const int8_t* iq, size_t nSamples,
 
 /* tracking(fid, channel, settings) on the resident record — replaces
  * GPS/GPS_L1CA/include/tracking.m:88-368.
- *   sv[ch]        channel(ch).PRN (0 = channel off, tracking.m:136)
+ *   sv[ch]        channel(ch).PRN (0 = channel off, tracking.m:136); GLONASS: channel(ch).K
+ *                 (GC_SV_NONE = channel off).  GLONASS uses the 3-coefficient carrier filter of
+ *                 Common/calcLoopCoefCarr.m (GLO_GL1/include/tracking.m:281-285) and swaps I/Q (:227).
  *   acqFreq[ch]   channel(ch).acquiredFreq        codePhase[ch]  channel(ch).codePhase (1-based)
  *   nEpochs       settings.msToProcess (code periods)
  *   out           [nCh][GC_TRACK_NFIELDS][nEpochs] doubles; rows pre-filled like tracking.m:51-77

@@ -1,12 +1,21 @@
 function cfg = gnsscorr_config(settings)
 %GNSSCORR_CONFIG  settings struct (initSettings.m) -> the field names of gc_config (gnsscorr.h).
 cfg.device = 0;
+if isfield(settings, 'freqSpacing')      % GLO/GLO_GL1, GLO/GLO_GL2
+    cfg.signal = 1;  cfg.freq_spacing = settings.freqSpacing;
+else                                    % GPS/GPS_L1CA
+    cfg.signal = 0;  cfg.freq_spacing = 0;
+end
 cfg.file_type = settings.fileType;
 cfg.sample_bytes = 1;
 cfg.code_length = settings.codeLength;
 cfg.acq_noncoh_time = settings.acqNonCohTime;
 cfg.cno_vsm_interval = settings.CNo.VSMinterval;
-cfg.skip_number_of_bytes = settings.skipNumberOfBytes;
+if isfield(settings, 'skipNumberOfSamples')   % the GLONASS folders' name for the same offset
+    cfg.skip_number_of_bytes = settings.skipNumberOfSamples;
+else
+    cfg.skip_number_of_bytes = settings.skipNumberOfBytes;
+end
 cfg.sampling_freq = settings.samplingFreq;
 cfg.IF = settings.IF;
 cfg.code_freq_basis = settings.codeFreqBasis;

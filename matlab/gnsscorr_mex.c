@@ -10,8 +10,8 @@
  *   r = gnsscorr_mex('acquire', cfg, iq_int8, svList)
  *         cfg     : struct with the gc_config field names (doubles)
  *         iq_int8 : int8 vector, I,Q interleaved (longSignal as stored in the file)
- *         svList  : double vector of PRNs
- *         r       : struct carrFreq, codePhase, peakMetric (1x32 double)
+ *         svList  : double vector of PRNs (GLONASS: frequency numbers K)
+ *         r       : struct carrFreq, codePhase, peakMetric (1x32 double; GLONASS 1x21, index K+8)
  *   r = gnsscorr_mex('track', cfg, path, prn, acqFreq, codePhase, nEpochs)
  *         r       : struct out (nEpochs x 15 x nCh double, MATLAB column-major view of the
  *                   C [nCh][15][nEpochs] block), vsmValue, vsmIndex, epochsDone
@@ -35,7 +35,8 @@ static void fill_config(const mxArray* s, gc_config* c)
     memset(c, 0, sizeof(*c));
     c->abi_version = GC_ABI_VERSION;
     c->device = (int32_t)field(s, "device");
-    c->signal = GC_SIG_GPS_L1CA;
+    c->signal = (int32_t)field(s, "signal");
+    c->freq_spacing = field(s, "freq_spacing");
     c->file_type = (int32_t)field(s, "file_type");
     c->sample_bytes = (int32_t)field(s, "sample_bytes");
     c->code_length = (int32_t)field(s, "code_length");
@@ -105,7 +106,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
         mxArray *out, *vv, *vi, *done;
         mwSize i;
         if (nrhs != 7 || mxGetString(prhs[2], path, sizeof(path)) || nCh > 256) { gc_destroy(h); mexErrMsgIdAndTxt("gnsscorr:args", "track: bad arguments"); }
-        for (i = 0; i < nCh; ++i) prn[i] = (int32_t)prnd[i];
+        for (i = 0; i < nCh; ++i) prn[i] = (prnd[i] != prnd[i]) ? GC_SV_NONE : (int32_t)prnd[i];   /* NaN = channel off (GLONASS) */
         dims[0] = nEpochs; dims[1] = GC_TRACK_NFIELDS; dims[2] = nCh;
         out = mxCreateNumericArray(3, dims, mxDOUBLE_CLASS, mxREAL);
         vv = mxCreateDoubleMatrix(nV, nCh, mxREAL);

@@ -35,6 +35,8 @@ typedef struct {
     double dllDampingRatio, dllNoiseBandwidth, dllCorrelatorSpacing; /* :100-102 */
     double pllDampingRatio, pllNoiseBandwidth, intTime;            /* :105-108 */
     double CNo_accTime; int CNo_VSMinterval;                       /* :133-135 */
+    double freqSpacing;                                            /* GLO/GLO_GL1/initSettings.m:72 */
+    int    glo;            /* 0: GPS/GPS_L1CA files; 1: GLO/GLO_GL1 (= GLO_GL2) files, cited as "GLO :line" */
 } orc_settings;
 
 /* ---------------------------------------------------------------- helpers */
@@ -72,6 +74,44 @@ void orc_generateCAcode(int PRN, double* CAcode /*1023*/)
     for (int i = 0; i < 1023; i++) {
         int src = (i < g2shift) ? (1023 - g2shift + i) : (i - g2shift);
         CAcode[i] = -(g1[i] * g2[src]);
+    }
+}
+
+/* GLO/GLO_GL1/include/generateCAcode.m:95-108 — 511-chip ST code (PRN == 0 branch) */
+void orc_glo_code(double* code /*511*/)
+{
+    double reg[9];
+    for (int i = 0; i < 9; i++) reg[i] = -1;
+    for (int i = 0; i < 511; i++) {
+        code[i] = reg[6];
+        double save1 = reg[4] * reg[8];
+        for (int j = 8; j >= 1; j--) reg[j] = reg[j - 1];
+        reg[0] = save1;
+    }
+}
+
+/* element k of MATLAB 0:d:b (colonop), n+1 elements, last element c */
+static void colon0_setup(double d, double b, long* n_out, double* c_out)
+{
+    double tol = 2.0 * 2.220446049250313e-16 * fabs(b);
+    long n;
+    if (d == 1) n = (long)floor(b);
+    else if (d == floor(d)) n = (long)trunc(b / d);
+    else { n = (long)m_round(b / d); if ((0.0 + n * d - b) > tol) n -= 1; }
+    double c = 0.0 + n * d;
+    if ((c - b) > -tol) c = b;
+    *n_out = n; *c_out = c;
+}
+/* GLO generateCAcode.m:110-116 — samples = floor(0:stepSize:(num*stepSize)-stepSize) wrapped to 511 */
+void orc_glo_sampled_code(double sampFreq, long numSamples, double* out)
+{
+    double code[511]; orc_glo_code(code);
+    double stepSize = 511e3 / sampFreq;
+    long n; double c;
+    colon0_setup(stepSize, (numSamples * stepSize) - stepSize, &n, &c);
+    for (long k = 0; k <= n && k < numSamples; k++) {
+        double v = (2 * k < n) ? 0.0 + (double)k * stepSize : (2 * k > n) ? c - (double)(n - k) * stepSize : (0.0 + c) / 2;
+        out[k] = code[(long)fmod(floor(v), 511)];
     }
 }
 
@@ -174,11 +214,15 @@ int orc_acquisition(const int8_t* iq, size_t nSamplesAvail, const orc_settings* 
     const double fineSearchStep = 25;                                            /* :138 */
     const int nFine = (int)m_round(s->acqSearchStep / fineSearchStep) + 1;       /* :140 */
     const int nonCoh = s->acqNonCohTime;
-    for (int i = 0; i < 32; i++) { carrFreq[i] = codePhaseOut[i] = peakMetric[i] = 0; coarseBin[i] = coarseCodePhase[i] = 0; }
+    const int nRes = s->glo ? 21 : 32;                      /* GLO acquisition.m:138-142 */
+    for (int i = 0; i < nRes; i++) { carrFreq[i] = codePhaseOut[i] = peakMetric[i] = 0; coarseBin[i] = coarseCodePhase[i] = 0; }
 
     size_t Ltot = (size_t)codeLen * N;
     cplx* sig = (cplx*)malloc(sizeof(cplx) * Ltot);
-    for (size_t i = 0; i < Ltot; i++) sig[i] = (double)iq[2 * i] + I * (double)iq[2 * i + 1];
+    for (size_t i = 0; i < Ltot; i++)                        /* GLO postProcessing.m:94: data2 + 1i*data1 */
+        sig[i] = s->glo ? (double)iq[2 * i + 1] + I * (double)iq[2 * i] : (double)iq[2 * i] + I * (double)iq[2 * i + 1];
+    double* glo40 = NULL;                                    /* GLO acquisition.m:164 caCode40ms */
+    if (s->glo) { glo40 = (double*)malloc(sizeof(double) * 40 * (size_t)N); orc_glo_sampled_code(s->samplingFreq, 40L * N, glo40); }
     double* phasePoints = (double*)malloc(sizeof(double) * L2);
     for (int n = 0; n < L2; n++) phasePoints[n] = (double)n * 2 * M_PI * ts;     /* :122 */
 
@@ -202,12 +246,15 @@ int orc_acquisition(const int8_t* iq, size_t nSamplesAvail, const orc_settings* 
         cplx* carr = (cplx*)malloc(sizeof(cplx) * L2);
         double* results = (double*)calloc((size_t)nBins * L2, sizeof(double));   /* :162 */
         double* coarseFreqBin = (double*)malloc(sizeof(double) * nBins);
-        orc_makeCaTable(PRN, s, table);                                          /* :158 */
+        if (s->glo) orc_glo_sampled_code(s->samplingFreq, N, table);             /* GLO :145 */
+        else orc_makeCaTable(PRN, s, table);                                     /* :158 */
+        const int ri = s->glo ? PRN + 7 : PRN - 1;                               /* result slot: K+8 / PRN (1-based) */
         for (int n = 0; n < L2; n++) codeF[n] = n < N ? table[n] : 0.0;          /* :160 */
         fft_exec(&plan, codeF, tmp, -1);
         for (int n = 0; n < L2; n++) codeF[n] = conj(codeF[n]);                  /* :164 */
         for (int k = 1; k <= nBins; k++) {                                       /* :167 */
-            coarseFreqBin[k - 1] = s->IF + s->acqSearchBand - s->acqSearchStep * (k - 1);   /* :169 */
+            coarseFreqBin[k - 1] = s->glo ? s->IF - s->freqSpacing * PRN + s->acqSearchBand - s->acqSearchStep * (k - 1)   /* GLO :181 */
+                                          : s->IF + s->acqSearchBand - s->acqSearchStep * (k - 1);                   /* :169 */
             for (int n = 0; n < L2; n++) {
                 double a = coarseFreqBin[k - 1] * phasePoints[n];
                 carr[n] = cos(a) - I * sin(a);                                   /* :172 */
@@ -236,10 +283,10 @@ int orc_acquisition(const int8_t* iq, size_t nSamplesAvail, const orc_settings* 
             for (int k = 1; k < nBins; k++) if (results[(size_t)k * L2 + n] > cm) cm = results[(size_t)k * L2 + n];
             if (cm > peak) { peak = cm; cp = n + 1; }
         }
-        peakMetric[PRN - 1] = peak / sigPower / nonCoh;                          /* :200 */
-        coarseBin[PRN - 1] = bin; coarseCodePhase[PRN - 1] = cp;
-        if (peakMetric[PRN - 1] > s->acqThreshold) {                             /* :206 */
-            double ca[1023]; orc_generateCAcode(PRN, ca);                        /* :213 */
+        peakMetric[ri] = peak / sigPower / nonCoh;                               /* :200 */
+        coarseBin[ri] = bin; coarseCodePhase[ri] = cp;
+        if (peakMetric[ri] > s->acqThreshold) {                                  /* :206 */
+            double ca[1023]; if (!s->glo) orc_generateCAcode(PRN, ca);           /* :213 */
             double bestFine = -1; int bestJ = 1; double bestFreq = 0;
             for (int j = 1; j <= nFine; j++) {                                   /* :224 */
                 double f = coarseFreqBin[bin - 1] + s->acqSearchStep / 2 - fineSearchStep * (j - 1);  /* :227 */
@@ -248,8 +295,12 @@ int orc_acquisition(const int8_t* iq, size_t nSamplesAvail, const orc_settings* 
                     cplx acc = 0;
                     for (int n = 0; n < N; n++) {
                         long gi = (long)c * N + n;
-                        long idx = (long)floor((ts * (double)gi) / (1 / s->codeFreqBasis));      /* :215 */
-                        double chip = ca[idx % (long)s->codeLength];                           /* :218 */
+                        double chip;
+                        if (s->glo) chip = glo40[gi];                                          /* GLO :164,236 */
+                        else {
+                            long idx = (long)floor((ts * (double)gi) / (1 / s->codeFreqBasis));  /* :215 */
+                            chip = ca[idx % (long)s->codeLength];                              /* :218 */
+                        }
                         double a = f * ((double)gi * 2 * M_PI * ts);                           /* :148,:230 */
                         cplx cw = cos(a) - I * sin(a);
                         acc += (sig[(size_t)(cp - 1) + gi] * chip) * cw;                       /* :221,:232,:236 */
@@ -258,20 +309,27 @@ int orc_acquisition(const int8_t* iq, size_t nSamplesAvail, const orc_settings* 
                 }
                 double maxPower = 0;
                 for (int c = 0; c < 20; c++) {                                   /* :243 */
-                    cplx t = 0; for (int q = c; q < c + 20; q++) t += sumPerCode[q];
+                    cplx t = 0;
+                    if (!s->glo) { for (int q = c; q < c + 20; q++) t += sumPerCode[q]; }
+                    else {                                                       /* GLO :250-251: sum(c:c+9) - sum(c+10:c+19) */
+                        cplx t1 = 0, t2 = 0;
+                        for (int q = c; q < c + 10; q++) t1 += sumPerCode[q];
+                        for (int q = c + 10; q < c + 20; q++) t2 += sumPerCode[q];
+                        t = t1 - t2;
+                    }
                     double pw = cabs(t);                                         /* :245 */
                     if (pw > maxPower) maxPower = pw;                            /* :247 */
                 }
                 if (maxPower > bestFine) { bestFine = maxPower; bestJ = j; bestFreq = f; }       /* :253 */
             }
             (void)bestJ;
-            carrFreq[PRN - 1] = bestFreq;                                        /* :254 */
-            codePhaseOut[PRN - 1] = cp;                                          /* :256 */
-            if (carrFreq[PRN - 1] == 0) carrFreq[PRN - 1] = 1;                   /* :258 */
+            carrFreq[ri] = bestFreq;                                             /* :254 */
+            codePhaseOut[ri] = cp;                                               /* :256 */
+            if (carrFreq[ri] == 0) carrFreq[ri] = 1;                             /* :258 */
         }
         free(table); free(codeF); free(buf); free(tmp); free(carr); free(results); free(coarseFreqBin);
     }
-    plan_free(&plan); free(sig); free(phasePoints);
+    plan_free(&plan); free(sig); free(phasePoints); free(glo40);
     return rc;
 }
 
@@ -336,6 +394,9 @@ int orc_tracking(const int8_t* iq, size_t nBytes, const orc_settings* s, int nCh
     double tau1code, tau2code, tau1carr, tau2carr;
     calcLoopCoef(s->dllNoiseBandwidth, s->dllDampingRatio, 1.0, &tau1code, &tau2code);   /* :100 */
     calcLoopCoef(s->pllNoiseBandwidth, s->pllDampingRatio, 0.25, &tau1carr, &tau2carr);  /* :109 */
+    /* GLO Common/calcLoopCoefCarr.m:41-56 (GLO tracking.m:110) */
+    const double WnC = 1.2 * s->pllNoiseBandwidth;
+    const double pf3 = pow(WnC, 3) * pow(s->intTime, 2), pf2 = 2 * pow(WnC, 2) * s->intTime, pf1 = 2 * WnC;
     const int L = (int)s->codeLength;
     const int nV = nEpochs / s->CNo_VSMinterval;
     /* result init (tracking.m:48-83): zeros for absoluteSample and I/Q, inf elsewhere */
@@ -351,13 +412,15 @@ int orc_tracking(const int8_t* iq, size_t nBytes, const orc_settings* s, int nCh
     volatile int abortAll = 0;
 #pragma omp parallel for schedule(dynamic, 1) if (parallel)
     for (int ch = 0; ch < nCh; ch++) {                                           /* :133 */
-        if (PRN[ch] == 0) continue;                                              /* :136 */
+        if (s->glo ? (PRN[ch] == INT32_MIN) : (PRN[ch] == 0)) continue;          /* :136 ; GLO :137 status ~= '-' (INT32_MIN = off) */
         if (!parallel && abortAll) continue;   /* sequential semantics: return ends all later channels */
         double* o = out + (size_t)ch * ORC_NFIELDS * nEpochs;
 #define F(i) (o + (size_t)(i) * nEpochs)
         size_t pos = (size_t)(2 * ((long)s->skipNumberOfBytes + (long)codePhase[ch] - 1));   /* :150 */
         double ca[1023], caCode[1025];
-        orc_generateCAcode(PRN[ch], ca);                                         /* :156 */
+        if (s->glo) orc_glo_code(ca);                                            /* GLO :88 */
+        else orc_generateCAcode(PRN[ch], ca);                                    /* :156 */
+        double d2CarrError = 0, dCarrError = 0;                                  /* GLO :171-172 */
         caCode[0] = ca[L - 1]; memcpy(caCode + 1, ca, sizeof(double) * L); caCode[L + 1] = ca[0];   /* :158 */
         double codeFreq = s->codeFreqBasis, remCodePhase = 0.0;                  /* :163-165 */
         double carrFreq = acquiredFreq[ch], carrFreqBasis = acquiredFreq[ch], remCarrPhase = 0.0;   /* :167-170 */
@@ -387,6 +450,7 @@ int orc_tracking(const int8_t* iq, size_t nBytes, const orc_settings* s, int nCh
                 double trig = (w * ((double)n / s->samplingFreq)) + remCarrPhase;            /* :280-281 */
                 double c = cos(trig), sn = sin(trig);                            /* :287 exp(-1i*trig) = c - i*sn */
                 double xr = raw[2 * n], xi = raw[2 * n + 1];                     /* :233-235 */
+                if (s->glo) { double t_ = xr; xr = xi; xi = t_; }                /* GLO :227 rawSignal2 + 1i*rawSignal1 */
                 double iBB = c * xr + sn * xi, qBB = c * xi - sn * xr;           /* :291-292 */
                 I_E += e * iBB; Q_E += e * qBB; I_P += p * iBB; Q_P += p * qBB; I_L += l * iBB; Q_L += l * qBB;   /* :295-300 */
             }
@@ -394,8 +458,15 @@ int orc_tracking(const int8_t* iq, size_t nBytes, const orc_settings* s, int nCh
             double trigEnd = (w * ((double)blksize / s->samplingFreq)) + remCarrPhase;
             remCarrPhase = fmod(trigEnd, 2 * M_PI);                              /* :283 */
             double carrError = atan(Q_P / I_P) / (2.0 * M_PI);                   /* :305 */
-            double carrNco = oldCarrNco + (tau2carr / tau1carr) * (carrError - oldCarrError) + carrError * (PDIcarr / tau1carr);   /* :308 */
-            oldCarrNco = carrNco; oldCarrError = carrError;
+            double carrNco;
+            if (!s->glo) {
+                carrNco = oldCarrNco + (tau2carr / tau1carr) * (carrError - oldCarrError) + carrError * (PDIcarr / tau1carr);   /* :308 */
+                oldCarrNco = carrNco; oldCarrError = carrError;
+            } else {                                                             /* GLO :282-285 */
+                d2CarrError = d2CarrError + carrError * pf3;
+                dCarrError = d2CarrError + carrError * pf2 + dCarrError;
+                carrNco = dCarrError + carrError * pf1;
+            }
             F(2)[loopCnt - 1] = carrFreq;                                        /* :314 */
             carrFreq = carrFreqBasis + carrNco;                                  /* :317 */
             double sE = sqrt(I_E * I_E + Q_E * Q_E), sL = sqrt(I_L * I_L + Q_L * Q_L);
@@ -423,7 +494,7 @@ int orc_tracking(const int8_t* iq, size_t nBytes, const orc_settings* s, int nCh
     if (parallel) {
         int failed = -1;
         for (int ch = 0; ch < nCh && failed < 0; ch++)
-            if (PRN[ch] != 0 && epochsDone[ch] < nEpochs) failed = ch;
+            if (!(s->glo ? (PRN[ch] == INT32_MIN) : (PRN[ch] == 0)) && epochsDone[ch] < nEpochs) failed = ch;
         for (int ch = failed + 1; failed >= 0 && ch < nCh; ch++) {
             double* o = out + (size_t)ch * ORC_NFIELDS * nEpochs;
             for (int f = 0; f < ORC_NFIELDS; f++) {

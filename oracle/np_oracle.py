@@ -74,6 +74,7 @@ class Settings:
     intTime: float = 0.001              # :108
     CNo_accTime: float = 0.001          # :133
     CNo_VSMinterval: int = 40           # :135
+    freqSpacing: float = 0.0            # GLO/GLO_GL1/initSettings.m:72 (GLONASS only)
 
 
 def matlab_round(x: float) -> float:
@@ -409,4 +410,204 @@ def tracking(raw: np.ndarray, channel: list, s: Settings):
                                                     s.CNo_accTime)   # :353
                 tr["VSMIndex"][vsmCnt - 1] = loopCnt               # :356
         tr["status"] = channel[ch]["status"]                       # :365
+    return out
+
+
+# ===========================================================================
+# GLONASS L1/L2 (GLO/GLO_GL1 and GLO/GLO_GL2: identical code, different freqSpacing)
+# paths below relative to /root/reference/GLO/GLO_GL1/
+# ===========================================================================
+def glo_settings(**kw) -> Settings:
+    """GLO/GLO_GL1/initSettings.m:44-146 defaults (hot-path fields)."""
+    s = Settings(IF=0.0, samplingFreq=12e6, codeFreqBasis=0.511e6, codeLength=511.0,
+                 acqSatelliteList=list(range(-7, 7)), acqSearchBand=5000.0, acqThreshold=2.0,
+                 dllNoiseBandwidth=2.0, pllNoiseBandwidth=25.0, freqSpacing=562.5e3)
+    for k, v in kw.items():
+        setattr(s, k, v)
+    return s
+
+
+def glo_code() -> np.ndarray:
+    """include/generateCAcode.m:95-108 — 511-chip ST code, +-1 (PRN == 0 branch)."""
+    reg = -np.ones(9)
+    code = np.zeros(511)
+    for i in range(511):
+        code[i] = reg[6]
+        save1 = reg[4] * reg[8]
+        reg[1:9] = reg[0:8].copy()
+        reg[0] = save1
+    return code
+
+
+def generateCAcode_glo(sampFreq: float, numSamples: int) -> np.ndarray:
+    """include/generateCAcode.m:110-116 — the code resampled with a floating-point colon vector."""
+    code = glo_code()
+    stepSize = 511e3 / sampFreq
+    samples = colonop(0.0, stepSize, (numSamples * stepSize) - stepSize)
+    samples = np.fmod(np.floor(samples), 511).astype(np.int64)
+    return code[samples]
+
+
+def read_acq_signal_glo(raw: np.ndarray, s: Settings) -> np.ndarray:
+    """include/postProcessing.m:83-96 — note data = data2 + 1i*data1 (Q + iI)."""
+    N = samples_per_code(s)
+    codeLen = max(42, s.acqNonCohTime + 2)
+    off = 2 * s.skipNumberOfBytes
+    data = raw[off: off + 2 * codeLen * N].astype(np.float64)
+    return data[1::2] + 1j * data[0::2]
+
+
+def acquisition_glo(longSignal: np.ndarray, s: Settings, workers: int = 1):
+    """include/acquisition.m:121-292.  Result vectors are 1x21, indexed K+8 (0-based K+7)."""
+    N = samples_per_code(s)                                        # :121
+    ts = 1 / s.samplingFreq
+    phasePoints = np.arange(0, 2 * N, dtype=np.float64) * 2 * np.pi * ts       # :127
+    nBins = int(matlab_round(s.acqSearchBand * 2 / s.acqSearchStep)) + 1       # :129
+    coarseFreqBin = np.zeros(nBins)
+    res = dict(carrFreq=np.zeros(21), codePhase=np.zeros(21), peakMetric=np.zeros(21),
+               coarseBin=np.zeros(21, dtype=np.int64), coarseCodePhase=np.zeros(21, dtype=np.int64))
+    caCode = generateCAcode_glo(s.samplingFreq, N)                 # :145
+    caCodeFreqDom = np.conj(_FFT(np.concatenate([caCode, np.zeros(N)])))       # :147-149
+    fineSearchStep = 25
+    numOfFineBins = int(matlab_round(s.acqSearchStep / fineSearchStep)) + 1
+    caCode40ms = generateCAcode_glo(s.samplingFreq, N * 40)        # :164
+    finePhasePoints = np.arange(0, 40 * N, dtype=np.float64) * 2 * np.pi * ts  # :166
+    x = longSignal[:N]
+    sigPower = math.sqrt(np.sum(np.abs(x - np.mean(x)) ** 2) / (N - 1) * N)    # :169
+    res["sigPower"] = sigPower
+    for K in s.acqSatelliteList:                                   # :173
+        results = np.zeros((nBins, 2 * N))
+        for k in range(1, nBins + 1):
+            coarseFreqBin[k - 1] = s.IF - s.freqSpacing * K + s.acqSearchBand - s.acqSearchStep * (k - 1)   # :181
+            sigCarr = np.exp(-1j * coarseFreqBin[k - 1] * phasePoints)
+            win = np.stack([longSignal[(m - 1) * N: (m + 1) * N] for m in range(1, s.acqNonCohTime + 1)])
+            coh = np.abs(_IFFT(_FFT(sigCarr[None, :] * win, workers) * caCodeFreqDom[None, :], workers))    # :190-202
+            for m in range(coh.shape[0]):
+                results[k - 1, :] += coh[m]
+        acqCoarseBin = int(np.argmax(results.max(axis=1))) + 1     # :208
+        colmax = results.max(axis=0)
+        codePhase = int(np.argmax(colmax)) + 1                     # :210
+        i = K + 7
+        res["peakMetric"][i] = colmax[codePhase - 1] / sigPower / s.acqNonCohTime   # :212
+        res["coarseBin"][i] = acqCoarseBin
+        res["coarseCodePhase"][i] = codePhase
+        if res["peakMetric"][i] > s.acqThreshold:                  # :218
+            sig40 = longSignal[codePhase - 1: codePhase - 1 + 40 * N]   # :226
+            fineFreqBins = np.zeros(numOfFineBins)
+            fineResult = np.zeros(numOfFineBins)
+            for j in range(1, numOfFineBins + 1):
+                fineFreqBins[j - 1] = coarseFreqBin[acqCoarseBin - 1] + s.acqSearchStep / 2 - fineSearchStep * (j - 1)   # :232
+                basebandSig = sig40 * caCode40ms * np.exp(-1j * fineFreqBins[j - 1] * finePhasePoints)   # :235-237
+                sumPerCode = basebandSig.reshape(40, N).sum(axis=1)   # :240-243
+                maxPower = 0.0
+                for c in range(1, 21):                             # :248
+                    comPower = abs(np.sum(sumPerCode[c - 1: c + 9]) - np.sum(sumPerCode[c + 9: c + 19]))   # :250
+                    maxPower = max(maxPower, comPower)
+                fineResult[j - 1] = maxPower
+            maxFinBin = int(np.argmax(fineResult)) + 1             # :258
+            res["carrFreq"][i] = fineFreqBins[maxFinBin - 1]       # :259
+            res["codePhase"][i] = codePhase                        # :261
+            if res["carrFreq"][i] == 0:
+                res["carrFreq"][i] = 1
+    return res
+
+
+def preRun_glo(acq: dict, s: Settings):
+    """include/preRun.m:44-72 — channels carry the frequency number K = Kindexes(ii)-8."""
+    chans = [dict(K=0, acquiredFreq=0.0, codePhase=0, status="-") for _ in range(s.numberOfChannels)]
+    order = np.argsort(-acq["peakMetric"], kind="stable")
+    n = min(s.numberOfChannels, int(np.sum(acq["carrFreq"] != 0)))
+    for ii in range(n):
+        p = int(order[ii])
+        chans[ii] = dict(K=p + 1 - 8, acquiredFreq=float(acq["carrFreq"][p]), codePhase=int(acq["codePhase"][p]), status="T")
+    return chans
+
+
+def calcLoopCoefCarr(s: Settings):
+    """GLO/GLO_GL1/Common/calcLoopCoefCarr.m:41-56."""
+    Wn = 1.2 * s.pllNoiseBandwidth
+    return Wn ** 3 * s.intTime ** 2, 2 * Wn ** 2 * s.intTime, 2 * Wn     # pf3, pf2, pf1
+
+
+def tracking_glo(raw: np.ndarray, channel: list, s: Settings):
+    """include/tracking.m:45-358: as GPS L1 C/A except the shared 511-chip code (:88-90), the channel
+    test status ~= '-' (:137), rawSignal = Q + 1i*I (:227) and the carrier loop filter (:281-285)."""
+    nE = s.msToProcess
+    out = []
+    for _ in range(s.numberOfChannels):
+        tr = dict(status="-", PRN=None)
+        tr["absoluteSample"] = np.zeros(nE)
+        for f in ("codeFreq", "carrFreq", "dllDiscr", "dllDiscrFilt", "pllDiscr", "pllDiscrFilt", "remCodePhase", "remCarrPhase"):
+            tr[f] = np.full(nE, np.inf)
+        for f in ("I_P", "I_E", "I_L", "Q_E", "Q_P", "Q_L"):
+            tr[f] = np.zeros(nE)
+        tr["VSMValue"] = np.zeros(nE // s.CNo_VSMinterval)
+        tr["VSMIndex"] = np.zeros(nE // s.CNo_VSMinterval)
+        out.append(tr)
+    caCode = glo_code()                                            # :88 (generateCAcode(0, codeFreqBasis, 511))
+    caCode = np.concatenate([[caCode[510]], caCode, [caCode[0]]])  # :90
+    earlyLateSpc = s.dllCorrelatorSpacing
+    PDIcode = s.intTime
+    tau1code, tau2code = calcLoopCoef(s.dllNoiseBandwidth, s.dllDampingRatio, 1.0)     # :104
+    pf3, pf2, pf1 = calcLoopCoefCarr(s)                            # :110
+    for ch in range(s.numberOfChannels):
+        if channel[ch]["status"] == "-":                           # :137
+            continue
+        tr = out[ch]
+        tr["PRN"] = channel[ch]["K"]                               # :141
+        pos = 2 * (s.skipNumberOfBytes + channel[ch]["codePhase"] - 1)     # :148
+        codeFreq = s.codeFreqBasis; remCodePhase = 0.0
+        carrFreq = channel[ch]["acquiredFreq"]; carrFreqBasis = channel[ch]["acquiredFreq"]; remCarrPhase = 0.0
+        oldCodeNco = oldCodeError = 0.0
+        d2CarrError = dCarrError = 0.0                             # :171-172
+        vsmCnt = 0
+        for loopCnt in range(1, nE + 1):
+            tr["absoluteSample"][loopCnt - 1] = pos / 2            # :206
+            codePhaseStep = codeFreq / s.samplingFreq
+            blksize = int(math.ceil((s.codeLength - remCodePhase) / codePhaseStep))
+            chunk = raw[pos: pos + 2 * blksize]
+            pos += chunk.size
+            if chunk.size != 2 * blksize:                          # :232-236
+                return out
+            rawSignal = chunk[1::2].astype(np.float64) + 1j * chunk[0::2].astype(np.float64)   # :227 (Q + iI)
+            tr["remCodePhase"][loopCnt - 1] = remCodePhase
+            tE = colonop(remCodePhase - earlyLateSpc, codePhaseStep, (blksize - 1) * codePhaseStep + remCodePhase - earlyLateSpc)
+            tL = colonop(remCodePhase + earlyLateSpc, codePhaseStep, (blksize - 1) * codePhaseStep + remCodePhase + earlyLateSpc)
+            tP = colonop(remCodePhase, codePhaseStep, (blksize - 1) * codePhaseStep + remCodePhase)
+            earlyCode = caCode[np.ceil(tE).astype(np.int64)]
+            lateCode = caCode[np.ceil(tL).astype(np.int64)]
+            promptCode = caCode[np.ceil(tP).astype(np.int64)]
+            remCodePhase = (tP[blksize - 1] + codePhaseStep) - s.codeLength
+            tr["remCarrPhase"][loopCnt - 1] = remCarrPhase
+            time = np.arange(0, blksize + 1, dtype=np.float64) / s.samplingFreq
+            trigarg = ((carrFreq * 2.0 * np.pi) * time) + remCarrPhase
+            remCarrPhase = math.fmod(trigarg[blksize], 2 * np.pi)
+            bb = np.exp(-1j * trigarg[:blksize]) * rawSignal
+            I_E = float(np.sum(earlyCode * bb.real)); Q_E = float(np.sum(earlyCode * bb.imag))
+            I_P = float(np.sum(promptCode * bb.real)); Q_P = float(np.sum(promptCode * bb.imag))
+            I_L = float(np.sum(lateCode * bb.real)); Q_L = float(np.sum(lateCode * bb.imag))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                carrError = float(np.arctan(np.float64(Q_P) / np.float64(I_P)) / (2.0 * np.pi))
+            d2CarrError = d2CarrError + carrError * pf3            # :282
+            dCarrError = d2CarrError + carrError * pf2 + dCarrError   # :283
+            carrNco = dCarrError + carrError * pf1                 # :285
+            tr["carrFreq"][loopCnt - 1] = carrFreq
+            carrFreq = carrFreqBasis + carrNco
+            sE = math.sqrt(I_E * I_E + Q_E * Q_E); sL = math.sqrt(I_L * I_L + Q_L * Q_L)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                codeError = float((np.float64(sE) - sL) / (np.float64(sE) + sL))
+            codeNco = oldCodeNco + (tau2code / tau1code) * (codeError - oldCodeError) + codeError * (PDIcode / tau1code)
+            oldCodeNco = codeNco; oldCodeError = codeError
+            tr["codeFreq"][loopCnt - 1] = codeFreq
+            codeFreq = s.codeFreqBasis - codeNco
+            tr["dllDiscr"][loopCnt - 1] = codeError; tr["dllDiscrFilt"][loopCnt - 1] = codeNco
+            tr["pllDiscr"][loopCnt - 1] = carrError; tr["pllDiscrFilt"][loopCnt - 1] = carrNco
+            tr["I_E"][loopCnt - 1] = I_E; tr["I_P"][loopCnt - 1] = I_P; tr["I_L"][loopCnt - 1] = I_L
+            tr["Q_E"][loopCnt - 1] = Q_E; tr["Q_P"][loopCnt - 1] = Q_P; tr["Q_L"][loopCnt - 1] = Q_L
+            if loopCnt % s.CNo_VSMinterval == 0:
+                vsmCnt += 1
+                lo = loopCnt - s.CNo_VSMinterval
+                tr["VSMValue"][vsmCnt - 1] = CNoVSM(tr["I_P"][lo:loopCnt], tr["Q_P"][lo:loopCnt], s.CNo_accTime)
+                tr["VSMIndex"][vsmCnt - 1] = loopCnt
+        tr["status"] = channel[ch]["status"]
     return out

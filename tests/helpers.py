@@ -18,7 +18,7 @@ class OrcSettings(C.Structure):
                 [("acqNonCohTime", C.c_int), ("skipNumberOfBytes", C.c_int)] +
                 [(n, C.c_double) for n in ["dllDampingRatio", "dllNoiseBandwidth", "dllCorrelatorSpacing",
                                            "pllDampingRatio", "pllNoiseBandwidth", "intTime", "CNo_accTime"]] +
-                [("CNo_VSMinterval", C.c_int)])
+                [("CNo_VSMinterval", C.c_int), ("freqSpacing", C.c_double), ("glo", C.c_int)])
 
 
 _orc = None
@@ -36,7 +36,8 @@ def orc_settings(s) -> OrcSettings:
     return OrcSettings(s.samplingFreq, s.IF, s.codeFreqBasis, s.codeLength, s.acqSearchBand, s.acqSearchStep,
                        s.acqThreshold, s.acqNonCohTime, s.skipNumberOfBytes, s.dllDampingRatio,
                        s.dllNoiseBandwidth, s.dllCorrelatorSpacing, s.pllDampingRatio, s.pllNoiseBandwidth,
-                       s.intTime, s.CNo_accTime, s.CNo_VSMinterval)
+                       s.intTime, s.CNo_accTime, s.CNo_VSMinterval, float(getattr(s, "freqSpacing", 0.0)),
+                       1 if float(getattr(s, "freqSpacing", 0.0)) != 0.0 else 0)
 
 
 def to_oracle_settings(s: Settings) -> "O.Settings":
@@ -55,8 +56,9 @@ def c_acquisition(raw: np.ndarray, s, prns):
     """C oracle acquisition; raw starts at the skip point."""
     cs = orc_settings(s)
     prn = np.asarray(prns, dtype=np.int32)
-    cf, cp, pm = np.zeros(32), np.zeros(32), np.zeros(32)
-    cb, ccp = np.zeros(32, dtype=np.int32), np.zeros(32, dtype=np.int32)
+    nres = 21 if cs.glo else 32
+    cf, cp, pm = np.zeros(nres), np.zeros(nres), np.zeros(nres)
+    cb, ccp = np.zeros(nres, dtype=np.int32), np.zeros(nres, dtype=np.int32)
     sp = C.c_double()
     rc = orc().orc_acquisition(P(raw), C.c_size_t(raw.size // 2), C.byref(cs), P(prn), int(prn.size),
                                P(cf), P(cp), P(pm), P(cb), P(ccp), C.byref(sp))

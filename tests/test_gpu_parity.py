@@ -288,3 +288,95 @@ def test_full_size_tracking_properties():
     errs = track_rel_err(out[:, :, :n0], ref)
     assert errs["I_P"] < IQ_TOL and errs["Q_P"] < IQ_TOL, errs
     eng.close()
+
+
+# ------------------------------------------------------------------------------- GLONASS (GLO_GL1 / GLO_GL2)
+from cu_sdr_collection_b200.engine import GC_SV_NONE  # noqa: E402
+
+
+def _glo_check_acq(got, ref, ks):
+    idx = np.array(ks) + 7
+    assert got["carrFreq"].shape == (21,)
+    assert np.array_equal(got["carrFreq"] != 0, ref["carrFreq"] != 0), "acquired channel set differs"
+    assert np.array_equal(got["coarseBin"][idx], ref["coarseBin"][idx])
+    assert np.array_equal(got["codePhase"], ref["codePhase"])
+    assert np.array_equal(got["carrFreq"], ref["carrFreq"])
+    rel = np.abs(got["peakMetric"][idx] - ref["peakMetric"][idx]) / ref["peakMetric"][idx]
+    assert rel.max() < METRIC_TOL, rel.max()
+
+
+@pytest.mark.parametrize("signal,fs,nonCoh", [("GLO_GL1", 12e6, 20), ("GLO_GL2", 2.4e6, 4)])
+def test_glonass_acquisition_vs_oracle(signal, fs, nonCoh):
+    """GLO_GL1 at the reference defaults (12 Msps, FFT length 24000, 14 frequency channels x 21 bins x 20
+    blocks) and GLO_GL2 spacing at a small rate; both through the generic mixed-radix path."""
+    spacing = 562.5e3 if signal == "GLO_GL1" else 437.5e3
+    sc = synth.default_scene_glo(fs=fs, nsat=4, seed=17, freqSpacing=spacing)
+    for x in sc.sats:
+        x.cn0 = 47
+    if fs < 5e6:                                           # keep the channels inside the sampled band
+        for i, x in enumerate(sc.sats):
+            x.prn = [-2, -1, 1, 2][i]
+    ks = sorted({x.prn for x in sc.sats} | {0}) if fs < 5e6 else list(range(-7, 7))
+    s = init_settings(signal, samplingFreq=fs, acqNonCohTime=nonCoh, acqSatelliteList=ks)
+    so = O.glo_settings(samplingFreq=fs, acqNonCohTime=nonCoh, acqSatelliteList=ks, freqSpacing=spacing)
+    N = O.samples_per_code(so)
+    raw = synth.make_record(sc, N * max(42, nonCoh + 2) + 64)
+    eng = Engine(s)
+    got = eng.acquire(ks, host_iq=raw)
+    ref = c_acquisition(raw, so, ks)
+    _glo_check_acq(got, ref, ks)
+    for sat in sc.sats:
+        assert got["carrFreq"][sat.prn + 7] != 0
+        assert abs(got["carrFreq"][sat.prn + 7] - (s.IF - spacing * sat.prn + sat.doppler)) <= 25
+    eng.close()
+
+
+def test_glonass_tracking_and_wrappers_vs_oracle(tmp_path):
+    """acquisition() -> preRun() -> tracking() on a GLONASS record, against the GLONASS oracle."""
+    fs, nms = 12e6, 300
+    sc = synth.default_scene_glo(fs=fs, nsat=3, seed=23)
+    for x in sc.sats:
+        x.cn0 = 47
+    ks = sorted({x.prn for x in sc.sats} | {5, -6})
+    s = init_settings("GLO_GL1", samplingFreq=fs, acqSatelliteList=ks, acqNonCohTime=6, msToProcess=nms, numberOfChannels=4)
+    so = O.glo_settings(samplingFreq=fs, acqSatelliteList=ks, acqNonCohTime=6, msToProcess=nms, numberOfChannels=4)
+    N = 12000
+    raw = synth.make_record(sc, N * (nms + 50))
+    path = tmp_path / "glo.bin"
+    raw.tofile(path)
+    longSignal = O.read_acq_signal_glo(raw, so)            # Q + 1i*I, as the GLONASS postProcessing.m builds it
+    acq = acquisition(longSignal, s, verbose=True)
+    ref_acq = O.acquisition_glo(longSignal, so)
+    _glo_check_acq(acq, ref_acq, ks)
+    ch = preRun(acq, s)
+    ref_ch = O.preRun_glo(ref_acq, so)
+    assert [(c["K"], c["status"]) for c in ch] == [(c["K"], c["status"]) for c in ref_ch]
+    assert sorted(c["K"] for c in ch if c["status"] == "T") == sorted(x.prn for x in sc.sats)
+    with open(path, "rb") as fid:
+        tr, _ = tracking(fid, ch, s)
+    sv = [c["K"] if c["status"] != "-" else GC_SV_NONE for c in ch]
+    ref, rvv, rvi, rdone = c_tracking(raw, so, sv, [c["acquiredFreq"] for c in ch], [float(c["codePhase"]) for c in ch], nms)
+    for i, c in enumerate(ch):
+        if c["status"] == "-":
+            assert tr[i]["status"] == "-" and tr[i]["epochsDone"] == 0 and np.all(tr[i]["I_P"] == 0)
+            continue
+        assert tr[i]["status"] == "T" and tr[i]["PRN"] == c["K"] and tr[i]["epochsDone"] == nms
+        assert np.array_equal(tr[i]["absoluteSample"], ref[i, 0])
+        sc_ = np.hypot(ref[i, 3], ref[i, 7])
+        for f, name in ((3, "I_P"), (7, "Q_P"), (4, "I_E"), (5, "I_L"), (6, "Q_E"), (8, "Q_L")):
+            assert np.max(np.abs(tr[i][name] - ref[i, f]) / sc_) < IQ_TOL, name
+        assert np.max(np.abs(tr[i]["carrFreq"] - ref[i, 2])) < 1e-4
+        assert np.allclose(tr[i]["CNo"]["VSMValue"], rvv[i], rtol=1e-5)
+    # one-CTA and 8-CTA-cluster variants agree for GLONASS too
+    eng = Engine(s)
+    eng.set_record(raw)
+    out8, _, _, d8 = eng.track(sv, [c["acquiredFreq"] for c in ch], [float(c["codePhase"]) for c in ch], nms)
+    os.environ["GC_TRACK_CLUSTER"] = "1"
+    try:
+        out1, _, _, d1 = eng.track(sv, [c["acquiredFreq"] for c in ch], [float(c["codePhase"]) for c in ch], nms)
+    finally:
+        del os.environ["GC_TRACK_CLUSTER"]
+    assert np.array_equal(d1, d8) and np.array_equal(out1[:, 0], out8[:, 0])
+    live = np.array(sv) != GC_SV_NONE
+    assert track_rel_err(out1[live], out8[live])["I_P"] < IQ_TOL
+    eng.close()

@@ -24,8 +24,8 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert set(engine.EXPORTS) == declared
-    assert lib.gc_abi_version() == 1 and lib.gc_build_arch() == b"sm_100a"
-    assert lib.gc_acq_result_len(0) == 32
+    assert lib.gc_abi_version() == 2 and lib.gc_build_arch() == b"sm_100a"
+    assert lib.gc_acq_result_len(0) == 32 and lib.gc_acq_result_len(1) == 21
 
 
 def test_config_struct_layout_matches_header():

@@ -148,3 +148,67 @@ def test_golden_vectors():
     live = g["chPRN"] != 0
     assert np.max(np.abs(out[live][:, 3:9] - ref[live][:, 3:9]) / sc_[live]) < 1e-8
     assert np.array_equal(out[live][:, 0], ref[live][:, 0])          # absoluteSample exact
+
+
+# ------------------------------------------------------------------------------- GLONASS (GLO_GL1 / GLO_GL2)
+GLO_NONE = -2147483648
+
+
+def _glo_case():
+    fs = 2.4e6                       # N = 2400 samples per code, FFT length 4800 = 2^6*3*5^2 (fast on the CPU)
+    sc = synth.default_scene_glo(fs=fs, nsat=3, seed=5)
+    for x in sc.sats:
+        x.cn0 = 48
+    ks = sorted({x.prn for x in sc.sats} | {6})
+    s = O.glo_settings(samplingFreq=fs, acqNonCohTime=4, msToProcess=100, numberOfChannels=4, acqSatelliteList=ks)
+    N = O.samples_per_code(s)
+    raw = synth.make_record(sc, N * 150)
+    return sc, s, N, raw
+
+
+def test_glonass_code_is_an_m_sequence():
+    c = O.glo_code()
+    assert c.size == 511 and int(c.sum()) == -1
+    r = np.array([np.dot(c, np.roll(c, k)) for k in range(1, 511)])
+    assert np.all(r == -1)                                   # maximal-length sequence: two-valued autocorrelation
+    assert np.array_equal(c.astype(np.int8), codes.glo_code())
+    cc = np.zeros(511)
+    orc().orc_glo_code(P(cc))
+    assert np.array_equal(cc, c)
+    # resampled replica: 0:stepSize:... colon vector, floor, wrap (generateCAcode.m:110-116)
+    t = O.generateCAcode_glo(12e6, 12000)
+    ct = np.zeros(12000)
+    orc().orc_glo_sampled_code(C.c_double(12e6), C.c_long(12000), P(ct))
+    assert np.array_equal(t, ct) and np.array_equal(t[:24], np.full(24, c[0]))    # 23.48 samples per chip
+
+
+def test_glonass_oracles_agree_and_find_injected_channels():
+    sc, s, N, raw = _glo_case()
+    a = O.acquisition_glo(O.read_acq_signal_glo(raw, s), s)
+    c = c_acquisition(raw, s, s.acqSatelliteList)
+    for k in ("carrFreq", "codePhase", "coarseBin", "coarseCodePhase"):
+        assert np.array_equal(a[k], c[k]), k
+    idx = np.array(s.acqSatelliteList) + 7
+    assert np.allclose(a["peakMetric"][idx], c["peakMetric"][idx], rtol=1e-12)
+    for sat in sc.sats:
+        i = sat.prn + 7
+        assert a["carrFreq"][i] != 0
+        assert abs(a["carrFreq"][i] - (s.IF - s.freqSpacing * sat.prn + sat.doppler)) <= 25
+    assert a["carrFreq"][6 + 7] == 0 or 6 in {x.prn for x in sc.sats}
+    ch = O.preRun_glo(a, s)
+    assert sorted(c_["K"] for c_ in ch if c_["status"] == "T") == sorted(x.prn for x in sc.sats)
+    tr = O.tracking_glo(raw, ch, s)
+    sv = [c_["K"] if c_["status"] != "-" else GLO_NONE for c_ in ch]
+    out, vv, vi, done = c_tracking(raw, s, sv, [c_["acquiredFreq"] for c_ in ch], [c_["codePhase"] for c_ in ch], s.msToProcess)
+    for i, c_ in enumerate(ch):
+        if c_["status"] == "-":
+            assert done[i] == 0
+            continue
+        assert done[i] == s.msToProcess and tr[i]["status"] == "T" and tr[i]["PRN"] == c_["K"]
+        P_ = np.hypot(tr[i]["I_P"], tr[i]["Q_P"])
+        for f, fname in enumerate(O.TRACK_FIELDS):
+            d = np.abs(out[i, f] - tr[i][fname])
+            scale = P_ if 3 <= f <= 8 else np.maximum(np.abs(tr[i][fname]), 1e-9)
+            assert np.max(d / scale) < 1e-8, (fname, np.max(d / scale))
+        # carrier loop still pulling in after 100 ms (25 Hz loop from up to 12.5 Hz off): power mostly in-phase
+        assert np.mean(np.abs(tr[i]["I_P"][60:])) > 2 * np.mean(np.abs(tr[i]["Q_P"][60:]))
