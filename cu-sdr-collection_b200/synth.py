@@ -121,7 +121,12 @@ def make_record_torch(scene: Scene, nsamples: int, device="cuda", chunk: int = 1
     out = torch.empty(2 * nsamples, dtype=torch.int8, device=device)
     g = torch.Generator(device=device)
     g.manual_seed(scene.seed)
-    codes = {s.prn: torch.tensor(ca_code(s.prn).astype(np.float32), device=device) for s in scene.sats}
+    if scene.glonass:
+        clen, crate, carrier = 511, 511e3, 1602e6
+        codes = {s.prn: torch.tensor(glo_code().astype(np.float32), device=device) for s in scene.sats}
+    else:
+        clen, crate, carrier = 1023, 1.023e6, L1
+        codes = {s.prn: torch.tensor(ca_code(s.prn).astype(np.float32), device=device) for s in scene.sats}
     bits = {s.prn: torch.tensor(nav_bits(s, int(nsamples / scene.fs * 50) + 5).astype(np.float32), device=device)
             for s in scene.sats}
     for c0 in range(0, nsamples, chunk):
@@ -131,17 +136,23 @@ def make_record_torch(scene: Scene, nsamples: int, device="cuda", chunk: int = 1
         re = torch.zeros(m, dtype=torch.float32, device=device)
         im = torch.zeros(m, dtype=torch.float32, device=device)
         for s in scene.sats:
-            fcode = 1.023e6 * (1 + s.doppler / L1)
+            fcode = crate * (1 + s.doppler / carrier)
             chips = fcode * t + s.code_phase
-            period = torch.floor(chips / 1023.0)
-            idx = torch.floor(chips - period * 1023.0).to(torch.int64) % 1023
-            d = bits[s.prn][((period.to(torch.int64) + s.bit_offset) // 20)]
+            period = torch.floor(chips / clen)
+            idx = torch.floor(chips - period * float(clen)).to(torch.int64) % clen
+            pint = period.to(torch.int64) + s.bit_offset
+            d = bits[s.prn][pint // 20]
+            if scene.glonass:
+                d = d * torch.where((pint % 20) < 10, 1.0, -1.0).to(torch.float32)
             a = _amp(s.cn0, scene.sigma, scene.fs) * d * codes[s.prn][idx]
-            ph = (2 * np.pi) * torch.frac((scene.IF + s.doppler) * t) + s.phi0
+            fc = (scene.IF - scene.freqSpacing * s.prn + s.doppler) if scene.glonass else (scene.IF + s.doppler)
+            ph = (2 * np.pi) * torch.frac(fc * t) + s.phi0
             re += a * torch.cos(ph).to(torch.float32)
             im += a * torch.sin(ph).to(torch.float32)
         re += scene.sigma * torch.randn(m, device=device, generator=g)
         im += scene.sigma * torch.randn(m, device=device, generator=g)
+        if scene.glonass:
+            re, im = im, re                     # GLONASS files are read as Q + 1i*I
         out[2 * c0: 2 * (c0 + m): 2] = torch.clamp(torch.round(re), -127, 127).to(torch.int8)
         out[2 * c0 + 1: 2 * (c0 + m): 2] = torch.clamp(torch.round(im), -127, 127).to(torch.int8)
     return out
