@@ -5,10 +5,13 @@
 
 namespace gc {
 
-// ---- fused 33 x (32 x 31) path, FFT length 32736 -------------------------------------------
-constexpr int kFusedC = 33;
-constexpr int kFusedR = 992;
-constexpr int kFusedL = kFusedC * kFusedR;
+// ---- fused plans L = C x 32 x RB (acq_fused.cu) ------------------------------------------------
+struct FusedPlanInfo {
+    int L, C, RA, RB, R;
+    int pfa;                  // 1: gcd(C, R) = 1, no twiddle between the passes; 0: [C][R] twiddle table needed
+    int parts;                // column tiles per (SV, bin) in the partial-maximum arrays
+};
+bool fused_plan_info(int L, FusedPlanInfo* out);   // false: no fused plan for this length
 
 struct FwdColsParams {
     const int8_t* rec;        // resident record (int8 I,Q)
@@ -17,34 +20,35 @@ struct FwdColsParams {
     int nonCoh;
     int swapIQ;               // GLONASS: rawSignal = Q + 1i*I (GLO_GL1/include/postProcessing.m:94)
     const uint64_t* dphi;     // [nBins] carrier phase increment per sample (turns, 0.64 fixed point)
-    const int8_t* codeTab;    // [nPrn][N] +-1 resampled replicas (code mode)
-    float2* out;              // [nRows][33][992]  (k1, n2*31 + n3)
+    const int8_t* codeTab;    // [nReplicas][N] +-1 resampled replicas (code mode)
+    float2* out;              // [nRows][C][R]
+    const float2* tw;         // [C][R] w_L^(j1*m(p)) (plans with pfa == 0), else unused
 };
 
 struct RowsParams {
-    float2* X;                // forward: rows transformed in place; inverse: spectra [nBins*nonCoh][33][992]
-    const float2* Cc;         // [nPrnSlots][33][992] conj(FFT(code))/L
-    float2* W;                // inverse output [nPrnChunk][nBins][nonCoh][33][992]
+    float2* X;                // forward: rows transformed in place; inverse: spectra [nBins*nonCoh][C][R]
+    const float2* Cc;         // [nReplicas][C][R] conj(FFT(code))/L
+    float2* W;                // inverse output [nPrnChunk][nBins][nonCoh][C][R]
+    const float2* tw;         // as above
     long long nRows;          // forward only
     int nonCoh, nBins;
     int prnPerCta, mPerCta;   // warps of an inverse CTA = prnPerCta x mPerCta (same row j1, same bin)
     int nPrnChunk, prnSlot0;  // list slots [prnSlot0, prnSlot0 + nPrnChunk) are processed by this launch
-    const int* prnList;       // [nSv] PRN-1 per list slot (index into Cc)
+    const int* prnList;       // [nSv] replica index per list slot (index into Cc)
 };
 
 struct InvColsParams {
     const float2* W;
     int nBins, nonCoh, nPrnChunk, prnSlot0;
-    float* partMax;           // [nPrnSlots][nBins][parts]
+    float* partMax;           // [nSv][nBins][parts]
     int* partIdx;
 };
 
-int fused_col_parts();
-cudaError_t launch_fwd_cols(const FwdColsParams& p, int nRows, bool codeMode, cudaStream_t s);
-cudaError_t launch_fwd_rows(const RowsParams& p, cudaStream_t s);
-cudaError_t launch_inv_rows(const RowsParams& p, cudaStream_t s);
-cudaError_t launch_finish_replica(float2* Cc, size_t n, cudaStream_t s);
-cudaError_t launch_inv_cols(const InvColsParams& p, cudaStream_t s);
+cudaError_t launch_fwd_cols(int L, const FwdColsParams& p, int nRows, bool codeMode, cudaStream_t s);
+cudaError_t launch_fwd_rows(int L, const RowsParams& p, cudaStream_t s);
+cudaError_t launch_inv_rows(int L, const RowsParams& p, cudaStream_t s);
+cudaError_t launch_finish_replica(float2* Cc, size_t n, int L, cudaStream_t s);
+cudaError_t launch_inv_cols(int L, const InvColsParams& p, cudaStream_t s);
 
 // ---- generic mixed-radix path (any length whose prime factors are <= 64) --------------------
 struct GenericPlan {

@@ -1,26 +1,32 @@
-// Acquisition, fused path for FFT length 32736 = 33 x 32 x 31 (2*samplesPerCode at 16.368 Msps).
+// Acquisition, fused transform plans for FFT lengths L = C x RA x RB (2*samplesPerCode):
+//
+//      32736 = 33 x 32 x 31   (16.368 Msps, 1 ms codes)      40000 = 50 x 32 x 25   (20 Msps)
+//      36000 = 45 x 32 x 25   (18 Msps: the reference default of six signal folders)
+//      24000 = 30 x 32 x 25   (12 Msps: GLONASS default)     32000 = 40 x 32 x 25   (16 Msps)
 //
 // Replaces the PRN x Doppler x non-coherent-block loop of
-// GPS/GPS_L1CA/include/acquisition.m:155-200.  The 2N-point transforms the reference does with
-// MATLAB's fft/ifft are computed exactly at that length (no power-of-two padding, so the
-// code-phase index space 1..2N is the reference's own) as a four-step transform
+// GPS/GPS_L1CA/include/acquisition.m:155-200 (and the same loop of the other variant-A folders).
+// The 2N-point transforms the reference does with MATLAB's fft/ifft are computed exactly at that
+// length (no power-of-two padding, so the code-phase index space 1..2N is the reference's own).
 //
-//      L = 33 x 32 x 31, pairwise coprime  ->  Good-Thomas prime-factor algorithm: with the time /
-//      lag index n = (992*n1 + 1023*n2 + 1056*n3) mod L and the frequency index addressed by its
-//      residues (j mod 33, j mod 32, j mod 31) the transform is a plain 3-D DFT, no twiddles.
+//   rows   R = RA x RB with gcd(RA, RB) = 1: Good-Thomas prime-factor mapping, no twiddles:
+//          row time index m = (RB*a + RA*b) mod R, row frequency index addressed by residues.
+//   cols   C against R: prime-factor mapping again when gcd(C, R) = 1 (32736: a plain 3-D DFT, no
+//          twiddle anywhere); otherwise one Cooley-Tukey twiddle w_L^(j1*m) between the passes,
+//          read from a [C][R] table laid out like the data.
 //
 //   forward  (wipe-off + FFT, PRN independent, acquisition.m:169-183):
-//      fwd_cols : one thread per (n2, n3): 33 gathered int8 I/Q samples, carrier wipe-off with a
-//                 64-bit fixed-point phase, 33-point DFT in registers (3 x 11 codelet)
-//      fwd_rows : one warp per row k1: 32-point DFTs (31 lanes), shared-memory transpose,
-//                 31-point DFTs (32 lanes)
-//      spectrum layout X[k1][k3][k2]; the replica spectra use the same layout, so no index map
-//      is ever applied in the frequency domain.
+//      fwd_cols : one thread per row position: C gathered int8 I/Q samples, carrier wipe-off with a
+//                 64-bit fixed-point phase, C-point DFT in registers
+//      fwd_rows : one warp per row: RA-point DFTs on RB lanes, shared-memory transpose, RB-point
+//                 DFTs on RA lanes
+//      spectrum layout X[j1][kb][ka]; the replica spectra use the same layout, so no index map is
+//      ever applied in the frequency domain.
 //   inverse  (acquisition.m:186-190):
-//      inv_rows : one warp per row: load X*conj(FFT(code))/L, 31-point then 32-point inverse DFTs
-//      inv_cols : one thread per (t2, t3): for each non-coherent block 33-point inverse DFT,
+//      inv_rows : one warp per row: load X*conj(FFT(code))/L, RB-point then RA-point inverse DFTs
+//      inv_cols : one thread per row position: for each non-coherent block C-point inverse DFT,
 //                 |.|, accumulate in registers; after the last block the running maximum /
-//                 first arg-max over the thread's 33 code phases (992*t1 + 1023*t2 + 1056*t3) mod L.
+//                 first arg-max over the thread's C code phases.
 //   `results(freqBin, :)` (acquisition.m:162,190) is therefore never written to memory.
 #include "acq.h"
 #include "common.cuh"
@@ -30,32 +36,43 @@ namespace gc {
 
 namespace {
 
-constexpr int C = kFusedC;       // 33
-constexpr int R = kFusedR;       // 992
-constexpr int RA = 32, RB = 31;  // R = RA * RB
-constexpr int L = C * R;         // 32736
-constexpr int kPitchF = RA + 1;  // smem pitch (float2) of the forward 31 x 32 exchange
-constexpr int kPitchI = RB;      // smem pitch of the inverse 32 x 31 exchange
-constexpr int kRowWarps = 8;     // warps (= rows in flight) per CTA in the row kernels
-// Good-Thomas index maps (33, 32, 31 pairwise coprime): time / lag index
-//   n = (992*n1 + 1023*n2 + 1056*n3) mod 32736,   992 = L/33, 1023 = L/32, 1056 = L/31
-// while the frequency index j is addressed by its residues (j mod 33, j mod 32, j mod 31).
-// With these maps the 32736-point DFT is a plain 33 x 32 x 31 three-dimensional DFT: no twiddle
-// factors between the passes.
-constexpr int kM1 = R, kM2 = L / RA, kM3 = L / RB;
+constexpr int kRowWarps = 8;     // warps (= rows in flight) per CTA in the forward row kernel
+
+constexpr int gcd_c(int a, int b) { return b == 0 ? a : gcd_c(b, a % b); }
+
+template <int C_, int RA_, int RB_>
+struct Plan {
+    static constexpr int C = C_, RA = RA_, RB = RB_;
+    static constexpr int R = RA * RB, L = C * R;
+    static constexpr bool kPfa = gcd_c(C, R) == 1;        // no twiddle between column and row pass
+    static_assert(gcd_c(RA, RB) == 1 && RA == 32 && RB < 32, "row = 32 x RB with RB coprime to 32");
+    // row position p = a*RB + b  ->  its part of the time / lag index
+    __device__ static __forceinline__ int row_index(int p)
+    {
+        const int a = p / RB, b = p % RB;
+        return kPfa ? ((L / RA) * a + (L / RB) * b) % L     // 3-D prime-factor map: contribution to n mod L
+                    : (RB * a + RA * b) % R;                // 2-D map inside the row
+    }
+    // global time / lag index of (column index i1, row part)
+    __device__ static __forceinline__ int index(int i1, int rowPart)
+    {
+        if (kPfa) { const int n = rowPart + R * i1; return n >= L ? n - L : n; }   // rowPart < L, R*i1 < L
+        return rowPart + R * i1;
+    }
+};
 
 // ------------------------------------------------------------------ column pass (forward)
-// grid (ceil(R/128), nRows), block 128; thread = (n2, n3) = p / 31, p % 31.
+// grid (ceil(R/128), nRows), block 128; thread = row position p.
 // MODE 0: IF samples with carrier wipe-off; MODE 1: code table.
-template <int MODE>
+template <class P, int MODE>
 __global__ void __launch_bounds__(128)
 fwd_cols_kernel(FwdColsParams p)
 {
+    constexpr int C = P::C, R = P::R, L = P::L;
     const int pp = blockIdx.x * 128 + threadIdx.x;
     if (pp >= R) return;
-    const int n2 = pp / RB, n3 = pp % RB;
-    const int row = blockIdx.y;               // MODE 0: km = k*nonCoh + m ; MODE 1: prn slot
-    const int base = (kM2 * n2 + kM3 * n3) % L;
+    const int row = blockIdx.y;               // MODE 0: km = k*nonCoh + m ; MODE 1: replica slot
+    const int base = P::row_index(pp);
     float2 x[C];
     if (MODE == 0) {
         const int k = row / p.nonCoh, m = row % p.nonCoh;
@@ -63,8 +80,7 @@ fwd_cols_kernel(FwdColsParams p)
         const int8_t* src = p.rec + 2 * ((size_t)p.winStart + (size_t)m * p.N);   // window x((m-1)N+1 : (m+1)N)
 #pragma unroll
         for (int n1 = 0; n1 < C; ++n1) {
-            int n = base + kM1 * n1;
-            n -= (n >= L) ? L : 0;
+            const int n = P::index(n1, base);
             const char2 s = *reinterpret_cast<const char2*>(src + 2 * (size_t)n);
             float sn, cs;
             fix_sincos(dphi * (uint64_t)n, &sn, &cs);          // exp(-1i*f*phasePoints(n)), :172
@@ -75,51 +91,60 @@ fwd_cols_kernel(FwdColsParams p)
         const int8_t* code = p.codeTab + (size_t)row * p.N;    // caCodesTable, zero padded to 2N (:160)
 #pragma unroll
         for (int n1 = 0; n1 < C; ++n1) {
-            int n = base + kM1 * n1;
-            n -= (n >= L) ? L : 0;
+            const int n = P::index(n1, base);
             x[n1] = make_float2(n < p.N ? (float)code[n] : 0.f, 0.f);
         }
     }
     float2* dst = p.out + (size_t)row * L + pp;
-    codelet::dft33_fwd(x, [&](int k1, float re, float im) { dst[(size_t)k1 * R] = make_float2(re, im); });
+    const float2* tw = p.tw + pp;
+    codelet::dft<C, false>(x, [&](int k1, float re, float im) {
+        float2 v = make_float2(re, im);
+        if (!P::kPfa) v = cmul(v, __ldg(tw + (size_t)k1 * R));   // w_L^(j1*m)
+        dst[(size_t)k1 * R] = v;
+    });
 }
 
 // ------------------------------------------------------------------ row pass, forward
-// One warp per row (fixed k1): 32 x 31 two-dimensional DFT over (n2, n3) in place.
-// in : element (n2, n3) at n2*31 + n3       out: element (k2, k3) at k3*32 + k2
+// One warp per row (fixed j1): RA x RB two-dimensional DFT over (a, b) in place.
+// in : element (a, b) at a*RB + b       out: element (ka, kb) at kb*RA + ka
+template <class P>
 __global__ void __launch_bounds__(kRowWarps * 32)
 fwd_rows_kernel(RowsParams p)
 {
+    constexpr int RA = P::RA, RB = P::RB, R = P::R;
+    constexpr int kPitchF = RA + 1;                              // conflict-free pitch of the RB x RA exchange
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float2* s_x = reinterpret_cast<float2*>(smem_raw) + warp * (RB * kPitchF);
     const long long row = (long long)blockIdx.x * kRowWarps + warp;
     if (row >= p.nRows) return;
     float2* io = p.X + row * R;
-    if (lane < RB) {                                             // lane = n3: DFT-32 over n2
+    if (lane < RB) {                                             // lane = b: DFT-RA over a
         float2 v[RA];
 #pragma unroll
-        for (int n2 = 0; n2 < RA; ++n2) v[n2] = io[n2 * RB + lane];
-        codelet::dft32_fwd(v, [&](int k2, float re, float im) { s_x[lane * kPitchF + k2] = make_float2(re, im); });
+        for (int a = 0; a < RA; ++a) v[a] = io[a * RB + lane];
+        codelet::dft<RA, false>(v, [&](int ka, float re, float im) { s_x[lane * kPitchF + ka] = make_float2(re, im); });
     }
     __syncwarp();
-    {                                                            // lane = k2: DFT-31 over n3
+    {                                                            // lane = ka: DFT-RB over b
         float2 u[RB];
 #pragma unroll
-        for (int n3 = 0; n3 < RB; ++n3) u[n3] = s_x[n3 * kPitchF + lane];
-        codelet::dft31_fwd(u, [&](int k3, float re, float im) { io[k3 * RA + lane] = make_float2(re, im); });
+        for (int b = 0; b < RB; ++b) u[b] = s_x[b * kPitchF + lane];
+        codelet::dft<RB, false>(u, [&](int kb, float re, float im) { io[kb * RA + lane] = make_float2(re, im); });
     }
 }
 
 // ------------------------------------------------------------------ row pass, inverse (dominant kernel)
-// One warp per row of one (PRN, bin, block): X .* Cc, inverse 31 x 32 DFT over (k3, k2) -> (t3, t2).
-// in : element (k2, k3) at k3*32 + k2       out: element (t2, t3) at t2*31 + t3
-// grid: x = k1 (33 rows), y = PRN group, z = bin * mGroups + block group, so that CTAs scheduled
+// One warp per row of one (PRN, bin, block): X .* Cc, inverse RB x RA DFT over (kb, ka) -> (tb, ta).
+// in : element (ka, kb) at kb*RA + ka       out: element (ta, tb) at ta*RB + tb
+// grid: x = j1 (C rows), y = PRN group, z = bin * mGroups + block group, so that CTAs scheduled
 // together share one X slice (L1/L2 hits) while the replica spectra stay L2 resident.
-template <int WARPS, int MINB>
+template <class P, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 inv_rows_kernel(RowsParams p)
 {
+    constexpr int C = P::C, RA = P::RA, RB = P::RB, R = P::R;
+    constexpr int kPitchI = RB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float2* s_x = reinterpret_cast<float2*>(smem_raw) + warp * (RA * kPitchI);
@@ -132,19 +157,24 @@ inv_rows_kernel(RowsParams p)
     const float2* src = p.X + ((size_t)(k * p.nonCoh + m) * C + k1) * R;
     const float2* mul = p.Cc + ((size_t)p.prnList[p.prnSlot0 + pi] * C + k1) * R;
     float2* dst = p.W + (((size_t)(pi * p.nBins + k) * p.nonCoh + m) * C + k1) * R;
-    {                                                            // lane = k2: DFT-31 over k3
+    {                                                            // lane = ka: DFT-RB over kb
         float2 u[RB];
 #pragma unroll
-        for (int k3 = 0; k3 < RB; ++k3)                          // IQfreqDom .* caCodeFreqDom (:186)
-            u[k3] = cmul(src[k3 * RA + lane], __ldg(mul + k3 * RA + lane));
-        codelet::dft31_inv(u, [&](int t3, float re, float im) { s_x[lane * kPitchI + t3] = make_float2(re, im); });
+        for (int kb = 0; kb < RB; ++kb)                          // IQfreqDom .* caCodeFreqDom (:186)
+            u[kb] = cmul(src[kb * RA + lane], __ldg(mul + kb * RA + lane));
+        codelet::dft<RB, true>(u, [&](int tb, float re, float im) { s_x[lane * kPitchI + tb] = make_float2(re, im); });
     }
     __syncwarp();
-    if (lane < RB) {                                             // lane = t3: DFT-32 over k2
+    if (lane < RB) {                                             // lane = tb: DFT-RA over ka
         float2 v[RA];
 #pragma unroll
-        for (int k2 = 0; k2 < RA; ++k2) v[k2] = s_x[k2 * kPitchI + lane];
-        codelet::dft32_inv(v, [&](int t2, float re, float im) { __stcs(dst + t2 * RB + lane, make_float2(re, im)); });
+        for (int ka = 0; ka < RA; ++ka) v[ka] = s_x[ka * kPitchI + lane];
+        const float2* tw = p.tw + (size_t)k1 * R + lane;
+        codelet::dft<RA, true>(v, [&](int ta, float re, float im) {
+            float2 t = make_float2(re, im);
+            if (!P::kPfa) t = cmul_conj(t, __ldg(tw + ta * RB));  // conj(w_L^(j1*tau2))
+            __stcs(dst + ta * RB + lane, t);
+        });
     }
 }
 
@@ -159,10 +189,12 @@ __global__ void finish_replica_kernel(float2* Cc, size_t n, float scale)
 }
 
 // ------------------------------------------------------------------ column pass (inverse) + |.| + sum + max
-// grid (ceil(R/128), nBins, nPrnChunk), block 128: thread = (t2, t3) column of one (PRN, bin).
+// grid (ceil(R/128), nBins, nPrnChunk), block 128: thread = row position (ta, tb) of one (PRN, bin).
+template <class P>
 __global__ void __launch_bounds__(128)
 inv_cols_kernel(InvColsParams p)
 {
+    constexpr int C = P::C, R = P::R, L = P::L;
     const int pp = blockIdx.x * 128 + threadIdx.x;
     const int k = blockIdx.y, pi = blockIdx.z;
     float acc[C];
@@ -174,7 +206,7 @@ inv_cols_kernel(InvColsParams p)
             float2 x[C];
 #pragma unroll
             for (int k1 = 0; k1 < C; ++k1) x[k1] = __ldcs(base + (size_t)m * L + (size_t)k1 * R);
-            codelet::dft33_inv(x, [&](int t1, float re, float im) {
+            codelet::dft<C, true>(x, [&](int t1, float re, float im) {
                 acc[t1] += sqrtf(fmaf(re, re, im * im));        // abs(ifft(.)) summed over blocks (:188-190)
             });
         }
@@ -183,11 +215,10 @@ inv_cols_kernel(InvColsParams p)
     float best = -1.f;
     int bidx = 0x7fffffff;
     if (pp < R) {
-        const int rest = (kM2 * (pp / RB) + kM3 * (pp % RB)) % L;
+        const int rest = P::row_index(pp);
 #pragma unroll
         for (int t1 = 0; t1 < C; ++t1) {
-            int idx = rest + kM1 * t1;                          // lag = (992*t1 + 1023*t2 + 1056*t3) mod L
-            idx -= (idx >= L) ? L : 0;
+            const int idx = P::index(t1, rest);                 // code phase (lag) of this output
             if (acc[t1] > best || (acc[t1] == best && idx < bidx)) { best = acc[t1]; bidx = idx; }
         }
     }
@@ -210,63 +241,95 @@ inv_cols_kernel(InvColsParams p)
     }
 }
 
+// ------------------------------------------------------------------ host side, per plan
+template <class P>
+struct Launch {
+    static cudaError_t fwd_cols(const FwdColsParams& p, int nRows, bool codeMode, cudaStream_t s)
+    {
+        dim3 grid((P::R + 127) / 128, nRows);
+        if (codeMode) fwd_cols_kernel<P, 1><<<grid, 128, 0, s>>>(p);
+        else fwd_cols_kernel<P, 0><<<grid, 128, 0, s>>>(p);
+        return cudaGetLastError();
+    }
+    static cudaError_t fwd_rows(const RowsParams& p, cudaStream_t s)
+    {
+        const int smem = (int)(sizeof(float2) * kRowWarps * P::RB * (P::RA + 1));
+        cudaError_t e = cudaFuncSetAttribute(fwd_rows_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        const unsigned grid = (unsigned)((p.nRows + kRowWarps - 1) / kRowWarps);
+        fwd_rows_kernel<P><<<grid, kRowWarps * 32, smem, s>>>(p);
+        return cudaGetLastError();
+    }
+    template <int WARPS, int MINB>
+    static cudaError_t inv_rows_t(const RowsParams& p, cudaStream_t s)
+    {
+        const int smem = (int)(sizeof(float2) * WARPS * P::RA * P::RB);
+        cudaError_t e = cudaFuncSetAttribute(inv_rows_kernel<P, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        const int mGroups = (p.nonCoh + p.mPerCta - 1) / p.mPerCta;
+        const int pGroups = (p.nPrnChunk + p.prnPerCta - 1) / p.prnPerCta;
+        dim3 grid(P::C, pGroups, p.nBins * mGroups);
+        inv_rows_kernel<P, WARPS, MINB><<<grid, WARPS * 32, smem, s>>>(p);
+        return cudaGetLastError();
+    }
+    // p.prnPerCta * p.mPerCta warps per CTA: 5 (96 registers, 20 warps/SM) or 8 (128 registers, 16 warps/SM)
+    static cudaError_t inv_rows(const RowsParams& p, cudaStream_t s)
+    {
+        return (p.prnPerCta * p.mPerCta == 8) ? inv_rows_t<8, 2>(p, s) : inv_rows_t<5, 4>(p, s);
+    }
+    static cudaError_t inv_cols(const InvColsParams& p, cudaStream_t s)
+    {
+        dim3 grid((P::R + 127) / 128, p.nBins, p.nPrnChunk);
+        inv_cols_kernel<P><<<grid, 128, 0, s>>>(p);
+        return cudaGetLastError();
+    }
+};
+
+using P32736 = Plan<33, 32, 31>;
+using P36000 = Plan<45, 32, 25>;
+using P24000 = Plan<30, 32, 25>;
+using P32000 = Plan<40, 32, 25>;
+using P40000 = Plan<50, 32, 25>;
+
+#define GC_PLAN_DISPATCH(LEN, CALL)                             \
+    switch (LEN) {                                              \
+        case P32736::L: return Launch<P32736>::CALL;            \
+        case P36000::L: return Launch<P36000>::CALL;            \
+        case P24000::L: return Launch<P24000>::CALL;            \
+        case P32000::L: return Launch<P32000>::CALL;            \
+        case P40000::L: return Launch<P40000>::CALL;            \
+        default: return cudaErrorInvalidValue;                  \
+    }
+
+template <class P>
+void fill_info(FusedPlanInfo* o)
+{
+    o->L = P::L; o->C = P::C; o->RA = P::RA; o->RB = P::RB; o->R = P::R; o->pfa = P::kPfa ? 1 : 0;
+    o->parts = (P::R + 127) / 128;
+}
+
 }  // namespace
 
-int fused_col_parts() { return (R + 127) / 128; }
-
-cudaError_t launch_fwd_cols(const FwdColsParams& p, int nRows, bool codeMode, cudaStream_t s)
+bool fused_plan_info(int L, FusedPlanInfo* o)
 {
-    dim3 grid((R + 127) / 128, nRows);
-    if (codeMode) fwd_cols_kernel<1><<<grid, 128, 0, s>>>(p);
-    else fwd_cols_kernel<0><<<grid, 128, 0, s>>>(p);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_fwd_rows(const RowsParams& p, cudaStream_t s)
-{
-    const int smem = (int)(sizeof(float2) * kRowWarps * RB * kPitchF);
-    cudaError_t e = cudaFuncSetAttribute(fwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    const unsigned grid = (unsigned)((p.nRows + kRowWarps - 1) / kRowWarps);
-    fwd_rows_kernel<<<grid, kRowWarps * 32, smem, s>>>(p);
-    return cudaGetLastError();
-}
-
-template <int WARPS, int MINB>
-static cudaError_t launch_inv_rows_t(const RowsParams& p, cudaStream_t s)
-{
-    const int smem = (int)(sizeof(float2) * WARPS * RA * kPitchI);
-    cudaError_t e = cudaFuncSetAttribute(inv_rows_kernel<WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    const int mGroups = (p.nonCoh + p.mPerCta - 1) / p.mPerCta;
-    const int pGroups = (p.nPrnChunk + p.prnPerCta - 1) / p.prnPerCta;
-    dim3 grid(C, pGroups, p.nBins * mGroups);
-    inv_rows_kernel<WARPS, MINB><<<grid, WARPS * 32, smem, s>>>(p);
-    return cudaGetLastError();
-}
-
-// p.prnPerCta * p.mPerCta warps per CTA: 8 (2 x 4, 128 registers, 16 warps/SM), 6 (1 x 6 or 2 x 3,
-// 96 registers, 18 warps/SM) or 5 (1 x 5, 96 registers, 20 warps/SM)
-cudaError_t launch_inv_rows(const RowsParams& p, cudaStream_t s)
-{
-    switch (p.prnPerCta * p.mPerCta) {
-        case 5: return launch_inv_rows_t<5, 4>(p, s);
-        case 6: return launch_inv_rows_t<6, 3>(p, s);
-        case 10: return launch_inv_rows_t<10, 2>(p, s);
-        default: return launch_inv_rows_t<8, 2>(p, s);
+    switch (L) {
+        case P32736::L: fill_info<P32736>(o); return true;
+        case P36000::L: fill_info<P36000>(o); return true;
+        case P24000::L: fill_info<P24000>(o); return true;
+        case P32000::L: fill_info<P32000>(o); return true;
+        case P40000::L: fill_info<P40000>(o); return true;
+        default: return false;
     }
 }
 
-cudaError_t launch_finish_replica(float2* Cc, size_t n, cudaStream_t s)
+cudaError_t launch_fwd_cols(int L, const FwdColsParams& p, int nRows, bool codeMode, cudaStream_t s) { GC_PLAN_DISPATCH(L, fwd_cols(p, nRows, codeMode, s)) }
+cudaError_t launch_fwd_rows(int L, const RowsParams& p, cudaStream_t s) { GC_PLAN_DISPATCH(L, fwd_rows(p, s)) }
+cudaError_t launch_inv_rows(int L, const RowsParams& p, cudaStream_t s) { GC_PLAN_DISPATCH(L, inv_rows(p, s)) }
+cudaError_t launch_inv_cols(int L, const InvColsParams& p, cudaStream_t s) { GC_PLAN_DISPATCH(L, inv_cols(p, s)) }
+
+cudaError_t launch_finish_replica(float2* Cc, size_t n, int L, cudaStream_t s)
 {
     finish_replica_kernel<<<148 * 2, 256, 0, s>>>(Cc, n, 1.0f / (float)L);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_inv_cols(const InvColsParams& p, cudaStream_t s)
-{
-    dim3 grid((R + 127) / 128, p.nBins, p.nPrnChunk);
-    inv_cols_kernel<<<grid, 128, 0, s>>>(p);
     return cudaGetLastError();
 }
 

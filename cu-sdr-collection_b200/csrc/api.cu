@@ -62,6 +62,8 @@ struct gc_handle {
     int N = 0, L = 0, nBins = 0, nFine = 0, nonCoh = 0;
     double ts = 0;
     bool fused = false;
+    FusedPlanInfo fp{};
+    DevBuf<float2> twFused;      // [C][R] twiddles of fused plans with a Cooley-Tukey column/row link
 
     // resident record
     const int8_t* rec = nullptr;
@@ -169,12 +171,12 @@ int build_replicas(gc_handle* h)
     GC_CUDA(h, h->Cc.reserve((size_t)nRep * L));
     if (h->fused) {
         FwdColsParams fp{};
-        fp.N = N; fp.codeTab = h->codeTab.p; fp.out = h->Cc.p;
-        GC_CUDA(h, launch_fwd_cols(fp, nRep, true, h->stream));
+        fp.N = N; fp.codeTab = h->codeTab.p; fp.out = h->Cc.p; fp.tw = h->twFused.p;
+        GC_CUDA(h, launch_fwd_cols(L, fp, nRep, true, h->stream));
         RowsParams rp{};
-        rp.X = h->Cc.p; rp.nRows = (long long)nRep * kFusedC;
-        GC_CUDA(h, launch_fwd_rows(rp, h->stream));
-        GC_CUDA(h, launch_finish_replica(h->Cc.p, (size_t)nRep * L, h->stream));
+        rp.X = h->Cc.p; rp.nRows = (long long)nRep * h->fp.C;
+        GC_CUDA(h, launch_fwd_rows(L, rp, h->stream));
+        GC_CUDA(h, launch_finish_replica(h->Cc.p, (size_t)nRep * L, L, h->stream));
     } else {
         GC_CUDA(h, h->T1.reserve((size_t)std::max(nRep, h->nBins * h->nonCoh) * L));
         GC_CUDA(h, h->T2.reserve((size_t)std::max(nRep, h->nBins * h->nonCoh) * L));
@@ -244,13 +246,26 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     h->nBins = (int)m_round(cfg->acq_search_band * 2 / cfg->acq_search_step) + 1;
     h->nFine = (int)m_round(cfg->acq_search_step / 25.0) + 1;
     h->nonCoh = cfg->acq_noncoh_time;
-    h->fused = (h->L == kFusedL) && !getenv("GC_FORCE_GENERIC");
+    h->fused = fused_plan_info(h->L, &h->fp) && !getenv("GC_FORCE_GENERIC");
     h->stats.fft_len = h->L;
-    h->stats.acq_path = h->fused ? 1 : 0;
+    h->stats.acq_path = h->fused ? 1 : 0;   // 1 = fused C x 32 x RB plan, 0 = generic mixed-radix passes
 
     auto setup = [&]() -> int {
         if (h->fused) {
-            h->parts = fused_col_parts();
+            h->parts = h->fp.parts;
+            if (!h->fp.pfa) {   // w_L^(j1 * m(p)), row position p = a*RB + b <-> m = (RB*a + RA*b) mod R
+                const FusedPlanInfo& f = h->fp;
+                std::vector<float2> tw((size_t)f.C * f.R);
+                const long double two_pi = 6.283185307179586476925286766559005768L;
+                for (int j1 = 0; j1 < f.C; ++j1)
+                    for (int p = 0; p < f.R; ++p) {
+                        const int m = (f.RB * (p / f.RB) + f.RA * (p % f.RB)) % f.R;
+                        const long long e = ((long long)j1 * m) % f.L;
+                        const long double a = -two_pi * (long double)e / (long double)f.L;
+                        tw[(size_t)j1 * f.R + p] = make_float2((float)cosl(a), (float)sinl(a));
+                    }
+                GC_CUDA(h, upload(h->twFused, tw, h->stream));
+            }
         } else {
             h->plan.L = h->L; h->plan.nf = 0;
             int m = h->L;
@@ -284,7 +299,7 @@ void gc_destroy(gc_handle* h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->recOwned.release();
     h->twGen.release(); h->X.release(); h->T1.release(); h->T2.release();
-    h->chipIdx.release();
+    h->chipIdx.release(); h->twFused.release();
     h->Cc.release(); h->W.release(); h->dphi.release(); h->fdphi.release(); h->codeTab.release(); h->chips.release();
     h->prnList.release(); h->partIdx.release(); h->fineCodePhase.release(); h->fineBest.release(); h->partMax.release();
     h->peaks.release(); h->sigPower.release(); h->fineSums.release(); h->fineResult.release(); h->fineProd.release();
@@ -391,11 +406,11 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         if (h->fused) {
             FwdColsParams fp{};
             fp.rec = h->rec; fp.winStart = winStart; fp.N = N; fp.nonCoh = nonCoh; fp.swapIQ = h->glo ? 1 : 0;
-            fp.dphi = h->dphi.p; fp.out = h->X.p;
-            GC_CUDA(h, launch_fwd_cols(fp, nKm, false, st)); ++launches;
+            fp.dphi = h->dphi.p; fp.out = h->X.p; fp.tw = h->twFused.p;
+            GC_CUDA(h, launch_fwd_cols(L, fp, nKm, false, st)); ++launches;
             RowsParams rp{};
-            rp.X = h->X.p; rp.nRows = (long long)nKm * kFusedC;
-            GC_CUDA(h, launch_fwd_rows(rp, st)); ++launches;
+            rp.X = h->X.p; rp.nRows = (long long)nKm * h->fp.C;
+            GC_CUDA(h, launch_fwd_rows(L, rp, st)); ++launches;
             fwdEv.push_back({f0, mark()});
             // PRN chunks sized so the inverse work buffer stays below ~2.5 GB
             int chunk = (int)std::max<long long>(1, (long long)(2.5e9 / ((double)nKm * L * sizeof(float2))));
@@ -405,21 +420,21 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
             for (int s0 = g0; s0 < g1; s0 += chunk) {
                 const int nc = std::min(chunk, g1 - s0);
                 RowsParams ip{};
-                ip.X = h->X.p; ip.Cc = h->Cc.p; ip.W = h->W.p;
+                ip.X = h->X.p; ip.Cc = h->Cc.p; ip.W = h->W.p; ip.tw = h->twFused.p;
                 ip.nonCoh = nonCoh; ip.nBins = nBins; ip.prnPerCta = 1; ip.mPerCta = 5;   // 5 warps, 96 registers, 20 warps/SM
                 if (const char* e = getenv("GC_ROWS_VARIANT")) {   // "PxM" warps per CTA = P PRNs x M blocks
                     int P = 0, M = 0;
-                    if (sscanf(e, "%dx%d", &P, &M) == 2 && (P * M == 5 || P * M == 6 || P * M == 8 || P * M == 10)) { ip.prnPerCta = P; ip.mPerCta = M; }
+                    if (sscanf(e, "%dx%d", &P, &M) == 2 && (P * M == 5 || P * M == 8)) { ip.prnPerCta = P; ip.mPerCta = M; }
                 }
                 ip.nPrnChunk = nc; ip.prnSlot0 = s0; ip.prnList = h->prnList.p;
                 if (evn > kEvents - 12) drain_events();
                 const int a = mark();
-                GC_CUDA(h, launch_inv_rows(ip, st)); ++launches;
+                GC_CUDA(h, launch_inv_rows(L, ip, st)); ++launches;
                 const int b = mark();
                 InvColsParams cp{};
                 cp.W = h->W.p; cp.nBins = nBins; cp.nonCoh = nonCoh; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
                 cp.partMax = h->partMax.p; cp.partIdx = h->partIdx.p;
-                GC_CUDA(h, launch_inv_cols(cp, st)); ++launches;
+                GC_CUDA(h, launch_inv_cols(L, cp, st)); ++launches;
                 const int d = mark();
                 rowEv.push_back({a, b}); colEv.push_back({b, d}); ++nRowLaunches;
             }

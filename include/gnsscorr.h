@@ -169,7 +169,8 @@ typedef struct gc_stats {
     int32_t acq_launches;      /* kernels launched by the last gc_acquire                           */
     int32_t track_launches;    /* kernels launched by the last gc_track                             */
     int32_t fft_len;           /* 2*samplesPerCode                                                  */
-    int32_t acq_path;          /* 0 = generic mixed-radix path, 1 = fused 33x32x31 path (len 32736) */
+    int32_t acq_path;          /* 0 = generic mixed-radix passes, 1 = fused C x 32 x RB plan (lengths
+                                  32736, 36000, 24000, 32000, 40000)                                */
     int32_t n_acquired;        /* PRNs above threshold in the last gc_acquire                       */
     float corr_rows_ms;        /* dominant kernel: spectrum multiply + inverse row FFT              */
     float corr_cols_ms;        /* inverse column DFT + |.| + non-coherent sum + row max             */

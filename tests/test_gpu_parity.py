@@ -62,14 +62,17 @@ def test_acquisition_fused_matches_numpy_oracle_too():
     _check_acq(got, ref, s.acqSatelliteList)
 
 
-@pytest.mark.parametrize("fs,nonCoh", [(2.046e6, 4), (18e6, 2), (4.092e6, 20)])
-def test_acquisition_generic_lengths(fs, nonCoh):
-    """Other FFT lengths go through the generic mixed-radix path: 4092, 36000 (reference default
-    18 Msps), 8184."""
+@pytest.mark.parametrize("fs,nonCoh,path", [(2.046e6, 4, 0), (18e6, 2, 0), (4.092e6, 20, 0),
+                                            (18e6, 3, 1), (16e6, 2, 1), (20e6, 2, 1)])
+def test_acquisition_other_lengths(fs, nonCoh, path, monkeypatch):
+    """Other FFT lengths: generic mixed-radix passes (4092, 8184, and 36000 when forced) and the fused
+    C x 32 x 25 plans with a Cooley-Tukey column/row link (36000 = reference default 18 Msps, 32000, 40000)."""
+    if path == 0:
+        monkeypatch.setenv("GC_FORCE_GENERIC", "1")
     sc, s, N, raw = _acq_case(fs, nsat=3, seed=13, sv_extra=[4], nonCoh=nonCoh, cn0=47, band=6000.0)
     eng = Engine(s)
     got = eng.acquire(s.acqSatelliteList, host_iq=raw)
-    assert eng.stats()["acq_path"] == 0
+    assert eng.stats()["acq_path"] == path
     ref = c_acquisition(raw, s, s.acqSatelliteList)
     _check_acq(got, ref, s.acqSatelliteList)
     eng.close()
