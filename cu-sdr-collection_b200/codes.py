@@ -66,3 +66,35 @@ def glo_code() -> np.ndarray:
         fb = reg[4] ^ reg[8]
         reg = [fb] + reg[:8]
     return out
+
+
+B3I_INIT = (4, 11, 13, 22, 30, 36, 44, 48, 88, 104, 116, 129, 376, 418, 458, 682, 696, 707, 1078, 2069,
+            2248, 2574, 2596, 2731, 4294, 4436, 4647, 4978, 4986, 1, 5209, 5539, 6061, 6488, 7130, 7165,
+            7403, 5879, 1681, 5080, 5938, 3983, 6208, 7223, 2996, 1814, 6906, 6144, 4713, 7406, 7264, 1766,
+            5347, 3515, 7951, 7054, 3884, 6067, 4230, 3803, 869, 3683, 1205)
+
+
+@lru_cache(maxsize=None)
+def b3i_code(prn: int) -> np.ndarray:
+    """+-1 BeiDou B3I chips (int8, 10230): truncated 13-stage G1 (taps 1,3,4,13, reloaded at state
+    1111111111100) times G2 (taps 1,5,6,7,9,10,12,13) advanced by a per-PRN step count
+    (BDS/B3I/include/generateB3Icode.m:33-86; bit 1 <-> -1)."""
+    def step(reg, taps):
+        fb = 0
+        for t in taps:
+            fb ^= reg[t - 1]
+        return [fb] + reg[:12]
+    reset = [1] * 11 + [0, 0]
+    a = [1] * 13
+    ca = np.empty(10230, dtype=np.int8)
+    for i in range(10230):
+        ca[i] = a[12]
+        a = [1] * 13 if a == reset else step(a, (1, 3, 4, 13))
+    b = [1] * 13
+    for _ in range(B3I_INIT[prn - 1]):
+        b = step(b, (1, 5, 6, 7, 9, 10, 12, 13))
+    out = np.empty(10230, dtype=np.int8)
+    for i in range(10230):
+        out[i] = -1 if (b[12] ^ ca[i]) else 1
+        b = step(b, (1, 5, 6, 7, 9, 10, 12, 13))
+    return out

@@ -86,7 +86,9 @@ struct FineParams {
     int nFine;                // numOfFineBins (:140)
     int codeLen;              // 1023 (511 GLONASS)
     int swapIQ;               // GLONASS I/Q swap
-    int splitHalves;          // 0: |sum of 20 codes| (acquisition.m:245); 1: |sum of 10 - sum of next 10| (GLO :246-252)
+    int combine;              // 0: max_c |sum of 20 codes| (acquisition.m:243-248); 1: |sum of 10 - sum of next 10| (GLO :246-252);
+                              // 2: B3I NH-code / GEO 2-ms-bit search over 20 codes (BDS/B3I/include/acquisition.m:193-211)
+    const int* svId;          // [nAcq] PRN of each acquired SV (combine 2 depends on it)
     const int16_t* chipIdx;   // [nPeriods*N] sample -> chip index of the 40 ms replica (host table, :215-218)
     const int8_t* chips;      // [nAcq][codeLen] +-1 chips of the acquired PRNs
     const int* codePhase;     // [nAcq] 1-based coarse code phase (:221)

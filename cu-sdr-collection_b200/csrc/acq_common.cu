@@ -145,24 +145,53 @@ fine_sum_kernel(FineParams p)
 }
 
 // nav-bit-edge search and arg-max over the fine bins (acquisition.m:240-253): for each bin the
-// maximum over the 20 start offsets of |sum of 20 consecutive per-code sums|.
+// maximum over the 20 start offsets of |sum of 20 consecutive per-code sums| (GLONASS: the two
+// 10 ms meander halves enter with opposite sign).  B3I (BDS/B3I/include/acquisition.m:193-211):
+// GEO PRNs (1-5, 59-63) carry 2 ms bits, the others the 20-bit Neumann-Hoffman code.
 __global__ void fine_select_kernel(FineParams p)
 {
     const int a = blockIdx.x;
     const int half = p.nPeriods / 2;
+    const double NH[20] = {1, 1, 1, 1, 1, -1, 1, 1, -1, -1, 1, -1, 1, -1, 1, 1, -1, -1, -1, 1};   // :127
     for (int j = threadIdx.x; j < p.nFine; j += blockDim.x) {
         const double* s = p.sums + ((size_t)a * p.nFine + j) * p.nPeriods * 2;
         double maxPower = 0;
-        for (int c = 0; c < half; ++c) {
-            double r = 0, i = 0;
-            if (!p.splitHalves) {
-                for (int q = c; q < c + half; ++q) { r += s[2 * q]; i += s[2 * q + 1]; }
-            } else {                                             // 10 ms meander halves of opposite sign (GLO :246-252)
-                for (int q = c; q < c + half / 2; ++q) { r += s[2 * q]; i += s[2 * q + 1]; }
-                for (int q = c + half / 2; q < c + half; ++q) { r -= s[2 * q]; i -= s[2 * q + 1]; }
+        if (p.combine == 2) {
+            const int prn = p.svId[a];
+            if ((prn >= 1 && prn <= 5) || (prn >= 59 && prn <= 63)) {               // :193-198
+                double c1 = 0, c2 = 0;
+                for (int q = 0; q < 20; q += 2) c1 += hypot(s[2 * q] + s[2 * q + 2], s[2 * q + 1] + s[2 * q + 3]);
+                c2 = hypot(s[0], s[1]) + hypot(s[38], s[39]);
+                for (int q = 1; q < 19; q += 2) c2 += hypot(s[2 * q] + s[2 * q + 2], s[2 * q + 1] + s[2 * q + 3]);
+                maxPower = c1 > c2 ? c1 : c2;
+            } else {                                                                 // :199-210
+                double r = 0, i = 0;
+                for (int q = 0; q < 20; ++q) { r += s[2 * q] * NH[q]; i += s[2 * q + 1] * NH[q]; }
+                maxPower = hypot(r, i);
+                for (int c = 1; c <= 19; ++c) {
+                    // NHcodeShift = circshift(NHcode', c)': element q takes NH[(q - c) mod 20]
+                    double r1 = 0, i1 = 0, r2 = 0, i2 = 0;
+                    for (int q = 0; q < 20; ++q) {
+                        const double nh = NH[(q - c + 20) % 20];
+                        if (q < c) { r1 += s[2 * q] * nh; i1 += s[2 * q + 1] * nh; }
+                        else { r2 += s[2 * q] * nh; i2 += s[2 * q + 1] * nh; }
+                    }
+                    const double pw = hypot(r1, i1) + hypot(r2, i2);
+                    if (pw > maxPower) maxPower = pw;
+                }
             }
-            const double pw = sqrt(r * r + i * i);
-            if (pw > maxPower) maxPower = pw;
+        } else {
+            for (int c = 0; c < half; ++c) {
+                double r = 0, i = 0;
+                if (p.combine == 0) {
+                    for (int q = c; q < c + half; ++q) { r += s[2 * q]; i += s[2 * q + 1]; }
+                } else {                                             // 10 ms meander halves of opposite sign (GLO :246-252)
+                    for (int q = c; q < c + half / 2; ++q) { r += s[2 * q]; i += s[2 * q + 1]; }
+                    for (int q = c + half / 2; q < c + half; ++q) { r -= s[2 * q]; i -= s[2 * q + 1]; }
+                }
+                const double pw = sqrt(r * r + i * i);
+                if (pw > maxPower) maxPower = pw;
+            }
         }
         p.fineResult[a * p.nFine + j] = maxPower;
     }

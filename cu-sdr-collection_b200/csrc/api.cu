@@ -40,7 +40,7 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-constexpr int kMaxSv = 32;            // most SVs a list can hold / replica slots
+constexpr int kMaxSv = 63;            // most SVs a list can hold / replica slots
 constexpr int kEvents = 160;
 
 }  // namespace
@@ -53,9 +53,11 @@ struct gc_handle {
     gc_stats stats{};
 
     // per-signal description
-    bool glo = false;            // GLONASS: FDMA channels K, one shared code, I/Q swapped, 3-coefficient carrier filter
-    int nReplicas = 32;          // replica spectra held (32 GPS PRNs; 1 GLONASS)
+    bool glo = false;            // GLONASS: FDMA channels K, one shared code, I/Q swapped
+    bool b3i = false;            // BeiDou B3I: 63 PRNs, 10230-chip codes, carrier-aided code NCO, NH/GEO fine search
+    int nReplicas = 32;          // replica spectra held (32 GPS PRNs; 1 GLONASS; 63 B3I)
     int resultLen = 32;          // length of the acqResults vectors
+    int nFinePeriods = 40;       // code periods of the fine-frequency search (40 GPS/GLONASS, 20 B3I)
     DevBuf<int16_t> chipIdx;     // sample -> chip index of the 40-period fine-search replica
 
     // derived (acquisition.m:116-124,138-140)
@@ -74,7 +76,7 @@ struct gc_handle {
     DevBuf<float2> twGen, X, T1, T2, Cc, W;
     DevBuf<uint64_t> dphi, fdphi;
     DevBuf<int8_t> codeTab, chips;
-    DevBuf<int> prnList, partIdx, fineCodePhase, fineBest;
+    DevBuf<int> prnList, partIdx, fineCodePhase, fineBest, fineSv;
     DevBuf<float> partMax;
     DevBuf<PeakOut> peaks;
     DevBuf<double> sigPower, fineSums, fineResult;
@@ -136,7 +138,7 @@ void calcLoopCoef(double LBW, double zeta, double k, double* tau1, double* tau2)
 }
 
 // SV id -> (valid, result index, replica slot, carrier offset)
-bool sv_ok(const gc_handle* h, int sv) { return h->glo ? (sv >= -7 && sv <= 13) : (sv >= 1 && sv <= kMaxSv); }
+bool sv_ok(const gc_handle* h, int sv) { return h->glo ? (sv >= -7 && sv <= 13) : (sv >= 1 && sv <= h->resultLen); }
 int sv_result_index(const gc_handle* h, int sv) { return h->glo ? sv + 7 : sv - 1; }       // MATLAB K+8 / PRN, 0-based
 int sv_replica(const gc_handle* h, int sv) { return h->glo ? 0 : sv - 1; }
 double sv_freq_offset(const gc_handle* h, int sv) { return h->glo ? -h->cfg.freq_spacing * (double)sv : 0.0; }
@@ -144,7 +146,7 @@ double sv_freq_offset(const gc_handle* h, int sv) { return h->glo ? -h->cfg.freq
 // +-1 chips of one code period for an SV (tracking / fine-search replica)
 void sv_chips(const gc_handle* h, int sv, int8_t* out)
 {
-    if (h->glo) glo_code(out); else ca_code(sv, out);
+    if (h->glo) glo_code(out); else if (h->b3i) b3i_code(sv, out); else ca_code(sv, out);
 }
 
 // Replica spectra conj(fft([code zeros(1,N)]))/L (acquisition.m:158-164; GLO acquisition.m:145-149) and
@@ -153,8 +155,15 @@ int build_replicas(gc_handle* h)
 {
     const int N = h->N, L = h->L, nRep = h->nReplicas, codeLen = h->cfg.code_length;
     std::vector<int8_t> tab((size_t)nRep * N);
-    std::vector<int16_t> idx40((size_t)40 * N);
-    if (h->glo) {
+    std::vector<int16_t> idx40((size_t)h->nFinePeriods * N);
+    if (h->b3i) {                                            // makeB3ITable.m:38-52; acquisition.m:170-173
+        std::vector<int8_t> chips(codeLen);
+        for (int prn = 1; prn <= nRep; ++prn) {
+            b3i_code(prn, chips.data());
+            make_code_table(chips.data(), h->cfg.sampling_freq, h->cfg.code_freq_basis, codeLen, N, tab.data() + (size_t)(prn - 1) * N);
+        }
+        gps_fine_index(h->cfg.sampling_freq, h->cfg.code_freq_basis, codeLen, (long long)h->nFinePeriods * N, idx40.data());
+    } else if (h->glo) {
         int8_t chips[511];
         glo_code(chips);
         std::vector<int16_t> idx(N);
@@ -201,7 +210,10 @@ extern "C" {
 
 int gc_abi_version(void) { return GC_ABI_VERSION; }
 const char* gc_build_arch(void) { return "sm_100a"; }
-int gc_acq_result_len(int32_t signal) { return signal == GC_SIG_GPS_L1CA ? 32 : signal == GC_SIG_GLO_G1G2 ? 21 : 0; }
+int gc_acq_result_len(int32_t signal)
+{
+    return signal == GC_SIG_GPS_L1CA ? 32 : signal == GC_SIG_GLO_G1G2 ? 21 : signal == GC_SIG_BDS_B3I ? 63 : 0;
+}
 
 const char* gc_last_error(const gc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -210,12 +222,13 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     if (!out || !cfg) return fail(nullptr, GC_ERR_ARG, "gc_create: null argument");
     *out = nullptr;
     if (cfg->abi_version != GC_ABI_VERSION) return fail(nullptr, GC_ERR_ARG, "gc_create: abi_version mismatch");
-    if (cfg->signal != GC_SIG_GPS_L1CA && cfg->signal != GC_SIG_GLO_G1G2)
-        return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: only GC_SIG_GPS_L1CA and GC_SIG_GLO_G1G2 are implemented");
+    if (cfg->signal != GC_SIG_GPS_L1CA && cfg->signal != GC_SIG_GLO_G1G2 && cfg->signal != GC_SIG_BDS_B3I)
+        return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: signal not implemented (GPS L1CA, GLONASS G1/G2, BDS B3I are)");
     if (cfg->file_type != 2 || cfg->sample_bytes != 1)
         return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: only fileType 2 (I/Q) with dataType 'schar' is implemented");
     if (!(cfg->sampling_freq > 0) || !(cfg->code_freq_basis > 0) ||
-        cfg->code_length != (cfg->signal == GC_SIG_GLO_G1G2 ? 511 : 1023) || cfg->acq_noncoh_time < 1 ||
+        cfg->code_length != (cfg->signal == GC_SIG_GLO_G1G2 ? 511 : cfg->signal == GC_SIG_BDS_B3I ? 10230 : 1023) ||
+        cfg->acq_noncoh_time < 1 ||
         !(cfg->acq_search_step > 0) || cfg->cno_vsm_interval < 2)
         return fail(nullptr, GC_ERR_ARG, "gc_create: invalid settings");
     int ndev = 0;
@@ -231,7 +244,9 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     gc_handle* h = new gc_handle();
     h->cfg = *cfg;
     h->glo = (cfg->signal == GC_SIG_GLO_G1G2);
-    h->nReplicas = h->glo ? 1 : kMaxSv;
+    h->b3i = (cfg->signal == GC_SIG_BDS_B3I);
+    h->nReplicas = h->glo ? 1 : h->b3i ? 63 : 32;
+    h->nFinePeriods = h->b3i ? 20 : 40;                      // BDS/B3I/include/acquisition.m:131-133
     h->resultLen = gc_acq_result_len(cfg->signal);
     auto bail = [&](int rc) { g_create_error = h->err; gc_destroy(h); return rc; };
     if (cudaSetDevice(cfg->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(GC_ERR_CUDA); }
@@ -301,7 +316,7 @@ void gc_destroy(gc_handle* h)
     h->twGen.release(); h->X.release(); h->T1.release(); h->T2.release();
     h->chipIdx.release(); h->twFused.release();
     h->Cc.release(); h->W.release(); h->dphi.release(); h->fdphi.release(); h->codeTab.release(); h->chips.release();
-    h->prnList.release(); h->partIdx.release(); h->fineCodePhase.release(); h->fineBest.release(); h->partMax.release();
+    h->prnList.release(); h->partIdx.release(); h->fineCodePhase.release(); h->fineBest.release(); h->fineSv.release(); h->partMax.release();
     h->peaks.release(); h->sigPower.release(); h->fineSums.release(); h->fineResult.release(); h->fineProd.release();
     h->chans.release(); h->trackCodes.release(); h->trackOut.release(); h->epochsDone.release();
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
@@ -343,11 +358,12 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
     if (nSv < 1 || nSv > kMaxSv || !svList || !carrFreq || !codePhase || !peakMetric)
         return fail(h, GC_ERR_ARG, "gc_acquire: bad argument");
     for (int i = 0; i < nSv; ++i)
-        if (!sv_ok(h, svList[i])) return fail(h, GC_ERR_ARG, h->glo ? "gc_acquire: frequency number out of range -7..13" : "gc_acquire: PRN out of range 1..32");
-    const int nPeriodsAcq = std::max(42, nonCoh + 2);                                // postProcessing.m:86
+        if (!sv_ok(h, svList[i])) return fail(h, GC_ERR_ARG, h->glo ? "gc_acquire: frequency number out of range -7..13" : "gc_acquire: PRN out of range");
+    // postProcessing.m:86 reads max(42, nonCoh+2) code periods (B3I: max(22, nonCoh+1), BDS/B3I/include/postProcessing.m:86)
+    const int nPeriodsAcq = h->b3i ? std::max(22, nonCoh + 1) : std::max(42, nonCoh + 2);
     const long long recSamples = (long long)(h->recBytes / 2);
     if (winStart < 0 || winStart + (long long)nPeriodsAcq * N > recSamples)
-        return fail(h, GC_ERR_SHORT_RECORD, "gc_acquire: record shorter than max(42, acqNonCohTime+2) code periods");
+        return fail(h, GC_ERR_SHORT_RECORD, "gc_acquire: record shorter than the acquisition window (max(42, acqNonCohTime+2) code periods; B3I max(22, acqNonCohTime+1))");
     cudaSetDevice(c.device);
     cudaStream_t st = h->stream;
     int launches = 0, evn = 0, nRowLaunches = 0;
@@ -493,7 +509,10 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
     h->stats.n_acquired = nAcq;
     float fineMs = 0;
     if (nAcq > 0) {
-        const int nPeriods = 40;                                                     // :146-148
+        const int nPeriods = h->nFinePeriods;                                        // :146-148 (B3I :131-133)
+        std::vector<int> svIds(nAcq);
+        for (int a = 0; a < nAcq; ++a) svIds[a] = svList[order[acq[a]]];
+        GC_CUDA(h, upload(h->fineSv, svIds, st));
         std::vector<int8_t> chips((size_t)nAcq * codeLen);
         std::vector<int> cps(nAcq);
         std::vector<uint64_t> fd((size_t)nAcq * h->nFine);
@@ -516,7 +535,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         GC_CUDA(h, h->fineBest.reserve(nAcq));
         FineParams fp{};
         fp.rec = h->rec; fp.winStart = winStart; fp.N = N; fp.nPeriods = nPeriods; fp.nFine = h->nFine; fp.codeLen = codeLen;
-        fp.swapIQ = h->glo ? 1 : 0; fp.splitHalves = h->glo ? 1 : 0; fp.chipIdx = h->chipIdx.p;
+        fp.swapIQ = h->glo ? 1 : 0; fp.combine = h->glo ? 1 : h->b3i ? 2 : 0; fp.chipIdx = h->chipIdx.p; fp.svId = h->fineSv.p;
         fp.chips = h->chips.p; fp.codePhase = h->fineCodePhase.p; fp.dphi = h->fdphi.p; fp.prod = h->fineProd.p;
         fp.sums = h->fineSums.p; fp.best = h->fineBest.p; fp.fineResult = h->fineResult.p;
         const int fa = mark();
@@ -585,7 +604,7 @@ static double cno_vsm(const double* I, const double* Q, int n, double T)
 }
 
 int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq, const double* codePhase,
-             int32_t nEpochs, double* out, double* vsmValue, double* vsmIndex, int32_t* epochsDone)
+             const double* codeFreq0, int32_t nEpochs, double* out, double* vsmValue, double* vsmIndex, int32_t* epochsDone)
 {
     if (!h) return GC_ERR_ARG;
     const gc_config& c = h->cfg;
@@ -604,6 +623,7 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
         live[ch] = active;
         chans[ch].prn = sv[ch]; chans[ch].pad = active ? 1 : 0;
         chans[ch].acqFreq = acqFreq[ch];
+        chans[ch].codeFreq0 = codeFreq0 ? codeFreq0[ch] : c.code_freq_basis;   // channel.codeFreq (B3I tracking.m:57)
         // fseek(fid, dataAdaptCoeff*(skipNumberOfBytes + codePhase-1)) (tracking.m:150)
         chans[ch].startSample = (long long)c.skip_number_of_bytes + (long long)codePhase[ch] - 1;
         if (active) {
@@ -627,7 +647,7 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
         p.pf2 = 2 * std::pow(Wn, 2) * c.int_time;
         p.pf1 = 2 * Wn;
     }
-    p.loopType = h->glo ? 1 : 0;
+    p.loopType = (h->glo || h->b3i) ? 1 : 0;
     p.swapIQ = h->glo ? 1 : 0;
     p.nEpochs = nEpochs;
     p.exactDisc = getenv("GC_TRACK_EXACT_DISC") ? 1 : 0;
@@ -715,8 +735,8 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
 }
 
 int gc_track_file(gc_handle* h, const char* path, int32_t nCh, const int32_t* sv, const double* acqFreq,
-                  const double* codePhase, int32_t nEpochs, double* out, double* vsmValue, double* vsmIndex,
-                  int32_t* epochsDone)
+                  const double* codePhase, const double* codeFreq0, int32_t nEpochs, double* out, double* vsmValue,
+                  double* vsmIndex, int32_t* epochsDone)
 {
     if (!h || !path) return fail(h, GC_ERR_ARG, "gc_track_file: bad argument");
     FILE* f = fopen(path, "rb");
@@ -733,7 +753,7 @@ int gc_track_file(gc_handle* h, const char* path, int32_t nCh, const int32_t* sv
     int rc = (got == (size_t)sz) ? gc_set_record_host(h, pinned, (size_t)sz) : fail(h, GC_ERR_IO, "gc_track_file: short read");
     cudaFreeHost(pinned);
     if (rc != GC_OK) return rc;
-    return gc_track(h, nCh, sv, acqFreq, codePhase, nEpochs, out, vsmValue, vsmIndex, epochsDone);
+    return gc_track(h, nCh, sv, acqFreq, codePhase, codeFreq0, nEpochs, out, vsmValue, vsmIndex, epochsDone);
 }
 
 void* gc_get_stream(const gc_handle* h) { return h ? (void*)h->stream : nullptr; }

@@ -3,6 +3,7 @@
 #include "codes.h"
 
 #include <cmath>
+#include <initializer_list>
 
 namespace gc {
 
@@ -38,15 +39,54 @@ void ca_code(int prn, int8_t* out)
     }
 }
 
+void make_code_table(const int8_t* chips, double fs, double codeFreqBasis, int codeLength, int N, int8_t* out)
+{
+    const double ts = 1 / fs, tc = 1 / codeFreqBasis;
+    for (int n = 1; n <= N; ++n) {
+        int idx = (int)std::ceil((ts * (double)n) / tc);                               // makeCaTable.m:59, makeB3ITable.m:47
+        if (n == N) idx = codeLength;                                                  // :62 / :50
+        out[n - 1] = chips[idx - 1];
+    }
+}
+
 void make_ca_table(int prn, double fs, double codeFreqBasis, int codeLength, int N, int8_t* out)
 {
     int8_t chips[1023];
     ca_code(prn, chips);
-    const double ts = 1 / fs, tc = 1 / codeFreqBasis;
-    for (int n = 1; n <= N; ++n) {
-        int idx = (int)std::ceil((ts * (double)n) / tc);                               // makeCaTable.m:59
-        if (n == N) idx = codeLength;                                                  // :62
-        out[n - 1] = chips[idx - 1];
+    make_code_table(chips, fs, codeFreqBasis, codeLength, N, out);
+}
+
+// BeiDou B3I: two 13-stage registers.  G1 (taps 1,3,4,13) is cut short: when it reaches the state
+// 1111111111100 it is reloaded with all ones (period 8190); G2 (taps 1,5,6,7,9,10,12,13) is advanced
+// by a PRN-specific number of steps before the first chip (generateB3Icode.m:36-84).  The reference
+// works with +-1 values loaded with -1, so -1 <-> bit 1 and a product is an xor.
+void b3i_code(int prn, int8_t* out)
+{
+    static const int kInit[63] = {4, 11, 13, 22, 30, 36, 44, 48, 88, 104, 116, 129, 376, 418, 458, 682, 696, 707, 1078, 2069,
+                                  2248, 2574, 2596, 2731, 4294, 4436, 4647, 4978, 4986, 1, 5209, 5539, 6061, 6488, 7130, 7165,
+                                  7403, 5879, 1681, 5080, 5938, 3983, 6208, 7223, 2996, 1814, 6906, 6144, 4713, 7406, 7264, 1766,
+                                  5347, 3515, 7951, 7054, 3884, 6067, 4230, 3803, 869, 3683, 1205};
+    auto tap = [](unsigned reg, std::initializer_list<int> stages) {
+        unsigned f = 0;
+        for (int st : stages) f ^= (reg >> (st - 1)) & 1u;     // bit i-1 = stage i
+        return f;
+    };
+    const unsigned all = 0x1fff;
+    // reset_state = [-1 x11, 1, 1] for stages 1..13  ->  bits 1 for stages 1..11, 0 for stages 12, 13
+    const unsigned resetState = 0x07ff;
+    unsigned a = all;
+    uint8_t ca[10230];
+    for (int i = 0; i < 10230; ++i) {
+        ca[i] = (a >> 12) & 1u;                                // stage 13
+        if (a == resetState) a = all;
+        else a = ((a << 1) | tap(a, {1, 3, 4, 13})) & all;
+    }
+    unsigned b = all;
+    for (int i = 0; i < kInit[prn - 1]; ++i) b = ((b << 1) | tap(b, {1, 5, 6, 7, 9, 10, 12, 13})) & all;
+    for (int i = 0; i < 10230; ++i) {
+        const unsigned cb = (b >> 12) & 1u;
+        b = ((b << 1) | tap(b, {1, 5, 6, 7, 9, 10, 12, 13})) & all;
+        out[i] = (cb ^ ca[i]) ? -1 : 1;                        // CB .* CA with -1 <-> bit 1
     }
 }
 

@@ -11,6 +11,13 @@ void ca_code(int prn, int8_t* out);
 // GPS/GPS_L1CA/include/makeCaTable.m:43-67 (index = ceil(ts*n/tc), last index forced to 1023).
 void make_ca_table(int prn, double fs, double codeFreqBasis, int codeLength, int N, int8_t* out);
 
+// +-1 BeiDou B3I chips of one PRN (1..63), 10230 values.  BDS/B3I/include/generateB3Icode.m:33-86.
+void b3i_code(int prn, int8_t* out);
+
+// A code resampled to the sampling frequency like makeCaTable.m / makeB3ITable.m: index = ceil(ts*n/tc),
+// last index forced to codeLength.
+void make_code_table(const int8_t* chips, double fs, double codeFreqBasis, int codeLength, int N, int8_t* out);
+
 // +-1 GLONASS ST-code chips (511, 9-stage register, taps 5 and 9, output of stage 7).
 // GLO/GLO_GL1/include/generateCAcode.m:95-108.
 void glo_code(int8_t* out);

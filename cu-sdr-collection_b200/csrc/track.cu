@@ -276,7 +276,7 @@ track_kernel(TrackParams p)
         s_issued[0] = s_issued[1] = 0;
         // :163-170 codeFreq = codeFreqBasis, remCodePhase = 0, carrFreq = acquiredFreq, remCarrPhase = 0; :150 fseek
         double inv0 = 0.0;
-        plan_epoch(p, p.codeFreqBasis, 0.0, 0.0, 0ull, cinfo.startSample, s_ep[0], inv0);
+        plan_epoch(p, cinfo.codeFreq0, 0.0, 0.0, 0ull, cinfo.startSample, s_ep[0], inv0);
         plan_carrier(p, cinfo.acqFreq, s_ep[0]);
     }
     __syncthreads();
@@ -552,7 +552,7 @@ track_kernel(TrackParams p)
                 // :335 codeFreq of the next block, then its geometry
                 NextPhases nx;
                 end_phases(p, ep, nx);
-                plan_epoch(p, __dsub_rn(p.codeFreqBasis, codeNco), nx.remCodePhase, nx.remCarrPhase, nx.phase0,
+                plan_epoch(p, __dsub_rn(cinfo.codeFreq0, codeNco), nx.remCodePhase, nx.remCarrPhase, nx.phase0,
                            pos + blk, s_ep[stage ^ 1], invStep);
             }
         }

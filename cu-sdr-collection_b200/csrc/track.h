@@ -12,6 +12,7 @@ struct TrackChan {
     int32_t prn;             // PRN (GPS) or frequency number K (GLONASS)
     int32_t pad;             // 1 = channel active, 0 = channel off
     double acqFreq;          // channel.acquiredFreq
+    double codeFreq0;        // centre of the code NCO: settings.codeFreqBasis, or channel.codeFreq (B3I tracking.m:57,146)
     long long startSample;   // skipNumberOfBytes + codePhase - 1   (tracking.m:150)
 };
 

@@ -34,7 +34,7 @@ class gc_config(C.Structure):
                 ("freq_spacing", C.c_double)]
 
 
-GC_SIG_GPS_L1CA, GC_SIG_GLO_G1G2 = 0, 1
+GC_SIG_GPS_L1CA, GC_SIG_GLO_G1G2, GC_SIG_BDS_B3I = 0, 1, 2
 GC_SV_NONE = -2147483648
 
 
@@ -76,8 +76,8 @@ def load_lib():
     lib.gc_set_record_device.argtypes = [vp, vp, C.c_size_t]
     lib.gc_acquire.argtypes = [vp, C.c_int32, i32p, dp, dp, dp, i32p, i32p]
     lib.gc_acquire_host.argtypes = [vp, vp, C.c_size_t, C.c_int32, i32p, dp, dp, dp, i32p, i32p]
-    lib.gc_track.argtypes = [vp, C.c_int32, i32p, dp, dp, C.c_int32, dp, dp, dp, i32p]
-    lib.gc_track_file.argtypes = [vp, C.c_char_p, C.c_int32, i32p, dp, dp, C.c_int32, dp, dp, dp, i32p]
+    lib.gc_track.argtypes = [vp, C.c_int32, i32p, dp, dp, dp, C.c_int32, dp, dp, dp, i32p]
+    lib.gc_track_file.argtypes = [vp, C.c_char_p, C.c_int32, i32p, dp, dp, dp, C.c_int32, dp, dp, dp, i32p]
     lib.gc_get_stats.argtypes = [vp, C.POINTER(gc_stats)]
     lib.gc_get_stream.argtypes = [vp]
     lib.gc_get_stream.restype = C.c_void_p
@@ -85,13 +85,17 @@ def load_lib():
     return lib
 
 
+def signal_id(s: Settings) -> int:
+    return GC_SIG_GLO_G1G2 if s.is_glonass else GC_SIG_BDS_B3I if s.signal == "BDS_B3I" else GC_SIG_GPS_L1CA
+
+
 def config_from_settings(s: Settings, device: int = 0) -> gc_config:
-    if s.resamplingflag != 0:
+    if s.resamplingflag != 0:   # (B3I spells it resamplingFlag, BDS/B3I/initSettings.m:88)
         raise GnssCorrError("resamplingflag == 1 is outside the accelerated path "
                             "(acquisition.m:50-111); run the reference for that case")
     if s.fileType != 2 or s.dataType != "schar":
         raise GnssCorrError("only fileType 2 with dataType 'schar' is implemented")
-    sig = GC_SIG_GLO_G1G2 if s.is_glonass else GC_SIG_GPS_L1CA
+    sig = signal_id(s)
     return gc_config(abi_version=2, device=device, signal=sig, freq_spacing=float(s.freqSpacing),
                      file_type=s.fileType, sample_bytes=1,
                      code_length=int(s.codeLength), acq_noncoh_time=int(s.acqNonCohTime),
@@ -157,7 +161,7 @@ class Engine:
     def acquire(self, sv_list=None, host_iq=None):
         s = self.settings
         sv = np.asarray(list(sv_list if sv_list is not None else s.acqSatelliteList), dtype=np.int32)
-        n = self.lib.gc_acq_result_len(GC_SIG_GLO_G1G2 if s.is_glonass else GC_SIG_GPS_L1CA)
+        n = self.lib.gc_acq_result_len(signal_id(s))
         carr, cph, pm = np.zeros(n), np.zeros(n), np.zeros(n)
         cbin, ccp = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
         if host_iq is not None:
@@ -171,21 +175,23 @@ class Engine:
         return dict(carrFreq=carr, codePhase=cph, peakMetric=pm, coarseBin=cbin, coarseCodePhase=ccp)
 
     # ---- tracking -----------------------------------------------------------------------
-    def track(self, prn, acq_freq, code_phase, n_epochs, path=None):
+    def track(self, prn, acq_freq, code_phase, n_epochs, path=None, code_freq0=None):
         prn = np.asarray(prn, dtype=np.int32)
         af = np.asarray(acq_freq, dtype=np.float64)
         cp = np.asarray(code_phase, dtype=np.float64)
+        cf0 = None if code_freq0 is None else np.ascontiguousarray(code_freq0, dtype=np.float64)
+        cf0p = _dp(cf0) if cf0 is not None else None
         nch = prn.size
         nv = n_epochs // int(self.settings.CNo_VSMinterval)
         out = np.empty((nch, GC_TRACK_NFIELDS, n_epochs))
         vv, vi = np.zeros((nch, nv)), np.zeros((nch, nv))
         done = np.zeros(nch, dtype=np.int32)
         if path is not None:
-            rc = self.lib.gc_track_file(self._h, os.fsencode(path), nch, _ip(prn), _dp(af), _dp(cp), n_epochs,
+            rc = self.lib.gc_track_file(self._h, os.fsencode(path), nch, _ip(prn), _dp(af), _dp(cp), cf0p, n_epochs,
                                         _dp(out), _dp(vv), _dp(vi), _ip(done))
             self._check(rc, "gc_track_file")
         else:
-            rc = self.lib.gc_track(self._h, nch, _ip(prn), _dp(af), _dp(cp), n_epochs,
+            rc = self.lib.gc_track(self._h, nch, _ip(prn), _dp(af), _dp(cp), cf0p, n_epochs,
                                    _dp(out), _dp(vv), _dp(vi), _ip(done))
             self._check(rc, "gc_track")
         return out, vv, vi, done

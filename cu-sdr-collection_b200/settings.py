@@ -38,6 +38,7 @@ class Settings:
     CNo_accTime: float = 0.001          # :133
     CNo_VSMinterval: int = 40           # :135
     freqSpacing: float = 0.0            # GLONASS only: FDMA channel spacing (GLO_GL1/initSettings.m:72)
+    carrFreqBasis: float = 0.0          # B3I: RF carrier used to aid the code NCO (BDS/B3I/initSettings.m:132)
 
     @property
     def is_glonass(self) -> bool:
@@ -51,6 +52,13 @@ _GLO_DEFAULTS = dict(fileName="../../../GL1_IF0KHz_FS12MHz.bin", IF=0.0, samplin
                      dllNoiseBandwidth=2.0, pllNoiseBandwidth=25.0, freqSpacing=562.5e3)
 
 
+# BDS/B3I/initSettings.m:44-132
+_B3I_DEFAULTS = dict(numberOfChannels=15, fileName="../../../B3I_IF20KHz_FS18MHz.bin", codeLength=10230.0,
+                     codeFreqBasis=10.23e6, acqSatelliteList=list(range(1, 64)), acqSearchBand=5000.0, acqNonCohTime=10,
+                     acqThreshold=3.0, resamplingThreshold=45e6, dllNoiseBandwidth=2.0, pllNoiseBandwidth=15.0,
+                     carrFreqBasis=1268.520e6)
+
+
 def init_settings(signal: str = "GPS_L1CA", **overrides) -> Settings:
     """``settings = initSettings()`` of the given signal folder (GPS/GPS_L1CA/init.m:56,
     GLO/GLO_GL1, GLO/GLO_GL2) with optional field overrides."""
@@ -61,11 +69,16 @@ def init_settings(signal: str = "GPS_L1CA", **overrides) -> Settings:
         if signal == "GLO_GL2":
             s.freqSpacing = 437.5e3
             s.fileName = "../../../GL2_IF0KHz_FS12MHz.bin"
+    elif signal == "BDS_B3I":
+        for k, v in _B3I_DEFAULTS.items():
+            setattr(s, k, list(v) if isinstance(v, list) else v)
     elif signal != "GPS_L1CA":
         raise ValueError(f"signal {signal!r} is not implemented")
     for k, v in overrides.items():
         if k == "skipNumberOfSamples":
             k = "skipNumberOfBytes"
+        if k == "resamplingFlag":
+            k = "resamplingflag"
         if not hasattr(s, k):
             raise AttributeError(f"settings has no field {k!r}")
         setattr(s, k, v)

@@ -16,7 +16,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from .codes import ca_code, glo_code
+from .codes import b3i_code, ca_code, glo_code
 
 L1 = 1575.42e6
 
@@ -44,6 +44,9 @@ class Scene:
     # 10 ms meander halves (+b, -b) of 20 ms bits.
     glonass: bool = False
     freqSpacing: float = 562.5e3
+    # BeiDou B3I scenes: 10230-chip codes at 10.23 Mcps; PRN 6-58 carry the 20-bit Neumann-Hoffman
+    # secondary code on 20 ms bits, GEO PRNs (1-5, 59-63) carry 2 ms bits.
+    b3i: bool = False
 
 
 def default_scene(fs: float = 16.368e6, IF: float = 20e3, nsat: int = 8, seed: int = 20260101) -> Scene:
@@ -76,6 +79,18 @@ def default_scene_glo(fs: float = 12e6, IF: float = 0.0, nsat: int = 5, seed: in
     return Scene(fs=fs, IF=IF, seed=seed, sats=sats, glonass=True, freqSpacing=freqSpacing)
 
 
+_NH20 = np.array([1, 1, 1, 1, 1, -1, 1, 1, -1, -1, 1, -1, 1, -1, 1, 1, -1, -1, -1, 1], dtype=np.float64)
+
+
+def default_scene_b3i(fs: float = 18e6, IF: float = 20e3, nsat: int = 5, seed: int = 20260101) -> Scene:
+    rng = np.random.default_rng(seed)
+    prns = rng.choice(np.arange(1, 64), size=nsat, replace=False)
+    sats = [Sat(prn=int(p), doppler=float(rng.uniform(-4000, 4000)), code_phase=float(rng.uniform(0, 10230)),
+                cn0=float(rng.uniform(40, 50)), phi0=float(rng.uniform(0, 2 * np.pi)), bit_seed=int(rng.integers(1 << 30)),
+                bit_offset=int(rng.integers(0, 20))) for p in prns]
+    return Scene(fs=fs, IF=IF, seed=seed, sats=sats, b3i=True)
+
+
 def make_record(scene: Scene, nsamples: int, start: int = 0) -> np.ndarray:
     """int8 array of length 2*nsamples (I0,Q0,I1,Q1,...), samples start..start+nsamples-1."""
     n = np.arange(start, start + nsamples, dtype=np.float64)
@@ -86,6 +101,10 @@ def make_record(scene: Scene, nsamples: int, start: int = 0) -> np.ndarray:
             clen, crate, carrier = 511, 511e3, 1602e6
             fc = scene.IF - scene.freqSpacing * s.prn + s.doppler
             chipseq = glo_code().astype(np.float64)
+        elif scene.b3i:
+            clen, crate, carrier = 10230, 10.23e6, 1268.52e6
+            fc = scene.IF + s.doppler
+            chipseq = b3i_code(s.prn).astype(np.float64)
         else:
             clen, crate, carrier = 1023, 1.023e6, L1
             fc = scene.IF + s.doppler
@@ -99,6 +118,12 @@ def make_record(scene: Scene, nsamples: int, start: int = 0) -> np.ndarray:
         d = bits[(period + s.bit_offset) // 20]
         if scene.glonass:                       # meander: second 10 ms of every bit is inverted
             d = d * np.where(((period + s.bit_offset) % 20) < 10, 1.0, -1.0)
+        if scene.b3i:
+            if (1 <= s.prn <= 5) or (59 <= s.prn <= 63):     # GEO: 2 ms bits
+                gbits = nav_bits(s, int(period.max() // 2) + 12)
+                d = gbits[(period + s.bit_offset) // 2]
+            else:                                             # NH secondary code on every 20 ms bit
+                d = d * _NH20[(period + s.bit_offset) % 20]
         ph = 2 * np.pi * (fc * t % 1.0) + s.phi0
         sig += _amp(s.cn0, scene.sigma, scene.fs) * d * code * np.exp(1j * ph)
     # noise is a function of (seed, absolute chunk) so records can be made piecewise

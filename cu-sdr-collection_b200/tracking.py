@@ -31,7 +31,8 @@ def tracking(fid, channel: list, settings: Settings, engine: Engine | None = Non
         af = [float(c["acquiredFreq"]) for c in channel[:nch]]
         cp = [float(c["codePhase"]) for c in channel[:nch]]
         path = fid.name if fid is not None else None
-        out, vv, vi, done = eng.track(prn, af, cp, n, path=path)
+        cf0 = [float(c["codeFreq"]) for c in channel[:nch]] if settings.signal == "BDS_B3I" else None   # B3I tracking.m:57
+        out, vv, vi, done = eng.track(prn, af, cp, n, path=path, code_freq0=cf0)
     finally:
         if own:
             eng.close()

@@ -30,9 +30,9 @@ extern "C" {
 
 #define GC_ABI_VERSION 2
 
-/* signal ids (reference folders).  Implemented: GPS/GPS_L1CA and GLO/GLO_GL1 + GLO/GLO_GL2 (the two
- * GLONASS folders differ only in settings.freqSpacing and the file name). */
-enum { GC_SIG_GPS_L1CA = 0, GC_SIG_GLO_G1G2 = 1 };
+/* signal ids (reference folders).  Implemented: GPS/GPS_L1CA, GLO/GLO_GL1 + GLO/GLO_GL2 (the two
+ * GLONASS folders differ only in settings.freqSpacing and the file name) and BDS/B3I. */
+enum { GC_SIG_GPS_L1CA = 0, GC_SIG_GLO_G1G2 = 1, GC_SIG_BDS_B3I = 2 };
 
 /* "no satellite on this channel" for gc_track: GPS uses PRN 0 (tracking.m:136); a GLONASS channel is
  * identified by its frequency number K, for which 0 is valid, so unused channels carry GC_SV_NONE
@@ -92,7 +92,8 @@ enum {
 };
 
 /* Length of the acqResults vectors for a signal: 32 for GPS L1CA indexed PRN-1 (acquisition.m:130-134),
- * 21 for GLONASS indexed K+7, i.e. MATLAB's K+8 (GLO_GL1/include/acquisition.m:138-142,212). */
+ * 21 for GLONASS indexed K+7, i.e. MATLAB's K+8 (GLO_GL1/include/acquisition.m:138-142,212),
+ * 63 for BeiDou B3I indexed PRN-1 (BDS/B3I/include/acquisition.m:118-122). */
 int gc_acq_result_len(int32_t signal);
 
 /* Create / destroy an engine bound to one GPU.  Builds the FFT plan and twiddle tables for
@@ -139,6 +140,9 @@ int gc_acquire_host(gc_handle* h, const int8_t* iq, size_t nSamples,
  *                 (GC_SV_NONE = channel off).  GLONASS uses the 3-coefficient carrier filter of
  *                 Common/calcLoopCoefCarr.m (GLO_GL1/include/tracking.m:281-285) and swaps I/Q (:227).
  *   acqFreq[ch]   channel(ch).acquiredFreq        codePhase[ch]  channel(ch).codePhase (1-based)
+ *   codeFreq0[ch] channel(ch).codeFreq, the carrier-aided centre of the code NCO that preRun.m computes
+ *                 for B3I (BDS/B3I/include/preRun.m:71-73, tracking.m:57,146); NULL = settings.codeFreqBasis
+ *                 (GPS L1CA, GLONASS)
  *   nEpochs       settings.msToProcess (code periods)
  *   out           [nCh][GC_TRACK_NFIELDS][nEpochs] doubles; rows pre-filled like tracking.m:51-77
  *                 (zeros for absoluteSample and I/Q, +inf for the rest)
@@ -147,7 +151,7 @@ int gc_acquire_host(gc_handle* h, const int8_t* iq, size_t nSamples,
  *                 as in the reference the whole call stops there and later channels stay untouched,
  *                 and `status` must be left '-' for every channel with epochsDone < nEpochs. */
 int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq,
-             const double* codePhase, int32_t nEpochs,
+             const double* codePhase, const double* codeFreq0, int32_t nEpochs,
              double* out, double* vsmValue, double* vsmIndex, int32_t* epochsDone);
 
 /* Convenience for the MATLAB wrapper: tracking() receives an open fid, which a MEX cannot use;
@@ -155,7 +159,7 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
  * into pinned memory, makes it resident, then gc_track. */
 int gc_track_file(gc_handle* h, const char* path,
                   int32_t nCh, const int32_t* sv, const double* acqFreq,
-                  const double* codePhase, int32_t nEpochs,
+                  const double* codePhase, const double* codeFreq0, int32_t nEpochs,
                   double* out, double* vsmValue, double* vsmIndex, int32_t* epochsDone);
 
 /* Device-side timing of the most recent gc_acquire / gc_track, measured with CUDA events on the

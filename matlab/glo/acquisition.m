@@ -15,7 +15,7 @@ end
 iq = zeros(1, 2 * numel(longSignal), 'int8');
 iq(1:2:end) = int8(imag(longSignal));     % I
 iq(2:2:end) = int8(real(longSignal));     % Q
-r = gnsscorr_mex('acquire', gnsscorr_config(settings), iq, double(settings.acqSatelliteList));
+r = gnsscorr_mex('acquire', gnsscorr_config(settings, 'GLO'), iq, double(settings.acqSatelliteList));
 acqResults.carrFreq   = r.carrFreq;
 acqResults.codePhase  = r.codePhase;
 acqResults.peakMetric = r.peakMetric;

@@ -11,7 +11,7 @@ for ch = 1:nCh
         K(ch) = channel(ch).K;
     end
 end
-r = gnsscorr_mex('track', gnsscorr_config(settings), fname, K, ...
+r = gnsscorr_mex('track', gnsscorr_config(settings, 'GLO'), fname, K, ...
                  double([channel(1:nCh).acquiredFreq]), double([channel(1:nCh).codePhase]), n);
 names = {'absoluteSample', 'codeFreq', 'carrFreq', 'I_P', 'I_E', 'I_L', 'Q_E', 'Q_P', 'Q_L', ...
          'dllDiscr', 'dllDiscrFilt', 'pllDiscr', 'pllDiscrFilt', 'remCodePhase', 'remCarrPhase'};

@@ -1,10 +1,13 @@
-function cfg = gnsscorr_config(settings)
+function cfg = gnsscorr_config(settings, signal)
 %GNSSCORR_CONFIG  settings struct (initSettings.m) -> the field names of gc_config (gnsscorr.h).
+%   signal: 'GPS_L1CA' (default), 'GLO' (GLO_GL1 / GLO_GL2) or 'BDS_B3I' - the wrapper of each signal
+%   folder passes its own.
+if nargin < 2, signal = 'GPS_L1CA'; end
 cfg.device = 0;
-if isfield(settings, 'freqSpacing')      % GLO/GLO_GL1, GLO/GLO_GL2
-    cfg.signal = 1;  cfg.freq_spacing = settings.freqSpacing;
-else                                    % GPS/GPS_L1CA
-    cfg.signal = 0;  cfg.freq_spacing = 0;
+switch signal
+    case 'GLO',     cfg.signal = 1;  cfg.freq_spacing = settings.freqSpacing;
+    case 'BDS_B3I', cfg.signal = 2;  cfg.freq_spacing = 0;
+    otherwise,      cfg.signal = 0;  cfg.freq_spacing = 0;
 end
 cfg.file_type = settings.fileType;
 cfg.sample_bytes = 1;

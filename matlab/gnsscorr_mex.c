@@ -12,7 +12,7 @@
  *         iq_int8 : int8 vector, I,Q interleaved (longSignal as stored in the file)
  *         svList  : double vector of PRNs (GLONASS: frequency numbers K)
  *         r       : struct carrFreq, codePhase, peakMetric (1x32 double; GLONASS 1x21, index K+8)
- *   r = gnsscorr_mex('track', cfg, path, prn, acqFreq, codePhase, nEpochs)
+ *   r = gnsscorr_mex('track', cfg, path, prn, acqFreq, codePhase, nEpochs [, codeFreq0])
  *         r       : struct out (nEpochs x 15 x nCh double, MATLAB column-major view of the
  *                   C [nCh][15][nEpochs] block), vsmValue, vsmIndex, epochsDone
  *
@@ -105,14 +105,15 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
         int32_t prn[256];
         mxArray *out, *vv, *vi, *done;
         mwSize i;
-        if (nrhs != 7 || mxGetString(prhs[2], path, sizeof(path)) || nCh > 256) { gc_destroy(h); mexErrMsgIdAndTxt("gnsscorr:args", "track: bad arguments"); }
+        if ((nrhs != 7 && nrhs != 8) || mxGetString(prhs[2], path, sizeof(path)) || nCh > 256) { gc_destroy(h); mexErrMsgIdAndTxt("gnsscorr:args", "track: bad arguments"); }
         for (i = 0; i < nCh; ++i) prn[i] = (prnd[i] != prnd[i]) ? GC_SV_NONE : (int32_t)prnd[i];   /* NaN = channel off (GLONASS) */
         dims[0] = nEpochs; dims[1] = GC_TRACK_NFIELDS; dims[2] = nCh;
         out = mxCreateNumericArray(3, dims, mxDOUBLE_CLASS, mxREAL);
         vv = mxCreateDoubleMatrix(nV, nCh, mxREAL);
         vi = mxCreateDoubleMatrix(nV, nCh, mxREAL);
         done = mxCreateNumericMatrix(1, nCh, mxINT32_CLASS, mxREAL);
-        check(h, gc_track_file(h, path, (int32_t)nCh, prn, mxGetDoubles(prhs[4]), mxGetDoubles(prhs[5]), nEpochs,
+        check(h, gc_track_file(h, path, (int32_t)nCh, prn, mxGetDoubles(prhs[4]), mxGetDoubles(prhs[5]),
+                               nrhs == 8 ? mxGetDoubles(prhs[7]) : NULL, nEpochs,
                                mxGetDoubles(out), mxGetDoubles(vv), mxGetDoubles(vi), (int32_t*)mxGetInt32s(done)),
               "gc_track_file");
         plhs[0] = mxCreateStructMatrix(1, 1, 4, names);

@@ -36,7 +36,7 @@ typedef struct {
     double pllDampingRatio, pllNoiseBandwidth, intTime;            /* :105-108 */
     double CNo_accTime; int CNo_VSMinterval;                       /* :133-135 */
     double freqSpacing;                                            /* GLO/GLO_GL1/initSettings.m:72 */
-    int    glo;            /* 0: GPS/GPS_L1CA files; 1: GLO/GLO_GL1 (= GLO_GL2) files, cited as "GLO :line" */
+    int    glo;            /* 0: GPS/GPS_L1CA files; 1: GLO/GLO_GL1 (= GLO_GL2), cited "GLO :line"; 2: BDS/B3I, cited "B3I :line" */
 } orc_settings;
 
 /* ---------------------------------------------------------------- helpers */
@@ -74,6 +74,35 @@ void orc_generateCAcode(int PRN, double* CAcode /*1023*/)
     for (int i = 0; i < 1023; i++) {
         int src = (i < g2shift) ? (1023 - g2shift + i) : (i - g2shift);
         CAcode[i] = -(g1[i] * g2[src]);
+    }
+}
+
+/* BDS/B3I/include/generateB3Icode.m:33-86 — +-1 chips (10230) */
+static const int B3I_INIT[63] = {4, 11, 13, 22, 30, 36, 44, 48, 88, 104, 116, 129, 376, 418, 458, 682, 696, 707, 1078, 2069,
+                                 2248, 2574, 2596, 2731, 4294, 4436, 4647, 4978, 4986, 1, 5209, 5539, 6061, 6488, 7130, 7165,
+                                 7403, 5879, 1681, 5080, 5938, 3983, 6208, 7223, 2996, 1814, 6906, 6144, 4713, 7406, 7264, 1766,
+                                 5347, 3515, 7951, 7054, 3884, 6067, 4230, 3803, 869, 3683, 1205};
+void orc_generateB3Icode(int PRN, double* code /*10230*/)
+{
+    static const double reset_state[13] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 1, 1};
+    double reg[13], CA[10230];
+    for (int i = 0; i < 13; i++) reg[i] = -1;
+    for (int ind = 0; ind < 10230; ind++) {                        /* :40-49 */
+        CA[ind] = reg[12];
+        int eq = 1; for (int i = 0; i < 13; i++) if (reg[i] != reset_state[i]) eq = 0;
+        if (eq) { for (int i = 0; i < 13; i++) reg[i] = -1; }
+        else {
+            double fb = reg[0] * reg[2] * reg[3] * reg[12];
+            for (int j = 12; j >= 1; j--) reg[j] = reg[j - 1];
+            reg[0] = fb;
+        }
+    }
+    for (int i = 0; i < 13; i++) reg[i] = -1;
+    for (int step = 0; step < B3I_INIT[PRN - 1] + 10230; step++) { /* :68-80 */
+        if (step >= B3I_INIT[PRN - 1]) code[step - B3I_INIT[PRN - 1]] = reg[12] * CA[step - B3I_INIT[PRN - 1]];
+        double fb = reg[0] * reg[4] * reg[5] * reg[6] * reg[8] * reg[9] * reg[11] * reg[12];
+        for (int j = 12; j >= 1; j--) reg[j] = reg[j - 1];
+        reg[0] = fb;
     }
 }
 
@@ -207,22 +236,26 @@ int orc_acquisition(const int8_t* iq, size_t nSamplesAvail, const orc_settings* 
 {
     const int N = orc_samples_per_code(s);
     const int L2 = 2 * N;
-    const int codeLen = (42 > s->acqNonCohTime + 2) ? 42 : s->acqNonCohTime + 2;
+    const int b3i = (s->glo == 2);
+    /* postProcessing.m:86 max(42, nonCoh+2); B3I postProcessing.m:86 max(22, nonCoh+1) */
+    const int codeLen = b3i ? ((22 > s->acqNonCohTime + 1) ? 22 : s->acqNonCohTime + 1)
+                            : ((42 > s->acqNonCohTime + 2) ? 42 : s->acqNonCohTime + 2);
+    const int nFinePer = b3i ? 20 : 40;                                          /* B3I acquisition.m:131-133 */
     if (nSamplesAvail < (size_t)codeLen * N) return -1;
     const double ts = 1 / s->samplingFreq;                                       /* :119 */
     const int nBins = (int)m_round(s->acqSearchBand * 2 / s->acqSearchStep) + 1; /* :124 */
     const double fineSearchStep = 25;                                            /* :138 */
     const int nFine = (int)m_round(s->acqSearchStep / fineSearchStep) + 1;       /* :140 */
     const int nonCoh = s->acqNonCohTime;
-    const int nRes = s->glo ? 21 : 32;                      /* GLO acquisition.m:138-142 */
+    const int nRes = s->glo == 1 ? 21 : b3i ? 63 : 32;      /* GLO acquisition.m:138-142 ; B3I :118-122 */
     for (int i = 0; i < nRes; i++) { carrFreq[i] = codePhaseOut[i] = peakMetric[i] = 0; coarseBin[i] = coarseCodePhase[i] = 0; }
 
     size_t Ltot = (size_t)codeLen * N;
     cplx* sig = (cplx*)malloc(sizeof(cplx) * Ltot);
     for (size_t i = 0; i < Ltot; i++)                        /* GLO postProcessing.m:94: data2 + 1i*data1 */
-        sig[i] = s->glo ? (double)iq[2 * i + 1] + I * (double)iq[2 * i] : (double)iq[2 * i] + I * (double)iq[2 * i + 1];
+        sig[i] = s->glo == 1 ? (double)iq[2 * i + 1] + I * (double)iq[2 * i] : (double)iq[2 * i] + I * (double)iq[2 * i + 1];
     double* glo40 = NULL;                                    /* GLO acquisition.m:164 caCode40ms */
-    if (s->glo) { glo40 = (double*)malloc(sizeof(double) * 40 * (size_t)N); orc_glo_sampled_code(s->samplingFreq, 40L * N, glo40); }
+    if (s->glo == 1) { glo40 = (double*)malloc(sizeof(double) * 40 * (size_t)N); orc_glo_sampled_code(s->samplingFreq, 40L * N, glo40); }
     double* phasePoints = (double*)malloc(sizeof(double) * L2);
     for (int n = 0; n < L2; n++) phasePoints[n] = (double)n * 2 * M_PI * ts;     /* :122 */
 
@@ -246,14 +279,21 @@ int orc_acquisition(const int8_t* iq, size_t nSamplesAvail, const orc_settings* 
         cplx* carr = (cplx*)malloc(sizeof(cplx) * L2);
         double* results = (double*)calloc((size_t)nBins * L2, sizeof(double));   /* :162 */
         double* coarseFreqBin = (double*)malloc(sizeof(double) * nBins);
-        if (s->glo) orc_glo_sampled_code(s->samplingFreq, N, table);             /* GLO :145 */
+        double* b3code = NULL;
+        if (s->glo == 1) orc_glo_sampled_code(s->samplingFreq, N, table);        /* GLO :145 */
+        else if (b3i) {                                                          /* B3I makeB3ITable.m:38-52 */
+            b3code = (double*)malloc(sizeof(double) * 10230);
+            orc_generateB3Icode(PRN, b3code);
+            double ts_ = 1 / s->samplingFreq, tc_ = 1 / s->codeFreqBasis;
+            for (int n = 1; n <= N; n++) { int idx = (int)ceil((ts_ * (double)n) / tc_); if (n == N) idx = 10230; table[n - 1] = b3code[idx - 1]; }
+        }
         else orc_makeCaTable(PRN, s, table);                                     /* :158 */
-        const int ri = s->glo ? PRN + 7 : PRN - 1;                               /* result slot: K+8 / PRN (1-based) */
+        const int ri = s->glo == 1 ? PRN + 7 : PRN - 1;                          /* result slot: K+8 / PRN (1-based) */
         for (int n = 0; n < L2; n++) codeF[n] = n < N ? table[n] : 0.0;          /* :160 */
         fft_exec(&plan, codeF, tmp, -1);
         for (int n = 0; n < L2; n++) codeF[n] = conj(codeF[n]);                  /* :164 */
         for (int k = 1; k <= nBins; k++) {                                       /* :167 */
-            coarseFreqBin[k - 1] = s->glo ? s->IF - s->freqSpacing * PRN + s->acqSearchBand - s->acqSearchStep * (k - 1)   /* GLO :181 */
+            coarseFreqBin[k - 1] = s->glo == 1 ? s->IF - s->freqSpacing * PRN + s->acqSearchBand - s->acqSearchStep * (k - 1)   /* GLO :181 */
                                           : s->IF + s->acqSearchBand - s->acqSearchStep * (k - 1);                   /* :169 */
             for (int n = 0; n < L2; n++) {
                 double a = coarseFreqBin[k - 1] * phasePoints[n];
@@ -286,17 +326,21 @@ int orc_acquisition(const int8_t* iq, size_t nSamplesAvail, const orc_settings* 
         peakMetric[ri] = peak / sigPower / nonCoh;                               /* :200 */
         coarseBin[ri] = bin; coarseCodePhase[ri] = cp;
         if (peakMetric[ri] > s->acqThreshold) {                                  /* :206 */
-            double ca[1023]; if (!s->glo) orc_generateCAcode(PRN, ca);           /* :213 */
+            double ca[1023]; if (s->glo == 0) orc_generateCAcode(PRN, ca);       /* :213 */
             double bestFine = -1; int bestJ = 1; double bestFreq = 0;
             for (int j = 1; j <= nFine; j++) {                                   /* :224 */
                 double f = coarseFreqBin[bin - 1] + s->acqSearchStep / 2 - fineSearchStep * (j - 1);  /* :227 */
                 cplx sumPerCode[40];
-                for (int c = 0; c < 40; c++) {
+                for (int c = 0; c < nFinePer; c++) {
                     cplx acc = 0;
                     for (int n = 0; n < N; n++) {
                         long gi = (long)c * N + n;
                         double chip;
-                        if (s->glo) chip = glo40[gi];                                          /* GLO :164,236 */
+                        if (s->glo == 1) chip = glo40[gi];                                     /* GLO :164,236 */
+                        else if (b3i) {                                                        /* B3I :174-177 */
+                            long idx = (long)floor((ts * (double)gi) / (1 / s->codeFreqBasis));
+                            chip = b3code[idx % 10230];
+                        }
                         else {
                             long idx = (long)floor((ts * (double)gi) / (1 / s->codeFreqBasis));  /* :215 */
                             chip = ca[idx % (long)s->codeLength];                              /* :218 */
@@ -308,9 +352,27 @@ int orc_acquisition(const int8_t* iq, size_t nSamplesAvail, const orc_settings* 
                     sumPerCode[c] = acc;
                 }
                 double maxPower = 0;
-                for (int c = 0; c < 20; c++) {                                   /* :243 */
+                if (b3i) {                                                       /* B3I :193-211 */
+                    static const double NH[20] = {1, 1, 1, 1, 1, -1, 1, 1, -1, -1, 1, -1, 1, -1, 1, 1, -1, -1, -1, 1};
+                    if ((PRN >= 1 && PRN <= 5) || (PRN >= 59 && PRN <= 63)) {
+                        double c1 = 0, c2 = cabs(sumPerCode[0]) + cabs(sumPerCode[19]);
+                        for (int q = 0; q < 20; q += 2) c1 += cabs(sumPerCode[q] + sumPerCode[q + 1]);
+                        for (int q = 1; q < 19; q += 2) c2 += cabs(sumPerCode[q] + sumPerCode[q + 1]);
+                        maxPower = c1 > c2 ? c1 : c2;
+                    } else {
+                        cplx t = 0; for (int q = 0; q < 20; q++) t += sumPerCode[q] * NH[q];
+                        maxPower = cabs(t);
+                        for (int ci = 1; ci <= 19; ci++) {
+                            cplx t1 = 0, t2 = 0;
+                            for (int q = 0; q < 20; q++) { cplx v_ = sumPerCode[q] * NH[(q - ci + 20) % 20]; if (q < ci) t1 += v_; else t2 += v_; }
+                            double pw = cabs(t1) + cabs(t2);
+                            if (pw > maxPower) maxPower = pw;
+                        }
+                    }
+                }
+                for (int c = 0; c < 20 && !b3i; c++) {                           /* :243 */
                     cplx t = 0;
-                    if (!s->glo) { for (int q = c; q < c + 20; q++) t += sumPerCode[q]; }
+                    if (s->glo == 0) { for (int q = c; q < c + 20; q++) t += sumPerCode[q]; }
                     else {                                                       /* GLO :250-251: sum(c:c+9) - sum(c+10:c+19) */
                         cplx t1 = 0, t2 = 0;
                         for (int q = c; q < c + 10; q++) t1 += sumPerCode[q];
@@ -327,7 +389,7 @@ int orc_acquisition(const int8_t* iq, size_t nSamplesAvail, const orc_settings* 
             codePhaseOut[ri] = cp;                                               /* :256 */
             if (carrFreq[ri] == 0) carrFreq[ri] = 1;                             /* :258 */
         }
-        free(table); free(codeF); free(buf); free(tmp); free(carr); free(results); free(coarseFreqBin);
+        free(table); free(codeF); free(buf); free(tmp); free(carr); free(results); free(coarseFreqBin); free(b3code);
     }
     plan_free(&plan); free(sig); free(phasePoints); free(glo40);
     return rc;
@@ -385,7 +447,7 @@ static void colon_setup(double a, double d, double b, int* n_out, double* c_out)
 /* tracking.m:88-368 for fileType 2 / schar.  iq = whole file bytes (int8 I,Q interleaved), nBytes its size.
  * Returns 0; epochsDone[ch] = completed epochs; a short read stops the WHOLE call (tracking.m:241-245). */
 int orc_tracking(const int8_t* iq, size_t nBytes, const orc_settings* s, int nCh,
-                 const int* PRN, const double* acquiredFreq, const double* codePhase,
+                 const int* PRN, const double* acquiredFreq, const double* codePhase, const double* codeFreq0 /* B3I channel.codeFreq, else NULL */,
                  int nEpochs, double* out /* nCh*15*nEpochs */, double* vsmValue, double* vsmIndex /* nCh*floor(nE/VSMint) */,
                  int* epochsDone, int parallel)
 {
@@ -412,17 +474,20 @@ int orc_tracking(const int8_t* iq, size_t nBytes, const orc_settings* s, int nCh
     volatile int abortAll = 0;
 #pragma omp parallel for schedule(dynamic, 1) if (parallel)
     for (int ch = 0; ch < nCh; ch++) {                                           /* :133 */
-        if (s->glo ? (PRN[ch] == INT32_MIN) : (PRN[ch] == 0)) continue;          /* :136 ; GLO :137 status ~= '-' (INT32_MIN = off) */
+        if (s->glo == 1 ? (PRN[ch] == INT32_MIN) : (PRN[ch] == 0)) continue;          /* :136 ; GLO :137 status ~= '-' (INT32_MIN = off) */
         if (!parallel && abortAll) continue;   /* sequential semantics: return ends all later channels */
         double* o = out + (size_t)ch * ORC_NFIELDS * nEpochs;
 #define F(i) (o + (size_t)(i) * nEpochs)
         size_t pos = (size_t)(2 * ((long)s->skipNumberOfBytes + (long)codePhase[ch] - 1));   /* :150 */
-        double ca[1023], caCode[1025];
-        if (s->glo) orc_glo_code(ca);                                            /* GLO :88 */
+        double* ca = (double*)malloc(sizeof(double) * 10230);
+        double* caCode = (double*)malloc(sizeof(double) * 10232);
+        if (s->glo == 1) orc_glo_code(ca);                                       /* GLO :88 */
+        else if (s->glo == 2) orc_generateB3Icode(PRN[ch], ca);                  /* B3I :55 */
         else orc_generateCAcode(PRN[ch], ca);                                    /* :156 */
+        const double codeFreqCentre = (s->glo == 2 && codeFreq0) ? codeFreq0[ch] : s->codeFreqBasis;   /* B3I :57 */
         double d2CarrError = 0, dCarrError = 0;                                  /* GLO :171-172 */
         caCode[0] = ca[L - 1]; memcpy(caCode + 1, ca, sizeof(double) * L); caCode[L + 1] = ca[0];   /* :158 */
-        double codeFreq = s->codeFreqBasis, remCodePhase = 0.0;                  /* :163-165 */
+        double codeFreq = codeFreqCentre, remCodePhase = 0.0;                    /* :163-165 */
         double carrFreq = acquiredFreq[ch], carrFreqBasis = acquiredFreq[ch], remCarrPhase = 0.0;   /* :167-170 */
         double oldCodeNco = 0, oldCodeError = 0, oldCarrNco = 0, oldCarrError = 0;           /* :173-178 */
         int vsmCnt = 0;
@@ -450,7 +515,7 @@ int orc_tracking(const int8_t* iq, size_t nBytes, const orc_settings* s, int nCh
                 double trig = (w * ((double)n / s->samplingFreq)) + remCarrPhase;            /* :280-281 */
                 double c = cos(trig), sn = sin(trig);                            /* :287 exp(-1i*trig) = c - i*sn */
                 double xr = raw[2 * n], xi = raw[2 * n + 1];                     /* :233-235 */
-                if (s->glo) { double t_ = xr; xr = xi; xi = t_; }                /* GLO :227 rawSignal2 + 1i*rawSignal1 */
+                if (s->glo == 1) { double t_ = xr; xr = xi; xi = t_; }                /* GLO :227 rawSignal2 + 1i*rawSignal1 */
                 double iBB = c * xr + sn * xi, qBB = c * xi - sn * xr;           /* :291-292 */
                 I_E += e * iBB; Q_E += e * qBB; I_P += p * iBB; Q_P += p * qBB; I_L += l * iBB; Q_L += l * qBB;   /* :295-300 */
             }
@@ -459,7 +524,7 @@ int orc_tracking(const int8_t* iq, size_t nBytes, const orc_settings* s, int nCh
             remCarrPhase = fmod(trigEnd, 2 * M_PI);                              /* :283 */
             double carrError = atan(Q_P / I_P) / (2.0 * M_PI);                   /* :305 */
             double carrNco;
-            if (!s->glo) {
+            if (s->glo == 0) {
                 carrNco = oldCarrNco + (tau2carr / tau1carr) * (carrError - oldCarrError) + carrError * (PDIcarr / tau1carr);   /* :308 */
                 oldCarrNco = carrNco; oldCarrError = carrError;
             } else {                                                             /* GLO :282-285 */
@@ -474,7 +539,7 @@ int orc_tracking(const int8_t* iq, size_t nBytes, const orc_settings* s, int nCh
             double codeNco = oldCodeNco + (tau2code / tau1code) * (codeError - oldCodeError) + codeError * (PDIcode / tau1code);   /* :326 */
             oldCodeNco = codeNco; oldCodeError = codeError;
             F(1)[loopCnt - 1] = codeFreq;                                        /* :332 */
-            codeFreq = s->codeFreqBasis - codeNco;                               /* :335 */
+            codeFreq = codeFreqCentre - codeNco;                                 /* :335 ; B3I :146 */
             F(9)[loopCnt - 1] = codeError; F(10)[loopCnt - 1] = codeNco;         /* :338-341 */
             F(11)[loopCnt - 1] = carrError; F(12)[loopCnt - 1] = carrNco;
             F(4)[loopCnt - 1] = I_E; F(3)[loopCnt - 1] = I_P; F(5)[loopCnt - 1] = I_L;       /* :343-348 */
@@ -487,6 +552,7 @@ int orc_tracking(const int8_t* iq, size_t nBytes, const orc_settings* s, int nCh
             }
             epochsDone[ch] = loopCnt;
         }
+        free(ca); free(caCode);
 #undef F
     }
     /* MATLAB `return` on a short read ends the whole function: channels after the first one that
@@ -494,7 +560,7 @@ int orc_tracking(const int8_t* iq, size_t nBytes, const orc_settings* s, int nCh
     if (parallel) {
         int failed = -1;
         for (int ch = 0; ch < nCh && failed < 0; ch++)
-            if (!(s->glo ? (PRN[ch] == INT32_MIN) : (PRN[ch] == 0)) && epochsDone[ch] < nEpochs) failed = ch;
+            if (!(s->glo == 1 ? (PRN[ch] == INT32_MIN) : (PRN[ch] == 0)) && epochsDone[ch] < nEpochs) failed = ch;
         for (int ch = failed + 1; failed >= 0 && ch < nCh; ch++) {
             double* o = out + (size_t)ch * ORC_NFIELDS * nEpochs;
             for (int f = 0; f < ORC_NFIELDS; f++) {

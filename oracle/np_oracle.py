@@ -75,6 +75,7 @@ class Settings:
     CNo_accTime: float = 0.001          # :133
     CNo_VSMinterval: int = 40           # :135
     freqSpacing: float = 0.0            # GLO/GLO_GL1/initSettings.m:72 (GLONASS only)
+    carrFreqBasis: float = 0.0          # BDS/B3I/initSettings.m:132 (B3I only)
 
 
 def matlab_round(x: float) -> float:
@@ -530,8 +531,20 @@ def calcLoopCoefCarr(s: Settings):
 
 
 def tracking_glo(raw: np.ndarray, channel: list, s: Settings):
-    """include/tracking.m:45-358: as GPS L1 C/A except the shared 511-chip code (:88-90), the channel
-    test status ~= '-' (:137), rawSignal = Q + 1i*I (:227) and the carrier loop filter (:281-285)."""
+    """GLO/GLO_GL1/include/tracking.m:45-358: as GPS L1 C/A except the shared 511-chip code (:88-90), the
+    channel test status ~= '-' (:137), rawSignal = Q + 1i*I (:227) and the carrier loop filter (:281-285)."""
+    return _tracking_pf(raw, channel, s, "GLO")
+
+
+def tracking_b3i(raw: np.ndarray, channel: list, s: Settings):
+    """BDS/B3I/include/tracking.m:45-352: the GLONASS-style loop with the per-PRN 10230-chip code (:55-56),
+    the PRN ~= 0 channel test (:44), no I/Q swap (:96) and the carrier-aided code NCO centre
+    channel.codeFreq (:57, :146)."""
+    return _tracking_pf(raw, channel, s, "B3I")
+
+
+def _tracking_pf(raw: np.ndarray, channel: list, s: Settings, mode: str):
+    glo = mode == "GLO"
     nE = s.msToProcess
     out = []
     for _ in range(s.numberOfChannels):
@@ -544,19 +557,30 @@ def tracking_glo(raw: np.ndarray, channel: list, s: Settings):
         tr["VSMValue"] = np.zeros(nE // s.CNo_VSMinterval)
         tr["VSMIndex"] = np.zeros(nE // s.CNo_VSMinterval)
         out.append(tr)
-    caCode = glo_code()                                            # :88 (generateCAcode(0, codeFreqBasis, 511))
-    caCode = np.concatenate([[caCode[510]], caCode, [caCode[0]]])  # :90
+    if glo:
+        caCode = glo_code()                                        # GLO :88 (generateCAcode(0, codeFreqBasis, 511))
+        caCode = np.concatenate([[caCode[510]], caCode, [caCode[0]]])  # GLO :90
     earlyLateSpc = s.dllCorrelatorSpacing
     PDIcode = s.intTime
     tau1code, tau2code = calcLoopCoef(s.dllNoiseBandwidth, s.dllDampingRatio, 1.0)     # :104
     pf3, pf2, pf1 = calcLoopCoefCarr(s)                            # :110
     for ch in range(s.numberOfChannels):
-        if channel[ch]["status"] == "-":                           # :137
-            continue
-        tr = out[ch]
-        tr["PRN"] = channel[ch]["K"]                               # :141
+        if glo:
+            if channel[ch]["status"] == "-":                       # GLO :137
+                continue
+            tr = out[ch]
+            tr["PRN"] = channel[ch]["K"]                           # GLO :141
+            codeFreqCentre = s.codeFreqBasis
+        else:
+            if channel[ch]["PRN"] == 0:                            # B3I :44
+                continue
+            tr = out[ch]
+            tr["PRN"] = channel[ch]["PRN"]
+            code = generateB3Icode(channel[ch]["PRN"])             # B3I :55
+            caCode = np.concatenate([[code[-1]], code, [code[0]]])  # B3I :56
+            codeFreqCentre = channel[ch]["codeFreq"]               # B3I :57
         pos = 2 * (s.skipNumberOfBytes + channel[ch]["codePhase"] - 1)     # :148
-        codeFreq = s.codeFreqBasis; remCodePhase = 0.0
+        codeFreq = codeFreqCentre; remCodePhase = 0.0
         carrFreq = channel[ch]["acquiredFreq"]; carrFreqBasis = channel[ch]["acquiredFreq"]; remCarrPhase = 0.0
         oldCodeNco = oldCodeError = 0.0
         d2CarrError = dCarrError = 0.0                             # :171-172
@@ -569,7 +593,10 @@ def tracking_glo(raw: np.ndarray, channel: list, s: Settings):
             pos += chunk.size
             if chunk.size != 2 * blksize:                          # :232-236
                 return out
-            rawSignal = chunk[1::2].astype(np.float64) + 1j * chunk[0::2].astype(np.float64)   # :227 (Q + iI)
+            if glo:
+                rawSignal = chunk[1::2].astype(np.float64) + 1j * chunk[0::2].astype(np.float64)   # GLO :227 (Q + iI)
+            else:
+                rawSignal = chunk[0::2].astype(np.float64) + 1j * chunk[1::2].astype(np.float64)   # B3I :96
             tr["remCodePhase"][loopCnt - 1] = remCodePhase
             tE = colonop(remCodePhase - earlyLateSpc, codePhaseStep, (blksize - 1) * codePhaseStep + remCodePhase - earlyLateSpc)
             tL = colonop(remCodePhase + earlyLateSpc, codePhaseStep, (blksize - 1) * codePhaseStep + remCodePhase + earlyLateSpc)
@@ -599,7 +626,7 @@ def tracking_glo(raw: np.ndarray, channel: list, s: Settings):
             codeNco = oldCodeNco + (tau2code / tau1code) * (codeError - oldCodeError) + codeError * (PDIcode / tau1code)
             oldCodeNco = codeNco; oldCodeError = codeError
             tr["codeFreq"][loopCnt - 1] = codeFreq
-            codeFreq = s.codeFreqBasis - codeNco
+            codeFreq = codeFreqCentre - codeNco                    # GLO :313 codeFreqBasis ; B3I :146 channel.codeFreq
             tr["dllDiscr"][loopCnt - 1] = codeError; tr["dllDiscrFilt"][loopCnt - 1] = codeNco
             tr["pllDiscr"][loopCnt - 1] = carrError; tr["pllDiscrFilt"][loopCnt - 1] = carrNco
             tr["I_E"][loopCnt - 1] = I_E; tr["I_P"][loopCnt - 1] = I_P; tr["I_L"][loopCnt - 1] = I_L
@@ -611,3 +638,154 @@ def tracking_glo(raw: np.ndarray, channel: list, s: Settings):
                 tr["VSMIndex"][vsmCnt - 1] = loopCnt
         tr["status"] = channel[ch]["status"]
     return out
+
+
+# ===========================================================================
+# BeiDou B3I (BDS/B3I); paths below relative to /root/reference/BDS/B3I/
+# ===========================================================================
+def b3i_settings(**kw) -> Settings:
+    """initSettings.m:44-132 defaults (hot-path fields)."""
+    s = Settings(numberOfChannels=15, codeLength=10230.0, codeFreqBasis=10.23e6, acqSatelliteList=list(range(1, 64)),
+                 acqSearchBand=5000.0, acqNonCohTime=10, acqThreshold=3.0, dllNoiseBandwidth=2.0, pllNoiseBandwidth=15.0,
+                 carrFreqBasis=1268.520e6)
+    for k, v in kw.items():
+        setattr(s, k, v)
+    return s
+
+
+_B3I_INIT = [4, 11, 13, 22, 30, 36, 44, 48, 88, 104, 116, 129, 376, 418, 458, 682, 696, 707, 1078, 2069,
+             2248, 2574, 2596, 2731, 4294, 4436, 4647, 4978, 4986, 1, 5209, 5539, 6061, 6488, 7130, 7165,
+             7403, 5879, 1681, 5080, 5938, 3983, 6208, 7223, 2996, 1814, 6906, 6144, 4713, 7406, 7264, 1766,
+             5347, 3515, 7951, 7054, 3884, 6067, 4230, 3803, 869, 3683, 1205]
+_B3I_CACHE = {}
+
+
+def generateB3Icode(PRN: int) -> np.ndarray:
+    """include/generateB3Icode.m:33-86 — +-1 chips (10230)."""
+    if PRN in _B3I_CACHE:
+        return _B3I_CACHE[PRN]
+    CodeLength = 10230
+    ca_reg = -np.ones(13)
+    CA = np.zeros(CodeLength)
+    reset_state = np.array([-1] * 11 + [1, 1], dtype=np.float64)
+    for ind in range(CodeLength):                                 # :40-49
+        CA[ind] = ca_reg[-1]
+        if np.array_equal(ca_reg, reset_state):
+            ca_reg = -np.ones(13)
+        else:
+            feedback = ca_reg[0] * ca_reg[2] * ca_reg[3] * ca_reg[12]
+            ca_reg = np.roll(ca_reg, 1)
+            ca_reg[0] = feedback
+    cb_reg = -np.ones(13)
+    CB = np.zeros(CodeLength)
+    fb_pos = [0, 4, 5, 6, 8, 9, 11, 12]
+    for _ in range(_B3I_INIT[PRN - 1]):                           # :68-72
+        feedback = np.prod(cb_reg[fb_pos])
+        cb_reg = np.roll(cb_reg, 1)
+        cb_reg[0] = feedback
+    for ind in range(CodeLength):                                 # :75-80
+        CB[ind] = cb_reg[-1]
+        feedback = np.prod(cb_reg[fb_pos])
+        cb_reg = np.roll(cb_reg, 1)
+        cb_reg[0] = feedback
+    _B3I_CACHE[PRN] = CB * CA                                     # :83
+    return _B3I_CACHE[PRN]
+
+
+def makeB3ITable(PRN: int, s: Settings) -> np.ndarray:
+    """include/makeB3ITable.m:38-52."""
+    N = samples_per_code(s)
+    ts = 1 / s.samplingFreq
+    tc = 1 / s.codeFreqBasis
+    code = generateB3Icode(PRN)
+    idx = np.ceil((ts * np.arange(1, N + 1, dtype=np.float64)) / tc).astype(np.int64)
+    idx[-1] = 10230
+    return code[idx - 1]
+
+
+def read_acq_signal_b3i(raw: np.ndarray, s: Settings) -> np.ndarray:
+    """include/postProcessing.m:80-94 — max(22, acqNonCohTime+1) code periods."""
+    N = samples_per_code(s)
+    codeLen = max(22, s.acqNonCohTime + 1)
+    off = 2 * s.skipNumberOfBytes
+    data = raw[off: off + 2 * codeLen * N].astype(np.float64)
+    return data[0::2] + 1j * data[1::2]
+
+
+_NH = np.array([1, 1, 1, 1, 1, -1, 1, 1, -1, -1, 1, -1, 1, -1, 1, 1, -1, -1, -1, 1], dtype=np.float64)   # acquisition.m:127
+
+
+def acquisition_b3i(longSignal: np.ndarray, s: Settings, workers: int = 1):
+    """include/acquisition.m:107-237 (resampling branch not restated, resamplingFlag == 0)."""
+    N = samples_per_code(s)
+    ts = 1 / s.samplingFreq
+    phasePoints = np.arange(0, 2 * N, dtype=np.float64) * 2 * np.pi * ts
+    nBins = int(matlab_round(s.acqSearchBand * 2 / s.acqSearchStep)) + 1
+    coarseFreqBin = np.zeros(nBins)
+    res = dict(carrFreq=np.zeros(63), codePhase=np.zeros(63), peakMetric=np.zeros(63),
+               coarseBin=np.zeros(63, dtype=np.int64), coarseCodePhase=np.zeros(63, dtype=np.int64))
+    fineSearchStep = 25
+    numOfFineBins = int(matlab_round(s.acqSearchStep / fineSearchStep)) + 1
+    finePhasePoints = np.arange(0, 20 * N, dtype=np.float64) * 2 * np.pi * ts       # :133
+    x = longSignal[:N]
+    sigPower = math.sqrt(np.sum(np.abs(x - np.mean(x)) ** 2) / (N - 1) * N)         # :135
+    res["sigPower"] = sigPower
+    for PRN in s.acqSatelliteList:                                                    # :139
+        table = makeB3ITable(PRN, s)
+        codeFreqDom = np.conj(_FFT(np.concatenate([table, np.zeros(N)])))             # :142-146
+        results = np.zeros((nBins, 2 * N))
+        for k in range(1, nBins + 1):
+            coarseFreqBin[k - 1] = s.IF + s.acqSearchBand - s.acqSearchStep * (k - 1)
+            sigCarr = np.exp(-1j * coarseFreqBin[k - 1] * phasePoints)
+            win = np.stack([longSignal[(m - 1) * N: (m + 1) * N] for m in range(1, s.acqNonCohTime + 1)])
+            coh = np.abs(_IFFT(_FFT(sigCarr[None, :] * win, workers) * codeFreqDom[None, :], workers))
+            for m in range(coh.shape[0]):
+                results[k - 1, :] += coh[m]
+        acqCoarseBin = int(np.argmax(results.max(axis=1))) + 1                       # :164
+        colmax = results.max(axis=0)
+        codePhase = int(np.argmax(colmax)) + 1                                       # :166
+        res["peakMetric"][PRN - 1] = colmax[codePhase - 1] / sigPower / s.acqNonCohTime   # :168
+        res["coarseBin"][PRN - 1] = acqCoarseBin
+        res["coarseCodePhase"][PRN - 1] = codePhase
+        if res["peakMetric"][PRN - 1] > s.acqThreshold:                              # :170
+            code = generateB3Icode(PRN)
+            codeValueIndex = np.floor((ts * np.arange(0, 20 * N, dtype=np.float64)) / (1 / s.codeFreqBasis)).astype(np.int64)
+            code20 = code[np.fmod(codeValueIndex, int(s.codeLength))]                # :174-177
+            sig20 = longSignal[codePhase - 1: codePhase - 1 + 20 * N]                # :179
+            fineFreqBins = np.zeros(numOfFineBins)
+            fineResult = np.zeros(numOfFineBins)
+            for j in range(1, numOfFineBins + 1):
+                fineFreqBins[j - 1] = coarseFreqBin[acqCoarseBin - 1] + s.acqSearchStep / 2 - fineSearchStep * (j - 1)
+                basebandSig = sig20 * code20 * np.exp(-1j * fineFreqBins[j - 1] * finePhasePoints)
+                sumPerCode = basebandSig.reshape(20, N).sum(axis=1)                  # :188-191
+                if (1 <= PRN <= 5) or (59 <= PRN <= 63):                             # :193 GEO: 2 ms bits
+                    comPower1 = np.sum(np.abs(sumPerCode.reshape(10, 2).sum(axis=1)))
+                    comPower2 = np.sum(np.abs(sumPerCode[[0, 19]])) + np.sum(np.abs(sumPerCode[1:19].reshape(9, 2).sum(axis=1)))
+                    maxPower = max(comPower1, comPower2)
+                else:                                                                # :199 MEO/IGSO: NH code
+                    maxPower = abs(np.sum(sumPerCode * _NH))
+                    for comIndex in range(1, 20):
+                        NHshift = np.roll(_NH, comIndex)
+                        sNH = sumPerCode * NHshift
+                        comPower = abs(np.sum(sNH[:comIndex])) + abs(np.sum(sNH[comIndex:]))
+                        maxPower = max(maxPower, comPower)
+                fineResult[j - 1] = maxPower
+            maxFinBin = int(np.argmax(fineResult)) + 1
+            res["carrFreq"][PRN - 1] = fineFreqBins[maxFinBin - 1]                   # :216
+            res["codePhase"][PRN - 1] = codePhase
+            if res["carrFreq"][PRN - 1] == 0:
+                res["carrFreq"][PRN - 1] = 1
+    return res
+
+
+def preRun_b3i(acq: dict, s: Settings):
+    """include/preRun.m:44-77 — adds the carrier-aided code NCO centre channel.codeFreq (:71-73)."""
+    chans = [dict(PRN=0, acquiredFreq=0.0, codePhase=0, codeFreq=0.0, status="-") for _ in range(s.numberOfChannels)]
+    order = np.argsort(-acq["peakMetric"], kind="stable")
+    n = min(s.numberOfChannels, int(np.sum(acq["carrFreq"] != 0)))
+    for ii in range(n):
+        p = int(order[ii])
+        af = float(acq["carrFreq"][p])
+        chans[ii] = dict(PRN=p + 1, acquiredFreq=af, codePhase=int(acq["codePhase"][p]),
+                         codeFreq=s.codeFreqBasis + (af - s.IF) / s.carrFreqBasis * s.codeFreqBasis, status="T")
+    return chans

@@ -37,7 +37,14 @@ def orc_settings(s) -> OrcSettings:
                        s.acqThreshold, s.acqNonCohTime, s.skipNumberOfBytes, s.dllDampingRatio,
                        s.dllNoiseBandwidth, s.dllCorrelatorSpacing, s.pllDampingRatio, s.pllNoiseBandwidth,
                        s.intTime, s.CNo_accTime, s.CNo_VSMinterval, float(getattr(s, "freqSpacing", 0.0)),
-                       1 if float(getattr(s, "freqSpacing", 0.0)) != 0.0 else 0)
+                       oracle_mode(s))
+
+
+def oracle_mode(s) -> int:
+    """0 = GPS L1CA files, 1 = GLO_GL1/GL2, 2 = BDS B3I (the `glo` field of the C oracle's settings)."""
+    if float(getattr(s, "freqSpacing", 0.0)) != 0.0:
+        return 1
+    return 2 if int(s.codeLength) == 10230 else 0
 
 
 def to_oracle_settings(s: Settings) -> "O.Settings":
@@ -56,7 +63,7 @@ def c_acquisition(raw: np.ndarray, s, prns):
     """C oracle acquisition; raw starts at the skip point."""
     cs = orc_settings(s)
     prn = np.asarray(prns, dtype=np.int32)
-    nres = 21 if cs.glo else 32
+    nres = {0: 32, 1: 21, 2: 63}[cs.glo]
     cf, cp, pm = np.zeros(nres), np.zeros(nres), np.zeros(nres)
     cb, ccp = np.zeros(nres, dtype=np.int32), np.zeros(nres, dtype=np.int32)
     sp = C.c_double()
@@ -66,7 +73,7 @@ def c_acquisition(raw: np.ndarray, s, prns):
     return dict(carrFreq=cf, codePhase=cp, peakMetric=pm, coarseBin=cb, coarseCodePhase=ccp, sigPower=sp.value)
 
 
-def c_tracking(raw: np.ndarray, s, prn, acq_freq, code_phase, n_epochs, parallel=1):
+def c_tracking(raw: np.ndarray, s, prn, acq_freq, code_phase, n_epochs, parallel=1, code_freq0=None):
     cs = orc_settings(s)
     prn = np.asarray(prn, dtype=np.int32)
     af = np.asarray(acq_freq, dtype=np.float64)
@@ -76,7 +83,9 @@ def c_tracking(raw: np.ndarray, s, prn, acq_freq, code_phase, n_epochs, parallel
     out = np.zeros((nch, 15, n_epochs))
     vv, vi = np.zeros((nch, nv)), np.zeros((nch, nv))
     done = np.zeros(nch, dtype=np.int32)
-    orc().orc_tracking(P(raw), C.c_size_t(raw.size), C.byref(cs), nch, P(prn), P(af), P(cp), n_epochs,
+    cf0 = None if code_freq0 is None else np.ascontiguousarray(code_freq0, dtype=np.float64)
+    orc().orc_tracking(P(raw), C.c_size_t(raw.size), C.byref(cs), nch, P(prn), P(af), P(cp),
+                       P(cf0) if cf0 is not None else None, n_epochs,
                        P(out), P(vv), P(vi), P(done), parallel)
     return out, vv, vi, done
 

@@ -383,3 +383,46 @@ def test_glonass_tracking_and_wrappers_vs_oracle(tmp_path):
     live = np.array(sv) != GC_SV_NONE
     assert track_rel_err(out1[live], out8[live])["I_P"] < IQ_TOL
     eng.close()
+
+
+# ------------------------------------------------------------------------------- BeiDou B3I (BDS/B3I)
+def test_b3i_acquisition_tracking_and_wrappers_vs_oracle(tmp_path):
+    """BDS/B3I at the reference's sampling rate (18 Msps, FFT length 36000, fused 45 x 32 x 25 plan):
+    acquisition() with the NH-code / GEO fine search, preRun() with the carrier-aided code NCO centre,
+    tracking() with the 3-coefficient carrier filter, against the B3I oracle."""
+    fs, nms = 18e6, 200
+    sc = synth.default_scene_b3i(fs=fs, nsat=4, seed=9)
+    for x, p in zip(sc.sats, (3, 20, 41, 60)):           # two GEO (2 ms bits) and two NH-coded satellites
+        x.prn, x.cn0 = p, 48
+    sv = [3, 20, 41, 60, 7, 33]
+    s = init_settings("BDS_B3I", samplingFreq=fs, acqSatelliteList=sv, acqNonCohTime=5, msToProcess=nms, numberOfChannels=5)
+    so = O.b3i_settings(samplingFreq=fs, acqSatelliteList=sv, acqNonCohTime=5, msToProcess=nms, numberOfChannels=5)
+    N = 18000
+    raw = synth.make_record(sc, N * (nms + 40))
+    path = tmp_path / "b3i.bin"
+    raw.tofile(path)
+    longSignal = O.read_acq_signal_b3i(raw, so)
+    acq = acquisition(longSignal, s, verbose=True)
+    assert acq["carrFreq"].shape == (63,)
+    ref = c_acquisition(raw, so, sv)
+    _check_acq(acq, ref, sv)
+    assert {p for p in sv if acq["carrFreq"][p - 1] != 0} == {3, 20, 41, 60}
+    ch = preRun(acq, s)
+    ref_ch = O.preRun_b3i(ref, so)
+    assert [(c["PRN"], c["codeFreq"]) for c in ch] == [(c["PRN"], c["codeFreq"]) for c in ref_ch]
+    with open(path, "rb") as fid:
+        tr, _ = tracking(fid, ch, s)
+    rout, rvv, rvi, rdone = c_tracking(raw, so, [c["PRN"] for c in ch], [c["acquiredFreq"] for c in ch],
+                                       [float(c["codePhase"]) for c in ch], nms, code_freq0=[c["codeFreq"] for c in ch])
+    for i, c in enumerate(ch):
+        if c["PRN"] == 0:
+            assert tr[i]["status"] == "-" and tr[i]["epochsDone"] == 0
+            continue
+        assert tr[i]["status"] == "T" and tr[i]["epochsDone"] == nms == rdone[i]
+        assert np.array_equal(tr[i]["absoluteSample"], rout[i, 0])
+        assert tr[i]["codeFreq"][0] == c["codeFreq"]
+        sc_ = np.hypot(rout[i, 3], rout[i, 7])
+        for f, name in ((3, "I_P"), (7, "Q_P"), (4, "I_E"), (5, "I_L"), (6, "Q_E"), (8, "Q_L")):
+            assert np.max(np.abs(tr[i][name] - rout[i, f]) / sc_) < IQ_TOL, name
+        assert np.max(np.abs(tr[i]["codeFreq"] - rout[i, 1])) < 1e-4
+        assert np.allclose(tr[i]["CNo"]["VSMValue"], rvv[i], rtol=1e-5)
