@@ -50,6 +50,21 @@ cudaError_t launch_inv_rows(int L, const RowsParams& p, cudaStream_t s);
 cudaError_t launch_finish_replica(float2* Cc, size_t n, int L, cudaStream_t s);
 cudaError_t launch_inv_cols(int L, const InvColsParams& p, cudaStream_t s);
 
+// ---- correlation stage as one cluster kernel (acq_cluster.cu) ----------------------------------
+struct CorrParams {
+    const float2* X;          // [nGroups][nBins*nonCoh][C][R] wiped-off spectra per carrier grid
+    const float2* Cc;         // [nReplicas][C][R] conj(FFT(code))/L
+    const float2* tw;         // [C][R] (plans with pfa == 0)
+    int nonCoh, nBins, nSlots;
+    int nRep, repStride;      // replicas summed per SV (1, or 2 = data + pilot) and their distance in Cc
+    const int* slotReplica;   // [nSlots] first replica of the SV in list slot s
+    const int* slotGroup;     // [nSlots] carrier grid (X group) of slot s
+    float* partMax;           // [nSlots][nBins][parts]
+    int* partIdx;
+};
+constexpr int kCorrClusterParts = 4;   // partial maxima per (SV, bin): one per CTA of the largest cluster
+cudaError_t launch_corr_cluster(int L, const CorrParams& p, cudaStream_t s);
+
 // ---- generic mixed-radix path (any length whose prime factors are <= 64) --------------------
 struct GenericPlan {
     int L;                    // FFT length

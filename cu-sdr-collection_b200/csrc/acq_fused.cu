@@ -31,35 +31,13 @@
 #include "acq.h"
 #include "common.cuh"
 #include "fft_codelets.cuh"
+#include "acq_plan.cuh"
 
 namespace gc {
 
 namespace {
 
 constexpr int kRowWarps = 8;     // warps (= rows in flight) per CTA in the forward row kernel
-
-constexpr int gcd_c(int a, int b) { return b == 0 ? a : gcd_c(b, a % b); }
-
-template <int C_, int RA_, int RB_>
-struct Plan {
-    static constexpr int C = C_, RA = RA_, RB = RB_;
-    static constexpr int R = RA * RB, L = C * R;
-    static constexpr bool kPfa = gcd_c(C, R) == 1;        // no twiddle between column and row pass
-    static_assert(gcd_c(RA, RB) == 1 && RA == 32 && RB < 32, "row = 32 x RB with RB coprime to 32");
-    // row position p = a*RB + b  ->  its part of the time / lag index
-    __device__ static __forceinline__ int row_index(int p)
-    {
-        const int a = p / RB, b = p % RB;
-        return kPfa ? ((L / RA) * a + (L / RB) * b) % L     // 3-D prime-factor map: contribution to n mod L
-                    : (RB * a + RA * b) % R;                // 2-D map inside the row
-    }
-    // global time / lag index of (column index i1, row part)
-    __device__ static __forceinline__ int index(int i1, int rowPart)
-    {
-        if (kPfa) { const int n = rowPart + R * i1; return n >= L ? n - L : n; }   // rowPart < L, R*i1 < L
-        return rowPart + R * i1;
-    }
-};
 
 // ------------------------------------------------------------------ column pass (forward)
 // grid (ceil(R/128), nRows), block 128; thread = row position p.
@@ -207,7 +185,7 @@ inv_cols_kernel(InvColsParams p)
 #pragma unroll
             for (int k1 = 0; k1 < C; ++k1) x[k1] = __ldcs(base + (size_t)m * L + (size_t)k1 * R);
             codelet::dft<C, true>(x, [&](int t1, float re, float im) {
-                acc[t1] += sqrtf(fmaf(re, re, im * im));        // abs(ifft(.)) summed over blocks (:188-190)
+                acc[t1] += cabs_fast(re, im);        // abs(ifft(.)) summed over blocks (:188-190)
             });
         }
     }
@@ -284,22 +262,6 @@ struct Launch {
         return cudaGetLastError();
     }
 };
-
-using P32736 = Plan<33, 32, 31>;
-using P36000 = Plan<45, 32, 25>;
-using P24000 = Plan<30, 32, 25>;
-using P32000 = Plan<40, 32, 25>;
-using P40000 = Plan<50, 32, 25>;
-
-#define GC_PLAN_DISPATCH(LEN, CALL)                             \
-    switch (LEN) {                                              \
-        case P32736::L: return Launch<P32736>::CALL;            \
-        case P36000::L: return Launch<P36000>::CALL;            \
-        case P24000::L: return Launch<P24000>::CALL;            \
-        case P32000::L: return Launch<P32000>::CALL;            \
-        case P40000::L: return Launch<P40000>::CALL;            \
-        default: return cudaErrorInvalidValue;                  \
-    }
 
 template <class P>
 void fill_info(FusedPlanInfo* o)

@@ -1,0 +1,48 @@
+// Transform plans of the fused acquisition kernels: FFT length L = C x RA x RB (2*samplesPerCode),
+// rows R = RA x RB by the Good-Thomas prime-factor mapping, columns C against R by the prime-factor
+// mapping when gcd(C, R) = 1 and by one Cooley-Tukey twiddle otherwise (see acq_fused.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace gc {
+
+constexpr int gcd_c(int a, int b) { return b == 0 ? a : gcd_c(b, a % b); }
+
+template <int C_, int RA_, int RB_>
+struct Plan {
+    static constexpr int C = C_, RA = RA_, RB = RB_;
+    static constexpr int R = RA * RB, L = C * R;
+    static constexpr bool kPfa = gcd_c(C, R) == 1;        // no twiddle between column and row pass
+    static_assert(gcd_c(RA, RB) == 1 && RA == 32 && RB < 32, "row = 32 x RB with RB coprime to 32");
+    // row position p = a*RB + b  ->  its part of the time / lag index
+    __device__ static __forceinline__ int row_index(int p)
+    {
+        const int a = p / RB, b = p % RB;
+        return kPfa ? ((L / RA) * a + (L / RB) * b) % L     // 3-D prime-factor map: contribution to n mod L
+                    : (RB * a + RA * b) % R;                // 2-D map inside the row
+    }
+    // global time / lag index of (column index i1, row part)
+    __device__ static __forceinline__ int index(int i1, int rowPart)
+    {
+        if (kPfa) { const int n = rowPart + R * i1; return n >= L ? n - L : n; }   // rowPart < L, R*i1 < L
+        return rowPart + R * i1;
+    }
+};
+
+using P32736 = Plan<33, 32, 31>;   // 16.368 Msps, 1 ms codes
+using P36000 = Plan<45, 32, 25>;   // 18 Msps: the reference default of six signal folders
+using P24000 = Plan<30, 32, 25>;   // 12 Msps: GLONASS default
+using P32000 = Plan<40, 32, 25>;   // 16 Msps
+using P40000 = Plan<50, 32, 25>;   // 20 Msps
+
+#define GC_PLAN_DISPATCH(LEN, CALL)                             \
+    switch (LEN) {                                              \
+        case P32736::L: return Launch<P32736>::CALL;            \
+        case P36000::L: return Launch<P36000>::CALL;            \
+        case P24000::L: return Launch<P24000>::CALL;            \
+        case P32000::L: return Launch<P32000>::CALL;            \
+        case P40000::L: return Launch<P40000>::CALL;            \
+        default: return cudaErrorInvalidValue;                  \
+    }
+
+}  // namespace gc

@@ -64,6 +64,7 @@ struct gc_handle {
     int N = 0, L = 0, nBins = 0, nFine = 0, nonCoh = 0;
     double ts = 0;
     bool fused = false;
+    bool cluster = false;        // correlation stage as one cluster kernel (acq_cluster.cu); else inv_rows + inv_cols
     FusedPlanInfo fp{};
     DevBuf<float2> twFused;      // [C][R] twiddles of fused plans with a Cooley-Tukey column/row link
 
@@ -76,7 +77,7 @@ struct gc_handle {
     DevBuf<float2> twGen, X, T1, T2, Cc, W;
     DevBuf<uint64_t> dphi, fdphi;
     DevBuf<int8_t> codeTab, chips;
-    DevBuf<int> prnList, partIdx, fineCodePhase, fineBest, fineSv;
+    DevBuf<int> prnList, slotGroup, partIdx, fineCodePhase, fineBest, fineSv;
     DevBuf<float> partMax;
     DevBuf<PeakOut> peaks;
     DevBuf<double> sigPower, fineSums, fineResult;
@@ -263,11 +264,17 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     h->nonCoh = cfg->acq_noncoh_time;
     h->fused = fused_plan_info(h->L, &h->fp) && !getenv("GC_FORCE_GENERIC");
     h->stats.fft_len = h->L;
-    h->stats.acq_path = h->fused ? 1 : 0;   // 1 = fused C x 32 x RB plan, 0 = generic mixed-radix passes
+    {   // GC_ACQ_PATH=cluster selects the one-kernel correlation stage (acq_cluster.cu, transform resident
+        // in a cluster's shared memory); the default is inverse rows + inverse columns through a work buffer
+        const char* e = getenv("GC_ACQ_PATH");
+        h->cluster = h->fused && e && strcmp(e, "cluster") == 0;
+    }
+    h->stats.acq_path = h->cluster ? 2 : h->fused ? 1 : 0;   // 2 = fused plan + cluster correlation kernel, 1 = fused plan, split
+                                                             // correlation stage, 0 = generic mixed-radix passes
 
     auto setup = [&]() -> int {
         if (h->fused) {
-            h->parts = h->fp.parts;
+            h->parts = h->cluster ? kCorrClusterParts : h->fp.parts;
             if (!h->fp.pfa) {   // w_L^(j1 * m(p)), row position p = a*RB + b <-> m = (RB*a + RA*b) mod R
                 const FusedPlanInfo& f = h->fp;
                 std::vector<float2> tw((size_t)f.C * f.R);
@@ -316,7 +323,7 @@ void gc_destroy(gc_handle* h)
     h->twGen.release(); h->X.release(); h->T1.release(); h->T2.release();
     h->chipIdx.release(); h->twFused.release();
     h->Cc.release(); h->W.release(); h->dphi.release(); h->fdphi.release(); h->codeTab.release(); h->chips.release();
-    h->prnList.release(); h->partIdx.release(); h->fineCodePhase.release(); h->fineBest.release(); h->fineSv.release(); h->partMax.release();
+    h->prnList.release(); h->slotGroup.release(); h->partIdx.release(); h->fineCodePhase.release(); h->fineBest.release(); h->fineSv.release(); h->partMax.release();
     h->peaks.release(); h->sigPower.release(); h->fineSums.release(); h->fineResult.release(); h->fineProd.release();
     h->chans.release(); h->trackCodes.release(); h->trackOut.release(); h->epochsDone.release();
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
@@ -397,14 +404,57 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
     GC_CUDA(h, h->partIdx.reserve((size_t)nSv * nBins * h->parts));
     GC_CUDA(h, h->peaks.reserve(nSv));
     GC_CUDA(h, h->sigPower.reserve(1));
-    GC_CUDA(h, h->X.reserve((size_t)nKm * L));
-    GC_CUDA(h, h->dphi.reserve(nBins));
+    // carrier grids: runs of list slots with the same offset
+    std::vector<int> groupStart;
+    std::vector<int> slotGroup(nSv);
+    for (int s = 0; s < nSv; ++s) {
+        if (s == 0 || sv_freq_offset(h, svList[order[s]]) != sv_freq_offset(h, svList[order[s - 1]])) groupStart.push_back(s);
+        slotGroup[s] = (int)groupStart.size() - 1;
+    }
+    const int nGroups = (int)groupStart.size();
+    groupStart.push_back(nSv);
+    GC_CUDA(h, h->X.reserve((size_t)(h->cluster ? nGroups : 1) * nKm * L));
+    GC_CUDA(h, h->dphi.reserve((size_t)nGroups * nBins));
     std::vector<std::vector<double>> coarseFreqOf(nSv);   // per list slot: the bin frequencies it was searched on
 
     const int e0 = mark();
     GC_CUDA(h, launch_sig_power(h->rec, winStart, N, h->sigPower.p, st)); ++launches;   // :151
     mark();                                           // event 1 (re-recorded at the end of the coarse search)
-    for (int g0 = 0; g0 < nSv;) {
+    if (h->cluster) {
+        // forward spectra of every carrier grid, then the whole SV x bin grid in one cluster launch
+        std::vector<uint64_t> dphi((size_t)nGroups * nBins);
+        for (int gi = 0; gi < nGroups; ++gi) {
+            const double off = sv_freq_offset(h, svList[order[groupStart[gi]]]);
+            std::vector<double> coarseFreq(nBins);
+            for (int k = 0; k < nBins; ++k) {
+                coarseFreq[k] = (c.IF + off) + c.acq_search_band - c.acq_search_step * k;   // :169 (GLO :181-182)
+                dphi[(size_t)gi * nBins + k] = turns_to_fix(coarseFreq[k] * h->ts);
+            }
+            for (int s = groupStart[gi]; s < groupStart[gi + 1]; ++s) coarseFreqOf[s] = coarseFreq;
+        }
+        GC_CUDA(h, cudaMemcpyAsync(h->dphi.p, dphi.data(), dphi.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        GC_CUDA(h, upload(h->slotGroup, slotGroup, st));
+        const int f0 = mark();
+        for (int gi = 0; gi < nGroups; ++gi) {
+            FwdColsParams fp{};
+            fp.rec = h->rec; fp.winStart = winStart; fp.N = N; fp.nonCoh = nonCoh; fp.swapIQ = h->glo ? 1 : 0;
+            fp.dphi = h->dphi.p + (size_t)gi * nBins; fp.out = h->X.p + (size_t)gi * nKm * L; fp.tw = h->twFused.p;
+            GC_CUDA(h, launch_fwd_cols(L, fp, nKm, false, st)); ++launches;
+        }
+        RowsParams rp{};
+        rp.X = h->X.p; rp.nRows = (long long)nGroups * nKm * h->fp.C;
+        GC_CUDA(h, launch_fwd_rows(L, rp, st)); ++launches;
+        const int f1 = mark();
+        fwdEv.push_back({f0, f1});
+        CorrParams cp{};
+        cp.X = h->X.p; cp.Cc = h->Cc.p; cp.tw = h->twFused.p;
+        cp.nonCoh = nonCoh; cp.nBins = nBins; cp.nSlots = nSv; cp.nRep = 1; cp.repStride = 0;
+        cp.slotReplica = h->prnList.p; cp.slotGroup = h->slotGroup.p;
+        cp.partMax = h->partMax.p; cp.partIdx = h->partIdx.p;
+        GC_CUDA(h, launch_corr_cluster(L, cp, st)); ++launches;
+        rowEv.push_back({f1, mark()}); ++nRowLaunches;
+    }
+    for (int g0 = 0; g0 < nSv && !h->cluster;) {
         int g1 = g0 + 1;
         const double off = sv_freq_offset(h, svList[order[g0]]);
         while (g1 < nSv && sv_freq_offset(h, svList[order[g1]]) == off) ++g1;

@@ -38,6 +38,20 @@ def test_config_struct_layout_matches_header():
     assert names == [f for f, _ in engine.gc_stats._fields_]
 
 
+def test_generated_codelets_match_direct_dft(tmp_path):
+    """The packed-fp32x2 register DFT codelets (tools/gen_codelets.py -> csrc/fft_codelets.cuh) compiled for
+    the host with stub intrinsics: every length, forward and inverse, against a float64 direct DFT."""
+    exe = str(tmp_path / "codelet_host_check")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", os.path.join(ROOT, "cu-sdr-collection_b200", "csrc"),
+                           "-o", exe, os.path.join(ROOT, "tests", "host_src", "codelet_host_check.cpp")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert out.stdout.count("max err") == 8
+    gen = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_codelets.py")], capture_output=True, text=True, check=True)
+    assert gen.stdout == open(os.path.join(ROOT, "cu-sdr-collection_b200", "csrc", "fft_codelets.cuh")).read(), \
+        "fft_codelets.cuh is stale: regenerate with tools/gen_codelets.py"
+
+
 def test_no_gpu_means_loud_failure_not_fallback():
     import torch
     if torch.cuda.is_available():

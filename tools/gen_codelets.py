@@ -1,16 +1,25 @@
 #!/usr/bin/env python3
-"""Generates cu-sdr-collection_b200/csrc/fft_codelets.cuh: straight-line register DFT codelets.
+"""Generates cu-sdr-collection_b200/csrc/fft_codelets.cuh: straight-line register DFT codelets
+written in Blackwell's packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2).
+
+A complex value is one float2 = one 64-bit register pair, so a complex add is ONE FADD2 and
+"real constant times complex, accumulate" is ONE FFMA2 with a literal broadcast scalar.  The packed
+instructions carry operand swizzles (`.LO_HI`, per-half negate), so a + i*b, a - i*b and a - b are
+single instructions as well, and a multiplication by a literal complex twiddle is two
+(FMUL2 by the real part, FFMA2 of the rotated value by the imaginary part).  The FMA pipe does
+the same number of lane operations as the scalar form, but every floating-point instruction
+takes one issue slot instead of two - and the issue slot is what bounds the transform kernels
+(profiles/: 71 % issue-active against 62 % FMA pipe for the scalar codelets).
 
 Every codelet works on a register array ``float2 (&x)[N]`` and hands each output to a functor
-``emit(k, re, im)`` with a literal output index ``k`` (so stores/accumulations are resolved at
-compile time after inlining).  All twiddles are literal constants, which lets ptxas use the
-immediate form of FFMA.
+``emit(k, re, im)`` with a literal output index ``k``.  The code is emitted in SSA form (every
+intermediate is a fresh ``const float2``); all index maps are resolved at generation time.
 
-  * odd primes P: direct DFT using the (x_j + x_{P-j}, x_j - x_{P-j}) symmetry - 4*((P-1)/2)^2 FMAs
-  * powers of two: radix-2 decimation-in-frequency network, trivial twiddles special-cased
-  * composites: recursive - coprime factors by the Good-Thomas prime-factor mapping (no twiddles),
-    repeated factors (9 = 3x3, 25 = 5x5) by Cooley-Tukey with literal twiddles; all index maps are
-    resolved at generation time, so the emitted code is flat register arithmetic.
+  * odd primes P: direct DFT with the (x_j + x_{P-j}, x_j - x_{P-j}) symmetry:
+    A_k = x_0 + sum_j cos(2 pi jk/P) s_j,  B_k = sum_j sin(2 pi jk/P) d_j,  X_k = A_k -/+ i B_k
+  * powers of two: radix-2 decimation in time (a +/- w*b as two FFMA2 chains; w = 1, -i free)
+  * composites: coprime factors by the Good-Thomas prime-factor mapping (no twiddles), repeated
+    factors (9 = 3x3, 25 = 5x5) by Cooley-Tukey with literal twiddles.
 
 Run:  python tools/gen_codelets.py > cu-sdr-collection_b200/csrc/fft_codelets.cuh
 """
@@ -18,16 +27,11 @@ import math
 import sys
 
 OUT = []
-_uid = [0]
+_n = [0]
 
 
 def w(s=""):
     OUT.append(s)
-
-
-def uid():
-    _uid[0] += 1
-    return f"t{_uid[0]}_"
 
 
 def lit(v):
@@ -36,20 +40,19 @@ def lit(v):
     return repr(float(format(v, ".9g"))) + "f"
 
 
+def new(expr):
+    _n[0] += 1
+    name = f"v{_n[0]}"
+    w(f"    const float2 {name} = {expr};")
+    return name
+
+
 def is_pow2(n):
     return n & (n - 1) == 0
 
 
 def is_prime(n):
     return n > 1 and all(n % p for p in range(2, int(n ** 0.5) + 1))
-
-
-def bitrev(i, n):
-    r = 0
-    for _ in range(n.bit_length() - 1):
-        r = (r << 1) | (i & 1)
-        i >>= 1
-    return r
 
 
 def split(n):
@@ -72,150 +75,116 @@ def split(n):
     return p, n // p, False
 
 
-def prime_block(P, slots, inv, omap):
-    """DFT of odd prime length P over x[slots[j]].  omap = list -> emit(omap[k]); None -> in place
-    (returns pos with x[slots[pos[k]]] holding output k)."""
-    tag = uid()
+def cmul_const(v, wr, wi):
+    """v * (wr + i*wi) with literal wr, wi."""
+    if abs(wi) < 1e-15:
+        if abs(wr - 1) < 1e-15:
+            return v
+        return new(f"f2scale({v}, {lit(wr)})")
+    if abs(wr) < 1e-15:
+        return new(f"f2scale(f2rot({v}), {lit(wi)})")
+    return new(f"f2cmulc({v}, {lit(wr)}, {lit(wi)})")
+
+
+def prime_block(P, vals, inv):
     h = (P - 1) // 2
-    X = [f"x[{i}]" for i in slots]
-    w(f"    {{ // DFT-{P} ({'inv' if inv else 'fwd'}) on slots {slots}")
+    s = [None] + [new(f"f2add({vals[j]}, {vals[P - j]})") for j in range(1, h + 1)]
+    d = [None] + [new(f"f2sub({vals[j]}, {vals[P - j]})") for j in range(1, h + 1)]
+    out = [None] * P
+    acc = vals[0]
     for j in range(1, h + 1):
-        a, b = X[j], X[P - j]
-        w(f"        {{ const float2 t = {a}; {a}.x = t.x + {b}.x; {a}.y = t.y + {b}.y; "
-          f"{b}.x = t.x - {b}.x; {b}.y = t.y - {b}.y; }}")
-    sr = " + ".join([f"{X[0]}.x"] + [f"{X[j]}.x" for j in range(1, h + 1)])
-    si = " + ".join([f"{X[0]}.y"] + [f"{X[j]}.y" for j in range(1, h + 1)])
-    outs = {}
-    w(f"        const float {tag}r0 = {sr};")
-    w(f"        const float {tag}i0 = {si};")
-    outs[0] = (f"{tag}r0", f"{tag}i0")
+        acc = new(f"f2add({acc}, {s[j]})")
+    out[0] = acc
     for k in range(1, h + 1):
-        ar, ai, br, bi = f"{tag}ar{k}", f"{tag}ai{k}", f"{tag}br{k}", f"{tag}bi{k}"
-        w(f"        float {ar} = {X[0]}.x, {ai} = {X[0]}.y, {br}, {bi};")
+        a = vals[0]
+        b = None
         for j in range(1, h + 1):
             q = (j * k) % P
             c = math.cos(2 * math.pi * q / P)
-            s = math.sin(2 * math.pi * q / P)
-            w(f"        {ar} = fmaf({X[j]}.x, {lit(c)}, {ar}); {ai} = fmaf({X[j]}.y, {lit(c)}, {ai});")
-            if j == 1:
-                w(f"        {br} = {X[P - j]}.x * {lit(s)}; {bi} = {X[P - j]}.y * {lit(s)};")
-            else:
-                w(f"        {br} = fmaf({X[P - j]}.x, {lit(s)}, {br}); {bi} = fmaf({X[P - j]}.y, {lit(s)}, {bi});")
-        lo = (f"{ar} + {bi}", f"{ai} - {br}")      # forward: X_k = A - iB ; X_{P-k} = A + iB
-        hi = (f"{ar} - {bi}", f"{ai} + {br}")
+            sn = math.sin(2 * math.pi * q / P)
+            a = new(f"f2fma({s[j]}, {lit(c)}, {a})")
+            b = new(f"f2scale({d[j]}, {lit(sn)})") if b is None else new(f"f2fma({d[j]}, {lit(sn)}, {b})")
+        lo = new(f"f2subi({a}, {b})")        # A - iB: forward X_k, inverse X_{P-k}
+        hi = new(f"f2addi({a}, {b})")
         if inv:
             lo, hi = hi, lo
-        outs[k] = lo
-        outs[P - k] = hi
-        if omap is not None:
-            w(f"        emit({omap[k]}, {lo[0]}, {lo[1]});")
-            w(f"        emit({omap[P - k]}, {hi[0]}, {hi[1]});")
-    if omap is not None:
-        w(f"        emit({omap[0]}, {tag}r0, {tag}i0);")
-        w("    }")
-        return None
-    for k in range(P):
-        w(f"        const float {tag}yr{k} = {outs[k][0]}, {tag}yi{k} = {outs[k][1]};")
-    for k in range(P):
-        w(f"        {X[k]}.x = {tag}yr{k}; {X[k]}.y = {tag}yi{k};")
-    w("    }")
-    return list(range(P))
+        out[k] = lo
+        out[P - k] = hi
+    return out
 
 
-def pow2_block(N, slots, inv, omap):
-    """radix-2 DIF network in place over x[slots[i]]; x[slots[i]] ends holding X[bitrev(i)]."""
+def bitrev(i, bits):
+    r = 0
+    for _ in range(bits):
+        r = (r << 1) | (i & 1)
+        i >>= 1
+    return r
+
+
+def pow2_block(N, vals, inv):
+    """radix-2 decimation in time."""
     sgn = 1.0 if inv else -1.0
-    X = [f"x[{i}]" for i in slots]
-    span = N // 2
-    w(f"    // DFT-{N} ({'inv' if inv else 'fwd'}) radix-2 DIF on slots {slots}")
-    while span >= 1:
-        for g in range(0, N, 2 * span):
-            for j in range(span):
-                a, b = X[g + j], X[g + j + span]
-                ang = sgn * 2 * math.pi * j / (2 * span)
-                wr, wi = math.cos(ang), math.sin(ang)
-                w(f"    {{ const float tr = {a}.x - {b}.x, ti = {a}.y - {b}.y; {a}.x += {b}.x; {a}.y += {b}.y;")
-                if j == 0:
-                    w(f"      {b}.x = tr; {b}.y = ti; }}")
-                elif 4 * j == 2 * span:      # w = -i (fwd) / +i (inv)
+    bits = N.bit_length() - 1
+    cur = [vals[bitrev(i, bits)] for i in range(N)]
+    half = 1
+    while half < N:
+        nxt = list(cur)
+        for g in range(0, N, 2 * half):
+            for j in range(half):
+                a, b = cur[g + j], cur[g + j + half]
+                num, den = j, 2 * half                     # w = exp(sgn * 2 pi i * j / (2*half))
+                if num == 0:
+                    nxt[g + j] = new(f"f2add({a}, {b})")
+                    nxt[g + j + half] = new(f"f2sub({a}, {b})")
+                elif 4 * num == den:                       # w = -i (fwd) / +i (inv)
                     if inv:
-                        w(f"      {b}.x = -ti; {b}.y = tr; }}")
+                        nxt[g + j] = new(f"f2addi({a}, {b})")
+                        nxt[g + j + half] = new(f"f2subi({a}, {b})")
                     else:
-                        w(f"      {b}.x = ti; {b}.y = -tr; }}")
-                elif 8 * j == 2 * span or 8 * j == 3 * 2 * span:
-                    r2 = lit(math.sqrt(0.5))
-                    re = f"({'' if wr > 0 else '-'}tr {'-' if wi > 0 else '+'} ti) * {r2}"
-                    im = f"({'' if wi > 0 else '-'}tr {'+' if wr > 0 else '-'} ti) * {r2}"
-                    w(f"      {b}.x = {re}; {b}.y = {im}; }}")
+                        nxt[g + j] = new(f"f2subi({a}, {b})")
+                        nxt[g + j + half] = new(f"f2addi({a}, {b})")
                 else:
-                    w(f"      {b}.x = fmaf(tr, {lit(wr)}, -ti * {lit(wi)}); {b}.y = fmaf(tr, {lit(wi)}, ti * {lit(wr)}); }}")
-        span //= 2
-    pos = [0] * N
-    for i in range(N):
-        pos[bitrev(i, N)] = i
-    if omap is not None:
-        for k in range(N):
-            w(f"    emit({omap[k]}, {X[pos[k]]}.x, {X[pos[k]]}.y);")
-        return None
-    return pos
+                    ang = sgn * 2 * math.pi * num / den
+                    wr, wi = math.cos(ang), math.sin(ang)
+                    nxt[g + j] = new(f"f2bfly({a}, {b}, {lit(wr)}, {lit(wi)})")
+                    nxt[g + j + half] = new(f"f2bfly({a}, {b}, {lit(-wr)}, {lit(-wi)})")
+        cur = nxt
+        half *= 2
+    return cur
 
 
-def gen(N, slots, inv, omap):
-    """DFT-N over x[slots[n]], n = 0..N-1.  omap: emit outputs as emit(omap[k], ..); None: in place,
-    returns pos (x[slots[pos[k]]] = output k)."""
+def dft(N, vals, inv):
+    """DFT-N of the SSA values vals[0..N-1]; returns the outputs in natural order."""
     if N == 1:
-        if omap is not None:
-            w(f"    emit({omap[0]}, x[{slots[0]}].x, x[{slots[0]}].y);")
-            return None
-        return [0]
+        return list(vals)
     if is_pow2(N):
-        return pow2_block(N, slots, inv, omap)
+        return pow2_block(N, vals, inv)
     if is_prime(N):
-        return prime_block(N, slots, inv, omap)
+        return prime_block(N, vals, inv)
     n1, n2, coprime = split(N)
     sgn = 1.0 if inv else -1.0
+    out = [None] * N
     if coprime:
         # Good-Thomas: n = (n2*a + n1*b) mod N ; k = (c1*k1 + c2*k2) mod N
         c1 = n2 * pow(n2, -1, n1) % N
         c2 = n1 * pow(n1, -1, n2) % N
-        pos1 = {}
-        for b in range(n2):
-            sub = [slots[(n2 * a + n1 * b) % N] for a in range(n1)]
-            pos1[b] = gen(n1, sub, inv, None)
-        out_pos = [None] * N
+        cols = [dft(n1, [vals[(n2 * a + n1 * b) % N] for a in range(n1)], inv) for b in range(n2)]
         for k1 in range(n1):
-            sub = [slots[(n2 * pos1[b][k1] + n1 * b) % N] for b in range(n2)]
-            if omap is not None:
-                gen(n2, sub, inv, [omap[(c1 * k1 + c2 * k2) % N] for k2 in range(n2)])
-            else:
-                p2 = gen(n2, sub, inv, None)
-                for k2 in range(n2):
-                    b = p2[k2]
-                    out_pos[(c1 * k1 + c2 * k2) % N] = (n2 * pos1[b][k1] + n1 * b) % N
-        return None if omap is not None else out_pos
-    # Cooley-Tukey with literal twiddles: n = n2*a + b ; k = k1 + n1*k2
-    pos1 = {}
-    for b in range(n2):
-        sub = [slots[n2 * a + b] for a in range(n1)]
-        pos1[b] = gen(n1, sub, inv, None)
-    for b in range(1, n2):
-        for k1 in range(1, n1):
-            ang = sgn * 2 * math.pi * k1 * b / N
-            wr, wi = math.cos(ang), math.sin(ang)
-            s = f"x[{slots[n2 * pos1[b][k1] + b]}]"
-            w(f"    {{ const float tr = {s}.x, ti = {s}.y; {s}.x = fmaf(tr, {lit(wr)}, -ti * {lit(wi)}); "
-              f"{s}.y = fmaf(tr, {lit(wi)}, ti * {lit(wr)}); }}")
-    out_pos = [None] * N
-    for k1 in range(n1):
-        sub = [slots[n2 * pos1[b][k1] + b] for b in range(n2)]
-        if omap is not None:
-            gen(n2, sub, inv, [omap[k1 + n1 * k2] for k2 in range(n2)])
-        else:
-            p2 = gen(n2, sub, inv, None)
+            row = dft(n2, [cols[b][k1] for b in range(n2)], inv)
             for k2 in range(n2):
-                b = p2[k2]
-                out_pos[k1 + n1 * k2] = n2 * pos1[b][k1] + b
-    return None if omap is not None else out_pos
+                out[(c1 * k1 + c2 * k2) % N] = row[k2]
+        return out
+    # Cooley-Tukey with literal twiddles: n = n2*a + b ; k = k1 + n1*k2
+    cols = [dft(n1, [vals[n2 * a + b] for a in range(n1)], inv) for b in range(n2)]
+    for k1 in range(n1):
+        rowin = []
+        for b in range(n2):
+            ang = sgn * 2 * math.pi * k1 * b / N
+            rowin.append(cmul_const(cols[b][k1], math.cos(ang), math.sin(ang)))
+        row = dft(n2, rowin, inv)
+        for k2 in range(n2):
+            out[k1 + n1 * k2] = row[k2]
+    return out
 
 
 def gen_codelet(N):
@@ -223,19 +192,46 @@ def gen_codelet(N):
         nm = f"dft{N}_{'inv' if inv else 'fwd'}"
         w(f"template <class F> __device__ __forceinline__ void {nm}(float2 (&x)[{N}], F&& emit)")
         w("{")
-        gen(N, list(range(N)), inv, list(range(N)))
+        res = dft(N, [f"x[{i}]" for i in range(N)], inv)
+        for k in range(N):
+            w(f"    emit({k}, {res[k]}.x, {res[k]}.y);")
         w("}")
         w()
 
 
+PRELUDE = r"""
+// packed fp32x2 primitives (one instruction each on sm_100a; the swizzled / negated operands fold
+// into the FADD2 / FFMA2 operand modifiers)
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 f2addi(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.y, b.x)); }   // a + i*b
+__device__ __forceinline__ float2 f2subi(float2 a, float2 b) { return __fadd2_rn(a, make_float2(b.y, -b.x)); }   // a - i*b
+__device__ __forceinline__ float2 f2rot(float2 a) { return make_float2(-a.y, a.x); }                              // i*a
+__device__ __forceinline__ float2 f2scale(float2 a, float c) { return __fmul2_rn(a, make_float2(c, c)); }
+__device__ __forceinline__ float2 f2fma(float2 a, float c, float2 b) { return __ffma2_rn(a, make_float2(c, c), b); }   // a*c + b
+// t * (wr + i*wi)
+__device__ __forceinline__ float2 f2cmulc(float2 t, float wr, float wi)
+{
+    return __ffma2_rn(f2rot(t), make_float2(wi, wi), __fmul2_rn(t, make_float2(wr, wr)));
+}
+// a + b * (wr + i*wi)
+__device__ __forceinline__ float2 f2bfly(float2 a, float2 b, float wr, float wi)
+{
+    return __ffma2_rn(f2rot(b), make_float2(wi, wi), __ffma2_rn(b, make_float2(wr, wr), a));
+}
+"""
+
+
 def main():
-    w("// GENERATED by tools/gen_codelets.py - do not edit.  Register DFT codelets (fp32).")
+    w("// GENERATED by tools/gen_codelets.py - do not edit.  Register DFT codelets in packed fp32x2 arithmetic.")
     w("#pragma once")
+    w("#ifndef CODELET_HOST_CHECK   // tests/test_host.py compiles this header for the host with stub intrinsics")
     w("#include <cuda_runtime.h>")
+    w("#endif")
     w()
     w("namespace gc { namespace codelet {")
-    w()
-    sizes = (2, 3, 4, 5, 7, 8, 9, 11, 13, 16, 25, 30, 31, 32, 33, 40, 45, 50)
+    w(PRELUDE)
+    sizes = (25, 30, 31, 32, 33, 40, 45, 50)
     for N in sizes:
         gen_codelet(N)
     w("// compile-time dispatch: dft<N, INV>(x, emit)")
