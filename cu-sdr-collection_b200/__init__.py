@@ -6,7 +6,7 @@ The compute lives in ``libgnsscorr.so`` (hand-written sm_100a CUDA behind the C 
 interface for that path: same function names, argument meaning and result fields.  There is
 no CPU fallback: every compute call raises if the library or a B200 is missing.
 """
-from .settings import Settings, init_settings            # noqa: F401
+from .settings import Settings, init_settings, num_to_process   # noqa: F401
 from .engine import Engine, GnssCorrError, lib_path       # noqa: F401
 from .acquisition import acquisition                      # noqa: F401
 from .tracking import tracking, TRACK_FIELDS              # noqa: F401

@@ -98,3 +98,42 @@ def b3i_code(prn: int) -> np.ndarray:
         out[i] = -1 if (b[12] ^ ca[i]) else 1
         b = step(b, (1, 5, 6, 7, 9, 10, 12, 13))
     return out
+
+
+# ---- Galileo E1 memory codes -------------------------------------------------------------------------
+# The E1-B / E1-C primary codes are ICD tables, not LFSR output; the reference keeps them as data files
+# next to its sources and reads them at run time (GAL/GAL_E1C/include/generateE1Bcode.m:44-55,
+# generateE1Ccode.m).  The engine therefore takes them from the caller (gc_set_code).
+def load_e1_codes(code_dir: str) -> dict:
+    """{PRN: (e1b, e1c)} for PRN 1..50 from ``E1b.dat`` / ``E1c.dat`` in ``code_dir`` (the format the reference
+    reads with fscanf '%d': 50 x 4092 whitespace-separated 0/1 digits); values are the +-1 primary chips
+    ``1 - 2*bit`` (generateE1Bcode.m:55)."""
+    import os
+    tabs = []
+    for name in ("E1b.dat", "E1c.dat"):
+        with open(os.path.join(code_dir, name)) as f:
+            v = np.array(f.read().split(), dtype=np.int8)
+        if v.size < 50 * 4092:
+            raise ValueError(f"{name}: expected 50 x 4092 digits, found {v.size}")
+        tabs.append((1 - 2 * v[: 50 * 4092]).astype(np.int8).reshape(50, 4092))
+    return {prn: (tabs[0][prn - 1], tabs[1][prn - 1]) for prn in range(1, 51)}
+
+
+def standin_e1_codes(seed: int = 20260101) -> dict:
+    """Seeded random +-1 tables with the shape of the E1 memory codes, for synthetic records where the real
+    tables are not at hand (tests and benchmarks on the GPU box): {PRN: (e1b, e1c)}."""
+    rng = np.random.default_rng(seed)
+    t = (1 - 2 * rng.integers(0, 2, size=(2, 50, 4092))).astype(np.int8)
+    return {prn: (t[0, prn - 1], t[1, prn - 1]) for prn in range(1, 51)}
+
+
+def boc11(primary: np.ndarray) -> np.ndarray:
+    """BOC(1,1) sub-chips [c -c] of a +-1 primary code (generateE1Bcode.m:58-64)."""
+    out = np.empty(2 * primary.size, dtype=np.int8)
+    out[0::2] = primary
+    out[1::2] = -primary
+    return out
+
+
+E1_SECONDARY = np.array([1, 1, -1, -1, -1, 1, 1, 1, 1, 1, 1, 1, -1, 1, -1, 1, -1, -1, 1, -1, -1, 1, 1, -1, 1],
+                        dtype=np.int8)     # CS25 '380AD90', antipodal (GAL_E1C/include/acquisition.m:135)

@@ -79,7 +79,8 @@ cudaError_t launch_generic_wipe(const int8_t* rec, long long winStart, int N, in
                                 const uint64_t* dphi, float2* out, int L, cudaStream_t st);
 cudaError_t launch_generic_code(const int8_t* codeTab, int N, int nPrn, float2* out, int L, cudaStream_t st);
 cudaError_t launch_generic_mul(const float2* X, const float2* Cc, float2* out, int L, long long nKm, cudaStream_t st);
-cudaError_t launch_generic_absacc(const float2* W, int L, int nBins, int nonCoh, int parts,
+// W2 != nullptr: second replica of a data + pilot pair, abs(ifft(.)) of both summed (GAL_E1C acquisition.m:192)
+cudaError_t launch_generic_absacc(const float2* W, const float2* W2, int L, int nBins, int nonCoh, int parts,
                                   float* partMax, int* partIdx, size_t outBase, cudaStream_t st);
 cudaError_t launch_generic_conj_scale(float2* Cc, size_t n, float scale, cudaStream_t st);
 
@@ -103,6 +104,7 @@ struct FineParams {
     int swapIQ;               // GLONASS I/Q swap
     int combine;              // 0: max_c |sum of 20 codes| (acquisition.m:243-248); 1: |sum of 10 - sum of next 10| (GLO :246-252);
                               // 2: B3I NH-code / GEO 2-ms-bit search over 20 codes (BDS/B3I/include/acquisition.m:193-211)
+                              // 3: Galileo E1 25-chip secondary code, 25 alignments (GAL_E1C/include/acquisition.m:236-252)
     const int* svId;          // [nAcq] PRN of each acquired SV (combine 2 depends on it)
     const int16_t* chipIdx;   // [nPeriods*N] sample -> chip index of the 40 ms replica (host table, :215-218)
     const int8_t* chips;      // [nAcq][codeLen] +-1 chips of the acquired PRNs

@@ -156,7 +156,25 @@ __global__ void fine_select_kernel(FineParams p)
     for (int j = threadIdx.x; j < p.nFine; j += blockDim.x) {
         const double* s = p.sums + ((size_t)a * p.nFine + j) * p.nPeriods * 2;
         double maxPower = 0;
-        if (p.combine == 2) {
+        if (p.combine == 3) {
+            // Galileo E1: 25 code periods against the 25-chip pilot secondary code '380AD90', aligned and at
+            // the 24 other edges (GAL_E1C/include/acquisition.m:135, 236-252)
+            const double SEC[25] = {1, 1, -1, -1, -1, 1, 1, 1, 1, 1, 1, 1, -1, 1, -1, 1, -1, -1, 1, -1, -1, 1, 1, -1, 1};
+            double r = 0, i = 0;
+            for (int q = 0; q < 25; ++q) { r += s[2 * q] * SEC[q]; i += s[2 * q + 1] * SEC[q]; }
+            maxPower = hypot(r, i);
+            for (int c = 1; c <= 24; ++c) {
+                // code2ndShift = circshift(secondaryCode', c)': element q takes SEC[(q - c) mod 25]
+                double r1 = 0, i1 = 0, r2 = 0, i2 = 0;
+                for (int q = 0; q < 25; ++q) {
+                    const double sc = SEC[(q - c + 25) % 25];
+                    if (q < c) { r1 += s[2 * q] * sc; i1 += s[2 * q + 1] * sc; }
+                    else { r2 += s[2 * q] * sc; i2 += s[2 * q + 1] * sc; }
+                }
+                const double pw = hypot(r1, i1) + hypot(r2, i2);
+                if (pw > maxPower) maxPower = pw;
+            }
+        } else if (p.combine == 2) {
             const int prn = p.svId[a];
             if ((prn >= 1 && prn <= 5) || (prn >= 59 && prn <= 63)) {               // :193-198
                 double c1 = 0, c2 = 0;

@@ -87,7 +87,7 @@ __global__ void conj_scale_kernel(float2* Cc, size_t n, float scale)
 
 // results(k,:) = sum_m abs(W[k][m][:]) and the per-tile maximum / first arg-max (:188-198)
 __global__ void __launch_bounds__(256)
-absacc_kernel(const float2* W, int L, int nonCoh, int parts, float* partMax, int* partIdx, size_t outBase)
+absacc_kernel(const float2* W, const float2* W2, int L, int nonCoh, int parts, float* partMax, int* partIdx, size_t outBase)
 {
     const int k = blockIdx.y, part = blockIdx.x;
     const int per = (L + parts - 1) / parts;
@@ -97,7 +97,12 @@ absacc_kernel(const float2* W, int L, int nonCoh, int parts, float* partMax, int
         float acc = 0.f;
         for (int m = 0; m < nonCoh; ++m) {
             const float2 v = W[((size_t)k * nonCoh + m) * L + n];
-            acc += sqrtf(fmaf(v.x, v.x, v.y * v.y));
+            float coh = sqrtf(fmaf(v.x, v.x, v.y * v.y));
+            if (W2) {                                       // abs(ifft(convE1bIQ)) + abs(ifft(convE1cIQ)), GAL_E1C acquisition.m:192
+                const float2 u = W2[((size_t)k * nonCoh + m) * L + n];
+                coh += sqrtf(fmaf(u.x, u.x, u.y * u.y));
+            }
+            acc += coh;
         }
         if (acc > best) { best = acc; bidx = n; }      // n ascending per thread: first max kept
     }
@@ -162,11 +167,11 @@ cudaError_t launch_generic_mul(const float2* X, const float2* Cc, float2* out, i
     return cudaGetLastError();
 }
 
-cudaError_t launch_generic_absacc(const float2* W, int L, int nBins, int nonCoh, int parts,
+cudaError_t launch_generic_absacc(const float2* W, const float2* W2, int L, int nBins, int nonCoh, int parts,
                                   float* partMax, int* partIdx, size_t outBase, cudaStream_t st)
 {
     dim3 grid(parts, nBins);
-    absacc_kernel<<<grid, 256, 0, st>>>(W, L, nonCoh, parts, partMax, partIdx, outBase);
+    absacc_kernel<<<grid, 256, 0, st>>>(W, W2, L, nonCoh, parts, partMax, partIdx, outBase);
     return cudaGetLastError();
 }
 

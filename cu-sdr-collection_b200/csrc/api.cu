@@ -55,6 +55,12 @@ struct gc_handle {
     // per-signal description
     bool glo = false;            // GLONASS: FDMA channels K, one shared code, I/Q swapped
     bool b3i = false;            // BeiDou B3I: 63 PRNs, 10230-chip codes, carrier-aided code NCO, NH/GEO fine search
+    bool e1c = false;            // Galileo E1: 50 PRNs, caller-supplied 4092-chip memory codes, BOC(1,1) sub-chip tables,
+                                 // E1B + E1C replicas summed in acquisition, 25-chip secondary-code fine search, pilot tracking
+    int sub = 1;                 // table entries per chip (2 = BOC(1,1) sub-chips)
+    int nRep = 1;                // replicas summed per SV in acquisition (2 = data + pilot)
+    double fineStep = 25.0;      // fine-search bin width in Hz (acquisition.m:138; GAL_E1C acquisition.m:138: 10)
+    std::vector<int8_t> hostCode[2][50];   // caller-supplied codes as BOC(1,1) sub-chips: [component][PRN-1]
     int nReplicas = 32;          // replica spectra held (32 GPS PRNs; 1 GLONASS; 63 B3I)
     int resultLen = 32;          // length of the acqResults vectors
     int nFinePeriods = 40;       // code periods of the fine-frequency search (40 GPS/GLONASS, 20 B3I)
@@ -74,7 +80,7 @@ struct gc_handle {
     DevBuf<int8_t> recOwned;
 
     // acquisition
-    DevBuf<float2> twGen, X, T1, T2, Cc, W;
+    DevBuf<float2> twGen, X, T1, T2, T3, Cc, W;
     DevBuf<uint64_t> dphi, fdphi;
     DevBuf<int8_t> codeTab, chips;
     DevBuf<int> prnList, slotGroup, partIdx, fineCodePhase, fineBest, fineSv;
@@ -88,7 +94,7 @@ struct gc_handle {
 
     // tracking
     DevBuf<TrackChan> chans;
-    DevBuf<int8_t> trackCodes;
+    DevBuf<int8_t> trackCodes, trackPilot;
     DevBuf<double> trackOut;
     DevBuf<int32_t> epochsDone;
     double tau1code = 0, tau2code = 0, tau1carr = 0, tau2carr = 0;
@@ -141,13 +147,19 @@ void calcLoopCoef(double LBW, double zeta, double k, double* tau1, double* tau2)
 // SV id -> (valid, result index, replica slot, carrier offset)
 bool sv_ok(const gc_handle* h, int sv) { return h->glo ? (sv >= -7 && sv <= 13) : (sv >= 1 && sv <= h->resultLen); }
 int sv_result_index(const gc_handle* h, int sv) { return h->glo ? sv + 7 : sv - 1; }       // MATLAB K+8 / PRN, 0-based
-int sv_replica(const gc_handle* h, int sv) { return h->glo ? 0 : sv - 1; }
+int sv_replica(const gc_handle* h, int sv) { return h->glo ? 0 : (sv - 1) * h->nRep; }
 double sv_freq_offset(const gc_handle* h, int sv) { return h->glo ? -h->cfg.freq_spacing * (double)sv : 0.0; }
 
-// +-1 chips of one code period for an SV (tracking / fine-search replica)
-void sv_chips(const gc_handle* h, int sv, int8_t* out)
+// +-1 table entries (chips, or BOC sub-chips) of one code period for an SV: the tracking replica of
+// `component` (0 data, 1 pilot); the fine search uses the pilot component where there is one
+void sv_chips(const gc_handle* h, int sv, int8_t* out, int component = 0)
 {
-    if (h->glo) glo_code(out); else if (h->b3i) b3i_code(sv, out); else ca_code(sv, out);
+    if (h->e1c) { const std::vector<int8_t>& c = h->hostCode[component][sv - 1]; std::copy(c.begin(), c.end(), out); }
+    else if (h->glo) glo_code(out); else if (h->b3i) b3i_code(sv, out); else ca_code(sv, out);
+}
+bool sv_has_code(const gc_handle* h, int sv)
+{
+    return !h->e1c || (!h->hostCode[0][sv - 1].empty() && !h->hostCode[1][sv - 1].empty());
 }
 
 // Replica spectra conj(fft([code zeros(1,N)]))/L (acquisition.m:158-164; GLO acquisition.m:145-149) and
@@ -157,7 +169,15 @@ int build_replicas(gc_handle* h)
     const int N = h->N, L = h->L, nRep = h->nReplicas, codeLen = h->cfg.code_length;
     std::vector<int8_t> tab((size_t)nRep * N);
     std::vector<int16_t> idx40((size_t)h->nFinePeriods * N);
-    if (h->b3i) {                                            // makeB3ITable.m:38-52; acquisition.m:170-173
+    if (h->e1c) {                                            // makeE1BTable.m / makeE1CTable.m; GAL_E1C acquisition.m:160-172, 209-214
+        for (int prn = 1; prn <= nRep / 2; ++prn) {
+            if (!sv_has_code(h, prn)) continue;              // replica stays zero; gc_acquire refuses SVs without codes
+            for (int r = 0; r < 2; ++r)
+                make_boc_table(h->hostCode[r][prn - 1].data(), h->cfg.sampling_freq, h->cfg.code_freq_basis, codeLen, N,
+                               tab.data() + (size_t)((prn - 1) * 2 + r) * N);
+        }
+        boc_fine_index(h->cfg.sampling_freq, h->cfg.code_freq_basis, codeLen, (long long)h->nFinePeriods * N, idx40.data());
+    } else if (h->b3i) {                                     // makeB3ITable.m:38-52; acquisition.m:170-173
         std::vector<int8_t> chips(codeLen);
         for (int prn = 1; prn <= nRep; ++prn) {
             b3i_code(prn, chips.data());
@@ -213,7 +233,8 @@ int gc_abi_version(void) { return GC_ABI_VERSION; }
 const char* gc_build_arch(void) { return "sm_100a"; }
 int gc_acq_result_len(int32_t signal)
 {
-    return signal == GC_SIG_GPS_L1CA ? 32 : signal == GC_SIG_GLO_G1G2 ? 21 : signal == GC_SIG_BDS_B3I ? 63 : 0;
+    return signal == GC_SIG_GPS_L1CA ? 32 : signal == GC_SIG_GLO_G1G2 ? 21 : signal == GC_SIG_BDS_B3I ? 63 :
+           signal == GC_SIG_GAL_E1C ? 50 : 0;
 }
 
 const char* gc_last_error(const gc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -223,12 +244,14 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     if (!out || !cfg) return fail(nullptr, GC_ERR_ARG, "gc_create: null argument");
     *out = nullptr;
     if (cfg->abi_version != GC_ABI_VERSION) return fail(nullptr, GC_ERR_ARG, "gc_create: abi_version mismatch");
-    if (cfg->signal != GC_SIG_GPS_L1CA && cfg->signal != GC_SIG_GLO_G1G2 && cfg->signal != GC_SIG_BDS_B3I)
-        return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: signal not implemented (GPS L1CA, GLONASS G1/G2, BDS B3I are)");
+    if (cfg->signal != GC_SIG_GPS_L1CA && cfg->signal != GC_SIG_GLO_G1G2 && cfg->signal != GC_SIG_BDS_B3I &&
+        cfg->signal != GC_SIG_GAL_E1C)
+        return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: signal not implemented (GPS L1CA, GLONASS G1/G2, BDS B3I, GAL E1C are)");
     if (cfg->file_type != 2 || cfg->sample_bytes != 1)
         return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: only fileType 2 (I/Q) with dataType 'schar' is implemented");
     if (!(cfg->sampling_freq > 0) || !(cfg->code_freq_basis > 0) ||
-        cfg->code_length != (cfg->signal == GC_SIG_GLO_G1G2 ? 511 : cfg->signal == GC_SIG_BDS_B3I ? 10230 : 1023) ||
+        cfg->code_length != (cfg->signal == GC_SIG_GLO_G1G2 ? 511 : cfg->signal == GC_SIG_BDS_B3I ? 10230 :
+                             cfg->signal == GC_SIG_GAL_E1C ? 4092 : 1023) ||
         cfg->acq_noncoh_time < 1 ||
         !(cfg->acq_search_step > 0) || cfg->cno_vsm_interval < 2)
         return fail(nullptr, GC_ERR_ARG, "gc_create: invalid settings");
@@ -246,8 +269,12 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     h->cfg = *cfg;
     h->glo = (cfg->signal == GC_SIG_GLO_G1G2);
     h->b3i = (cfg->signal == GC_SIG_BDS_B3I);
-    h->nReplicas = h->glo ? 1 : h->b3i ? 63 : 32;
-    h->nFinePeriods = h->b3i ? 20 : 40;                      // BDS/B3I/include/acquisition.m:131-133
+    h->e1c = (cfg->signal == GC_SIG_GAL_E1C);
+    h->sub = h->e1c ? 2 : 1;
+    h->nRep = h->e1c ? 2 : 1;                                // E1B + E1C (GAL_E1C acquisition.m:186-192)
+    h->fineStep = h->e1c ? 10.0 : 25.0;                      // GAL_E1C acquisition.m:138
+    h->nReplicas = h->glo ? 1 : h->b3i ? 63 : h->e1c ? 100 : 32;
+    h->nFinePeriods = h->b3i ? 20 : h->e1c ? 25 : 40;        // BDS/B3I/include/acquisition.m:131-133; GAL_E1C :148
     h->resultLen = gc_acq_result_len(cfg->signal);
     auto bail = [&](int rc) { g_create_error = h->err; gc_destroy(h); return rc; };
     if (cudaSetDevice(cfg->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(GC_ERR_CUDA); }
@@ -260,9 +287,9 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     h->L = 2 * h->N;
     h->ts = 1 / cfg->sampling_freq;
     h->nBins = (int)m_round(cfg->acq_search_band * 2 / cfg->acq_search_step) + 1;
-    h->nFine = (int)m_round(cfg->acq_search_step / 25.0) + 1;
+    h->nFine = (int)m_round(cfg->acq_search_step / h->fineStep) + 1;
     h->nonCoh = cfg->acq_noncoh_time;
-    h->fused = fused_plan_info(h->L, &h->fp) && !getenv("GC_FORCE_GENERIC");
+    h->fused = fused_plan_info(h->L, &h->fp) && !getenv("GC_FORCE_GENERIC") && h->nRep == 1;
     h->stats.fft_len = h->L;
     {   // GC_ACQ_PATH=cluster selects the one-kernel correlation stage (acq_cluster.cu, transform resident
         // in a cluster's shared memory); the default is inverse rows + inverse columns through a work buffer
@@ -303,8 +330,10 @@ int gc_create(gc_handle** out, const gc_config* cfg)
         }
         calcLoopCoef(cfg->dll_noise_bandwidth, cfg->dll_damping_ratio, 1.0, &h->tau1code, &h->tau2code);    // tracking.m:100
         calcLoopCoef(cfg->pll_noise_bandwidth, cfg->pll_damping_ratio, 0.25, &h->tau1carr, &h->tau2carr);   // tracking.m:109
-        int rc = build_replicas(h);
-        if (rc != GC_OK) return rc;
+        if (!h->e1c) {                                       // caller-supplied codes: replicas are built by the first gc_acquire
+            int rc = build_replicas(h);
+            if (rc != GC_OK) return rc;
+        }
         GC_CUDA(h, cudaStreamSynchronize(h->stream));
         return GC_OK;
     };
@@ -320,15 +349,30 @@ void gc_destroy(gc_handle* h)
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->recOwned.release();
-    h->twGen.release(); h->X.release(); h->T1.release(); h->T2.release();
+    h->twGen.release(); h->X.release(); h->T1.release(); h->T2.release(); h->T3.release();
     h->chipIdx.release(); h->twFused.release();
     h->Cc.release(); h->W.release(); h->dphi.release(); h->fdphi.release(); h->codeTab.release(); h->chips.release();
     h->prnList.release(); h->slotGroup.release(); h->partIdx.release(); h->fineCodePhase.release(); h->fineBest.release(); h->fineSv.release(); h->partMax.release();
     h->peaks.release(); h->sigPower.release(); h->fineSums.release(); h->fineResult.release(); h->fineProd.release();
-    h->chans.release(); h->trackCodes.release(); h->trackOut.release(); h->epochsDone.release();
+    h->chans.release(); h->trackCodes.release(); h->trackPilot.release(); h->trackOut.release(); h->epochsDone.release();
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
+}
+
+int gc_set_code(gc_handle* h, int32_t sv, int32_t component, const int8_t* chips, int32_t nChips)
+{
+    if (!h) return GC_ERR_ARG;
+    if (!h->e1c) return fail(h, GC_ERR_ARG, "gc_set_code: this signal generates its own codes");
+    if (sv < 1 || sv > 50 || component < 0 || component > 1 || !chips || nChips != h->cfg.code_length)
+        return fail(h, GC_ERR_ARG, "gc_set_code: bad argument (PRN 1..50, component 0/1, code_length chips)");
+    for (int i = 0; i < nChips; ++i)
+        if (chips[i] != 1 && chips[i] != -1) return fail(h, GC_ERR_ARG, "gc_set_code: chips must be +-1");
+    std::vector<int8_t>& c = h->hostCode[component][sv - 1];
+    c.resize((size_t)2 * nChips);
+    boc11(chips, nChips, c.data());                           // generateE1Bcode.m:58-64
+    h->replicasReady = false;
+    return GC_OK;
 }
 
 int gc_set_record_host(gc_handle* h, const void* bytes, size_t nbytes)
@@ -366,6 +410,13 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         return fail(h, GC_ERR_ARG, "gc_acquire: bad argument");
     for (int i = 0; i < nSv; ++i)
         if (!sv_ok(h, svList[i])) return fail(h, GC_ERR_ARG, h->glo ? "gc_acquire: frequency number out of range -7..13" : "gc_acquire: PRN out of range");
+    for (int i = 0; i < nSv; ++i)
+        if (!sv_has_code(h, svList[i])) return fail(h, GC_ERR_ARG, "gc_acquire: no code set for an SV of the list (gc_set_code)");
+    if (!h->replicasReady) {
+        cudaSetDevice(c.device);
+        int rc = build_replicas(h);
+        if (rc != GC_OK) return rc;
+    }
     // postProcessing.m:86 reads max(42, nonCoh+2) code periods (B3I: max(22, nonCoh+1), BDS/B3I/include/postProcessing.m:86)
     const int nPeriodsAcq = h->b3i ? std::max(22, nonCoh + 1) : std::max(42, nonCoh + 2);
     const long long recSamples = (long long)(h->recBytes / 2);
@@ -517,18 +568,28 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
             }
             GC_CUDA(h, cudaMemcpyAsync(h->X.p, src, (size_t)nKm * L * sizeof(float2), cudaMemcpyDeviceToDevice, st));
             fwdEv.push_back({f0, mark()});
+            if (h->nRep > 1) GC_CUDA(h, h->T3.reserve((size_t)nKm * L));
             for (int sl = g0; sl < g1; ++sl) {
                 if (evn > kEvents - 12) drain_events();
                 const int a = mark();
-                GC_CUDA(h, launch_generic_mul(h->X.p, h->Cc.p + (size_t)slotReplica[sl] * L, h->T1.p, L, nKm, st)); ++launches;
-                src = h->T1.p; dst = h->T2.p; n = L; s = 1;
-                for (int f = 0; f < h->plan.nf; ++f) {
-                    GC_CUDA(h, launch_generic_stage(h->plan, f, n, s, true, src, dst, nKm, st)); ++launches;
-                    n /= h->plan.fac[f]; s *= h->plan.fac[f];
-                    std::swap(src, dst);
+                const float2* Wr[2] = {nullptr, nullptr};           // abs(ifft(X .* C_r)) inputs, one per replica
+                for (int r = 0; r < h->nRep; ++r) {
+                    GC_CUDA(h, launch_generic_mul(h->X.p, h->Cc.p + (size_t)(slotReplica[sl] + r) * L, h->T1.p, L, nKm, st)); ++launches;
+                    src = h->T1.p; dst = h->T2.p; n = L; s = 1;
+                    for (int f = 0; f < h->plan.nf; ++f) {
+                        GC_CUDA(h, launch_generic_stage(h->plan, f, n, s, true, src, dst, nKm, st)); ++launches;
+                        n /= h->plan.fac[f]; s *= h->plan.fac[f];
+                        std::swap(src, dst);
+                    }
+                    if (r + 1 < h->nRep) {                          // keep the data-replica result while the pilot one is computed
+                        GC_CUDA(h, cudaMemcpyAsync(h->T3.p, src, (size_t)nKm * L * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+                        Wr[r] = h->T3.p;
+                    } else {
+                        Wr[r] = src;
+                    }
                 }
                 const int b = mark();
-                GC_CUDA(h, launch_generic_absacc(src, L, nBins, nonCoh, h->parts, h->partMax.p, h->partIdx.p,
+                GC_CUDA(h, launch_generic_absacc(Wr[0], Wr[1], L, nBins, nonCoh, h->parts, h->partMax.p, h->partIdx.p,
                                                  (size_t)sl * nBins * h->parts, st)); ++launches;
                 const int d = mark();
                 rowEv.push_back({a, b}); colEv.push_back({b, d}); ++nRowLaunches;
@@ -563,16 +624,17 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         std::vector<int> svIds(nAcq);
         for (int a = 0; a < nAcq; ++a) svIds[a] = svList[order[acq[a]]];
         GC_CUDA(h, upload(h->fineSv, svIds, st));
-        std::vector<int8_t> chips((size_t)nAcq * codeLen);
+        const int tabLen = codeLen * h->sub;                 // chips, or BOC sub-chips, per code period
+        std::vector<int8_t> chips((size_t)nAcq * tabLen);
         std::vector<int> cps(nAcq);
         std::vector<uint64_t> fd((size_t)nAcq * h->nFine);
         std::vector<double> fineFreq((size_t)nAcq * h->nFine);
         for (int a = 0; a < nAcq; ++a) {
             const int s = acq[a];
-            sv_chips(h, svList[order[s]], chips.data() + (size_t)a * codeLen);       // :213
+            sv_chips(h, svList[order[s]], chips.data() + (size_t)a * tabLen, h->nRep - 1);   // :213 (E1: the pilot code, GAL_E1C :209)
             cps[a] = peaks[s].codePhase;
             for (int j = 0; j < h->nFine; ++j) {
-                fineFreq[(size_t)a * h->nFine + j] = coarseFreqOf[s][peaks[s].bin - 1] + c.acq_search_step / 2 - 25.0 * j;   // :227
+                fineFreq[(size_t)a * h->nFine + j] = coarseFreqOf[s][peaks[s].bin - 1] + c.acq_search_step / 2 - h->fineStep * j;   // :227
                 fd[(size_t)a * h->nFine + j] = turns_to_fix(fineFreq[(size_t)a * h->nFine + j] * h->ts);
             }
         }
@@ -584,8 +646,8 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         GC_CUDA(h, h->fineResult.reserve((size_t)nAcq * h->nFine));
         GC_CUDA(h, h->fineBest.reserve(nAcq));
         FineParams fp{};
-        fp.rec = h->rec; fp.winStart = winStart; fp.N = N; fp.nPeriods = nPeriods; fp.nFine = h->nFine; fp.codeLen = codeLen;
-        fp.swapIQ = h->glo ? 1 : 0; fp.combine = h->glo ? 1 : h->b3i ? 2 : 0; fp.chipIdx = h->chipIdx.p; fp.svId = h->fineSv.p;
+        fp.rec = h->rec; fp.winStart = winStart; fp.N = N; fp.nPeriods = nPeriods; fp.nFine = h->nFine; fp.codeLen = tabLen;
+        fp.swapIQ = h->glo ? 1 : 0; fp.combine = h->glo ? 1 : h->b3i ? 2 : h->e1c ? 3 : 0; fp.chipIdx = h->chipIdx.p; fp.svId = h->fineSv.p;
         fp.chips = h->chips.p; fp.codePhase = h->fineCodePhase.p; fp.dphi = h->fdphi.p; fp.prod = h->fineProd.p;
         fp.sums = h->fineSums.p; fp.best = h->fineBest.p; fp.fineResult = h->fineResult.p;
         const int fa = mark();
@@ -663,10 +725,11 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
         return fail(h, GC_ERR_ARG, "gc_track: bad argument");
     cudaSetDevice(c.device);
     cudaStream_t st = h->stream;
-    const int codeLen = c.code_length;
+    const int codeLen = c.code_length * h->sub;               // table entries per code period (BOC: sub-chips)
     const int stride = (codeLen + 2 + 15) & ~15;
+    const bool pilot = h->e1c && c.pilot_trk_flag == 1;       // GAL_E1C tracking.m:127
     std::vector<TrackChan> chans(nCh);
-    std::vector<int8_t> tabs((size_t)nCh * stride, 0);
+    std::vector<int8_t> tabs((size_t)nCh * stride, 0), ptabs(pilot ? (size_t)nCh * stride : 0, 0);
     std::vector<char> live(nCh, 0);
     for (int ch = 0; ch < nCh; ++ch) {
         const bool active = h->glo ? (sv[ch] != GC_SV_NONE) : (sv[ch] != 0);   // tracking.m:136; GLO tracking.m:137
@@ -678,16 +741,22 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
         chans[ch].startSample = (long long)c.skip_number_of_bytes + (long long)codePhase[ch] - 1;
         if (active) {
             if (!sv_ok(h, sv[ch])) return fail(h, GC_ERR_ARG, "gc_track: SV id out of range");
+            if (!sv_has_code(h, sv[ch])) return fail(h, GC_ERR_ARG, "gc_track: no code set for a channel's SV (gc_set_code)");
             if (chans[ch].startSample < 0) return fail(h, GC_ERR_ARG, "gc_track: codePhase must be >= 1");
             int8_t* t = tabs.data() + (size_t)ch * stride;
             sv_chips(h, sv[ch], t + 1);                    // tracking.m:156 (GLO tracking.m:88)
             t[0] = t[codeLen]; t[codeLen + 1] = t[1];      // [c(L) c c(1)]  :158
+            if (pilot) {                                   // GAL_E1C tracking.m:127-130
+                int8_t* u = ptabs.data() + (size_t)ch * stride;
+                sv_chips(h, sv[ch], u + 1, 1);
+                u[0] = u[codeLen]; u[codeLen + 1] = u[1];
+            }
         }
     }
     TrackParams p{};
     p.rec = h->rec;
     p.recSamples = (long long)(h->recBytes / 2);
-    p.fs = c.sampling_freq; p.invFs = 1.0 / c.sampling_freq; p.codeFreqBasis = c.code_freq_basis; p.codeLength = (double)codeLen;
+    p.fs = c.sampling_freq; p.invFs = 1.0 / c.sampling_freq; p.codeFreqBasis = c.code_freq_basis; p.codeLength = (double)c.code_length;
     p.spc = c.dll_correlator_spacing;
     p.cA = h->tau2code / h->tau1code; p.cB = c.int_time / h->tau1code;     // tracking.m:326
     p.pA = h->tau2carr / h->tau1carr; p.pB = c.int_time / h->tau1carr;     // tracking.m:308
@@ -697,7 +766,7 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
         p.pf2 = 2 * std::pow(Wn, 2) * c.int_time;
         p.pf1 = 2 * Wn;
     }
-    p.loopType = (h->glo || h->b3i) ? 1 : 0;
+    p.loopType = (h->glo || h->b3i || h->e1c) ? 1 : 0;
     p.swapIQ = h->glo ? 1 : 0;
     p.nEpochs = nEpochs;
     p.exactDisc = getenv("GC_TRACK_EXACT_DISC") ? 1 : 0;
@@ -710,16 +779,20 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
         if (nCh * g <= 148) { cluster = g; break; }
     if (const char* e = getenv("GC_TRACK_CLUSTER")) { const int g = atoi(e); if (g == 1 || g == 2 || g == 4 || g == 8) cluster = g; }
     (void)nLive;
+    p.codeLen = codeLen; p.codeStride = stride; p.subChip = h->sub; p.pilot = pilot ? 1 : 0;
+    // long code periods (Galileo E1: 4 ms = 72000+ samples): spread the block over enough CTAs for the
+    // double-buffered window to fit in shared memory
+    while (cluster < 8 && track_smem_bytes(track_buf_bytes(h->N + 64, cluster), codeLen, p.pilot) > 227 * 1024) cluster *= 2;
     p.bufBytes = track_buf_bytes(h->N + 64, cluster);
-    p.codeLen = codeLen; p.codeStride = stride;
-    if (track_smem_bytes(p.bufBytes, codeLen) > 227 * 1024)
+    if (track_smem_bytes(p.bufBytes, codeLen, p.pilot) > 227 * 1024)
         return fail(h, GC_ERR_UNSUPPORTED, "gc_track: one code period of samples does not fit in shared memory");
     GC_CUDA(h, upload(h->chans, chans, st));
     GC_CUDA(h, upload(h->trackCodes, tabs, st));
+    if (pilot) GC_CUDA(h, upload(h->trackPilot, ptabs, st));
     const size_t nOut = (size_t)nCh * GC_TRACK_NFIELDS * nEpochs;
     GC_CUDA(h, h->trackOut.reserve(nOut));
     GC_CUDA(h, h->epochsDone.reserve(nCh));
-    p.codeTables = h->trackCodes.p; p.chans = h->chans.p; p.out = h->trackOut.p; p.epochsDone = h->epochsDone.p;
+    p.codeTables = h->trackCodes.p; p.pilotTables = h->trackPilot.p; p.chans = h->chans.p; p.out = h->trackOut.p; p.epochsDone = h->epochsDone.p;
     long long* dbg = nullptr;
     if (getenv("GC_TRACK_DEBUG")) { cudaMalloc(&dbg, 96 * sizeof(long long)); cudaMemset(dbg, 0, 96 * sizeof(long long)); }
     p.dbg = dbg;

@@ -49,6 +49,29 @@ void make_code_table(const int8_t* chips, double fs, double codeFreqBasis, int c
     }
 }
 
+void boc11(const int8_t* primary, int codeLength, int8_t* out)
+{
+    for (int i = 0; i < codeLength; ++i) { out[2 * i] = primary[i]; out[2 * i + 1] = (int8_t)-primary[i]; }
+}
+
+void make_boc_table(const int8_t* subchips, double fs, double codeFreqBasis, int codeLength, int N, int8_t* out)
+{
+    const double ts = 1 / fs, tc = 1 / codeFreqBasis / 2;                              // makeE1BTable.m:42-43
+    for (int n = 1; n <= N; ++n) {
+        int idx = (int)std::ceil((ts * (double)n) / tc);                               // :51
+        if (n == N) idx = codeLength * 2;                                              // :54
+        if (n == 1) idx = 1;                                                           // :55
+        out[n - 1] = subchips[idx - 1];
+    }
+}
+
+void boc_fine_index(double fs, double codeFreqBasis, int codeLength, long long numSamples, int16_t* idx)
+{
+    const double ts = 1 / fs, tc = 1 / codeFreqBasis / 2;
+    for (long long k = 0; k < numSamples; ++k)
+        idx[k] = (int16_t)((long long)std::floor((ts * (double)k) / tc) % (2LL * codeLength));
+}
+
 void make_ca_table(int prn, double fs, double codeFreqBasis, int codeLength, int N, int8_t* out)
 {
     int8_t chips[1023];

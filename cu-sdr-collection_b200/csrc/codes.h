@@ -18,6 +18,18 @@ void b3i_code(int prn, int8_t* out);
 // last index forced to codeLength.
 void make_code_table(const int8_t* chips, double fs, double codeFreqBasis, int codeLength, int N, int8_t* out);
 
+// Galileo E1 BOC(1,1): primary chips c -> sub-chips [c -c] (GAL/GAL_E1C/include/generateE1Bcode.m:58-64),
+// 2*codeLength values.
+void boc11(const int8_t* primary, int codeLength, int8_t* out);
+
+// BOC(1,1) sub-chip code resampled like makeE1BTable.m:42-55 / makeE1CTable.m: tc = 1/codeFreqBasis/2,
+// index = ceil(ts*n/tc), last index forced to 2*codeLength, FIRST index forced to 1.
+void make_boc_table(const int8_t* subchips, double fs, double codeFreqBasis, int codeLength, int N, int8_t* out);
+
+// codeValueIndex of the E1 fine search: floor((ts*(0:num-1)) / (1/codeFreqBasis/2)) rem (codeLength*2)
+// (GAL_E1C/include/acquisition.m:211-214), 0-based.
+void boc_fine_index(double fs, double codeFreqBasis, int codeLength, long long numSamples, int16_t* idx);
+
 // +-1 GLONASS ST-code chips (511, 9-stage register, taps 5 and 9, output of stage 7).
 // GLO/GLO_GL1/include/generateCAcode.m:95-108.
 void glo_code(int8_t* out);

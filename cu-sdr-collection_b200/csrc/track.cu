@@ -157,7 +157,7 @@ __device__ void plan_epoch(const TrackParams& p, double codeFreq, double remCode
     }
     // fast path: the three vectors share n, and the samples masked just outside the block still index the
     // zero padding of the code table
-    ep.generic = !(ep.nE == blk - 1 && ep.nP == blk - 1 && ep.nL == blk - 1) || !(8.0 * step + p.spc + 2.0 < (double)kPad);
+    ep.generic = !(ep.nE == blk - 1 && ep.nP == blk - 1 && ep.nL == blk - 1) || !((8.0 * step + p.spc) * (double)p.subChip + 2.0 < (double)kPad);
     ep.mE = __dmul_rn(__dadd_rn(ep.aE, ep.cE), 0.5);
     ep.mP = __dmul_rn(__dadd_rn(ep.aP, ep.cP), 0.5);
     ep.mL = __dmul_rn(__dadd_rn(ep.aL, ep.cL), 0.5);
@@ -215,11 +215,12 @@ __device__ __forceinline__ void dsmem_push(double* local, uint64_t* bar, uint32_
 
 }  // namespace
 
-// G = CTAs per channel (cluster size), T = threads per CTA
-template <int G, int T>
+// G = CTAs per channel (cluster size), T = threads per CTA, PILOT = data + pilot replicas (12 sums)
+template <int G, int T, bool PILOT>
 __global__ void __launch_bounds__(T, 1)
 track_kernel(TrackParams p)
 {
+    constexpr int NS = PILOT ? 12 : 6;                           // correlator sums per epoch
     constexpr int kThreads = T;
     constexpr int kWarps = T / 32;
     // Role threads.  The 8-CTA variant carries three spare warps so that the TMA issue, the one
@@ -233,9 +234,11 @@ track_kernel(TrackParams p)
     int8_t* const buf0 = reinterpret_cast<int8_t*>(smem_raw);
     float* s_code_raw = reinterpret_cast<float*>(smem_raw + 2 * (size_t)p.bufBytes);
     float* s_code = s_code_raw + kPad;                           // index 0 = c(L) of the wrapped table
-    double* s_part = reinterpret_cast<double*>(s_code_raw + ((p.codeLen + 2 + 2 * kPad + 3) & ~3));
-    double* s_cl = s_part + kMaxWarps * 6;                       // [2][kMaxCluster][6] per-CTA partial sums (pushed by peers)
-    double* s_stage = s_cl + 2 * kMaxCluster * 6;                // [15][kStage]
+    const int tabFloats = (p.codeLen + 2 + 2 * kPad + 3) & ~3;
+    float* s_pilot = s_code + (PILOT ? tabFloats : 0);           // pilot table right behind the data table
+    double* s_part = reinterpret_cast<double*>(s_code_raw + (PILOT ? 2 : 1) * tabFloats);
+    double* s_cl = s_part + kMaxWarps * NS;                      // [2][kMaxCluster][NS] per-CTA partial sums (pushed by peers)
+    double* s_stage = s_cl + 2 * kMaxCluster * NS;               // [15][kStage]
     EpochParams* s_ep = reinterpret_cast<EpochParams*>(s_stage + GC_TRACK_ROWS * kStage);   // [2]
     NextPhases* s_nx = reinterpret_cast<NextPhases*>(s_ep + 2);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_nx + 1);     // 2 mbarriers (TMA stages) + 2 (partial-sum exchange)
@@ -257,6 +260,7 @@ track_kernel(TrackParams p)
     for (int i = tid; i < p.codeLen + 2 + 2 * kPad; i += kThreads) {
         const int j = i - kPad;
         s_code_raw[i] = (j >= 0 && j < p.codeLen + 2) ? (float)p.codeTables[(size_t)ch * p.codeStride + j] : 0.f;
+        if (PILOT) s_code_raw[tabFloats + i] = (j >= 0 && j < p.codeLen + 2) ? (float)p.pilotTables[(size_t)ch * p.codeStride + j] : 0.f;
     }
 
     // byte selectors: sample bytes are I,Q,I,Q; GLONASS takes rawSignal = Q + 1i*I (GLO tracking.m:227)
@@ -320,7 +324,7 @@ track_kernel(TrackParams p)
         const uint64_t dphi = ep.dphi, phase0 = ep.phase0;
         // window of epoch e+1 starts where this one ends; fetch it while we correlate
         if (tid == kLoader && e + 1 < p.nEpochs) prefetch(pos + blk, stage ^ 1, e + 1);
-        if (G > 1 && tid == kPllTid) mbar_expect_tx(&s_xbar[e & 1], 48u * G);   // G CTAs x 6 doubles will arrive
+        if (G > 1 && tid == kPllTid) mbar_expect_tx(&s_xbar[e & 1], 8u * NS * G);   // G CTAs x NS doubles will arrive
         GC_TICK(0)
         if (staged) { mbar_wait(&s_bar[stage], phase[stage]); phase[stage] ^= 1u; }
         GC_TICK(1)
@@ -345,12 +349,16 @@ track_kernel(TrackParams p)
         const bool inBuf = fits && staged;
         const int8_t* src = buf0 + (size_t)stage * p.bufBytes - (size_t)c_lo * 16;
         const int8_t* gsrc = p.rec + ((pos * 2) & ~15LL);
-        const double d = ep.d;
-        const double aE = ep.aE, aP = ep.aP, aL = ep.aL, cE = ep.cE, cP = ep.cP, cL = ep.cL;
+        // table index = ceil(tcode * subChip): the scaling by 1 or 2 is exact, so the scaled colon vector is
+        // element for element the reference's (rem -/+ spc)*2 : step*2 : (...)*2  (GAL_E1C tracking.m:236-262)
+        const double sc = (double)p.subChip;
+        const double d = ep.d * sc;
+        const double aE = ep.aE * sc, aP = ep.aP * sc, aL = ep.aL * sc, cE = ep.cE * sc, cP = ep.cP * sc, cL = ep.cL * sc;
         const bool generic = ep.generic != 0;
 
         float aIE = 0, aQE = 0, aIP = 0, aQP = 0, aIL = 0, aQL = 0;
-        const double mE = ep.mE, mP = ep.mP, mL = ep.mL;
+        float bIE = 0, bQE = 0, bIP = 0, bQP = 0, bIL = 0, bQL = 0;     // pilot sums
+        const double mE = ep.mE * sc, mP = ep.mP * sc, mL = ep.mL * sc;
         const int nE_ = ep.nE, nP_ = ep.nP, nL_ = ep.nL;
         // One 16-byte chunk = 8 consecutive samples.  SPECIAL = per-sample left/right/middle selection
         // (the chunk holding the middle of the colon vector, or every chunk of a `generic` block).
@@ -373,6 +381,7 @@ track_kernel(TrackParams p)
                     if ((unsigned)(k0 + j) >= (unsigned)blk) { xi[j] = 0.f; xq[j] = 0.f; }
             }
             float pIE = 0, pQE = 0, pIP = 0, pQP = 0, pIL = 0, pQL = 0;
+            float qIE = 0, qQE = 0, qIP = 0, qQP = 0, qIL = 0, qQL = 0;
             if (!SPECIAL) {
                 // whole chunk in the left half (t = a + k*d) or in the right half (t = c - (n-k)*d).
                 // Samples masked above may have k < 0 or k >= blk; their code index stays inside
@@ -386,15 +395,22 @@ track_kernel(TrackParams p)
                 for (int j = 0; j < 8; ++j) {
                     const double st = __dmul_rn(__fma_rn(sg, (double)j, f0), ds);   // (+-)(k or n-k)*d, exact integer factor
                     // code replicas (tracking.m:252-270): ceil(tcode) indexes [c(L) c c(1)] 0-based
-                    const float vE = s_code[ceil_idx(__dadd_rn(bE, st))];
-                    const float vP = s_code[ceil_idx(__dadd_rn(bP, st))];
-                    const float vL = s_code[ceil_idx(__dadd_rn(bL, st))];
+                    const int iE = ceil_idx(__dadd_rn(bE, st)), iP = ceil_idx(__dadd_rn(bP, st)), iL = ceil_idx(__dadd_rn(bL, st));
+                    const float vE = s_code[iE];
+                    const float vP = s_code[iP];
+                    const float vL = s_code[iL];
                     // x * e^{-i*j*dphi}   (tracking.m:287-292 with the chunk phase factored out)
                     const float ur = fmaf(wc[j], xi[j], ws[j] * xq[j]);
                     const float ui = fmaf(wc[j], xq[j], -ws[j] * xi[j]);
                     pIE = fmaf(vE, ur, pIE); pQE = fmaf(vE, ui, pQE);                 // :295-300
                     pIP = fmaf(vP, ur, pIP); pQP = fmaf(vP, ui, pQP);
                     pIL = fmaf(vL, ur, pIL); pQL = fmaf(vL, ui, pQL);
+                    if (PILOT) {                                  // same code phase, pilot table (GAL_E1C tracking.m:241-262)
+                        const float uE = s_pilot[iE], uP = s_pilot[iP], uL = s_pilot[iL];
+                        qIE = fmaf(uE, ur, qIE); qQE = fmaf(uE, ui, qQE);
+                        qIP = fmaf(uP, ur, qIP); qQP = fmaf(uP, ui, qQP);
+                        qIL = fmaf(uL, ur, qIL); qQL = fmaf(uL, ui, qQL);
+                    }
                 }
             } else {
 #pragma unroll
@@ -412,12 +428,19 @@ track_kernel(TrackParams p)
                         tP = colon_elem(aP, d, cP, nP_, kc);
                         tL = colon_elem(aL, d, cL, nL_, kc);
                     }
-                    const float vE = s_code[ceil_idx(tE)], vP = s_code[ceil_idx(tP)], vL = s_code[ceil_idx(tL)];
+                    const int iE = ceil_idx(tE), iP = ceil_idx(tP), iL = ceil_idx(tL);
+                    const float vE = s_code[iE], vP = s_code[iP], vL = s_code[iL];
                     const float ur = fmaf(wc[j], xi[j], ws[j] * xq[j]);
                     const float ui = fmaf(wc[j], xq[j], -ws[j] * xi[j]);
                     pIE = fmaf(vE, ur, pIE); pQE = fmaf(vE, ui, pQE);
                     pIP = fmaf(vP, ur, pIP); pQP = fmaf(vP, ui, pQP);
                     pIL = fmaf(vL, ur, pIL); pQL = fmaf(vL, ui, pQL);
+                    if (PILOT) {
+                        const float uE = s_pilot[iE], uP = s_pilot[iP], uL = s_pilot[iL];
+                        qIE = fmaf(uE, ur, qIE); qQE = fmaf(uE, ui, qQE);
+                        qIP = fmaf(uP, ur, qIP); qQP = fmaf(uP, ui, qQP);
+                        qIL = fmaf(uL, ur, qIL); qQL = fmaf(uL, ui, qQL);
+                    }
                 }
             }
             // rotate the chunk sums by e^{-i*phase(k0)}
@@ -426,6 +449,11 @@ track_kernel(TrackParams p)
             aIE += fmaf(c0, pIE, s0 * pQE); aQE += fmaf(c0, pQE, -s0 * pIE);
             aIP += fmaf(c0, pIP, s0 * pQP); aQP += fmaf(c0, pQP, -s0 * pIP);
             aIL += fmaf(c0, pIL, s0 * pQL); aQL += fmaf(c0, pQL, -s0 * pIL);
+            if (PILOT) {
+                bIE += fmaf(c0, qIE, s0 * qQE); bQE += fmaf(c0, qQE, -s0 * qIE);
+                bIP += fmaf(c0, qIP, s0 * qQP); bQP += fmaf(c0, qQP, -s0 * qIP);
+                bIL += fmaf(c0, qIL, s0 * qQL); bQL += fmaf(c0, qQL, -s0 * qIL);
+            }
         };
         using TagFast = std::false_type;
         using TagSpecial = std::true_type;
@@ -445,36 +473,38 @@ track_kernel(TrackParams p)
         // cross-thread reduction in float64: warp shuffle, then warps 0 and 1 over the warp partials
         // (the 32 lane partials of a warp are combined in fp32 - they are fp32 sums of <= 32 samples each -
         //  and everything from the warp partials on is float64)
-        float vf[6] = {aIE, aQE, aIP, aQP, aIL, aQL};
+        float vf[12] = {aIE, aQE, aIP, aQP, aIL, aQL, bIE, bQE, bIP, bQP, bIL, bQL};
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-            for (int q = 0; q < 6; ++q) vf[q] += __shfl_down_sync(0xffffffffu, vf[q], o);
-        double v[6] = {(double)vf[0], (double)vf[1], (double)vf[2], (double)vf[3], (double)vf[4], (double)vf[5]};
+            for (int q = 0; q < NS; ++q) vf[q] += __shfl_down_sync(0xffffffffu, vf[q], o);
+        double v[NS];
+#pragma unroll
+        for (int q = 0; q < NS; ++q) v[q] = (double)vf[q];
         if (lane == 0)
 #pragma unroll
-            for (int q = 0; q < 6; ++q) s_part[warp * 6 + q] = v[q];
+            for (int q = 0; q < NS; ++q) s_part[warp * NS + q] = v[q];
         __syncthreads();
         GC_TICK(3)
         if (G > 1) {
             // CTA partial -> every CTA of the cluster (slot [epoch parity][my rank]), then one barrier
-            double* slot = s_cl + ((e & 1) * kMaxCluster + (int)crank) * 6;
+            double* slot = s_cl + ((e & 1) * kMaxCluster + (int)crank) * NS;
             if (warp == 0) {
 #pragma unroll
-                for (int q = 0; q < 6; ++q) v[q] = (lane < kWarps) ? s_part[lane * 6 + q] : 0.0;
+                for (int q = 0; q < NS; ++q) v[q] = (lane < kWarps) ? s_part[lane * NS + q] : 0.0;
 #pragma unroll
                 for (int o = kMaxWarps / 2; o > 0; o >>= 1)
 #pragma unroll
-                    for (int q = 0; q < 6; ++q) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
-                double b[6];
+                    for (int q = 0; q < NS; ++q) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
+                double b[NS];
 #pragma unroll
-                for (int q = 0; q < 6; ++q) b[q] = __shfl_sync(0xffffffffu, v[q], 0);
-                for (int i = lane; i < 6 * G; i += 32) {
-                    const int q = i % 6;
+                for (int q = 0; q < NS; ++q) b[q] = __shfl_sync(0xffffffffu, v[q], 0);
+                for (int i = lane; i < NS * G; i += 32) {
+                    const int q = i % NS;
                     double val = b[0];
 #pragma unroll
-                    for (int t = 1; t < 6; ++t) val = (q == t) ? b[t] : val;
-                    dsmem_push(slot + q, &s_xbar[e & 1], (uint32_t)(i / 6), val);
+                    for (int t = 1; t < NS; ++t) val = (q == t) ? b[t] : val;
+                    dsmem_push(slot + q, &s_xbar[e & 1], (uint32_t)(i / NS), val);
                 }
             }
         }
@@ -484,12 +514,12 @@ track_kernel(TrackParams p)
                 mbar_wait(&s_xbar[e & 1], xphase[e & 1]);       // all G partial sets have landed here
                 xphase[e & 1] ^= 1u;
                 // every CTA adds the G partials in the same (pairwise) order -> identical sums everywhere
-                const double* sl = s_cl + (e & 1) * kMaxCluster * 6;
+                const double* sl = s_cl + (e & 1) * kMaxCluster * NS;
 #pragma unroll
-                for (int q = 0; q < 6; ++q) {
+                for (int q = 0; q < NS; ++q) {
                     double t[G];
 #pragma unroll
-                    for (int r = 0; r < G; ++r) t[r] = sl[r * 6 + q];
+                    for (int r = 0; r < G; ++r) t[r] = sl[r * NS + q];
 #pragma unroll
                     for (int w = G / 2; w > 0; w >>= 1)
 #pragma unroll
@@ -498,11 +528,11 @@ track_kernel(TrackParams p)
                 }
             } else {
 #pragma unroll
-                for (int q = 0; q < 6; ++q) v[q] = (lane < kWarps) ? s_part[lane * 6 + q] : 0.0;
+                for (int q = 0; q < NS; ++q) v[q] = (lane < kWarps) ? s_part[lane * NS + q] : 0.0;
 #pragma unroll
                 for (int o = kMaxWarps / 2; o > 0; o >>= 1)
 #pragma unroll
-                    for (int q = 0; q < 6; ++q) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
+                    for (int q = 0; q < NS; ++q) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
             }
             const double I_E = v[0], Q_E = v[1], I_P = v[2], Q_P = v[3], I_L = v[4], Q_L = v[5];
             double* sg = s_stage + (e % kStage);
@@ -510,8 +540,13 @@ track_kernel(TrackParams p)
                 // PLL (tracking.m:305-317)
                 // The discriminator is evaluated in fp32: its inputs are sums of fp32 products, so float64
                 // would not make it more accurate, and a float64 atan is ~1000 dependent cycles per epoch.
-                const double carrError = p.exactDisc ? atan(__ddiv_rn(Q_P, I_P)) / kTwoPi
-                                                     : (double)atanf((float)Q_P / (float)I_P) * 0.15915494309189535;
+                double carrError = p.exactDisc ? atan(__ddiv_rn(Q_P, I_P)) / kTwoPi
+                                               : (double)atanf((float)Q_P / (float)I_P) * 0.15915494309189535;
+                if (PILOT) {                                     // GAL_E1C tracking.m:297-300
+                    const double cP2 = p.exactDisc ? atan(__ddiv_rn(v[NS - 3], v[NS - 4])) / kTwoPi
+                                                   : (double)atanf((float)v[NS - 3] / (float)v[NS - 4]) * 0.15915494309189535;
+                    carrError = __dmul_rn(__dadd_rn(carrError, cP2), 0.5);
+                }
                 double carrNco;
                 if (p.loopType == 0) {
                     carrNco = __dadd_rn(__dadd_rn(lm.oldCarrNco, __dmul_rn(p.pA, __dsub_rn(carrError, lm.oldCarrError))),
@@ -543,6 +578,19 @@ track_kernel(TrackParams p)
                 } else {
                     const float sE = sqrtf((float)pE), sL = sqrtf((float)pL);
                     codeError = (double)((sE - sL) / (sE + sL));
+                }
+                if (PILOT) {                                     // GAL_E1C tracking.m:327-333
+                    const double qE = __dadd_rn(__dmul_rn(v[NS - 6], v[NS - 6]), __dmul_rn(v[NS - 5], v[NS - 5]));
+                    const double qL = __dadd_rn(__dmul_rn(v[NS - 2], v[NS - 2]), __dmul_rn(v[NS - 1], v[NS - 1]));
+                    double ce2;
+                    if (p.exactDisc) {
+                        const double sE = sqrt(qE), sL = sqrt(qL);
+                        ce2 = __ddiv_rn(__dsub_rn(sE, sL), __dadd_rn(sE, sL));
+                    } else {
+                        const float sE = sqrtf((float)qE), sL = sqrtf((float)qL);
+                        ce2 = (double)((sE - sL) / (sE + sL));
+                    }
+                    codeError = __dmul_rn(__dadd_rn(codeError, ce2), 0.5);
                 }
                 const double codeNco = __dadd_rn(__dadd_rn(lm.oldCodeNco, __dmul_rn(p.cA, __dsub_rn(codeError, lm.oldCodeError))),
                                                  __dmul_rn(codeError, p.cB));
@@ -586,20 +634,21 @@ track_kernel(TrackParams p)
     if (G > 1) cluster_sync_all();                               // nobody leaves while a peer may still push to it
 }
 
-size_t track_smem_bytes(int bufBytes, int codeLen)
+size_t track_smem_bytes(int bufBytes, int codeLen, int pilot)
 {
+    const int ns = pilot ? 12 : 6;
     size_t s = 2 * (size_t)bufBytes;
-    s += sizeof(float) * ((codeLen + 2 + 2 * kPad + 3) & ~3);
-    s += sizeof(double) * (kMaxWarps * 6 + 2 * kMaxCluster * 6 + GC_TRACK_ROWS * kStage);
+    s += sizeof(float) * ((codeLen + 2 + 2 * kPad + 3) & ~3) * (pilot ? 2 : 1);
+    s += sizeof(double) * (kMaxWarps * ns + 2 * kMaxCluster * ns + GC_TRACK_ROWS * kStage);
     s += 2 * sizeof(EpochParams) + sizeof(NextPhases) + 4 * sizeof(uint64_t) + 2 * sizeof(int) + 64;
     return s;
 }
 
-template <int G, int T>
+template <int G, int T, bool PILOT>
 static cudaError_t launch_track_g(const TrackParams& p, int nCh, cudaStream_t stream)
 {
-    const size_t smem = track_smem_bytes(p.bufBytes, p.codeLen);
-    cudaError_t err = cudaFuncSetAttribute(track_kernel<G, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = track_smem_bytes(p.bufBytes, p.codeLen, PILOT ? 1 : 0);
+    cudaError_t err = cudaFuncSetAttribute(track_kernel<G, T, PILOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nCh * G);
@@ -611,17 +660,25 @@ static cudaError_t launch_track_g(const TrackParams& p, int nCh, cudaStream_t st
     attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, track_kernel<G, T>, p);
+    return cudaLaunchKernelEx(&cfg, track_kernel<G, T, PILOT>, p);
 }
 
 // p.bufBytes must be the per-CTA staging size for `cluster` CTAs per channel (track_buf_bytes)
 cudaError_t launch_track(const TrackParams& p, int nCh, int cluster, cudaStream_t stream)
 {
+    if (p.pilot) {
+        switch (cluster) {
+            case 8: return launch_track_g<8, 352, true>(p, nCh, stream);
+            case 4: return launch_track_g<4, 512, true>(p, nCh, stream);
+            case 2: return launch_track_g<2, 512, true>(p, nCh, stream);
+            default: return launch_track_g<1, 512, true>(p, nCh, stream);
+        }
+    }
     switch (cluster) {
-        case 8: return launch_track_g<8, 352>(p, nCh, stream);
-        case 4: return launch_track_g<4, 512>(p, nCh, stream);
-        case 2: return launch_track_g<2, 512>(p, nCh, stream);
-        default: return launch_track_g<1, 512>(p, nCh, stream);
+        case 8: return launch_track_g<8, 352, false>(p, nCh, stream);
+        case 4: return launch_track_g<4, 512, false>(p, nCh, stream);
+        case 2: return launch_track_g<2, 512, false>(p, nCh, stream);
+        default: return launch_track_g<1, 512, false>(p, nCh, stream);
     }
 }
 

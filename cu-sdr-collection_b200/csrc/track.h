@@ -28,16 +28,21 @@ struct TrackParams {
     int nEpochs;
     int exactDisc;           // 1: float64 atan/sqrt/divide in the discriminators (GC_TRACK_EXACT_DISC), 0: fp32-seeded
     int bufBytes;            // bytes staged per epoch by ONE CTA (multiple of 16)
-    int codeLen;             // chips per code period
-    int codeStride;          // bytes between channels in codeTables
+    int codeLen;             // entries of one code period in the tables: chips x subChip
+    int subChip;             // table entries per chip: 1, or 2 for the BOC(1,1) tables of Galileo E1
+                             // (tcode*2 in GAL/GAL_E1C/include/tracking.m:236-262)
+    int pilot;               // 1: a second (pilot) replica is correlated with the same code phase and both
+                             // discriminators are averaged (GAL_E1C tracking.m:241-333, settings.pilotTRKflag)
+    int codeStride;          // bytes between channels in codeTables / pilotTables
     const int8_t* codeTables;   // [nCh][codeStride]: wrapped +-1 table [c(L) c(1..L) c(1)]
+    const int8_t* pilotTables;  // same layout, pilot component (pilot == 1)
     const TrackChan* chans;
     double* out;             // [nCh][15][nEpochs]
     int32_t* epochsDone;
     long long* dbg;          // optional [4][8] phase-timing accumulators (GC_TRACK_DEBUG), else nullptr
 };
 
-size_t track_smem_bytes(int bufBytes, int codeLen);
+size_t track_smem_bytes(int bufBytes, int codeLen, int pilot);
 cudaError_t launch_track(const TrackParams& p, int nCh, int cluster, cudaStream_t stream);
 int track_buf_bytes(int maxBlockSamples, int cluster);
 cudaError_t launch_track_fill(double* out, int nCh, int nEpochs, cudaStream_t stream);

@@ -31,10 +31,10 @@ class gc_config(C.Structure):
                 ("dll_damping_ratio", C.c_double), ("dll_noise_bandwidth", C.c_double),
                 ("dll_correlator_spacing", C.c_double), ("pll_damping_ratio", C.c_double),
                 ("pll_noise_bandwidth", C.c_double), ("int_time", C.c_double), ("cno_acc_time", C.c_double),
-                ("freq_spacing", C.c_double)]
+                ("freq_spacing", C.c_double), ("pilot_trk_flag", C.c_int32), ("reserved0", C.c_int32)]
 
 
-GC_SIG_GPS_L1CA, GC_SIG_GLO_G1G2, GC_SIG_BDS_B3I = 0, 1, 2
+GC_SIG_GPS_L1CA, GC_SIG_GLO_G1G2, GC_SIG_BDS_B3I, GC_SIG_GAL_E1C = 0, 1, 2, 3
 GC_SV_NONE = -2147483648
 
 
@@ -47,7 +47,7 @@ class gc_stats(C.Structure):
 
 
 EXPORTS = ["gc_abi_version", "gc_build_arch", "gc_acq_result_len", "gc_create", "gc_destroy",
-           "gc_last_error", "gc_set_record_host", "gc_set_record_device", "gc_acquire",
+           "gc_last_error", "gc_set_code", "gc_set_record_host", "gc_set_record_device", "gc_acquire",
            "gc_acquire_host", "gc_track", "gc_track_file", "gc_get_stats", "gc_get_stream"]
 
 _lib = None
@@ -72,6 +72,7 @@ def load_lib():
     lib.gc_destroy.restype = None
     lib.gc_last_error.argtypes = [vp]
     lib.gc_last_error.restype = C.c_char_p
+    lib.gc_set_code.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_int32]
     lib.gc_set_record_host.argtypes = [vp, vp, C.c_size_t]
     lib.gc_set_record_device.argtypes = [vp, vp, C.c_size_t]
     lib.gc_acquire.argtypes = [vp, C.c_int32, i32p, dp, dp, dp, i32p, i32p]
@@ -86,7 +87,8 @@ def load_lib():
 
 
 def signal_id(s: Settings) -> int:
-    return GC_SIG_GLO_G1G2 if s.is_glonass else GC_SIG_BDS_B3I if s.signal == "BDS_B3I" else GC_SIG_GPS_L1CA
+    return (GC_SIG_GLO_G1G2 if s.is_glonass else GC_SIG_BDS_B3I if s.signal == "BDS_B3I" else
+            GC_SIG_GAL_E1C if s.signal == "GAL_E1C" else GC_SIG_GPS_L1CA)
 
 
 def config_from_settings(s: Settings, device: int = 0) -> gc_config:
@@ -96,7 +98,7 @@ def config_from_settings(s: Settings, device: int = 0) -> gc_config:
     if s.fileType != 2 or s.dataType != "schar":
         raise GnssCorrError("only fileType 2 with dataType 'schar' is implemented")
     sig = signal_id(s)
-    return gc_config(abi_version=2, device=device, signal=sig, freq_spacing=float(s.freqSpacing),
+    return gc_config(abi_version=3, device=device, pilot_trk_flag=int(s.pilotTRKflag), signal=sig, freq_spacing=float(s.freqSpacing),
                      file_type=s.fileType, sample_bytes=1,
                      code_length=int(s.codeLength), acq_noncoh_time=int(s.acqNonCohTime),
                      cno_vsm_interval=int(s.CNo_VSMinterval), skip_number_of_bytes=int(s.skipNumberOfBytes),
@@ -119,7 +121,10 @@ def _ip(a):
 class Engine:
     """One engine = one GPU: owns the FFT plan, replica spectra and the resident IF record."""
 
-    def __init__(self, settings: Settings, device: int = 0):
+    def __init__(self, settings: Settings, device: int = 0, codes: dict | None = None):
+        """``codes``: Galileo E1 only - {PRN: (e1b, e1c)} +-1 primary chips (codes.load_e1_codes /
+        codes.standin_e1_codes); default: read E1b.dat / E1c.dat from ``settings.codeDir`` as the reference
+        does from its include/ folder (generateE1Bcode.m:44)."""
         self.lib = load_lib()
         self.settings = settings
         self._h = C.c_void_p()
@@ -128,6 +133,20 @@ class Engine:
         if rc != 0:
             raise GnssCorrError(f"gc_create failed ({rc}): {self.lib.gc_last_error(None).decode()}")
         self._keep = None
+        if settings.signal == "GAL_E1C":
+            if codes is None:
+                from .codes import load_e1_codes
+                if not settings.codeDir:
+                    raise GnssCorrError("Galileo E1 needs the memory codes: pass codes= or set settings.codeDir "
+                                        "to the folder with E1b.dat / E1c.dat")
+                codes = load_e1_codes(settings.codeDir)
+            self.set_codes(codes)
+
+    def set_codes(self, codes: dict):
+        for prn, (b, c) in codes.items():
+            for comp, chips in ((0, b), (1, c)):
+                a = np.ascontiguousarray(chips, dtype=np.int8)
+                self._check(self.lib.gc_set_code(self._h, int(prn), comp, a.ctypes.data, a.size), "gc_set_code")
 
     def close(self):
         if self._h:

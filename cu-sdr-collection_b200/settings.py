@@ -39,6 +39,8 @@ class Settings:
     CNo_VSMinterval: int = 40           # :135
     freqSpacing: float = 0.0            # GLONASS only: FDMA channel spacing (GLO_GL1/initSettings.m:72)
     carrFreqBasis: float = 0.0          # B3I: RF carrier used to aid the code NCO (BDS/B3I/initSettings.m:132)
+    pilotTRKflag: int = 0               # Galileo E1: track the pilot component too (GAL/GAL_E1C/initSettings.m:113)
+    codeDir: str = ""                   # Galileo E1: directory holding E1b.dat / E1c.dat (the reference keeps them in include/)
 
     @property
     def is_glonass(self) -> bool:
@@ -59,6 +61,12 @@ _B3I_DEFAULTS = dict(numberOfChannels=15, fileName="../../../B3I_IF20KHz_FS18MHz
                      carrFreqBasis=1268.520e6)
 
 
+# GAL/GAL_E1C/initSettings.m:44-140
+_E1C_DEFAULTS = dict(codeLength=4092.0, acqSatelliteList=list(range(1, 37)), acqSearchBand=7000.0, acqNonCohTime=1,
+                     acqSearchStep=150.0, acqThreshold=10.0, resamplingThreshold=50e6, dllCorrelatorSpacing=0.3,
+                     pllNoiseBandwidth=15.0, intTime=0.004, pilotTRKflag=1, CNo_accTime=0.004, CNo_VSMinterval=400)
+
+
 def init_settings(signal: str = "GPS_L1CA", **overrides) -> Settings:
     """``settings = initSettings()`` of the given signal folder (GPS/GPS_L1CA/init.m:56,
     GLO/GLO_GL1, GLO/GLO_GL2) with optional field overrides."""
@@ -72,6 +80,9 @@ def init_settings(signal: str = "GPS_L1CA", **overrides) -> Settings:
     elif signal == "BDS_B3I":
         for k, v in _B3I_DEFAULTS.items():
             setattr(s, k, list(v) if isinstance(v, list) else v)
+    elif signal == "GAL_E1C":
+        for k, v in _E1C_DEFAULTS.items():
+            setattr(s, k, list(v) if isinstance(v, list) else v)
     elif signal != "GPS_L1CA":
         raise ValueError(f"signal {signal!r} is not implemented")
     for k, v in overrides.items():
@@ -83,6 +94,16 @@ def init_settings(signal: str = "GPS_L1CA", **overrides) -> Settings:
             raise AttributeError(f"settings has no field {k!r}")
         setattr(s, k, v)
     return s
+
+
+def num_to_process(s: Settings) -> int:
+    """Integration periods tracking() runs: msToProcess for the 1 ms signals, round(msToProcess/1000/intTime)
+    for Galileo E1 (GAL/GAL_E1C/include/tracking.m:48)."""
+    import math
+    if s.signal == "GAL_E1C":
+        x = s.msToProcess / 1000 / s.intTime
+        return int(math.floor(x + 0.5))
+    return int(s.msToProcess)
 
 
 def samples_per_code(s: Settings) -> int:

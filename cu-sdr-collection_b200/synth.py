@@ -16,7 +16,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from .codes import b3i_code, ca_code, glo_code
+from .codes import E1_SECONDARY, b3i_code, boc11, ca_code, glo_code
 
 L1 = 1575.42e6
 
@@ -47,6 +47,11 @@ class Scene:
     # BeiDou B3I scenes: 10230-chip codes at 10.23 Mcps; PRN 6-58 carry the 20-bit Neumann-Hoffman
     # secondary code on 20 ms bits, GEO PRNs (1-5, 59-63) carry 2 ms bits.
     b3i: bool = False
+    # Galileo E1 scenes: E1-B (250 sps data symbols, one per 4 ms code period) minus E1-C (25-chip secondary
+    # code) on the same carrier, each a 4092-chip memory code with the BOC(1,1) sub-carrier; ``codes`` =
+    # {PRN: (e1b, e1c)} +-1 primary chips (codes.load_e1_codes or codes.standin_e1_codes).
+    e1c: bool = False
+    codes: dict = None
 
 
 def default_scene(fs: float = 16.368e6, IF: float = 20e3, nsat: int = 8, seed: int = 20260101) -> Scene:
@@ -91,6 +96,15 @@ def default_scene_b3i(fs: float = 18e6, IF: float = 20e3, nsat: int = 5, seed: i
     return Scene(fs=fs, IF=IF, seed=seed, sats=sats, b3i=True)
 
 
+def default_scene_e1c(codes: dict, fs: float = 18e6, IF: float = 20e3, nsat: int = 4, seed: int = 20260101) -> Scene:
+    rng = np.random.default_rng(seed)
+    prns = rng.choice(np.arange(1, 37), size=nsat, replace=False)
+    sats = [Sat(prn=int(p), doppler=float(rng.uniform(-4000, 4000)), code_phase=float(rng.uniform(0, 4092)),
+                cn0=float(rng.uniform(42, 50)), phi0=float(rng.uniform(0, 2 * np.pi)), bit_seed=int(rng.integers(1 << 30)),
+                bit_offset=int(rng.integers(0, 25))) for p in prns]
+    return Scene(fs=fs, IF=IF, seed=seed, sats=sats, e1c=True, codes=codes)
+
+
 def make_record(scene: Scene, nsamples: int, start: int = 0) -> np.ndarray:
     """int8 array of length 2*nsamples (I0,Q0,I1,Q1,...), samples start..start+nsamples-1."""
     n = np.arange(start, start + nsamples, dtype=np.float64)
@@ -105,6 +119,20 @@ def make_record(scene: Scene, nsamples: int, start: int = 0) -> np.ndarray:
             clen, crate, carrier = 10230, 10.23e6, 1268.52e6
             fc = scene.IF + s.doppler
             chipseq = b3i_code(s.prn).astype(np.float64)
+        elif scene.e1c:
+            clen, crate, carrier = 4092, 1.023e6, L1
+            fc = scene.IF + s.doppler
+            fcode = crate * (1 + s.doppler / carrier)
+            chips = fcode * t + s.code_phase
+            period = np.floor(chips / clen).astype(np.int64)
+            sub = np.floor(2.0 * (chips - period * float(clen))).astype(np.int64) % (2 * clen)
+            cB = boc11(scene.codes[s.prn][0]).astype(np.float64)[sub]
+            cC = boc11(scene.codes[s.prn][1]).astype(np.float64)[sub]
+            dB = nav_bits(s, int(period.max()) + 30)[period + s.bit_offset]
+            dC = E1_SECONDARY.astype(np.float64)[(period + s.bit_offset) % 25]
+            ph = 2 * np.pi * (fc * t % 1.0) + s.phi0
+            sig += _amp(s.cn0, scene.sigma, scene.fs) * (dB * cB - dC * cC) / np.sqrt(2.0) * np.exp(1j * ph)
+            continue
         else:
             clen, crate, carrier = 1023, 1.023e6, L1
             fc = scene.IF + s.doppler
@@ -149,11 +177,16 @@ def make_record_torch(scene: Scene, nsamples: int, device="cuda", chunk: int = 1
     if scene.glonass:
         clen, crate, carrier = 511, 511e3, 1602e6
         codes = {s.prn: torch.tensor(glo_code().astype(np.float32), device=device) for s in scene.sats}
+    elif scene.e1c:
+        clen, crate, carrier = 4092, 1.023e6, L1
+        codes = {s.prn: torch.tensor(boc11(scene.codes[s.prn][0]).astype(np.float32), device=device) for s in scene.sats}
+        pcodes = {s.prn: torch.tensor(boc11(scene.codes[s.prn][1]).astype(np.float32), device=device) for s in scene.sats}
+        sec = torch.tensor(E1_SECONDARY.astype(np.float32), device=device)
     else:
         clen, crate, carrier = 1023, 1.023e6, L1
         codes = {s.prn: torch.tensor(ca_code(s.prn).astype(np.float32), device=device) for s in scene.sats}
-    bits = {s.prn: torch.tensor(nav_bits(s, int(nsamples / scene.fs * 50) + 5).astype(np.float32), device=device)
-            for s in scene.sats}
+    bits = {s.prn: torch.tensor(nav_bits(s, int(nsamples / scene.fs * (250 if scene.e1c else 50)) + 30).astype(np.float32),
+                                device=device) for s in scene.sats}
     for c0 in range(0, nsamples, chunk):
         m = min(chunk, nsamples - c0)
         n = torch.arange(c0, c0 + m, dtype=torch.float64, device=device)
@@ -166,6 +199,14 @@ def make_record_torch(scene: Scene, nsamples: int, device="cuda", chunk: int = 1
             period = torch.floor(chips / clen)
             idx = torch.floor(chips - period * float(clen)).to(torch.int64) % clen
             pint = period.to(torch.int64) + s.bit_offset
+            if scene.e1c:
+                sub = torch.floor(2.0 * (chips - period * float(clen))).to(torch.int64) % (2 * clen)
+                a = _amp(s.cn0, scene.sigma, scene.fs) * 0.7071067811865476 * \
+                    (bits[s.prn][pint] * codes[s.prn][sub] - sec[pint % 25] * pcodes[s.prn][sub])
+                ph = (2 * np.pi) * torch.frac((scene.IF + s.doppler) * t) + s.phi0
+                re += a * torch.cos(ph).to(torch.float32)
+                im += a * torch.sin(ph).to(torch.float32)
+                continue
             d = bits[s.prn][pint // 20]
             if scene.glonass:
                 d = d * torch.where((pint % 20) < 10, 1.0, -1.0).to(torch.float32)

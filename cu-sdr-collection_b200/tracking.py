@@ -6,7 +6,7 @@ from __future__ import annotations
 import numpy as np
 
 from .engine import GC_SV_NONE, Engine
-from .settings import Settings
+from .settings import Settings, num_to_process
 
 # row order of the C ABI's output block == GC_F_* in include/gnsscorr.h
 TRACK_FIELDS = ["absoluteSample", "codeFreq", "carrFreq", "I_P", "I_E", "I_L", "Q_E", "Q_P", "Q_L",
@@ -22,7 +22,7 @@ def tracking(fid, channel: list, settings: Settings, engine: Engine | None = Non
     own = engine is None
     eng = engine or Engine(settings)
     try:
-        n = settings.msToProcess                                            # tracking.m:90
+        n = num_to_process(settings)                                        # tracking.m:90 (GAL_E1C tracking.m:48)
         nch = settings.numberOfChannels
         if settings.is_glonass:     # a GLONASS channel is live when status ~= '-' and is identified by K (GLO tracking.m:137-141)
             prn = [int(c["K"]) if c["status"] != "-" else GC_SV_NONE for c in channel[:nch]]

@@ -28,11 +28,13 @@
 extern "C" {
 #endif
 
-#define GC_ABI_VERSION 2
+#define GC_ABI_VERSION 3
 
 /* signal ids (reference folders).  Implemented: GPS/GPS_L1CA, GLO/GLO_GL1 + GLO/GLO_GL2 (the two
- * GLONASS folders differ only in settings.freqSpacing and the file name) and BDS/B3I. */
-enum { GC_SIG_GPS_L1CA = 0, GC_SIG_GLO_G1G2 = 1, GC_SIG_BDS_B3I = 2 };
+ * GLONASS folders differ only in settings.freqSpacing and the file name), BDS/B3I and GAL/GAL_E1C
+ * (E1B + E1C BOC(1,1) replicas summed in acquisition, 25-chip secondary-code fine search, 4 ms
+ * data + pilot tracking). */
+enum { GC_SIG_GPS_L1CA = 0, GC_SIG_GLO_G1G2 = 1, GC_SIG_BDS_B3I = 2, GC_SIG_GAL_E1C = 3 };
 
 /* "no satellite on this channel" for gc_track: GPS uses PRN 0 (tracking.m:136); a GLONASS channel is
  * identified by its frequency number K, for which 0 is valid, so unused channels carry GC_SV_NONE
@@ -78,6 +80,9 @@ typedef struct gc_config {
     double cno_acc_time;         /* settings.CNo.accTime (:133)                                     */
     double freq_spacing;         /* GLONASS only: settings.freqSpacing, FDMA channel spacing in Hz
                                     (GLO/GLO_GL1/initSettings.m: 562.5e3, GLO_GL2: 437.5e3)         */
+    int32_t pilot_trk_flag;      /* settings.pilotTRKflag (GAL/GAL_E1C/initSettings.m:113): 1 = track the
+                                    pilot component too and average the discriminators                */
+    int32_t reserved0;
 } gc_config;
 
 typedef struct gc_handle gc_handle;
@@ -93,7 +98,8 @@ enum {
 
 /* Length of the acqResults vectors for a signal: 32 for GPS L1CA indexed PRN-1 (acquisition.m:130-134),
  * 21 for GLONASS indexed K+7, i.e. MATLAB's K+8 (GLO_GL1/include/acquisition.m:138-142,212),
- * 63 for BeiDou B3I indexed PRN-1 (BDS/B3I/include/acquisition.m:118-122). */
+ * 63 for BeiDou B3I indexed PRN-1 (BDS/B3I/include/acquisition.m:118-122),
+ * 50 for Galileo E1 indexed PRN-1 (GAL/GAL_E1C/include/acquisition.m:127-131). */
 int gc_acq_result_len(int32_t signal);
 
 /* Create / destroy an engine bound to one GPU.  Builds the FFT plan and twiddle tables for
@@ -102,6 +108,17 @@ int  gc_create(gc_handle** out, const gc_config* cfg);
 void gc_destroy(gc_handle* h);
 /* Text of the last error on this handle (or of the last failed gc_create when h == NULL). */
 const char* gc_last_error(const gc_handle* h);
+
+/* Memory-code signals (Galileo E1): the primary codes are ICD tables that the reference reads at run time
+ * from include/E1b.dat / include/E1c.dat (GAL/GAL_E1C/include/generateE1Bcode.m:44-55,
+ * generateE1Ccode.m), so the caller hands them over instead of the library embedding them:
+ *   sv         PRN 1..50
+ *   component  0 = data (E1B), 1 = pilot (E1C)
+ *   chips      the +-1 primary chips (1 - 2*bit, generateE1Bcode.m:55), nChips == code_length (4092);
+ *              the BOC(1,1) sub-carrier (:58-64) is applied by the library.
+ * Every SV named in gc_acquire / gc_track must have both components set.  Signals with generated
+ * codes (GPS L1CA, GLONASS, B3I) return GC_ERR_ARG. */
+int gc_set_code(gc_handle* h, int32_t sv, int32_t component, const int8_t* chips, int32_t nChips);
 
 /* Make an IF record resident in HBM.  `bytes` is the raw file image from byte 0
  * (what fopen/fread see, postProcessing.m:59-96): int8 I,Q interleaved for fileType 2.
@@ -143,7 +160,8 @@ int gc_acquire_host(gc_handle* h, const int8_t* iq, size_t nSamples,
  *   codeFreq0[ch] channel(ch).codeFreq, the carrier-aided centre of the code NCO that preRun.m computes
  *                 for B3I (BDS/B3I/include/preRun.m:71-73, tracking.m:57,146); NULL = settings.codeFreqBasis
  *                 (GPS L1CA, GLONASS)
- *   nEpochs       settings.msToProcess (code periods)
+ *   nEpochs       integration periods to process: settings.msToProcess for the 1 ms signals,
+ *                 round(msToProcess/1000/intTime) for Galileo E1 (GAL_E1C/include/tracking.m:48)
  *   out           [nCh][GC_TRACK_NFIELDS][nEpochs] doubles; rows pre-filled like tracking.m:51-77
  *                 (zeros for absoluteSample and I/Q, +inf for the rest)
  *   vsmValue/vsmIndex  [nCh][nEpochs / cno_vsm_interval]  (trackResults.CNo, tracking.m:80-83,351-358)
@@ -174,7 +192,8 @@ typedef struct gc_stats {
     int32_t track_launches;    /* kernels launched by the last gc_track                             */
     int32_t fft_len;           /* 2*samplesPerCode                                                  */
     int32_t acq_path;          /* 0 = generic mixed-radix passes, 1 = fused C x 32 x RB plan (lengths
-                                  32736, 36000, 24000, 32000, 40000)                                */
+                                  32736, 36000, 24000, 32000, 40000), 2 = fused plan with the one-kernel
+                                  cluster correlation stage (GC_ACQ_PATH=cluster)                   */
     int32_t n_acquired;        /* PRNs above threshold in the last gc_acquire                       */
     float corr_rows_ms;        /* dominant kernel: spectrum multiply + inverse row FFT              */
     float corr_cols_ms;        /* inverse column DFT + |.| + non-coherent sum + row max             */

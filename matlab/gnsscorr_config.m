@@ -1,12 +1,13 @@
 function cfg = gnsscorr_config(settings, signal)
 %GNSSCORR_CONFIG  settings struct (initSettings.m) -> the field names of gc_config (gnsscorr.h).
-%   signal: 'GPS_L1CA' (default), 'GLO' (GLO_GL1 / GLO_GL2) or 'BDS_B3I' - the wrapper of each signal
+%   signal: 'GPS_L1CA' (default), 'GLO' (GLO_GL1 / GLO_GL2), 'BDS_B3I' or 'GAL_E1C' - the wrapper of each signal
 %   folder passes its own.
 if nargin < 2, signal = 'GPS_L1CA'; end
 cfg.device = 0;
 switch signal
     case 'GLO',     cfg.signal = 1;  cfg.freq_spacing = settings.freqSpacing;
     case 'BDS_B3I', cfg.signal = 2;  cfg.freq_spacing = 0;
+    case 'GAL_E1C', cfg.signal = 3;  cfg.freq_spacing = 0;
     otherwise,      cfg.signal = 0;  cfg.freq_spacing = 0;
 end
 cfg.file_type = settings.fileType;
@@ -32,4 +33,9 @@ cfg.pll_damping_ratio = settings.pllDampingRatio;
 cfg.pll_noise_bandwidth = settings.pllNoiseBandwidth;
 cfg.int_time = settings.intTime;
 cfg.cno_acc_time = settings.CNo.accTime;
+if isfield(settings, 'pilotTRKflag')
+    cfg.pilot_trk_flag = settings.pilotTRKflag;
+else
+    cfg.pilot_trk_flag = 0;
+end
 end

@@ -12,9 +12,12 @@
  *         iq_int8 : int8 vector, I,Q interleaved (longSignal as stored in the file)
  *         svList  : double vector of PRNs (GLONASS: frequency numbers K)
  *         r       : struct carrFreq, codePhase, peakMetric (1x32 double; GLONASS 1x21, index K+8)
- *   r = gnsscorr_mex('track', cfg, path, prn, acqFreq, codePhase, nEpochs [, codeFreq0])
+ *   r = gnsscorr_mex('track', cfg, path, prn, acqFreq, codePhase, nEpochs [, codeFreq0 [, codes]])
  *         r       : struct out (nEpochs x 15 x nCh double, MATLAB column-major view of the
  *                   C [nCh][15][nEpochs] block), vsmValue, vsmIndex, epochsDone
+ *   Galileo E1 (memory codes, gc_set_code): 'acquire' takes a 5th and 'track' a 9th argument
+ *         codes   : struct sv (double vector of PRNs), data, pilot (int8, codeLength x numel(sv), one
+ *                   column of +-1 primary chips per PRN - generateE1Bcode(PRN)(1:2:end) etc.)
  *
  * This file cannot be exercised in the build image (no MATLAB); it is compile-checked against
  * matlab/stub/mex.h and the same C entry points are exercised from Python (ctypes).
@@ -56,6 +59,31 @@ static void fill_config(const mxArray* s, gc_config* c)
     c->pll_noise_bandwidth = field(s, "pll_noise_bandwidth");
     c->int_time = field(s, "int_time");
     c->cno_acc_time = field(s, "cno_acc_time");
+    c->pilot_trk_flag = mxGetField(s, 0, "pilot_trk_flag") ? (int32_t)field(s, "pilot_trk_flag") : 0;
+}
+
+/* codes struct -> gc_set_code for every listed PRN (Galileo E1) */
+static void set_codes(gc_handle* h, const gc_config* cfg, const mxArray* codes)
+{
+    const mxArray *sv = mxGetField(codes, 0, "sv"), *d = mxGetField(codes, 0, "data"), *p = mxGetField(codes, 0, "pilot");
+    mwSize i, n;
+    if (!sv || !d || !p || !mxIsInt8(d) || !mxIsInt8(p)) { gc_destroy(h); mexErrMsgIdAndTxt("gnsscorr:args", "codes: struct with sv, data (int8), pilot (int8)"); }
+    n = mxGetNumberOfElements(sv);
+    if (mxGetNumberOfElements(d) != n * (mwSize)cfg->code_length || mxGetNumberOfElements(p) != n * (mwSize)cfg->code_length) {
+        gc_destroy(h);
+        mexErrMsgIdAndTxt("gnsscorr:args", "codes: data and pilot must be codeLength x numel(sv)");
+    }
+    for (i = 0; i < n; ++i) {
+        int rc = gc_set_code(h, (int32_t)mxGetDoubles(sv)[i], 0, (const int8_t*)mxGetInt8s(d) + i * cfg->code_length, cfg->code_length);
+        if (rc == GC_OK) rc = gc_set_code(h, (int32_t)mxGetDoubles(sv)[i], 1, (const int8_t*)mxGetInt8s(p) + i * cfg->code_length, cfg->code_length);
+        if (rc != GC_OK) {
+            char msg[512];
+            strncpy(msg, gc_last_error(h), sizeof(msg) - 1);
+            msg[sizeof(msg) - 1] = 0;
+            gc_destroy(h);
+            mexErrMsgIdAndTxt("gnsscorr:fail", "gc_set_code failed (%d): %s", rc, msg);
+        }
+    }
 }
 
 static void check(gc_handle* h, int rc, const char* what)
@@ -86,7 +114,8 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
         const double* svd = mxGetDoubles(prhs[3]);
         int32_t sv[64];
         mwSize i;
-        if (nrhs != 4 || !mxIsInt8(prhs[2]) || nSv > 64) { gc_destroy(h); mexErrMsgIdAndTxt("gnsscorr:args", "acquire: bad arguments"); }
+        if ((nrhs != 4 && nrhs != 5) || !mxIsInt8(prhs[2]) || nSv > 64) { gc_destroy(h); mexErrMsgIdAndTxt("gnsscorr:args", "acquire: bad arguments"); }
+        if (nrhs == 5) set_codes(h, &cfg, prhs[4]);
         for (i = 0; i < nSv; ++i) sv[i] = (int32_t)svd[i];
         plhs[0] = mxCreateStructMatrix(1, 1, 3, names);
         for (i = 0; i < 3; ++i) mxSetField(plhs[0], 0, names[i], mxCreateDoubleMatrix(1, n, mxREAL));
@@ -105,7 +134,8 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
         int32_t prn[256];
         mxArray *out, *vv, *vi, *done;
         mwSize i;
-        if ((nrhs != 7 && nrhs != 8) || mxGetString(prhs[2], path, sizeof(path)) || nCh > 256) { gc_destroy(h); mexErrMsgIdAndTxt("gnsscorr:args", "track: bad arguments"); }
+        if (nrhs < 7 || nrhs > 9 || mxGetString(prhs[2], path, sizeof(path)) || nCh > 256) { gc_destroy(h); mexErrMsgIdAndTxt("gnsscorr:args", "track: bad arguments"); }
+        if (nrhs == 9) set_codes(h, &cfg, prhs[8]);
         for (i = 0; i < nCh; ++i) prn[i] = (prnd[i] != prnd[i]) ? GC_SV_NONE : (int32_t)prnd[i];   /* NaN = channel off (GLONASS) */
         dims[0] = nEpochs; dims[1] = GC_TRACK_NFIELDS; dims[2] = nCh;
         out = mxCreateNumericArray(3, dims, mxDOUBLE_CLASS, mxREAL);
@@ -113,7 +143,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
         vi = mxCreateDoubleMatrix(nV, nCh, mxREAL);
         done = mxCreateNumericMatrix(1, nCh, mxINT32_CLASS, mxREAL);
         check(h, gc_track_file(h, path, (int32_t)nCh, prn, mxGetDoubles(prhs[4]), mxGetDoubles(prhs[5]),
-                               nrhs == 8 ? mxGetDoubles(prhs[7]) : NULL, nEpochs,
+                               (nrhs >= 8 && !mxIsEmpty(prhs[7])) ? mxGetDoubles(prhs[7]) : NULL, nEpochs,
                                mxGetDoubles(out), mxGetDoubles(vv), mxGetDoubles(vi), (int32_t*)mxGetInt32s(done)),
               "gc_track_file");
         plhs[0] = mxCreateStructMatrix(1, 1, 4, names);

@@ -17,6 +17,7 @@ double* mxGetDoubles(const mxArray*);
 int8_t* mxGetInt8s(const mxArray*);
 int32_t* mxGetInt32s(const mxArray*);
 int mxIsInt8(const mxArray*);
+int mxIsEmpty(const mxArray*);
 mxArray* mxCreateStructMatrix(mwSize, mwSize, int, const char**);
 mxArray* mxCreateDoubleMatrix(mwSize, mwSize, mxComplexity);
 mxArray* mxCreateNumericArray(mwSize, const mwSize*, mxClassID, mxComplexity);

@@ -36,7 +36,9 @@ typedef struct {
     double pllDampingRatio, pllNoiseBandwidth, intTime;            /* :105-108 */
     double CNo_accTime; int CNo_VSMinterval;                       /* :133-135 */
     double freqSpacing;                                            /* GLO/GLO_GL1/initSettings.m:72 */
-    int    glo;            /* 0: GPS/GPS_L1CA files; 1: GLO/GLO_GL1 (= GLO_GL2), cited "GLO :line"; 2: BDS/B3I, cited "B3I :line" */
+    int    glo;            /* 0: GPS/GPS_L1CA files; 1: GLO/GLO_GL1 (= GLO_GL2), cited "GLO :line"; 2: BDS/B3I, cited "B3I :line";
+                              3: GAL/GAL_E1C, cited "E1C :line" (pilotTRKflag below) */
+    int    pilotTRKflag;   /* GAL/GAL_E1C/initSettings.m:113 */
 } orc_settings;
 
 /* ---------------------------------------------------------------- helpers */
@@ -223,6 +225,28 @@ int orc_fft(double* reim /*interleaved, n*/, int n, int dir)
     return 0;
 }
 
+/* Galileo E1 memory codes: DATA the reference reads at run time from include/E1b.dat / E1c.dat
+ * (E1C generateE1Bcode.m:44-55); the caller hands the 0/1 tables [50][4092] over before using mode 3. */
+static const int8_t* g_e1bits[2] = {NULL, NULL};
+void orc_set_e1_codes(const int8_t* e1b, const int8_t* e1c) { g_e1bits[0] = e1b; g_e1bits[1] = e1c; }
+/* E1C generateE1Bcode.m:55-64 / generateE1Ccode.m: 1-2*bit with the BOC(1,1) sub-carrier [c -c], 8184 values */
+static void e1_code(int PRN, int comp, double* out /*8184*/)
+{
+    const int8_t* b = g_e1bits[comp] + (size_t)(PRN - 1) * 4092;
+    for (int i = 0; i < 4092; i++) { double c = 1.0 - 2.0 * (double)b[i]; out[2 * i] = c; out[2 * i + 1] = -c; }
+}
+/* E1C makeE1BTable.m:38-58 / makeE1CTable.m */
+static void e1_table(const double* code, const orc_settings* s, int N, double* table)
+{
+    double ts = 1 / s->samplingFreq, tc = 1 / s->codeFreqBasis / 2;
+    for (int n = 1; n <= N; n++) {
+        int idx = (int)ceil((ts * (double)n) / tc);
+        if (n == N) idx = (int)s->codeLength * 2;
+        if (n == 1) idx = 1;
+        table[n - 1] = code[idx - 1];
+    }
+}
+
 /* --------------------------------------------------------------- acquisition
  * acquisition.m:113-292 (resampling branch :50-111 not restated, resamplingflag==0).
  * iq: int8 interleaved I,Q record bytes AFTER the fseek of postProcessing.m:74; the first
@@ -237,17 +261,19 @@ int orc_acquisition(const int8_t* iq, size_t nSamplesAvail, const orc_settings* 
     const int N = orc_samples_per_code(s);
     const int L2 = 2 * N;
     const int b3i = (s->glo == 2);
+    const int e1c = (s->glo == 3);
     /* postProcessing.m:86 max(42, nonCoh+2); B3I postProcessing.m:86 max(22, nonCoh+1) */
     const int codeLen = b3i ? ((22 > s->acqNonCohTime + 1) ? 22 : s->acqNonCohTime + 1)
                             : ((42 > s->acqNonCohTime + 2) ? 42 : s->acqNonCohTime + 2);
-    const int nFinePer = b3i ? 20 : 40;                                          /* B3I acquisition.m:131-133 */
+    const int nFinePer = b3i ? 20 : e1c ? 25 : 40;                               /* B3I acquisition.m:131-133; E1C :148 */
     if (nSamplesAvail < (size_t)codeLen * N) return -1;
     const double ts = 1 / s->samplingFreq;                                       /* :119 */
     const int nBins = (int)m_round(s->acqSearchBand * 2 / s->acqSearchStep) + 1; /* :124 */
-    const double fineSearchStep = 25;                                            /* :138 */
+    const double fineSearchStep = e1c ? 10 : 25;                                 /* :138; E1C :138 */
     const int nFine = (int)m_round(s->acqSearchStep / fineSearchStep) + 1;       /* :140 */
     const int nonCoh = s->acqNonCohTime;
-    const int nRes = s->glo == 1 ? 21 : b3i ? 63 : 32;      /* GLO acquisition.m:138-142 ; B3I :118-122 */
+    const int nRes = s->glo == 1 ? 21 : b3i ? 63 : e1c ? 50 : 32;   /* GLO acquisition.m:138-142 ; B3I :118-122 ; E1C :127-131 */
+    if (e1c && (!g_e1bits[0] || !g_e1bits[1])) return -3;
     for (int i = 0; i < nRes; i++) { carrFreq[i] = codePhaseOut[i] = peakMetric[i] = 0; coarseBin[i] = coarseCodePhase[i] = 0; }
 
     size_t Ltot = (size_t)codeLen * N;
@@ -280,7 +306,22 @@ int orc_acquisition(const int8_t* iq, size_t nSamplesAvail, const orc_settings* 
         double* results = (double*)calloc((size_t)nBins * L2, sizeof(double));   /* :162 */
         double* coarseFreqBin = (double*)malloc(sizeof(double) * nBins);
         double* b3code = NULL;
-        if (s->glo == 1) orc_glo_sampled_code(s->samplingFreq, N, table);        /* GLO :145 */
+        double* e1code = NULL; cplx* codeF2 = NULL; cplx* buf2 = NULL;          /* E1C: pilot (E1C) code and its spectrum */
+        if (e1c) {                                                               /* E1C :158-171 */
+            e1code = (double*)malloc(sizeof(double) * 8184);
+            codeF2 = (cplx*)malloc(sizeof(cplx) * L2);
+            buf2 = (cplx*)malloc(sizeof(cplx) * L2);
+            e1_code(PRN, 1, e1code);
+            e1_table(e1code, s, N, table);
+            for (int n = 0; n < L2; n++) codeF2[n] = n < N ? table[n] : 0.0;
+            fft_exec(&plan, codeF2, tmp, -1);
+            for (int n = 0; n < L2; n++) codeF2[n] = conj(codeF2[n]);
+            double* e1b = (double*)malloc(sizeof(double) * 8184);
+            e1_code(PRN, 0, e1b);
+            e1_table(e1b, s, N, table);
+            free(e1b);
+        }
+        else if (s->glo == 1) orc_glo_sampled_code(s->samplingFreq, N, table);   /* GLO :145 */
         else if (b3i) {                                                          /* B3I makeB3ITable.m:38-52 */
             b3code = (double*)malloc(sizeof(double) * 10230);
             orc_generateB3Icode(PRN, b3code);
@@ -303,10 +344,12 @@ int orc_acquisition(const int8_t* iq, size_t nSamplesAvail, const orc_settings* 
                 const cplx* w = sig + (size_t)(m - 1) * N;                       /* :177 */
                 for (int n = 0; n < L2; n++) buf[n] = carr[n] * w[n];            /* :180-181 */
                 fft_exec(&plan, buf, tmp, -1);                                   /* :183 */
+                if (e1c) { for (int n = 0; n < L2; n++) buf2[n] = buf[n] * codeF2[n]; fft_exec(&plan, buf2, tmp, +1); }   /* E1C :194 */
                 for (int n = 0; n < L2; n++) buf[n] *= codeF[n];                 /* :186 */
                 fft_exec(&plan, buf, tmp, +1);
                 double* row = results + (size_t)(k - 1) * L2;
-                for (int n = 0; n < L2; n++) row[n] += cabs(buf[n]) / L2;        /* :188-190 */
+                if (e1c) for (int n = 0; n < L2; n++) row[n] += cabs(buf[n]) / L2 + cabs(buf2[n]) / L2;   /* E1C :196-198 */
+                else for (int n = 0; n < L2; n++) row[n] += cabs(buf[n]) / L2;   /* :188-190 */
             }
         }
         /* :196  [~,bin] = max(max(results,[],2))   — first maximal row */
@@ -327,6 +370,7 @@ int orc_acquisition(const int8_t* iq, size_t nSamplesAvail, const orc_settings* 
         coarseBin[ri] = bin; coarseCodePhase[ri] = cp;
         if (peakMetric[ri] > s->acqThreshold) {                                  /* :206 */
             double ca[1023]; if (s->glo == 0) orc_generateCAcode(PRN, ca);       /* :213 */
+            if (e1c) e1_code(PRN, 1, e1code);                                    /* E1C :209 */
             double bestFine = -1; int bestJ = 1; double bestFreq = 0;
             for (int j = 1; j <= nFine; j++) {                                   /* :224 */
                 double f = coarseFreqBin[bin - 1] + s->acqSearchStep / 2 - fineSearchStep * (j - 1);  /* :227 */
@@ -337,6 +381,10 @@ int orc_acquisition(const int8_t* iq, size_t nSamplesAvail, const orc_settings* 
                         long gi = (long)c * N + n;
                         double chip;
                         if (s->glo == 1) chip = glo40[gi];                                     /* GLO :164,236 */
+                        else if (e1c) {                                                        /* E1C :211-214 */
+                            long idx = (long)floor((ts * (double)gi) / (1 / s->codeFreqBasis / 2));
+                            chip = e1code[idx % 8184];
+                        }
                         else if (b3i) {                                                        /* B3I :174-177 */
                             long idx = (long)floor((ts * (double)gi) / (1 / s->codeFreqBasis));
                             chip = b3code[idx % 10230];
@@ -352,6 +400,17 @@ int orc_acquisition(const int8_t* iq, size_t nSamplesAvail, const orc_settings* 
                     sumPerCode[c] = acc;
                 }
                 double maxPower = 0;
+                if (e1c) {                                                       /* E1C :236-252 */
+                    static const double SEC[25] = {1, 1, -1, -1, -1, 1, 1, 1, 1, 1, 1, 1, -1, 1, -1, 1, -1, -1, 1, -1, -1, 1, 1, -1, 1};
+                    cplx t = 0; for (int q = 0; q < 25; q++) t += sumPerCode[q] * SEC[q];
+                    maxPower = cabs(t);
+                    for (int ci = 1; ci <= 24; ci++) {
+                        cplx t1 = 0, t2 = 0;
+                        for (int q = 0; q < 25; q++) { cplx v_ = sumPerCode[q] * SEC[(q - ci + 25) % 25]; if (q < ci) t1 += v_; else t2 += v_; }
+                        double pw = cabs(t1) + cabs(t2);
+                        if (pw > maxPower) maxPower = pw;
+                    }
+                }
                 if (b3i) {                                                       /* B3I :193-211 */
                     static const double NH[20] = {1, 1, 1, 1, 1, -1, 1, 1, -1, -1, 1, -1, 1, -1, 1, 1, -1, -1, -1, 1};
                     if ((PRN >= 1 && PRN <= 5) || (PRN >= 59 && PRN <= 63)) {
@@ -370,7 +429,7 @@ int orc_acquisition(const int8_t* iq, size_t nSamplesAvail, const orc_settings* 
                         }
                     }
                 }
-                for (int c = 0; c < 20 && !b3i; c++) {                           /* :243 */
+                for (int c = 0; c < 20 && !b3i && !e1c; c++) {                   /* :243 */
                     cplx t = 0;
                     if (s->glo == 0) { for (int q = c; q < c + 20; q++) t += sumPerCode[q]; }
                     else {                                                       /* GLO :250-251: sum(c:c+9) - sum(c+10:c+19) */
@@ -390,6 +449,7 @@ int orc_acquisition(const int8_t* iq, size_t nSamplesAvail, const orc_settings* 
             if (carrFreq[ri] == 0) carrFreq[ri] = 1;                             /* :258 */
         }
         free(table); free(codeF); free(buf); free(tmp); free(carr); free(results); free(coarseFreqBin); free(b3code);
+        free(e1code); free(codeF2); free(buf2);
     }
     plan_free(&plan); free(sig); free(phasePoints); free(glo40);
     return rc;
@@ -459,8 +519,12 @@ int orc_tracking(const int8_t* iq, size_t nBytes, const orc_settings* s, int nCh
     /* GLO Common/calcLoopCoefCarr.m:41-56 (GLO tracking.m:110) */
     const double WnC = 1.2 * s->pllNoiseBandwidth;
     const double pf3 = pow(WnC, 3) * pow(s->intTime, 2), pf2 = 2 * pow(WnC, 2) * s->intTime, pf1 = 2 * WnC;
-    const int L = (int)s->codeLength;
+    const int e1c = (s->glo == 3);
+    const double sub = e1c ? 2.0 : 1.0;                  /* E1C tracking.m:236-262: tcode*2 into the BOC(1,1) sub-chip table */
+    const int pilot = e1c && s->pilotTRKflag == 1;       /* E1C :127 */
+    const int L = (int)s->codeLength * (e1c ? 2 : 1);    /* table entries per code period */
     const int nV = nEpochs / s->CNo_VSMinterval;
+    if (e1c && (!g_e1bits[0] || !g_e1bits[1])) return -3;
     /* result init (tracking.m:48-83): zeros for absoluteSample and I/Q, inf elsewhere */
     for (int ch = 0; ch < nCh; ch++) {
         double* o = out + (size_t)ch * ORC_NFIELDS * nEpochs;
@@ -481,7 +545,13 @@ int orc_tracking(const int8_t* iq, size_t nBytes, const orc_settings* s, int nCh
         size_t pos = (size_t)(2 * ((long)s->skipNumberOfBytes + (long)codePhase[ch] - 1));   /* :150 */
         double* ca = (double*)malloc(sizeof(double) * 10230);
         double* caCode = (double*)malloc(sizeof(double) * 10232);
-        if (s->glo == 1) orc_glo_code(ca);                                       /* GLO :88 */
+        double* pCode = pilot ? (double*)malloc(sizeof(double) * 10232) : NULL;
+        if (e1c) {                                                               /* E1C :125-130 */
+            e1_code(PRN[ch], 0, ca);
+            if (pilot) { double* t_ = (double*)malloc(sizeof(double) * 8184); e1_code(PRN[ch], 1, t_);
+                         pCode[0] = t_[L - 1]; memcpy(pCode + 1, t_, sizeof(double) * L); pCode[L + 1] = t_[0]; free(t_); }
+        }
+        else if (s->glo == 1) orc_glo_code(ca);                                  /* GLO :88 */
         else if (s->glo == 2) orc_generateB3Icode(PRN[ch], ca);                  /* B3I :55 */
         else orc_generateCAcode(PRN[ch], ca);                                    /* :156 */
         const double codeFreqCentre = (s->glo == 2 && codeFreq0) ? codeFreq0[ch] : s->codeFreqBasis;   /* B3I :57 */
@@ -502,27 +572,39 @@ int orc_tracking(const int8_t* iq, size_t nBytes, const orc_settings* s, int nCh
             double aL = remCodePhase + earlyLateSpc, bL = (blksize - 1) * codePhaseStep + remCodePhase + earlyLateSpc;   /* :259 */
             double aP = remCodePhase, bP = (blksize - 1) * codePhaseStep + remCodePhase;                                 /* :266 */
             int nE_, nL_, nP_; double cE, cL, cP;
-            colon_setup(aE, codePhaseStep, bE, &nE_, &cE);
-            colon_setup(aL, codePhaseStep, bL, &nL_, &cL);
-            colon_setup(aP, codePhaseStep, bP, &nP_, &cP);
+            /* E1C :236-256: the three vectors are (rem -/+ spc)*2 : step*2 : (...)*2 */
+            aE *= sub; bE *= sub; aL *= sub; bL *= sub; aP *= sub; bP *= sub;
+            const double tstep = codePhaseStep * sub;
+            colon_setup(aE, tstep, bE, &nE_, &cE);
+            colon_setup(aL, tstep, bL, &nL_, &cL);
+            colon_setup(aP, tstep, bP, &nP_, &cP);
             F(14)[loopCnt - 1] = remCarrPhase;                                   /* :277 */
             double w = carrFreq * 2.0 * M_PI;                                    /* :281 */
             double I_E = 0, Q_E = 0, I_P = 0, Q_P = 0, I_L = 0, Q_L = 0;
+            double I_Ec = 0, Q_Ec = 0, I_Pc = 0, Q_Pc = 0, I_Lc = 0, Q_Lc = 0;                /* E1C pilot sums :285-290 */
             for (int n = 0; n < blksize; n++) {
-                double e = caCode[(int)ceil(colon_elem(aE, codePhaseStep, cE, nE_, n))];     /* :255-256 */
-                double l = caCode[(int)ceil(colon_elem(aL, codePhaseStep, cL, nL_, n))];     /* :262-263 */
-                double p = caCode[(int)ceil(colon_elem(aP, codePhaseStep, cP, nP_, n))];     /* :269-270 */
+                const int iE = (int)ceil(colon_elem(aE, tstep, cE, nE_, n));
+                const int iL = (int)ceil(colon_elem(aL, tstep, cL, nL_, n));
+                const int iP = (int)ceil(colon_elem(aP, tstep, cP, nP_, n));
+                double e = caCode[iE];                                           /* :255-256 */
+                double l = caCode[iL];                                           /* :262-263 */
+                double p = caCode[iP];                                           /* :269-270 */
                 double trig = (w * ((double)n / s->samplingFreq)) + remCarrPhase;            /* :280-281 */
                 double c = cos(trig), sn = sin(trig);                            /* :287 exp(-1i*trig) = c - i*sn */
                 double xr = raw[2 * n], xi = raw[2 * n + 1];                     /* :233-235 */
                 if (s->glo == 1) { double t_ = xr; xr = xi; xi = t_; }                /* GLO :227 rawSignal2 + 1i*rawSignal1 */
                 double iBB = c * xr + sn * xi, qBB = c * xi - sn * xr;           /* :291-292 */
                 I_E += e * iBB; Q_E += e * qBB; I_P += p * iBB; Q_P += p * qBB; I_L += l * iBB; Q_L += l * qBB;   /* :295-300 */
+                if (pilot) {
+                    I_Ec += pCode[iE] * iBB; Q_Ec += pCode[iE] * qBB; I_Pc += pCode[iP] * iBB; Q_Pc += pCode[iP] * qBB;
+                    I_Lc += pCode[iL] * iBB; Q_Lc += pCode[iL] * qBB;
+                }
             }
-            remCodePhase = (colon_elem(aP, codePhaseStep, cP, nP_, blksize - 1) + codePhaseStep) - s->codeLength;  /* :273 */
+            remCodePhase = (colon_elem(aP, tstep, cP, nP_, blksize - 1) / sub + codePhaseStep) - s->codeLength;  /* :273; E1C :263 */
             double trigEnd = (w * ((double)blksize / s->samplingFreq)) + remCarrPhase;
             remCarrPhase = fmod(trigEnd, 2 * M_PI);                              /* :283 */
             double carrError = atan(Q_P / I_P) / (2.0 * M_PI);                   /* :305 */
+            if (pilot) carrError = (carrError + atan(Q_Pc / I_Pc) / (2.0 * M_PI)) / 2;       /* E1C :297-300 */
             double carrNco;
             if (s->glo == 0) {
                 carrNco = oldCarrNco + (tau2carr / tau1carr) * (carrError - oldCarrError) + carrError * (PDIcarr / tau1carr);   /* :308 */
@@ -536,6 +618,10 @@ int orc_tracking(const int8_t* iq, size_t nBytes, const orc_settings* s, int nCh
             carrFreq = carrFreqBasis + carrNco;                                  /* :317 */
             double sE = sqrt(I_E * I_E + Q_E * Q_E), sL = sqrt(I_L * I_L + Q_L * Q_L);
             double codeError = (sE - sL) / (sE + sL);                            /* :322 */
+            if (pilot) {                                                         /* E1C :327-333 */
+                double sEc = sqrt(I_Ec * I_Ec + Q_Ec * Q_Ec), sLc = sqrt(I_Lc * I_Lc + Q_Lc * Q_Lc);
+                codeError = (codeError + (sEc - sLc) / (sEc + sLc)) / 2;
+            }
             double codeNco = oldCodeNco + (tau2code / tau1code) * (codeError - oldCodeError) + codeError * (PDIcode / tau1code);   /* :326 */
             oldCodeNco = codeNco; oldCodeError = codeError;
             F(1)[loopCnt - 1] = codeFreq;                                        /* :332 */
@@ -552,7 +638,7 @@ int orc_tracking(const int8_t* iq, size_t nBytes, const orc_settings* s, int nCh
             }
             epochsDone[ch] = loopCnt;
         }
-        free(ca); free(caCode);
+        free(ca); free(caCode); free(pCode);
 #undef F
     }
     /* MATLAB `return` on a short read ends the whole function: channels after the first one that

@@ -789,3 +789,216 @@ def preRun_b3i(acq: dict, s: Settings):
         chans[ii] = dict(PRN=p + 1, acquiredFreq=af, codePhase=int(acq["codePhase"][p]),
                          codeFreq=s.codeFreqBasis + (af - s.IF) / s.carrFreqBasis * s.codeFreqBasis, status="T")
     return chans
+
+
+# ===========================================================================
+# Galileo E1 (GAL/GAL_E1C); paths below relative to /root/reference/GAL/GAL_E1C/
+# ===========================================================================
+# The primary codes are the ICD memory codes; the reference reads them at run time from
+# include/E1b.dat / include/E1c.dat (generateE1Bcode.m:44-55).  They are DATA, not algorithm: the
+# restatement takes them as an argument (``codes[PRN] = (e1b_bits, e1c_bits)``, 0/1 arrays of 4092),
+# so tests can run on the real tables where the reference tree is mounted and on seeded stand-in
+# tables on the GPU box.
+def e1c_settings(**kw) -> Settings:
+    """initSettings.m:44-140 defaults (hot-path fields)."""
+    s = Settings(codeLength=4092.0, acqSatelliteList=list(range(1, 37)), acqSearchBand=7000.0, acqNonCohTime=1,
+                 acqSearchStep=150.0, acqThreshold=10.0, resamplingThreshold=50e6, dllCorrelatorSpacing=0.3,
+                 pllNoiseBandwidth=15.0, intTime=0.004, CNo_accTime=0.004, CNo_VSMinterval=400)
+    s.pilotTRKflag = 1                                             # :113
+    for k, v in kw.items():
+        setattr(s, k, v)
+    return s
+
+
+def read_e1_dat(path: str) -> np.ndarray:
+    """fscanf(fid, '%d', 4092*50) of E1b.dat / E1c.dat (generateE1Bcode.m:47-51) -> [50][4092] 0/1."""
+    with open(path) as f:
+        v = np.array(f.read().split(), dtype=np.int64)
+    return v[: 4092 * 50].reshape(50, 4092)
+
+
+def generateE1code(bits: np.ndarray) -> np.ndarray:
+    """generateE1Bcode.m:55-64 / generateE1Ccode.m: 1-2*bit, then the BOC(1,1) sub-carrier [c -c] -> 8184 values."""
+    raw = 1.0 - 2.0 * np.asarray(bits, dtype=np.float64)
+    out = np.empty(2 * raw.size)
+    out[0::2] = raw
+    out[1::2] = -raw
+    return out
+
+
+def makeE1Table(code: np.ndarray, s: Settings) -> np.ndarray:
+    """makeE1BTable.m:38-58 / makeE1CTable.m (``code`` = the 8184-value BOC code)."""
+    N = samples_per_code(s)
+    ts = 1 / s.samplingFreq
+    tc = 1 / s.codeFreqBasis / 2                                   # :43
+    idx = np.ceil((ts * np.arange(1, N + 1, dtype=np.float64)) / tc).astype(np.int64)   # :51
+    idx[-1] = int(s.codeLength) * 2                                # :54
+    idx[0] = 1                                                     # :55
+    return code[idx - 1]
+
+
+_E1_SECONDARY = np.array([1, 1, -1, -1, -1, 1, 1, 1, 1, 1, 1, 1, -1, 1, -1, 1, -1, -1, 1, -1, -1, 1, 1, -1, 1],
+                         dtype=np.float64)                         # acquisition.m:135 ('380AD90')
+
+
+def acquisition_e1c(longSignal: np.ndarray, s: Settings, codes: dict, workers: int = 1):
+    """include/acquisition.m:112-292 (resampling branch not restated, resamplingflag == 0)."""
+    N = samples_per_code(s)                                        # :114
+    ts = 1 / s.samplingFreq
+    phasePoints = np.arange(0, 2 * N, dtype=np.float64) * 2 * np.pi * ts   # :120
+    nBins = int(matlab_round(s.acqSearchBand * 2 / s.acqSearchStep)) + 1   # :122
+    coarseFreqBin = np.zeros(nBins)
+    res = dict(carrFreq=np.zeros(50), codePhase=np.zeros(50), peakMetric=np.zeros(50),
+               coarseBin=np.zeros(50, dtype=np.int64), coarseCodePhase=np.zeros(50, dtype=np.int64))
+    fineSearchStep = 10                                            # :138
+    numOfFineBins = int(matlab_round(s.acqSearchStep / fineSearchStep)) + 1   # :140
+    finePhasePoints = np.arange(0, 25 * N, dtype=np.float64) * 2 * np.pi * ts   # :148
+    x = longSignal[:N]
+    sigPower = math.sqrt(np.sum(np.abs(x - np.mean(x)) ** 2) / (N - 1) * N)     # :151
+    res["sigPower"] = sigPower
+    for PRN in s.acqSatelliteList:                                 # :155
+        E1bCode = generateE1code(codes[PRN][0])
+        E1cCode = generateE1code(codes[PRN][1])
+        E1bFreqDom = np.conj(_FFT(np.concatenate([makeE1Table(E1bCode, s), np.zeros(N)])))   # :158-171
+        E1cFreqDom = np.conj(_FFT(np.concatenate([makeE1Table(E1cCode, s), np.zeros(N)])))
+        results = np.zeros((nBins, 2 * N))
+        for k in range(1, nBins + 1):                              # :174
+            coarseFreqBin[k - 1] = s.IF + s.acqSearchBand - s.acqSearchStep * (k - 1)   # :176
+            sigCarr = np.exp(-1j * coarseFreqBin[k - 1] * phasePoints)                   # :179
+            for m in range(1, s.acqNonCohTime + 1):                # :182
+                signal = longSignal[(m - 1) * N: (m + 1) * N]      # :184
+                IQfreqDom = _FFT(sigCarr * signal, workers)        # :186-189
+                coh = np.abs(_IFFT(IQfreqDom * E1bFreqDom, workers)) + np.abs(_IFFT(IQfreqDom * E1cFreqDom, workers))   # :192-196
+                results[k - 1, :] += coh                           # :198
+        acqCoarseBin = int(np.argmax(results.max(axis=1))) + 1     # :204
+        colmax = results.max(axis=0)
+        codePhase = int(np.argmax(colmax)) + 1                     # :206
+        res["peakMetric"][PRN - 1] = colmax[codePhase - 1] / sigPower / s.acqNonCohTime   # :208
+        res["coarseBin"][PRN - 1] = acqCoarseBin
+        res["coarseCodePhase"][PRN - 1] = codePhase
+        if res["peakMetric"][PRN - 1] > s.acqThreshold:            # :212
+            codeValueIndex = np.floor((ts * np.arange(0, 25 * N, dtype=np.float64)) /
+                                      (1 / s.codeFreqBasis / 2)).astype(np.int64)        # :219
+            E1cCode25ms = E1cCode[np.fmod(codeValueIndex, int(s.codeLength) * 2)]        # :222
+            sig25ms = longSignal[codePhase - 1: codePhase - 1 + 25 * N]                  # :224
+            fineFreqBins = np.zeros(numOfFineBins)
+            fineResult = np.zeros(numOfFineBins)
+            for j in range(1, numOfFineBins + 1):                  # :227
+                fineFreqBins[j - 1] = coarseFreqBin[acqCoarseBin - 1] + s.acqSearchStep / 2 - fineSearchStep * (j - 1)   # :230
+                basebandSig = sig25ms * E1cCode25ms * np.exp(-1j * fineFreqBins[j - 1] * finePhasePoints)   # :233-235
+                sumPerCode = basebandSig.reshape(25, N).sum(axis=1)                      # :237-240
+                maxPower = abs(np.sum(sumPerCode * _E1_SECONDARY))                       # :246
+                for comIndex in range(1, 25):                                            # :248
+                    s2 = sumPerCode * np.roll(_E1_SECONDARY, comIndex)                   # :250-252
+                    comPower = abs(np.sum(s2[:comIndex])) + abs(np.sum(s2[comIndex:]))   # :254
+                    maxPower = max(maxPower, comPower)
+                fineResult[j - 1] = maxPower
+            maxFinBin = int(np.argmax(fineResult)) + 1             # :263
+            res["carrFreq"][PRN - 1] = fineFreqBins[maxFinBin - 1]
+            res["codePhase"][PRN - 1] = codePhase
+            if res["carrFreq"][PRN - 1] == 0:
+                res["carrFreq"][PRN - 1] = 1
+    return res
+
+
+def tracking_e1c(raw: np.ndarray, channel: list, s: Settings, codes: dict):
+    """include/tracking.m:45-383: 4 ms epochs, BOC(1,1) sub-chip tables indexed by ceil(tcode*2)+1 (:236-262),
+    pilot component correlated with the same code phase and both discriminators averaged when
+    settings.pilotTRKflag == 1 (:297-300, :327-333), three-coefficient carrier filter (:303-305)."""
+    nE = int(matlab_round(s.msToProcess / 1000 / s.intTime))       # :48
+    nV = int(math.floor(s.msToProcess / 4 / s.CNo_VSMinterval))    # :70-73
+    out = []
+    for _ in range(s.numberOfChannels):
+        tr = dict(status="-", PRN=0)
+        tr["absoluteSample"] = np.zeros(nE)
+        for f in ("codeFreq", "carrFreq", "dllDiscr", "dllDiscrFilt", "pllDiscr", "pllDiscrFilt", "remCodePhase", "remCarrPhase"):
+            tr[f] = np.full(nE, np.inf)
+        for f in ("I_P", "I_E", "I_L", "Q_E", "Q_P", "Q_L"):
+            tr[f] = np.zeros(nE)
+        tr["VSMValue"] = np.zeros(nV)
+        tr["VSMIndex"] = np.zeros(nV)
+        out.append(tr)
+    earlyLateSpc = s.dllCorrelatorSpacing                          # :82
+    PDIcode = s.intTime                                            # :85
+    tau1code, tau2code = calcLoopCoef(s.dllNoiseBandwidth, s.dllDampingRatio, 1.0)   # :88
+    pf3, pf2, pf1 = calcLoopCoefCarr(s)                            # :92
+    pilot = int(getattr(s, "pilotTRKflag", 1)) == 1
+    L2 = int(s.codeLength) * 2
+    for ch in range(s.numberOfChannels):
+        if channel[ch]["PRN"] == 0:                                # :116
+            continue
+        tr = out[ch]
+        PRN = channel[ch]["PRN"]
+        tr["PRN"] = PRN
+        pos = 2 * (s.skipNumberOfBytes + channel[ch]["codePhase"] - 1)    # :120
+        c = generateE1code(codes[PRN][0])
+        E1bCode = np.concatenate([[c[L2 - 1]], c, [c[0]]])         # :125-126
+        if pilot:
+            c = generateE1code(codes[PRN][1])
+            E1cCode = np.concatenate([[c[L2 - 1]], c, [c[0]]])     # :128-130
+        codeFreq = s.codeFreqBasis; remCodePhase = 0.0             # :133-135
+        carrFreq = channel[ch]["acquiredFreq"]; carrFreqBasis = channel[ch]["acquiredFreq"]; remCarrPhase = 0.0
+        oldCodeNco = oldCodeError = 0.0
+        d2CarrError = dCarrError = 0.0
+        vsmCnt = 0
+        for loopCnt in range(1, nE + 1):                           # :154
+            tr["absoluteSample"][loopCnt - 1] = pos / 2            # :207
+            codePhaseStep = codeFreq / s.samplingFreq              # :211
+            blksize = int(math.ceil((s.codeLength - remCodePhase) / codePhaseStep))   # :214
+            chunk = raw[pos: pos + 2 * blksize]
+            pos += chunk.size
+            if chunk.size != 2 * blksize:                          # :228-232
+                return out
+            rawSignal = chunk[0::2].astype(np.float64) + 1j * chunk[1::2].astype(np.float64)
+            tr["remCodePhase"][loopCnt - 1] = remCodePhase         # :234
+            tE = colonop((remCodePhase - earlyLateSpc) * 2, codePhaseStep * 2,
+                         ((blksize - 1) * codePhaseStep + remCodePhase - earlyLateSpc) * 2)      # :236-238
+            iE = np.ceil(tE).astype(np.int64)                      # tcode2 = ceil(tcode) + 1, 1-based
+            tL = colonop((remCodePhase + earlyLateSpc) * 2, codePhaseStep * 2,
+                         ((blksize - 1) * codePhaseStep + remCodePhase + earlyLateSpc) * 2)      # :245-247
+            iL = np.ceil(tL).astype(np.int64)
+            tP = colonop(remCodePhase * 2, codePhaseStep * 2, ((blksize - 1) * codePhaseStep + remCodePhase) * 2)   # :254-256
+            iP = np.ceil(tP).astype(np.int64)
+            remCodePhase = tP[blksize - 1] / 2 + codePhaseStep - s.codeLength   # :263
+            tr["remCarrPhase"][loopCnt - 1] = remCarrPhase
+            time = np.arange(0, blksize + 1, dtype=np.float64) / s.samplingFreq
+            trigarg = ((carrFreq * 2.0 * np.pi) * time) + remCarrPhase
+            remCarrPhase = math.fmod(trigarg[blksize], 2 * np.pi)
+            bb = np.exp(-1j * trigarg[:blksize]) * rawSignal
+            iB, qB = bb.real, bb.imag
+            I_E = float(np.sum(E1bCode[iE] * iB)); Q_E = float(np.sum(E1bCode[iE] * qB))
+            I_P = float(np.sum(E1bCode[iP] * iB)); Q_P = float(np.sum(E1bCode[iP] * qB))
+            I_L = float(np.sum(E1bCode[iL] * iB)); Q_L = float(np.sum(E1bCode[iL] * qB))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                carrError = float(np.arctan(np.float64(Q_P) / np.float64(I_P)) / (2.0 * np.pi))   # :296
+                sE = math.sqrt(I_E * I_E + Q_E * Q_E); sL = math.sqrt(I_L * I_L + Q_L * Q_L)
+                codeError = float((np.float64(sE) - sL) / (np.float64(sE) + sL))                # :322-323
+                if pilot:
+                    I_Ec = float(np.sum(E1cCode[iE] * iB)); Q_Ec = float(np.sum(E1cCode[iE] * qB))
+                    I_Pc = float(np.sum(E1cCode[iP] * iB)); Q_Pc = float(np.sum(E1cCode[iP] * qB))
+                    I_Lc = float(np.sum(E1cCode[iL] * iB)); Q_Lc = float(np.sum(E1cCode[iL] * qB))
+                    carrErrorE1c = float(np.arctan(np.float64(Q_Pc) / np.float64(I_Pc)) / (2.0 * np.pi))   # :298
+                    carrError = (carrError + carrErrorE1c) / 2     # :299
+                    sEc = math.sqrt(I_Ec * I_Ec + Q_Ec * Q_Ec); sLc = math.sqrt(I_Lc * I_Lc + Q_Lc * Q_Lc)
+                    codeErrorE1c = float((np.float64(sEc) - sLc) / (np.float64(sEc) + sLc))     # :328-329
+                    codeError = (codeError + codeErrorE1c) / 2     # :331
+            d2CarrError = d2CarrError + carrError * pf3            # :303
+            dCarrError = d2CarrError + carrError * pf2 + dCarrError
+            carrNco = dCarrError + carrError * pf1
+            tr["carrFreq"][loopCnt - 1] = carrFreq
+            carrFreq = carrFreqBasis + carrNco                     # :311
+            codeNco = oldCodeNco + (tau2code / tau1code) * (codeError - oldCodeError) + codeError * (PDIcode / tau1code)   # :335-336
+            oldCodeNco = codeNco; oldCodeError = codeError
+            tr["codeFreq"][loopCnt - 1] = codeFreq
+            codeFreq = s.codeFreqBasis - codeNco                   # :343
+            tr["dllDiscr"][loopCnt - 1] = codeError; tr["dllDiscrFilt"][loopCnt - 1] = codeNco
+            tr["pllDiscr"][loopCnt - 1] = carrError; tr["pllDiscrFilt"][loopCnt - 1] = carrNco
+            tr["I_E"][loopCnt - 1] = I_E; tr["I_P"][loopCnt - 1] = I_P; tr["I_L"][loopCnt - 1] = I_L
+            tr["Q_E"][loopCnt - 1] = Q_E; tr["Q_P"][loopCnt - 1] = Q_P; tr["Q_L"][loopCnt - 1] = Q_L
+            if loopCnt % s.CNo_VSMinterval == 0:                   # :360-368
+                vsmCnt += 1
+                lo = loopCnt - s.CNo_VSMinterval
+                tr["VSMValue"][vsmCnt - 1] = CNoVSM(tr["I_P"][lo:loopCnt], tr["Q_P"][lo:loopCnt], s.CNo_accTime)
+                tr["VSMIndex"][vsmCnt - 1] = loopCnt
+        tr["status"] = channel[ch]["status"]
+    return out

@@ -18,7 +18,7 @@ class OrcSettings(C.Structure):
                 [("acqNonCohTime", C.c_int), ("skipNumberOfBytes", C.c_int)] +
                 [(n, C.c_double) for n in ["dllDampingRatio", "dllNoiseBandwidth", "dllCorrelatorSpacing",
                                            "pllDampingRatio", "pllNoiseBandwidth", "intTime", "CNo_accTime"]] +
-                [("CNo_VSMinterval", C.c_int), ("freqSpacing", C.c_double), ("glo", C.c_int)])
+                [("CNo_VSMinterval", C.c_int), ("freqSpacing", C.c_double), ("glo", C.c_int), ("pilotTRKflag", C.c_int)])
 
 
 _orc = None
@@ -37,14 +37,33 @@ def orc_settings(s) -> OrcSettings:
                        s.acqThreshold, s.acqNonCohTime, s.skipNumberOfBytes, s.dllDampingRatio,
                        s.dllNoiseBandwidth, s.dllCorrelatorSpacing, s.pllDampingRatio, s.pllNoiseBandwidth,
                        s.intTime, s.CNo_accTime, s.CNo_VSMinterval, float(getattr(s, "freqSpacing", 0.0)),
-                       oracle_mode(s))
+                       oracle_mode(s), int(getattr(s, "pilotTRKflag", 0)))
 
 
 def oracle_mode(s) -> int:
-    """0 = GPS L1CA files, 1 = GLO_GL1/GL2, 2 = BDS B3I (the `glo` field of the C oracle's settings)."""
+    """0 = GPS L1CA files, 1 = GLO_GL1/GL2, 2 = BDS B3I, 3 = GAL E1C (the `glo` field of the C oracle's settings)."""
     if float(getattr(s, "freqSpacing", 0.0)) != 0.0:
         return 1
-    return 2 if int(s.codeLength) == 10230 else 0
+    return 2 if int(s.codeLength) == 10230 else 3 if int(s.codeLength) == 4092 else 0
+
+
+_e1_keep = None
+
+
+def orc_set_e1_codes(codes: dict):
+    """Hand the E1 memory codes ({PRN: (e1b, e1c)} +-1 primary chips) to the C oracle as its 0/1 tables."""
+    global _e1_keep
+    tabs = [np.zeros((50, 4092), dtype=np.int8), np.zeros((50, 4092), dtype=np.int8)]
+    for prn, (b, c) in codes.items():
+        tabs[0][prn - 1] = (1 - np.asarray(b, dtype=np.int64)) // 2
+        tabs[1][prn - 1] = (1 - np.asarray(c, dtype=np.int64)) // 2
+    _e1_keep = tabs
+    orc().orc_set_e1_codes(P(tabs[0]), P(tabs[1]))
+
+
+def oracle_codes(codes: dict) -> dict:
+    """{PRN: (e1b_bits, e1c_bits)} 0/1 tables for the NumPy oracle from the +-1 chips."""
+    return {prn: ((1 - np.asarray(b, dtype=np.int64)) // 2, (1 - np.asarray(c, dtype=np.int64)) // 2) for prn, (b, c) in codes.items()}
 
 
 def to_oracle_settings(s: Settings) -> "O.Settings":
@@ -63,7 +82,7 @@ def c_acquisition(raw: np.ndarray, s, prns):
     """C oracle acquisition; raw starts at the skip point."""
     cs = orc_settings(s)
     prn = np.asarray(prns, dtype=np.int32)
-    nres = {0: 32, 1: 21, 2: 63}[cs.glo]
+    nres = {0: 32, 1: 21, 2: 63, 3: 50}[cs.glo]
     cf, cp, pm = np.zeros(nres), np.zeros(nres), np.zeros(nres)
     cb, ccp = np.zeros(nres, dtype=np.int32), np.zeros(nres, dtype=np.int32)
     sp = C.c_double()
@@ -84,9 +103,10 @@ def c_tracking(raw: np.ndarray, s, prn, acq_freq, code_phase, n_epochs, parallel
     vv, vi = np.zeros((nch, nv)), np.zeros((nch, nv))
     done = np.zeros(nch, dtype=np.int32)
     cf0 = None if code_freq0 is None else np.ascontiguousarray(code_freq0, dtype=np.float64)
-    orc().orc_tracking(P(raw), C.c_size_t(raw.size), C.byref(cs), nch, P(prn), P(af), P(cp),
-                       P(cf0) if cf0 is not None else None, n_epochs,
-                       P(out), P(vv), P(vi), P(done), parallel)
+    rc = orc().orc_tracking(P(raw), C.c_size_t(raw.size), C.byref(cs), nch, P(prn), P(af), P(cp),
+                            P(cf0) if cf0 is not None else None, n_epochs,
+                            P(out), P(vv), P(vi), P(done), parallel)
+    assert rc == 0, rc
     return out, vv, vi, done
 
 

@@ -9,7 +9,8 @@ import pytest
 
 import np_oracle as O
 from cu_sdr_collection_b200 import Engine, acquisition, init_settings, preRun, synth, tracking
-from helpers import ROOT, c_acquisition, c_tracking, scene, to_oracle_settings, track_rel_err
+from cu_sdr_collection_b200.codes import standin_e1_codes
+from helpers import ROOT, c_acquisition, c_tracking, orc_set_e1_codes, scene, to_oracle_settings, track_rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -431,3 +432,79 @@ def test_b3i_acquisition_tracking_and_wrappers_vs_oracle(tmp_path):
             assert np.max(np.abs(tr[i][name] - rout[i, f]) / sc_) < IQ_TOL, name
         assert np.max(np.abs(tr[i]["codeFreq"] - rout[i, 1])) < 1e-4
         assert np.allclose(tr[i]["CNo"]["VSMValue"], rvv[i], rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------- Galileo E1 (GAL/GAL_E1C)
+def _e1c_case(fs, nsat, seed, extra, band, ms, nch, cn0=48, **kw):
+    codes = standin_e1_codes()
+    sc = synth.default_scene_e1c(codes, fs=fs, nsat=nsat, seed=seed)
+    for x in sc.sats:
+        x.cn0 = cn0
+    sv = sorted({x.prn for x in sc.sats} | set(extra))
+    s = init_settings("GAL_E1C", samplingFreq=fs, acqSatelliteList=sv, acqSearchBand=band, msToProcess=ms, numberOfChannels=nch, **kw)
+    so = to_oracle_settings(s)
+    so.pilotTRKflag = s.pilotTRKflag
+    orc_set_e1_codes(codes)
+    return codes, sc, s, so, sv
+
+
+@pytest.mark.parametrize("fs,band", [(4.092e6, 4500.0), (18e6, 4200.0)])
+def test_e1c_acquisition_vs_oracle(fs, band):
+    """GAL_E1C acquisition (E1B + E1C BOC(1,1) replicas summed, 10 Hz fine search over 25 periods against the
+    25-chip secondary code) on caller-supplied memory codes: a small rate and the reference's 18 Msps
+    (FFT length 144000, generic mixed-radix path)."""
+    codes, sc, s, so, sv = _e1c_case(fs, nsat=2, seed=4, extra=[7], band=band, ms=80, nch=2)
+    N = O.samples_per_code(so)
+    raw = synth.make_record(sc, N * 42 + 64)
+    eng = Engine(s, codes=codes)
+    got = eng.acquire(sv, host_iq=raw)
+    assert got["carrFreq"].shape == (50,) and eng.stats()["fft_len"] == 2 * N
+    ref = c_acquisition(raw, s, sv)
+    _check_acq(got, ref, sv)
+    for sat in sc.sats:                                   # closed loop: injected signals come back on the 10 Hz grid
+        assert got["carrFreq"][sat.prn - 1] != 0
+        assert abs(got["carrFreq"][sat.prn - 1] - (s.IF + sat.doppler)) <= 10
+        start = (4092 - sat.code_phase) * (fs / 1.023e6)
+        assert abs((got["codePhase"][sat.prn - 1] - 1 - start + N / 2) % N - N / 2) <= 2
+    assert got["carrFreq"][7 - 1] == 0
+    with pytest.raises(Exception, match="no code set"):
+        Engine(s, codes={sv[0]: codes[sv[0]]}).acquire(sv, host_iq=raw)
+    eng.close()
+
+
+@pytest.mark.parametrize("fs,nE,pilot", [(4.092e6, 120, 1), (4.092e6, 60, 0), (18e6, 25, 1)])
+def test_e1c_tracking_and_wrappers_vs_oracle(fs, nE, pilot, tmp_path):
+    """acquisition() -> preRun() -> tracking() on a Galileo E1 record: 4 ms epochs, ceil(tcode*2) sub-chip
+    tables, data + pilot discriminators averaged (pilotTRKflag), against the E1C oracle."""
+    codes, sc, s, so, sv = _e1c_case(fs, nsat=2, seed=4, extra=[], band=4500.0, ms=4 * nE, nch=3,
+                                     pilotTRKflag=pilot, CNo_VSMinterval=20)
+    N = O.samples_per_code(so)
+    raw = synth.make_record(sc, N * (nE + 4) + 64)
+    # channel hand-off values as acquisition would give them
+    ch = []
+    for sat in sc.sats:
+        start = (4092 - sat.code_phase) * (fs / 1.023e6)
+        ch.append(dict(PRN=sat.prn, acquiredFreq=round((s.IF + sat.doppler) / 10.0) * 10.0,
+                       codePhase=int(round(start)) % N + 1, status="T"))
+    ch.append(dict(PRN=0, acquiredFreq=0.0, codePhase=0, status="-"))
+    path = tmp_path / "e1.bin"
+    raw.tofile(path)
+    eng = Engine(s, codes=codes)
+    with open(path, "rb") as fid:
+        tr, _ = tracking(fid, ch, s, engine=eng)
+    rout, rvv, rvi, rdone = c_tracking(raw, s, [c["PRN"] for c in ch], [c["acquiredFreq"] for c in ch],
+                                       [float(c["codePhase"]) for c in ch], nE)
+    assert tr[2]["status"] == "-" and tr[2]["epochsDone"] == 0
+    for i in range(2):
+        assert tr[i]["status"] == "T" and tr[i]["epochsDone"] == nE == rdone[i]
+        assert np.array_equal(tr[i]["absoluteSample"], rout[i, 0])
+        sc_ = np.hypot(rout[i, 3], rout[i, 7])
+        for f, name in ((3, "I_P"), (7, "Q_P"), (4, "I_E"), (5, "I_L"), (6, "Q_E"), (8, "Q_L")):
+            assert np.max(np.abs(tr[i][name] - rout[i, f]) / sc_) < IQ_TOL, name
+        assert np.max(np.abs(tr[i]["carrFreq"] - rout[i, 2])) < 1e-4
+        assert np.max(np.abs(tr[i]["codeFreq"] - rout[i, 1])) < 1e-4
+        assert np.max(np.abs(tr[i]["remCodePhase"] - rout[i, 13])) < 1e-6      # chips; follows codeFreq (fp32 discriminators)
+        assert np.allclose(tr[i]["CNo"]["VSMValue"], rvv[i], rtol=1e-5)
+        if nE >= 100:                                     # the loops have pulled in: prompt energy sits in I
+            assert np.mean(np.abs(tr[i]["I_P"][60:])) > 4 * np.mean(np.abs(tr[i]["Q_P"][60:]))
+    eng.close()

@@ -24,14 +24,14 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert set(engine.EXPORTS) == declared
-    assert lib.gc_abi_version() == 2 and lib.gc_build_arch() == b"sm_100a"
-    assert lib.gc_acq_result_len(0) == 32 and lib.gc_acq_result_len(1) == 21
+    assert lib.gc_abi_version() == 3 and lib.gc_build_arch() == b"sm_100a"
+    assert lib.gc_acq_result_len(0) == 32 and lib.gc_acq_result_len(1) == 21 and lib.gc_acq_result_len(3) == 50
 
 
 def test_config_struct_layout_matches_header():
     hdr = open(os.path.join(ROOT, "include", "gnsscorr.h")).read()
     body = re.search(r"typedef struct gc_config \{(.*?)\} gc_config;", hdr, re.S).group(1)
-    names = re.findall(r"^\s*(?:int32_t|int64_t|double)\s+([A-Za-z_]+);", body, re.M)
+    names = re.findall(r"^\s*(?:int32_t|int64_t|double)\s+([A-Za-z_0-9]+);", body, re.M)
     assert names == [f for f, _ in engine.gc_config._fields_]
     body = re.search(r"typedef struct gc_stats \{(.*?)\} gc_stats;", hdr, re.S).group(1)
     names = re.findall(r"^\s*(?:int32_t|float)\s+([A-Za-z_]+);", body, re.M)

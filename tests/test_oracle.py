@@ -274,3 +274,63 @@ def test_b3i_oracles_agree_and_find_injected_signals():
             scale = P_ if 3 <= f <= 8 else np.maximum(np.abs(tr[i][fname]), 1e-9)
             assert np.max(d / scale) < 1e-8, (fname, np.max(d / scale))
         assert tr[i]["codeFreq"][0] == c_["codeFreq"]                  # aided start value (tracking.m:57)
+
+
+# ------------------------------------------------------------------------------- Galileo E1 (GAL/GAL_E1C)
+def test_e1c_oracles_agree_and_closed_loop():
+    """NumPy and C restatements of GAL_E1C acquisition.m / tracking.m agree, and a synthetic E1-B/E1-C record
+    comes back: PRN set, code phase, Doppler on the 10 Hz grid, tracking in lock (prompt energy in I)."""
+    from cu_sdr_collection_b200 import init_settings
+    from helpers import oracle_codes, orc_set_e1_codes, to_oracle_settings
+    tabs = codes.standin_e1_codes()
+    fs, N = 4.092e6, 16368
+    sc = synth.default_scene_e1c(tabs, fs=fs, nsat=2, seed=4)
+    for x in sc.sats:
+        x.cn0 = 48
+    sv = sorted({x.prn for x in sc.sats} | {7})
+    s = init_settings("GAL_E1C", samplingFreq=fs, acqSearchBand=4500.0, acqSatelliteList=sv, msToProcess=480,
+                      numberOfChannels=3, CNo_VSMinterval=20)
+    so = to_oracle_settings(s)
+    so.pilotTRKflag = 1
+    assert O.samples_per_code(so) == N
+    raw = synth.make_record(sc, N * 125)
+    ref = O.acquisition_e1c(O.read_acq_signal(raw, so), so, oracle_codes(tabs), workers=os.cpu_count() or 1)
+    orc_set_e1_codes(tabs)
+    cref = c_acquisition(raw, s, sv)
+    idx = np.array(sv) - 1
+    assert np.array_equal(ref["carrFreq"], cref["carrFreq"]) and np.array_equal(ref["codePhase"], cref["codePhase"])
+    assert np.array_equal(ref["coarseBin"][idx], cref["coarseBin"][idx])
+    assert np.allclose(ref["peakMetric"][idx], cref["peakMetric"][idx], rtol=1e-9)
+    assert ref["carrFreq"].shape == (50,) and ref["carrFreq"][7 - 1] == 0
+    for sat in sc.sats:
+        assert abs(ref["carrFreq"][sat.prn - 1] - (s.IF + sat.doppler)) <= 10
+        start = (4092 - sat.code_phase) * (fs / 1.023e6)
+        assert abs((ref["codePhase"][sat.prn - 1] - 1 - start + N / 2) % N - N / 2) <= 2
+    ch = O.preRun(ref, so)
+    assert [c["PRN"] for c in ch][:2] == [int(p) + 1 for p in np.argsort(-ref["peakMetric"], kind="stable")[:2]]
+    nE = 120
+    tr = O.tracking_e1c(raw, ch, so, oracle_codes(tabs))
+    out, vv, vi, done = c_tracking(raw, s, [c["PRN"] for c in ch], [c["acquiredFreq"] for c in ch],
+                                   [float(c["codePhase"]) for c in ch], nE)
+    assert list(done) == [nE, nE, 0]
+    for i in range(2):
+        assert tr[i]["status"] == "T" and np.array_equal(tr[i]["absoluteSample"], out[i, 0])
+        for f, name in ((3, "I_P"), (7, "Q_P"), (4, "I_E"), (8, "Q_L"), (13, "remCodePhase"), (2, "carrFreq"), (1, "codeFreq")):
+            assert np.allclose(tr[i][name], out[i, f], rtol=1e-8, atol=1e-6), name
+        assert np.allclose(tr[i]["VSMValue"], vv[i], rtol=1e-8)
+        assert np.mean(np.abs(tr[i]["I_P"][60:])) > 4 * np.mean(np.abs(tr[i]["Q_P"][60:]))
+    assert tr[2]["status"] == "-"
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/GAL/GAL_E1C/include/E1b.dat"),
+                    reason="the reference tree (E1b.dat / E1c.dat) is only mounted in the build container")
+def test_e1_memory_code_loader_known_answer():
+    """The loader reads the reference's own E1b.dat / E1c.dat: 50 x 4092 chips; E1-B code 1 starts with
+    hex F5D710 (Galileo OS SIS ICD, Annex C)."""
+    tabs = codes.load_e1_codes("/root/reference/GAL/GAL_E1C/include")
+    assert sorted(tabs) == list(range(1, 51)) and tabs[1][0].shape == (4092,) and set(np.unique(tabs[50][1])) == {-1, 1}
+    bits = (1 - tabs[1][0][:24].astype(int)) // 2
+    assert int("".join(map(str, bits)), 2) == 0xF5D710
+    o = O.read_e1_dat("/root/reference/GAL/GAL_E1C/include/E1b.dat")
+    assert np.array_equal(1 - 2 * o[0], tabs[1][0])
+    assert np.array_equal(codes.boc11(tabs[3][1])[:4], [tabs[3][1][0], -tabs[3][1][0], tabs[3][1][1], -tabs[3][1][1]])
