@@ -137,3 +137,18 @@ def boc11(primary: np.ndarray) -> np.ndarray:
 
 E1_SECONDARY = np.array([1, 1, -1, -1, -1, 1, 1, 1, 1, 1, 1, 1, -1, 1, -1, 1, -1, -1, 1, -1, -1, 1, 1, -1, 1],
                         dtype=np.int8)     # CS25 '380AD90', antipodal (GAL_E1C/include/acquisition.m:135)
+
+
+def standin_codes(signal: str, seed: int = 20260101) -> dict:
+    """Seeded random +-1 stand-ins for the generated 10230-chip codes of GPS L5C (I5/Q5), GAL E5a/E5b (I/Q) and
+    BDS B2a (data/pilot): {PRN: (data, pilot, pilot_secondary)} for PRN 1..63.  The engine takes these codes from
+    the caller (the MATLAB wrappers pass what generateL5Icode.m etc. return); synthetic records and the parity
+    tests only need *some* codes that both sides share.  ``pilot_secondary`` (100 chips) is the per-PRN code
+    GAL E5a's fine search uses; GPS L5C pilots carry the fixed NH20 code instead."""
+    rng = np.random.default_rng([seed, sum(map(ord, signal))])
+    t = (1 - 2 * rng.integers(0, 2, size=(2, 63, 10230))).astype(np.int8)
+    sec = (1 - 2 * rng.integers(0, 2, size=(63, 100))).astype(np.int8)
+    return {prn: (t[0, prn - 1], t[1, prn - 1], sec[prn - 1]) for prn in range(1, 64)}
+
+
+NH20 = np.array([1, 1, 1, 1, 1, -1, 1, 1, -1, -1, 1, -1, 1, -1, 1, 1, -1, -1, -1, 1], dtype=np.int8)

@@ -32,6 +32,8 @@ struct RowsParams {
     const float2* tw;         // as above
     long long nRows;          // forward only
     int nonCoh, nBins;
+    int nRep, repStride;      // inverse: replicas summed per SV (1, or 2 = data + pilot) and their distance in Cc; the
+                              // work buffer then holds nonCoh*nRep transforms per (SV, bin), replica index fastest
     int prnPerCta, mPerCta;   // warps of an inverse CTA = prnPerCta x mPerCta (same row j1, same bin)
     int nPrnChunk, prnSlot0;  // list slots [prnSlot0, prnSlot0 + nPrnChunk) are processed by this launch
     const int* prnList;       // [nSv] replica index per list slot (index into Cc)
@@ -105,6 +107,11 @@ struct FineParams {
     int combine;              // 0: max_c |sum of 20 codes| (acquisition.m:243-248); 1: |sum of 10 - sum of next 10| (GLO :246-252);
                               // 2: B3I NH-code / GEO 2-ms-bit search over 20 codes (BDS/B3I/include/acquisition.m:193-211)
                               // 3: Galileo E1 25-chip secondary code, 25 alignments (GAL_E1C/include/acquisition.m:236-252)
+                              // 4: pilot secondary code, max over all circular shifts of |sum_q s(q)*sec(q - c)| (GPS_L5C
+                              //    acquisition.m:214-219 with NH20, GAL_E5a :211-216 with the per-PRN 100-chip code)
+                              // 5: sum_q |s_data(q)| + sum_q |s_pilot(q)| (BDS/B2a/include/acquisition.m:226-228)
+    int nAcq;                 // acquired SVs; entries [nAcq, 2*nAcq) of chips/prod/sums are the pilot-code ones of combine 5
+    const int8_t* secondary;  // [nAcq][nPeriods] +-1 secondary code (combine 4)
     const int* svId;          // [nAcq] PRN of each acquired SV (combine 2 depends on it)
     const int16_t* chipIdx;   // [nPeriods*N] sample -> chip index of the 40 ms replica (host table, :215-218)
     const int8_t* chips;      // [nAcq][codeLen] +-1 chips of the acquired PRNs
@@ -115,6 +122,6 @@ struct FineParams {
     int* best;                // [nAcq] arg-max fine bin, 0-based (:253)
     double* fineResult;       // [nAcq][nFine]
 };
-cudaError_t launch_fine(const FineParams& p, int nAcq, cudaStream_t s);
+cudaError_t launch_fine(const FineParams& p, int nEntries, int nAcq, cudaStream_t s);
 
 }  // namespace gc

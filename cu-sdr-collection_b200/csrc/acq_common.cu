@@ -156,7 +156,25 @@ __global__ void fine_select_kernel(FineParams p)
     for (int j = threadIdx.x; j < p.nFine; j += blockDim.x) {
         const double* s = p.sums + ((size_t)a * p.nFine + j) * p.nPeriods * 2;
         double maxPower = 0;
-        if (p.combine == 3) {
+        if (p.combine == 4) {
+            // secondary code of the pilot, every circular alignment (GPS_L5C acquisition.m:214-219: the code is rotated
+            // by one element per step, after step c it holds sec(q - c))
+            const int8_t* sec = p.secondary + (size_t)a * p.nPeriods;
+            for (int c = 0; c < p.nPeriods; ++c) {
+                double r = 0, i = 0;
+                for (int q = 0; q < p.nPeriods; ++q) {
+                    const double sc = (double)sec[(q - c + p.nPeriods) % p.nPeriods];
+                    r += s[2 * q] * sc; i += s[2 * q + 1] * sc;
+                }
+                const double pw = hypot(r, i);
+                if (pw > maxPower) maxPower = pw;
+            }
+        } else if (p.combine == 5) {
+            const double* s2 = p.sums + ((size_t)(a + p.nAcq) * p.nFine + j) * p.nPeriods * 2;
+            double t1 = 0, t2 = 0;
+            for (int q = 0; q < p.nPeriods; ++q) { t1 += hypot(s[2 * q], s[2 * q + 1]); t2 += hypot(s2[2 * q], s2[2 * q + 1]); }
+            maxPower = t1 + t2;
+        } else if (p.combine == 3) {
             // Galileo E1: 25 code periods against the 25-chip pilot secondary code '380AD90', aligned and at
             // the 24 other edges (GAL_E1C/include/acquisition.m:135, 236-252)
             const double SEC[25] = {1, 1, -1, -1, -1, 1, 1, 1, 1, 1, 1, 1, -1, 1, -1, 1, -1, -1, 1, -1, -1, 1, 1, -1, 1};
@@ -237,11 +255,11 @@ cudaError_t launch_peak_select(const float* partMax, const int* partIdx, int nPr
     return cudaGetLastError();
 }
 
-cudaError_t launch_fine(const FineParams& p, int nAcq, cudaStream_t s)
+cudaError_t launch_fine(const FineParams& p, int nEntries, int nAcq, cudaStream_t s)
 {
-    dim3 g1(148 * 2, nAcq);
+    dim3 g1(148 * 2, nEntries);
     fine_prep_kernel<<<g1, 256, 0, s>>>(p);
-    dim3 g2(p.nPeriods, nAcq, (p.nFine + kFineBins - 1) / kFineBins);
+    dim3 g2(p.nPeriods, nEntries, (p.nFine + kFineBins - 1) / kFineBins);
     fine_sum_kernel<<<g2, 256, 0, s>>>(p);
     fine_select_kernel<<<nAcq, 64, 0, s>>>(p);
     return cudaGetLastError();

@@ -127,14 +127,16 @@ inv_rows_kernel(RowsParams p)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float2* s_x = reinterpret_cast<float2*>(smem_raw) + warp * (RA * kPitchI);
     const int k1 = blockIdx.x, pg = blockIdx.y;
-    const int mGroups = (p.nonCoh + p.mPerCta - 1) / p.mPerCta;
+    const int M = p.nonCoh * p.nRep;                             // transforms per (SV, bin): blocks x replicas
+    const int mGroups = (M + p.mPerCta - 1) / p.mPerCta;
     const int k = blockIdx.z / mGroups, mg = blockIdx.z % mGroups;
     const int pi = pg * p.prnPerCta + warp / p.mPerCta;         // list slot within this launch's chunk
-    const int m = mg * p.mPerCta + warp % p.mPerCta;
-    if (pi >= p.nPrnChunk || m >= p.nonCoh) return;
+    const int mv = mg * p.mPerCta + warp % p.mPerCta;
+    if (pi >= p.nPrnChunk || mv >= M) return;
+    const int m = mv / p.nRep, r = mv - m * p.nRep;             // block, replica (data / pilot, GPS_L5C acquisition.m:171-175)
     const float2* src = p.X + ((size_t)(k * p.nonCoh + m) * C + k1) * R;
-    const float2* mul = p.Cc + ((size_t)p.prnList[p.prnSlot0 + pi] * C + k1) * R;
-    float2* dst = p.W + (((size_t)(pi * p.nBins + k) * p.nonCoh + m) * C + k1) * R;
+    const float2* mul = p.Cc + ((size_t)(p.prnList[p.prnSlot0 + pi] + r * p.repStride) * C + k1) * R;
+    float2* dst = p.W + (((size_t)(pi * p.nBins + k) * M + mv) * C + k1) * R;
     {                                                            // lane = ka: DFT-RB over kb
         float2 u[RB];
 #pragma unroll
@@ -244,7 +246,7 @@ struct Launch {
         const int smem = (int)(sizeof(float2) * WARPS * P::RA * P::RB);
         cudaError_t e = cudaFuncSetAttribute(inv_rows_kernel<P, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        const int mGroups = (p.nonCoh + p.mPerCta - 1) / p.mPerCta;
+        const int mGroups = (p.nonCoh * p.nRep + p.mPerCta - 1) / p.mPerCta;
         const int pGroups = (p.nPrnChunk + p.prnPerCta - 1) / p.prnPerCta;
         dim3 grid(P::C, pGroups, p.nBins * mGroups);
         inv_rows_kernel<P, WARPS, MINB><<<grid, WARPS * 32, smem, s>>>(p);

@@ -60,7 +60,17 @@ struct gc_handle {
     int sub = 1;                 // table entries per chip (2 = BOC(1,1) sub-chips)
     int nRep = 1;                // replicas summed per SV in acquisition (2 = data + pilot)
     double fineStep = 25.0;      // fine-search bin width in Hz (acquisition.m:138; GAL_E1C acquisition.m:138: 10)
-    std::vector<int8_t> hostCode[2][50];   // caller-supplied codes as BOC(1,1) sub-chips: [component][PRN-1]
+    bool fam5 = false;           // GPS L5C, GAL E5a, GAL E5b, BDS B2a: 10230-chip data + pilot codes supplied by the caller, two
+                                 // replicas summed in acquisition, quadrature pilot tracking, carrier-aided code NCO
+    bool hostCodes = false;      // codes come from gc_set_code (e1c, fam5)
+    int acqMinPeriods = 42, acqExtraPeriods = 2;   // longSignal = max(acqMinPeriods, nonCoh + acqExtraPeriods) code periods
+    int fineCombine = 0;         // FineParams::combine
+    int fineIdx0 = 0;            // first sample index of the fine-search code map (0: ts*(0:n-1), 1: ts*(1:n))
+    bool fineTwoCodes = false;   // B2a: data and pilot codes both wiped off, |.| summed per period
+    bool noFine = false;         // E5b: carrFreq = coarse bin frequency (GAL_E5b acquisition.m:203)
+    int pilotMode = 0;           // tracking: 0 no pilot, 1 same-phase pilot (E1C), 2 quadrature pilot (L5C/E5a/E5b/B2a)
+    std::vector<int8_t> hostCode[3][63];   // caller-supplied codes [component: 0 data, 1 pilot, 2 pilot secondary][PRN-1]
+                                           // (E1: stored as BOC(1,1) sub-chips)
     int nReplicas = 32;          // replica spectra held (32 GPS PRNs; 1 GLONASS; 63 B3I)
     int resultLen = 32;          // length of the acqResults vectors
     int nFinePeriods = 40;       // code periods of the fine-frequency search (40 GPS/GLONASS, 20 B3I)
@@ -82,7 +92,7 @@ struct gc_handle {
     // acquisition
     DevBuf<float2> twGen, X, T1, T2, T3, Cc, W;
     DevBuf<uint64_t> dphi, fdphi;
-    DevBuf<int8_t> codeTab, chips;
+    DevBuf<int8_t> codeTab, chips, fineSecondary;
     DevBuf<int> prnList, slotGroup, partIdx, fineCodePhase, fineBest, fineSv;
     DevBuf<float> partMax;
     DevBuf<PeakOut> peaks;
@@ -154,12 +164,14 @@ double sv_freq_offset(const gc_handle* h, int sv) { return h->glo ? -h->cfg.freq
 // `component` (0 data, 1 pilot); the fine search uses the pilot component where there is one
 void sv_chips(const gc_handle* h, int sv, int8_t* out, int component = 0)
 {
-    if (h->e1c) { const std::vector<int8_t>& c = h->hostCode[component][sv - 1]; std::copy(c.begin(), c.end(), out); }
+    if (h->hostCodes) { const std::vector<int8_t>& c = h->hostCode[component][sv - 1]; std::copy(c.begin(), c.end(), out); }
     else if (h->glo) glo_code(out); else if (h->b3i) b3i_code(sv, out); else ca_code(sv, out);
 }
 bool sv_has_code(const gc_handle* h, int sv)
 {
-    return !h->e1c || (!h->hostCode[0][sv - 1].empty() && !h->hostCode[1][sv - 1].empty());
+    if (!h->hostCodes) return true;
+    if (h->cfg.signal == GC_SIG_GAL_E5A && h->hostCode[2][sv - 1].empty()) return false;   // per-PRN pilot secondary code
+    return !h->hostCode[0][sv - 1].empty() && !h->hostCode[1][sv - 1].empty();
 }
 
 // Replica spectra conj(fft([code zeros(1,N)]))/L (acquisition.m:158-164; GLO acquisition.m:145-149) and
@@ -177,6 +189,14 @@ int build_replicas(gc_handle* h)
                                tab.data() + (size_t)((prn - 1) * 2 + r) * N);
         }
         boc_fine_index(h->cfg.sampling_freq, h->cfg.code_freq_basis, codeLen, (long long)h->nFinePeriods * N, idx40.data());
+    } else if (h->fam5) {                                    // makeL5ITable.m / makeL5QTable.m (and the E5a/E5b/B2a twins)
+        for (int prn = 1; prn <= nRep / 2; ++prn) {
+            if (!sv_has_code(h, prn)) continue;
+            for (int r = 0; r < 2; ++r)
+                make_code_table(h->hostCode[r][prn - 1].data(), h->cfg.sampling_freq, h->cfg.code_freq_basis, codeLen, N,
+                                tab.data() + (size_t)((prn - 1) * 2 + r) * N);
+        }
+        gps_fine_index(h->cfg.sampling_freq, h->cfg.code_freq_basis, codeLen, (long long)h->nFinePeriods * N, idx40.data(), h->fineIdx0);
     } else if (h->b3i) {                                     // makeB3ITable.m:38-52; acquisition.m:170-173
         std::vector<int8_t> chips(codeLen);
         for (int prn = 1; prn <= nRep; ++prn) {
@@ -234,7 +254,8 @@ const char* gc_build_arch(void) { return "sm_100a"; }
 int gc_acq_result_len(int32_t signal)
 {
     return signal == GC_SIG_GPS_L1CA ? 32 : signal == GC_SIG_GLO_G1G2 ? 21 : signal == GC_SIG_BDS_B3I ? 63 :
-           signal == GC_SIG_GAL_E1C ? 50 : 0;
+           signal == GC_SIG_GAL_E1C ? 50 : signal == GC_SIG_GPS_L5C ? 32 : signal == GC_SIG_GAL_E5A ? 50 :
+           signal == GC_SIG_GAL_E5B ? 50 : signal == GC_SIG_BDS_B2A ? 63 : 0;
 }
 
 const char* gc_last_error(const gc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -244,14 +265,13 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     if (!out || !cfg) return fail(nullptr, GC_ERR_ARG, "gc_create: null argument");
     *out = nullptr;
     if (cfg->abi_version != GC_ABI_VERSION) return fail(nullptr, GC_ERR_ARG, "gc_create: abi_version mismatch");
-    if (cfg->signal != GC_SIG_GPS_L1CA && cfg->signal != GC_SIG_GLO_G1G2 && cfg->signal != GC_SIG_BDS_B3I &&
-        cfg->signal != GC_SIG_GAL_E1C)
-        return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: signal not implemented (GPS L1CA, GLONASS G1/G2, BDS B3I, GAL E1C are)");
+    if (cfg->signal < GC_SIG_GPS_L1CA || cfg->signal > GC_SIG_BDS_B2A)
+        return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: signal not implemented (GPS L1CA/L5C, GLONASS G1/G2, BDS B3I/B2a, GAL E1C/E5a/E5b are)");
     if (cfg->file_type != 2 || cfg->sample_bytes != 1)
         return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: only fileType 2 (I/Q) with dataType 'schar' is implemented");
     if (!(cfg->sampling_freq > 0) || !(cfg->code_freq_basis > 0) ||
-        cfg->code_length != (cfg->signal == GC_SIG_GLO_G1G2 ? 511 : cfg->signal == GC_SIG_BDS_B3I ? 10230 :
-                             cfg->signal == GC_SIG_GAL_E1C ? 4092 : 1023) ||
+        cfg->code_length != (cfg->signal == GC_SIG_GLO_G1G2 ? 511 : cfg->signal == GC_SIG_GAL_E1C ? 4092 :
+                             cfg->signal == GC_SIG_GPS_L1CA ? 1023 : 10230) ||
         cfg->acq_noncoh_time < 1 ||
         !(cfg->acq_search_step > 0) || cfg->cno_vsm_interval < 2)
         return fail(nullptr, GC_ERR_ARG, "gc_create: invalid settings");
@@ -270,11 +290,29 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     h->glo = (cfg->signal == GC_SIG_GLO_G1G2);
     h->b3i = (cfg->signal == GC_SIG_BDS_B3I);
     h->e1c = (cfg->signal == GC_SIG_GAL_E1C);
+    h->fam5 = (cfg->signal == GC_SIG_GPS_L5C || cfg->signal == GC_SIG_GAL_E5A || cfg->signal == GC_SIG_GAL_E5B ||
+               cfg->signal == GC_SIG_BDS_B2A);
+    h->hostCodes = h->e1c || h->fam5;
     h->sub = h->e1c ? 2 : 1;
-    h->nRep = h->e1c ? 2 : 1;                                // E1B + E1C (GAL_E1C acquisition.m:186-192)
+    h->nRep = h->hostCodes ? 2 : 1;                          // data + pilot replicas (GAL_E1C acquisition.m:186-192, GPS_L5C :171-175)
     h->fineStep = h->e1c ? 10.0 : 25.0;                      // GAL_E1C acquisition.m:138
-    h->nReplicas = h->glo ? 1 : h->b3i ? 63 : h->e1c ? 100 : 32;
     h->nFinePeriods = h->b3i ? 20 : h->e1c ? 25 : 40;        // BDS/B3I/include/acquisition.m:131-133; GAL_E1C :148
+    h->fineCombine = h->glo ? 1 : h->b3i ? 2 : h->e1c ? 3 : 0;
+    h->pilotMode = (h->e1c && cfg->pilot_trk_flag == 1) ? 1 : 0;
+    if (h->b3i) { h->acqMinPeriods = 22; h->acqExtraPeriods = 1; }               // BDS/B3I/include/postProcessing.m:86
+    if (h->fam5) {
+        h->fineIdx0 = 1;                                     // codeValueIndex = floor(ts*(1:n*samplesPerCode)/tc), GPS_L5C acquisition.m:196
+        h->pilotMode = cfg->pilot_trk_flag == 1 ? 2 : 0;     // GPS_L5C tracking.m:277-281
+        switch (cfg->signal) {
+            case GC_SIG_GPS_L5C: h->nFinePeriods = 20; h->fineCombine = 4; break;                          // GPS_L5C acquisition.m:136-150
+            case GC_SIG_GAL_E5A: h->nFinePeriods = 100; h->fineStep = 5.0; h->fineCombine = 4;             // GAL_E5a acquisition.m:136-142
+                                 h->acqMinPeriods = 102; break;                                            // GAL_E5a postProcessing.m:88
+            case GC_SIG_GAL_E5B: h->noFine = true; h->nFinePeriods = 1; h->acqMinPeriods = 102; break;     // GAL_E5b acquisition.m:203; postProcessing.m:89
+            default:             h->nFinePeriods = std::max(10, (int)cfg->acq_noncoh_time); h->fineCombine = 5;   // BDS/B2a acquisition.m:140
+                                 h->fineTwoCodes = true; h->acqMinPeriods = 12; break;                     // B2a postProcessing.m:86
+        }
+    }
+    h->nReplicas = h->glo ? 1 : h->b3i ? 63 : h->hostCodes ? 2 * gc_acq_result_len(cfg->signal) : 32;
     h->resultLen = gc_acq_result_len(cfg->signal);
     auto bail = [&](int rc) { g_create_error = h->err; gc_destroy(h); return rc; };
     if (cudaSetDevice(cfg->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(GC_ERR_CUDA); }
@@ -289,7 +327,7 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     h->nBins = (int)m_round(cfg->acq_search_band * 2 / cfg->acq_search_step) + 1;
     h->nFine = (int)m_round(cfg->acq_search_step / h->fineStep) + 1;
     h->nonCoh = cfg->acq_noncoh_time;
-    h->fused = fused_plan_info(h->L, &h->fp) && !getenv("GC_FORCE_GENERIC") && h->nRep == 1;
+    h->fused = fused_plan_info(h->L, &h->fp) && !getenv("GC_FORCE_GENERIC");
     h->stats.fft_len = h->L;
     {   // GC_ACQ_PATH=cluster selects the one-kernel correlation stage (acq_cluster.cu, transform resident
         // in a cluster's shared memory); the default is inverse rows + inverse columns through a work buffer
@@ -330,7 +368,7 @@ int gc_create(gc_handle** out, const gc_config* cfg)
         }
         calcLoopCoef(cfg->dll_noise_bandwidth, cfg->dll_damping_ratio, 1.0, &h->tau1code, &h->tau2code);    // tracking.m:100
         calcLoopCoef(cfg->pll_noise_bandwidth, cfg->pll_damping_ratio, 0.25, &h->tau1carr, &h->tau2carr);   // tracking.m:109
-        if (!h->e1c) {                                       // caller-supplied codes: replicas are built by the first gc_acquire
+        if (!h->hostCodes) {                                 // caller-supplied codes: replicas are built by the first gc_acquire
             int rc = build_replicas(h);
             if (rc != GC_OK) return rc;
         }
@@ -351,7 +389,7 @@ void gc_destroy(gc_handle* h)
     h->recOwned.release();
     h->twGen.release(); h->X.release(); h->T1.release(); h->T2.release(); h->T3.release();
     h->chipIdx.release(); h->twFused.release();
-    h->Cc.release(); h->W.release(); h->dphi.release(); h->fdphi.release(); h->codeTab.release(); h->chips.release();
+    h->Cc.release(); h->W.release(); h->dphi.release(); h->fdphi.release(); h->codeTab.release(); h->chips.release(); h->fineSecondary.release();
     h->prnList.release(); h->slotGroup.release(); h->partIdx.release(); h->fineCodePhase.release(); h->fineBest.release(); h->fineSv.release(); h->partMax.release();
     h->peaks.release(); h->sigPower.release(); h->fineSums.release(); h->fineResult.release(); h->fineProd.release();
     h->chans.release(); h->trackCodes.release(); h->trackPilot.release(); h->trackOut.release(); h->epochsDone.release();
@@ -363,15 +401,22 @@ void gc_destroy(gc_handle* h)
 int gc_set_code(gc_handle* h, int32_t sv, int32_t component, const int8_t* chips, int32_t nChips)
 {
     if (!h) return GC_ERR_ARG;
-    if (!h->e1c) return fail(h, GC_ERR_ARG, "gc_set_code: this signal generates its own codes");
-    if (sv < 1 || sv > 50 || component < 0 || component > 1 || !chips || nChips != h->cfg.code_length)
-        return fail(h, GC_ERR_ARG, "gc_set_code: bad argument (PRN 1..50, component 0/1, code_length chips)");
+    if (!h->hostCodes) return fail(h, GC_ERR_ARG, "gc_set_code: this signal generates its own codes");
+    const bool secondary = (component == 2);
+    if (secondary && h->cfg.signal != GC_SIG_GAL_E5A) return fail(h, GC_ERR_ARG, "gc_set_code: only GAL E5a takes a pilot secondary code");
+    if (sv < 1 || sv > h->resultLen || component < 0 || component > 2 || !chips ||
+        nChips != (secondary ? 100 : h->cfg.code_length))
+        return fail(h, GC_ERR_ARG, "gc_set_code: bad argument (PRN in range, component 0/1 with code_length chips, or 2 with 100)");
     for (int i = 0; i < nChips; ++i)
         if (chips[i] != 1 && chips[i] != -1) return fail(h, GC_ERR_ARG, "gc_set_code: chips must be +-1");
     std::vector<int8_t>& c = h->hostCode[component][sv - 1];
-    c.resize((size_t)2 * nChips);
-    boc11(chips, nChips, c.data());                           // generateE1Bcode.m:58-64
-    h->replicasReady = false;
+    if (h->e1c) {
+        c.resize((size_t)2 * nChips);
+        boc11(chips, nChips, c.data());                       // generateE1Bcode.m:58-64
+    } else {
+        c.assign(chips, chips + nChips);
+    }
+    if (!secondary) h->replicasReady = false;
     return GC_OK;
 }
 
@@ -418,7 +463,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         if (rc != GC_OK) return rc;
     }
     // postProcessing.m:86 reads max(42, nonCoh+2) code periods (B3I: max(22, nonCoh+1), BDS/B3I/include/postProcessing.m:86)
-    const int nPeriodsAcq = h->b3i ? std::max(22, nonCoh + 1) : std::max(42, nonCoh + 2);
+    const int nPeriodsAcq = std::max(h->acqMinPeriods, nonCoh + h->acqExtraPeriods);
     const long long recSamples = (long long)(h->recBytes / 2);
     if (winStart < 0 || winStart + (long long)nPeriodsAcq * N > recSamples)
         return fail(h, GC_ERR_SHORT_RECORD, "gc_acquire: record shorter than the acquisition window (max(42, acqNonCohTime+2) code periods; B3I max(22, acqNonCohTime+1))");
@@ -499,7 +544,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         fwdEv.push_back({f0, f1});
         CorrParams cp{};
         cp.X = h->X.p; cp.Cc = h->Cc.p; cp.tw = h->twFused.p;
-        cp.nonCoh = nonCoh; cp.nBins = nBins; cp.nSlots = nSv; cp.nRep = 1; cp.repStride = 0;
+        cp.nonCoh = nonCoh; cp.nBins = nBins; cp.nSlots = nSv; cp.nRep = h->nRep; cp.repStride = 1;
         cp.slotReplica = h->prnList.p; cp.slotGroup = h->slotGroup.p;
         cp.partMax = h->partMax.p; cp.partIdx = h->partIdx.p;
         GC_CUDA(h, launch_corr_cluster(L, cp, st)); ++launches;
@@ -530,15 +575,16 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
             GC_CUDA(h, launch_fwd_rows(L, rp, st)); ++launches;
             fwdEv.push_back({f0, mark()});
             // PRN chunks sized so the inverse work buffer stays below ~2.5 GB
-            int chunk = (int)std::max<long long>(1, (long long)(2.5e9 / ((double)nKm * L * sizeof(float2))));
+            int chunk = (int)std::max<long long>(1, (long long)(2.5e9 / ((double)nKm * h->nRep * L * sizeof(float2))));
             if (const char* e = getenv("GC_ACQ_CHUNK_PRNS")) chunk = std::max(1, atoi(e));
             chunk = std::min(chunk, g1 - g0);
-            GC_CUDA(h, h->W.reserve((size_t)chunk * nKm * L));
+            GC_CUDA(h, h->W.reserve((size_t)chunk * nKm * h->nRep * L));
             for (int s0 = g0; s0 < g1; s0 += chunk) {
                 const int nc = std::min(chunk, g1 - s0);
                 RowsParams ip{};
                 ip.X = h->X.p; ip.Cc = h->Cc.p; ip.W = h->W.p; ip.tw = h->twFused.p;
                 ip.nonCoh = nonCoh; ip.nBins = nBins; ip.prnPerCta = 1; ip.mPerCta = 5;   // 5 warps, 96 registers, 20 warps/SM
+                ip.nRep = h->nRep; ip.repStride = 1;
                 if (const char* e = getenv("GC_ROWS_VARIANT")) {   // "PxM" warps per CTA = P PRNs x M blocks
                     int P = 0, M = 0;
                     if (sscanf(e, "%dx%d", &P, &M) == 2 && (P * M == 5 || P * M == 8)) { ip.prnPerCta = P; ip.mPerCta = M; }
@@ -549,7 +595,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
                 GC_CUDA(h, launch_inv_rows(L, ip, st)); ++launches;
                 const int b = mark();
                 InvColsParams cp{};
-                cp.W = h->W.p; cp.nBins = nBins; cp.nonCoh = nonCoh; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
+                cp.W = h->W.p; cp.nBins = nBins; cp.nonCoh = nonCoh * h->nRep; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
                 cp.partMax = h->partMax.p; cp.partIdx = h->partIdx.p;
                 GC_CUDA(h, launch_inv_cols(L, cp, st)); ++launches;
                 const int d = mark();
@@ -619,39 +665,60 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
     const int nAcq = (int)acq.size();
     h->stats.n_acquired = nAcq;
     float fineMs = 0;
-    if (nAcq > 0) {
+    if (nAcq > 0 && h->noFine) {                                                     // GAL_E5b acquisition.m:203-205
+        for (int a = 0; a < nAcq; ++a) {
+            const int ri = sv_result_index(h, svList[order[acq[a]]]);
+            carrFreq[ri] = coarseFreqOf[acq[a]][peaks[acq[a]].bin - 1];
+            codePhase[ri] = peaks[acq[a]].codePhase;
+        }
+    } else if (nAcq > 0) {
         const int nPeriods = h->nFinePeriods;                                        // :146-148 (B3I :131-133)
+        // fine-search entries: one per acquired SV; B2a wipes off the data AND the pilot code (two entries per SV,
+        // the pilot ones in the second half: BDS/B2a/include/acquisition.m:208-228)
+        const int nEnt = nAcq * (h->fineTwoCodes ? 2 : 1);
         std::vector<int> svIds(nAcq);
         for (int a = 0; a < nAcq; ++a) svIds[a] = svList[order[acq[a]]];
         GC_CUDA(h, upload(h->fineSv, svIds, st));
         const int tabLen = codeLen * h->sub;                 // chips, or BOC sub-chips, per code period
-        std::vector<int8_t> chips((size_t)nAcq * tabLen);
-        std::vector<int> cps(nAcq);
-        std::vector<uint64_t> fd((size_t)nAcq * h->nFine);
+        std::vector<int8_t> chips((size_t)nEnt * tabLen);
+        std::vector<int8_t> secondary;                       // [nAcq][nPeriods] pilot secondary code (combine 4)
+        std::vector<int> cps(nEnt);
+        std::vector<uint64_t> fd((size_t)nEnt * h->nFine);
         std::vector<double> fineFreq((size_t)nAcq * h->nFine);
-        for (int a = 0; a < nAcq; ++a) {
+        if (h->fineCombine == 4) secondary.resize((size_t)nAcq * nPeriods);
+        for (int e = 0; e < nEnt; ++e) {
+            const int a = e % nAcq, comp = h->fineTwoCodes ? e / nAcq : h->nRep - 1;
             const int s = acq[a];
-            sv_chips(h, svList[order[s]], chips.data() + (size_t)a * tabLen, h->nRep - 1);   // :213 (E1: the pilot code, GAL_E1C :209)
-            cps[a] = peaks[s].codePhase;
+            sv_chips(h, svList[order[s]], chips.data() + (size_t)e * tabLen, comp);   // :213 (pilot code where there is one, GAL_E1C :209)
+            cps[e] = peaks[s].codePhase;
             for (int j = 0; j < h->nFine; ++j) {
-                fineFreq[(size_t)a * h->nFine + j] = coarseFreqOf[s][peaks[s].bin - 1] + c.acq_search_step / 2 - h->fineStep * j;   // :227
-                fd[(size_t)a * h->nFine + j] = turns_to_fix(fineFreq[(size_t)a * h->nFine + j] * h->ts);
+                const double f = coarseFreqOf[s][peaks[s].bin - 1] + c.acq_search_step / 2 - h->fineStep * j;   // :227
+                if (e < nAcq) fineFreq[(size_t)a * h->nFine + j] = f;
+                fd[(size_t)e * h->nFine + j] = turns_to_fix(f * h->ts);
+            }
+            if (h->fineCombine == 4 && e < nAcq) {
+                static const int8_t NH20[20] = {1, 1, 1, 1, 1, -1, 1, 1, -1, -1, 1, -1, 1, -1, 1, 1, -1, -1, -1, 1};   // GPS_L5C acquisition.m:134
+                for (int q = 0; q < nPeriods; ++q)
+                    secondary[(size_t)a * nPeriods + q] = (c.signal == GC_SIG_GAL_E5A) ? h->hostCode[2][svList[order[s]] - 1][q]   // generateE5aQ_secondary
+                                                                                         : NH20[q % 20];
             }
         }
         GC_CUDA(h, upload(h->chips, chips, st));
         GC_CUDA(h, upload(h->fineCodePhase, cps, st));
         GC_CUDA(h, upload(h->fdphi, fd, st));
-        GC_CUDA(h, h->fineProd.reserve((size_t)nAcq * nPeriods * N));
-        GC_CUDA(h, h->fineSums.reserve((size_t)nAcq * h->nFine * nPeriods * 2));
+        if (!secondary.empty()) GC_CUDA(h, upload(h->fineSecondary, secondary, st));
+        GC_CUDA(h, h->fineProd.reserve((size_t)nEnt * nPeriods * N));
+        GC_CUDA(h, h->fineSums.reserve((size_t)nEnt * h->nFine * nPeriods * 2));
         GC_CUDA(h, h->fineResult.reserve((size_t)nAcq * h->nFine));
         GC_CUDA(h, h->fineBest.reserve(nAcq));
         FineParams fp{};
         fp.rec = h->rec; fp.winStart = winStart; fp.N = N; fp.nPeriods = nPeriods; fp.nFine = h->nFine; fp.codeLen = tabLen;
-        fp.swapIQ = h->glo ? 1 : 0; fp.combine = h->glo ? 1 : h->b3i ? 2 : h->e1c ? 3 : 0; fp.chipIdx = h->chipIdx.p; fp.svId = h->fineSv.p;
+        fp.swapIQ = h->glo ? 1 : 0; fp.combine = h->fineCombine; fp.chipIdx = h->chipIdx.p; fp.svId = h->fineSv.p;
         fp.chips = h->chips.p; fp.codePhase = h->fineCodePhase.p; fp.dphi = h->fdphi.p; fp.prod = h->fineProd.p;
         fp.sums = h->fineSums.p; fp.best = h->fineBest.p; fp.fineResult = h->fineResult.p;
+        fp.nAcq = nAcq; fp.secondary = h->fineSecondary.p;
         const int fa = mark();
-        GC_CUDA(h, launch_fine(fp, nAcq, st)); launches += 3;
+        GC_CUDA(h, launch_fine(fp, nEnt, nAcq, st)); launches += 3;
         std::vector<int> best(nAcq);
         GC_CUDA(h, cudaMemcpyAsync(best.data(), h->fineBest.p, nAcq * sizeof(int), cudaMemcpyDeviceToHost, st));
         const int fb = mark();
@@ -715,6 +782,8 @@ static double cno_vsm(const double* I, const double* Q, int n, double T)
     return 10 * std::log10(num / den);
 }
 
+int gc_track_nfields(const gc_handle* h) { return (h && h->pilotMode == 2) ? GC_TRACK_NFIELDS_PILOT : GC_TRACK_NFIELDS; }
+
 int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq, const double* codePhase,
              const double* codeFreq0, int32_t nEpochs, double* out, double* vsmValue, double* vsmIndex, int32_t* epochsDone)
 {
@@ -727,7 +796,7 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
     cudaStream_t st = h->stream;
     const int codeLen = c.code_length * h->sub;               // table entries per code period (BOC: sub-chips)
     const int stride = (codeLen + 2 + 15) & ~15;
-    const bool pilot = h->e1c && c.pilot_trk_flag == 1;       // GAL_E1C tracking.m:127
+    const bool pilot = h->pilotMode != 0;                     // GAL_E1C tracking.m:127; GPS_L5C tracking.m:167
     std::vector<TrackChan> chans(nCh);
     std::vector<int8_t> tabs((size_t)nCh * stride, 0), ptabs(pilot ? (size_t)nCh * stride : 0, 0);
     std::vector<char> live(nCh, 0);
@@ -766,7 +835,7 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
         p.pf2 = 2 * std::pow(Wn, 2) * c.int_time;
         p.pf1 = 2 * Wn;
     }
-    p.loopType = (h->glo || h->b3i || h->e1c) ? 1 : 0;
+    p.loopType = (h->glo || h->b3i || h->hostCodes) ? 1 : 0;
     p.swapIQ = h->glo ? 1 : 0;
     p.nEpochs = nEpochs;
     p.exactDisc = getenv("GC_TRACK_EXACT_DISC") ? 1 : 0;
@@ -779,7 +848,8 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
         if (nCh * g <= 148) { cluster = g; break; }
     if (const char* e = getenv("GC_TRACK_CLUSTER")) { const int g = atoi(e); if (g == 1 || g == 2 || g == 4 || g == 8) cluster = g; }
     (void)nLive;
-    p.codeLen = codeLen; p.codeStride = stride; p.subChip = h->sub; p.pilot = pilot ? 1 : 0;
+    p.codeLen = codeLen; p.codeStride = stride; p.subChip = h->sub; p.pilot = h->pilotMode;
+    p.nRows = gc_track_nfields(h);
     // long code periods (Galileo E1: 4 ms = 72000+ samples): spread the block over enough CTAs for the
     // double-buffered window to fit in shared memory
     while (cluster < 8 && track_smem_bytes(track_buf_bytes(h->N + 64, cluster), codeLen, p.pilot) > 227 * 1024) cluster *= 2;
@@ -789,14 +859,15 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
     GC_CUDA(h, upload(h->chans, chans, st));
     GC_CUDA(h, upload(h->trackCodes, tabs, st));
     if (pilot) GC_CUDA(h, upload(h->trackPilot, ptabs, st));
-    const size_t nOut = (size_t)nCh * GC_TRACK_NFIELDS * nEpochs;
+    const int nRows = gc_track_nfields(h);
+    const size_t nOut = (size_t)nCh * nRows * nEpochs;
     GC_CUDA(h, h->trackOut.reserve(nOut));
     GC_CUDA(h, h->epochsDone.reserve(nCh));
     p.codeTables = h->trackCodes.p; p.pilotTables = h->trackPilot.p; p.chans = h->chans.p; p.out = h->trackOut.p; p.epochsDone = h->epochsDone.p;
     long long* dbg = nullptr;
     if (getenv("GC_TRACK_DEBUG")) { cudaMalloc(&dbg, 96 * sizeof(long long)); cudaMemset(dbg, 0, 96 * sizeof(long long)); }
     p.dbg = dbg;
-    GC_CUDA(h, launch_track_fill(h->trackOut.p, nCh, nEpochs, st));
+    GC_CUDA(h, launch_track_fill(h->trackOut.p, nCh, nRows, nEpochs, st));
     cudaEventRecord(h->ev[0], st);
     GC_CUDA(h, launch_track(p, nCh, cluster, st));
     cudaEventRecord(h->ev[1], st);
@@ -832,9 +903,9 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
         if (live[ch] && epochsDone[ch] < nEpochs) failed = ch;
     const double inf = std::numeric_limits<double>::infinity();
     for (int ch = failed + 1; failed >= 0 && ch < nCh; ++ch) {
-        double* o = out + (size_t)ch * GC_TRACK_NFIELDS * nEpochs;
-        for (int f = 0; f < GC_TRACK_NFIELDS; ++f) {
-            const double fill = (f == GC_F_ABSOLUTE_SAMPLE || (f >= GC_F_I_P && f <= GC_F_Q_L)) ? 0.0 : inf;
+        double* o = out + (size_t)ch * nRows * nEpochs;
+        for (int f = 0; f < nRows; ++f) {
+            const double fill = (f == GC_F_ABSOLUTE_SAMPLE || (f >= GC_F_I_P && f <= GC_F_Q_L) || f >= GC_TRACK_NFIELDS) ? 0.0 : inf;
             std::fill(o + (size_t)f * nEpochs, o + (size_t)(f + 1) * nEpochs, fill);
         }
         epochsDone[ch] = 0;
@@ -846,7 +917,7 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
         std::fill(vsmIndex, vsmIndex + (size_t)nCh * nV, 0.0);
         for (int ch = 0; ch < nCh; ++ch) {
             if (!live[ch]) continue;
-            const double* o = out + (size_t)ch * GC_TRACK_NFIELDS * nEpochs;
+            const double* o = out + (size_t)ch * nRows * nEpochs;
             for (int v = 1; v <= nV && v * vint <= epochsDone[ch]; ++v) {
                 const int lo = v * vint - vint;
                 vsmValue[(size_t)ch * nV + v - 1] = cno_vsm(o + (size_t)GC_F_I_P * nEpochs + lo, o + (size_t)GC_F_Q_P * nEpochs + lo, vint, c.cno_acc_time);

@@ -151,11 +151,11 @@ void glo_sample_index(double codeRate, double fs, int codeLength, long long numS
     for (long long k = n + 1; k < numSamples; ++k) idx[k] = 0;   // (never happens: n == numSamples-1)
 }
 
-void gps_fine_index(double fs, double codeFreqBasis, int codeLength, long long numSamples, int16_t* idx)
+void gps_fine_index(double fs, double codeFreqBasis, int codeLength, long long numSamples, int16_t* idx, int first)
 {
     const double ts = 1 / fs, tc = 1 / codeFreqBasis;
     for (long long k = 0; k < numSamples; ++k)
-        idx[k] = (int16_t)((long long)std::floor((ts * (double)k) / tc) % codeLength);
+        idx[k] = (int16_t)((long long)std::floor((ts * (double)(k + first)) / tc) % codeLength);
 }
 
 }  // namespace gc

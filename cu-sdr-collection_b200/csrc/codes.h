@@ -39,7 +39,8 @@ void glo_code(int8_t* out);
 void glo_sample_index(double codeRate, double fs, int codeLength, long long numSamples, int16_t* idx);
 
 // codeValueIndex of the GPS fine search: floor((ts*(0:num-1)) / (1/codeFreqBasis)) mod codeLength
-// (GPS/GPS_L1CA/include/acquisition.m:215-218), 0-based.
-void gps_fine_index(double fs, double codeFreqBasis, int codeLength, long long numSamples, int16_t* idx);
+// (GPS/GPS_L1CA/include/acquisition.m:215-218), 0-based.  first = 1: the sample index runs 1..num
+// (floor(ts*(1:num)/tc), GPS/GPS_L5C/include/acquisition.m:196).
+void gps_fine_index(double fs, double codeFreqBasis, int codeLength, long long numSamples, int16_t* idx, int first = 0);
 
 }  // namespace gc

@@ -254,7 +254,7 @@ track_kernel(TrackParams p)
         return;
     }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double* out = p.out + (size_t)ch * GC_TRACK_ROWS * p.nEpochs;
+    double* out = p.out + (size_t)ch * p.nRows * p.nEpochs;
 
     // wrapped code table [c(L) c(1..L) c(1)]  (tracking.m:156-158)
     for (int i = tid; i < p.codeLen + 2 + 2 * kPad; i += kThreads) {
@@ -543,9 +543,17 @@ track_kernel(TrackParams p)
                 double carrError = p.exactDisc ? atan(__ddiv_rn(Q_P, I_P)) / kTwoPi
                                                : (double)atanf((float)Q_P / (float)I_P) * 0.15915494309189535;
                 if (PILOT) {                                     // GAL_E1C tracking.m:297-300
-                    const double cP2 = p.exactDisc ? atan(__ddiv_rn(v[NS - 3], v[NS - 4])) / kTwoPi
-                                                   : (double)atanf((float)v[NS - 3] / (float)v[NS - 4]) * 0.15915494309189535;
+                    double num = v[NS - 3], den = v[NS - 4];     // Q_P, I_P of the pilot
+                    if (p.pilot == 2) {
+                        // QI = (I + 1i*Q) * exp(-1i*pi/2), exp(-1i*pi/2) = 6.123e-17 - 1i in float64 (GPS_L5C tracking.m:278-279)
+                        const double eps = 6.123233995736766e-17;
+                        num = __dsub_rn(__dmul_rn(v[NS - 3], eps), v[NS - 4]);    // imag(QI) = Q*eps - I
+                        den = __dadd_rn(__dmul_rn(v[NS - 4], eps), v[NS - 3]);    // real(QI) = I*eps + Q
+                    }
+                    const double cP2 = p.exactDisc ? atan(__ddiv_rn(num, den)) / kTwoPi
+                                                   : (double)atanf((float)num / (float)den) * 0.15915494309189535;
                     carrError = __dmul_rn(__dadd_rn(carrError, cP2), 0.5);
+                    if (p.pilot == 2) { sg[15 * kStage] = v[NS - 4]; sg[16 * kStage] = v[NS - 3]; }   // Pilot_I_P, Pilot_Q_P (GPS_L5C :323-324)
                 }
                 double carrNco;
                 if (p.loopType == 0) {
@@ -610,7 +618,7 @@ track_kernel(TrackParams p)
         // coalesced flush of the staged rows every kStage epochs
         if (leader && (e % kStage) == kStage - 1) {
             const int e0 = e - (kStage - 1);
-            for (int i = tid; i < GC_TRACK_ROWS * kStage; i += kThreads) {
+            for (int i = tid; i < p.nRows * kStage; i += kThreads) {
                 const int f = i / kStage, q = i % kStage;
                 out[(size_t)f * p.nEpochs + e0 + q] = s_stage[f * kStage + q];
             }
@@ -621,7 +629,7 @@ track_kernel(TrackParams p)
     const int rem = e % kStage;
     if (leader && rem) {
         const int e0 = e - rem;
-        for (int i = tid; i < GC_TRACK_ROWS * kStage; i += kThreads) {
+        for (int i = tid; i < p.nRows * kStage; i += kThreads) {
             const int f = i / kStage, q = i % kStage;
             if (q < rem) out[(size_t)f * p.nEpochs + e0 + q] = s_stage[f * kStage + q];
         }
@@ -690,19 +698,19 @@ int track_buf_bytes(int maxBlockSamples, int cluster)
 }
 
 // out rows pre-fill (tracking.m:51-77): zeros for absoluteSample and the six I/Q rows, +inf elsewhere
-__global__ void track_fill_kernel(double* out, int nCh, int nEpochs)
+__global__ void track_fill_kernel(double* out, int nCh, int nRows, int nEpochs)
 {
-    const size_t total = (size_t)nCh * GC_TRACK_ROWS * nEpochs;
+    const size_t total = (size_t)nCh * nRows * nEpochs;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int f = (int)((i / nEpochs) % GC_TRACK_ROWS);
-        out[i] = (f == GC_F_ABSOLUTE_SAMPLE || (f >= GC_F_I_P && f <= GC_F_Q_L)) ? 0.0 : inf;
+        const int f = (int)((i / nEpochs) % nRows);
+        out[i] = (f == GC_F_ABSOLUTE_SAMPLE || (f >= GC_F_I_P && f <= GC_F_Q_L) || f >= GC_TRACK_NFIELDS) ? 0.0 : inf;
     }
 }
 
-cudaError_t launch_track_fill(double* out, int nCh, int nEpochs, cudaStream_t stream)
+cudaError_t launch_track_fill(double* out, int nCh, int nRows, int nEpochs, cudaStream_t stream)
 {
-    track_fill_kernel<<<148 * 4, 256, 0, stream>>>(out, nCh, nEpochs);
+    track_fill_kernel<<<148 * 4, 256, 0, stream>>>(out, nCh, nRows, nEpochs);
     return cudaGetLastError();
 }
 

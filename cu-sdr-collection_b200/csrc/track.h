@@ -4,7 +4,7 @@
 #include <stdint.h>
 #include "../../include/gnsscorr.h"
 
-#define GC_TRACK_ROWS GC_TRACK_NFIELDS
+#define GC_TRACK_ROWS GC_TRACK_NFIELDS_PILOT   /* most rows a channel records per epoch (staging size) */
 
 namespace gc {
 
@@ -32,12 +32,15 @@ struct TrackParams {
     int subChip;             // table entries per chip: 1, or 2 for the BOC(1,1) tables of Galileo E1
                              // (tcode*2 in GAL/GAL_E1C/include/tracking.m:236-262)
     int pilot;               // 1: a second (pilot) replica is correlated with the same code phase and both
-                             // discriminators are averaged (GAL_E1C tracking.m:241-333, settings.pilotTRKflag)
+                             // discriminators are averaged (GAL_E1C tracking.m:241-333, settings.pilotTRKflag);
+                             // 2: same, the pilot is in quadrature - its prompt is rotated by -pi/2 before the atan
+                             // (GPS_L5C tracking.m:277-281) - and Pilot_I_P / Pilot_Q_P are recorded (rows 15, 16)
+    int nRows;               // rows recorded per epoch: GC_TRACK_NFIELDS, or GC_TRACK_NFIELDS_PILOT with pilot == 2
     int codeStride;          // bytes between channels in codeTables / pilotTables
     const int8_t* codeTables;   // [nCh][codeStride]: wrapped +-1 table [c(L) c(1..L) c(1)]
     const int8_t* pilotTables;  // same layout, pilot component (pilot == 1)
     const TrackChan* chans;
-    double* out;             // [nCh][15][nEpochs]
+    double* out;             // [nCh][nRows][nEpochs]
     int32_t* epochsDone;
     long long* dbg;          // optional [4][8] phase-timing accumulators (GC_TRACK_DEBUG), else nullptr
 };
@@ -45,6 +48,6 @@ struct TrackParams {
 size_t track_smem_bytes(int bufBytes, int codeLen, int pilot);
 cudaError_t launch_track(const TrackParams& p, int nCh, int cluster, cudaStream_t stream);
 int track_buf_bytes(int maxBlockSamples, int cluster);
-cudaError_t launch_track_fill(double* out, int nCh, int nEpochs, cudaStream_t stream);
+cudaError_t launch_track_fill(double* out, int nCh, int nRows, int nEpochs, cudaStream_t stream);
 
 }  // namespace gc

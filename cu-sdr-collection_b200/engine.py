@@ -35,6 +35,8 @@ class gc_config(C.Structure):
 
 
 GC_SIG_GPS_L1CA, GC_SIG_GLO_G1G2, GC_SIG_BDS_B3I, GC_SIG_GAL_E1C = 0, 1, 2, 3
+GC_SIG_GPS_L5C, GC_SIG_GAL_E5A, GC_SIG_GAL_E5B, GC_SIG_BDS_B2A = 4, 5, 6, 7
+_FAM5_IDS = {"GPS_L5C": GC_SIG_GPS_L5C, "GAL_E5a": GC_SIG_GAL_E5A, "GAL_E5b": GC_SIG_GAL_E5B, "BDS_B2a": GC_SIG_BDS_B2A}
 GC_SV_NONE = -2147483648
 
 
@@ -48,7 +50,7 @@ class gc_stats(C.Structure):
 
 EXPORTS = ["gc_abi_version", "gc_build_arch", "gc_acq_result_len", "gc_create", "gc_destroy",
            "gc_last_error", "gc_set_code", "gc_set_record_host", "gc_set_record_device", "gc_acquire",
-           "gc_acquire_host", "gc_track", "gc_track_file", "gc_get_stats", "gc_get_stream"]
+           "gc_acquire_host", "gc_track_nfields", "gc_track", "gc_track_file", "gc_get_stats", "gc_get_stream"]
 
 _lib = None
 
@@ -77,6 +79,7 @@ def load_lib():
     lib.gc_set_record_device.argtypes = [vp, vp, C.c_size_t]
     lib.gc_acquire.argtypes = [vp, C.c_int32, i32p, dp, dp, dp, i32p, i32p]
     lib.gc_acquire_host.argtypes = [vp, vp, C.c_size_t, C.c_int32, i32p, dp, dp, dp, i32p, i32p]
+    lib.gc_track_nfields.argtypes = [vp]
     lib.gc_track.argtypes = [vp, C.c_int32, i32p, dp, dp, dp, C.c_int32, dp, dp, dp, i32p]
     lib.gc_track_file.argtypes = [vp, C.c_char_p, C.c_int32, i32p, dp, dp, dp, C.c_int32, dp, dp, dp, i32p]
     lib.gc_get_stats.argtypes = [vp, C.POINTER(gc_stats)]
@@ -87,6 +90,8 @@ def load_lib():
 
 
 def signal_id(s: Settings) -> int:
+    if s.signal in _FAM5_IDS:
+        return _FAM5_IDS[s.signal]
     return (GC_SIG_GLO_G1G2 if s.is_glonass else GC_SIG_BDS_B3I if s.signal == "BDS_B3I" else
             GC_SIG_GAL_E1C if s.signal == "GAL_E1C" else GC_SIG_GPS_L1CA)
 
@@ -133,6 +138,11 @@ class Engine:
         if rc != 0:
             raise GnssCorrError(f"gc_create failed ({rc}): {self.lib.gc_last_error(None).decode()}")
         self._keep = None
+        if settings.is_fam5:
+            if codes is None:
+                raise GnssCorrError(f"{settings.signal} takes its primary codes from the caller: pass codes= "
+                                    "{PRN: (data, pilot[, pilot_secondary])} (what generateL5Icode.m etc. return)")
+            self.set_codes(codes)
         if settings.signal == "GAL_E1C":
             if codes is None:
                 from .codes import load_e1_codes
@@ -143,8 +153,13 @@ class Engine:
             self.set_codes(codes)
 
     def set_codes(self, codes: dict):
-        for prn, (b, c) in codes.items():
-            for comp, chips in ((0, b), (1, c)):
+        nmax = self.lib.gc_acq_result_len(signal_id(self.settings))
+        for prn, comps in codes.items():
+            if prn > nmax:
+                continue
+            for comp, chips in enumerate(comps):
+                if comp == 2 and self.settings.signal != "GAL_E5a":
+                    continue                                     # only E5a's fine search uses a per-PRN secondary code
                 a = np.ascontiguousarray(chips, dtype=np.int8)
                 self._check(self.lib.gc_set_code(self._h, int(prn), comp, a.ctypes.data, a.size), "gc_set_code")
 
@@ -202,7 +217,7 @@ class Engine:
         cf0p = _dp(cf0) if cf0 is not None else None
         nch = prn.size
         nv = n_epochs // int(self.settings.CNo_VSMinterval)
-        out = np.empty((nch, GC_TRACK_NFIELDS, n_epochs))
+        out = np.empty((nch, int(self.lib.gc_track_nfields(self._h)), n_epochs))
         vv, vi = np.zeros((nch, nv)), np.zeros((nch, nv))
         done = np.zeros(nch, dtype=np.int32)
         if path is not None:

@@ -46,6 +46,11 @@ class Settings:
     def is_glonass(self) -> bool:
         return self.signal in ("GLO_GL1", "GLO_GL2")
 
+    @property
+    def is_fam5(self) -> bool:
+        """One of the four 10230-chip data + pilot signals (L5C, E5a, E5b, B2a)."""
+        return self.signal in ("GPS_L5C", "GAL_E5a", "GAL_E5b", "BDS_B2a")
+
 
 # GLO/GLO_GL1/initSettings.m:44-146 (GLO_GL2 differs in freqSpacing and fileName only).  The GLONASS
 # folders call the record offset `skipNumberOfSamples`; it is the same quantity as skipNumberOfBytes.
@@ -67,6 +72,25 @@ _E1C_DEFAULTS = dict(codeLength=4092.0, acqSatelliteList=list(range(1, 37)), acq
                      pllNoiseBandwidth=15.0, intTime=0.004, pilotTRKflag=1, CNo_accTime=0.004, CNo_VSMinterval=400)
 
 
+# GPS/GPS_L5C, GAL/GAL_E5a, GAL/GAL_E5b, BDS/B2a initSettings.m (hot-path fields).  B2a's settings.CNoInterval (:128)
+# takes the place of CNo.VSMinterval.
+_FAM5_BASE = dict(codeLength=10230.0, codeFreqBasis=10.23e6, acqSearchBand=5000.0, acqSearchStep=500.0, acqThreshold=4.5,
+                  pllNoiseBandwidth=15.0, carrFreqBasis=1176.45e6)
+_FAM5 = {
+    "GPS_L5C": dict(acqSatelliteList=list(range(1, 33)), acqNonCohTime=25, dllNoiseBandwidth=2.0, CNo_VSMinterval=400,
+                    resamplingThreshold=50e6, pilotTRKflag=0, fileName="../../../L5_IF20KHz_FS18MHz.bin"),
+    "GAL_E5a": dict(acqSatelliteList=list(range(1, 37)), acqNonCohTime=15, dllNoiseBandwidth=1.5, CNo_VSMinterval=100,
+                    resamplingThreshold=45e6, pilotTRKflag=1, fileName="../../../L5_IF20KHz_FS18MHz.bin"),
+    "GAL_E5b": dict(acqSatelliteList=list(range(1, 37)), acqNonCohTime=15, acqSearchStep=60.0, dllNoiseBandwidth=1.5,
+                    pllNoiseBandwidth=25.0, CNo_VSMinterval=100, resamplingThreshold=45e6, carrFreqBasis=1207.14e6,
+                    pilotTRKflag=1, fileName="../../../E5b_IF20KHz_FS18MHz.bin"),
+    "BDS_B2a": dict(acqSatelliteList=list(range(19, 31)) + list(range(32, 47)) + [59, 60], acqNonCohTime=15,
+                    acqThreshold=5.0, dllNoiseBandwidth=2.0, CNo_VSMinterval=200, resamplingThreshold=50e6, pilotTRKflag=0,
+                    fileName="../../../L5_IF20KHz_FS18MHz.bin"),
+}
+FAM5_SIGNALS = tuple(_FAM5)
+
+
 def init_settings(signal: str = "GPS_L1CA", **overrides) -> Settings:
     """``settings = initSettings()`` of the given signal folder (GPS/GPS_L1CA/init.m:56,
     GLO/GLO_GL1, GLO/GLO_GL2) with optional field overrides."""
@@ -79,6 +103,9 @@ def init_settings(signal: str = "GPS_L1CA", **overrides) -> Settings:
             s.fileName = "../../../GL2_IF0KHz_FS12MHz.bin"
     elif signal == "BDS_B3I":
         for k, v in _B3I_DEFAULTS.items():
+            setattr(s, k, list(v) if isinstance(v, list) else v)
+    elif signal in _FAM5:
+        for k, v in {**_FAM5_BASE, **_FAM5[signal]}.items():
             setattr(s, k, list(v) if isinstance(v, list) else v)
     elif signal == "GAL_E1C":
         for k, v in _E1C_DEFAULTS.items():

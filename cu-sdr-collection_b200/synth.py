@@ -16,7 +16,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from .codes import E1_SECONDARY, b3i_code, boc11, ca_code, glo_code
+from .codes import E1_SECONDARY, NH20, b3i_code, boc11, ca_code, glo_code
 
 L1 = 1575.42e6
 
@@ -52,6 +52,10 @@ class Scene:
     # {PRN: (e1b, e1c)} +-1 primary chips (codes.load_e1_codes or codes.standin_e1_codes).
     e1c: bool = False
     codes: dict = None
+    # GPS L5C / GAL E5a / GAL E5b / BDS B2a scenes (``fam5`` = the signal name): 10230-chip codes at 10.23 Mcps, the
+    # data component in phase (one random symbol per 1 ms code period) and the pilot in quadrature carrying its
+    # secondary code (NH20 for L5C, the PRN's 100-chip code otherwise); ``codes`` = {PRN: (data, pilot, secondary)}.
+    fam5: str = ""
 
 
 def default_scene(fs: float = 16.368e6, IF: float = 20e3, nsat: int = 8, seed: int = 20260101) -> Scene:
@@ -105,6 +109,20 @@ def default_scene_e1c(codes: dict, fs: float = 18e6, IF: float = 20e3, nsat: int
     return Scene(fs=fs, IF=IF, seed=seed, sats=sats, e1c=True, codes=codes)
 
 
+def default_scene_fam5(signal: str, codes: dict, fs: float = 18e6, IF: float = 20e3, nsat: int = 4, seed: int = 20260101) -> Scene:
+    rng = np.random.default_rng(seed)
+    pool = np.arange(19, 31) if signal == "BDS_B2a" else np.arange(1, 33)
+    prns = rng.choice(pool, size=nsat, replace=False)
+    sats = [Sat(prn=int(p), doppler=float(rng.uniform(-4000, 4000)), code_phase=float(rng.uniform(0, 10230)),
+                cn0=float(rng.uniform(42, 50)), phi0=float(rng.uniform(0, 2 * np.pi)), bit_seed=int(rng.integers(1 << 30)),
+                bit_offset=int(rng.integers(0, 100))) for p in prns]
+    return Scene(fs=fs, IF=IF, seed=seed, sats=sats, fam5=signal, codes=codes)
+
+
+def _fam5_secondary(scene: Scene, prn: int) -> np.ndarray:
+    return NH20.astype(np.float64) if scene.fam5 == "GPS_L5C" else np.asarray(scene.codes[prn][2], dtype=np.float64)
+
+
 def make_record(scene: Scene, nsamples: int, start: int = 0) -> np.ndarray:
     """int8 array of length 2*nsamples (I0,Q0,I1,Q1,...), samples start..start+nsamples-1."""
     n = np.arange(start, start + nsamples, dtype=np.float64)
@@ -119,6 +137,22 @@ def make_record(scene: Scene, nsamples: int, start: int = 0) -> np.ndarray:
             clen, crate, carrier = 10230, 10.23e6, 1268.52e6
             fc = scene.IF + s.doppler
             chipseq = b3i_code(s.prn).astype(np.float64)
+        elif scene.fam5:
+            clen, crate = 10230, 10.23e6
+            carrier = 1207.14e6 if scene.fam5 == "GAL_E5b" else 1176.45e6
+            fc = scene.IF + s.doppler
+            fcode = crate * (1 + s.doppler / carrier)
+            chips = fcode * t + s.code_phase
+            period = np.floor(chips / clen).astype(np.int64)
+            idx = np.floor(chips - period * float(clen)).astype(np.int64) % clen
+            cD = np.asarray(scene.codes[s.prn][0], dtype=np.float64)[idx]
+            cP = np.asarray(scene.codes[s.prn][1], dtype=np.float64)[idx]
+            sec = _fam5_secondary(scene, s.prn)
+            dD = nav_bits(s, int(period.max()) + 130)[period + s.bit_offset]
+            dP = sec[(period + s.bit_offset) % sec.size]
+            ph = 2 * np.pi * (fc * t % 1.0) + s.phi0
+            sig += _amp(s.cn0, scene.sigma, scene.fs) * (dD * cD + 1j * dP * cP) / np.sqrt(2.0) * np.exp(1j * ph)
+            continue
         elif scene.e1c:
             clen, crate, carrier = 4092, 1.023e6, L1
             fc = scene.IF + s.doppler

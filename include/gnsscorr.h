@@ -34,7 +34,9 @@ extern "C" {
  * GLONASS folders differ only in settings.freqSpacing and the file name), BDS/B3I and GAL/GAL_E1C
  * (E1B + E1C BOC(1,1) replicas summed in acquisition, 25-chip secondary-code fine search, 4 ms
  * data + pilot tracking). */
-enum { GC_SIG_GPS_L1CA = 0, GC_SIG_GLO_G1G2 = 1, GC_SIG_BDS_B3I = 2, GC_SIG_GAL_E1C = 3 };
+enum { GC_SIG_GPS_L1CA = 0, GC_SIG_GLO_G1G2 = 1, GC_SIG_BDS_B3I = 2, GC_SIG_GAL_E1C = 3,
+       /* the four 10230-chip data + pilot signals (variant A with two replicas, quadrature-pilot tracking): */
+       GC_SIG_GPS_L5C = 4, GC_SIG_GAL_E5A = 5, GC_SIG_GAL_E5B = 6, GC_SIG_BDS_B2A = 7 };
 
 /* "no satellite on this channel" for gc_track: GPS uses PRN 0 (tracking.m:136); a GLONASS channel is
  * identified by its frequency number K, for which 0 is valid, so unused channels carry GC_SV_NONE
@@ -90,6 +92,9 @@ typedef struct gc_handle gc_handle;
 /* Number of per-epoch result rows gc_track writes per channel and their order
  * (trackResults fields, GPS/GPS_L1CA/include/tracking.m:48-77). */
 #define GC_TRACK_NFIELDS 15
+/* With a quadrature pilot tracked (GPS L5C, GAL E5a/E5b, BDS B2a and pilot_trk_flag == 1) two more rows follow:
+ * Pilot_I_P, Pilot_Q_P (GPS/GPS_L5C/include/tracking.m:57-60, 323-324); gc_track_nfields() tells which. */
+#define GC_TRACK_NFIELDS_PILOT 17
 enum {
     GC_F_ABSOLUTE_SAMPLE = 0, GC_F_CODE_FREQ, GC_F_CARR_FREQ, GC_F_I_P, GC_F_I_E, GC_F_I_L,
     GC_F_Q_E, GC_F_Q_P, GC_F_Q_L, GC_F_DLL_DISCR, GC_F_DLL_DISCR_FILT, GC_F_PLL_DISCR,
@@ -116,7 +121,11 @@ const char* gc_last_error(const gc_handle* h);
  *   component  0 = data (E1B), 1 = pilot (E1C)
  *   chips      the +-1 primary chips (1 - 2*bit, generateE1Bcode.m:55), nChips == code_length (4092);
  *              the BOC(1,1) sub-carrier (:58-64) is applied by the library.
- * Every SV named in gc_acquire / gc_track must have both components set.  Signals with generated
+ * The 10230-chip data + pilot signals (GPS L5C I5/Q5, GAL E5a/E5b I/Q, BDS B2a data/pilot) take their codes
+ * the same way - the wrapper passes what the reference's own generateL5Icode / generateL5Qcode /
+ * generateE5aIcode ... return (component 0 = data, 1 = pilot, nChips == 10230); GAL E5a also takes
+ * component 2 = the PRN's 100-chip pilot secondary code (generateE5aQ_secondary.m) for the fine search.
+ * Every SV named in gc_acquire / gc_track must have its components set.  Signals with generated
  * codes (GPS L1CA, GLONASS, B3I) return GC_ERR_ARG. */
 int gc_set_code(gc_handle* h, int32_t sv, int32_t component, const int8_t* chips, int32_t nChips);
 
@@ -162,12 +171,13 @@ int gc_acquire_host(gc_handle* h, const int8_t* iq, size_t nSamples,
  *                 (GPS L1CA, GLONASS)
  *   nEpochs       integration periods to process: settings.msToProcess for the 1 ms signals,
  *                 round(msToProcess/1000/intTime) for Galileo E1 (GAL_E1C/include/tracking.m:48)
- *   out           [nCh][GC_TRACK_NFIELDS][nEpochs] doubles; rows pre-filled like tracking.m:51-77
+ *   out           [nCh][gc_track_nfields(h)][nEpochs] doubles; rows pre-filled like tracking.m:51-77
  *                 (zeros for absoluteSample and I/Q, +inf for the rest)
  *   vsmValue/vsmIndex  [nCh][nEpochs / cno_vsm_interval]  (trackResults.CNo, tracking.m:80-83,351-358)
  *   epochsDone    [nCh] completed epochs; < nEpochs means the record ran out (tracking.m:241-245):
  *                 as in the reference the whole call stops there and later channels stay untouched,
  *                 and `status` must be left '-' for every channel with epochsDone < nEpochs. */
+int gc_track_nfields(const gc_handle* h);   /* rows per channel in `out`: GC_TRACK_NFIELDS or GC_TRACK_NFIELDS_PILOT */
 int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq,
              const double* codePhase, const double* codeFreq0, int32_t nEpochs,
              double* out, double* vsmValue, double* vsmIndex, int32_t* epochsDone);

@@ -1,6 +1,7 @@
 function cfg = gnsscorr_config(settings, signal)
 %GNSSCORR_CONFIG  settings struct (initSettings.m) -> the field names of gc_config (gnsscorr.h).
-%   signal: 'GPS_L1CA' (default), 'GLO' (GLO_GL1 / GLO_GL2), 'BDS_B3I' or 'GAL_E1C' - the wrapper of each signal
+%   signal: 'GPS_L1CA' (default), 'GLO' (GLO_GL1 / GLO_GL2), 'BDS_B3I', 'GAL_E1C', 'GPS_L5C', 'GAL_E5a', 'GAL_E5b'
+%   or 'BDS_B2a' - the wrapper of each signal
 %   folder passes its own.
 if nargin < 2, signal = 'GPS_L1CA'; end
 cfg.device = 0;
@@ -8,13 +9,23 @@ switch signal
     case 'GLO',     cfg.signal = 1;  cfg.freq_spacing = settings.freqSpacing;
     case 'BDS_B3I', cfg.signal = 2;  cfg.freq_spacing = 0;
     case 'GAL_E1C', cfg.signal = 3;  cfg.freq_spacing = 0;
+    case 'GPS_L5C', cfg.signal = 4;  cfg.freq_spacing = 0;
+    case 'GAL_E5a', cfg.signal = 5;  cfg.freq_spacing = 0;
+    case 'GAL_E5b', cfg.signal = 6;  cfg.freq_spacing = 0;
+    case 'BDS_B2a', cfg.signal = 7;  cfg.freq_spacing = 0;
     otherwise,      cfg.signal = 0;  cfg.freq_spacing = 0;
 end
 cfg.file_type = settings.fileType;
 cfg.sample_bytes = 1;
 cfg.code_length = settings.codeLength;
 cfg.acq_noncoh_time = settings.acqNonCohTime;
-cfg.cno_vsm_interval = settings.CNo.VSMinterval;
+if isfield(settings, 'CNo')
+    cfg.cno_vsm_interval = settings.CNo.VSMinterval;
+    cfg.cno_acc_time = settings.CNo.accTime;
+else                                  % BDS/B2a: settings.CNoInterval (initSettings.m:128), Calc_CNo_PLD on the host
+    cfg.cno_vsm_interval = settings.CNoInterval;
+    cfg.cno_acc_time = settings.intTime;
+end
 if isfield(settings, 'skipNumberOfSamples')   % the GLONASS folders' name for the same offset
     cfg.skip_number_of_bytes = settings.skipNumberOfSamples;
 else
@@ -32,7 +43,6 @@ cfg.dll_correlator_spacing = settings.dllCorrelatorSpacing;
 cfg.pll_damping_ratio = settings.pllDampingRatio;
 cfg.pll_noise_bandwidth = settings.pllNoiseBandwidth;
 cfg.int_time = settings.intTime;
-cfg.cno_acc_time = settings.CNo.accTime;
 if isfield(settings, 'pilotTRKflag')
     cfg.pilot_trk_flag = settings.pilotTRKflag;
 else

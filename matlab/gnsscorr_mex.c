@@ -15,9 +15,12 @@
  *   r = gnsscorr_mex('track', cfg, path, prn, acqFreq, codePhase, nEpochs [, codeFreq0 [, codes]])
  *         r       : struct out (nEpochs x 15 x nCh double, MATLAB column-major view of the
  *                   C [nCh][15][nEpochs] block), vsmValue, vsmIndex, epochsDone
- *   Galileo E1 (memory codes, gc_set_code): 'acquire' takes a 5th and 'track' a 9th argument
+ *   Signals with caller-supplied codes (gc_set_code: GAL E1C, GPS L5C, GAL E5a/E5b, BDS B2a): 'acquire' takes a
+ *   5th and 'track' a 9th argument
  *         codes   : struct sv (double vector of PRNs), data, pilot (int8, codeLength x numel(sv), one
- *                   column of +-1 primary chips per PRN - generateE1Bcode(PRN)(1:2:end) etc.)
+ *                   column of +-1 primary chips per PRN - generateE1Bcode(PRN)(1:2:end), generateL5Icode(PRN, settings),
+ *                   ...) and for GAL E5a secondary (int8, 100 x numel(sv), generateE5aQ_secondary(PRN));
+ *         with a quadrature pilot tracked r.out is nEpochs x 17 x nCh (rows 16, 17 = Pilot_I_P, Pilot_Q_P)
  *
  * This file cannot be exercised in the build image (no MATLAB); it is compile-checked against
  * matlab/stub/mex.h and the same C entry points are exercised from Python (ctypes).
@@ -66,6 +69,7 @@ static void fill_config(const mxArray* s, gc_config* c)
 static void set_codes(gc_handle* h, const gc_config* cfg, const mxArray* codes)
 {
     const mxArray *sv = mxGetField(codes, 0, "sv"), *d = mxGetField(codes, 0, "data"), *p = mxGetField(codes, 0, "pilot");
+    const mxArray* sec = mxGetField(codes, 0, "secondary");   /* GAL E5a only: int8 100 x numel(sv) */
     mwSize i, n;
     if (!sv || !d || !p || !mxIsInt8(d) || !mxIsInt8(p)) { gc_destroy(h); mexErrMsgIdAndTxt("gnsscorr:args", "codes: struct with sv, data (int8), pilot (int8)"); }
     n = mxGetNumberOfElements(sv);
@@ -76,6 +80,8 @@ static void set_codes(gc_handle* h, const gc_config* cfg, const mxArray* codes)
     for (i = 0; i < n; ++i) {
         int rc = gc_set_code(h, (int32_t)mxGetDoubles(sv)[i], 0, (const int8_t*)mxGetInt8s(d) + i * cfg->code_length, cfg->code_length);
         if (rc == GC_OK) rc = gc_set_code(h, (int32_t)mxGetDoubles(sv)[i], 1, (const int8_t*)mxGetInt8s(p) + i * cfg->code_length, cfg->code_length);
+        if (rc == GC_OK && sec && mxIsInt8(sec) && mxGetNumberOfElements(sec) == n * 100)
+            rc = gc_set_code(h, (int32_t)mxGetDoubles(sv)[i], 2, (const int8_t*)mxGetInt8s(sec) + i * 100, 100);
         if (rc != GC_OK) {
             char msg[512];
             strncpy(msg, gc_last_error(h), sizeof(msg) - 1);
@@ -137,7 +143,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
         if (nrhs < 7 || nrhs > 9 || mxGetString(prhs[2], path, sizeof(path)) || nCh > 256) { gc_destroy(h); mexErrMsgIdAndTxt("gnsscorr:args", "track: bad arguments"); }
         if (nrhs == 9) set_codes(h, &cfg, prhs[8]);
         for (i = 0; i < nCh; ++i) prn[i] = (prnd[i] != prnd[i]) ? GC_SV_NONE : (int32_t)prnd[i];   /* NaN = channel off (GLONASS) */
-        dims[0] = nEpochs; dims[1] = GC_TRACK_NFIELDS; dims[2] = nCh;
+        dims[0] = nEpochs; dims[1] = gc_track_nfields(h); dims[2] = nCh;   /* 15, or 17 with Pilot_I_P / Pilot_Q_P */
         out = mxCreateNumericArray(3, dims, mxDOUBLE_CLASS, mxREAL);
         vv = mxCreateDoubleMatrix(nV, nCh, mxREAL);
         vi = mxCreateDoubleMatrix(nV, nCh, mxREAL);

@@ -75,7 +75,9 @@ class Settings:
     CNo_accTime: float = 0.001          # :133
     CNo_VSMinterval: int = 40           # :135
     freqSpacing: float = 0.0            # GLO/GLO_GL1/initSettings.m:72 (GLONASS only)
-    carrFreqBasis: float = 0.0          # BDS/B3I/initSettings.m:132 (B3I only)
+    carrFreqBasis: float = 0.0          # BDS/B3I/initSettings.m:132 (B3I, L5C, E5a, E5b, B2a)
+    pilotTRKflag: int = 0               # GAL/GAL_E1C/initSettings.m:113 (E1C, L5C, E5a, E5b, B2a)
+    signal: str = "GPS_L1CA"            # which reference folder these settings belong to
 
 
 def matlab_round(x: float) -> float:
@@ -996,6 +998,245 @@ def tracking_e1c(raw: np.ndarray, channel: list, s: Settings, codes: dict):
             tr["I_E"][loopCnt - 1] = I_E; tr["I_P"][loopCnt - 1] = I_P; tr["I_L"][loopCnt - 1] = I_L
             tr["Q_E"][loopCnt - 1] = Q_E; tr["Q_P"][loopCnt - 1] = Q_P; tr["Q_L"][loopCnt - 1] = Q_L
             if loopCnt % s.CNo_VSMinterval == 0:                   # :360-368
+                vsmCnt += 1
+                lo = loopCnt - s.CNo_VSMinterval
+                tr["VSMValue"][vsmCnt - 1] = CNoVSM(tr["I_P"][lo:loopCnt], tr["Q_P"][lo:loopCnt], s.CNo_accTime)
+                tr["VSMIndex"][vsmCnt - 1] = loopCnt
+        tr["status"] = channel[ch]["status"]
+    return out
+
+
+# ===========================================================================
+# The four 10230-chip data + pilot signals: GPS L5C, Galileo E5a, Galileo E5b, BeiDou B2a
+# (GPS/GPS_L5C, GAL/GAL_E5a, GAL/GAL_E5b, BDS/B2a; "L5C :n" etc. cite <folder>/include/<file>.m)
+# ===========================================================================
+# Their acquisition.m / tracking.m are one algorithm with per-signal constants; the primary codes come
+# from per-signal generators built on ICD tables (generateL5Icode.m, generateE5aIcode.m, ...), which are
+# DATA here: ``codes[PRN] = (data_chips, pilot_chips[, pilot_secondary])`` as +-1 arrays.
+def fam5_settings(signal: str, **kw) -> Settings:
+    """initSettings.m of the signal (hot-path fields)."""
+    base = dict(codeLength=10230.0, codeFreqBasis=10.23e6, acqSearchBand=5000.0, acqSearchStep=500.0, acqThreshold=4.5,
+                pllNoiseBandwidth=15.0, carrFreqBasis=1176.45e6)
+    per = {
+        "GPS_L5C": dict(acqSatelliteList=list(range(1, 33)), acqNonCohTime=25, dllNoiseBandwidth=2.0, CNo_VSMinterval=400,
+                        resamplingThreshold=50e6),
+        "GAL_E5a": dict(acqSatelliteList=list(range(1, 37)), acqNonCohTime=15, dllNoiseBandwidth=1.5, CNo_VSMinterval=100,
+                        resamplingThreshold=45e6),
+        "GAL_E5b": dict(acqSatelliteList=list(range(1, 37)), acqNonCohTime=15, acqSearchStep=60.0, dllNoiseBandwidth=1.5,
+                        pllNoiseBandwidth=25.0, CNo_VSMinterval=100, resamplingThreshold=45e6, carrFreqBasis=1207.14e6),
+        "BDS_B2a": dict(acqSatelliteList=list(range(19, 31)) + list(range(32, 47)) + [59, 60], acqNonCohTime=15,
+                        acqThreshold=5.0, dllNoiseBandwidth=2.0, CNo_VSMinterval=200, resamplingThreshold=50e6),
+    }[signal]
+    s = Settings(**{**base, **per})
+    s.signal = signal
+    s.pilotTRKflag = 1 if signal in ("GAL_E5a", "GAL_E5b") else 0      # L5C initSettings.m:113, B2a :112: 0
+    for k, v in kw.items():
+        setattr(s, k, v)
+    return s
+
+
+_FAM5_RESLEN = {"GPS_L5C": 32, "GAL_E5a": 50, "GAL_E5b": 50, "BDS_B2a": None}    # B2a: max(acqSatelliteList) (B2a :128-132)
+_FAM5_MINPER = {"GPS_L5C": 42, "GAL_E5a": 102, "GAL_E5b": 102, "BDS_B2a": 12}    # postProcessing.m codeLen = max(., nonCoh+2)
+
+
+def read_acq_signal_fam5(raw: np.ndarray, s: Settings) -> np.ndarray:
+    """postProcessing.m: max(42 | 102 | 12, acqNonCohTime+2) code periods (L5C :88, E5a :88, E5b :89, B2a :86)."""
+    N = samples_per_code(s)
+    codeLen = max(_FAM5_MINPER[s.signal], s.acqNonCohTime + 2)
+    off = 2 * s.skipNumberOfBytes
+    data = raw[off: off + 2 * codeLen * N].astype(np.float64)
+    return data[0::2] + 1j * data[1::2]
+
+
+def make_code_table(code: np.ndarray, s: Settings) -> np.ndarray:
+    """makeL5ITable.m / makeL5QTable.m / makeE5aITable.m ...: index = ceil(ts*(1:N)/tc), last forced to codeLength."""
+    N = samples_per_code(s)
+    ts = 1 / s.samplingFreq
+    tc = 1 / s.codeFreqBasis
+    idx = np.ceil((ts * np.arange(1, N + 1, dtype=np.float64)) / tc).astype(np.int64)
+    idx[-1] = int(s.codeLength)
+    return np.asarray(code, dtype=np.float64)[idx - 1]
+
+
+def acquisition_fam5(longSignal: np.ndarray, s: Settings, codes: dict, workers: int = 1):
+    """L5C acquisition.m:118-300, E5a :118-290, E5b :118-230, B2a :116-300 (resampling branch not restated)."""
+    sig = s.signal
+    N = samples_per_code(s)
+    ts = 1 / s.samplingFreq
+    phasePoints = np.arange(0, 2 * N, dtype=np.float64) * 2 * np.pi * ts
+    nBins = int(matlab_round(s.acqSearchBand * 2 / s.acqSearchStep)) + 1
+    coarseFreqBin = np.zeros(nBins)
+    nRes = _FAM5_RESLEN[sig] or max(s.acqSatelliteList)
+    res = dict(carrFreq=np.zeros(nRes), codePhase=np.zeros(nRes), peakMetric=np.zeros(nRes),
+               coarseBin=np.zeros(nRes, dtype=np.int64), coarseCodePhase=np.zeros(nRes, dtype=np.int64))
+    NHcode = np.array([1, 1, 1, 1, 1, -1, 1, 1, -1, -1, 1, -1, 1, -1, 1, 1, -1, -1, -1, 1], dtype=np.float64)   # L5C :134
+    fineSearchStep = 5 if sig in ("GAL_E5a", "GAL_E5b") else 25                 # E5a :136; L5C :136; B2a :135
+    numOfFineBins = int(matlab_round(s.acqSearchStep / fineSearchStep)) + 1
+    nPer = {"GPS_L5C": 20, "GAL_E5a": 100, "GAL_E5b": 100, "BDS_B2a": max(10, s.acqNonCohTime)}[sig]   # L5C :146; E5a :142; B2a :140
+    finePhasePoints = np.arange(0, nPer * N, dtype=np.float64) * 2 * np.pi * ts
+    x = longSignal[:N]
+    sigPower = math.sqrt(np.sum(np.abs(x - np.mean(x)) ** 2) / (N - 1) * N)
+    res["sigPower"] = sigPower
+    for PRN in s.acqSatelliteList:
+        dcode = np.asarray(codes[PRN][0], dtype=np.float64)
+        pcode = np.asarray(codes[PRN][1], dtype=np.float64)
+        IFreqDom = np.conj(_FFT(np.concatenate([make_code_table(dcode, s), np.zeros(N)])))     # L5C :158-167
+        QFreqDom = np.conj(_FFT(np.concatenate([make_code_table(pcode, s), np.zeros(N)])))
+        results = np.zeros((nBins, 2 * N))
+        for k in range(1, nBins + 1):
+            coarseFreqBin[k - 1] = s.IF + s.acqSearchBand - s.acqSearchStep * (k - 1)
+            sigCarr = np.exp(-1j * coarseFreqBin[k - 1] * phasePoints)
+            for m in range(1, s.acqNonCohTime + 1):
+                IQfreqDom = _FFT(sigCarr * longSignal[(m - 1) * N: (m + 1) * N], workers)
+                coh = np.abs(_IFFT(IQfreqDom * IFreqDom, workers)) + np.abs(_IFFT(IQfreqDom * QFreqDom, workers))   # L5C :186-190
+                results[k - 1, :] += coh
+        acqCoarseBin = int(np.argmax(results.max(axis=1))) + 1
+        colmax = results.max(axis=0)
+        codePhase = int(np.argmax(colmax)) + 1
+        res["peakMetric"][PRN - 1] = colmax[codePhase - 1] / sigPower / s.acqNonCohTime
+        res["coarseBin"][PRN - 1] = acqCoarseBin
+        res["coarseCodePhase"][PRN - 1] = codePhase
+        if res["peakMetric"][PRN - 1] > s.acqThreshold:
+            if sig == "GAL_E5b":                                                # E5b :203-205: no fine search
+                res["carrFreq"][PRN - 1] = coarseFreqBin[acqCoarseBin - 1]
+                res["codePhase"][PRN - 1] = codePhase
+                continue
+            codeValueIndex = np.floor((ts * np.arange(1, nPer * N + 1, dtype=np.float64)) / (1 / s.codeFreqBasis)).astype(np.int64)   # L5C :196 (1-based sample index)
+            longP = pcode[np.fmod(codeValueIndex, int(s.codeLength))]          # L5C :198
+            longD = dcode[np.fmod(codeValueIndex, int(s.codeLength))]          # B2a :210
+            sigF = longSignal[codePhase - 1: codePhase - 1 + nPer * N]         # L5C :200
+            fineFreqBins = np.zeros(numOfFineBins)
+            fineResult = np.zeros(numOfFineBins)
+            sec = NHcode if sig == "GPS_L5C" else np.asarray(codes[PRN][2], dtype=np.float64) if sig == "GAL_E5a" else None
+            for j in range(1, numOfFineBins + 1):
+                fineFreqBins[j - 1] = coarseFreqBin[acqCoarseBin - 1] + s.acqSearchStep / 2 - fineSearchStep * (j - 1)
+                carr = np.exp(-1j * fineFreqBins[j - 1] * finePhasePoints)
+                sumPerCode = (longP * carr * sigF).reshape(nPer, N).sum(axis=1)                 # L5C :208-212
+                if sig == "BDS_B2a":                                                            # B2a :216-228
+                    sum1 = (longD * carr * sigF).reshape(nPer, N).sum(axis=1)
+                    fineResult[j - 1] = np.sum(np.abs(sum1)) + np.sum(np.abs(sumPerCode))
+                    continue
+                maxPower = 0.0
+                for c in range(nPer):                                                           # L5C :214-219
+                    maxPower = max(maxPower, abs(np.sum(sumPerCode * np.roll(sec, c))))
+                fineResult[j - 1] = maxPower
+            maxFinBin = int(np.argmax(fineResult)) + 1
+            res["carrFreq"][PRN - 1] = fineFreqBins[maxFinBin - 1]
+            res["codePhase"][PRN - 1] = codePhase
+            if res["carrFreq"][PRN - 1] == 0:
+                res["carrFreq"][PRN - 1] = 1
+    return res
+
+
+def preRun_fam5(acq: dict, s: Settings):
+    """preRun.m:44-78 of the four folders: strongest peaks first; channel.codeFreq is the carrier-aided code
+    NCO centre codeFreqBasis + (acquiredFreq - IF)/carrFreqBasis*codeFreqBasis (L5C :69-71)."""
+    chans = [dict(PRN=0, acquiredFreq=0.0, codePhase=0, codeFreq=0.0, status="-") for _ in range(s.numberOfChannels)]
+    order = np.argsort(-acq["peakMetric"], kind="stable")
+    n = min(s.numberOfChannels, int(np.sum(acq["carrFreq"] != 0)))
+    for ii in range(n):
+        p = int(order[ii])
+        af = float(acq["carrFreq"][p])
+        chans[ii] = dict(PRN=p + 1, acquiredFreq=af, codePhase=int(acq["codePhase"][p]),
+                         codeFreq=s.codeFreqBasis + (af - s.IF) / s.carrFreqBasis * s.codeFreqBasis, status="T")
+    return chans
+
+
+def tracking_fam5(raw: np.ndarray, channel: list, s: Settings, codes: dict):
+    """L5C tracking.m:45-424 (E5a/E5b/B2a: the same loop): 1 ms epochs, code NCO centred on channel.codeFreq,
+    three-coefficient carrier filter, and with pilotTRKflag == 1 the pilot replica on the same code phase: its
+    prompt is rotated by -pi/2 before the atan (:277-281), both discriminators are averaged, and Pilot_I_P /
+    Pilot_Q_P are recorded (:323-324)."""
+    nE = s.msToProcess
+    pilot = int(getattr(s, "pilotTRKflag", 0)) == 1
+    out = []
+    for _ in range(s.numberOfChannels):
+        tr = dict(status="-", PRN=0)
+        tr["absoluteSample"] = np.zeros(nE)
+        for f in ("codeFreq", "carrFreq", "dllDiscr", "dllDiscrFilt", "pllDiscr", "pllDiscrFilt", "remCodePhase", "remCarrPhase"):
+            tr[f] = np.full(nE, np.inf)
+        for f in ("I_P", "I_E", "I_L", "Q_E", "Q_P", "Q_L", "Pilot_I_P", "Pilot_Q_P"):
+            tr[f] = np.zeros(nE)
+        tr["VSMValue"] = np.zeros(nE // s.CNo_VSMinterval)
+        tr["VSMIndex"] = np.zeros(nE // s.CNo_VSMinterval)
+        out.append(tr)
+    earlyLateSpc = s.dllCorrelatorSpacing
+    PDIcode = s.intTime
+    tau1code, tau2code = calcLoopCoef(s.dllNoiseBandwidth, s.dllDampingRatio, 1.0)
+    pf3, pf2, pf1 = calcLoopCoefCarr(s)
+    Lc = int(s.codeLength)
+    rot = np.exp(-1j * np.pi / 2)                                  # :278
+    for ch in range(s.numberOfChannels):
+        if channel[ch]["PRN"] == 0:
+            continue
+        tr = out[ch]
+        PRN = channel[ch]["PRN"]
+        tr["PRN"] = PRN
+        pos = 2 * (s.skipNumberOfBytes + channel[ch]["codePhase"] - 1)
+        c = np.asarray(codes[PRN][0], dtype=np.float64)
+        ICode = np.concatenate([[c[Lc - 1]], c, [c[0]]])           # :164-165
+        if pilot:
+            c = np.asarray(codes[PRN][1], dtype=np.float64)
+            QCode = np.concatenate([[c[Lc - 1]], c, [c[0]]])       # :167-169
+        codeFreq = channel[ch]["codeFreq"]; remCodePhase = 0.0     # :173-175
+        carrFreq = channel[ch]["acquiredFreq"]; carrFreqBasis = channel[ch]["acquiredFreq"]; remCarrPhase = 0.0
+        oldCodeNco = oldCodeError = 0.0
+        d2CarrError = dCarrError = 0.0
+        vsmCnt = 0
+        for loopCnt in range(1, nE + 1):
+            tr["absoluteSample"][loopCnt - 1] = pos / 2
+            codePhaseStep = codeFreq / s.samplingFreq
+            blksize = int(math.ceil((s.codeLength - remCodePhase) / codePhaseStep))
+            chunk = raw[pos: pos + 2 * blksize]
+            pos += chunk.size
+            if chunk.size != 2 * blksize:
+                return out
+            rawSignal = chunk[0::2].astype(np.float64) + 1j * chunk[1::2].astype(np.float64)
+            tr["remCodePhase"][loopCnt - 1] = remCodePhase
+            tE = colonop(remCodePhase - earlyLateSpc, codePhaseStep, (blksize - 1) * codePhaseStep + remCodePhase - earlyLateSpc)
+            tL = colonop(remCodePhase + earlyLateSpc, codePhaseStep, (blksize - 1) * codePhaseStep + remCodePhase + earlyLateSpc)
+            tP = colonop(remCodePhase, codePhaseStep, (blksize - 1) * codePhaseStep + remCodePhase)
+            iE = np.ceil(tE).astype(np.int64); iL = np.ceil(tL).astype(np.int64); iP = np.ceil(tP).astype(np.int64)
+            remCodePhase = (tP[blksize - 1] + codePhaseStep) - s.codeLength
+            tr["remCarrPhase"][loopCnt - 1] = remCarrPhase
+            time = np.arange(0, blksize + 1, dtype=np.float64) / s.samplingFreq
+            trigarg = ((carrFreq * 2.0 * np.pi) * time) + remCarrPhase
+            remCarrPhase = math.fmod(trigarg[blksize], 2 * np.pi)
+            bb = np.exp(-1j * trigarg[:blksize]) * rawSignal
+            iB, qB = bb.real, bb.imag
+            I_E = float(np.sum(ICode[iE] * iB)); Q_E = float(np.sum(ICode[iE] * qB))
+            I_P = float(np.sum(ICode[iP] * iB)); Q_P = float(np.sum(ICode[iP] * qB))
+            I_L = float(np.sum(ICode[iL] * iB)); Q_L = float(np.sum(ICode[iL] * qB))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                carrError = float(np.arctan(np.float64(Q_P) / np.float64(I_P)) / (2.0 * np.pi))
+                sE = math.sqrt(I_E * I_E + Q_E * Q_E); sL = math.sqrt(I_L * I_L + Q_L * Q_L)
+                codeError = float((np.float64(sE) - sL) / (np.float64(sE) + sL))
+                if pilot:
+                    I_EQ = float(np.sum(QCode[iE] * iB)); Q_EQ = float(np.sum(QCode[iE] * qB))
+                    I_PQ = float(np.sum(QCode[iP] * iB)); Q_PQ = float(np.sum(QCode[iP] * qB))
+                    I_LQ = float(np.sum(QCode[iL] * iB)); Q_LQ = float(np.sum(QCode[iL] * qB))
+                    QI = (I_PQ + 1j * Q_PQ) * rot                                               # :278
+                    carrErrorQ = float(np.arctan(np.float64(QI.imag) / np.float64(QI.real)) / (2.0 * np.pi))   # :279
+                    carrError = (carrError + carrErrorQ) / 2                                    # :280
+                    sEq = math.sqrt(I_EQ ** 2 + Q_EQ ** 2); sLq = math.sqrt(I_LQ ** 2 + Q_LQ ** 2)
+                    codeErrorQ = float((np.float64(sEq) - sLq) / (np.float64(sEq) + sLq))     # :298-299
+                    codeError = (codeError + codeErrorQ) / 2
+            d2CarrError = d2CarrError + carrError * pf3
+            dCarrError = d2CarrError + carrError * pf2 + dCarrError
+            carrNco = dCarrError + carrError * pf1
+            tr["carrFreq"][loopCnt - 1] = carrFreq
+            carrFreq = carrFreqBasis + carrNco
+            codeNco = oldCodeNco + (tau2code / tau1code) * (codeError - oldCodeError) + codeError * (PDIcode / tau1code)
+            oldCodeNco = codeNco; oldCodeError = codeError
+            tr["codeFreq"][loopCnt - 1] = codeFreq
+            codeFreq = channel[ch]["codeFreq"] - codeNco           # :309
+            tr["dllDiscr"][loopCnt - 1] = codeError; tr["dllDiscrFilt"][loopCnt - 1] = codeNco
+            tr["pllDiscr"][loopCnt - 1] = carrError; tr["pllDiscrFilt"][loopCnt - 1] = carrNco
+            tr["I_E"][loopCnt - 1] = I_E; tr["I_P"][loopCnt - 1] = I_P; tr["I_L"][loopCnt - 1] = I_L
+            tr["Q_E"][loopCnt - 1] = Q_E; tr["Q_P"][loopCnt - 1] = Q_P; tr["Q_L"][loopCnt - 1] = Q_L
+            if pilot:
+                tr["Pilot_I_P"][loopCnt - 1] = I_PQ; tr["Pilot_Q_P"][loopCnt - 1] = Q_PQ   # :323-324
+            if loopCnt % s.CNo_VSMinterval == 0:                   # :328-335 (B2a computes DataCNo/PLD from the same rows instead)
                 vsmCnt += 1
                 lo = loopCnt - s.CNo_VSMinterval
                 tr["VSMValue"][vsmCnt - 1] = CNoVSM(tr["I_P"][lo:loopCnt], tr["Q_P"][lo:loopCnt], s.CNo_accTime)

@@ -137,3 +137,27 @@ def track_rel_err(got, ref):
         e = np.where(d == 0, 0.0, e)
         errs[f] = float(np.nanmax(e))
     return errs
+
+
+def first_illconditioned_epoch(rem_code_phase, code_freq, abs_sample, fs, spacing, sub=1.0, margin=2e-9):
+    """First epoch in which one sample's code phase (early, prompt or late) lies within `margin` chips of a chip
+    boundary, or len() if none.  There ceil(tcode) - hence one sample's replica chip, 1e-4..1e-3 of a correlator sum
+    at low SNR per sample - depends on the 10th decimal of remCodePhase, which no implementation that accumulates
+    differently from MATLAB's float64 sums can reproduce; closed-loop comparisons are only meaningful up to it.
+    (16.368 Msps / 1.023 Mcps puts 16 samples on a chip and never gets there; 18 Msps / 10.23 Mcps has 18000
+    distinct code-phase fractions per epoch and meets such a point every ~1e5 epochs.)"""
+    n = len(rem_code_phase)
+    for e in range(n):
+        if not np.isfinite(rem_code_phase[e]):
+            return e
+        blk = int(abs_sample[e + 1] - abs_sample[e]) if e + 1 < n and abs_sample[e + 1] > 0 else int(np.ceil(fs / code_freq[e] * 10230)) + 2
+        step = code_freq[e] / fs
+        k = np.arange(blk, dtype=np.float64)
+        for off in (-spacing, 0.0, spacing):
+            t = (rem_code_phase[e] + off + k * step) * sub
+            d = np.abs(t - np.rint(t))
+            if e == 0:
+                d = d[1:]                  # remCodePhase starts at exactly 0: sample 0 of the prompt replica is on an edge for everyone
+            if np.min(d) < margin:
+                return e
+    return n

@@ -10,7 +10,8 @@ import pytest
 import np_oracle as O
 from cu_sdr_collection_b200 import Engine, acquisition, init_settings, preRun, synth, tracking
 from cu_sdr_collection_b200.codes import standin_e1_codes
-from helpers import ROOT, c_acquisition, c_tracking, orc_set_e1_codes, scene, to_oracle_settings, track_rel_err
+from helpers import (ROOT, c_acquisition, c_tracking, first_illconditioned_epoch, orc_set_e1_codes, scene,
+                     to_oracle_settings, track_rel_err)
 
 pytestmark = pytest.mark.gpu
 
@@ -507,4 +508,103 @@ def test_e1c_tracking_and_wrappers_vs_oracle(fs, nE, pilot, tmp_path):
         assert np.allclose(tr[i]["CNo"]["VSMValue"], rvv[i], rtol=1e-5)
         if nE >= 100:                                     # the loops have pulled in: prompt energy sits in I
             assert np.mean(np.abs(tr[i]["I_P"][60:])) > 4 * np.mean(np.abs(tr[i]["Q_P"][60:]))
+    eng.close()
+
+
+# ------------------------------------------------------------- GPS L5C, GAL E5a, GAL E5b, BDS B2a (10230-chip data + pilot)
+def _fam5_case(signal, nsat, seed, extra, nonCoh, ms, nch, cn0=50, **kw):
+    from cu_sdr_collection_b200.codes import standin_codes
+    codes = standin_codes(signal)
+    sc = synth.default_scene_fam5(signal, codes, fs=18e6, nsat=nsat, seed=seed)
+    for x in sc.sats:
+        x.cn0 = cn0
+    sv = sorted({x.prn for x in sc.sats} | set(extra))
+    s = init_settings(signal, acqSatelliteList=sv, acqNonCohTime=nonCoh, msToProcess=ms, numberOfChannels=nch, **kw)
+    so = to_oracle_settings(s)
+    return codes, sc, s, so, sv
+
+
+@pytest.mark.parametrize("signal,path", [("GPS_L5C", "split"), ("GPS_L5C", "cluster"), ("GPS_L5C", "generic"),
+                                         ("GAL_E5a", "split"), ("GAL_E5b", "split"), ("BDS_B2a", "split")])
+def test_fam5_acquisition_vs_oracle(signal, path, monkeypatch):
+    """Two-replica variant-A acquisition (abs(ifft(X.*C_data)) + abs(ifft(X.*C_pilot))) at the reference's 18 Msps
+    (FFT length 36000, fused 45 x 32 x 25 plan) with each signal's fine search: L5C NH20 over 20 periods, E5a the
+    PRN's 100-chip secondary code over 100 periods on a 5 Hz grid, E5b none, B2a data + pilot non-coherent."""
+    if path == "cluster":
+        monkeypatch.setenv("GC_ACQ_PATH", "cluster")
+    if path == "generic":
+        monkeypatch.setenv("GC_FORCE_GENERIC", "1")
+    kw = dict(acqSearchBand=4500.0)
+    if signal == "GAL_E5b":
+        kw = dict(acqSearchBand=4200.0, acqSearchStep=300.0)
+    codes, sc, s, so, sv = _fam5_case(signal, nsat=2, seed=5, extra=[25], nonCoh=3, ms=60, nch=3, **kw)
+    N = 18000
+    raw = synth.make_record(sc, N * (max(O._FAM5_MINPER[signal], 5) + 2))
+    longSignal = O.read_acq_signal_fam5(raw, so)
+    eng = Engine(s, codes=codes)
+    got = acquisition(longSignal, s, engine=eng, verbose=False)
+    st = eng.stats()
+    assert st["fft_len"] == 36000 and st["acq_path"] == {"split": 1, "cluster": 2, "generic": 0}[path]
+    ref = O.acquisition_fam5(longSignal, so, codes, workers=os.cpu_count() or 1)
+    assert got["carrFreq"].shape == ref["carrFreq"].shape
+    _check_acq(got, ref, sv)
+    for sat in sc.sats:
+        # B2a sums |per-period sums| non-coherently, which barely resolves frequency inside a coarse bin
+        step = {"GAL_E5a": 5, "GAL_E5b": 300, "BDS_B2a": 250}.get(signal, 25)
+        assert got["carrFreq"][sat.prn - 1] != 0 and abs(got["carrFreq"][sat.prn - 1] - (s.IF + sat.doppler)) <= step
+    assert got["carrFreq"][25 - 1] == 0
+    eng.close()
+
+
+@pytest.mark.parametrize("signal,pilot", [("GPS_L5C", 1), ("GPS_L5C", 0), ("GAL_E5a", 1), ("GAL_E5b", 1), ("BDS_B2a", 1)])
+def test_fam5_tracking_and_wrappers_vs_oracle(signal, pilot, tmp_path):
+    """preRun() (carrier-aided code NCO centre) -> tracking() with the quadrature pilot (prompt rotated by -pi/2
+    before the atan, discriminators averaged, Pilot_I_P / Pilot_Q_P recorded), against the NumPy oracle."""
+    nE = 240
+    codes, sc, s, so, sv = _fam5_case(signal, nsat=2, seed=5, extra=[], nonCoh=3, ms=nE, nch=3, pilotTRKflag=pilot,
+                                      CNo_VSMinterval=40)
+    N = 18000
+    raw = synth.make_record(sc, N * (nE + 4))
+    acq = dict(carrFreq=np.zeros(63), codePhase=np.zeros(63), peakMetric=np.zeros(63))
+    for i, sat in enumerate(sc.sats):
+        start = (10230 - sat.code_phase) * (18e6 / 10.23e6)
+        acq["carrFreq"][sat.prn - 1] = round((s.IF + sat.doppler) / 25.0) * 25.0
+        acq["codePhase"][sat.prn - 1] = int(round(start)) % N + 1
+        acq["peakMetric"][sat.prn - 1] = 10.0 - i
+    ch = preRun(acq, s)
+    ref_ch = O.preRun_fam5(acq, so)
+    assert [(c["PRN"], c["codeFreq"], c["status"]) for c in ch] == [(c["PRN"], c["codeFreq"], c["status"]) for c in ref_ch]
+    path = tmp_path / "fam5.bin"
+    raw.tofile(path)
+    eng = Engine(s, codes=codes)
+    with open(path, "rb") as fid:
+        tr, _ = tracking(fid, ch, s, engine=eng)
+    ref = O.tracking_fam5(raw, ref_ch, so, codes)
+    assert tr[2]["status"] == "-" and tr[2]["epochsDone"] == 0
+    for i in range(2):
+        assert tr[i]["status"] == "T" == ref[i]["status"] and tr[i]["epochsDone"] == nE
+        assert np.array_equal(tr[i]["absoluteSample"], ref[i]["absoluteSample"])
+        sc_ = np.hypot(ref[i]["I_P"], ref[i]["Q_P"])
+        names = ["I_P", "Q_P", "I_E", "I_L", "Q_E", "Q_L"] + (["Pilot_I_P", "Pilot_Q_P"] if pilot else [])
+        # 18000 distinct code-phase fractions per epoch: now and then a sample sits within 1e-9 chips of a chip edge
+        # and its replica chip hangs on the 10th decimal of remCodePhase (helpers.first_illconditioned_epoch); the
+        # 1e-6 comparison runs up to the first such epoch, after it the trajectories may differ by one sample's worth
+        ok = first_illconditioned_epoch(ref[i]["remCodePhase"], ref[i]["codeFreq"], ref[i]["absoluteSample"], 18e6,
+                                        s.dllCorrelatorSpacing)
+        assert ok >= 20
+        for name in names:
+            assert np.max(np.abs(tr[i][name][:ok] - ref[i][name][:ok]) / sc_[:ok]) < IQ_TOL, name
+            assert np.max(np.abs(tr[i][name] - ref[i][name]) / sc_) < 1e-2, name
+        assert ("Pilot_I_P" in tr[i]) == bool(pilot)
+        assert np.max(np.abs(tr[i]["carrFreq"][:ok] - ref[i]["carrFreq"][:ok])) < 1e-4
+        assert np.max(np.abs(tr[i]["codeFreq"][:ok] - ref[i]["codeFreq"][:ok])) < 1e-4
+        assert np.max(np.abs(tr[i]["carrFreq"] - ref[i]["carrFreq"])) < 0.05
+        if signal == "BDS_B2a":
+            assert tr[i]["DataCNo"].shape == (nE // 40,) and np.all(np.isfinite(tr[i]["DataCNo"])) and "PilotCNo" in tr[i]
+        else:
+            nv = ok // 40
+            assert np.allclose(tr[i]["CNo"]["VSMValue"][:nv], ref[i]["VSMValue"][:nv], rtol=1e-5)
+        assert np.mean(np.abs(tr[i]["I_P"][150:])) > 2 * np.mean(np.abs(tr[i]["Q_P"][150:]))     # pulling in: data in phase,
+        if pilot:
+            assert np.mean(np.abs(tr[i]["Pilot_Q_P"][150:])) > 2 * np.mean(np.abs(tr[i]["Pilot_I_P"][150:]))   # pilot in quadrature
     eng.close()

@@ -334,3 +334,44 @@ def test_e1_memory_code_loader_known_answer():
     o = O.read_e1_dat("/root/reference/GAL/GAL_E1C/include/E1b.dat")
     assert np.array_equal(1 - 2 * o[0], tabs[1][0])
     assert np.array_equal(codes.boc11(tabs[3][1])[:4], [tabs[3][1][0], -tabs[3][1][0], tabs[3][1][1], -tabs[3][1][1]])
+
+
+# ------------------------------------------------------------- GPS L5C, GAL E5a, GAL E5b, BDS B2a (10230-chip data + pilot)
+@pytest.mark.parametrize("signal", ["GPS_L5C", "GAL_E5b", "BDS_B2a"])
+def test_fam5_oracle_closed_loop(signal):
+    """Closed-loop known answers for the two-replica variant-A restatement (oracle/np_oracle.py acquisition_fam5 /
+    tracking_fam5): the injected PRNs come back with code phase and Doppler, an absent PRN stays below threshold,
+    tracking pulls the data component into I and the quadrature pilot into Pilot_Q_P."""
+    from cu_sdr_collection_b200 import init_settings
+    from helpers import to_oracle_settings
+    tabs = codes.standin_codes(signal)
+    fs, N, nE = 18e6, 18000, 200
+    sc = synth.default_scene_fam5(signal, tabs, fs=fs, nsat=2, seed=5)
+    for x in sc.sats:
+        x.cn0 = 50
+    sv = sorted({x.prn for x in sc.sats} | {25})
+    kw = dict(acqSearchBand=4200.0, acqSearchStep=300.0) if signal == "GAL_E5b" else dict(acqSearchBand=4500.0)
+    s = init_settings(signal, acqSatelliteList=sv, acqNonCohTime=3, msToProcess=nE, numberOfChannels=3, pilotTRKflag=1,
+                      CNo_VSMinterval=40, **kw)
+    so = to_oracle_settings(s)
+    assert so.signal == signal and so.pilotTRKflag == 1
+    raw = synth.make_record(sc, N * (nE + 4))
+    ref = O.acquisition_fam5(O.read_acq_signal_fam5(raw, so), so, tabs, workers=os.cpu_count() or 1)
+    assert ref["carrFreq"].shape == ({"GPS_L5C": 32, "GAL_E5b": 50}.get(signal, max(sv)),)
+    assert ref["carrFreq"][25 - 1] == 0
+    for sat in sc.sats:
+        step = {"GAL_E5b": 300, "BDS_B2a": 250}.get(signal, 25)
+        assert ref["carrFreq"][sat.prn - 1] != 0 and abs(ref["carrFreq"][sat.prn - 1] - (s.IF + sat.doppler)) <= step
+        start = (10230 - sat.code_phase) * (fs / 10.23e6)
+        assert abs((ref["codePhase"][sat.prn - 1] - 1 - start + N / 2) % N - N / 2) <= 2
+    ch = O.preRun_fam5(ref, so)
+    assert ch[0]["codeFreq"] == so.codeFreqBasis + (ch[0]["acquiredFreq"] - so.IF) / so.carrFreqBasis * so.codeFreqBasis
+    if signal == "GAL_E5b":            # the coarse grid leaves up to 150 Hz: start the loops from the 25 Hz hand-off instead
+        for c, sat in zip(ch, sorted(sc.sats, key=lambda x: -ref["peakMetric"][x.prn - 1])):
+            c["acquiredFreq"] = round((s.IF + sat.doppler) / 25.0) * 25.0
+    tr = O.tracking_fam5(raw, ch, so, tabs)
+    for i in range(2):
+        assert tr[i]["status"] == "T"
+        assert np.mean(np.abs(tr[i]["I_P"][150:])) > 1.5 * np.mean(np.abs(tr[i]["Q_P"][150:]))
+        assert np.mean(np.abs(tr[i]["Pilot_Q_P"][150:])) > 1.5 * np.mean(np.abs(tr[i]["Pilot_I_P"][150:]))
+    assert tr[2]["status"] == "-"
