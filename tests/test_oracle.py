@@ -345,7 +345,7 @@ def test_fam5_oracle_closed_loop(signal):
     from cu_sdr_collection_b200 import init_settings
     from helpers import to_oracle_settings
     tabs = codes.standin_codes(signal)
-    fs, N, nE = 18e6, 18000, 200
+    fs, N, nE = 18e6, 18000, 400
     sc = synth.default_scene_fam5(signal, tabs, fs=fs, nsat=2, seed=5)
     for x in sc.sats:
         x.cn0 = 50
@@ -366,12 +366,14 @@ def test_fam5_oracle_closed_loop(signal):
         assert abs((ref["codePhase"][sat.prn - 1] - 1 - start + N / 2) % N - N / 2) <= 2
     ch = O.preRun_fam5(ref, so)
     assert ch[0]["codeFreq"] == so.codeFreqBasis + (ch[0]["acquiredFreq"] - so.IF) / so.carrFreqBasis * so.codeFreqBasis
-    if signal == "GAL_E5b":            # the coarse grid leaves up to 150 Hz: start the loops from the 25 Hz hand-off instead
-        for c, sat in zip(ch, sorted(sc.sats, key=lambda x: -ref["peakMetric"][x.prn - 1])):
-            c["acquiredFreq"] = round((s.IF + sat.doppler) / 25.0) * 25.0
+    if signal in ("GAL_E5b", "BDS_B2a"):   # their acquisition leaves up to 150-250 Hz: start the loops from a 25 Hz hand-off instead
+        for c in ch:
+            for sat in sc.sats:
+                if sat.prn == c["PRN"]:
+                    c["acquiredFreq"] = round((s.IF + sat.doppler) / 25.0) * 25.0
     tr = O.tracking_fam5(raw, ch, so, tabs)
     for i in range(2):
         assert tr[i]["status"] == "T"
-        assert np.mean(np.abs(tr[i]["I_P"][150:])) > 1.5 * np.mean(np.abs(tr[i]["Q_P"][150:]))
-        assert np.mean(np.abs(tr[i]["Pilot_Q_P"][150:])) > 1.5 * np.mean(np.abs(tr[i]["Pilot_I_P"][150:]))
+        assert np.mean(np.abs(tr[i]["I_P"][300:])) > 1.5 * np.mean(np.abs(tr[i]["Q_P"][300:]))
+        assert np.mean(np.abs(tr[i]["Pilot_Q_P"][300:])) > 1.5 * np.mean(np.abs(tr[i]["Pilot_I_P"][300:]))
     assert tr[2]["status"] == "-"
