@@ -152,3 +152,16 @@ def standin_codes(signal: str, seed: int = 20260101) -> dict:
 
 
 NH20 = np.array([1, 1, 1, 1, 1, -1, 1, 1, -1, -1, 1, -1, 1, -1, 1, 1, -1, -1, -1, 1], dtype=np.int8)
+
+
+def standin_varb_codes(signal: str, seed: int = 20260101) -> dict:
+    """Seeded stand-ins for the codes of the variant-B signals, {PRN: (code,)}: BDS B1I 2046 +-1 chips (what
+    generateCAcode53.m returns), GPS L2C the 20460-entry return-to-zero CM sequence generateCMcode.m returns
+    (chip, 0, chip, 0, ...)."""
+    rng = np.random.default_rng([seed, sum(map(ord, signal))])
+    if signal == "BDS_B1I":
+        t = (1 - 2 * rng.integers(0, 2, size=(63, 2046))).astype(np.int8)
+        return {prn: (t[prn - 1],) for prn in range(1, 59)}
+    t = np.zeros((32, 20460), dtype=np.int8)
+    t[:, 0::2] = 1 - 2 * rng.integers(0, 2, size=(32, 10230))
+    return {prn: (t[prn - 1],) for prn in range(1, 33)}

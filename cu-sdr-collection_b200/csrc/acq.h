@@ -86,6 +86,18 @@ cudaError_t launch_generic_absacc(const float2* W, const float2* W2, int L, int 
                                   float* partMax, int* partIdx, size_t outBase, cudaStream_t st);
 cudaError_t launch_generic_conj_scale(float2* Cc, size_t n, float scale, cudaStream_t st);
 
+// ---- acquisition variant B (acq_varb.cu): circularly shifted spectra, best row kept ----------------
+struct VarbRow {
+    int src;                  // spectrum row in X: shift * nBlocks + block
+    int rep;                  // replica row in Cc
+    int shift;                // circshift amount = frqBinIndex - 1
+    int pad;
+};
+cudaError_t launch_varb_mulshift(const float2* X, const float2* Cc, const VarbRow* rows, int nRows, float2* out, int L, cudaStream_t st);
+cudaError_t launch_varb_rowpeak(const float2* W, int nRows, int L, float* peak, int* idx, cudaStream_t st);
+cudaError_t launch_varb_segmax(const float2* W, int nRows, int L, const int4* seg, float* out, cudaStream_t st);
+cudaError_t launch_varb_pad(const int8_t* tab, int n, int nRows, float2* out, int L, cudaStream_t st);
+
 // ---- shared by both paths -------------------------------------------------------------------
 struct PeakOut {              // one per PRN slot
     double peak;              // max(max(results))                      acquisition.m:198

@@ -1,0 +1,115 @@
+// Acquisition variant B (BDS/B1I/include/acquisition.m:4-176, GPS/GPS_L2C/include/acquisition.m:4-118):
+// one carrier wipe-off + forward FFT per sub-bin shift, the Doppler bins are circular shifts of that
+// spectrum (IQfreqDomShift = circshift(IQfreqDom, frqBinIndex-1)), every (shift, bin, block) row is
+// correlated with abs(ifft(. .* codeFreqDom)) and only the row holding the largest peak is kept; the
+// metric is that peak over the second peak outside +-1 chip.  The transforms run on the generic
+// mixed-radix passes (acq_generic.cu); this file adds the shifted spectrum multiply and the row reductions.
+#include <algorithm>
+#include "acq.h"
+#include "common.cuh"
+
+namespace gc {
+
+namespace {
+
+// out[r][j] = X[src(r)][(j - shift(r)) mod L] * Cc[rep(r)][j]      (acquisition.m:71-74 / B1I :107-113)
+__global__ void __launch_bounds__(256)
+mulshift_kernel(const float2* __restrict__ X, const float2* __restrict__ Cc, const VarbRow* __restrict__ rows,
+                float2* __restrict__ out, int L)
+{
+    const VarbRow r = rows[blockIdx.y];
+    const float2* x = X + (size_t)r.src * L;
+    const float2* c = Cc + (size_t)r.rep * L;
+    float2* o = out + (size_t)blockIdx.y * L;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < L; j += gridDim.x * blockDim.x) {
+        int i = j - r.shift;
+        if (i < 0) i += L;
+        o[j] = cmul(x[i], __ldg(c + j));
+    }
+}
+
+// per row: max(abs(W)) and its first index            (currmax = max(acqRes), acquisition.m:77; [maxPeak, codePhase] = max(corrVec), :90)
+__global__ void __launch_bounds__(1024)
+rowpeak_kernel(const float2* __restrict__ W, int L, float* peak, int* idx)
+{
+    const float2* w = W + (size_t)blockIdx.x * L;
+    float best = -1.f;
+    int bi = 0x7fffffff;
+    for (int j = threadIdx.x; j < L; j += blockDim.x) {
+        const float2 v = w[j];
+        const float a = sqrtf(fmaf(v.x, v.x, v.y * v.y));
+        if (a > best) { best = a; bi = j; }                 // j ascending per thread: first maximum kept
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_down_sync(0xffffffffu, best, o);
+        const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    __shared__ float sb[32];
+    __shared__ int si[32];
+    if ((threadIdx.x & 31) == 0) { sb[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < (int)(blockDim.x >> 5); ++q)
+            if (sb[q] > best || (sb[q] == best && si[q] < bi)) { best = sb[q]; bi = si[q]; }
+        peak[blockIdx.x] = best;
+        idx[blockIdx.x] = bi;
+    }
+}
+
+// per row: max(abs(W)) over up to two 0-based index ranges [lo, hi]        (secondPeakSize = max(corrVec(codePhaseRange)), :108)
+__global__ void __launch_bounds__(1024)
+segmax_kernel(const float2* __restrict__ W, int L, const int4* __restrict__ seg, float* out)
+{
+    const float2* w = W + (size_t)blockIdx.x * L;
+    const int4 s = seg[blockIdx.x];
+    float best = -1.f;
+    for (int j = s.x + threadIdx.x; j <= s.y; j += blockDim.x) { const float2 v = w[j]; best = fmaxf(best, sqrtf(fmaf(v.x, v.x, v.y * v.y))); }
+    for (int j = s.z + threadIdx.x; j <= s.w; j += blockDim.x) { const float2 v = w[j]; best = fmaxf(best, sqrtf(fmaf(v.x, v.x, v.y * v.y))); }
+    for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_down_sync(0xffffffffu, best, o));
+    __shared__ float sb[32];
+    if ((threadIdx.x & 31) == 0) sb[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < (int)(blockDim.x >> 5); ++q) best = fmaxf(best, sb[q]);
+        out[blockIdx.x] = best;
+    }
+}
+
+// replica tables of variant B into complex rows zero padded to L (code_kernel of acq_generic.cu, any table length)
+__global__ void pad_kernel(const int8_t* tab, int n, float2* out, int L)
+{
+    const int r = blockIdx.y;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < L; j += gridDim.x * blockDim.x)
+        out[(size_t)r * L + j] = make_float2(j < n ? (float)tab[(size_t)r * n + j] : 0.f, 0.f);
+}
+
+}  // namespace
+
+cudaError_t launch_varb_mulshift(const float2* X, const float2* Cc, const VarbRow* rows, int nRows, float2* out, int L, cudaStream_t st)
+{
+    dim3 grid(std::min((L + 255) / 256, 148 * 2), nRows);
+    mulshift_kernel<<<grid, 256, 0, st>>>(X, Cc, rows, out, L);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_varb_rowpeak(const float2* W, int nRows, int L, float* peak, int* idx, cudaStream_t st)
+{
+    rowpeak_kernel<<<nRows, 1024, 0, st>>>(W, L, peak, idx);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_varb_segmax(const float2* W, int nRows, int L, const int4* seg, float* out, cudaStream_t st)
+{
+    segmax_kernel<<<nRows, 1024, 0, st>>>(W, L, seg, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_varb_pad(const int8_t* tab, int n, int nRows, float2* out, int L, cudaStream_t st)
+{
+    dim3 grid(std::min((L + 255) / 256, 148 * 2), nRows);
+    pad_kernel<<<grid, 256, 0, st>>>(tab, n, out, L);
+    return cudaGetLastError();
+}
+
+}  // namespace gc

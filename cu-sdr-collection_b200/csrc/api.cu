@@ -62,7 +62,22 @@ struct gc_handle {
     double fineStep = 25.0;      // fine-search bin width in Hz (acquisition.m:138; GAL_E1C acquisition.m:138: 10)
     bool fam5 = false;           // GPS L5C, GAL E5a, GAL E5b, BDS B2a: 10230-chip data + pilot codes supplied by the caller, two
                                  // replicas summed in acquisition, quadrature pilot tracking, carrier-aided code NCO
-    bool hostCodes = false;      // codes come from gc_set_code (e1c, fam5)
+    bool varB = false;           // acquisition variant B (BDS B1I, GPS L2C): circularly shifted spectra, best row kept
+    struct {                     // variant B geometry (BDS/B1I/include/acquisition.m:6-40, GPS/GPS_L2C/include/acquisition.m:5-24)
+        int Lb = 0;              // samplesPerBlock = transform length
+        int nSig = 1;            // consecutive signal blocks searched (B1I: 2, the better one is kept)
+        int tabLen = 0;          // replica samples before the zero padding
+        int nShifts = 1, nBins = 0;
+        int sign = 1;            // initFreqShift = initFreq + sign*(binIter-1)*freqResolution/Nshifts
+        int chipSamples = 0;     // samplesPerCodeChip: the +-1 chip excluded around the peak
+        int N1 = 0;              // samplesPerBlock/Nblocks: the code-phase range of the second-peak search
+        double freqRes = 0, initFreq = 0;
+    } vb;
+    DevBuf<VarbRow> vbRows;
+    DevBuf<float> vbPeak;
+    DevBuf<int> vbIdx;
+    DevBuf<int4> vbSeg;
+    bool hostCodes = false;      // codes come from gc_set_code (e1c, fam5, varB)
     int acqMinPeriods = 42, acqExtraPeriods = 2;   // longSignal = max(acqMinPeriods, nonCoh + acqExtraPeriods) code periods
     int fineCombine = 0;         // FineParams::combine
     int fineIdx0 = 0;            // first sample index of the fine-search code map (0: ts*(0:n-1), 1: ts*(1:n))
@@ -171,6 +186,7 @@ bool sv_has_code(const gc_handle* h, int sv)
 {
     if (!h->hostCodes) return true;
     if (h->cfg.signal == GC_SIG_GAL_E5A && h->hostCode[2][sv - 1].empty()) return false;   // per-PRN pilot secondary code
+    if (h->varB) return !h->hostCode[0][sv - 1].empty();
     return !h->hostCode[0][sv - 1].empty() && !h->hostCode[1][sv - 1].empty();
 }
 
@@ -255,7 +271,8 @@ int gc_acq_result_len(int32_t signal)
 {
     return signal == GC_SIG_GPS_L1CA ? 32 : signal == GC_SIG_GLO_G1G2 ? 21 : signal == GC_SIG_BDS_B3I ? 63 :
            signal == GC_SIG_GAL_E1C ? 50 : signal == GC_SIG_GPS_L5C ? 32 : signal == GC_SIG_GAL_E5A ? 50 :
-           signal == GC_SIG_GAL_E5B ? 50 : signal == GC_SIG_BDS_B2A ? 63 : 0;
+           signal == GC_SIG_GAL_E5B ? 50 : signal == GC_SIG_BDS_B2A ? 63 : signal == GC_SIG_BDS_B1I ? 58 :
+           signal == GC_SIG_GPS_L2C ? 32 : 0;
 }
 
 const char* gc_last_error(const gc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -265,14 +282,14 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     if (!out || !cfg) return fail(nullptr, GC_ERR_ARG, "gc_create: null argument");
     *out = nullptr;
     if (cfg->abi_version != GC_ABI_VERSION) return fail(nullptr, GC_ERR_ARG, "gc_create: abi_version mismatch");
-    if (cfg->signal < GC_SIG_GPS_L1CA || cfg->signal > GC_SIG_BDS_B2A)
-        return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: signal not implemented (GPS L1CA/L5C, GLONASS G1/G2, BDS B3I/B2a, GAL E1C/E5a/E5b are)");
+    if (cfg->signal < GC_SIG_GPS_L1CA || cfg->signal > GC_SIG_GPS_L2C)
+        return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: signal not implemented (GPS L1CA/L5C/L2C, GLONASS G1/G2, BDS B1I/B3I/B2a, GAL E1C/E5a/E5b are)");
     if (cfg->file_type != 2 || cfg->sample_bytes != 1)
         return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: only fileType 2 (I/Q) with dataType 'schar' is implemented");
     if (!(cfg->sampling_freq > 0) || !(cfg->code_freq_basis > 0) ||
         cfg->code_length != (cfg->signal == GC_SIG_GLO_G1G2 ? 511 : cfg->signal == GC_SIG_GAL_E1C ? 4092 :
-                             cfg->signal == GC_SIG_GPS_L1CA ? 1023 : 10230) ||
-        cfg->acq_noncoh_time < 1 ||
+                             cfg->signal == GC_SIG_GPS_L1CA ? 1023 : cfg->signal == GC_SIG_BDS_B1I ? 2046 : 10230) ||
+        (cfg->acq_noncoh_time < 1 && cfg->signal != GC_SIG_BDS_B1I && cfg->signal != GC_SIG_GPS_L2C) ||
         !(cfg->acq_search_step > 0) || cfg->cno_vsm_interval < 2)
         return fail(nullptr, GC_ERR_ARG, "gc_create: invalid settings");
     int ndev = 0;
@@ -292,9 +309,10 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     h->e1c = (cfg->signal == GC_SIG_GAL_E1C);
     h->fam5 = (cfg->signal == GC_SIG_GPS_L5C || cfg->signal == GC_SIG_GAL_E5A || cfg->signal == GC_SIG_GAL_E5B ||
                cfg->signal == GC_SIG_BDS_B2A);
-    h->hostCodes = h->e1c || h->fam5;
+    h->varB = (cfg->signal == GC_SIG_BDS_B1I || cfg->signal == GC_SIG_GPS_L2C);
+    h->hostCodes = h->e1c || h->fam5 || h->varB;
     h->sub = h->e1c ? 2 : 1;
-    h->nRep = h->hostCodes ? 2 : 1;                          // data + pilot replicas (GAL_E1C acquisition.m:186-192, GPS_L5C :171-175)
+    h->nRep = (h->e1c || h->fam5) ? 2 : 1;                   // data + pilot replicas (GAL_E1C acquisition.m:186-192, GPS_L5C :171-175)
     h->fineStep = h->e1c ? 10.0 : 25.0;                      // GAL_E1C acquisition.m:138
     h->nFinePeriods = h->b3i ? 20 : h->e1c ? 25 : 40;        // BDS/B3I/include/acquisition.m:131-133; GAL_E1C :148
     h->fineCombine = h->glo ? 1 : h->b3i ? 2 : h->e1c ? 3 : 0;
@@ -323,11 +341,29 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     // acquisition.m:116-124,138-140
     h->N = (int)m_round(cfg->sampling_freq / (cfg->code_freq_basis / (double)cfg->code_length));
     h->L = 2 * h->N;
+    if (h->varB) {
+        const bool b1i = cfg->signal == GC_SIG_BDS_B1I;
+        const int nBlocks = b1i ? 4 : 2;                                                   // B1I :7 ; L2C :5
+        h->vb.Lb = b1i ? (int)m_round(cfg->sampling_freq / (cfg->code_freq_basis / (nBlocks * (double)cfg->code_length)))   // B1I :9-10
+                       : h->N * nBlocks;                                                    // L2C :10
+        h->vb.nSig = b1i ? 2 : 1;                                                           // B1I :13-14
+        h->vb.tabLen = b1i ? (int)m_round(cfg->sampling_freq / (cfg->code_freq_basis / (2 * (double)cfg->code_length))) : h->N;   // makeCaTableDMA.m:9-10
+        h->vb.freqRes = cfg->sampling_freq / h->vb.Lb;                                      // B1I :20
+        h->vb.nBins = (int)m_round(cfg->acq_search_band * 1e3 / h->vb.freqRes) + 1;         // :22 (acqSearchBand in kHz)
+        const double ns = h->vb.freqRes / cfg->acq_search_step;                             // :40 Nshifts = freqResolution/stepSize
+        h->vb.nShifts = (int)m_round(ns);
+        if (h->vb.nShifts < 1 || std::fabs(ns - h->vb.nShifts) > 1e-9) { h->err = "gc_create: freqResolution/stepSize must be a whole number"; return bail(GC_ERR_ARG); }
+        h->vb.sign = b1i ? 1 : -1;                                                          // B1I :64 ; L2C :62
+        h->vb.chipSamples = (int)m_round(cfg->sampling_freq / cfg->code_freq_basis);        // B1I :126 ; L2C :7
+        h->vb.N1 = h->vb.Lb / nBlocks;
+        h->vb.initFreq = cfg->IF + (cfg->acq_search_band / 2) * 1000;                       // B1I :50
+        h->L = h->vb.Lb;
+    }
     h->ts = 1 / cfg->sampling_freq;
-    h->nBins = (int)m_round(cfg->acq_search_band * 2 / cfg->acq_search_step) + 1;
+    h->nBins = h->varB ? h->vb.nBins : (int)m_round(cfg->acq_search_band * 2 / cfg->acq_search_step) + 1;
     h->nFine = (int)m_round(cfg->acq_search_step / h->fineStep) + 1;
-    h->nonCoh = cfg->acq_noncoh_time;
-    h->fused = fused_plan_info(h->L, &h->fp) && !getenv("GC_FORCE_GENERIC");
+    h->nonCoh = h->varB ? 1 : cfg->acq_noncoh_time;
+    h->fused = !h->varB && fused_plan_info(h->L, &h->fp) && !getenv("GC_FORCE_GENERIC");
     h->stats.fft_len = h->L;
     {   // GC_ACQ_PATH=cluster selects the one-kernel correlation stage (acq_cluster.cu, transform resident
         // in a cluster's shared memory); the default is inverse rows + inverse columns through a work buffer
@@ -392,6 +428,7 @@ void gc_destroy(gc_handle* h)
     h->Cc.release(); h->W.release(); h->dphi.release(); h->fdphi.release(); h->codeTab.release(); h->chips.release(); h->fineSecondary.release();
     h->prnList.release(); h->slotGroup.release(); h->partIdx.release(); h->fineCodePhase.release(); h->fineBest.release(); h->fineSv.release(); h->partMax.release();
     h->peaks.release(); h->sigPower.release(); h->fineSums.release(); h->fineResult.release(); h->fineProd.release();
+    h->vbRows.release(); h->vbPeak.release(); h->vbIdx.release(); h->vbSeg.release();
     h->chans.release(); h->trackCodes.release(); h->trackPilot.release(); h->trackOut.release(); h->epochsDone.release();
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -404,11 +441,12 @@ int gc_set_code(gc_handle* h, int32_t sv, int32_t component, const int8_t* chips
     if (!h->hostCodes) return fail(h, GC_ERR_ARG, "gc_set_code: this signal generates its own codes");
     const bool secondary = (component == 2);
     if (secondary && h->cfg.signal != GC_SIG_GAL_E5A) return fail(h, GC_ERR_ARG, "gc_set_code: only GAL E5a takes a pilot secondary code");
-    if (sv < 1 || sv > h->resultLen || component < 0 || component > 2 || !chips ||
-        nChips != (secondary ? 100 : h->cfg.code_length))
+    const bool l2c = h->cfg.signal == GC_SIG_GPS_L2C;        // CM code as generateCMcode.m returns it: 2*codeLength entries, return-to-zero
+    if (sv < 1 || sv > h->resultLen || component < 0 || component > 2 || !chips || (h->varB && component != 0) ||
+        nChips != (secondary ? 100 : l2c ? 2 * h->cfg.code_length : h->cfg.code_length))
         return fail(h, GC_ERR_ARG, "gc_set_code: bad argument (PRN in range, component 0/1 with code_length chips, or 2 with 100)");
     for (int i = 0; i < nChips; ++i)
-        if (chips[i] != 1 && chips[i] != -1) return fail(h, GC_ERR_ARG, "gc_set_code: chips must be +-1");
+        if (chips[i] != 1 && chips[i] != -1 && !(l2c && chips[i] == 0)) return fail(h, GC_ERR_ARG, "gc_set_code: chips must be +-1");
     std::vector<int8_t>& c = h->hostCode[component][sv - 1];
     if (h->e1c) {
         c.resize((size_t)2 * nChips);
@@ -443,6 +481,198 @@ int gc_set_record_device(gc_handle* h, const void* dptr, size_t nbytes)
     return GC_OK;
 }
 
+// ---- acquisition variant B (BDS/B1I/include/acquisition.m:42-176, GPS/GPS_L2C/include/acquisition.m:26-118) -------
+static int varb_build_replicas(gc_handle* h)
+{
+    const gc_config& c = h->cfg;
+    const int Lb = h->vb.Lb, S = h->vb.tabLen, nRep = h->resultLen;
+    const bool b1i = c.signal == GC_SIG_BDS_B1I;
+    std::vector<int8_t> tab((size_t)nRep * S, 0);
+    const double ts = 1 / c.sampling_freq;
+    for (int prn = 1; prn <= nRep; ++prn) {
+        const std::vector<int8_t>& code = h->hostCode[0][prn - 1];
+        if (code.empty()) continue;
+        int8_t* t = tab.data() + (size_t)(prn - 1) * S;
+        if (b1i) {                                            // makeCaTableDMA.m:13-19: [caCode caCode] sampled over two periods
+            const double tc = 1 / c.code_freq_basis;
+            for (int n = 1; n <= S; ++n) {
+                int idx = (int)std::ceil((ts * (double)n) / tc);
+                if (n == S) idx = 2 * c.code_length;
+                t[n - 1] = code[(idx - 1) % c.code_length];
+            }
+        } else {                                              // makeCMTable.m:8-15 (return-to-zero CM code, 2*codeLength entries)
+            const double tc = 1 / (c.code_freq_basis * 2);
+            for (int n = 0; n < S; ++n) {
+                int idx = (int)std::ceil((ts * (double)n) / tc);
+                if (n == S - 1) idx = c.code_length * 2;
+                if (n == 0) idx = 1;
+                t[n] = code[idx - 1];
+            }
+        }
+    }
+    cudaStream_t st = h->stream;
+    GC_CUDA(h, upload(h->codeTab, tab, st));
+    GC_CUDA(h, h->Cc.reserve((size_t)nRep * Lb));
+    GC_CUDA(h, h->T1.reserve((size_t)nRep * Lb));
+    GC_CUDA(h, h->T2.reserve((size_t)nRep * Lb));
+    GC_CUDA(h, launch_varb_pad(h->codeTab.p, S, nRep, h->T1.p, Lb, st));           // [table zeros] (B1I :58, L2C :47)
+    float2 *src = h->T1.p, *dst = h->T2.p;
+    int n = Lb, sd = 1;
+    for (int f = 0; f < h->plan.nf; ++f) {
+        GC_CUDA(h, launch_generic_stage(h->plan, f, n, sd, false, src, dst, nRep, st));
+        n /= h->plan.fac[f]; sd *= h->plan.fac[f];
+        std::swap(src, dst);
+    }
+    GC_CUDA(h, cudaMemcpyAsync(h->Cc.p, src, (size_t)nRep * Lb * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    GC_CUDA(h, launch_generic_conj_scale(h->Cc.p, (size_t)nRep * Lb, 1.0f / (float)Lb, st));   // conj(fft(.)) with ifft's 1/L
+    h->replicasReady = true;
+    return GC_OK;
+}
+
+static int acquire_varb(gc_handle* h, long long winStart, int32_t nSv, const int32_t* svList,
+                        double* carrFreq, double* codePhase, double* peakMetric, int32_t* coarseBin, int32_t* coarseCodePhase)
+{
+    const gc_config& c = h->cfg;
+    const int Lb = h->vb.Lb, nSig = h->vb.nSig, nShifts = h->vb.nShifts, nBins = h->vb.nBins;
+    const bool b1i = c.signal == GC_SIG_BDS_B1I;
+    cudaStream_t st = h->stream;
+    const long long recSamples = (long long)(h->recBytes / 2);
+    if (winStart < 0 || winStart + (long long)nSig * Lb > recSamples)
+        return fail(h, GC_ERR_SHORT_RECORD, "gc_acquire: record shorter than the acquisition blocks");
+    for (int i = 0; i < h->resultLen; ++i) {
+        carrFreq[i] = codePhase[i] = peakMetric[i] = 0;
+        if (coarseBin) coarseBin[i] = 0;
+        if (coarseCodePhase) coarseCodePhase[i] = 0;
+    }
+    cudaEventRecord(h->ev[0], st);
+    int launches = 0;
+    // wiped-off spectra of every sub-bin shift and block (B1I :62-76, L2C :60-68)
+    std::vector<uint64_t> dphi(nShifts);
+    for (int b = 0; b < nShifts; ++b)
+        dphi[b] = turns_to_fix((h->vb.initFreq + h->vb.sign * b * (h->vb.freqRes / nShifts)) / c.sampling_freq);
+    GC_CUDA(h, h->dphi.reserve(nShifts));
+    GC_CUDA(h, cudaMemcpyAsync(h->dphi.p, dphi.data(), nShifts * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    const int nX = nShifts * nSig;
+    const int nRows = nShifts * nBins * nSig;
+    const size_t bufRows = (size_t)std::max(std::max(nRows, nX), std::max((int)nSv, h->resultLen));
+    GC_CUDA(h, h->X.reserve((size_t)nX * Lb));
+    GC_CUDA(h, h->T1.reserve(bufRows * Lb));
+    GC_CUDA(h, h->T2.reserve(bufRows * Lb));
+    GC_CUDA(h, launch_generic_wipe(h->rec, winStart, Lb, nSig, nShifts, 0, h->dphi.p, h->T1.p, Lb, st)); ++launches;
+    float2 *src = h->T1.p, *dst = h->T2.p;
+    int n = Lb, sd = 1;
+    for (int f = 0; f < h->plan.nf; ++f) {
+        GC_CUDA(h, launch_generic_stage(h->plan, f, n, sd, false, src, dst, nX, st)); ++launches;
+        n /= h->plan.fac[f]; sd *= h->plan.fac[f];
+        std::swap(src, dst);
+    }
+    GC_CUDA(h, cudaMemcpyAsync(h->X.p, src, (size_t)nX * Lb * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    cudaEventRecord(h->ev[2], st);
+
+    // every (shift, bin, block) row of every SV: peak of abs(ifft(circshift(X) .* codeFreqDom))
+    GC_CUDA(h, h->vbRows.reserve((size_t)std::max(nRows, (int)nSv)));
+    GC_CUDA(h, h->vbPeak.reserve((size_t)nSv * nRows));
+    GC_CUDA(h, h->vbIdx.reserve((size_t)std::max(nRows, (int)nSv)));
+    std::vector<VarbRow> rows(nRows);
+    auto inverse = [&](int batch, float2** result) -> int {
+        float2 *a = h->T1.p, *b = h->T2.p;
+        int nn = Lb, ss = 1;
+        for (int f = 0; f < h->plan.nf; ++f) {
+            GC_CUDA(h, launch_generic_stage(h->plan, f, nn, ss, true, a, b, batch, st)); ++launches;
+            nn /= h->plan.fac[f]; ss *= h->plan.fac[f];
+            std::swap(a, b);
+        }
+        *result = a;
+        return GC_OK;
+    };
+    for (int s = 0; s < nSv; ++s) {
+        for (int b = 0; b < nShifts; ++b)
+            for (int k = 0; k < nBins; ++k)
+                for (int g = 0; g < nSig; ++g)
+                    rows[(b * nBins + k) * nSig + g] = VarbRow{b * nSig + g, svList[s] - 1, k, 0};
+        GC_CUDA(h, cudaMemcpyAsync(h->vbRows.p, rows.data(), nRows * sizeof(VarbRow), cudaMemcpyHostToDevice, st));
+        GC_CUDA(h, launch_varb_mulshift(h->X.p, h->Cc.p, h->vbRows.p, nRows, h->T1.p, Lb, st)); ++launches;
+        float2* W = nullptr;
+        int rc = inverse(nRows, &W);
+        if (rc != GC_OK) return rc;
+        GC_CUDA(h, launch_varb_rowpeak(W, nRows, Lb, h->vbPeak.p + (size_t)s * nRows, h->vbIdx.p, st)); ++launches;
+        GC_CUDA(h, cudaStreamSynchronize(st));                // rows (pageable host vector) is rewritten for the next SV
+    }
+    std::vector<float> peaks((size_t)nSv * nRows);
+    GC_CUDA(h, cudaMemcpyAsync(peaks.data(), h->vbPeak.p, peaks.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+    GC_CUDA(h, cudaStreamSynchronize(st));
+
+    // the reference's running comparison, in its loop order (B1I :60-123, L2C :58-86)
+    std::vector<VarbRow> win(nSv);
+    std::vector<int> winShift(nSv), winBin(nSv);
+    for (int s = 0; s < nSv; ++s) {
+        float prevmax = 0.f;
+        int fbin = 0, fshift = 0, fsig = 0;
+        for (int b = 0; b < nShifts; ++b)
+            for (int k = 0; k < nBins; ++k) {
+                if (k == nBins - 1 && b > 0) continue;                                     // B1I :79-81
+                const float* pk = peaks.data() + (size_t)s * nRows + (size_t)(b * nBins + k) * nSig;
+                if (nSig == 2) {
+                    if (pk[0] > prevmax || pk[1] > prevmax) {                              // B1I :101-114
+                        if (pk[0] > pk[1]) { prevmax = pk[0]; fsig = 0; } else { prevmax = pk[1]; fsig = 1; }
+                        fshift = b; fbin = k;
+                    }
+                } else if (pk[0] > prevmax) { prevmax = pk[0]; fshift = b; fbin = k; fsig = 0; }   // L2C :78-83
+            }
+        win[s] = VarbRow{fshift * nSig + fsig, svList[s] - 1, fbin, 0};
+        winShift[s] = fshift; winBin[s] = fbin;
+    }
+    // corrVec of the winning rows again, then its first maximum and the second peak outside +-1 chip
+    GC_CUDA(h, cudaMemcpyAsync(h->vbRows.p, win.data(), nSv * sizeof(VarbRow), cudaMemcpyHostToDevice, st));
+    GC_CUDA(h, launch_varb_mulshift(h->X.p, h->Cc.p, h->vbRows.p, nSv, h->T1.p, Lb, st)); ++launches;
+    float2* W = nullptr;
+    int rc = inverse(nSv, &W);
+    if (rc != GC_OK) return rc;
+    GC_CUDA(h, launch_varb_rowpeak(W, nSv, Lb, h->vbPeak.p, h->vbIdx.p, st)); ++launches;
+    std::vector<float> maxPeak(nSv), second(nSv);
+    std::vector<int> cp0(nSv);
+    GC_CUDA(h, cudaMemcpyAsync(maxPeak.data(), h->vbPeak.p, nSv * sizeof(float), cudaMemcpyDeviceToHost, st));
+    GC_CUDA(h, cudaMemcpyAsync(cp0.data(), h->vbIdx.p, nSv * sizeof(int), cudaMemcpyDeviceToHost, st));
+    GC_CUDA(h, cudaStreamSynchronize(st));
+    std::vector<int4> seg(nSv);
+    for (int s = 0; s < nSv; ++s) {
+        const int cp = cp0[s] + 1;                                                         // 1-based codePhase (:125)
+        const int e1 = cp - h->vb.chipSamples, e2 = cp + h->vb.chipSamples, N1 = h->vb.N1; // :127-128
+        int a1, b1, a2 = 1, b2 = 0;                                                        // 1-based inclusive ranges; second one empty by default
+        if (e1 < 2) { a1 = e2; b1 = N1 + e1; }                                             // :131-133
+        else if (e2 >= N1) { a1 = e2 - N1 + 1; b1 = e1; }                                  // :134-136
+        else { a1 = 1; b1 = e1; a2 = e2; b2 = N1; }                                        // :137-139
+        seg[s] = make_int4(std::max(a1, 1) - 1, std::min(b1, Lb) - 1, std::max(a2, 1) - 1, std::min(b2, Lb) - 1);
+    }
+    GC_CUDA(h, h->vbSeg.reserve(nSv));
+    GC_CUDA(h, cudaMemcpyAsync(h->vbSeg.p, seg.data(), nSv * sizeof(int4), cudaMemcpyHostToDevice, st));
+    GC_CUDA(h, launch_varb_segmax(W, nSv, Lb, h->vbSeg.p, h->vbPeak.p, st)); ++launches;
+    GC_CUDA(h, cudaMemcpyAsync(second.data(), h->vbPeak.p, nSv * sizeof(float), cudaMemcpyDeviceToHost, st));
+    cudaEventRecord(h->ev[1], st);
+    GC_CUDA(h, cudaStreamSynchronize(st));
+    int nAcq = 0;
+    for (int s = 0; s < nSv; ++s) {
+        const int ri = svList[s] - 1;
+        peakMetric[ri] = (double)maxPeak[s] / (double)second[s];                           // :142
+        if (coarseBin) coarseBin[ri] = winBin[s] + 1;
+        if (coarseCodePhase) coarseCodePhase[ri] = cp0[s] + 1;
+        if (peakMetric[ri] > c.acq_threshold) {                                            // :145
+            ++nAcq;
+            codePhase[ri] = cp0[s] + 1;
+            carrFreq[ri] = h->vb.initFreq - h->vb.freqRes * winBin[s] + h->vb.sign * (h->vb.freqRes / nShifts) * winShift[s];   // B1I :150 ; L2C :95
+        }
+    }
+    (void)b1i;
+    float total = 0, fwd = 0;
+    cudaEventElapsedTime(&total, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&fwd, h->ev[0], h->ev[2]);
+    h->stats.n_acquired = nAcq;
+    h->stats.acq_fwd_ms = fwd; h->stats.acq_corr_ms = total - fwd; h->stats.acq_fine_ms = 0; h->stats.acq_total_ms = total;
+    h->stats.corr_rows_ms = total - fwd; h->stats.corr_cols_ms = 0; h->stats.corr_row_launches = nSv;
+    h->stats.acq_launches = launches;
+    return GC_OK;
+}
+
 static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int32_t* svList,
                         double* carrFreq, double* codePhase, double* peakMetric,
                         int32_t* coarseBin, int32_t* coarseCodePhase)
@@ -459,8 +689,12 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         if (!sv_has_code(h, svList[i])) return fail(h, GC_ERR_ARG, "gc_acquire: no code set for an SV of the list (gc_set_code)");
     if (!h->replicasReady) {
         cudaSetDevice(c.device);
-        int rc = build_replicas(h);
+        int rc = h->varB ? varb_build_replicas(h) : build_replicas(h);
         if (rc != GC_OK) return rc;
+    }
+    if (h->varB) {
+        cudaSetDevice(c.device);
+        return acquire_varb(h, winStart, nSv, svList, carrFreq, codePhase, peakMetric, coarseBin, coarseCodePhase);
     }
     // postProcessing.m:86 reads max(42, nonCoh+2) code periods (B3I: max(22, nonCoh+1), BDS/B3I/include/postProcessing.m:86)
     const int nPeriodsAcq = std::max(h->acqMinPeriods, nonCoh + h->acqExtraPeriods);
@@ -790,6 +1024,8 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
     if (!h) return GC_ERR_ARG;
     const gc_config& c = h->cfg;
     if (!h->rec) return fail(h, GC_ERR_NO_RECORD, "gc_track: no record resident");
+    if (c.signal == GC_SIG_GPS_L2C)
+        return fail(h, GC_ERR_UNSUPPORTED, "gc_track: GPS L2C tracking (20 ms CM/CL epochs) is not implemented yet");
     if (nCh < 1 || nEpochs < 1 || !sv || !acqFreq || !codePhase || !out || !epochsDone)
         return fail(h, GC_ERR_ARG, "gc_track: bad argument");
     cudaSetDevice(c.device);

@@ -7,7 +7,7 @@ import os
 
 import numpy as np
 
-from .settings import Settings
+from .settings import Settings, varb_step
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 GC_TRACK_NFIELDS = 15
@@ -36,7 +36,9 @@ class gc_config(C.Structure):
 
 GC_SIG_GPS_L1CA, GC_SIG_GLO_G1G2, GC_SIG_BDS_B3I, GC_SIG_GAL_E1C = 0, 1, 2, 3
 GC_SIG_GPS_L5C, GC_SIG_GAL_E5A, GC_SIG_GAL_E5B, GC_SIG_BDS_B2A = 4, 5, 6, 7
-_FAM5_IDS = {"GPS_L5C": GC_SIG_GPS_L5C, "GAL_E5a": GC_SIG_GAL_E5A, "GAL_E5b": GC_SIG_GAL_E5B, "BDS_B2a": GC_SIG_BDS_B2A}
+GC_SIG_BDS_B1I, GC_SIG_GPS_L2C = 8, 9
+_FAM5_IDS = {"GPS_L5C": GC_SIG_GPS_L5C, "GAL_E5a": GC_SIG_GAL_E5A, "GAL_E5b": GC_SIG_GAL_E5B, "BDS_B2a": GC_SIG_BDS_B2A,
+             "BDS_B1I": GC_SIG_BDS_B1I, "GPS_L2C": GC_SIG_GPS_L2C}
 GC_SV_NONE = -2147483648
 
 
@@ -108,7 +110,7 @@ def config_from_settings(s: Settings, device: int = 0) -> gc_config:
                      code_length=int(s.codeLength), acq_noncoh_time=int(s.acqNonCohTime),
                      cno_vsm_interval=int(s.CNo_VSMinterval), skip_number_of_bytes=int(s.skipNumberOfBytes),
                      sampling_freq=s.samplingFreq, IF=s.IF, code_freq_basis=s.codeFreqBasis,
-                     acq_search_band=s.acqSearchBand, acq_search_step=s.acqSearchStep,
+                     acq_search_band=s.acqSearchBand, acq_search_step=varb_step(s) if s.is_varb else s.acqSearchStep,
                      acq_threshold=s.acqThreshold, dll_damping_ratio=s.dllDampingRatio,
                      dll_noise_bandwidth=s.dllNoiseBandwidth, dll_correlator_spacing=s.dllCorrelatorSpacing,
                      pll_damping_ratio=s.pllDampingRatio, pll_noise_bandwidth=s.pllNoiseBandwidth,
@@ -138,7 +140,7 @@ class Engine:
         if rc != 0:
             raise GnssCorrError(f"gc_create failed ({rc}): {self.lib.gc_last_error(None).decode()}")
         self._keep = None
-        if settings.is_fam5:
+        if settings.is_fam5 or settings.is_varb:
             if codes is None:
                 raise GnssCorrError(f"{settings.signal} takes its primary codes from the caller: pass codes= "
                                     "{PRN: (data, pilot[, pilot_secondary])} (what generateL5Icode.m etc. return)")
@@ -160,6 +162,8 @@ class Engine:
             for comp, chips in enumerate(comps):
                 if comp == 2 and self.settings.signal != "GAL_E5a":
                     continue                                     # only E5a's fine search uses a per-PRN secondary code
+                if comp >= 1 and self.settings.is_varb:
+                    continue                                     # B1I / L2C: one code per SV
                 a = np.ascontiguousarray(chips, dtype=np.int8)
                 self._check(self.lib.gc_set_code(self._h, int(prn), comp, a.ctypes.data, a.size), "gc_set_code")
 

@@ -41,10 +41,18 @@ class Settings:
     carrFreqBasis: float = 0.0          # B3I: RF carrier used to aid the code NCO (BDS/B3I/initSettings.m:132)
     pilotTRKflag: int = 0               # Galileo E1: track the pilot component too (GAL/GAL_E1C/initSettings.m:113)
     codeDir: str = ""                   # Galileo E1: directory holding E1b.dat / E1c.dat (the reference keeps them in include/)
+    stepSize: float = 0.0               # BDS B1I: sub-bin step request (BDS/B1I/initSettings.m:96; 0 = [] = derive it)
+    acqStep: float = 0.0                # GPS L2C: sub-bin step (GPS/GPS_L2C/initSettings.m:94)
+    acqCohT: int = 20                   # GPS L2C: coherent time in ms (:91)
 
     @property
     def is_glonass(self) -> bool:
         return self.signal in ("GLO_GL1", "GLO_GL2")
+
+    @property
+    def is_varb(self) -> bool:
+        """Acquisition variant B (circularly shifted spectra, best row kept): BDS B1I, GPS L2C."""
+        return self.signal in ("BDS_B1I", "GPS_L2C")
 
     @property
     def is_fam5(self) -> bool:
@@ -91,6 +99,37 @@ _FAM5 = {
 FAM5_SIGNALS = tuple(_FAM5)
 
 
+# BDS/B1I/initSettings.m and GPS/GPS_L2C/initSettings.m (hot-path fields); acqSearchBand is in kHz in these two folders
+_B1I_DEFAULTS = dict(codeFreqBasis=2.046e6, codeLength=2046.0, acqSatelliteList=list(range(6, 59)), acqSearchBand=10.0,
+                     acqThreshold=2.0, resamplingThreshold=9e6, stepSize=125.0, dllNoiseBandwidth=4.0, pllNoiseBandwidth=35.0,
+                     CNo_VSMinterval=400, fileName="../../../B1I_IF20KHz_FS18MHz.bin")
+_L2C_DEFAULTS = dict(samplingFreq=8e6, codeFreqBasis=0.5115e6, codeLength=10230.0, acqSearchBand=10.0, acqThreshold=1.5,
+                     resamplingThreshold=6e6, acqStep=12.5, acqCohT=20, dllNoiseBandwidth=4.0, dllCorrelatorSpacing=0.25,
+                     pllNoiseBandwidth=10.0, intTime=0.02, CNo_accTime=0.02, CNo_VSMinterval=40,
+                     fileName="../../../L2_IF20KHz_FS8MHz.bin")
+
+
+def varb_step(s: "Settings") -> float:
+    """Sub-bin step of the variant-B acquisitions: settings.acqStep for L2C; for B1I settings.stepSize resolved the way
+    BDS/B1I/include/acquisition.m:24-39 does ([] -> 0.5/(4 ms); == freqResolution -> itself; else the nearest divisor of
+    freqResolution on a 0.25 Hz raster that does not exceed it)."""
+    import math
+    import numpy as np
+    if s.signal == "GPS_L2C":
+        return float(s.acqStep)
+    spb = int(math.floor(s.samplingFreq / (s.codeFreqBasis / (4 * s.codeLength)) + 0.5))
+    res = s.samplingFreq / spb
+    if not s.stepSize:
+        return 0.5 / (4 * s.codeLength / s.codeFreqBasis)
+    if s.stepSize == res:
+        return float(s.stepSize)
+    steps = np.arange(1, res / 2 + 1e-12, 0.25)
+    steps = steps[np.fmod(res, steps) == 0]
+    diff = steps - s.stepSize
+    k = int(np.argmin(np.abs(diff)))
+    return float(steps[k - 1] if diff[k] > 0 else steps[k])
+
+
 def init_settings(signal: str = "GPS_L1CA", **overrides) -> Settings:
     """``settings = initSettings()`` of the given signal folder (GPS/GPS_L1CA/init.m:56,
     GLO/GLO_GL1, GLO/GLO_GL2) with optional field overrides."""
@@ -106,6 +145,9 @@ def init_settings(signal: str = "GPS_L1CA", **overrides) -> Settings:
             setattr(s, k, list(v) if isinstance(v, list) else v)
     elif signal in _FAM5:
         for k, v in {**_FAM5_BASE, **_FAM5[signal]}.items():
+            setattr(s, k, list(v) if isinstance(v, list) else v)
+    elif signal in ("BDS_B1I", "GPS_L2C"):
+        for k, v in (_B1I_DEFAULTS if signal == "BDS_B1I" else _L2C_DEFAULTS).items():
             setattr(s, k, list(v) if isinstance(v, list) else v)
     elif signal == "GAL_E1C":
         for k, v in _E1C_DEFAULTS.items():

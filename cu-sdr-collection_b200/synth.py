@@ -56,6 +56,10 @@ class Scene:
     # data component in phase (one random symbol per 1 ms code period) and the pilot in quadrature carrying its
     # secondary code (NH20 for L5C, the PRN's 100-chip code otherwise); ``codes`` = {PRN: (data, pilot, secondary)}.
     fam5: str = ""
+    # BDS B1I / GPS L2C scenes (``varb`` = the signal name): one caller-supplied code per SV, ``codes`` = {PRN: (code,)};
+    # B1I: 2046 chips at 2.046 Mcps, 20 ms bits with the NH20 secondary code; L2C: the 20460-entry return-to-zero CM
+    # sequence at 1.023 M entries/s (the CL slots stay empty), one data symbol per 20 ms code period.
+    varb: str = ""
 
 
 def default_scene(fs: float = 16.368e6, IF: float = 20e3, nsat: int = 8, seed: int = 20260101) -> Scene:
@@ -119,6 +123,17 @@ def default_scene_fam5(signal: str, codes: dict, fs: float = 18e6, IF: float = 2
     return Scene(fs=fs, IF=IF, seed=seed, sats=sats, fam5=signal, codes=codes)
 
 
+def default_scene_varb(signal: str, codes: dict, fs: float, IF: float = 20e3, nsat: int = 3, seed: int = 20260101) -> Scene:
+    rng = np.random.default_rng(seed)
+    pool = np.arange(6, 59) if signal == "BDS_B1I" else np.arange(1, 33)
+    clen = 2046 if signal == "BDS_B1I" else 20460
+    prns = rng.choice(pool, size=nsat, replace=False)
+    sats = [Sat(prn=int(p), doppler=float(rng.uniform(-4000, 4000)), code_phase=float(rng.uniform(0, clen)),
+                cn0=float(rng.uniform(42, 50)), phi0=float(rng.uniform(0, 2 * np.pi)), bit_seed=int(rng.integers(1 << 30)),
+                bit_offset=int(rng.integers(0, 20))) for p in prns]
+    return Scene(fs=fs, IF=IF, seed=seed, sats=sats, varb=signal, codes=codes)
+
+
 def _fam5_secondary(scene: Scene, prn: int) -> np.ndarray:
     return NH20.astype(np.float64) if scene.fam5 == "GPS_L5C" else np.asarray(scene.codes[prn][2], dtype=np.float64)
 
@@ -137,6 +152,22 @@ def make_record(scene: Scene, nsamples: int, start: int = 0) -> np.ndarray:
             clen, crate, carrier = 10230, 10.23e6, 1268.52e6
             fc = scene.IF + s.doppler
             chipseq = b3i_code(s.prn).astype(np.float64)
+        elif scene.varb:
+            b1i = scene.varb == "BDS_B1I"
+            clen, crate, carrier = (2046, 2.046e6, 1561.098e6) if b1i else (20460, 1.023e6, 1227.6e6)
+            fc = scene.IF + s.doppler
+            fcode = crate * (1 + s.doppler / carrier)
+            chips = fcode * t + s.code_phase
+            period = np.floor(chips / clen).astype(np.int64)
+            idx = np.floor(chips - period * float(clen)).astype(np.int64) % clen
+            code = np.asarray(scene.codes[s.prn][0], dtype=np.float64)[idx]
+            if b1i:
+                d = nav_bits(s, int(period.max() // 20) + 3)[(period + s.bit_offset) // 20] * _NH20[(period + s.bit_offset) % 20]
+            else:
+                d = nav_bits(s, int(period.max()) + 30)[period + s.bit_offset]
+            ph = 2 * np.pi * (fc * t % 1.0) + s.phi0
+            sig += _amp(s.cn0, scene.sigma, scene.fs) * (np.sqrt(2.0) if not b1i else 1.0) * d * code * np.exp(1j * ph)
+            continue
         elif scene.fam5:
             clen, crate = 10230, 10.23e6
             carrier = 1207.14e6 if scene.fam5 == "GAL_E5b" else 1176.45e6

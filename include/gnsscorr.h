@@ -36,7 +36,12 @@ extern "C" {
  * data + pilot tracking). */
 enum { GC_SIG_GPS_L1CA = 0, GC_SIG_GLO_G1G2 = 1, GC_SIG_BDS_B3I = 2, GC_SIG_GAL_E1C = 3,
        /* the four 10230-chip data + pilot signals (variant A with two replicas, quadrature-pilot tracking): */
-       GC_SIG_GPS_L5C = 4, GC_SIG_GAL_E5A = 5, GC_SIG_GAL_E5B = 6, GC_SIG_BDS_B2A = 7 };
+       GC_SIG_GPS_L5C = 4, GC_SIG_GAL_E5A = 5, GC_SIG_GAL_E5B = 6, GC_SIG_BDS_B2A = 7,
+       /* acquisition variant B (Doppler bins by circshift of one spectrum, best row kept, peak / second-peak
+        * metric): BDS B1I (two 4 ms blocks, + 1 ms tracking) and GPS L2C (acquisition only so far).
+        * For these acq_search_band is in kHz as in their initSettings.m and acq_search_step is the sub-bin
+        * step (settings.stepSize resolved as BDS/B1I/include/acquisition.m:24-39 / settings.acqStep). */
+       GC_SIG_BDS_B1I = 8, GC_SIG_GPS_L2C = 9 };
 
 /* "no satellite on this channel" for gc_track: GPS uses PRN 0 (tracking.m:136); a GLONASS channel is
  * identified by its frequency number K, for which 0 is valid, so unused channels carry GC_SV_NONE

@@ -13,12 +13,18 @@ switch signal
     case 'GAL_E5a', cfg.signal = 5;  cfg.freq_spacing = 0;
     case 'GAL_E5b', cfg.signal = 6;  cfg.freq_spacing = 0;
     case 'BDS_B2a', cfg.signal = 7;  cfg.freq_spacing = 0;
+    case 'BDS_B1I', cfg.signal = 8;  cfg.freq_spacing = 0;
+    case 'GPS_L2C', cfg.signal = 9;  cfg.freq_spacing = 0;
     otherwise,      cfg.signal = 0;  cfg.freq_spacing = 0;
 end
 cfg.file_type = settings.fileType;
 cfg.sample_bytes = 1;
 cfg.code_length = settings.codeLength;
-cfg.acq_noncoh_time = settings.acqNonCohTime;
+if isfield(settings, 'acqNonCohTime')
+    cfg.acq_noncoh_time = settings.acqNonCohTime;
+else
+    cfg.acq_noncoh_time = 1;           % variant-B folders (B1I, L2C) have no non-coherent sum
+end
 if isfield(settings, 'CNo')
     cfg.cno_vsm_interval = settings.CNo.VSMinterval;
     cfg.cno_acc_time = settings.CNo.accTime;
@@ -35,7 +41,11 @@ cfg.sampling_freq = settings.samplingFreq;
 cfg.IF = settings.IF;
 cfg.code_freq_basis = settings.codeFreqBasis;
 cfg.acq_search_band = settings.acqSearchBand;
-cfg.acq_search_step = settings.acqSearchStep;
+if isfield(settings, 'acqSearchStep')
+    cfg.acq_search_step = settings.acqSearchStep;
+else
+    cfg.acq_search_step = 0;           % set by the variant-B wrappers (resolved sub-bin step)
+end
 cfg.acq_threshold = settings.acqThreshold;
 cfg.dll_damping_ratio = settings.dllDampingRatio;
 cfg.dll_noise_bandwidth = settings.dllNoiseBandwidth;

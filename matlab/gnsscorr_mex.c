@@ -72,14 +72,17 @@ static void set_codes(gc_handle* h, const gc_config* cfg, const mxArray* codes)
     const mxArray* sec = mxGetField(codes, 0, "secondary");   /* GAL E5a only: int8 100 x numel(sv) */
     mwSize i, n;
     if (!sv || !d || !p || !mxIsInt8(d) || !mxIsInt8(p)) { gc_destroy(h); mexErrMsgIdAndTxt("gnsscorr:args", "codes: struct with sv, data (int8), pilot (int8)"); }
+    const int single = (cfg->signal == GC_SIG_BDS_B1I || cfg->signal == GC_SIG_GPS_L2C);   /* one code per SV */
+    mwSize len;
     n = mxGetNumberOfElements(sv);
-    if (mxGetNumberOfElements(d) != n * (mwSize)cfg->code_length || mxGetNumberOfElements(p) != n * (mwSize)cfg->code_length) {
+    len = n ? mxGetNumberOfElements(d) / n : 0;         /* codeLength, or 2*codeLength for the return-to-zero L2C CM code */
+    if (n == 0 || mxGetNumberOfElements(d) != n * len || mxGetNumberOfElements(p) != n * len) {
         gc_destroy(h);
-        mexErrMsgIdAndTxt("gnsscorr:args", "codes: data and pilot must be codeLength x numel(sv)");
+        mexErrMsgIdAndTxt("gnsscorr:args", "codes: data and pilot must be nChips x numel(sv)");
     }
     for (i = 0; i < n; ++i) {
-        int rc = gc_set_code(h, (int32_t)mxGetDoubles(sv)[i], 0, (const int8_t*)mxGetInt8s(d) + i * cfg->code_length, cfg->code_length);
-        if (rc == GC_OK) rc = gc_set_code(h, (int32_t)mxGetDoubles(sv)[i], 1, (const int8_t*)mxGetInt8s(p) + i * cfg->code_length, cfg->code_length);
+        int rc = gc_set_code(h, (int32_t)mxGetDoubles(sv)[i], 0, (const int8_t*)mxGetInt8s(d) + i * len, (int32_t)len);
+        if (rc == GC_OK && !single) rc = gc_set_code(h, (int32_t)mxGetDoubles(sv)[i], 1, (const int8_t*)mxGetInt8s(p) + i * len, (int32_t)len);
         if (rc == GC_OK && sec && mxIsInt8(sec) && mxGetNumberOfElements(sec) == n * 100)
             rc = gc_set_code(h, (int32_t)mxGetDoubles(sv)[i], 2, (const int8_t*)mxGetInt8s(sec) + i * 100, 100);
         if (rc != GC_OK) {

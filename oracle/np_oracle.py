@@ -1243,3 +1243,166 @@ def tracking_fam5(raw: np.ndarray, channel: list, s: Settings, codes: dict):
                 tr["VSMIndex"][vsmCnt - 1] = loopCnt
         tr["status"] = channel[ch]["status"]
     return out
+
+
+# ===========================================================================
+# Acquisition variant B: BeiDou B1I (BDS/B1I) and GPS L2C (GPS/GPS_L2C)
+# ===========================================================================
+def varb_settings(signal: str, **kw) -> Settings:
+    """initSettings.m of BDS/B1I and GPS/GPS_L2C (hot-path fields); acqSearchBand is in kHz there."""
+    if signal == "BDS_B1I":
+        s = Settings(codeFreqBasis=2.046e6, codeLength=2046.0, acqSatelliteList=list(range(6, 59)), acqSearchBand=10.0,
+                     acqThreshold=2.0, dllNoiseBandwidth=4.0, pllNoiseBandwidth=35.0, CNo_VSMinterval=400)
+        s.stepSize = 125.0
+    else:
+        s = Settings(samplingFreq=8e6, codeFreqBasis=0.5115e6, codeLength=10230.0, acqSearchBand=10.0, acqThreshold=1.5,
+                     dllNoiseBandwidth=4.0, dllCorrelatorSpacing=0.25, pllNoiseBandwidth=10.0, intTime=0.02,
+                     CNo_accTime=0.02, CNo_VSMinterval=40)
+        s.acqStep = (1000 / 2) / 20 / 2
+    s.signal = signal
+    for k, v in kw.items():
+        setattr(s, k, v)
+    return s
+
+
+def read_acq_signal_varb(raw: np.ndarray, s: Settings) -> np.ndarray:
+    """B1I postProcessing.m:98: 11 code periods; L2C postProcessing.m:88-90: max(42, acqCohT+2) code periods."""
+    N = samples_per_code(s)
+    codeLen = 11 if s.signal == "BDS_B1I" else max(42, int(getattr(s, "acqCohT", 20)) + 2)
+    off = 2 * s.skipNumberOfBytes
+    data = raw[off: off + 2 * codeLen * N].astype(np.float64)
+    return data[0::2] + 1j * data[1::2]
+
+
+def _varb_second_peak(corrVec: np.ndarray, codePhase: int, chip: int, N1: int) -> float:
+    """B1I acquisition.m:127-141 / L2C :89-103 with MATLAB's 1-based colon ranges."""
+    e1, e2 = codePhase - chip, codePhase + chip
+    if e1 < 2:
+        rng = np.arange(e2, N1 + e1 + 1)
+    elif e2 >= N1:
+        rng = np.arange(e2 - N1 + 1, e1 + 1)
+    else:
+        rng = np.concatenate([np.arange(1, e1 + 1), np.arange(e2, N1 + 1)])
+    return float(np.max(corrVec[rng - 1]))
+
+
+def acquisition_b1i(longSignal: np.ndarray, s: Settings, codes: dict, workers: int = 1):
+    """BDS/B1I/include/acquisition.m:4-176 (resampling branch not restated).  codes[PRN][0] = the 2046 chips
+    generateCAcode53.m returns."""
+    Ncodes, Nblocks = 2, 4                                         # :6-7
+    spb = int(matlab_round(s.samplingFreq / (s.codeFreqBasis / (Nblocks * s.codeLength))))   # :9
+    signal1, signal2 = longSignal[:spb], longSignal[spb: 2 * spb]  # :13-14
+    ts = 1 / s.samplingFreq
+    phasePoints = np.arange(0, spb, dtype=np.float64) * 2 * np.pi * ts
+    freqResolution = s.samplingFreq / spb                           # :20
+    nBins = int(matlab_round(s.acqSearchBand * 1e3 / freqResolution)) + 1   # :22
+    stepSize = getattr(s, "stepSize", None)
+    if not stepSize:                                                # :24-39
+        stepSize = 0.5 / (Nblocks * s.codeLength / s.codeFreqBasis)
+    elif stepSize != freqResolution:
+        steps = np.arange(1, freqResolution / 2 + 1e-12, 0.25)
+        steps = steps[np.fmod(freqResolution, steps) == 0]
+        diff = steps - stepSize
+        k = int(np.argmin(np.abs(diff)))
+        stepSize = steps[k - 1] if diff[k] > 0 else steps[k]
+    Nshifts = int(matlab_round(freqResolution / stepSize))          # :40
+    spc2 = int(matlab_round(s.samplingFreq / (s.codeFreqBasis / (Ncodes * s.codeLength))))   # makeCaTableDMA.m:9
+    tc = 1 / s.codeFreqBasis
+    idx = np.ceil((ts * np.arange(1, spc2 + 1, dtype=np.float64)) / tc).astype(np.int64)
+    idx[-1] = Ncodes * 2046
+    res = dict(carrFreq=np.zeros(58), codePhase=np.zeros(58), peakMetric=np.zeros(58),
+               coarseBin=np.zeros(58, dtype=np.int64), coarseCodePhase=np.zeros(58, dtype=np.int64))
+    initFreq = s.IF + (s.acqSearchBand / 2) * 1000                  # :50
+    chip = int(matlab_round(s.samplingFreq / s.codeFreqBasis))      # :126
+    for PRN in s.acqSatelliteList:
+        c = np.asarray(codes[PRN][0], dtype=np.float64)
+        table = np.concatenate([c, c])[idx - 1]                     # makeCaTableDMA.m:15-18
+        codeFreqDom = np.conj(_FFT(np.concatenate([table, np.zeros(spb // Ncodes)])))   # :58
+        prevmax = 0.0
+        corrVec = np.zeros(spb)
+        frequencyBinIndex = freqShift = 0
+        for binIter in range(1, Nshifts + 1):
+            f0 = initFreq + (binIter - 1) * (freqResolution / Nshifts)   # :64
+            sigCarr = np.exp(-1j * f0 * phasePoints)
+            F1 = _FFT(sigCarr * signal1, workers)
+            F2 = _FFT(sigCarr * signal2, workers)
+            sh = np.arange(nBins if binIter == 1 else nBins - 1)    # :79-81 the last bin is skipped for binIter > 1
+            A1 = np.abs(_IFFT(np.stack([np.roll(F1, k) for k in sh]) * codeFreqDom[None, :], workers))   # :83-90
+            A2 = np.abs(_IFFT(np.stack([np.roll(F2, k) for k in sh]) * codeFreqDom[None, :], workers))
+            p1, p2 = A1.max(axis=1), A2.max(axis=1)
+            for k in sh:                                            # :101-116
+                if p1[k] > prevmax or p2[k] > prevmax:
+                    if p1[k] > p2[k]:
+                        prevmax = p1[k]; corrVec = A1[k]
+                    else:
+                        prevmax = p2[k]; corrVec = A2[k]
+                    freqShift = binIter
+                    frequencyBinIndex = int(k) + 1
+        codePhase = int(np.argmax(corrVec)) + 1                     # :125
+        maxPeak = corrVec[codePhase - 1]
+        second = _varb_second_peak(corrVec, codePhase, chip, spb // Nblocks)
+        res["peakMetric"][PRN - 1] = maxPeak / second               # :142
+        res["coarseBin"][PRN - 1] = frequencyBinIndex
+        res["coarseCodePhase"][PRN - 1] = codePhase
+        if maxPeak / second > s.acqThreshold:                       # :145-150
+            res["codePhase"][PRN - 1] = codePhase
+            res["carrFreq"][PRN - 1] = initFreq - freqResolution * (frequencyBinIndex - 1) + (freqResolution / Nshifts) * (freqShift - 1)
+    return res
+
+
+def acquisition_l2c(longSignal: np.ndarray, s: Settings, codes: dict, workers: int = 1):
+    """GPS/GPS_L2C/include/acquisition.m:4-118 without the CL phase search of :120-166 (pilotTRKflag == 0, the
+    folder's default).  codes[PRN][0] = the 20460-entry return-to-zero CM sequence generateCMcode.m returns."""
+    Nblocks = 2
+    N = samples_per_code(s)
+    chip = int(matlab_round(s.samplingFreq / s.codeFreqBasis))      # :7
+    spb = N * Nblocks
+    signal = longSignal[:spb]
+    ts = 1 / s.samplingFreq
+    phasePoints = np.arange(0, spb, dtype=np.float64) * 2 * np.pi * ts
+    freqResolution = s.samplingFreq / spb
+    nBins = int(matlab_round(s.acqSearchBand * 1e3 / freqResolution)) + 1
+    Nshifts = int(matlab_round(freqResolution / s.acqStep))         # :24
+    tc = 1 / (s.codeFreqBasis * 2)                                   # makeCMTable.m:8
+    idx = np.ceil((ts * np.arange(0, N, dtype=np.float64)) / tc).astype(np.int64)
+    idx[-1] = int(s.codeLength) * 2
+    idx[0] = 1
+    res = dict(carrFreq=np.zeros(32), codePhase=np.zeros(32), peakMetric=np.zeros(32),
+               coarseBin=np.zeros(32, dtype=np.int64), coarseCodePhase=np.zeros(32, dtype=np.int64))
+    initFreq = s.IF + (s.acqSearchBand / 2) * 1000
+    for PRN in s.acqSatelliteList:
+        cm = np.asarray(codes[PRN][0], dtype=np.float64)
+        cmFreqDom = np.conj(_FFT(np.concatenate([cm[idx - 1], np.zeros(N)])))   # :44-48
+        prevmax = 0.0
+        corrVec = np.zeros(spb)
+        frequencyBinIndex = freqShift = 0
+        for binIter in range(1, Nshifts + 1):
+            f0 = initFreq - (binIter - 1) * (freqResolution / Nshifts)   # :62
+            F = _FFT(np.exp(-1j * f0 * phasePoints) * signal, workers)
+            last = nBins if binIter == 1 else nBins - 1
+            for k0 in range(0, last, 64):                            # batches of rows to bound memory
+                sh = np.arange(k0, min(last, k0 + 64))
+                A = np.abs(_IFFT(np.stack([np.roll(F, k) for k in sh]) * cmFreqDom[None, :], workers))
+                pk = A.max(axis=1)
+                for i, k in enumerate(sh):                           # :78-83
+                    if pk[i] > prevmax:
+                        prevmax = pk[i]; corrVec = A[i].copy(); frequencyBinIndex = int(k) + 1; freqShift = binIter
+        codePhase = int(np.argmax(corrVec)) + 1
+        maxPeak = corrVec[codePhase - 1]
+        second = _varb_second_peak(corrVec, codePhase, chip, spb // Nblocks)
+        res["peakMetric"][PRN - 1] = maxPeak / second
+        res["coarseBin"][PRN - 1] = frequencyBinIndex
+        res["coarseCodePhase"][PRN - 1] = codePhase
+        if maxPeak / second > s.acqThreshold:
+            res["carrFreq"][PRN - 1] = initFreq - freqResolution * (frequencyBinIndex - 1) - (freqResolution / Nshifts) * (freqShift - 1)   # :95
+            res["codePhase"][PRN - 1] = codePhase
+    return res
+
+
+def tracking_b1i(raw: np.ndarray, channel: list, s: Settings, codes: dict):
+    """BDS/B1I/include/tracking.m: the B3I loop (three-coefficient carrier filter, 1 ms epochs) with the 2046-chip code
+    generateCAcode53(PRN) (:50) and the code NCO centred on settings.codeFreqBasis (:52, :139)."""
+    ch = [dict(c, codeFreq=s.codeFreqBasis) for c in channel]
+    s2 = Settings(**{k: getattr(s, k) for k in Settings.__dataclass_fields__})
+    s2.pilotTRKflag = 0
+    return tracking_fam5(raw, ch, s2, {p: (c[0], c[0]) for p, c in codes.items()})

@@ -139,25 +139,26 @@ def track_rel_err(got, ref):
     return errs
 
 
-def first_illconditioned_epoch(rem_code_phase, code_freq, abs_sample, fs, spacing, sub=1.0, margin=2e-9):
-    """First epoch in which one sample's code phase (early, prompt or late) lies within `margin` chips of a chip
-    boundary, or len() if none.  There ceil(tcode) - hence one sample's replica chip, 1e-4..1e-3 of a correlator sum
-    at low SNR per sample - depends on the 10th decimal of remCodePhase, which no implementation that accumulates
-    differently from MATLAB's float64 sums can reproduce; closed-loop comparisons are only meaningful up to it.
+def first_illconditioned_epoch(ref_rem, ref_cf, got_rem, got_cf, abs_sample, fs, spacing, sub=1.0, safety=8.0):
+    """First epoch in which a sample's code phase (early, prompt or late) lies closer to a chip edge than the two
+    implementations' code phases differ there (times `safety`), or len() if none.  tcode(k) = remCodePhase -/+ spacing +
+    k*codeFreq/fs feeds ceil(); the engine's remCodePhase / codeFreq follow the reference's to ~1e-10 chips / ~1e-7 Hz
+    (fp32 correlator sums feed the discriminators), so where |tcode(k) - integer| is below that the replica chip of
+    one sample - 1e-4..1e-3 of a correlator sum at these SNRs - is not determined by the algorithm but by the 10th
+    decimal of the loop state; closed-loop comparisons at 1e-6 are only meaningful up to such an epoch.
     (16.368 Msps / 1.023 Mcps puts 16 samples on a chip and never gets there; 18 Msps / 10.23 Mcps has 18000
-    distinct code-phase fractions per epoch and meets such a point every ~1e5 epochs.)"""
-    n = len(rem_code_phase)
+    distinct code-phase fractions per epoch and meets such a point every ~1e5 epoch-correlators.)"""
+    n = len(ref_rem)
     for e in range(n):
-        if not np.isfinite(rem_code_phase[e]):
+        if not (np.isfinite(ref_rem[e]) and np.isfinite(got_rem[e])):
             return e
-        blk = int(abs_sample[e + 1] - abs_sample[e]) if e + 1 < n and abs_sample[e + 1] > 0 else int(np.ceil(fs / code_freq[e] * 10230)) + 2
-        step = code_freq[e] / fs
+        blk = int(abs_sample[e + 1] - abs_sample[e]) if e + 1 < n and abs_sample[e + 1] > 0 else int(np.ceil(fs / ref_cf[e] * 10230)) + 2
+        step = ref_cf[e] / fs
+        d_rem, d_step = abs(got_rem[e] - ref_rem[e]), abs(got_cf[e] - ref_cf[e]) / fs
         k = np.arange(blk, dtype=np.float64)
+        tol = safety * (d_rem + k * d_step) * sub          # zero where the two states are bit-identical: nothing to flag
         for off in (-spacing, 0.0, spacing):
-            t = (rem_code_phase[e] + off + k * step) * sub
-            d = np.abs(t - np.rint(t))
-            if e == 0:
-                d = d[1:]                  # remCodePhase starts at exactly 0: sample 0 of the prompt replica is on an edge for everyone
-            if np.min(d) < margin:
+            t = (ref_rem[e] + off + k * step) * sub
+            if np.any(np.abs(t - np.rint(t)) < tol):
                 return e
     return n

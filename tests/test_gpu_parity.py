@@ -589,9 +589,9 @@ def test_fam5_tracking_and_wrappers_vs_oracle(signal, pilot, tmp_path):
         # 18000 distinct code-phase fractions per epoch: now and then a sample sits within 1e-9 chips of a chip edge
         # and its replica chip hangs on the 10th decimal of remCodePhase (helpers.first_illconditioned_epoch); the
         # 1e-6 comparison runs up to the first such epoch, after it the trajectories may differ by one sample's worth
-        ok = first_illconditioned_epoch(ref[i]["remCodePhase"], ref[i]["codeFreq"], ref[i]["absoluteSample"], 18e6,
-                                        s.dllCorrelatorSpacing)
-        assert ok >= 20
+        ok = first_illconditioned_epoch(ref[i]["remCodePhase"], ref[i]["codeFreq"], tr[i]["remCodePhase"], tr[i]["codeFreq"],
+                                        ref[i]["absoluteSample"], 18e6, s.dllCorrelatorSpacing)
+        assert ok >= 10
         for name in names:
             assert np.max(np.abs(tr[i][name][:ok] - ref[i][name][:ok]) / sc_[:ok]) < IQ_TOL, name
             assert np.max(np.abs(tr[i][name] - ref[i][name]) / sc_) < 1e-2, name
@@ -607,4 +607,81 @@ def test_fam5_tracking_and_wrappers_vs_oracle(signal, pilot, tmp_path):
         assert np.mean(np.abs(tr[i]["I_P"][150:])) > 2 * np.mean(np.abs(tr[i]["Q_P"][150:]))     # pulling in: data in phase,
         if pilot:
             assert np.mean(np.abs(tr[i]["Pilot_Q_P"][150:])) > 2 * np.mean(np.abs(tr[i]["Pilot_I_P"][150:]))   # pilot in quadrature
+    eng.close()
+
+
+# ------------------------------------------------------------- acquisition variant B: BDS B1I, GPS L2C
+def _varb_case(signal, fs, nsat, seed, extra, cn0, **kw):
+    from cu_sdr_collection_b200.codes import standin_varb_codes
+    codes = standin_varb_codes(signal)
+    sc = synth.default_scene_varb(signal, codes, fs=fs, nsat=nsat, seed=seed)
+    for x in sc.sats:
+        x.cn0 = cn0
+    sv = sorted({x.prn for x in sc.sats} | set(extra))
+    s = init_settings(signal, samplingFreq=fs, acqSatelliteList=sv, **kw)
+    so = to_oracle_settings(s)
+    so.stepSize, so.acqStep = s.stepSize, s.acqStep
+    return codes, sc, s, so, sv
+
+
+@pytest.mark.parametrize("signal,fs", [("BDS_B1I", 18e6), ("GPS_L2C", 2.046e6)])
+def test_varb_acquisition_vs_oracle(signal, fs):
+    """Variant B: one wipe-off + FFT per sub-bin shift, Doppler bins by circshift of the spectrum, abs(ifft) per row,
+    the row with the largest peak kept (two 4 ms blocks for B1I), metric = peak / second peak outside +-1 chip."""
+    codes, sc, s, so, sv = _varb_case(signal, fs, nsat=2, seed=3, extra=[30], cn0=48 if signal == "BDS_B1I" else 45,
+                                      **({} if signal == "BDS_B1I" else dict(acqSearchBand=9.0)))
+    N = O.samples_per_code(so)
+    if signal == "BDS_B1I":
+        raw = synth.make_record(sc, N * 11)
+        longSignal = O.read_acq_signal_varb(raw, so)
+        ref = O.acquisition_b1i(longSignal, so, codes, workers=os.cpu_count() or 1)
+    else:
+        raw = synth.make_record(sc, N * 3)
+        longSignal = (raw[0::2] + 1j * raw[1::2]).astype(np.complex128)
+        ref = O.acquisition_l2c(longSignal, so, codes, workers=os.cpu_count() or 1)
+    eng = Engine(s, codes=codes)
+    got = acquisition(longSignal, s, engine=eng, verbose=False)
+    assert got["carrFreq"].shape == ref["carrFreq"].shape and eng.stats()["acq_path"] == 0
+    idx = np.array(sv) - 1
+    assert np.array_equal(got["carrFreq"], ref["carrFreq"]), "carrier frequency differs"
+    assert np.array_equal(got["codePhase"], ref["codePhase"]), "code phase differs"
+    assert np.array_equal(got["coarseBin"][idx], ref["coarseBin"][idx]) and np.array_equal(got["coarseCodePhase"][idx], ref["coarseCodePhase"][idx])
+    rel = np.abs(got["peakMetric"][idx] - ref["peakMetric"][idx]) / ref["peakMetric"][idx]
+    assert rel.max() < 1e-5, rel.max()          # a ratio of two fp32 magnitudes
+    for sat in sc.sats:
+        assert got["carrFreq"][sat.prn - 1] != 0
+    assert got["carrFreq"][30 - 1] == 0
+    eng.close()
+
+
+def test_b1i_tracking_and_wrappers_vs_oracle(tmp_path):
+    """BDS B1I tracking() (1 ms epochs, 2046-chip code from the caller, three-coefficient carrier filter) vs the oracle."""
+    nE = 200
+    codes, sc, s, so, sv = _varb_case("BDS_B1I", 18e6, nsat=2, seed=3, extra=[], cn0=48, msToProcess=nE, numberOfChannels=3,
+                                      CNo_VSMinterval=40)
+    N = 18000
+    raw = synth.make_record(sc, N * (nE + 4))
+    ch = []
+    for sat in sc.sats:
+        start = (2046 - sat.code_phase) * (18e6 / 2.046e6)
+        ch.append(dict(PRN=sat.prn, acquiredFreq=round((s.IF + sat.doppler) / 25.0) * 25.0, codePhase=int(round(start)) % N + 1, status="T"))
+    ch.append(dict(PRN=0, acquiredFreq=0.0, codePhase=0, status="-"))
+    path = tmp_path / "b1i.bin"
+    raw.tofile(path)
+    eng = Engine(s, codes=codes)
+    with open(path, "rb") as fid:
+        tr, _ = tracking(fid, ch, s, engine=eng)
+    ref = O.tracking_b1i(raw, ch, so, codes)
+    for i in range(2):
+        assert tr[i]["status"] == "T" == ref[i]["status"] and tr[i]["epochsDone"] == nE
+        assert np.array_equal(tr[i]["absoluteSample"], ref[i]["absoluteSample"])
+        ok = first_illconditioned_epoch(ref[i]["remCodePhase"], ref[i]["codeFreq"], tr[i]["remCodePhase"], tr[i]["codeFreq"],
+                                        ref[i]["absoluteSample"], 18e6, s.dllCorrelatorSpacing)
+        assert ok >= 10
+        sc_ = np.hypot(ref[i]["I_P"], ref[i]["Q_P"])
+        for name in ("I_P", "Q_P", "I_E", "I_L", "Q_E", "Q_L"):
+            assert np.max(np.abs(tr[i][name][:ok] - ref[i][name][:ok]) / sc_[:ok]) < IQ_TOL, name
+        assert np.max(np.abs(tr[i]["carrFreq"][:ok] - ref[i]["carrFreq"][:ok])) < 1e-4
+        assert "Pilot_I_P" not in tr[i]
+    assert tr[2]["status"] == "-"
     eng.close()

@@ -377,3 +377,50 @@ def test_fam5_oracle_closed_loop(signal):
         assert np.mean(np.abs(tr[i]["I_P"][300:])) > 1.5 * np.mean(np.abs(tr[i]["Q_P"][300:]))
         assert np.mean(np.abs(tr[i]["Pilot_Q_P"][300:])) > 1.5 * np.mean(np.abs(tr[i]["Pilot_I_P"][300:]))
     assert tr[2]["status"] == "-"
+
+
+# ------------------------------------------------------------- acquisition variant B: BDS B1I, GPS L2C
+def test_varb_oracle_closed_loop():
+    """Closed-loop known answers for the variant-B restatements (circularly shifted spectra, best row kept, peak /
+    second-peak metric): injected SVs come back on the sub-bin grid with their code phase, an absent one does not;
+    the B1I sub-bin step rule (acquisition.m:24-39) resolves the default request to 125 Hz."""
+    from cu_sdr_collection_b200 import init_settings
+    from cu_sdr_collection_b200.settings import varb_step
+    from helpers import to_oracle_settings
+    assert varb_step(init_settings("BDS_B1I")) == 125.0 and varb_step(init_settings("GPS_L2C")) == 12.5
+    assert varb_step(init_settings("BDS_B1I", stepSize=0.0)) == 125.0 and varb_step(init_settings("BDS_B1I", stepSize=250.0)) == 250.0
+    assert varb_step(init_settings("BDS_B1I", stepSize=60.0)) == 50.0
+    # B1I at the reference's 18 Msps: two 4 ms blocks of 72000 samples
+    tabs = codes.standin_varb_codes("BDS_B1I")
+    sc = synth.default_scene_varb("BDS_B1I", tabs, fs=18e6, nsat=2, seed=3)
+    for x in sc.sats:
+        x.cn0 = 48
+    sv = sorted({x.prn for x in sc.sats} | {30})
+    s = init_settings("BDS_B1I", acqSatelliteList=sv)
+    so = to_oracle_settings(s)
+    so.stepSize = s.stepSize
+    raw = synth.make_record(sc, 18000 * 11)
+    ref = O.acquisition_b1i(O.read_acq_signal_varb(raw, so), so, tabs, workers=os.cpu_count() or 1)
+    assert ref["carrFreq"].shape == (58,) and ref["carrFreq"][30 - 1] == 0 and ref["peakMetric"][30 - 1] < 2
+    for sat in sc.sats:
+        assert ref["carrFreq"][sat.prn - 1] != 0 and abs(ref["carrFreq"][sat.prn - 1] - (s.IF + sat.doppler)) <= 200
+        start = (2046 - sat.code_phase) * (18e6 / 2.046e6)
+        assert abs((ref["codePhase"][sat.prn - 1] - 1 - start + 9000) % 18000 - 9000) <= 2
+    # L2C at a reduced rate (one 40 ms block)
+    tabs = codes.standin_varb_codes("GPS_L2C")
+    fs = 2.046e6
+    sc = synth.default_scene_varb("GPS_L2C", tabs, fs=fs, nsat=2, seed=3)
+    for x in sc.sats:
+        x.cn0 = 45
+    sv = sorted({x.prn for x in sc.sats} | {30})
+    s = init_settings("GPS_L2C", samplingFreq=fs, acqSatelliteList=sv, acqSearchBand=9.0)
+    so = to_oracle_settings(s)
+    so.acqStep = s.acqStep
+    N = O.samples_per_code(so)
+    raw = synth.make_record(sc, N * 3)
+    ref = O.acquisition_l2c((raw[0::2] + 1j * raw[1::2]).astype(np.complex128), so, tabs, workers=os.cpu_count() or 1)
+    assert ref["carrFreq"][30 - 1] == 0
+    for sat in sc.sats:
+        assert abs(ref["carrFreq"][sat.prn - 1] - (s.IF + sat.doppler)) <= 12.5
+        start = (20460 - sat.code_phase) * (fs / 1.023e6)
+        assert abs((ref["codePhase"][sat.prn - 1] - 1 - start + N / 2) % N - N / 2) <= 2
