@@ -43,7 +43,7 @@ def acquisition(longSignal, settings: Settings, engine: Engine | None = None, ve
     finally:
         if own:
             eng.close()
-    if settings.signal == "BDS_B2a":              # acqResults vectors are 1 x max(acqSatelliteList) (BDS/B2a/include/acquisition.m:128-132)
+    if settings.signal in ("BDS_B2a", "BDS_B1C"):  # acqResults vectors are 1 x max(acqSatelliteList) (BDS/B2a/include/acquisition.m:128-132)
         n = max(settings.acqSatelliteList)
         r = {k: v[:n] for k, v in r.items()}
     if verbose:                                   # acquisition.m:154,209,286,292

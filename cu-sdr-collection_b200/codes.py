@@ -165,3 +165,20 @@ def standin_varb_codes(signal: str, seed: int = 20260101) -> dict:
     t = np.zeros((32, 20460), dtype=np.int8)
     t[:, 0::2] = 1 - 2 * rng.integers(0, 2, size=(32, 10230))
     return {prn: (t[prn - 1],) for prn in range(1, 33)}
+
+
+def standin_b1c_codes(seed: int = 20260101) -> dict:
+    """Seeded stand-ins for the BDS B1C BOC(1,1) sub-chip sequences generateDataBOC11.m / generatePilotBOC11.m return
+    (20460 entries, [-c +c] per primary chip): {PRN: (data, pilot)} for PRN 1..63."""
+    rng = np.random.default_rng([seed, 0xB1C])
+    prim = (1 - 2 * rng.integers(0, 2, size=(2, 63, 10230))).astype(np.int8)
+    out = {}
+    for prn in range(1, 64):
+        comps = []
+        for r in range(2):
+            c = np.empty(20460, dtype=np.int8)
+            c[0::2] = -prim[r, prn - 1]
+            c[1::2] = prim[r, prn - 1]
+            comps.append(c)
+        out[prn] = tuple(comps)
+    return out

@@ -76,6 +76,79 @@ segmax_kernel(const float2* __restrict__ W, int L, const int4* __restrict__ seg,
     }
 }
 
+// variant C (BDS/B1C/include/acquisition.m:205-216): results(bin, :) = abs(ifft(X_shift .* Data)), with the pilot replica
+// (results*sqrt(11) + abs(ifft(X_shift .* Pilot))*sqrt(29))/sqrt(40); per bin the maximum and its first index.
+// W rows: bin*nRep + r.
+__global__ void __launch_bounds__(1024)
+varc_combine_kernel(const float2* __restrict__ W, int L, int nRep, float* partMax, int* partIdx, size_t outBase)
+{
+    const float2* a = W + (size_t)blockIdx.x * nRep * L;
+    const float2* b = a + L;
+    float best = -1.f;
+    int bi = 0x7fffffff;
+    for (int j = threadIdx.x; j < L; j += blockDim.x) {
+        const float2 v = a[j];
+        float r = sqrtf(fmaf(v.x, v.x, v.y * v.y));
+        if (nRep == 2) {
+            const float2 u = b[j];
+            r = (r * 3.3166247903554f + sqrtf(fmaf(u.x, u.x, u.y * u.y)) * 5.385164807134504f) / 6.324555320336759f;
+        }
+        if (r > best) { best = r; bi = j; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_down_sync(0xffffffffu, best, o);
+        const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    __shared__ float sb[32];
+    __shared__ int si[32];
+    if ((threadIdx.x & 31) == 0) { sb[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < (int)(blockDim.x >> 5); ++q)
+            if (sb[q] > best || (sb[q] == best && si[q] < bi)) { best = sb[q]; bi = si[q]; }
+        partMax[outBase + blockIdx.x] = best;
+        partIdx[outBase + blockIdx.x] = bi;
+    }
+}
+
+// variant C fine search (:236-250): FineResult(j) = abs(sum(signal0DC .* DataPriTable .* exp(-1i*f_j*t)))
+// [*11 + the same with PilotPriTable *29, /40]; grid (nFine, nAcq), one 10 ms period per block.
+__global__ void __launch_bounds__(1024)
+varc_fine_kernel(const int8_t* rec, long long winStart, int N, int nRep, const int8_t* tabs /*[slot][N]*/,
+                 const int* tabSlot, const int* codePhase, const uint64_t* dphi, int nFine, double* fineResult)
+{
+    const int j = blockIdx.x, a = blockIdx.y;
+    const char2* x = reinterpret_cast<const char2*>(rec) + winStart + (codePhase[a] - 1);
+    const int8_t* d = tabs + (size_t)tabSlot[a] * N;
+    const int8_t* pl = d + N;
+    const uint64_t dp = dphi[a * nFine + j];
+    double dr = 0, di = 0, pr = 0, pi = 0;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        const char2 v = x[n];
+        float sn, cs;
+        fix_sincos(dp * (uint64_t)n, &sn, &cs);
+        const float re = fmaf(cs, (float)v.x, sn * (float)v.y), im = fmaf(cs, (float)v.y, -sn * (float)v.x);
+        const float cd = (float)d[n];
+        dr += (double)(cd * re); di += (double)(cd * im);
+        if (nRep == 2) { const float cp = (float)pl[n]; pr += (double)(cp * re); pi += (double)(cp * im); }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        dr += __shfl_down_sync(0xffffffffu, dr, o); di += __shfl_down_sync(0xffffffffu, di, o);
+        pr += __shfl_down_sync(0xffffffffu, pr, o); pi += __shfl_down_sync(0xffffffffu, pi, o);
+    }
+    __shared__ double sh[32][4];
+    if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5][0] = dr; sh[threadIdx.x >> 5][1] = di; sh[threadIdx.x >> 5][2] = pr; sh[threadIdx.x >> 5][3] = pi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        dr = di = pr = pi = 0;
+        for (int q = 0; q < (int)(blockDim.x >> 5); ++q) { dr += sh[q][0]; di += sh[q][1]; pr += sh[q][2]; pi += sh[q][3]; }
+        double r = hypot(dr, di);
+        if (nRep == 2) r = (r * 11 + hypot(pr, pi) * 29) / 40;                           // :246-249
+        fineResult[a * nFine + j] = r;
+    }
+}
+
 // replica tables of variant B into complex rows zero padded to L (code_kernel of acq_generic.cu, any table length)
 __global__ void pad_kernel(const int8_t* tab, int n, float2* out, int L)
 {
@@ -102,6 +175,20 @@ cudaError_t launch_varb_rowpeak(const float2* W, int nRows, int L, float* peak, 
 cudaError_t launch_varb_segmax(const float2* W, int nRows, int L, const int4* seg, float* out, cudaStream_t st)
 {
     segmax_kernel<<<nRows, 1024, 0, st>>>(W, L, seg, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_varc_combine(const float2* W, int nBins, int L, int nRep, float* partMax, int* partIdx, size_t outBase, cudaStream_t st)
+{
+    varc_combine_kernel<<<nBins, 1024, 0, st>>>(W, L, nRep, partMax, partIdx, outBase);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_varc_fine(const int8_t* rec, long long winStart, int N, int nRep, const int8_t* tabs, const int* tabSlot,
+                             const int* codePhase, const uint64_t* dphi, int nFine, int nAcq, double* fineResult, cudaStream_t st)
+{
+    dim3 grid(nFine, nAcq);
+    varc_fine_kernel<<<grid, 1024, 0, st>>>(rec, winStart, N, nRep, tabs, tabSlot, codePhase, dphi, nFine, fineResult);
     return cudaGetLastError();
 }
 

@@ -77,7 +77,10 @@ struct gc_handle {
     DevBuf<float> vbPeak;
     DevBuf<int> vbIdx;
     DevBuf<int4> vbSeg;
-    bool hostCodes = false;      // codes come from gc_set_code (e1c, fam5, varB)
+    bool varC = false;           // acquisition variant C (BDS B1C): one spectrum, bins by circshift, weighted data + pilot, 2-D max
+    struct { int Lc = 0, xLen = 0, nFine = 0; double initFreq = 0; } vc;   // len10PlusXms, samplesXmsLen (B1C acquisition.m:131-134)
+    DevBuf<int> vcSlot;
+    bool hostCodes = false;      // codes come from gc_set_code (e1c, fam5, varB, varC)
     int acqMinPeriods = 42, acqExtraPeriods = 2;   // longSignal = max(acqMinPeriods, nonCoh + acqExtraPeriods) code periods
     int fineCombine = 0;         // FineParams::combine
     int fineIdx0 = 0;            // first sample index of the fine-search code map (0: ts*(0:n-1), 1: ts*(1:n))
@@ -187,6 +190,7 @@ bool sv_has_code(const gc_handle* h, int sv)
     if (!h->hostCodes) return true;
     if (h->cfg.signal == GC_SIG_GAL_E5A && h->hostCode[2][sv - 1].empty()) return false;   // per-PRN pilot secondary code
     if (h->varB) return !h->hostCode[0][sv - 1].empty();
+    if (h->varC) return !h->hostCode[0][sv - 1].empty() && (h->nRep == 1 || !h->hostCode[1][sv - 1].empty());
     return !h->hostCode[0][sv - 1].empty() && !h->hostCode[1][sv - 1].empty();
 }
 
@@ -272,7 +276,7 @@ int gc_acq_result_len(int32_t signal)
     return signal == GC_SIG_GPS_L1CA ? 32 : signal == GC_SIG_GLO_G1G2 ? 21 : signal == GC_SIG_BDS_B3I ? 63 :
            signal == GC_SIG_GAL_E1C ? 50 : signal == GC_SIG_GPS_L5C ? 32 : signal == GC_SIG_GAL_E5A ? 50 :
            signal == GC_SIG_GAL_E5B ? 50 : signal == GC_SIG_BDS_B2A ? 63 : signal == GC_SIG_BDS_B1I ? 58 :
-           signal == GC_SIG_GPS_L2C ? 32 : 0;
+           signal == GC_SIG_GPS_L2C ? 32 : signal == GC_SIG_BDS_B1C ? 63 : 0;
 }
 
 const char* gc_last_error(const gc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -282,14 +286,14 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     if (!out || !cfg) return fail(nullptr, GC_ERR_ARG, "gc_create: null argument");
     *out = nullptr;
     if (cfg->abi_version != GC_ABI_VERSION) return fail(nullptr, GC_ERR_ARG, "gc_create: abi_version mismatch");
-    if (cfg->signal < GC_SIG_GPS_L1CA || cfg->signal > GC_SIG_GPS_L2C)
-        return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: signal not implemented (GPS L1CA/L5C/L2C, GLONASS G1/G2, BDS B1I/B3I/B2a, GAL E1C/E5a/E5b are)");
+    if (cfg->signal < GC_SIG_GPS_L1CA || cfg->signal > GC_SIG_BDS_B1C)
+        return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: signal not implemented (GPS L1CA/L5C/L2C, GLONASS G1/G2, BDS B1I/B1C/B3I/B2a, GAL E1C/E5a/E5b are)");
     if (cfg->file_type != 2 || cfg->sample_bytes != 1)
         return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: only fileType 2 (I/Q) with dataType 'schar' is implemented");
     if (!(cfg->sampling_freq > 0) || !(cfg->code_freq_basis > 0) ||
         cfg->code_length != (cfg->signal == GC_SIG_GLO_G1G2 ? 511 : cfg->signal == GC_SIG_GAL_E1C ? 4092 :
                              cfg->signal == GC_SIG_GPS_L1CA ? 1023 : cfg->signal == GC_SIG_BDS_B1I ? 2046 : 10230) ||
-        (cfg->acq_noncoh_time < 1 && cfg->signal != GC_SIG_BDS_B1I && cfg->signal != GC_SIG_GPS_L2C) ||
+        (cfg->acq_noncoh_time < 1 && cfg->signal != GC_SIG_BDS_B1I && cfg->signal != GC_SIG_GPS_L2C && cfg->signal != GC_SIG_BDS_B1C) ||
         !(cfg->acq_search_step > 0) || cfg->cno_vsm_interval < 2)
         return fail(nullptr, GC_ERR_ARG, "gc_create: invalid settings");
     int ndev = 0;
@@ -310,9 +314,10 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     h->fam5 = (cfg->signal == GC_SIG_GPS_L5C || cfg->signal == GC_SIG_GAL_E5A || cfg->signal == GC_SIG_GAL_E5B ||
                cfg->signal == GC_SIG_BDS_B2A);
     h->varB = (cfg->signal == GC_SIG_BDS_B1I || cfg->signal == GC_SIG_GPS_L2C);
-    h->hostCodes = h->e1c || h->fam5 || h->varB;
+    h->varC = (cfg->signal == GC_SIG_BDS_B1C);
+    h->hostCodes = h->e1c || h->fam5 || h->varB || h->varC;
     h->sub = h->e1c ? 2 : 1;
-    h->nRep = (h->e1c || h->fam5) ? 2 : 1;                   // data + pilot replicas (GAL_E1C acquisition.m:186-192, GPS_L5C :171-175)
+    h->nRep = (h->e1c || h->fam5) ? 2 : 1;                   // data + pilot replicas (B1C: set below from pilotACQflag) (GAL_E1C acquisition.m:186-192, GPS_L5C :171-175)
     h->fineStep = h->e1c ? 10.0 : 25.0;                      // GAL_E1C acquisition.m:138
     h->nFinePeriods = h->b3i ? 20 : h->e1c ? 25 : 40;        // BDS/B3I/include/acquisition.m:131-133; GAL_E1C :148
     h->fineCombine = h->glo ? 1 : h->b3i ? 2 : h->e1c ? 3 : 0;
@@ -341,6 +346,15 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     // acquisition.m:116-124,138-140
     h->N = (int)m_round(cfg->sampling_freq / (cfg->code_freq_basis / (double)cfg->code_length));
     h->L = 2 * h->N;
+    if (h->varC) {
+        if (cfg->acq_coh_t < 1 || cfg->acq_coh_t > 10) { h->err = "gc_create: acqCohT must be 1..10 ms"; return bail(GC_ERR_ARG); }
+        h->vc.xLen = (int)m_round((double)h->N / 10 * cfg->acq_coh_t);                      // samplesXmsLen, B1C acquisition.m:131
+        h->vc.Lc = (int)m_round((double)h->N / 10 * (10 + cfg->acq_coh_t));                 // len10PlusXms, :133
+        h->vc.nFine = (int)m_round(cfg->acq_search_step / 25) * 2 + 1;                      // :155
+        h->vc.initFreq = cfg->IF + cfg->acq_search_band;                                    // :166
+        h->L = h->vc.Lc;
+        h->nRep = cfg->pilot_acq_flag == 1 ? 2 : 1;
+    }
     if (h->varB) {
         const bool b1i = cfg->signal == GC_SIG_BDS_B1I;
         const int nBlocks = b1i ? 4 : 2;                                                   // B1I :7 ; L2C :5
@@ -362,8 +376,8 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     h->ts = 1 / cfg->sampling_freq;
     h->nBins = h->varB ? h->vb.nBins : (int)m_round(cfg->acq_search_band * 2 / cfg->acq_search_step) + 1;
     h->nFine = (int)m_round(cfg->acq_search_step / h->fineStep) + 1;
-    h->nonCoh = h->varB ? 1 : cfg->acq_noncoh_time;
-    h->fused = !h->varB && fused_plan_info(h->L, &h->fp) && !getenv("GC_FORCE_GENERIC");
+    h->nonCoh = (h->varB || h->varC) ? 1 : cfg->acq_noncoh_time;
+    h->fused = !h->varB && !h->varC && fused_plan_info(h->L, &h->fp) && !getenv("GC_FORCE_GENERIC");
     h->stats.fft_len = h->L;
     {   // GC_ACQ_PATH=cluster selects the one-kernel correlation stage (acq_cluster.cu, transform resident
         // in a cluster's shared memory); the default is inverse rows + inverse columns through a work buffer
@@ -428,7 +442,7 @@ void gc_destroy(gc_handle* h)
     h->Cc.release(); h->W.release(); h->dphi.release(); h->fdphi.release(); h->codeTab.release(); h->chips.release(); h->fineSecondary.release();
     h->prnList.release(); h->slotGroup.release(); h->partIdx.release(); h->fineCodePhase.release(); h->fineBest.release(); h->fineSv.release(); h->partMax.release();
     h->peaks.release(); h->sigPower.release(); h->fineSums.release(); h->fineResult.release(); h->fineProd.release();
-    h->vbRows.release(); h->vbPeak.release(); h->vbIdx.release(); h->vbSeg.release();
+    h->vcSlot.release(); h->vbRows.release(); h->vbPeak.release(); h->vbIdx.release(); h->vbSeg.release();
     h->chans.release(); h->trackCodes.release(); h->trackPilot.release(); h->trackOut.release(); h->epochsDone.release();
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -441,12 +455,13 @@ int gc_set_code(gc_handle* h, int32_t sv, int32_t component, const int8_t* chips
     if (!h->hostCodes) return fail(h, GC_ERR_ARG, "gc_set_code: this signal generates its own codes");
     const bool secondary = (component == 2);
     if (secondary && h->cfg.signal != GC_SIG_GAL_E5A) return fail(h, GC_ERR_ARG, "gc_set_code: only GAL E5a takes a pilot secondary code");
-    const bool l2c = h->cfg.signal == GC_SIG_GPS_L2C;        // CM code as generateCMcode.m returns it: 2*codeLength entries, return-to-zero
+    const bool l2c = h->cfg.signal == GC_SIG_GPS_L2C || h->cfg.signal == GC_SIG_BDS_B1C;   // 2*codeLength entries: the return-to-zero CM code
+                                                                                            // (generateCMcode.m) / B1C BOC(1,1) sub-chips (generateDataBOC11.m)
     if (sv < 1 || sv > h->resultLen || component < 0 || component > 2 || !chips || (h->varB && component != 0) ||
         nChips != (secondary ? 100 : l2c ? 2 * h->cfg.code_length : h->cfg.code_length))
         return fail(h, GC_ERR_ARG, "gc_set_code: bad argument (PRN in range, component 0/1 with code_length chips, or 2 with 100)");
     for (int i = 0; i < nChips; ++i)
-        if (chips[i] != 1 && chips[i] != -1 && !(l2c && chips[i] == 0)) return fail(h, GC_ERR_ARG, "gc_set_code: chips must be +-1");
+        if (chips[i] != 1 && chips[i] != -1 && !(h->cfg.signal == GC_SIG_GPS_L2C && chips[i] == 0)) return fail(h, GC_ERR_ARG, "gc_set_code: chips must be +-1");
     std::vector<int8_t>& c = h->hostCode[component][sv - 1];
     if (h->e1c) {
         c.resize((size_t)2 * nChips);
@@ -673,9 +688,171 @@ static int acquire_varb(gc_handle* h, long long winStart, int32_t nSv, const int
     return GC_OK;
 }
 
+// ---- acquisition variant C (BDS/B1C/include/acquisition.m:128-276) -------------------------------------------------
+static int varc_build_replicas(gc_handle* h)
+{
+    const gc_config& c = h->cfg;
+    const int N = h->N, Lc = h->vc.Lc, xLen = h->vc.xLen, nSvMax = h->resultLen, nRep = h->nRep;
+    // sampled BOC(1,1) tables (makeDataTable.m / makePilotTable.m): [sv][rep][N]; kept on the device for the fine search
+    std::vector<int8_t> tab((size_t)nSvMax * 2 * N, 0);
+    for (int prn = 1; prn <= nSvMax; ++prn)
+        for (int r = 0; r < nRep; ++r)
+            if (!h->hostCode[r][prn - 1].empty())
+                make_boc_table(h->hostCode[r][prn - 1].data(), c.sampling_freq, c.code_freq_basis, c.code_length, N,
+                               tab.data() + ((size_t)(prn - 1) * 2 + r) * N);
+    cudaStream_t st = h->stream;
+    GC_CUDA(h, upload(h->codeTab, tab, st));
+    // local replicas [table(1:samplesXmsLen) zeros] -> conj(fft(.))/L   (:176-185); rows (prn-1)*2 + r
+    const int rows = nSvMax * 2;
+    std::vector<int8_t> head((size_t)rows * xLen);
+    for (int r = 0; r < rows; ++r) std::copy(tab.begin() + (size_t)r * N, tab.begin() + (size_t)r * N + xLen, head.begin() + (size_t)r * xLen);
+    GC_CUDA(h, upload(h->chips, head, st));
+    GC_CUDA(h, h->Cc.reserve((size_t)rows * Lc));
+    const int chunk = 32;                                       // transform the replicas in chunks to bound the scratch buffers
+    GC_CUDA(h, h->T1.reserve((size_t)chunk * Lc));
+    GC_CUDA(h, h->T2.reserve((size_t)chunk * Lc));
+    for (int r0 = 0; r0 < rows; r0 += chunk) {
+        const int nr = std::min(chunk, rows - r0);
+        GC_CUDA(h, launch_varb_pad(h->chips.p + (size_t)r0 * xLen, xLen, nr, h->T1.p, Lc, st));
+        float2 *src = h->T1.p, *dst = h->T2.p;
+        int n = Lc, sd = 1;
+        for (int f = 0; f < h->plan.nf; ++f) {
+            GC_CUDA(h, launch_generic_stage(h->plan, f, n, sd, false, src, dst, nr, st));
+            n /= h->plan.fac[f]; sd *= h->plan.fac[f];
+            std::swap(src, dst);
+        }
+        GC_CUDA(h, cudaMemcpyAsync(h->Cc.p + (size_t)r0 * Lc, src, (size_t)nr * Lc * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    }
+    GC_CUDA(h, launch_generic_conj_scale(h->Cc.p, (size_t)rows * Lc, 1.0f / (float)Lc, st));
+    GC_CUDA(h, cudaStreamSynchronize(st));
+    h->replicasReady = true;
+    return GC_OK;
+}
+
+static int acquire_varc(gc_handle* h, long long winStart, long long longLen, int32_t nSv, const int32_t* svList,
+                        double* carrFreq, double* codePhase, double* peakMetric, int32_t* coarseBin, int32_t* coarseCodePhase)
+{
+    const gc_config& c = h->cfg;
+    const int N = h->N, Lc = h->vc.Lc, nBins = h->nBins, nRep = h->nRep, nFine = h->vc.nFine;
+    cudaStream_t st = h->stream;
+    if (longLen <= 0) longLen = 2LL * N;                     // postProcessing.m:33 reads two code periods
+    const long long recSamples = (long long)(h->recBytes / 2);
+    if (winStart < 0 || winStart + std::max<long long>(Lc, longLen) > recSamples || longLen < Lc)
+        return fail(h, GC_ERR_SHORT_RECORD, "gc_acquire: record shorter than (10 + acqCohT) ms");
+    for (int i = 0; i < h->resultLen; ++i) {
+        carrFreq[i] = codePhase[i] = peakMetric[i] = 0;
+        if (coarseBin) coarseBin[i] = 0;
+        if (coarseCodePhase) coarseCodePhase[i] = 0;
+    }
+    int launches = 0;
+    cudaEventRecord(h->ev[0], st);
+    GC_CUDA(h, h->sigPower.reserve(1));
+    GC_CUDA(h, launch_sig_power(h->rec, winStart, h->vc.xLen, h->sigPower.p, st)); ++launches;   // :163
+    const uint64_t dphi0 = turns_to_fix(h->vc.initFreq / c.sampling_freq);
+    GC_CUDA(h, h->dphi.reserve(1));
+    GC_CUDA(h, cudaMemcpyAsync(h->dphi.p, &dphi0, sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    const int nRows = nBins * nRep;
+    GC_CUDA(h, h->X.reserve((size_t)Lc));
+    GC_CUDA(h, h->T1.reserve((size_t)std::max(nRows, 32) * Lc));
+    GC_CUDA(h, h->T2.reserve((size_t)std::max(nRows, 32) * Lc));
+    GC_CUDA(h, launch_generic_wipe(h->rec, winStart, Lc, 1, 1, 0, h->dphi.p, h->T1.p, Lc, st)); ++launches;   // :168-172
+    {
+        float2 *src = h->T1.p, *dst = h->T2.p;
+        int n = Lc, sd = 1;
+        for (int f = 0; f < h->plan.nf; ++f) {
+            GC_CUDA(h, launch_generic_stage(h->plan, f, n, sd, false, src, dst, 1, st)); ++launches;
+            n /= h->plan.fac[f]; sd *= h->plan.fac[f];
+            std::swap(src, dst);
+        }
+        GC_CUDA(h, cudaMemcpyAsync(h->X.p, src, (size_t)Lc * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    }
+    cudaEventRecord(h->ev[2], st);
+    GC_CUDA(h, h->vbRows.reserve(nRows));
+    GC_CUDA(h, h->partMax.reserve((size_t)nSv * nBins));
+    GC_CUDA(h, h->partIdx.reserve((size_t)nSv * nBins));
+    GC_CUDA(h, h->peaks.reserve(nSv));
+    std::vector<VarbRow> rows(nRows);
+    for (int s = 0; s < nSv; ++s) {
+        for (int k = 0; k < nBins; ++k)
+            for (int r = 0; r < nRep; ++r) rows[k * nRep + r] = VarbRow{0, (svList[s] - 1) * 2 + r, k, 0};   // circshift(IQfreqDom, k) (:203)
+        GC_CUDA(h, cudaMemcpyAsync(h->vbRows.p, rows.data(), nRows * sizeof(VarbRow), cudaMemcpyHostToDevice, st));
+        GC_CUDA(h, launch_varb_mulshift(h->X.p, h->Cc.p, h->vbRows.p, nRows, h->T1.p, Lc, st)); ++launches;
+        float2 *a = h->T1.p, *b = h->T2.p;
+        int nn = Lc, ss = 1;
+        for (int f = 0; f < h->plan.nf; ++f) {
+            GC_CUDA(h, launch_generic_stage(h->plan, f, nn, ss, true, a, b, nRows, st)); ++launches;
+            nn /= h->plan.fac[f]; ss *= h->plan.fac[f];
+            std::swap(a, b);
+        }
+        GC_CUDA(h, launch_varc_combine(a, nBins, Lc, nRep, h->partMax.p, h->partIdx.p, (size_t)s * nBins, st)); ++launches;
+        GC_CUDA(h, cudaStreamSynchronize(st));
+    }
+    GC_CUDA(h, launch_peak_select(h->partMax.p, h->partIdx.p, nSv, nBins, 1, h->peaks.p, st)); ++launches;   // :221-225
+    std::vector<PeakOut> peaks(nSv);
+    double sigPower = 0;
+    GC_CUDA(h, cudaMemcpyAsync(peaks.data(), h->peaks.p, nSv * sizeof(PeakOut), cudaMemcpyDeviceToHost, st));
+    GC_CUDA(h, cudaMemcpyAsync(&sigPower, h->sigPower.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    cudaEventRecord(h->ev[1], st);
+    GC_CUDA(h, cudaStreamSynchronize(st));
+    std::vector<int> acq;
+    std::vector<int> cps, slots;
+    std::vector<double> selFreq;
+    for (int s = 0; s < nSv; ++s) {
+        const int ri = svList[s] - 1;
+        peakMetric[ri] = peaks[s].peak / sigPower;                                         // :227
+        int cp = peaks[s].codePhase;
+        if ((long long)cp + N - 1 > longLen) cp -= N;                                      // :229-231
+        if (coarseBin) coarseBin[ri] = peaks[s].bin;
+        if (coarseCodePhase) coarseCodePhase[ri] = cp;
+        if (peakMetric[ri] > c.acq_threshold) {                                            // :234
+            acq.push_back(s); cps.push_back(cp); slots.push_back((svList[s] - 1) * 2);
+            selFreq.push_back(h->vc.initFreq - (peaks[s].bin - 1) * c.acq_search_step);    // :223
+        }
+    }
+    const int nAcq = (int)acq.size();
+    float fineMs = 0;
+    if (nAcq > 0) {
+        std::vector<uint64_t> fd((size_t)nAcq * nFine);
+        std::vector<double> ff((size_t)nAcq * nFine);
+        for (int a = 0; a < nAcq; ++a)
+            for (int j = 0; j < nFine; ++j) {
+                ff[(size_t)a * nFine + j] = selFreq[a] + c.acq_search_step - 25.0 * j;     // :244
+                fd[(size_t)a * nFine + j] = turns_to_fix(ff[(size_t)a * nFine + j] / c.sampling_freq);
+            }
+        GC_CUDA(h, upload(h->fdphi, fd, st));
+        GC_CUDA(h, upload(h->fineCodePhase, cps, st));
+        GC_CUDA(h, upload(h->vcSlot, slots, st));
+        GC_CUDA(h, h->fineResult.reserve((size_t)nAcq * nFine));
+        cudaEventRecord(h->ev[3], st);
+        GC_CUDA(h, launch_varc_fine(h->rec, winStart, N, nRep, h->codeTab.p, h->vcSlot.p, h->fineCodePhase.p, h->fdphi.p, nFine, nAcq,
+                                    h->fineResult.p, st)); ++launches;
+        std::vector<double> fr((size_t)nAcq * nFine);
+        GC_CUDA(h, cudaMemcpyAsync(fr.data(), h->fineResult.p, fr.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+        cudaEventRecord(h->ev[4], st);
+        GC_CUDA(h, cudaStreamSynchronize(st));
+        cudaEventElapsedTime(&fineMs, h->ev[3], h->ev[4]);
+        for (int a = 0; a < nAcq; ++a) {
+            int best = 0;
+            for (int j = 1; j < nFine; ++j) if (fr[(size_t)a * nFine + j] > fr[(size_t)a * nFine + best]) best = j;   // :252
+            const int ri = svList[acq[a]] - 1;
+            carrFreq[ri] = ff[(size_t)a * nFine + best];                                   // :253
+            if (carrFreq[ri] == 0) carrFreq[ri] = 1;
+            codePhase[ri] = cps[a];                                                        // :258
+        }
+    }
+    float total = 0, fwd = 0;
+    cudaEventElapsedTime(&total, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&fwd, h->ev[0], h->ev[2]);
+    h->stats.n_acquired = nAcq;
+    h->stats.acq_fwd_ms = fwd; h->stats.acq_corr_ms = total - fwd; h->stats.acq_fine_ms = fineMs; h->stats.acq_total_ms = total + fineMs;
+    h->stats.corr_rows_ms = total - fwd; h->stats.corr_cols_ms = 0; h->stats.corr_row_launches = nSv;
+    h->stats.acq_launches = launches;
+    return GC_OK;
+}
+
 static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int32_t* svList,
                         double* carrFreq, double* codePhase, double* peakMetric,
-                        int32_t* coarseBin, int32_t* coarseCodePhase)
+                        int32_t* coarseBin, int32_t* coarseCodePhase, long long longLen = 0 /* length(longSignal), B1C only */)
 {
     const gc_config& c = h->cfg;
     const int N = h->N, L = h->L, nBins = h->nBins, nonCoh = h->nonCoh, nKm = nBins * nonCoh;
@@ -689,12 +866,16 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         if (!sv_has_code(h, svList[i])) return fail(h, GC_ERR_ARG, "gc_acquire: no code set for an SV of the list (gc_set_code)");
     if (!h->replicasReady) {
         cudaSetDevice(c.device);
-        int rc = h->varB ? varb_build_replicas(h) : build_replicas(h);
+        int rc = h->varB ? varb_build_replicas(h) : h->varC ? varc_build_replicas(h) : build_replicas(h);
         if (rc != GC_OK) return rc;
     }
     if (h->varB) {
         cudaSetDevice(c.device);
         return acquire_varb(h, winStart, nSv, svList, carrFreq, codePhase, peakMetric, coarseBin, coarseCodePhase);
+    }
+    if (h->varC) {
+        cudaSetDevice(c.device);
+        return acquire_varc(h, winStart, longLen, nSv, svList, carrFreq, codePhase, peakMetric, coarseBin, coarseCodePhase);
     }
     // postProcessing.m:86 reads max(42, nonCoh+2) code periods (B3I: max(22, nonCoh+1), BDS/B3I/include/postProcessing.m:86)
     const int nPeriodsAcq = std::max(h->acqMinPeriods, nonCoh + h->acqExtraPeriods);
@@ -993,7 +1174,7 @@ int gc_acquire_host(gc_handle* h, const int8_t* iq, size_t nSamples, int32_t nSv
     if (!h || !iq) return fail(h, GC_ERR_ARG, "gc_acquire_host: bad argument");
     int rc = gc_set_record_host(h, iq, nSamples * 2);
     if (rc != GC_OK) return rc;
-    return acquire_impl(h, 0, nSv, svList, carrFreq, codePhase, peakMetric, coarseBin, coarseCodePhase);
+    return acquire_impl(h, 0, nSv, svList, carrFreq, codePhase, peakMetric, coarseBin, coarseCodePhase, (long long)nSamples);
 }
 
 // Common/CNoVSM.m:38-47 on the host (40 values every 40 epochs — scalar work)
@@ -1024,8 +1205,8 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
     if (!h) return GC_ERR_ARG;
     const gc_config& c = h->cfg;
     if (!h->rec) return fail(h, GC_ERR_NO_RECORD, "gc_track: no record resident");
-    if (c.signal == GC_SIG_GPS_L2C)
-        return fail(h, GC_ERR_UNSUPPORTED, "gc_track: GPS L2C tracking (20 ms CM/CL epochs) is not implemented yet");
+    if (c.signal == GC_SIG_GPS_L2C || c.signal == GC_SIG_BDS_B1C)
+        return fail(h, GC_ERR_UNSUPPORTED, "gc_track: GPS L2C (20 ms CM/CL epochs) and BDS B1C (10 ms NB/WB) tracking are not implemented yet");
     if (nCh < 1 || nEpochs < 1 || !sv || !acqFreq || !codePhase || !out || !epochsDone)
         return fail(h, GC_ERR_ARG, "gc_track: bad argument");
     cudaSetDevice(c.device);

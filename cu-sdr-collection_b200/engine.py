@@ -31,14 +31,15 @@ class gc_config(C.Structure):
                 ("dll_damping_ratio", C.c_double), ("dll_noise_bandwidth", C.c_double),
                 ("dll_correlator_spacing", C.c_double), ("pll_damping_ratio", C.c_double),
                 ("pll_noise_bandwidth", C.c_double), ("int_time", C.c_double), ("cno_acc_time", C.c_double),
-                ("freq_spacing", C.c_double), ("pilot_trk_flag", C.c_int32), ("reserved0", C.c_int32)]
+                ("freq_spacing", C.c_double), ("pilot_trk_flag", C.c_int32), ("acq_coh_t", C.c_int32),
+                ("pilot_acq_flag", C.c_int32), ("reserved1", C.c_int32)]
 
 
 GC_SIG_GPS_L1CA, GC_SIG_GLO_G1G2, GC_SIG_BDS_B3I, GC_SIG_GAL_E1C = 0, 1, 2, 3
 GC_SIG_GPS_L5C, GC_SIG_GAL_E5A, GC_SIG_GAL_E5B, GC_SIG_BDS_B2A = 4, 5, 6, 7
-GC_SIG_BDS_B1I, GC_SIG_GPS_L2C = 8, 9
+GC_SIG_BDS_B1I, GC_SIG_GPS_L2C, GC_SIG_BDS_B1C = 8, 9, 10
 _FAM5_IDS = {"GPS_L5C": GC_SIG_GPS_L5C, "GAL_E5a": GC_SIG_GAL_E5A, "GAL_E5b": GC_SIG_GAL_E5B, "BDS_B2a": GC_SIG_BDS_B2A,
-             "BDS_B1I": GC_SIG_BDS_B1I, "GPS_L2C": GC_SIG_GPS_L2C}
+             "BDS_B1I": GC_SIG_BDS_B1I, "GPS_L2C": GC_SIG_GPS_L2C, "BDS_B1C": GC_SIG_BDS_B1C}
 GC_SV_NONE = -2147483648
 
 
@@ -105,12 +106,13 @@ def config_from_settings(s: Settings, device: int = 0) -> gc_config:
     if s.fileType != 2 or s.dataType != "schar":
         raise GnssCorrError("only fileType 2 with dataType 'schar' is implemented")
     sig = signal_id(s)
-    return gc_config(abi_version=3, device=device, pilot_trk_flag=int(s.pilotTRKflag), signal=sig, freq_spacing=float(s.freqSpacing),
+    return gc_config(abi_version=3, device=device, pilot_trk_flag=int(s.pilotTRKflag), acq_coh_t=int(s.acqCohT),
+                     pilot_acq_flag=int(s.pilotACQflag), signal=sig, freq_spacing=float(s.freqSpacing),
                      file_type=s.fileType, sample_bytes=1,
                      code_length=int(s.codeLength), acq_noncoh_time=int(s.acqNonCohTime),
                      cno_vsm_interval=int(s.CNo_VSMinterval), skip_number_of_bytes=int(s.skipNumberOfBytes),
                      sampling_freq=s.samplingFreq, IF=s.IF, code_freq_basis=s.codeFreqBasis,
-                     acq_search_band=s.acqSearchBand, acq_search_step=varb_step(s) if s.is_varb else s.acqSearchStep,
+                     acq_search_band=s.acqSearchBand, acq_search_step=varb_step(s) if s.is_varb else s.acqStep if s.signal == "BDS_B1C" else s.acqSearchStep,
                      acq_threshold=s.acqThreshold, dll_damping_ratio=s.dllDampingRatio,
                      dll_noise_bandwidth=s.dllNoiseBandwidth, dll_correlator_spacing=s.dllCorrelatorSpacing,
                      pll_damping_ratio=s.pllDampingRatio, pll_noise_bandwidth=s.pllNoiseBandwidth,
@@ -140,7 +142,7 @@ class Engine:
         if rc != 0:
             raise GnssCorrError(f"gc_create failed ({rc}): {self.lib.gc_last_error(None).decode()}")
         self._keep = None
-        if settings.is_fam5 or settings.is_varb:
+        if settings.is_fam5 or settings.is_varb or settings.signal == "BDS_B1C":
             if codes is None:
                 raise GnssCorrError(f"{settings.signal} takes its primary codes from the caller: pass codes= "
                                     "{PRN: (data, pilot[, pilot_secondary])} (what generateL5Icode.m etc. return)")

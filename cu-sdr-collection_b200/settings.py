@@ -43,7 +43,8 @@ class Settings:
     codeDir: str = ""                   # Galileo E1: directory holding E1b.dat / E1c.dat (the reference keeps them in include/)
     stepSize: float = 0.0               # BDS B1I: sub-bin step request (BDS/B1I/initSettings.m:96; 0 = [] = derive it)
     acqStep: float = 0.0                # GPS L2C: sub-bin step (GPS/GPS_L2C/initSettings.m:94)
-    acqCohT: int = 20                   # GPS L2C: coherent time in ms (:91)
+    acqCohT: int = 20                   # GPS L2C: coherent time in ms (:91); BDS B1C: BDS/B1C/initSettings.m:97 (10)
+    pilotACQflag: int = 0               # BDS B1C: the pilot replica joins the acquisition (BDS/B1C/initSettings.m:74)
 
     @property
     def is_glonass(self) -> bool:
@@ -109,6 +110,12 @@ _L2C_DEFAULTS = dict(samplingFreq=8e6, codeFreqBasis=0.5115e6, codeLength=10230.
                      fileName="../../../L2_IF20KHz_FS8MHz.bin")
 
 
+# BDS/B1C/initSettings.m (hot-path fields of the acquisition)
+_B1C_DEFAULTS = dict(numberOfChannels=15, codeLength=10230.0, codeFreqBasis=1.023e6, acqSatelliteList=list(range(1, 63)),
+                     acqSearchBand=5000.0, acqCohT=10, acqStep=50.0, acqThreshold=10.0, resamplingThreshold=15e6, pilotACQflag=1,
+                     pilotTRKflag=1, intTime=0.01, CNo_VSMinterval=50, fileName="../../../B1C_IF20KHz_FS18MHz.bin")
+
+
 def varb_step(s: "Settings") -> float:
     """Sub-bin step of the variant-B acquisitions: settings.acqStep for L2C; for B1I settings.stepSize resolved the way
     BDS/B1I/include/acquisition.m:24-39 does ([] -> 0.5/(4 ms); == freqResolution -> itself; else the nearest divisor of
@@ -145,6 +152,9 @@ def init_settings(signal: str = "GPS_L1CA", **overrides) -> Settings:
             setattr(s, k, list(v) if isinstance(v, list) else v)
     elif signal in _FAM5:
         for k, v in {**_FAM5_BASE, **_FAM5[signal]}.items():
+            setattr(s, k, list(v) if isinstance(v, list) else v)
+    elif signal == "BDS_B1C":
+        for k, v in _B1C_DEFAULTS.items():
             setattr(s, k, list(v) if isinstance(v, list) else v)
     elif signal in ("BDS_B1I", "GPS_L2C"):
         for k, v in (_B1I_DEFAULTS if signal == "BDS_B1I" else _L2C_DEFAULTS).items():

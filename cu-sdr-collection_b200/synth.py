@@ -126,7 +126,7 @@ def default_scene_fam5(signal: str, codes: dict, fs: float = 18e6, IF: float = 2
 def default_scene_varb(signal: str, codes: dict, fs: float, IF: float = 20e3, nsat: int = 3, seed: int = 20260101) -> Scene:
     rng = np.random.default_rng(seed)
     pool = np.arange(6, 59) if signal == "BDS_B1I" else np.arange(1, 33)
-    clen = 2046 if signal == "BDS_B1I" else 20460
+    clen = 2046 if signal == "BDS_B1I" else 20460       # (B1C: 20460 BOC sub-chips per 10 ms)
     prns = rng.choice(pool, size=nsat, replace=False)
     sats = [Sat(prn=int(p), doppler=float(rng.uniform(-4000, 4000)), code_phase=float(rng.uniform(0, clen)),
                 cn0=float(rng.uniform(42, 50)), phi0=float(rng.uniform(0, 2 * np.pi)), bit_seed=int(rng.integers(1 << 30)),
@@ -152,6 +152,22 @@ def make_record(scene: Scene, nsamples: int, start: int = 0) -> np.ndarray:
             clen, crate, carrier = 10230, 10.23e6, 1268.52e6
             fc = scene.IF + s.doppler
             chipseq = b3i_code(s.prn).astype(np.float64)
+        elif scene.varb == "BDS_B1C":
+            # data (amplitude sqrt(11/40)) and pilot (sqrt(29/40), in quadrature) BOC(1,1) sub-chip codes, 10 ms periods
+            clen, crate, carrier = 20460, 2.046e6, 1575.42e6
+            fc = scene.IF + s.doppler
+            fcode = crate * (1 + s.doppler / carrier)
+            chips = fcode * t + s.code_phase
+            period = np.floor(chips / clen).astype(np.int64)
+            idx = np.floor(chips - period * float(clen)).astype(np.int64) % clen
+            cD = np.asarray(scene.codes[s.prn][0], dtype=np.float64)[idx]
+            cP = np.asarray(scene.codes[s.prn][1], dtype=np.float64)[idx]
+            bits = nav_bits(s, int(period.max()) + 60)
+            dD = bits[period + s.bit_offset]
+            dP = bits[::-1][period + s.bit_offset]
+            ph = 2 * np.pi * (fc * t % 1.0) + s.phi0
+            sig += _amp(s.cn0, scene.sigma, scene.fs) * (np.sqrt(11 / 40) * dD * cD + 1j * np.sqrt(29 / 40) * dP * cP) * np.exp(1j * ph)
+            continue
         elif scene.varb:
             b1i = scene.varb == "BDS_B1I"
             clen, crate, carrier = (2046, 2.046e6, 1561.098e6) if b1i else (20460, 1.023e6, 1227.6e6)

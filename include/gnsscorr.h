@@ -41,7 +41,11 @@ enum { GC_SIG_GPS_L1CA = 0, GC_SIG_GLO_G1G2 = 1, GC_SIG_BDS_B3I = 2, GC_SIG_GAL_
         * metric): BDS B1I (two 4 ms blocks, + 1 ms tracking) and GPS L2C (acquisition only so far).
         * For these acq_search_band is in kHz as in their initSettings.m and acq_search_step is the sub-bin
         * step (settings.stepSize resolved as BDS/B1I/include/acquisition.m:24-39 / settings.acqStep). */
-       GC_SIG_BDS_B1I = 8, GC_SIG_GPS_L2C = 9 };
+       GC_SIG_BDS_B1I = 8, GC_SIG_GPS_L2C = 9,
+       /* acquisition variant C (BDS/B1C/include/acquisition.m:128-276): ONE wipe-off + FFT of (10 + acqCohT) ms, Doppler
+        * bins by circshift, data and pilot BOC(1,1) replicas combined (d*sqrt(11) + p*sqrt(29))/sqrt(40), 2-D maximum,
+        * 25 Hz fine search over one 10 ms period.  Acquisition only so far (NB/WB tracking: not yet). */
+       GC_SIG_BDS_B1C = 10 };
 
 /* "no satellite on this channel" for gc_track: GPS uses PRN 0 (tracking.m:136); a GLONASS channel is
  * identified by its frequency number K, for which 0 is valid, so unused channels carry GC_SV_NONE
@@ -89,7 +93,9 @@ typedef struct gc_config {
                                     (GLO/GLO_GL1/initSettings.m: 562.5e3, GLO_GL2: 437.5e3)         */
     int32_t pilot_trk_flag;      /* settings.pilotTRKflag (GAL/GAL_E1C/initSettings.m:113): 1 = track the
                                     pilot component too and average the discriminators                */
-    int32_t reserved0;
+    int32_t acq_coh_t;           /* settings.acqCohT in ms (BDS/B1C/initSettings.m:97; B1C only)                     */
+    int32_t pilot_acq_flag;      /* settings.pilotACQflag (BDS/B1C/initSettings.m:74): 1 = pilot replica joins the search */
+    int32_t reserved1;
 } gc_config;
 
 typedef struct gc_handle gc_handle;

@@ -15,6 +15,7 @@ switch signal
     case 'BDS_B2a', cfg.signal = 7;  cfg.freq_spacing = 0;
     case 'BDS_B1I', cfg.signal = 8;  cfg.freq_spacing = 0;
     case 'GPS_L2C', cfg.signal = 9;  cfg.freq_spacing = 0;
+    case 'BDS_B1C', cfg.signal = 10; cfg.freq_spacing = 0;
     otherwise,      cfg.signal = 0;  cfg.freq_spacing = 0;
 end
 cfg.file_type = settings.fileType;
@@ -25,6 +26,7 @@ if isfield(settings, 'acqNonCohTime')
 else
     cfg.acq_noncoh_time = 1;           % variant-B folders (B1I, L2C) have no non-coherent sum
 end
+cfg.acq_coh_t = 0;  cfg.pilot_acq_flag = 0;   % BDS B1C only (set by its wrapper)
 if isfield(settings, 'CNo')
     cfg.cno_vsm_interval = settings.CNo.VSMinterval;
     cfg.cno_acc_time = settings.CNo.accTime;

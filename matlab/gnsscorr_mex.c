@@ -63,6 +63,8 @@ static void fill_config(const mxArray* s, gc_config* c)
     c->int_time = field(s, "int_time");
     c->cno_acc_time = field(s, "cno_acc_time");
     c->pilot_trk_flag = mxGetField(s, 0, "pilot_trk_flag") ? (int32_t)field(s, "pilot_trk_flag") : 0;
+    c->acq_coh_t = mxGetField(s, 0, "acq_coh_t") ? (int32_t)field(s, "acq_coh_t") : 0;
+    c->pilot_acq_flag = mxGetField(s, 0, "pilot_acq_flag") ? (int32_t)field(s, "pilot_acq_flag") : 0;
 }
 
 /* codes struct -> gc_set_code for every listed PRN (Galileo E1) */
@@ -73,6 +75,7 @@ static void set_codes(gc_handle* h, const gc_config* cfg, const mxArray* codes)
     mwSize i, n;
     if (!sv || !d || !p || !mxIsInt8(d) || !mxIsInt8(p)) { gc_destroy(h); mexErrMsgIdAndTxt("gnsscorr:args", "codes: struct with sv, data (int8), pilot (int8)"); }
     const int single = (cfg->signal == GC_SIG_BDS_B1I || cfg->signal == GC_SIG_GPS_L2C);   /* one code per SV */
+    /* (B1C passes the 2*codeLength BOC(1,1) sub-chip sequences of generateDataBOC11 / generatePilotBOC11) */
     mwSize len;
     n = mxGetNumberOfElements(sv);
     len = n ? mxGetNumberOfElements(d) / n : 0;         /* codeLength, or 2*codeLength for the return-to-zero L2C CM code */

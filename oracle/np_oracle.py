@@ -1406,3 +1406,81 @@ def tracking_b1i(raw: np.ndarray, channel: list, s: Settings, codes: dict):
     s2 = Settings(**{k: getattr(s, k) for k in Settings.__dataclass_fields__})
     s2.pilotTRKflag = 0
     return tracking_fam5(raw, ch, s2, {p: (c[0], c[0]) for p, c in codes.items()})
+
+
+# ===========================================================================
+# Acquisition variant C: BeiDou B1C (BDS/B1C)
+# ===========================================================================
+def b1c_settings(**kw) -> Settings:
+    """BDS/B1C/initSettings.m (acquisition fields)."""
+    s = Settings(numberOfChannels=15, codeLength=10230.0, codeFreqBasis=1.023e6, acqSatelliteList=list(range(1, 63)),
+                 acqSearchBand=5000.0, acqThreshold=10.0, intTime=0.01)
+    s.acqCohT, s.acqStep, s.pilotACQflag, s.signal = 10, 1000 / 10 / 2, 1, "BDS_B1C"
+    for k, v in kw.items():
+        setattr(s, k, v)
+    return s
+
+
+def acquisition_b1c(longSignal: np.ndarray, s: Settings, codes: dict, workers: int = 1):
+    """BDS/B1C/include/acquisition.m:128-276 (resampling branch :50-126 not restated).  codes[PRN] = (data, pilot) BOC(1,1)
+    sub-chip sequences as generateDataBOC11.m / generatePilotBOC11.m return them (20460 entries)."""
+    N = samples_per_code(s)
+    xLen = int(matlab_round(N / 10 * s.acqCohT))                   # :131
+    Lc = int(matlab_round(N / 10 * (10 + s.acqCohT)))              # :133
+    sig = longSignal[:Lc]                                          # :136
+    ts = 1 / s.samplingFreq
+    phasePoints = np.arange(0, Lc, dtype=np.float64) * 2 * np.pi * ts
+    nBins = int(matlab_round(s.acqSearchBand * 2 / s.acqStep)) + 1   # :142
+    nRes = max(s.acqSatelliteList)
+    res = dict(carrFreq=np.zeros(nRes), codePhase=np.zeros(nRes), peakMetric=np.zeros(nRes),
+               coarseBin=np.zeros(nRes, dtype=np.int64), coarseCodePhase=np.zeros(nRes, dtype=np.int64))
+    fineStep = 25
+    nFine = int(matlab_round(s.acqStep / 25)) * 2 + 1              # :155
+    finePhasePoints = np.arange(0, N, dtype=np.float64) * 2 * np.pi * ts
+    x = sig[:xLen]
+    sigPower = math.sqrt(np.sum(np.abs(x - np.mean(x)) ** 2) / (xLen - 1) * xLen)   # :163
+    initFreq = s.IF + s.acqSearchBand                              # :166
+    IQfreqDom = _FFT(np.exp(-1j * initFreq * phasePoints) * sig, workers)   # :168-172
+    tc = 1 / s.codeFreqBasis / 2                                   # makeDataTable.m:9
+    idx = np.ceil((ts * np.arange(1, N + 1, dtype=np.float64)) / tc).astype(np.int64)
+    idx[-1] = int(s.codeLength) * 2
+    idx[0] = 1
+    pilot = int(getattr(s, "pilotACQflag", 1)) == 1
+    for PRN in s.acqSatelliteList:
+        DataTab = np.asarray(codes[PRN][0], dtype=np.float64)[idx - 1]
+        DataF = np.conj(_FFT(np.concatenate([DataTab[:xLen], np.zeros(Lc - xLen)])))   # :176-179
+        if pilot:
+            PilotTab = np.asarray(codes[PRN][1], dtype=np.float64)[idx - 1]
+            PilotF = np.conj(_FFT(np.concatenate([PilotTab[:xLen], np.zeros(Lc - xLen)])))
+        results = np.zeros((nBins, Lc))
+        for k0 in range(0, nBins, 32):
+            sh = np.arange(k0, min(nBins, k0 + 32))
+            S = np.stack([np.roll(IQfreqDom, k) for k in sh])      # :203
+            r = np.abs(_IFFT(S * DataF[None, :], workers))         # :205-207
+            if pilot:
+                r = (r * math.sqrt(11) + np.abs(_IFFT(S * PilotF[None, :], workers)) * math.sqrt(29)) / math.sqrt(40)   # :211-214
+            results[sh] = r
+        frequencyBinIndex = int(np.argmax(results.max(axis=1))) + 1   # :221
+        selFreq = initFreq - (frequencyBinIndex - 1) * s.acqStep
+        colmax = results.max(axis=0)
+        codePhase = int(np.argmax(colmax)) + 1                     # :225
+        res["peakMetric"][PRN - 1] = colmax[codePhase - 1] / sigPower
+        if codePhase + N - 1 > longSignal.size:                    # :229-231
+            codePhase -= N
+        res["coarseBin"][PRN - 1] = frequencyBinIndex
+        res["coarseCodePhase"][PRN - 1] = codePhase
+        if res["peakMetric"][PRN - 1] > s.acqThreshold:            # :234
+            signal0DC = longSignal[codePhase - 1: codePhase - 1 + N]
+            xCarrier = signal0DC * DataTab
+            fineFrq = np.zeros(nFine); fineRes = np.zeros(nFine)
+            for j in range(1, nFine + 1):
+                fineFrq[j - 1] = selFreq + s.acqStep - fineStep * (j - 1)   # :244
+                carr = np.exp(-1j * fineFrq[j - 1] * finePhasePoints)
+                fineRes[j - 1] = abs(np.sum(xCarrier * carr))
+                if pilot:
+                    fineRes[j - 1] = (fineRes[j - 1] * 11 + abs(np.sum(signal0DC * PilotTab * carr)) * 29) / 40   # :247-249
+            res["carrFreq"][PRN - 1] = fineFrq[int(np.argmax(fineRes))]
+            if res["carrFreq"][PRN - 1] == 0:
+                res["carrFreq"][PRN - 1] = 1
+            res["codePhase"][PRN - 1] = codePhase
+    return res

@@ -685,3 +685,32 @@ def test_b1i_tracking_and_wrappers_vs_oracle(tmp_path):
         assert "Pilot_I_P" not in tr[i]
     assert tr[2]["status"] == "-"
     eng.close()
+
+
+# ------------------------------------------------------------- acquisition variant C: BDS B1C
+@pytest.mark.parametrize("fs,pilot", [(4.092e6, 1), (4.092e6, 0), (18e6, 1)])
+def test_b1c_acquisition_vs_oracle(fs, pilot):
+    """Variant C: one wipe-off + FFT of 20 ms, Doppler bins by circshift, (|data|*sqrt(11) + |pilot|*sqrt(29))/sqrt(40),
+    2-D maximum over bins x code phases, 25 Hz fine search over one 10 ms period (FFT length 360000 at 18 Msps)."""
+    from cu_sdr_collection_b200.codes import standin_b1c_codes
+    codes = standin_b1c_codes()
+    sc = synth.default_scene_varb("BDS_B1C", codes, fs=fs, nsat=2, seed=3)
+    for x in sc.sats:
+        x.cn0 = 46
+    sv = sorted({x.prn for x in sc.sats} | {30})
+    s = init_settings("BDS_B1C", samplingFreq=fs, acqSatelliteList=sv, acqSearchBand=4500.0 if fs < 10e6 else 4000.0, pilotACQflag=pilot)
+    so = to_oracle_settings(s)
+    so.acqStep, so.pilotACQflag, so.acqCohT = s.acqStep, s.pilotACQflag, s.acqCohT
+    N = O.samples_per_code(so)
+    raw = synth.make_record(sc, N * 2)
+    longSignal = (raw[0::2] + 1j * raw[1::2]).astype(np.complex128)
+    ref = O.acquisition_b1c(longSignal, so, codes, workers=os.cpu_count() or 1)
+    eng = Engine(s, codes=codes)
+    got = acquisition(longSignal, s, engine=eng, verbose=False)
+    assert got["carrFreq"].shape == ref["carrFreq"].shape == (max(sv),) and eng.stats()["fft_len"] == 2 * N
+    _check_acq(got, ref, sv)
+    for sat in sc.sats:
+        if pilot:           # the data component alone carries 11/40 of the power and stays under the threshold of 10 here
+            assert got["carrFreq"][sat.prn - 1] != 0 and abs(got["carrFreq"][sat.prn - 1] - (s.IF + sat.doppler)) <= 25
+    assert got["carrFreq"][30 - 1] == 0
+    eng.close()

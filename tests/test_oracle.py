@@ -424,3 +424,26 @@ def test_varb_oracle_closed_loop():
         assert abs(ref["carrFreq"][sat.prn - 1] - (s.IF + sat.doppler)) <= 12.5
         start = (20460 - sat.code_phase) * (fs / 1.023e6)
         assert abs((ref["codePhase"][sat.prn - 1] - 1 - start + N / 2) % N - N / 2) <= 2
+
+
+def test_b1c_oracle_closed_loop():
+    """Variant C (BDS B1C) restatement: injected SVs come back with code phase and Doppler on the 25 Hz fine grid."""
+    from cu_sdr_collection_b200 import init_settings
+    from helpers import to_oracle_settings
+    tabs = codes.standin_b1c_codes()
+    fs = 4.092e6
+    sc = synth.default_scene_varb("BDS_B1C", tabs, fs=fs, nsat=2, seed=3)
+    for x in sc.sats:
+        x.cn0 = 46
+    sv = sorted({x.prn for x in sc.sats} | {30})
+    s = init_settings("BDS_B1C", samplingFreq=fs, acqSatelliteList=sv, acqSearchBand=4500.0)
+    so = to_oracle_settings(s)
+    so.acqStep, so.pilotACQflag, so.acqCohT = s.acqStep, s.pilotACQflag, s.acqCohT
+    N = O.samples_per_code(so)
+    raw = synth.make_record(sc, N * 2)
+    ref = O.acquisition_b1c((raw[0::2] + 1j * raw[1::2]).astype(np.complex128), so, tabs, workers=os.cpu_count() or 1)
+    assert ref["carrFreq"].shape == (max(sv),) and ref["carrFreq"][30 - 1] == 0
+    for sat in sc.sats:
+        assert abs(ref["carrFreq"][sat.prn - 1] - (s.IF + sat.doppler)) <= 25
+        start = (20460 - sat.code_phase) * (fs / 2.046e6)
+        assert abs((ref["codePhase"][sat.prn - 1] - 1 - start + N / 2) % N - N / 2) <= 2
