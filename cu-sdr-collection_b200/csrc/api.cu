@@ -1205,13 +1205,18 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
     if (!h) return GC_ERR_ARG;
     const gc_config& c = h->cfg;
     if (!h->rec) return fail(h, GC_ERR_NO_RECORD, "gc_track: no record resident");
-    if (c.signal == GC_SIG_GPS_L2C || c.signal == GC_SIG_BDS_B1C)
-        return fail(h, GC_ERR_UNSUPPORTED, "gc_track: GPS L2C (20 ms CM/CL epochs) and BDS B1C (10 ms NB/WB) tracking are not implemented yet");
+    if (c.signal == GC_SIG_BDS_B1C)
+        return fail(h, GC_ERR_UNSUPPORTED, "gc_track: BDS B1C (10 ms NB/WB) tracking is not implemented yet");
+    const bool l2c = c.signal == GC_SIG_GPS_L2C;
+    if (l2c && c.pilot_trk_flag != 0)
+        return fail(h, GC_ERR_UNSUPPORTED, "gc_track: GPS L2C tracking with the CL pilot (pilotTRKflag) is not implemented yet");
     if (nCh < 1 || nEpochs < 1 || !sv || !acqFreq || !codePhase || !out || !epochsDone)
         return fail(h, GC_ERR_ARG, "gc_track: bad argument");
     cudaSetDevice(c.device);
     cudaStream_t st = h->stream;
-    const int codeLen = c.code_length * h->sub;               // table entries per code period (BOC: sub-chips)
+    // table entries per code period (BOC: sub-chips).  GPS L2C works in half chips throughout: codeLength*2 entries of the
+    // return-to-zero CM code, code NCO at 2*codeFreqBasis, spacing*2 (GPS_L2C/include/tracking.m:93-94, 171)
+    const int codeLen = c.code_length * h->sub * (c.signal == GC_SIG_GPS_L2C ? 2 : 1);
     const int stride = (codeLen + 2 + 15) & ~15;
     const bool pilot = h->pilotMode != 0;                     // GAL_E1C tracking.m:127; GPS_L5C tracking.m:167
     std::vector<TrackChan> chans(nCh);
@@ -1222,9 +1227,9 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
         live[ch] = active;
         chans[ch].prn = sv[ch]; chans[ch].pad = active ? 1 : 0;
         chans[ch].acqFreq = acqFreq[ch];
-        chans[ch].codeFreq0 = codeFreq0 ? codeFreq0[ch] : c.code_freq_basis;   // channel.codeFreq (B3I tracking.m:57)
-        // fseek(fid, dataAdaptCoeff*(skipNumberOfBytes + codePhase-1)) (tracking.m:150)
-        chans[ch].startSample = (long long)c.skip_number_of_bytes + (long long)codePhase[ch] - 1;
+        chans[ch].codeFreq0 = codeFreq0 ? codeFreq0[ch] : c.code_freq_basis * (l2c ? 2 : 1);   // channel.codeFreq (B3I tracking.m:57)
+        // fseek(fid, dataAdaptCoeff*(skipNumberOfBytes + codePhase-1)) (tracking.m:150); L2C seeks to codePhase (GPS_L2C tracking.m:153)
+        chans[ch].startSample = (long long)c.skip_number_of_bytes + (long long)codePhase[ch] - (l2c ? 0 : 1);
         if (active) {
             if (!sv_ok(h, sv[ch])) return fail(h, GC_ERR_ARG, "gc_track: SV id out of range");
             if (!sv_has_code(h, sv[ch])) return fail(h, GC_ERR_ARG, "gc_track: no code set for a channel's SV (gc_set_code)");
@@ -1242,8 +1247,8 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
     TrackParams p{};
     p.rec = h->rec;
     p.recSamples = (long long)(h->recBytes / 2);
-    p.fs = c.sampling_freq; p.invFs = 1.0 / c.sampling_freq; p.codeFreqBasis = c.code_freq_basis; p.codeLength = (double)c.code_length;
-    p.spc = c.dll_correlator_spacing;
+    p.fs = c.sampling_freq; p.invFs = 1.0 / c.sampling_freq; p.codeFreqBasis = c.code_freq_basis * (l2c ? 2 : 1); p.codeLength = (double)c.code_length * (l2c ? 2 : 1);
+    p.spc = c.dll_correlator_spacing * (l2c ? 2 : 1);
     p.cA = h->tau2code / h->tau1code; p.cB = c.int_time / h->tau1code;     // tracking.m:326
     p.pA = h->tau2carr / h->tau1carr; p.pB = c.int_time / h->tau1carr;     // tracking.m:308
     {   // Common/calcLoopCoefCarr.m:41-56 (GLONASS carrier filter)

@@ -179,7 +179,7 @@ def num_to_process(s: Settings) -> int:
     """Integration periods tracking() runs: msToProcess for the 1 ms signals, round(msToProcess/1000/intTime)
     for Galileo E1 (GAL/GAL_E1C/include/tracking.m:48)."""
     import math
-    if s.signal == "GAL_E1C":
+    if s.signal in ("GAL_E1C", "GPS_L2C"):             # GPS_L2C/include/tracking.m:51
         x = s.msToProcess / 1000 / s.intTime
         return int(math.floor(x + 0.5))
     return int(s.msToProcess)

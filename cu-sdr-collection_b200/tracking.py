@@ -41,6 +41,15 @@ def tracking(fid, channel: list, settings: Settings, engine: Engine | None = Non
         tr = {"status": "-"}
         for i, f in enumerate(TRACK_FIELDS):
             tr[f] = out[ch, i]
+        if settings.signal == "GPS_L2C":
+            # the loop runs in half chips (code NCO at 2*codeFreqBasis); the recorded values are chips, and absoluteSample
+            # is the fractional sample of the code start (GPS_L2C/include/tracking.m:223, 250, 376, 382-383)
+            e = int(done[ch])
+            step = tr["codeFreq"][:e] / settings.samplingFreq
+            tr["absoluteSample"] = tr["absoluteSample"].copy()
+            tr["absoluteSample"][:e] = tr["absoluteSample"][:e] + 1 - tr["remCodePhase"][:e] / step
+            for f in ("remCodePhase", "codeFreq", "dllDiscr", "dllDiscrFilt"):
+                tr[f] = tr[f] / 2
         if out.shape[1] == 17:                                             # GPS_L5C tracking.m:57-60, 323-324
             tr["Pilot_I_P"], tr["Pilot_Q_P"] = out[ch, 15], out[ch, 16]
         if settings.signal == "BDS_B2a":                                   # BDS/B2a/include/tracking.m:66-72, 336-352

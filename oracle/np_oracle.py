@@ -1484,3 +1484,88 @@ def acquisition_b1c(longSignal: np.ndarray, s: Settings, codes: dict, workers: i
                 res["carrFreq"][PRN - 1] = 1
             res["codePhase"][PRN - 1] = codePhase
     return res
+
+
+def tracking_l2c(raw: np.ndarray, channel: list, s: Settings, codes: dict):
+    """GPS/GPS_L2C/include/tracking.m:45-395 with settings.pilotTRKflag == 0 (the folder's default; the CL branch is not
+    restated): 20 ms epochs in half-chip units - the return-to-zero CM table of 2*codeLength entries, code NCO at
+    2*codeFreqBasis, spacing*2 (:93-94, :171) - fseek to codePhase (not codePhase-1, :153), fractional absoluteSample
+    (:223), and remCodePhase, codeFreq, dllDiscr, dllDiscrFilt recorded halved (:250, :376, :382-383)."""
+    nE = int(matlab_round(s.msToProcess / 1000 / s.intTime))       # :51
+    nV = int(math.floor(s.msToProcess / s.CNo_VSMinterval / 20))   # :80-83
+    out = []
+    for _ in range(s.numberOfChannels):
+        tr = dict(status="-", PRN=0)
+        tr["absoluteSample"] = np.zeros(nE)
+        for f in ("codeFreq", "carrFreq", "dllDiscr", "dllDiscrFilt", "pllDiscr", "pllDiscrFilt", "remCodePhase", "remCarrPhase"):
+            tr[f] = np.full(nE, np.inf)
+        for f in ("I_P", "I_E", "I_L", "Q_E", "Q_P", "Q_L"):
+            tr[f] = np.zeros(nE)
+        tr["VSMValue"] = np.zeros(nV); tr["VSMIndex"] = np.zeros(nV)
+        out.append(tr)
+    earlyLateSpc = s.dllCorrelatorSpacing * 2                      # :93
+    codeLength = int(s.codeLength) * 2                             # :94
+    PDIcode = s.intTime
+    tau1code, tau2code = calcLoopCoef(s.dllNoiseBandwidth, s.dllDampingRatio, 1.0)
+    pf3, pf2, pf1 = calcLoopCoefCarr(s)
+    for ch in range(s.numberOfChannels):
+        if channel[ch]["PRN"] == 0:
+            continue
+        tr = out[ch]
+        tr["PRN"] = channel[ch]["PRN"]
+        pos = 2 * (s.skipNumberOfBytes + channel[ch]["codePhase"])   # :153
+        c = np.asarray(codes[channel[ch]["PRN"]][0], dtype=np.float64)
+        cmCode = np.concatenate([[c[codeLength - 1]], c, [c[0]]])  # :155-156
+        codeFreq = s.codeFreqBasis * 2; remCodePhase = 0.0         # :171-173
+        carrFreq = channel[ch]["acquiredFreq"]; carrFreqBasis = channel[ch]["acquiredFreq"]; remCarrPhase = 0.0
+        oldCodeNco = oldCodeError = 0.0
+        d2CarrError = dCarrError = 0.0
+        vsmCnt = 0
+        for loopCnt in range(1, nE + 1):
+            codePhaseStep = codeFreq / s.samplingFreq              # :220
+            tr["absoluteSample"][loopCnt - 1] = (pos / 2) / 1 + 1 - remCodePhase / codePhaseStep   # :223
+            blksize = int(math.ceil((codeLength - remCodePhase) / codePhaseStep))   # :226
+            chunk = raw[pos: pos + 2 * blksize]
+            pos += chunk.size
+            if chunk.size != 2 * blksize:
+                return out
+            rawSignal = chunk[0::2].astype(np.float64) + 1j * chunk[1::2].astype(np.float64)
+            tr["remCodePhase"][loopCnt - 1] = remCodePhase / 2     # :250
+            tE = colonop(remCodePhase - earlyLateSpc, codePhaseStep, (blksize - 1) * codePhaseStep + remCodePhase - earlyLateSpc)
+            tL = colonop(remCodePhase + earlyLateSpc, codePhaseStep, (blksize - 1) * codePhaseStep + remCodePhase + earlyLateSpc)
+            tP = colonop(remCodePhase, codePhaseStep, (blksize - 1) * codePhaseStep + remCodePhase)
+            iE = np.ceil(tE).astype(np.int64); iL = np.ceil(tL).astype(np.int64); iP = np.ceil(tP).astype(np.int64)
+            remCodePhase = (tP[blksize - 1] + codePhaseStep) - codeLength   # :288
+            tr["remCarrPhase"][loopCnt - 1] = remCarrPhase
+            time = np.arange(0, blksize + 1, dtype=np.float64) / s.samplingFreq
+            trigarg = ((carrFreq * 2.0 * np.pi) * time) + remCarrPhase
+            remCarrPhase = math.fmod(trigarg[blksize], 2 * np.pi)
+            bb = np.exp(-1j * trigarg[:blksize]) * rawSignal
+            iB, qB = bb.real, bb.imag
+            I_E = float(np.sum(cmCode[iE] * iB)); Q_E = float(np.sum(cmCode[iE] * qB))
+            I_P = float(np.sum(cmCode[iP] * iB)); Q_P = float(np.sum(cmCode[iP] * qB))
+            I_L = float(np.sum(cmCode[iL] * iB)); Q_L = float(np.sum(cmCode[iL] * qB))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                carrError = float(np.arctan(np.float64(Q_P) / np.float64(I_P)) / (2.0 * np.pi))
+                sE = math.sqrt(I_E ** 2 + Q_E ** 2); sL = math.sqrt(I_L ** 2 + Q_L ** 2)
+                codeError = float((np.float64(sE) - sL) / (np.float64(sE) + sL))
+            d2CarrError = d2CarrError + carrError * pf3
+            dCarrError = d2CarrError + carrError * pf2 + dCarrError
+            carrNco = dCarrError + carrError * pf1
+            tr["carrFreq"][loopCnt - 1] = carrFreq
+            carrFreq = carrFreqBasis + carrNco
+            codeNco = oldCodeNco + (tau2code / tau1code) * (codeError - oldCodeError) + codeError * (PDIcode / tau1code)
+            oldCodeNco = codeNco; oldCodeError = codeError
+            tr["codeFreq"][loopCnt - 1] = codeFreq / 2             # :376
+            codeFreq = s.codeFreqBasis * 2 - codeNco               # :379
+            tr["dllDiscr"][loopCnt - 1] = codeError / 2; tr["dllDiscrFilt"][loopCnt - 1] = codeNco / 2   # :382-383
+            tr["pllDiscr"][loopCnt - 1] = carrError; tr["pllDiscrFilt"][loopCnt - 1] = carrNco
+            tr["I_E"][loopCnt - 1] = I_E; tr["I_P"][loopCnt - 1] = I_P; tr["I_L"][loopCnt - 1] = I_L
+            tr["Q_E"][loopCnt - 1] = Q_E; tr["Q_P"][loopCnt - 1] = Q_P; tr["Q_L"][loopCnt - 1] = Q_L
+            if loopCnt % s.CNo_VSMinterval == 0:
+                vsmCnt += 1
+                lo = loopCnt - s.CNo_VSMinterval
+                tr["VSMValue"][vsmCnt - 1] = CNoVSM(tr["I_P"][lo:loopCnt], tr["Q_P"][lo:loopCnt], s.CNo_accTime)
+                tr["VSMIndex"][vsmCnt - 1] = loopCnt
+        tr["status"] = channel[ch]["status"]
+    return out

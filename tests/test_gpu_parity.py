@@ -714,3 +714,39 @@ def test_b1c_acquisition_vs_oracle(fs, pilot):
             assert got["carrFreq"][sat.prn - 1] != 0 and abs(got["carrFreq"][sat.prn - 1] - (s.IF + sat.doppler)) <= 25
     assert got["carrFreq"][30 - 1] == 0
     eng.close()
+
+
+@pytest.mark.parametrize("fs,nE", [(2.046e6, 60), (8e6, 12)])
+def test_l2c_tracking_and_wrappers_vs_oracle(fs, nE, tmp_path):
+    """GPS L2C tracking() with pilotTRKflag == 0: 20 ms epochs (160000 samples at 8 Msps) in half-chip units on the
+    return-to-zero CM table, fseek to codePhase, fractional absoluteSample, halved recorded code quantities."""
+    codes, sc, s, so, sv = _varb_case("GPS_L2C", fs, nsat=2, seed=3, extra=[], cn0=45, msToProcess=20 * nE, numberOfChannels=3,
+                                      CNo_VSMinterval=10)
+    N = O.samples_per_code(so)
+    raw = synth.make_record(sc, N * (nE + 2))
+    ch = []
+    for sat in sc.sats:
+        start = (20460 - sat.code_phase) * (fs / 1.023e6)
+        ch.append(dict(PRN=sat.prn, acquiredFreq=round((s.IF + sat.doppler) / 12.5) * 12.5, codePhase=int(round(start)) % N, status="T"))
+    ch.append(dict(PRN=0, acquiredFreq=0.0, codePhase=0, status="-"))
+    path = tmp_path / "l2c.bin"
+    raw.tofile(path)
+    eng = Engine(s, codes=codes)
+    with open(path, "rb") as fid:
+        tr, _ = tracking(fid, ch, s, engine=eng)
+    ref = O.tracking_l2c(raw, ch, so, codes)
+    for i in range(2):
+        assert tr[i]["status"] == "T" == ref[i]["status"] and tr[i]["epochsDone"] == nE
+        ok = first_illconditioned_epoch(2 * ref[i]["remCodePhase"], 2 * ref[i]["codeFreq"], 2 * tr[i]["remCodePhase"], 2 * tr[i]["codeFreq"],
+                                        np.floor(ref[i]["absoluteSample"]), fs, 2 * s.dllCorrelatorSpacing)
+        assert ok >= min(10, nE)
+        sc_ = np.hypot(ref[i]["I_P"], ref[i]["Q_P"])
+        for name in ("I_P", "Q_P", "I_E", "I_L", "Q_E", "Q_L"):
+            assert np.max(np.abs(tr[i][name][:ok] - ref[i][name][:ok]) / sc_[:ok]) < IQ_TOL, name
+        assert np.max(np.abs(tr[i]["absoluteSample"][:ok] - ref[i]["absoluteSample"][:ok])) < 1e-5      # fractional samples
+        assert np.max(np.abs(tr[i]["carrFreq"][:ok] - ref[i]["carrFreq"][:ok])) < 1e-4
+        assert np.max(np.abs(tr[i]["codeFreq"][:ok] - ref[i]["codeFreq"][:ok])) < 1e-4
+        assert np.max(np.abs(tr[i]["remCodePhase"][:ok] - ref[i]["remCodePhase"][:ok])) < 1e-6
+        assert np.allclose(tr[i]["CNo"]["VSMValue"][: ok // 10], ref[i]["VSMValue"][: ok // 10], rtol=1e-5)
+    assert tr[2]["status"] == "-"
+    eng.close()
