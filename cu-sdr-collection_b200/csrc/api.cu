@@ -354,6 +354,8 @@ int gc_create(gc_handle** out, const gc_config* cfg)
         h->vc.initFreq = cfg->IF + cfg->acq_search_band;                                    // :166
         h->L = h->vc.Lc;
         h->nRep = cfg->pilot_acq_flag == 1 ? 2 : 1;
+        h->sub = 2;                                                                         // BOC(1,1) sub-chip tables (NB_tracking.m:225-246)
+        h->pilotMode = cfg->pilot_trk_flag == 1 ? 3 : 0;
     }
     if (h->varB) {
         const bool b1i = cfg->signal == GC_SIG_BDS_B1I;
@@ -1197,7 +1199,7 @@ static double cno_vsm(const double* I, const double* Q, int n, double T)
     return 10 * std::log10(num / den);
 }
 
-int gc_track_nfields(const gc_handle* h) { return (h && h->pilotMode == 2) ? GC_TRACK_NFIELDS_PILOT : GC_TRACK_NFIELDS; }
+int gc_track_nfields(const gc_handle* h) { return (h && h->pilotMode >= 2) ? GC_TRACK_NFIELDS_PILOT : GC_TRACK_NFIELDS; }
 
 int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq, const double* codePhase,
              const double* codeFreq0, int32_t nEpochs, double* out, double* vsmValue, double* vsmIndex, int32_t* epochsDone)
@@ -1205,8 +1207,8 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
     if (!h) return GC_ERR_ARG;
     const gc_config& c = h->cfg;
     if (!h->rec) return fail(h, GC_ERR_NO_RECORD, "gc_track: no record resident");
-    if (c.signal == GC_SIG_BDS_B1C)
-        return fail(h, GC_ERR_UNSUPPORTED, "gc_track: BDS B1C (10 ms NB/WB) tracking is not implemented yet");
+    if (c.signal == GC_SIG_BDS_B1C && c.pilot_trk_flag != 1)
+        return fail(h, GC_ERR_UNSUPPORTED, "gc_track: BDS B1C tracking is implemented for pilotTRKflag == 1 (NB_tracking.m); WB_tracking.m is not");
     const bool l2c = c.signal == GC_SIG_GPS_L2C;
     if (l2c && c.pilot_trk_flag != 0)
         return fail(h, GC_ERR_UNSUPPORTED, "gc_track: GPS L2C tracking with the CL pilot (pilotTRKflag) is not implemented yet");
@@ -1276,7 +1278,8 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
     // double-buffered window to fit in shared memory
     while (cluster < 8 && track_smem_bytes(track_buf_bytes(h->N + 64, cluster), codeLen, p.pilot) > 227 * 1024) cluster *= 2;
     p.bufBytes = track_buf_bytes(h->N + 64, cluster);
-    if (track_smem_bytes(p.bufBytes, codeLen, p.pilot) > 227 * 1024)
+    p.singleBuf = track_smem_bytes(p.bufBytes, codeLen, p.pilot) > 227 * 1024 ? 1 : 0;   // B1C: 45 KB windows + two 82 KB tables
+    if (track_smem_bytes(p.bufBytes, codeLen, p.pilot, p.singleBuf) > 227 * 1024)
         return fail(h, GC_ERR_UNSUPPORTED, "gc_track: one code period of samples does not fit in shared memory");
     GC_CUDA(h, upload(h->chans, chans, st));
     GC_CUDA(h, upload(h->trackCodes, tabs, st));

@@ -232,7 +232,7 @@ track_kernel(TrackParams p)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // layout: [buf0 | buf1 | code table (float) | warp partials | staging | params | mbarriers]
     int8_t* const buf0 = reinterpret_cast<int8_t*>(smem_raw);
-    float* s_code_raw = reinterpret_cast<float*>(smem_raw + 2 * (size_t)p.bufBytes);
+    float* s_code_raw = reinterpret_cast<float*>(smem_raw + (p.singleBuf ? 1 : 2) * (size_t)p.bufBytes);
     float* s_code = s_code_raw + kPad;                           // index 0 = c(L) of the wrapped table
     const int tabFloats = (p.codeLen + 2 + 2 * kPad + 3) & ~3;
     float* s_pilot = s_code + (PILOT ? tabFloats : 0);           // pilot table right behind the data table
@@ -295,7 +295,7 @@ track_kernel(TrackParams p)
         if (b0 + n > recBytesUp) n = recBytesUp - b0;
         if (b0 < 0 || n <= 0) return false;                      // this CTA's slice lies beyond the record
         mbar_expect_tx(&s_bar[stage], (uint32_t)n);
-        bulk_g2s(buf0 + (size_t)stage * p.bufBytes, p.rec + b0, (uint32_t)n, &s_bar[stage]);
+        bulk_g2s(buf0 + (p.singleBuf ? 0 : (size_t)stage * p.bufBytes), p.rec + b0, (uint32_t)n, &s_bar[stage]);
         s_issued[stage] = epoch + 1;
         return true;
     };
@@ -323,7 +323,7 @@ track_kernel(TrackParams p)
         const long long pos = ep.pos;
         const uint64_t dphi = ep.dphi, phase0 = ep.phase0;
         // window of epoch e+1 starts where this one ends; fetch it while we correlate
-        if (tid == kLoader && e + 1 < p.nEpochs) prefetch(pos + blk, stage ^ 1, e + 1);
+        if (!p.singleBuf && tid == kLoader && e + 1 < p.nEpochs) prefetch(pos + blk, stage ^ 1, e + 1);
         if (G > 1 && tid == kPllTid) mbar_expect_tx(&s_xbar[e & 1], 8u * NS * G);   // G CTAs x NS doubles will arrive
         GC_TICK(0)
         if (staged) { mbar_wait(&s_bar[stage], phase[stage]); phase[stage] ^= 1u; }
@@ -347,7 +347,7 @@ track_kernel(TrackParams p)
         const int c_begin = fits ? c_lo : (int)crank, c_end = fits ? min(nChunks, c_lo + cpc) : nChunks;
         const int c_step = fits ? kThreads : kThreads * G;
         const bool inBuf = fits && staged;
-        const int8_t* src = buf0 + (size_t)stage * p.bufBytes - (size_t)c_lo * 16;
+        const int8_t* src = buf0 + (p.singleBuf ? 0 : (size_t)stage * p.bufBytes) - (size_t)c_lo * 16;
         const int8_t* gsrc = p.rec + ((pos * 2) & ~15LL);
         // table index = ceil(tcode * subChip): the scaling by 1 or 2 is exact, so the scaled colon vector is
         // element for element the reference's (rem -/+ spc)*2 : step*2 : (...)*2  (GAL_E1C tracking.m:236-262)
@@ -486,6 +486,8 @@ track_kernel(TrackParams p)
             for (int q = 0; q < NS; ++q) s_part[warp * NS + q] = v[q];
         __syncthreads();
         GC_TICK(3)
+        // one-window mode: every thread of this CTA has consumed its samples, the window of the next epoch may land now
+        if (p.singleBuf && tid == kLoader && e + 1 < p.nEpochs) prefetch(pos + blk, stage ^ 1, e + 1);
         if (G > 1) {
             // CTA partial -> every CTA of the cluster (slot [epoch parity][my rank]), then one barrier
             double* slot = s_cl + ((e & 1) * kMaxCluster + (int)crank) * NS;
@@ -550,10 +552,12 @@ track_kernel(TrackParams p)
                         num = __dsub_rn(__dmul_rn(v[NS - 3], eps), v[NS - 4]);    // imag(QI) = Q*eps - I
                         den = __dadd_rn(__dmul_rn(v[NS - 4], eps), v[NS - 3]);    // real(QI) = I*eps + Q
                     }
+                    if (p.pilot == 3) { num = -v[NS - 4]; den = v[NS - 3]; }      // atan(-p11_I_P/p11_Q_P), B1C NB_tracking.m:301
                     const double cP2 = p.exactDisc ? atan(__ddiv_rn(num, den)) / kTwoPi
                                                    : (double)atanf((float)num / (float)den) * 0.15915494309189535;
-                    carrError = __dmul_rn(__dadd_rn(carrError, cP2), 0.5);
-                    if (p.pilot == 2) { sg[15 * kStage] = v[NS - 4]; sg[16 * kStage] = v[NS - 3]; }   // Pilot_I_P, Pilot_Q_P (GPS_L5C :323-324)
+                    carrError = (p.pilot == 3) ? __ddiv_rn(__dadd_rn(__dmul_rn(carrError, 11.0), __dmul_rn(cP2, 29.0)), 40.0)   // :302
+                                               : __dmul_rn(__dadd_rn(carrError, cP2), 0.5);
+                    if (p.pilot >= 2) { sg[15 * kStage] = v[NS - 4]; sg[16 * kStage] = v[NS - 3]; }   // Pilot_I_P, Pilot_Q_P (GPS_L5C :323-324)
                 }
                 double carrNco;
                 if (p.loopType == 0) {
@@ -598,7 +602,12 @@ track_kernel(TrackParams p)
                         const float sE = sqrtf((float)qE), sL = sqrtf((float)qL);
                         ce2 = (double)((sE - sL) / (sE + sL));
                     }
-                    codeError = __dmul_rn(__dadd_rn(codeError, ce2), 0.5);
+                    if (p.pilot == 3) {                          // B1C NB_tracking.m:313-318: both scaled by (1 - spacing), weights 11/40, 29/40
+                        const double sc1 = __dsub_rn(1.0, p.spc);
+                        codeError = __ddiv_rn(__dadd_rn(__dmul_rn(__dmul_rn(codeError, sc1), 11.0), __dmul_rn(__dmul_rn(ce2, sc1), 29.0)), 40.0);
+                    } else {
+                        codeError = __dmul_rn(__dadd_rn(codeError, ce2), 0.5);
+                    }
                 }
                 const double codeNco = __dadd_rn(__dadd_rn(lm.oldCodeNco, __dmul_rn(p.cA, __dsub_rn(codeError, lm.oldCodeError))),
                                                  __dmul_rn(codeError, p.cB));
@@ -642,10 +651,10 @@ track_kernel(TrackParams p)
     if (G > 1) cluster_sync_all();                               // nobody leaves while a peer may still push to it
 }
 
-size_t track_smem_bytes(int bufBytes, int codeLen, int pilot)
+size_t track_smem_bytes(int bufBytes, int codeLen, int pilot, int singleBuf)
 {
     const int ns = pilot ? 12 : 6;
-    size_t s = 2 * (size_t)bufBytes;
+    size_t s = (singleBuf ? 1 : 2) * (size_t)bufBytes;
     s += sizeof(float) * ((codeLen + 2 + 2 * kPad + 3) & ~3) * (pilot ? 2 : 1);
     s += sizeof(double) * (kMaxWarps * ns + 2 * kMaxCluster * ns + GC_TRACK_ROWS * kStage);
     s += 2 * sizeof(EpochParams) + sizeof(NextPhases) + 4 * sizeof(uint64_t) + 2 * sizeof(int) + 64;
@@ -655,7 +664,7 @@ size_t track_smem_bytes(int bufBytes, int codeLen, int pilot)
 template <int G, int T, bool PILOT>
 static cudaError_t launch_track_g(const TrackParams& p, int nCh, cudaStream_t stream)
 {
-    const size_t smem = track_smem_bytes(p.bufBytes, p.codeLen, PILOT ? 1 : 0);
+    const size_t smem = track_smem_bytes(p.bufBytes, p.codeLen, PILOT ? 1 : 0, p.singleBuf);
     cudaError_t err = cudaFuncSetAttribute(track_kernel<G, T, PILOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     cudaLaunchConfig_t cfg{};

@@ -35,6 +35,10 @@ struct TrackParams {
                              // discriminators are averaged (GAL_E1C tracking.m:241-333, settings.pilotTRKflag);
                              // 2: same, the pilot is in quadrature - its prompt is rotated by -pi/2 before the atan
                              // (GPS_L5C tracking.m:277-281) - and Pilot_I_P / Pilot_Q_P are recorded (rows 15, 16)
+                             // 3: quadrature pilot weighted 11/40 : 29/40, pilot discriminator atan(-I/Q), code discriminators
+                             // scaled by (1 - spacing) (BDS/B1C/include/NB_tracking.m:300-320); Pilot rows recorded
+    int singleBuf;           // 1: one sample window in shared memory instead of two (long epochs whose double-buffered window
+                             // would not fit next to the code tables: B1C, 10 ms = 180000 samples with two 20460-entry tables)
     int nRows;               // rows recorded per epoch: GC_TRACK_NFIELDS, or GC_TRACK_NFIELDS_PILOT with pilot == 2
     int codeStride;          // bytes between channels in codeTables / pilotTables
     const int8_t* codeTables;   // [nCh][codeStride]: wrapped +-1 table [c(L) c(1..L) c(1)]
@@ -45,7 +49,7 @@ struct TrackParams {
     long long* dbg;          // optional [4][8] phase-timing accumulators (GC_TRACK_DEBUG), else nullptr
 };
 
-size_t track_smem_bytes(int bufBytes, int codeLen, int pilot);
+size_t track_smem_bytes(int bufBytes, int codeLen, int pilot, int singleBuf = 0);
 cudaError_t launch_track(const TrackParams& p, int nCh, int cluster, cudaStream_t stream);
 int track_buf_bytes(int maxBlockSamples, int cluster);
 cudaError_t launch_track_fill(double* out, int nCh, int nRows, int nEpochs, cudaStream_t stream);

@@ -26,10 +26,10 @@ def preRun(acqResults: dict, settings: Settings) -> list:
         p = int(order[ii])
         channel[ii] = dict(PRN=p + 1, acquiredFreq=float(acqResults["carrFreq"][p]),
                            codePhase=int(acqResults["codePhase"][p]), status="T")              # :66-71
-        if settings.signal == "BDS_B3I" or settings.is_fam5:   # carrier-aided code NCO centre (BDS/B3I/include/preRun.m:71-73, GPS_L5C :69-71)
+        if settings.signal in ("BDS_B3I", "BDS_B1C") or settings.is_fam5:   # carrier-aided code NCO centre (BDS/B3I/include/preRun.m:71-73, GPS_L5C :69-71)
             channel[ii]["codeFreq"] = settings.codeFreqBasis + \
                 (channel[ii]["acquiredFreq"] - settings.IF) / settings.carrFreqBasis * settings.codeFreqBasis
-    if settings.signal == "BDS_B3I" or settings.is_fam5:
+    if settings.signal in ("BDS_B3I", "BDS_B1C") or settings.is_fam5:
         for c in channel:
             c.setdefault("codeFreq", 0.0)
     return channel

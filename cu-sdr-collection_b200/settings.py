@@ -113,7 +113,9 @@ _L2C_DEFAULTS = dict(samplingFreq=8e6, codeFreqBasis=0.5115e6, codeLength=10230.
 # BDS/B1C/initSettings.m (hot-path fields of the acquisition)
 _B1C_DEFAULTS = dict(numberOfChannels=15, codeLength=10230.0, codeFreqBasis=1.023e6, acqSatelliteList=list(range(1, 63)),
                      acqSearchBand=5000.0, acqCohT=10, acqStep=50.0, acqThreshold=10.0, resamplingThreshold=15e6, pilotACQflag=1,
-                     pilotTRKflag=1, intTime=0.01, CNo_VSMinterval=50, fileName="../../../B1C_IF20KHz_FS18MHz.bin")
+                     pilotTRKflag=1, intTime=0.01, CNo_VSMinterval=50, CNo_accTime=0.01, carrFreqBasis=1575.42e6,
+                     dllNoiseBandwidth=1.0, dllCorrelatorSpacing=0.06, pllNoiseBandwidth=18.0,
+                     fileName="../../../B1C_IF20KHz_FS18MHz.bin")
 
 
 def varb_step(s: "Settings") -> float:
@@ -179,7 +181,7 @@ def num_to_process(s: Settings) -> int:
     """Integration periods tracking() runs: msToProcess for the 1 ms signals, round(msToProcess/1000/intTime)
     for Galileo E1 (GAL/GAL_E1C/include/tracking.m:48)."""
     import math
-    if s.signal in ("GAL_E1C", "GPS_L2C"):             # GPS_L2C/include/tracking.m:51
+    if s.signal in ("GAL_E1C", "GPS_L2C", "BDS_B1C"):  # GPS_L2C/include/tracking.m:51, BDS/B1C/include/NB_tracking.m:49
         x = s.msToProcess / 1000 / s.intTime
         return int(math.floor(x + 0.5))
     return int(s.msToProcess)

@@ -31,7 +31,7 @@ def tracking(fid, channel: list, settings: Settings, engine: Engine | None = Non
         af = [float(c["acquiredFreq"]) for c in channel[:nch]]
         cp = [float(c["codePhase"]) for c in channel[:nch]]
         path = fid.name if fid is not None else None
-        cf0 = [float(c["codeFreq"]) for c in channel[:nch]] if (settings.signal == "BDS_B3I" or settings.is_fam5) else None   # B3I tracking.m:57, GPS_L5C :173
+        cf0 = [float(c["codeFreq"]) for c in channel[:nch]] if (settings.signal in ("BDS_B3I", "BDS_B1C") or settings.is_fam5) else None   # B3I tracking.m:57, GPS_L5C :173, B1C NB_tracking.m:163
         out, vv, vi, done = eng.track(prn, af, cp, n, path=path, code_freq0=cf0)
     finally:
         if own:
@@ -52,7 +52,7 @@ def tracking(fid, channel: list, settings: Settings, engine: Engine | None = Non
                 tr[f] = tr[f] / 2
         if out.shape[1] == 17:                                             # GPS_L5C tracking.m:57-60, 323-324
             tr["Pilot_I_P"], tr["Pilot_Q_P"] = out[ch, 15], out[ch, 16]
-        if settings.signal == "BDS_B2a":                                   # BDS/B2a/include/tracking.m:66-72, 336-352
+        if settings.signal in ("BDS_B2a", "BDS_B1C"):                      # BDS/B2a/include/tracking.m:66-72, 336-352; B1C NB_tracking.m:65-69, 340-355
             tr.update(_b2a_cno_pld(tr, settings, int(done[ch])))
         else:
             tr["CNo"] = {"VSMValue": vv[ch], "VSMIndex": vi[ch]}
@@ -73,11 +73,12 @@ def _b2a_cno_pld(tr: dict, settings: Settings, done: int) -> dict:
     rows - BDS/B2a/include/Calc_CNo_PLD.m:38-76 and the 0.5/0.5 smoothing of tracking.m:340-349.  Scalar host work
     on rows the GPU produced (40..200 values per call)."""
     n_int = int(settings.CNo_VSMinterval)
-    nv = int(settings.msToProcess) // n_int
+    nv = num_to_process(settings) // n_int
     pilot = int(settings.pilotTRKflag) == 1
+    total = "B1C_CNo" if settings.signal == "BDS_B1C" else "B2a_CNo"
     res = {"DataCNo": np.zeros(nv), "DataPLD": np.zeros(nv)}
     if pilot:
-        res.update(PilotCNo=np.zeros(nv), PilotPLD=np.zeros(nv), B2a_CNo=np.zeros(nv))
+        res.update({"PilotCNo": np.zeros(nv), "PilotPLD": np.zeros(nv), total: np.zeros(nv)})
     T = settings.intTime
     prev = np.zeros(3)
 
@@ -109,6 +110,6 @@ def _b2a_cno_pld(tr: dict, settings: Settings, done: int) -> dict:
         res["DataPLD"][v - 1] = d_pld
         if pilot:
             res["PilotCNo"][v - 1] = cur[1] * 0.5 + prev[1] * 0.5
-            res["B2a_CNo"][v - 1] = cur[2] * 0.5 + prev[2] * 0.5
+            res[total][v - 1] = cur[2] * 0.5 + prev[2] * 0.5
         prev = cur
     return res

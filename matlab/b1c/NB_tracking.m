@@ -1,0 +1,55 @@
+function [trackResults, channel] = NB_tracking(fid, channel, settings)
+%NB_TRACKING  Drop-in for BDS/B1C/include/NB_tracking.m (same signature and trackResults struct, settings.pilotTRKflag == 1;
+%postProcessing.m:34-38 dispatches here) that runs the 10 ms data + pilot correlate-and-dump loops of all channels on a B200.
+%WB_tracking.m (pilotTRKflag == 2, BOC(6,1) component, 18 sums) is not accelerated yet.
+fastPath = settings.fileType == 2 && strcmp(settings.dataType, 'schar') && settings.pilotTRKflag == 1;
+if ~fastPath
+    [trackResults, channel] = NB_tracking_reference(fid, channel, settings);
+    return
+end
+fname = fopen(fid);
+nCh = settings.numberOfChannels;
+n   = round(settings.msToProcess / 1000 / settings.intTime);          % NB_tracking.m:49
+prn = double([channel(1:nCh).PRN]);
+sv = unique(prn(prn > 0));
+codes.sv = sv;
+codes.data  = zeros(2 * settings.codeLength, numel(sv), 'int8');
+codes.pilot = zeros(2 * settings.codeLength, numel(sv), 'int8');
+for k = 1:numel(sv)
+    codes.data(:, k)  = int8(generateDataBOC11(settings, sv(k)));
+    codes.pilot(:, k) = int8(generatePilotBOC11(settings, sv(k)));
+end
+cfg = gnsscorr_config(settings, 'BDS_B1C');
+cfg.acq_search_step = settings.acqStep;  cfg.acq_coh_t = settings.acqCohT;  cfg.pilot_acq_flag = settings.pilotACQflag;
+r = gnsscorr_mex('track', cfg, fname, prn, double([channel(1:nCh).acquiredFreq]), double([channel(1:nCh).codePhase]), n, ...
+                 double([channel(1:nCh).codeFreq]), codes);
+names = {'absoluteSample', 'codeFreq', 'carrFreq', 'I_P', 'I_E', 'I_L', 'Q_E', 'Q_P', 'Q_L', ...
+         'dllDiscr', 'dllDiscrFilt', 'pllDiscr', 'pllDiscrFilt', 'remCodePhase', 'remCarrPhase'};
+nv = floor(n / settings.CNoInterval);
+shortRead = false;
+for ch = nCh:-1:1
+    t = struct('status', '-');
+    for k = 1:15, t.(names{k}) = r.out(:, k, ch).'; end
+    t.Pilot_I_P = r.out(:, 16, ch).';
+    t.Pilot_Q_P = r.out(:, 17, ch).';
+    t.DataCNo = zeros(1, nv);  t.DataPLD = zeros(1, nv);  t.PilotCNo = zeros(1, nv);  t.PilotPLD = zeros(1, nv);  t.B1C_CNo = zeros(1, nv);
+    prev = zeros(1, 3);                                               % NB_tracking.m:340-357 on the returned rows
+    for v = 1:floor(double(r.epochsDone(ch)) / settings.CNoInterval)
+        [cno, pld] = Calc_CNo_PLD(t, settings, v * settings.CNoInterval);
+        t.DataCNo(v) = cno(1) * 0.5 + prev(1) * 0.5;   t.DataPLD(v) = pld(1);
+        t.PilotCNo(v) = cno(2) * 0.5 + prev(2) * 0.5;  t.PilotPLD(v) = pld(2);
+        t.B1C_CNo(v) = cno(3) * 0.5 + prev(3) * 0.5;
+        prev = cno;
+    end
+    if channel(ch).PRN ~= 0
+        t.PRN = channel(ch).PRN;
+        if r.epochsDone(ch) == n, t.status = channel(ch).status; else, shortRead = true; end
+    else
+        t.PRN = [];
+    end
+    trackResults(ch) = t; %#ok<AGROW>
+end
+if shortRead
+    disp('Not able to read the specified number of samples  for tracking, exiting!')
+end
+end

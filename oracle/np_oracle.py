@@ -1569,3 +1569,92 @@ def tracking_l2c(raw: np.ndarray, channel: list, s: Settings, codes: dict):
                 tr["VSMIndex"][vsmCnt - 1] = loopCnt
         tr["status"] = channel[ch]["status"]
     return out
+
+
+def tracking_b1c_nb(raw: np.ndarray, channel: list, s: Settings, codes: dict):
+    """BDS/B1C/include/NB_tracking.m:47-365 (settings.pilotTRKflag == 1): 10 ms epochs, BOC(1,1) sub-chip tables indexed by
+    ceil(tcode*2)+1 (:225-246), code NCO centred on channel.codeFreq, the pilot in quadrature with atan(-I/Q) (:301), carrier
+    and code discriminators weighted 11/40 : 29/40 (:302, :318), code discriminators scaled by (1 - spacing) (:313-317),
+    Pilot_I_P / Pilot_Q_P recorded.  The DataCNo / PLD block (Calc_CNo_PLD.m) is host post-processing of these rows."""
+    nE = int(matlab_round(s.msToProcess / 1000 / s.intTime))       # :49
+    out = []
+    for _ in range(s.numberOfChannels):
+        tr = dict(status="-", PRN=0)
+        tr["absoluteSample"] = np.zeros(nE)
+        for f in ("codeFreq", "carrFreq", "dllDiscr", "dllDiscrFilt", "pllDiscr", "pllDiscrFilt", "remCodePhase", "remCarrPhase"):
+            tr[f] = np.full(nE, np.inf)
+        for f in ("I_P", "I_E", "I_L", "Q_E", "Q_P", "Q_L", "Pilot_I_P", "Pilot_Q_P"):
+            tr[f] = np.zeros(nE)
+        out.append(tr)
+    spc = s.dllCorrelatorSpacing
+    codeLength = int(s.codeLength)
+    PDIcode = s.intTime
+    tau1code, tau2code = calcLoopCoef(s.dllNoiseBandwidth, s.dllDampingRatio, 1.0)
+    pf3, pf2, pf1 = calcLoopCoefCarr(s)
+    for ch in range(s.numberOfChannels):
+        if channel[ch]["PRN"] == 0:
+            continue
+        tr = out[ch]
+        PRN = channel[ch]["PRN"]
+        tr["PRN"] = PRN
+        pos = 2 * (s.skipNumberOfBytes + channel[ch]["codePhase"] - 1)
+        c = np.asarray(codes[PRN][0], dtype=np.float64)
+        D = np.concatenate([[c[2 * codeLength - 1]], c, [c[0]]])   # :155-156
+        c = np.asarray(codes[PRN][1], dtype=np.float64)
+        P11 = np.concatenate([[c[2 * codeLength - 1]], c, [c[0]]])
+        codeFreq = channel[ch]["codeFreq"]; remCodePhase = 0.0     # :163
+        carrFreq = channel[ch]["acquiredFreq"]; carrFreqBasis = channel[ch]["acquiredFreq"]; remCarrPhase = 0.0
+        oldCodeNco = oldCodeError = 0.0
+        d2CarrError = dCarrError = 0.0
+        for loopCnt in range(1, nE + 1):
+            tr["absoluteSample"][loopCnt - 1] = pos / 2
+            step = codeFreq / s.samplingFreq
+            blksize = int(math.ceil((codeLength - remCodePhase) / step))
+            chunk = raw[pos: pos + 2 * blksize]
+            pos += chunk.size
+            if chunk.size != 2 * blksize:
+                return out
+            rawSignal = chunk[0::2].astype(np.float64) + 1j * chunk[1::2].astype(np.float64)
+            tr["remCodePhase"][loopCnt - 1] = remCodePhase
+            tE = colonop((remCodePhase - spc) * 2, step * 2, ((blksize - 1) * step + remCodePhase - spc) * 2)
+            tL = colonop((remCodePhase + spc) * 2, step * 2, ((blksize - 1) * step + remCodePhase + spc) * 2)
+            tP = colonop(remCodePhase * 2, step * 2, ((blksize - 1) * step + remCodePhase) * 2)
+            iE = np.ceil(tE).astype(np.int64); iL = np.ceil(tL).astype(np.int64); iP = np.ceil(tP).astype(np.int64)
+            remCodePhase = tP[blksize - 1] / 2 + step - codeLength   # :248
+            tr["remCarrPhase"][loopCnt - 1] = remCarrPhase
+            time = np.arange(0, blksize + 1, dtype=np.float64) / s.samplingFreq
+            trigarg = ((carrFreq * 2.0 * np.pi) * time) + remCarrPhase
+            remCarrPhase = math.fmod(trigarg[blksize], 2 * np.pi)
+            bb = np.exp(-1j * trigarg[:blksize]) * rawSignal
+            iB, qB = bb.real, bb.imag
+            I_E = float(np.sum(D[iE] * iB)); Q_E = float(np.sum(D[iE] * qB))
+            I_P = float(np.sum(D[iP] * iB)); Q_P = float(np.sum(D[iP] * qB))
+            I_L = float(np.sum(D[iL] * iB)); Q_L = float(np.sum(D[iL] * qB))
+            pI_E = float(np.sum(P11[iE] * iB)); pQ_E = float(np.sum(P11[iE] * qB))
+            pI_P = float(np.sum(P11[iP] * iB)); pQ_P = float(np.sum(P11[iP] * qB))
+            pI_L = float(np.sum(P11[iL] * iB)); pQ_L = float(np.sum(P11[iL] * qB))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                carrError = float(np.arctan(np.float64(Q_P) / np.float64(I_P)) / (2.0 * np.pi))
+                p11_carrError = float(np.arctan(-np.float64(pI_P) / np.float64(pQ_P)) / (2.0 * np.pi))   # :301
+                carrError = (carrError * 11 + p11_carrError * 29) / 40                                   # :302
+                sE = math.sqrt(I_E ** 2 + Q_E ** 2); sL = math.sqrt(I_L ** 2 + Q_L ** 2)
+                codeError = float((np.float64(sE) - sL) / (np.float64(sE) + sL)) * (1 - spc)             # :313-314
+                sEp = math.sqrt(pI_E ** 2 + pQ_E ** 2); sLp = math.sqrt(pI_L ** 2 + pQ_L ** 2)
+                p11_codeError = float((np.float64(sEp) - sLp) / (np.float64(sEp) + sLp)) * (1 - spc)     # :315-317
+                codeError = (codeError * 11 + p11_codeError * 29) / 40                                   # :318
+            d2CarrError = d2CarrError + carrError * pf3
+            dCarrError = d2CarrError + carrError * pf2 + dCarrError
+            carrNco = dCarrError + carrError * pf1
+            tr["carrFreq"][loopCnt - 1] = carrFreq
+            carrFreq = carrFreqBasis + carrNco
+            codeNco = oldCodeNco + (tau2code / tau1code) * (codeError - oldCodeError) + codeError * (PDIcode / tau1code)
+            oldCodeNco = codeNco; oldCodeError = codeError
+            tr["codeFreq"][loopCnt - 1] = codeFreq
+            codeFreq = channel[ch]["codeFreq"] - codeNco
+            tr["dllDiscr"][loopCnt - 1] = codeError; tr["dllDiscrFilt"][loopCnt - 1] = codeNco
+            tr["pllDiscr"][loopCnt - 1] = carrError; tr["pllDiscrFilt"][loopCnt - 1] = carrNco
+            tr["I_E"][loopCnt - 1] = I_E; tr["I_P"][loopCnt - 1] = I_P; tr["I_L"][loopCnt - 1] = I_L
+            tr["Q_E"][loopCnt - 1] = Q_E; tr["Q_P"][loopCnt - 1] = Q_P; tr["Q_L"][loopCnt - 1] = Q_L
+            tr["Pilot_I_P"][loopCnt - 1] = pI_P; tr["Pilot_Q_P"][loopCnt - 1] = pQ_P
+        tr["status"] = channel[ch]["status"]
+    return out

@@ -750,3 +750,48 @@ def test_l2c_tracking_and_wrappers_vs_oracle(fs, nE, tmp_path):
         assert np.allclose(tr[i]["CNo"]["VSMValue"][: ok // 10], ref[i]["VSMValue"][: ok // 10], rtol=1e-5)
     assert tr[2]["status"] == "-"
     eng.close()
+
+
+@pytest.mark.parametrize("fs,nE", [(4.092e6, 40), (18e6, 8)])
+def test_b1c_nb_tracking_and_wrappers_vs_oracle(fs, nE, tmp_path):
+    """BDS B1C NB_tracking (pilotTRKflag 1): 10 ms epochs (180000 samples at 18 Msps, one sample window in shared memory
+    next to the two BOC(1,1) tables), carrier-aided code NCO, quadrature pilot atan(-I/Q), 11/40 : 29/40 weights,
+    (1 - spacing)-scaled code discriminators, Pilot rows, DataCNo / PLD block on the host."""
+    from cu_sdr_collection_b200.codes import standin_b1c_codes
+    codes = standin_b1c_codes()
+    sc = synth.default_scene_varb("BDS_B1C", codes, fs=fs, nsat=2, seed=3)
+    for x in sc.sats:
+        x.cn0 = 46
+    s = init_settings("BDS_B1C", samplingFreq=fs, acqSatelliteList=sorted(x.prn for x in sc.sats), msToProcess=10 * nE,
+                      numberOfChannels=3, CNo_VSMinterval=4)
+    so = to_oracle_settings(s)
+    N = O.samples_per_code(so)
+    raw = synth.make_record(sc, N * (nE + 2))
+    acq = dict(carrFreq=np.zeros(63), codePhase=np.zeros(63), peakMetric=np.zeros(63))
+    for i, sat in enumerate(sc.sats):
+        start = (20460 - sat.code_phase) * (fs / 2.046e6)
+        acq["carrFreq"][sat.prn - 1] = round((s.IF + sat.doppler) / 25.0) * 25.0
+        acq["codePhase"][sat.prn - 1] = int(round(start)) % N + 1
+        acq["peakMetric"][sat.prn - 1] = 20.0 - i
+    ch = preRun(acq, s)
+    assert ch[0]["codeFreq"] == s.codeFreqBasis + (ch[0]["acquiredFreq"] - s.IF) / s.carrFreqBasis * s.codeFreqBasis
+    path = tmp_path / "b1c.bin"
+    raw.tofile(path)
+    eng = Engine(s, codes=codes)
+    with open(path, "rb") as fid:
+        tr, _ = tracking(fid, ch, s, engine=eng)
+    ref = O.tracking_b1c_nb(raw, ch, so, codes)
+    for i in range(2):
+        assert tr[i]["status"] == "T" == ref[i]["status"] and tr[i]["epochsDone"] == nE
+        assert np.array_equal(tr[i]["absoluteSample"], ref[i]["absoluteSample"])
+        ok = first_illconditioned_epoch(ref[i]["remCodePhase"], ref[i]["codeFreq"], tr[i]["remCodePhase"], tr[i]["codeFreq"],
+                                        ref[i]["absoluteSample"], fs, s.dllCorrelatorSpacing, sub=2.0)
+        assert ok >= min(8, nE)
+        sc_ = np.hypot(ref[i]["Pilot_I_P"], ref[i]["Pilot_Q_P"])
+        for name in ("I_P", "Q_P", "I_E", "I_L", "Q_E", "Q_L", "Pilot_I_P", "Pilot_Q_P"):
+            assert np.max(np.abs(tr[i][name][:ok] - ref[i][name][:ok]) / sc_[:ok]) < IQ_TOL, name
+        assert np.max(np.abs(tr[i]["carrFreq"][:ok] - ref[i]["carrFreq"][:ok])) < 1e-4
+        assert np.max(np.abs(tr[i]["codeFreq"][:ok] - ref[i]["codeFreq"][:ok])) < 1e-4
+        assert tr[i]["DataCNo"].shape == (nE // 4,) and "B1C_CNo" in tr[i] and np.all(np.isfinite(tr[i]["PilotCNo"]))
+    assert tr[2]["status"] == "-"
+    eng.close()
