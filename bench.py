@@ -404,6 +404,59 @@ def main():
             "n_acquired": int(lst["n_acquired"]), "acq_path": int(lst["acq_path"])}
         leng.close()
         del lrec
+    # ---- BASELINE configs[4]: every constellation's acquisition at the reference's default initSettings.m, one after the
+    #      other on this GPU (per rank; N ranks = N independent receivers).  Cells = SVs x Doppler rows searched. ---------
+    if not args.no_tracking and widened is not None:
+        from cu_sdr_collection_b200.codes import standin_b1c_codes, standin_varb_codes
+        from cu_sdr_collection_b200.settings import samples_per_code
+        allc = {}
+        tot_cells, tot_ms = 0, 0.0
+
+        def run_sig(name, st_, codes_, scene_, periods, cells):
+            nonlocal tot_cells, tot_ms
+            n_ = samples_per_code(st_)
+            r_ = torch.from_numpy(synth.make_record(scene_, n_ * periods + 64)).to(dev)
+            e_ = Engine(st_, device=local, codes=codes_) if codes_ is not None else Engine(st_, device=local)
+            e_.set_record(r_)
+            for _ in range(2):
+                e_.acquire()
+            ms_ = max_over_ranks(e_.stats()["acq_total_ms"])
+            allc[name] = {"cells": cells, "ms": ms_, "fft_len": int(e_.stats()["fft_len"]), "n_acquired": int(e_.stats()["n_acquired"])}
+            tot_cells += cells; tot_ms += ms_
+            e_.close()
+            del r_
+
+        sd = 20260101 + rank
+        st_ = init_settings("GPS_L1CA")
+        run_sig("GPS_L1CA", st_, None, synth.default_scene(fs=18e6, nsat=6, seed=sd), 42, 32 * 29)
+        st_ = init_settings("GLO_GL1")
+        run_sig("GLO_GL1", st_, None, synth.default_scene_glo(fs=12e6, nsat=5, seed=sd), 42, 14 * 21)
+        st_ = init_settings("GLO_GL2")
+        run_sig("GLO_GL2", st_, None, synth.default_scene_glo(fs=12e6, nsat=5, seed=sd + 1, freqSpacing=437.5e3), 42, 14 * 21)
+        st_ = init_settings("BDS_B3I")
+        run_sig("BDS_B3I", st_, None, synth.default_scene_b3i(fs=18e6, nsat=5, seed=sd), 22, 63 * 21)
+        st_ = init_settings("GAL_E1C")
+        run_sig("GAL_E1C", st_, e1codes, synth.default_scene_e1c(e1codes, fs=18e6, nsat=4, seed=sd), 42, 36 * 94)
+        for sg, per, bins in (("GPS_L5C", 42, 21), ("GAL_E5a", 102, 21), ("GAL_E5b", 102, 168), ("BDS_B2a", 17, 21)):
+            cd = standin_codes(sg)
+            st_ = init_settings(sg)
+            run_sig(sg, st_, cd, synth.default_scene_fam5(sg, cd, fs=18e6, nsat=4, seed=sd), per, len(st_.acqSatelliteList) * bins)
+        cd = standin_varb_codes("BDS_B1I")
+        st_ = init_settings("BDS_B1I")
+        run_sig("BDS_B1I", st_, cd, synth.default_scene_varb("BDS_B1I", cd, fs=18e6, nsat=4, seed=sd), 11, 53 * 81)
+        cd = standin_varb_codes("GPS_L2C")
+        st_ = init_settings("GPS_L2C")
+        run_sig("GPS_L2C", st_, cd, synth.default_scene_varb("GPS_L2C", cd, fs=8e6, nsat=3, seed=sd), 3, 32 * 801)
+        cd = standin_b1c_codes()
+        st_ = init_settings("BDS_B1C")
+        run_sig("BDS_B1C", st_, cd, synth.default_scene_varb("BDS_B1C", cd, fs=18e6, nsat=3, seed=sd), 2, 62 * 201)
+        widened["all_constellation_acquisition"] = {
+            "value": tot_cells * world / (tot_ms * 1e-3), "unit": "cells/s", "cells": tot_cells, "ms": tot_ms,
+            "sv_signal_pairs": 32 + 14 + 14 + 63 + 36 + 32 + 36 + 36 + 29 + 53 + 32 + 62,
+            "workload": "BASELINE.json configs[4]: the twelve signal folders' acquisitions at their default initSettings.m, run "
+                        "back to back on one GPU per rank (cells = SVs x Doppler rows; fused plans for 36000/24000, generic "
+                        "passes for 144000/72000/320000/360000; stand-in codes where the reference's are data)",
+            "per_signal": allc}
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- CPU baseline (oracle on the host cores; rank 0, N = 1 only) -------------------------

@@ -126,18 +126,41 @@ struct FineParams {
                               // 4: pilot secondary code, max over all circular shifts of |sum_q s(q)*sec(q - c)| (GPS_L5C
                               //    acquisition.m:214-219 with NH20, GAL_E5a :211-216 with the per-PRN 100-chip code)
                               // 5: sum_q |s_data(q)| + sum_q |s_pilot(q)| (BDS/B2a/include/acquisition.m:226-228)
-    int nAcq;                 // acquired SVs; entries [nAcq, 2*nAcq) of chips/prod/sums are the pilot-code ones of combine 5
+    const int* nAcqDev;       // device: number of acquired SVs (written by fine_setup_kernel); entries [nAcq, 2*nAcq) of
+                              // chipRow/prod/sums are the pilot-code ones of combine 5
+    int nCodes;               // codes wiped off per acquired SV (2 for combine 5, else 1)
     const int8_t* secondary;  // [nAcq][nPeriods] +-1 secondary code (combine 4)
     const int* svId;          // [nAcq] PRN of each acquired SV (combine 2 depends on it)
     const int16_t* chipIdx;   // [nPeriods*N] sample -> chip index of the 40 ms replica (host table, :215-218)
-    const int8_t* chips;      // [nAcq][codeLen] +-1 chips of the acquired PRNs
-    const int* codePhase;     // [nAcq] 1-based coarse code phase (:221)
-    const uint64_t* dphi;     // [nAcq][nFine] fine-bin phase increments
+    const int8_t* chips;      // [rows][codeLen] +-1 chips of every SV / component of the handle
+    const int* chipRow;       // [entries] row of `chips` each entry wipes off
+    const int* codePhase;     // [entries] 1-based coarse code phase (:221)
+    const uint64_t* dphi;     // [entries][nFine] fine-bin phase increments
     short2* prod;             // [nAcq][nPeriods*N] scratch: sig40cm .* caCode40ms (:232)
     double* sums;             // [nAcq][nFine][nPeriods][2]  sumPerCode (:235-238)
     int* best;                // [nAcq] arg-max fine bin, 0-based (:253)
     double* fineResult;       // [nAcq][nFine]
 };
-cudaError_t launch_fine(const FineParams& p, int nEntries, int nAcq, cudaStream_t s);
+cudaError_t launch_fine(const FineParams& p, int maxEntries, int maxAcq, cudaStream_t s);
+
+// Threshold test and fine-search set-up on the device (acquisition.m:200-206, 221-227), so that gc_acquire needs no
+// host round trip between the coarse and the fine stage.
+struct FineSetup {
+    const PeakOut* peaks;     // [nSv] from peak_select_kernel
+    const double* sigPower;
+    int nSv, nonCoh, nFine, nCodes, nPeriods;
+    int pilotComp;            // component wiped off when nCodes == 1 (nRep - 1)
+    double threshold, step, fineStep, ts;
+    const double* slotFreq0;  // [nSv] (IF + offset) + acqSearchBand: frequency of coarse bin 1 for the slot
+    const int* slotChipRow;   // [nSv] first chip row of the slot's SV (component 0; component c at +c)
+    const int* slotSv;        // [nSv] SV id of the slot
+    const int8_t* slotSecondary;   // [nSv][nPeriods] or nullptr
+    // outputs
+    double* metric;           // [nSv] peakMetric
+    int* nAcq;                // [1]
+    int* acqSlot;             // [nSv] list slots above threshold, ascending
+    int* chipRow; int* codePhase; uint64_t* dphi; int* svId; int8_t* secondary;   // the FineParams arrays
+};
+cudaError_t launch_fine_setup(const FineSetup& p, cudaStream_t s);
 
 }  // namespace gc

@@ -76,9 +76,10 @@ __global__ void fine_prep_kernel(FineParams p)
 {
     short2* prod = p.prod;
     const int a = blockIdx.y;
+    if (a >= *p.nAcqDev * p.nCodes) return;
     const long long total = (long long)p.nPeriods * p.N;
     const char2* x = reinterpret_cast<const char2*>(p.rec) + p.winStart + (p.codePhase[a] - 1);   // :221
-    const int8_t* chips = p.chips + (size_t)a * p.codeLen;
+    const int8_t* chips = p.chips + (size_t)p.chipRow[a] * p.codeLen;
     for (long long gi = blockIdx.x * (long long)blockDim.x + threadIdx.x; gi < total; gi += (long long)gridDim.x * blockDim.x) {
         const int c = chips[p.chipIdx[gi]];                      // caCode40ms (:215-218; GLO generateCAcode.m:110-116)
         char2 v = x[gi];
@@ -94,6 +95,7 @@ fine_sum_kernel(FineParams p)
 {
     const short2* prod = p.prod;
     const int c = blockIdx.x, a = blockIdx.y, j0 = blockIdx.z * kFineBins;
+    if (a >= *p.nAcqDev * p.nCodes) return;
     const long long total = (long long)p.nPeriods * p.N;
     const short2* x = prod + (size_t)a * total + (size_t)c * p.N;
     uint64_t dphi[kFineBins];
@@ -151,6 +153,8 @@ fine_sum_kernel(FineParams p)
 __global__ void fine_select_kernel(FineParams p)
 {
     const int a = blockIdx.x;
+    const int nAcq = *p.nAcqDev;
+    if (a >= nAcq) return;
     const int half = p.nPeriods / 2;
     const double NH[20] = {1, 1, 1, 1, 1, -1, 1, 1, -1, -1, 1, -1, 1, -1, 1, 1, -1, -1, -1, 1};   // :127
     for (int j = threadIdx.x; j < p.nFine; j += blockDim.x) {
@@ -170,7 +174,7 @@ __global__ void fine_select_kernel(FineParams p)
                 if (pw > maxPower) maxPower = pw;
             }
         } else if (p.combine == 5) {
-            const double* s2 = p.sums + ((size_t)(a + p.nAcq) * p.nFine + j) * p.nPeriods * 2;
+            const double* s2 = p.sums + ((size_t)(a + nAcq) * p.nFine + j) * p.nPeriods * 2;
             double t1 = 0, t2 = 0;
             for (int q = 0; q < p.nPeriods; ++q) { t1 += hypot(s[2 * q], s[2 * q + 1]); t2 += hypot(s2[2 * q], s2[2 * q + 1]); }
             maxPower = t1 + t2;
@@ -252,6 +256,51 @@ cudaError_t launch_peak_select(const float* partMax, const int* partIdx, int nPr
                                PeakOut* out, cudaStream_t s)
 {
     peak_select_kernel<<<nPrnSlots, 32, 0, s>>>(partMax, partIdx, nBins, parts, out);
+    return cudaGetLastError();
+}
+
+// one block: metric and threshold per slot (acquisition.m:200, 206), the list of acquired slots in list order, and per
+// fine-search entry its chip row, code phase and the phase increments of the fine bins (:221-227)
+__global__ void __launch_bounds__(128)
+fine_setup_kernel(FineSetup p)
+{
+    __shared__ int s_n;
+    if (threadIdx.x == 0) {
+        int n = 0;
+        const double sp = *p.sigPower;
+        for (int s = 0; s < p.nSv; ++s) {
+            const double m = __ddiv_rn(__ddiv_rn(p.peaks[s].peak, sp), (double)p.nonCoh);     // :200
+            p.metric[s] = m;
+            if (m > p.threshold) p.acqSlot[n++] = s;                                          // :206
+        }
+        *p.nAcq = n;
+        s_n = n;
+    }
+    __syncthreads();
+    const int nAcq = s_n;
+    for (int e = threadIdx.x; e < nAcq * p.nCodes; e += blockDim.x) {
+        const int a = e % nAcq, comp = p.nCodes == 2 ? e / nAcq : p.pilotComp;
+        const int s = p.acqSlot[a];
+        p.chipRow[e] = p.slotChipRow[s] + comp;
+        p.codePhase[e] = p.peaks[s].codePhase;
+        if (e < nAcq) p.svId[a] = p.slotSv[s];
+    }
+    for (int i = threadIdx.x; i < nAcq * p.nCodes * p.nFine; i += blockDim.x) {
+        const int e = i / p.nFine, j = i - e * p.nFine;
+        const int s = p.acqSlot[e % nAcq];
+        // coarseFreqBin(bin) + acqSearchStep/2 - fineSearchStep*(j-1), every operation rounded as the host does (:169, :227)
+        const double coarse = __dsub_rn(p.slotFreq0[s], __dmul_rn(p.step, (double)(p.peaks[s].bin - 1)));
+        const double f = __dsub_rn(__dadd_rn(coarse, __ddiv_rn(p.step, 2.0)), __dmul_rn(p.fineStep, (double)j));
+        p.dphi[i] = turns_to_fix(__dmul_rn(f, p.ts));
+    }
+    if (p.slotSecondary)
+        for (int i = threadIdx.x; i < nAcq * p.nPeriods; i += blockDim.x)
+            p.secondary[i] = p.slotSecondary[(size_t)p.acqSlot[i / p.nPeriods] * p.nPeriods + i % p.nPeriods];
+}
+
+cudaError_t launch_fine_setup(const FineSetup& p, cudaStream_t s)
+{
+    fine_setup_kernel<<<1, 128, 0, s>>>(p);
     return cudaGetLastError();
 }
 

@@ -110,7 +110,9 @@ struct gc_handle {
     // acquisition
     DevBuf<float2> twGen, X, T1, T2, T3, Cc, W;
     DevBuf<uint64_t> dphi, fdphi;
-    DevBuf<int8_t> codeTab, chips, fineSecondary;
+    DevBuf<int8_t> codeTab, chips, fineSecondary, slotSecondary;
+    DevBuf<double> slotFreq0, metricDev;
+    DevBuf<int> slotChipRow, slotSv, nAcqDev, acqSlot, fineChipRow;
     DevBuf<int> prnList, slotGroup, partIdx, fineCodePhase, fineBest, fineSv;
     DevBuf<float> partMax;
     DevBuf<PeakOut> peaks;
@@ -238,6 +240,17 @@ int build_replicas(gc_handle* h)
     }
     GC_CUDA(h, upload(h->codeTab, tab, h->stream));
     GC_CUDA(h, upload(h->chipIdx, idx40, h->stream));
+    {   // chips of every SV / component for the fine search: row = result index * 2 + component (GLONASS: row 0)
+        const int tabLen = codeLen * h->sub;
+        const int nSvRows = h->glo ? 1 : h->resultLen;
+        std::vector<int8_t> all((size_t)nSvRows * 2 * tabLen, 0);
+        for (int i = 0; i < nSvRows; ++i) {
+            const int sv = h->glo ? 0 : i + 1;
+            if (!h->glo && !sv_has_code(h, sv)) continue;
+            for (int comp = 0; comp < (h->nRep == 2 ? 2 : 1); ++comp) sv_chips(h, sv, all.data() + ((size_t)i * 2 + comp) * tabLen, comp);
+        }
+        GC_CUDA(h, upload(h->chips, all, h->stream));
+    }
     GC_CUDA(h, h->Cc.reserve((size_t)nRep * L));
     if (h->fused) {
         FwdColsParams fp{};
@@ -441,7 +454,8 @@ void gc_destroy(gc_handle* h)
     h->recOwned.release();
     h->twGen.release(); h->X.release(); h->T1.release(); h->T2.release(); h->T3.release();
     h->chipIdx.release(); h->twFused.release();
-    h->Cc.release(); h->W.release(); h->dphi.release(); h->fdphi.release(); h->codeTab.release(); h->chips.release(); h->fineSecondary.release();
+    h->Cc.release(); h->W.release(); h->dphi.release(); h->fdphi.release(); h->codeTab.release(); h->chips.release(); h->fineSecondary.release(); h->slotSecondary.release();
+    h->slotFreq0.release(); h->metricDev.release(); h->slotChipRow.release(); h->slotSv.release(); h->nAcqDev.release(); h->acqSlot.release(); h->fineChipRow.release();
     h->prnList.release(); h->slotGroup.release(); h->partIdx.release(); h->fineCodePhase.release(); h->fineBest.release(); h->fineSv.release(); h->partMax.release();
     h->peaks.release(); h->sigPower.release(); h->fineSums.release(); h->fineResult.release(); h->fineProd.release();
     h->vcSlot.release(); h->vbRows.release(); h->vbPeak.release(); h->vbIdx.release(); h->vbSeg.release();
@@ -1062,16 +1076,86 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
     }
     GC_CUDA(h, launch_peak_select(h->partMax.p, h->partIdx.p, nSv, nBins, h->parts, h->peaks.p, st)); ++launches;
     cudaEventRecord(h->ev[1], st);
+    // threshold (:200-206) and fine search (:211-253) follow on the device without a host round trip: fine_setup_kernel
+    // decides which list slots are above the threshold and prepares their fine-search entries, the fine kernels are
+    // launched for the worst case (every slot acquired) and idle blocks leave at once
+    const int nCodes = h->fineTwoCodes ? 2 : 1;
+    const int nPeriods = h->nFinePeriods;                                            // :146-148 (B3I :131-133)
+    const int tabLen = codeLen * h->sub;                                             // chips, or BOC sub-chips, per code period
+    int fa = -1, fb = -1;
+    if (!h->noFine) {
+        std::vector<double> slotFreq0(nSv);
+        std::vector<int> slotChipRow(nSv), slotSv(nSv);
+        std::vector<int8_t> slotSec;
+        if (h->fineCombine == 4) slotSec.resize((size_t)nSv * nPeriods);
+        for (int s = 0; s < nSv; ++s) {
+            const int sv = svList[order[s]];
+            slotFreq0[s] = (c.IF + sv_freq_offset(h, sv)) + c.acq_search_band;       // coarseFreqBin(1), :169 (GLO :181-182)
+            slotChipRow[s] = h->glo ? 0 : sv_result_index(h, sv) * 2;
+            slotSv[s] = sv;
+            if (h->fineCombine == 4) {
+                static const int8_t NH20[20] = {1, 1, 1, 1, 1, -1, 1, 1, -1, -1, 1, -1, 1, -1, 1, 1, -1, -1, -1, 1};   // GPS_L5C acquisition.m:134
+                for (int q = 0; q < nPeriods; ++q)
+                    slotSec[(size_t)s * nPeriods + q] = (c.signal == GC_SIG_GAL_E5A) ? h->hostCode[2][sv - 1][q]   // generateE5aQ_secondary
+                                                                                       : NH20[q % 20];
+            }
+        }
+        GC_CUDA(h, upload(h->slotFreq0, slotFreq0, st));
+        GC_CUDA(h, upload(h->slotChipRow, slotChipRow, st));
+        GC_CUDA(h, upload(h->slotSv, slotSv, st));
+        if (!slotSec.empty()) GC_CUDA(h, upload(h->slotSecondary, slotSec, st));
+        const int maxEnt = nSv * nCodes;
+        GC_CUDA(h, h->metricDev.reserve(nSv));
+        GC_CUDA(h, h->nAcqDev.reserve(1));
+        GC_CUDA(h, h->acqSlot.reserve(nSv));
+        GC_CUDA(h, h->fineChipRow.reserve(maxEnt));
+        GC_CUDA(h, h->fineCodePhase.reserve(maxEnt));
+        GC_CUDA(h, h->fdphi.reserve((size_t)maxEnt * h->nFine));
+        GC_CUDA(h, h->fineSv.reserve(nSv));
+        GC_CUDA(h, h->fineSecondary.reserve((size_t)nSv * nPeriods));
+        GC_CUDA(h, h->fineProd.reserve((size_t)maxEnt * nPeriods * N));
+        GC_CUDA(h, h->fineSums.reserve((size_t)maxEnt * h->nFine * nPeriods * 2));
+        GC_CUDA(h, h->fineResult.reserve((size_t)nSv * h->nFine));
+        GC_CUDA(h, h->fineBest.reserve(nSv));
+        FineSetup fs{};
+        fs.peaks = h->peaks.p; fs.sigPower = h->sigPower.p; fs.nSv = nSv; fs.nonCoh = nonCoh; fs.nFine = h->nFine; fs.nCodes = nCodes;
+        fs.nPeriods = nPeriods; fs.pilotComp = h->nRep - 1; fs.threshold = c.acq_threshold; fs.step = c.acq_search_step;
+        fs.fineStep = h->fineStep; fs.ts = h->ts; fs.slotFreq0 = h->slotFreq0.p; fs.slotChipRow = h->slotChipRow.p; fs.slotSv = h->slotSv.p;
+        fs.slotSecondary = slotSec.empty() ? nullptr : h->slotSecondary.p;
+        fs.metric = h->metricDev.p; fs.nAcq = h->nAcqDev.p; fs.acqSlot = h->acqSlot.p; fs.chipRow = h->fineChipRow.p;
+        fs.codePhase = h->fineCodePhase.p; fs.dphi = h->fdphi.p; fs.svId = h->fineSv.p; fs.secondary = h->fineSecondary.p;
+        fa = mark();
+        GC_CUDA(h, launch_fine_setup(fs, st)); ++launches;
+        FineParams fp{};
+        fp.rec = h->rec; fp.winStart = winStart; fp.N = N; fp.nPeriods = nPeriods; fp.nFine = h->nFine; fp.codeLen = tabLen;
+        fp.swapIQ = h->glo ? 1 : 0; fp.combine = h->fineCombine; fp.chipIdx = h->chipIdx.p; fp.svId = h->fineSv.p;
+        fp.chips = h->chips.p; fp.chipRow = h->fineChipRow.p; fp.codePhase = h->fineCodePhase.p; fp.dphi = h->fdphi.p; fp.prod = h->fineProd.p;
+        fp.sums = h->fineSums.p; fp.best = h->fineBest.p; fp.fineResult = h->fineResult.p;
+        fp.nAcqDev = h->nAcqDev.p; fp.nCodes = nCodes; fp.secondary = h->fineSecondary.p;
+        GC_CUDA(h, launch_fine(fp, maxEnt, nSv, st)); launches += 3;
+        fb = mark();
+    }
     std::vector<PeakOut> peaks(nSv);
+    std::vector<int> best(nSv, 0);
     double sigPower = 0;
+    int nAcqDevice = -1;
     GC_CUDA(h, cudaMemcpyAsync(peaks.data(), h->peaks.p, nSv * sizeof(PeakOut), cudaMemcpyDeviceToHost, st));
     GC_CUDA(h, cudaMemcpyAsync(&sigPower, h->sigPower.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (!h->noFine) {
+        GC_CUDA(h, cudaMemcpyAsync(best.data(), h->fineBest.p, nSv * sizeof(int), cudaMemcpyDeviceToHost, st));
+        GC_CUDA(h, cudaMemcpyAsync(&nAcqDevice, h->nAcqDev.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    float fineMs = 0;
+    {
+        const int fa_ = fa, fb_ = fb;
+        cudaStreamSynchronize(st);
+        if (fa_ >= 0) cudaEventElapsedTime(&fineMs, h->ev[fa_], h->ev[fb_]);
+    }
     drain_events();
     float coarseMs = 0;
     cudaEventElapsedTime(&coarseMs, h->ev[e0], h->ev[1]);
 
-    // threshold (:200-206) and fine search for the SVs above it
-    std::vector<int> acq;   // device list slots
+    std::vector<int> acq;   // list slots above the threshold, in list order (what fine_setup_kernel found too)
     for (int s = 0; s < nSv; ++s) {
         const int ri = sv_result_index(h, svList[order[s]]);
         peakMetric[ri] = peaks[s].peak / sigPower / nonCoh;                          // :200
@@ -1081,72 +1165,15 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
     }
     const int nAcq = (int)acq.size();
     h->stats.n_acquired = nAcq;
-    float fineMs = 0;
-    if (nAcq > 0 && h->noFine) {                                                     // GAL_E5b acquisition.m:203-205
-        for (int a = 0; a < nAcq; ++a) {
-            const int ri = sv_result_index(h, svList[order[acq[a]]]);
-            carrFreq[ri] = coarseFreqOf[acq[a]][peaks[acq[a]].bin - 1];
-            codePhase[ri] = peaks[acq[a]].codePhase;
-        }
-    } else if (nAcq > 0) {
-        const int nPeriods = h->nFinePeriods;                                        // :146-148 (B3I :131-133)
-        // fine-search entries: one per acquired SV; B2a wipes off the data AND the pilot code (two entries per SV,
-        // the pilot ones in the second half: BDS/B2a/include/acquisition.m:208-228)
-        const int nEnt = nAcq * (h->fineTwoCodes ? 2 : 1);
-        std::vector<int> svIds(nAcq);
-        for (int a = 0; a < nAcq; ++a) svIds[a] = svList[order[acq[a]]];
-        GC_CUDA(h, upload(h->fineSv, svIds, st));
-        const int tabLen = codeLen * h->sub;                 // chips, or BOC sub-chips, per code period
-        std::vector<int8_t> chips((size_t)nEnt * tabLen);
-        std::vector<int8_t> secondary;                       // [nAcq][nPeriods] pilot secondary code (combine 4)
-        std::vector<int> cps(nEnt);
-        std::vector<uint64_t> fd((size_t)nEnt * h->nFine);
-        std::vector<double> fineFreq((size_t)nAcq * h->nFine);
-        if (h->fineCombine == 4) secondary.resize((size_t)nAcq * nPeriods);
-        for (int e = 0; e < nEnt; ++e) {
-            const int a = e % nAcq, comp = h->fineTwoCodes ? e / nAcq : h->nRep - 1;
-            const int s = acq[a];
-            sv_chips(h, svList[order[s]], chips.data() + (size_t)e * tabLen, comp);   // :213 (pilot code where there is one, GAL_E1C :209)
-            cps[e] = peaks[s].codePhase;
-            for (int j = 0; j < h->nFine; ++j) {
-                const double f = coarseFreqOf[s][peaks[s].bin - 1] + c.acq_search_step / 2 - h->fineStep * j;   // :227
-                if (e < nAcq) fineFreq[(size_t)a * h->nFine + j] = f;
-                fd[(size_t)e * h->nFine + j] = turns_to_fix(f * h->ts);
-            }
-            if (h->fineCombine == 4 && e < nAcq) {
-                static const int8_t NH20[20] = {1, 1, 1, 1, 1, -1, 1, 1, -1, -1, 1, -1, 1, -1, 1, 1, -1, -1, -1, 1};   // GPS_L5C acquisition.m:134
-                for (int q = 0; q < nPeriods; ++q)
-                    secondary[(size_t)a * nPeriods + q] = (c.signal == GC_SIG_GAL_E5A) ? h->hostCode[2][svList[order[s]] - 1][q]   // generateE5aQ_secondary
-                                                                                         : NH20[q % 20];
-            }
-        }
-        GC_CUDA(h, upload(h->chips, chips, st));
-        GC_CUDA(h, upload(h->fineCodePhase, cps, st));
-        GC_CUDA(h, upload(h->fdphi, fd, st));
-        if (!secondary.empty()) GC_CUDA(h, upload(h->fineSecondary, secondary, st));
-        GC_CUDA(h, h->fineProd.reserve((size_t)nEnt * nPeriods * N));
-        GC_CUDA(h, h->fineSums.reserve((size_t)nEnt * h->nFine * nPeriods * 2));
-        GC_CUDA(h, h->fineResult.reserve((size_t)nAcq * h->nFine));
-        GC_CUDA(h, h->fineBest.reserve(nAcq));
-        FineParams fp{};
-        fp.rec = h->rec; fp.winStart = winStart; fp.N = N; fp.nPeriods = nPeriods; fp.nFine = h->nFine; fp.codeLen = tabLen;
-        fp.swapIQ = h->glo ? 1 : 0; fp.combine = h->fineCombine; fp.chipIdx = h->chipIdx.p; fp.svId = h->fineSv.p;
-        fp.chips = h->chips.p; fp.codePhase = h->fineCodePhase.p; fp.dphi = h->fdphi.p; fp.prod = h->fineProd.p;
-        fp.sums = h->fineSums.p; fp.best = h->fineBest.p; fp.fineResult = h->fineResult.p;
-        fp.nAcq = nAcq; fp.secondary = h->fineSecondary.p;
-        const int fa = mark();
-        GC_CUDA(h, launch_fine(fp, nEnt, nAcq, st)); launches += 3;
-        std::vector<int> best(nAcq);
-        GC_CUDA(h, cudaMemcpyAsync(best.data(), h->fineBest.p, nAcq * sizeof(int), cudaMemcpyDeviceToHost, st));
-        const int fb = mark();
-        GC_CUDA(h, cudaStreamSynchronize(st));
-        cudaEventElapsedTime(&fineMs, h->ev[fa], h->ev[fb]);
-        for (int a = 0; a < nAcq; ++a) {
-            const int ri = sv_result_index(h, svList[order[acq[a]]]);
-            carrFreq[ri] = fineFreq[(size_t)a * h->nFine + best[a]];                 // :254
-            codePhase[ri] = peaks[acq[a]].codePhase;                                 // :256
-            if (carrFreq[ri] == 0) carrFreq[ri] = 1;                                 // :258
-        }
+    if (!h->noFine && nAcqDevice != nAcq) return fail(h, GC_ERR_CUDA, "gc_acquire: device and host disagree on the acquired set");
+    for (int a = 0; a < nAcq; ++a) {
+        const int s = acq[a];
+        const int ri = sv_result_index(h, svList[order[s]]);
+        const double coarse = coarseFreqOf[s][peaks[s].bin - 1];
+        carrFreq[ri] = h->noFine ? coarse                                            // GAL_E5b acquisition.m:203-205
+                                 : coarse + c.acq_search_step / 2 - h->fineStep * best[a];   // :227, :254
+        codePhase[ri] = peaks[s].codePhase;                                          // :256
+        if (!h->noFine && carrFreq[ri] == 0) carrFreq[ri] = 1;                       // :258
     }
     h->stats.acq_fwd_ms = fwdMs;
     h->stats.acq_corr_ms = coarseMs - fwdMs;
