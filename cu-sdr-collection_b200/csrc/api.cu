@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <string>
 #include <vector>
@@ -419,14 +420,27 @@ int gc_create(gc_handle** out, const gc_config* cfg)
                 GC_CUDA(h, upload(h->twFused, tw, h->stream));
             }
         } else {
+            // fewest passes over the radices that have a kernel: register codelets (8 .. 50) and small primes / 4
             h->plan.L = h->L; h->plan.nf = 0;
-            int m = h->L;
-            while (m % 4 == 0) { h->plan.fac[h->plan.nf++] = 4; m /= 4; }
-            for (int f = 2; m > 1; ++f)
-                while (m % f == 0) {
-                    if (f > 64 || h->plan.nf >= 32) return fail(h, GC_ERR_UNSUPPORTED, "FFT length 2*samplesPerCode has a prime factor > 64");
-                    h->plan.fac[h->plan.nf++] = f; m /= f;
+            {
+                static const int kRadix[] = {50, 45, 40, 33, 32, 30, 25, 16, 8, 31, 13, 11, 7, 5, 4, 3, 2};
+                std::vector<int> best, cur;
+                std::function<void(int)> rec = [&](int m) {
+                    if (m == 1) { if (best.empty() || cur.size() < best.size()) best = cur; return; }
+                    if (!best.empty() && cur.size() + 1 >= best.size()) return;
+                    for (int r : kRadix)
+                        if (m % r == 0) { cur.push_back(r); rec(m / r); cur.pop_back(); }
+                };
+                if (!getenv("GC_GENERIC_SMALL_RADIX")) rec(h->L);
+                if (best.empty()) {                              // other primes up to 64 (run-time radix kernel) / the original
+                    int m = h->L;                                // pass structure: radix 4, then primes
+                    while (m % 4 == 0) { best.push_back(4); m /= 4; }
+                    for (int f = 2; m > 1 && f <= 64; ++f) while (m % f == 0) { best.push_back(f); m /= f; }
+                    if (m > 1) best.clear();
                 }
+                if (best.empty() || best.size() > 32) return fail(h, GC_ERR_UNSUPPORTED, "FFT length 2*samplesPerCode has a prime factor > 64");
+                for (int r : best) h->plan.fac[h->plan.nf++] = r;
+            }
             GC_CUDA(h, upload(h->twGen, tw_table_2d(2, h->L, h->L), h->stream));
             h->plan.tw = h->twGen.p + h->L;   // row 1 of the [2][L] table = w_L^t
             h->parts = 8;
