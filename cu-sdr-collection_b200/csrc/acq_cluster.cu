@@ -214,7 +214,9 @@ template <class P>
 struct Launch {
     static cudaError_t corr(const CorrParams& p, cudaStream_t s)
     {
-        if constexpr (Geo<P, 2>::kSmem + 1024 <= kSmemMax) {
+        if constexpr (P::kBig) {
+            return cudaErrorNotSupported;                     // two-level columns: only the two-kernel path
+        } else if constexpr (Geo<P, 2>::kSmem + 1024 <= kSmemMax) {
             return launch_t<P, 2>(p, s);
         } else {
             static_assert(Geo<P, 4>::kSmem + 1024 <= kSmemMax, "transform does not fit a 4-CTA cluster");

@@ -221,15 +221,164 @@ inv_cols_kernel(InvColsParams p)
     }
 }
 
+// ------------------------------------------------------------------ column passes for long columns (C = C1 x C2)
+// Cooley-Tukey inside the pass: input index n1 = C2*a + b, output index k1 = ka + C1*kb.
+//   phase 1: thread (b, col): C1-point DFT over a, times w_C^(ka*b), into shared memory Y[ka][b][col]
+//   phase 2: thread (ka, col): C2-point DFT over b -> outputs k1 = ka + C1*kb
+// A CTA handles TC adjacent row positions (columns), so global accesses are TC*8-byte runs.
+template <class P> struct BigGeo {
+    static constexpr int C1 = P::C1, C2 = P::C2;
+    static constexpr int TC = (C1 > C2 ? C1 : C2) * 32 <= 1024 ? 32 : 16;     // columns per CTA
+    static constexpr int NT = (C1 > C2 ? C1 : C2) * TC;                        // threads: max of the two phases
+    static constexpr size_t kSmem = sizeof(float2) * P::C * TC;
+};
+
+// w_C^(+-ka*b): computed once per thread (one sincospif)
+__device__ __forceinline__ float2 unit_root(int num, int den, bool inverse)
+{
+    float s, c;
+    sincospif(2.0f * (float)num / (float)den, &s, &c);
+    return make_float2(c, inverse ? s : -s);
+}
+
+template <class P, int MODE>
+__global__ void __launch_bounds__(BigGeo<P>::NT)
+fwd_cols_big_kernel(FwdColsParams p)
+{
+    using G = BigGeo<P>;
+    constexpr int C = P::C, C1 = P::C1, C2 = P::C2, R = P::R, L = P::L, TC = G::TC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* Y = reinterpret_cast<float2*>(smem_raw);            // [ka][b][col]
+    const int row = blockIdx.y;
+    const int col = threadIdx.x % TC, q = threadIdx.x / TC;
+    const int pp = blockIdx.x * TC + col;
+    const bool in = pp < R;
+    const int base = in ? P::row_index(pp) : 0;
+    if (q < C2 && in) {                                         // phase 1: q = b
+        float2 x[C1];
+        if (MODE == 0) {
+            const int k = row / p.nonCoh, m = row % p.nonCoh;
+            const uint64_t dphi = p.dphi[k];
+            const int8_t* src = p.rec + 2 * ((size_t)p.winStart + (size_t)m * p.N);
+#pragma unroll
+            for (int a = 0; a < C1; ++a) {
+                const int n = P::index(C2 * a + q, base);
+                const char2 sv = *reinterpret_cast<const char2*>(src + 2 * (size_t)n);
+                float sn, cs;
+                fix_sincos(dphi * (uint64_t)n, &sn, &cs);
+                const float I = p.swapIQ ? (float)sv.y : (float)sv.x, Q = p.swapIQ ? (float)sv.x : (float)sv.y;
+                x[a] = make_float2(fmaf(cs, I, sn * Q), fmaf(cs, Q, -sn * I));
+            }
+        } else {
+            const int8_t* code = p.codeTab + (size_t)row * p.N;
+#pragma unroll
+            for (int a = 0; a < C1; ++a) {
+                const int n = P::index(C2 * a + q, base);
+                x[a] = make_float2(n < p.N ? (float)code[n] : 0.f, 0.f);
+            }
+        }
+        codelet::dft<C1, false>(x, [&](int ka, float re, float im) {
+            Y[(ka * C2 + q) * TC + col] = cmul(make_float2(re, im), unit_root(ka * q, C, false));
+        });
+    }
+    __syncthreads();
+    if (q < C1 && in) {                                         // phase 2: q = ka
+        float2 y[C2];
+#pragma unroll
+        for (int b = 0; b < C2; ++b) y[b] = Y[(q * C2 + b) * TC + col];
+        float2* dst = p.out + (size_t)row * L + pp;
+        const float2* tw = p.tw + pp;
+        codelet::dft<C2, false>(y, [&](int kb, float re, float im) {
+            const int k1 = q + C1 * kb;
+            dst[(size_t)k1 * R] = cmul(make_float2(re, im), __ldg(tw + (size_t)k1 * R));      // w_L^(j1*m)
+        });
+    }
+}
+
+// inverse column pass + |.| + sum over blocks/replicas + max: grid (ceil(R/TC), nBins, nPrnChunk)
+template <class P>
+__global__ void __launch_bounds__(BigGeo<P>::NT)
+inv_cols_big_kernel(InvColsParams p)
+{
+    using G = BigGeo<P>;
+    constexpr int C = P::C, C1 = P::C1, C2 = P::C2, R = P::R, L = P::L, TC = G::TC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* Y = reinterpret_cast<float2*>(smem_raw);            // [ta][beta][col]
+    const int col = threadIdx.x % TC, q = threadIdx.x / TC;
+    const int pp = blockIdx.x * TC + col;
+    const bool in = pp < R;
+    const int k = blockIdx.y, pi = blockIdx.z;
+    float acc[C2];
+#pragma unroll
+    for (int i = 0; i < C2; ++i) acc[i] = 0.f;
+    const float2* base = p.W + ((size_t)(pi * p.nBins + k) * p.nonCoh) * L + pp;
+    for (int m = 0; m < p.nonCoh; ++m) {
+        if (q < C2 && in) {                                     // phase 1: q = beta, input k1 = C2*alpha + beta
+            float2 x[C1];
+#pragma unroll
+            for (int a = 0; a < C1; ++a) x[a] = __ldcs(base + (size_t)m * L + (size_t)(C2 * a + q) * R);
+            codelet::dft<C1, true>(x, [&](int ta, float re, float im) {
+                Y[(ta * C2 + q) * TC + col] = cmul(make_float2(re, im), unit_root(ta * q, C, true));
+            });
+        }
+        __syncthreads();
+        if (q < C1 && in) {                                     // phase 2: q = ta, outputs t1 = ta + C1*tb
+            float2 y[C2];
+#pragma unroll
+            for (int b = 0; b < C2; ++b) y[b] = Y[(q * C2 + b) * TC + col];
+            codelet::dft<C2, true>(y, [&](int tb, float re, float im) { acc[tb] += cabs_fast(re, im); });
+        }
+        __syncthreads();
+    }
+    float best = -1.f;
+    int bidx = 0x7fffffff;
+    if (q < C1 && in) {
+        const int rest = P::row_index(pp);
+#pragma unroll
+        for (int tb = 0; tb < C2; ++tb) {
+            const int idx = P::index(q + C1 * tb, rest);
+            if (acc[tb] > best || (acc[tb] == best && idx < bidx)) { best = acc[tb]; bidx = idx; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_down_sync(0xffffffffu, best, o);
+        const int oi = __shfl_down_sync(0xffffffffu, bidx, o);
+        if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+    __shared__ float s_b[32];
+    __shared__ int s_i[32];
+    if ((threadIdx.x & 31) == 0) { s_b[threadIdx.x >> 5] = best; s_i[threadIdx.x >> 5] = bidx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            if (s_b[w] > best || (s_b[w] == best && s_i[w] < bidx)) { best = s_b[w]; bidx = s_i[w]; }
+        const size_t o = ((size_t)(p.prnSlot0 + pi) * p.nBins + k) * gridDim.x + blockIdx.x;
+        p.partMax[o] = best;
+        p.partIdx[o] = bidx;
+    }
+}
+
 // ------------------------------------------------------------------ host side, per plan
 template <class P>
 struct Launch {
     static cudaError_t fwd_cols(const FwdColsParams& p, int nRows, bool codeMode, cudaStream_t s)
     {
-        dim3 grid((P::R + 127) / 128, nRows);
-        if (codeMode) fwd_cols_kernel<P, 1><<<grid, 128, 0, s>>>(p);
-        else fwd_cols_kernel<P, 0><<<grid, 128, 0, s>>>(p);
-        return cudaGetLastError();
+        if constexpr (P::kBig) {
+            using G = BigGeo<P>;
+            dim3 grid((P::R + G::TC - 1) / G::TC, nRows);
+            cudaError_t e = cudaFuncSetAttribute(codeMode ? fwd_cols_big_kernel<P, 1> : fwd_cols_big_kernel<P, 0>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::kSmem);
+            if (e != cudaSuccess) return e;
+            if (codeMode) fwd_cols_big_kernel<P, 1><<<grid, G::NT, G::kSmem, s>>>(p);
+            else fwd_cols_big_kernel<P, 0><<<grid, G::NT, G::kSmem, s>>>(p);
+            return cudaGetLastError();
+        } else {
+            dim3 grid((P::R + 127) / 128, nRows);
+            if (codeMode) fwd_cols_kernel<P, 1><<<grid, 128, 0, s>>>(p);
+            else fwd_cols_kernel<P, 0><<<grid, 128, 0, s>>>(p);
+            return cudaGetLastError();
+        }
     }
     static cudaError_t fwd_rows(const RowsParams& p, cudaStream_t s)
     {
@@ -259,9 +408,18 @@ struct Launch {
     }
     static cudaError_t inv_cols(const InvColsParams& p, cudaStream_t s)
     {
-        dim3 grid((P::R + 127) / 128, p.nBins, p.nPrnChunk);
-        inv_cols_kernel<P><<<grid, 128, 0, s>>>(p);
-        return cudaGetLastError();
+        if constexpr (P::kBig) {
+            using G = BigGeo<P>;
+            dim3 grid((P::R + G::TC - 1) / G::TC, p.nBins, p.nPrnChunk);
+            cudaError_t e = cudaFuncSetAttribute(inv_cols_big_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::kSmem);
+            if (e != cudaSuccess) return e;
+            inv_cols_big_kernel<P><<<grid, G::NT, G::kSmem, s>>>(p);
+            return cudaGetLastError();
+        } else {
+            dim3 grid((P::R + 127) / 128, p.nBins, p.nPrnChunk);
+            inv_cols_kernel<P><<<grid, 128, 0, s>>>(p);
+            return cudaGetLastError();
+        }
     }
 };
 
@@ -269,7 +427,8 @@ template <class P>
 void fill_info(FusedPlanInfo* o)
 {
     o->L = P::L; o->C = P::C; o->RA = P::RA; o->RB = P::RB; o->R = P::R; o->pfa = P::kPfa ? 1 : 0;
-    o->parts = (P::R + 127) / 128;
+    if constexpr (P::kBig) o->parts = (P::R + BigGeo<P>::TC - 1) / BigGeo<P>::TC;
+    else o->parts = (P::R + 127) / 128;
 }
 
 }  // namespace
@@ -282,6 +441,8 @@ bool fused_plan_info(int L, FusedPlanInfo* o)
         case P24000::L: fill_info<P24000>(o); return true;
         case P32000::L: fill_info<P32000>(o); return true;
         case P40000::L: fill_info<P40000>(o); return true;
+        case P160000::L: fill_info<P160000>(o); return true;
+        case P144000::L: fill_info<P144000>(o); return true;
         default: return false;
     }
 }

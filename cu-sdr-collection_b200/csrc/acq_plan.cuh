@@ -8,9 +8,14 @@ namespace gc {
 
 constexpr int gcd_c(int a, int b) { return b == 0 ? a : gcd_c(b, a % b); }
 
-template <int C_, int RA_, int RB_>
+// C1 > 0: the column length C = C1 x C2 is too long for one register codelet and is done in two levels through shared
+// memory (Cooley-Tukey inside the column pass: Galileo E1's 160000 = (8 x 25) x 800 and 144000 = (20 x 9) x 800).
+template <int C_, int RA_, int RB_, int C1_ = 0>
 struct Plan {
     static constexpr int C = C_, RA = RA_, RB = RB_;
+    static constexpr int C1 = C1_, C2 = C1_ ? C_ / C1_ : 0;
+    static constexpr bool kBig = C1_ != 0;
+    static_assert(C1_ == 0 || C_ % C1_ == 0, "C = C1 x C2");
     static constexpr int R = RA * RB, L = C * R;
     static constexpr bool kPfa = gcd_c(C, R) == 1;        // no twiddle between column and row pass
     static_assert(gcd_c(RA, RB) == 1 && RA == 32 && RB < 32, "row = 32 x RB with RB coprime to 32");
@@ -34,6 +39,8 @@ using P36000 = Plan<45, 32, 25>;   // 18 Msps: the reference default of six sign
 using P24000 = Plan<30, 32, 25>;   // 12 Msps: GLONASS default
 using P32000 = Plan<40, 32, 25>;   // 16 Msps
 using P40000 = Plan<50, 32, 25>;   // 20 Msps
+using P160000 = Plan<200, 32, 25, 8>;    // Galileo E1 (4 ms codes) at 20 Msps: columns 200 = 8 x 25
+using P144000 = Plan<180, 32, 25, 20>;   // Galileo E1 at 18 Msps (reference default): columns 180 = 20 x 9
 
 #define GC_PLAN_DISPATCH(LEN, CALL)                             \
     switch (LEN) {                                              \
@@ -42,6 +49,8 @@ using P40000 = Plan<50, 32, 25>;   // 20 Msps
         case P24000::L: return Launch<P24000>::CALL;            \
         case P32000::L: return Launch<P32000>::CALL;            \
         case P40000::L: return Launch<P40000>::CALL;            \
+        case P160000::L: return Launch<P160000>::CALL;          \
+        case P144000::L: return Launch<P144000>::CALL;          \
         default: return cudaErrorInvalidValue;                  \
     }
 

@@ -1030,6 +1030,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
                 ip.X = h->X.p; ip.Cc = h->Cc.p; ip.W = h->W.p; ip.tw = h->twFused.p;
                 ip.nonCoh = nonCoh; ip.nBins = nBins; ip.prnPerCta = 1; ip.mPerCta = 5;   // 5 warps, 96 registers, 20 warps/SM
                 ip.nRep = h->nRep; ip.repStride = 1;
+                if (nonCoh * h->nRep < 5) { ip.prnPerCta = 5; ip.mPerCta = 1; }       // few transforms per cell (Galileo E1: 2): fill the CTA with SVs
                 if (const char* e = getenv("GC_ROWS_VARIANT")) {   // "PxM" warps per CTA = P PRNs x M blocks
                     int P = 0, M = 0;
                     if (sscanf(e, "%dx%d", &P, &M) == 2 && (P * M == 5 || P * M == 8)) { ip.prnPerCta = P; ip.mPerCta = M; }

@@ -449,17 +449,20 @@ def _e1c_case(fs, nsat, seed, extra, band, ms, nch, cn0=48, **kw):
     return codes, sc, s, so, sv
 
 
-@pytest.mark.parametrize("fs,band", [(4.092e6, 4500.0), (18e6, 4200.0)])
-def test_e1c_acquisition_vs_oracle(fs, band):
+@pytest.mark.parametrize("fs,band,generic", [(4.092e6, 4500.0, 0), (18e6, 4200.0, 0), (18e6, 4200.0, 1), (20e6, 4200.0, 0)])
+def test_e1c_acquisition_vs_oracle(fs, band, generic, monkeypatch):
     """GAL_E1C acquisition (E1B + E1C BOC(1,1) replicas summed, 10 Hz fine search over 25 periods against the
     25-chip secondary code) on caller-supplied memory codes: a small rate and the reference's 18 Msps
-    (FFT length 144000, generic mixed-radix path)."""
+    (FFT length 144000: fused 180 x 32 x 25 plan with two-level columns; GC_FORCE_GENERIC covers the generic passes)."""
+    if generic:
+        monkeypatch.setenv("GC_FORCE_GENERIC", "1")
     codes, sc, s, so, sv = _e1c_case(fs, nsat=2, seed=4, extra=[7], band=band, ms=80, nch=2)
     N = O.samples_per_code(so)
     raw = synth.make_record(sc, N * 42 + 64)
     eng = Engine(s, codes=codes)
     got = eng.acquire(sv, host_iq=raw)
     assert got["carrFreq"].shape == (50,) and eng.stats()["fft_len"] == 2 * N
+    assert eng.stats()["acq_path"] == (0 if generic else 1)      # 32736, 144000 and 160000 all have fused plans
     ref = c_acquisition(raw, s, sv)
     _check_acq(got, ref, sv)
     for sat in sc.sats:                                   # closed loop: injected signals come back on the 10 Hz grid
