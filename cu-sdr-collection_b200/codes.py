@@ -167,6 +167,28 @@ def standin_varb_codes(signal: str, seed: int = 20260101) -> dict:
     return {prn: (t[prn - 1],) for prn in range(1, 33)}
 
 
+def standin_l2c_cl_codes(prns, seed: int = 20260101) -> dict:
+    """Seeded stand-ins for the GPS L2C CL sequences generateCLcode.m returns: 2*767250 entries, return-to-zero with the
+    CL chips in the slots the CM sequence leaves empty (0, chip, 0, chip, ...).  {PRN: (cm, cl)} for the PRNs asked
+    for (1.5 MB each), cm as in ``standin_varb_codes``."""
+    cm = standin_varb_codes("GPS_L2C", seed)
+    out = {}
+    for prn in prns:
+        rng = np.random.default_rng([seed, 0xC1, int(prn)])
+        cl = np.zeros(2 * 767250, dtype=np.int8)
+        cl[1::2] = 1 - 2 * rng.integers(0, 2, size=767250)
+        out[int(prn)] = (cm[int(prn)][0], cl)
+    return out
+
+
+def boc61_from_boc11(pilot_boc11: np.ndarray) -> np.ndarray:
+    """Pilot BOC(6,1) sequence of generatePilotBOC61.m:60-66 ((-1)^ii * Primary(jj), ii = 1..12) from the BOC(1,1)
+    sub-chips ([-c +c] per primary chip, so Primary = the odd entries)."""
+    prim = np.asarray(pilot_boc11, dtype=np.int8)[1::2]
+    sub = np.array([-1, 1] * 6, dtype=np.int8)
+    return (prim[:, None] * sub[None, :]).reshape(-1)
+
+
 def standin_b1c_codes(seed: int = 20260101) -> dict:
     """Seeded stand-ins for the BDS B1C BOC(1,1) sub-chip sequences generateDataBOC11.m / generatePilotBOC11.m return
     (20460 entries, [-c +c] per primary chip): {PRN: (data, pilot)} for PRN 1..63."""

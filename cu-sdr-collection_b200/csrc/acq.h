@@ -97,6 +97,9 @@ cudaError_t launch_varb_mulshift(const float2* X, const float2* Cc, const VarbRo
 cudaError_t launch_varb_rowpeak(const float2* W, int nRows, int L, float* peak, int* idx, cudaStream_t st);
 cudaError_t launch_varb_segmax(const float2* W, int nRows, int L, const int4* seg, float* out, cudaStream_t st);
 cudaError_t launch_varb_pad(const int8_t* tab, int n, int nRows, float2* out, int L, cudaStream_t st);
+// GPS L2C: |sum((x - mean) .* CL segment .* carrier)| for the 75 CL segments (acquisition.m:100-137); codeIdx 1-based [N]
+cudaError_t launch_l2c_clphase(const int8_t* rec, long long start, int N, const int8_t* cl, int segLen, const int* codeIdx,
+                               uint64_t dphi, double* power, cudaStream_t st);
 // variant C (BDS B1C): weighted data + pilot magnitudes per Doppler bin -> (max, first index); one-period fine search
 cudaError_t launch_varc_combine(const float2* W, int nBins, int L, int nRep, float* partMax, int* partIdx, size_t outBase, cudaStream_t st);
 cudaError_t launch_varc_fine(const int8_t* rec, long long winStart, int N, int nRep, const int8_t* tabs, const int* tabSlot,

@@ -149,6 +149,45 @@ varc_fine_kernel(const int8_t* rec, long long winStart, int N, int nRep, const i
     }
 }
 
+// GPS L2C CL code phase (GPS/GPS_L2C/include/acquisition.m:100-137): powerArray(ind) = abs(sum(signal0DC .* CLCodeSample .* sigCarr))
+// for the 75 CM-period segments of the CL sequence; signal0DC = x - mean(x) over one CM period starting at codePhase.
+// sum((x - mu) .* c .* e) = sum(x .* c .* e) - mu * sum(c .* e); one block per segment.
+__global__ void __launch_bounds__(1024)
+l2c_clphase_kernel(const int8_t* rec, long long start, int N, const int8_t* cl, int segLen, const int* codeIdx, uint64_t dphi, double* power)
+{
+    const int ind = blockIdx.x;
+    const char2* x = reinterpret_cast<const char2*>(rec) + start;
+    const int8_t* c = cl + (size_t)ind * segLen;
+    double s[6] = {0, 0, 0, 0, 0, 0};            // sum x.c.e (re, im), sum c.e (re, im), sum x (re, im)
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        const char2 v = x[n];
+        float sn, cs;
+        fix_sincos(dphi * (uint64_t)n, &sn, &cs);
+        const float cv = (float)c[codeIdx[n] - 1];
+        const float re = fmaf(cs, (float)v.x, sn * (float)v.y), im = fmaf(cs, (float)v.y, -sn * (float)v.x);
+        s[0] += (double)(cv * re); s[1] += (double)(cv * im);
+        s[2] += (double)(cv * cs); s[3] -= (double)(cv * sn);
+        s[4] += (double)v.x; s[5] += (double)v.y;
+    }
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int q = 0; q < 6; ++q) s[q] += __shfl_down_sync(0xffffffffu, s[q], o);
+    __shared__ double sh[32][6];
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+        for (int q = 0; q < 6; ++q) sh[threadIdx.x >> 5][q] = s[q];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) s[q] = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w)
+#pragma unroll
+            for (int q = 0; q < 6; ++q) s[q] += sh[w][q];
+        const double mr = s[4] / N, mi = s[5] / N;           // mean(signal0DC), :103
+        power[ind] = hypot(s[0] - (mr * s[2] - mi * s[3]), s[1] - (mr * s[3] + mi * s[2]));
+    }
+}
+
 // replica tables of variant B into complex rows zero padded to L (code_kernel of acq_generic.cu, any table length)
 __global__ void pad_kernel(const int8_t* tab, int n, float2* out, int L)
 {
@@ -189,6 +228,13 @@ cudaError_t launch_varc_fine(const int8_t* rec, long long winStart, int N, int n
 {
     dim3 grid(nFine, nAcq);
     varc_fine_kernel<<<grid, 1024, 0, st>>>(rec, winStart, N, nRep, tabs, tabSlot, codePhase, dphi, nFine, fineResult);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_l2c_clphase(const int8_t* rec, long long start, int N, const int8_t* cl, int segLen, const int* codeIdx,
+                               uint64_t dphi, double* power, cudaStream_t st)
+{
+    l2c_clphase_kernel<<<75, 1024, 0, st>>>(rec, start, N, cl, segLen, codeIdx, dphi, power);
     return cudaGetLastError();
 }
 

@@ -87,7 +87,13 @@ struct gc_handle {
     int fineIdx0 = 0;            // first sample index of the fine-search code map (0: ts*(0:n-1), 1: ts*(1:n))
     bool fineTwoCodes = false;   // B2a: data and pilot codes both wiped off, |.| summed per period
     bool noFine = false;         // E5b: carrFreq = coarse bin frequency (GAL_E5b acquisition.m:203)
-    int pilotMode = 0;           // tracking: 0 no pilot, 1 same-phase pilot (E1C), 2 quadrature pilot (L5C/E5a/E5b/B2a)
+    int pilotMode = 0;           // tracking: 0 no pilot, 1 same-phase pilot (E1C), 2 quadrature pilot (L5C/E5a/E5b/B2a), 3 B1C narrow band,
+                                 // 4 GPS L2C CL pilot, 5 B1C full band (TrackParams::pilot)
+    double wbFactor = -1.0;      // GC_PARAM_B1C_WB_FACTOR (CalcWeighingFactor.m), < 0 = not set
+    std::vector<int32_t> clPhaseIn;          // channel.CLCodePhase for the next gc_track (GPS L2C CL pilot)
+    int32_t clPhaseOut[32] = {0};            // acqResults.CLCodePhase of the last gc_acquire
+    DevBuf<int8_t> clDev; DevBuf<int> clIdx; DevBuf<double> clPower;
+    DevBuf<int8_t> trackP61;
     std::vector<int8_t> hostCode[3][63];   // caller-supplied codes [component: 0 data, 1 pilot, 2 pilot secondary][PRN-1]
                                            // (E1: stored as BOC(1,1) sub-chips)
     int nReplicas = 32;          // replica spectra held (32 GPS PRNs; 1 GLONASS; 63 B3I)
@@ -369,7 +375,7 @@ int gc_create(gc_handle** out, const gc_config* cfg)
         h->L = h->vc.Lc;
         h->nRep = cfg->pilot_acq_flag == 1 ? 2 : 1;
         h->sub = 2;                                                                         // BOC(1,1) sub-chip tables (NB_tracking.m:225-246)
-        h->pilotMode = cfg->pilot_trk_flag == 1 ? 3 : 0;
+        h->pilotMode = cfg->pilot_trk_flag == 1 ? 3 : cfg->pilot_trk_flag == 2 ? 5 : 0;          // NB_tracking.m / WB_tracking.m (B1C postProcessing.m:34-38)
     }
     if (h->varB) {
         const bool b1i = cfg->signal == GC_SIG_BDS_B1I;
@@ -388,6 +394,7 @@ int gc_create(gc_handle** out, const gc_config* cfg)
         h->vb.N1 = h->vb.Lb / nBlocks;
         h->vb.initFreq = cfg->IF + (cfg->acq_search_band / 2) * 1000;                       // B1I :50
         h->L = h->vb.Lb;
+        if (!b1i && cfg->pilot_trk_flag == 1) h->pilotMode = 4;                            // GPS_L2C tracking.m:160-167
     }
     h->ts = 1 / cfg->sampling_freq;
     h->nBins = h->varB ? h->vb.nBins : (int)m_round(cfg->acq_search_band * 2 / cfg->acq_search_step) + 1;
@@ -484,9 +491,26 @@ int gc_set_code(gc_handle* h, int32_t sv, int32_t component, const int8_t* chips
     if (!h) return GC_ERR_ARG;
     if (!h->hostCodes) return fail(h, GC_ERR_ARG, "gc_set_code: this signal generates its own codes");
     const bool secondary = (component == 2);
-    if (secondary && h->cfg.signal != GC_SIG_GAL_E5A) return fail(h, GC_ERR_ARG, "gc_set_code: only GAL E5a takes a pilot secondary code");
+    if (secondary && h->cfg.signal != GC_SIG_GAL_E5A && h->cfg.signal != GC_SIG_BDS_B1C) return fail(h, GC_ERR_ARG, "gc_set_code: only GAL E5a takes a pilot secondary code");
     const bool l2c = h->cfg.signal == GC_SIG_GPS_L2C || h->cfg.signal == GC_SIG_BDS_B1C;   // 2*codeLength entries: the return-to-zero CM code
                                                                                             // (generateCMcode.m) / B1C BOC(1,1) sub-chips (generateDataBOC11.m)
+    const bool isL2C = h->cfg.signal == GC_SIG_GPS_L2C, isB1C = h->cfg.signal == GC_SIG_BDS_B1C;
+    if (isL2C && component == 1) {                            // the return-to-zero CL sequence, 75 CM periods (generateCLcode.m)
+        if (sv < 1 || sv > h->resultLen || !chips || nChips != 150 * h->cfg.code_length)
+            return fail(h, GC_ERR_ARG, "gc_set_code: the GPS L2C CL component takes 2*75*code_length entries");
+        for (int i = 0; i < nChips; ++i)
+            if (chips[i] < -1 || chips[i] > 1) return fail(h, GC_ERR_ARG, "gc_set_code: CL entries must be +-1 or 0");
+        h->hostCode[1][sv - 1].assign(chips, chips + nChips);
+        return GC_OK;
+    }
+    if (isB1C && component == 2) {                            // pilot BOC(6,1) sequence, 12 entries per chip (generatePilotBOC61.m)
+        if (sv < 1 || sv > h->resultLen || !chips || nChips != 12 * h->cfg.code_length)
+            return fail(h, GC_ERR_ARG, "gc_set_code: the BDS B1C BOC(6,1) component takes 12*code_length entries");
+        for (int i = 0; i < nChips; ++i)
+            if (chips[i] != 1 && chips[i] != -1) return fail(h, GC_ERR_ARG, "gc_set_code: chips must be +-1");
+        h->hostCode[2][sv - 1].assign(chips, chips + nChips);
+        return GC_OK;
+    }
     if (sv < 1 || sv > h->resultLen || component < 0 || component > 2 || !chips || (h->varB && component != 0) ||
         nChips != (secondary ? 100 : l2c ? 2 * h->cfg.code_length : h->cfg.code_length))
         return fail(h, GC_ERR_ARG, "gc_set_code: bad argument (PRN in range, component 0/1 with code_length chips, or 2 with 100)");
@@ -707,7 +731,34 @@ static int acquire_varb(gc_handle* h, long long winStart, int32_t nSv, const int
             carrFreq[ri] = h->vb.initFreq - h->vb.freqRes * winBin[s] + h->vb.sign * (h->vb.freqRes / nShifts) * winShift[s];   // B1I :150 ; L2C :95
         }
     }
-    (void)b1i;
+    std::fill(h->clPhaseOut, h->clPhaseOut + 32, 0);
+    if (!b1i && c.pilot_trk_flag == 1 && nAcq > 0) {
+        // L2CL code phase from the detected CM code phase (GPS_L2C acquisition.m:100-137)
+        const int N = h->N, segLen = 2 * c.code_length;
+        std::vector<int> idx(N);
+        const double ts = 1.0 / c.sampling_freq, tc = 1.0 / (c.code_freq_basis * 2);          // :117
+        for (int i = 0; i < N; ++i) idx[i] = (int)std::ceil((ts * (double)i) / tc);          // :124
+        idx[0] = 1;                                                                           // :127
+        idx[N - 1] = (c.acq_coh_t > 0 && c.acq_coh_t <= 10) ? c.code_length : 2 * c.code_length;   // :128-133
+        GC_CUDA(h, upload(h->clIdx, idx, st));
+        GC_CUDA(h, h->clPower.reserve(75));
+        for (int s = 0; s < nSv; ++s) {
+            const int ri = svList[s] - 1;
+            if (carrFreq[ri] == 0) continue;
+            const std::vector<int8_t>& cl = h->hostCode[1][ri];
+            if ((int)cl.size() != 75 * segLen) return fail(h, GC_ERR_ARG, "gc_acquire: pilotTRKflag == 1 needs the CL code of every SV (gc_set_code component 1)");
+            const long long start = winStart + (long long)codePhase[ri] - 1;
+            if (start + N > recSamples) return fail(h, GC_ERR_SHORT_RECORD, "gc_acquire: record too short for the CL phase search");
+            GC_CUDA(h, upload(h->clDev, cl, st));
+            GC_CUDA(h, launch_l2c_clphase(h->rec, start, N, h->clDev.p, segLen, h->clIdx.p, turns_to_fix(carrFreq[ri] * ts), h->clPower.p, st)); ++launches;
+            double pw[75];
+            GC_CUDA(h, cudaMemcpyAsync(pw, h->clPower.p, sizeof(pw), cudaMemcpyDeviceToHost, st));
+            GC_CUDA(h, cudaStreamSynchronize(st));
+            int best = 0;
+            for (int i = 1; i < 75; ++i) if (pw[i] > pw[best]) best = i;                      // [~, CLCodePhase] = max(powerArray), :136
+            h->clPhaseOut[ri] = best + 1;
+        }
+    }
     float total = 0, fwd = 0;
     cudaEventElapsedTime(&total, h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&fwd, h->ev[0], h->ev[2]);
@@ -1241,7 +1292,37 @@ static double cno_vsm(const double* I, const double* Q, int n, double T)
     return 10 * std::log10(num / den);
 }
 
-int gc_track_nfields(const gc_handle* h) { return (h && h->pilotMode >= 2) ? GC_TRACK_NFIELDS_PILOT : GC_TRACK_NFIELDS; }
+int gc_track_nfields(const gc_handle* h)
+{
+    if (!h) return GC_TRACK_NFIELDS;
+    return h->pilotMode >= 4 ? GC_TRACK_NFIELDS_PILOT6 : h->pilotMode >= 2 ? GC_TRACK_NFIELDS_PILOT : GC_TRACK_NFIELDS;
+}
+
+int gc_set_param(gc_handle* h, int32_t key, double value)
+{
+    if (!h) return GC_ERR_ARG;
+    if (key == GC_PARAM_B1C_WB_FACTOR) {
+        if (!(value >= 0.0 && value <= 1.0)) return fail(h, GC_ERR_ARG, "gc_set_param: the B1C weighting factor lies in [0, 1]");
+        h->wbFactor = value;
+        return GC_OK;
+    }
+    return fail(h, GC_ERR_ARG, "gc_set_param: unknown key");
+}
+
+int gc_get_cl_code_phase(const gc_handle* h, int32_t* clCodePhase)
+{
+    if (!h || !clCodePhase || h->cfg.signal != GC_SIG_GPS_L2C) return GC_ERR_ARG;
+    std::copy(h->clPhaseOut, h->clPhaseOut + 32, clCodePhase);
+    return GC_OK;
+}
+
+int gc_set_cl_code_phase(gc_handle* h, int32_t nCh, const int32_t* clCodePhase)
+{
+    if (!h) return GC_ERR_ARG;
+    if (h->cfg.signal != GC_SIG_GPS_L2C || nCh < 1 || !clCodePhase) return fail(h, GC_ERR_ARG, "gc_set_cl_code_phase: GPS L2C only, nCh >= 1");
+    h->clPhaseIn.assign(clCodePhase, clCodePhase + nCh);
+    return GC_OK;
+}
 
 int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq, const double* codePhase,
              const double* codeFreq0, int32_t nEpochs, double* out, double* vsmValue, double* vsmIndex, int32_t* epochsDone)
@@ -1249,11 +1330,13 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
     if (!h) return GC_ERR_ARG;
     const gc_config& c = h->cfg;
     if (!h->rec) return fail(h, GC_ERR_NO_RECORD, "gc_track: no record resident");
-    if (c.signal == GC_SIG_BDS_B1C && c.pilot_trk_flag != 1)
-        return fail(h, GC_ERR_UNSUPPORTED, "gc_track: BDS B1C tracking is implemented for pilotTRKflag == 1 (NB_tracking.m); WB_tracking.m is not");
+    if (c.signal == GC_SIG_BDS_B1C && c.pilot_trk_flag != 1 && c.pilot_trk_flag != 2)
+        return fail(h, GC_ERR_UNSUPPORTED, "gc_track: BDS B1C tracking needs pilotTRKflag 1 (NB_tracking.m) or 2 (WB_tracking.m), B1C postProcessing.m:34-38");
     const bool l2c = c.signal == GC_SIG_GPS_L2C;
-    if (l2c && c.pilot_trk_flag != 0)
-        return fail(h, GC_ERR_UNSUPPORTED, "gc_track: GPS L2C tracking with the CL pilot (pilotTRKflag) is not implemented yet");
+    if (h->pilotMode == 5 && h->wbFactor < 0)
+        return fail(h, GC_ERR_ARG, "gc_track: B1C full-band tracking needs gc_set_param(GC_PARAM_B1C_WB_FACTOR) first");
+    if (h->pilotMode == 4 && (int)h->clPhaseIn.size() != nCh)
+        return fail(h, GC_ERR_ARG, "gc_track: GPS L2C CL pilot needs gc_set_cl_code_phase for these channels first");
     if (nCh < 1 || nEpochs < 1 || !sv || !acqFreq || !codePhase || !out || !epochsDone)
         return fail(h, GC_ERR_ARG, "gc_track: bad argument");
     cudaSetDevice(c.device);
@@ -1264,7 +1347,11 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
     const int stride = (codeLen + 2 + 15) & ~15;
     const bool pilot = h->pilotMode != 0;                     // GAL_E1C tracking.m:127; GPS_L5C tracking.m:167
     std::vector<TrackChan> chans(nCh);
-    std::vector<int8_t> tabs((size_t)nCh * stride, 0), ptabs(pilot ? (size_t)nCh * stride : 0, 0);
+    const int clLen = 150 * c.code_length;                   // padded CL sequence [CL(end) CL CL(1)] per channel (GPS_L2C tracking.m:164-166)
+    const int pstride = h->pilotMode == 4 ? ((clLen + 2 + 15) & ~15) : stride;
+    const int p61stride = (codeLen * 6 + 2 + 15) & ~15;
+    std::vector<int8_t> tabs((size_t)nCh * stride, 0), ptabs(pilot ? (size_t)nCh * pstride : 0, 0);
+    std::vector<int8_t> p61(h->pilotMode == 5 ? (size_t)nCh * p61stride : 0, 0);
     std::vector<char> live(nCh, 0);
     for (int ch = 0; ch < nCh; ++ch) {
         const bool active = h->glo ? (sv[ch] != GC_SV_NONE) : (sv[ch] != 0);   // tracking.m:136; GLO tracking.m:137
@@ -1281,10 +1368,26 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
             int8_t* t = tabs.data() + (size_t)ch * stride;
             sv_chips(h, sv[ch], t + 1);                    // tracking.m:156 (GLO tracking.m:88)
             t[0] = t[codeLen]; t[codeLen + 1] = t[1];      // [c(L) c c(1)]  :158
-            if (pilot) {                                   // GAL_E1C tracking.m:127-130
+            if (h->pilotMode == 4) {
+                const std::vector<int8_t>& cl = h->hostCode[1][sv[ch] - 1];
+                if ((int)cl.size() != clLen) return fail(h, GC_ERR_ARG, "gc_track: no CL code set for a channel's SV (gc_set_code component 1)");
+                if (h->clPhaseIn[ch] < 1 || h->clPhaseIn[ch] > 75) return fail(h, GC_ERR_ARG, "gc_track: CLCodePhase must be 1..75");
+                chans[ch].clPhase = h->clPhaseIn[ch];
+                int8_t* u = ptabs.data() + (size_t)ch * pstride;
+                std::copy(cl.begin(), cl.end(), u + 1);
+                u[0] = u[clLen]; u[clLen + 1] = u[1];
+            } else if (pilot) {                            // GAL_E1C tracking.m:127-130
+                if (h->hostCode[1][sv[ch] - 1].empty()) return fail(h, GC_ERR_ARG, "gc_track: no pilot code set for a channel's SV (gc_set_code component 1)");
                 int8_t* u = ptabs.data() + (size_t)ch * stride;
                 sv_chips(h, sv[ch], u + 1, 1);
                 u[0] = u[codeLen]; u[codeLen + 1] = u[1];
+            }
+            if (h->pilotMode == 5) {                       // B1C WB_tracking.m:181-183
+                const std::vector<int8_t>& b = h->hostCode[2][sv[ch] - 1];
+                if ((int)b.size() != codeLen * 6) return fail(h, GC_ERR_ARG, "gc_track: no pilot BOC(6,1) code set for a channel's SV (gc_set_code component 2)");
+                int8_t* u = p61.data() + (size_t)ch * p61stride;
+                std::copy(b.begin(), b.end(), u + 1);
+                u[0] = u[codeLen * 6]; u[codeLen * 6 + 1] = u[1];
             }
         }
     }
@@ -1314,7 +1417,9 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
         if (nCh * g <= 148) { cluster = g; break; }
     if (const char* e = getenv("GC_TRACK_CLUSTER")) { const int g = atoi(e); if (g == 1 || g == 2 || g == 4 || g == 8) cluster = g; }
     (void)nLive;
-    p.codeLen = codeLen; p.codeStride = stride; p.subChip = h->sub; p.pilot = h->pilotMode;
+    p.codeLen = codeLen; p.codeStride = stride; p.pilotStride = pstride; p.p61Stride = p61stride; p.subChip = h->sub; p.pilot = h->pilotMode;
+    p.wbFactor = h->wbFactor;
+    if (h->pilotMode == 5) cluster = 8;                       // three tables + the window only fit with the block spread over 8 CTAs
     p.nRows = gc_track_nfields(h);
     // long code periods (Galileo E1: 4 ms = 72000+ samples): spread the block over enough CTAs for the
     // double-buffered window to fit in shared memory
@@ -1326,11 +1431,12 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
     GC_CUDA(h, upload(h->chans, chans, st));
     GC_CUDA(h, upload(h->trackCodes, tabs, st));
     if (pilot) GC_CUDA(h, upload(h->trackPilot, ptabs, st));
+    if (h->pilotMode == 5) GC_CUDA(h, upload(h->trackP61, p61, st));
     const int nRows = gc_track_nfields(h);
     const size_t nOut = (size_t)nCh * nRows * nEpochs;
     GC_CUDA(h, h->trackOut.reserve(nOut));
     GC_CUDA(h, h->epochsDone.reserve(nCh));
-    p.codeTables = h->trackCodes.p; p.pilotTables = h->trackPilot.p; p.chans = h->chans.p; p.out = h->trackOut.p; p.epochsDone = h->epochsDone.p;
+    p.codeTables = h->trackCodes.p; p.pilotTables = h->trackPilot.p; p.p61Tables = h->trackP61.p; p.chans = h->chans.p; p.out = h->trackOut.p; p.epochsDone = h->epochsDone.p;
     long long* dbg = nullptr;
     if (getenv("GC_TRACK_DEBUG")) { cudaMalloc(&dbg, 96 * sizeof(long long)); cudaMemset(dbg, 0, 96 * sizeof(long long)); }
     p.dbg = dbg;

@@ -39,6 +39,7 @@ namespace {
 constexpr int kMaxWarps = 16;
 constexpr int kMaxCluster = 8;
 constexpr int kPad = 16;     // zero entries on both sides of the code table (masked out-of-block samples index them)
+constexpr int kPad61 = 96;   // same for the BOC(6,1) table, whose index runs six times as fast
 constexpr int kStage = 16;   // epochs of results staged in smem before a coalesced flush
 constexpr double kCeilMagic = 6755399441055744.0;   // 1.5 * 2^52: t + magic stays in [2^52, 2^53) for |t| < 2^51
 
@@ -157,7 +158,8 @@ __device__ void plan_epoch(const TrackParams& p, double codeFreq, double remCode
     }
     // fast path: the three vectors share n, and the samples masked just outside the block still index the
     // zero padding of the code table
-    ep.generic = !(ep.nE == blk - 1 && ep.nP == blk - 1 && ep.nL == blk - 1) || !((8.0 * step + p.spc) * (double)p.subChip + 2.0 < (double)kPad);
+    ep.generic = !(ep.nE == blk - 1 && ep.nP == blk - 1 && ep.nL == blk - 1) || !((8.0 * step + p.spc) * (double)p.subChip + 2.0 < (double)kPad) ||
+                 (p.pilot == 5 && !((8.0 * step + p.spc) * (double)p.subChip * 6.0 + 2.0 < (double)kPad61));
     ep.mE = __dmul_rn(__dadd_rn(ep.aE, ep.cE), 0.5);
     ep.mP = __dmul_rn(__dadd_rn(ep.aP, ep.cP), 0.5);
     ep.mL = __dmul_rn(__dadd_rn(ep.aL, ep.cL), 0.5);
@@ -215,12 +217,15 @@ __device__ __forceinline__ void dsmem_push(double* local, uint64_t* bar, uint32_
 
 }  // namespace
 
-// G = CTAs per channel (cluster size), T = threads per CTA, PILOT = data + pilot replicas (12 sums)
-template <int G, int T, bool PILOT>
+// G = CTAs per channel (cluster size), T = threads per CTA, NSET = replicas correlated (1 data; 2 data + pilot, 12 sums;
+// 3 data + pilot BOC(1,1) + pilot BOC(6,1), 18 sums - B1C WB_tracking.m), TT = storage type of the code tables in
+// shared memory (float, or int8_t where three tables have to fit)
+template <int G, int T, int NSET, typename TT>
 __global__ void __launch_bounds__(T, 1)
 track_kernel(TrackParams p)
 {
-    constexpr int NS = PILOT ? 12 : 6;                           // correlator sums per epoch
+    constexpr bool PILOT = NSET >= 2;
+    constexpr int NS = 6 * NSET;                                 // correlator sums per epoch
     constexpr int kThreads = T;
     constexpr int kWarps = T / 32;
     // Role threads.  The 8-CTA variant carries three spare warps so that the TMA issue, the one
@@ -232,11 +237,13 @@ track_kernel(TrackParams p)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // layout: [buf0 | buf1 | code table (float) | warp partials | staging | params | mbarriers]
     int8_t* const buf0 = reinterpret_cast<int8_t*>(smem_raw);
-    float* s_code_raw = reinterpret_cast<float*>(smem_raw + (p.singleBuf ? 1 : 2) * (size_t)p.bufBytes);
-    float* s_code = s_code_raw + kPad;                           // index 0 = c(L) of the wrapped table
-    const int tabFloats = (p.codeLen + 2 + 2 * kPad + 3) & ~3;
-    float* s_pilot = s_code + (PILOT ? tabFloats : 0);           // pilot table right behind the data table
-    double* s_part = reinterpret_cast<double*>(s_code_raw + (PILOT ? 2 : 1) * tabFloats);
+    TT* s_code_raw = reinterpret_cast<TT*>(smem_raw + (p.singleBuf ? 1 : 2) * (size_t)p.bufBytes);
+    TT* s_code = s_code_raw + kPad;                              // index 0 = c(L) of the wrapped table
+    const int tabFloats = (p.codeLen + 2 + 2 * kPad + 15) & ~15; // entries per table
+    TT* s_pilot = s_code + (PILOT ? tabFloats : 0);              // pilot table right behind the data table
+    const int tab61 = (NSET == 3) ? ((p.codeLen * 6 + 2 + 2 * kPad61 + 15) & ~15) : 0;
+    TT* s_p61 = s_code_raw + 2 * tabFloats + kPad61;             // BOC(6,1) pilot table, 6 entries per BOC(1,1) entry (NSET == 3)
+    double* s_part = reinterpret_cast<double*>(s_code_raw + (PILOT ? 2 : 1) * tabFloats + tab61);
     double* s_cl = s_part + kMaxWarps * NS;                      // [2][kMaxCluster][NS] per-CTA partial sums (pushed by peers)
     double* s_stage = s_cl + 2 * kMaxCluster * NS;               // [15][kStage]
     EpochParams* s_ep = reinterpret_cast<EpochParams*>(s_stage + GC_TRACK_ROWS * kStage);   // [2]
@@ -259,9 +266,14 @@ track_kernel(TrackParams p)
     // wrapped code table [c(L) c(1..L) c(1)]  (tracking.m:156-158)
     for (int i = tid; i < p.codeLen + 2 + 2 * kPad; i += kThreads) {
         const int j = i - kPad;
-        s_code_raw[i] = (j >= 0 && j < p.codeLen + 2) ? (float)p.codeTables[(size_t)ch * p.codeStride + j] : 0.f;
-        if (PILOT) s_code_raw[tabFloats + i] = (j >= 0 && j < p.codeLen + 2) ? (float)p.pilotTables[(size_t)ch * p.codeStride + j] : 0.f;
+        s_code_raw[i] = (j >= 0 && j < p.codeLen + 2) ? (TT)p.codeTables[(size_t)ch * p.codeStride + j] : (TT)0;
+        if (PILOT) s_code_raw[tabFloats + i] = (p.pilot != 4 && j >= 0 && j < p.codeLen + 2) ? (TT)p.pilotTables[(size_t)ch * p.pilotStride + j] : (TT)0;
     }
+    if (NSET == 3)                                               // [p61(12L) p61 p61(1)] (B1C WB_tracking.m:181-183)
+        for (int i = tid; i < p.codeLen * 6 + 2 + 2 * kPad61; i += kThreads) {
+            const int j = i - kPad61;
+            s_code_raw[2 * tabFloats + i] = (j >= 0 && j < p.codeLen * 6 + 2) ? (TT)p.p61Tables[(size_t)ch * p.p61Stride + j] : (TT)0;
+        }
 
     // byte selectors: sample bytes are I,Q,I,Q; GLONASS takes rawSignal = Q + 1i*I (GLO tracking.m:227)
     const uint32_t selI0 = p.swapIQ ? 0x7651u : 0x7650u, selQ0 = p.swapIQ ? 0x7650u : 0x7651u;
@@ -322,6 +334,15 @@ track_kernel(TrackParams p)
         const int blk = ep.blk, n = ep.n;
         const long long pos = ep.pos;
         const uint64_t dphi = ep.dphi, phase0 = ep.phase0;
+        if (PILOT && p.pilot == 4) {
+            // GPS L2C: the pilot table of this epoch is one 20 ms segment of the padded CL sequence,
+            // CLCode(tcode2 + codeLength*(CLCodePhase-1)), CLCodePhase stepping 1..75 with the epochs (GPS_L2C tracking.m:261, 363-366).
+            // Every thread finished the previous epoch's lookups at the barrier that ended it.
+            const int seg = (cinfo.clPhase - 1 + e) % 75;
+            const int8_t* cl = p.pilotTables + (size_t)ch * p.pilotStride + (size_t)seg * p.codeLen;
+            for (int i = tid; i < p.codeLen + 2; i += kThreads) s_pilot[i] = (TT)cl[i];
+            __syncthreads();
+        }
         // window of epoch e+1 starts where this one ends; fetch it while we correlate
         if (!p.singleBuf && tid == kLoader && e + 1 < p.nEpochs) prefetch(pos + blk, stage ^ 1, e + 1);
         if (G > 1 && tid == kPllTid) mbar_expect_tx(&s_xbar[e & 1], 8u * NS * G);   // G CTAs x NS doubles will arrive
@@ -358,6 +379,7 @@ track_kernel(TrackParams p)
 
         float aIE = 0, aQE = 0, aIP = 0, aQP = 0, aIL = 0, aQL = 0;
         float bIE = 0, bQE = 0, bIP = 0, bQP = 0, bIL = 0, bQL = 0;     // pilot sums
+        float cIE = 0, cQE = 0, cIP = 0, cQP = 0, cIL = 0, cQL = 0;     // pilot BOC(6,1) sums (NSET == 3)
         const double mE = ep.mE * sc, mP = ep.mP * sc, mL = ep.mL * sc;
         const int nE_ = ep.nE, nP_ = ep.nP, nL_ = ep.nL;
         // One 16-byte chunk = 8 consecutive samples.  SPECIAL = per-sample left/right/middle selection
@@ -382,6 +404,7 @@ track_kernel(TrackParams p)
             }
             float pIE = 0, pQE = 0, pIP = 0, pQP = 0, pIL = 0, pQL = 0;
             float qIE = 0, qQE = 0, qIP = 0, qQP = 0, qIL = 0, qQL = 0;
+            float rIE = 0, rQE = 0, rIP = 0, rQP = 0, rIL = 0, rQL = 0;
             if (!SPECIAL) {
                 // whole chunk in the left half (t = a + k*d) or in the right half (t = c - (n-k)*d).
                 // Samples masked above may have k < 0 or k >= blk; their code index stays inside
@@ -395,10 +418,11 @@ track_kernel(TrackParams p)
                 for (int j = 0; j < 8; ++j) {
                     const double st = __dmul_rn(__fma_rn(sg, (double)j, f0), ds);   // (+-)(k or n-k)*d, exact integer factor
                     // code replicas (tracking.m:252-270): ceil(tcode) indexes [c(L) c c(1)] 0-based
-                    const int iE = ceil_idx(__dadd_rn(bE, st)), iP = ceil_idx(__dadd_rn(bP, st)), iL = ceil_idx(__dadd_rn(bL, st));
-                    const float vE = s_code[iE];
-                    const float vP = s_code[iP];
-                    const float vL = s_code[iL];
+                    const double tE = __dadd_rn(bE, st), tP = __dadd_rn(bP, st), tL = __dadd_rn(bL, st);
+                    const int iE = ceil_idx(tE), iP = ceil_idx(tP), iL = ceil_idx(tL);
+                    const float vE = (float)s_code[iE];
+                    const float vP = (float)s_code[iP];
+                    const float vL = (float)s_code[iL];
                     // x * e^{-i*j*dphi}   (tracking.m:287-292 with the chunk phase factored out)
                     const float ur = fmaf(wc[j], xi[j], ws[j] * xq[j]);
                     const float ui = fmaf(wc[j], xq[j], -ws[j] * xi[j]);
@@ -406,10 +430,17 @@ track_kernel(TrackParams p)
                     pIP = fmaf(vP, ur, pIP); pQP = fmaf(vP, ui, pQP);
                     pIL = fmaf(vL, ur, pIL); pQL = fmaf(vL, ui, pQL);
                     if (PILOT) {                                  // same code phase, pilot table (GAL_E1C tracking.m:241-262)
-                        const float uE = s_pilot[iE], uP = s_pilot[iP], uL = s_pilot[iL];
+                        const float uE = (float)s_pilot[iE], uP = (float)s_pilot[iP], uL = (float)s_pilot[iL];
                         qIE = fmaf(uE, ur, qIE); qQE = fmaf(uE, ui, qQE);
                         qIP = fmaf(uP, ur, qIP); qQP = fmaf(uP, ui, qQP);
                         qIL = fmaf(uL, ur, qIL); qQL = fmaf(uL, ui, qQL);
+                    }
+                    if (NSET == 3) {                              // pilotBOC61(ceil(tcode * 6) + 1), B1C WB_tracking.m:283,294,305
+                        const float wE = (float)s_p61[ceil_idx(__dmul_rn(tE, 6.0))], wP = (float)s_p61[ceil_idx(__dmul_rn(tP, 6.0))],
+                                    wL = (float)s_p61[ceil_idx(__dmul_rn(tL, 6.0))];
+                        rIE = fmaf(wE, ur, rIE); rQE = fmaf(wE, ui, rQE);
+                        rIP = fmaf(wP, ur, rIP); rQP = fmaf(wP, ui, rQP);
+                        rIL = fmaf(wL, ur, rIL); rQL = fmaf(wL, ui, rQL);
                     }
                 }
             } else {
@@ -429,17 +460,24 @@ track_kernel(TrackParams p)
                         tL = colon_elem(aL, d, cL, nL_, kc);
                     }
                     const int iE = ceil_idx(tE), iP = ceil_idx(tP), iL = ceil_idx(tL);
-                    const float vE = s_code[iE], vP = s_code[iP], vL = s_code[iL];
+                    const float vE = (float)s_code[iE], vP = (float)s_code[iP], vL = (float)s_code[iL];
                     const float ur = fmaf(wc[j], xi[j], ws[j] * xq[j]);
                     const float ui = fmaf(wc[j], xq[j], -ws[j] * xi[j]);
                     pIE = fmaf(vE, ur, pIE); pQE = fmaf(vE, ui, pQE);
                     pIP = fmaf(vP, ur, pIP); pQP = fmaf(vP, ui, pQP);
                     pIL = fmaf(vL, ur, pIL); pQL = fmaf(vL, ui, pQL);
                     if (PILOT) {
-                        const float uE = s_pilot[iE], uP = s_pilot[iP], uL = s_pilot[iL];
+                        const float uE = (float)s_pilot[iE], uP = (float)s_pilot[iP], uL = (float)s_pilot[iL];
                         qIE = fmaf(uE, ur, qIE); qQE = fmaf(uE, ui, qQE);
                         qIP = fmaf(uP, ur, qIP); qQP = fmaf(uP, ui, qQP);
                         qIL = fmaf(uL, ur, qIL); qQL = fmaf(uL, ui, qQL);
+                    }
+                    if (NSET == 3) {
+                        const float wE = (float)s_p61[ceil_idx(__dmul_rn(tE, 6.0))], wP = (float)s_p61[ceil_idx(__dmul_rn(tP, 6.0))],
+                                    wL = (float)s_p61[ceil_idx(__dmul_rn(tL, 6.0))];
+                        rIE = fmaf(wE, ur, rIE); rQE = fmaf(wE, ui, rQE);
+                        rIP = fmaf(wP, ur, rIP); rQP = fmaf(wP, ui, rQP);
+                        rIL = fmaf(wL, ur, rIL); rQL = fmaf(wL, ui, rQL);
                     }
                 }
             }
@@ -453,6 +491,11 @@ track_kernel(TrackParams p)
                 bIE += fmaf(c0, qIE, s0 * qQE); bQE += fmaf(c0, qQE, -s0 * qIE);
                 bIP += fmaf(c0, qIP, s0 * qQP); bQP += fmaf(c0, qQP, -s0 * qIP);
                 bIL += fmaf(c0, qIL, s0 * qQL); bQL += fmaf(c0, qQL, -s0 * qIL);
+            }
+            if (NSET == 3) {
+                cIE += fmaf(c0, rIE, s0 * rQE); cQE += fmaf(c0, rQE, -s0 * rIE);
+                cIP += fmaf(c0, rIP, s0 * rQP); cQP += fmaf(c0, rQP, -s0 * rIP);
+                cIL += fmaf(c0, rIL, s0 * rQL); cQL += fmaf(c0, rQL, -s0 * rIL);
             }
         };
         using TagFast = std::false_type;
@@ -473,7 +516,7 @@ track_kernel(TrackParams p)
         // cross-thread reduction in float64: warp shuffle, then warps 0 and 1 over the warp partials
         // (the 32 lane partials of a warp are combined in fp32 - they are fp32 sums of <= 32 samples each -
         //  and everything from the warp partials on is float64)
-        float vf[12] = {aIE, aQE, aIP, aQP, aIL, aQL, bIE, bQE, bIP, bQP, bIL, bQL};
+        float vf[18] = {aIE, aQE, aIP, aQP, aIL, aQL, bIE, bQE, bIP, bQP, bIL, bQL, cIE, cQE, cIP, cQP, cIL, cQL};
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
@@ -537,6 +580,21 @@ track_kernel(TrackParams p)
                     for (int q = 0; q < NS; ++q) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
             }
             const double I_E = v[0], Q_E = v[1], I_P = v[2], Q_P = v[3], I_L = v[4], Q_L = v[5];
+            double pv[6] = {0, 0, 0, 0, 0, 0};                   // pilot I_E, Q_E, I_P, Q_P, I_L, Q_L as the discriminators see them
+            if (PILOT) {
+                if (NSET == 3) {
+                    // composite pilot: -sqrt(4/33) * p61 +- sqrt(29/33) * p11 cross terms (B1C WB_tracking.m:339-344)
+                    const double a61 = -0.3481553119113957, b11 = 0.937436866561092;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        pv[2 * q] = __dadd_rn(__dmul_rn(a61, v[12 + 2 * q]), __dmul_rn(b11, v[7 + 2 * q]));
+                        pv[2 * q + 1] = __dsub_rn(__dmul_rn(a61, v[13 + 2 * q]), __dmul_rn(b11, v[6 + 2 * q]));
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) pv[q] = v[6 + q];
+                }
+            }
             double* sg = s_stage + (e % kStage);
             if (tid == kPllTid) {
                 // PLL (tracking.m:305-317)
@@ -545,19 +603,24 @@ track_kernel(TrackParams p)
                 double carrError = p.exactDisc ? atan(__ddiv_rn(Q_P, I_P)) / kTwoPi
                                                : (double)atanf((float)Q_P / (float)I_P) * 0.15915494309189535;
                 if (PILOT) {                                     // GAL_E1C tracking.m:297-300
-                    double num = v[NS - 3], den = v[NS - 4];     // Q_P, I_P of the pilot
+                    double num = pv[3], den = pv[2];             // Q_P, I_P of the pilot
                     if (p.pilot == 2) {
                         // QI = (I + 1i*Q) * exp(-1i*pi/2), exp(-1i*pi/2) = 6.123e-17 - 1i in float64 (GPS_L5C tracking.m:278-279)
                         const double eps = 6.123233995736766e-17;
-                        num = __dsub_rn(__dmul_rn(v[NS - 3], eps), v[NS - 4]);    // imag(QI) = Q*eps - I
-                        den = __dadd_rn(__dmul_rn(v[NS - 4], eps), v[NS - 3]);    // real(QI) = I*eps + Q
+                        num = __dsub_rn(__dmul_rn(pv[3], eps), pv[2]);    // imag(QI) = Q*eps - I
+                        den = __dadd_rn(__dmul_rn(pv[2], eps), pv[3]);    // real(QI) = I*eps + Q
                     }
-                    if (p.pilot == 3) { num = -v[NS - 4]; den = v[NS - 3]; }      // atan(-p11_I_P/p11_Q_P), B1C NB_tracking.m:301
+                    if (p.pilot == 3) { num = -pv[2]; den = pv[3]; }      // atan(-p11_I_P/p11_Q_P), B1C NB_tracking.m:301
                     const double cP2 = p.exactDisc ? atan(__ddiv_rn(num, den)) / kTwoPi
                                                    : (double)atanf((float)num / (float)den) * 0.15915494309189535;
                     carrError = (p.pilot == 3) ? __ddiv_rn(__dadd_rn(__dmul_rn(carrError, 11.0), __dmul_rn(cP2, 29.0)), 40.0)   // :302
+                              : (p.pilot == 5) ? __ddiv_rn(__dadd_rn(carrError, __dmul_rn(cP2, 3.0)), 4.0)                     // B1C WB_tracking.m:356
                                                : __dmul_rn(__dadd_rn(carrError, cP2), 0.5);
-                    if (p.pilot >= 2) { sg[15 * kStage] = v[NS - 4]; sg[16 * kStage] = v[NS - 3]; }   // Pilot_I_P, Pilot_Q_P (GPS_L5C :323-324)
+                    if (p.pilot >= 2) { sg[GC_F_PILOT_I_P * kStage] = pv[2]; sg[GC_F_PILOT_Q_P * kStage] = pv[3]; }   // Pilot_I_P, Pilot_Q_P (GPS_L5C :323-324)
+                    if (p.pilot >= 4) {                          // GPS_L2C tracking.m:396-402; B1C WB_tracking.m:409-414
+                        sg[GC_F_PILOT_I_E * kStage] = pv[0]; sg[GC_F_PILOT_I_L * kStage] = pv[4];
+                        sg[GC_F_PILOT_Q_E * kStage] = pv[1]; sg[GC_F_PILOT_Q_L * kStage] = pv[5];
+                    }
                 }
                 double carrNco;
                 if (p.loopType == 0) {
@@ -592,8 +655,8 @@ track_kernel(TrackParams p)
                     codeError = (double)((sE - sL) / (sE + sL));
                 }
                 if (PILOT) {                                     // GAL_E1C tracking.m:327-333
-                    const double qE = __dadd_rn(__dmul_rn(v[NS - 6], v[NS - 6]), __dmul_rn(v[NS - 5], v[NS - 5]));
-                    const double qL = __dadd_rn(__dmul_rn(v[NS - 2], v[NS - 2]), __dmul_rn(v[NS - 1], v[NS - 1]));
+                    const double qE = __dadd_rn(__dmul_rn(pv[0], pv[0]), __dmul_rn(pv[1], pv[1]));
+                    const double qL = __dadd_rn(__dmul_rn(pv[4], pv[4]), __dmul_rn(pv[5], pv[5]));
                     double ce2;
                     if (p.exactDisc) {
                         const double sE = sqrt(qE), sL = sqrt(qL);
@@ -605,6 +668,9 @@ track_kernel(TrackParams p)
                     if (p.pilot == 3) {                          // B1C NB_tracking.m:313-318: both scaled by (1 - spacing), weights 11/40, 29/40
                         const double sc1 = __dsub_rn(1.0, p.spc);
                         codeError = __ddiv_rn(__dadd_rn(__dmul_rn(__dmul_rn(codeError, sc1), 11.0), __dmul_rn(__dmul_rn(ce2, sc1), 29.0)), 40.0);
+                    } else if (p.pilot == 5) {                   // B1C WB_tracking.m:366-374: weighted by CalcWeighingFactor.m's factor
+                        const double sc1 = __dsub_rn(1.0, p.spc);
+                        codeError = __dadd_rn(__dmul_rn(__dmul_rn(codeError, sc1), p.wbFactor), __dmul_rn(__dmul_rn(ce2, sc1), __dsub_rn(1.0, p.wbFactor)));
                     } else {
                         codeError = __dmul_rn(__dadd_rn(codeError, ce2), 0.5);
                     }
@@ -653,19 +719,21 @@ track_kernel(TrackParams p)
 
 size_t track_smem_bytes(int bufBytes, int codeLen, int pilot, int singleBuf)
 {
-    const int ns = pilot ? 12 : 6;
+    const int nset = pilot == 5 ? 3 : pilot ? 2 : 1;
+    const int ns = 6 * nset;
     size_t s = (singleBuf ? 1 : 2) * (size_t)bufBytes;
-    s += sizeof(float) * ((codeLen + 2 + 2 * kPad + 3) & ~3) * (pilot ? 2 : 1);
+    s += (pilot == 5 ? sizeof(int8_t) : sizeof(float)) * ((codeLen + 2 + 2 * kPad + 15) & ~15) * (pilot ? 2 : 1);
+    if (pilot == 5) s += (codeLen * 6 + 2 + 2 * kPad61 + 15) & ~15;
     s += sizeof(double) * (kMaxWarps * ns + 2 * kMaxCluster * ns + GC_TRACK_ROWS * kStage);
     s += 2 * sizeof(EpochParams) + sizeof(NextPhases) + 4 * sizeof(uint64_t) + 2 * sizeof(int) + 64;
     return s;
 }
 
-template <int G, int T, bool PILOT>
+template <int G, int T, int NSET, typename TT = float>
 static cudaError_t launch_track_g(const TrackParams& p, int nCh, cudaStream_t stream)
 {
-    const size_t smem = track_smem_bytes(p.bufBytes, p.codeLen, PILOT ? 1 : 0, p.singleBuf);
-    cudaError_t err = cudaFuncSetAttribute(track_kernel<G, T, PILOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = track_smem_bytes(p.bufBytes, p.codeLen, p.pilot, p.singleBuf);
+    cudaError_t err = cudaFuncSetAttribute(track_kernel<G, T, NSET, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nCh * G);
@@ -677,25 +745,29 @@ static cudaError_t launch_track_g(const TrackParams& p, int nCh, cudaStream_t st
     attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, track_kernel<G, T, PILOT>, p);
+    return cudaLaunchKernelEx(&cfg, track_kernel<G, T, NSET, TT>, p);
 }
 
 // p.bufBytes must be the per-CTA staging size for `cluster` CTAs per channel (track_buf_bytes)
 cudaError_t launch_track(const TrackParams& p, int nCh, int cluster, cudaStream_t stream)
 {
+    if (p.pilot == 5) {                                          // three int8 tables; 18 accumulators want the 352-thread register budget
+        if (cluster != 8) return cudaErrorInvalidValue;
+        return launch_track_g<8, 352, 3, int8_t>(p, nCh, stream);
+    }
     if (p.pilot) {
         switch (cluster) {
-            case 8: return launch_track_g<8, 352, true>(p, nCh, stream);
-            case 4: return launch_track_g<4, 512, true>(p, nCh, stream);
-            case 2: return launch_track_g<2, 512, true>(p, nCh, stream);
-            default: return launch_track_g<1, 512, true>(p, nCh, stream);
+            case 8: return launch_track_g<8, 352, 2>(p, nCh, stream);
+            case 4: return launch_track_g<4, 512, 2>(p, nCh, stream);
+            case 2: return launch_track_g<2, 512, 2>(p, nCh, stream);
+            default: return launch_track_g<1, 512, 2>(p, nCh, stream);
         }
     }
     switch (cluster) {
-        case 8: return launch_track_g<8, 352, false>(p, nCh, stream);
-        case 4: return launch_track_g<4, 512, false>(p, nCh, stream);
-        case 2: return launch_track_g<2, 512, false>(p, nCh, stream);
-        default: return launch_track_g<1, 512, false>(p, nCh, stream);
+        case 8: return launch_track_g<8, 352, 1>(p, nCh, stream);
+        case 4: return launch_track_g<4, 512, 1>(p, nCh, stream);
+        case 2: return launch_track_g<2, 512, 1>(p, nCh, stream);
+        default: return launch_track_g<1, 512, 1>(p, nCh, stream);
     }
 }
 

@@ -4,7 +4,7 @@
 #include <stdint.h>
 #include "../../include/gnsscorr.h"
 
-#define GC_TRACK_ROWS GC_TRACK_NFIELDS_PILOT   /* most rows a channel records per epoch (staging size) */
+#define GC_TRACK_ROWS GC_TRACK_NFIELDS_PILOT6   /* most rows a channel records per epoch (staging size) */
 
 namespace gc {
 
@@ -14,6 +14,8 @@ struct TrackChan {
     double acqFreq;          // channel.acquiredFreq
     double codeFreq0;        // centre of the code NCO: settings.codeFreqBasis, or channel.codeFreq (B3I tracking.m:57,146)
     long long startSample;   // skipNumberOfBytes + codePhase - 1   (tracking.m:150)
+    int32_t clPhase;         // GPS L2C with the CL pilot: channel.CLCodePhase, 1..75 (GPS_L2C tracking.m:162)
+    int32_t pad2;
 };
 
 struct TrackParams {
@@ -37,10 +39,19 @@ struct TrackParams {
                              // (GPS_L5C tracking.m:277-281) - and Pilot_I_P / Pilot_Q_P are recorded (rows 15, 16)
                              // 3: quadrature pilot weighted 11/40 : 29/40, pilot discriminator atan(-I/Q), code discriminators
                              // scaled by (1 - spacing) (BDS/B1C/include/NB_tracking.m:300-320); Pilot rows recorded
+                             // 4: GPS L2C CL pilot - the pilot table is reloaded every epoch with the CL segment CLCodePhase points at
+                             // (pilotTables = [nCh][pilotStride] padded CL sequences), plain average of both discriminators,
+                             // six Pilot rows recorded (GPS_L2C tracking.m:259-366)
+                             // 5: BDS B1C full band - data BOC(1,1), pilot BOC(1,1) and pilot BOC(6,1) tables (18 sums), composite
+                             // pilot correlations, carrier 1:3, code weighted by wbFactor (B1C WB_tracking.m:270-374)
     int singleBuf;           // 1: one sample window in shared memory instead of two (long epochs whose double-buffered window
                              // would not fit next to the code tables: B1C, 10 ms = 180000 samples with two 20460-entry tables)
-    int nRows;               // rows recorded per epoch: GC_TRACK_NFIELDS, or GC_TRACK_NFIELDS_PILOT with pilot == 2
-    int codeStride;          // bytes between channels in codeTables / pilotTables
+    int nRows;               // rows recorded per epoch: GC_TRACK_NFIELDS, GC_TRACK_NFIELDS_PILOT (pilot 2, 3) or GC_TRACK_NFIELDS_PILOT6 (pilot 4, 5)
+    int codeStride;          // bytes between channels in codeTables
+    int pilotStride;         // bytes between channels in pilotTables (codeStride, or the padded CL length for pilot == 4)
+    int p61Stride;           // bytes between channels in p61Tables
+    double wbFactor;         // pilot == 5: weight of the data channel in the code discriminator (CalcWeighingFactor.m)
+    const int8_t* p61Tables; // pilot == 5: [nCh][p61Stride] wrapped pilot BOC(6,1) tables, 12 entries per chip
     const int8_t* codeTables;   // [nCh][codeStride]: wrapped +-1 table [c(L) c(1..L) c(1)]
     const int8_t* pilotTables;  // same layout, pilot component (pilot == 1)
     const TrackChan* chans;

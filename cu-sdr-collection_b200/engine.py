@@ -41,6 +41,7 @@ GC_SIG_BDS_B1I, GC_SIG_GPS_L2C, GC_SIG_BDS_B1C = 8, 9, 10
 _FAM5_IDS = {"GPS_L5C": GC_SIG_GPS_L5C, "GAL_E5a": GC_SIG_GAL_E5A, "GAL_E5b": GC_SIG_GAL_E5B, "BDS_B2a": GC_SIG_BDS_B2A,
              "BDS_B1I": GC_SIG_BDS_B1I, "GPS_L2C": GC_SIG_GPS_L2C, "BDS_B1C": GC_SIG_BDS_B1C}
 GC_SV_NONE = -2147483648
+GC_PARAM_B1C_WB_FACTOR = 1
 
 
 class gc_stats(C.Structure):
@@ -53,7 +54,8 @@ class gc_stats(C.Structure):
 
 EXPORTS = ["gc_abi_version", "gc_build_arch", "gc_acq_result_len", "gc_create", "gc_destroy",
            "gc_last_error", "gc_set_code", "gc_set_record_host", "gc_set_record_device", "gc_acquire",
-           "gc_acquire_host", "gc_track_nfields", "gc_track", "gc_track_file", "gc_get_stats", "gc_get_stream"]
+           "gc_acquire_host", "gc_track_nfields", "gc_track", "gc_track_file", "gc_get_stats", "gc_get_stream",
+           "gc_set_param", "gc_get_cl_code_phase", "gc_set_cl_code_phase"]
 
 _lib = None
 
@@ -83,6 +85,9 @@ def load_lib():
     lib.gc_acquire.argtypes = [vp, C.c_int32, i32p, dp, dp, dp, i32p, i32p]
     lib.gc_acquire_host.argtypes = [vp, vp, C.c_size_t, C.c_int32, i32p, dp, dp, dp, i32p, i32p]
     lib.gc_track_nfields.argtypes = [vp]
+    lib.gc_set_param.argtypes = [vp, C.c_int32, C.c_double]
+    lib.gc_get_cl_code_phase.argtypes = [vp, i32p]
+    lib.gc_set_cl_code_phase.argtypes = [vp, C.c_int32, i32p]
     lib.gc_track.argtypes = [vp, C.c_int32, i32p, dp, dp, dp, C.c_int32, dp, dp, dp, i32p]
     lib.gc_track_file.argtypes = [vp, C.c_char_p, C.c_int32, i32p, dp, dp, dp, C.c_int32, dp, dp, dp, i32p]
     lib.gc_get_stats.argtypes = [vp, C.POINTER(gc_stats)]
@@ -106,7 +111,7 @@ def config_from_settings(s: Settings, device: int = 0) -> gc_config:
     if s.fileType != 2 or s.dataType != "schar":
         raise GnssCorrError("only fileType 2 with dataType 'schar' is implemented")
     sig = signal_id(s)
-    return gc_config(abi_version=3, device=device, pilot_trk_flag=int(s.pilotTRKflag), acq_coh_t=int(s.acqCohT),
+    return gc_config(abi_version=4, device=device, pilot_trk_flag=int(s.pilotTRKflag), acq_coh_t=int(s.acqCohT),
                      pilot_acq_flag=int(s.pilotACQflag), signal=sig, freq_spacing=float(s.freqSpacing),
                      file_type=s.fileType, sample_bytes=1,
                      code_length=int(s.codeLength), acq_noncoh_time=int(s.acqNonCohTime),
@@ -162,10 +167,11 @@ class Engine:
             if prn > nmax:
                 continue
             for comp, chips in enumerate(comps):
-                if comp == 2 and self.settings.signal != "GAL_E5a":
-                    continue                                     # only E5a's fine search uses a per-PRN secondary code
-                if comp >= 1 and self.settings.is_varb:
-                    continue                                     # B1I / L2C: one code per SV
+                sig = self.settings.signal
+                if comp == 2 and not (sig == "GAL_E5a" or (sig == "BDS_B1C" and int(self.settings.pilotTRKflag) == 2)):
+                    continue                                     # E5a: per-PRN secondary code; B1C full band: pilot BOC(6,1)
+                if comp >= 1 and self.settings.is_varb and not (sig == "GPS_L2C" and comp == 1 and int(self.settings.pilotTRKflag) == 1):
+                    continue                                     # B1I / L2C: one code per SV (+ the CL sequence with the L2C pilot)
                 a = np.ascontiguousarray(chips, dtype=np.int8)
                 self._check(self.lib.gc_set_code(self._h, int(prn), comp, a.ctypes.data, a.size), "gc_set_code")
 
@@ -212,11 +218,22 @@ class Engine:
         else:
             rc = self.lib.gc_acquire(self._h, sv.size, _ip(sv), _dp(carr), _dp(cph), _dp(pm), _ip(cbin), _ip(ccp))
             self._check(rc, "gc_acquire")
-        return dict(carrFreq=carr, codePhase=cph, peakMetric=pm, coarseBin=cbin, coarseCodePhase=ccp)
+        r = dict(carrFreq=carr, codePhase=cph, peakMetric=pm, coarseBin=cbin, coarseCodePhase=ccp)
+        if s.signal == "GPS_L2C" and int(s.pilotTRKflag) == 1:       # acqResults.CLCodePhase (GPS_L2C acquisition.m:136)
+            cl = np.zeros(32, dtype=np.int32)
+            self._check(self.lib.gc_get_cl_code_phase(self._h, _ip(cl)), "gc_get_cl_code_phase")
+            r["CLCodePhase"] = cl
+        return r
 
     # ---- tracking -----------------------------------------------------------------------
-    def track(self, prn, acq_freq, code_phase, n_epochs, path=None, code_freq0=None):
+    def set_param(self, key: int, value: float):
+        self._check(self.lib.gc_set_param(self._h, int(key), float(value)), "gc_set_param")
+
+    def track(self, prn, acq_freq, code_phase, n_epochs, path=None, code_freq0=None, cl_code_phase=None):
         prn = np.asarray(prn, dtype=np.int32)
+        if cl_code_phase is not None:                                # channel.CLCodePhase (GPS_L2C tracking.m:162)
+            cl = np.ascontiguousarray(cl_code_phase, dtype=np.int32)
+            self._check(self.lib.gc_set_cl_code_phase(self._h, cl.size, _ip(cl)), "gc_set_cl_code_phase")
         af = np.asarray(acq_freq, dtype=np.float64)
         cp = np.asarray(code_phase, dtype=np.float64)
         cf0 = None if code_freq0 is None else np.ascontiguousarray(code_freq0, dtype=np.float64)

@@ -26,6 +26,8 @@ def preRun(acqResults: dict, settings: Settings) -> list:
         p = int(order[ii])
         channel[ii] = dict(PRN=p + 1, acquiredFreq=float(acqResults["carrFreq"][p]),
                            codePhase=int(acqResults["codePhase"][p]), status="T")              # :66-71
+        if settings.signal == "GPS_L2C" and "CLCodePhase" in acqResults:     # GPS_L2C/include/preRun.m: channel.CLCodePhase
+            channel[ii]["CLCodePhase"] = int(acqResults["CLCodePhase"][p])
         if settings.signal in ("BDS_B3I", "BDS_B1C") or settings.is_fam5:   # carrier-aided code NCO centre (BDS/B3I/include/preRun.m:71-73, GPS_L5C :69-71)
             channel[ii]["codeFreq"] = settings.codeFreqBasis + \
                 (channel[ii]["acquiredFreq"] - settings.IF) / settings.carrFreqBasis * settings.codeFreqBasis

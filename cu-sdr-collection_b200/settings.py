@@ -45,6 +45,8 @@ class Settings:
     acqStep: float = 0.0                # GPS L2C: sub-bin step (GPS/GPS_L2C/initSettings.m:94)
     acqCohT: int = 20                   # GPS L2C: coherent time in ms (:91); BDS B1C: BDS/B1C/initSettings.m:97 (10)
     pilotACQflag: int = 0               # BDS B1C: the pilot replica joins the acquisition (BDS/B1C/initSettings.m:74)
+    FEBW: float = 27e6                  # BDS B1C: front-end bandwidth (BDS/B1C/initSettings.m:59), input of CalcWeighingFactor.m
+    wbFactor: float | None = None       # BDS B1C full band: CalcWeighingFactor(settings) if the caller already has it
 
     @property
     def is_glonass(self) -> bool:

@@ -166,6 +166,13 @@ def make_record(scene: Scene, nsamples: int, start: int = 0) -> np.ndarray:
             dD = bits[period + s.bit_offset]
             dP = bits[::-1][period + s.bit_offset]
             ph = 2 * np.pi * (fc * t % 1.0) + s.phi0
+            if len(scene.codes[s.prn]) > 2:
+                # full-band signal: the pilot is QMBOC - BOC(1,1) in quadrature at sqrt(29/44), BOC(6,1) in phase at -sqrt(1/11) -
+                # next to the data component at 1/2; the combination B1C WB_tracking.m:339-344 is built for
+                idx6 = np.floor(6.0 * (chips - period * float(clen))).astype(np.int64) % (6 * clen)
+                c61 = np.asarray(scene.codes[s.prn][2], dtype=np.float64)[idx6]
+                sig += _amp(s.cn0, scene.sigma, scene.fs) * (0.5 * dD * cD + 1j * np.sqrt(29 / 44) * dP * cP - np.sqrt(1 / 11) * dP * c61) * np.exp(1j * ph)
+                continue
             sig += _amp(s.cn0, scene.sigma, scene.fs) * (np.sqrt(11 / 40) * dD * cD + 1j * np.sqrt(29 / 40) * dP * cP) * np.exp(1j * ph)
             continue
         elif scene.varb:
@@ -182,6 +189,13 @@ def make_record(scene: Scene, nsamples: int, start: int = 0) -> np.ndarray:
             else:
                 d = nav_bits(s, int(period.max()) + 30)[period + s.bit_offset]
             ph = 2 * np.pi * (fc * t % 1.0) + s.phi0
+            if not b1i and len(scene.codes[s.prn]) > 1:
+                # L2C with its CL pilot: CM (data) and CL chips time-multiplexed - the CL sequence fills the half chips the
+                # return-to-zero CM sequence leaves empty and runs over 75 CM periods; segment (bit_offset % 75) at period 0
+                cl = np.asarray(scene.codes[s.prn][1], dtype=np.float64)
+                idx_cl = (idx + ((period + s.bit_offset) % 75) * clen)
+                code = d * code + cl[idx_cl]
+                d = 1.0
             sig += _amp(s.cn0, scene.sigma, scene.fs) * (np.sqrt(2.0) if not b1i else 1.0) * d * code * np.exp(1j * ph)
             continue
         elif scene.fam5:

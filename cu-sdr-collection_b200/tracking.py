@@ -5,7 +5,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .engine import GC_SV_NONE, Engine
+from .engine import GC_PARAM_B1C_WB_FACTOR, GC_SV_NONE, Engine
 from .settings import Settings, num_to_process
 
 # row order of the C ABI's output block == GC_F_* in include/gnsscorr.h
@@ -32,7 +32,11 @@ def tracking(fid, channel: list, settings: Settings, engine: Engine | None = Non
         cp = [float(c["codePhase"]) for c in channel[:nch]]
         path = fid.name if fid is not None else None
         cf0 = [float(c["codeFreq"]) for c in channel[:nch]] if (settings.signal in ("BDS_B3I", "BDS_B1C") or settings.is_fam5) else None   # B3I tracking.m:57, GPS_L5C :173, B1C NB_tracking.m:163
-        out, vv, vi, done = eng.track(prn, af, cp, n, path=path, code_freq0=cf0)
+        l2c_pilot = settings.signal == "GPS_L2C" and int(settings.pilotTRKflag) == 1
+        clp = [int(c.get("CLCodePhase", 0)) if c["PRN"] != 0 else 1 for c in channel[:nch]] if l2c_pilot else None
+        if settings.signal == "BDS_B1C" and int(settings.pilotTRKflag) == 2:   # factor = CalcWeighingFactor(settings), WB_tracking.m:124
+            eng.set_param(GC_PARAM_B1C_WB_FACTOR, settings.wbFactor if settings.wbFactor is not None else calc_weighing_factor(settings))
+        out, vv, vi, done = eng.track(prn, af, cp, n, path=path, code_freq0=cf0, cl_code_phase=clp)
     finally:
         if own:
             eng.close()
@@ -50,8 +54,10 @@ def tracking(fid, channel: list, settings: Settings, engine: Engine | None = Non
             tr["absoluteSample"][:e] = tr["absoluteSample"][:e] + 1 - tr["remCodePhase"][:e] / step
             for f in ("remCodePhase", "codeFreq", "dllDiscr", "dllDiscrFilt"):
                 tr[f] = tr[f] / 2
-        if out.shape[1] == 17:                                             # GPS_L5C tracking.m:57-60, 323-324
+        if out.shape[1] >= 17:                                             # GPS_L5C tracking.m:57-60, 323-324
             tr["Pilot_I_P"], tr["Pilot_Q_P"] = out[ch, 15], out[ch, 16]
+        if out.shape[1] == 21:                                             # GPS_L2C tracking.m:396-402; B1C WB_tracking.m:409-414
+            tr["Pilot_I_E"], tr["Pilot_I_L"], tr["Pilot_Q_E"], tr["Pilot_Q_L"] = out[ch, 17], out[ch, 18], out[ch, 19], out[ch, 20]
         if settings.signal in ("BDS_B2a", "BDS_B1C"):                      # BDS/B2a/include/tracking.m:66-72, 336-352; B1C NB_tracking.m:65-69, 340-355
             tr.update(_b2a_cno_pld(tr, settings, int(done[ch])))
         else:
@@ -68,13 +74,37 @@ def tracking(fid, channel: list, settings: Settings, engine: Engine | None = Non
     return results, channel
 
 
+def calc_weighing_factor(settings: Settings) -> float:
+    """``factor = CalcWeighingFactor(settings)`` (BDS/B1C/include/CalcWeighingFactor.m:45-82): weight of the data channel in
+    the full-band code discriminator, from the BOC(1,1) and QMBOC power spectra integrated over the front-end bandwidth
+    ``settings.FEBW``.  A settings-derived scalar (host side; the MATLAB wrapper calls the reference's own function)."""
+    from scipy.integrate import quad
+    fc = settings.codeFreqBasis
+    Tc, Br = 1 / fc, settings.FEBW
+
+    def boc(f, m):
+        a = np.pi / (2 * m)
+        return Tc * (np.sin(a * f / fc) * np.sin(np.pi * f / fc) / np.cos(a * f / fc) * fc / f / np.pi) ** 2
+
+    def integ(g):
+        return 2 * quad(g, 0, Br / 2, limit=400, epsabs=0, epsrel=1e-12)[0]
+
+    g11 = lambda f: boc(f, 1)
+    gp = lambda f: 29 / 33 * boc(f, 1) + 4 / 33 * boc(f, 6)
+    p11, p11_2 = integ(g11), integ(lambda f: g11(f) * f ** 2)
+    pp, pp_2 = integ(gp), integ(lambda f: gp(f) * f ** 2)
+    t1 = 11 * p11 * (p11_2 / p11)
+    t2 = 33 * pp * (pp_2 / pp)
+    return float(t1 / (t1 + t2))
+
+
 def _b2a_cno_pld(tr: dict, settings: Settings, done: int) -> dict:
     """DataCNo / DataPLD (/ PilotCNo / PilotPLD / B2a_CNo) every settings.CNoInterval epochs from the recorded prompt
     rows - BDS/B2a/include/Calc_CNo_PLD.m:38-76 and the 0.5/0.5 smoothing of tracking.m:340-349.  Scalar host work
     on rows the GPU produced (40..200 values per call)."""
     n_int = int(settings.CNo_VSMinterval)
     nv = num_to_process(settings) // n_int
-    pilot = int(settings.pilotTRKflag) == 1
+    pilot = int(settings.pilotTRKflag) >= 1
     total = "B1C_CNo" if settings.signal == "BDS_B1C" else "B2a_CNo"
     res = {"DataCNo": np.zeros(nv), "DataPLD": np.zeros(nv)}
     if pilot:
@@ -101,7 +131,11 @@ def _b2a_cno_pld(tr: dict, settings: Settings, done: int) -> dict:
             d_cno, d_pld = one(tr["I_P"][hi - n_int:hi], tr["Q_P"][hi - n_int:hi])
             cur[0] = 10 * np.log10(d_cno)
             p_cno = 0.0
-            if pilot:                                  # Calc_CNo_PLD.m:60-61: the pilot rows swap roles
+            if pilot and int(settings.pilotTRKflag) == 2:   # B1C Calc_CNo_PLD.m: the composite full-band pilot is in phase
+                p_cno, p_pld = one(tr["Pilot_I_P"][hi - n_int:hi], tr["Pilot_Q_P"][hi - n_int:hi])
+                cur[1] = 10 * np.log10(p_cno)
+                res["PilotPLD"][v - 1] = p_pld
+            elif pilot:                                # Calc_CNo_PLD.m:60-61: the pilot rows swap roles
                 p_cno, p_pld = one(tr["Pilot_Q_P"][hi - n_int:hi], tr["Pilot_I_P"][hi - n_int:hi])
                 cur[1] = 10 * np.log10(p_cno)
                 res["PilotPLD"][v - 1] = p_pld

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GC_ABI_VERSION 3
+#define GC_ABI_VERSION 4
 
 /* signal ids (reference folders).  Implemented: GPS/GPS_L1CA, GLO/GLO_GL1 + GLO/GLO_GL2 (the two
  * GLONASS folders differ only in settings.freqSpacing and the file name), BDS/B3I and GAL/GAL_E1C
@@ -106,10 +106,15 @@ typedef struct gc_handle gc_handle;
 /* With a quadrature pilot tracked (GPS L5C, GAL E5a/E5b, BDS B2a and pilot_trk_flag == 1) two more rows follow:
  * Pilot_I_P, Pilot_Q_P (GPS/GPS_L5C/include/tracking.m:57-60, 323-324); gc_track_nfields() tells which. */
 #define GC_TRACK_NFIELDS_PILOT 17
+/* GPS L2C with the CL pilot (pilot_trk_flag == 1, GPS/GPS_L2C/include/tracking.m:72-83, 396-402) and BDS B1C full-band
+ * tracking (pilot_trk_flag == 2, BDS/B1C/include/WB_tracking.m:60-67, 409-414) record all six pilot correlators:
+ * four more rows Pilot_I_E, Pilot_I_L, Pilot_Q_E, Pilot_Q_L. */
+#define GC_TRACK_NFIELDS_PILOT6 21
 enum {
     GC_F_ABSOLUTE_SAMPLE = 0, GC_F_CODE_FREQ, GC_F_CARR_FREQ, GC_F_I_P, GC_F_I_E, GC_F_I_L,
     GC_F_Q_E, GC_F_Q_P, GC_F_Q_L, GC_F_DLL_DISCR, GC_F_DLL_DISCR_FILT, GC_F_PLL_DISCR,
-    GC_F_PLL_DISCR_FILT, GC_F_REM_CODE_PHASE, GC_F_REM_CARR_PHASE
+    GC_F_PLL_DISCR_FILT, GC_F_REM_CODE_PHASE, GC_F_REM_CARR_PHASE,
+    GC_F_PILOT_I_P, GC_F_PILOT_Q_P, GC_F_PILOT_I_E, GC_F_PILOT_I_L, GC_F_PILOT_Q_E, GC_F_PILOT_Q_L
 };
 
 /* Length of the acqResults vectors for a signal: 32 for GPS L1CA indexed PRN-1 (acquisition.m:130-134),
@@ -136,9 +141,26 @@ const char* gc_last_error(const gc_handle* h);
  * the same way - the wrapper passes what the reference's own generateL5Icode / generateL5Qcode /
  * generateE5aIcode ... return (component 0 = data, 1 = pilot, nChips == 10230); GAL E5a also takes
  * component 2 = the PRN's 100-chip pilot secondary code (generateE5aQ_secondary.m) for the fine search.
+ * GPS L2C takes component 0 = the 20460-entry return-to-zero CM sequence (generateCMcode.m) and, when pilot_trk_flag == 1,
+ * component 1 = the 1534500-entry return-to-zero CL sequence (generateCLcode.m; entries +-1 and 0).  BDS B1C takes
+ * components 0 / 1 = the 20460 BOC(1,1) sub-chips of generateDataBOC11.m / generatePilotBOC11.m and, for full-band
+ * tracking (pilot_trk_flag == 2), component 2 = the 122760-entry pilot BOC(6,1) sequence of generatePilotBOC61.m.
  * Every SV named in gc_acquire / gc_track must have its components set.  Signals with generated
  * codes (GPS L1CA, GLONASS, B3I) return GC_ERR_ARG. */
 int gc_set_code(gc_handle* h, int32_t sv, int32_t component, const int8_t* chips, int32_t nChips);
+
+/* Scalar settings outside gc_config.  GC_PARAM_B1C_WB_FACTOR: the data-channel weight of the composite code
+ * discriminator in B1C full-band tracking, `factor = CalcWeighingFactor(settings)` (BDS/B1C/include/WB_tracking.m:124,
+ * CalcWeighingFactor.m:45-82 - adaptive quadrature of the BOC / QMBOC spectra over settings.FEBW, done by the caller);
+ * required before gc_track when pilot_trk_flag == 2. */
+enum { GC_PARAM_B1C_WB_FACTOR = 1 };
+int gc_set_param(gc_handle* h, int32_t key, double value);
+
+/* GPS L2C with pilot_trk_flag == 1: acqResults.CLCodePhase (1..75, 0 = not acquired; GPS_L2C/include/acquisition.m:100-137)
+ * of the last gc_acquire, indexed PRN-1 (32 entries), and channel(ch).CLCodePhase for the next gc_track (nCh entries,
+ * GPS_L2C/include/tracking.m:162; preRun.m copies it from acqResults). */
+int gc_get_cl_code_phase(const gc_handle* h, int32_t* clCodePhase);
+int gc_set_cl_code_phase(gc_handle* h, int32_t nCh, const int32_t* clCodePhase);
 
 /* Make an IF record resident in HBM.  `bytes` is the raw file image from byte 0
  * (what fopen/fread see, postProcessing.m:59-96): int8 I,Q interleaved for fileType 2.
@@ -188,7 +210,7 @@ int gc_acquire_host(gc_handle* h, const int8_t* iq, size_t nSamples,
  *   epochsDone    [nCh] completed epochs; < nEpochs means the record ran out (tracking.m:241-245):
  *                 as in the reference the whole call stops there and later channels stay untouched,
  *                 and `status` must be left '-' for every channel with epochsDone < nEpochs. */
-int gc_track_nfields(const gc_handle* h);   /* rows per channel in `out`: GC_TRACK_NFIELDS or GC_TRACK_NFIELDS_PILOT */
+int gc_track_nfields(const gc_handle* h);   /* rows per channel in `out`: GC_TRACK_NFIELDS, GC_TRACK_NFIELDS_PILOT or GC_TRACK_NFIELDS_PILOT6 */
 int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq,
              const double* codePhase, const double* codeFreq0, int32_t nEpochs,
              double* out, double* vsmValue, double* vsmIndex, int32_t* epochsDone);

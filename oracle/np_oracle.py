@@ -1351,8 +1351,9 @@ def acquisition_b1i(longSignal: np.ndarray, s: Settings, codes: dict, workers: i
 
 
 def acquisition_l2c(longSignal: np.ndarray, s: Settings, codes: dict, workers: int = 1):
-    """GPS/GPS_L2C/include/acquisition.m:4-118 without the CL phase search of :120-166 (pilotTRKflag == 0, the
-    folder's default).  codes[PRN][0] = the 20460-entry return-to-zero CM sequence generateCMcode.m returns."""
+    """GPS/GPS_L2C/include/acquisition.m:4-145.  codes[PRN][0] = the 20460-entry return-to-zero CM sequence
+    generateCMcode.m returns; with settings.pilotTRKflag == 1 the CL code phase search of :100-137 runs on the acquired
+    PRNs (codes[PRN][1] = the 1534500-entry return-to-zero CL sequence of generateCLcode.m) and CLCodePhase is returned."""
     Nblocks = 2
     N = samples_per_code(s)
     chip = int(matlab_round(s.samplingFreq / s.codeFreqBasis))      # :7
@@ -1368,7 +1369,8 @@ def acquisition_l2c(longSignal: np.ndarray, s: Settings, codes: dict, workers: i
     idx[-1] = int(s.codeLength) * 2
     idx[0] = 1
     res = dict(carrFreq=np.zeros(32), codePhase=np.zeros(32), peakMetric=np.zeros(32),
-               coarseBin=np.zeros(32, dtype=np.int64), coarseCodePhase=np.zeros(32, dtype=np.int64))
+               coarseBin=np.zeros(32, dtype=np.int64), coarseCodePhase=np.zeros(32, dtype=np.int64),
+               CLCodePhase=np.zeros(32, dtype=np.int64))
     initFreq = s.IF + (s.acqSearchBand / 2) * 1000
     for PRN in s.acqSatelliteList:
         cm = np.asarray(codes[PRN][0], dtype=np.float64)
@@ -1396,6 +1398,20 @@ def acquisition_l2c(longSignal: np.ndarray, s: Settings, codes: dict, workers: i
         if maxPeak / second > s.acqThreshold:
             res["carrFreq"][PRN - 1] = initFreq - freqResolution * (frequencyBinIndex - 1) - (freqResolution / Nshifts) * (freqShift - 1)   # :95
             res["codePhase"][PRN - 1] = codePhase
+            if int(getattr(s, "pilotTRKflag", 0)) == 1:              # :100-137
+                signal0DC = longSignal[codePhase - 1: codePhase - 1 + N]
+                signal0DC = signal0DC - np.mean(signal0DC)
+                phasePointsCL = np.arange(0, N, dtype=np.float64) * 2 * np.pi * ts
+                sigCarr = np.exp(-1j * res["carrFreq"][PRN - 1] * phasePointsCL)
+                CLCode = np.asarray(codes[PRN][1], dtype=np.float64)
+                cvi = np.ceil((ts * np.arange(0, N, dtype=np.float64)) / tc).astype(np.int64)   # :124
+                cvi[0] = 1
+                cvi[-1] = int(s.codeLength) if getattr(s, "acqCohT", 20) <= 10 else int(s.codeLength) * 2   # :128-133
+                powerArray = np.zeros(75)
+                for ind in range(1, 76):
+                    CLCodeSample = CLCode[cvi + int(s.codeLength) * 2 * (ind - 1) - 1]
+                    powerArray[ind - 1] = abs(np.sum(signal0DC * CLCodeSample * sigCarr))
+                res["CLCodePhase"][PRN - 1] = int(np.argmax(powerArray)) + 1
     return res
 
 
@@ -1487,10 +1503,13 @@ def acquisition_b1c(longSignal: np.ndarray, s: Settings, codes: dict, workers: i
 
 
 def tracking_l2c(raw: np.ndarray, channel: list, s: Settings, codes: dict):
-    """GPS/GPS_L2C/include/tracking.m:45-395 with settings.pilotTRKflag == 0 (the folder's default; the CL branch is not
-    restated): 20 ms epochs in half-chip units - the return-to-zero CM table of 2*codeLength entries, code NCO at
+    """GPS/GPS_L2C/include/tracking.m:45-405: 20 ms epochs in half-chip units - the return-to-zero CM table of 2*codeLength entries, code NCO at
     2*codeFreqBasis, spacing*2 (:93-94, :171) - fseek to codePhase (not codePhase-1, :153), fractional absoluteSample
-    (:223), and remCodePhase, codeFreq, dllDiscr, dllDiscrFilt recorded halved (:250, :376, :382-383)."""
+    (:223), and remCodePhase, codeFreq, dllDiscr, dllDiscrFilt recorded halved (:250, :376, :382-383).  With
+    settings.pilotTRKflag == 1 the CL pilot is correlated too: CLCode(tcode2 + codeLength*(CLCodePhase-1)) from the padded
+    CL sequence codes[PRN][1], CLCodePhase = channel.CLCodePhase stepping 1..75 every epoch (:259-286, :363-366), both
+    discriminator pairs averaged (:335-339, :359-361) and six Pilot_* rows recorded (:396-402)."""
+    pilotOn = int(getattr(s, "pilotTRKflag", 0)) == 1
     nE = int(matlab_round(s.msToProcess / 1000 / s.intTime))       # :51
     nV = int(math.floor(s.msToProcess / s.CNo_VSMinterval / 20))   # :80-83
     out = []
@@ -1501,6 +1520,9 @@ def tracking_l2c(raw: np.ndarray, channel: list, s: Settings, codes: dict):
             tr[f] = np.full(nE, np.inf)
         for f in ("I_P", "I_E", "I_L", "Q_E", "Q_P", "Q_L"):
             tr[f] = np.zeros(nE)
+        if pilotOn:                                                # :72-83
+            for f in ("Pilot_I_P", "Pilot_I_E", "Pilot_I_L", "Pilot_Q_E", "Pilot_Q_P", "Pilot_Q_L"):
+                tr[f] = np.zeros(nE)
         tr["VSMValue"] = np.zeros(nV); tr["VSMIndex"] = np.zeros(nV)
         out.append(tr)
     earlyLateSpc = s.dllCorrelatorSpacing * 2                      # :93
@@ -1516,6 +1538,10 @@ def tracking_l2c(raw: np.ndarray, channel: list, s: Settings, codes: dict):
         pos = 2 * (s.skipNumberOfBytes + channel[ch]["codePhase"])   # :153
         c = np.asarray(codes[channel[ch]["PRN"]][0], dtype=np.float64)
         cmCode = np.concatenate([[c[codeLength - 1]], c, [c[0]]])  # :155-156
+        if pilotOn:                                                # :160-167
+            CLCodePhase = int(channel[ch]["CLCodePhase"])
+            c = np.asarray(codes[channel[ch]["PRN"]][1], dtype=np.float64)
+            CLCode = np.concatenate([[c[-1]], c, [c[0]]])
         codeFreq = s.codeFreqBasis * 2; remCodePhase = 0.0         # :171-173
         carrFreq = channel[ch]["acquiredFreq"]; carrFreqBasis = channel[ch]["acquiredFreq"]; remCarrPhase = 0.0
         oldCodeNco = oldCodeError = 0.0
@@ -1545,10 +1571,24 @@ def tracking_l2c(raw: np.ndarray, channel: list, s: Settings, codes: dict):
             I_E = float(np.sum(cmCode[iE] * iB)); Q_E = float(np.sum(cmCode[iE] * qB))
             I_P = float(np.sum(cmCode[iP] * iB)); Q_P = float(np.sum(cmCode[iP] * qB))
             I_L = float(np.sum(cmCode[iL] * iB)); Q_L = float(np.sum(cmCode[iL] * qB))
+            if pilotOn:                                            # :261-285, :319-324
+                o = codeLength * (CLCodePhase - 1)
+                I_ECL = float(np.sum(CLCode[iE + o] * iB)); Q_ECL = float(np.sum(CLCode[iE + o] * qB))
+                I_PCL = float(np.sum(CLCode[iP + o] * iB)); Q_PCL = float(np.sum(CLCode[iP + o] * qB))
+                I_LCL = float(np.sum(CLCode[iL + o] * iB)); Q_LCL = float(np.sum(CLCode[iL + o] * qB))
             with np.errstate(divide="ignore", invalid="ignore"):
                 carrError = float(np.arctan(np.float64(Q_P) / np.float64(I_P)) / (2.0 * np.pi))
                 sE = math.sqrt(I_E ** 2 + Q_E ** 2); sL = math.sqrt(I_L ** 2 + Q_L ** 2)
                 codeError = float((np.float64(sE) - sL) / (np.float64(sE) + sL))
+                if pilotOn:
+                    carrErrorCL = float(np.arctan(np.float64(Q_PCL) / np.float64(I_PCL)) / (2.0 * np.pi))   # :335
+                    carrError = (carrError + carrErrorCL) / 2                                              # :339
+                    sEc = math.sqrt(I_ECL ** 2 + Q_ECL ** 2); sLc = math.sqrt(I_LCL ** 2 + Q_LCL ** 2)
+                    codeErrorCL = float((np.float64(sEc) - sLc) / (np.float64(sEc) + sLc))                # :359
+                    codeError = (codeError + codeErrorCL) / 2                                              # :361
+                    CLCodePhase = CLCodePhase + 1                                                          # :363-366
+                    if CLCodePhase >= 76:
+                        CLCodePhase = 1
             d2CarrError = d2CarrError + carrError * pf3
             dCarrError = d2CarrError + carrError * pf2 + dCarrError
             carrNco = dCarrError + carrError * pf1
@@ -1556,6 +1596,9 @@ def tracking_l2c(raw: np.ndarray, channel: list, s: Settings, codes: dict):
             carrFreq = carrFreqBasis + carrNco
             codeNco = oldCodeNco + (tau2code / tau1code) * (codeError - oldCodeError) + codeError * (PDIcode / tau1code)
             oldCodeNco = codeNco; oldCodeError = codeError
+            if pilotOn:                                            # :396-402
+                tr["Pilot_I_E"][loopCnt - 1] = I_ECL; tr["Pilot_I_P"][loopCnt - 1] = I_PCL; tr["Pilot_I_L"][loopCnt - 1] = I_LCL
+                tr["Pilot_Q_E"][loopCnt - 1] = Q_ECL; tr["Pilot_Q_P"][loopCnt - 1] = Q_PCL; tr["Pilot_Q_L"][loopCnt - 1] = Q_LCL
             tr["codeFreq"][loopCnt - 1] = codeFreq / 2             # :376
             codeFreq = s.codeFreqBasis * 2 - codeNco               # :379
             tr["dllDiscr"][loopCnt - 1] = codeError / 2; tr["dllDiscrFilt"][loopCnt - 1] = codeNco / 2   # :382-383
@@ -1572,6 +1615,40 @@ def tracking_l2c(raw: np.ndarray, channel: list, s: Settings, codes: dict):
 
 
 def tracking_b1c_nb(raw: np.ndarray, channel: list, s: Settings, codes: dict):
+    return _tracking_b1c(raw, channel, s, codes, False, 0.0)
+
+
+def CalcWeighingFactor(s: Settings) -> float:
+    """BDS/B1C/include/CalcWeighingFactor.m:45-82: data-channel weight of the full-band code discriminator from the BOC(1,1)
+    and QMBOC power spectra integrated over the front-end bandwidth settings.FEBW.  MATLAB's `integral` (adaptive
+    Gauss-Kronrod, RelTol 1e-6) and scipy's `quad` agree to ~1e-9 relative here; the factor is a settings-derived scalar
+    that the engine takes from its caller."""
+    from scipy.integrate import quad
+    fc = s.codeFreqBasis; Tc = 1 / fc; Br = s.FEBW
+    def boc(f, m):                                                  # BOC(m,1) spectrum, m = 1 -> pi/2, m = 6 -> pi/12
+        a = np.pi / (2 * m)
+        return Tc * (np.sin(a * f / fc) * np.sin(np.pi * f / fc) / np.cos(a * f / fc) * fc / f / np.pi) ** 2
+    G11 = lambda f: boc(f, 1)
+    Gp = lambda f: 29 / 33 * boc(f, 1) + 4 / 33 * boc(f, 6)
+    def I(g):                                                       # even integrand, removable singularity at 0
+        return 2 * quad(g, 0, Br / 2, limit=400, epsabs=0, epsrel=1e-12)[0]
+    P11 = I(G11); P11_2 = I(lambda f: G11(f) * f ** 2)
+    Pp = I(Gp); Pp_2 = I(lambda f: Gp(f) * f ** 2)
+    rms11 = (P11_2 / P11) ** 0.5; rmsp = (Pp_2 / Pp) ** 0.5
+    temp1 = 11 * P11 * rms11 ** 2
+    temp2 = 33 * Pp * rmsp ** 2
+    return float(temp1 / (temp1 + temp2))
+
+
+def tracking_b1c_wb(raw: np.ndarray, channel: list, s: Settings, codes: dict, factor: float):
+    """BDS/B1C/include/WB_tracking.m:47-474 (settings.pilotTRKflag == 2): as NB_tracking plus the pilot BOC(6,1) table
+    codes[PRN][2] (122760 entries) indexed by ceil(tcode*6)+1 (:283-305), 18 sums, composite pilot correlations
+    -sqrt(4/33)*p61 +- sqrt(29/33)*p11 cross terms (:339-344), carrier error (data + 3*pilot)/4 (:356), code error weighted by
+    `factor` = CalcWeighingFactor(settings) (:374), six composite Pilot_* rows recorded (:409-414)."""
+    return _tracking_b1c(raw, channel, s, codes, True, factor)
+
+
+def _tracking_b1c(raw: np.ndarray, channel: list, s: Settings, codes: dict, wb: bool, factor: float):
     """BDS/B1C/include/NB_tracking.m:47-365 (settings.pilotTRKflag == 1): 10 ms epochs, BOC(1,1) sub-chip tables indexed by
     ceil(tcode*2)+1 (:225-246), code NCO centred on channel.codeFreq, the pilot in quadrature with atan(-I/Q) (:301), carrier
     and code discriminators weighted 11/40 : 29/40 (:302, :318), code discriminators scaled by (1 - spacing) (:313-317),
@@ -1585,6 +1662,9 @@ def tracking_b1c_nb(raw: np.ndarray, channel: list, s: Settings, codes: dict):
             tr[f] = np.full(nE, np.inf)
         for f in ("I_P", "I_E", "I_L", "Q_E", "Q_P", "Q_L", "Pilot_I_P", "Pilot_Q_P"):
             tr[f] = np.zeros(nE)
+        if wb:
+            for f in ("Pilot_I_E", "Pilot_I_L", "Pilot_Q_E", "Pilot_Q_L"):
+                tr[f] = np.zeros(nE)
         out.append(tr)
     spc = s.dllCorrelatorSpacing
     codeLength = int(s.codeLength)
@@ -1602,6 +1682,9 @@ def tracking_b1c_nb(raw: np.ndarray, channel: list, s: Settings, codes: dict):
         D = np.concatenate([[c[2 * codeLength - 1]], c, [c[0]]])   # :155-156
         c = np.asarray(codes[PRN][1], dtype=np.float64)
         P11 = np.concatenate([[c[2 * codeLength - 1]], c, [c[0]]])
+        if wb:                                                     # WB_tracking.m:181-183
+            c = np.asarray(codes[PRN][2], dtype=np.float64)
+            P61 = np.concatenate([[c[12 * codeLength - 1]], c, [c[0]]])
         codeFreq = channel[ch]["codeFreq"]; remCodePhase = 0.0     # :163
         carrFreq = channel[ch]["acquiredFreq"]; carrFreqBasis = channel[ch]["acquiredFreq"]; remCarrPhase = 0.0
         oldCodeNco = oldCodeError = 0.0
@@ -1633,15 +1716,34 @@ def tracking_b1c_nb(raw: np.ndarray, channel: list, s: Settings, codes: dict):
             pI_E = float(np.sum(P11[iE] * iB)); pQ_E = float(np.sum(P11[iE] * qB))
             pI_P = float(np.sum(P11[iP] * iB)); pQ_P = float(np.sum(P11[iP] * qB))
             pI_L = float(np.sum(P11[iL] * iB)); pQ_L = float(np.sum(P11[iL] * qB))
-            with np.errstate(divide="ignore", invalid="ignore"):
-                carrError = float(np.arctan(np.float64(Q_P) / np.float64(I_P)) / (2.0 * np.pi))
-                p11_carrError = float(np.arctan(-np.float64(pI_P) / np.float64(pQ_P)) / (2.0 * np.pi))   # :301
-                carrError = (carrError * 11 + p11_carrError * 29) / 40                                   # :302
-                sE = math.sqrt(I_E ** 2 + Q_E ** 2); sL = math.sqrt(I_L ** 2 + Q_L ** 2)
-                codeError = float((np.float64(sE) - sL) / (np.float64(sE) + sL)) * (1 - spc)             # :313-314
-                sEp = math.sqrt(pI_E ** 2 + pQ_E ** 2); sLp = math.sqrt(pI_L ** 2 + pQ_L ** 2)
-                p11_codeError = float((np.float64(sEp) - sLp) / (np.float64(sEp) + sLp)) * (1 - spc)     # :315-317
-                codeError = (codeError * 11 + p11_codeError * 29) / 40                                   # :318
+            if wb:
+                jE = np.ceil(tE * 6).astype(np.int64); jL = np.ceil(tL * 6).astype(np.int64); jP = np.ceil(tP * 6).astype(np.int64)   # :283,294,305
+                sI_E = float(np.sum(P61[jE] * iB)); sQ_E = float(np.sum(P61[jE] * qB))
+                sI_P = float(np.sum(P61[jP] * iB)); sQ_P = float(np.sum(P61[jP] * qB))
+                sI_L = float(np.sum(P61[jL] * iB)); sQ_L = float(np.sum(P61[jL] * qB))
+                a61 = -math.sqrt(4 / 33); b11 = math.sqrt(29 / 33)
+                cI_E = a61 * sI_E + b11 * pQ_E; cQ_E = a61 * sQ_E - b11 * pI_E    # :339-344
+                cI_P = a61 * sI_P + b11 * pQ_P; cQ_P = a61 * sQ_P - b11 * pI_P
+                cI_L = a61 * sI_L + b11 * pQ_L; cQ_L = a61 * sQ_L - b11 * pI_L
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    carrError = float(np.arctan(np.float64(Q_P) / np.float64(I_P)) / (2.0 * np.pi))
+                    p_carrError = float(np.arctan(np.float64(cQ_P) / np.float64(cI_P)) / (2.0 * np.pi))       # :353
+                    carrError = (carrError * 1 + p_carrError * 3) / 4                                         # :356
+                    sE = math.sqrt(I_E ** 2 + Q_E ** 2); sL = math.sqrt(I_L ** 2 + Q_L ** 2)
+                    codeError = float((np.float64(sE) - sL) / (np.float64(sE) + sL)) * (1 - spc)              # :366-367
+                    sEp = math.sqrt(cI_E ** 2 + cQ_E ** 2); sLp = math.sqrt(cI_L ** 2 + cQ_L ** 2)
+                    p_codeError = float((np.float64(sEp) - sLp) / (np.float64(sEp) + sLp)) * (1 - spc)        # :371-372
+                    codeError = codeError * factor + p_codeError * (1 - factor)                               # :374
+            if not wb:
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    carrError = float(np.arctan(np.float64(Q_P) / np.float64(I_P)) / (2.0 * np.pi))
+                    p11_carrError = float(np.arctan(-np.float64(pI_P) / np.float64(pQ_P)) / (2.0 * np.pi))   # :301
+                    carrError = (carrError * 11 + p11_carrError * 29) / 40                                   # :302
+                    sE = math.sqrt(I_E ** 2 + Q_E ** 2); sL = math.sqrt(I_L ** 2 + Q_L ** 2)
+                    codeError = float((np.float64(sE) - sL) / (np.float64(sE) + sL)) * (1 - spc)             # :313-314
+                    sEp = math.sqrt(pI_E ** 2 + pQ_E ** 2); sLp = math.sqrt(pI_L ** 2 + pQ_L ** 2)
+                    p11_codeError = float((np.float64(sEp) - sLp) / (np.float64(sEp) + sLp)) * (1 - spc)     # :315-317
+                    codeError = (codeError * 11 + p11_codeError * 29) / 40                                   # :318
             d2CarrError = d2CarrError + carrError * pf3
             dCarrError = d2CarrError + carrError * pf2 + dCarrError
             carrNco = dCarrError + carrError * pf1
@@ -1655,6 +1757,11 @@ def tracking_b1c_nb(raw: np.ndarray, channel: list, s: Settings, codes: dict):
             tr["pllDiscr"][loopCnt - 1] = carrError; tr["pllDiscrFilt"][loopCnt - 1] = carrNco
             tr["I_E"][loopCnt - 1] = I_E; tr["I_P"][loopCnt - 1] = I_P; tr["I_L"][loopCnt - 1] = I_L
             tr["Q_E"][loopCnt - 1] = Q_E; tr["Q_P"][loopCnt - 1] = Q_P; tr["Q_L"][loopCnt - 1] = Q_L
-            tr["Pilot_I_P"][loopCnt - 1] = pI_P; tr["Pilot_Q_P"][loopCnt - 1] = pQ_P
+            if wb:                                                 # WB_tracking.m:409-414: the composite pilot correlations
+                tr["Pilot_I_E"][loopCnt - 1] = cI_E; tr["Pilot_Q_E"][loopCnt - 1] = cQ_E
+                tr["Pilot_I_P"][loopCnt - 1] = cI_P; tr["Pilot_Q_P"][loopCnt - 1] = cQ_P
+                tr["Pilot_I_L"][loopCnt - 1] = cI_L; tr["Pilot_Q_L"][loopCnt - 1] = cQ_L
+            else:
+                tr["Pilot_I_P"][loopCnt - 1] = pI_P; tr["Pilot_Q_P"][loopCnt - 1] = pQ_P
         tr["status"] = channel[ch]["status"]
     return out

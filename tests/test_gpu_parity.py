@@ -755,6 +755,139 @@ def test_l2c_tracking_and_wrappers_vs_oracle(fs, nE, tmp_path):
     eng.close()
 
 
+def _l2c_pilot_case(fs, nE, cn0=45):
+    """GPS L2C scene with the CL pilot time-multiplexed into the CM signal; settings with pilotTRKflag = 1."""
+    from cu_sdr_collection_b200.codes import standin_varb_codes, standin_l2c_cl_codes
+    sc = synth.default_scene_varb("GPS_L2C", standin_varb_codes("GPS_L2C"), fs=fs, nsat=2, seed=3)
+    codes = standin_l2c_cl_codes([x.prn for x in sc.sats] + [30])
+    sc.codes = codes
+    for x in sc.sats:
+        x.cn0 = cn0
+    sv = sorted({x.prn for x in sc.sats} | {30})
+    s = init_settings("GPS_L2C", samplingFreq=fs, acqSatelliteList=sv, acqSearchBand=9.0, pilotTRKflag=1, msToProcess=20 * nE,
+                      numberOfChannels=3, CNo_VSMinterval=10)
+    so = to_oracle_settings(s)
+    so.stepSize, so.acqStep, so.acqCohT = s.stepSize, s.acqStep, s.acqCohT
+    return codes, sc, s, so, sv
+
+
+def test_l2c_cl_phase_search_vs_oracle():
+    """GPS L2C acquisition with pilotTRKflag == 1: the 75-way CL code phase search on the acquired PRNs
+    (GPS_L2C acquisition.m:100-137) returns the oracle's CLCodePhase, which is the segment the scene put there."""
+    fs = 2.046e6
+    codes, sc, s, so, sv = _l2c_pilot_case(fs, 4)
+    N = O.samples_per_code(so)
+    raw = synth.make_record(sc, N * 3)
+    longSignal = (raw[0::2] + 1j * raw[1::2]).astype(np.complex128)
+    ref = O.acquisition_l2c(longSignal, so, codes, workers=os.cpu_count() or 1)
+    eng = Engine(s, codes=codes)
+    got = acquisition(longSignal, s, engine=eng, verbose=False)
+    assert np.array_equal(got["carrFreq"], ref["carrFreq"]) and np.array_equal(got["codePhase"], ref["codePhase"])
+    assert np.array_equal(got["CLCodePhase"], ref["CLCodePhase"]), (got["CLCodePhase"], ref["CLCodePhase"])
+    for sat in sc.sats:
+        assert got["carrFreq"][sat.prn - 1] != 0
+        assert got["CLCodePhase"][sat.prn - 1] == (sat.bit_offset + 1) % 75 + 1       # the CM period that starts inside the record
+    assert got["CLCodePhase"][30 - 1] == 0
+    ch = preRun(got, s)
+    assert ch[0]["CLCodePhase"] == got["CLCodePhase"][ch[0]["PRN"] - 1]
+    eng.close()
+
+
+@pytest.mark.parametrize("fs,nE", [(2.046e6, 80), (8e6, 10)])
+def test_l2c_cl_pilot_tracking_vs_oracle(fs, nE, tmp_path):
+    """GPS L2C tracking() with the CL pilot (pilotTRKflag == 1): the pilot table is the CL segment CLCodePhase points at,
+    reloaded every 20 ms epoch and stepping 1..75 (past the wrap here); both discriminator pairs averaged; six Pilot rows."""
+    codes, sc, s, so, sv = _l2c_pilot_case(fs, nE)
+    N = O.samples_per_code(so)
+    raw = synth.make_record(sc, N * (nE + 2))
+    ch = []
+    for sat in sc.sats:
+        start = (20460 - sat.code_phase) * (fs / 1.023e6)
+        ch.append(dict(PRN=sat.prn, acquiredFreq=float(round(s.IF + sat.doppler)), codePhase=int(round(start)) % N, status="T",
+                       CLCodePhase=(sat.bit_offset + 1) % 75 + 1))
+    ch.append(dict(PRN=0, acquiredFreq=0.0, codePhase=0, status="-", CLCodePhase=0))
+    path = tmp_path / "l2c.bin"
+    raw.tofile(path)
+    eng = Engine(s, codes=codes)
+    with open(path, "rb") as fid:
+        tr, _ = tracking(fid, ch, s, engine=eng)
+    ref = O.tracking_l2c(raw, ch, so, codes)
+    for i in range(2):
+        assert tr[i]["status"] == "T" == ref[i]["status"] and tr[i]["epochsDone"] == nE
+        ok = first_illconditioned_epoch(2 * ref[i]["remCodePhase"], 2 * ref[i]["codeFreq"], 2 * tr[i]["remCodePhase"], 2 * tr[i]["codeFreq"],
+                                        np.floor(ref[i]["absoluteSample"]), fs, 2 * s.dllCorrelatorSpacing)
+        assert ok >= min(10, nE)
+        sc_ = np.hypot(ref[i]["I_P"], ref[i]["Q_P"])
+        for name in ("I_P", "Q_P", "I_E", "I_L", "Q_E", "Q_L", "Pilot_I_P", "Pilot_Q_P", "Pilot_I_E", "Pilot_I_L", "Pilot_Q_E", "Pilot_Q_L"):
+            assert np.max(np.abs(tr[i][name][:ok] - ref[i][name][:ok]) / sc_[:ok]) < IQ_TOL, name
+        assert np.max(np.abs(tr[i]["carrFreq"][:ok] - ref[i]["carrFreq"][:ok])) < 1e-4
+        assert np.max(np.abs(tr[i]["codeFreq"][:ok] - ref[i]["codeFreq"][:ok])) < 1e-4
+        # the pilot carries the CL chips: its prompt correlator is as strong as the data one and in phase with it
+        # (8 samples per half chip; at 2 the return-to-zero triangle is too coarse for the loops to settle)
+        pw = np.hypot(tr[i]["Pilot_I_P"], tr[i]["Pilot_Q_P"]), np.hypot(tr[i]["I_P"], tr[i]["Q_P"])
+        assert np.mean(pw[0]) > 0.5 * np.mean(pw[1])
+        if fs == 8e6:
+            assert np.mean(np.abs(tr[i]["Pilot_I_P"][nE // 2:])) > 2 * np.mean(np.abs(tr[i]["Pilot_Q_P"][nE // 2:]))
+    assert tr[2]["status"] == "-"
+    eng.close()
+
+
+@pytest.mark.parametrize("fs,nE", [(4.092e6, 40), (18e6, 6)])
+def test_b1c_wb_tracking_vs_oracle(fs, nE, tmp_path):
+    """BDS B1C WB_tracking (pilotTRKflag 2): data BOC(1,1), pilot BOC(1,1) and pilot BOC(6,1) tables (int8, 18 sums), the
+    BOC(6,1) index ceil(tcode*6)+1, composite pilot correlations, carrier (data + 3 pilot)/4, code error weighted by
+    CalcWeighingFactor's factor, six composite Pilot rows."""
+    from cu_sdr_collection_b200.codes import standin_b1c_codes, boc61_from_boc11
+    from cu_sdr_collection_b200.tracking import calc_weighing_factor
+    base = standin_b1c_codes()
+    sc = synth.default_scene_varb("BDS_B1C", base, fs=fs, nsat=2, seed=3)
+    codes = {x.prn: (base[x.prn][0], base[x.prn][1], boc61_from_boc11(base[x.prn][1])) for x in sc.sats}
+    sc.codes = codes
+    for x in sc.sats:
+        x.cn0 = 46
+    s = init_settings("BDS_B1C", samplingFreq=fs, acqSatelliteList=sorted(x.prn for x in sc.sats), msToProcess=10 * nE,
+                      numberOfChannels=3, CNo_VSMinterval=2, pilotTRKflag=2)
+    so = to_oracle_settings(s)
+    so.FEBW = s.FEBW
+    factor = calc_weighing_factor(s)
+    assert abs(factor - O.CalcWeighingFactor(so)) < 1e-12 and 0.1 < factor < 0.25
+    N = O.samples_per_code(so)
+    raw = synth.make_record(sc, N * (nE + 2))
+    acq = dict(carrFreq=np.zeros(63), codePhase=np.zeros(63), peakMetric=np.zeros(63))
+    for i, sat in enumerate(sc.sats):
+        start = (20460 - sat.code_phase) * (fs / 2.046e6)
+        acq["carrFreq"][sat.prn - 1] = round((s.IF + sat.doppler) / 25.0) * 25.0
+        acq["codePhase"][sat.prn - 1] = int(round(start)) % N + 1
+        acq["peakMetric"][sat.prn - 1] = 20.0 - i
+    ch = preRun(acq, s)
+    path = tmp_path / "b1c.bin"
+    raw.tofile(path)
+    eng = Engine(s, codes=codes)
+    with open(path, "rb") as fid:
+        tr, _ = tracking(fid, ch, s, engine=eng)
+    ref = O.tracking_b1c_wb(raw, ch, so, codes, factor)
+    names = ("I_P", "Q_P", "I_E", "I_L", "Q_E", "Q_L", "Pilot_I_P", "Pilot_Q_P", "Pilot_I_E", "Pilot_I_L", "Pilot_Q_E", "Pilot_Q_L")
+    for i in range(2):
+        assert tr[i]["status"] == "T" == ref[i]["status"] and tr[i]["epochsDone"] == nE
+        assert np.array_equal(tr[i]["absoluteSample"], ref[i]["absoluteSample"])
+        ok = first_illconditioned_epoch(ref[i]["remCodePhase"], ref[i]["codeFreq"], tr[i]["remCodePhase"], tr[i]["codeFreq"],
+                                        ref[i]["absoluteSample"], fs, s.dllCorrelatorSpacing, sub=12.0)
+        assert ok >= min(6, nE)
+        sc_ = np.hypot(ref[i]["Pilot_I_P"], ref[i]["Pilot_Q_P"])
+        for name in names:
+            assert np.max(np.abs(tr[i][name][:ok] - ref[i][name][:ok]) / sc_[:ok]) < IQ_TOL, name
+        assert np.max(np.abs(tr[i]["carrFreq"][:ok] - ref[i]["carrFreq"][:ok])) < 1e-4
+        assert np.max(np.abs(tr[i]["codeFreq"][:ok] - ref[i]["codeFreq"][:ok])) < 1e-4
+        assert np.max(np.abs(tr[i]["dllDiscr"][:ok] - ref[i]["dllDiscr"][:ok])) < 1e-5
+        # the composite pilot is in phase (atan(p_Q_P / p_I_P), :353) and carries 3/4 of the power
+        if nE >= 40:                                   # (6 epochs are not enough to pull in from a 25 Hz grid)
+            assert np.mean(np.abs(tr[i]["Pilot_I_P"][nE // 2:])) > 2 * np.mean(np.abs(tr[i]["Pilot_Q_P"][nE // 2:]))
+        assert np.mean(np.hypot(tr[i]["Pilot_I_P"], tr[i]["Pilot_Q_P"])) > 1.2 * np.mean(np.hypot(tr[i]["I_P"], tr[i]["Q_P"]))
+        assert tr[i]["DataCNo"].shape == (nE // 2,) and np.all(np.isfinite(tr[i]["PilotCNo"][1:]))
+    assert tr[2]["status"] == "-"
+    eng.close()
+
+
 @pytest.mark.parametrize("fs,nE", [(4.092e6, 40), (18e6, 8)])
 def test_b1c_nb_tracking_and_wrappers_vs_oracle(fs, nE, tmp_path):
     """BDS B1C NB_tracking (pilotTRKflag 1): 10 ms epochs (180000 samples at 18 Msps, one sample window in shared memory

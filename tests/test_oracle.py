@@ -447,3 +447,83 @@ def test_b1c_oracle_closed_loop():
         assert abs(ref["carrFreq"][sat.prn - 1] - (s.IF + sat.doppler)) <= 25
         start = (20460 - sat.code_phase) * (fs / 2.046e6)
         assert abs((ref["codePhase"][sat.prn - 1] - 1 - start + N / 2) % N - N / 2) <= 2
+
+
+def test_l2c_cl_pilot_oracle_closed_loop():
+    """GPS L2C with the CL pilot (pilotTRKflag == 1): the CL phase search of acquisition.m:100-137 returns the CL segment
+    the scene multiplexed in, and the tracking restatement with the CL pilot locks with both prompts in phase."""
+    from cu_sdr_collection_b200 import init_settings
+    from helpers import to_oracle_settings
+    fs = 2.046e6
+    sc = synth.default_scene_varb("GPS_L2C", codes.standin_varb_codes("GPS_L2C"), fs=fs, nsat=1, seed=3)
+    tabs = codes.standin_l2c_cl_codes([x.prn for x in sc.sats])
+    sc.codes = tabs
+    sat = sc.sats[0]
+    sat.cn0 = 45
+    nE = 40
+    s = init_settings("GPS_L2C", samplingFreq=fs, acqSatelliteList=[sat.prn], acqSearchBand=9.0, pilotTRKflag=1, msToProcess=20 * nE,
+                      numberOfChannels=1, CNo_VSMinterval=10)
+    so = to_oracle_settings(s)
+    so.acqStep, so.acqCohT = s.acqStep, s.acqCohT
+    assert tabs[sat.prn][1].size == 2 * 767250 and not np.any(tabs[sat.prn][1][0::2]) and not np.any(tabs[sat.prn][0][1::2])
+    N = O.samples_per_code(so)
+    raw = synth.make_record(sc, N * (nE + 3))
+    acq = O.acquisition_l2c((raw[0::2] + 1j * raw[1::2]).astype(np.complex128)[: 3 * N], so, tabs, workers=os.cpu_count() or 1)
+    want = (sat.bit_offset + 1) % 75 + 1
+    assert acq["carrFreq"][sat.prn - 1] != 0 and acq["CLCodePhase"][sat.prn - 1] == want
+    # tracking at the folder's 8 Msps (8 samples per half chip; at 2 samples the return-to-zero triangle is too coarse to pull in)
+    fs = 8e6
+    sc.fs = fs
+    s = init_settings("GPS_L2C", samplingFreq=fs, acqSatelliteList=[sat.prn], pilotTRKflag=1, msToProcess=20 * nE,
+                      numberOfChannels=1, CNo_VSMinterval=10)
+    so = to_oracle_settings(s)
+    N = O.samples_per_code(so)
+    raw = synth.make_record(sc, N * (nE + 2))
+    start = (20460 - sat.code_phase) * (fs / 1.023e6)
+    # (hand-off within 1 Hz: with 20 ms epochs the two-quadrant atan pulls in over less than the 6 Hz the 12.5 Hz grid leaves)
+    ch = [dict(PRN=sat.prn, acquiredFreq=float(round(s.IF + sat.doppler)), codePhase=int(round(start)) % N, status="T", CLCodePhase=want)]
+    tr = O.tracking_l2c(raw, ch, so, tabs)[0]
+    assert tr["status"] == "T"
+    h = nE // 2
+    assert np.mean(np.abs(tr["I_P"][h:])) > 3 * np.mean(np.abs(tr["Q_P"][h:]))
+    assert np.mean(np.abs(tr["Pilot_I_P"][h:])) > 3 * np.mean(np.abs(tr["Pilot_Q_P"][h:]))
+    assert np.all(np.sign(tr["Pilot_I_P"][h:]) == np.sign(tr["Pilot_I_P"][h]))           # dataless pilot: no sign flips
+    # a wrong CL phase leaves the pilot correlators with noise only
+    ch[0]["CLCodePhase"] = want % 75 + 1
+    bad = O.tracking_l2c(raw[: 2 * N * 6], ch, so, tabs)[0]
+    assert np.mean(np.abs(bad["Pilot_I_P"][:5])) < 0.2 * np.mean(np.abs(tr["Pilot_I_P"][:5]))
+
+
+def test_b1c_wb_oracle_closed_loop():
+    """BDS B1C full-band restatement (WB_tracking.m): on a QMBOC pilot the composite pilot prompt is in phase and about
+    sqrt(3) times the data prompt; CalcWeighingFactor's factor is the ratio the reference's formula gives."""
+    from cu_sdr_collection_b200 import init_settings
+    from cu_sdr_collection_b200.tracking import calc_weighing_factor
+    from helpers import to_oracle_settings
+    base = codes.standin_b1c_codes()
+    fs = 4.092e6
+    sc = synth.default_scene_varb("BDS_B1C", base, fs=fs, nsat=1, seed=3)
+    sat = sc.sats[0]
+    sat.cn0 = 46
+    tabs = {sat.prn: (base[sat.prn][0], base[sat.prn][1], codes.boc61_from_boc11(base[sat.prn][1]))}
+    assert tabs[sat.prn][2].size == 122760 and np.array_equal(tabs[sat.prn][2][:12], -base[sat.prn][1][0] * np.array([-1, 1] * 6))
+    sc.codes = tabs
+    nE = 40
+    s = init_settings("BDS_B1C", samplingFreq=fs, acqSatelliteList=[sat.prn], msToProcess=10 * nE, numberOfChannels=1, pilotTRKflag=2)
+    so = to_oracle_settings(s)
+    so.FEBW = s.FEBW
+    factor = O.CalcWeighingFactor(so)
+    assert abs(factor - calc_weighing_factor(s)) < 1e-12 and 0.1 < factor < 0.25
+    N = O.samples_per_code(so)
+    raw = synth.make_record(sc, N * (nE + 2))
+    start = (20460 - sat.code_phase) * (fs / 2.046e6)
+    cf = round((s.IF + sat.doppler) / 25.0) * 25.0
+    ch = [dict(PRN=sat.prn, acquiredFreq=cf, codePhase=int(round(start)) % N + 1, status="T",
+               codeFreq=s.codeFreqBasis + (cf - s.IF) / s.carrFreqBasis * s.codeFreqBasis)]
+    tr = O.tracking_b1c_wb(raw, ch, so, tabs, factor)[0]
+    h = nE // 2
+    assert tr["status"] == "T"
+    assert np.mean(np.abs(tr["I_P"][h:])) > 3 * np.mean(np.abs(tr["Q_P"][h:]))
+    assert np.mean(np.abs(tr["Pilot_I_P"][h:])) > 3 * np.mean(np.abs(tr["Pilot_Q_P"][h:]))
+    ratio = np.mean(np.abs(tr["Pilot_I_P"][h:])) / np.mean(np.abs(tr["I_P"][h:]))
+    assert 1.5 < ratio < 2.0, ratio                                                     # sqrt(3) = 1.73
