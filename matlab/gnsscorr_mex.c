@@ -72,6 +72,9 @@ static void set_codes(gc_handle* h, const gc_config* cfg, const mxArray* codes)
 {
     const mxArray *sv = mxGetField(codes, 0, "sv"), *d = mxGetField(codes, 0, "data"), *p = mxGetField(codes, 0, "pilot");
     const mxArray* sec = mxGetField(codes, 0, "secondary");   /* GAL E5a only: int8 100 x numel(sv) */
+    const mxArray* cl = mxGetField(codes, 0, "cl");           /* GPS L2C with pilotTRKflag: int8 (150*codeLength) x numel(sv) */
+    const mxArray* b61 = mxGetField(codes, 0, "boc61");       /* BDS B1C with pilotTRKflag == 2: int8 (12*codeLength) x numel(sv) */
+    const mwSize clLen = (mwSize)150 * cfg->code_length, b61Len = (mwSize)12 * cfg->code_length;
     mwSize i, n;
     if (!sv || !d || !p || !mxIsInt8(d) || !mxIsInt8(p)) { gc_destroy(h); mexErrMsgIdAndTxt("gnsscorr:args", "codes: struct with sv, data (int8), pilot (int8)"); }
     const int single = (cfg->signal == GC_SIG_BDS_B1I || cfg->signal == GC_SIG_GPS_L2C);   /* one code per SV */
@@ -88,6 +91,10 @@ static void set_codes(gc_handle* h, const gc_config* cfg, const mxArray* codes)
         if (rc == GC_OK && !single) rc = gc_set_code(h, (int32_t)mxGetDoubles(sv)[i], 1, (const int8_t*)mxGetInt8s(p) + i * len, (int32_t)len);
         if (rc == GC_OK && sec && mxIsInt8(sec) && mxGetNumberOfElements(sec) == n * 100)
             rc = gc_set_code(h, (int32_t)mxGetDoubles(sv)[i], 2, (const int8_t*)mxGetInt8s(sec) + i * 100, 100);
+        if (rc == GC_OK && cl && mxIsInt8(cl) && mxGetNumberOfElements(cl) == n * clLen)      /* GPS L2C CL pilot (generateCLcode.m) */
+            rc = gc_set_code(h, (int32_t)mxGetDoubles(sv)[i], 1, (const int8_t*)mxGetInt8s(cl) + i * clLen, (int32_t)clLen);
+        if (rc == GC_OK && b61 && mxIsInt8(b61) && mxGetNumberOfElements(b61) == n * b61Len)   /* BDS B1C full band (generatePilotBOC61.m) */
+            rc = gc_set_code(h, (int32_t)mxGetDoubles(sv)[i], 2, (const int8_t*)mxGetInt8s(b61) + i * b61Len, (int32_t)b61Len);
         if (rc != GC_OK) {
             char msg[512];
             strncpy(msg, gc_last_error(h), sizeof(msg) - 1);
@@ -120,7 +127,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
     check(NULL, gc_create(&h, &cfg), "gc_create");
 
     if (!strcmp(cmd, "acquire")) {
-        const char* names[] = {"carrFreq", "codePhase", "peakMetric"};
+        const char* names[] = {"carrFreq", "codePhase", "peakMetric", "CLCodePhase"};
         const int n = gc_acq_result_len(cfg.signal);
         const mwSize nSv = mxGetNumberOfElements(prhs[3]);
         const double* svd = mxGetDoubles(prhs[3]);
@@ -129,12 +136,18 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
         if ((nrhs != 4 && nrhs != 5) || !mxIsInt8(prhs[2]) || nSv > 64) { gc_destroy(h); mexErrMsgIdAndTxt("gnsscorr:args", "acquire: bad arguments"); }
         if (nrhs == 5) set_codes(h, &cfg, prhs[4]);
         for (i = 0; i < nSv; ++i) sv[i] = (int32_t)svd[i];
-        plhs[0] = mxCreateStructMatrix(1, 1, 3, names);
-        for (i = 0; i < 3; ++i) mxSetField(plhs[0], 0, names[i], mxCreateDoubleMatrix(1, n, mxREAL));
+        plhs[0] = mxCreateStructMatrix(1, 1, 4, names);
+        for (i = 0; i < 4; ++i) mxSetField(plhs[0], 0, names[i], mxCreateDoubleMatrix(1, n, mxREAL));
         check(h, gc_acquire_host(h, (const int8_t*)mxGetInt8s(prhs[2]), mxGetNumberOfElements(prhs[2]) / 2, (int32_t)nSv, sv,
                                  mxGetDoubles(mxGetField(plhs[0], 0, "carrFreq")), mxGetDoubles(mxGetField(plhs[0], 0, "codePhase")),
                                  mxGetDoubles(mxGetField(plhs[0], 0, "peakMetric")), NULL, NULL),
               "gc_acquire_host");
+        if (cfg.signal == GC_SIG_GPS_L2C && cfg.pilot_trk_flag == 1) {     /* acqResults.CLCodePhase (GPS_L2C acquisition.m:136) */
+            int32_t clp[32];
+            double* o = mxGetDoubles(mxGetField(plhs[0], 0, "CLCodePhase"));
+            check(h, gc_get_cl_code_phase(h, clp), "gc_get_cl_code_phase");
+            for (i = 0; i < 32 && i < (mwSize)n; ++i) o[i] = (double)clp[i];
+        }
     } else if (!strcmp(cmd, "track")) {
         const char* names[] = {"out", "vsmValue", "vsmIndex", "epochsDone"};
         char path[4096];
@@ -148,8 +161,17 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
         mwSize i;
         if (nrhs < 7 || nrhs > 9 || mxGetString(prhs[2], path, sizeof(path)) || nCh > 256) { gc_destroy(h); mexErrMsgIdAndTxt("gnsscorr:args", "track: bad arguments"); }
         if (nrhs == 9) set_codes(h, &cfg, prhs[8]);
+        if (mxGetField(prhs[1], 0, "wb_factor"))                          /* factor = CalcWeighingFactor(settings), B1C WB_tracking.m:124 */
+            check(h, gc_set_param(h, GC_PARAM_B1C_WB_FACTOR, field(prhs[1], "wb_factor")), "gc_set_param");
+        if (nrhs == 9 && mxGetField(prhs[8], 0, "clCodePhase")) {         /* channel.CLCodePhase (GPS_L2C tracking.m:162) */
+            const mxArray* a = mxGetField(prhs[8], 0, "clCodePhase");
+            int32_t clp[256];
+            if (mxGetNumberOfElements(a) != nCh) { gc_destroy(h); mexErrMsgIdAndTxt("gnsscorr:args", "track: clCodePhase must have one entry per channel"); }
+            for (i = 0; i < nCh; ++i) clp[i] = (int32_t)mxGetDoubles(a)[i];
+            check(h, gc_set_cl_code_phase(h, (int32_t)nCh, clp), "gc_set_cl_code_phase");
+        }
         for (i = 0; i < nCh; ++i) prn[i] = (prnd[i] != prnd[i]) ? GC_SV_NONE : (int32_t)prnd[i];   /* NaN = channel off (GLONASS) */
-        dims[0] = nEpochs; dims[1] = gc_track_nfields(h); dims[2] = nCh;   /* 15, or 17 with Pilot_I_P / Pilot_Q_P */
+        dims[0] = nEpochs; dims[1] = gc_track_nfields(h); dims[2] = nCh;   /* 15, 17 with Pilot_I_P / Pilot_Q_P, 21 with all six pilot rows */
         out = mxCreateNumericArray(3, dims, mxDOUBLE_CLASS, mxREAL);
         vv = mxCreateDoubleMatrix(nV, nCh, mxREAL);
         vi = mxCreateDoubleMatrix(nV, nCh, mxREAL);
