@@ -34,7 +34,10 @@ struct RowsParams {
     int nonCoh, nBins;
     int nRep, repStride;      // inverse: replicas summed per SV (1, or 2 = data + pilot) and their distance in Cc; the
                               // work buffer then holds nonCoh*nRep transforms per (SV, bin), replica index fastest
-    int prnPerCta, mPerCta;   // warps of an inverse CTA = prnPerCta x mPerCta (same row j1, same bin)
+    int prnPerCta, mPerCta;   // warps of an inverse CTA = binPerCta x prnPerCta x mPerCta (same row j1)
+    int binPerCta;            // bins per CTA (0 = 1); > 1 where a (SV, bin) cell has too few transforms to fill a CTA
+    const int2* binMap;       // optional [nBins]: .x = spectrum row in X (instead of bin*nonCoh + block), .y = circular shift of
+                              // the spectrum, circshift(IQfreqDom, y) (acquisition variants B and C); nullptr = variant A
     int nPrnChunk, prnSlot0;  // list slots [prnSlot0, prnSlot0 + nPrnChunk) are processed by this launch
     const int* prnList;       // [nSv] replica index per list slot (index into Cc)
 };
@@ -44,6 +47,9 @@ struct InvColsParams {
     int nBins, nonCoh, nPrnChunk, prnSlot0;
     float* partMax;           // [nSv][nBins][parts]
     int* partIdx;
+    int weighted;             // 1: magnitudes of even / odd transforms are weighted w0 / w1 and the sum scaled by wScale
+    float w0, w1, wScale;     // (BDS B1C: (|data|*sqrt(11) + |pilot|*sqrt(29)) / sqrt(40), acquisition.m:213-214)
+    float* magOut;            // optional [nPrnChunk][nBins][L]: the summed magnitudes in natural lag order (corrVec of variant B)
 };
 
 cudaError_t launch_fwd_cols(int L, const FwdColsParams& p, int nRows, bool codeMode, cudaStream_t s);
@@ -96,6 +102,7 @@ struct VarbRow {
 cudaError_t launch_varb_mulshift(const float2* X, const float2* Cc, const VarbRow* rows, int nRows, float2* out, int L, cudaStream_t st);
 cudaError_t launch_varb_rowpeak(const float2* W, int nRows, int L, float* peak, int* idx, cudaStream_t st);
 cudaError_t launch_varb_segmax(const float2* W, int nRows, int L, const int4* seg, float* out, cudaStream_t st);
+cudaError_t launch_varb_segmax_mag(const float* mag, int nRows, int L, const int4* seg, float* out, cudaStream_t st);
 cudaError_t launch_varb_pad(const int8_t* tab, int n, int nRows, float2* out, int L, cudaStream_t st);
 // GPS L2C: |sum((x - mean) .* CL segment .* carrier)| for the 75 CL segments (acquisition.m:100-137); codeIdx 1-based [N]
 cudaError_t launch_l2c_clphase(const int8_t* rec, long long start, int N, const int8_t* cl, int segLen, const int* codeIdx,

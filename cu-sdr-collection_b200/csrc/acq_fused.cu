@@ -129,19 +129,40 @@ inv_rows_kernel(RowsParams p)
     const int k1 = blockIdx.x, pg = blockIdx.y;
     const int M = p.nonCoh * p.nRep;                             // transforms per (SV, bin): blocks x replicas
     const int mGroups = (M + p.mPerCta - 1) / p.mPerCta;
-    const int k = blockIdx.z / mGroups, mg = blockIdx.z % mGroups;
-    const int pi = pg * p.prnPerCta + warp / p.mPerCta;         // list slot within this launch's chunk
-    const int mv = mg * p.mPerCta + warp % p.mPerCta;
-    if (pi >= p.nPrnChunk || mv >= M) return;
+    const int wpb = p.prnPerCta * p.mPerCta;                     // warps per bin
+    const int bpc = p.binPerCta > 1 ? p.binPerCta : 1;
+    const int k = (blockIdx.z / mGroups) * bpc + warp / wpb, mg = blockIdx.z % mGroups;
+    const int wl = warp % wpb;
+    const int pi = pg * p.prnPerCta + wl / p.mPerCta;           // list slot within this launch's chunk
+    const int mv = mg * p.mPerCta + wl % p.mPerCta;
+    if (pi >= p.nPrnChunk || mv >= M || k >= p.nBins) return;
     const int m = mv / p.nRep, r = mv - m * p.nRep;             // block, replica (data / pilot, GPS_L5C acquisition.m:171-175)
-    const float2* src = p.X + ((size_t)(k * p.nonCoh + m) * C + k1) * R;
+    // circshift(IQfreqDom, s) (BDS/B1I acquisition.m:88, GPS_L2C :73, B1C :203): product element j takes spectrum element j - s.
+    // With j = j1 + C*j2 (row j1, in-row frequency j2 held by its residues mod RA and mod RB) that is row (j1 - s) mod C
+    // and j2 - floor-part, i.e. a fixed source row and a circular shift of both residues.
+    int xrow = k * p.nonCoh + m, srow = k1, sa = 0, sb = 0;
+    if constexpr (!P::kPfa) {                                    // (the variant B / C lengths all have Cooley-Tukey plans)
+        if (p.binMap != nullptr) {
+            const int2 bm = p.binMap[k];
+            xrow = bm.x * p.nonCoh + m;
+            const int s1 = bm.y % C;
+            int s2 = bm.y / C;
+            srow = k1 - s1;
+            if (srow < 0) { srow += C; s2 += 1; }
+            sa = s2 % RA; sb = s2 % RB;
+        }
+    }
+    const float2* src = p.X + ((size_t)xrow * C + srow) * R;
     const float2* mul = p.Cc + ((size_t)(p.prnList[p.prnSlot0 + pi] + r * p.repStride) * C + k1) * R;
     float2* dst = p.W + (((size_t)(pi * p.nBins + k) * M + mv) * C + k1) * R;
     {                                                            // lane = ka: DFT-RB over kb
         float2 u[RB];
 #pragma unroll
-        for (int kb = 0; kb < RB; ++kb)                          // IQfreqDom .* caCodeFreqDom (:186)
-            u[kb] = cmul(src[kb * RA + lane], __ldg(mul + kb * RA + lane));
+        for (int kb = 0; kb < RB; ++kb) {                        // IQfreqDom .* caCodeFreqDom (:186)
+            int ks = kb - sb;
+            if (ks < 0) ks += RB;
+            u[kb] = cmul(src[ks * RA + ((lane - sa) & (RA - 1))], __ldg(mul + kb * RA + lane));
+        }
         codelet::dft<RB, true>(u, [&](int tb, float re, float im) { s_x[lane * kPitchI + tb] = make_float2(re, im); });
     }
     __syncwarp();
@@ -186,10 +207,14 @@ inv_cols_kernel(InvColsParams p)
             float2 x[C];
 #pragma unroll
             for (int k1 = 0; k1 < C; ++k1) x[k1] = __ldcs(base + (size_t)m * L + (size_t)k1 * R);
+            const float wm = p.weighted ? ((m & 1) ? p.w1 : p.w0) : 1.f;
             codelet::dft<C, true>(x, [&](int t1, float re, float im) {
-                acc[t1] += cabs_fast(re, im);        // abs(ifft(.)) summed over blocks (:188-190)
+                acc[t1] = fmaf(wm, cabs_fast(re, im), acc[t1]);        // abs(ifft(.)) summed over blocks (:188-190)
             });
         }
+        if (p.weighted)
+#pragma unroll
+            for (int i = 0; i < C; ++i) acc[i] *= p.wScale;
     }
     // running maximum with MATLAB first-index tie breaking (smaller code phase wins)
     float best = -1.f;
@@ -199,6 +224,7 @@ inv_cols_kernel(InvColsParams p)
 #pragma unroll
         for (int t1 = 0; t1 < C; ++t1) {
             const int idx = P::index(t1, rest);                 // code phase (lag) of this output
+            if (p.magOut) p.magOut[(size_t)(pi * p.nBins + k) * L + idx] = acc[t1];
             if (acc[t1] > best || (acc[t1] == best && idx < bidx)) { best = acc[t1]; bidx = idx; }
         }
     }
@@ -228,7 +254,8 @@ inv_cols_kernel(InvColsParams p)
 // A CTA handles TC adjacent row positions (columns), so global accesses are TC*8-byte runs.
 template <class P> struct BigGeo {
     static constexpr int C1 = P::C1, C2 = P::C2;
-    static constexpr int TC = (C1 > C2 ? C1 : C2) * 32 <= 1024 ? 32 : 16;     // columns per CTA
+    // columns per CTA: 32, or 16 where a 25-point phase would otherwise run at 800 threads (80 registers: spills)
+    static constexpr int TC = ((C1 > C2 ? C1 : C2) * 32 <= 640 && sizeof(float2) * P::C * 32 <= 110 * 1024) ? 32 : 16;
     static constexpr int NT = (C1 > C2 ? C1 : C2) * TC;                        // threads: max of the two phases
     static constexpr size_t kSmem = sizeof(float2) * P::C * TC;
 };
@@ -326,7 +353,8 @@ inv_cols_big_kernel(InvColsParams p)
             float2 y[C2];
 #pragma unroll
             for (int b = 0; b < C2; ++b) y[b] = Y[(q * C2 + b) * TC + col];
-            codelet::dft<C2, true>(y, [&](int tb, float re, float im) { acc[tb] += cabs_fast(re, im); });
+            const float wm = p.weighted ? ((m & 1) ? p.w1 : p.w0) : 1.f;
+            codelet::dft<C2, true>(y, [&](int tb, float re, float im) { acc[tb] = fmaf(wm, cabs_fast(re, im), acc[tb]); });
         }
         __syncthreads();
     }
@@ -337,6 +365,8 @@ inv_cols_big_kernel(InvColsParams p)
 #pragma unroll
         for (int tb = 0; tb < C2; ++tb) {
             const int idx = P::index(q + C1 * tb, rest);
+            if (p.weighted) acc[tb] *= p.wScale;
+            if (p.magOut) p.magOut[(size_t)(pi * p.nBins + k) * L + idx] = acc[tb];
             if (acc[tb] > best || (acc[tb] == best && idx < bidx)) { best = acc[tb]; bidx = idx; }
         }
     }
@@ -397,14 +427,15 @@ struct Launch {
         if (e != cudaSuccess) return e;
         const int mGroups = (p.nonCoh * p.nRep + p.mPerCta - 1) / p.mPerCta;
         const int pGroups = (p.nPrnChunk + p.prnPerCta - 1) / p.prnPerCta;
-        dim3 grid(P::C, pGroups, p.nBins * mGroups);
+        const int bpc = p.binPerCta > 1 ? p.binPerCta : 1;
+        dim3 grid(P::C, pGroups, ((p.nBins + bpc - 1) / bpc) * mGroups);
         inv_rows_kernel<P, WARPS, MINB><<<grid, WARPS * 32, smem, s>>>(p);
         return cudaGetLastError();
     }
     // p.prnPerCta * p.mPerCta warps per CTA: 5 (96 registers, 20 warps/SM) or 8 (128 registers, 16 warps/SM)
     static cudaError_t inv_rows(const RowsParams& p, cudaStream_t s)
     {
-        return (p.prnPerCta * p.mPerCta == 8) ? inv_rows_t<8, 2>(p, s) : inv_rows_t<5, 4>(p, s);
+        return ((p.binPerCta > 1 ? p.binPerCta : 1) * p.prnPerCta * p.mPerCta == 8) ? inv_rows_t<8, 2>(p, s) : inv_rows_t<5, 4>(p, s);
     }
     static cudaError_t inv_cols(const InvColsParams& p, cudaStream_t s)
     {
@@ -443,6 +474,9 @@ bool fused_plan_info(int L, FusedPlanInfo* o)
         case P40000::L: fill_info<P40000>(o); return true;
         case P160000::L: fill_info<P160000>(o); return true;
         case P144000::L: fill_info<P144000>(o); return true;
+        case P320000::L: fill_info<P320000>(o); return true;
+        case P360000::L: fill_info<P360000>(o); return true;
+        case P72000::L: fill_info<P72000>(o); return true;
         default: return false;
     }
 }

@@ -41,6 +41,9 @@ using P32000 = Plan<40, 32, 25>;   // 16 Msps
 using P40000 = Plan<50, 32, 25>;   // 20 Msps
 using P160000 = Plan<200, 32, 25, 8>;    // Galileo E1 (4 ms codes) at 20 Msps: columns 200 = 8 x 25
 using P144000 = Plan<180, 32, 25, 20>;   // Galileo E1 at 18 Msps (reference default): columns 180 = 20 x 9
+using P320000 = Plan<400, 32, 25, 16>;   // GPS L2C at 8 Msps (40 ms block): columns 400 = 16 x 25
+using P360000 = Plan<450, 32, 25, 18>;   // BDS B1C at 18 Msps (20 ms): columns 450 = 18 x 25
+using P72000 = Plan<90, 32, 25, 10>;     // BDS B1I at 18 Msps (4 ms blocks): columns 90 = 10 x 9
 
 #define GC_PLAN_DISPATCH(LEN, CALL)                             \
     switch (LEN) {                                              \
@@ -51,6 +54,9 @@ using P144000 = Plan<180, 32, 25, 20>;   // Galileo E1 at 18 Msps (reference def
         case P40000::L: return Launch<P40000>::CALL;            \
         case P160000::L: return Launch<P160000>::CALL;          \
         case P144000::L: return Launch<P144000>::CALL;          \
+        case P320000::L: return Launch<P320000>::CALL;          \
+        case P360000::L: return Launch<P360000>::CALL;          \
+        case P72000::L: return Launch<P72000>::CALL;            \
         default: return cudaErrorInvalidValue;                  \
     }
 

@@ -76,6 +76,25 @@ segmax_kernel(const float2* __restrict__ W, int L, const int4* __restrict__ seg,
     }
 }
 
+// same on a row of magnitudes (the fused path writes corrVec itself)
+__global__ void __launch_bounds__(1024)
+segmax_mag_kernel(const float* __restrict__ mag, int L, const int4* __restrict__ seg, float* out)
+{
+    const float* w = mag + (size_t)blockIdx.x * L;
+    const int4 s = seg[blockIdx.x];
+    float best = -1.f;
+    for (int j = s.x + threadIdx.x; j <= s.y; j += blockDim.x) best = fmaxf(best, w[j]);
+    for (int j = s.z + threadIdx.x; j <= s.w; j += blockDim.x) best = fmaxf(best, w[j]);
+    for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_down_sync(0xffffffffu, best, o));
+    __shared__ float sb[32];
+    if ((threadIdx.x & 31) == 0) sb[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < (int)(blockDim.x >> 5); ++q) best = fmaxf(best, sb[q]);
+        out[blockIdx.x] = best;
+    }
+}
+
 // variant C (BDS/B1C/include/acquisition.m:205-216): results(bin, :) = abs(ifft(X_shift .* Data)), with the pilot replica
 // (results*sqrt(11) + abs(ifft(X_shift .* Pilot))*sqrt(29))/sqrt(40); per bin the maximum and its first index.
 // W rows: bin*nRep + r.
@@ -214,6 +233,12 @@ cudaError_t launch_varb_rowpeak(const float2* W, int nRows, int L, float* peak, 
 cudaError_t launch_varb_segmax(const float2* W, int nRows, int L, const int4* seg, float* out, cudaStream_t st)
 {
     segmax_kernel<<<nRows, 1024, 0, st>>>(W, L, seg, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_varb_segmax_mag(const float* mag, int nRows, int L, const int4* seg, float* out, cudaStream_t st)
+{
+    segmax_mag_kernel<<<nRows, 1024, 0, st>>>(mag, L, seg, out);
     return cudaGetLastError();
 }
 

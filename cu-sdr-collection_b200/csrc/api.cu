@@ -78,6 +78,8 @@ struct gc_handle {
     DevBuf<float> vbPeak;
     DevBuf<int> vbIdx;
     DevBuf<int4> vbSeg;
+    DevBuf<int2> vbMap;          // fused variant B / C: spectrum row and circular shift per searched row
+    DevBuf<float> vbMag;         // corrVec of the winning rows
     bool varC = false;           // acquisition variant C (BDS B1C): one spectrum, bins by circshift, weighted data + pilot, 2-D max
     struct { int Lc = 0, xLen = 0, nFine = 0; double initFreq = 0; } vc;   // len10PlusXms, samplesXmsLen (B1C acquisition.m:131-134)
     DevBuf<int> vcSlot;
@@ -400,7 +402,7 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     h->nBins = h->varB ? h->vb.nBins : (int)m_round(cfg->acq_search_band * 2 / cfg->acq_search_step) + 1;
     h->nFine = (int)m_round(cfg->acq_search_step / h->fineStep) + 1;
     h->nonCoh = (h->varB || h->varC) ? 1 : cfg->acq_noncoh_time;
-    h->fused = !h->varB && !h->varC && fused_plan_info(h->L, &h->fp) && !getenv("GC_FORCE_GENERIC");
+    h->fused = fused_plan_info(h->L, &h->fp) && !getenv("GC_FORCE_GENERIC") && !((h->varB || h->varC) && h->fp.pfa);   // (spectrum shifts: Cooley-Tukey plans)
     h->stats.fft_len = h->L;
     {   // GC_ACQ_PATH=cluster selects the one-kernel correlation stage (acq_cluster.cu, transform resident
         // in a cluster's shared memory); the default is inverse rows + inverse columns through a work buffer
@@ -582,6 +584,17 @@ static int varb_build_replicas(gc_handle* h)
     cudaStream_t st = h->stream;
     GC_CUDA(h, upload(h->codeTab, tab, st));
     GC_CUDA(h, h->Cc.reserve((size_t)nRep * Lb));
+    if (h->fused) {                                          // [table zeros] (B1I :58, L2C :47) -> conj(fft(.))/L in the plan's layout
+        FwdColsParams fp{};
+        fp.N = S; fp.codeTab = h->codeTab.p; fp.out = h->Cc.p; fp.tw = h->twFused.p;
+        GC_CUDA(h, launch_fwd_cols(Lb, fp, nRep, true, st));
+        RowsParams rp{};
+        rp.X = h->Cc.p; rp.nRows = (long long)nRep * h->fp.C;
+        GC_CUDA(h, launch_fwd_rows(Lb, rp, st));
+        GC_CUDA(h, launch_finish_replica(h->Cc.p, (size_t)nRep * Lb, Lb, st));
+        h->replicasReady = true;
+        return GC_OK;
+    }
     GC_CUDA(h, h->T1.reserve((size_t)nRep * Lb));
     GC_CUDA(h, h->T2.reserve((size_t)nRep * Lb));
     GC_CUDA(h, launch_varb_pad(h->codeTab.p, S, nRep, h->T1.p, Lb, st));           // [table zeros] (B1I :58, L2C :47)
@@ -623,102 +636,182 @@ static int acquire_varb(gc_handle* h, long long winStart, int32_t nSv, const int
     GC_CUDA(h, cudaMemcpyAsync(h->dphi.p, dphi.data(), nShifts * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     const int nX = nShifts * nSig;
     const int nRows = nShifts * nBins * nSig;
-    const size_t bufRows = (size_t)std::max(std::max(nRows, nX), std::max((int)nSv, h->resultLen));
-    GC_CUDA(h, h->X.reserve((size_t)nX * Lb));
-    GC_CUDA(h, h->T1.reserve(bufRows * Lb));
-    GC_CUDA(h, h->T2.reserve(bufRows * Lb));
-    GC_CUDA(h, launch_generic_wipe(h->rec, winStart, Lb, nSig, nShifts, 0, h->dphi.p, h->T1.p, Lb, st)); ++launches;
-    float2 *src = h->T1.p, *dst = h->T2.p;
-    int n = Lb, sd = 1;
-    for (int f = 0; f < h->plan.nf; ++f) {
-        GC_CUDA(h, launch_generic_stage(h->plan, f, n, sd, false, src, dst, nX, st)); ++launches;
-        n /= h->plan.fac[f]; sd *= h->plan.fac[f];
-        std::swap(src, dst);
-    }
-    GC_CUDA(h, cudaMemcpyAsync(h->X.p, src, (size_t)nX * Lb * sizeof(float2), cudaMemcpyDeviceToDevice, st));
-    cudaEventRecord(h->ev[2], st);
-
-    // every (shift, bin, block) row of every SV: peak of abs(ifft(circshift(X) .* codeFreqDom))
-    GC_CUDA(h, h->vbRows.reserve((size_t)std::max(nRows, (int)nSv)));
-    GC_CUDA(h, h->vbPeak.reserve((size_t)nSv * nRows));
-    GC_CUDA(h, h->vbIdx.reserve((size_t)std::max(nRows, (int)nSv)));
-    std::vector<VarbRow> rows(nRows);
-    auto inverse = [&](int batch, float2** result) -> int {
-        float2 *a = h->T1.p, *b = h->T2.p;
-        int nn = Lb, ss = 1;
-        for (int f = 0; f < h->plan.nf; ++f) {
-            GC_CUDA(h, launch_generic_stage(h->plan, f, nn, ss, true, a, b, batch, st)); ++launches;
-            nn /= h->plan.fac[f]; ss *= h->plan.fac[f];
-            std::swap(a, b);
-        }
-        *result = a;
-        return GC_OK;
-    };
-    for (int s = 0; s < nSv; ++s) {
-        for (int b = 0; b < nShifts; ++b)
-            for (int k = 0; k < nBins; ++k)
-                for (int g = 0; g < nSig; ++g)
-                    rows[(b * nBins + k) * nSig + g] = VarbRow{b * nSig + g, svList[s] - 1, k, 0};
-        GC_CUDA(h, cudaMemcpyAsync(h->vbRows.p, rows.data(), nRows * sizeof(VarbRow), cudaMemcpyHostToDevice, st));
-        GC_CUDA(h, launch_varb_mulshift(h->X.p, h->Cc.p, h->vbRows.p, nRows, h->T1.p, Lb, st)); ++launches;
-        float2* W = nullptr;
-        int rc = inverse(nRows, &W);
-        if (rc != GC_OK) return rc;
-        GC_CUDA(h, launch_varb_rowpeak(W, nRows, Lb, h->vbPeak.p + (size_t)s * nRows, h->vbIdx.p, st)); ++launches;
-        GC_CUDA(h, cudaStreamSynchronize(st));                // rows (pageable host vector) is rewritten for the next SV
-    }
     std::vector<float> peaks((size_t)nSv * nRows);
-    GC_CUDA(h, cudaMemcpyAsync(peaks.data(), h->vbPeak.p, peaks.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
-    GC_CUDA(h, cudaStreamSynchronize(st));
-
-    // the reference's running comparison, in its loop order (B1I :60-123, L2C :58-86)
     std::vector<VarbRow> win(nSv);
     std::vector<int> winShift(nSv), winBin(nSv);
-    for (int s = 0; s < nSv; ++s) {
-        float prevmax = 0.f;
-        int fbin = 0, fshift = 0, fsig = 0;
-        for (int b = 0; b < nShifts; ++b)
-            for (int k = 0; k < nBins; ++k) {
-                if (k == nBins - 1 && b > 0) continue;                                     // B1I :79-81
-                const float* pk = peaks.data() + (size_t)s * nRows + (size_t)(b * nBins + k) * nSig;
-                if (nSig == 2) {
-                    if (pk[0] > prevmax || pk[1] > prevmax) {                              // B1I :101-114
-                        if (pk[0] > pk[1]) { prevmax = pk[0]; fsig = 0; } else { prevmax = pk[1]; fsig = 1; }
-                        fshift = b; fbin = k;
-                    }
-                } else if (pk[0] > prevmax) { prevmax = pk[0]; fshift = b; fbin = k; fsig = 0; }   // L2C :78-83
-            }
-        win[s] = VarbRow{fshift * nSig + fsig, svList[s] - 1, fbin, 0};
-        winShift[s] = fshift; winBin[s] = fbin;
-    }
-    // corrVec of the winning rows again, then its first maximum and the second peak outside +-1 chip
-    GC_CUDA(h, cudaMemcpyAsync(h->vbRows.p, win.data(), nSv * sizeof(VarbRow), cudaMemcpyHostToDevice, st));
-    GC_CUDA(h, launch_varb_mulshift(h->X.p, h->Cc.p, h->vbRows.p, nSv, h->T1.p, Lb, st)); ++launches;
-    float2* W = nullptr;
-    int rc = inverse(nSv, &W);
-    if (rc != GC_OK) return rc;
-    GC_CUDA(h, launch_varb_rowpeak(W, nSv, Lb, h->vbPeak.p, h->vbIdx.p, st)); ++launches;
     std::vector<float> maxPeak(nSv), second(nSv);
     std::vector<int> cp0(nSv);
-    GC_CUDA(h, cudaMemcpyAsync(maxPeak.data(), h->vbPeak.p, nSv * sizeof(float), cudaMemcpyDeviceToHost, st));
-    GC_CUDA(h, cudaMemcpyAsync(cp0.data(), h->vbIdx.p, nSv * sizeof(int), cudaMemcpyDeviceToHost, st));
-    GC_CUDA(h, cudaStreamSynchronize(st));
-    std::vector<int4> seg(nSv);
-    for (int s = 0; s < nSv; ++s) {
-        const int cp = cp0[s] + 1;                                                         // 1-based codePhase (:125)
-        const int e1 = cp - h->vb.chipSamples, e2 = cp + h->vb.chipSamples, N1 = h->vb.N1; // :127-128
-        int a1, b1, a2 = 1, b2 = 0;                                                        // 1-based inclusive ranges; second one empty by default
-        if (e1 < 2) { a1 = e2; b1 = N1 + e1; }                                             // :131-133
-        else if (e2 >= N1) { a1 = e2 - N1 + 1; b1 = e1; }                                  // :134-136
-        else { a1 = 1; b1 = e1; a2 = e2; b2 = N1; }                                        // :137-139
-        seg[s] = make_int4(std::max(a1, 1) - 1, std::min(b1, Lb) - 1, std::max(a2, 1) - 1, std::min(b2, Lb) - 1);
+    // the reference's running comparison, in its loop order (B1I :60-123, L2C :58-86)
+    auto pick_winners = [&]() {
+        for (int s = 0; s < nSv; ++s) {
+            float prevmax = 0.f;
+            int fbin = 0, fshift = 0, fsig = 0;
+            for (int b = 0; b < nShifts; ++b)
+                for (int k = 0; k < nBins; ++k) {
+                    if (k == nBins - 1 && b > 0) continue;                                     // B1I :79-81
+                    const float* pk = peaks.data() + (size_t)s * nRows + (size_t)(b * nBins + k) * nSig;
+                    if (nSig == 2) {
+                        if (pk[0] > prevmax || pk[1] > prevmax) {                              // B1I :101-114
+                            if (pk[0] > pk[1]) { prevmax = pk[0]; fsig = 0; } else { prevmax = pk[1]; fsig = 1; }
+                            fshift = b; fbin = k;
+                        }
+                    } else if (pk[0] > prevmax) { prevmax = pk[0]; fshift = b; fbin = k; fsig = 0; }   // L2C :78-83
+                }
+            win[s] = VarbRow{fshift * nSig + fsig, svList[s] - 1, fbin, 0};
+            winShift[s] = fshift; winBin[s] = fbin;
+        }
+    };
+    // code-phase ranges of the second-peak search outside +-1 chip of the peak (:127-139), 0-based inclusive
+    auto second_peak_ranges = [&](std::vector<int4>& seg) {
+        for (int s = 0; s < nSv; ++s) {
+            const int cp = cp0[s] + 1;                                                         // 1-based codePhase (:125)
+            const int e1 = cp - h->vb.chipSamples, e2 = cp + h->vb.chipSamples, N1 = h->vb.N1; // :127-128
+            int a1, b1, a2 = 1, b2 = 0;                                                        // 1-based inclusive ranges; second one empty by default
+            if (e1 < 2) { a1 = e2; b1 = N1 + e1; }                                             // :131-133
+            else if (e2 >= N1) { a1 = e2 - N1 + 1; b1 = e1; }                                  // :134-136
+            else { a1 = 1; b1 = e1; a2 = e2; b2 = N1; }                                        // :137-139
+            seg[s] = make_int4(std::max(a1, 1) - 1, std::min(b1, Lb) - 1, std::max(a2, 1) - 1, std::min(b2, Lb) - 1);
+        }
+    };
+    if (h->fused) {
+        // the plan's kernels: forward spectra of every (shift, block); per SV every (shift, bin, block) row as X(j - bin) .* C,
+        // inverse rows -> work buffer -> inverse columns + |.| + tile maxima; the winning rows once more with corrVec written out
+        const int parts = h->fp.parts, C = h->fp.C;
+        GC_CUDA(h, h->X.reserve((size_t)nX * Lb));
+        FwdColsParams fp{};
+        fp.rec = h->rec; fp.winStart = winStart; fp.N = Lb; fp.nonCoh = nSig; fp.swapIQ = 0;
+        fp.dphi = h->dphi.p; fp.out = h->X.p; fp.tw = h->twFused.p;
+        GC_CUDA(h, launch_fwd_cols(Lb, fp, nX, false, st)); ++launches;
+        RowsParams rp{};
+        rp.X = h->X.p; rp.nRows = (long long)nX * C;
+        GC_CUDA(h, launch_fwd_rows(Lb, rp, st)); ++launches;
+        cudaEventRecord(h->ev[2], st);
+        std::vector<int2> map((size_t)nRows + nSv);
+        for (int b = 0; b < nShifts; ++b)
+            for (int k = 0; k < nBins; ++k)
+                for (int g = 0; g < nSig; ++g) map[(b * nBins + k) * nSig + g] = make_int2(b * nSig + g, k);
+        GC_CUDA(h, h->vbMap.reserve(map.size()));
+        GC_CUDA(h, cudaMemcpyAsync(h->vbMap.p, map.data(), nRows * sizeof(int2), cudaMemcpyHostToDevice, st));
+        std::vector<int> slotRep(nSv);
+        for (int s = 0; s < nSv; ++s) slotRep[s] = svList[s] - 1;
+        GC_CUDA(h, upload(h->prnList, slotRep, st));
+        GC_CUDA(h, h->partMax.reserve((size_t)nSv * nRows * parts));
+        GC_CUDA(h, h->partIdx.reserve((size_t)nSv * nRows * parts));
+        GC_CUDA(h, h->peaks.reserve((size_t)nSv * nRows));
+        int chunk = (int)std::max<long long>(1, (long long)(2.5e9 / ((double)nRows * Lb * sizeof(float2))));
+        chunk = std::min(chunk, (int)nSv);
+        GC_CUDA(h, h->W.reserve((size_t)chunk * nRows * Lb));
+        auto correlate = [&](int s0, int nc, int nB, const int2* bm, float* magOut) -> int {
+            RowsParams ip{};
+            ip.X = h->X.p; ip.Cc = h->Cc.p; ip.W = h->W.p; ip.tw = h->twFused.p;
+            ip.nonCoh = 1; ip.nBins = nB; ip.nRep = 1; ip.repStride = 1;
+            ip.prnPerCta = 1; ip.mPerCta = 1; ip.binPerCta = 5; ip.binMap = bm;
+            ip.nPrnChunk = nc; ip.prnSlot0 = s0; ip.prnList = h->prnList.p;
+            GC_CUDA(h, launch_inv_rows(Lb, ip, st)); ++launches;
+            InvColsParams cp{};
+            cp.W = h->W.p; cp.nBins = nB; cp.nonCoh = 1; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
+            cp.partMax = h->partMax.p; cp.partIdx = h->partIdx.p; cp.magOut = magOut;
+            GC_CUDA(h, launch_inv_cols(Lb, cp, st)); ++launches;
+            return GC_OK;
+        };
+        for (int s0 = 0; s0 < nSv; s0 += chunk) {
+            const int rc = correlate(s0, std::min(chunk, (int)nSv - s0), nRows, h->vbMap.p, nullptr);
+            if (rc != GC_OK) return rc;
+        }
+        GC_CUDA(h, launch_peak_select(h->partMax.p, h->partIdx.p, nSv * nRows, 1, parts, h->peaks.p, st)); ++launches;
+        std::vector<PeakOut> po((size_t)nSv * nRows);
+        GC_CUDA(h, cudaMemcpyAsync(po.data(), h->peaks.p, po.size() * sizeof(PeakOut), cudaMemcpyDeviceToHost, st));
+        GC_CUDA(h, cudaStreamSynchronize(st));
+        for (size_t i = 0; i < po.size(); ++i) peaks[i] = (float)po[i].peak;
+        pick_winners();
+        for (int s = 0; s < nSv; ++s) map[nRows + s] = make_int2(win[s].src, win[s].shift);
+        GC_CUDA(h, cudaMemcpyAsync(h->vbMap.p + nRows, map.data() + nRows, nSv * sizeof(int2), cudaMemcpyHostToDevice, st));
+        GC_CUDA(h, h->vbMag.reserve((size_t)nSv * Lb));
+        for (int s = 0; s < nSv; ++s) {                       // corrVec of the winning row of each SV (partial maxima land in slot s, one bin)
+            const int rc = correlate(s, 1, 1, h->vbMap.p + nRows + s, h->vbMag.p + (size_t)s * Lb);
+            if (rc != GC_OK) return rc;
+        }
+        GC_CUDA(h, launch_peak_select(h->partMax.p, h->partIdx.p, nSv, 1, parts, h->peaks.p, st)); ++launches;
+        GC_CUDA(h, cudaMemcpyAsync(po.data(), h->peaks.p, nSv * sizeof(PeakOut), cudaMemcpyDeviceToHost, st));
+        GC_CUDA(h, cudaStreamSynchronize(st));
+        for (int s = 0; s < nSv; ++s) { maxPeak[s] = (float)po[s].peak; cp0[s] = po[s].codePhase - 1; }
+        std::vector<int4> seg(nSv);
+        second_peak_ranges(seg);
+        GC_CUDA(h, h->vbSeg.reserve(nSv));
+        GC_CUDA(h, h->vbPeak.reserve(nSv));
+        GC_CUDA(h, cudaMemcpyAsync(h->vbSeg.p, seg.data(), nSv * sizeof(int4), cudaMemcpyHostToDevice, st));
+        GC_CUDA(h, launch_varb_segmax_mag(h->vbMag.p, nSv, Lb, h->vbSeg.p, h->vbPeak.p, st)); ++launches;
+        GC_CUDA(h, cudaMemcpyAsync(second.data(), h->vbPeak.p, nSv * sizeof(float), cudaMemcpyDeviceToHost, st));
+        cudaEventRecord(h->ev[1], st);
+        GC_CUDA(h, cudaStreamSynchronize(st));
+    } else {
+        const size_t bufRows = (size_t)std::max(std::max(nRows, nX), std::max((int)nSv, h->resultLen));
+        GC_CUDA(h, h->X.reserve((size_t)nX * Lb));
+        GC_CUDA(h, h->T1.reserve(bufRows * Lb));
+        GC_CUDA(h, h->T2.reserve(bufRows * Lb));
+        GC_CUDA(h, launch_generic_wipe(h->rec, winStart, Lb, nSig, nShifts, 0, h->dphi.p, h->T1.p, Lb, st)); ++launches;
+        float2 *src = h->T1.p, *dst = h->T2.p;
+        int n = Lb, sd = 1;
+        for (int f = 0; f < h->plan.nf; ++f) {
+            GC_CUDA(h, launch_generic_stage(h->plan, f, n, sd, false, src, dst, nX, st)); ++launches;
+            n /= h->plan.fac[f]; sd *= h->plan.fac[f];
+            std::swap(src, dst);
+        }
+        GC_CUDA(h, cudaMemcpyAsync(h->X.p, src, (size_t)nX * Lb * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+        cudaEventRecord(h->ev[2], st);
+
+        // every (shift, bin, block) row of every SV: peak of abs(ifft(circshift(X) .* codeFreqDom))
+        GC_CUDA(h, h->vbRows.reserve((size_t)std::max(nRows, (int)nSv)));
+        GC_CUDA(h, h->vbPeak.reserve((size_t)nSv * nRows));
+        GC_CUDA(h, h->vbIdx.reserve((size_t)std::max(nRows, (int)nSv)));
+        std::vector<VarbRow> rows(nRows);
+        auto inverse = [&](int batch, float2** result) -> int {
+            float2 *a = h->T1.p, *b = h->T2.p;
+            int nn = Lb, ss = 1;
+            for (int f = 0; f < h->plan.nf; ++f) {
+                GC_CUDA(h, launch_generic_stage(h->plan, f, nn, ss, true, a, b, batch, st)); ++launches;
+                nn /= h->plan.fac[f]; ss *= h->plan.fac[f];
+                std::swap(a, b);
+            }
+            *result = a;
+            return GC_OK;
+        };
+        for (int s = 0; s < nSv; ++s) {
+            for (int b = 0; b < nShifts; ++b)
+                for (int k = 0; k < nBins; ++k)
+                    for (int g = 0; g < nSig; ++g)
+                        rows[(b * nBins + k) * nSig + g] = VarbRow{b * nSig + g, svList[s] - 1, k, 0};
+            GC_CUDA(h, cudaMemcpyAsync(h->vbRows.p, rows.data(), nRows * sizeof(VarbRow), cudaMemcpyHostToDevice, st));
+            GC_CUDA(h, launch_varb_mulshift(h->X.p, h->Cc.p, h->vbRows.p, nRows, h->T1.p, Lb, st)); ++launches;
+            float2* W = nullptr;
+            int rc = inverse(nRows, &W);
+            if (rc != GC_OK) return rc;
+            GC_CUDA(h, launch_varb_rowpeak(W, nRows, Lb, h->vbPeak.p + (size_t)s * nRows, h->vbIdx.p, st)); ++launches;
+            GC_CUDA(h, cudaStreamSynchronize(st));                // rows (pageable host vector) is rewritten for the next SV
+        }
+        GC_CUDA(h, cudaMemcpyAsync(peaks.data(), h->vbPeak.p, peaks.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+        GC_CUDA(h, cudaStreamSynchronize(st));
+
+        pick_winners();
+        // corrVec of the winning rows again, then its first maximum and the second peak outside +-1 chip
+        GC_CUDA(h, cudaMemcpyAsync(h->vbRows.p, win.data(), nSv * sizeof(VarbRow), cudaMemcpyHostToDevice, st));
+        GC_CUDA(h, launch_varb_mulshift(h->X.p, h->Cc.p, h->vbRows.p, nSv, h->T1.p, Lb, st)); ++launches;
+        float2* W = nullptr;
+        int rc = inverse(nSv, &W);
+        if (rc != GC_OK) return rc;
+        GC_CUDA(h, launch_varb_rowpeak(W, nSv, Lb, h->vbPeak.p, h->vbIdx.p, st)); ++launches;
+        GC_CUDA(h, cudaMemcpyAsync(maxPeak.data(), h->vbPeak.p, nSv * sizeof(float), cudaMemcpyDeviceToHost, st));
+        GC_CUDA(h, cudaMemcpyAsync(cp0.data(), h->vbIdx.p, nSv * sizeof(int), cudaMemcpyDeviceToHost, st));
+        GC_CUDA(h, cudaStreamSynchronize(st));
+        std::vector<int4> seg(nSv);
+        second_peak_ranges(seg);
+        GC_CUDA(h, h->vbSeg.reserve(nSv));
+        GC_CUDA(h, cudaMemcpyAsync(h->vbSeg.p, seg.data(), nSv * sizeof(int4), cudaMemcpyHostToDevice, st));
+        GC_CUDA(h, launch_varb_segmax(W, nSv, Lb, h->vbSeg.p, h->vbPeak.p, st)); ++launches;
+        GC_CUDA(h, cudaMemcpyAsync(second.data(), h->vbPeak.p, nSv * sizeof(float), cudaMemcpyDeviceToHost, st));
+        cudaEventRecord(h->ev[1], st);
+        GC_CUDA(h, cudaStreamSynchronize(st));
     }
-    GC_CUDA(h, h->vbSeg.reserve(nSv));
-    GC_CUDA(h, cudaMemcpyAsync(h->vbSeg.p, seg.data(), nSv * sizeof(int4), cudaMemcpyHostToDevice, st));
-    GC_CUDA(h, launch_varb_segmax(W, nSv, Lb, h->vbSeg.p, h->vbPeak.p, st)); ++launches;
-    GC_CUDA(h, cudaMemcpyAsync(second.data(), h->vbPeak.p, nSv * sizeof(float), cudaMemcpyDeviceToHost, st));
-    cudaEventRecord(h->ev[1], st);
-    GC_CUDA(h, cudaStreamSynchronize(st));
     int nAcq = 0;
     for (int s = 0; s < nSv; ++s) {
         const int ri = svList[s] - 1;
@@ -789,6 +882,18 @@ static int varc_build_replicas(gc_handle* h)
     for (int r = 0; r < rows; ++r) std::copy(tab.begin() + (size_t)r * N, tab.begin() + (size_t)r * N + xLen, head.begin() + (size_t)r * xLen);
     GC_CUDA(h, upload(h->chips, head, st));
     GC_CUDA(h, h->Cc.reserve((size_t)rows * Lc));
+    if (h->fused) {
+        FwdColsParams fp{};
+        fp.N = xLen; fp.codeTab = h->chips.p; fp.out = h->Cc.p; fp.tw = h->twFused.p;
+        GC_CUDA(h, launch_fwd_cols(Lc, fp, rows, true, st));
+        RowsParams rp{};
+        rp.X = h->Cc.p; rp.nRows = (long long)rows * h->fp.C;
+        GC_CUDA(h, launch_fwd_rows(Lc, rp, st));
+        GC_CUDA(h, launch_finish_replica(h->Cc.p, (size_t)rows * Lc, Lc, st));
+        GC_CUDA(h, cudaStreamSynchronize(st));
+        h->replicasReady = true;
+        return GC_OK;
+    }
     const int chunk = 32;                                       // transform the replicas in chunks to bound the scratch buffers
     GC_CUDA(h, h->T1.reserve((size_t)chunk * Lc));
     GC_CUDA(h, h->T2.reserve((size_t)chunk * Lc));
@@ -832,43 +937,85 @@ static int acquire_varc(gc_handle* h, long long winStart, long long longLen, int
     const uint64_t dphi0 = turns_to_fix(h->vc.initFreq / c.sampling_freq);
     GC_CUDA(h, h->dphi.reserve(1));
     GC_CUDA(h, cudaMemcpyAsync(h->dphi.p, &dphi0, sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-    const int nRows = nBins * nRep;
-    GC_CUDA(h, h->X.reserve((size_t)Lc));
-    GC_CUDA(h, h->T1.reserve((size_t)std::max(nRows, 32) * Lc));
-    GC_CUDA(h, h->T2.reserve((size_t)std::max(nRows, 32) * Lc));
-    GC_CUDA(h, launch_generic_wipe(h->rec, winStart, Lc, 1, 1, 0, h->dphi.p, h->T1.p, Lc, st)); ++launches;   // :168-172
-    {
-        float2 *src = h->T1.p, *dst = h->T2.p;
-        int n = Lc, sd = 1;
-        for (int f = 0; f < h->plan.nf; ++f) {
-            GC_CUDA(h, launch_generic_stage(h->plan, f, n, sd, false, src, dst, 1, st)); ++launches;
-            n /= h->plan.fac[f]; sd *= h->plan.fac[f];
-            std::swap(src, dst);
+    int parts = 1;
+    if (h->fused) {
+        // the plan's kernels: one forward spectrum; per SV the (bin, replica) rows as X(j - bin) .* C, inverse rows -> work buffer ->
+        // inverse columns with the data / pilot magnitudes weighted sqrt(11) : sqrt(29) and scaled by 1/sqrt(40) (:213-214)
+        parts = h->fp.parts;
+        GC_CUDA(h, h->X.reserve((size_t)Lc));
+        FwdColsParams fp{};
+        fp.rec = h->rec; fp.winStart = winStart; fp.N = Lc; fp.nonCoh = 1; fp.swapIQ = 0;
+        fp.dphi = h->dphi.p; fp.out = h->X.p; fp.tw = h->twFused.p;
+        GC_CUDA(h, launch_fwd_cols(Lc, fp, 1, false, st)); ++launches;                      // :168-179
+        RowsParams rp{};
+        rp.X = h->X.p; rp.nRows = h->fp.C;
+        GC_CUDA(h, launch_fwd_rows(Lc, rp, st)); ++launches;
+        cudaEventRecord(h->ev[2], st);
+        std::vector<int2> map(nBins);
+        for (int k = 0; k < nBins; ++k) map[k] = make_int2(0, k);                          // circshift(IQfreqDom, k) (:203)
+        GC_CUDA(h, upload(h->vbMap, map, st));
+        std::vector<int> slotRep(nSv);
+        for (int s = 0; s < nSv; ++s) slotRep[s] = (svList[s] - 1) * 2;
+        GC_CUDA(h, upload(h->prnList, slotRep, st));
+        GC_CUDA(h, h->partMax.reserve((size_t)nSv * nBins * parts));
+        GC_CUDA(h, h->partIdx.reserve((size_t)nSv * nBins * parts));
+        GC_CUDA(h, h->peaks.reserve(nSv));
+        int chunk = (int)std::max<long long>(1, (long long)(2.5e9 / ((double)nBins * nRep * Lc * sizeof(float2))));
+        chunk = std::min(chunk, (int)nSv);
+        GC_CUDA(h, h->W.reserve((size_t)chunk * nBins * nRep * Lc));
+        for (int s0 = 0; s0 < nSv; s0 += chunk) {
+            const int nc = std::min(chunk, (int)nSv - s0);
+            RowsParams ip{};
+            ip.X = h->X.p; ip.Cc = h->Cc.p; ip.W = h->W.p; ip.tw = h->twFused.p;
+            ip.nonCoh = 1; ip.nBins = nBins; ip.nRep = nRep; ip.repStride = 1;
+            ip.prnPerCta = 1; ip.mPerCta = 1; ip.binPerCta = 5; ip.binMap = h->vbMap.p;
+            ip.nPrnChunk = nc; ip.prnSlot0 = s0; ip.prnList = h->prnList.p;
+            GC_CUDA(h, launch_inv_rows(Lc, ip, st)); ++launches;
+            InvColsParams cp{};
+            cp.W = h->W.p; cp.nBins = nBins; cp.nonCoh = nRep; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
+            cp.partMax = h->partMax.p; cp.partIdx = h->partIdx.p;
+            if (nRep == 2) { cp.weighted = 1; cp.w0 = 3.3166247903554f; cp.w1 = 5.385164807134504f; cp.wScale = 1.0f / 6.324555320336759f; }
+            GC_CUDA(h, launch_inv_cols(Lc, cp, st)); ++launches;
         }
-        GC_CUDA(h, cudaMemcpyAsync(h->X.p, src, (size_t)Lc * sizeof(float2), cudaMemcpyDeviceToDevice, st));
-    }
-    cudaEventRecord(h->ev[2], st);
-    GC_CUDA(h, h->vbRows.reserve(nRows));
-    GC_CUDA(h, h->partMax.reserve((size_t)nSv * nBins));
-    GC_CUDA(h, h->partIdx.reserve((size_t)nSv * nBins));
-    GC_CUDA(h, h->peaks.reserve(nSv));
-    std::vector<VarbRow> rows(nRows);
-    for (int s = 0; s < nSv; ++s) {
-        for (int k = 0; k < nBins; ++k)
-            for (int r = 0; r < nRep; ++r) rows[k * nRep + r] = VarbRow{0, (svList[s] - 1) * 2 + r, k, 0};   // circshift(IQfreqDom, k) (:203)
-        GC_CUDA(h, cudaMemcpyAsync(h->vbRows.p, rows.data(), nRows * sizeof(VarbRow), cudaMemcpyHostToDevice, st));
-        GC_CUDA(h, launch_varb_mulshift(h->X.p, h->Cc.p, h->vbRows.p, nRows, h->T1.p, Lc, st)); ++launches;
-        float2 *a = h->T1.p, *b = h->T2.p;
-        int nn = Lc, ss = 1;
-        for (int f = 0; f < h->plan.nf; ++f) {
-            GC_CUDA(h, launch_generic_stage(h->plan, f, nn, ss, true, a, b, nRows, st)); ++launches;
-            nn /= h->plan.fac[f]; ss *= h->plan.fac[f];
-            std::swap(a, b);
+    } else {
+        const int nRows = nBins * nRep;
+        GC_CUDA(h, h->X.reserve((size_t)Lc));
+        GC_CUDA(h, h->T1.reserve((size_t)std::max(nRows, 32) * Lc));
+        GC_CUDA(h, h->T2.reserve((size_t)std::max(nRows, 32) * Lc));
+        GC_CUDA(h, launch_generic_wipe(h->rec, winStart, Lc, 1, 1, 0, h->dphi.p, h->T1.p, Lc, st)); ++launches;   // :168-172
+        {
+            float2 *src = h->T1.p, *dst = h->T2.p;
+            int n = Lc, sd = 1;
+            for (int f = 0; f < h->plan.nf; ++f) {
+                GC_CUDA(h, launch_generic_stage(h->plan, f, n, sd, false, src, dst, 1, st)); ++launches;
+                n /= h->plan.fac[f]; sd *= h->plan.fac[f];
+                std::swap(src, dst);
+            }
+            GC_CUDA(h, cudaMemcpyAsync(h->X.p, src, (size_t)Lc * sizeof(float2), cudaMemcpyDeviceToDevice, st));
         }
-        GC_CUDA(h, launch_varc_combine(a, nBins, Lc, nRep, h->partMax.p, h->partIdx.p, (size_t)s * nBins, st)); ++launches;
-        GC_CUDA(h, cudaStreamSynchronize(st));
+        cudaEventRecord(h->ev[2], st);
+        GC_CUDA(h, h->vbRows.reserve(nRows));
+        GC_CUDA(h, h->partMax.reserve((size_t)nSv * nBins));
+        GC_CUDA(h, h->partIdx.reserve((size_t)nSv * nBins));
+        GC_CUDA(h, h->peaks.reserve(nSv));
+        std::vector<VarbRow> rows(nRows);
+        for (int s = 0; s < nSv; ++s) {
+            for (int k = 0; k < nBins; ++k)
+                for (int r = 0; r < nRep; ++r) rows[k * nRep + r] = VarbRow{0, (svList[s] - 1) * 2 + r, k, 0};   // circshift(IQfreqDom, k) (:203)
+            GC_CUDA(h, cudaMemcpyAsync(h->vbRows.p, rows.data(), nRows * sizeof(VarbRow), cudaMemcpyHostToDevice, st));
+            GC_CUDA(h, launch_varb_mulshift(h->X.p, h->Cc.p, h->vbRows.p, nRows, h->T1.p, Lc, st)); ++launches;
+            float2 *a = h->T1.p, *b = h->T2.p;
+            int nn = Lc, ss = 1;
+            for (int f = 0; f < h->plan.nf; ++f) {
+                GC_CUDA(h, launch_generic_stage(h->plan, f, nn, ss, true, a, b, nRows, st)); ++launches;
+                nn /= h->plan.fac[f]; ss *= h->plan.fac[f];
+                std::swap(a, b);
+            }
+            GC_CUDA(h, launch_varc_combine(a, nBins, Lc, nRep, h->partMax.p, h->partIdx.p, (size_t)s * nBins, st)); ++launches;
+            GC_CUDA(h, cudaStreamSynchronize(st));
+        }
     }
-    GC_CUDA(h, launch_peak_select(h->partMax.p, h->partIdx.p, nSv, nBins, 1, h->peaks.p, st)); ++launches;   // :221-225
+    GC_CUDA(h, launch_peak_select(h->partMax.p, h->partIdx.p, nSv, nBins, parts, h->peaks.p, st)); ++launches;   // :221-225
     std::vector<PeakOut> peaks(nSv);
     double sigPower = 0;
     GC_CUDA(h, cudaMemcpyAsync(peaks.data(), h->peaks.p, nSv * sizeof(PeakOut), cudaMemcpyDeviceToHost, st));

@@ -27,5 +27,5 @@ template <int N> double check()
     printf("N=%d max err %.3g\n", N, worst);
     return worst;
 }
-int main() { double w = 0; w = std::max(w, check<4>()); w = std::max(w, check<8>()); w = std::max(w, check<9>()); w = std::max(w, check<20>()); w = std::max(w, check<16>()); w = std::max(w, check<25>()); w = std::max(w, check<30>()); w = std::max(w, check<31>()); w = std::max(w, check<32>());
+int main() { double w = 0; w = std::max(w, check<4>()); w = std::max(w, check<8>()); w = std::max(w, check<9>()); w = std::max(w, check<10>()); w = std::max(w, check<18>()); w = std::max(w, check<20>()); w = std::max(w, check<16>()); w = std::max(w, check<25>()); w = std::max(w, check<30>()); w = std::max(w, check<31>()); w = std::max(w, check<32>());
   w = std::max(w, check<33>()); w = std::max(w, check<40>()); w = std::max(w, check<45>()); w = std::max(w, check<50>()); return w < 5e-6 ? 0 : 1; }

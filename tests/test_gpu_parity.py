@@ -627,13 +627,16 @@ def _varb_case(signal, fs, nsat, seed, extra, cn0, **kw):
     return codes, sc, s, so, sv
 
 
-@pytest.mark.parametrize("signal,fs", [("BDS_B1I", 18e6), ("GPS_L2C", 2.046e6)])
+@pytest.mark.parametrize("signal,fs", [("BDS_B1I", 18e6), ("GPS_L2C", 2.046e6), ("GPS_L2C", 8e6), ("BDS_B1I", 4.092e6)])
 def test_varb_acquisition_vs_oracle(signal, fs):
     """Variant B: one wipe-off + FFT per sub-bin shift, Doppler bins by circshift of the spectrum, abs(ifft) per row,
     the row with the largest peak kept (two 4 ms blocks for B1I), metric = peak / second peak outside +-1 chip."""
     codes, sc, s, so, sv = _varb_case(signal, fs, nsat=2, seed=3, extra=[30], cn0=48 if signal == "BDS_B1I" else 45,
-                                      **({} if signal == "BDS_B1I" else dict(acqSearchBand=9.0)))
+                                      **({} if signal == "BDS_B1I" else dict(acqSearchBand=9.0 if fs < 8e6 else 4.0)))
     N = O.samples_per_code(so)
+    if fs == 8e6:                               # keep the Dopplers inside the reduced +-2 kHz band of this case
+        for x in sc.sats:
+            x.doppler /= 2.5
     if signal == "BDS_B1I":
         raw = synth.make_record(sc, N * 11)
         longSignal = O.read_acq_signal_varb(raw, so)
@@ -644,7 +647,8 @@ def test_varb_acquisition_vs_oracle(signal, fs):
         ref = O.acquisition_l2c(longSignal, so, codes, workers=os.cpu_count() or 1)
     eng = Engine(s, codes=codes)
     got = acquisition(longSignal, s, engine=eng, verbose=False)
-    assert got["carrFreq"].shape == ref["carrFreq"].shape and eng.stats()["acq_path"] == 0
+    # 72000 = 90 x 800 (B1I at 18 Msps) and 320000 = 400 x 800 (L2C at 8 Msps) have fused plans (spectrum shift = row + residue shift)
+    assert got["carrFreq"].shape == ref["carrFreq"].shape and eng.stats()["acq_path"] == (1 if fs in (18e6, 8e6) else 0)
     idx = np.array(sv) - 1
     assert np.array_equal(got["carrFreq"], ref["carrFreq"]), "carrier frequency differs"
     assert np.array_equal(got["codePhase"], ref["codePhase"]), "code phase differs"
@@ -711,6 +715,7 @@ def test_b1c_acquisition_vs_oracle(fs, pilot):
     eng = Engine(s, codes=codes)
     got = acquisition(longSignal, s, engine=eng, verbose=False)
     assert got["carrFreq"].shape == ref["carrFreq"].shape == (max(sv),) and eng.stats()["fft_len"] == 2 * N
+    assert eng.stats()["acq_path"] == (1 if fs == 18e6 else 0)          # 360000 = 450 x 800 has a fused plan
     _check_acq(got, ref, sv)
     for sat in sc.sats:
         if pilot:           # the data component alone carries 11/40 of the power and stays under the threshold of 10 here

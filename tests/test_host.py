@@ -46,7 +46,7 @@ def test_generated_codelets_match_direct_dft(tmp_path):
                            "-o", exe, os.path.join(ROOT, "tests", "host_src", "codelet_host_check.cpp")])
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
-    assert out.stdout.count("max err") == 13
+    assert out.stdout.count("max err") == 15
     gen = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_codelets.py")], capture_output=True, text=True, check=True)
     assert gen.stdout == open(os.path.join(ROOT, "cu-sdr-collection_b200", "csrc", "fft_codelets.cuh")).read(), \
         "fft_codelets.cuh is stale: regenerate with tools/gen_codelets.py"

@@ -231,7 +231,7 @@ def main():
     w()
     w("namespace gc { namespace codelet {")
     w(PRELUDE)
-    sizes = (4, 8, 9, 16, 20, 25, 30, 31, 32, 33, 40, 45, 50)
+    sizes = (4, 8, 9, 10, 16, 18, 20, 25, 30, 31, 32, 33, 40, 45, 50)
     for N in sizes:
         gen_codelet(N)
     w("// compile-time dispatch: dft<N, INV>(x, emit)")
