@@ -382,7 +382,7 @@ def main():
         widened["gal_e1c_acquisition"] = {
             "value": ecells * world / (max_over_ranks(est["acq_total_ms"]) * 1e-3), "unit": "cells/s", "ms": est["acq_total_ms"],
             "workload": "GAL_E1C 36 PRN x 81 Doppler x 1 block x 2 replicas (E1B + E1C), FFT length 160000 @ 20 Msps "
-                        "(BASELINE.json configs[3] grid; fused 200 x 32 x 25 plan with two-level columns, stand-in memory codes)",
+                        "(BASELINE.json configs[3] grid; fused 200 x 32 x 25 plan with two-level 20 x 10 columns, stand-in memory codes)",
             "n_acquired": int(est["n_acquired"]), "acq_path": int(est["acq_path"])}
         eeng.close()
         del erec
@@ -454,8 +454,8 @@ def main():
             "value": tot_cells * world / (tot_ms * 1e-3), "unit": "cells/s", "cells": tot_cells, "ms": tot_ms,
             "sv_signal_pairs": 32 + 14 + 14 + 63 + 36 + 32 + 36 + 36 + 29 + 53 + 32 + 62,
             "workload": "BASELINE.json configs[4]: the twelve signal folders' acquisitions at their default initSettings.m, run "
-                        "back to back on one GPU per rank (cells = SVs x Doppler rows; fused plans for 36000/24000/144000, codelet "
-                        "Stockham passes for 72000/320000/360000; stand-in codes where the reference's are data)",
+                        "back to back on one GPU per rank (cells = SVs x Doppler rows; every length has a fused plan: 36000, 24000, 144000, "
+                        "72000, 320000, 360000; stand-in codes where the reference's are data)",
             "per_signal": allc}
     clocks = sampler.stop() if rank == 0 else None
 

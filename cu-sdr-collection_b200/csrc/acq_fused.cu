@@ -254,10 +254,11 @@ inv_cols_kernel(InvColsParams p)
 // A CTA handles TC adjacent row positions (columns), so global accesses are TC*8-byte runs.
 template <class P> struct BigGeo {
     static constexpr int C1 = P::C1, C2 = P::C2;
-    // columns per CTA: 32, or 16 where a 25-point phase would otherwise run at 800 threads (80 registers: spills)
-    static constexpr int TC = ((C1 > C2 ? C1 : C2) * 32 <= 640 && sizeof(float2) * P::C * 32 <= 110 * 1024) ? 32 : 16;
+    // columns per CTA: 32 (256-byte runs) while the CTA stays within 1024 threads and half the shared memory
+    static constexpr int TC = ((C1 > C2 ? C1 : C2) * 32 <= 1024 && sizeof(float2) * P::C * 32 <= 120 * 1024) ? 32 : 16;
     static constexpr int NT = (C1 > C2 ? C1 : C2) * TC;                        // threads: max of the two phases
     static constexpr size_t kSmem = sizeof(float2) * P::C * TC;
+    static constexpr size_t kSmemInv = kSmem + sizeof(float2) * P::C;          // + the w_C^(ta*beta) table of the inverse pass
 };
 
 // w_C^(+-ka*b): computed once per thread (one sincospif)
@@ -331,6 +332,9 @@ inv_cols_big_kernel(InvColsParams p)
     constexpr int C = P::C, C1 = P::C1, C2 = P::C2, R = P::R, L = P::L, TC = G::TC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* Y = reinterpret_cast<float2*>(smem_raw);            // [ta][beta][col]
+    float2* TW = Y + C * TC;                                     // [ta][beta] = w_C^(-ta*beta): one sincospif per entry and CTA
+    for (int i = threadIdx.x; i < C; i += G::NT) TW[i] = unit_root((i / C2) * (i % C2), C, true);
+    __syncthreads();
     const int col = threadIdx.x % TC, q = threadIdx.x / TC;
     const int pp = blockIdx.x * TC + col;
     const bool in = pp < R;
@@ -345,7 +349,7 @@ inv_cols_big_kernel(InvColsParams p)
 #pragma unroll
             for (int a = 0; a < C1; ++a) x[a] = __ldcs(base + (size_t)m * L + (size_t)(C2 * a + q) * R);
             codelet::dft<C1, true>(x, [&](int ta, float re, float im) {
-                Y[(ta * C2 + q) * TC + col] = cmul(make_float2(re, im), unit_root(ta * q, C, true));
+                Y[(ta * C2 + q) * TC + col] = cmul(make_float2(re, im), TW[ta * C2 + q]);
             });
         }
         __syncthreads();
@@ -442,9 +446,9 @@ struct Launch {
         if constexpr (P::kBig) {
             using G = BigGeo<P>;
             dim3 grid((P::R + G::TC - 1) / G::TC, p.nBins, p.nPrnChunk);
-            cudaError_t e = cudaFuncSetAttribute(inv_cols_big_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::kSmem);
+            cudaError_t e = cudaFuncSetAttribute(inv_cols_big_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::kSmemInv);
             if (e != cudaSuccess) return e;
-            inv_cols_big_kernel<P><<<grid, G::NT, G::kSmem, s>>>(p);
+            inv_cols_big_kernel<P><<<grid, G::NT, G::kSmemInv, s>>>(p);
             return cudaGetLastError();
         } else {
             dim3 grid((P::R + 127) / 128, p.nBins, p.nPrnChunk);

@@ -9,7 +9,8 @@ namespace gc {
 constexpr int gcd_c(int a, int b) { return b == 0 ? a : gcd_c(b, a % b); }
 
 // C1 > 0: the column length C = C1 x C2 is too long for one register codelet and is done in two levels through shared
-// memory (Cooley-Tukey inside the column pass: Galileo E1's 160000 = (8 x 25) x 800 and 144000 = (20 x 9) x 800).
+// memory (Cooley-Tukey inside the column pass: Galileo E1's 160000 = (20 x 10) x 800 and 144000 = (20 x 9) x 800, GPS L2C's
+// 320000 = (20 x 20) x 800, BDS B1C's 360000 = (25 x 18) x 800, BDS B1I's 72000 = (10 x 9) x 800).
 template <int C_, int RA_, int RB_, int C1_ = 0>
 struct Plan {
     static constexpr int C = C_, RA = RA_, RB = RB_;
@@ -39,10 +40,10 @@ using P36000 = Plan<45, 32, 25>;   // 18 Msps: the reference default of six sign
 using P24000 = Plan<30, 32, 25>;   // 12 Msps: GLONASS default
 using P32000 = Plan<40, 32, 25>;   // 16 Msps
 using P40000 = Plan<50, 32, 25>;   // 20 Msps
-using P160000 = Plan<200, 32, 25, 8>;    // Galileo E1 (4 ms codes) at 20 Msps: columns 200 = 8 x 25
+using P160000 = Plan<200, 32, 25, 20>;   // Galileo E1 (4 ms codes) at 20 Msps: columns 200 = 20 x 10
 using P144000 = Plan<180, 32, 25, 20>;   // Galileo E1 at 18 Msps (reference default): columns 180 = 20 x 9
-using P320000 = Plan<400, 32, 25, 16>;   // GPS L2C at 8 Msps (40 ms block): columns 400 = 16 x 25
-using P360000 = Plan<450, 32, 25, 18>;   // BDS B1C at 18 Msps (20 ms): columns 450 = 18 x 25
+using P320000 = Plan<400, 32, 25, 20>;   // GPS L2C at 8 Msps (40 ms block): columns 400 = 20 x 20
+using P360000 = Plan<450, 32, 25, 25>;   // BDS B1C at 18 Msps (20 ms): columns 450 = 25 x 18
 using P72000 = Plan<90, 32, 25, 10>;     // BDS B1I at 18 Msps (4 ms blocks): columns 90 = 10 x 9
 
 #define GC_PLAN_DISPATCH(LEN, CALL)                             \
