@@ -11,19 +11,28 @@ from .engine import Engine, GnssCorrError
 from .settings import Settings
 
 
-def _to_int8_iq(longSignal: np.ndarray, swapped: bool = False) -> np.ndarray:
-    """Complex longSignal -> the file's int8 I,Q byte order.  ``swapped``: the GLONASS read path
-    builds ``data2 + 1i*data1`` (GLO_GL1/include/postProcessing.m:94), so real/imag are Q/I."""
+def _to_file_samples(longSignal: np.ndarray, settings: Settings, swapped: bool = False) -> np.ndarray:
+    """longSignal -> the file's own samples: int8 or int16 (settings.dataType), I,Q interleaved for fileType 2, one value
+    per sample for fileType 1 (postProcessing.m:83-96).  ``swapped``: the GLONASS read path builds ``data2 + 1i*data1``
+    (GLO_GL1/include/postProcessing.m:94), so real/imag are Q/I."""
     x = np.asarray(longSignal)
+    dt = np.int16 if settings.dataType == "int16" else np.int8
+    lim = 32768 if dt is np.int16 else 128
+    if settings.fileType == 1:
+        if np.iscomplexobj(x):
+            raise GnssCorrError("fileType 1 expects a real-valued longSignal")
+        if not (np.all(x == np.rint(x)) and np.max(np.abs(x)) <= lim):
+            raise GnssCorrError("longSignal is not integer valued in the range of settings.dataType")
+        return x.astype(dt)
     if not np.iscomplexobj(x):
-        raise GnssCorrError("real-valued longSignal (fileType 1) is not implemented")
+        raise GnssCorrError("fileType 2 expects a complex longSignal (I + 1i*Q)")
     re, im = x.real, x.imag
     if not (np.all(re == np.rint(re)) and np.all(im == np.rint(im)) and
-            np.max(np.abs(re)) <= 128 and np.max(np.abs(im)) <= 128):
-        raise GnssCorrError("longSignal is not 8-bit integer valued; the accelerated path needs the raw 'schar' samples")
-    iq = np.empty(2 * x.size, dtype=np.int8)
-    iq[0::2] = (im if swapped else re).astype(np.int8)
-    iq[1::2] = (re if swapped else im).astype(np.int8)
+            np.max(np.abs(re)) <= lim and np.max(np.abs(im)) <= lim):
+        raise GnssCorrError("longSignal is not integer valued in the range of settings.dataType; the accelerated path needs the raw samples")
+    iq = np.empty(2 * x.size, dtype=dt)
+    iq[0::2] = (im if swapped else re).astype(dt)
+    iq[1::2] = (re if swapped else im).astype(dt)
     return iq
 
 
@@ -38,7 +47,7 @@ def acquisition(longSignal, settings: Settings, engine: Engine | None = None, ve
     eng = engine or Engine(settings)
     try:
         x = np.asarray(longSignal)
-        iq = x if x.dtype == np.int8 else _to_int8_iq(x, swapped=settings.is_glonass)
+        iq = x if x.dtype in (np.int8, np.int16) else _to_file_samples(x, settings, swapped=settings.is_glonass and settings.fileType == 2)
         r = eng.acquire(settings.acqSatelliteList, host_iq=iq)
     finally:
         if own:

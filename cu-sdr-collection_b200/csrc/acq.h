@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "rec.h"
 
 namespace gc {
 
@@ -14,7 +15,7 @@ struct FusedPlanInfo {
 bool fused_plan_info(int L, FusedPlanInfo* out);   // false: no fused plan for this length
 
 struct FwdColsParams {
-    const int8_t* rec;        // resident record (int8 I,Q)
+    Rec rec;                  // resident record
     long long winStart;       // sample index of longSignal(1) in the record
     int N;                    // samplesPerCode
     int nonCoh;
@@ -83,7 +84,7 @@ struct GenericPlan {
 // one Stockham pass over `batch` transforms: src -> dst
 cudaError_t launch_generic_stage(const GenericPlan& pl, int stage, int n, int s, bool inverse,
                                  const float2* src, float2* dst, long long batch, cudaStream_t st);
-cudaError_t launch_generic_wipe(const int8_t* rec, long long winStart, int N, int nonCoh, int nBins, int swapIQ,
+cudaError_t launch_generic_wipe(Rec rec, long long winStart, int N, int nonCoh, int nBins, int swapIQ,
                                 const uint64_t* dphi, float2* out, int L, cudaStream_t st);
 cudaError_t launch_generic_code(const int8_t* codeTab, int N, int nPrn, float2* out, int L, cudaStream_t st);
 cudaError_t launch_generic_mul(const float2* X, const float2* Cc, float2* out, int L, long long nKm, cudaStream_t st);
@@ -105,11 +106,11 @@ cudaError_t launch_varb_segmax(const float2* W, int nRows, int L, const int4* se
 cudaError_t launch_varb_segmax_mag(const float* mag, int nRows, int L, const int4* seg, float* out, cudaStream_t st);
 cudaError_t launch_varb_pad(const int8_t* tab, int n, int nRows, float2* out, int L, cudaStream_t st);
 // GPS L2C: |sum((x - mean) .* CL segment .* carrier)| for the 75 CL segments (acquisition.m:100-137); codeIdx 1-based [N]
-cudaError_t launch_l2c_clphase(const int8_t* rec, long long start, int N, const int8_t* cl, int segLen, const int* codeIdx,
+cudaError_t launch_l2c_clphase(Rec rec, long long start, int N, const int8_t* cl, int segLen, const int* codeIdx,
                                uint64_t dphi, double* power, cudaStream_t st);
 // variant C (BDS B1C): weighted data + pilot magnitudes per Doppler bin -> (max, first index); one-period fine search
 cudaError_t launch_varc_combine(const float2* W, int nBins, int L, int nRep, float* partMax, int* partIdx, size_t outBase, cudaStream_t st);
-cudaError_t launch_varc_fine(const int8_t* rec, long long winStart, int N, int nRep, const int8_t* tabs, const int* tabSlot,
+cudaError_t launch_varc_fine(Rec rec, long long winStart, int N, int nRep, const int8_t* tabs, const int* tabSlot,
                              const int* codePhase, const uint64_t* dphi, int nFine, int nAcq, double* fineResult, cudaStream_t st);
 
 // ---- shared by both paths -------------------------------------------------------------------
@@ -118,12 +119,12 @@ struct PeakOut {              // one per PRN slot
     int bin;                  // acqCoarseBin, 1-based                  :196
     int codePhase;            // 1-based                                :198
 };
-cudaError_t launch_sig_power(const int8_t* rec, long long winStart, int N, double* out, cudaStream_t s);
+cudaError_t launch_sig_power(Rec rec, long long winStart, int N, double* out, cudaStream_t s);
 cudaError_t launch_peak_select(const float* partMax, const int* partIdx, int nPrnSlots, int nBins, int parts,
                                PeakOut* out, cudaStream_t s);
 
 struct FineParams {
-    const int8_t* rec;
+    Rec rec;
     long long winStart;
     int N;                    // samplesPerCode
     int nPeriods;             // 40   (acquisition.m:146-148)

@@ -10,13 +10,12 @@ namespace {
 // sigPower = sqrt(var(longSignal(1:N)) * N), var of a complex vector with N-1 (acquisition.m:151).
 // The samples are small integers, so the three sums are exact in 64-bit integers.
 __global__ void __launch_bounds__(1024)
-sig_power_kernel(const int8_t* rec, long long winStart, int N, double* out)
+sig_power_kernel(Rec rec, long long winStart, int N, double* out)
 {
     long long sI = 0, sQ = 0, s2 = 0;
-    const char2* x = reinterpret_cast<const char2*>(rec) + winStart;
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        const char2 v = x[i];
-        sI += v.x; sQ += v.y; s2 += (int)v.x * v.x + (int)v.y * v.y;
+        const short2 v = rec.load(winStart + i);
+        sI += v.x; sQ += v.y; s2 += (long long)((int)v.x * v.x) + (long long)((int)v.y * v.y);
     }
     for (int o = 16; o > 0; o >>= 1) {
         sI += __shfl_down_sync(0xffffffffu, sI, o);
@@ -78,12 +77,12 @@ __global__ void fine_prep_kernel(FineParams p)
     const int a = blockIdx.y;
     if (a >= *p.nAcqDev * p.nCodes) return;
     const long long total = (long long)p.nPeriods * p.N;
-    const char2* x = reinterpret_cast<const char2*>(p.rec) + p.winStart + (p.codePhase[a] - 1);   // :221
+    const long long x0 = p.winStart + (p.codePhase[a] - 1);                                      // :221
     const int8_t* chips = p.chips + (size_t)p.chipRow[a] * p.codeLen;
     for (long long gi = blockIdx.x * (long long)blockDim.x + threadIdx.x; gi < total; gi += (long long)gridDim.x * blockDim.x) {
         const int c = chips[p.chipIdx[gi]];                      // caCode40ms (:215-218; GLO generateCAcode.m:110-116)
-        char2 v = x[gi];
-        if (p.swapIQ) v = make_char2(v.y, v.x);
+        short2 v = p.rec.load(x0 + gi);
+        if (p.swapIQ) v = make_short2(v.y, v.x);
         prod[(size_t)a * total + gi] = make_short2((short)(v.x * c), (short)(v.y * c));
     }
 }
@@ -246,7 +245,7 @@ __global__ void fine_select_kernel(FineParams p)
 
 }  // namespace
 
-cudaError_t launch_sig_power(const int8_t* rec, long long winStart, int N, double* out, cudaStream_t s)
+cudaError_t launch_sig_power(Rec rec, long long winStart, int N, double* out, cudaStream_t s)
 {
     sig_power_kernel<<<1, 1024, 0, s>>>(rec, winStart, N, out);
     return cudaGetLastError();

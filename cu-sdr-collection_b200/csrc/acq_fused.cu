@@ -55,11 +55,11 @@ fwd_cols_kernel(FwdColsParams p)
     if (MODE == 0) {
         const int k = row / p.nonCoh, m = row % p.nonCoh;
         const uint64_t dphi = p.dphi[k];
-        const int8_t* src = p.rec + 2 * ((size_t)p.winStart + (size_t)m * p.N);   // window x((m-1)N+1 : (m+1)N)
+        const long long x0 = p.winStart + (long long)m * p.N;                       // window x((m-1)N+1 : (m+1)N)
 #pragma unroll
         for (int n1 = 0; n1 < C; ++n1) {
             const int n = P::index(n1, base);
-            const char2 s = *reinterpret_cast<const char2*>(src + 2 * (size_t)n);
+            const short2 s = p.rec.load(x0 + n);
             float sn, cs;
             fix_sincos(dphi * (uint64_t)n, &sn, &cs);          // exp(-1i*f*phasePoints(n)), :172
             const float I = p.swapIQ ? (float)s.y : (float)s.x, Q = p.swapIQ ? (float)s.x : (float)s.y;
@@ -287,11 +287,11 @@ fwd_cols_big_kernel(FwdColsParams p)
         if (MODE == 0) {
             const int k = row / p.nonCoh, m = row % p.nonCoh;
             const uint64_t dphi = p.dphi[k];
-            const int8_t* src = p.rec + 2 * ((size_t)p.winStart + (size_t)m * p.N);
+            const long long x0 = p.winStart + (long long)m * p.N;
 #pragma unroll
             for (int a = 0; a < C1; ++a) {
                 const int n = P::index(C2 * a + q, base);
-                const char2 sv = *reinterpret_cast<const char2*>(src + 2 * (size_t)n);
+                const short2 sv = p.rec.load(x0 + n);
                 float sn, cs;
                 fix_sincos(dphi * (uint64_t)n, &sn, &cs);
                 const float I = p.swapIQ ? (float)sv.y : (float)sv.x, Q = p.swapIQ ? (float)sv.x : (float)sv.y;

@@ -13,14 +13,14 @@ namespace gc {
 namespace {
 
 // out[(k*nonCoh+m)][n] = longSignal(m*N + n) * exp(-1i*f_k*phasePoints(n))   (acquisition.m:172-181)
-__global__ void wipe_kernel(const int8_t* rec, long long winStart, int N, int nonCoh, int swapIQ,
+__global__ void wipe_kernel(Rec rec, long long winStart, int N, int nonCoh, int swapIQ,
                             const uint64_t* dphi, float2* out, int L)
 {
     const int km = blockIdx.y, k = km / nonCoh, m = km % nonCoh;
-    const char2* x = reinterpret_cast<const char2*>(rec) + winStart + (long long)m * N;
+    const long long x0 = winStart + (long long)m * N;
     const uint64_t d = dphi[k];
     for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < L; n += gridDim.x * blockDim.x) {
-        const char2 s = x[n];
+        const short2 s = rec.load(x0 + n);
         float sn, cs;
         fix_sincos(d * (uint64_t)n, &sn, &cs);
         const float I = swapIQ ? (float)s.y : (float)s.x, Q = swapIQ ? (float)s.x : (float)s.y;
@@ -185,7 +185,7 @@ cudaError_t launch_generic_stage(const GenericPlan& pl, int stage, int n, int s,
     return cudaGetLastError();
 }
 
-cudaError_t launch_generic_wipe(const int8_t* rec, long long winStart, int N, int nonCoh, int nBins, int swapIQ,
+cudaError_t launch_generic_wipe(Rec rec, long long winStart, int N, int nonCoh, int nBins, int swapIQ,
                                 const uint64_t* dphi, float2* out, int L, cudaStream_t st)
 {
     dim3 grid((L + 255) / 256, nBins * nonCoh);

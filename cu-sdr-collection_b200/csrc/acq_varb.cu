@@ -134,17 +134,17 @@ varc_combine_kernel(const float2* __restrict__ W, int L, int nRep, float* partMa
 // variant C fine search (:236-250): FineResult(j) = abs(sum(signal0DC .* DataPriTable .* exp(-1i*f_j*t)))
 // [*11 + the same with PilotPriTable *29, /40]; grid (nFine, nAcq), one 10 ms period per block.
 __global__ void __launch_bounds__(1024)
-varc_fine_kernel(const int8_t* rec, long long winStart, int N, int nRep, const int8_t* tabs /*[slot][N]*/,
+varc_fine_kernel(Rec rec, long long winStart, int N, int nRep, const int8_t* tabs /*[slot][N]*/,
                  const int* tabSlot, const int* codePhase, const uint64_t* dphi, int nFine, double* fineResult)
 {
     const int j = blockIdx.x, a = blockIdx.y;
-    const char2* x = reinterpret_cast<const char2*>(rec) + winStart + (codePhase[a] - 1);
+    const long long x0 = winStart + (codePhase[a] - 1);
     const int8_t* d = tabs + (size_t)tabSlot[a] * N;
     const int8_t* pl = d + N;
     const uint64_t dp = dphi[a * nFine + j];
     double dr = 0, di = 0, pr = 0, pi = 0;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
-        const char2 v = x[n];
+        const short2 v = rec.load(x0 + n);
         float sn, cs;
         fix_sincos(dp * (uint64_t)n, &sn, &cs);
         const float re = fmaf(cs, (float)v.x, sn * (float)v.y), im = fmaf(cs, (float)v.y, -sn * (float)v.x);
@@ -172,14 +172,13 @@ varc_fine_kernel(const int8_t* rec, long long winStart, int N, int nRep, const i
 // for the 75 CM-period segments of the CL sequence; signal0DC = x - mean(x) over one CM period starting at codePhase.
 // sum((x - mu) .* c .* e) = sum(x .* c .* e) - mu * sum(c .* e); one block per segment.
 __global__ void __launch_bounds__(1024)
-l2c_clphase_kernel(const int8_t* rec, long long start, int N, const int8_t* cl, int segLen, const int* codeIdx, uint64_t dphi, double* power)
+l2c_clphase_kernel(Rec rec, long long start, int N, const int8_t* cl, int segLen, const int* codeIdx, uint64_t dphi, double* power)
 {
     const int ind = blockIdx.x;
-    const char2* x = reinterpret_cast<const char2*>(rec) + start;
     const int8_t* c = cl + (size_t)ind * segLen;
     double s[6] = {0, 0, 0, 0, 0, 0};            // sum x.c.e (re, im), sum c.e (re, im), sum x (re, im)
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
-        const char2 v = x[n];
+        const short2 v = rec.load(start + n);
         float sn, cs;
         fix_sincos(dphi * (uint64_t)n, &sn, &cs);
         const float cv = (float)c[codeIdx[n] - 1];
@@ -248,7 +247,7 @@ cudaError_t launch_varc_combine(const float2* W, int nBins, int L, int nRep, flo
     return cudaGetLastError();
 }
 
-cudaError_t launch_varc_fine(const int8_t* rec, long long winStart, int N, int nRep, const int8_t* tabs, const int* tabSlot,
+cudaError_t launch_varc_fine(Rec rec, long long winStart, int N, int nRep, const int8_t* tabs, const int* tabSlot,
                              const int* codePhase, const uint64_t* dphi, int nFine, int nAcq, double* fineResult, cudaStream_t st)
 {
     dim3 grid(nFine, nAcq);
@@ -256,7 +255,7 @@ cudaError_t launch_varc_fine(const int8_t* rec, long long winStart, int N, int n
     return cudaGetLastError();
 }
 
-cudaError_t launch_l2c_clphase(const int8_t* rec, long long start, int N, const int8_t* cl, int segLen, const int* codeIdx,
+cudaError_t launch_l2c_clphase(Rec rec, long long start, int N, const int8_t* cl, int segLen, const int* codeIdx,
                                uint64_t dphi, double* power, cudaStream_t st)
 {
     l2c_clphase_kernel<<<75, 1024, 0, st>>>(rec, start, N, cl, segLen, codeIdx, dphi, power);

@@ -114,6 +114,7 @@ struct gc_handle {
     // resident record
     const int8_t* rec = nullptr;
     size_t recBytes = 0;
+    int fmt = 0;                 // Rec::fmt from settings.fileType / dataType
     DevBuf<int8_t> recOwned;
 
     // acquisition
@@ -188,6 +189,11 @@ bool sv_ok(const gc_handle* h, int sv) { return h->glo ? (sv >= -7 && sv <= 13) 
 int sv_result_index(const gc_handle* h, int sv) { return h->glo ? sv + 7 : sv - 1; }       // MATLAB K+8 / PRN, 0-based
 int sv_replica(const gc_handle* h, int sv) { return h->glo ? 0 : (sv - 1) * h->nRep; }
 double sv_freq_offset(const gc_handle* h, int sv) { return h->glo ? -h->cfg.freq_spacing * (double)sv : 0.0; }
+Rec rec_of(const gc_handle* h) { return Rec{h->rec, h->fmt}; }
+// settings.skipNumberOfBytes as a sample offset: the reference seeks dataAdaptCoeff*skip BYTES (postProcessing.m:74,
+// tracking.m:145-151), which is `skip` samples of 'schar' data and skip/2 samples of 'int16' data
+long long skip_samples(const gc_handle* h) { return (long long)h->cfg.skip_number_of_bytes / ((h->fmt & 1) ? 2 : 1); }
+long long rec_samples(const gc_handle* h) { return (long long)(h->recBytes / (size_t)rec_of(h).bytes_per_sample()); }
 
 // +-1 table entries (chips, or BOC sub-chips) of one code period for an SV: the tracking replica of
 // `component` (0 data, 1 pilot); the fine search uses the pilot component where there is one
@@ -310,8 +316,8 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     if (cfg->abi_version != GC_ABI_VERSION) return fail(nullptr, GC_ERR_ARG, "gc_create: abi_version mismatch");
     if (cfg->signal < GC_SIG_GPS_L1CA || cfg->signal > GC_SIG_BDS_B1C)
         return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: signal not implemented (GPS L1CA/L5C/L2C, GLONASS G1/G2, BDS B1I/B1C/B3I/B2a, GAL E1C/E5a/E5b are)");
-    if (cfg->file_type != 2 || cfg->sample_bytes != 1)
-        return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: only fileType 2 (I/Q) with dataType 'schar' is implemented");
+    if ((cfg->file_type != 1 && cfg->file_type != 2) || (cfg->sample_bytes != 1 && cfg->sample_bytes != 2))
+        return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: fileType must be 1 (real) or 2 (I/Q) and dataType 'schar' (1 byte) or 'int16' (2 bytes)");
     if (!(cfg->sampling_freq > 0) || !(cfg->code_freq_basis > 0) ||
         cfg->code_length != (cfg->signal == GC_SIG_GLO_G1G2 ? 511 : cfg->signal == GC_SIG_GAL_E1C ? 4092 :
                              cfg->signal == GC_SIG_GPS_L1CA ? 1023 : cfg->signal == GC_SIG_BDS_B1I ? 2046 : 10230) ||
@@ -330,6 +336,8 @@ int gc_create(gc_handle** out, const gc_config* cfg)
 
     gc_handle* h = new gc_handle();
     h->cfg = *cfg;
+    h->fmt = (cfg->sample_bytes == 2 ? 1 : 0) | (cfg->file_type == 1 ? 2 : 0);
+    if ((h->fmt & 1) && (cfg->skip_number_of_bytes & 1)) { delete h; return fail(nullptr, GC_ERR_ARG, "gc_create: with 'int16' data skipNumberOfBytes must be even (the seek would land inside a sample)"); }
     h->glo = (cfg->signal == GC_SIG_GLO_G1G2);
     h->b3i = (cfg->signal == GC_SIG_BDS_B3I);
     h->e1c = (cfg->signal == GC_SIG_GAL_E1C);
@@ -618,7 +626,7 @@ static int acquire_varb(gc_handle* h, long long winStart, int32_t nSv, const int
     const int Lb = h->vb.Lb, nSig = h->vb.nSig, nShifts = h->vb.nShifts, nBins = h->vb.nBins;
     const bool b1i = c.signal == GC_SIG_BDS_B1I;
     cudaStream_t st = h->stream;
-    const long long recSamples = (long long)(h->recBytes / 2);
+    const long long recSamples = rec_samples(h);
     if (winStart < 0 || winStart + (long long)nSig * Lb > recSamples)
         return fail(h, GC_ERR_SHORT_RECORD, "gc_acquire: record shorter than the acquisition blocks");
     for (int i = 0; i < h->resultLen; ++i) {
@@ -679,7 +687,7 @@ static int acquire_varb(gc_handle* h, long long winStart, int32_t nSv, const int
         const int parts = h->fp.parts, C = h->fp.C;
         GC_CUDA(h, h->X.reserve((size_t)nX * Lb));
         FwdColsParams fp{};
-        fp.rec = h->rec; fp.winStart = winStart; fp.N = Lb; fp.nonCoh = nSig; fp.swapIQ = 0;
+        fp.rec = rec_of(h); fp.winStart = winStart; fp.N = Lb; fp.nonCoh = nSig; fp.swapIQ = 0;
         fp.dphi = h->dphi.p; fp.out = h->X.p; fp.tw = h->twFused.p;
         GC_CUDA(h, launch_fwd_cols(Lb, fp, nX, false, st)); ++launches;
         RowsParams rp{};
@@ -749,7 +757,7 @@ static int acquire_varb(gc_handle* h, long long winStart, int32_t nSv, const int
         GC_CUDA(h, h->X.reserve((size_t)nX * Lb));
         GC_CUDA(h, h->T1.reserve(bufRows * Lb));
         GC_CUDA(h, h->T2.reserve(bufRows * Lb));
-        GC_CUDA(h, launch_generic_wipe(h->rec, winStart, Lb, nSig, nShifts, 0, h->dphi.p, h->T1.p, Lb, st)); ++launches;
+        GC_CUDA(h, launch_generic_wipe(rec_of(h), winStart, Lb, nSig, nShifts, 0, h->dphi.p, h->T1.p, Lb, st)); ++launches;
         float2 *src = h->T1.p, *dst = h->T2.p;
         int n = Lb, sd = 1;
         for (int f = 0; f < h->plan.nf; ++f) {
@@ -843,7 +851,7 @@ static int acquire_varb(gc_handle* h, long long winStart, int32_t nSv, const int
             const long long start = winStart + (long long)codePhase[ri] - 1;
             if (start + N > recSamples) return fail(h, GC_ERR_SHORT_RECORD, "gc_acquire: record too short for the CL phase search");
             GC_CUDA(h, upload(h->clDev, cl, st));
-            GC_CUDA(h, launch_l2c_clphase(h->rec, start, N, h->clDev.p, segLen, h->clIdx.p, turns_to_fix(carrFreq[ri] * ts), h->clPower.p, st)); ++launches;
+            GC_CUDA(h, launch_l2c_clphase(rec_of(h), start, N, h->clDev.p, segLen, h->clIdx.p, turns_to_fix(carrFreq[ri] * ts), h->clPower.p, st)); ++launches;
             double pw[75];
             GC_CUDA(h, cudaMemcpyAsync(pw, h->clPower.p, sizeof(pw), cudaMemcpyDeviceToHost, st));
             GC_CUDA(h, cudaStreamSynchronize(st));
@@ -922,7 +930,7 @@ static int acquire_varc(gc_handle* h, long long winStart, long long longLen, int
     const int N = h->N, Lc = h->vc.Lc, nBins = h->nBins, nRep = h->nRep, nFine = h->vc.nFine;
     cudaStream_t st = h->stream;
     if (longLen <= 0) longLen = 2LL * N;                     // postProcessing.m:33 reads two code periods
-    const long long recSamples = (long long)(h->recBytes / 2);
+    const long long recSamples = rec_samples(h);
     if (winStart < 0 || winStart + std::max<long long>(Lc, longLen) > recSamples || longLen < Lc)
         return fail(h, GC_ERR_SHORT_RECORD, "gc_acquire: record shorter than (10 + acqCohT) ms");
     for (int i = 0; i < h->resultLen; ++i) {
@@ -933,7 +941,7 @@ static int acquire_varc(gc_handle* h, long long winStart, long long longLen, int
     int launches = 0;
     cudaEventRecord(h->ev[0], st);
     GC_CUDA(h, h->sigPower.reserve(1));
-    GC_CUDA(h, launch_sig_power(h->rec, winStart, h->vc.xLen, h->sigPower.p, st)); ++launches;   // :163
+    GC_CUDA(h, launch_sig_power(rec_of(h), winStart, h->vc.xLen, h->sigPower.p, st)); ++launches;   // :163
     const uint64_t dphi0 = turns_to_fix(h->vc.initFreq / c.sampling_freq);
     GC_CUDA(h, h->dphi.reserve(1));
     GC_CUDA(h, cudaMemcpyAsync(h->dphi.p, &dphi0, sizeof(uint64_t), cudaMemcpyHostToDevice, st));
@@ -944,7 +952,7 @@ static int acquire_varc(gc_handle* h, long long winStart, long long longLen, int
         parts = h->fp.parts;
         GC_CUDA(h, h->X.reserve((size_t)Lc));
         FwdColsParams fp{};
-        fp.rec = h->rec; fp.winStart = winStart; fp.N = Lc; fp.nonCoh = 1; fp.swapIQ = 0;
+        fp.rec = rec_of(h); fp.winStart = winStart; fp.N = Lc; fp.nonCoh = 1; fp.swapIQ = 0;
         fp.dphi = h->dphi.p; fp.out = h->X.p; fp.tw = h->twFused.p;
         GC_CUDA(h, launch_fwd_cols(Lc, fp, 1, false, st)); ++launches;                      // :168-179
         RowsParams rp{};
@@ -982,7 +990,7 @@ static int acquire_varc(gc_handle* h, long long winStart, long long longLen, int
         GC_CUDA(h, h->X.reserve((size_t)Lc));
         GC_CUDA(h, h->T1.reserve((size_t)std::max(nRows, 32) * Lc));
         GC_CUDA(h, h->T2.reserve((size_t)std::max(nRows, 32) * Lc));
-        GC_CUDA(h, launch_generic_wipe(h->rec, winStart, Lc, 1, 1, 0, h->dphi.p, h->T1.p, Lc, st)); ++launches;   // :168-172
+        GC_CUDA(h, launch_generic_wipe(rec_of(h), winStart, Lc, 1, 1, 0, h->dphi.p, h->T1.p, Lc, st)); ++launches;   // :168-172
         {
             float2 *src = h->T1.p, *dst = h->T2.p;
             int n = Lc, sd = 1;
@@ -1052,7 +1060,7 @@ static int acquire_varc(gc_handle* h, long long winStart, long long longLen, int
         GC_CUDA(h, upload(h->vcSlot, slots, st));
         GC_CUDA(h, h->fineResult.reserve((size_t)nAcq * nFine));
         cudaEventRecord(h->ev[3], st);
-        GC_CUDA(h, launch_varc_fine(h->rec, winStart, N, nRep, h->codeTab.p, h->vcSlot.p, h->fineCodePhase.p, h->fdphi.p, nFine, nAcq,
+        GC_CUDA(h, launch_varc_fine(rec_of(h), winStart, N, nRep, h->codeTab.p, h->vcSlot.p, h->fineCodePhase.p, h->fdphi.p, nFine, nAcq,
                                     h->fineResult.p, st)); ++launches;
         std::vector<double> fr((size_t)nAcq * nFine);
         GC_CUDA(h, cudaMemcpyAsync(fr.data(), h->fineResult.p, fr.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1107,7 +1115,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
     }
     // postProcessing.m:86 reads max(42, nonCoh+2) code periods (B3I: max(22, nonCoh+1), BDS/B3I/include/postProcessing.m:86)
     const int nPeriodsAcq = std::max(h->acqMinPeriods, nonCoh + h->acqExtraPeriods);
-    const long long recSamples = (long long)(h->recBytes / 2);
+    const long long recSamples = rec_samples(h);
     if (winStart < 0 || winStart + (long long)nPeriodsAcq * N > recSamples)
         return fail(h, GC_ERR_SHORT_RECORD, "gc_acquire: record shorter than the acquisition window (max(42, acqNonCohTime+2) code periods; B3I max(22, acqNonCohTime+1))");
     cudaSetDevice(c.device);
@@ -1157,7 +1165,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
     std::vector<std::vector<double>> coarseFreqOf(nSv);   // per list slot: the bin frequencies it was searched on
 
     const int e0 = mark();
-    GC_CUDA(h, launch_sig_power(h->rec, winStart, N, h->sigPower.p, st)); ++launches;   // :151
+    GC_CUDA(h, launch_sig_power(rec_of(h), winStart, N, h->sigPower.p, st)); ++launches;   // :151
     mark();                                           // event 1 (re-recorded at the end of the coarse search)
     if (h->cluster) {
         // forward spectra of every carrier grid, then the whole SV x bin grid in one cluster launch
@@ -1176,7 +1184,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         const int f0 = mark();
         for (int gi = 0; gi < nGroups; ++gi) {
             FwdColsParams fp{};
-            fp.rec = h->rec; fp.winStart = winStart; fp.N = N; fp.nonCoh = nonCoh; fp.swapIQ = h->glo ? 1 : 0;
+            fp.rec = rec_of(h); fp.winStart = winStart; fp.N = N; fp.nonCoh = nonCoh; fp.swapIQ = (h->glo && !(h->fmt & 2)) ? 1 : 0;
             fp.dphi = h->dphi.p + (size_t)gi * nBins; fp.out = h->X.p + (size_t)gi * nKm * L; fp.tw = h->twFused.p;
             GC_CUDA(h, launch_fwd_cols(L, fp, nKm, false, st)); ++launches;
         }
@@ -1210,7 +1218,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         const int f0 = mark();
         if (h->fused) {
             FwdColsParams fp{};
-            fp.rec = h->rec; fp.winStart = winStart; fp.N = N; fp.nonCoh = nonCoh; fp.swapIQ = h->glo ? 1 : 0;
+            fp.rec = rec_of(h); fp.winStart = winStart; fp.N = N; fp.nonCoh = nonCoh; fp.swapIQ = (h->glo && !(h->fmt & 2)) ? 1 : 0;
             fp.dphi = h->dphi.p; fp.out = h->X.p; fp.tw = h->twFused.p;
             GC_CUDA(h, launch_fwd_cols(L, fp, nKm, false, st)); ++launches;
             RowsParams rp{};
@@ -1248,7 +1256,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         } else {
             GC_CUDA(h, h->T1.reserve((size_t)std::max(h->nReplicas, nKm) * L));
             GC_CUDA(h, h->T2.reserve((size_t)std::max(h->nReplicas, nKm) * L));
-            GC_CUDA(h, launch_generic_wipe(h->rec, winStart, N, nonCoh, nBins, h->glo ? 1 : 0, h->dphi.p, h->T1.p, L, st)); ++launches;
+            GC_CUDA(h, launch_generic_wipe(rec_of(h), winStart, N, nonCoh, nBins, (h->glo && !(h->fmt & 2)) ? 1 : 0, h->dphi.p, h->T1.p, L, st)); ++launches;
             float2 *src = h->T1.p, *dst = h->T2.p;
             int n = L, s = 1;
             for (int f = 0; f < h->plan.nf; ++f) {
@@ -1340,8 +1348,8 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         fa = mark();
         GC_CUDA(h, launch_fine_setup(fs, st)); ++launches;
         FineParams fp{};
-        fp.rec = h->rec; fp.winStart = winStart; fp.N = N; fp.nPeriods = nPeriods; fp.nFine = h->nFine; fp.codeLen = tabLen;
-        fp.swapIQ = h->glo ? 1 : 0; fp.combine = h->fineCombine; fp.chipIdx = h->chipIdx.p; fp.svId = h->fineSv.p;
+        fp.rec = rec_of(h); fp.winStart = winStart; fp.N = N; fp.nPeriods = nPeriods; fp.nFine = h->nFine; fp.codeLen = tabLen;
+        fp.swapIQ = (h->glo && !(h->fmt & 2)) ? 1 : 0; fp.combine = h->fineCombine; fp.chipIdx = h->chipIdx.p; fp.svId = h->fineSv.p;
         fp.chips = h->chips.p; fp.chipRow = h->fineChipRow.p; fp.codePhase = h->fineCodePhase.p; fp.dphi = h->fdphi.p; fp.prod = h->fineProd.p;
         fp.sums = h->fineSums.p; fp.best = h->fineBest.p; fp.fineResult = h->fineResult.p;
         fp.nAcqDev = h->nAcqDev.p; fp.nCodes = nCodes; fp.secondary = h->fineSecondary.p;
@@ -1405,7 +1413,7 @@ int gc_acquire(gc_handle* h, int32_t nSv, const int32_t* svList,
 {
     if (!h) return GC_ERR_ARG;
     // fseek(fid, dataAdaptCoeff*skipNumberOfBytes) (postProcessing.m:74): skip counts complex samples
-    return acquire_impl(h, (long long)h->cfg.skip_number_of_bytes, nSv, svList, carrFreq, codePhase, peakMetric,
+    return acquire_impl(h, skip_samples(h), nSv, svList, carrFreq, codePhase, peakMetric,
                         coarseBin, coarseCodePhase);
 }
 
@@ -1414,7 +1422,7 @@ int gc_acquire_host(gc_handle* h, const int8_t* iq, size_t nSamples, int32_t nSv
                     int32_t* coarseBin, int32_t* coarseCodePhase)
 {
     if (!h || !iq) return fail(h, GC_ERR_ARG, "gc_acquire_host: bad argument");
-    int rc = gc_set_record_host(h, iq, nSamples * 2);
+    int rc = gc_set_record_host(h, iq, nSamples * (size_t)rec_of(h).bytes_per_sample());
     if (rc != GC_OK) return rc;
     return acquire_impl(h, 0, nSv, svList, carrFreq, codePhase, peakMetric, coarseBin, coarseCodePhase, (long long)nSamples);
 }
@@ -1507,7 +1515,7 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
         chans[ch].acqFreq = acqFreq[ch];
         chans[ch].codeFreq0 = codeFreq0 ? codeFreq0[ch] : c.code_freq_basis * (l2c ? 2 : 1);   // channel.codeFreq (B3I tracking.m:57)
         // fseek(fid, dataAdaptCoeff*(skipNumberOfBytes + codePhase-1)) (tracking.m:150); L2C seeks to codePhase (GPS_L2C tracking.m:153)
-        chans[ch].startSample = (long long)c.skip_number_of_bytes + (long long)codePhase[ch] - (l2c ? 0 : 1);
+        chans[ch].startSample = skip_samples(h) + (long long)codePhase[ch] - (l2c ? 0 : 1);
         if (active) {
             if (!sv_ok(h, sv[ch])) return fail(h, GC_ERR_ARG, "gc_track: SV id out of range");
             if (!sv_has_code(h, sv[ch])) return fail(h, GC_ERR_ARG, "gc_track: no code set for a channel's SV (gc_set_code)");
@@ -1539,8 +1547,8 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
         }
     }
     TrackParams p{};
-    p.rec = h->rec;
-    p.recSamples = (long long)(h->recBytes / 2);
+    p.rec = h->rec; p.fmt = h->fmt;
+    p.recSamples = rec_samples(h);
     p.fs = c.sampling_freq; p.invFs = 1.0 / c.sampling_freq; p.codeFreqBasis = c.code_freq_basis * (l2c ? 2 : 1); p.codeLength = (double)c.code_length * (l2c ? 2 : 1);
     p.spc = c.dll_correlator_spacing * (l2c ? 2 : 1);
     p.cA = h->tau2code / h->tau1code; p.cB = c.int_time / h->tau1code;     // tracking.m:326
@@ -1552,7 +1560,7 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
         p.pf1 = 2 * Wn;
     }
     p.loopType = (h->glo || h->b3i || h->hostCodes) ? 1 : 0;
-    p.swapIQ = h->glo ? 1 : 0;
+    p.swapIQ = (h->glo && !(h->fmt & 2)) ? 1 : 0;
     p.nEpochs = nEpochs;
     p.exactDisc = getenv("GC_TRACK_EXACT_DISC") ? 1 : 0;
     // CTAs per channel: spread few channels over the chip (thread-block clusters), 1 CTA per channel once

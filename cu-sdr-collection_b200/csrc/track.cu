@@ -302,6 +302,7 @@ track_kernel(TrackParams p)
     const int cpc = p.bufBytes / 16;                             // chunks per CTA (bufBytes is per CTA)
     const int c_lo = (int)crank * cpc;
     auto prefetch = [&](long long startSample, int stage, int epoch) {      // one thread only
+        if (p.fmt != 0) return false;                            // only int8 I,Q windows are staged
         const long long b0 = ((startSample * 2) & ~15LL) + (long long)c_lo * 16;
         long long n = p.bufBytes;
         if (b0 + n > recBytesUp) n = recBytesUp - b0;
@@ -386,17 +387,28 @@ track_kernel(TrackParams p)
         // (the chunk holding the middle of the colon vector, or every chunk of a `generic` block).
         auto do_chunk = [&](int c, auto special_tag) {
             constexpr bool SPECIAL = decltype(special_tag)::value;
-            int4 raw;
-            if (inBuf) raw = *reinterpret_cast<const int4*>(src + (size_t)c * 16);
-            else raw = __ldg(reinterpret_cast<const int4*>(gsrc + (size_t)c * 16));   // not staged: straight from L2
             const int k0 = c * 8 - off;
-            const uint32_t w0 = (uint32_t)raw.x ^ 0x80808080u, w1 = (uint32_t)raw.y ^ 0x80808080u,
-                           w2 = (uint32_t)raw.z ^ 0x80808080u, w3 = (uint32_t)raw.w ^ 0x80808080u;
             float xi[8], xq[8];                                   // tracking.m:233-235
-            xi[0] = byte_to_float(w0, selI0); xq[0] = byte_to_float(w0, selQ0); xi[1] = byte_to_float(w0, selI1); xq[1] = byte_to_float(w0, selQ1);
-            xi[2] = byte_to_float(w1, selI0); xq[2] = byte_to_float(w1, selQ0); xi[3] = byte_to_float(w1, selI1); xq[3] = byte_to_float(w1, selQ1);
-            xi[4] = byte_to_float(w2, selI0); xq[4] = byte_to_float(w2, selQ0); xi[5] = byte_to_float(w2, selI1); xq[5] = byte_to_float(w2, selQ1);
-            xi[6] = byte_to_float(w3, selI0); xq[6] = byte_to_float(w3, selQ0); xi[7] = byte_to_float(w3, selI1); xq[7] = byte_to_float(w3, selQ1);
+            if (p.fmt == 0) {
+                int4 raw;
+                if (inBuf) raw = *reinterpret_cast<const int4*>(src + (size_t)c * 16);
+                else raw = __ldg(reinterpret_cast<const int4*>(gsrc + (size_t)c * 16));   // not staged: straight from L2
+                const uint32_t w0 = (uint32_t)raw.x ^ 0x80808080u, w1 = (uint32_t)raw.y ^ 0x80808080u,
+                               w2 = (uint32_t)raw.z ^ 0x80808080u, w3 = (uint32_t)raw.w ^ 0x80808080u;
+                xi[0] = byte_to_float(w0, selI0); xq[0] = byte_to_float(w0, selQ0); xi[1] = byte_to_float(w0, selI1); xq[1] = byte_to_float(w0, selQ1);
+                xi[2] = byte_to_float(w1, selI0); xq[2] = byte_to_float(w1, selQ0); xi[3] = byte_to_float(w1, selI1); xq[3] = byte_to_float(w1, selQ1);
+                xi[4] = byte_to_float(w2, selI0); xq[4] = byte_to_float(w2, selQ0); xi[5] = byte_to_float(w2, selI1); xq[5] = byte_to_float(w2, selQ1);
+                xi[6] = byte_to_float(w3, selI0); xq[6] = byte_to_float(w3, selQ0); xi[7] = byte_to_float(w3, selI1); xq[7] = byte_to_float(w3, selQ1);
+            } else {                                              // int16 and / or real samples (tracking.m:145-149, 229-240)
+                const Rec rec{p.rec, p.fmt};
+                const bool swap = p.swapIQ && !(p.fmt & 2);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const long long si = min(max(pos + k0 + j, 0LL), p.recSamples - 1);
+                    const short2 v = rec.load(si);
+                    xi[j] = (float)(swap ? v.y : v.x); xq[j] = (float)(swap ? v.x : v.y);
+                }
+            }
             if (k0 < 0 || k0 + 7 >= blk) {                        // first / last chunk of the block: drop the samples outside it
 #pragma unroll
                 for (int j = 0; j < 8; ++j)

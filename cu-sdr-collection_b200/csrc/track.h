@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/gnsscorr.h"
+#include "rec.h"
 
 #define GC_TRACK_ROWS GC_TRACK_NFIELDS_PILOT6   /* most rows a channel records per epoch (staging size) */
 
@@ -19,8 +20,10 @@ struct TrackChan {
 };
 
 struct TrackParams {
-    const int8_t* rec;       // resident IF record, int8 I,Q interleaved, 16-byte aligned
-    long long recSamples;    // complex samples in the record
+    const int8_t* rec;       // resident IF record, 16-byte aligned
+    int fmt;                 // Rec::fmt; 0 (int8 I,Q) is staged through shared memory by bulk copies, the other formats
+                             // (int16, real: tracking.m:141-153, 229-240) are read through the generic accessor from L2
+    long long recSamples;    // samples in the record
     double fs, invFs, codeFreqBasis, codeLength, spc;
     double cA, cB;           // tau2code/tau1code, PDIcode/tau1code  (tracking.m:326)
     double pA, pB;           // tau2carr/tau1carr, PDIcarr/tau1carr  (tracking.m:308)

@@ -108,12 +108,12 @@ def config_from_settings(s: Settings, device: int = 0) -> gc_config:
     if s.resamplingflag != 0:   # (B3I spells it resamplingFlag, BDS/B3I/initSettings.m:88)
         raise GnssCorrError("resamplingflag == 1 is outside the accelerated path "
                             "(acquisition.m:50-111); run the reference for that case")
-    if s.fileType != 2 or s.dataType != "schar":
-        raise GnssCorrError("only fileType 2 with dataType 'schar' is implemented")
+    if s.fileType not in (1, 2) or s.dataType not in ("schar", "int16"):
+        raise GnssCorrError("fileType must be 1 (real) or 2 (I/Q) and dataType 'schar' or 'int16' (initSettings.m:63-68)")
     sig = signal_id(s)
     return gc_config(abi_version=4, device=device, pilot_trk_flag=int(s.pilotTRKflag), acq_coh_t=int(s.acqCohT),
                      pilot_acq_flag=int(s.pilotACQflag), signal=sig, freq_spacing=float(s.freqSpacing),
-                     file_type=s.fileType, sample_bytes=1,
+                     file_type=s.fileType, sample_bytes=2 if s.dataType == "int16" else 1,
                      code_length=int(s.codeLength), acq_noncoh_time=int(s.acqNonCohTime),
                      cno_vsm_interval=int(s.CNo_VSMinterval), skip_number_of_bytes=int(s.skipNumberOfBytes),
                      sampling_freq=s.samplingFreq, IF=s.IF, code_freq_basis=s.codeFreqBasis,
@@ -175,6 +175,11 @@ class Engine:
                 a = np.ascontiguousarray(chips, dtype=np.int8)
                 self._check(self.lib.gc_set_code(self._h, int(prn), comp, a.ctypes.data, a.size), "gc_set_code")
 
+    @property
+    def sample_dtype(self):
+        """numpy dtype of one stored value of the record: settings.dataType 'schar' / 'int16' (initSettings.m:63)."""
+        return np.int16 if self.settings.dataType == "int16" else np.int8
+
     def close(self):
         if self._h:
             self.lib.gc_destroy(self._h)
@@ -195,12 +200,12 @@ class Engine:
         """Make an IF record resident.  ``data``: int8 numpy array (copied host->device) or an
         int8 CUDA torch tensor (adopted without a copy; kept alive by the engine)."""
         if isinstance(data, np.ndarray):
-            a = np.ascontiguousarray(data, dtype=np.int8)
-            self._check(self.lib.gc_set_record_host(self._h, a.ctypes.data, a.size), "gc_set_record_host")
+            a = np.ascontiguousarray(data, dtype=self.sample_dtype)
+            self._check(self.lib.gc_set_record_host(self._h, a.ctypes.data, a.nbytes), "gc_set_record_host")
             self._keep = None
         else:  # torch tensor on the GPU
-            assert data.is_cuda and data.element_size() == 1 and data.is_contiguous()
-            self._check(self.lib.gc_set_record_device(self._h, data.data_ptr(), data.numel()), "gc_set_record_device")
+            assert data.is_cuda and data.element_size() == np.dtype(self.sample_dtype).itemsize and data.is_contiguous()
+            self._check(self.lib.gc_set_record_device(self._h, data.data_ptr(), data.numel() * data.element_size()), "gc_set_record_device")
             self._keep = data
 
     # ---- acquisition --------------------------------------------------------------------
@@ -211,8 +216,8 @@ class Engine:
         carr, cph, pm = np.zeros(n), np.zeros(n), np.zeros(n)
         cbin, ccp = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
         if host_iq is not None:
-            a = np.ascontiguousarray(host_iq, dtype=np.int8)
-            rc = self.lib.gc_acquire_host(self._h, a.ctypes.data, a.size // 2, sv.size, _ip(sv),
+            a = np.ascontiguousarray(host_iq, dtype=self.sample_dtype)       # the file's own sample format
+            rc = self.lib.gc_acquire_host(self._h, a.ctypes.data, a.size // (1 if s.fileType == 1 else 2), sv.size, _ip(sv),
                                           _dp(carr), _dp(cph), _dp(pm), _ip(cbin), _ip(ccp))
             self._check(rc, "gc_acquire_host")
         else:

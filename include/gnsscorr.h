@@ -163,7 +163,10 @@ int gc_get_cl_code_phase(const gc_handle* h, int32_t* clCodePhase);
 int gc_set_cl_code_phase(gc_handle* h, int32_t nCh, const int32_t* clCodePhase);
 
 /* Make an IF record resident in HBM.  `bytes` is the raw file image from byte 0
- * (what fopen/fread see, postProcessing.m:59-96): int8 I,Q interleaved for fileType 2.
+ * (what fopen/fread see, postProcessing.m:59-96): I,Q interleaved for fileType 2, one value per sample for fileType 1,
+ * int8 for dataType 'schar' (sample_bytes 1), little-endian int16 for 'int16' (sample_bytes 2; the dataAdaptCoeff and
+ * int16 branches of postProcessing.m:66-96 and tracking.m:141-153, 229-240).  int8 I,Q is the fast path (bulk-copied
+ * windows in tracking); the other formats go through a per-sample accessor.
  * _host copies host->device (pinned or pageable memory); _device adopts a device pointer without
  * copying (must be 16-byte aligned with its capacity rounded up to a multiple of 16 bytes, which
  * every cudaMalloc/torch allocation satisfies) — the caller keeps it alive. */
@@ -184,8 +187,9 @@ int gc_acquire(gc_handle* h, int32_t nSv, const int32_t* svList,
                double* carrFreq, double* codePhase, double* peakMetric,
                int32_t* coarseBin, int32_t* coarseCodePhase);
 
-/* Same, but with longSignal supplied from HOST memory as int8 I,Q pairs (what the MEX gateway
- * passes after checking the complex-double longSignal is integer valued): copies it to the GPU,
+/* Same, but with longSignal supplied from HOST memory in the record's own sample format - int8 I,Q pairs for
+ * fileType 2 / 'schar' (what the MEX gateway passes after checking the complex-double longSignal is integer valued),
+ * int16 pairs for 'int16', single values for fileType 1; nSamples counts samples, not bytes: copies it to the GPU,
  * runs gc_acquire on it (skip ignored — longSignal already starts at the skip point), copies the
  * results back.  This is the reference-facing call and the one bench.py times as `e2e`. */
 int gc_acquire_host(gc_handle* h, const int8_t* iq, size_t nSamples,

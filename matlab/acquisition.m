@@ -7,18 +7,25 @@ function acqResults = acquisition(longSignal, settings)
 % Put this folder ahead of the signal's include/ on the MATLAB path (init.m:39-40 adds include
 % then Common).  Cases outside the accelerated path are handed to the original function, which
 % must then be reachable as acquisition_reference (a renamed copy of the reference file).
-fastPath = settings.resamplingflag == 0 && settings.fileType == 2 && ...
-           strcmp(settings.dataType, 'schar') && ~isreal(longSignal) && ...
+% The engine takes the file's own samples: int8 ('schar') or int16, I,Q pairs (fileType 2) or real values (fileType 1).
+is16 = strcmp(settings.dataType, 'int16');
+if is16, cls = 'int16'; lim = 32768; else, cls = 'int8'; lim = 128; end
+fastPath = settings.resamplingflag == 0 && (is16 || strcmp(settings.dataType, 'schar')) && ...
+           isreal(longSignal) == (settings.fileType == 1) && ...
            all(real(longSignal) == round(real(longSignal))) && ...
            all(imag(longSignal) == round(imag(longSignal))) && ...
-           max(abs(real(longSignal))) <= 128 && max(abs(imag(longSignal))) <= 128;
+           max(abs(real(longSignal))) <= lim && max(abs(imag(longSignal))) <= lim;
 if ~fastPath
     acqResults = acquisition_reference(longSignal, settings);
     return
 end
-iq = zeros(1, 2 * numel(longSignal), 'int8');
-iq(1:2:end) = int8(real(longSignal));
-iq(2:2:end) = int8(imag(longSignal));
+if settings.fileType == 1
+    iq = cast(longSignal, cls);
+else
+    iq = zeros(1, 2 * numel(longSignal), cls);
+    iq(1:2:end) = cast(real(longSignal), cls);
+    iq(2:2:end) = cast(imag(longSignal), cls);
+end
 r = gnsscorr_mex('acquire', gnsscorr_config(settings), iq, double(settings.acqSatelliteList));
 acqResults.carrFreq   = r.carrFreq;
 acqResults.codePhase  = r.codePhase;

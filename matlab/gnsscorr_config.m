@@ -19,7 +19,7 @@ switch signal
     otherwise,      cfg.signal = 0;  cfg.freq_spacing = 0;
 end
 cfg.file_type = settings.fileType;
-cfg.sample_bytes = 1;
+if strcmp(settings.dataType, 'int16'), cfg.sample_bytes = 2; else, cfg.sample_bytes = 1; end   % initSettings.m:63
 cfg.code_length = settings.codeLength;
 if isfield(settings, 'acqNonCohTime')
     cfg.acq_noncoh_time = settings.acqNonCohTime;

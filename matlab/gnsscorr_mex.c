@@ -133,12 +133,15 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
         const double* svd = mxGetDoubles(prhs[3]);
         int32_t sv[64];
         mwSize i;
-        if ((nrhs != 4 && nrhs != 5) || !mxIsInt8(prhs[2]) || nSv > 64) { gc_destroy(h); mexErrMsgIdAndTxt("gnsscorr:args", "acquire: bad arguments"); }
+        /* longSignal in the file's own samples: int8 or int16 (cfg.sample_bytes), I,Q pairs or real values (cfg.file_type) */
+        const int is16 = cfg.sample_bytes == 2;
+        const size_t perSample = cfg.file_type == 1 ? 1 : 2;
+        if ((nrhs != 4 && nrhs != 5) || !(is16 ? mxIsInt16(prhs[2]) : mxIsInt8(prhs[2])) || nSv > 64) { gc_destroy(h); mexErrMsgIdAndTxt("gnsscorr:args", "acquire: bad arguments"); }
         if (nrhs == 5) set_codes(h, &cfg, prhs[4]);
         for (i = 0; i < nSv; ++i) sv[i] = (int32_t)svd[i];
         plhs[0] = mxCreateStructMatrix(1, 1, 4, names);
         for (i = 0; i < 4; ++i) mxSetField(plhs[0], 0, names[i], mxCreateDoubleMatrix(1, n, mxREAL));
-        check(h, gc_acquire_host(h, (const int8_t*)mxGetInt8s(prhs[2]), mxGetNumberOfElements(prhs[2]) / 2, (int32_t)nSv, sv,
+        check(h, gc_acquire_host(h, (const int8_t*)mxGetData(prhs[2]), mxGetNumberOfElements(prhs[2]) / perSample, (int32_t)nSv, sv,
                                  mxGetDoubles(mxGetField(plhs[0], 0, "carrFreq")), mxGetDoubles(mxGetField(plhs[0], 0, "codePhase")),
                                  mxGetDoubles(mxGetField(plhs[0], 0, "peakMetric")), NULL, NULL),
               "gc_acquire_host");

@@ -17,6 +17,8 @@ double* mxGetDoubles(const mxArray*);
 int8_t* mxGetInt8s(const mxArray*);
 int32_t* mxGetInt32s(const mxArray*);
 int mxIsInt8(const mxArray*);
+int mxIsInt16(const mxArray*);
+void* mxGetData(const mxArray*);
 int mxIsEmpty(const mxArray*);
 mxArray* mxCreateStructMatrix(mwSize, mwSize, int, const char**);
 mxArray* mxCreateDoubleMatrix(mwSize, mwSize, mxComplexity);

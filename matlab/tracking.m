@@ -6,7 +6,8 @@ function [trackResults, channel] = tracking(fid, channel, settings)
 %
 % A MEX file cannot use MATLAB's fid, so the file name is recovered with fopen(fid) and the
 % library reads the record itself.
-fastPath = settings.fileType == 2 && strcmp(settings.dataType, 'schar');
+fastPath = (settings.fileType == 1 || settings.fileType == 2) && ...
+           (strcmp(settings.dataType, 'schar') || strcmp(settings.dataType, 'int16'));
 if ~fastPath
     [trackResults, channel] = tracking_reference(fid, channel, settings);
     return

@@ -176,7 +176,9 @@ def read_acq_signal(raw: np.ndarray, s: Settings) -> np.ndarray:
     N = samples_per_code(s)
     coef = 1 if s.fileType == 1 else 2
     codeLen = max(42, s.acqNonCohTime + 2)
-    off = coef * s.skipNumberOfBytes
+    off = coef * s.skipNumberOfBytes                           # fseek in bytes (:74); int16 values are two bytes each
+    if getattr(s, "dataType", "schar") == "int16":
+        off //= 2
     data = raw[off: off + coef * codeLen * N].astype(np.float64)
     if coef == 2:
         data = data[0::2] + 1j * data[1::2]
@@ -311,9 +313,11 @@ TRACK_FIELDS = ["absoluteSample", "codeFreq", "carrFreq", "I_P", "I_E", "I_L",
 # tracking (GPS/GPS_L1CA/include/tracking.m:45-371)
 # ---------------------------------------------------------------------------
 def tracking(raw: np.ndarray, channel: list, s: Settings):
-    """Line-by-line restatement of tracking.m:45-371 for fileType 2 /
-    dataType schar.  ``raw`` plays the role of the open file (int8 bytes);
-    fseek/ftell/fread are restated as a byte cursor.  A short read ends the
+    """Line-by-line restatement of tracking.m:45-371.  ``raw`` plays the role of the open file: the array of stored
+    values (int8 for dataType 'schar', int16 for 'int16'; I,Q interleaved for fileType 2, one value per sample for
+    fileType 1); fseek/ftell/fread are restated as a cursor in VALUES - for 'int16' the reference's byte offsets
+    dataAdaptCoeff*(skip + (codePhase-1)*2) (:145-148) and ftell/dataAdaptCoeff/2 (:212-213) are the same cursor divided by the
+    two bytes of a value.  A short read ends the
     whole call with partially filled results and status left '-'
     (tracking.m:241-245)."""
     nE = s.msToProcess
@@ -335,14 +339,17 @@ def tracking(raw: np.ndarray, channel: list, s: Settings):
     PDIcarr = s.intTime                                            # :106
     tau1carr, tau2carr = calcLoopCoef(s.pllNoiseBandwidth, s.pllDampingRatio, 0.25)  # :109
     coef = 1 if s.fileType == 1 else 2                             # :126-130
-    assert coef == 2 and s.dataType == "schar"
+    is16 = getattr(s, "dataType", "schar") == "int16"
     L = int(s.codeLength)
     for ch in range(s.numberOfChannels):                           # :133
         if channel[ch]["PRN"] == 0:                                # :136
             continue
         tr = out[ch]
         tr["PRN"] = channel[ch]["PRN"]                             # :138
-        pos = coef * (s.skipNumberOfBytes + channel[ch]["codePhase"] - 1)   # :150 (byte cursor)
+        if is16:                                                   # :145-148, bytes -> int16 values
+            pos = (coef * (s.skipNumberOfBytes + (channel[ch]["codePhase"] - 1) * 2)) // 2
+        else:
+            pos = coef * (s.skipNumberOfBytes + channel[ch]["codePhase"] - 1)   # :150 (byte cursor)
         caCode = generateCAcode(channel[ch]["PRN"])                # :156
         caCode = np.concatenate([[caCode[L - 1]], caCode, [caCode[0]]])     # :158
         codeFreq = s.codeFreqBasis                                 # :163
@@ -363,7 +370,10 @@ def tracking(raw: np.ndarray, channel: list, s: Settings):
             pos += samplesRead
             if samplesRead != nbytes:                              # :241-245
                 return out
-            rawSignal = chunk[0::2].astype(np.float64) + 1j * chunk[1::2].astype(np.float64)  # :233-235
+            if coef == 2:
+                rawSignal = chunk[0::2].astype(np.float64) + 1j * chunk[1::2].astype(np.float64)  # :233-235
+            else:
+                rawSignal = chunk.astype(np.float64)
             tr["remCodePhase"][loopCnt - 1] = remCodePhase         # :249
             tcode = colonop(remCodePhase - earlyLateSpc, codePhaseStep,
                             (blksize - 1) * codePhaseStep + remCodePhase - earlyLateSpc)   # :252

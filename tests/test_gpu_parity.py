@@ -613,6 +613,53 @@ def test_fam5_tracking_and_wrappers_vs_oracle(signal, pilot, tmp_path):
     eng.close()
 
 
+# ------------------------------------------------------------- sample formats: int16 and real records
+@pytest.mark.parametrize("fileType,dataType", [(2, "int16"), (1, "schar"), (1, "int16")])
+def test_sample_formats_vs_oracle(fileType, dataType, tmp_path):
+    """GPS L1CA acquisition + tracking on int16 and on real (fileType 1) records - the dataAdaptCoeff / int16 branches of
+    postProcessing.m:66-96 and tracking.m:141-153, 229-240.  The int16 samples exceed the int8 range (x 90), so nothing can
+    pass through an 8-bit path unnoticed."""
+    fs = 16.368e6
+    sc = scene(fs, nsat=3, seed=11, cn0=47)
+    nE = 120
+    s = init_settings(samplingFreq=fs, fileType=fileType, dataType=dataType, msToProcess=nE, numberOfChannels=4, acqSatelliteList=sorted({x.prn for x in sc.sats} | {30}))
+    so = to_oracle_settings(s)
+    so.fileType = fileType
+    N = O.samples_per_code(so)
+    iq8 = synth.make_record(sc, N * (nE + 44))
+    scale = 90 if dataType == "int16" else 1
+    dt = np.int16 if dataType == "int16" else np.int8
+    if fileType == 2:
+        raw = (iq8.astype(np.int32) * scale).astype(dt)
+    else:
+        raw = (iq8[0::2].astype(np.int32) * scale).astype(dt)    # real record: the in-phase samples only
+    longSignal = O.read_acq_signal(raw, so)
+    assert np.iscomplexobj(longSignal) == (fileType == 2)
+    ref = O.acquisition(longSignal, so, workers=os.cpu_count() or 1)
+    eng = Engine(s)
+    got = acquisition(longSignal, s, engine=eng, verbose=False)
+    _check_acq(got, ref, s.acqSatelliteList)
+    for sat in sc.sats:
+        assert got["carrFreq"][sat.prn - 1] != 0
+    assert got["carrFreq"][30 - 1] == 0
+    ch = preRun(got, s)
+    path = tmp_path / "rec.bin"
+    raw.tofile(path)
+    with open(path, "rb") as fid:
+        tr, _ = tracking(fid, ch, s, engine=eng)
+    ref_tr = O.tracking(raw, ch, so)
+    for i in range(3):
+        assert tr[i]["status"] == "T" == ref_tr[i]["status"] and tr[i]["epochsDone"] == nE
+        assert np.array_equal(tr[i]["absoluteSample"], ref_tr[i]["absoluteSample"])
+        sc_ = np.hypot(ref_tr[i]["I_P"], ref_tr[i]["Q_P"])
+        for name in ("I_P", "Q_P", "I_E", "I_L", "Q_E", "Q_L"):
+            assert np.max(np.abs(tr[i][name] - ref_tr[i][name]) / sc_) < IQ_TOL, name
+        assert np.max(np.abs(tr[i]["carrFreq"] - ref_tr[i]["carrFreq"])) < 1e-4
+        assert np.max(np.abs(tr[i]["remCodePhase"] - ref_tr[i]["remCodePhase"])) < 1e-7
+    assert tr[3]["status"] == "-"
+    eng.close()
+
+
 # ------------------------------------------------------------- acquisition variant B: BDS B1I, GPS L2C
 def _varb_case(signal, fs, nsat, seed, extra, cn0, **kw):
     from cu_sdr_collection_b200.codes import standin_varb_codes

@@ -101,15 +101,30 @@ def test_prerun_orders_by_peak_metric():
     assert [c["PRN"] for c in ch] == [9, 20]
 
 
-def test_acquisition_rejects_non_integer_signal():
-    from cu_sdr_collection_b200.acquisition import _to_int8_iq
+def test_acquisition_sample_conversion():
+    """longSignal -> the file's own samples for the four fileType / dataType combinations; non-integer or out-of-range
+    input is refused (the accelerated path needs the raw samples)."""
+    from cu_sdr_collection_b200.acquisition import _to_file_samples
+    s8 = init_settings()
     x = (np.arange(8) - 4) + 1j * (np.arange(8) - 3)
-    iq = _to_int8_iq(x.astype(np.complex128))
+    iq = _to_file_samples(x.astype(np.complex128), s8)
     assert iq.dtype == np.int8 and list(iq[:4]) == [-4, -3, -3, -2]
     with pytest.raises(engine.GnssCorrError):
-        _to_int8_iq(x + 0.5)
+        _to_file_samples(x + 0.5, s8)
     with pytest.raises(engine.GnssCorrError):
-        _to_int8_iq(np.arange(8, dtype=np.float64))
+        _to_file_samples(np.arange(8, dtype=np.float64), s8)
+    with pytest.raises(engine.GnssCorrError):
+        _to_file_samples(300.0 * x, s8)
+    s16 = init_settings(dataType="int16")
+    iq = _to_file_samples(300.0 * x, s16)
+    assert iq.dtype == np.int16 and list(iq[:4]) == [-1200, -900, -900, -600]
+    sr = init_settings(fileType=1)
+    r = _to_file_samples(np.arange(8, dtype=np.float64) - 4, sr)
+    assert r.dtype == np.int8 and r.size == 8 and r[0] == -4
+    with pytest.raises(engine.GnssCorrError):
+        _to_file_samples(x, sr)
+    cfg = engine.config_from_settings(init_settings(fileType=1, dataType="int16"))
+    assert cfg.file_type == 1 and cfg.sample_bytes == 2
 
 
 def test_shard_units_partition():
