@@ -36,6 +36,9 @@ struct RowsParams {
     int nRep, repStride;      // inverse: replicas summed per SV (1, or 2 = data + pilot) and their distance in Cc; the
                               // work buffer then holds nonCoh*nRep transforms per (SV, bin), replica index fastest
     int prnPerCta, mPerCta;   // warps of an inverse CTA = binPerCta x prnPerCta x mPerCta (same row j1)
+    int bin0;                 // first bin of this launch: nBins counts the bins of the launch (and of the W layout), the spectra
+                              // and binMap are addressed with bin0 + local bin
+    int keepL2;               // 1: W is written with default caching (an L2-resident chunk), 0: streaming stores
     int binPerCta;            // bins per CTA (0 = 1); > 1 where a (SV, bin) cell has too few transforms to fill a CTA
     const int2* binMap;       // optional [nBins]: .x = spectrum row in X (instead of bin*nonCoh + block), .y = circular shift of
                               // the spectrum, circshift(IQfreqDom, y) (acquisition variants B and C); nullptr = variant A
@@ -46,7 +49,8 @@ struct RowsParams {
 struct InvColsParams {
     const float2* W;
     int nBins, nonCoh, nPrnChunk, prnSlot0;
-    float* partMax;           // [nSv][nBins][parts]
+    int bin0, nBinsTotal;     // the launch covers bins [bin0, bin0 + nBins) of nBinsTotal (0 = nBins) in partMax / partIdx
+    float* partMax;           // [nSv][nBinsTotal][parts]
     int* partIdx;
     int weighted;             // 1: magnitudes of even / odd transforms are weighted w0 / w1 and the sum scaled by wScale
     float w0, w1, wScale;     // (BDS B1C: (|data|*sqrt(11) + |pilot|*sqrt(29)) / sqrt(40), acquisition.m:213-214)

@@ -140,10 +140,10 @@ inv_rows_kernel(RowsParams p)
     // circshift(IQfreqDom, s) (BDS/B1I acquisition.m:88, GPS_L2C :73, B1C :203): product element j takes spectrum element j - s.
     // With j = j1 + C*j2 (row j1, in-row frequency j2 held by its residues mod RA and mod RB) that is row (j1 - s) mod C
     // and j2 - floor-part, i.e. a fixed source row and a circular shift of both residues.
-    int xrow = k * p.nonCoh + m, srow = k1, sa = 0, sb = 0;
+    int xrow = (p.bin0 + k) * p.nonCoh + m, srow = k1, sa = 0, sb = 0;
     if constexpr (!P::kPfa) {                                    // (the variant B / C lengths all have Cooley-Tukey plans)
         if (p.binMap != nullptr) {
-            const int2 bm = p.binMap[k];
+            const int2 bm = p.binMap[p.bin0 + k];
             xrow = bm.x * p.nonCoh + m;
             const int s1 = bm.y % C;
             int s2 = bm.y / C;
@@ -174,7 +174,7 @@ inv_rows_kernel(RowsParams p)
         codelet::dft<RA, true>(v, [&](int ta, float re, float im) {
             float2 t = make_float2(re, im);
             if (!P::kPfa) t = cmul_conj(t, __ldg(tw + ta * RB));  // conj(w_L^(j1*tau2))
-            __stcs(dst + ta * RB + lane, t);
+            if (p.keepL2) dst[ta * RB + lane] = t; else __stcs(dst + ta * RB + lane, t);
         });
     }
 }
@@ -241,7 +241,7 @@ inv_cols_kernel(InvColsParams p)
     if (threadIdx.x == 0) {
         for (int w = 1; w < 4; ++w)
             if (s_b[w] > best || (s_b[w] == best && s_i[w] < bidx)) { best = s_b[w]; bidx = s_i[w]; }
-        const size_t o = ((size_t)(p.prnSlot0 + pi) * p.nBins + k) * gridDim.x + blockIdx.x;
+        const size_t o = ((size_t)(p.prnSlot0 + pi) * (p.nBinsTotal ? p.nBinsTotal : p.nBins) + p.bin0 + k) * gridDim.x + blockIdx.x;
         p.partMax[o] = best;
         p.partIdx[o] = bidx;
     }
@@ -387,7 +387,7 @@ inv_cols_big_kernel(InvColsParams p)
     if (threadIdx.x == 0) {
         for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
             if (s_b[w] > best || (s_b[w] == best && s_i[w] < bidx)) { best = s_b[w]; bidx = s_i[w]; }
-        const size_t o = ((size_t)(p.prnSlot0 + pi) * p.nBins + k) * gridDim.x + blockIdx.x;
+        const size_t o = ((size_t)(p.prnSlot0 + pi) * (p.nBinsTotal ? p.nBinsTotal : p.nBins) + p.bin0 + k) * gridDim.x + blockIdx.x;
         p.partMax[o] = best;
         p.partIdx[o] = bidx;
     }

@@ -50,6 +50,9 @@ struct gc_handle {
     gc_config cfg{};
     std::string err;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;          // column passes of the split correlation stage when they overlap the next chunk's row pass
+    cudaEvent_t evRows[2]{}, evCols[2]{};    // hand-offs between the two streams (no timing)
+    DevBuf<float2> W2;                       // second work buffer of the overlapped pipeline
     cudaEvent_t ev[kEvents]{};
     gc_stats stats{};
 
@@ -107,6 +110,7 @@ struct gc_handle {
     int N = 0, L = 0, nBins = 0, nFine = 0, nonCoh = 0;
     double ts = 0;
     bool fused = false;
+    bool overlap = false;        // split correlation stage pipelined over two streams (GC_ACQ_OVERLAP)
     bool cluster = false;        // correlation stage as one cluster kernel (acq_cluster.cu); else inv_rows + inv_cols
     FusedPlanInfo fp{};
     DevBuf<float2> twFused;      // [C][R] twiddles of fused plans with a Cooley-Tukey column/row link
@@ -372,6 +376,9 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(GC_ERR_CUDA); }
     for (auto& e : h->ev)
         if (cudaEventCreate(&e) != cudaSuccess) { h->err = "cudaEventCreate failed"; return bail(GC_ERR_CUDA); }
+    if (cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(GC_ERR_CUDA); }
+    for (int i = 0; i < 2; ++i)
+        if (cudaEventCreateWithFlags(&h->evRows[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->evCols[i], cudaEventDisableTiming) != cudaSuccess) { h->err = "cudaEventCreate failed"; return bail(GC_ERR_CUDA); }
 
     // acquisition.m:116-124,138-140
     h->N = (int)m_round(cfg->sampling_freq / (cfg->code_freq_basis / (double)cfg->code_length));
@@ -416,6 +423,8 @@ int gc_create(gc_handle** out, const gc_config* cfg)
         // in a cluster's shared memory); the default is inverse rows + inverse columns through a work buffer
         const char* e = getenv("GC_ACQ_PATH");
         h->cluster = h->fused && e && strcmp(e, "cluster") == 0;
+        const char* o = getenv("GC_ACQ_OVERLAP");
+        h->overlap = h->fused && !h->cluster && o && atoi(o) != 0;
     }
     h->stats.acq_path = h->cluster ? 2 : h->fused ? 1 : 0;   // 2 = fused plan + cluster correlation kernel, 1 = fused plan, split
                                                              // correlation stage, 0 = generic mixed-radix passes
@@ -492,6 +501,8 @@ void gc_destroy(gc_handle* h)
     h->vcSlot.release(); h->vbRows.release(); h->vbPeak.release(); h->vbIdx.release(); h->vbSeg.release();
     h->chans.release(); h->trackCodes.release(); h->trackPilot.release(); h->trackOut.release(); h->epochsDone.release();
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) { if (h->evRows[i]) cudaEventDestroy(h->evRows[i]); if (h->evCols[i]) cudaEventDestroy(h->evCols[i]); }
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -1225,16 +1236,29 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
             rp.X = h->X.p; rp.nRows = (long long)nKm * h->fp.C;
             GC_CUDA(h, launch_fwd_rows(L, rp, st)); ++launches;
             fwdEv.push_back({f0, mark()});
-            // PRN chunks sized so the inverse work buffer stays below ~2.5 GB
-            int chunk = (int)std::max<long long>(1, (long long)(2.5e9 / ((double)nKm * h->nRep * L * sizeof(float2))));
+            // PRN chunks sized so the inverse work buffer stays below ~2.5 GB.  With GC_ACQ_OVERLAP the chunks are halved and
+            // pipelined over two work buffers: the column pass of chunk c (HBM bound) runs on a second stream while the row
+            // pass of chunk c+1 (FP32 bound) runs on the first.
+            const bool overlap = h->overlap;
+            int chunk = (int)std::max<long long>(1, (long long)((overlap ? 1.25e9 : 2.5e9) / ((double)nKm * h->nRep * L * sizeof(float2))));
             if (const char* e = getenv("GC_ACQ_CHUNK_PRNS")) chunk = std::max(1, atoi(e));
             chunk = std::min(chunk, g1 - g0);
             GC_CUDA(h, h->W.reserve((size_t)chunk * nKm * h->nRep * L));
-            for (int s0 = g0; s0 < g1; s0 += chunk) {
+            if (overlap) GC_CUDA(h, h->W2.reserve((size_t)chunk * nKm * h->nRep * L));
+            // GC_ACQ_CHUNK_BINS: bins per launch; with a PRN x bin chunk small enough for the L2 (126 MB) the work buffer never
+            // reaches HBM: written by the row pass with default caching, read back by the column pass that follows
+            int binChunk = nBins;
+            if (const char* e = getenv("GC_ACQ_CHUNK_BINS")) binChunk = std::min(nBins, std::max(1, atoi(e)));
+            const bool keepL2 = binChunk < nBins && !overlap;
+            int ci = 0;
+            for (int b0 = 0; b0 < nBins; b0 += binChunk)
+            for (int s0 = g0; s0 < g1; s0 += chunk, ++ci) {
+                const int nb = std::min(binChunk, nBins - b0);
                 const int nc = std::min(chunk, g1 - s0);
+                float2* Wc = (overlap && (ci & 1)) ? h->W2.p : h->W.p;
                 RowsParams ip{};
-                ip.X = h->X.p; ip.Cc = h->Cc.p; ip.W = h->W.p; ip.tw = h->twFused.p;
-                ip.nonCoh = nonCoh; ip.nBins = nBins; ip.prnPerCta = 1; ip.mPerCta = 5;   // 5 warps, 96 registers, 20 warps/SM
+                ip.X = h->X.p; ip.Cc = h->Cc.p; ip.W = Wc; ip.tw = h->twFused.p;
+                ip.nonCoh = nonCoh; ip.nBins = nb; ip.bin0 = b0; ip.keepL2 = keepL2 ? 1 : 0; ip.prnPerCta = 1; ip.mPerCta = 5;   // 5 warps, 96 registers, 20 warps/SM
                 ip.nRep = h->nRep; ip.repStride = 1;
                 if (nonCoh * h->nRep < 5) { ip.prnPerCta = 5; ip.mPerCta = 1; }       // few transforms per cell (Galileo E1: 2): fill the CTA with SVs
                 if (const char* e = getenv("GC_ROWS_VARIANT")) {   // "PxM" warps per CTA = P PRNs x M blocks
@@ -1243,16 +1267,27 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
                 }
                 ip.nPrnChunk = nc; ip.prnSlot0 = s0; ip.prnList = h->prnList.p;
                 if (evn > kEvents - 12) drain_events();
+                if (overlap && ci >= 2) GC_CUDA(h, cudaStreamWaitEvent(st, h->evCols[ci & 1], 0));   // this buffer's previous columns are done
                 const int a = mark();
                 GC_CUDA(h, launch_inv_rows(L, ip, st)); ++launches;
                 const int b = mark();
                 InvColsParams cp{};
-                cp.W = h->W.p; cp.nBins = nBins; cp.nonCoh = nonCoh * h->nRep; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
+                cp.W = Wc; cp.nBins = nb; cp.bin0 = b0; cp.nBinsTotal = nBins; cp.nonCoh = nonCoh * h->nRep; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
                 cp.partMax = h->partMax.p; cp.partIdx = h->partIdx.p;
-                GC_CUDA(h, launch_inv_cols(L, cp, st)); ++launches;
-                const int d = mark();
-                rowEv.push_back({a, b}); colEv.push_back({b, d}); ++nRowLaunches;
+                if (overlap) {
+                    GC_CUDA(h, cudaEventRecord(h->evRows[ci & 1], st));
+                    GC_CUDA(h, cudaStreamWaitEvent(h->stream2, h->evRows[ci & 1], 0));
+                    GC_CUDA(h, launch_inv_cols(L, cp, h->stream2)); ++launches;
+                    GC_CUDA(h, cudaEventRecord(h->evCols[ci & 1], h->stream2));
+                    rowEv.push_back({a, b}); ++nRowLaunches;
+                } else {
+                    GC_CUDA(h, launch_inv_cols(L, cp, st)); ++launches;
+                    const int d = mark();
+                    rowEv.push_back({a, b}); colEv.push_back({b, d}); ++nRowLaunches;
+                }
             }
+            if (overlap)                                       // the peak search waits for every column pass
+                for (int i = 0; i < std::min(ci, 2); ++i) GC_CUDA(h, cudaStreamWaitEvent(st, h->evCols[i], 0));
         } else {
             GC_CUDA(h, h->T1.reserve((size_t)std::max(h->nReplicas, nKm) * L));
             GC_CUDA(h, h->T2.reserve((size_t)std::max(h->nReplicas, nKm) * L));
