@@ -16,6 +16,7 @@
 #include "codes.h"
 #include "common.cuh"
 #include "track.h"
+#include "nav.h"
 
 using namespace gc;
 
@@ -141,6 +142,8 @@ struct gc_handle {
     DevBuf<int8_t> trackCodes, trackPilot;
     DevBuf<double> trackOut;
     DevBuf<int32_t> epochsDone;
+    DevBuf<uint8_t> navCand, navBits;
+    DevBuf<int> navInt;
     double tau1code = 0, tau2code = 0, tau1carr = 0, tau2carr = 0;
 };
 
@@ -1711,6 +1714,32 @@ int gc_track_file(gc_handle* h, const char* path, int32_t nCh, const int32_t* sv
     cudaFreeHost(pinned);
     if (rc != GC_OK) return rc;
     return gc_track(h, nCh, sv, acqFreq, codePhase, codeFreq0, nEpochs, out, vsmValue, vsmIndex, epochsDone);
+}
+
+int gc_nav_sync(gc_handle* h, int32_t nCh, int32_t nEpochs, const double* I_P, int32_t* subFrameStart, uint8_t* navBits, int32_t* bitsValid)
+{
+    if (!h) return GC_ERR_ARG;
+    if (h->cfg.signal != GC_SIG_GPS_L1CA) return fail(h, GC_ERR_UNSUPPORTED, "gc_nav_sync: GPS L1 C/A only");
+    if (nCh < 1 || nEpochs < 1 || !I_P || !subFrameStart || !navBits || !bitsValid) return fail(h, GC_ERR_ARG, "gc_nav_sync: bad argument");
+    cudaSetDevice(h->cfg.device);
+    cudaStream_t st = h->stream;
+    const size_t n = (size_t)nCh * nEpochs;
+    GC_CUDA(h, h->trackOut.reserve(n));                       // the I_P rows
+    GC_CUDA(h, h->navCand.reserve(n));
+    GC_CUDA(h, h->navBits.reserve((size_t)nCh * GC_NAV_BITS));
+    GC_CUDA(h, h->navInt.reserve(2 * (size_t)nCh));
+    GC_CUDA(h, cudaMemcpyAsync(h->trackOut.p, I_P, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    GC_CUDA(h, launch_nav_sync(h->trackOut.p, nCh, nEpochs, 0 /* searchStartOffset, NAVdecoding.m:66 */, nEpochs, h->navCand.p,
+                               h->navInt.p, h->navBits.p, h->navInt.p + nCh, st));
+    std::vector<int> hi(2 * (size_t)nCh);
+    GC_CUDA(h, cudaMemcpyAsync(hi.data(), h->navInt.p, hi.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+    GC_CUDA(h, cudaMemcpyAsync(navBits, h->navBits.p, (size_t)nCh * GC_NAV_BITS, cudaMemcpyDeviceToHost, st));
+    GC_CUDA(h, cudaStreamSynchronize(st));
+    for (int ch = 0; ch < nCh; ++ch) {
+        subFrameStart[ch] = hi[ch] == 0x7fffffff ? 0 : hi[ch];
+        bitsValid[ch] = hi[nCh + ch];
+    }
+    return GC_OK;
 }
 
 void* gc_get_stream(const gc_handle* h) { return h ? (void*)h->stream : nullptr; }

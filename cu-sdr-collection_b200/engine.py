@@ -55,7 +55,7 @@ class gc_stats(C.Structure):
 EXPORTS = ["gc_abi_version", "gc_build_arch", "gc_acq_result_len", "gc_create", "gc_destroy",
            "gc_last_error", "gc_set_code", "gc_set_record_host", "gc_set_record_device", "gc_acquire",
            "gc_acquire_host", "gc_track_nfields", "gc_track", "gc_track_file", "gc_get_stats", "gc_get_stream",
-           "gc_set_param", "gc_get_cl_code_phase", "gc_set_cl_code_phase"]
+           "gc_set_param", "gc_get_cl_code_phase", "gc_set_cl_code_phase", "gc_nav_sync"]
 
 _lib = None
 
@@ -91,6 +91,7 @@ def load_lib():
     lib.gc_track.argtypes = [vp, C.c_int32, i32p, dp, dp, dp, C.c_int32, dp, dp, dp, i32p]
     lib.gc_track_file.argtypes = [vp, C.c_char_p, C.c_int32, i32p, dp, dp, dp, C.c_int32, dp, dp, dp, i32p]
     lib.gc_get_stats.argtypes = [vp, C.POINTER(gc_stats)]
+    lib.gc_nav_sync.argtypes = [vp, C.c_int32, C.c_int32, dp, i32p, C.POINTER(C.c_uint8), i32p]
     lib.gc_get_stream.argtypes = [vp]
     lib.gc_get_stream.restype = C.c_void_p
     _lib = lib

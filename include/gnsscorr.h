@@ -227,6 +227,21 @@ int gc_track_file(gc_handle* h, const char* path,
                   const double* codePhase, const double* codeFreq0, int32_t nEpochs,
                   double* out, double* vsmValue, double* vsmIndex, int32_t* epochsDone);
 
+/* Bit and frame synchronisation front end of postNavigation for GPS L1 C/A - replaces
+ * GPS/GPS_L1CA/include/NAVdecoding.m:69-170 (with Common/navPartyChk.m): sign of the prompt outputs, cross-correlation with the
+ * 8-bit TLM preamble at 20 values per bit, candidates |xcorr| > 153 with 40 < index < msToProcess - 1199, for every
+ * candidate that has another one 6000 ms later the parity of the TLM and HOW words on 20 ms bit sums, and the navigation
+ * bits summed from subFrameStart - 20 (GC_NAV_BITS = 1501: the last bit of the previous subframe and five subframes).
+ *   I_P            [nCh][nEpochs] trackResults(ch).I_P (host)
+ *   subFrameStart  [nCh] first index (1-based) that passes, 0 = 'Could not find valid preambles in channel!' (:143-146)
+ *   navBits        [nCh][GC_NAV_BITS] bits as 0/1 (:152-166), zero when bitsValid[ch] == 0
+ *   bitsValid      [nCh] 1 when subFrameStart - 20 .. subFrameStart + 29999 lies inside the record (the reference
+ *                  indexes out of range otherwise)
+ * GPS L1 C/A only (GC_ERR_UNSUPPORTED for the other signals, whose messages have their own framing). */
+#define GC_NAV_BITS 1501
+int gc_nav_sync(gc_handle* h, int32_t nCh, int32_t nEpochs, const double* I_P,
+                int32_t* subFrameStart, uint8_t* navBits, int32_t* bitsValid);
+
 /* Device-side timing of the most recent gc_acquire / gc_track, measured with CUDA events on the
  * engine's own stream (the stream the kernels are launched on). */
 typedef struct gc_stats {

@@ -188,6 +188,23 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
         mxSetField(plhs[0], 0, "vsmValue", vv);
         mxSetField(plhs[0], 0, "vsmIndex", vi);
         mxSetField(plhs[0], 0, "epochsDone", done);
+    } else if (!strcmp(cmd, "navsync")) {
+        /* r = gnsscorr_mex('navsync', cfg, I_P)  with I_P = nEpochs x nCh (one column per channel): the front end of
+         * NAVdecoding.m:69-170 -> r.subFrameStart (1 x nCh, 0 = none), r.navBits (GC_NAV_BITS x nCh uint8), r.bitsValid */
+        const char* names[] = {"subFrameStart", "navBits", "bitsValid"};
+        mxArray *sfs, *bits, *valid;
+        mwSize nE, nCh;
+        if (nrhs != 3 || !mxIsDouble(prhs[2])) { gc_destroy(h); mexErrMsgIdAndTxt("gnsscorr:args", "navsync: I_P must be a double matrix"); }
+        nE = mxGetM(prhs[2]); nCh = mxGetN(prhs[2]);
+        sfs = mxCreateNumericMatrix(1, nCh, mxINT32_CLASS, mxREAL);
+        bits = mxCreateNumericMatrix(GC_NAV_BITS, nCh, mxUINT8_CLASS, mxREAL);
+        valid = mxCreateNumericMatrix(1, nCh, mxINT32_CLASS, mxREAL);
+        check(h, gc_nav_sync(h, (int32_t)nCh, (int32_t)nE, mxGetDoubles(prhs[2]), (int32_t*)mxGetInt32s(sfs), (uint8_t*)mxGetData(bits),
+                             (int32_t*)mxGetInt32s(valid)), "gc_nav_sync");
+        plhs[0] = mxCreateStructMatrix(1, 1, 3, names);
+        mxSetField(plhs[0], 0, "subFrameStart", sfs);
+        mxSetField(plhs[0], 0, "navBits", bits);
+        mxSetField(plhs[0], 0, "bitsValid", valid);
     } else {
         gc_destroy(h);
         mexErrMsgIdAndTxt("gnsscorr:args", "unknown command %s", cmd);

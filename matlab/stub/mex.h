@@ -7,12 +7,15 @@
 typedef struct mxArray_tag mxArray;
 typedef size_t mwSize;
 typedef enum { mxREAL, mxCOMPLEX } mxComplexity;
-typedef enum { mxDOUBLE_CLASS = 6, mxINT8_CLASS = 8, mxINT32_CLASS = 12 } mxClassID;
+typedef enum { mxDOUBLE_CLASS = 6, mxINT8_CLASS = 8, mxUINT8_CLASS = 9, mxINT32_CLASS = 12 } mxClassID;
 mxArray* mxGetField(const mxArray*, mwSize, const char*);
 void mxSetField(mxArray*, mwSize, const char*, mxArray*);
 double mxGetScalar(const mxArray*);
 int mxGetString(const mxArray*, char*, mwSize);
 mwSize mxGetNumberOfElements(const mxArray*);
+mwSize mxGetM(const mxArray*);
+mwSize mxGetN(const mxArray*);
+int mxIsDouble(const mxArray*);
 double* mxGetDoubles(const mxArray*);
 int8_t* mxGetInt8s(const mxArray*);
 int32_t* mxGetInt32s(const mxArray*);

@@ -1775,3 +1775,62 @@ def _tracking_b1c(raw: np.ndarray, channel: list, s: Settings, codes: dict, wb: 
                 tr["Pilot_I_P"][loopCnt - 1] = pI_P; tr["Pilot_Q_P"][loopCnt - 1] = pQ_P
         tr["status"] = channel[ch]["status"]
     return out
+
+
+# ---------------------------------------------------------------------------
+# navigation-bit front end (GPS/GPS_L1CA/include/NAVdecoding.m:69-170, Common/navPartyChk.m)
+# ---------------------------------------------------------------------------
+def navPartyChk(ndat) -> int:
+    """Common/navPartyChk.m: ndat = [D29* D30* d1..d24 D25..D30] as +-1 (32 values); returns -D30* when the six parity
+    equations of IS-GPS-200 table 20-XIV hold, else 0."""
+    n = [0] + [int(v) for v in ndat]                               # 1-based like the reference
+    if n[2] != 1:
+        for i in range(3, 27):
+            n[i] = -n[i]
+    sets = [
+        (1, 3, 4, 5, 7, 8, 12, 13, 14, 15, 16, 19, 20, 22, 25),
+        (2, 4, 5, 6, 8, 9, 13, 14, 15, 16, 17, 20, 21, 23, 26),
+        (1, 3, 5, 6, 7, 9, 10, 14, 15, 16, 17, 18, 21, 22, 24),
+        (2, 4, 6, 7, 8, 10, 11, 15, 16, 17, 18, 19, 22, 23, 25),
+        (2, 3, 5, 7, 8, 9, 11, 12, 16, 17, 18, 19, 20, 23, 24, 26),
+        (1, 5, 7, 8, 10, 11, 12, 13, 15, 17, 21, 24, 25, 26)]
+    parity = [int(np.prod([n[i] for i in st])) for st in sets]
+    if sum(int(parity[k] == n[27 + k]) for k in range(6)) == 6:
+        return -1 * n[2]
+    return 0
+
+
+def nav_sync(I_P: np.ndarray, msToProcess: int):
+    """NAVdecoding.m:69-170: (subFrameStart, navBits).  subFrameStart is the 1-based index of the first preamble-like pattern
+    with another one 6000 ms later whose TLM and HOW words pass the parity check (0 when there is none); navBits the 1501
+    bits summed over 20 ms from subFrameStart-20 (the last bit of the previous subframe, then five subframes) (None when that range leaves the record)."""
+    searchStartOffset = 0                                          # :66
+    preamble_bits = np.array([1, -1, -1, -1, 1, -1, 1, 1])
+    preamble_ms = np.kron(preamble_bits, np.ones(20))             # :73
+    bits = np.asarray(I_P, dtype=np.float64)[searchStartOffset:].copy()
+    bits[bits > 0] = 1                                             # :82-83
+    bits[bits <= 0] = -1
+    n = bits.size
+    # xcorr(bits, preamble_ms), non-negative lags (:86, :93-96): sum_j bits(l+j) preamble_ms(j)
+    full = np.correlate(np.concatenate([bits, np.zeros(preamble_ms.size)]), preamble_ms, mode="valid")[:n]
+    index = np.nonzero(np.abs(full) > 153)[0] + 1 + searchStartOffset
+    index = index[(index > 40) & (index < msToProcess - (20 * 60 - 1))]   # :101
+    subFrameStart = 0
+    iset = set(int(v) for v in index)
+    for i in index:                                                # :104-141
+        if int(i) + 6000 in iset:
+            b = np.asarray(I_P, dtype=np.float64)[int(i) - 40 - 1: int(i) + 20 * 60 - 1]
+            b = b.reshape(-1, 20)
+            sums = np.array([float(np.sum(row)) for row in b])
+            sb = np.where(sums > 0, 1, -1)
+            if navPartyChk(sb[0:32]) != 0 and navPartyChk(sb[30:62]) != 0:
+                subFrameStart = int(i)
+                break
+    if subFrameStart == 0:
+        return 0, None
+    lo, hi = subFrameStart - 20 - 1, subFrameStart + 1500 * 20 - 1
+    if lo < 0 or hi > np.asarray(I_P).size:
+        return subFrameStart, None
+    s = np.asarray(I_P, dtype=np.float64)[lo:hi].reshape(-1, 20)
+    navBits = (np.array([float(np.sum(row)) for row in s]) > 0).astype(np.uint8)   # :152-166
+    return subFrameStart, navBits

@@ -162,3 +162,47 @@ def first_illconditioned_epoch(ref_rem, ref_cf, got_rem, got_cf, abs_sample, fs,
             if np.any(np.abs(t - np.rint(t)) < tol):
                 return e
     return n
+
+
+# IS-GPS-200 table 20-XIV: source data bits d1..d24 entering D25..D30 and which of D29*, D30* joins them
+_NAV_SETS = [
+    (0, (1, 2, 3, 5, 6, 10, 11, 12, 13, 14, 17, 18, 20, 23)),
+    (1, (2, 3, 4, 6, 7, 11, 12, 13, 14, 15, 18, 19, 21, 24)),
+    (0, (1, 3, 4, 5, 7, 8, 12, 13, 14, 15, 16, 19, 20, 22)),
+    (1, (2, 4, 5, 6, 8, 9, 13, 14, 15, 16, 17, 20, 21, 23)),
+    (1, (1, 3, 5, 6, 7, 9, 10, 14, 15, 16, 17, 18, 21, 22, 24)),
+    (0, (3, 5, 6, 8, 9, 10, 11, 13, 15, 19, 22, 23, 24))]
+
+
+def nav_message_bits(n_subframes: int, seed: int) -> np.ndarray:
+    """A GPS L1 C/A bit stream (0/1) of whole subframes with the TLM preamble 10001011 and valid word parity: random source
+    data, transmitted D1..D24 = d xor D30*, D25..D30 from the table above."""
+    rng = np.random.default_rng(seed)
+    out = []
+    star = [0, 0]                                                  # D29*, D30* of the previous word
+    for _ in range(n_subframes):
+        for w in range(10):
+            d = rng.integers(0, 2, size=24)
+            if w == 0:
+                d[:8] = [1, 0, 0, 0, 1, 0, 1, 1]
+            par = [(star[s] + int(np.sum(d[np.array(ix) - 1]))) % 2 for s, ix in _NAV_SETS]
+            word = [int(b) ^ star[1] for b in d] + par
+            out += word
+            star = word[28:30]
+    return np.array(out, dtype=np.int64)
+
+
+def nav_prompt_row(bits: np.ndarray, start: int, n: int, amp: float, sigma: float, seed: int, polarity: int = 1) -> np.ndarray:
+    """trackResults.I_P for a channel whose first bit edge of `bits` falls on 1-based index `start`: 20 values per bit,
+    binary 1 -> -amp (the mapping navPartyChk.m assumes, D30* set <=> -1), noise sigma, random data before `start`."""
+    rng = np.random.default_rng(seed)
+    x = np.repeat(1 - 2 * bits, 20).astype(np.float64)
+    row = np.empty(n)
+    head = np.repeat(1 - 2 * rng.integers(0, 2, size=start // 20 + 1), 20)[-(start - 1):] if start > 1 else np.empty(0)
+    row[: start - 1] = head
+    row[max(start - 41, 0): start - 1] = 1.0                       # D29*, D30* before the first word: binary 0, as the generator assumed
+    m = min(n - (start - 1), x.size)
+    row[start - 1: start - 1 + m] = x[:m]
+    if start - 1 + m < n:
+        row[start - 1 + m:] = np.repeat(1 - 2 * rng.integers(0, 2, size=(n - start - m) // 20 + 2), 20)[: n - (start - 1 + m)]
+    return polarity * amp * row + sigma * rng.standard_normal(n)

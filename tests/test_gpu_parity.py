@@ -983,3 +983,30 @@ def test_b1c_nb_tracking_and_wrappers_vs_oracle(fs, nE, tmp_path):
         assert tr[i]["DataCNo"].shape == (nE // 4,) and "B1C_CNo" in tr[i] and np.all(np.isfinite(tr[i]["PilotCNo"]))
     assert tr[2]["status"] == "-"
     eng.close()
+
+
+# ------------------------------------------------------------- navigation-bit front end
+def test_nav_front_end_vs_oracle():
+    """gc_nav_sync against the NAVdecoding.m:69-170 restatement: clean, noisy / inverted, late (bits do not fit), weak
+    (bit errors break the parity of the first candidates) and random channels - subFrameStart and all 1501 bits exact."""
+    from helpers import nav_message_bits, nav_prompt_row
+    from cu_sdr_collection_b200.navsync import nav_sync
+    n = 60000
+    s = init_settings(samplingFreq=16.368e6, msToProcess=n, numberOfChannels=6)
+    rows = [nav_prompt_row(nav_message_bits(9, seed=5), 1234, n, 2000.0, 300.0, seed=1),
+            nav_prompt_row(nav_message_bits(9, seed=6), 4321, n, 1500.0, 400.0, seed=2, polarity=-1),
+            nav_prompt_row(nav_message_bits(9, seed=7), 40000, n, 2000.0, 100.0, seed=3),
+            nav_prompt_row(nav_message_bits(9, seed=8), 777, n, 1000.0, 4000.0, seed=4),
+            2000.0 * (1 - 2 * np.random.default_rng(3).integers(0, 2, size=3000)).repeat(20).astype(np.float64),
+            np.zeros(n)]
+    tr = [dict(I_P=r) for r in rows]
+    eng = Engine(s)
+    sfs, bits = nav_sync(tr, s, eng)
+    for ch, r in enumerate(rows):
+        want_sfs, want_bits = O.nav_sync(r, n)
+        assert sfs[ch] == want_sfs, (ch, sfs[ch], want_sfs)
+        assert (bits[ch] is None) == (want_bits is None)
+        if want_bits is not None:
+            assert np.array_equal(bits[ch], want_bits), ch
+    assert sfs[0] == 1234 and sfs[1] == 4321 and sfs[2] == 40000 and bits[2] is None and sfs[4] == 0 and sfs[5] == 0
+    eng.close()

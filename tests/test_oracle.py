@@ -527,3 +527,27 @@ def test_b1c_wb_oracle_closed_loop():
     assert np.mean(np.abs(tr["Pilot_I_P"][h:])) > 3 * np.mean(np.abs(tr["Pilot_Q_P"][h:]))
     ratio = np.mean(np.abs(tr["Pilot_I_P"][h:])) / np.mean(np.abs(tr["I_P"][h:]))
     assert 1.5 < ratio < 2.0, ratio                                                     # sqrt(3) = 1.73
+
+
+def test_nav_front_end_oracle_known_answers():
+    """NAVdecoding.m:69-170 restatement: a bit stream with valid TLM / HOW parity is found at the planted index in either
+    carrier polarity and its 1500 bits come back; a corrupted parity bit or a record of random bits yields nothing."""
+    from helpers import nav_message_bits, nav_prompt_row
+    bits = nav_message_bits(9, seed=5)
+    w = 1 - 2 * bits[30:60]                                        # second word as +-1 (binary 1 -> -1)
+    ndat = np.concatenate([1 - 2 * bits[28:30], w])
+    assert O.navPartyChk(ndat) == -ndat[1] and O.navPartyChk(-ndat) == ndat[1]     # both polarities pass, status = -D30*
+    bad = ndat.copy(); bad[10] = -bad[10]
+    assert O.navPartyChk(bad) == 0
+    n = 60000
+    for start, pol in ((1234, 1), (4321, -1)):
+        row = nav_prompt_row(bits, start, n, amp=2000.0, sigma=300.0, seed=start, polarity=pol)
+        sfs, nb = O.nav_sync(row, n)
+        assert sfs == start
+        want = bits[:1500] if pol == 1 else 1 - bits[:1500]       # navBits = (sum > 0): +amp <-> 1
+        assert nb.size == 1501 and np.array_equal(nb[1:], 1 - want) and nb[0] == (1 if pol == 1 else 0)   # planted D30* = binary 0
+    rnd = 2000.0 * (1 - 2 * np.random.default_rng(3).integers(0, 2, size=3000)).repeat(20).astype(np.float64)
+    assert O.nav_sync(rnd, n) == (0, None)
+    late = nav_prompt_row(bits, 40000, n, amp=2000.0, sigma=0.0, seed=1)     # found, but 30000 ms of bits do not fit
+    sfs, nb = O.nav_sync(late, n)
+    assert sfs == 40000 and nb is None
