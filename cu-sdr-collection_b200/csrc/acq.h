@@ -38,7 +38,6 @@ struct RowsParams {
     int prnPerCta, mPerCta;   // warps of an inverse CTA = binPerCta x prnPerCta x mPerCta (same row j1)
     int bin0;                 // first bin of this launch: nBins counts the bins of the launch (and of the W layout), the spectra
                               // and binMap are addressed with bin0 + local bin
-    int keepL2;               // 1: W is written with default caching (an L2-resident chunk), 0: streaming stores
     int binPerCta;            // bins per CTA (0 = 1); > 1 where a (SV, bin) cell has too few transforms to fill a CTA
     const int2* binMap;       // optional [nBins]: .x = spectrum row in X (instead of bin*nonCoh + block), .y = circular shift of
                               // the spectrum, circshift(IQfreqDom, y) (acquisition variants B and C); nullptr = variant A

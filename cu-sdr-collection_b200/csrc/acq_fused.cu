@@ -129,14 +129,21 @@ inv_rows_kernel(RowsParams p)
     const int k1 = blockIdx.x, pg = blockIdx.y;
     const int M = p.nonCoh * p.nRep;                             // transforms per (SV, bin): blocks x replicas
     const int mGroups = (M + p.mPerCta - 1) / p.mPerCta;
-    const int wpb = p.prnPerCta * p.mPerCta;                     // warps per bin
-    const int bpc = p.binPerCta > 1 ? p.binPerCta : 1;
-    const int k = (blockIdx.z / mGroups) * bpc + warp / wpb, mg = blockIdx.z % mGroups;
-    const int wl = warp % wpb;
-    const int pi = pg * p.prnPerCta + wl / p.mPerCta;           // list slot within this launch's chunk
-    const int mv = mg * p.mPerCta + wl % p.mPerCta;
+    // (a warp does this index arithmetic once per 1100-instruction row: the run-time divisions are kept to the cases that need them)
+    int k = blockIdx.z / mGroups;
+    const int mg = blockIdx.z - k * mGroups;
+    int wl = warp;
+    if (p.binPerCta > 1) {                                       // several bins per CTA (variants B / C)
+        const int wpb = p.prnPerCta * p.mPerCta;                 // warps per bin
+        const int kb = warp / wpb;
+        k = k * p.binPerCta + kb;
+        wl = warp - kb * wpb;
+    }
+    const int pq = (p.mPerCta == 1) ? wl : wl / p.mPerCta;
+    const int pi = pg * p.prnPerCta + pq;                       // list slot within this launch's chunk
+    const int mv = mg * p.mPerCta + (wl - pq * p.mPerCta);
     if (pi >= p.nPrnChunk || mv >= M || k >= p.nBins) return;
-    const int m = mv / p.nRep, r = mv - m * p.nRep;             // block, replica (data / pilot, GPS_L5C acquisition.m:171-175)
+    const int m = (p.nRep == 1) ? mv : mv / p.nRep, r = mv - m * p.nRep;   // block, replica (data / pilot, GPS_L5C acquisition.m:171-175)
     // circshift(IQfreqDom, s) (BDS/B1I acquisition.m:88, GPS_L2C :73, B1C :203): product element j takes spectrum element j - s.
     // With j = j1 + C*j2 (row j1, in-row frequency j2 held by its residues mod RA and mod RB) that is row (j1 - s) mod C
     // and j2 - floor-part, i.e. a fixed source row and a circular shift of both residues.
@@ -174,7 +181,7 @@ inv_rows_kernel(RowsParams p)
         codelet::dft<RA, true>(v, [&](int ta, float re, float im) {
             float2 t = make_float2(re, im);
             if (!P::kPfa) t = cmul_conj(t, __ldg(tw + ta * RB));  // conj(w_L^(j1*tau2))
-            if (p.keepL2) dst[ta * RB + lane] = t; else __stcs(dst + ta * RB + lane, t);
+            __stcs(dst + ta * RB + lane, t);
         });
     }
 }

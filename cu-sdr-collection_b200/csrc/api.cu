@@ -1248,11 +1248,10 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
             chunk = std::min(chunk, g1 - g0);
             GC_CUDA(h, h->W.reserve((size_t)chunk * nKm * h->nRep * L));
             if (overlap) GC_CUDA(h, h->W2.reserve((size_t)chunk * nKm * h->nRep * L));
-            // GC_ACQ_CHUNK_BINS: bins per launch; with a PRN x bin chunk small enough for the L2 (126 MB) the work buffer never
-            // reaches HBM: written by the row pass with default caching, read back by the column pass that follows
+            // GC_ACQ_CHUNK_BINS: bins per launch (experiment: PRN x bin chunks small enough for the 126 MB L2; the launches get too
+            // short to pay, profiles/r01_l2_overlap_experiments.md)
             int binChunk = nBins;
             if (const char* e = getenv("GC_ACQ_CHUNK_BINS")) binChunk = std::min(nBins, std::max(1, atoi(e)));
-            const bool keepL2 = binChunk < nBins && !overlap;
             int ci = 0;
             for (int b0 = 0; b0 < nBins; b0 += binChunk)
             for (int s0 = g0; s0 < g1; s0 += chunk, ++ci) {
@@ -1261,7 +1260,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
                 float2* Wc = (overlap && (ci & 1)) ? h->W2.p : h->W.p;
                 RowsParams ip{};
                 ip.X = h->X.p; ip.Cc = h->Cc.p; ip.W = Wc; ip.tw = h->twFused.p;
-                ip.nonCoh = nonCoh; ip.nBins = nb; ip.bin0 = b0; ip.keepL2 = keepL2 ? 1 : 0; ip.prnPerCta = 1; ip.mPerCta = 5;   // 5 warps, 96 registers, 20 warps/SM
+                ip.nonCoh = nonCoh; ip.nBins = nb; ip.bin0 = b0; ip.prnPerCta = 1; ip.mPerCta = 5;   // 5 warps, 96 registers, 20 warps/SM
                 ip.nRep = h->nRep; ip.repStride = 1;
                 if (nonCoh * h->nRep < 5) { ip.prnPerCta = 5; ip.mPerCta = 1; }       // few transforms per cell (Galileo E1: 2): fill the CTA with SVs
                 if (const char* e = getenv("GC_ROWS_VARIANT")) {   // "PxM" warps per CTA = P PRNs x M blocks

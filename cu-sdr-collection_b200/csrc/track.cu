@@ -220,7 +220,9 @@ __device__ __forceinline__ void dsmem_push(double* local, uint64_t* bar, uint32_
 // G = CTAs per channel (cluster size), T = threads per CTA, NSET = replicas correlated (1 data; 2 data + pilot, 12 sums;
 // 3 data + pilot BOC(1,1) + pilot BOC(6,1), 18 sums - B1C WB_tracking.m), TT = storage type of the code tables in
 // shared memory (float, or int8_t where three tables have to fit)
-template <int G, int T, int NSET, typename TT>
+// FMT0 = the record is int8 I,Q (bulk-copied windows, byte-permute conversion); false = the per-sample accessor for the
+// int16 / real formats (a separate instantiation, so that the fast path's code is not touched by it)
+template <int G, int T, int NSET, typename TT, bool FMT0>
 __global__ void __launch_bounds__(T, 1)
 track_kernel(TrackParams p)
 {
@@ -302,7 +304,7 @@ track_kernel(TrackParams p)
     const int cpc = p.bufBytes / 16;                             // chunks per CTA (bufBytes is per CTA)
     const int c_lo = (int)crank * cpc;
     auto prefetch = [&](long long startSample, int stage, int epoch) {      // one thread only
-        if (p.fmt != 0) return false;                            // only int8 I,Q windows are staged
+        if (!FMT0) return false;                                 // only int8 I,Q windows are staged
         const long long b0 = ((startSample * 2) & ~15LL) + (long long)c_lo * 16;
         long long n = p.bufBytes;
         if (b0 + n > recBytesUp) n = recBytesUp - b0;
@@ -389,7 +391,7 @@ track_kernel(TrackParams p)
             constexpr bool SPECIAL = decltype(special_tag)::value;
             const int k0 = c * 8 - off;
             float xi[8], xq[8];                                   // tracking.m:233-235
-            if (p.fmt == 0) {
+            if (FMT0) {
                 int4 raw;
                 if (inBuf) raw = *reinterpret_cast<const int4*>(src + (size_t)c * 16);
                 else raw = __ldg(reinterpret_cast<const int4*>(gsrc + (size_t)c * 16));   // not staged: straight from L2
@@ -741,11 +743,11 @@ size_t track_smem_bytes(int bufBytes, int codeLen, int pilot, int singleBuf)
     return s;
 }
 
-template <int G, int T, int NSET, typename TT = float>
-static cudaError_t launch_track_g(const TrackParams& p, int nCh, cudaStream_t stream)
+template <int G, int T, int NSET, typename TT, bool FMT0>
+static cudaError_t launch_track_f(const TrackParams& p, int nCh, cudaStream_t stream)
 {
     const size_t smem = track_smem_bytes(p.bufBytes, p.codeLen, p.pilot, p.singleBuf);
-    cudaError_t err = cudaFuncSetAttribute(track_kernel<G, T, NSET, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = cudaFuncSetAttribute(track_kernel<G, T, NSET, TT, FMT0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nCh * G);
@@ -757,7 +759,13 @@ static cudaError_t launch_track_g(const TrackParams& p, int nCh, cudaStream_t st
     attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, track_kernel<G, T, NSET, TT>, p);
+    return cudaLaunchKernelEx(&cfg, track_kernel<G, T, NSET, TT, FMT0>, p);
+}
+
+template <int G, int T, int NSET, typename TT = float>
+static cudaError_t launch_track_g(const TrackParams& p, int nCh, cudaStream_t stream)
+{
+    return p.fmt == 0 ? launch_track_f<G, T, NSET, TT, true>(p, nCh, stream) : launch_track_f<G, T, NSET, TT, false>(p, nCh, stream);
 }
 
 // p.bufBytes must be the per-CTA staging size for `cluster` CTAs per channel (track_buf_bytes)
