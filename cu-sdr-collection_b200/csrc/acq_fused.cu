@@ -262,7 +262,11 @@ inv_cols_kernel(InvColsParams p)
 template <class P> struct BigGeo {
     static constexpr int C1 = P::C1, C2 = P::C2;
     // columns per CTA: 32 (256-byte runs) while the CTA stays within 1024 threads and half the shared memory
+#ifdef GC_BIG_TC16
+    static constexpr int TC = 16;
+#else
     static constexpr int TC = ((C1 > C2 ? C1 : C2) * 32 <= 1024 && sizeof(float2) * P::C * 32 <= 120 * 1024) ? 32 : 16;
+#endif
     static constexpr int NT = (C1 > C2 ? C1 : C2) * TC;                        // threads: max of the two phases
     static constexpr size_t kSmem = sizeof(float2) * P::C * TC;
     static constexpr size_t kSmemInv = kSmem + sizeof(float2) * P::C;          // + the w_C^(ta*beta) table of the inverse pass
