@@ -261,12 +261,10 @@ inv_cols_kernel(InvColsParams p)
 // A CTA handles TC adjacent row positions (columns), so global accesses are TC*8-byte runs.
 template <class P> struct BigGeo {
     static constexpr int C1 = P::C1, C2 = P::C2;
-    // columns per CTA: 32 (256-byte runs) while the CTA stays within 1024 threads and half the shared memory
-#ifdef GC_BIG_TC16
+    // 16 columns per CTA (128-byte runs) and at least two CTAs per SM: one CTA's loads overlap the other's DFT phases
+    // (one 640-thread CTA per SM measured 10-25 % slower: its load, DFT and barrier phases serialise)
     static constexpr int TC = 16;
-#else
-    static constexpr int TC = ((C1 > C2 ? C1 : C2) * 32 <= 1024 && sizeof(float2) * P::C * 32 <= 120 * 1024) ? 32 : 16;
-#endif
+    static constexpr int kMinCtas = 2;
     static constexpr int NT = (C1 > C2 ? C1 : C2) * TC;                        // threads: max of the two phases
     static constexpr size_t kSmem = sizeof(float2) * P::C * TC;
     static constexpr size_t kSmemInv = kSmem + sizeof(float2) * P::C;          // + the w_C^(ta*beta) table of the inverse pass
@@ -281,7 +279,7 @@ __device__ __forceinline__ float2 unit_root(int num, int den, bool inverse)
 }
 
 template <class P, int MODE>
-__global__ void __launch_bounds__(BigGeo<P>::NT)
+__global__ void __launch_bounds__(BigGeo<P>::NT, BigGeo<P>::kMinCtas)
 fwd_cols_big_kernel(FwdColsParams p)
 {
     using G = BigGeo<P>;
@@ -336,7 +334,7 @@ fwd_cols_big_kernel(FwdColsParams p)
 
 // inverse column pass + |.| + sum over blocks/replicas + max: grid (ceil(R/TC), nBins, nPrnChunk)
 template <class P>
-__global__ void __launch_bounds__(BigGeo<P>::NT)
+__global__ void __launch_bounds__(BigGeo<P>::NT, BigGeo<P>::kMinCtas)
 inv_cols_big_kernel(InvColsParams p)
 {
     using G = BigGeo<P>;
