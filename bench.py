@@ -481,7 +481,7 @@ def main():
                                    "32736 @ 16.368 Msps, 8-bit complex IF (BASELINE.json configs[1]); per GPU",
                        "record": f"synthetic 60 s IF record per rank, {rec.numel()} B resident in HBM, seed 20260101+rank "
                                  f"(generated in {t_gen:.1f} s, untimed)",
-                       "l2": "flushed between timed steps (256 MiB memset); per-step working set 2.6 GB > 126 MB L2",
+                       "l2": "flushed between timed steps (256 MiB memset); per-step working set 5 GB > 126 MB L2",
                        "timing": "CUDA events on the engine's stream per step, max over ranks",
                        "parallelism": f"{world} x (full grid on own record) + 1 NCCL all-gather of per-PRN metrics"},
             "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": 2 * n_acq_samples,

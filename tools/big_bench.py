@@ -15,6 +15,10 @@ for name in want:
         cd = standin_e1_codes()
         st = init_settings("GAL_E1C", samplingFreq=fs, **(dict(acqSatelliteList=list(range(1, 37)), acqSearchBand=8000.0, acqSearchStep=200.0) if fs == 20e6 else {}))
         sc, per = synth.default_scene_e1c(cd, fs=fs, nsat=4), 42
+    elif name == "E5B":
+        from cu_sdr_collection_b200.codes import standin_codes
+        cd = standin_codes("GAL_E5b"); st = init_settings("GAL_E5b")
+        sc, per = synth.default_scene_fam5("GAL_E5b", cd, fs=18e6, nsat=4), 102
     elif name == "L2C":
         cd = standin_varb_codes("GPS_L2C"); st = init_settings("GPS_L2C")
         sc, per = synth.default_scene_varb("GPS_L2C", cd, fs=8e6, nsat=3), 3
