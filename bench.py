@@ -472,7 +472,10 @@ def main():
         achieved = cells_per_launch * BYTES_PER_CELL / (rows_launch_ms * 1e-3) / 1e9
         step_ach = CELLS * BYTES_PER_CELL / (step_ms * 1e-3) / 1e9
         prof = os.path.join(ROOT, "profiles", "r01_traffic.json")   # ncu --set full capture of the dominant kernel
-        traffic = json.load(open(prof)).get("inv_rows_dram_bytes_per_launch") if os.path.exists(prof) else None
+        traffic = None
+        if os.path.exists(prof):                                    # per launch like `achieved`: bytes per cell x cells of one launch
+            tj = json.load(open(prof))
+            traffic = tj["inv_rows_dram_bytes_per_cell"] * cells_per_launch if "inv_rows_dram_bytes_per_cell" in tj else tj.get("inv_rows_dram_bytes_per_launch")
         line = {
             "metric": "acquisition PRNxDoppler cells/s", "value": value, "unit": "cells/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
