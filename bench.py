@@ -32,6 +32,9 @@ BYTES_PER_CELL = N_NONCOH * 2 * N_CODE * 2 + 2 * N_CODE * 8          # 1,571,328
 BYTES_PER_CHANNEL_MS = N_CODE * 2 + 15 * 8                            # 32,856
 
 
+_OUT = sys.stdout
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -117,7 +120,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 # --------------------------------------------------------------------------------- CPU baselines
@@ -165,6 +168,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tracking", action="store_true")
     args = ap.parse_args()
+    # ONE JSON line on stdout: keep the real stdout for it and send everything else that writes to fd 1 (NCCL's version banner,
+    # library chatter) to stderr
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -508,7 +517,7 @@ def main():
             "glonass": glonass,
             "widened": widened,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
