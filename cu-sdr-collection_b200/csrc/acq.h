@@ -56,6 +56,19 @@ struct InvColsParams {
     float* magOut;            // optional [nPrnChunk][nBins][L]: the summed magnitudes in natural lag order (corrVec of variant B)
 };
 
+// correlation stage as one persistent kernel with an ordered work queue (acq_fused.cu, experimental: GC_ACQ_PATH=queue)
+struct QueueParams {
+    const float2* X; const float2* Cc; float2* W; const float2* tw;
+    int nonCoh, nBins, nRep, repStride;
+    int nPrn, prnSlot0;       // cells = nPrn x nBins, bin-major (the spectra of a bin are shared by consecutive cells)
+    const int* prnList;
+    int nSlots, lag;          // W is a ring of nSlots cells; the column items of a cell are queued `lag` cells after its row items
+    float* partMax; int* partIdx; int parts;   // [nSv][nBins][parts], parts = ceil(R / 160)
+    float* partial;           // [nSlots][ceil(M/5)][C][R] partial magnitude sums of the column items (L2 resident)
+    int* ctrl;                // zeroed by the caller: [0] queue head, [1] abort flag, [2 ..) rowsDone[nCells], colsDone[nCells],
+                              // tileDone[nCells * parts]
+};
+cudaError_t launch_corr_queue(int L, const QueueParams& p, cudaStream_t s);
 cudaError_t launch_fwd_cols(int L, const FwdColsParams& p, int nRows, bool codeMode, cudaStream_t s);
 cudaError_t launch_fwd_rows(int L, const RowsParams& p, cudaStream_t s);
 cudaError_t launch_inv_rows(int L, const RowsParams& p, cudaStream_t s);

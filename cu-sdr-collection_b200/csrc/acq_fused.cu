@@ -402,6 +402,174 @@ inv_cols_big_kernel(InvColsParams p)
     }
 }
 
+// ------------------------------------------------------------------ correlation stage as ONE persistent kernel (experimental)
+// The split stage writes the inverse-row output W to HBM and reads it back (2 x 8 B per transform point: the bound of the
+// two-kernel design).  Here CTAs pull work items from one ordered queue: "rows" items (cell, row j1, group of 5 transforms) write
+// into a ring of nSlots cells, "cols" items (cell, tile of 160 row positions) consume a cell `lag` cells later, so that W lives
+// in the 126 MB L2 only.  Every item's prerequisites sit EARLIER in the queue and items are taken in order, so the oldest
+// unfinished item never waits on a younger one (no deadlock); waits are bounded and raise an abort flag instead of hanging.
+__device__ __forceinline__ int ld_acquire(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <class P>
+__global__ void __launch_bounds__(160, 4)
+corr_queue_kernel(QueueParams p)
+{
+    constexpr int C = P::C, RA = P::RA, RB = P::RB, R = P::R, L = P::L;
+    constexpr int kPitchI = RB;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_item, s_ok;
+    __shared__ float s_b[5];
+    __shared__ int s_i[5];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float2* s_x = reinterpret_cast<float2*>(smem_raw) + warp * (RA * kPitchI);
+    const int M = p.nonCoh * p.nRep;
+    const int mGroups = (M + 4) / 5;
+    // a column item covers one tile of 160 row positions and one GROUP of 5 transforms (short items: the ring slot of a cell is
+    // free again only when its last column item has finished); the group partial sums meet in an L2-resident buffer and the
+    // item that finishes a tile last adds them in group order - the sum does not depend on who that is
+    const int rowItems = C * mGroups, colItems = p.parts * mGroups, stepItems = rowItems + colItems;
+    const int nCells = p.nPrn * p.nBins;
+    const int total = (nCells + p.lag) * stepItems;
+    int* rowsDone = p.ctrl + 2;
+    int* colsDone = rowsDone + nCells;
+    int* tileDone = colsDone + nCells;
+    __shared__ int s_last;
+    auto wait_for = [&](const int* ctr, int want) {             // thread 0 spins (bounded), then everybody knows the outcome
+        if (tid == 0) {
+            int ok = 1;
+            long long spins = 0;
+            while (ld_acquire(ctr) < want) {
+                if (++spins > 4000000 || ld_acquire(p.ctrl + 1) != 0) { atomicExch(p.ctrl + 1, 1); ok = 0; break; }
+                __nanosleep(64);
+            }
+            s_ok = ok;
+        }
+        __syncthreads();
+        return s_ok != 0;
+    };
+    for (;;) {
+        __syncthreads();                                         // s_item / s_ok / shared buffers of the previous item are free
+        if (tid == 0) s_item = atomicAdd(p.ctrl, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= total) break;
+        const int step = item / stepItems, r = item - step * stepItems;
+        if (r < rowItems) {
+            // ---- rows item: X .* Cc and the inverse RB x RA row DFTs of 5 transforms of cell `step`, row j1
+            const int c = step;
+            if (c >= nCells) continue;
+            if (c >= p.nSlots && !wait_for(colsDone + (c - p.nSlots), p.parts)) break;   // the ring slot is free again
+            const int k1 = r / mGroups, mg = r - k1 * mGroups;
+            const int mv = mg * 5 + warp;
+            const int k = c / p.nPrn, pi = c - k * p.nPrn;
+            if (mv < M) {
+                const int m = (p.nRep == 1) ? mv : mv / p.nRep, rep = mv - m * p.nRep;
+                const float2* src = p.X + ((size_t)(k * p.nonCoh + m) * C + k1) * R;
+                const float2* mul = p.Cc + ((size_t)(p.prnList[p.prnSlot0 + pi] + rep * p.repStride) * C + k1) * R;
+                float2* dst = p.W + (((size_t)(c % p.nSlots) * M + mv) * C + k1) * R;
+                {
+                    float2 u[RB];
+#pragma unroll
+                    for (int kb = 0; kb < RB; ++kb) u[kb] = cmul(__ldcs(src + kb * RA + lane), __ldg(mul + kb * RA + lane));
+                    codelet::dft<RB, true>(u, [&](int tb, float re, float im) { s_x[lane * kPitchI + tb] = make_float2(re, im); });
+                }
+                __syncwarp();
+                if (lane < RB) {
+                    float2 v[RA];
+#pragma unroll
+                    for (int ka = 0; ka < RA; ++ka) v[ka] = s_x[ka * kPitchI + lane];
+                    const float2* tw = p.tw + (size_t)k1 * R + lane;
+                    codelet::dft<RA, true>(v, [&](int ta, float re, float im) {
+                        float2 t = make_float2(re, im);
+                        if (!P::kPfa) t = cmul_conj(t, __ldg(tw + ta * RB));
+                        __stcg(dst + ta * RB + lane, t);          // L2 only: the column item of this cell reads it back from there
+                    });
+                }
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicAdd(rowsDone + c, 1);
+        } else {
+            // ---- cols item: inverse column DFTs, |.|, sum over the cell's transforms, tile maximum
+            const int c = step - p.lag;
+            if (c < 0 || c >= nCells) continue;
+            if (!wait_for(rowsDone + c, rowItems)) break;
+            const int tq = r - rowItems;
+            const int t = tq / mGroups, grp = tq - t * mGroups;
+            const int k = c / p.nPrn, pi = c - k * p.nPrn;
+            const int pp = t * 160 + tid;
+            const int slot = c % p.nSlots;
+            float acc[C];
+#pragma unroll
+            for (int i = 0; i < C; ++i) acc[i] = 0.f;
+            if (pp < R) {
+                const float2* base = p.W + ((size_t)slot * M) * L + pp;
+                const int m1 = min(M, grp * 5 + 5);
+                for (int m = grp * 5; m < m1; ++m) {
+                    float2 x[C];
+#pragma unroll
+                    for (int k1 = 0; k1 < C; ++k1) x[k1] = __ldcg(base + (size_t)m * L + (size_t)k1 * R);
+                    codelet::dft<C, true>(x, [&](int t1, float re, float im) { acc[t1] += cabs_fast(re, im); });
+                }
+            }
+            bool last = true;
+            if (mGroups > 1) {
+                float* pb = p.partial + ((size_t)slot * mGroups) * L;
+                if (pp < R)
+#pragma unroll
+                    for (int t1 = 0; t1 < C; ++t1) __stcg(pb + ((size_t)grp * C + t1) * R + pp, acc[t1]);
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) { s_last = (atomicAdd(tileDone + (size_t)c * p.parts + t, 1) == mGroups - 1); __threadfence(); }
+                __syncthreads();
+                last = s_last != 0;
+                if (last && pp < R) {
+#pragma unroll
+                    for (int t1 = 0; t1 < C; ++t1) {
+                        float a = 0.f;
+                        for (int g = 0; g < mGroups; ++g) a += __ldcg(pb + ((size_t)g * C + t1) * R + pp);
+                        acc[t1] = a;
+                    }
+                }
+            }
+            if (last) {
+                float best = -1.f;
+                int bidx = 0x7fffffff;
+                if (pp < R) {
+                    const int rest = P::row_index(pp);
+#pragma unroll
+                    for (int t1 = 0; t1 < C; ++t1) {
+                        const int idx = P::index(t1, rest);
+                        if (acc[t1] > best || (acc[t1] == best && idx < bidx)) { best = acc[t1]; bidx = idx; }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ob = __shfl_down_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_down_sync(0xffffffffu, bidx, o);
+                    if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+                }
+                if (lane == 0) { s_b[warp] = best; s_i[warp] = bidx; }
+                __syncthreads();
+                if (tid == 0) {
+                    for (int w = 1; w < 5; ++w)
+                        if (s_b[w] > best || (s_b[w] == best && s_i[w] < bidx)) { best = s_b[w]; bidx = s_i[w]; }
+                    const size_t o = ((size_t)(p.prnSlot0 + pi) * p.nBins + k) * p.parts + t;
+                    p.partMax[o] = best;
+                    p.partIdx[o] = bidx;
+                    __threadfence();
+                    atomicAdd(colsDone + c, 1);
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ host side, per plan
 template <class P>
 struct Launch {
@@ -449,6 +617,23 @@ struct Launch {
     static cudaError_t inv_rows(const RowsParams& p, cudaStream_t s)
     {
         return ((p.binPerCta > 1 ? p.binPerCta : 1) * p.prnPerCta * p.mPerCta == 8) ? inv_rows_t<8, 2>(p, s) : inv_rows_t<5, 4>(p, s);
+    }
+    static cudaError_t corr_queue(const QueueParams& p, cudaStream_t s)
+    {
+        if constexpr (P::kBig) return cudaErrorNotSupported;
+        else {
+            const int smem = (int)(sizeof(float2) * 5 * P::RA * P::RB);
+            cudaError_t e = cudaFuncSetAttribute(corr_queue_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            int perSm = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, corr_queue_kernel<P>, 160, smem);
+            if (e != cudaSuccess) return e;
+            int dev = 0, sms = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            corr_queue_kernel<P><<<sms * (perSm > 0 ? perSm : 1), 160, smem, s>>>(p);   // all CTAs resident: the queue order is the schedule
+            return cudaGetLastError();
+        }
     }
     static cudaError_t inv_cols(const InvColsParams& p, cudaStream_t s)
     {
@@ -498,6 +683,7 @@ cudaError_t launch_fwd_cols(int L, const FwdColsParams& p, int nRows, bool codeM
 cudaError_t launch_fwd_rows(int L, const RowsParams& p, cudaStream_t s) { GC_PLAN_DISPATCH(L, fwd_rows(p, s)) }
 cudaError_t launch_inv_rows(int L, const RowsParams& p, cudaStream_t s) { GC_PLAN_DISPATCH(L, inv_rows(p, s)) }
 cudaError_t launch_inv_cols(int L, const InvColsParams& p, cudaStream_t s) { GC_PLAN_DISPATCH(L, inv_cols(p, s)) }
+cudaError_t launch_corr_queue(int L, const QueueParams& p, cudaStream_t s) { GC_PLAN_DISPATCH(L, corr_queue(p, s)) }
 
 cudaError_t launch_finish_replica(float2* Cc, size_t n, int L, cudaStream_t s)
 {

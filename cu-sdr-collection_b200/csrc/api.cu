@@ -115,6 +115,8 @@ struct gc_handle {
     double ts = 0;
     bool fused = false;
     bool overlap = false;        // split correlation stage pipelined over two streams (GC_ACQ_OVERLAP)
+    bool queue = false;          // correlation stage as one persistent kernel with an ordered work queue (GC_ACQ_PATH=queue)
+    DevBuf<int> qctrl;
     bool cluster = false;        // correlation stage as one cluster kernel (acq_cluster.cu); else inv_rows + inv_cols
     FusedPlanInfo fp{};
     DevBuf<float2> twFused;      // [C][R] twiddles of fused plans with a Cooley-Tukey column/row link
@@ -431,13 +433,14 @@ int gc_create(gc_handle** out, const gc_config* cfg)
         h->cluster = h->fused && e && strcmp(e, "cluster") == 0;
         const char* o = getenv("GC_ACQ_OVERLAP");
         h->overlap = h->fused && !h->cluster && o && atoi(o) != 0;
+        h->queue = h->fused && e && strcmp(e, "queue") == 0 && h->fp.C <= 50 && !h->varB && !h->varC;
     }
-    h->stats.acq_path = h->cluster ? 2 : h->fused ? 1 : 0;   // 2 = fused plan + cluster correlation kernel, 1 = fused plan, split
+    h->stats.acq_path = h->cluster ? 2 : h->queue ? 3 : h->fused ? 1 : 0;   // 2 = fused plan + cluster correlation kernel, 1 = fused plan, split
                                                              // correlation stage, 0 = generic mixed-radix passes
 
     auto setup = [&]() -> int {
         if (h->fused) {
-            h->parts = h->cluster ? kCorrClusterParts : h->fp.parts;
+            h->parts = h->cluster ? kCorrClusterParts : h->queue ? (h->fp.R + 159) / 160 : h->fp.parts;
             if (!h->fp.pfa) {   // w_L^(j1 * m(p)), row position p = a*RB + b <-> m = (RB*a + RA*b) mod R
                 const FusedPlanInfo& f = h->fp;
                 std::vector<float2> tw((size_t)f.C * f.R);
@@ -1242,6 +1245,34 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
             rp.X = h->X.p; rp.nRows = (long long)nKm * h->fp.C;
             GC_CUDA(h, launch_fwd_rows(L, rp, st)); ++launches;
             fwdEv.push_back({f0, mark()});
+            if (h->queue) {
+                // one persistent kernel for the whole SV x bin grid of this carrier grid: W is a ring of nSlots cells in L2
+                const int nCells = (g1 - g0) * nBins, Mq = nonCoh * h->nRep;
+                int nSlots = 12, lag = 6;
+                if (const char* e = getenv("GC_Q_SLOTS")) nSlots = std::max(2, atoi(e));
+                if (const char* e = getenv("GC_Q_LAG")) lag = std::max(1, atoi(e));
+                lag = std::min(lag, nSlots - 1);
+                GC_CUDA(h, h->W.reserve((size_t)nSlots * Mq * L));
+                const size_t nCtrl = 2 + (2 + (size_t)h->parts) * nCells;
+                GC_CUDA(h, h->qctrl.reserve(nCtrl));
+                GC_CUDA(h, cudaMemsetAsync(h->qctrl.p, 0, nCtrl * sizeof(int), st));
+                GC_CUDA(h, h->vbMag.reserve((size_t)nSlots * ((Mq + 4) / 5) * L));
+                QueueParams qp{};
+                qp.X = h->X.p; qp.Cc = h->Cc.p; qp.W = h->W.p; qp.tw = h->twFused.p;
+                qp.nonCoh = nonCoh; qp.nBins = nBins; qp.nRep = h->nRep; qp.repStride = 1;
+                qp.nPrn = g1 - g0; qp.prnSlot0 = g0; qp.prnList = h->prnList.p;
+                qp.nSlots = nSlots; qp.lag = lag;
+                qp.partMax = h->partMax.p; qp.partIdx = h->partIdx.p; qp.parts = h->parts; qp.ctrl = h->qctrl.p; qp.partial = h->vbMag.p;
+                const int a = mark();
+                GC_CUDA(h, launch_corr_queue(L, qp, st)); ++launches;
+                rowEv.push_back({a, mark()}); ++nRowLaunches;
+                int flag = 0;
+                GC_CUDA(h, cudaMemcpyAsync(&flag, h->qctrl.p + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+                GC_CUDA(h, cudaStreamSynchronize(st));
+                if (flag) return fail(h, GC_ERR_CUDA, "gc_acquire: the work-queue correlation kernel gave up waiting (GC_ACQ_PATH=queue)");
+                g0 = g1;
+                continue;
+            }
             // PRN chunks sized so the inverse work buffer stays below kWorkBytes.  With GC_ACQ_OVERLAP the chunks are halved and
             // pipelined over two work buffers: the column pass of chunk c (HBM bound) runs on a second stream while the row
             // pass of chunk c+1 (FP32 bound) runs on the first.

@@ -254,8 +254,9 @@ typedef struct gc_stats {
     int32_t track_launches;    /* kernels launched by the last gc_track                             */
     int32_t fft_len;           /* 2*samplesPerCode                                                  */
     int32_t acq_path;          /* 0 = generic mixed-radix passes, 1 = fused C x 32 x RB plan (lengths
-                                  32736, 36000, 24000, 32000, 40000), 2 = fused plan with the one-kernel
-                                  cluster correlation stage (GC_ACQ_PATH=cluster)                   */
+                                  32736, 36000, 24000, 32000, 40000, 72000, 144000, 160000, 320000, 360000),
+                                  2 = fused plan with the one-kernel cluster correlation stage (GC_ACQ_PATH=cluster),
+                                  3 = fused plan with the persistent work-queue correlation kernel (GC_ACQ_PATH=queue) */
     int32_t n_acquired;        /* PRNs above threshold in the last gc_acquire                       */
     float corr_rows_ms;        /* dominant kernel: spectrum multiply + inverse row FFT              */
     float corr_cols_ms;        /* inverse column DFT + |.| + non-coherent sum + row max             */

@@ -66,16 +66,22 @@ def test_acquisition_fused_matches_numpy_oracle_too():
 
 @pytest.mark.parametrize("fs,nonCoh,path", [(2.046e6, 4, 0), (18e6, 2, 0), (4.092e6, 20, 0),
                                             (18e6, 3, 1), (16e6, 2, 1), (20e6, 2, 1), (16.368e6, 3, 2),
-                                            (18e6, 3, 2), (16e6, 2, 2), (20e6, 2, 2), (12e6, 2, 2)])
+                                            (18e6, 3, 2), (16e6, 2, 2), (20e6, 2, 2), (12e6, 2, 2),
+                                            (16.368e6, 7, 3), (18e6, 3, 3), (12e6, 12, 3)])
 def test_acquisition_other_lengths(fs, nonCoh, path, monkeypatch):
     """Other FFT lengths: generic mixed-radix passes (4092, 8184, and 36000 when forced) and the fused
     C x 32 x 25 plans with a Cooley-Tukey column/row link (36000 = reference default 18 Msps, 32000, 40000,
     24000), each with the two-kernel inverse rows / inverse columns correlation stage (path 1, the default)
-    and with the one-kernel cluster version (path 2, GC_ACQ_PATH=cluster)."""
+    and with the one-kernel cluster version (path 2, GC_ACQ_PATH=cluster) and the persistent work-queue version (path 3,
+    GC_ACQ_PATH=queue: row and column items of one ordered queue, the work buffer a ring in L2)."""
     if path == 0:
         monkeypatch.setenv("GC_FORCE_GENERIC", "1")
     if path == 2:
         monkeypatch.setenv("GC_ACQ_PATH", "cluster")
+    if path == 3:
+        monkeypatch.setenv("GC_ACQ_PATH", "queue")
+        monkeypatch.setenv("GC_Q_SLOTS", "5")           # a ring shorter than the grid, so that slots are reused and waited for
+        monkeypatch.setenv("GC_Q_LAG", "2")
     sc, s, N, raw = _acq_case(fs, nsat=3, seed=13, sv_extra=[4], nonCoh=nonCoh, cn0=47, band=6000.0)
     eng = Engine(s)
     got = eng.acquire(s.acqSatelliteList, host_iq=raw)
