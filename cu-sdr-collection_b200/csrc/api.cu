@@ -148,6 +148,7 @@ struct gc_handle {
     DevBuf<double> trackOut;
     DevBuf<int32_t> epochsDone;
     DevBuf<uint8_t> navCand, navBits;
+    DevBuf<double> vsmDev;
     DevBuf<int> navInt;
     double tau1code = 0, tau2code = 0, tau1carr = 0, tau2carr = 0;
 };
@@ -1498,26 +1499,6 @@ int gc_acquire_host(gc_handle* h, const int8_t* iq, size_t nSamples, int32_t nSv
     return acquire_impl(h, 0, nSv, svList, carrFreq, codePhase, peakMetric, coarseBin, coarseCodePhase, (long long)nSamples);
 }
 
-// Common/CNoVSM.m:38-47 on the host (40 values every 40 epochs — scalar work)
-static double cno_vsm(const double* I, const double* Q, int n, double T)
-{
-    std::vector<double> Z(n);
-    double Zm = 0;
-    for (int i = 0; i < n; ++i) { Z[i] = I[i] * I[i] + Q[i] * Q[i]; Zm += Z[i]; }
-    Zm /= n;
-    double Zv = 0;
-    for (int i = 0; i < n; ++i) Zv += (Z[i] - Zm) * (Z[i] - Zm);
-    Zv /= (n - 1);
-    // MATLAB sqrt of a negative number is complex: Pav = sqrt(Zm^2 - Zv)
-    const double d = Zm * Zm - Zv;
-    double pr, pi;
-    if (d >= 0) { pr = std::sqrt(d); pi = 0; } else { pr = 0; pi = std::sqrt(-d); }
-    // Nv = 0.5*(Zm - Pav);  CNo = 10*log10(abs((1/T)*Pav/(2*Nv)))
-    const double nr = 0.5 * (Zm - pr), ni = 0.5 * (-pi);
-    const double num = std::hypot(pr, pi) * (1 / T), den = 2 * std::hypot(nr, ni);
-    return 10 * std::log10(num / den);
-}
-
 int gc_track_nfields(const gc_handle* h)
 {
     if (!h) return GC_TRACK_NFIELDS;
@@ -1670,6 +1651,15 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
     cudaEventRecord(h->ev[0], st);
     GC_CUDA(h, launch_track(p, nCh, cluster, st));
     cudaEventRecord(h->ev[1], st);
+    const int vint = c.cno_vsm_interval, nV = nEpochs / vint;
+    const bool wantVsm = vsmValue && vsmIndex && nV > 0;
+    if (wantVsm) {                                               // C/N0 on the device, straight from the rows the kernel just wrote
+        GC_CUDA(h, h->vsmDev.reserve(2 * (size_t)nCh * nV));
+        GC_CUDA(h, launch_cno_vsm(h->trackOut.p, nCh, nRows, nEpochs, vint, c.cno_acc_time, h->epochsDone.p, h->vsmDev.p,
+                                  h->vsmDev.p + (size_t)nCh * nV, st));
+        GC_CUDA(h, cudaMemcpyAsync(vsmValue, h->vsmDev.p, (size_t)nCh * nV * sizeof(double), cudaMemcpyDeviceToHost, st));
+        GC_CUDA(h, cudaMemcpyAsync(vsmIndex, h->vsmDev.p + (size_t)nCh * nV, (size_t)nCh * nV * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
     GC_CUDA(h, cudaMemcpyAsync(out, h->trackOut.p, nOut * sizeof(double), cudaMemcpyDeviceToHost, st));
     GC_CUDA(h, cudaMemcpyAsync(epochsDone, h->epochsDone.p, nCh * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     GC_CUDA(h, cudaStreamSynchronize(st));
@@ -1709,22 +1699,40 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
         }
         epochsDone[ch] = 0;
     }
-    // C/N0 every VSMinterval epochs over the last VSMinterval prompt values (tracking.m:351-358)
-    const int vint = c.cno_vsm_interval, nV = nEpochs / vint;
-    if (vsmValue && vsmIndex) {
-        std::fill(vsmValue, vsmValue + (size_t)nCh * nV, 0.0);
-        std::fill(vsmIndex, vsmIndex + (size_t)nCh * nV, 0.0);
-        for (int ch = 0; ch < nCh; ++ch) {
-            if (!live[ch]) continue;
-            const double* o = out + (size_t)ch * nRows * nEpochs;
-            for (int v = 1; v <= nV && v * vint <= epochsDone[ch]; ++v) {
-                const int lo = v * vint - vint;
-                vsmValue[(size_t)ch * nV + v - 1] = cno_vsm(o + (size_t)GC_F_I_P * nEpochs + lo, o + (size_t)GC_F_Q_P * nEpochs + lo, vint, c.cno_acc_time);
-                vsmIndex[(size_t)ch * nV + v - 1] = v * vint;
+    // C/N0 (tracking.m:351-358) came from the device; channels after one that ran out of data stay as initialised
+    if (wantVsm)
+        for (int ch = 0; ch < nCh; ++ch)
+            if (!live[ch] || (failed >= 0 && ch > failed)) {
+                std::fill(vsmValue + (size_t)ch * nV, vsmValue + (size_t)(ch + 1) * nV, 0.0);
+                std::fill(vsmIndex + (size_t)ch * nV, vsmIndex + (size_t)(ch + 1) * nV, 0.0);
             }
-        }
-    }
     return GC_OK;
+}
+
+int gc_acquire_track(gc_handle* h, int32_t nSv, const int32_t* svList, int32_t nChannels, int32_t nEpochs,
+                     double* carrFreq, double* codePhase, double* peakMetric,
+                     int32_t* chanSv, double* chanAcqFreq, double* chanCodePhase,
+                     double* out, double* vsmValue, double* vsmIndex, int32_t* epochsDone)
+{
+    if (!h) return GC_ERR_ARG;
+    if (h->cfg.signal != GC_SIG_GPS_L1CA) return fail(h, GC_ERR_UNSUPPORTED, "gc_acquire_track: GPS L1 C/A only");
+    if (nChannels < 1 || !chanSv || !chanAcqFreq || !chanCodePhase) return fail(h, GC_ERR_ARG, "gc_acquire_track: bad argument");
+    int rc = gc_acquire(h, nSv, svList, carrFreq, codePhase, peakMetric, nullptr, nullptr);
+    if (rc != GC_OK) return rc;
+    // preRun.m:44-72: [~, PRNindexes] = sort(peakMetric, 'descend') (stable), the first min(numberOfChannels, #acquired) of them
+    const int n = h->resultLen;
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return peakMetric[a] > peakMetric[b]; });
+    int nAcq = 0;
+    for (int i = 0; i < n; ++i) nAcq += (carrFreq[i] != 0);
+    for (int ch = 0; ch < nChannels; ++ch) {
+        const bool on = ch < std::min(nChannels, nAcq);
+        chanSv[ch] = on ? order[ch] + 1 : 0;
+        chanAcqFreq[ch] = on ? carrFreq[order[ch]] : 0.0;
+        chanCodePhase[ch] = on ? codePhase[order[ch]] : 0.0;
+    }
+    return gc_track(h, nChannels, chanSv, chanAcqFreq, chanCodePhase, nullptr, nEpochs, out, vsmValue, vsmIndex, epochsDone);
 }
 
 int gc_track_file(gc_handle* h, const char* path, int32_t nCh, const int32_t* sv, const double* acqFreq,

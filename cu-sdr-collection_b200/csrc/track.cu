@@ -809,6 +809,48 @@ __global__ void track_fill_kernel(double* out, int nCh, int nRows, int nEpochs)
     }
 }
 
+// C/N0 by the variance summing method on the recorded prompt rows (Common/CNoVSM.m:38-47; tracking.m:351-358): one thread per
+// (channel, VSM interval), the sums in the reference's order
+__global__ void cno_vsm_kernel(const double* out, int nCh, int nRows, int nEpochs, int vint, double T, const int32_t* epochsDone,
+                               double* vsmValue, double* vsmIndex)
+{
+    const int nV = nEpochs / vint;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nCh * nV) return;
+    const int ch = i / nV, v = i % nV + 1;
+    double val = 0.0, idx = 0.0;
+    if (v * vint <= epochsDone[ch]) {
+        const double* I = out + ((size_t)ch * nRows + GC_F_I_P) * nEpochs + (size_t)(v - 1) * vint;
+        const double* Q = out + ((size_t)ch * nRows + GC_F_Q_P) * nEpochs + (size_t)(v - 1) * vint;
+        double Zm = 0;
+        for (int k = 0; k < vint; ++k) Zm = __dadd_rn(Zm, __dadd_rn(__dmul_rn(I[k], I[k]), __dmul_rn(Q[k], Q[k])));   // Z = I.^2 + Q.^2
+        Zm = __ddiv_rn(Zm, (double)vint);                                                                       // mean(Z)
+        double Zv = 0;
+        for (int k = 0; k < vint; ++k) {
+            const double d = __dsub_rn(__dadd_rn(__dmul_rn(I[k], I[k]), __dmul_rn(Q[k], Q[k])), Zm);
+            Zv = __dadd_rn(Zv, __dmul_rn(d, d));
+        }
+        Zv = __ddiv_rn(Zv, (double)(vint - 1));                                                                 // var(Z)
+        // MATLAB's sqrt of a negative number is complex: Pav = sqrt(Zm^2 - Zv), Nv = 0.5*(Zm - Pav), CNo = 10*log10(abs((1/T)*Pav/(2*Nv)))
+        const double d = __dsub_rn(__dmul_rn(Zm, Zm), Zv);
+        const double pr = d >= 0 ? sqrt(d) : 0.0, pi = d >= 0 ? 0.0 : sqrt(-d);
+        const double nr = __dmul_rn(0.5, __dsub_rn(Zm, pr)), ni = __dmul_rn(0.5, -pi);
+        const double num = __dmul_rn(hypot(pr, pi), __ddiv_rn(1.0, T)), den = __dmul_rn(2.0, hypot(nr, ni));
+        val = __dmul_rn(10.0, log10(__ddiv_rn(num, den)));
+        idx = (double)(v * vint);
+    }
+    vsmValue[i] = val;
+    vsmIndex[i] = idx;
+}
+
+cudaError_t launch_cno_vsm(const double* out, int nCh, int nRows, int nEpochs, int vint, double T, const int32_t* epochsDone,
+                           double* vsmValue, double* vsmIndex, cudaStream_t stream)
+{
+    const int n = nCh * (nEpochs / vint);
+    if (n > 0) cno_vsm_kernel<<<(n + 127) / 128, 128, 0, stream>>>(out, nCh, nRows, nEpochs, vint, T, epochsDone, vsmValue, vsmIndex);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_track_fill(double* out, int nCh, int nRows, int nEpochs, cudaStream_t stream)
 {
     track_fill_kernel<<<148 * 4, 256, 0, stream>>>(out, nCh, nRows, nEpochs);

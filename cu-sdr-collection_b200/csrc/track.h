@@ -67,5 +67,8 @@ size_t track_smem_bytes(int bufBytes, int codeLen, int pilot, int singleBuf = 0)
 cudaError_t launch_track(const TrackParams& p, int nCh, int cluster, cudaStream_t stream);
 int track_buf_bytes(int maxBlockSamples, int cluster);
 cudaError_t launch_track_fill(double* out, int nCh, int nRows, int nEpochs, cudaStream_t stream);
+// trackResults.CNo.VSMValue / VSMIndex from the recorded prompt rows, on the device
+cudaError_t launch_cno_vsm(const double* out, int nCh, int nRows, int nEpochs, int vint, double T, const int32_t* epochsDone,
+                           double* vsmValue, double* vsmIndex, cudaStream_t stream);
 
 }  // namespace gc

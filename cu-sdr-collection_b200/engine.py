@@ -55,7 +55,7 @@ class gc_stats(C.Structure):
 EXPORTS = ["gc_abi_version", "gc_build_arch", "gc_acq_result_len", "gc_create", "gc_destroy",
            "gc_last_error", "gc_set_code", "gc_set_record_host", "gc_set_record_device", "gc_acquire",
            "gc_acquire_host", "gc_track_nfields", "gc_track", "gc_track_file", "gc_get_stats", "gc_get_stream",
-           "gc_set_param", "gc_get_cl_code_phase", "gc_set_cl_code_phase", "gc_nav_sync"]
+           "gc_set_param", "gc_get_cl_code_phase", "gc_set_cl_code_phase", "gc_nav_sync", "gc_acquire_track"]
 
 _lib = None
 
@@ -91,6 +91,7 @@ def load_lib():
     lib.gc_track.argtypes = [vp, C.c_int32, i32p, dp, dp, dp, C.c_int32, dp, dp, dp, i32p]
     lib.gc_track_file.argtypes = [vp, C.c_char_p, C.c_int32, i32p, dp, dp, dp, C.c_int32, dp, dp, dp, i32p]
     lib.gc_get_stats.argtypes = [vp, C.POINTER(gc_stats)]
+    lib.gc_acquire_track.argtypes = [vp, C.c_int32, i32p, C.c_int32, C.c_int32, dp, dp, dp, i32p, dp, dp, dp, dp, dp, i32p]
     lib.gc_nav_sync.argtypes = [vp, C.c_int32, C.c_int32, dp, i32p, C.POINTER(C.c_uint8), i32p]
     lib.gc_get_stream.argtypes = [vp]
     lib.gc_get_stream.restype = C.c_void_p
@@ -258,6 +259,25 @@ class Engine:
                                    _dp(out), _dp(vv), _dp(vi), _ip(done))
             self._check(rc, "gc_track")
         return out, vv, vi, done
+
+    def acquire_track(self, n_channels: int, n_epochs: int, sv_list=None):
+        """acquisition -> preRun -> tracking on the resident record in one library call (GPS L1 C/A).  Returns
+        ``(acqResults, channel, out, vsmValue, vsmIndex, epochsDone)``."""
+        s = self.settings
+        sv = np.asarray(list(sv_list if sv_list is not None else s.acqSatelliteList), dtype=np.int32)
+        n = self.lib.gc_acq_result_len(signal_id(s))
+        carr, cph, pm = np.zeros(n), np.zeros(n), np.zeros(n)
+        csv = np.zeros(n_channels, dtype=np.int32)
+        caf, ccp = np.zeros(n_channels), np.zeros(n_channels)
+        nv = n_epochs // int(s.CNo_VSMinterval)
+        out = np.empty((n_channels, int(self.lib.gc_track_nfields(self._h)), n_epochs))
+        vv, vi = np.zeros((n_channels, nv)), np.zeros((n_channels, nv))
+        done = np.zeros(n_channels, dtype=np.int32)
+        rc = self.lib.gc_acquire_track(self._h, sv.size, _ip(sv), n_channels, n_epochs, _dp(carr), _dp(cph), _dp(pm),
+                                       _ip(csv), _dp(caf), _dp(ccp), _dp(out), _dp(vv), _dp(vi), _ip(done))
+        self._check(rc, "gc_acquire_track")
+        channel = [dict(PRN=int(csv[i]), acquiredFreq=float(caf[i]), codePhase=int(ccp[i]), status="T" if csv[i] else "-") for i in range(n_channels)]
+        return dict(carrFreq=carr, codePhase=cph, peakMetric=pm), channel, out, vv, vi, done
 
     @property
     def stream_ptr(self) -> int:

@@ -227,6 +227,19 @@ int gc_track_file(gc_handle* h, const char* path,
                   const double* codePhase, const double* codeFreq0, int32_t nEpochs,
                   double* out, double* vsmValue, double* vsmIndex, int32_t* epochsDone);
 
+/* acquisition -> preRun -> tracking in ONE call, the hand-off done inside the library (postProcessing.m:100-124 with
+ * preRun.m:44-72: channels in descending peakMetric order, first index wins ties, at most nChannels of the acquired PRNs,
+ * the other channels off).  For callers that do not need to stop between the two hot functions (the MATLAB drop-in keeps
+ * the two separate signatures).  GPS L1 C/A only: the carrier-aided signals need settings.carrFreqBasis for
+ * channel.codeFreq, which gc_config does not carry.
+ *   carrFreq, codePhase, peakMetric   acqResults (length 32)
+ *   chanSv, chanAcqFreq, chanCodePhase   [nChannels] channel(ch).PRN / acquiredFreq / codePhase as preRun.m leaves them
+ *   out, vsmValue, vsmIndex, epochsDone  as gc_track */
+int gc_acquire_track(gc_handle* h, int32_t nSv, const int32_t* svList, int32_t nChannels, int32_t nEpochs,
+                     double* carrFreq, double* codePhase, double* peakMetric,
+                     int32_t* chanSv, double* chanAcqFreq, double* chanCodePhase,
+                     double* out, double* vsmValue, double* vsmIndex, int32_t* epochsDone);
+
 /* Bit and frame synchronisation front end of postNavigation for GPS L1 C/A - replaces
  * GPS/GPS_L1CA/include/NAVdecoding.m:69-170 (with Common/navPartyChk.m): sign of the prompt outputs, cross-correlation with the
  * 8-bit TLM preamble at 20 values per bit, candidates |xcorr| > 153 with 40 < index < msToProcess - 1199, for every

@@ -1016,3 +1016,34 @@ def test_nav_front_end_vs_oracle():
             assert np.array_equal(bits[ch], want_bits), ch
     assert sfs[0] == 1234 and sfs[1] == 4321 and sfs[2] == 40000 and bits[2] is None and sfs[4] == 0 and sfs[5] == 0
     eng.close()
+
+
+def test_acquire_track_one_call_matches_two_calls():
+    """gc_acquire_track (acquisition -> preRun -> tracking inside the library) returns exactly what
+    acquisition(), preRun() and tracking() return one after the other; C/N0 (now computed on the device) matches the oracle."""
+    fs = 16.368e6
+    sc = scene(fs, nsat=3, seed=11, cn0=47)
+    nE = 120
+    s = init_settings(samplingFreq=fs, msToProcess=nE, numberOfChannels=5, acqSatelliteList=sorted({x.prn for x in sc.sats} | {30}), CNo_VSMinterval=40)
+    N = 16368
+    raw = synth.make_record(sc, N * (nE + 44))
+    eng = Engine(s)
+    eng.set_record(raw)
+    acq2 = eng.acquire()
+    ch2 = preRun(acq2, s)
+    tr2, _ = tracking(None, ch2, s, engine=eng)
+    acq1, ch1, out, vv, vi, done = eng.acquire_track(s.numberOfChannels, nE)
+    for k in ("carrFreq", "codePhase", "peakMetric"):
+        assert np.array_equal(acq1[k], acq2[k]), k
+    assert [c["PRN"] for c in ch1] == [c["PRN"] for c in ch2] and [c["codePhase"] for c in ch1] == [c["codePhase"] for c in ch2]
+    assert [c["PRN"] for c in ch1][3:] == [0, 0]
+    from cu_sdr_collection_b200.tracking import TRACK_FIELDS
+    for i in range(5):
+        for j, f in enumerate(TRACK_FIELDS):
+            assert np.array_equal(out[i, j], tr2[i][f]), (i, f)
+        assert np.array_equal(vv[i], tr2[i]["CNo"]["VSMValue"]) and np.array_equal(vi[i], tr2[i]["CNo"]["VSMIndex"])
+    ref = O.tracking(raw, ch2, to_oracle_settings(s))
+    for i in range(3):
+        assert np.allclose(vv[i], ref[i]["VSMValue"], rtol=1e-5) and np.array_equal(vi[i], ref[i]["VSMIndex"]) and vi[i][-1] == 120
+    assert not np.any(vv[3:]) and not np.any(vi[3:])
+    eng.close()
