@@ -16,6 +16,9 @@ def _to_file_samples(longSignal: np.ndarray, settings: Settings, swapped: bool =
     per sample for fileType 1 (postProcessing.m:83-96).  ``swapped``: the GLONASS read path builds ``data2 + 1i*data1``
     (GLO_GL1/include/postProcessing.m:94), so real/imag are Q/I."""
     x = np.asarray(longSignal)
+    if settings.fileType == 3:
+        from .synth import pack_cplx2
+        return pack_cplx2(x)
     dt = np.int16 if settings.dataType == "int16" else np.int8
     lim = 32768 if dt is np.int16 else 128
     if settings.fileType == 1:
@@ -47,7 +50,7 @@ def acquisition(longSignal, settings: Settings, engine: Engine | None = None, ve
     eng = engine or Engine(settings)
     try:
         x = np.asarray(longSignal)
-        iq = x if x.dtype in (np.int8, np.int16) else _to_file_samples(x, settings, swapped=settings.is_glonass and settings.fileType == 2)
+        iq = x if x.dtype in (np.int8, np.int16, np.uint8) else _to_file_samples(x, settings, swapped=settings.is_glonass and settings.fileType == 2)
         r = eng.acquire(settings.acqSatelliteList, host_iq=iq)
     finally:
         if own:

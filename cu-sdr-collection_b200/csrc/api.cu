@@ -205,8 +205,8 @@ double sv_freq_offset(const gc_handle* h, int sv) { return h->glo ? -h->cfg.freq
 Rec rec_of(const gc_handle* h) { return Rec{h->rec, h->fmt}; }
 // settings.skipNumberOfBytes as a sample offset: the reference seeks dataAdaptCoeff*skip BYTES (postProcessing.m:74,
 // tracking.m:145-151), which is `skip` samples of 'schar' data and skip/2 samples of 'int16' data
-long long skip_samples(const gc_handle* h) { return (long long)h->cfg.skip_number_of_bytes / ((h->fmt & 1) ? 2 : 1); }
-long long rec_samples(const gc_handle* h) { return (long long)(h->recBytes / (size_t)rec_of(h).bytes_per_sample()); }
+long long skip_samples(const gc_handle* h) { return (long long)h->cfg.skip_number_of_bytes / ((h->fmt == 1 || h->fmt == 3) ? 2 : 1); }
+long long rec_samples(const gc_handle* h) { return rec_of(h).samples_in((long long)h->recBytes); }
 
 // +-1 table entries (chips, or BOC sub-chips) of one code period for an SV: the tracking replica of
 // `component` (0 data, 1 pilot); the fine search uses the pilot component where there is one
@@ -329,8 +329,9 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     if (cfg->abi_version != GC_ABI_VERSION) return fail(nullptr, GC_ERR_ARG, "gc_create: abi_version mismatch");
     if (cfg->signal < GC_SIG_GPS_L1CA || cfg->signal > GC_SIG_BDS_B1C)
         return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: signal not implemented (GPS L1CA/L5C/L2C, GLONASS G1/G2, BDS B1I/B1C/B3I/B2a, GAL E1C/E5a/E5b are)");
-    if ((cfg->file_type != 1 && cfg->file_type != 2) || (cfg->sample_bytes != 1 && cfg->sample_bytes != 2))
-        return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: fileType must be 1 (real) or 2 (I/Q) and dataType 'schar' (1 byte) or 'int16' (2 bytes)");
+    if ((cfg->file_type != 1 && cfg->file_type != 2 && cfg->file_type != GC_FILE_PACKED2) || (cfg->sample_bytes != 1 && cfg->sample_bytes != 2) ||
+        (cfg->file_type == GC_FILE_PACKED2 && cfg->sample_bytes != 1))
+        return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: fileType must be 1 (real), 2 (I/Q) or GC_FILE_PACKED2 and dataType 'schar' (1 byte) or 'int16' (2 bytes)");
     if (!(cfg->sampling_freq > 0) || !(cfg->code_freq_basis > 0) ||
         cfg->code_length != (cfg->signal == GC_SIG_GLO_G1G2 ? 511 : cfg->signal == GC_SIG_GAL_E1C ? 4092 :
                              cfg->signal == GC_SIG_GPS_L1CA ? 1023 : cfg->signal == GC_SIG_BDS_B1I ? 2046 : 10230) ||
@@ -349,8 +350,8 @@ int gc_create(gc_handle** out, const gc_config* cfg)
 
     gc_handle* h = new gc_handle();
     h->cfg = *cfg;
-    h->fmt = (cfg->sample_bytes == 2 ? 1 : 0) | (cfg->file_type == 1 ? 2 : 0);
-    if ((h->fmt & 1) && (cfg->skip_number_of_bytes & 1)) { delete h; return fail(nullptr, GC_ERR_ARG, "gc_create: with 'int16' data skipNumberOfBytes must be even (the seek would land inside a sample)"); }
+    h->fmt = cfg->file_type == GC_FILE_PACKED2 ? 4 : (cfg->sample_bytes == 2 ? 1 : 0) | (cfg->file_type == 1 ? 2 : 0);
+    if ((h->fmt == 1 || h->fmt == 3) && (cfg->skip_number_of_bytes & 1)) { delete h; return fail(nullptr, GC_ERR_ARG, "gc_create: with 'int16' data skipNumberOfBytes must be even (the seek would land inside a sample)"); }
     h->glo = (cfg->signal == GC_SIG_GLO_G1G2);
     h->b3i = (cfg->signal == GC_SIG_BDS_B3I);
     h->e1c = (cfg->signal == GC_SIG_GAL_E1C);
@@ -1205,7 +1206,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         const int f0 = mark();
         for (int gi = 0; gi < nGroups; ++gi) {
             FwdColsParams fp{};
-            fp.rec = rec_of(h); fp.winStart = winStart; fp.N = N; fp.nonCoh = nonCoh; fp.swapIQ = (h->glo && !(h->fmt & 2)) ? 1 : 0;
+            fp.rec = rec_of(h); fp.winStart = winStart; fp.N = N; fp.nonCoh = nonCoh; fp.swapIQ = (h->glo && h->fmt != 2 && h->fmt != 3) ? 1 : 0;
             fp.dphi = h->dphi.p + (size_t)gi * nBins; fp.out = h->X.p + (size_t)gi * nKm * L; fp.tw = h->twFused.p;
             GC_CUDA(h, launch_fwd_cols(L, fp, nKm, false, st)); ++launches;
         }
@@ -1239,7 +1240,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         const int f0 = mark();
         if (h->fused) {
             FwdColsParams fp{};
-            fp.rec = rec_of(h); fp.winStart = winStart; fp.N = N; fp.nonCoh = nonCoh; fp.swapIQ = (h->glo && !(h->fmt & 2)) ? 1 : 0;
+            fp.rec = rec_of(h); fp.winStart = winStart; fp.N = N; fp.nonCoh = nonCoh; fp.swapIQ = (h->glo && h->fmt != 2 && h->fmt != 3) ? 1 : 0;
             fp.dphi = h->dphi.p; fp.out = h->X.p; fp.tw = h->twFused.p;
             GC_CUDA(h, launch_fwd_cols(L, fp, nKm, false, st)); ++launches;
             RowsParams rp{};
@@ -1328,7 +1329,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         } else {
             GC_CUDA(h, h->T1.reserve((size_t)std::max(h->nReplicas, nKm) * L));
             GC_CUDA(h, h->T2.reserve((size_t)std::max(h->nReplicas, nKm) * L));
-            GC_CUDA(h, launch_generic_wipe(rec_of(h), winStart, N, nonCoh, nBins, (h->glo && !(h->fmt & 2)) ? 1 : 0, h->dphi.p, h->T1.p, L, st)); ++launches;
+            GC_CUDA(h, launch_generic_wipe(rec_of(h), winStart, N, nonCoh, nBins, (h->glo && h->fmt != 2 && h->fmt != 3) ? 1 : 0, h->dphi.p, h->T1.p, L, st)); ++launches;
             float2 *src = h->T1.p, *dst = h->T2.p;
             int n = L, s = 1;
             for (int f = 0; f < h->plan.nf; ++f) {
@@ -1421,7 +1422,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         GC_CUDA(h, launch_fine_setup(fs, st)); ++launches;
         FineParams fp{};
         fp.rec = rec_of(h); fp.winStart = winStart; fp.N = N; fp.nPeriods = nPeriods; fp.nFine = h->nFine; fp.codeLen = tabLen;
-        fp.swapIQ = (h->glo && !(h->fmt & 2)) ? 1 : 0; fp.combine = h->fineCombine; fp.chipIdx = h->chipIdx.p; fp.svId = h->fineSv.p;
+        fp.swapIQ = (h->glo && h->fmt != 2 && h->fmt != 3) ? 1 : 0; fp.combine = h->fineCombine; fp.chipIdx = h->chipIdx.p; fp.svId = h->fineSv.p;
         fp.chips = h->chips.p; fp.chipRow = h->fineChipRow.p; fp.codePhase = h->fineCodePhase.p; fp.dphi = h->fdphi.p; fp.prod = h->fineProd.p;
         fp.sums = h->fineSums.p; fp.best = h->fineBest.p; fp.fineResult = h->fineResult.p;
         fp.nAcqDev = h->nAcqDev.p; fp.nCodes = nCodes; fp.secondary = h->fineSecondary.p;
@@ -1494,7 +1495,7 @@ int gc_acquire_host(gc_handle* h, const int8_t* iq, size_t nSamples, int32_t nSv
                     int32_t* coarseBin, int32_t* coarseCodePhase)
 {
     if (!h || !iq) return fail(h, GC_ERR_ARG, "gc_acquire_host: bad argument");
-    int rc = gc_set_record_host(h, iq, nSamples * (size_t)rec_of(h).bytes_per_sample());
+    int rc = gc_set_record_host(h, iq, (size_t)rec_of(h).bytes_of((long long)nSamples));
     if (rc != GC_OK) return rc;
     return acquire_impl(h, 0, nSv, svList, carrFreq, codePhase, peakMetric, coarseBin, coarseCodePhase, (long long)nSamples);
 }
@@ -1612,7 +1613,7 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
         p.pf1 = 2 * Wn;
     }
     p.loopType = (h->glo || h->b3i || h->hostCodes) ? 1 : 0;
-    p.swapIQ = (h->glo && !(h->fmt & 2)) ? 1 : 0;
+    p.swapIQ = (h->glo && h->fmt != 2 && h->fmt != 3) ? 1 : 0;
     p.nEpochs = nEpochs;
     p.exactDisc = getenv("GC_TRACK_EXACT_DISC") ? 1 : 0;
     // CTAs per channel: spread few channels over the chip (thread-block clusters), 1 CTA per channel once

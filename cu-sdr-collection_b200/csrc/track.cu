@@ -403,7 +403,7 @@ track_kernel(TrackParams p)
                 xi[6] = byte_to_float(w3, selI0); xq[6] = byte_to_float(w3, selQ0); xi[7] = byte_to_float(w3, selI1); xq[7] = byte_to_float(w3, selQ1);
             } else {                                              // int16 and / or real samples (tracking.m:145-149, 229-240)
                 const Rec rec{p.rec, p.fmt};
-                const bool swap = p.swapIQ && !(p.fmt & 2);
+                const bool swap = p.swapIQ != 0;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const long long si = min(max(pos + k0 + j, 0LL), p.recSamples - 1);

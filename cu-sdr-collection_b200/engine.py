@@ -110,8 +110,8 @@ def config_from_settings(s: Settings, device: int = 0) -> gc_config:
     if s.resamplingflag != 0:   # (B3I spells it resamplingFlag, BDS/B3I/initSettings.m:88)
         raise GnssCorrError("resamplingflag == 1 is outside the accelerated path "
                             "(acquisition.m:50-111); run the reference for that case")
-    if s.fileType not in (1, 2) or s.dataType not in ("schar", "int16"):
-        raise GnssCorrError("fileType must be 1 (real) or 2 (I/Q) and dataType 'schar' or 'int16' (initSettings.m:63-68)")
+    if s.fileType not in (1, 2, 3) or s.dataType not in ("schar", "int16") or (s.fileType == 3 and s.dataType != "schar"):
+        raise GnssCorrError("fileType must be 1 (real), 2 (I/Q) or 3 (2-bit packed I/Q, unpack_cplx.m) and dataType 'schar' or 'int16' (initSettings.m:63-68)")
     sig = signal_id(s)
     return gc_config(abi_version=4, device=device, pilot_trk_flag=int(s.pilotTRKflag), acq_coh_t=int(s.acqCohT),
                      pilot_acq_flag=int(s.pilotACQflag), signal=sig, freq_spacing=float(s.freqSpacing),
@@ -180,6 +180,8 @@ class Engine:
     @property
     def sample_dtype(self):
         """numpy dtype of one stored value of the record: settings.dataType 'schar' / 'int16' (initSettings.m:63)."""
+        if self.settings.fileType == 3:
+            return np.uint8                                          # 2-bit packed: two complex samples per byte
         return np.int16 if self.settings.dataType == "int16" else np.int8
 
     def close(self):
@@ -219,7 +221,7 @@ class Engine:
         cbin, ccp = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
         if host_iq is not None:
             a = np.ascontiguousarray(host_iq, dtype=self.sample_dtype)       # the file's own sample format
-            rc = self.lib.gc_acquire_host(self._h, a.ctypes.data, a.size // (1 if s.fileType == 1 else 2), sv.size, _ip(sv),
+            rc = self.lib.gc_acquire_host(self._h, a.ctypes.data, {1: a.size, 2: a.size // 2, 3: a.size * 2}[s.fileType], sv.size, _ip(sv),
                                           _dp(carr), _dp(cph), _dp(pm), _ip(cbin), _ip(ccp))
             self._check(rc, "gc_acquire_host")
         else:

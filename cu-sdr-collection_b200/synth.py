@@ -317,3 +317,25 @@ def make_record_torch(scene: Scene, nsamples: int, device="cuda", chunk: int = 1
         out[2 * c0: 2 * (c0 + m): 2] = torch.clamp(torch.round(re), -127, 127).to(torch.int8)
         out[2 * c0 + 1: 2 * (c0 + m): 2] = torch.clamp(torch.round(im), -127, 127).to(torch.int8)
     return out
+
+
+def pack_cplx2(x: np.ndarray) -> np.ndarray:
+    """Complex samples with I, Q in {+-1, +-3} -> the 2-bit packed bytes that include/unpack_cplx.m reads (two samples per
+    byte; per component a sign bit and a magnitude bit: first sample I = bits (0, 2), Q = bits (1, 3), second sample I = bits
+    (4, 6), Q = bits (5, 7); its four 256-entry tables, unpack_cplx.m:17-20, are exactly that)."""
+    x = np.asarray(x)
+    re, im = np.rint(x.real).astype(np.int64), np.rint(x.imag).astype(np.int64)
+    if not (np.all(np.isin(np.abs(re), (1, 3))) and np.all(np.isin(np.abs(im), (1, 3))) and np.all(re == x.real) and np.all(im == x.imag)):
+        from .engine import GnssCorrError
+        raise GnssCorrError("2-bit packed records hold I, Q in {+-1, +-3}")
+    if x.size % 2:
+        re, im = np.append(re, 1), np.append(im, 1)
+    nib = (re < 0).astype(np.uint8) | ((im < 0).astype(np.uint8) << 1) | ((np.abs(re) == 3).astype(np.uint8) << 2) | ((np.abs(im) == 3).astype(np.uint8) << 3)
+    return (nib[0::2] | (nib[1::2] << 4)).astype(np.uint8)
+
+
+def quantize2(iq8: np.ndarray, step: float = 20.0) -> np.ndarray:
+    """An int8 I,Q record quantised to the four levels of a 2-bit front end (+-1 within +-step, +-3 beyond), as complex."""
+    v = iq8.astype(np.float64)
+    q = np.where(np.abs(v) > step, 3.0, 1.0) * np.where(v < 0, -1.0, 1.0)
+    return q[0::2] + 1j * q[1::2]

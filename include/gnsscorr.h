@@ -63,13 +63,16 @@ enum {
     GC_ERR_IO = -6            /* gc_track_file: open/read failure (postProcessing.m:155-158)       */
 };
 
+#define GC_FILE_PACKED2 3   /* file_type: two complex samples per byte, values +-1 / +-3 (GPS_L2C/include/unpack_cplx.m:17-20) */
+
 /* POD image of the hot-path fields of the reference's `settings` struct
  * (GPS/GPS_L1CA/initSettings.m:44-136).  Filled by the MATLAB wrapper / Python mirror. */
 typedef struct gc_config {
     int32_t abi_version;         /* GC_ABI_VERSION                                                  */
     int32_t device;              /* CUDA device ordinal                                             */
     int32_t signal;              /* GC_SIG_*                                                        */
-    int32_t file_type;           /* settings.fileType: 1 = real, 2 = I/Q interleaved (:68)          */
+    int32_t file_type;           /* settings.fileType: 1 = real, 2 = I/Q interleaved (:68); GC_FILE_PACKED2 = the 2-bit packed
+                                    I/Q records that include/unpack_cplx.m converts to 'schar' files, decoded on the fly */
     int32_t sample_bytes;        /* settings.dataType: 1 = 'schar', 2 = 'int16' (:63)               */
     int32_t code_length;         /* settings.codeLength (:76)                                       */
     int32_t acq_noncoh_time;     /* settings.acqNonCohTime (:88)                                    */

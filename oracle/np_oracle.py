@@ -1834,3 +1834,19 @@ def nav_sync(I_P: np.ndarray, msToProcess: int):
     s = np.asarray(I_P, dtype=np.float64)[lo:hi].reshape(-1, 20)
     navBits = (np.array([float(np.sum(row)) for row in s]) > 0).astype(np.uint8)   # :152-166
     return subFrameStart, navBits
+
+
+def unpack_cplx(data: np.ndarray) -> np.ndarray:
+    """GPS/GPS_L2C/include/unpack_cplx.m:17-31: every byte of the 2-bit packed record becomes four schar values I1 Q1 I2 Q2
+    through four 256-entry tables.  The tables are periodic patterns - LUT_I_long1 = [1 -1 1 -1 3 -3 3 -3] repeated,
+    LUT_Q_long1 = [1 1 -1 -1 1 1 -1 -1 3 3 -3 -3 3 3 -3 -3] repeated, LUT_I_long2 / LUT_Q_long2 the same patterns stretched by 16 -
+    restated here as such; returns the int8 I,Q interleaved record the reference then processes with fileType 2."""
+    b = np.asarray(data, dtype=np.uint8).astype(np.int64)
+    pat_i = np.array([1, -1, 1, -1, 3, -3, 3, -3])
+    pat_q = np.array([1, 1, -1, -1, 1, 1, -1, -1, 3, 3, -3, -3, 3, 3, -3, -3])
+    idx = np.arange(256)
+    lut_i1, lut_q1 = pat_i[idx % 8], pat_q[idx % 16]
+    lut_i2, lut_q2 = pat_i[(idx // 16) % 8], pat_q[(idx // 16) % 16]
+    out = np.empty(4 * b.size, dtype=np.int8)
+    out[0::4] = lut_i1[b]; out[1::4] = lut_q1[b]; out[2::4] = lut_i2[b]; out[3::4] = lut_q2[b]
+    return out

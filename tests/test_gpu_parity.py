@@ -1047,3 +1047,48 @@ def test_acquire_track_one_call_matches_two_calls():
         assert np.allclose(vv[i], ref[i]["VSMValue"], rtol=1e-5) and np.array_equal(vi[i], ref[i]["VSMIndex"]) and vi[i][-1] == 120
     assert not np.any(vv[3:]) and not np.any(vi[3:])
     eng.close()
+
+
+def test_packed_2bit_record_equals_unpacked_schar_record(tmp_path):
+    """fileType GC_FILE_PACKED2: the 2-bit packed I/Q record (the input of unpack_cplx.m) decoded on the fly gives exactly what
+    the engine gives on the 'schar' file unpack_cplx.m would write - acquisition results and every tracking row - and that
+    matches the oracle on the unpacked record."""
+    fs = 16.368e6
+    sc = scene(fs, nsat=3, seed=11, cn0=50)
+    nE = 80
+    sv = sorted({x.prn for x in sc.sats} | {30})
+    N = 16368
+    x = synth.quantize2(synth.make_record(sc, N * (nE + 44)))
+    packed = synth.pack_cplx2(x)
+    unpacked = O.unpack_cplx(packed)
+    res = {}
+    for ft, rec in ((3, packed), (2, unpacked)):
+        s = init_settings(samplingFreq=fs, fileType=ft, msToProcess=nE, numberOfChannels=4, acqSatelliteList=sv)
+        eng = Engine(s)
+        eng.set_record(rec)
+        acq = eng.acquire()
+        ch = preRun(acq, s)
+        path = tmp_path / ("rec%d.bin" % ft)
+        rec.tofile(path)
+        with open(path, "rb") as fid:
+            tr, _ = tracking(fid, ch, s, engine=eng)
+        res[ft] = (acq, ch, tr)
+        eng.close()
+    for k in ("carrFreq", "codePhase", "coarseBin"):
+        assert np.array_equal(res[3][0][k], res[2][0][k]), k
+    assert np.allclose(res[3][0]["peakMetric"], res[2][0]["peakMetric"], rtol=1e-12)
+    from cu_sdr_collection_b200.tracking import TRACK_FIELDS
+    for i in range(4):
+        for f in TRACK_FIELDS:
+            a, b = res[3][2][i][f], res[2][2][i][f]
+            assert np.allclose(a, b, rtol=1e-9, atol=1e-9, equal_nan=True), (i, f)
+    so = to_oracle_settings(init_settings(samplingFreq=fs, msToProcess=nE, numberOfChannels=4, acqSatelliteList=sv))
+    ref = O.acquisition(O.read_acq_signal(unpacked, so), so, workers=os.cpu_count() or 1)
+    _check_acq(res[3][0], ref, sv)
+    for sat in sc.sats:
+        assert res[3][0]["carrFreq"][sat.prn - 1] != 0
+    ref_tr = O.tracking(unpacked, res[3][1], so)
+    for i in range(3):
+        sc_ = np.hypot(ref_tr[i]["I_P"], ref_tr[i]["Q_P"])
+        for name in ("I_P", "Q_P", "I_E", "I_L", "Q_E", "Q_L"):
+            assert np.max(np.abs(res[3][2][i][name] - ref_tr[i][name]) / sc_) < IQ_TOL, name

@@ -551,3 +551,23 @@ def test_nav_front_end_oracle_known_answers():
     late = nav_prompt_row(bits, 40000, n, amp=2000.0, sigma=0.0, seed=1)     # found, but 30000 ms of bits do not fit
     sfs, nb = O.nav_sync(late, n)
     assert sfs == 40000 and nb is None
+
+
+def test_unpack_cplx_restatement():
+    """The 2-bit packed record format: pack/unpack round trip, and - where the reference tree is mounted - the restated
+    periodic patterns against the four literal 256-entry tables of GPS_L2C/include/unpack_cplx.m:17-20."""
+    import re
+    rng = np.random.default_rng(0)
+    x = rng.choice([-3, -1, 1, 3], size=1001) + 1j * rng.choice([-3, -1, 1, 3], size=1001)
+    b = synth.pack_cplx2(x)
+    u = O.unpack_cplx(b)
+    assert b.size == 501 and np.array_equal(u[0:2002:2], x.real) and np.array_equal(u[1:2002:2], x.imag)
+    ref = "/root/reference/GPS/GPS_L2C/include/unpack_cplx.m"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree not mounted")
+    txt = open(ref).read()
+    allb = O.unpack_cplx(np.arange(256, dtype=np.uint8)).reshape(256, 4)
+    for col, name in enumerate(("LUT_I_long1", "LUT_Q_long1", "LUT_I_long2", "LUT_Q_long2")):
+        m = re.search(name + r"\s*=\s*\[([^\]]*)\]", txt)
+        lut = np.array([int(v) for v in m.group(1).split(";") if v.strip()])
+        assert lut.size == 256 and np.array_equal(lut, allb[:, col]), name
