@@ -36,6 +36,8 @@ struct RowsParams {
     int nRep, repStride;      // inverse: replicas summed per SV (1, or 2 = data + pilot) and their distance in Cc; the
                               // work buffer then holds nonCoh*nRep transforms per (SV, bin), replica index fastest
     int prnPerCta, mPerCta;   // warps of an inverse CTA = binPerCta x prnPerCta x mPerCta (same row j1)
+    const int* slotGroup;     // optional [nSv]: carrier grid of each list slot (GLONASS frequency numbers): the spectra of grid g start
+    int groupRows;            // groupRows rows into X (nBins x nonCoh); nullptr = one grid
     int bin0;                 // first bin of this launch: nBins counts the bins of the launch (and of the W layout), the spectra
                               // and binMap are addressed with bin0 + local bin
     int binPerCta;            // bins per CTA (0 = 1); > 1 where a (SV, bin) cell has too few transforms to fill a CTA

@@ -148,6 +148,7 @@ inv_rows_kernel(RowsParams p)
     // With j = j1 + C*j2 (row j1, in-row frequency j2 held by its residues mod RA and mod RB) that is row (j1 - s) mod C
     // and j2 - floor-part, i.e. a fixed source row and a circular shift of both residues.
     int xrow = (p.bin0 + k) * p.nonCoh + m, srow = k1, sa = 0, sb = 0;
+    if (p.slotGroup != nullptr) xrow += p.slotGroup[p.prnSlot0 + pi] * p.groupRows;     // this SV's carrier grid
     if constexpr (!P::kPfa) {                                    // (the variant B / C lengths all have Cooley-Tukey plans)
         if (p.binMap != nullptr) {
             const int2 bm = p.binMap[p.bin0 + k];

@@ -1182,7 +1182,10 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
     }
     const int nGroups = (int)groupStart.size();
     groupStart.push_back(nSv);
-    GC_CUDA(h, h->X.reserve((size_t)(h->cluster ? nGroups : 1) * nKm * L));
+    // several carrier grids (GLONASS: one per frequency number) are transformed and searched in ONE pass each instead of grid by grid
+    const bool batchGroups = h->fused && !h->cluster && !h->queue && !h->overlap && nGroups > 1 && !getenv("GC_ACQ_CHUNK_BINS") &&
+                             (double)nGroups * nKm * L * sizeof(float2) <= kWorkBytes;
+    GC_CUDA(h, h->X.reserve((size_t)((h->cluster || batchGroups) ? nGroups : 1) * nKm * L));
     GC_CUDA(h, h->dphi.reserve((size_t)nGroups * nBins));
     std::vector<std::vector<double>> coarseFreqOf(nSv);   // per list slot: the bin frequencies it was searched on
 
@@ -1223,7 +1226,53 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         GC_CUDA(h, launch_corr_cluster(L, cp, st)); ++launches;
         rowEv.push_back({f1, mark()}); ++nRowLaunches;
     }
-    for (int g0 = 0; g0 < nSv && !h->cluster;) {
+    if (batchGroups) {
+        std::vector<uint64_t> dphi((size_t)nGroups * nBins);
+        for (int gi = 0; gi < nGroups; ++gi) {
+            const double off = sv_freq_offset(h, svList[order[groupStart[gi]]]);
+            std::vector<double> coarseFreq(nBins);
+            for (int k = 0; k < nBins; ++k) {
+                coarseFreq[k] = (c.IF + off) + c.acq_search_band - c.acq_search_step * k;   // :169 (GLO :181-182)
+                dphi[(size_t)gi * nBins + k] = turns_to_fix(coarseFreq[k] * h->ts);
+            }
+            for (int s = groupStart[gi]; s < groupStart[gi + 1]; ++s) coarseFreqOf[s] = coarseFreq;
+        }
+        GC_CUDA(h, cudaMemcpyAsync(h->dphi.p, dphi.data(), dphi.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        GC_CUDA(h, upload(h->slotGroup, slotGroup, st));
+        const int f0 = mark();
+        FwdColsParams fp{};
+        fp.rec = rec_of(h); fp.winStart = winStart; fp.N = N; fp.nonCoh = nonCoh; fp.swapIQ = (h->glo && h->fmt != 2 && h->fmt != 3) ? 1 : 0;
+        fp.dphi = h->dphi.p; fp.out = h->X.p; fp.tw = h->twFused.p;          // row (grid, bin, block): the phase table is indexed grid*nBins + bin
+        GC_CUDA(h, launch_fwd_cols(L, fp, nGroups * nKm, false, st)); ++launches;
+        RowsParams rp{};
+        rp.X = h->X.p; rp.nRows = (long long)nGroups * nKm * h->fp.C;
+        GC_CUDA(h, launch_fwd_rows(L, rp, st)); ++launches;
+        fwdEv.push_back({f0, mark()});
+        int chunk = (int)std::max<long long>(1, (long long)(kWorkBytes / ((double)nKm * h->nRep * L * sizeof(float2))));
+        chunk = std::min(chunk, (int)nSv);
+        GC_CUDA(h, h->W.reserve((size_t)chunk * nKm * h->nRep * L));
+        for (int s0 = 0; s0 < nSv; s0 += chunk) {
+            const int nc = std::min(chunk, (int)nSv - s0);
+            RowsParams ip{};
+            ip.X = h->X.p; ip.Cc = h->Cc.p; ip.W = h->W.p; ip.tw = h->twFused.p;
+            ip.nonCoh = nonCoh; ip.nBins = nBins; ip.prnPerCta = 1; ip.mPerCta = 5;
+            ip.nRep = h->nRep; ip.repStride = 1;
+            if (nonCoh * h->nRep < 5) { ip.prnPerCta = 5; ip.mPerCta = 1; }
+            ip.nPrnChunk = nc; ip.prnSlot0 = s0; ip.prnList = h->prnList.p;
+            ip.slotGroup = h->slotGroup.p; ip.groupRows = nKm;
+            if (evn > kEvents - 12) drain_events();
+            const int a = mark();
+            GC_CUDA(h, launch_inv_rows(L, ip, st)); ++launches;
+            const int b = mark();
+            InvColsParams cp{};
+            cp.W = h->W.p; cp.nBins = nBins; cp.nonCoh = nonCoh * h->nRep; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
+            cp.partMax = h->partMax.p; cp.partIdx = h->partIdx.p;
+            GC_CUDA(h, launch_inv_cols(L, cp, st)); ++launches;
+            const int d = mark();
+            rowEv.push_back({a, b}); colEv.push_back({b, d}); ++nRowLaunches;
+        }
+    }
+    for (int g0 = 0; g0 < nSv && !h->cluster && !batchGroups;) {
         int g1 = g0 + 1;
         const double off = sv_freq_offset(h, svList[order[g0]]);
         while (g1 < nSv && sv_freq_offset(h, svList[order[g1]]) == off) ++g1;
