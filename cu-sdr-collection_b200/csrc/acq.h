@@ -43,6 +43,7 @@ struct RowsParams {
     int binPerCta;            // bins per CTA (0 = 1); > 1 where a (SV, bin) cell has too few transforms to fill a CTA
     const int2* binMap;       // optional [nBins]: .x = spectrum row in X (instead of bin*nonCoh + block), .y = circular shift of
                               // the spectrum, circshift(IQfreqDom, y) (acquisition variants B and C); nullptr = variant A
+    int binMapSlotStride;     // 0: one map for every list slot; else slot s uses binMap[s * binMapSlotStride + bin]
     int nPrnChunk, prnSlot0;  // list slots [prnSlot0, prnSlot0 + nPrnChunk) are processed by this launch
     const int* prnList;       // [nSv] replica index per list slot (index into Cc)
 };

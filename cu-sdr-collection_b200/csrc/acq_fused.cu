@@ -151,7 +151,7 @@ inv_rows_kernel(RowsParams p)
     if (p.slotGroup != nullptr) xrow += p.slotGroup[p.prnSlot0 + pi] * p.groupRows;     // this SV's carrier grid
     if constexpr (!P::kPfa) {                                    // (the variant B / C lengths all have Cooley-Tukey plans)
         if (p.binMap != nullptr) {
-            const int2 bm = p.binMap[p.bin0 + k];
+            const int2 bm = p.binMap[(p.binMapSlotStride ? (p.prnSlot0 + pi) * p.binMapSlotStride : 0) + p.bin0 + k];
             xrow = bm.x * p.nonCoh + m;
             const int s1 = bm.y % C;
             int s2 = bm.y / C;

@@ -730,12 +730,13 @@ static int acquire_varb(gc_handle* h, long long winStart, int32_t nSv, const int
         GC_CUDA(h, h->peaks.reserve((size_t)nSv * nRows));
         int chunk = (int)std::max<long long>(1, (long long)(kWorkBytes / ((double)nRows * Lb * sizeof(float2))));
         chunk = std::min(chunk, (int)nSv);
-        GC_CUDA(h, h->W.reserve((size_t)chunk * nRows * Lb));
-        auto correlate = [&](int s0, int nc, int nB, const int2* bm, float* magOut) -> int {
+        GC_CUDA(h, h->W.reserve(std::max((size_t)chunk * nRows, (size_t)nSv) * Lb));   // (the winner pass holds one row per SV)
+        auto correlate = [&](int s0, int nc, int nB, const int2* bm, int bmStride, float* magOut) -> int {
             RowsParams ip{};
             ip.X = h->X.p; ip.Cc = h->Cc.p; ip.W = h->W.p; ip.tw = h->twFused.p;
             ip.nonCoh = 1; ip.nBins = nB; ip.nRep = 1; ip.repStride = 1;
-            ip.prnPerCta = 1; ip.mPerCta = 1; ip.binPerCta = 5; ip.binMap = bm;
+            ip.prnPerCta = 1; ip.mPerCta = 1; ip.binPerCta = 5; ip.binMap = bm; ip.binMapSlotStride = bmStride;
+            if (nB == 1) { ip.prnPerCta = 5; ip.binPerCta = 1; }       // one row per SV: fill the CTA with SVs instead of bins
             ip.nPrnChunk = nc; ip.prnSlot0 = s0; ip.prnList = h->prnList.p;
             GC_CUDA(h, launch_inv_rows(Lb, ip, st)); ++launches;
             InvColsParams cp{};
@@ -745,7 +746,7 @@ static int acquire_varb(gc_handle* h, long long winStart, int32_t nSv, const int
             return GC_OK;
         };
         for (int s0 = 0; s0 < nSv; s0 += chunk) {
-            const int rc = correlate(s0, std::min(chunk, (int)nSv - s0), nRows, h->vbMap.p, nullptr);
+            const int rc = correlate(s0, std::min(chunk, (int)nSv - s0), nRows, h->vbMap.p, 0, nullptr);
             if (rc != GC_OK) return rc;
         }
         GC_CUDA(h, launch_peak_select(h->partMax.p, h->partIdx.p, nSv * nRows, 1, parts, h->peaks.p, st)); ++launches;
@@ -757,8 +758,8 @@ static int acquire_varb(gc_handle* h, long long winStart, int32_t nSv, const int
         for (int s = 0; s < nSv; ++s) map[nRows + s] = make_int2(win[s].src, win[s].shift);
         GC_CUDA(h, cudaMemcpyAsync(h->vbMap.p + nRows, map.data() + nRows, nSv * sizeof(int2), cudaMemcpyHostToDevice, st));
         GC_CUDA(h, h->vbMag.reserve((size_t)nSv * Lb));
-        for (int s = 0; s < nSv; ++s) {                       // corrVec of the winning row of each SV (partial maxima land in slot s, one bin)
-            const int rc = correlate(s, 1, 1, h->vbMap.p + nRows + s, h->vbMag.p + (size_t)s * Lb);
+        {                                                     // corrVec of the winning row of every SV in one pass: slot s reads its own map
+            const int rc = correlate(0, nSv, 1, h->vbMap.p + nRows, 1, h->vbMag.p);   // entry (partial maxima land in slot s, one bin)
             if (rc != GC_OK) return rc;
         }
         GC_CUDA(h, launch_peak_select(h->partMax.p, h->partIdx.p, nSv, 1, parts, h->peaks.p, st)); ++launches;
