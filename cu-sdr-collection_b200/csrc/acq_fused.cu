@@ -262,10 +262,12 @@ inv_cols_kernel(InvColsParams p)
 // A CTA handles TC adjacent row positions (columns), so global accesses are TC*8-byte runs.
 template <class P> struct BigGeo {
     static constexpr int C1 = P::C1, C2 = P::C2;
-    // 16 columns per CTA (128-byte runs) and at least two CTAs per SM: one CTA's loads overlap the other's DFT phases
+    // 16 columns per CTA (128-byte runs) and several CTAs per SM: one CTA's loads overlap the other's DFT phases
     // (one 640-thread CTA per SM measured 10-25 % slower: its load, DFT and barrier phases serialise)
     static constexpr int TC = 16;
-    static constexpr int kMinCtas = 2;
+    // three CTAs per SM (64 registers) where both phases are at most 20 points (E1 36 x 81 grid 6.0 -> 5.4 ms, L2C 43 -> 41 ms);
+    // a 25-point phase spills at that budget (B1C 46 -> 58 ms) and stays at two
+    static constexpr int kMinCtas = (C1 > C2 ? C1 : C2) <= 20 ? 3 : 2;
     static constexpr int NT = (C1 > C2 ? C1 : C2) * TC;                        // threads: max of the two phases
     static constexpr size_t kSmem = sizeof(float2) * P::C * TC;
     static constexpr size_t kSmemInv = kSmem + sizeof(float2) * P::C;          // + the w_C^(ta*beta) table of the inverse pass
