@@ -32,6 +32,8 @@ struct TrackParams {
     int swapIQ;              // GLONASS: rawSignal = Q + 1i*I (GLO tracking.m:227)
     int nEpochs;
     int exactDisc;           // 1: float64 atan/sqrt/divide in the discriminators (GC_TRACK_EXACT_DISC), 0: fp32-seeded
+    int exact;               // 1: the float64 checking mode (GC_PARAM_TRACK_EXACT_SUMS): per-sample float64 carrier, products and sums,
+                             // rem(trigarg, 2*pi) recurrence; implies exactDisc
     int bufBytes;            // bytes staged per epoch by ONE CTA (multiple of 16)
     int codeLen;             // entries of one code period in the tables: chips x subChip
     int subChip;             // table entries per chip: 1, or 2 for the BOC(1,1) tables of Galileo E1

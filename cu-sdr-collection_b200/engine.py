@@ -42,6 +42,8 @@ _FAM5_IDS = {"GPS_L5C": GC_SIG_GPS_L5C, "GAL_E5a": GC_SIG_GAL_E5A, "GAL_E5b": GC
              "BDS_B1I": GC_SIG_BDS_B1I, "GPS_L2C": GC_SIG_GPS_L2C, "BDS_B1C": GC_SIG_BDS_B1C}
 GC_SV_NONE = -2147483648
 GC_PARAM_B1C_WB_FACTOR = 1
+GC_PARAM_TRACK_EXACT_SUMS = 2     # float64 checking mode of the tracking kernel (include/gnsscorr.h)
+GC_PARAM_TRACK_FAST_DISC = 3      # fp32 discriminators (default: float64)
 
 
 class gc_stats(C.Structure):

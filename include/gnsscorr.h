@@ -156,7 +156,16 @@ int gc_set_code(gc_handle* h, int32_t sv, int32_t component, const int8_t* chips
  * discriminator in B1C full-band tracking, `factor = CalcWeighingFactor(settings)` (BDS/B1C/include/WB_tracking.m:124,
  * CalcWeighingFactor.m:45-82 - adaptive quadrature of the BOC / QMBOC spectra over settings.FEBW, done by the caller);
  * required before gc_track when pilot_trk_flag == 2. */
-enum { GC_PARAM_B1C_WB_FACTOR = 1 };
+enum { GC_PARAM_B1C_WB_FACTOR = 1,
+       /* 1 = tracking in the float64 CHECKING mode: carrier exp(-1i*trigarg) per sample in float64 from the reference's own
+        * expression (tracking.m:280-287), float64 products and sums, rem(trigarg, 2*pi) recurrence for remCarrPhase.  Several times
+        * slower; the recorded loop state then follows the float64 reference to ~1e-13 instead of ~1e-10, which the parity tests
+        * use to show that what separates the default mode from the reference at 18 Msps is the conditioning of ceil(tcode) alone.
+        * Also switched on by GC_TRACK_EXACT_SUMS=1 in the environment when the handle is created. */
+       GC_PARAM_TRACK_EXACT_SUMS = 2,
+       /* 1 = discriminators atan(Q/I), sqrt, divide evaluated in fp32 (their inputs are fp32-accumulated sums anyway); the default
+        * is float64 as the reference evaluates them (tracking.m:305, 322), which costs 1.5 % */
+       GC_PARAM_TRACK_FAST_DISC = 3 };
 int gc_set_param(gc_handle* h, int32_t key, double value);
 
 /* GPS L2C with pilot_trk_flag == 1: acqResults.CLCodePhase (1..75, 0 = not acquired; GPS_L2C/include/acquisition.m:100-137)

@@ -21,3 +21,24 @@ def _oracle_lib():
     if not os.path.exists(so):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
     return so
+
+
+def pytest_terminal_summary(terminalreporter):
+    """Observed parity of the closed-loop tracking comparisons (tests/helpers.windowed_iq_compare): how many epochs the 1e-6
+    window covered and the worst error inside / after it; also written to gpurun_out/ for profiles/."""
+    try:
+        from helpers import PARITY_REPORT
+    except Exception:
+        return
+    if not PARITY_REPORT:
+        return
+    lines = ["%-72s window %6d / %6d   inside %.2e   after %.2e" % r for r in PARITY_REPORT]
+    terminalreporter.write_sep("-", "closed-loop parity windows (1e-6 of |P| inside)")
+    for ln in lines:
+        terminalreporter.write_line(ln)
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "parity_windows.txt"), "w") as f:
+            f.write("\n".join(lines) + "\n")
+    except OSError:
+        pass

@@ -164,6 +164,37 @@ def first_illconditioned_epoch(ref_rem, ref_cf, got_rem, got_cf, abs_sample, fs,
     return n
 
 
+PARITY_REPORT = []      # (label, window epochs, total epochs, worst pre-window error, worst post-window error): printed by conftest
+
+
+def windowed_iq_compare(label, tr, ref, names, fs, spacing, sub=1.0, rem_scale=1.0, scale_keys=("I_P", "Q_P"), iq_tol=1e-6,
+                        post_tol=1e-2, min_frac=0.0, exact=False, abs_sample=None):
+    """The closed-loop I/Q comparison of the trackers whose ceil(tcode) can be ill conditioned (18 Msps / 10.23 Mcps, BOC tables):
+    every correlator row within `iq_tol` of |P| up to the first ill-conditioned epoch (first_illconditioned_epoch), `post_tol`
+    after it; the window must cover at least `min_frac` of the run.  With exact=True (the engine's float64 checking mode) there is
+    no window: `iq_tol` holds over the whole run - that is the proof that the window is conditioning and not an error.
+    Returns (window, worst error inside, worst error after) and records them for the test report."""
+    nE = len(ref["I_P"])
+    sc_ = np.hypot(ref[scale_keys[0]], ref[scale_keys[1]])
+    err = np.zeros(nE)
+    for name in names:
+        err = np.maximum(err, np.abs(tr[name] - ref[name]) / sc_)
+    if exact:
+        ok = nE
+    else:
+        a = ref["absoluteSample"] if abs_sample is None else abs_sample
+        ok = first_illconditioned_epoch(rem_scale * ref["remCodePhase"], rem_scale * ref["codeFreq"], rem_scale * tr["remCodePhase"],
+                                        rem_scale * tr["codeFreq"], a, fs, rem_scale * spacing, sub=sub)
+    pre = float(err[:ok].max()) if ok else 0.0
+    post = float(err[ok:].max()) if ok < nE else 0.0
+    PARITY_REPORT.append((label + (" [float64 checking mode]" if exact else ""), ok, nE, pre, post))
+    print(f"[parity] {PARITY_REPORT[-1][0]}: 1e-6 window {ok}/{nE} epochs, worst |dIQ|/|P| inside {pre:.2e}, after {post:.2e}")
+    assert pre < iq_tol, (label, "inside the window", pre)
+    assert post < post_tol, (label, "after the window", post)
+    assert ok >= min_frac * nE, (label, "window", ok, nE)
+    return ok, pre, post
+
+
 # IS-GPS-200 table 20-XIV: source data bits d1..d24 entering D25..D30 and which of D29*, D30* joins them
 _NAV_SETS = [
     (0, (1, 2, 3, 5, 6, 10, 11, 12, 13, 14, 17, 18, 20, 23)),

@@ -11,12 +11,22 @@ import np_oracle as O
 from cu_sdr_collection_b200 import Engine, acquisition, init_settings, preRun, synth, tracking
 from cu_sdr_collection_b200.codes import standin_e1_codes
 from helpers import (ROOT, c_acquisition, c_tracking, first_illconditioned_epoch, orc_set_e1_codes, scene,
-                     to_oracle_settings, track_rel_err)
+                     to_oracle_settings, track_rel_err, windowed_iq_compare)
+from cu_sdr_collection_b200.engine import GC_PARAM_TRACK_EXACT_SUMS
 
 pytestmark = pytest.mark.gpu
 
 IQ_TOL = 1e-6        # north_star: floating-point I_P/Q_P within 1e-6 relative
 METRIC_TOL = 1e-6
+# Variant B (BDS B1I, GPS L2C): peakMetric = peak / SECOND peak of one fp32 correlation row.  The second peak is a noise-floor
+# value (~1/30 of the row's largest spectral products at these SNRs), so the fp32 transform's error - 1e-7 of the LARGE values -
+# is a few 1e-6 of it; the measured worst case is printed by the test and recorded in DESIGN.md.  Indices stay exact.
+VARB_METRIC_TOL = 1e-5
+# The 60000-epoch closed-loop comparison needs correlator sums that follow the float64 reference far below 1e-6: whenever the code
+# phase of a block start passes a sample-grid alignment, ~1000 samples of that block lie within 1e-6 chips of a chip edge at once,
+# and a loop state that is off by 1e-10 chips (fp32 sums) flips one of them about once per channel-minute, after which the two
+# closed loops separate for good (profiles/r02_parity_60000.md).  1 = run it in the float64 checking mode.
+FULL_SIZE_EXACT = 1
 
 
 def _acq_case(fs, nsat, seed, sv_extra, nonCoh=20, cn0=None, band=7000.0):
@@ -254,13 +264,15 @@ def test_full_size_acquisition_grid_vs_oracle():
     ref = c_acquisition(raw, s, s.acqSatelliteList)
     worst = _check_acq(got, ref, s.acqSatelliteList)
     assert int(np.sum(got["carrFreq"] != 0)) >= 8
-    assert np.array_equal(got["coarseCodePhase"], ref["coarseCodePhase"]) or worst < METRIC_TOL
+    # PRNs that are not acquired too: the coarse code phase of a noise-only cell is the arg max of 32736 nearly equal values
+    assert np.array_equal(got["coarseCodePhase"], ref["coarseCodePhase"])
+    print(f"[parity] full 32 x 29 grid: worst peakMetric error {worst:.2e}")
     eng.close()
 
 
 def test_full_size_tracking_properties():
     """BASELINE configs[2] at full size (12 channels x 60000 ms on a 60 s record generated on the GPU):
-    size-independent properties + the oracle on the first 400 epochs of every channel."""
+    size-independent properties + the C oracle on every one of the 12 x 60000 epochs."""
     import torch
     fs, nms = 16.368e6, 60000
     sc = scene(fs, nsat=12, seed=77)
@@ -276,6 +288,7 @@ def test_full_size_tracking_properties():
     found = {c["PRN"] for c in ch if c["PRN"]}
     assert found == {x.prn for x in sc.sats}
     prn = [c["PRN"] for c in ch]; af = [c["acquiredFreq"] for c in ch]; cp = [float(c["codePhase"]) for c in ch]
+    eng.set_param(GC_PARAM_TRACK_EXACT_SUMS, FULL_SIZE_EXACT)
     out, vv, vi, done = eng.track(prn, af, cp, nms)
     assert np.all(done == nms)
     sat_of = {x.prn: x for x in sc.sats}
@@ -296,13 +309,23 @@ def test_full_size_tracking_properties():
         assert np.all(np.hypot(out[c, 3], out[c, 7]) > 0)
         # C/N0 estimate within 3 dB of the injected value
         assert abs(np.median(vv[c, 10:]) - sat.cn0) < 3.0, (np.median(vv[c, 10:]), sat.cn0)
-    # same bytes through the oracle for the first 400 epochs
-    n0 = 400
-    raw = rec[: 2 * N * (n0 + 50)].cpu().numpy()
-    ref, _, _, rdone = c_tracking(raw, s, prn, af, cp, n0)
-    assert np.array_equal(out[:, 0, :n0], ref[:, 0])
-    errs = track_rel_err(out[:, :, :n0], ref)
-    assert errs["I_P"] < IQ_TOL and errs["Q_P"] < IQ_TOL, errs
+    # the same bytes through the C oracle for ALL 60000 epochs of all 12 channels (OpenMP over channels, about half a minute):
+    # block boundaries exact, every correlator sum within 1e-6 of |P|, the NCO rows at their own bars
+    raw = rec.cpu().numpy()
+    ref, rvv, rvi, rdone = c_tracking(raw, s, prn, af, cp, nms, parallel=1)
+    assert np.array_equal(done, rdone)
+    assert np.array_equal(out[:, 0], ref[:, 0]), "absoluteSample differs somewhere in the minute"
+    errs = track_rel_err(out, ref)
+    print("[parity] configs[2] 12 x 60000 epochs vs C oracle:", {k: float("%.3g" % v) for k, v in errs.items()})
+    for f in ("I_P", "Q_P", "I_E", "Q_E", "I_L", "Q_L"):
+        assert errs[f] < IQ_TOL, (f, errs[f])
+    assert errs["codeFreq"] < 1e-9 and errs["carrFreq"] < 1e-6, errs
+    d = np.abs(out[:, 14] - ref[:, 14])
+    d = np.minimum(d, np.abs(d - 2 * np.pi))
+    assert d.max() < 1e-6 and np.abs(out[:, 13] - ref[:, 13]).max() < 1e-7, (d.max(), np.abs(out[:, 13] - ref[:, 13]).max())
+    assert np.allclose(vv, rvv, rtol=1e-5) and np.array_equal(vi, rvi)
+    from helpers import PARITY_REPORT
+    PARITY_REPORT.append(("GPS_L1CA configs[2] 12 ch x 60000 ms vs C oracle (no window needed)", nms, nms, max(errs["I_P"], errs["Q_P"]), 0.0))
     eng.close()
 
 
@@ -565,11 +588,12 @@ def test_fam5_acquisition_vs_oracle(signal, path, monkeypatch):
     eng.close()
 
 
-@pytest.mark.parametrize("signal,pilot", [("GPS_L5C", 1), ("GPS_L5C", 0), ("GAL_E5a", 1), ("GAL_E5b", 1), ("BDS_B2a", 1)])
-def test_fam5_tracking_and_wrappers_vs_oracle(signal, pilot, tmp_path):
+@pytest.mark.parametrize("signal,pilot,nE,exact", [("GPS_L5C", 1, 1200, 0), ("GPS_L5C", 1, 1200, 1), ("GPS_L5C", 0, 240, 0), ("GAL_E5a", 1, 240, 0),
+                                                   ("GAL_E5a", 1, 240, 1), ("GAL_E5b", 1, 240, 0), ("BDS_B2a", 1, 240, 0), ("BDS_B2a", 1, 240, 1)])
+def test_fam5_tracking_and_wrappers_vs_oracle(signal, pilot, nE, exact, tmp_path):
     """preRun() (carrier-aided code NCO centre) -> tracking() with the quadrature pilot (prompt rotated by -pi/2
-    before the atan, discriminators averaged, Pilot_I_P / Pilot_Q_P recorded), against the NumPy oracle."""
-    nE = 240
+    before the atan, discriminators averaged, Pilot_I_P / Pilot_Q_P recorded), against the NumPy oracle.
+    exact = the engine's float64 checking mode: 1e-6 over the whole run, no window."""
     codes, sc, s, so, sv = _fam5_case(signal, nsat=2, seed=5, extra=[], nonCoh=3, ms=nE, nch=3, pilotTRKflag=pilot,
                                       CNo_VSMinterval=40)
     N = 18000
@@ -586,6 +610,7 @@ def test_fam5_tracking_and_wrappers_vs_oracle(signal, pilot, tmp_path):
     path = tmp_path / "fam5.bin"
     raw.tofile(path)
     eng = Engine(s, codes=codes)
+    eng.set_param(GC_PARAM_TRACK_EXACT_SUMS, exact)
     with open(path, "rb") as fid:
         tr, _ = tracking(fid, ch, s, engine=eng)
     ref = O.tracking_fam5(raw, ref_ch, so, codes)
@@ -593,21 +618,20 @@ def test_fam5_tracking_and_wrappers_vs_oracle(signal, pilot, tmp_path):
     for i in range(2):
         assert tr[i]["status"] == "T" == ref[i]["status"] and tr[i]["epochsDone"] == nE
         assert np.array_equal(tr[i]["absoluteSample"], ref[i]["absoluteSample"])
-        sc_ = np.hypot(ref[i]["I_P"], ref[i]["Q_P"])
         names = ["I_P", "Q_P", "I_E", "I_L", "Q_E", "Q_L"] + (["Pilot_I_P", "Pilot_Q_P"] if pilot else [])
         # 18000 distinct code-phase fractions per epoch: now and then a sample sits within 1e-9 chips of a chip edge
         # and its replica chip hangs on the 10th decimal of remCodePhase (helpers.first_illconditioned_epoch); the
         # 1e-6 comparison runs up to the first such epoch, after it the trajectories may differ by one sample's worth
-        ok = first_illconditioned_epoch(ref[i]["remCodePhase"], ref[i]["codeFreq"], tr[i]["remCodePhase"], tr[i]["codeFreq"],
-                                        ref[i]["absoluteSample"], 18e6, s.dllCorrelatorSpacing)
-        assert ok >= 10
-        for name in names:
-            assert np.max(np.abs(tr[i][name][:ok] - ref[i][name][:ok]) / sc_[:ok]) < IQ_TOL, name
-            assert np.max(np.abs(tr[i][name] - ref[i][name]) / sc_) < 1e-2, name
+        ok, _, _ = windowed_iq_compare(f"{signal} pilot={pilot} ch{i} 18 Msps", tr[i], ref[i], names, 18e6, s.dllCorrelatorSpacing, exact=bool(exact))
         assert ("Pilot_I_P" in tr[i]) == bool(pilot)
         assert np.max(np.abs(tr[i]["carrFreq"][:ok] - ref[i]["carrFreq"][:ok])) < 1e-4
         assert np.max(np.abs(tr[i]["codeFreq"][:ok] - ref[i]["codeFreq"][:ok])) < 1e-4
         assert np.max(np.abs(tr[i]["carrFreq"] - ref[i]["carrFreq"])) < 0.05
+        if exact:                                          # the loop state follows the float64 reference closely
+            assert np.max(np.abs(tr[i]["remCodePhase"] - ref[i]["remCodePhase"])) < 1e-11
+            assert np.max(np.abs(tr[i]["codeFreq"] - ref[i]["codeFreq"])) < 1e-8 and np.max(np.abs(tr[i]["carrFreq"] - ref[i]["carrFreq"])) < 1e-8
+            d = np.abs(tr[i]["remCarrPhase"] - ref[i]["remCarrPhase"])
+            assert np.max(d) < 1e-9, np.max(d)
         if signal == "BDS_B2a":
             assert tr[i]["DataCNo"].shape == (nE // 40,) and np.all(np.isfinite(tr[i]["DataCNo"])) and "PilotCNo" in tr[i]
         else:
@@ -707,16 +731,17 @@ def test_varb_acquisition_vs_oracle(signal, fs):
     assert np.array_equal(got["codePhase"], ref["codePhase"]), "code phase differs"
     assert np.array_equal(got["coarseBin"][idx], ref["coarseBin"][idx]) and np.array_equal(got["coarseCodePhase"][idx], ref["coarseCodePhase"][idx])
     rel = np.abs(got["peakMetric"][idx] - ref["peakMetric"][idx]) / ref["peakMetric"][idx]
-    assert rel.max() < 1e-5, rel.max()          # a ratio of two fp32 magnitudes
+    print(f"[parity] {signal} {fs / 1e6:g} Msps variant B peakMetric: worst relative error {rel.max():.2e}")
+    assert rel.max() < VARB_METRIC_TOL, rel.max()
     for sat in sc.sats:
         assert got["carrFreq"][sat.prn - 1] != 0
     assert got["carrFreq"][30 - 1] == 0
     eng.close()
 
 
-def test_b1i_tracking_and_wrappers_vs_oracle(tmp_path):
+@pytest.mark.parametrize("nE,exact", [(1200, 0), (1200, 1)])
+def test_b1i_tracking_and_wrappers_vs_oracle(nE, exact, tmp_path):
     """BDS B1I tracking() (1 ms epochs, 2046-chip code from the caller, three-coefficient carrier filter) vs the oracle."""
-    nE = 200
     codes, sc, s, so, sv = _varb_case("BDS_B1I", 18e6, nsat=2, seed=3, extra=[], cn0=48, msToProcess=nE, numberOfChannels=3,
                                       CNo_VSMinterval=40)
     N = 18000
@@ -729,19 +754,17 @@ def test_b1i_tracking_and_wrappers_vs_oracle(tmp_path):
     path = tmp_path / "b1i.bin"
     raw.tofile(path)
     eng = Engine(s, codes=codes)
+    eng.set_param(GC_PARAM_TRACK_EXACT_SUMS, exact)
     with open(path, "rb") as fid:
         tr, _ = tracking(fid, ch, s, engine=eng)
     ref = O.tracking_b1i(raw, ch, so, codes)
     for i in range(2):
         assert tr[i]["status"] == "T" == ref[i]["status"] and tr[i]["epochsDone"] == nE
         assert np.array_equal(tr[i]["absoluteSample"], ref[i]["absoluteSample"])
-        ok = first_illconditioned_epoch(ref[i]["remCodePhase"], ref[i]["codeFreq"], tr[i]["remCodePhase"], tr[i]["codeFreq"],
-                                        ref[i]["absoluteSample"], 18e6, s.dllCorrelatorSpacing)
-        assert ok >= 10
-        sc_ = np.hypot(ref[i]["I_P"], ref[i]["Q_P"])
-        for name in ("I_P", "Q_P", "I_E", "I_L", "Q_E", "Q_L"):
-            assert np.max(np.abs(tr[i][name][:ok] - ref[i][name][:ok]) / sc_[:ok]) < IQ_TOL, name
+        ok, _, _ = windowed_iq_compare(f"BDS_B1I ch{i} 18 Msps", tr[i], ref[i], ("I_P", "Q_P", "I_E", "I_L", "Q_E", "Q_L"), 18e6,
+                                       s.dllCorrelatorSpacing, exact=bool(exact))
         assert np.max(np.abs(tr[i]["carrFreq"][:ok] - ref[i]["carrFreq"][:ok])) < 1e-4
+        assert np.max(np.abs(tr[i]["carrFreq"] - ref[i]["carrFreq"])) < 0.05
         assert "Pilot_I_P" not in tr[i]
     assert tr[2]["status"] == "-"
     eng.close()
@@ -777,8 +800,8 @@ def test_b1c_acquisition_vs_oracle(fs, pilot):
     eng.close()
 
 
-@pytest.mark.parametrize("fs,nE", [(2.046e6, 60), (8e6, 12)])
-def test_l2c_tracking_and_wrappers_vs_oracle(fs, nE, tmp_path):
+@pytest.mark.parametrize("fs,nE,exact", [(2.046e6, 60, 0), (8e6, 12, 0), (8e6, 12, 1)])
+def test_l2c_tracking_and_wrappers_vs_oracle(fs, nE, exact, tmp_path):
     """GPS L2C tracking() with pilotTRKflag == 0: 20 ms epochs (160000 samples at 8 Msps) in half-chip units on the
     return-to-zero CM table, fseek to codePhase, fractional absoluteSample, halved recorded code quantities."""
     codes, sc, s, so, sv = _varb_case("GPS_L2C", fs, nsat=2, seed=3, extra=[], cn0=45, msToProcess=20 * nE, numberOfChannels=3,
@@ -793,17 +816,14 @@ def test_l2c_tracking_and_wrappers_vs_oracle(fs, nE, tmp_path):
     path = tmp_path / "l2c.bin"
     raw.tofile(path)
     eng = Engine(s, codes=codes)
+    eng.set_param(GC_PARAM_TRACK_EXACT_SUMS, exact)
     with open(path, "rb") as fid:
         tr, _ = tracking(fid, ch, s, engine=eng)
     ref = O.tracking_l2c(raw, ch, so, codes)
     for i in range(2):
         assert tr[i]["status"] == "T" == ref[i]["status"] and tr[i]["epochsDone"] == nE
-        ok = first_illconditioned_epoch(2 * ref[i]["remCodePhase"], 2 * ref[i]["codeFreq"], 2 * tr[i]["remCodePhase"], 2 * tr[i]["codeFreq"],
-                                        np.floor(ref[i]["absoluteSample"]), fs, 2 * s.dllCorrelatorSpacing)
-        assert ok >= min(10, nE)
-        sc_ = np.hypot(ref[i]["I_P"], ref[i]["Q_P"])
-        for name in ("I_P", "Q_P", "I_E", "I_L", "Q_E", "Q_L"):
-            assert np.max(np.abs(tr[i][name][:ok] - ref[i][name][:ok]) / sc_[:ok]) < IQ_TOL, name
+        ok, _, _ = windowed_iq_compare(f"GPS_L2C ch{i} {fs / 1e6:g} Msps", tr[i], ref[i], ("I_P", "Q_P", "I_E", "I_L", "Q_E", "Q_L"), fs,
+                                       s.dllCorrelatorSpacing, rem_scale=2.0, abs_sample=np.floor(ref[i]["absoluteSample"]), exact=bool(exact))
         assert np.max(np.abs(tr[i]["absoluteSample"][:ok] - ref[i]["absoluteSample"][:ok])) < 1e-5      # fractional samples
         assert np.max(np.abs(tr[i]["carrFreq"][:ok] - ref[i]["carrFreq"][:ok])) < 1e-4
         assert np.max(np.abs(tr[i]["codeFreq"][:ok] - ref[i]["codeFreq"][:ok])) < 1e-4
@@ -851,8 +871,8 @@ def test_l2c_cl_phase_search_vs_oracle():
     eng.close()
 
 
-@pytest.mark.parametrize("fs,nE", [(2.046e6, 80), (8e6, 10)])
-def test_l2c_cl_pilot_tracking_vs_oracle(fs, nE, tmp_path):
+@pytest.mark.parametrize("fs,nE,exact", [(2.046e6, 80, 0), (8e6, 10, 0), (8e6, 10, 1)])
+def test_l2c_cl_pilot_tracking_vs_oracle(fs, nE, exact, tmp_path):
     """GPS L2C tracking() with the CL pilot (pilotTRKflag == 1): the pilot table is the CL segment CLCodePhase points at,
     reloaded every 20 ms epoch and stepping 1..75 (past the wrap here); both discriminator pairs averaged; six Pilot rows."""
     codes, sc, s, so, sv = _l2c_pilot_case(fs, nE)
@@ -867,17 +887,15 @@ def test_l2c_cl_pilot_tracking_vs_oracle(fs, nE, tmp_path):
     path = tmp_path / "l2c.bin"
     raw.tofile(path)
     eng = Engine(s, codes=codes)
+    eng.set_param(GC_PARAM_TRACK_EXACT_SUMS, exact)
     with open(path, "rb") as fid:
         tr, _ = tracking(fid, ch, s, engine=eng)
     ref = O.tracking_l2c(raw, ch, so, codes)
     for i in range(2):
         assert tr[i]["status"] == "T" == ref[i]["status"] and tr[i]["epochsDone"] == nE
-        ok = first_illconditioned_epoch(2 * ref[i]["remCodePhase"], 2 * ref[i]["codeFreq"], 2 * tr[i]["remCodePhase"], 2 * tr[i]["codeFreq"],
-                                        np.floor(ref[i]["absoluteSample"]), fs, 2 * s.dllCorrelatorSpacing)
-        assert ok >= min(10, nE)
-        sc_ = np.hypot(ref[i]["I_P"], ref[i]["Q_P"])
-        for name in ("I_P", "Q_P", "I_E", "I_L", "Q_E", "Q_L", "Pilot_I_P", "Pilot_Q_P", "Pilot_I_E", "Pilot_I_L", "Pilot_Q_E", "Pilot_Q_L"):
-            assert np.max(np.abs(tr[i][name][:ok] - ref[i][name][:ok]) / sc_[:ok]) < IQ_TOL, name
+        ok, _, _ = windowed_iq_compare(f"GPS_L2C CL pilot ch{i} {fs / 1e6:g} Msps", tr[i], ref[i],
+                                       ("I_P", "Q_P", "I_E", "I_L", "Q_E", "Q_L", "Pilot_I_P", "Pilot_Q_P", "Pilot_I_E", "Pilot_I_L", "Pilot_Q_E", "Pilot_Q_L"),
+                                       fs, s.dllCorrelatorSpacing, rem_scale=2.0, abs_sample=np.floor(ref[i]["absoluteSample"]), exact=bool(exact))
         assert np.max(np.abs(tr[i]["carrFreq"][:ok] - ref[i]["carrFreq"][:ok])) < 1e-4
         assert np.max(np.abs(tr[i]["codeFreq"][:ok] - ref[i]["codeFreq"][:ok])) < 1e-4
         # the pilot carries the CL chips: its prompt correlator is as strong as the data one and in phase with it
@@ -890,8 +908,8 @@ def test_l2c_cl_pilot_tracking_vs_oracle(fs, nE, tmp_path):
     eng.close()
 
 
-@pytest.mark.parametrize("fs,nE", [(4.092e6, 40), (18e6, 6)])
-def test_b1c_wb_tracking_vs_oracle(fs, nE, tmp_path):
+@pytest.mark.parametrize("fs,nE,exact", [(4.092e6, 40, 0), (18e6, 6, 0), (18e6, 6, 1)])
+def test_b1c_wb_tracking_vs_oracle(fs, nE, exact, tmp_path):
     """BDS B1C WB_tracking (pilotTRKflag 2): data BOC(1,1), pilot BOC(1,1) and pilot BOC(6,1) tables (int8, 18 sums), the
     BOC(6,1) index ceil(tcode*6)+1, composite pilot correlations, carrier (data + 3 pilot)/4, code error weighted by
     CalcWeighingFactor's factor, six composite Pilot rows."""
@@ -921,6 +939,7 @@ def test_b1c_wb_tracking_vs_oracle(fs, nE, tmp_path):
     path = tmp_path / "b1c.bin"
     raw.tofile(path)
     eng = Engine(s, codes=codes)
+    eng.set_param(GC_PARAM_TRACK_EXACT_SUMS, exact)
     with open(path, "rb") as fid:
         tr, _ = tracking(fid, ch, s, engine=eng)
     ref = O.tracking_b1c_wb(raw, ch, so, codes, factor)
@@ -928,12 +947,8 @@ def test_b1c_wb_tracking_vs_oracle(fs, nE, tmp_path):
     for i in range(2):
         assert tr[i]["status"] == "T" == ref[i]["status"] and tr[i]["epochsDone"] == nE
         assert np.array_equal(tr[i]["absoluteSample"], ref[i]["absoluteSample"])
-        ok = first_illconditioned_epoch(ref[i]["remCodePhase"], ref[i]["codeFreq"], tr[i]["remCodePhase"], tr[i]["codeFreq"],
-                                        ref[i]["absoluteSample"], fs, s.dllCorrelatorSpacing, sub=12.0)
-        assert ok >= min(6, nE)
-        sc_ = np.hypot(ref[i]["Pilot_I_P"], ref[i]["Pilot_Q_P"])
-        for name in names:
-            assert np.max(np.abs(tr[i][name][:ok] - ref[i][name][:ok]) / sc_[:ok]) < IQ_TOL, name
+        ok, _, _ = windowed_iq_compare(f"BDS_B1C WB ch{i} {fs / 1e6:g} Msps", tr[i], ref[i], names, fs, s.dllCorrelatorSpacing, sub=12.0,
+                                       scale_keys=("Pilot_I_P", "Pilot_Q_P"), exact=bool(exact))
         assert np.max(np.abs(tr[i]["carrFreq"][:ok] - ref[i]["carrFreq"][:ok])) < 1e-4
         assert np.max(np.abs(tr[i]["codeFreq"][:ok] - ref[i]["codeFreq"][:ok])) < 1e-4
         assert np.max(np.abs(tr[i]["dllDiscr"][:ok] - ref[i]["dllDiscr"][:ok])) < 1e-5
@@ -946,8 +961,8 @@ def test_b1c_wb_tracking_vs_oracle(fs, nE, tmp_path):
     eng.close()
 
 
-@pytest.mark.parametrize("fs,nE", [(4.092e6, 40), (18e6, 8)])
-def test_b1c_nb_tracking_and_wrappers_vs_oracle(fs, nE, tmp_path):
+@pytest.mark.parametrize("fs,nE,exact", [(4.092e6, 40, 0), (18e6, 8, 0), (18e6, 8, 1)])
+def test_b1c_nb_tracking_and_wrappers_vs_oracle(fs, nE, exact, tmp_path):
     """BDS B1C NB_tracking (pilotTRKflag 1): 10 ms epochs (180000 samples at 18 Msps, one sample window in shared memory
     next to the two BOC(1,1) tables), carrier-aided code NCO, quadrature pilot atan(-I/Q), 11/40 : 29/40 weights,
     (1 - spacing)-scaled code discriminators, Pilot rows, DataCNo / PLD block on the host."""
@@ -972,18 +987,15 @@ def test_b1c_nb_tracking_and_wrappers_vs_oracle(fs, nE, tmp_path):
     path = tmp_path / "b1c.bin"
     raw.tofile(path)
     eng = Engine(s, codes=codes)
+    eng.set_param(GC_PARAM_TRACK_EXACT_SUMS, exact)
     with open(path, "rb") as fid:
         tr, _ = tracking(fid, ch, s, engine=eng)
     ref = O.tracking_b1c_nb(raw, ch, so, codes)
     for i in range(2):
         assert tr[i]["status"] == "T" == ref[i]["status"] and tr[i]["epochsDone"] == nE
         assert np.array_equal(tr[i]["absoluteSample"], ref[i]["absoluteSample"])
-        ok = first_illconditioned_epoch(ref[i]["remCodePhase"], ref[i]["codeFreq"], tr[i]["remCodePhase"], tr[i]["codeFreq"],
-                                        ref[i]["absoluteSample"], fs, s.dllCorrelatorSpacing, sub=2.0)
-        assert ok >= min(8, nE)
-        sc_ = np.hypot(ref[i]["Pilot_I_P"], ref[i]["Pilot_Q_P"])
-        for name in ("I_P", "Q_P", "I_E", "I_L", "Q_E", "Q_L", "Pilot_I_P", "Pilot_Q_P"):
-            assert np.max(np.abs(tr[i][name][:ok] - ref[i][name][:ok]) / sc_[:ok]) < IQ_TOL, name
+        ok, _, _ = windowed_iq_compare(f"BDS_B1C NB ch{i} {fs / 1e6:g} Msps", tr[i], ref[i], ("I_P", "Q_P", "I_E", "I_L", "Q_E", "Q_L", "Pilot_I_P", "Pilot_Q_P"),
+                                       fs, s.dllCorrelatorSpacing, sub=2.0, scale_keys=("Pilot_I_P", "Pilot_Q_P"), exact=bool(exact))
         assert np.max(np.abs(tr[i]["carrFreq"][:ok] - ref[i]["carrFreq"][:ok])) < 1e-4
         assert np.max(np.abs(tr[i]["codeFreq"][:ok] - ref[i]["codeFreq"][:ok])) < 1e-4
         assert tr[i]["DataCNo"].shape == (nE // 4,) and "B1C_CNo" in tr[i] and np.all(np.isfinite(tr[i]["PilotCNo"]))
