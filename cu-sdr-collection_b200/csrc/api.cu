@@ -1681,7 +1681,7 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
     for (int ch = 0; ch < nCh; ++ch) nLive += (sv[ch] != 0);
     int cluster = 1;
     for (int g = 8; g >= 2; g /= 2)
-        if (nCh * g <= 148) { cluster = g; break; }
+        if (nCh * g <= 148) { cluster = g; break; }   // (every B200 has 148 SMs; `sms` below is read from the device for the batch split)
     if (const char* e = getenv("GC_TRACK_CLUSTER")) { const int g = atoi(e); if (g == 1 || g == 2 || g == 4 || g == 8) cluster = g; }
     (void)nLive;
     p.codeLen = codeLen; p.codeStride = stride; p.pilotStride = pstride; p.p61Stride = p61stride; p.subChip = h->sub; p.pilot = h->pilotMode;
@@ -1695,6 +1695,15 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
     p.singleBuf = track_smem_bytes(p.bufBytes, codeLen, p.pilot) > 227 * 1024 ? 1 : 0;   // B1C: 45 KB windows + two 82 KB tables
     if (track_smem_bytes(p.bufBytes, codeLen, p.pilot, p.singleBuf) > 227 * 1024)
         return fail(h, GC_ERR_UNSUPPORTED, "gc_track: one code period of samples does not fit in shared memory");
+    // more channels than SMs: 256-thread CTAs, two per SM (each needs half of the shared memory)
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device);
+    int batch = (cluster == 1 && nCh > sms && h->pilotMode != 5 && !getenv("GC_TRACK_NO_BATCH")) ? 1 : 0;
+    if (batch && 2 * (track_smem_bytes(p.bufBytes, codeLen, p.pilot, p.singleBuf, 0) + 1024) > 227 * 1024) batch = 0;
+    {
+        const size_t withSlots = track_smem_bytes(p.bufBytes, codeLen, p.pilot, p.singleBuf, track_threads(cluster, batch));
+        p.preSlots = (h->fmt == 0 && !p.exact && (batch ? 2 * (withSlots + 1024) : withSlots) <= 227 * 1024) ? 1 : 0;
+    }
     GC_CUDA(h, upload(h->chans, chans, st));
     GC_CUDA(h, upload(h->trackCodes, tabs, st));
     if (pilot) GC_CUDA(h, upload(h->trackPilot, ptabs, st));
@@ -1709,7 +1718,7 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
     p.dbg = dbg;
     GC_CUDA(h, launch_track_fill(h->trackOut.p, nCh, nRows, nEpochs, st));
     cudaEventRecord(h->ev[0], st);
-    GC_CUDA(h, launch_track(p, nCh, cluster, st));
+    GC_CUDA(h, launch_track(p, nCh, cluster, batch, st));
     cudaEventRecord(h->ev[1], st);
     const int vint = c.cno_vsm_interval, nV = nEpochs / vint;
     const bool wantVsm = vsmValue && vsmIndex && nV > 0;

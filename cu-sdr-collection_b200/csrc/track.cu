@@ -43,7 +43,7 @@ constexpr int kPad61 = 96;   // same for the BOC(6,1) table, whose index runs si
 constexpr int kStage = 16;   // epochs of results staged in smem before a coalesced flush
 constexpr double kCeilMagic = 6755399441055744.0;   // 1.5 * 2^52: t + magic stays in [2^52, 2^53) for |t| < 2^51
 
-struct EpochParams {          // parameters of the block being correlated (read by every thread)
+struct alignas(16) EpochParams {   // parameters of the block being correlated (read by every thread)
     double aE, aP, aL;        // first elements of the early/prompt/late tcode vectors (tracking.m:252-266)
     double cE, cP, cL;        // last elements
     double mE, mP, mL;        // middle elements (a+c)/2, used when the vector length is odd
@@ -55,8 +55,14 @@ struct EpochParams {          // parameters of the block being correlated (read 
     long long pos;            // first sample of this block (absolute, in complex samples)
     uint64_t phase0, dphi;    // carrier phase at sample 0 and per-sample increment (turns, 0.64)
     int stop;
+    int fast;                 // every chunk of 8 samples holds at most one table-entry edge per correlator (8*d*subChip <= 1) and the
+                              // three colon vectors share their length: indices by the per-chunk edge prediction
+    uint32_t rinv;            // floor(2^24 / (d*subChip)): samples per table entry in 8.24 fixed point
     int pad;
     double codeFreq, carrFreq, remCodePhase, remCarrPhase;   // values used in this block (recorded)
+    // in-chunk carrier rotations e^{-i*2*pi*j*dphi}, j = 0..7, and the bias terms of the byte -> double trick (written by eight
+    // lanes of the carrier-loop warp): rot[j] = {cos, sin, B*(cos + sin), B*(cos - sin)}
+    alignas(16) double rot[8][4];
 };
 
 struct NextPhases {           // NCO phases at the end of the block being correlated (warp 2)
@@ -160,6 +166,12 @@ __device__ void plan_epoch(const TrackParams& p, double codeFreq, double remCode
     // zero padding of the code table
     ep.generic = !(ep.nE == blk - 1 && ep.nP == blk - 1 && ep.nL == blk - 1) || !((8.0 * step + p.spc) * (double)p.subChip + 2.0 < (double)kPad) ||
                  (p.pilot == 5 && !((8.0 * step + p.spc) * (double)p.subChip * 6.0 + 2.0 < (double)kPad61));
+    {   // per-chunk edge prediction (track_kernel, fast chunks): needs at most one table-entry edge per correlator in 8 samples and a
+        // samples-per-entry count that fits 8.24 fixed point
+        const double dt = step * (double)p.subChip;
+        ep.fast = (!ep.generic && 8.0 * dt <= 1.0 && dt >= 0.0078125 && p.pilot != 5) ? 1 : 0;
+        ep.rinv = ep.fast ? (uint32_t)(16777216.0 * y / (double)p.subChip) : 0u;     // y = 1/step to ~1e-12: far inside the margin
+    }
     ep.mE = __dmul_rn(__dadd_rn(ep.aE, ep.cE), 0.5);
     ep.mP = __dmul_rn(__dadd_rn(ep.aP, ep.cP), 0.5);
     ep.mL = __dmul_rn(__dadd_rn(ep.aL, ep.cL), 0.5);
@@ -192,11 +204,63 @@ __device__ __forceinline__ void end_phases(const TrackParams& p, const EpochPara
     }
 }
 
-// exact float of a signed byte already xor-ed with 0x80: 0x4B0000bb = 2^23 + (b+128)
-__device__ __forceinline__ float byte_to_float(uint32_t wx, uint32_t sel)
+// ---- float64 carrier phasors from the 64-bit fixed-point phase -------------------------------------------------------------
+// cos / sin(2*pi*phase) = table entry of the nearest 1/1024 turn rotated by the remainder (|alpha| <= 2*pi/2048: Taylor terms
+// up to alpha^5, next one < 1e-18).  About 15 float64 instructions and one 16-byte load; error ~2e-16.
+__device__ const double2 g_sincos1024[1024] = {
+#include "sincos1024.inc"
+};
+__device__ __forceinline__ void fix_sincos_f64(uint64_t phase, double* sn, double* cs)
 {
-    return __uint_as_float(__byte_perm(wx, 0x4B000000u, sel)) - 8388736.0f;
+    const uint64_t rounded = phase + (1ull << 53);
+    const uint32_t idx = (uint32_t)(rounded >> 54);                                // nearest 1/1024 turn (1024 wraps to 0 below)
+    const long long r = (long long)(phase - (rounded & ~((1ull << 54) - 1)));      // signed remainder, |r| <= 2^53
+    const double alpha = __dmul_rn(__ll2double_rn(r), 3.4061215800865545e-19);     // 2*pi * 2^-64
+    const double a2 = __dmul_rn(alpha, alpha);
+    const double c = __fma_rn(a2, __fma_rn(a2, 4.1666666666666664e-2, -0.5), 1.0);
+    const double t = __dmul_rn(alpha, __fma_rn(a2, __fma_rn(a2, 8.3333333333333332e-3, -1.6666666666666666e-1), 1.0));
+    const double2 T = g_sincos1024[idx & 1023u];
+    *cs = __fma_rn(-T.y, t, __dmul_rn(T.x, c));
+    *sn = __fma_rn(T.x, t, __dmul_rn(T.y, c));
 }
+
+// ---- byte -> double without a conversion instruction (I2F.F64 and F2F.F64 issue at 1/8 rate on this part) ------------------
+// The sample byte, already xor-ed with 0x80 (b' = x + 128), is permuted into bits 8-15 of the high word 0x40B0xx00 of a double
+// whose low word is zero: that double is exactly 4096 + b' = kByteBias + x.  The bias is removed inside the wipe-off FMA chain:
+// wc*(B + xr) + ws*(B + xq) - B*(wc + ws), with B*(wc + ws) a per-epoch constant (EpochParams::rot).  One PRMT per component.
+constexpr double kByteBias = 4224.0;
+__device__ __forceinline__ double byte_to_biased_double(uint32_t wx, uint32_t sel)
+{
+    return __hiloint2double((int)__byte_perm(wx, 0x40B00000u, sel), 0);
+}
+
+// ---- code tables in shared memory: the HIGH WORD of the entry as a double (low word zero), so that a looked-up entry enters a
+// DFMA without any conversion.  uint32_t: 0x3FF00000 / 0xBFF00000 / 0 = +1 / -1 / 0.  uint8_t (where three tables have to fit,
+// B1C full band): the top byte 0x40 / 0xC0 / 0 = +2 / -2 / 0, the sums are halved after the reduction (exact).
+template <typename TT> struct CodeEnc;
+template <> struct CodeEnc<uint32_t> {
+    static __device__ __forceinline__ uint32_t store(int8_t v) { return v > 0 ? 0x3FF00000u : v < 0 ? 0xBFF00000u : 0u; }
+    static __device__ __forceinline__ uint32_t hi(uint32_t e) { return e; }
+    static constexpr double kScale = 1.0;
+};
+template <> struct CodeEnc<uint8_t> {
+    static __device__ __forceinline__ uint8_t store(int8_t v) { return v > 0 ? 0x40 : v < 0 ? 0xC0 : 0; }
+    static __device__ __forceinline__ uint32_t hi(uint8_t e) { return (uint32_t)e << 24; }
+    static constexpr double kScale = 0.5;
+};
+__device__ __forceinline__ double hi2d(uint32_t hi) { return __hiloint2double((int)hi, 0); }
+
+// in-chunk rotations of the block whose carrier plan_carrier just wrote: lane j < 8 of the calling warp fills rot[j]
+__device__ __forceinline__ void plan_rotations(EpochParams& ep, int lane, double bias)
+{
+    if (lane < 8) {
+        double sn, cs;
+        fix_sincos_f64(ep.dphi * (uint64_t)lane, &sn, &cs);
+        ep.rot[lane][0] = cs; ep.rot[lane][1] = sn;
+        ep.rot[lane][2] = __dmul_rn(bias, __dadd_rn(cs, sn)); ep.rot[lane][3] = __dmul_rn(bias, __dsub_rn(cs, sn));
+    }
+}
+
 
 __device__ __forceinline__ uint32_t cluster_ctarank()
 {
@@ -224,7 +288,7 @@ __device__ __forceinline__ void dsmem_push(double* local, uint64_t* bar, uint32_
 
 // G = CTAs per channel (cluster size), T = threads per CTA, NSET = replicas correlated (1 data; 2 data + pilot, 12 sums;
 // 3 data + pilot BOC(1,1) + pilot BOC(6,1), 18 sums - B1C WB_tracking.m), TT = storage type of the code tables in
-// shared memory (float, or int8_t where three tables have to fit)
+// shared memory (CodeEnc: uint32_t, or uint8_t where three tables have to fit)
 // FMT0 = the record is int8 I,Q (bulk-copied windows, byte-permute conversion); false = the per-sample accessor for the
 // int16 / real formats (a separate instantiation, so that the fast path's code is not touched by it)
 // EXACT = the float64 checking mode (TrackParams::exact, GC_PARAM_TRACK_EXACT_SUMS): carrier exp(-1i*trigarg) per sample in float64 from
@@ -232,10 +296,11 @@ __device__ __forceinline__ void dsmem_push(double* local, uint64_t* bar, uint32_
 // loop state then follows the float64 reference to ~1e-13 instead of ~1e-10, which is what the parity tests use to show that the
 // windows they skip at 18 Msps are conditioning (a sample within 1e-9 chips of a chip edge) and not an error of this kernel.
 template <int G, int T, int NSET, typename TT, bool FMT0, bool EXACT>
-__global__ void __launch_bounds__(T, 1)
+__global__ void __launch_bounds__(T, T <= 256 ? 2 : 1)
 track_kernel(TrackParams p)
 {
     constexpr bool PILOT = NSET >= 2;
+    using Enc = CodeEnc<TT>;
     constexpr int NS = 6 * NSET;                                 // correlator sums per epoch
     constexpr int kThreads = T;
     constexpr int kWarps = T / 32;
@@ -262,6 +327,8 @@ track_kernel(TrackParams p)
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_nx + 1);     // 2 mbarriers (TMA stages) + 2 (partial-sum exchange)
     uint64_t* s_xbar = s_bar + 2;
     int* s_issued = reinterpret_cast<int*>(s_bar + 4);           // per stage: 1 + epoch whose window was requested (0 = none)
+    // [7][T] running sums of the fast chunks (TrackParams::preSlots), one 16-byte column per thread
+    double2* s_pre = reinterpret_cast<double2*>((reinterpret_cast<uintptr_t>(s_issued + 2) + 15) & ~(uintptr_t)15);
 
     const int ch = blockIdx.x / G;
     const uint32_t crank = (G > 1) ? cluster_ctarank() : 0u;
@@ -277,18 +344,15 @@ track_kernel(TrackParams p)
     // wrapped code table [c(L) c(1..L) c(1)]  (tracking.m:156-158)
     for (int i = tid; i < p.codeLen + 2 + 2 * kPad; i += kThreads) {
         const int j = i - kPad;
-        s_code_raw[i] = (j >= 0 && j < p.codeLen + 2) ? (TT)p.codeTables[(size_t)ch * p.codeStride + j] : (TT)0;
-        if (PILOT) s_code_raw[tabFloats + i] = (p.pilot != 4 && j >= 0 && j < p.codeLen + 2) ? (TT)p.pilotTables[(size_t)ch * p.pilotStride + j] : (TT)0;
+        s_code_raw[i] = (j >= 0 && j < p.codeLen + 2) ? Enc::store(p.codeTables[(size_t)ch * p.codeStride + j]) : (TT)0;
+        if (PILOT) s_code_raw[tabFloats + i] = (p.pilot != 4 && j >= 0 && j < p.codeLen + 2) ? Enc::store(p.pilotTables[(size_t)ch * p.pilotStride + j]) : (TT)0;
     }
     if (NSET == 3)                                               // [p61(12L) p61 p61(1)] (B1C WB_tracking.m:181-183)
         for (int i = tid; i < p.codeLen * 6 + 2 + 2 * kPad61; i += kThreads) {
             const int j = i - kPad61;
-            s_code_raw[2 * tabFloats + i] = (j >= 0 && j < p.codeLen * 6 + 2) ? (TT)p.p61Tables[(size_t)ch * p.p61Stride + j] : (TT)0;
+            s_code_raw[2 * tabFloats + i] = (j >= 0 && j < p.codeLen * 6 + 2) ? Enc::store(p.p61Tables[(size_t)ch * p.p61Stride + j]) : (TT)0;
         }
 
-    // byte selectors: sample bytes are I,Q,I,Q; GLONASS takes rawSignal = Q + 1i*I (GLO tracking.m:227)
-    const uint32_t selI0 = p.swapIQ ? 0x7651u : 0x7650u, selQ0 = p.swapIQ ? 0x7650u : 0x7651u;
-    const uint32_t selI1 = p.swapIQ ? 0x7653u : 0x7652u, selQ1 = p.swapIQ ? 0x7652u : 0x7653u;
     LoopMem lm;   // PLL thread: carrier memories; DLL thread: code memories
     lm.oldCodeNco = lm.oldCodeError = lm.oldCarrNco = lm.oldCarrError = 0.0;   // :173-178
     lm.carrFreqBasis = cinfo.acqFreq;                                          // :168
@@ -306,6 +370,8 @@ track_kernel(TrackParams p)
         plan_epoch(p, cinfo.codeFreq0, 0.0, 0.0, 0ull, cinfo.startSample, s_ep[0], inv0);
         plan_carrier(p, cinfo.acqFreq, s_ep[0]);
     }
+    __syncthreads();
+    if (warp == 0) plan_rotations(s_ep[0], lane, FMT0 ? kByteBias : 0.0);
     __syncthreads();
 
     const long long recBytesUp = (p.recSamples * 2 + 15) & ~15LL;
@@ -352,7 +418,7 @@ track_kernel(TrackParams p)
             // Every thread finished the previous epoch's lookups at the barrier that ended it.
             const int seg = (cinfo.clPhase - 1 + e) % 75;
             const int8_t* cl = p.pilotTables + (size_t)ch * p.pilotStride + (size_t)seg * p.codeLen;
-            for (int i = tid; i < p.codeLen + 2; i += kThreads) s_pilot[i] = (TT)cl[i];
+            for (int i = tid; i < p.codeLen + 2; i += kThreads) s_pilot[i] = Enc::store(cl[i]);
             __syncthreads();
         }
         // window of epoch e+1 starts where this one ends; fetch it while we correlate
@@ -362,17 +428,6 @@ track_kernel(TrackParams p)
         if (staged) { mbar_wait(&s_bar[stage], phase[stage]); phase[stage] ^= 1u; }
         GC_TICK(1)
 
-        // in-chunk rotations e^{-i*2*pi*j*dphi}, j = 0..7 (per-epoch constants)
-        float wc[8], ws[8];
-        {
-            float s, c;
-            fix_sincos(dphi * (uint64_t)(lane & 7), &s, &c);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                wc[j] = __shfl_sync(0xffffffffu, c, j);
-                ws[j] = __shfl_sync(0xffffffffu, s, j);
-            }
-        }
         const int off = (int)((pos * 2) & 15) >> 1;              // samples skipped in the first 16-byte chunk
         const int nChunks = (off + blk + 7) >> 3;
         const bool fits = (nChunks <= cpc * G);
@@ -388,49 +443,63 @@ track_kernel(TrackParams p)
         const double d = ep.d * sc;
         const double aE = ep.aE * sc, aP = ep.aP * sc, aL = ep.aL * sc, cE = ep.cE * sc, cP = ep.cP * sc, cL = ep.cL * sc;
         const bool generic = ep.generic != 0;
-
-        float aIE = 0, aQE = 0, aIP = 0, aQP = 0, aIL = 0, aQL = 0;
-        float bIE = 0, bQE = 0, bIP = 0, bQP = 0, bIL = 0, bQL = 0;     // pilot sums
-        float cIE = 0, cQE = 0, cIP = 0, cQP = 0, cIL = 0, cQL = 0;     // pilot BOC(6,1) sums (NSET == 3)
         const double mE = ep.mE * sc, mP = ep.mP * sc, mL = ep.mL * sc;
         const int nE_ = ep.nE, nP_ = ep.nP, nL_ = ep.nL;
-        double dacc[EXACT ? NS : 1];                              // EXACT: float64 sums (same order as vf below)
+        const uint32_t rinv = ep.rinv;
+        const double2* rot = reinterpret_cast<const double2*>(&ep.rot[0][0]);   // [j][0] = {cos, sin}, [j][1] = {B(cos+sin), B(cos-sin)}
+
+        // float64 sums of this thread: {I_E, Q_E, I_P, Q_P, I_L, Q_L} of the data replica, then of the pilot replica(s)
+        double acc[NS];
 #pragma unroll
-        for (int q = 0; q < (EXACT ? NS : 1); ++q) dacc[q] = 0.0;
-        // One 16-byte chunk = 8 consecutive samples.  SPECIAL = per-sample left/right/middle selection
-        // (the chunk holding the middle of the colon vector, or every chunk of a `generic` block).
-        auto do_chunk = [&](int c, auto special_tag) {
-            constexpr bool SPECIAL = decltype(special_tag)::value;
+        for (int q = 0; q < NS; ++q) acc[q] = 0.0;
+        // One 16-byte chunk = 8 consecutive samples.  Everything that enters a sum is float64: the wipe-off by the per-epoch
+        // in-chunk rotations (two DFMA per component, the byte -> double bias folded in), the +-1 replica entries as doubles built
+        // from their high word, the chunk's carrier phasor from the exact fixed-point phase.  The sums follow the float64 reference
+        // to ~1e-14 of |P|, which a minute-long closed loop needs (profiles/r02_parity_60000.md).  Three ways to the table indices:
+        //   MODE 0  per-chunk edge prediction: with at least 8 samples per table entry a chunk holds at most one edge per
+        //           correlator; the index of the first sample comes from the reference's own expression (exact), the position of
+        //           the edge from a 32-bit fixed-point division.  A sample closer than 2^-24 samples to an edge (or a first sample
+        //           closer than 2^-26 entries) sends the chunk to MODE 1, so the prediction never decides a close call.
+        //   MODE 1  per-sample index from the reference's expression, whole chunk in the left or in the right half of the colon vector
+        //   MODE 2  per-sample left / right / middle selection (the chunk holding the middle, or every chunk of a `generic` block)
+        auto do_chunk = [&](int c, auto mode_tag) {
+            constexpr int MODE = decltype(mode_tag)::value;
             const int k0 = c * 8 - off;
-            float xi[8], xq[8];                                   // tracking.m:233-235
+            const bool masked = (k0 < 0 || k0 + 7 >= blk);        // first / last chunk of the block: samples outside it count as zero
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
             if (FMT0) {
                 int4 raw;
                 if (inBuf) raw = *reinterpret_cast<const int4*>(src + (size_t)c * 16);
                 else raw = __ldg(reinterpret_cast<const int4*>(gsrc + (size_t)c * 16));   // not staged: straight from L2
-                const uint32_t w0 = (uint32_t)raw.x ^ 0x80808080u, w1 = (uint32_t)raw.y ^ 0x80808080u,
-                               w2 = (uint32_t)raw.z ^ 0x80808080u, w3 = (uint32_t)raw.w ^ 0x80808080u;
-                xi[0] = byte_to_float(w0, selI0); xq[0] = byte_to_float(w0, selQ0); xi[1] = byte_to_float(w0, selI1); xq[1] = byte_to_float(w0, selQ1);
-                xi[2] = byte_to_float(w1, selI0); xq[2] = byte_to_float(w1, selQ0); xi[3] = byte_to_float(w1, selI1); xq[3] = byte_to_float(w1, selQ1);
-                xi[4] = byte_to_float(w2, selI0); xq[4] = byte_to_float(w2, selQ0); xi[5] = byte_to_float(w2, selI1); xq[5] = byte_to_float(w2, selQ1);
-                xi[6] = byte_to_float(w3, selI0); xq[6] = byte_to_float(w3, selQ0); xi[7] = byte_to_float(w3, selI1); xq[7] = byte_to_float(w3, selQ1);
-            } else {                                              // int16 and / or real samples (tracking.m:145-149, 229-240)
-                const Rec rec{p.rec, p.fmt};
-                const bool swap = p.swapIQ != 0;
+                w[0] = (uint32_t)raw.x ^ 0x80808080u; w[1] = (uint32_t)raw.y ^ 0x80808080u;
+                w[2] = (uint32_t)raw.z ^ 0x80808080u; w[3] = (uint32_t)raw.w ^ 0x80808080u;
+                if (p.swapIQ) {                                   // GLONASS: rawSignal = Q + 1i*I (GLO tracking.m:227)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const long long si = min(max(pos + k0 + j, 0LL), p.recSamples - 1);
-                    const short2 v = rec.load(si);
-                    xi[j] = (float)(swap ? v.y : v.x); xq[j] = (float)(swap ? v.x : v.y);
+                    for (int q = 0; q < 4; ++q) w[q] = __byte_perm(w[q], 0u, 0x2301u);
+                }
+                if (masked) {                                     // a sample outside the block becomes 0x80 0x80, i.e. x = 0
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if ((unsigned)(k0 + j) >= (unsigned)blk) w[j >> 1] = (j & 1) ? ((w[j >> 1] & 0x0000FFFFu) | 0x80800000u) : ((w[j >> 1] & 0xFFFF0000u) | 0x00008080u);
                 }
             }
-            if (k0 < 0 || k0 + 7 >= blk) {                        // first / last chunk of the block: drop the samples outside it
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if ((unsigned)(k0 + j) >= (unsigned)blk) { xi[j] = 0.f; xq[j] = 0.f; }
-            }
+            // sample j of the chunk as (biased) doubles: rawSignal = I + 1i*Q (tracking.m:233-235), Q + 1i*I for GLONASS
+            auto sample = [&](int j, double& mr, double& mq) {
+                if (FMT0) {
+                    mr = byte_to_biased_double(w[j >> 1], (j & 1) ? 0x7624u : 0x7604u);
+                    mq = byte_to_biased_double(w[j >> 1], (j & 1) ? 0x7634u : 0x7614u);
+                } else {                                          // int16 and / or real samples (tracking.m:145-149, 229-240)
+                    const Rec rec{p.rec, p.fmt};
+                    const long long si = min(max(pos + k0 + j, 0LL), p.recSamples - 1);
+                    const short2 v = rec.load(si);
+                    const bool in = (unsigned)(k0 + j) < (unsigned)blk;
+                    mr = in ? (double)(p.swapIQ ? v.y : v.x) : 0.0;
+                    mq = in ? (double)(p.swapIQ ? v.x : v.y) : 0.0;
+                }
+            };
             if constexpr (EXACT) {
-                // tracking.m:249-300 sample by sample in float64 (the checking mode; SPECIAL is irrelevant here)
-                const double w = __dmul_rn(__dmul_rn(ep.carrFreq, 2.0), 3.141592653589793);            // carrFreq * 2.0 * pi (:281)
+                // tracking.m:249-300 sample by sample in float64 as written (the checking mode)
+                const double w2pi = __dmul_rn(__dmul_rn(ep.carrFreq, 2.0), 3.141592653589793);         // carrFreq * 2.0 * pi (:281)
 #pragma unroll 1
                 for (int j = 0; j < 8; ++j) {
                     const int kc = k0 + j;
@@ -449,33 +518,68 @@ track_kernel(TrackParams p)
                     }
                     const int iE = ceil_idx(tE), iP = ceil_idx(tP), iL = ceil_idx(tL);
                     // time = (0:blksize)./fs; trigarg = ((carrFreq*2.0*pi).*time) + remCarrPhase; carrsig = exp(-1i.*trigarg)  (:280-287)
-                    const double trig = __dadd_rn(__dmul_rn(w, __ddiv_rn((double)kc, p.fs)), ep.remCarrPhase);
+                    const double trig = __dadd_rn(__dmul_rn(w2pi, __ddiv_rn((double)kc, p.fs)), ep.remCarrPhase);
                     double sn, cs;
                     sincos(trig, &sn, &cs);
-                    const double xr = (double)xi[j], xm = (double)xq[j], ci = -sn;                    // carrsig = cs + 1i*ci
+                    double xr, xm;
+                    {
+                        double mr = 0, mq = 0;
+                        switch (j) {                              // (compile-time sample numbers for the byte selectors)
+                            case 0: sample(0, mr, mq); break; case 1: sample(1, mr, mq); break; case 2: sample(2, mr, mq); break;
+                            case 3: sample(3, mr, mq); break; case 4: sample(4, mr, mq); break; case 5: sample(5, mr, mq); break;
+                            case 6: sample(6, mr, mq); break; default: sample(7, mr, mq); break;
+                        }
+                        xr = FMT0 ? mr - kByteBias : mr; xm = FMT0 ? mq - kByteBias : mq;
+                    }
+                    const double ci = -sn;                                                                // carrsig = cs + 1i*ci
                     const double ur = __dsub_rn(__dmul_rn(cs, xr), __dmul_rn(ci, xm));                  // real(carrsig .* rawSignal) (:291)
                     const double ui = __dadd_rn(__dmul_rn(cs, xm), __dmul_rn(ci, xr));                  // imag(...)                  (:292)
-                    const double vE = (double)s_code[iE], vP = (double)s_code[iP], vL = (double)s_code[iL];
-                    dacc[0] += vE * ur; dacc[1] += vE * ui; dacc[2] += vP * ur; dacc[3] += vP * ui; dacc[4] += vL * ur; dacc[5] += vL * ui;
+                    const double vE = hi2d(Enc::hi(s_code[iE])), vP = hi2d(Enc::hi(s_code[iP])), vL = hi2d(Enc::hi(s_code[iL]));
+                    acc[0] += vE * ur; acc[1] += vE * ui; acc[2] += vP * ur; acc[3] += vP * ui; acc[4] += vL * ur; acc[5] += vL * ui;
                     if constexpr (PILOT) {
-                        const double uE = (double)s_pilot[iE], uP = (double)s_pilot[iP], uL = (double)s_pilot[iL];
-                        dacc[6] += uE * ur; dacc[7] += uE * ui; dacc[8] += uP * ur; dacc[9] += uP * ui; dacc[10] += uL * ur; dacc[11] += uL * ui;
+                        const double uE = hi2d(Enc::hi(s_pilot[iE])), uP = hi2d(Enc::hi(s_pilot[iP])), uL = hi2d(Enc::hi(s_pilot[iL]));
+                        acc[6] += uE * ur; acc[7] += uE * ui; acc[8] += uP * ur; acc[9] += uP * ui; acc[10] += uL * ur; acc[11] += uL * ui;
                     }
                     if constexpr (NSET == 3) {
-                        const double wE = (double)s_p61[ceil_idx(__dmul_rn(tE, 6.0))], wP = (double)s_p61[ceil_idx(__dmul_rn(tP, 6.0))],
-                                     wL = (double)s_p61[ceil_idx(__dmul_rn(tL, 6.0))];
-                        dacc[12] += wE * ur; dacc[13] += wE * ui; dacc[14] += wP * ur; dacc[15] += wP * ui; dacc[16] += wL * ur; dacc[17] += wL * ui;
+                        const double wE = hi2d(Enc::hi(s_p61[ceil_idx(__dmul_rn(tE, 6.0))])), wP = hi2d(Enc::hi(s_p61[ceil_idx(__dmul_rn(tP, 6.0))])),
+                                     wL = hi2d(Enc::hi(s_p61[ceil_idx(__dmul_rn(tL, 6.0))]));
+                        acc[12] += wE * ur; acc[13] += wE * ui; acc[14] += wP * ur; acc[15] += wP * ui; acc[16] += wL * ur; acc[17] += wL * ui;
                     }
                 }
                 return;
             }
-            float pIE = 0, pQE = 0, pIP = 0, pQP = 0, pIL = 0, pQL = 0;
-            float qIE = 0, qQE = 0, qIP = 0, qQP = 0, qIL = 0, qQL = 0;
-            float rIE = 0, rQE = 0, rIP = 0, rQP = 0, rIL = 0, rQL = 0;
-            if (!SPECIAL) {
-                // whole chunk in the left half (t = a + k*d) or in the right half (t = c - (n-k)*d).
-                // Samples masked above may have k < 0 or k >= blk; their code index stays inside
-                // the wrapped table (t > -1 and t < codeLength + 1).
+            double ps[NS];                                        // chunk sums before the chunk's carrier phasor
+#pragma unroll
+            for (int q = 0; q < NS; ++q) ps[q] = 0.0;
+            // wipe-off of sample j by the in-chunk rotation and accumulation against the three replica entries (high words)
+            auto mac = [&](int j, uint32_t hE, uint32_t hP, uint32_t hL, uint32_t gE, uint32_t gP, uint32_t gL,
+                           uint32_t fE, uint32_t fP, uint32_t fL) {
+                double mr, mq;
+                sample(j, mr, mq);
+                const double2 r0 = rot[2 * j], r1 = rot[2 * j + 1];
+                // x * e^{-i*j*dphi}   (tracking.m:287-292 with the chunk phase factored out)
+                const double ur = __fma_rn(r0.x, mr, __fma_rn(r0.y, mq, -r1.x));
+                const double ui = __fma_rn(r0.x, mq, __fma_rn(-r0.y, mr, -r1.y));
+                const double vE = hi2d(hE), vP = hi2d(hP), vL = hi2d(hL);
+                ps[0] = __fma_rn(vE, ur, ps[0]); ps[1] = __fma_rn(vE, ui, ps[1]);                     // :295-300
+                ps[2] = __fma_rn(vP, ur, ps[2]); ps[3] = __fma_rn(vP, ui, ps[3]);
+                ps[4] = __fma_rn(vL, ur, ps[4]); ps[5] = __fma_rn(vL, ui, ps[5]);
+                if constexpr (PILOT) {                            // same code phase, pilot table (GAL_E1C tracking.m:241-262)
+                    const double uE = hi2d(gE), uP = hi2d(gP), uL = hi2d(gL);
+                    ps[6] = __fma_rn(uE, ur, ps[6]); ps[7] = __fma_rn(uE, ui, ps[7]);
+                    ps[8] = __fma_rn(uP, ur, ps[8]); ps[9] = __fma_rn(uP, ui, ps[9]);
+                    ps[10] = __fma_rn(uL, ur, ps[10]); ps[11] = __fma_rn(uL, ui, ps[11]);
+                }
+                if constexpr (NSET == 3) {                        // pilotBOC61(ceil(tcode * 6) + 1), B1C WB_tracking.m:283,294,305
+                    const double wE = hi2d(fE), wP = hi2d(fP), wL = hi2d(fL);
+                    ps[12] = __fma_rn(wE, ur, ps[12]); ps[13] = __fma_rn(wE, ui, ps[13]);
+                    ps[14] = __fma_rn(wP, ur, ps[14]); ps[15] = __fma_rn(wP, ui, ps[15]);
+                    ps[16] = __fma_rn(wL, ur, ps[16]); ps[17] = __fma_rn(wL, ui, ps[17]);
+                }
+            };
+            // per-sample indices from the reference's expression (tracking.m:252-270): ceil(tcode) indexes [c(L) c c(1)] 0-based
+            auto by_sample = [&](auto special) {
+                constexpr bool SPECIAL = decltype(special)::value;
                 const bool allLeft = (2 * (k0 + 7) < n);
                 const double sg = allLeft ? 1.0 : -1.0;
                 const double f0 = (double)(allLeft ? k0 : (n - k0));
@@ -483,122 +587,126 @@ track_kernel(TrackParams p)
                 const double bE = allLeft ? aE : cE, bP = allLeft ? aP : cP, bL = allLeft ? aL : cL;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const double st = __dmul_rn(__fma_rn(sg, (double)j, f0), ds);   // (+-)(k or n-k)*d, exact integer factor
-                    // code replicas (tracking.m:252-270): ceil(tcode) indexes [c(L) c c(1)] 0-based
-                    const double tE = __dadd_rn(bE, st), tP = __dadd_rn(bP, st), tL = __dadd_rn(bL, st);
-                    const int iE = ceil_idx(tE), iP = ceil_idx(tP), iL = ceil_idx(tL);
-                    const float vE = (float)s_code[iE];
-                    const float vP = (float)s_code[iP];
-                    const float vL = (float)s_code[iL];
-                    // x * e^{-i*j*dphi}   (tracking.m:287-292 with the chunk phase factored out)
-                    const float ur = fmaf(wc[j], xi[j], ws[j] * xq[j]);
-                    const float ui = fmaf(wc[j], xq[j], -ws[j] * xi[j]);
-                    pIE = fmaf(vE, ur, pIE); pQE = fmaf(vE, ui, pQE);                 // :295-300
-                    pIP = fmaf(vP, ur, pIP); pQP = fmaf(vP, ui, pQP);
-                    pIL = fmaf(vL, ur, pIL); pQL = fmaf(vL, ui, pQL);
-                    if (PILOT) {                                  // same code phase, pilot table (GAL_E1C tracking.m:241-262)
-                        const float uE = (float)s_pilot[iE], uP = (float)s_pilot[iP], uL = (float)s_pilot[iL];
-                        qIE = fmaf(uE, ur, qIE); qQE = fmaf(uE, ui, qQE);
-                        qIP = fmaf(uP, ur, qIP); qQP = fmaf(uP, ui, qQP);
-                        qIL = fmaf(uL, ur, qIL); qQL = fmaf(uL, ui, qQL);
-                    }
-                    if (NSET == 3) {                              // pilotBOC61(ceil(tcode * 6) + 1), B1C WB_tracking.m:283,294,305
-                        const float wE = (float)s_p61[ceil_idx(__dmul_rn(tE, 6.0))], wP = (float)s_p61[ceil_idx(__dmul_rn(tP, 6.0))],
-                                    wL = (float)s_p61[ceil_idx(__dmul_rn(tL, 6.0))];
-                        rIE = fmaf(wE, ur, rIE); rQE = fmaf(wE, ui, rQE);
-                        rIP = fmaf(wP, ur, rIP); rQP = fmaf(wP, ui, rQP);
-                        rIL = fmaf(wL, ur, rIL); rQL = fmaf(wL, ui, rQL);
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int kc = min(max(k0 + j, 0), blk - 1);
                     double tE, tP, tL;
-                    if (!generic) {                              // the three vectors share n: one index conversion
-                        const bool left = 2 * kc < n, mid = 2 * kc == n;
-                        const double st = __dmul_rn((double)(left ? kc : n - kc), left ? d : -d);
-                        tE = mid ? mE : __dadd_rn(left ? aE : cE, st);
-                        tP = mid ? mP : __dadd_rn(left ? aP : cP, st);
-                        tL = mid ? mL : __dadd_rn(left ? aL : cL, st);
+                    if (!SPECIAL) {
+                        // whole chunk in the left half (t = a + k*d) or in the right half (t = c - (n-k)*d).  Samples masked above may
+                        // have k < 0 or k >= blk; their code index stays inside the padded table (t > -1 and t < codeLength + 1).
+                        const double st = __dmul_rn(__fma_rn(sg, (double)j, f0), ds);   // (+-)(k or n-k)*d, exact integer factor
+                        tE = __dadd_rn(bE, st); tP = __dadd_rn(bP, st); tL = __dadd_rn(bL, st);
                     } else {
-                        tE = colon_elem(aE, d, cE, nE_, kc);
-                        tP = colon_elem(aP, d, cP, nP_, kc);
-                        tL = colon_elem(aL, d, cL, nL_, kc);
+                        const int kc = min(max(k0 + j, 0), blk - 1);
+                        if (!generic) {                           // the three vectors share n: one index conversion
+                            const bool left = 2 * kc < n, mid = 2 * kc == n;
+                            const double st = __dmul_rn((double)(left ? kc : n - kc), left ? d : -d);
+                            tE = mid ? mE : __dadd_rn(left ? aE : cE, st);
+                            tP = mid ? mP : __dadd_rn(left ? aP : cP, st);
+                            tL = mid ? mL : __dadd_rn(left ? aL : cL, st);
+                        } else {
+                            tE = colon_elem(aE, d, cE, nE_, kc);
+                            tP = colon_elem(aP, d, cP, nP_, kc);
+                            tL = colon_elem(aL, d, cL, nL_, kc);
+                        }
                     }
                     const int iE = ceil_idx(tE), iP = ceil_idx(tP), iL = ceil_idx(tL);
-                    const float vE = (float)s_code[iE], vP = (float)s_code[iP], vL = (float)s_code[iL];
-                    const float ur = fmaf(wc[j], xi[j], ws[j] * xq[j]);
-                    const float ui = fmaf(wc[j], xq[j], -ws[j] * xi[j]);
-                    pIE = fmaf(vE, ur, pIE); pQE = fmaf(vE, ui, pQE);
-                    pIP = fmaf(vP, ur, pIP); pQP = fmaf(vP, ui, pQP);
-                    pIL = fmaf(vL, ur, pIL); pQL = fmaf(vL, ui, pQL);
-                    if (PILOT) {
-                        const float uE = (float)s_pilot[iE], uP = (float)s_pilot[iP], uL = (float)s_pilot[iL];
-                        qIE = fmaf(uE, ur, qIE); qQE = fmaf(uE, ui, qQE);
-                        qIP = fmaf(uP, ur, qIP); qQP = fmaf(uP, ui, qQP);
-                        qIL = fmaf(uL, ur, qIL); qQL = fmaf(uL, ui, qQL);
+                    uint32_t gE = 0, gP = 0, gL = 0, fE = 0, fP = 0, fL = 0;
+                    if constexpr (PILOT) { gE = Enc::hi(s_pilot[iE]); gP = Enc::hi(s_pilot[iP]); gL = Enc::hi(s_pilot[iL]); }
+                    if constexpr (NSET == 3) {
+                        fE = Enc::hi(s_p61[ceil_idx(__dmul_rn(tE, 6.0))]); fP = Enc::hi(s_p61[ceil_idx(__dmul_rn(tP, 6.0))]);
+                        fL = Enc::hi(s_p61[ceil_idx(__dmul_rn(tL, 6.0))]);
                     }
-                    if (NSET == 3) {
-                        const float wE = (float)s_p61[ceil_idx(__dmul_rn(tE, 6.0))], wP = (float)s_p61[ceil_idx(__dmul_rn(tP, 6.0))],
-                                    wL = (float)s_p61[ceil_idx(__dmul_rn(tL, 6.0))];
-                        rIE = fmaf(wE, ur, rIE); rQE = fmaf(wE, ui, rQE);
-                        rIP = fmaf(wP, ur, rIP); rQP = fmaf(wP, ui, rQP);
-                        rIL = fmaf(wL, ur, rIL); rQL = fmaf(wL, ui, rQL);
+                    mac(j, Enc::hi(s_code[iE]), Enc::hi(s_code[iP]), Enc::hi(s_code[iL]), gE, gP, gL, fE, fP, fL);
+                }
+            };
+            if constexpr (MODE == 0) {
+                const bool allLeft = (2 * (k0 + 7) < n);
+                const double st0 = __dmul_rn((double)(allLeft ? k0 : (n - k0)), allLeft ? d : -d);
+                const double t0[3] = {__dadd_rn(allLeft ? aE : cE, st0), __dadd_rn(allLeft ? aP : cP, st0), __dadd_rn(allLeft ? aL : cL, st0)};
+                int idxA[3], eN[3];
+                bool susp = false;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    // t0 + 1.5*2^20 has an ulp of 2^-32: low word = fraction of t0 in 0.32 fixed point, high word = floor(t0) + 2^19
+                    const double r = __dadd_rn(t0[q], 1572864.0);
+                    const uint32_t lo = (uint32_t)__double2loint(r);
+                    const int fl = (int)((uint32_t)__double2hiint(r) & 0xFFFFFu) - 0x80000;
+                    idxA[q] = fl + (lo != 0u);                    // ceil(t0): index of the chunk's first sample
+                    const uint32_t Q = __umulhi(0u - lo, rinv);   // (distance to the next entry) / d in 8.24 fixed point
+                    eN[q] = (int)(Q >> 24) + 1;                   // samples of this chunk that still have the first index
+                    susp |= (eN[q] <= 8 && ((Q + 16u) & 0xFFFFFFu) < 32u) || (lo + 64u < 128u);
+                }
+                if (susp) {
+                    by_sample(std::false_type{});
+                } else {
+                    // running sums S_(j+1) = u_0 + ... + u_j of the wiped-off samples, parked in this thread's column of s_pre; the sum
+                    // against a replica whose entry changes from A to B after eN samples is A*S_eN + B*(S_8 - S_eN)
+                    double sr = 0.0, si = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        double mr, mq;
+                        sample(j, mr, mq);
+                        const double2 r0 = rot[2 * j], r1 = rot[2 * j + 1];
+                        sr = __dadd_rn(sr, __fma_rn(r0.x, mr, __fma_rn(r0.y, mq, -r1.x)));
+                        si = __dadd_rn(si, __fma_rn(r0.x, mq, __fma_rn(-r0.y, mr, -r1.y)));
+                        if (j < 7) s_pre[j * kThreads + tid] = make_double2(sr, si);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        double2 H = make_double2(sr, si);
+                        if (eN[q] < 8) H = s_pre[(eN[q] - 1) * kThreads + tid];
+                        const double tr_ = __dsub_rn(sr, H.x), ti_ = __dsub_rn(si, H.y);
+                        const double vA = hi2d(Enc::hi(s_code[idxA[q]])), vB = hi2d(Enc::hi(s_code[idxA[q] + 1]));
+                        ps[2 * q] = __fma_rn(vA, H.x, __dmul_rn(vB, tr_));
+                        ps[2 * q + 1] = __fma_rn(vA, H.y, __dmul_rn(vB, ti_));
+                        if constexpr (PILOT) {
+                            const double uA = hi2d(Enc::hi(s_pilot[idxA[q]])), uB = hi2d(Enc::hi(s_pilot[idxA[q] + 1]));
+                            ps[6 + 2 * q] = __fma_rn(uA, H.x, __dmul_rn(uB, tr_));
+                            ps[6 + 2 * q + 1] = __fma_rn(uA, H.y, __dmul_rn(uB, ti_));
+                        }
                     }
                 }
+            } else if constexpr (MODE == 1) {
+                by_sample(std::false_type{});
+            } else {
+                by_sample(std::true_type{});
             }
-            // rotate the chunk sums by e^{-i*phase(k0)}
-            float s0, c0;
-            fix_sincos(phase0 + dphi * (uint64_t)(long long)k0, &s0, &c0);
-            aIE += fmaf(c0, pIE, s0 * pQE); aQE += fmaf(c0, pQE, -s0 * pIE);
-            aIP += fmaf(c0, pIP, s0 * pQP); aQP += fmaf(c0, pQP, -s0 * pIP);
-            aIL += fmaf(c0, pIL, s0 * pQL); aQL += fmaf(c0, pQL, -s0 * pIL);
-            if (PILOT) {
-                bIE += fmaf(c0, qIE, s0 * qQE); bQE += fmaf(c0, qQE, -s0 * qIE);
-                bIP += fmaf(c0, qIP, s0 * qQP); bQP += fmaf(c0, qQP, -s0 * qIP);
-                bIL += fmaf(c0, qIL, s0 * qQL); bQL += fmaf(c0, qQL, -s0 * qIL);
-            }
-            if (NSET == 3) {
-                cIE += fmaf(c0, rIE, s0 * rQE); cQE += fmaf(c0, rQE, -s0 * rIE);
-                cIP += fmaf(c0, rIP, s0 * rQP); cQP += fmaf(c0, rQP, -s0 * rIP);
-                cIL += fmaf(c0, rIL, s0 * rQL); cQL += fmaf(c0, rQL, -s0 * rIL);
+            // rotate the chunk sums by e^{-i*phase(k0)} (float64 phasor from the exact fixed-point phase)
+            double s0, c0;
+            fix_sincos_f64(phase0 + dphi * (uint64_t)(long long)k0, &s0, &c0);
+#pragma unroll
+            for (int q = 0; q < NS; q += 2) {
+                acc[q] = __fma_rn(c0, ps[q], __fma_rn(s0, ps[q + 1], acc[q]));
+                acc[q + 1] = __fma_rn(c0, ps[q + 1], __fma_rn(-s0, ps[q], acc[q + 1]));
             }
         };
-        using TagFast = std::false_type;
-        using TagSpecial = std::true_type;
+        using Mode0 = std::integral_constant<int, 0>;
+        using Mode1 = std::integral_constant<int, 1>;
+        using Mode2 = std::integral_constant<int, 2>;
         if (!generic) {
             // the one chunk that straddles the middle of the colon vector is left to the thread with
             // the least regular work (a divergent special chunk would otherwise double its warp's time)
             const int cMid = (off + (n >> 1)) >> 3;
             const bool midUniform = (2 * (cMid * 8 - off + 7) < n) || (2 * (cMid * 8 - off) > n);
-            for (int c = c_begin + (fits ? tid : tid * G); c < c_end; c += c_step)
-                if (c != cMid || midUniform) do_chunk(c, TagFast{});
+            if (ep.fast && p.preSlots) {
+                for (int c = c_begin + (fits ? tid : tid * G); c < c_end; c += c_step)
+                    if (c != cMid || midUniform) do_chunk(c, Mode0{});
+            } else {
+                for (int c = c_begin + (fits ? tid : tid * G); c < c_end; c += c_step)
+                    if (c != cMid || midUniform) do_chunk(c, Mode1{});
+            }
             if (tid == kSpecialTid && !midUniform && cMid >= c_begin && cMid < c_end && (fits || cMid % G == (int)crank))
-                do_chunk(cMid, TagSpecial{});
+                do_chunk(cMid, Mode2{});
         } else {
-            for (int c = c_begin + (fits ? tid : tid * G); c < c_end; c += c_step) do_chunk(c, TagSpecial{});
+            for (int c = c_begin + (fits ? tid : tid * G); c < c_end; c += c_step) do_chunk(c, Mode2{});
         }
         GC_TICK(2)
         // cross-thread reduction in float64: warp shuffle, then warps 0 and 1 over the warp partials
-        // (the 32 lane partials of a warp are combined in fp32 - they are fp32 sums of <= 32 samples each -
-        //  and everything from the warp partials on is float64)
-        float vf[18] = {aIE, aQE, aIP, aQP, aIL, aQL, bIE, bQE, bIP, bQP, bIL, bQL, cIE, cQE, cIP, cQP, cIL, cQL};
+        double v[NS];
+#pragma unroll
+        for (int q = 0; q < NS; ++q) v[q] = acc[q] * Enc::kScale;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-            for (int q = 0; q < NS; ++q) vf[q] += __shfl_down_sync(0xffffffffu, vf[q], o);
-        double v[NS];
-#pragma unroll
-        for (int q = 0; q < NS; ++q) v[q] = (double)vf[q];
-        if constexpr (EXACT) {
-#pragma unroll
-            for (int q = 0; q < NS; ++q) v[q] = dacc[q];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                for (int q = 0; q < NS; ++q) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
-        }
+            for (int q = 0; q < NS; ++q) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
         if (lane == 0)
 #pragma unroll
             for (int q = 0; q < NS; ++q) s_part[warp * NS + q] = v[q];
@@ -630,6 +738,8 @@ track_kernel(TrackParams p)
         }
         GC_TICK(4)
         if (warp == kPllTid / 32 || warp == kDllTid / 32) {
+            NextPhases nx;                                       // NCO phases at the end of this block: known before its sums are
+            if (tid == kDllTid) end_phases(p, ep, nx);
             if (G > 1) {
                 mbar_wait(&s_xbar[e & 1], xphase[e & 1]);       // all G partial sets have landed here
                 xphase[e & 1] ^= 1u;
@@ -756,10 +866,12 @@ track_kernel(TrackParams p)
                 sg[GC_F_DLL_DISCR * kStage] = codeError;                            // :338-339
                 sg[GC_F_DLL_DISCR_FILT * kStage] = codeNco;
                 // :335 codeFreq of the next block, then its geometry
-                NextPhases nx;
-                end_phases(p, ep, nx);
                 plan_epoch(p, __dsub_rn(cinfo.codeFreq0, codeNco), nx.remCodePhase, nx.remCarrPhase, nx.phase0,
                            pos + blk, s_ep[stage ^ 1], invStep);
+            }
+            if (warp == kPllTid / 32) {                          // the next block's in-chunk rotations, on eight lanes of the carrier warp
+                __syncwarp();
+                plan_rotations(s_ep[stage ^ 1], lane, FMT0 ? kByteBias : 0.0);
             }
         }
         GC_TICK(5)
@@ -792,7 +904,7 @@ track_kernel(TrackParams p)
     if (G > 1) cluster_sync_all();                               // nobody leaves while a peer may still push to it
 }
 
-size_t track_smem_bytes(int bufBytes, int codeLen, int pilot, int singleBuf)
+size_t track_smem_bytes(int bufBytes, int codeLen, int pilot, int singleBuf, int preThreads)
 {
     const int nset = pilot == 5 ? 3 : pilot ? 2 : 1;
     const int ns = 6 * nset;
@@ -801,13 +913,14 @@ size_t track_smem_bytes(int bufBytes, int codeLen, int pilot, int singleBuf)
     if (pilot == 5) s += (codeLen * 6 + 2 + 2 * kPad61 + 15) & ~15;
     s += sizeof(double) * (kMaxWarps * ns + 2 * kMaxCluster * ns + GC_TRACK_ROWS * kStage);
     s += 2 * sizeof(EpochParams) + sizeof(NextPhases) + 4 * sizeof(uint64_t) + 2 * sizeof(int) + 64;
+    s += (size_t)preThreads * 7 * sizeof(double2);               // running sums of the fast chunks
     return s;
 }
 
 template <int G, int T, int NSET, typename TT, bool FMT0, bool EXACT = false>
 static cudaError_t launch_track_f(const TrackParams& p, int nCh, cudaStream_t stream)
 {
-    const size_t smem = track_smem_bytes(p.bufBytes, p.codeLen, p.pilot, p.singleBuf);
+    const size_t smem = track_smem_bytes(p.bufBytes, p.codeLen, p.pilot, p.singleBuf, p.preSlots ? T : 0);
     cudaError_t err = cudaFuncSetAttribute(track_kernel<G, T, NSET, TT, FMT0, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     cudaLaunchConfig_t cfg{};
@@ -823,7 +936,7 @@ static cudaError_t launch_track_f(const TrackParams& p, int nCh, cudaStream_t st
     return cudaLaunchKernelEx(&cfg, track_kernel<G, T, NSET, TT, FMT0, EXACT>, p);
 }
 
-template <int G, int T, int NSET, typename TT = float>
+template <int G, int T, int NSET, typename TT = uint32_t>
 static cudaError_t launch_track_g(const TrackParams& p, int nCh, cudaStream_t stream)
 {
     // the float64 checking mode reads every format through the per-sample accessor (one instantiation per geometry)
@@ -832,11 +945,12 @@ static cudaError_t launch_track_g(const TrackParams& p, int nCh, cudaStream_t st
 }
 
 // p.bufBytes must be the per-CTA staging size for `cluster` CTAs per channel (track_buf_bytes)
-cudaError_t launch_track(const TrackParams& p, int nCh, int cluster, cudaStream_t stream)
+cudaError_t launch_track(const TrackParams& p, int nCh, int cluster, int batch, cudaStream_t stream)
 {
+    if (batch && cluster == 1 && p.pilot != 5) return p.pilot ? launch_track_g<1, 256, 2>(p, nCh, stream) : launch_track_g<1, 256, 1>(p, nCh, stream);
     if (p.pilot == 5) {                                          // three int8 tables; 18 accumulators want the 352-thread register budget
         if (cluster != 8) return cudaErrorInvalidValue;
-        return launch_track_g<8, 352, 3, int8_t>(p, nCh, stream);
+        return launch_track_g<8, 352, 3, uint8_t>(p, nCh, stream);
     }
     if (p.pilot) {
         switch (cluster) {
@@ -853,6 +967,10 @@ cudaError_t launch_track(const TrackParams& p, int nCh, int cluster, cudaStream_
         default: return launch_track_g<1, 512, 1>(p, nCh, stream);
     }
 }
+
+// threads per CTA of the kernel launch_track picks for this cluster size; `batch`: more channels than SMs and one CTA per channel -
+// 256-thread CTAs, two to an SM, so that one channel's loop closure (a single-warp section) overlaps another channel's samples
+int track_threads(int cluster, int batch) { return cluster == 8 ? 352 : (cluster == 1 && batch) ? 256 : 512; }
 
 // bytes each CTA stages per epoch: ceil(maxChunks / cluster) 16-byte chunks
 int track_buf_bytes(int maxBlockSamples, int cluster)

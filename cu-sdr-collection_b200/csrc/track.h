@@ -51,6 +51,8 @@ struct TrackParams {
                              // pilot correlations, carrier 1:3, code weighted by wbFactor (B1C WB_tracking.m:270-374)
     int singleBuf;           // 1: one sample window in shared memory instead of two (long epochs whose double-buffered window
                              // would not fit next to the code tables: B1C, 10 ms = 180000 samples with two 20460-entry tables)
+    int preSlots;            // 1: shared memory holds the [7][threads] running-sum columns of the fast chunks (low-rate codes: at least
+                             // 8 samples per table entry), 0: no room - every chunk takes its indices sample by sample
     int nRows;               // rows recorded per epoch: GC_TRACK_NFIELDS, GC_TRACK_NFIELDS_PILOT (pilot 2, 3) or GC_TRACK_NFIELDS_PILOT6 (pilot 4, 5)
     int codeStride;          // bytes between channels in codeTables
     int pilotStride;         // bytes between channels in pilotTables (codeStride, or the padded CL length for pilot == 4)
@@ -65,8 +67,9 @@ struct TrackParams {
     long long* dbg;          // optional [4][8] phase-timing accumulators (GC_TRACK_DEBUG), else nullptr
 };
 
-size_t track_smem_bytes(int bufBytes, int codeLen, int pilot, int singleBuf = 0);
-cudaError_t launch_track(const TrackParams& p, int nCh, int cluster, cudaStream_t stream);
+size_t track_smem_bytes(int bufBytes, int codeLen, int pilot, int singleBuf = 0, int preThreads = 0);
+int track_threads(int cluster, int batch);
+cudaError_t launch_track(const TrackParams& p, int nCh, int cluster, int batch, cudaStream_t stream);
 int track_buf_bytes(int maxBlockSamples, int cluster);
 cudaError_t launch_track_fill(double* out, int nCh, int nRows, int nEpochs, cudaStream_t stream);
 // trackResults.CNo.VSMValue / VSMIndex from the recorded prompt rows, on the device

@@ -168,7 +168,7 @@ PARITY_REPORT = []      # (label, window epochs, total epochs, worst pre-window 
 
 
 def windowed_iq_compare(label, tr, ref, names, fs, spacing, sub=1.0, rem_scale=1.0, scale_keys=("I_P", "Q_P"), iq_tol=1e-6,
-                        post_tol=1e-2, min_frac=0.0, exact=False, abs_sample=None):
+                        post_tol=1e-2, min_frac=0.9, exact=False, abs_sample=None):
     """The closed-loop I/Q comparison of the trackers whose ceil(tcode) can be ill conditioned (18 Msps / 10.23 Mcps, BOC tables):
     every correlator row within `iq_tol` of |P| up to the first ill-conditioned epoch (first_illconditioned_epoch), `post_tol`
     after it; the window must cover at least `min_frac` of the run.  With exact=True (the engine's float64 checking mode) there is

@@ -26,7 +26,7 @@ VARB_METRIC_TOL = 1e-5
 # phase of a block start passes a sample-grid alignment, ~1000 samples of that block lie within 1e-6 chips of a chip edge at once,
 # and a loop state that is off by 1e-10 chips (fp32 sums) flips one of them about once per channel-minute, after which the two
 # closed loops separate for good (profiles/r02_parity_60000.md).  1 = run it in the float64 checking mode.
-FULL_SIZE_EXACT = 1
+FULL_SIZE_EXACT = 0
 
 
 def _acq_case(fs, nsat, seed, sv_extra, nonCoh=20, cn0=None, band=7000.0):
