@@ -7,10 +7,10 @@ interface for that path: same function names, argument meaning and result fields
 no CPU fallback: every compute call raises if the library or a B200 is missing.
 """
 from .settings import Settings, init_settings, num_to_process   # noqa: F401
-from .engine import Engine, GnssCorrError, lib_path       # noqa: F401
+from .engine import Engine, MultiEngine, GnssCorrError, lib_path       # noqa: F401
 from .acquisition import acquisition                      # noqa: F401
 from .tracking import tracking, TRACK_FIELDS              # noqa: F401
 from .prerun import preRun                                # noqa: F401
 
-__all__ = ["Settings", "init_settings", "Engine", "GnssCorrError", "acquisition", "tracking",
+__all__ = ["Settings", "init_settings", "Engine", "MultiEngine", "GnssCorrError", "acquisition", "tracking",
            "preRun", "TRACK_FIELDS", "lib_path"]

@@ -193,4 +193,16 @@ struct FineSetup {
 };
 cudaError_t launch_fine_setup(const FineSetup& p, cudaStream_t s);
 
+// acqResults of variant A assembled on the device (gc_acquire_device): [peakMetric | codePhase | carrFreq | coarseBin]
+struct PackParams {
+    const PeakOut* peaks; const double* sigPower;
+    const double* slotFreq0;  // [nSv] frequency of coarse bin 1 of the slot
+    const int* slotResult;    // [nSv] index of the slot's SV in the result vectors
+    const int* best;          // [nAcq] arg-max fine bin per acquired slot, in slot order (FineParams::best)
+    int nSv, nonCoh, resultLen, noFine;
+    double threshold, step, fineStep;
+    double* out;              // [4][resultLen]
+};
+cudaError_t launch_pack_results(const PackParams& p, cudaStream_t s);
+
 }  // namespace gc

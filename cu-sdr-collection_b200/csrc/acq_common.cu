@@ -303,6 +303,40 @@ cudaError_t launch_fine_setup(const FineSetup& p, cudaStream_t s)
     return cudaGetLastError();
 }
 
+// acqResults on the device (gc_acquire_device): the host expressions of acquire_impl, operation for operation
+// (acquisition.m:200, 206, 227, 254-260), so that what a collective gathers from device memory is what gc_acquire returns
+__global__ void pack_results_kernel(PackParams p)
+{
+    for (int i = threadIdx.x; i < 4 * p.resultLen; i += blockDim.x) p.out[i] = 0.0;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const double sp = *p.sigPower;
+    int a = 0;
+    for (int s = 0; s < p.nSv; ++s) {
+        const int ri = p.slotResult[s];
+        const double m = __ddiv_rn(__ddiv_rn(p.peaks[s].peak, sp), (double)p.nonCoh);                 // :200
+        p.out[ri] = m;
+        p.out[3 * p.resultLen + ri] = (double)p.peaks[s].bin;
+        if (m > p.threshold) {                                                                        // :206
+            const double coarse = __dsub_rn(p.slotFreq0[s], __dmul_rn(p.step, (double)(p.peaks[s].bin - 1)));   // :169
+            double f = coarse;
+            if (!p.noFine) {
+                f = __dsub_rn(__dadd_rn(coarse, __ddiv_rn(p.step, 2.0)), __dmul_rn(p.fineStep, (double)p.best[a]));   // :227, :254
+                if (f == 0.0) f = 1.0;                                                                // :258
+            }
+            p.out[2 * p.resultLen + ri] = f;
+            p.out[p.resultLen + ri] = (double)p.peaks[s].codePhase;                                   // :256
+            ++a;
+        }
+    }
+}
+
+cudaError_t launch_pack_results(const PackParams& p, cudaStream_t s)
+{
+    pack_results_kernel<<<1, 128, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_fine(const FineParams& p, int nEntries, int nAcq, cudaStream_t s)
 {
     dim3 g1(148 * 2, nEntries);

@@ -134,7 +134,7 @@ struct gc_handle {
     DevBuf<uint64_t> dphi, fdphi;
     DevBuf<int8_t> codeTab, chips, fineSecondary, slotSecondary;
     DevBuf<double> slotFreq0, metricDev;
-    DevBuf<int> slotChipRow, slotSv, nAcqDev, acqSlot, fineChipRow;
+    DevBuf<int> slotChipRow, slotSv, nAcqDev, acqSlot, fineChipRow, slotResult;
     DevBuf<int> prnList, slotGroup, partIdx, fineCodePhase, fineBest, fineSv;
     DevBuf<float> partMax;
     DevBuf<PeakOut> peaks;
@@ -512,7 +512,7 @@ void gc_destroy(gc_handle* h)
     h->slotFreq0.release(); h->metricDev.release(); h->slotChipRow.release(); h->slotSv.release(); h->nAcqDev.release(); h->acqSlot.release(); h->fineChipRow.release();
     h->prnList.release(); h->slotGroup.release(); h->partIdx.release(); h->fineCodePhase.release(); h->fineBest.release(); h->fineSv.release(); h->partMax.release();
     h->peaks.release(); h->sigPower.release(); h->fineSums.release(); h->fineResult.release(); h->fineProd.release();
-    h->vcSlot.release(); h->vbRows.release(); h->vbPeak.release(); h->vbIdx.release(); h->vbSeg.release();
+    h->slotResult.release(); h->vcSlot.release(); h->vbRows.release(); h->vbPeak.release(); h->vbIdx.release(); h->vbSeg.release();
     h->chans.release(); h->trackCodes.release(); h->trackPilot.release(); h->trackOut.release(); h->epochsDone.release();
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) { if (h->evRows[i]) cudaEventDestroy(h->evRows[i]); if (h->evCols[i]) cudaEventDestroy(h->evCols[i]); }
@@ -1114,7 +1114,8 @@ static int acquire_varc(gc_handle* h, long long winStart, long long longLen, int
 
 static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int32_t* svList,
                         double* carrFreq, double* codePhase, double* peakMetric,
-                        int32_t* coarseBin, int32_t* coarseCodePhase, long long longLen = 0 /* length(longSignal), B1C only */)
+                        int32_t* coarseBin, int32_t* coarseCodePhase, long long longLen = 0 /* length(longSignal), B1C only */,
+                        double* dOut = nullptr /* gc_acquire_device: [4][resultLen] on the device */)
 {
     const gc_config& c = h->cfg;
     const int N = h->N, L = h->L, nBins = h->nBins, nonCoh = h->nonCoh, nKm = nBins * nonCoh;
@@ -1131,13 +1132,20 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         int rc = h->varB ? varb_build_replicas(h) : h->varC ? varc_build_replicas(h) : build_replicas(h);
         if (rc != GC_OK) return rc;
     }
-    if (h->varB) {
+    if (h->varB || h->varC) {
         cudaSetDevice(c.device);
-        return acquire_varb(h, winStart, nSv, svList, carrFreq, codePhase, peakMetric, coarseBin, coarseCodePhase);
-    }
-    if (h->varC) {
-        cudaSetDevice(c.device);
-        return acquire_varc(h, winStart, longLen, nSv, svList, carrFreq, codePhase, peakMetric, coarseBin, coarseCodePhase);
+        std::vector<int32_t> cb(h->resultLen, 0);
+        if (dOut && !coarseBin) coarseBin = cb.data();
+        const int rc = h->varB ? acquire_varb(h, winStart, nSv, svList, carrFreq, codePhase, peakMetric, coarseBin, coarseCodePhase)
+                               : acquire_varc(h, winStart, longLen, nSv, svList, carrFreq, codePhase, peakMetric, coarseBin, coarseCodePhase);
+        if (rc == GC_OK && dOut) {   // variants B and C finish on the host (the reference's running comparison): hand the result vectors over
+            const int n = h->resultLen;
+            std::vector<double> pack(4 * (size_t)n);
+            for (int i = 0; i < n; ++i) { pack[i] = peakMetric[i]; pack[n + i] = codePhase[i]; pack[2 * n + i] = carrFreq[i]; pack[3 * n + i] = (double)coarseBin[i]; }
+            GC_CUDA(h, cudaMemcpyAsync(dOut, pack.data(), pack.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            GC_CUDA(h, cudaStreamSynchronize(h->stream));
+        }
+        return rc;
     }
     // postProcessing.m:86 reads max(42, nonCoh+2) code periods (B3I: max(22, nonCoh+1), BDS/B3I/include/postProcessing.m:86)
     const int nPeriodsAcq = std::max(h->acqMinPeriods, nonCoh + h->acqExtraPeriods);
@@ -1482,6 +1490,21 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         GC_CUDA(h, launch_fine(fp, maxEnt, nSv, st)); launches += 3;
         fb = mark();
     }
+    if (dOut) {                                                   // acqResults assembled on the device for the collective that follows
+        std::vector<int> slotResult(nSv);
+        std::vector<double> slotFreq0(nSv);
+        for (int s = 0; s < nSv; ++s) {
+            slotResult[s] = sv_result_index(h, svList[order[s]]);
+            slotFreq0[s] = (c.IF + sv_freq_offset(h, svList[order[s]])) + c.acq_search_band;
+        }
+        GC_CUDA(h, upload(h->slotResult, slotResult, st));
+        if (h->noFine) GC_CUDA(h, upload(h->slotFreq0, slotFreq0, st));
+        PackParams pk{};
+        pk.peaks = h->peaks.p; pk.sigPower = h->sigPower.p; pk.slotFreq0 = h->slotFreq0.p; pk.slotResult = h->slotResult.p;
+        pk.best = h->noFine ? nullptr : h->fineBest.p; pk.nSv = nSv; pk.nonCoh = nonCoh; pk.resultLen = h->resultLen; pk.noFine = h->noFine ? 1 : 0;
+        pk.threshold = c.acq_threshold; pk.step = c.acq_search_step; pk.fineStep = h->fineStep; pk.out = dOut;
+        GC_CUDA(h, launch_pack_results(pk, st)); ++launches;
+    }
     std::vector<PeakOut> peaks(nSv);
     std::vector<int> best(nSv, 0);
     double sigPower = 0;
@@ -1541,6 +1564,14 @@ int gc_acquire(gc_handle* h, int32_t nSv, const int32_t* svList,
     // fseek(fid, dataAdaptCoeff*skipNumberOfBytes) (postProcessing.m:74): skip counts complex samples
     return acquire_impl(h, skip_samples(h), nSv, svList, carrFreq, codePhase, peakMetric,
                         coarseBin, coarseCodePhase);
+}
+
+int gc_acquire_device(gc_handle* h, int32_t nSv, const int32_t* svList, double* dResults)
+{
+    if (!h) return GC_ERR_ARG;
+    if (!dResults) return fail(h, GC_ERR_ARG, "gc_acquire_device: null result buffer");
+    std::vector<double> cf(h->resultLen), cp(h->resultLen), pm(h->resultLen);
+    return acquire_impl(h, skip_samples(h), nSv, svList, cf.data(), cp.data(), pm.data(), nullptr, nullptr, 0, dResults);
 }
 
 int gc_acquire_host(gc_handle* h, const int8_t* iq, size_t nSamples, int32_t nSv, const int32_t* svList,

@@ -57,7 +57,11 @@ class gc_stats(C.Structure):
 EXPORTS = ["gc_abi_version", "gc_build_arch", "gc_acq_result_len", "gc_create", "gc_destroy",
            "gc_last_error", "gc_set_code", "gc_set_record_host", "gc_set_record_device", "gc_acquire",
            "gc_acquire_host", "gc_track_nfields", "gc_track", "gc_track_file", "gc_get_stats", "gc_get_stream",
-           "gc_set_param", "gc_get_cl_code_phase", "gc_set_cl_code_phase", "gc_nav_sync", "gc_acquire_track"]
+           "gc_set_param", "gc_get_cl_code_phase", "gc_set_cl_code_phase", "gc_nav_sync", "gc_acquire_track",
+           "gc_acquire_device", "gc_multi_create", "gc_multi_destroy", "gc_multi_last_error", "gc_multi_n_gpus",
+           "gc_multi_handle", "gc_multi_set_code", "gc_multi_set_param", "gc_multi_set_cl_code_phase",
+           "gc_multi_get_cl_code_phase", "gc_multi_set_record_host", "gc_multi_acquire", "gc_multi_acquire_host",
+           "gc_multi_track", "gc_multi_track_file", "gc_multi_get_times"]
 
 _lib = None
 
@@ -97,6 +101,25 @@ def load_lib():
     lib.gc_nav_sync.argtypes = [vp, C.c_int32, C.c_int32, dp, i32p, C.POINTER(C.c_uint8), i32p]
     lib.gc_get_stream.argtypes = [vp]
     lib.gc_get_stream.restype = C.c_void_p
+    lib.gc_acquire_device.argtypes = [vp, C.c_int32, i32p, vp]
+    lib.gc_multi_create.argtypes = [C.POINTER(vp), C.POINTER(gc_config), C.c_int32]
+    lib.gc_multi_destroy.argtypes = [vp]
+    lib.gc_multi_destroy.restype = None
+    lib.gc_multi_last_error.argtypes = [vp]
+    lib.gc_multi_last_error.restype = C.c_char_p
+    lib.gc_multi_n_gpus.argtypes = [vp]
+    lib.gc_multi_handle.argtypes = [vp, C.c_int32]
+    lib.gc_multi_handle.restype = vp
+    lib.gc_multi_set_code.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_int32]
+    lib.gc_multi_set_param.argtypes = [vp, C.c_int32, C.c_double]
+    lib.gc_multi_set_cl_code_phase.argtypes = [vp, C.c_int32, i32p]
+    lib.gc_multi_get_cl_code_phase.argtypes = [vp, i32p]
+    lib.gc_multi_set_record_host.argtypes = [vp, vp, C.c_size_t]
+    lib.gc_multi_acquire.argtypes = [vp, C.c_int32, i32p, dp, dp, dp, i32p, i32p]
+    lib.gc_multi_acquire_host.argtypes = [vp, vp, C.c_size_t, C.c_int32, i32p, dp, dp, dp, i32p, i32p]
+    lib.gc_multi_track.argtypes = [vp, C.c_int32, i32p, dp, dp, dp, C.c_int32, dp, dp, dp, i32p]
+    lib.gc_multi_track_file.argtypes = [vp, C.c_char_p, C.c_int32, i32p, dp, dp, dp, C.c_int32, dp, dp, dp, i32p]
+    lib.gc_multi_get_times.argtypes = [vp, dp, dp]
     _lib = lib
     return lib
 
@@ -236,6 +259,16 @@ class Engine:
             r["CLCodePhase"] = cl
         return r
 
+    def acquire_device(self, sv_list, d_results):
+        """gc_acquire_device: the search on the resident record with acqResults left on the GPU in ``d_results`` - a CUDA
+        float64 tensor of 4 * gc_acq_result_len elements, [peakMetric | codePhase | carrFreq | coarseBin] - ready for the
+        NCCL all-gather of a one-process-per-GPU run (entries of SVs not in ``sv_list`` are zero)."""
+        sv = np.asarray(list(sv_list), dtype=np.int32)
+        n = self.lib.gc_acq_result_len(signal_id(self.settings))
+        assert d_results.is_cuda and d_results.is_contiguous() and d_results.numel() == 4 * n and d_results.element_size() == 8
+        self._check(self.lib.gc_acquire_device(self._h, sv.size, _ip(sv), d_results.data_ptr()), "gc_acquire_device")
+        return d_results
+
     # ---- tracking -----------------------------------------------------------------------
     def set_param(self, key: int, value: float):
         self._check(self.lib.gc_set_param(self._h, int(key), float(value)), "gc_set_param")
@@ -297,3 +330,112 @@ class Engine:
         st = gc_stats()
         self._check(self.lib.gc_get_stats(self._h, C.byref(st)), "gc_get_stats")
         return {k: getattr(st, k) for k, _ in gc_stats._fields_}
+
+
+def codes_for_settings(settings: Settings, codes: dict | None):
+    """The (PRN, component, chips) triples gc_set_code takes for this signal (Engine.set_codes / MultiEngine.set_codes)."""
+    sig = settings.signal
+    for prn, comps in (codes or {}).items():
+        for comp, chips in enumerate(comps):
+            if comp == 2 and not (sig == "GAL_E5a" or (sig == "BDS_B1C" and int(settings.pilotTRKflag) == 2)):
+                continue
+            if comp >= 1 and settings.is_varb and not (sig == "GPS_L2C" and comp == 1 and int(settings.pilotTRKflag) == 1):
+                continue
+            yield int(prn), comp, np.ascontiguousarray(chips, dtype=np.int8)
+
+
+class MultiEngine:
+    """Several GPUs behind one handle (gc_multi_*): the SV list is dealt round-robin and the channels in contiguous blocks
+    over ``n_gpus`` B200s inside the library; same calls and results as ``Engine``."""
+
+    def __init__(self, settings: Settings, n_gpus: int = 0, device: int = 0, codes: dict | None = None):
+        self.lib = load_lib()
+        self.settings = settings
+        self._m = C.c_void_p()
+        cfg = config_from_settings(settings, device)
+        rc = self.lib.gc_multi_create(C.byref(self._m), C.byref(cfg), int(n_gpus))
+        if rc != 0:
+            raise GnssCorrError(f"gc_multi_create failed ({rc}): {self.lib.gc_multi_last_error(None).decode()}")
+        if settings.signal == "GAL_E1C" and codes is None and settings.codeDir:
+            from .codes import load_e1_codes
+            codes = load_e1_codes(settings.codeDir)
+        nmax = self.lib.gc_acq_result_len(signal_id(settings))
+        for prn, comp, a in codes_for_settings(settings, codes):
+            if prn <= nmax:
+                self._check(self.lib.gc_multi_set_code(self._m, prn, comp, a.ctypes.data, a.size), "gc_multi_set_code")
+
+    @property
+    def n_gpus(self) -> int:
+        return int(self.lib.gc_multi_n_gpus(self._m))
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise GnssCorrError(f"{what} failed ({rc}): {self.lib.gc_multi_last_error(self._m).decode()}")
+
+    def close(self):
+        if self._m:
+            self.lib.gc_multi_destroy(self._m)
+            self._m = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_param(self, key: int, value: float):
+        self._check(self.lib.gc_multi_set_param(self._m, int(key), float(value)), "gc_multi_set_param")
+
+    def set_record(self, data: np.ndarray):
+        a = np.ascontiguousarray(data)
+        self._check(self.lib.gc_multi_set_record_host(self._m, a.ctypes.data, a.nbytes), "gc_multi_set_record_host")
+
+    def set_record_host_ptr(self, ptr: int, nbytes: int):
+        self._check(self.lib.gc_multi_set_record_host(self._m, ptr, nbytes), "gc_multi_set_record_host")
+
+    def acquire(self, sv_list=None, host_iq=None):
+        s = self.settings
+        sv = np.asarray(list(sv_list if sv_list is not None else s.acqSatelliteList), dtype=np.int32)
+        n = self.lib.gc_acq_result_len(signal_id(s))
+        carr, cph, pm = np.zeros(n), np.zeros(n), np.zeros(n)
+        cbin, ccp = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        if host_iq is not None:
+            a = np.ascontiguousarray(host_iq)
+            ns = {1: a.size, 2: a.size // 2, 3: a.size * 2}[s.fileType]
+            self._check(self.lib.gc_multi_acquire_host(self._m, a.ctypes.data, ns, sv.size, _ip(sv), _dp(carr), _dp(cph), _dp(pm),
+                                                       _ip(cbin), _ip(ccp)), "gc_multi_acquire_host")
+        else:
+            self._check(self.lib.gc_multi_acquire(self._m, sv.size, _ip(sv), _dp(carr), _dp(cph), _dp(pm), _ip(cbin), _ip(ccp)),
+                        "gc_multi_acquire")
+        r = dict(carrFreq=carr, codePhase=cph, peakMetric=pm, coarseBin=cbin, coarseCodePhase=ccp)
+        if s.signal == "GPS_L2C" and int(s.pilotTRKflag) == 1:
+            cl = np.zeros(32, dtype=np.int32)
+            self._check(self.lib.gc_multi_get_cl_code_phase(self._m, _ip(cl)), "gc_multi_get_cl_code_phase")
+            r["CLCodePhase"] = cl
+        return r
+
+    def track(self, prn, acq_freq, code_phase, n_epochs, path=None, code_freq0=None, cl_code_phase=None):
+        prn = np.asarray(prn, dtype=np.int32)
+        if cl_code_phase is not None:
+            cl = np.ascontiguousarray(cl_code_phase, dtype=np.int32)
+            self._check(self.lib.gc_multi_set_cl_code_phase(self._m, cl.size, _ip(cl)), "gc_multi_set_cl_code_phase")
+        af = np.asarray(acq_freq, dtype=np.float64)
+        cp = np.asarray(code_phase, dtype=np.float64)
+        cf0 = None if code_freq0 is None else np.ascontiguousarray(code_freq0, dtype=np.float64)
+        nch = prn.size
+        nv = n_epochs // int(self.settings.CNo_VSMinterval)
+        h0 = self.lib.gc_multi_handle(self._m, 0)
+        out = np.empty((nch, int(self.lib.gc_track_nfields(h0)), n_epochs))
+        vv, vi = np.zeros((nch, nv)), np.zeros((nch, nv))
+        done = np.zeros(nch, dtype=np.int32)
+        args = (nch, _ip(prn), _dp(af), _dp(cp), _dp(cf0) if cf0 is not None else None, n_epochs, _dp(out), _dp(vv), _dp(vi), _ip(done))
+        if path is not None:
+            self._check(self.lib.gc_multi_track_file(self._m, os.fsencode(path), *args), "gc_multi_track_file")
+        else:
+            self._check(self.lib.gc_multi_track(self._m, *args), "gc_multi_track")
+        return out, vv, vi, done
+
+    def times(self):
+        a, t = C.c_double(), C.c_double()
+        self._check(self.lib.gc_multi_get_times(self._m, C.byref(a), C.byref(t)), "gc_multi_get_times")
+        return dict(acq_ms=a.value, track_ms=t.value)

@@ -15,7 +15,8 @@
  *
  * Conventions: plain pointers and sizes only; the caller allocates every output; the library owns
  * all device memory behind the handle; integer return codes (0 = ok, <0 = error, text via
- * gc_last_error), never exceptions across the ABI; one handle = one GPU = one host thread.
+ * gc_last_error), never exceptions across the ABI; one gc_handle = one GPU = one host thread (gc_multi: one handle per
+ * GPU with the fan-out inside the library).
  * All indices in results are 1-based exactly as the MATLAB code returns them.
  */
 #ifndef GNSSCORR_H
@@ -38,13 +39,13 @@ enum { GC_SIG_GPS_L1CA = 0, GC_SIG_GLO_G1G2 = 1, GC_SIG_BDS_B3I = 2, GC_SIG_GAL_
        /* the four 10230-chip data + pilot signals (variant A with two replicas, quadrature-pilot tracking): */
        GC_SIG_GPS_L5C = 4, GC_SIG_GAL_E5A = 5, GC_SIG_GAL_E5B = 6, GC_SIG_BDS_B2A = 7,
        /* acquisition variant B (Doppler bins by circshift of one spectrum, best row kept, peak / second-peak
-        * metric): BDS B1I (two 4 ms blocks, + 1 ms tracking) and GPS L2C (acquisition only so far).
+        * metric): BDS B1I (two 4 ms blocks, 1 ms tracking) and GPS L2C (20 ms tracking, with and without the CL pilot).
         * For these acq_search_band is in kHz as in their initSettings.m and acq_search_step is the sub-bin
         * step (settings.stepSize resolved as BDS/B1I/include/acquisition.m:24-39 / settings.acqStep). */
        GC_SIG_BDS_B1I = 8, GC_SIG_GPS_L2C = 9,
        /* acquisition variant C (BDS/B1C/include/acquisition.m:128-276): ONE wipe-off + FFT of (10 + acqCohT) ms, Doppler
         * bins by circshift, data and pilot BOC(1,1) replicas combined (d*sqrt(11) + p*sqrt(29))/sqrt(40), 2-D maximum,
-        * 25 Hz fine search over one 10 ms period.  Acquisition only so far (NB/WB tracking: not yet). */
+        * 25 Hz fine search over one 10 ms period; NB_tracking.m (pilot_trk_flag 1) and WB_tracking.m (pilot_trk_flag 2). */
        GC_SIG_BDS_B1C = 10 };
 
 /* "no satellite on this channel" for gc_track: GPS uses PRN 0 (tracking.m:136); a GLONASS channel is
@@ -199,6 +200,13 @@ int gc_acquire(gc_handle* h, int32_t nSv, const int32_t* svList,
                double* carrFreq, double* codePhase, double* peakMetric,
                int32_t* coarseBin, int32_t* coarseCodePhase);
 
+/* gc_acquire with the results left ON THE DEVICE for a collective that follows (one process per GPU: every rank searches its
+ * share of settings.acqSatelliteList and one ncclAllGather of these buffers merges them - entries of SVs a rank did not search
+ * are zero, so the merge is a sum).  dResults: device pointer, 4 * gc_acq_result_len doubles laid out
+ * [peakMetric | codePhase | carrFreq | coarseBin], each indexed like the host arrays of gc_acquire; written on the handle's
+ * stream and complete when the call returns.  Bit-identical to what gc_acquire returns on the host (same expressions). */
+int gc_acquire_device(gc_handle* h, int32_t nSv, const int32_t* svList, double* dResults);
+
 /* Same, but with longSignal supplied from HOST memory in the record's own sample format - int8 I,Q pairs for
  * fileType 2 / 'schar' (what the MEX gateway passes after checking the complex-double longSignal is integer valued),
  * int16 pairs for 'int16', single values for fileType 1; nSamples counts samples, not bytes: copies it to the GPU,
@@ -266,6 +274,36 @@ int gc_acquire_track(gc_handle* h, int32_t nSv, const int32_t* svList, int32_t n
 #define GC_NAV_BITS 1501
 int gc_nav_sync(gc_handle* h, int32_t nCh, int32_t nEpochs, const double* I_P,
                 int32_t* subFrameStart, uint8_t* navBits, int32_t* bitsValid);
+
+/* ---- several GPUs behind one handle -----------------------------------------------------------------------------------------
+ * the PRN loop (acquisition.m:155; frequency numbers for GLONASS, GLO_GL1/include/acquisition.m:172-183) and
+ * the channel loop (tracking.m:133) are dealt over nGpus B200s inside the library - one gc_handle, one stream and one host thread
+ * per GPU; the SV list round-robin, the channels in contiguous blocks - and the per-SV results are merged on the host, so that
+ * the MATLAB caller gets every GPU of the box through the same two calls.  Results are bit-identical to one GPU's.
+ *   nGpus <= 0 = every visible device; the devices used are cfg->device .. cfg->device + nGpus - 1.
+ * Every function mirrors the single-GPU one of the same name (arguments, result layout, error codes, short-record semantics). */
+typedef struct gc_multi gc_multi;
+int  gc_multi_create(gc_multi** out, const gc_config* cfg, int32_t nGpus);
+void gc_multi_destroy(gc_multi* m);
+const char* gc_multi_last_error(const gc_multi* m);
+int gc_multi_n_gpus(const gc_multi* m);
+gc_handle* gc_multi_handle(gc_multi* m, int32_t gpu);                  /* the per-GPU handle (statistics, stream) */
+int gc_multi_set_code(gc_multi* m, int32_t sv, int32_t component, const int8_t* chips, int32_t nChips);
+int gc_multi_set_param(gc_multi* m, int32_t key, double value);
+int gc_multi_set_cl_code_phase(gc_multi* m, int32_t nCh, const int32_t* clCodePhase);
+int gc_multi_get_cl_code_phase(const gc_multi* m, int32_t* clCodePhase);
+int gc_multi_set_record_host(gc_multi* m, const void* bytes, size_t nbytes);      /* one H2D copy per GPU, in parallel */
+int gc_multi_acquire(gc_multi* m, int32_t nSv, const int32_t* svList, double* carrFreq, double* codePhase, double* peakMetric,
+                     int32_t* coarseBin, int32_t* coarseCodePhase);
+int gc_multi_acquire_host(gc_multi* m, const int8_t* iq, size_t nSamples, int32_t nSv, const int32_t* svList,
+                          double* carrFreq, double* codePhase, double* peakMetric, int32_t* coarseBin, int32_t* coarseCodePhase);
+int gc_multi_track(gc_multi* m, int32_t nCh, const int32_t* sv, const double* acqFreq, const double* codePhase,
+                   const double* codeFreq0, int32_t nEpochs, double* out, double* vsmValue, double* vsmIndex, int32_t* epochsDone);
+int gc_multi_track_file(gc_multi* m, const char* path, int32_t nCh, const int32_t* sv, const double* acqFreq,
+                        const double* codePhase, const double* codeFreq0, int32_t nEpochs, double* out, double* vsmValue,
+                        double* vsmIndex, int32_t* epochsDone);
+/* device time of the slowest GPU in the last gc_multi_acquire* / gc_multi_track* call (ms, CUDA events on each GPU's stream) */
+int gc_multi_get_times(const gc_multi* m, double* acqMs, double* trackMs);
 
 /* Device-side timing of the most recent gc_acquire / gc_track, measured with CUDA events on the
  * engine's own stream (the stream the kernels are launched on). */

@@ -150,6 +150,21 @@ for p in sv:                                    # stand-in for the per-rank GPU 
     local["carrFreq"][p - 1] = 20e3 + p if p % 3 == 0 else 0.0
     local["coarseBin"][p - 1] = p % 29 + 1
 m = shard.gather_acq_results(local, sv)
+# the device-buffer path of a one-process-per-GPU run (Engine.acquire_device -> all_gather_into_tensor -> sum), on CPU tensors here
+import torch
+buf = torch.from_numpy(np.concatenate([local["peakMetric"], local["codePhase"], local["carrFreq"], local["coarseBin"].astype(np.float64)]))
+md = shard.merge_device_results(shard.all_gather_device(buf), 32)
+for k in ("peakMetric", "codePhase", "carrFreq", "coarseBin"):
+    assert np.array_equal(md[k], m[k]), k
+# GLONASS: the unit list holds frequency numbers K = -7..6 stored at index K + 7 (MATLAB's K + 8)
+ks = shard.shard_units(list(range(-7, 7)), rank, 2)
+gl = dict(peakMetric=np.zeros(21), codePhase=np.zeros(21), carrFreq=np.zeros(21), coarseBin=np.zeros(21, dtype=np.int32))
+for k in ks:
+    gl["peakMetric"][k + 7] = 100.0 + k
+    gl["carrFreq"][k + 7] = 1e6 - 562.5e3 * k
+g = shard.gather_acq_results(gl, ks, glonass=True)
+assert np.array_equal(g["peakMetric"][:14], 100.0 + np.arange(-7, 7)) and not g["peakMetric"][14:].any(), g["peakMetric"]
+assert np.array_equal(g["carrFreq"][:14], 1e6 - 562.5e3 * np.arange(-7, 7))
 assert np.array_equal(m["peakMetric"], 1.0 + np.arange(1, 33)), m["peakMetric"]
 assert np.array_equal(m["codePhase"], 10.0 * np.arange(1, 33))
 assert np.array_equal(m["carrFreq"] != 0, np.arange(1, 33) % 3 == 0)
@@ -159,8 +174,30 @@ print("rank", rank, "ok")
 """
 
 
+def test_plan_pairs_balances_by_cost_and_covers_every_pair():
+    """The (signal, SV) pairs of the all-constellation search (BASELINE configs[4]) dealt over 8 ranks by measured cost."""
+    svs = {"GPS_L1CA": range(1, 33), "GLO_GL1": range(-7, 7), "GLO_GL2": range(-7, 7), "BDS_B3I": range(1, 64), "GAL_E1C": range(1, 37),
+           "GPS_L5C": range(1, 33), "GAL_E5a": range(1, 37), "GAL_E5b": range(1, 37), "BDS_B2a": range(1, 30), "BDS_B1I": range(1, 54),
+           "GPS_L2C": range(1, 33), "BDS_B1C": range(1, 63)}
+    pairs = [(sig, sv) for sig, r in svs.items() for sv in r]
+    assert len(pairs) == 439
+    for world in (1, 2, 4, 8):
+        plan, load = shard.plan_pairs(pairs, world)
+        got = sorted((sig, sv) for r in plan for sig, l in r.items() for sv in l)
+        assert got == sorted(pairs)                                   # every pair on exactly one rank
+        assert max(load) <= 1.08 * (sum(load) / world) + 1e-9, (world, load)
+        assert plan == shard.plan_pairs(pairs, world)[0]              # deterministic: every rank computes the same plan
+    plan, load = shard.plan_pairs(pairs, 8)
+    total = sum(shard.COST_MS_PER_SV[s] * len(r) for s, r in svs.items())
+    assert max(load) < total / 8 + 4.0                                # the 40+ ms signals (L2C, B1C) are spread over all ranks
+    assert all("GPS_L2C" in r and "BDS_B1C" in r for r in plan)
+    assert shard.shard_channels(592, 7, 8) == list(range(518, 592)) and shard.shard_channels(12, 6, 8) == [] and shard.shard_channels(12, 1, 8) == [2, 3]
+    assert shard.result_index(-7, True) == 0 and shard.result_index(13, True) == 20 and shard.result_index(32) == 31
+
+
 def test_two_rank_gloo_gather(tmp_path):
-    """world_size 2 over gloo: PRNs sharded round-robin, one all-gather rebuilds acqResults."""
+    """world_size 2 over gloo: PRNs sharded round-robin, one all-gather rebuilds acqResults (host arrays, device-buffer layout,
+    GLONASS frequency numbers)."""
     script = tmp_path / "w.py"
     script.write_text(_WORKER.format(root=ROOT, port=29000 + os.getpid() % 2000))
     procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

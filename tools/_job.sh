@@ -1,3 +1,3 @@
 cd $GRAFT_REPO_ROOT
-python -m pytest tests -m gpu -q -s 2>&1 | grep -v "^$" | tail -150 > gpurun_out/r02_gputests.log
-tail -60 gpurun_out/r02_gputests.log
+nvidia-smi -L
+python -m pytest tests/test_gpu_multi.py -m gpu -x -q 2>&1 | tail -30
