@@ -6,10 +6,13 @@
 
 Headline metric (BASELINE.json): acquisition PRN x Doppler cells/s on the GPS L1 C/A grid
 32 PRN x 29 Doppler bins, FFT length 2N = 32736 @ 16.368 Msps, 20 non-coherent blocks
-(configs[1]); the same JSON line carries the tracking leg (configs[2]: 12 channels x 60000 ms
-correlate-and-dump) under "tracking".  A "step" is one full pass of the acquisition grid over one
-record.  N > 1: every rank runs the full grid on its own record (weak scaling: the SV list grows
-with N), followed by one all-gather of the per-PRN peak metrics.
+(configs[1]).  A "step" is one full pass of that ONE grid over one record.  N > 1 (one process per
+GPU, torchrun): the 32 PRNs are dealt round-robin over the ranks, every rank searches its share on
+the same record (replicated), leaves acqResults on the device and ONE NCCL all-gather merges them -
+strong scaling of one grid.  The same line carries, as flat top-level keys the driver can read, the
+tracking leg (configs[2]: 12 channels x 60000 ms, channels dealt over the ranks; and the 592-channel
+batch), configs[3] (GAL E1C 36 x 81 at 20 Msps) and configs[4] (all twelve signals' acquisitions,
+439 (signal, SV) pairs dealt by measured cost), each sharded the same way.
 """
 import argparse
 import json
@@ -30,7 +33,8 @@ CELLS = N_PRN * N_BINS
 # + the replica spectrum 2N x 8 B; per channel-ms = blksize x 2 B read + 15 doubles written.
 BYTES_PER_CELL = N_NONCOH * 2 * N_CODE * 2 + 2 * N_CODE * 8          # 1,571,328
 BYTES_PER_CHANNEL_MS = N_CODE * 2 + 15 * 8                            # 32,856
-
+WORKLOAD = ("GPS_L1CA acquisition grid: 32 PRN x 29 Doppler x 20 non-coherent blocks, FFT length 32736 @ 16.368 Msps, "
+            "8-bit complex IF (BASELINE.json configs[1])")
 
 _OUT = sys.stdout
 
@@ -81,79 +85,96 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# --------------------------------------------------------------------------------- reference arm
+# --------------------------------------------------------------------------------- the reference's CPU path
+def cpu_acquisition_rate(raw_acq, prns, cores):
+    """The oracle's restatement of acquisition.m (NumPy/SciPy pocketfft, float64) over `prns`, one PRN per host thread - the
+    PRN loop of acquisition.m:155 is what a CPU build would parallelise.  Returns (cells/s, seconds, results)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import copy
+    from concurrent.futures import ThreadPoolExecutor
+    import np_oracle as O
+    so = O.Settings(samplingFreq=FS, acqSatelliteList=list(prns))
+    sig = O.read_acq_signal(raw_acq, so)
+
+    def one(prn):
+        s1 = copy.copy(so)
+        s1.acqSatelliteList = [prn]
+        return O.acquisition(sig, s1, workers=1)
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max(1, min(cores, len(prns)))) as ex:
+        res = list(ex.map(one, prns))
+    dt = time.perf_counter() - t0
+    return len(prns) * N_BINS / dt, dt, dict(zip(prns, res))
+
+
 def run_reference(args):
-    """The reference's CPU implementation of the path.  The reference is MATLAB (no MATLAB/Octave in
-    this image, nothing to compile into oracle/_ref), so this is the oracle port: the NumPy/SciPy
-    restatement of acquisition.m with pocketfft on all host threads.  Each step is a bounded sample
-    of the grid (SAMPLE_PRNS PRNs x 29 bins x 20 blocks)."""
+    """The reference's CPU implementation of the path.  The reference is MATLAB (no MATLAB/Octave in this image, nothing to
+    compile into oracle/_ref), so this is the oracle port on all host threads.  Each step is a bounded sample of the grid
+    (one PRN per host thread x 29 bins x 20 blocks; the work is exactly linear in PRNs)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import numpy as np
-    import np_oracle as O
     from cu_sdr_collection_b200 import synth
     cores = os.cpu_count() or 1
-    sample_prns = 2
     sc = synth.default_scene(fs=FS, nsat=8)
     raw = synth.make_record(sc, N_CODE * 42)
-    s = O.Settings(samplingFreq=FS, acqSatelliteList=[sc.sats[0].prn, 1 if sc.sats[0].prn != 1 else 2])
-    sig = O.read_acq_signal(raw, s)
+    prns = list(range(1, min(32, max(2, cores)) + 1))
     for _ in range(max(1, min(args.warmup, 1))):
-        O.acquisition(sig, s, workers=cores)
-    t0 = time.perf_counter()
+        cpu_acquisition_rate(raw, prns[:2], cores)
+    rates, secs = [], []
     for _ in range(args.steps):
-        O.acquisition(sig, s, workers=cores)
-    dt = (time.perf_counter() - t0) / args.steps
-    cells = sample_prns * N_BINS
-    value = cells / dt
+        r, dt, _ = cpu_acquisition_rate(raw, prns, cores)
+        rates.append(r); secs.append(dt)
+    value = len(prns) * N_BINS * len(secs) / sum(secs)
     line = {
         "impl": "reference", "metric": "acquisition PRNxDoppler cells/s", "value": value, "unit": "cells/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "GPS_L1CA acquisition grid: 32 PRN x 29 Doppler x 20 non-coherent blocks, "
-                               "FFT length 32736 @ 16.368 Msps", "sample_per_step": f"{sample_prns} PRN x 29 bins"},
-        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample_prns} PRN x 29 Doppler bins x 20 blocks per step (NumPy/SciPy pocketfft oracle, "
-                                   f"workers={cores}); work is linear in PRNs"},
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(secs) / len(secs) * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample_per_step": f"{len(prns)} PRN x 29 bins x 20 blocks"},
+        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": min(cores, len(prns)), "kind": "port",
+                         "sample": f"{len(prns)} PRN x 29 Doppler bins x 20 blocks per step, one PRN per host thread (NumPy/SciPy "
+                                   f"pocketfft oracle of acquisition.m, float64); work is linear in PRNs"},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), file=_OUT, flush=True)
 
 
-# --------------------------------------------------------------------------------- CPU baselines
-def cpu_baselines(raw_acq, raw_trk_host, settings, chans):
-    """Oracle timed on the host cores (rank 0, N = 1): bounded samples of both workloads."""
+def cpu_baselines_and_parity(raw_acq, raw_trk_host, settings, chans, gpu_acq, gpu_track_out):
+    """Oracle timed on the host cores (rank 0, N = 1): bounded samples of both workloads, and - since the same bytes went through
+    the GPU - the observed worst-case parity errors of this run."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import numpy as np
-    import np_oracle as O
-    from helpers import c_tracking, to_oracle_settings
+    from helpers import c_tracking, to_oracle_settings, orc, track_rel_err
     cores = os.cpu_count() or 1
-    so = to_oracle_settings(settings)
-    so.acqSatelliteList = [chans[0][0], chans[1][0]]
-    sig = O.read_acq_signal(raw_acq, so)
-    O.acquisition(sig, O.Settings(samplingFreq=FS, acqSatelliteList=[1], acqNonCohTime=1), workers=cores)   # warm pocketfft plans
-    t0 = time.perf_counter()
-    O.acquisition(sig, so, workers=cores)
-    dt = time.perf_counter() - t0
-    acq = {"value": 2 * N_BINS / dt, "unit": "cells/s", "cores": cores, "kind": "port",
-           "sample": f"2 PRN x 29 bins x 20 blocks of the same record in {dt:.2f} s "
-                     f"(NumPy/SciPy pocketfft oracle, workers={cores})"}
+    prns = sorted({c[0] for c in chans})[: max(2, min(cores, 8))]
+    cpu_acquisition_rate(raw_acq, prns[:1], 1)                       # warm pocketfft plans
+    rate, dt, res = cpu_acquisition_rate(raw_acq, prns, cores)
+    acq = {"value": rate, "unit": "cells/s", "cores": min(cores, len(prns)), "kind": "port",
+           "sample": f"{len(prns)} PRN x 29 bins x 20 blocks of the same record in {dt:.2f} s, one PRN per host thread "
+                     f"(NumPy/SciPy pocketfft oracle, float64)"}
+    pm_err, idx_ok = 0.0, True
+    for p in prns:
+        r = res[p]
+        pm_err = max(pm_err, abs(gpu_acq["peakMetric"][p - 1] - r["peakMetric"][p - 1]) / r["peakMetric"][p - 1])
+        idx_ok &= (gpu_acq["carrFreq"][p - 1] == r["carrFreq"][p - 1] and gpu_acq["codePhase"][p - 1] == r["codePhase"][p - 1]
+                   and gpu_acq["coarseBin"][p - 1] == r["coarseBin"][p - 1])
     n_ms = 1500
     prn = [c[0] for c in chans]; af = [c[1] for c in chans]; cp = [c[2] for c in chans]
-    settings_trk = to_oracle_settings(settings)
     t0 = time.perf_counter()
-    out, vv, vi, done = c_tracking(raw_trk_host, settings_trk, prn, af, cp, n_ms, parallel=1)
+    out, vv, vi, done = c_tracking(raw_trk_host, to_oracle_settings(settings), prn, af, cp, n_ms, parallel=1)
     dt = time.perf_counter() - t0
-    import ctypes
-    from helpers import orc
     thr = orc().orc_num_threads()
     trk = {"value": int(done.sum()) / dt, "unit": "channel-ms/s", "cores": min(thr, len(prn)), "kind": "port",
-           "sample": f"{len(prn)} channels x {n_ms} ms in {dt:.2f} s (C oracle, OpenMP over channels, {thr} threads)"}
-    return acq, trk
+           "sample": f"{len(prn)} channels x {n_ms} ms in {dt:.2f} s (C oracle of tracking.m, OpenMP over channels, {thr} threads)"}
+    errs = track_rel_err(gpu_track_out[:, :15, :n_ms], out)
+    parity = {"checked_against": "oracle (float64 restatement of acquisition.m / tracking.m) on the same bytes, in this run",
+              "acquisition": {"prns": len(prns), "indices_exact": bool(idx_ok), "peakMetric_max_rel_err": pm_err, "gate": 1e-6},
+              "tracking": {"channels": len(prn), "epochs": n_ms, "absoluteSample_exact": errs["absoluteSample"] == 0.0,
+                           "I_P_max_err_over_absP": errs["I_P"], "Q_P_max_err_over_absP": errs["Q_P"], "gate": 1e-6}}
+    return acq, trk, parity
 
 
 # --------------------------------------------------------------------------------- this engine
@@ -167,6 +188,7 @@ def main():
     ap.add_argument("--track-channels", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tracking", action="store_true")
+    ap.add_argument("--no-widened", action="store_true")
     args = ap.parse_args()
     # ONE JSON line on stdout: keep the real stdout for it and send everything else that writes to fd 1 (NCCL's version banner,
     # library chatter) to stderr
@@ -181,7 +203,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from cu_sdr_collection_b200 import Engine, init_settings, preRun, synth
+    from cu_sdr_collection_b200 import Engine, MultiEngine, init_settings, preRun, shard, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -205,9 +227,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- synthetic 60 s record, one per rank (seed + rank), generated on the GPU (untimed setup)
+    # ---- the ONE synthetic 60 s record, replicated: every rank generates the same bytes (same seed) on its GPU (untimed setup)
     settings = init_settings(samplingFreq=FS, msToProcess=args.track_ms, numberOfChannels=args.track_channels)
-    scene = synth.default_scene(fs=FS, nsat=10, seed=20260101 + rank)
+    scene = synth.default_scene(fs=FS, nsat=10, seed=20260101)
     for sat in scene.sats:                      # strong enough that >= 10 SVs clear acqThreshold
         sat.cn0 = max(sat.cn0, 44.0)
     n_samples = N_CODE * (args.track_ms + 60)
@@ -224,19 +246,19 @@ def main():
         with torch.cuda.stream(ext):
             flush_buf.zero_()
 
-    def gather_metrics(acq):
-        if world == 1:
-            return
-        t = torch.from_numpy(np.stack([acq["peakMetric"], acq["codePhase"], acq["carrFreq"],
-                                       acq["coarseBin"].astype(np.float64)])).to(dev)
-        outl = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(outl, t)                # the one NCCL all-gather of per-PRN peak metrics
+    sv_all = list(settings.acqSatelliteList)
+    my_sv = shard.shard_units(sv_all, rank, world)            # this rank's PRNs of the ONE grid
+    res_buf = torch.zeros(4 * N_PRN, dtype=torch.float64, device=dev)
+
+    def sharded_step():
+        """This rank's share of the grid, acqResults left on the device, ONE all-gather, merged acqResults on the host."""
+        eng.acquire_device(my_sv, res_buf)
+        return shard.merge_device_results(shard.all_gather_device(res_buf), N_PRN)
 
     sampler = ClockSampler(local)
     # ---- acquisition, device-timed with inputs resident in HBM ------------------------------
     for _ in range(args.warmup):
-        acq = eng.acquire()
-        gather_metrics(acq)
+        acq = sharded_step()
     barrier()
     if rank == 0:
         sampler.start()
@@ -247,20 +269,33 @@ def main():
     for i in range(args.steps):
         flush_l2()
         ev[i][0].record(ext)
-        acq = eng.acquire()
-        ev[i][1].record(ext)
-        gather_metrics(acq)
+        acq = sharded_step()
+        ev[i][1].record()                        # after the all-gather and the 1 KB D2H on torch's stream
         st = eng.stats()
         rows_ms += st["corr_rows_ms"]; cols_ms += st["corr_cols_ms"]; launches += st["acq_launches"]
     barrier()
     t_wall = time.perf_counter() - t_wall
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     step_ms = max_over_ranks(dev_ms / args.steps)
-    value = CELLS * world / (step_ms * 1e-3)
+    value = CELLS / (step_ms * 1e-3)
     st = eng.stats()
     n_chunks = max(1, st["corr_row_launches"])
     rows_launch_ms = rows_ms / args.steps / n_chunks
-    cells_per_launch = CELLS / n_chunks
+    cells_per_launch = len(my_sv) * N_BINS / n_chunks
+
+    # secondary number at N > 1: N independent replicas of the full grid (what round 1 reported)
+    replica_value = None
+    if world > 1:
+        for _ in range(2):
+            eng.acquire()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(3):
+            eng.acquire()
+        e1.record(ext)
+        torch.cuda.synchronize()
+        replica_value = CELLS * world / (max_over_ranks(e0.elapsed_time(e1) / 3) * 1e-3)
 
     # ---- acquisition end to end through the reference-facing call with HOST buffers ---------
     n_acq_samples = N_CODE * 42
@@ -268,21 +303,55 @@ def main():
     host_acq.copy_(rec[: 2 * n_acq_samples])
     host_acq_np = host_acq.numpy()
     eng_e2e = Engine(settings, device=local)
+
+    def e2e_step():
+        a = eng_e2e.acquire(my_sv, host_iq=host_acq_np)     # H2D of longSignal + search + D2H of acqResults (gc_acquire_host)
+        return shard.gather_acq_results(a, my_sv, device=dev) if world > 1 else a
     for _ in range(2):
-        eng_e2e.acquire(host_iq=host_acq_np)
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        a2 = eng_e2e.acquire(host_iq=host_acq_np)      # H2D of longSignal + search + D2H of acqResults
-        gather_metrics(a2)
+        a2 = e2e_step()
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) / args.steps * 1e3)
-    e2e_value = CELLS * world / (e2e_ms * 1e-3)
+    e2e_value = CELLS / (e2e_ms * 1e-3)
     d2h_acq = 32 * (3 * 8 + 2 * 4) + 32 * 16 + 8
     assert np.array_equal(a2["carrFreq"], acq["carrFreq"]) and np.array_equal(a2["codePhase"], acq["codePhase"])
+    assert np.array_equal(a2["peakMetric"], acq["peakMetric"])
     eng_e2e.close()
+    # one-shot cost of the drop-in: gc_create (context, plan, twiddles, replica spectra, work buffer) + gc_acquire_host + gc_destroy,
+    # which is what a MEX call without a cached handle pays (matlab/gnsscorr_mex.c keeps the handle; this is its first call)
+    cold = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        ec = Engine(settings, device=local)
+        ac = ec.acquire(my_sv, host_iq=host_acq_np)
+        if world > 1:
+            shard.gather_acq_results(ac, my_sv, device=dev)
+        ec.close()
+        cold.append(max_over_ranks(time.perf_counter() - t0))
+    e2e_cold_ms = sorted(cold)[1] * 1e3
+    # the same grid through the in-library fan-out (gc_multi_*: what the MATLAB caller gets, no torch.distributed): rank 0 drives all N GPUs
+    multi_abi = None
+    if world > 1:
+        barrier()
+        if rank == 0:
+            me = MultiEngine(settings, n_gpus=world)
+            for _ in range(2):
+                am = me.acquire(sv_all, host_iq=host_acq_np)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                am = me.acquire(sv_all, host_iq=host_acq_np)
+            mt = (time.perf_counter() - t0) / args.steps
+            assert np.array_equal(am["carrFreq"], acq["carrFreq"]) and np.array_equal(am["peakMetric"], acq["peakMetric"])
+            multi_abi = {"value": CELLS / mt, "unit": "cells/s", "ms_per_step": mt * 1e3,
+                         "call": f"gc_multi_acquire_host on {world} GPUs from one process (host longSignal -> merged acqResults)"}
+            me.close()
+        barrier()
 
-    # ---- tracking: 12 channels x 60000 ms (configs[2]) ---------------------------------------
+    # ---- tracking: 12 channels x 60000 ms (configs[2]), channels dealt over the ranks in blocks ---------------------------
     tracking = None
     chans = []
     ch = preRun(acq, settings)
@@ -292,189 +361,223 @@ def main():
     n_found = len(chans)
     while len(chans) < args.track_channels and n_found:       # fill the 12 channels (repeat SVs if fewer were found)
         chans.append(chans[len(chans) % n_found])
+    out = None
     if not args.no_tracking and chans:
-        prn = [c[0] for c in chans]; af = [c[1] for c in chans]; cp = [c[2] for c in chans]
-        eng.track(prn, af, cp, min(2000, args.track_ms))        # warm-up
+        mine = shard.shard_channels(len(chans), rank, world)
+        prn = [chans[i][0] for i in mine]; af = [chans[i][1] for i in mine]; cp = [chans[i][2] for i in mine]
+        if mine:
+            eng.track(prn, af, cp, min(2000, args.track_ms))        # warm-up
         barrier()
-        reps, kms, wall = 2, [], []
+        reps, kms = 2, []
+        units = 0
         for _ in range(reps):
             flush_l2()
             torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            out, vv, vi, done = eng.track(prn, af, cp, args.track_ms)
-            wall.append(time.perf_counter() - t0)
-            kms.append(eng.stats()["track_kernel_ms"])
+            if mine:
+                out, vv, vi, done = eng.track(prn, af, cp, args.track_ms)
+                kms.append(eng.stats()["track_kernel_ms"])
+                units = int(done.sum())
+            else:
+                kms.append(0.0)
         barrier()
         k_ms = max_over_ranks(sum(kms) / reps)
-        units = int(done.sum())
-        lock = float(np.mean(np.abs(out[:, 3, 100:])) / max(1e-9, np.mean(np.abs(out[:, 7, 100:]))))
-        # end to end: H2D of the whole record from pinned host memory + kernel + D2H of trackResults
-        host_rec = torch.empty(rec.numel(), dtype=torch.int8).pin_memory()
-        host_rec.copy_(rec)
-        eng_t = Engine(settings, device=local)
-        eng_t.set_record_host_ptr(host_rec.data_ptr(), host_rec.numel())      # untimed warm-up: the same call once, so that the
-        eng_t.track(prn, af, cp, args.track_ms)                               # timed one measures copies + kernel, not cudaMalloc
-        barrier()
-        t0 = time.perf_counter()
-        eng_t.set_record_host_ptr(host_rec.data_ptr(), host_rec.numel())
-        out2, _, _, done2 = eng_t.track(prn, af, cp, args.track_ms)
-        barrier()
-        e2e_t = max_over_ranks(time.perf_counter() - t0)
-        assert np.array_equal(done2, done)
-        eng_t.close()
+        if world > 1:
+            t = torch.tensor([float(units)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t)
+            units = int(t.item())
+        lock = float(np.mean(np.abs(out[:, 3, 100:])) / max(1e-9, np.mean(np.abs(out[:, 7, 100:])))) if out is not None else None
         pk, pk_src = peaks()
         t_ach = units * BYTES_PER_CHANNEL_MS / (k_ms * 1e-3) / 1e9
         tracking = {
-            "metric": "tracking channel-ms/s", "value": units * world / (k_ms * 1e-3), "unit": "channel-ms/s",
-            "channels": len(prn), "ms": args.track_ms, "kernel_ms": k_ms, "us_per_epoch": k_ms * 1e3 / args.track_ms,
-            "prompt_I_over_Q": lock,
-            "e2e": {"value": units * world / e2e_t, "unit": "channel-ms/s", "h2d_bytes_per_step": int(host_rec.numel()),
-                    "d2h_bytes_per_step": int(out2.nbytes)},
+            "metric": "tracking channel-ms/s", "value": units / (k_ms * 1e-3), "unit": "channel-ms/s", "dtype": "f64",
+            "channels": len(chans), "channels_per_rank": [len(shard.shard_channels(len(chans), r, world)) for r in range(world)],
+            "ms": args.track_ms, "kernel_ms": k_ms, "us_per_epoch": k_ms * 1e3 / args.track_ms, "prompt_I_over_Q": lock,
             "roofline": {"bound": "hbm", "achieved": t_ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": t_ach / pk["hbm_gbs"], "traffic": None,
-                         "note": "latency-bound: 60000-epoch loop-carried dependency per channel, 12 CTAs on 148 SMs"},
+                         "note": "latency-bound: 60000-epoch loop-carried dependency per channel (each channel already spread over 8 SMs); "
+                                 "more GPUs do not shorten the chain, they only free SMs"},
         }
-        # bandwidth regime: many independent channels (same kernel), 1000 ms
+        if world == 1:
+            # end to end: H2D of the whole record from pinned host memory + kernel + D2H of trackResults
+            host_rec = torch.empty(rec.numel(), dtype=torch.int8).pin_memory()
+            host_rec.copy_(rec)
+            eng_t = Engine(settings, device=local)
+            eng_t.set_record_host_ptr(host_rec.data_ptr(), host_rec.numel())      # untimed warm-up: the same call once, so that the
+            eng_t.track(prn, af, cp, args.track_ms)                               # timed one measures copies + kernel, not cudaMalloc
+            t0 = time.perf_counter()
+            eng_t.set_record_host_ptr(host_rec.data_ptr(), host_rec.numel())
+            out2, _, _, done2 = eng_t.track(prn, af, cp, args.track_ms)
+            e2e_t = time.perf_counter() - t0
+            assert np.array_equal(done2, done) and np.array_equal(out2, out)
+            eng_t.close()
+            del host_rec
+            tracking["e2e"] = {"value": units / e2e_t, "unit": "channel-ms/s", "h2d_bytes_per_step": int(rec.numel()),
+                               "d2h_bytes_per_step": int(out2.nbytes)}
+        # bandwidth regime: 592 independent channels x 1000 ms (same kernel), dealt over the ranks
         big = [chans[i % len(chans)] for i in range(592)]
-        eng.track([c[0] for c in big], [c[1] for c in big], [c[2] for c in big], 1000)
+        mineb = shard.shard_channels(592, rank, world)
+        eng.track([big[i][0] for i in mineb], [big[i][1] for i in mineb], [big[i][2] for i in mineb], 1000)
+        barrier()
+        eng.track([big[i][0] for i in mineb], [big[i][1] for i in mineb], [big[i][2] for i in mineb], 1000)
         bk = max_over_ranks(eng.stats()["track_kernel_ms"])
         b_ach = 592 * 1000 * BYTES_PER_CHANNEL_MS / (bk * 1e-3) / 1e9
-        tracking["batch_592ch_1000ms"] = {"value": 592 * 1000 * world / (bk * 1e-3), "unit": "channel-ms/s", "kernel_ms": bk,
-                                          "roofline_frac": b_ach / pk["hbm_gbs"], "achieved_gbs": b_ach}
-    # ---- widened rows: GLONASS L1 at the reference's default settings ----------
-    glonass = None
-    if not args.no_tracking:
-        gs = init_settings("GLO_GL1", msToProcess=5000, numberOfChannels=12)
-        gscene = synth.default_scene_glo(fs=gs.samplingFreq, nsat=8, seed=20260101 + rank)
-        for sat in gscene.sats:
-            sat.cn0 = max(sat.cn0, 44.0)
-        grec = synth.make_record_torch(gscene, 12000 * 5060, device=dev)
-        geng = Engine(gs, device=local)
-        geng.set_record(grec)
-        for _ in range(2):
-            gacq = geng.acquire()
-        gst = geng.stats()
-        gcells = len(gs.acqSatelliteList) * 21
-        gch = preRun(gacq, gs)
-        gsv = [c["K"] for c in gch if c["status"] == "T"]
-        glonass = {"acquisition": {"value": gcells * world / (max_over_ranks(gst["acq_total_ms"]) * 1e-3), "unit": "cells/s",
-                                   "workload": "GLO_GL1 defaults: 14 frequency channels x 21 Doppler x 20 blocks, FFT length 24000 "
-                                               "@ 12 Msps (fused 30 x 32 x 25 plan)", "ms": gst["acq_total_ms"],
-                                   "n_acquired": int(gst["n_acquired"])}}
-        if gsv:
-            while len(gsv) < 12:
-                gsv.append(gsv[len(gsv) % len(set(gsv))])
-            byK = {c["K"]: c for c in gch if c["status"] == "T"}
-            geng.track(gsv, [byK[k]["acquiredFreq"] for k in gsv], [float(byK[k]["codePhase"]) for k in gsv], 5000)
-            gk = max_over_ranks(geng.stats()["track_kernel_ms"])
-            glonass["tracking"] = {"value": 12 * 5000 * world / (gk * 1e-3), "unit": "channel-ms/s", "channels": 12, "ms": 5000,
-                                   "us_per_epoch": gk * 1e3 / 5000}
-        geng.close()
-        del grec
-    # ---- widened rows (BASELINE configs[3]): Galileo E1 36 PRN x 81 Doppler x 4 ms @ 20 Msps
-    #      (FFT length 160000, two replicas, fused 200 x 32 x 25 plan) and GPS L5C at the reference defaults
-    #      (32 PRN x 21 Doppler x 25 blocks x 2 replicas, FFT length 36000, fused plan) ----------------------
+        tracking["batch_592ch_1000ms"] = {"value": 592 * 1000 / (bk * 1e-3), "unit": "channel-ms/s", "kernel_ms": bk,
+                                          "channels_per_rank": len(mineb), "roofline_frac": b_ach / (pk["hbm_gbs"] * world),
+                                          "achieved_gbs": b_ach}
+
+    # ---- widened rows: configs[3] (GAL E1C 36 x 81 @ 20 Msps), GLONASS and GPS L5C at the reference defaults, configs[4] ----
     widened = None
-    if not args.no_tracking:
-        from cu_sdr_collection_b200.codes import standin_codes, standin_e1_codes
+    if not args.no_tracking and not args.no_widened:
+        from cu_sdr_collection_b200.codes import standin_b1c_codes, standin_codes, standin_e1_codes, standin_varb_codes
+        from cu_sdr_collection_b200.engine import signal_id
+        from cu_sdr_collection_b200.settings import samples_per_code
         widened = {}
+        sd = 20260101
         e1codes = standin_e1_codes()
+        # configs[3]: 36 PRNs dealt round-robin over the ranks, one all-gather
         es = init_settings("GAL_E1C", samplingFreq=20e6, acqSearchBand=6000.0, acqSearchStep=150.0)     # 81 bins
-        escene = synth.default_scene_e1c(e1codes, fs=20e6, nsat=6, seed=20260101 + rank)
+        escene = synth.default_scene_e1c(e1codes, fs=20e6, nsat=6, seed=sd)
         for sat in escene.sats:
             sat.cn0 = max(sat.cn0, 46.0)
         erec = synth.make_record_torch(escene, 80000 * 43, device=dev)
         eeng = Engine(es, device=local, codes=e1codes)
         eeng.set_record(erec)
+        esv = shard.shard_units(es.acqSatelliteList, rank, world)
+        ebuf = torch.zeros(4 * 50, dtype=torch.float64, device=dev)
+        eext = torch.cuda.ExternalStream(eeng.stream_ptr, device=dev)
         for _ in range(2):
-            eacq = eeng.acquire()
-        est = eeng.stats()
+            eeng.acquire_device(esv, ebuf)
+            eacq = shard.merge_device_results(shard.all_gather_device(ebuf), 50)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(eext)
+        for _ in range(3):
+            eeng.acquire_device(esv, ebuf)
+            eacq = shard.merge_device_results(shard.all_gather_device(ebuf), 50)
+        e1.record()
+        torch.cuda.synchronize()
+        ems = max_over_ranks(e0.elapsed_time(e1) / 3)
         ecells = len(es.acqSatelliteList) * 81
         widened["gal_e1c_acquisition"] = {
-            "value": ecells * world / (max_over_ranks(est["acq_total_ms"]) * 1e-3), "unit": "cells/s", "ms": est["acq_total_ms"],
-            "workload": "GAL_E1C 36 PRN x 81 Doppler x 1 block x 2 replicas (E1B + E1C), FFT length 160000 @ 20 Msps "
-                        "(BASELINE.json configs[3] grid; fused 200 x 32 x 25 plan with two-level 20 x 10 columns, stand-in memory codes)",
-            "n_acquired": int(est["n_acquired"]), "acq_path": int(est["acq_path"])}
+            "value": ecells / (ems * 1e-3), "unit": "cells/s", "ms": ems, "prns_per_rank": len(esv),
+            "workload": "GAL_E1C 36 PRN x 81 Doppler x 1 block x 2 replicas (E1B + E1C), FFT length 160000 @ 20 Msps (BASELINE.json "
+                        "configs[3]); PRNs dealt round-robin over the ranks, one all-gather; fused 200 x 32 x 25 plan, stand-in memory codes",
+            "n_acquired": int(np.count_nonzero(eacq["carrFreq"])), "acq_path": int(eeng.stats()["acq_path"])}
         eeng.close()
         del erec
-        lcodes = standin_codes("GPS_L5C")
-        ls = init_settings("GPS_L5C")
-        lscene = synth.default_scene_fam5("GPS_L5C", lcodes, fs=18e6, nsat=8, seed=20260101 + rank)
-        for sat in lscene.sats:
-            sat.cn0 = max(sat.cn0, 44.0)
-        lrec = torch.from_numpy(synth.make_record(lscene, 18000 * 44)).to(dev)
-        leng = Engine(ls, device=local, codes=lcodes)
-        leng.set_record(lrec)
-        for _ in range(2):
-            lacq = leng.acquire()
-        lst = leng.stats()
-        widened["gps_l5c_acquisition"] = {
-            "value": 32 * 21 * world / (max_over_ranks(lst["acq_total_ms"]) * 1e-3), "unit": "cells/s", "ms": lst["acq_total_ms"],
-            "workload": "GPS_L5C defaults: 32 PRN x 21 Doppler x 25 blocks x 2 replicas (I5 + Q5), FFT length 36000 @ 18 Msps "
-                        "(fused 45 x 32 x 25 plan, stand-in codes)",
-            "n_acquired": int(lst["n_acquired"]), "acq_path": int(lst["acq_path"])}
-        leng.close()
-        del lrec
-    # ---- BASELINE configs[4]: every constellation's acquisition at the reference's default initSettings.m, one after the
-    #      other on this GPU (per rank; N ranks = N independent receivers).  Cells = SVs x Doppler rows searched. ---------
-    if not args.no_tracking and widened is not None:
-        from cu_sdr_collection_b200.codes import standin_b1c_codes, standin_varb_codes
-        from cu_sdr_collection_b200.settings import samples_per_code
-        allc = {}
-        tot_cells, tot_ms = 0, 0.0
+        if world == 1:
+            gs = init_settings("GLO_GL1", msToProcess=5000, numberOfChannels=12)
+            gscene = synth.default_scene_glo(fs=gs.samplingFreq, nsat=8, seed=sd)
+            for sat in gscene.sats:
+                sat.cn0 = max(sat.cn0, 44.0)
+            grec = synth.make_record_torch(gscene, 12000 * 5060, device=dev)
+            geng = Engine(gs, device=local)
+            geng.set_record(grec)
+            for _ in range(2):
+                gacq = geng.acquire()
+            gst = geng.stats()
+            gch = preRun(gacq, gs)
+            gsv = [c["K"] for c in gch if c["status"] == "T"]
+            widened["glonass"] = {"acquisition": {"value": 14 * 21 / (gst["acq_total_ms"] * 1e-3), "unit": "cells/s", "ms": gst["acq_total_ms"],
+                                                  "workload": "GLO_GL1 defaults: 14 frequency channels x 21 Doppler x 20 blocks, FFT length 24000 @ 12 Msps",
+                                                  "n_acquired": int(gst["n_acquired"])}}
+            if gsv:
+                while len(gsv) < 12:
+                    gsv.append(gsv[len(gsv) % len(set(gsv))])
+                byK = {c["K"]: c for c in gch if c["status"] == "T"}
+                geng.track(gsv, [byK[k]["acquiredFreq"] for k in gsv], [float(byK[k]["codePhase"]) for k in gsv], 5000)
+                gk = geng.stats()["track_kernel_ms"]
+                widened["glonass"]["tracking"] = {"value": 12 * 5000 / (gk * 1e-3), "unit": "channel-ms/s", "channels": 12, "ms": 5000,
+                                                  "us_per_epoch": gk * 1e3 / 5000}
+            geng.close()
+            del grec
+        # configs[4]: every constellation's acquisition at the reference's default initSettings.m - 439 (signal, SV) pairs dealt
+        # over the ranks by measured per-pair cost (shard.plan_pairs), every rank runs its pairs signal after signal, ONE all-gather
+        sigs = {}
 
-        def run_sig(name, st_, codes_, scene_, periods, cells):
-            nonlocal tot_cells, tot_ms
+        def add_sig(name, st_, codes_, scene_, periods, bins):
+            sigs[name] = (st_, codes_, scene_, periods, bins)
+        add_sig("GPS_L1CA", init_settings("GPS_L1CA"), None, synth.default_scene(fs=18e6, nsat=6, seed=sd), 42, 29)
+        add_sig("GLO_GL1", init_settings("GLO_GL1"), None, synth.default_scene_glo(fs=12e6, nsat=5, seed=sd), 42, 21)
+        add_sig("GLO_GL2", init_settings("GLO_GL2"), None, synth.default_scene_glo(fs=12e6, nsat=5, seed=sd + 1, freqSpacing=437.5e3), 42, 21)
+        add_sig("BDS_B3I", init_settings("BDS_B3I"), None, synth.default_scene_b3i(fs=18e6, nsat=5, seed=sd), 22, 21)
+        add_sig("GAL_E1C", init_settings("GAL_E1C"), e1codes, synth.default_scene_e1c(e1codes, fs=18e6, nsat=4, seed=sd), 42, 94)
+        for sg, per, bins in (("GPS_L5C", 42, 21), ("GAL_E5a", 102, 21), ("GAL_E5b", 102, 168), ("BDS_B2a", 17, 21)):
+            cd = standin_codes(sg)
+            add_sig(sg, init_settings(sg), cd, synth.default_scene_fam5(sg, cd, fs=18e6, nsat=4, seed=sd), per, bins)
+        cd = standin_varb_codes("BDS_B1I")
+        add_sig("BDS_B1I", init_settings("BDS_B1I"), cd, synth.default_scene_varb("BDS_B1I", cd, fs=18e6, nsat=4, seed=sd), 11, 81)
+        cd = standin_varb_codes("GPS_L2C")
+        add_sig("GPS_L2C", init_settings("GPS_L2C"), cd, synth.default_scene_varb("GPS_L2C", cd, fs=8e6, nsat=3, seed=sd), 3, 801)
+        cd = standin_b1c_codes()
+        add_sig("BDS_B1C", init_settings("BDS_B1C"), cd, synth.default_scene_varb("BDS_B1C", cd, fs=18e6, nsat=3, seed=sd), 2, 201)
+        pairs = [(name, sv) for name, v in sigs.items() for sv in v[0].acqSatelliteList]
+        plan, load = shard.plan_pairs(pairs, world)
+        mine_plan = plan[rank]
+        engines, offs, total_len = {}, {}, 0
+        lib = eng.lib
+        for name, (st_, _, _, _, _) in sigs.items():
+            offs[name] = total_len
+            total_len += 4 * lib.gc_acq_result_len(signal_id(st_))
+        allbuf = torch.zeros(total_len, dtype=torch.float64, device=dev)
+        for name in mine_plan:
+            st_, codes_, scene_, periods, bins = sigs[name]
             n_ = samples_per_code(st_)
             r_ = torch.from_numpy(synth.make_record(scene_, n_ * periods + 64)).to(dev)
             e_ = Engine(st_, device=local, codes=codes_) if codes_ is not None else Engine(st_, device=local)
             e_.set_record(r_)
-            for _ in range(2):
-                e_.acquire()
-            ms_ = max_over_ranks(e_.stats()["acq_total_ms"])
-            allc[name] = {"cells": cells, "ms": ms_, "fft_len": int(e_.stats()["fft_len"]), "n_acquired": int(e_.stats()["n_acquired"])}
-            tot_cells += cells; tot_ms += ms_
-            e_.close()
-            del r_
+            engines[name] = (e_, r_)
 
-        sd = 20260101 + rank
-        st_ = init_settings("GPS_L1CA")
-        run_sig("GPS_L1CA", st_, None, synth.default_scene(fs=18e6, nsat=6, seed=sd), 42, 32 * 29)
-        st_ = init_settings("GLO_GL1")
-        run_sig("GLO_GL1", st_, None, synth.default_scene_glo(fs=12e6, nsat=5, seed=sd), 42, 14 * 21)
-        st_ = init_settings("GLO_GL2")
-        run_sig("GLO_GL2", st_, None, synth.default_scene_glo(fs=12e6, nsat=5, seed=sd + 1, freqSpacing=437.5e3), 42, 14 * 21)
-        st_ = init_settings("BDS_B3I")
-        run_sig("BDS_B3I", st_, None, synth.default_scene_b3i(fs=18e6, nsat=5, seed=sd), 22, 63 * 21)
-        st_ = init_settings("GAL_E1C")
-        run_sig("GAL_E1C", st_, e1codes, synth.default_scene_e1c(e1codes, fs=18e6, nsat=4, seed=sd), 42, 36 * 94)
-        for sg, per, bins in (("GPS_L5C", 42, 21), ("GAL_E5a", 102, 21), ("GAL_E5b", 102, 168), ("BDS_B2a", 17, 21)):
-            cd = standin_codes(sg)
-            st_ = init_settings(sg)
-            run_sig(sg, st_, cd, synth.default_scene_fam5(sg, cd, fs=18e6, nsat=4, seed=sd), per, len(st_.acqSatelliteList) * bins)
-        cd = standin_varb_codes("BDS_B1I")
-        st_ = init_settings("BDS_B1I")
-        run_sig("BDS_B1I", st_, cd, synth.default_scene_varb("BDS_B1I", cd, fs=18e6, nsat=4, seed=sd), 11, 53 * 81)
-        cd = standin_varb_codes("GPS_L2C")
-        st_ = init_settings("GPS_L2C")
-        run_sig("GPS_L2C", st_, cd, synth.default_scene_varb("GPS_L2C", cd, fs=8e6, nsat=3, seed=sd), 3, 32 * 801)
-        cd = standin_b1c_codes()
-        st_ = init_settings("BDS_B1C")
-        run_sig("BDS_B1C", st_, cd, synth.default_scene_varb("BDS_B1C", cd, fs=18e6, nsat=3, seed=sd), 2, 62 * 201)
+        def all_constellation_pass():
+            ms = {}
+            for name, svs in mine_plan.items():
+                e_ = engines[name][0]
+                nres = lib.gc_acq_result_len(signal_id(e_.settings))
+                e_.acquire_device(svs, allbuf[offs[name]: offs[name] + 4 * nres])
+                ms[name] = e_.stats()["acq_total_ms"]
+            g = shard.all_gather_device(allbuf)                    # ONE all-gather of every signal's acqResults
+            merged = g.sum(dim=0).cpu().numpy()
+            return ms, merged
+        for _ in range(2):
+            all_constellation_pass()
+        barrier()
+        t0 = time.perf_counter()
+        reps_ac = 3
+        for _ in range(reps_ac):
+            ms_sig, merged_all = all_constellation_pass()
+        torch.cuda.synchronize()
+        wall_ac = max_over_ranks((time.perf_counter() - t0) / reps_ac * 1e3)
+        dev_ac = max_over_ranks(sum(ms_sig.values()))
+        tot_cells = sum(len(v[0].acqSatelliteList) * v[4] for v in sigs.values())
+        per_rank_ms = None
+        if world > 1:
+            t = torch.zeros(world, dtype=torch.float64, device=dev)
+            t[rank] = sum(ms_sig.values())
+            dist.all_reduce(t)
+            per_rank_ms = [round(float(x), 3) for x in t.tolist()]
+        n_acq_all = 0
+        for name, (st_, _, _, _, _) in sigs.items():
+            nres = lib.gc_acq_result_len(signal_id(st_))
+            n_acq_all += int(np.count_nonzero(merged_all[offs[name] + 2 * nres: offs[name] + 3 * nres]))
         widened["all_constellation_acquisition"] = {
-            "value": tot_cells * world / (tot_ms * 1e-3), "unit": "cells/s", "cells": tot_cells, "ms": tot_ms,
-            "sv_signal_pairs": 32 + 14 + 14 + 63 + 36 + 32 + 36 + 36 + 29 + 53 + 32 + 62,
-            "workload": "BASELINE.json configs[4]: the twelve signal folders' acquisitions at their default initSettings.m, run "
-                        "back to back on one GPU per rank (cells = SVs x Doppler rows; every length has a fused plan: 36000, 24000, 144000, "
-                        "72000, 320000, 360000; stand-in codes where the reference's are data)",
-            "per_signal": allc}
+            "value": tot_cells / (wall_ac * 1e-3), "unit": "cells/s", "cells": tot_cells, "ms": wall_ac, "device_ms_slowest_rank": dev_ac,
+            "sv_signal_pairs": len(pairs), "pairs_per_rank": [sum(len(v) for v in p.values()) for p in plan],
+            "predicted_ms_per_rank": [round(x, 2) for x in load], "device_ms_per_rank": per_rank_ms, "n_acquired": n_acq_all,
+            "workload": "BASELINE.json configs[4]: the twelve signal folders' acquisitions at their default initSettings.m; the 439 "
+                        "(signal, SV) pairs dealt over the ranks by measured per-pair cost (longest first), each rank runs its pairs signal "
+                        "after signal, one all-gather of every signal's acqResults; ms = host wall clock of a whole pass incl. the gather "
+                        "(max over ranks); stand-in codes where the reference's are data",
+            "per_signal_ms_this_rank": {k: round(v, 3) for k, v in ms_sig.items()}}
+        for e_, r_ in engines.values():
+            e_.close()
+        engines.clear()
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- CPU baseline (oracle on the host cores; rank 0, N = 1 only) -------------------------
-    cpu_acq = cpu_trk = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and chans:
+    # ---- CPU baseline (oracle on the host cores; rank 0, N = 1 only) and the observed parity of this run ---------------
+    cpu_acq = cpu_trk = parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and chans and out is not None:
         raw_trk = rec[: 2 * N_CODE * 1600].cpu().numpy()
-        cpu_acq, cpu_trk = cpu_baselines(host_acq_np, raw_trk, settings, chans)
+        cpu_acq, cpu_trk, parity = cpu_baselines_and_parity(host_acq_np, raw_trk, settings, chans, acq, out)
         if tracking is not None:
             tracking["cpu_baseline"] = cpu_trk
 
@@ -482,7 +585,9 @@ def main():
         pk, pk_src = peaks()
         achieved = cells_per_launch * BYTES_PER_CELL / (rows_launch_ms * 1e-3) / 1e9
         step_ach = CELLS * BYTES_PER_CELL / (step_ms * 1e-3) / 1e9
-        prof = os.path.join(ROOT, "profiles", "r01_traffic.json")   # ncu --set full capture of the dominant kernel
+        prof = os.path.join(ROOT, "profiles", "r02_traffic.json")   # ncu --set full capture of the dominant kernel
+        if not os.path.exists(prof):
+            prof = os.path.join(ROOT, "profiles", "r01_traffic.json")
         traffic = None
         if os.path.exists(prof):                                    # per launch like `achieved`: bytes per cell x cells of one launch
             tj = json.load(open(prof))
@@ -490,33 +595,44 @@ def main():
         line = {
             "metric": "acquisition PRNxDoppler cells/s", "value": value, "unit": "cells/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "GPS_L1CA acquisition grid: 32 PRN x 29 Doppler x 20 non-coherent blocks, FFT length "
-                                   "32736 @ 16.368 Msps, 8-bit complex IF (BASELINE.json configs[1]); per GPU",
-                       "record": f"synthetic 60 s IF record per rank, {rec.numel()} B resident in HBM, seed 20260101+rank "
-                                 f"(generated in {t_gen:.1f} s, untimed)",
-                       "l2": "flushed between timed steps (256 MiB memset); per-step working set 5 GB > 126 MB L2",
-                       "timing": "CUDA events on the engine's stream per step, max over ranks",
-                       "parallelism": f"{world} x (full grid on own record) + 1 NCCL all-gather of per-PRN metrics"},
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD + "; ONE grid, its 32 PRNs dealt round-robin over the GPUs",
+                       "record": f"synthetic 60 s IF record, {rec.numel()} B resident in the HBM of every rank (same seed 20260101: the same bytes "
+                                 f"everywhere; generated in {t_gen:.1f} s, untimed)",
+                       "l2": "flushed between timed steps (256 MiB memset); per-step working set > 126 MB L2",
+                       "timing": "CUDA events per step from the engine's stream (start) to after the all-gather + 1 KB D2H (end), max over ranks",
+                       "parallelism": f"{world} rank(s) x {len(my_sv)} PRN x 29 bins, acqResults left on the device (gc_acquire_device), "
+                                      "1 NCCL all-gather of 4 x 32 doubles per rank, merge = sum"},
             "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": 2 * n_acq_samples,
                     "d2h_bytes_per_step": d2h_acq, "ms_per_step": e2e_ms,
-                    "call": "gc_acquire_host (host longSignal -> acqResults on host)"},
+                    "call": "gc_acquire_host per rank (host longSignal -> this rank's acqResults on the host)" +
+                            (" + all-gather of the result vectors" if world > 1 else "")},
+            "e2e_cold": {"value": CELLS / (e2e_cold_ms * 1e-3), "unit": "cells/s", "ms": e2e_cold_ms,
+                         "call": "gc_create + gc_acquire_host + gc_destroy, one shot (median of 3): CUDA context already up, everything "
+                                 "else - FFT plan, twiddles, 32 replica spectra, the work buffer cudaMalloc - inside"},
+            "e2e_multi_abi": multi_abi,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
                          "kernel": "inv_rows_kernel (spectrum multiply + inverse 31x32 row DFTs of the 33x32x31 prime-factor "
                                    "transform, packed fp32x2 codelets)",
                          "launch_ms": rows_launch_ms, "cells_per_launch": cells_per_launch, "peak_source": pk_src,
-                         "whole_step_achieved": step_ach, "whole_step_frac": step_ach / pk["hbm_gbs"],
+                         "whole_step_achieved": step_ach, "whole_step_frac": step_ach / (pk["hbm_gbs"] * world),
                          "kernel_share_of_step": {"inv_rows": rows_ms / args.steps / step_ms, "inv_cols": cols_ms / args.steps / step_ms},
                          "note": "FFT stages carry about 69 flop per algorithmic byte; the rows kernel is bound by FP32 issue and "
-                                 "L2 throughput, the column kernel by the HBM read of the work buffer (6.5 TB/s)"},
+                                 "L2 throughput, the column kernel by the HBM read of the work buffer"},
             "cpu_baseline": cpu_acq,
+            "parity": parity,
             "clocks": clocks,
-            "n_acquired": int(st["n_acquired"]),
-            "wall_ms_per_step_incl_flush_and_gather": t_wall / args.steps * 1e3,
+            "n_acquired": int(np.count_nonzero(acq["carrFreq"])),
+            "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
+            "replica_value": replica_value,
+            # the second half of BASELINE's metric as flat keys (tracking channel-ms/s at this N)
+            "tracking_value": tracking["value"] if tracking else None, "tracking_unit": "channel-ms/s",
+            "tracking_batch_value": tracking["batch_592ch_1000ms"]["value"] if tracking else None,
+            "gal_e1c_value": widened["gal_e1c_acquisition"]["value"] if widened else None,
+            "all_constellation_ms": widened["all_constellation_acquisition"]["ms"] if widened else None,
             "tracking": tracking,
-            "glonass": glonass,
             "widened": widened,
         }
         print(json.dumps(line), file=_OUT, flush=True)

@@ -147,19 +147,27 @@ inv_rows_kernel(RowsParams p)
     // circshift(IQfreqDom, s) (BDS/B1I acquisition.m:88, GPS_L2C :73, B1C :203): product element j takes spectrum element j - s.
     // With j = j1 + C*j2 (row j1, in-row frequency j2 held by its residues mod RA and mod RB) that is row (j1 - s) mod C
     // and j2 - floor-part, i.e. a fixed source row and a circular shift of both residues.
+    // Variant A whose Doppler step is a whole number of FFT bins (acqSearchStep * 2N / fs integer: 500 Hz at 16.368, 18 and 12 Msps)
+    // uses the same addressing: bin k of the grid is the spectrum of bin 0 shifted by k steps, so only nonCoh forward transforms
+    // exist (identity 2).  Prime-factor plans hold j by its three residues: each is rotated by the shift.
     int xrow = (p.bin0 + k) * p.nonCoh + m, srow = k1, sa = 0, sb = 0;
-    if (p.slotGroup != nullptr) xrow += p.slotGroup[p.prnSlot0 + pi] * p.groupRows;     // this SV's carrier grid
-    if constexpr (!P::kPfa) {                                    // (the variant B / C lengths all have Cooley-Tukey plans)
-        if (p.binMap != nullptr) {
-            const int2 bm = p.binMap[(p.binMapSlotStride ? (p.prnSlot0 + pi) * p.binMapSlotStride : 0) + p.bin0 + k];
-            xrow = bm.x * p.nonCoh + m;
+    const int grow = (p.slotGroup != nullptr) ? p.slotGroup[p.prnSlot0 + pi] * p.groupRows : 0;     // this SV's carrier grid
+    if (p.binMap != nullptr) {
+        const int2 bm = p.binMap[(p.binMapSlotStride ? (p.prnSlot0 + pi) * p.binMapSlotStride : 0) + p.bin0 + k];
+        xrow = bm.x * p.nonCoh + m;
+        if constexpr (!P::kPfa) {
             const int s1 = bm.y % C;
             int s2 = bm.y / C;
             srow = k1 - s1;
             if (srow < 0) { srow += C; s2 += 1; }
             sa = s2 % RA; sb = s2 % RB;
+        } else {
+            srow = k1 - bm.y % C;
+            if (srow < 0) srow += C;
+            sa = bm.y % RA; sb = bm.y % RB;
         }
     }
+    xrow += grow;
     const float2* src = p.X + ((size_t)xrow * C + srow) * R;
     const float2* mul = p.Cc + ((size_t)(p.prnList[p.prnSlot0 + pi] + r * p.repStride) * C + k1) * R;
     float2* dst = p.W + (((size_t)(pi * p.nBins + k) * M + mv) * C + k1) * R;

@@ -116,6 +116,8 @@ struct gc_handle {
     int N = 0, L = 0, nBins = 0, nFine = 0, nonCoh = 0;
     double ts = 0;
     bool fused = false;
+    int binShift = 0;            // variant A: acqSearchStep * L / fs when that is a whole number of FFT bins (else 0): the spectra of
+                                 // Doppler bin k are those of bin 0 shifted by k * binShift, so only bin 0 is transformed
     bool overlap = false;        // split correlation stage pipelined over two streams (GC_ACQ_OVERLAP)
     bool queue = false;          // correlation stage as one persistent kernel with an ordered work queue (GC_ACQ_PATH=queue)
     DevBuf<int> qctrl;
@@ -439,6 +441,11 @@ int gc_create(gc_handle** out, const gc_config* cfg)
         const char* o = getenv("GC_ACQ_OVERLAP");
         h->overlap = h->fused && !h->cluster && o && atoi(o) != 0;
         h->queue = h->fused && e && strcmp(e, "queue") == 0 && h->fp.C <= 50 && !h->varB && !h->varC;
+    }
+    if (h->fused && !h->cluster && !h->queue && !h->varB && !h->varC && !getenv("GC_ACQ_NO_SHIFT")) {
+        const double sh = cfg->acq_search_step * (double)h->L / cfg->sampling_freq;
+        const double shr = m_round(sh);
+        if (shr >= 1 && std::fabs(sh - shr) < 1e-9 && shr * (h->nBins - 1) < h->L) h->binShift = (int)shr;
     }
     h->stats.acq_path = h->cluster ? 2 : h->queue ? 3 : h->fused ? 1 : 0;   // 2 = fused plan + cluster correlation kernel, 1 = fused plan, split
                                                              // correlation stage, 0 = generic mixed-radix passes
@@ -1249,15 +1256,26 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
             }
             for (int s = groupStart[gi]; s < groupStart[gi + 1]; ++s) coarseFreqOf[s] = coarseFreq;
         }
-        GC_CUDA(h, cudaMemcpyAsync(h->dphi.p, dphi.data(), dphi.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        const bool shifted = h->binShift > 0;                // only bin 0 of every grid is transformed, the other bins are shifts of it
+        if (shifted) {
+            std::vector<uint64_t> d0(nGroups);
+            for (int gi = 0; gi < nGroups; ++gi) d0[gi] = dphi[(size_t)gi * nBins];
+            GC_CUDA(h, cudaMemcpyAsync(h->dphi.p, d0.data(), d0.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+            std::vector<int2> map(nBins);
+            for (int k = 0; k < nBins; ++k) map[k] = make_int2(0, k * h->binShift);
+            GC_CUDA(h, upload(h->vbMap, map, st));
+        } else {
+            GC_CUDA(h, cudaMemcpyAsync(h->dphi.p, dphi.data(), dphi.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        }
         GC_CUDA(h, upload(h->slotGroup, slotGroup, st));
         const int f0 = mark();
+        const int fwdRowsPerGroup = shifted ? nonCoh : nKm;
         FwdColsParams fp{};
         fp.rec = rec_of(h); fp.winStart = winStart; fp.N = N; fp.nonCoh = nonCoh; fp.swapIQ = (h->glo && h->fmt != 2 && h->fmt != 3) ? 1 : 0;
         fp.dphi = h->dphi.p; fp.out = h->X.p; fp.tw = h->twFused.p;          // row (grid, bin, block): the phase table is indexed grid*nBins + bin
-        GC_CUDA(h, launch_fwd_cols(L, fp, nGroups * nKm, false, st)); ++launches;
+        GC_CUDA(h, launch_fwd_cols(L, fp, nGroups * fwdRowsPerGroup, false, st)); ++launches;
         RowsParams rp{};
-        rp.X = h->X.p; rp.nRows = (long long)nGroups * nKm * h->fp.C;
+        rp.X = h->X.p; rp.nRows = (long long)nGroups * fwdRowsPerGroup * h->fp.C;
         GC_CUDA(h, launch_fwd_rows(L, rp, st)); ++launches;
         fwdEv.push_back({f0, mark()});
         int chunk = (int)std::max<long long>(1, (long long)(kWorkBytes / ((double)nKm * h->nRep * L * sizeof(float2))));
@@ -1271,7 +1289,8 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
             ip.nRep = h->nRep; ip.repStride = 1;
             if (nonCoh * h->nRep < 5) { ip.prnPerCta = 5; ip.mPerCta = 1; }
             ip.nPrnChunk = nc; ip.prnSlot0 = s0; ip.prnList = h->prnList.p;
-            ip.slotGroup = h->slotGroup.p; ip.groupRows = nKm;
+            ip.slotGroup = h->slotGroup.p; ip.groupRows = fwdRowsPerGroup;
+            if (shifted) ip.binMap = h->vbMap.p;
             if (evn > kEvents - 12) drain_events();
             const int a = mark();
             GC_CUDA(h, launch_inv_rows(L, ip, st)); ++launches;
@@ -1300,12 +1319,19 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         GC_CUDA(h, cudaMemcpyAsync(h->dphi.p, dphi.data(), nBins * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
         const int f0 = mark();
         if (h->fused) {
+            const bool shifted = h->binShift > 0;            // only bin 0 is transformed (dphi[0]); bin k = its spectrum shifted by k * binShift
+            if (shifted) {
+                std::vector<int2> map(nBins);
+                for (int k = 0; k < nBins; ++k) map[k] = make_int2(0, k * h->binShift);
+                GC_CUDA(h, upload(h->vbMap, map, st));
+            }
+            const int fwdRows = shifted ? nonCoh : nKm;
             FwdColsParams fp{};
             fp.rec = rec_of(h); fp.winStart = winStart; fp.N = N; fp.nonCoh = nonCoh; fp.swapIQ = (h->glo && h->fmt != 2 && h->fmt != 3) ? 1 : 0;
             fp.dphi = h->dphi.p; fp.out = h->X.p; fp.tw = h->twFused.p;
-            GC_CUDA(h, launch_fwd_cols(L, fp, nKm, false, st)); ++launches;
+            GC_CUDA(h, launch_fwd_cols(L, fp, fwdRows, false, st)); ++launches;
             RowsParams rp{};
-            rp.X = h->X.p; rp.nRows = (long long)nKm * h->fp.C;
+            rp.X = h->X.p; rp.nRows = (long long)fwdRows * h->fp.C;
             GC_CUDA(h, launch_fwd_rows(L, rp, st)); ++launches;
             fwdEv.push_back({f0, mark()});
             if (h->queue) {
@@ -1365,6 +1391,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
                     if (sscanf(e, "%dx%d", &P, &M) == 2 && (P * M == 5 || P * M == 8)) { ip.prnPerCta = P; ip.mPerCta = M; }
                 }
                 ip.nPrnChunk = nc; ip.prnSlot0 = s0; ip.prnList = h->prnList.p;
+                if (shifted) ip.binMap = h->vbMap.p;
                 if (evn > kEvents - 12) drain_events();
                 if (overlap && ci >= 2) GC_CUDA(h, cudaStreamWaitEvent(st, h->evCols[ci & 1], 0));   // this buffer's previous columns are done
                 const int a = mark();

@@ -8,7 +8,11 @@
 // semantics) carries over; the merged results are bit-identical to one GPU's because each SV / channel is computed by exactly
 // the same code on exactly the same data.
 #include <algorithm>
+#include <condition_variable>
 #include <cstdio>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -19,9 +23,53 @@
 
 #include "../../include/gnsscorr.h"
 
+namespace {
+// one persistent host thread per GPU (a fresh std::thread per call costs a CUDA per-thread set-up of several milliseconds)
+struct Worker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<int()> task;
+    int rc = 0;
+    bool busy = false, quit = false;
+    void loop()
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv.wait(lk, [&] { return busy || quit; });
+            if (quit) return;
+            lk.unlock();
+            const int r = task();
+            lk.lock();
+            rc = r; busy = false;
+            cv.notify_all();
+        }
+    }
+    void start() { th = std::thread([this] { loop(); }); }
+    void submit(std::function<int()> f)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        task = std::move(f); busy = true;
+        cv.notify_all();
+    }
+    int wait()
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return !busy; });
+        return rc;
+    }
+    void stop()
+    {
+        { std::lock_guard<std::mutex> lk(mu); quit = true; cv.notify_all(); }
+        if (th.joinable()) th.join();
+    }
+};
+}  // namespace
+
 struct gc_multi {
     gc_config cfg{};
     std::vector<gc_handle*> h;
+    std::vector<std::unique_ptr<Worker>> workers;   // workers[g] serves GPU g (GPU 0 runs on the calling thread)
     std::string err;
     std::vector<int32_t> clPhase;      // channel.CLCodePhase of the next gc_multi_track (GPS L2C CL pilot)
     double lastAcqMs = 0, lastTrackMs = 0;
@@ -46,10 +94,9 @@ template <class F>
 int for_each_gpu(gc_multi* m, int n, F fn)
 {
     std::vector<int> rc(n, GC_OK);
-    std::vector<std::thread> th;
-    for (int g = 1; g < n; ++g) th.emplace_back([&, g] { rc[g] = fn(g); });
+    for (int g = 1; g < n; ++g) m->workers[g]->submit([&fn, g] { return fn(g); });
     rc[0] = fn(0);
-    for (auto& t : th) t.join();
+    for (int g = 1; g < n; ++g) rc[g] = m->workers[g]->wait();
     for (int g = 0; g < n; ++g)
         if (rc[g] != GC_OK) {
             m->err = "GPU " + std::to_string(g) + ": " + gc_last_error(m->h[g]);
@@ -79,25 +126,28 @@ int gc_multi_create(gc_multi** out, const gc_config* cfg, int32_t nGpus)
     gc_multi* m = new gc_multi();
     m->cfg = *cfg;
     m->h.assign(nGpus, nullptr);
-    // the handles are created in parallel: each builds its FFT plan, twiddles and replica spectra on its own GPU
+    for (int g = 0; g < nGpus; ++g) {
+        m->workers.emplace_back(new Worker());
+        if (g > 0) m->workers[g]->start();
+    }
+    // the handles are created in parallel, each on the thread that will serve its GPU: FFT plan, twiddles, replica spectra
     std::vector<int> rc(nGpus, GC_OK);
     std::vector<std::string> msg(nGpus);
-    std::vector<std::thread> th;
     auto make = [&](int g) {
         gc_config c = *cfg;
         c.device = cfg->device + g;
         rc[g] = gc_create(&m->h[g], &c);
         if (rc[g] != GC_OK) msg[g] = gc_last_error(nullptr);
+        return rc[g];
     };
-    for (int g = 1; g < nGpus; ++g) th.emplace_back(make, g);
+    for (int g = 1; g < nGpus; ++g) m->workers[g]->submit([&make, g] { return make(g); });
     make(0);
-    for (auto& t : th) t.join();
+    for (int g = 1; g < nGpus; ++g) m->workers[g]->wait();
     for (int g = 0; g < nGpus; ++g)
         if (rc[g] != GC_OK) {
             const int code = rc[g];
             g_multi_create_error = "GPU " + std::to_string(g) + ": " + msg[g];
-            for (auto* hh : m->h) gc_destroy(hh);
-            delete m;
+            gc_multi_destroy(m);
             return code;
         }
     *out = m;
@@ -107,6 +157,7 @@ int gc_multi_create(gc_multi** out, const gc_config* cfg, int32_t nGpus)
 void gc_multi_destroy(gc_multi* m)
 {
     if (!m) return;
+    for (size_t g = 1; g < m->workers.size(); ++g) m->workers[g]->stop();
     for (auto* hh : m->h) gc_destroy(hh);
     delete m;
 }

@@ -1,3 +1,4 @@
 cd $GRAFT_REPO_ROOT
-nvidia-smi -L
-python -m pytest tests/test_gpu_multi.py -m gpu -x -q 2>&1 | tail -30
+python -m pytest tests -m gpu -x -q -k "acquisition or acquire or golden or multi or sharded or wrappers" 2>&1 | tail -8
+python tools/acq_bench.py 2>&1 | tail -12
+GC_ACQ_NO_SHIFT=1 python tools/acq_bench.py 2>&1 | tail -4
