@@ -60,4 +60,13 @@ if isfield(settings, 'pilotTRKflag')
 else
     cfg.pilot_trk_flag = 0;
 end
+% GPUs the library deals the PRNs / channels over (gc_multi_create): settings.gnsscorrGpus if the user set it, else the
+% environment variable GNSSCORR_NGPUS, else 1; 0 = every visible GPU.  The reference's settings struct is otherwise unchanged.
+if isfield(settings, 'gnsscorrGpus')
+    cfg.n_gpus = settings.gnsscorrGpus;
+elseif ~isempty(getenv('GNSSCORR_NGPUS'))
+    cfg.n_gpus = str2double(getenv('GNSSCORR_NGPUS'));
+else
+    cfg.n_gpus = 1;
+end
 end

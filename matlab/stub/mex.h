@@ -20,6 +20,11 @@ double* mxGetDoubles(const mxArray*);
 int8_t* mxGetInt8s(const mxArray*);
 int32_t* mxGetInt32s(const mxArray*);
 int mxIsInt8(const mxArray*);
+int mxIsUint8(const mxArray*);
+int mxIsChar(const mxArray*);
+int mxIsStruct(const mxArray*);
+size_t mxGetElementSize(const mxArray*);
+int mexAtExit(void (*fn)(void));
 int mxIsInt16(const mxArray*);
 void* mxGetData(const mxArray*);
 int mxIsEmpty(const mxArray*);
