@@ -152,7 +152,9 @@ struct gc_handle {
     DevBuf<double> trackOut;
     DevBuf<int32_t> epochsDone;
     DevBuf<uint8_t> navCand, navBits;
-    DevBuf<double> vsmDev;
+    DevBuf<double> vsmDev, cnoPldDev;
+    std::vector<double> cnoPld;  // [nCh][5][nV] of the last gc_track (BDS B2a / B1C)
+    int cnoPldCh = 0, cnoPldV = 0;
     DevBuf<int> navInt;
     double tau1code = 0, tau2code = 0, tau1carr = 0, tau2carr = 0;
 };
@@ -1787,6 +1789,16 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
         GC_CUDA(h, cudaMemcpyAsync(vsmValue, h->vsmDev.p, (size_t)nCh * nV * sizeof(double), cudaMemcpyDeviceToHost, st));
         GC_CUDA(h, cudaMemcpyAsync(vsmIndex, h->vsmDev.p + (size_t)nCh * nV, (size_t)nCh * nV * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
+    const bool pld = (c.signal == GC_SIG_BDS_B2A || c.signal == GC_SIG_BDS_B1C) && nV > 0;
+    h->cnoPldCh = h->cnoPldV = 0;
+    if (pld) {   // Calc_CNo_PLD.m on the device (BDS/B2a/include/tracking.m:409-431); pilot rows: B2a / B1C narrow band swap roles, B1C full band as recorded
+        const int pmode = h->pilotMode == 0 ? 0 : h->pilotMode == 5 ? 2 : 1;
+        GC_CUDA(h, h->cnoPldDev.reserve((size_t)nCh * GC_CNO_PLD_ROWS * nV));
+        GC_CUDA(h, launch_cno_pld(h->trackOut.p, nCh, nRows, nEpochs, vint, c.int_time, pmode, h->epochsDone.p, h->cnoPldDev.p, st));
+        h->cnoPld.assign((size_t)nCh * GC_CNO_PLD_ROWS * nV, 0.0);
+        GC_CUDA(h, cudaMemcpyAsync(h->cnoPld.data(), h->cnoPldDev.p, h->cnoPld.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+        h->cnoPldCh = nCh; h->cnoPldV = nV;
+    }
     GC_CUDA(h, cudaMemcpyAsync(out, h->trackOut.p, nOut * sizeof(double), cudaMemcpyDeviceToHost, st));
     GC_CUDA(h, cudaMemcpyAsync(epochsDone, h->epochsDone.p, nCh * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     GC_CUDA(h, cudaStreamSynchronize(st));
@@ -1826,6 +1838,10 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
         }
         epochsDone[ch] = 0;
     }
+    if (pld)
+        for (int ch = 0; ch < nCh; ++ch)
+            if (!live[ch] || (failed >= 0 && ch > failed))
+                std::fill(h->cnoPld.begin() + (size_t)ch * GC_CNO_PLD_ROWS * nV, h->cnoPld.begin() + (size_t)(ch + 1) * GC_CNO_PLD_ROWS * nV, 0.0);
     // C/N0 (tracking.m:351-358) came from the device; channels after one that ran out of data stay as initialised
     if (wantVsm)
         for (int ch = 0; ch < nCh; ++ch)
@@ -1836,14 +1852,24 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
     return GC_OK;
 }
 
+int gc_get_cno_pld(const gc_handle* h, int32_t nCh, int32_t nIntervals, double* out)
+{
+    if (!h || !out) return GC_ERR_ARG;
+    if (h->cnoPldCh == 0 || nCh != h->cnoPldCh || nIntervals != h->cnoPldV) return GC_ERR_ARG;   // no B2a / B1C gc_track of that shape before
+    std::copy(h->cnoPld.begin(), h->cnoPld.end(), out);
+    return GC_OK;
+}
+
 int gc_acquire_track(gc_handle* h, int32_t nSv, const int32_t* svList, int32_t nChannels, int32_t nEpochs,
                      double* carrFreq, double* codePhase, double* peakMetric,
                      int32_t* chanSv, double* chanAcqFreq, double* chanCodePhase,
                      double* out, double* vsmValue, double* vsmIndex, int32_t* epochsDone)
 {
     if (!h) return GC_ERR_ARG;
-    if (h->cfg.signal != GC_SIG_GPS_L1CA) return fail(h, GC_ERR_UNSUPPORTED, "gc_acquire_track: GPS L1 C/A only");
+    const gc_config& c = h->cfg;
     if (nChannels < 1 || !chanSv || !chanAcqFreq || !chanCodePhase) return fail(h, GC_ERR_ARG, "gc_acquire_track: bad argument");
+    const bool aided = h->b3i || h->fam5 || h->varC;           // channel.codeFreq from settings.carrFreqBasis (GPS_L5C preRun.m:69-71)
+    if (aided && !(c.carr_freq_basis > 0)) return fail(h, GC_ERR_ARG, "gc_acquire_track: this signal's code NCO is carrier aided - set cfg.carr_freq_basis (settings.carrFreqBasis)");
     int rc = gc_acquire(h, nSv, svList, carrFreq, codePhase, peakMetric, nullptr, nullptr);
     if (rc != GC_OK) return rc;
     // preRun.m:44-72: [~, PRNindexes] = sort(peakMetric, 'descend') (stable), the first min(numberOfChannels, #acquired) of them
@@ -1853,13 +1879,22 @@ int gc_acquire_track(gc_handle* h, int32_t nSv, const int32_t* svList, int32_t n
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return peakMetric[a] > peakMetric[b]; });
     int nAcq = 0;
     for (int i = 0; i < n; ++i) nAcq += (carrFreq[i] != 0);
+    std::vector<double> codeFreq0(nChannels, 0.0);
+    std::vector<int32_t> cl(nChannels, 1);
     for (int ch = 0; ch < nChannels; ++ch) {
         const bool on = ch < std::min(nChannels, nAcq);
-        chanSv[ch] = on ? order[ch] + 1 : 0;
+        chanSv[ch] = on ? (h->glo ? order[ch] - 7 : order[ch] + 1) : (h->glo ? GC_SV_NONE : 0);   // GLO preRun.m: Kindexes(ii) - 8
         chanAcqFreq[ch] = on ? carrFreq[order[ch]] : 0.0;
         chanCodePhase[ch] = on ? codePhase[order[ch]] : 0.0;
+        if (on && aided)
+            codeFreq0[ch] = c.code_freq_basis + (chanAcqFreq[ch] - c.IF) / c.carr_freq_basis * c.code_freq_basis;
+        if (on && h->pilotMode == 4) cl[ch] = h->clPhaseOut[order[ch]];                            // GPS_L2C preRun.m: channel.CLCodePhase
     }
-    return gc_track(h, nChannels, chanSv, chanAcqFreq, chanCodePhase, nullptr, nEpochs, out, vsmValue, vsmIndex, epochsDone);
+    if (h->pilotMode == 4) {
+        rc = gc_set_cl_code_phase(h, nChannels, cl.data());
+        if (rc != GC_OK) return rc;
+    }
+    return gc_track(h, nChannels, chanSv, chanAcqFreq, chanCodePhase, aided ? codeFreq0.data() : nullptr, nEpochs, out, vsmValue, vsmIndex, epochsDone);
 }
 
 int gc_track_file(gc_handle* h, const char* path, int32_t nCh, const int32_t* sv, const double* acqFreq,

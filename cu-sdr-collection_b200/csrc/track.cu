@@ -1024,6 +1024,79 @@ __global__ void cno_vsm_kernel(const double* out, int nCh, int nRows, int nEpoch
     vsmIndex[i] = idx;
 }
 
+// DataCNo / DataPLD / PilotCNo / PilotPLD / total C/N0 of BDS B2a and B1C (BDS/B2a/include/Calc_CNo_PLD.m:38-100, B1C's twin) with
+// the 0.5/0.5 smoothing of tracking.m:409-431: one thread per (channel, interval); it evaluates its own interval and the one before
+// (the smoothing partner) from the recorded prompt rows.  pilotMode: 0 none, 1 pilot rows swap roles (Calc_CNo_PLD.m:74-75), 2 as recorded.
+__device__ void cno_pld_one(const double* I, const double* Q, int n, double T, double* cno, double* pld)
+{
+    double Zm = 0, sp = 0, sn = 0, sq = 0;
+    for (int k = 0; k < n; ++k) {
+        Zm = __dadd_rn(Zm, __dadd_rn(__dmul_rn(I[k], I[k]), __dmul_rn(Q[k], Q[k])));              // Z = I.^2 + Q.^2
+        if (I[k] > 0) sp = __dadd_rn(sp, I[k]);
+        if (I[k] < 0) sn = __dadd_rn(sn, I[k]);
+        sq = __dadd_rn(sq, Q[k]);
+    }
+    Zm = __ddiv_rn(Zm, (double)n);
+    double Zv = 0;
+    for (int k = 0; k < n; ++k) {
+        const double d = __dsub_rn(__dadd_rn(__dmul_rn(I[k], I[k]), __dmul_rn(Q[k], Q[k])), Zm);
+        Zv = __dadd_rn(Zv, __dmul_rn(d, d));
+    }
+    Zv = __ddiv_rn(Zv, (double)(n - 1));
+    const double d = __dsub_rn(__dmul_rn(Zm, Zm), Zv);                                           // Pav = sqrt(Zm^2 - Zv), complex when negative
+    const double pr = d >= 0 ? sqrt(d) : 0.0, pi = d >= 0 ? 0.0 : sqrt(-d);
+    const double nr = __dmul_rn(0.5, __dsub_rn(Zm, pr)), ni = __dmul_rn(0.5, -pi);               // Nv = 0.5*(Zm - Pav)
+    *cno = __ddiv_rn(__dmul_rn(hypot(pr, pi), __ddiv_rn(1.0, T)), __dmul_rn(2.0, hypot(nr, ni)));  // abs((1/T)*Pav/(2*Nv))
+    const double a = __dsub_rn(sp, sn), a2 = __dmul_rn(a, a), q2 = __dmul_rn(sq, sq);            // (sum(I>0) - sum(I<0))^2, sum(Q)^2
+    *pld = __ddiv_rn(__dsub_rn(a2, q2), __dadd_rn(a2, q2));                                      // NBD / NBP
+}
+
+__global__ void cno_pld_kernel(const double* out, int nCh, int nRows, int nEpochs, int vint, double T, int pilotMode,
+                               const int32_t* epochsDone, double* res)
+{
+    const int nV = nEpochs / vint;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nCh * nV) return;
+    const int ch = i / nV, v = i % nV + 1;
+    double* r = res + (size_t)ch * 5 * nV + (v - 1);
+    for (int q = 0; q < 5; ++q) r[(size_t)q * nV] = 0.0;
+    if (v * vint > epochsDone[ch]) return;
+    double cur[3] = {0, 0, 0}, prev[3] = {0, 0, 0}, pldD = 0, pldP = 0;
+    for (int w = (v > 1 ? v - 1 : v); w <= v; ++w) {
+        const size_t e0 = (size_t)(w - 1) * vint;
+        const double* I = out + ((size_t)ch * nRows + GC_F_I_P) * nEpochs + e0;
+        const double* Q = out + ((size_t)ch * nRows + GC_F_Q_P) * nEpochs + e0;
+        double val[3] = {0, 0, 0}, dC, dP, pC = 0.0, pP = 0.0;
+        cno_pld_one(I, Q, vint, T, &dC, &dP);
+        val[0] = __dmul_rn(10.0, log10(dC));
+        if (pilotMode) {
+            const double* PI = out + ((size_t)ch * nRows + GC_F_PILOT_I_P) * nEpochs + e0;
+            const double* PQ = out + ((size_t)ch * nRows + GC_F_PILOT_Q_P) * nEpochs + e0;
+            if (pilotMode == 1) cno_pld_one(PQ, PI, vint, T, &pC, &pP);                          // I_P = Pilot_Q_P, Q_P = Pilot_I_P
+            else cno_pld_one(PI, PQ, vint, T, &pC, &pP);
+            val[1] = __dmul_rn(10.0, log10(pC));
+        }
+        val[2] = __dmul_rn(10.0, log10(__dadd_rn(dC, pC)));
+        if (w == v) { cur[0] = val[0]; cur[1] = val[1]; cur[2] = val[2]; pldD = dP; pldP = pP; }
+        else { prev[0] = val[0]; prev[1] = val[1]; prev[2] = val[2]; }
+    }
+    r[0] = __dadd_rn(__dmul_rn(cur[0], 0.5), __dmul_rn(prev[0], 0.5));
+    r[(size_t)nV] = pldD;
+    if (pilotMode) {
+        r[(size_t)2 * nV] = __dadd_rn(__dmul_rn(cur[1], 0.5), __dmul_rn(prev[1], 0.5));
+        r[(size_t)3 * nV] = pldP;
+        r[(size_t)4 * nV] = __dadd_rn(__dmul_rn(cur[2], 0.5), __dmul_rn(prev[2], 0.5));
+    }
+}
+
+cudaError_t launch_cno_pld(const double* out, int nCh, int nRows, int nEpochs, int vint, double T, int pilotMode,
+                           const int32_t* epochsDone, double* res, cudaStream_t stream)
+{
+    const int n = nCh * (nEpochs / vint);
+    if (n > 0) cno_pld_kernel<<<(n + 127) / 128, 128, 0, stream>>>(out, nCh, nRows, nEpochs, vint, T, pilotMode, epochsDone, res);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_cno_vsm(const double* out, int nCh, int nRows, int nEpochs, int vint, double T, const int32_t* epochsDone,
                            double* vsmValue, double* vsmIndex, cudaStream_t stream)
 {

@@ -76,4 +76,8 @@ cudaError_t launch_track_fill(double* out, int nCh, int nRows, int nEpochs, cuda
 cudaError_t launch_cno_vsm(const double* out, int nCh, int nRows, int nEpochs, int vint, double T, const int32_t* epochsDone,
                            double* vsmValue, double* vsmIndex, cudaStream_t stream);
 
+// DataCNo / DataPLD / PilotCNo / PilotPLD / total C/N0 of BDS B2a and B1C on the device (Calc_CNo_PLD.m + the smoothing of tracking.m)
+cudaError_t launch_cno_pld(const double* out, int nCh, int nRows, int nEpochs, int vint, double T, int pilotMode,
+                           const int32_t* epochsDone, double* res, cudaStream_t stream);
+
 }  // namespace gc

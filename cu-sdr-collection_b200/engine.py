@@ -32,7 +32,7 @@ class gc_config(C.Structure):
                 ("dll_correlator_spacing", C.c_double), ("pll_damping_ratio", C.c_double),
                 ("pll_noise_bandwidth", C.c_double), ("int_time", C.c_double), ("cno_acc_time", C.c_double),
                 ("freq_spacing", C.c_double), ("pilot_trk_flag", C.c_int32), ("acq_coh_t", C.c_int32),
-                ("pilot_acq_flag", C.c_int32), ("reserved1", C.c_int32)]
+                ("pilot_acq_flag", C.c_int32), ("reserved1", C.c_int32), ("carr_freq_basis", C.c_double)]
 
 
 GC_SIG_GPS_L1CA, GC_SIG_GLO_G1G2, GC_SIG_BDS_B3I, GC_SIG_GAL_E1C = 0, 1, 2, 3
@@ -58,7 +58,7 @@ EXPORTS = ["gc_abi_version", "gc_build_arch", "gc_acq_result_len", "gc_create", 
            "gc_last_error", "gc_set_code", "gc_set_record_host", "gc_set_record_device", "gc_acquire",
            "gc_acquire_host", "gc_track_nfields", "gc_track", "gc_track_file", "gc_get_stats", "gc_get_stream",
            "gc_set_param", "gc_get_cl_code_phase", "gc_set_cl_code_phase", "gc_nav_sync", "gc_acquire_track",
-           "gc_acquire_device", "gc_multi_create", "gc_multi_destroy", "gc_multi_last_error", "gc_multi_n_gpus",
+           "gc_acquire_device", "gc_get_cno_pld", "gc_multi_create", "gc_multi_destroy", "gc_multi_last_error", "gc_multi_n_gpus",
            "gc_multi_handle", "gc_multi_set_code", "gc_multi_set_param", "gc_multi_set_cl_code_phase",
            "gc_multi_get_cl_code_phase", "gc_multi_set_record_host", "gc_multi_acquire", "gc_multi_acquire_host",
            "gc_multi_track", "gc_multi_track_file", "gc_multi_get_times"]
@@ -102,6 +102,7 @@ def load_lib():
     lib.gc_get_stream.argtypes = [vp]
     lib.gc_get_stream.restype = C.c_void_p
     lib.gc_acquire_device.argtypes = [vp, C.c_int32, i32p, vp]
+    lib.gc_get_cno_pld.argtypes = [vp, C.c_int32, C.c_int32, dp]
     lib.gc_multi_create.argtypes = [C.POINTER(vp), C.POINTER(gc_config), C.c_int32]
     lib.gc_multi_destroy.argtypes = [vp]
     lib.gc_multi_destroy.restype = None
@@ -138,7 +139,7 @@ def config_from_settings(s: Settings, device: int = 0) -> gc_config:
     if s.fileType not in (1, 2, 3) or s.dataType not in ("schar", "int16") or (s.fileType == 3 and s.dataType != "schar"):
         raise GnssCorrError("fileType must be 1 (real), 2 (I/Q) or 3 (2-bit packed I/Q, unpack_cplx.m) and dataType 'schar' or 'int16' (initSettings.m:63-68)")
     sig = signal_id(s)
-    return gc_config(abi_version=4, device=device, pilot_trk_flag=int(s.pilotTRKflag), acq_coh_t=int(s.acqCohT),
+    return gc_config(abi_version=5, device=device, carr_freq_basis=float(getattr(s, 'carrFreqBasis', 0.0) or 0.0), pilot_trk_flag=int(s.pilotTRKflag), acq_coh_t=int(s.acqCohT),
                      pilot_acq_flag=int(s.pilotACQflag), signal=sig, freq_spacing=float(s.freqSpacing),
                      file_type=s.fileType, sample_bytes=2 if s.dataType == "int16" else 1,
                      code_length=int(s.codeLength), acq_noncoh_time=int(s.acqNonCohTime),
@@ -313,8 +314,20 @@ class Engine:
         rc = self.lib.gc_acquire_track(self._h, sv.size, _ip(sv), n_channels, n_epochs, _dp(carr), _dp(cph), _dp(pm),
                                        _ip(csv), _dp(caf), _dp(ccp), _dp(out), _dp(vv), _dp(vi), _ip(done))
         self._check(rc, "gc_acquire_track")
-        channel = [dict(PRN=int(csv[i]), acquiredFreq=float(caf[i]), codePhase=int(ccp[i]), status="T" if csv[i] else "-") for i in range(n_channels)]
+        if s.is_glonass:
+            channel = [dict(K=int(csv[i]) if csv[i] != GC_SV_NONE else 0, acquiredFreq=float(caf[i]), codePhase=int(ccp[i]),
+                            status="T" if csv[i] != GC_SV_NONE else "-") for i in range(n_channels)]
+        else:
+            channel = [dict(PRN=int(csv[i]), acquiredFreq=float(caf[i]), codePhase=int(ccp[i]), status="T" if csv[i] else "-") for i in range(n_channels)]
         return dict(carrFreq=carr, codePhase=cph, peakMetric=pm), channel, out, vv, vi, done
+
+    def cno_pld(self, n_channels: int, n_epochs: int):
+        """DataCNo, DataPLD, PilotCNo, PilotPLD, total C/N0 of the last track() (BDS B2a / B1C; Calc_CNo_PLD.m on the device):
+        array [n_channels][5][n_epochs // CNoInterval]."""
+        nv = n_epochs // int(self.settings.CNo_VSMinterval)
+        out = np.zeros((n_channels, 5, nv))
+        self._check(self.lib.gc_get_cno_pld(self._h, n_channels, nv, _dp(out)), "gc_get_cno_pld")
+        return out
 
     @property
     def stream_ptr(self) -> int:

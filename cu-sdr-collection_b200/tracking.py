@@ -37,6 +37,9 @@ def tracking(fid, channel: list, settings: Settings, engine: Engine | None = Non
         if settings.signal == "BDS_B1C" and int(settings.pilotTRKflag) == 2:   # factor = CalcWeighingFactor(settings), WB_tracking.m:124
             eng.set_param(GC_PARAM_B1C_WB_FACTOR, settings.wbFactor if settings.wbFactor is not None else calc_weighing_factor(settings))
         out, vv, vi, done = eng.track(prn, af, cp, n, path=path, code_freq0=cf0, cl_code_phase=clp)
+        # BDS B2a / B1C: DataCNo / DataPLD / PilotCNo / PilotPLD / B2a_CNo every CNoInterval epochs, computed on the device from the
+        # rows the kernel wrote (Calc_CNo_PLD.m:38-100 + the 0.5/0.5 smoothing of BDS/B2a/include/tracking.m:409-431)
+        pld = eng.cno_pld(nch, n) if settings.signal in ("BDS_B2a", "BDS_B1C") else None
     finally:
         if own:
             eng.close()
@@ -58,8 +61,11 @@ def tracking(fid, channel: list, settings: Settings, engine: Engine | None = Non
             tr["Pilot_I_P"], tr["Pilot_Q_P"] = out[ch, 15], out[ch, 16]
         if out.shape[1] == 21:                                             # GPS_L2C tracking.m:396-402; B1C WB_tracking.m:409-414
             tr["Pilot_I_E"], tr["Pilot_I_L"], tr["Pilot_Q_E"], tr["Pilot_Q_L"] = out[ch, 17], out[ch, 18], out[ch, 19], out[ch, 20]
-        if settings.signal in ("BDS_B2a", "BDS_B1C"):                      # BDS/B2a/include/tracking.m:66-72, 336-352; B1C NB_tracking.m:65-69, 340-355
-            tr.update(_b2a_cno_pld(tr, settings, int(done[ch])))
+        if pld is not None:                                                # BDS/B2a/include/tracking.m:66-72, 409-431; B1C NB_tracking.m:65-69, 400-418
+            tr["DataCNo"], tr["DataPLD"] = pld[ch, 0], pld[ch, 1]
+            if int(settings.pilotTRKflag) >= 1:
+                tr["PilotCNo"], tr["PilotPLD"] = pld[ch, 2], pld[ch, 3]
+                tr["B1C_CNo" if settings.signal == "BDS_B1C" else "B2a_CNo"] = pld[ch, 4]
         else:
             tr["CNo"] = {"VSMValue": vv[ch], "VSMIndex": vi[ch]}
         live = prn[ch] != (GC_SV_NONE if settings.is_glonass else 0)
@@ -96,54 +102,3 @@ def calc_weighing_factor(settings: Settings) -> float:
     t1 = 11 * p11 * (p11_2 / p11)
     t2 = 33 * pp * (pp_2 / pp)
     return float(t1 / (t1 + t2))
-
-
-def _b2a_cno_pld(tr: dict, settings: Settings, done: int) -> dict:
-    """DataCNo / DataPLD (/ PilotCNo / PilotPLD / B2a_CNo) every settings.CNoInterval epochs from the recorded prompt
-    rows - BDS/B2a/include/Calc_CNo_PLD.m:38-76 and the 0.5/0.5 smoothing of tracking.m:340-349.  Scalar host work
-    on rows the GPU produced (40..200 values per call)."""
-    n_int = int(settings.CNo_VSMinterval)
-    nv = num_to_process(settings) // n_int
-    pilot = int(settings.pilotTRKflag) >= 1
-    total = "B1C_CNo" if settings.signal == "BDS_B1C" else "B2a_CNo"
-    res = {"DataCNo": np.zeros(nv), "DataPLD": np.zeros(nv)}
-    if pilot:
-        res.update({"PilotCNo": np.zeros(nv), "PilotPLD": np.zeros(nv), total: np.zeros(nv)})
-    T = settings.intTime
-    prev = np.zeros(3)
-
-    def one(I, Q):
-        Z = I ** 2 + Q ** 2
-        Zm, Zv = np.mean(Z), np.var(Z, ddof=1)
-        with np.errstate(invalid="ignore", divide="ignore"):
-            Pav = np.sqrt(np.complex128(Zm ** 2 - Zv))
-            Nv = 0.5 * (Zm - Pav)
-            cno = np.abs((1 / T) * Pav / (2 * Nv))
-            a = (np.sum(I[I > 0]) - np.sum(I[I < 0])) ** 2
-            return cno, (a - np.sum(Q) ** 2) / (a + np.sum(Q) ** 2)
-
-    for v in range(1, nv + 1):
-        hi = v * n_int
-        if hi > done:
-            break
-        cur = np.zeros(3)
-        with np.errstate(invalid="ignore", divide="ignore"):
-            d_cno, d_pld = one(tr["I_P"][hi - n_int:hi], tr["Q_P"][hi - n_int:hi])
-            cur[0] = 10 * np.log10(d_cno)
-            p_cno = 0.0
-            if pilot and int(settings.pilotTRKflag) == 2:   # B1C Calc_CNo_PLD.m: the composite full-band pilot is in phase
-                p_cno, p_pld = one(tr["Pilot_I_P"][hi - n_int:hi], tr["Pilot_Q_P"][hi - n_int:hi])
-                cur[1] = 10 * np.log10(p_cno)
-                res["PilotPLD"][v - 1] = p_pld
-            elif pilot:                                # Calc_CNo_PLD.m:60-61: the pilot rows swap roles
-                p_cno, p_pld = one(tr["Pilot_Q_P"][hi - n_int:hi], tr["Pilot_I_P"][hi - n_int:hi])
-                cur[1] = 10 * np.log10(p_cno)
-                res["PilotPLD"][v - 1] = p_pld
-            cur[2] = 10 * np.log10(d_cno + p_cno)
-        res["DataCNo"][v - 1] = cur[0] * 0.5 + prev[0] * 0.5
-        res["DataPLD"][v - 1] = d_pld
-        if pilot:
-            res["PilotCNo"][v - 1] = cur[1] * 0.5 + prev[1] * 0.5
-            res[total][v - 1] = cur[2] * 0.5 + prev[2] * 0.5
-        prev = cur
-    return res

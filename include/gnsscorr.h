@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GC_ABI_VERSION 4
+#define GC_ABI_VERSION 5
 
 /* signal ids (reference folders).  Implemented: GPS/GPS_L1CA, GLO/GLO_GL1 + GLO/GLO_GL2 (the two
  * GLONASS folders differ only in settings.freqSpacing and the file name), BDS/B3I and GAL/GAL_E1C
@@ -100,6 +100,9 @@ typedef struct gc_config {
     int32_t acq_coh_t;           /* settings.acqCohT in ms (BDS/B1C/initSettings.m:97; B1C only)                     */
     int32_t pilot_acq_flag;      /* settings.pilotACQflag (BDS/B1C/initSettings.m:74): 1 = pilot replica joins the search */
     int32_t reserved1;
+    double carr_freq_basis;      /* settings.carrFreqBasis: the RF carrier of the carrier-aided signals (BDS/B3I/initSettings.m:132, GPS_L5C,
+                                    GAL_E5a/E5b, BDS_B2a/B1C); channel.codeFreq = codeFreqBasis + (acquiredFreq - IF) / carrFreqBasis *
+                                    codeFreqBasis (GPS_L5C/include/preRun.m:69-71), used by gc_acquire_track; 0 for the other signals   */
 } gc_config;
 
 typedef struct gc_handle gc_handle;
@@ -239,6 +242,16 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
              const double* codePhase, const double* codeFreq0, int32_t nEpochs,
              double* out, double* vsmValue, double* vsmIndex, int32_t* epochsDone);
 
+/* BDS B2a and B1C record DataCNo / DataPLD / PilotCNo / PilotPLD / B2a_CNo (B1C_CNo) every settings.CNoInterval epochs instead of
+ * CNo.VSMValue (BDS/B2a/include/tracking.m:409-431 with Calc_CNo_PLD.m:38-100: C/N0 by the variance-summing method and the
+ * narrow-band PLL lock detector on the data prompt and - pilot_trk_flag 1: with its I/Q roles swapped, 2: as recorded - the pilot
+ * prompt, C/N0 values smoothed 0.5/0.5 with the previous interval's).  gc_track computes them on the device from the rows it has
+ * just written (cfg.cno_vsm_interval = settings.CNoInterval); this returns them:
+ *   out   [nCh][5][nEpochs / cno_vsm_interval] doubles of the last gc_track: rows DataCNo, DataPLD, PilotCNo, PilotPLD, total C/N0
+ *         (zeros for intervals a channel did not complete, and for the pilot rows when pilot_trk_flag == 0) */
+#define GC_CNO_PLD_ROWS 5
+int gc_get_cno_pld(const gc_handle* h, int32_t nCh, int32_t nIntervals, double* out);
+
 /* Convenience for the MATLAB wrapper: tracking() receives an open fid, which a MEX cannot use;
  * the wrapper recovers the path with fopen(fid) and calls this.  Reads the file (from byte 0)
  * into pinned memory, makes it resident, then gc_track. */
@@ -248,12 +261,14 @@ int gc_track_file(gc_handle* h, const char* path,
                   double* out, double* vsmValue, double* vsmIndex, int32_t* epochsDone);
 
 /* acquisition -> preRun -> tracking in ONE call, the hand-off done inside the library (postProcessing.m:100-124 with
- * preRun.m:44-72: channels in descending peakMetric order, first index wins ties, at most nChannels of the acquired PRNs,
+ * preRun.m:44-72: channels in descending peakMetric order, first index wins ties, at most nChannels of the acquired SVs,
  * the other channels off).  For callers that do not need to stop between the two hot functions (the MATLAB drop-in keeps
- * the two separate signatures).  GPS L1 C/A only: the carrier-aided signals need settings.carrFreqBasis for
- * channel.codeFreq, which gc_config does not carry.
- *   carrFreq, codePhase, peakMetric   acqResults (length 32)
- *   chanSv, chanAcqFreq, chanCodePhase   [nChannels] channel(ch).PRN / acquiredFreq / codePhase as preRun.m leaves them
+ * the two separate signatures).  Every signal: GLONASS channels carry the frequency number K (GLO_GL1/include/preRun.m), the
+ * carrier-aided signals get channel.codeFreq from cfg.carr_freq_basis (GPS_L5C/include/preRun.m:69-71, BDS/B3I :71-73), GPS L2C
+ * with the CL pilot hands acqResults.CLCodePhase on to the channels.
+ *   carrFreq, codePhase, peakMetric   acqResults (length gc_acq_result_len)
+ *   chanSv, chanAcqFreq, chanCodePhase   [nChannels] channel(ch).PRN (K) / acquiredFreq / codePhase as preRun.m leaves them
+ *                                        (channel off: PRN 0, K GC_SV_NONE)
  *   out, vsmValue, vsmIndex, epochsDone  as gc_track */
 int gc_acquire_track(gc_handle* h, int32_t nSv, const int32_t* svList, int32_t nChannels, int32_t nEpochs,
                      double* carrFreq, double* codePhase, double* peakMetric,

@@ -38,14 +38,9 @@ for ch = nCh:-1:1
     t.Pilot_I_E = r.out(:, 18, ch).';  t.Pilot_I_L = r.out(:, 19, ch).';
     t.Pilot_Q_E = r.out(:, 20, ch).';  t.Pilot_Q_L = r.out(:, 21, ch).';
     t.DataCNo = zeros(1, nv);  t.DataPLD = zeros(1, nv);  t.PilotCNo = zeros(1, nv);  t.PilotPLD = zeros(1, nv);  t.B1C_CNo = zeros(1, nv);
-    prev = zeros(1, 3);                                               % WB_tracking.m:418-437 on the returned rows
-    for v = 1:floor(double(r.epochsDone(ch)) / settings.CNoInterval)
-        [cno, pld] = Calc_CNo_PLD(t, settings, v * settings.CNoInterval);
-        t.DataCNo(v) = cno(1) * 0.5 + prev(1) * 0.5;   t.DataPLD(v) = pld(1);
-        t.PilotCNo(v) = cno(2) * 0.5 + prev(2) * 0.5;  t.PilotPLD(v) = pld(2);
-        t.B1C_CNo(v) = cno(3) * 0.5 + prev(3) * 0.5;
-        prev = cno;
-    end
+    % Calc_CNo_PLD.m and the 0.5/0.5 smoothing were evaluated on the GPU from the same rows (r.cnoPld: nIntervals x 5 x nCh)
+    t.DataCNo = r.cnoPld(:, 1, ch).';   t.DataPLD = r.cnoPld(:, 2, ch).';
+    t.PilotCNo = r.cnoPld(:, 3, ch).';  t.PilotPLD = r.cnoPld(:, 4, ch).';  t.B1C_CNo = r.cnoPld(:, 5, ch).';
     if channel(ch).PRN ~= 0
         t.PRN = channel(ch).PRN;
         if r.epochsDone(ch) == n, t.status = channel(ch).status; else, shortRead = true; end

@@ -1,7 +1,7 @@
 function [trackResults, channel] = tracking(fid, channel, settings)
 %TRACKING  Drop-in for the tracking.m of GPS/GPS_L5C, GAL/GAL_E5a, GAL/GAL_E5b and BDS/B2a (same signature and
 %trackResults struct: code NCO centred on channel.codeFreq, Pilot_I_P / Pilot_Q_P when the pilot is tracked,
-%B2a's DataCNo / DataPLD block through the reference's own Calc_CNo_PLD) that runs the correlate-and-dump loops
+%B2a's DataCNo / DataPLD block from the device-side Calc_CNo_PLD, r.cnoPld) that runs the correlate-and-dump loops
 %of all channels on a B200.
 %
 %   [trackResults, channel] = tracking(fid, channel, settings)
@@ -36,14 +36,10 @@ for ch = nCh:-1:1
         nv = floor(n / settings.CNoInterval);
         t.DataCNo = zeros(1, nv);  t.DataPLD = zeros(1, nv);
         if pilot, t.PilotCNo = zeros(1, nv);  t.PilotPLD = zeros(1, nv);  t.B2a_CNo = zeros(1, nv); end
-        prev = zeros(1, 3);
-        for v = 1:floor(double(r.epochsDone(ch)) / settings.CNoInterval)
-            [cno, pld] = Calc_CNo_PLD(t, settings, v * settings.CNoInterval);
-            t.DataCNo(v) = cno(1) * 0.5 + prev(1) * 0.5;  t.DataPLD(v) = pld(1);
-            if pilot
-                t.PilotCNo(v) = cno(2) * 0.5 + prev(2) * 0.5;  t.B2a_CNo(v) = cno(3) * 0.5 + prev(3) * 0.5;  t.PilotPLD(v) = pld(2);
-            end
-            prev = cno;
+        % Calc_CNo_PLD.m:38-100 and the 0.5/0.5 smoothing of tracking.m:409-431 were evaluated on the GPU from the same rows
+        t.DataCNo = r.cnoPld(:, 1, ch).';  t.DataPLD = r.cnoPld(:, 2, ch).';
+        if pilot
+            t.PilotCNo = r.cnoPld(:, 3, ch).';  t.PilotPLD = r.cnoPld(:, 4, ch).';  t.B2a_CNo = r.cnoPld(:, 5, ch).';
         end
     else
         t.CNo.VSMValue = r.vsmValue(:, ch).';

@@ -221,7 +221,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
             for (i = 0; i < 32 && i < (mwSize)n; ++i) o[i] = (double)clp[i];
         }
     } else if (!strcmp(cmd, "track")) {
-        const char* names[] = {"out", "vsmValue", "vsmIndex", "epochsDone"};
+        const char* names[] = {"out", "vsmValue", "vsmIndex", "epochsDone", "cnoPld"};
         char path[4096];
         mwSize nCh, nV, i, dims[3];
         int32_t nEpochs;
@@ -257,7 +257,24 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
                                   (nrhs >= 8 && !mxIsEmpty(prhs[7])) ? mxGetDoubles(prhs[7]) : NULL, nEpochs,
                                   mxGetDoubles(out), mxGetDoubles(vv), mxGetDoubles(vi), (int32_t*)mxGetInt32s(done)),
               "gc_multi_track_file");
-        plhs[0] = mxCreateStructMatrix(1, 1, 4, names);
+        plhs[0] = mxCreateStructMatrix(1, 1, 5, names);
+        if (cfg.signal == GC_SIG_BDS_B2A || cfg.signal == GC_SIG_BDS_B1C) {
+            /* r.cnoPld: nIntervals x 5 x nCh = DataCNo, DataPLD, PilotCNo, PilotPLD, total C/N0 (Calc_CNo_PLD.m on the device); with
+             * several GPUs every GPU holds its own block of channels, in channel order */
+            mwSize d3[3], c0 = 0;
+            mxArray* pld;
+            int g;
+            const int nG = gc_multi_n_gpus(g_m);
+            const mwSize per = (nCh + nG - 1) / nG;
+            d3[0] = nV; d3[1] = GC_CNO_PLD_ROWS; d3[2] = nCh;
+            pld = mxCreateNumericArray(3, d3, mxDOUBLE_CLASS, mxREAL);
+            for (g = 0; g < nG && c0 < nCh; ++g, c0 += per) {
+                const mwSize nc = (nCh - c0 < per) ? nCh - c0 : per;
+                if (gc_get_cno_pld(gc_multi_handle(g_m, g), (int32_t)nc, (int32_t)nV, mxGetDoubles(pld) + c0 * GC_CNO_PLD_ROWS * nV) != GC_OK)
+                    fail_now(GC_ERR_ARG, "gc_get_cno_pld");
+            }
+            mxSetField(plhs[0], 0, "cnoPld", pld);
+        }
         mxSetField(plhs[0], 0, "out", out);
         mxSetField(plhs[0], 0, "vsmValue", vv);
         mxSetField(plhs[0], 0, "vsmIndex", vi);

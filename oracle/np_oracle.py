@@ -1850,3 +1850,67 @@ def unpack_cplx(data: np.ndarray) -> np.ndarray:
     out = np.empty(4 * b.size, dtype=np.int8)
     out[0::4] = lut_i1[b]; out[1::4] = lut_q1[b]; out[2::4] = lut_i2[b]; out[3::4] = lut_q2[b]
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# BDS/B2a/include/Calc_CNo_PLD.m (B1C's twin differs in the pilot branch only) and the block of tracking.m that calls it
+def Calc_CNo_PLD(trackResults: dict, s, loopCnt: int, signal: str = "BDS_B2a"):
+    """[CNo, PllDetector] = Calc_CNo_PLD(trackResults, settings, loopCnt) - BDS/B2a/include/Calc_CNo_PLD.m:38-100;
+    BDS/B1C/include/Calc_CNo_PLD.m:80-90 picks the pilot rows as recorded for pilotTRKflag == 2 and swapped for 1."""
+    CNo = np.zeros(3)
+    PllDetector = np.zeros(2)
+    T = s.intTime                                                              # :41
+    n = int(s.CNo_VSMinterval)                                                 # settings.CNoInterval
+    I_P = np.asarray(trackResults["I_P"][loopCnt - n: loopCnt], dtype=np.float64)   # :44-45
+    Q_P = np.asarray(trackResults["Q_P"][loopCnt - n: loopCnt], dtype=np.float64)
+
+    def est(I_P, Q_P):
+        Z = I_P ** 2 + Q_P ** 2                                                # :49
+        Zm = np.mean(Z)                                                        # :51
+        Zv = np.var(Z, ddof=1)                                                 # :52
+        with np.errstate(invalid="ignore", divide="ignore"):
+            Pav = np.sqrt(np.complex128(Zm ** 2 - Zv))                         # :54 (complex for a negative argument, as in MATLAB)
+            Nv = 0.5 * (Zm - Pav)                                              # :56
+            cno = np.abs((1 / T) * Pav / (2 * Nv))                             # :58
+            NBP = (np.sum(I_P[I_P > 0]) - np.sum(I_P[I_P < 0])) ** 2 + np.sum(Q_P) ** 2   # :63
+            NBD = (np.sum(I_P[I_P > 0]) - np.sum(I_P[I_P < 0])) ** 2 - np.sum(Q_P) ** 2   # :64
+            return float(cno), float(NBD / NBP)                                # :66
+
+    with np.errstate(invalid="ignore", divide="ignore"):
+        DataCNo, PllDetector[0] = est(I_P, Q_P)
+        CNo[0] = 10 * np.log10(DataCNo)                                        # :59
+        PilotCNo = 0.0                                                         # :70
+        flag = int(s.pilotTRKflag)
+        if flag == 2 and signal == "BDS_B1C":                                  # B1C Calc_CNo_PLD.m:80-83
+            PilotCNo, PllDetector[1] = est(np.asarray(trackResults["Pilot_I_P"][loopCnt - n: loopCnt]),
+                                           np.asarray(trackResults["Pilot_Q_P"][loopCnt - n: loopCnt]))
+            CNo[1] = 10 * np.log10(PilotCNo)
+        elif flag == 1:                                                        # :72-75: Q_P = Pilot_I_P, I_P = Pilot_Q_P
+            PilotCNo, PllDetector[1] = est(np.asarray(trackResults["Pilot_Q_P"][loopCnt - n: loopCnt]),
+                                           np.asarray(trackResults["Pilot_I_P"][loopCnt - n: loopCnt]))
+            CNo[1] = 10 * np.log10(PilotCNo)
+        CNo[2] = 10 * np.log10(DataCNo + PilotCNo)                             # :100
+    return CNo, PllDetector
+
+
+def cno_pld_rows(trackResults: dict, s, done: int, signal: str = "BDS_B2a") -> dict:
+    """DataCNo / DataPLD / PilotCNo / PilotPLD / total C/N0 as BDS/B2a/include/tracking.m:409-432 fills them: every CNoInterval
+    epochs, the C/N0 values smoothed 0.5/0.5 with the previous interval's (tempCNoValue starts at zeros(1,3), :192)."""
+    n = int(s.CNo_VSMinterval)
+    nE = len(trackResults["I_P"])
+    nv = nE // n
+    pilot = int(s.pilotTRKflag) >= 1
+    res = {"DataCNo": np.zeros(nv), "DataPLD": np.zeros(nv), "PilotCNo": np.zeros(nv), "PilotPLD": np.zeros(nv), "TotalCNo": np.zeros(nv)}
+    temp = np.zeros(3)                                                         # :192
+    for loopCnt in range(1, done + 1):
+        if loopCnt % n == 0:                                                   # :409
+            CNoValue, PllDetector = Calc_CNo_PLD(trackResults, s, loopCnt, signal)   # :411-412
+            c = loopCnt // n                                                   # :414
+            res["DataCNo"][c - 1] = CNoValue[0] * 0.5 + temp[0] * 0.5          # :418-419
+            res["DataPLD"][c - 1] = PllDetector[0]                             # :421
+            if pilot:                                                          # :424-430
+                res["PilotCNo"][c - 1] = CNoValue[1] * 0.5 + temp[1] * 0.5
+                res["TotalCNo"][c - 1] = CNoValue[2] * 0.5 + temp[2] * 0.5
+                res["PilotPLD"][c - 1] = PllDetector[1]
+            temp = CNoValue                                                    # :432
+    return res

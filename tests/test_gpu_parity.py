@@ -632,8 +632,12 @@ def test_fam5_tracking_and_wrappers_vs_oracle(signal, pilot, nE, exact, tmp_path
             assert np.max(np.abs(tr[i]["codeFreq"] - ref[i]["codeFreq"])) < 1e-8 and np.max(np.abs(tr[i]["carrFreq"] - ref[i]["carrFreq"])) < 1e-8
             d = np.abs(tr[i]["remCarrPhase"] - ref[i]["remCarrPhase"])
             assert np.max(d) < 1e-9, np.max(d)
-        if signal == "BDS_B2a":
-            assert tr[i]["DataCNo"].shape == (nE // 40,) and np.all(np.isfinite(tr[i]["DataCNo"])) and "PilotCNo" in tr[i]
+        if signal == "BDS_B2a":                           # Calc_CNo_PLD.m on the device vs its restatement on the oracle's rows
+            want = O.cno_pld_rows(ref[i], so, nE, "BDS_B2a")
+            assert tr[i]["DataCNo"].shape == (nE // 40,) and np.all(np.isfinite(tr[i]["DataCNo"]))
+            for got_k, want_k in (("DataCNo", "DataCNo"), ("DataPLD", "DataPLD"), ("PilotCNo", "PilotCNo"), ("PilotPLD", "PilotPLD"), ("B2a_CNo", "TotalCNo")):
+                assert np.allclose(tr[i][got_k], want[want_k], rtol=1e-7, atol=1e-9), (got_k, tr[i][got_k], want[want_k])
+            assert np.all(tr[i]["DataPLD"][-2:] > 0.8) and np.all(tr[i]["DataCNo"][1:] > 35)     # locked by the end of the run
         else:
             nv = ok // 40
             assert np.allclose(tr[i]["CNo"]["VSMValue"][:nv], ref[i]["VSMValue"][:nv], rtol=1e-5)
@@ -956,7 +960,10 @@ def test_b1c_wb_tracking_vs_oracle(fs, nE, exact, tmp_path):
         if nE >= 40:                                   # (6 epochs are not enough to pull in from a 25 Hz grid)
             assert np.mean(np.abs(tr[i]["Pilot_I_P"][nE // 2:])) > 2 * np.mean(np.abs(tr[i]["Pilot_Q_P"][nE // 2:]))
         assert np.mean(np.hypot(tr[i]["Pilot_I_P"], tr[i]["Pilot_Q_P"])) > 1.2 * np.mean(np.hypot(tr[i]["I_P"], tr[i]["Q_P"]))
-        assert tr[i]["DataCNo"].shape == (nE // 2,) and np.all(np.isfinite(tr[i]["PilotCNo"][1:]))
+        want = O.cno_pld_rows(ref[i], so, nE, "BDS_B1C")     # pilotTRKflag 2: the composite pilot rows as recorded
+        assert tr[i]["DataCNo"].shape == (nE // 2,)
+        for got_k, want_k in (("DataCNo", "DataCNo"), ("DataPLD", "DataPLD"), ("PilotCNo", "PilotCNo"), ("PilotPLD", "PilotPLD"), ("B1C_CNo", "TotalCNo")):
+            assert np.allclose(tr[i][got_k], want[want_k], rtol=1e-6, atol=1e-9, equal_nan=True), (got_k, tr[i][got_k], want[want_k])
     assert tr[2]["status"] == "-"
     eng.close()
 
@@ -998,7 +1005,10 @@ def test_b1c_nb_tracking_and_wrappers_vs_oracle(fs, nE, exact, tmp_path):
                                        fs, s.dllCorrelatorSpacing, sub=2.0, scale_keys=("Pilot_I_P", "Pilot_Q_P"), exact=bool(exact))
         assert np.max(np.abs(tr[i]["carrFreq"][:ok] - ref[i]["carrFreq"][:ok])) < 1e-4
         assert np.max(np.abs(tr[i]["codeFreq"][:ok] - ref[i]["codeFreq"][:ok])) < 1e-4
+        want = O.cno_pld_rows(ref[i], so, nE, "BDS_B1C")     # pilotTRKflag 1: the pilot rows swap roles
         assert tr[i]["DataCNo"].shape == (nE // 4,) and "B1C_CNo" in tr[i] and np.all(np.isfinite(tr[i]["PilotCNo"]))
+        for got_k, want_k in (("DataCNo", "DataCNo"), ("DataPLD", "DataPLD"), ("PilotCNo", "PilotCNo"), ("PilotPLD", "PilotPLD"), ("B1C_CNo", "TotalCNo")):
+            assert np.allclose(tr[i][got_k], want[want_k], rtol=1e-6, atol=1e-9, equal_nan=True), (got_k, tr[i][got_k], want[want_k])
     assert tr[2]["status"] == "-"
     eng.close()
 
@@ -1104,3 +1114,52 @@ def test_packed_2bit_record_equals_unpacked_schar_record(tmp_path):
         sc_ = np.hypot(ref_tr[i]["I_P"], ref_tr[i]["Q_P"])
         for name in ("I_P", "Q_P", "I_E", "I_L", "Q_E", "Q_L"):
             assert np.max(np.abs(res[3][2][i][name] - ref_tr[i][name]) / sc_) < IQ_TOL, name
+
+
+@pytest.mark.parametrize("signal", ["BDS_B3I", "GLO_GL1", "GPS_L5C", "BDS_B2a"])
+def test_acquire_track_one_call_other_signals(signal):
+    """gc_acquire_track for the carrier-aided signals (channel.codeFreq from cfg.carr_freq_basis, GPS_L5C/include/preRun.m:69-71)
+    and for GLONASS (channels carry K): the one call returns exactly what acquisition(), preRun() and tracking() return in turn."""
+    from cu_sdr_collection_b200.codes import standin_codes
+    from cu_sdr_collection_b200.engine import GC_SV_NONE
+    nE, codes = 60, None
+    if signal == "BDS_B3I":
+        sc = synth.default_scene_b3i(fs=18e6, nsat=3, seed=9)
+        for x, p in zip(sc.sats, (3, 20, 41)):
+            x.prn, x.cn0 = p, 48
+        sv, N, per = [3, 20, 41, 7], 18000, 40
+        s = init_settings(signal, samplingFreq=18e6, acqSatelliteList=sv, acqNonCohTime=5, msToProcess=nE, numberOfChannels=4)
+    elif signal == "GLO_GL1":
+        sc = synth.default_scene_glo(fs=12e6, nsat=3, seed=23)
+        for x in sc.sats:
+            x.cn0 = 47
+        sv, N, per = sorted({x.prn for x in sc.sats} | {5, -6}), 12000, 50
+        s = init_settings(signal, samplingFreq=12e6, acqSatelliteList=sv, acqNonCohTime=6, msToProcess=nE, numberOfChannels=4)
+    else:
+        codes = standin_codes(signal)
+        sc = synth.default_scene_fam5(signal, codes, fs=18e6, nsat=2, seed=5)
+        for x in sc.sats:
+            x.cn0 = 50
+        sv, N, per = sorted({x.prn for x in sc.sats} | {25}), 18000, 44
+        s = init_settings(signal, acqSatelliteList=sv, acqNonCohTime=3, msToProcess=nE, numberOfChannels=3, pilotTRKflag=1, CNo_VSMinterval=20)
+    raw = synth.make_record(sc, N * (nE + per))
+    eng = Engine(s, codes=codes) if codes is not None else Engine(s)
+    eng.set_record(raw)
+    acq2 = eng.acquire(sv)
+    ch2 = preRun(acq2, s)
+    tr2, _ = tracking(None, ch2, s, engine=eng)
+    acq1, ch1, out, vv, vi, done = eng.acquire_track(s.numberOfChannels, nE, sv_list=sv)
+    for k in ("carrFreq", "codePhase", "peakMetric"):
+        assert np.array_equal(acq1[k], acq2[k]), k
+    key = "K" if signal == "GLO_GL1" else "PRN"
+    assert [(c[key], c["status"], c["codePhase"]) for c in ch1] == [(c[key], c["status"], c["codePhase"]) for c in ch2]
+    assert sum(c["status"] == "T" for c in ch1) == len(sc.sats)
+    from cu_sdr_collection_b200.tracking import TRACK_FIELDS
+    for i in range(s.numberOfChannels):
+        for j, f in enumerate(TRACK_FIELDS):
+            assert np.array_equal(out[i, j], tr2[i][f]), (i, f)
+        assert done[i] == tr2[i]["epochsDone"]
+    if signal == "BDS_B2a":                                  # the device-side Calc_CNo_PLD block of the same call
+        pld = eng.cno_pld(s.numberOfChannels, nE)
+        assert np.array_equal(pld[0, 0], tr2[0]["DataCNo"]) and np.array_equal(pld[0, 4], tr2[0]["B2a_CNo"]) and not pld[2].any()
+    eng.close()

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert set(engine.EXPORTS) == declared
-    assert lib.gc_abi_version() == 4 and lib.gc_build_arch() == b"sm_100a"
+    assert lib.gc_abi_version() == 5 and lib.gc_build_arch() == b"sm_100a"
     assert lib.gc_acq_result_len(0) == 32 and lib.gc_acq_result_len(1) == 21 and lib.gc_acq_result_len(3) == 50
 
 
