@@ -428,19 +428,19 @@ def main():
     # ---- widened rows: configs[3] (GAL E1C 36 x 81 @ 20 Msps), GLONASS and GPS L5C at the reference defaults, configs[4] ----
     widened = None
     if not args.no_tracking and not args.no_widened:
-        from cu_sdr_collection_b200.codes import standin_b1c_codes, standin_codes, standin_e1_codes, standin_varb_codes
+        from cu_sdr_collection_b200.codes import icd_codes
         from cu_sdr_collection_b200.engine import signal_id
         from cu_sdr_collection_b200.settings import samples_per_code
         widened = {}
         sd = 20260101
-        e1codes = standin_e1_codes()
+        e1codes = icd_codes("GAL_E1C")
         # configs[3]: 36 PRNs dealt round-robin over the ranks, one all-gather
         es = init_settings("GAL_E1C", samplingFreq=20e6, acqSearchBand=6000.0, acqSearchStep=150.0)     # 81 bins
         escene = synth.default_scene_e1c(e1codes, fs=20e6, nsat=6, seed=sd)
         for sat in escene.sats:
             sat.cn0 = max(sat.cn0, 46.0)
         erec = synth.make_record_torch(escene, 80000 * 43, device=dev)
-        eeng = Engine(es, device=local, codes=e1codes)
+        eeng = Engine(es, device=local)                      # the engine decodes the E1-B / E1-C memory codes itself, on the device
         eeng.set_record(erec)
         esv = shard.shard_units(es.acqSatelliteList, rank, world)
         ebuf = torch.zeros(4 * 50, dtype=torch.float64, device=dev)
@@ -461,7 +461,7 @@ def main():
         widened["gal_e1c_acquisition"] = {
             "value": ecells / (ems * 1e-3), "unit": "cells/s", "ms": ems, "prns_per_rank": len(esv),
             "workload": "GAL_E1C 36 PRN x 81 Doppler x 1 block x 2 replicas (E1B + E1C), FFT length 160000 @ 20 Msps (BASELINE.json "
-                        "configs[3]); PRNs dealt round-robin over the ranks, one all-gather; fused 200 x 32 x 25 plan, stand-in memory codes",
+                        "configs[3]); PRNs dealt round-robin over the ranks, one all-gather; fused 200 x 32 x 25 plan, the real E1-B / E1-C memory codes",
             "n_acquired": int(np.count_nonzero(eacq["carrFreq"])), "acq_path": int(eeng.stats()["acq_path"])}
         eeng.close()
         del erec
@@ -503,13 +503,13 @@ def main():
         add_sig("BDS_B3I", init_settings("BDS_B3I"), None, synth.default_scene_b3i(fs=18e6, nsat=5, seed=sd), 22, 21)
         add_sig("GAL_E1C", init_settings("GAL_E1C"), e1codes, synth.default_scene_e1c(e1codes, fs=18e6, nsat=4, seed=sd), 42, 94)
         for sg, per, bins in (("GPS_L5C", 42, 21), ("GAL_E5a", 102, 21), ("GAL_E5b", 102, 168), ("BDS_B2a", 17, 21)):
-            cd = standin_codes(sg)
+            cd = icd_codes(sg)
             add_sig(sg, init_settings(sg), cd, synth.default_scene_fam5(sg, cd, fs=18e6, nsat=4, seed=sd), per, bins)
-        cd = standin_varb_codes("BDS_B1I")
+        cd = icd_codes("BDS_B1I")
         add_sig("BDS_B1I", init_settings("BDS_B1I"), cd, synth.default_scene_varb("BDS_B1I", cd, fs=18e6, nsat=4, seed=sd), 11, 81)
-        cd = standin_varb_codes("GPS_L2C")
+        cd = icd_codes("GPS_L2C")
         add_sig("GPS_L2C", init_settings("GPS_L2C"), cd, synth.default_scene_varb("GPS_L2C", cd, fs=8e6, nsat=3, seed=sd), 3, 801)
-        cd = standin_b1c_codes()
+        cd = icd_codes("BDS_B1C")
         add_sig("BDS_B1C", init_settings("BDS_B1C"), cd, synth.default_scene_varb("BDS_B1C", cd, fs=18e6, nsat=3, seed=sd), 2, 201)
         pairs = [(name, sv) for name, v in sigs.items() for sv in v[0].acqSatelliteList]
         plan, load = shard.plan_pairs(pairs, world)
@@ -524,7 +524,7 @@ def main():
             st_, codes_, scene_, periods, bins = sigs[name]
             n_ = samples_per_code(st_)
             r_ = torch.from_numpy(synth.make_record(scene_, n_ * periods + 64)).to(dev)
-            e_ = Engine(st_, device=local, codes=codes_) if codes_ is not None else Engine(st_, device=local)
+            e_ = Engine(st_, device=local)                   # every code generated inside the library (codegen_kernel)
             e_.set_record(r_)
             engines[name] = (e_, r_)
 
@@ -566,7 +566,7 @@ def main():
             "workload": "BASELINE.json configs[4]: the twelve signal folders' acquisitions at their default initSettings.m; the 439 "
                         "(signal, SV) pairs dealt over the ranks by measured per-pair cost (longest first), each rank runs its pairs signal "
                         "after signal, one all-gather of every signal's acqResults; ms = host wall clock of a whole pass incl. the gather "
-                        "(max over ranks); stand-in codes where the reference's are data",
+                        "(max over ranks); every code generated by the library (csrc/codegen.cu)",
             "per_signal_ms_this_rank": {k: round(v, 3) for k, v in ms_sig.items()}}
         for e_, r_ in engines.values():
             e_.close()

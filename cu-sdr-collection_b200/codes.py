@@ -204,3 +204,31 @@ def standin_b1c_codes(seed: int = 20260101) -> dict:
             comps.append(c)
         out[prn] = tuple(comps)
     return out
+
+
+def icd_codes(signal: str, prns=None, cl: bool = False, boc61: bool = False) -> dict:
+    """The signal's REAL primary codes from the library's generators (``gc_generate_code``: the reference's generate*code.m as
+    bit-packed registers, ICD tables included) in the {PRN: (component 0, component 1, ...)} layout the scene builders and
+    ``Engine(codes=...)`` take.  GAL E1C: (e1b, e1c) primary chips; GPS L5C / GAL E5a / GAL E5b / BDS B2a: (data, pilot, pilot
+    secondary code - NH20-free: E5a / E5b their own 100 chips, L5C and B2a a row of ones, used by scene synthesis only);
+    BDS B1I: (code,); GPS L2C: (cm,) or (cm, cl) with ``cl``; BDS B1C: (data, pilot) BOC(1,1) or with ``boc61`` also the pilot
+    BOC(6,1) sequence.  The engine does not need this dict - it generates whatever it is not given."""
+    from .engine import generate_code
+    pools = {"GAL_E1C": range(1, 51), "GPS_L5C": range(1, 33), "GAL_E5a": range(1, 51), "GAL_E5b": range(1, 51), "BDS_B2a": range(1, 64),
+             "BDS_B1I": range(1, 59), "GPS_L2C": range(1, 33), "BDS_B1C": range(1, 64)}
+    out = {}
+    for prn in (pools[signal] if prns is None else prns):
+        prn = int(prn)
+        if signal in ("GPS_L5C", "BDS_B2a"):
+            out[prn] = (generate_code(signal, prn, 0), generate_code(signal, prn, 1), np.ones(100, dtype=np.int8))
+        elif signal in ("GAL_E5a", "GAL_E5b"):
+            out[prn] = (generate_code(signal, prn, 0), generate_code(signal, prn, 1), generate_code(signal, prn, 2))
+        elif signal == "BDS_B1I":
+            out[prn] = (generate_code(signal, prn, 0),)
+        elif signal == "GPS_L2C":
+            out[prn] = (generate_code(signal, prn, 0),) + ((generate_code(signal, prn, 1),) if cl else ())
+        elif signal == "BDS_B1C":
+            out[prn] = (generate_code(signal, prn, 0), generate_code(signal, prn, 1)) + ((generate_code(signal, prn, 2),) if boc61 else ())
+        else:
+            out[prn] = (generate_code(signal, prn, 0), generate_code(signal, prn, 1))
+    return out

@@ -14,6 +14,7 @@
 #include "../../include/gnsscorr.h"
 #include "acq.h"
 #include "codes.h"
+#include "codegen_jobs.h"
 #include "common.cuh"
 #include "track.h"
 #include "nav.h"
@@ -594,6 +595,43 @@ int gc_set_record_device(gc_handle* h, const void* dptr, size_t nbytes)
     return GC_OK;
 }
 
+// Codes the caller has not supplied through gc_set_code are generated here, ON THE DEVICE (codegen.cu: one thread per SV and
+// component running the reference's generators as bit-packed registers), and then take the same path as caller-supplied ones.
+static int autofill_codes(gc_handle* h, int nSv, const int32_t* svList)
+{
+    if (!h->hostCodes) return GC_OK;
+    const gc_config& c = h->cfg;
+    std::vector<CodeJob> jobs;
+    std::vector<std::pair<int, int>> what;                     // (sv, component) of each job
+    for (int i = 0; i < nSv; ++i) {
+        const int sv = svList[i];
+        if (sv < 1 || sv > h->resultLen) continue;
+        for (int comp = 0; comp < 3; ++comp) {
+            bool need = comp <= 1;
+            if (c.signal == GC_SIG_BDS_B1I) need = comp == 0;
+            if (c.signal == GC_SIG_GPS_L2C) need = comp == 0 || (comp == 1 && c.pilot_trk_flag == 1);
+            if (c.signal == GC_SIG_BDS_B1C) need = comp <= 1 || (comp == 2 && c.pilot_trk_flag == 2);
+            if (c.signal == GC_SIG_GAL_E5A && comp == 2) need = true;
+            if (!need || !h->hostCode[comp][sv - 1].empty()) continue;
+            bool dup = false;
+            for (auto& w : what) dup |= (w.first == sv && w.second == comp);
+            CodeJob j;
+            if (dup || !make_code_job(c.signal, sv, comp, &j)) continue;
+            jobs.push_back(j);
+            what.push_back({sv, comp});
+        }
+    }
+    if (jobs.empty()) return GC_OK;
+    cudaSetDevice(c.device);
+    std::vector<int8_t> out;
+    GC_CUDA(h, run_code_jobs_device(jobs, out, h->stream));
+    for (size_t i = 0; i < jobs.size(); ++i) {
+        const int rc = gc_set_code(h, what[i].first, what[i].second, out.data() + jobs[i].outOff, jobs[i].n);
+        if (rc != GC_OK) return rc;
+    }
+    return GC_OK;
+}
+
 // ---- acquisition variant B (BDS/B1I/include/acquisition.m:42-176, GPS/GPS_L2C/include/acquisition.m:26-118) -------
 static int varb_build_replicas(gc_handle* h)
 {
@@ -1134,6 +1172,10 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         return fail(h, GC_ERR_ARG, "gc_acquire: bad argument");
     for (int i = 0; i < nSv; ++i)
         if (!sv_ok(h, svList[i])) return fail(h, GC_ERR_ARG, h->glo ? "gc_acquire: frequency number out of range -7..13" : "gc_acquire: PRN out of range");
+    {
+        const int rc = autofill_codes(h, nSv, svList);           // codes not supplied by the caller: generated on the device
+        if (rc != GC_OK) return rc;
+    }
     for (int i = 0; i < nSv; ++i)
         if (!sv_has_code(h, svList[i])) return fail(h, GC_ERR_ARG, "gc_acquire: no code set for an SV of the list (gc_set_code)");
     if (!h->replicasReady) {
@@ -1664,6 +1706,13 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
         return fail(h, GC_ERR_ARG, "gc_track: bad argument");
     cudaSetDevice(c.device);
     cudaStream_t st = h->stream;
+    {
+        std::vector<int32_t> need;
+        for (int ch = 0; ch < nCh; ++ch)
+            if (sv[ch] >= 1 && sv[ch] <= h->resultLen) need.push_back(sv[ch]);
+        const int rc = autofill_codes(h, (int)need.size(), need.data());
+        if (rc != GC_OK) return rc;
+    }
     // table entries per code period (BOC: sub-chips).  GPS L2C works in half chips throughout: codeLength*2 entries of the
     // return-to-zero CM code, code NCO at 2*codeFreqBasis, spacing*2 (GPS_L2C/include/tracking.m:93-94, 171)
     const int codeLen = c.code_length * h->sub * (c.signal == GC_SIG_GPS_L2C ? 2 : 1);
@@ -1943,6 +1992,41 @@ int gc_nav_sync(gc_handle* h, int32_t nCh, int32_t nEpochs, const double* I_P, i
         bitsValid[ch] = hi[nCh + ch];
     }
     return GC_OK;
+}
+
+int gc_code_entries(int32_t signal, int32_t component)
+{
+    if (signal == GC_SIG_GPS_L1CA) return component == 0 ? 1023 : 0;
+    if (signal == GC_SIG_GLO_G1G2) return component == 0 ? 511 : 0;
+    if (signal == GC_SIG_BDS_B3I) return component == 0 ? 10230 : 0;
+    return code_entries(signal, component);
+}
+
+int gc_generate_code(int32_t signal, int32_t sv, int32_t component, int8_t* out, int32_t nOut)
+{
+    const int n = gc_code_entries(signal, component);
+    if (!out || n == 0 || nOut < n) return GC_ERR_ARG;
+    if (signal == GC_SIG_GPS_L1CA) { if (sv < 1 || sv > 32) return GC_ERR_ARG; ca_code(sv, out); return n; }
+    if (signal == GC_SIG_GLO_G1G2) { glo_code(out); return n; }
+    if (signal == GC_SIG_BDS_B3I) { if (sv < 1 || sv > 63) return GC_ERR_ARG; b3i_code(sv, out); return n; }
+    CodeJob j;
+    if (!make_code_job(signal, sv, component, &j)) return GC_ERR_ARG;
+    run_code_job_host(j, out);
+    return n;
+}
+
+int gc_generate_code_device(int32_t device, int32_t signal, int32_t nSv, const int32_t* svList, int32_t component, int8_t* out)
+{
+    const int n = code_entries(signal, component);
+    if (!out || !svList || nSv < 1 || n == 0) return GC_ERR_ARG;
+    std::vector<CodeJob> jobs(nSv);
+    for (int i = 0; i < nSv; ++i)
+        if (!make_code_job(signal, svList[i], component, &jobs[i])) return GC_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return GC_ERR_CUDA;
+    std::vector<int8_t> host;
+    if (run_code_jobs_device(jobs, host, nullptr) != cudaSuccess) return GC_ERR_CUDA;
+    std::copy(host.begin(), host.end(), out);
+    return n;
 }
 
 void* gc_get_stream(const gc_handle* h) { return h ? (void*)h->stream : nullptr; }

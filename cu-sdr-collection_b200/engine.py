@@ -58,7 +58,7 @@ EXPORTS = ["gc_abi_version", "gc_build_arch", "gc_acq_result_len", "gc_create", 
            "gc_last_error", "gc_set_code", "gc_set_record_host", "gc_set_record_device", "gc_acquire",
            "gc_acquire_host", "gc_track_nfields", "gc_track", "gc_track_file", "gc_get_stats", "gc_get_stream",
            "gc_set_param", "gc_get_cl_code_phase", "gc_set_cl_code_phase", "gc_nav_sync", "gc_acquire_track",
-           "gc_acquire_device", "gc_get_cno_pld", "gc_multi_create", "gc_multi_destroy", "gc_multi_last_error", "gc_multi_n_gpus",
+           "gc_acquire_device", "gc_get_cno_pld", "gc_code_entries", "gc_generate_code", "gc_generate_code_device", "gc_multi_create", "gc_multi_destroy", "gc_multi_last_error", "gc_multi_n_gpus",
            "gc_multi_handle", "gc_multi_set_code", "gc_multi_set_param", "gc_multi_set_cl_code_phase",
            "gc_multi_get_cl_code_phase", "gc_multi_set_record_host", "gc_multi_acquire", "gc_multi_acquire_host",
            "gc_multi_track", "gc_multi_track_file", "gc_multi_get_times"]
@@ -103,6 +103,9 @@ def load_lib():
     lib.gc_get_stream.restype = C.c_void_p
     lib.gc_acquire_device.argtypes = [vp, C.c_int32, i32p, vp]
     lib.gc_get_cno_pld.argtypes = [vp, C.c_int32, C.c_int32, dp]
+    lib.gc_code_entries.argtypes = [C.c_int32, C.c_int32]
+    lib.gc_generate_code.argtypes = [C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32]
+    lib.gc_generate_code_device.argtypes = [C.c_int32, C.c_int32, C.c_int32, i32p, C.c_int32, vp]
     lib.gc_multi_create.argtypes = [C.POINTER(vp), C.POINTER(gc_config), C.c_int32]
     lib.gc_multi_destroy.argtypes = [vp]
     lib.gc_multi_destroy.restype = None
@@ -175,18 +178,12 @@ class Engine:
         if rc != 0:
             raise GnssCorrError(f"gc_create failed ({rc}): {self.lib.gc_last_error(None).decode()}")
         self._keep = None
-        if settings.is_fam5 or settings.is_varb or settings.signal == "BDS_B1C":
-            if codes is None:
-                raise GnssCorrError(f"{settings.signal} takes its primary codes from the caller: pass codes= "
-                                    "{PRN: (data, pilot[, pilot_secondary])} (what generateL5Icode.m etc. return)")
-            self.set_codes(codes)
-        if settings.signal == "GAL_E1C":
-            if codes is None:
-                from .codes import load_e1_codes
-                if not settings.codeDir:
-                    raise GnssCorrError("Galileo E1 needs the memory codes: pass codes= or set settings.codeDir "
-                                        "to the folder with E1b.dat / E1c.dat")
-                codes = load_e1_codes(settings.codeDir)
+        # codes= overrides the library's own generators (gc_generate_code: the reference's generate*code.m as device kernels);
+        # without it every code is generated inside the library the first time an SV is used
+        if settings.signal == "GAL_E1C" and codes is None and settings.codeDir:
+            from .codes import load_e1_codes
+            codes = load_e1_codes(settings.codeDir)
+        if codes is not None and (settings.is_fam5 or settings.is_varb or settings.signal in ("BDS_B1C", "GAL_E1C")):
             self.set_codes(codes)
 
     def set_codes(self, codes: dict):
@@ -452,3 +449,22 @@ class MultiEngine:
         a, t = C.c_double(), C.c_double()
         self._check(self.lib.gc_multi_get_times(self._m, C.byref(a), C.byref(t)), "gc_multi_get_times")
         return dict(acq_ms=a.value, track_ms=t.value)
+
+
+def generate_code(signal: str, sv: int, component: int = 0, device: int | None = None) -> np.ndarray:
+    """The library's own primary-code generators (``gc_generate_code``; ``device`` given: the same generators as a CUDA kernel,
+    ``gc_generate_code_device``).  ``signal``: a settings.signal name; returns the int8 entries in gc_set_code's layout."""
+    lib = load_lib()
+    sid = signal_id(Settings(signal=signal)) if not isinstance(signal, int) else int(signal)
+    n = lib.gc_code_entries(sid, component)
+    if n <= 0:
+        raise GnssCorrError(f"{signal} has no code component {component}")
+    out = np.zeros(n, dtype=np.int8)
+    if device is None:
+        rc = lib.gc_generate_code(sid, int(sv), component, out.ctypes.data, n)
+    else:
+        svl = np.asarray([sv], dtype=np.int32)
+        rc = lib.gc_generate_code_device(int(device), sid, 1, _ip(svl), component, out.ctypes.data)
+    if rc != n:
+        raise GnssCorrError(f"gc_generate_code({signal}, {sv}, {component}) failed ({rc})")
+    return out

@@ -152,9 +152,24 @@ const char* gc_last_error(const gc_handle* h);
  * component 1 = the 1534500-entry return-to-zero CL sequence (generateCLcode.m; entries +-1 and 0).  BDS B1C takes
  * components 0 / 1 = the 20460 BOC(1,1) sub-chips of generateDataBOC11.m / generatePilotBOC11.m and, for full-band
  * tracking (pilot_trk_flag == 2), component 2 = the 122760-entry pilot BOC(6,1) sequence of generatePilotBOC61.m.
- * Every SV named in gc_acquire / gc_track must have its components set.  Signals with generated
- * codes (GPS L1CA, GLONASS, B3I) return GC_ERR_ARG. */
+ * Components that are not set are generated by the library (gc_generate_code below): gc_set_code is an override.  Signals whose
+ * codes are always generated (GPS L1CA, GLONASS, B3I) return GC_ERR_ARG. */
 int gc_set_code(gc_handle* h, int32_t sv, int32_t component, const int8_t* chips, int32_t nChips);
+
+/* The primary codes themselves.  The reference builds them at run time inside acquisition.m / tracking.m (generateL5Icode.m,
+ * generateE5aIcode.m ..., generateB2aDataCode.m, generateCAcode53.m, generateCMcode.m / generateCLcode.m, generateDataBOC11.m /
+ * generatePilotBOC11.m / generatePilotBOC61.m with JacobiSymbol.m, generateE1Bcode.m reading E1b.dat); the library has the same
+ * generators (csrc/codegen.h, bit-packed registers; ICD tables extracted from those files) and runs them ON THE DEVICE for every
+ * (SV, component) the caller has not supplied through gc_set_code - gc_set_code stays as the override.
+ *   gc_code_entries          entries of a component in gc_set_code's layout (0 = no such component)
+ *   gc_generate_code         one code on the host (no GPU needed): returns the number of entries written, < 0 on error
+ *   gc_generate_code_device  the same generators as one kernel on GPU `device`, one thread per SV; out = nSv x entries, host memory
+ * Components: as gc_set_code (GAL E1C 0/1 = E1-B / E1-C primary chips; GPS L5C 0/1 = I5 / Q5; GAL E5a, E5b 0/1/2 = I, Q, the Q
+ * secondary code; BDS B2a 0/1 = data / pilot; BDS B1I 0; GPS L2C 0/1 = return-to-zero CM / CL; BDS B1C 0/1/2 = data BOC(1,1),
+ * pilot BOC(1,1), pilot BOC(6,1)); GPS L1CA, GLONASS and BDS B3I: component 0 (host only). */
+int gc_code_entries(int32_t signal, int32_t component);
+int gc_generate_code(int32_t signal, int32_t sv, int32_t component, int8_t* out, int32_t nOut);
+int gc_generate_code_device(int32_t device, int32_t signal, int32_t nSv, const int32_t* svList, int32_t component, int8_t* out);
 
 /* Scalar settings outside gc_config.  GC_PARAM_B1C_WB_FACTOR: the data-channel weight of the composite code
  * discriminator in B1C full-band tracking, `factor = CalcWeighingFactor(settings)` (BDS/B1C/include/WB_tracking.m:124,

@@ -1914,3 +1914,278 @@ def cno_pld_rows(trackResults: dict, s, done: int, signal: str = "BDS_B2a") -> d
                 res["PilotPLD"][c - 1] = PllDetector[1]
             temp = CNoValue                                                    # :432
     return res
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# Code generators of the nine signals whose primary codes the reference builds at run time.  Each function follows
+# its .m file statement by statement (+-1 registers, prod() feedback, circshift) - deliberately NOT the bit-packed form the library
+# uses (csrc/codegen.h), so that the two are independent witnesses.  The ICD constant tables come from oracle/icd_tables.py.
+import icd_tables as _icd
+
+
+def _circshift(v, k):
+    """circshift(v', k)' for a row vector."""
+    k %= len(v)
+    return v[-k:] + v[:-k] if k else list(v)
+
+
+def _prod(v, pos):
+    p = 1
+    for i in pos:
+        p *= v[i - 1]
+    return p
+
+
+def _l5_code(PRN, advance, codeLength=10230):
+    """GPS/GPS_L5C/include/generateL5Icode.m:44-133 (generateL5Qcode.m is the same with its own advance table)."""
+    xa_FeedbackPos = [9, 10, 12, 13]                                       # :47
+    xa_reg = [-1] * 13                                                     # :49
+    XA = [0] * codeLength
+    reset_state = [-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 1, -1]      # :53
+    for ind in range(codeLength):                                          # :55
+        XA[ind] = xa_reg[-1]
+        if xa_reg == reset_state:
+            xa_reg = [-1] * 13
+        else:
+            feedback = _prod(xa_reg, xa_FeedbackPos)
+            xa_reg = _circshift(xa_reg, 1)
+            xa_reg[0] = feedback
+    xbi_FeedbackPos = [1, 3, 4, 6, 7, 8, 12, 13]                           # :104
+    xbi_reg = [-1] * 13
+    XBI = [0] * codeLength
+    resetPos = advance[PRN - 1]                                            # :110
+    for _ in range(resetPos):                                              # :112-118
+        feedback = _prod(xbi_reg, xbi_FeedbackPos)
+        xbi_reg = _circshift(xbi_reg, 1)
+        xbi_reg[0] = feedback
+    for ind in range(codeLength):                                          # :121-129
+        XBI[ind] = xbi_reg[-1]
+        feedback = _prod(xbi_reg, xbi_FeedbackPos)
+        xbi_reg = _circshift(xbi_reg, 1)
+        xbi_reg[0] = feedback
+    return np.array(XBI, dtype=np.int64) * np.array(XA, dtype=np.int64)    # :132
+
+
+def generateL5Icode(PRN, codeLength=10230):
+    return _l5_code(PRN, _icd.L5I_ADVANCE, codeLength)
+
+
+def generateL5Qcode(PRN, codeLength=10230):
+    return _l5_code(PRN, _icd.L5Q_ADVANCE, codeLength)
+
+
+def _dec2bin(x):
+    """dec2bin(x) - 48: the binary digits without leading zeros."""
+    return [int(c) for c in bin(int(x))[2:]]
+
+
+def _gal_e5_primary(start_value, Feedback_Reg1, Feedback_Reg2):
+    """GAL/GAL_E5a/include/generateE5aIcode.m:45-97 (the E5a-Q, E5b-I and E5b-Q files differ in the tables and the octal
+    feedback strings only)."""
+    Register1 = [1] * 14                                                   # :47
+    taps1_coef = _dec2bin(int(Feedback_Reg1, 8))[:14]                      # :68-71 dec2bin(base2dec(.,8))-48, then (1:14)
+    taps2_coef = _dec2bin(int(Feedback_Reg2, 8))[:14]
+    StartValues = _dec2bin(start_value)                                    # :74-75
+    Register2 = [0] * 14                                                   # :76
+    Register2[14 - len(StartValues):] = StartValues                        # :77 Register2(end-length+1:end)
+    Pri = [0] * 10230
+    for ind in range(10230):                                               # :80
+        RegOut1 = [a * b for a, b in zip(Register1, taps1_coef)]
+        RegOut2 = [a * b for a, b in zip(Register2, taps2_coef)]
+        Pri[ind] = (1 - 2 * RegOut1[0]) * (1 - 2 * RegOut2[0])             # :84
+        feedback1, feedback2 = 1, 1
+        for v in RegOut1:
+            feedback1 *= (1 - 2 * v)                                       # :87 prod(1 - 2*RegOut1)
+        for v in RegOut2:
+            feedback2 *= (1 - 2 * v)
+        feedback1 = 0 if feedback1 == 1 else 1                             # :90-99
+        feedback2 = 0 if feedback2 == 1 else 1
+        Register1 = _circshift(Register1, -1)                              # :101 shift left
+        Register2 = _circshift(Register2, -1)
+        Register1[-1] = feedback1                                          # :104
+        Register2[-1] = feedback2
+    return np.array(Pri, dtype=np.int64)
+
+
+def generateE5aIcode(PRN):
+    return _gal_e5_primary(_icd.E5AI_START[PRN - 1], "40503", "50661")
+
+
+def generateE5aQcode(PRN):
+    return _gal_e5_primary(_icd.E5AQ_START[PRN - 1], "40503", "50661")
+
+
+def generateE5bIcode(PRN):
+    return _gal_e5_primary(_icd.E5BI_START[PRN - 1], "64021", "51445")
+
+
+def generateE5bQcode(PRN):
+    return _gal_e5_primary(_icd.E5BQ_START[PRN - 1], "64021", "43143")
+
+
+def _gal_secondary(code):
+    """GAL/GAL_E5a/include/generateE5aQ_secondary.m:73-87: 25 hex characters -> 100 chips, 1 - 2*bit."""
+    first_segement = [0] * (13 * 4)
+    second_segement = [0] * (12 * 4)
+    t = _dec2bin(int(code[:13], 16))
+    first_segement[len(first_segement) - len(t):] = t
+    t = _dec2bin(int(code[13:], 16))
+    second_segement[len(second_segement) - len(t):] = t
+    return 1 - 2 * np.array(first_segement + second_segement, dtype=np.int64)
+
+
+def generateE5aQ_secondary(PRN):
+    return _gal_secondary(_icd.E5AQ_SECONDARY[PRN - 1])
+
+
+def generateE5bQ_secondary(PRN):
+    return _gal_secondary(_icd.E5BQ_SECONDARY[PRN - 1])
+
+
+def _b2a_code(reg2_ini, reg1_FeedbackPos, reg2_FeedbackPos, codeLength=10230):
+    """BDS/B2a/include/generateB2aDataCode.m:111-138 (generateB2aPilotCode.m: other taps and initial states)."""
+    register1 = [-1] * 13                                                  # :116
+    bits = [(reg2_ini >> (12 - i)) & 1 for i in range(13)]                 # row PRN of B2aData_reg2_ini
+    register2 = [1 - 2 * b for b in bits]                                  # :117
+    code = [0] * codeLength
+    reset_index = 8190                                                     # :120
+    for ind in range(1, codeLength + 1):
+        code[ind - 1] = register1[-1] * register2[-1]                      # :123
+        feedback1 = _prod(register1, reg1_FeedbackPos)
+        register1 = _circshift(register1, 1)
+        register1[0] = feedback1
+        feedback2 = _prod(register2, reg2_FeedbackPos)
+        register2 = _circshift(register2, 1)
+        register2[0] = feedback2
+        if ind == reset_index:                                             # :135-137
+            register1 = [-1] * 13
+    return np.array(code, dtype=np.int64)
+
+
+def generateB2aDataCode(PRN):
+    return _b2a_code(_icd.B2AD_REG2[PRN - 1], [1, 5, 11, 13], [3, 5, 9, 11, 12, 13])
+
+
+def generateB2aPilotCode(PRN):
+    return _b2a_code(_icd.B2AP_REG2[PRN - 1], [3, 6, 7, 13], [1, 5, 7, 8, 12, 13])
+
+
+def generateCAcode53(PRN):
+    """BDS/B1I/include/generateCAcode53.m:38-103."""
+    g1 = [0] * 2046
+    reg = [-x for x in [-1, 1, -1, 1, -1, 1, -1, 1, -1, 1, -1]]            # :43
+    for i in range(2046):
+        g1[i] = reg[10]
+        saveBit = reg[0] * reg[6] * reg[7] * reg[8] * reg[9] * reg[10]     # :48
+        reg[1:11] = reg[0:10]
+        reg[0] = saveBit
+    g2 = [0] * 2046
+    reg = [-x for x in [-1, 1, -1, 1, -1, 1, -1, 1, -1, 1, -1]]
+    g2s1, g2s2, g2s3 = _icd.B1I_G2S1, _icd.B1I_G2S2, _icd.B1I_G2S3
+    for i in range(2046):
+        if PRN > 37:                                                       # :83-90
+            g2[i] = reg[g2s1[PRN - 1] - 1] * reg[g2s2[PRN - 1] - 1] * reg[g2s3[PRN - 37 - 1] - 1]
+        else:
+            g2[i] = reg[g2s1[PRN - 1] - 1] * reg[g2s2[PRN - 1] - 1]
+        saveBit = reg[0] * reg[1] * reg[2] * reg[3] * reg[4] * reg[7] * reg[8] * reg[10]
+        reg[1:11] = reg[0:10]
+        reg[0] = saveBit
+    return -(np.array(g1, dtype=np.int64) * np.array(g2, dtype=np.int64))  # :102
+
+
+def _l2c_code(code_init, CodeLength):
+    """GPS/GPS_L2C/include/generateCMcode.m:88-106: 27-stage register, taps multiplied by the output chip."""
+    RegPos = [4, 7, 9, 12, 15, 17, 19, 22, 23, 24, 25]                     # :41
+    reg = _dec2bin(code_init)                                              # :92 dec2bin(oct2dec(code_init)) - 48
+    reg = [0] * (27 - len(reg)) + reg                                      # :93
+    reg = [-1 if b else 1 for b in reg]                                    # :94-95
+    code = np.zeros(CodeLength, dtype=np.int64)
+    for index in range(CodeLength):
+        c = reg[-1]
+        code[index] = c                                                    # :99
+        reg = _circshift(reg, 1)                                           # :100
+        for p in RegPos:
+            reg[p - 1] *= c                                                # :101
+    return code
+
+
+def generateCMcode(PRN, codeLength=10230):
+    """The return-to-zero CM sequence [c1 0 c2 0 ...] (generateCMcode.m:108-111).  PRN 1..63."""
+    CM = _l2c_code(_icd.L2CM_INIT[PRN - 1], codeLength)
+    out = np.zeros(2 * codeLength, dtype=np.int64)
+    out[0::2] = CM
+    return out
+
+
+def generateCLcode(PRN, CLCodeLength=767250):
+    """[0 c1 0 c2 ...] (generateCLcode.m:107-110)."""
+    CL = _l2c_code(_icd.L2CL_INIT[PRN - 1], CLCodeLength)
+    out = np.zeros(2 * CLCodeLength, dtype=np.int64)
+    out[1::2] = CL
+    return out
+
+
+def JacobiSymbol_prime(a, N):
+    """JacobiSymbol(a, N) of BDS/B1C/include/JacobiSymbol.m for an odd prime N (all its callers pass 10243 or 3607): the
+    Legendre symbol, by Euler's criterion."""
+    if a % N == 0:
+        return 0
+    return 1 if pow(a, (N - 1) // 2, N) == 1 else -1
+
+
+def _weil_primary(w, p, N=10243, length=10230):
+    """BDS/B1C/include/generateDataBOC11.m:66-82."""
+    legendre = np.zeros(N, dtype=np.int64)
+    for ind in range(1, N):                                                # :68-70
+        legendre[ind] = JacobiSymbol_prime(ind, N)
+    legendre[legendre == -1] = 0                                           # :71
+    Primary = np.zeros(length, dtype=np.int64)
+    for ind in range(length):                                              # :77-80
+        k = (ind + p - 1) % N
+        Primary[ind] = legendre[k] ^ legendre[(k + w) % N]
+    return 1 - 2 * Primary                                                 # :82
+
+
+def generateDataBOC11(PRN):
+    P = _weil_primary(_icd.B1CD_W[PRN - 1], _icd.B1CD_P[PRN - 1])
+    out = np.zeros(2 * P.size, dtype=np.int64)
+    out[0::2] = -P                                                         # :86-89
+    out[1::2] = P
+    return out
+
+
+def generatePilotBOC11(PRN):
+    P = _weil_primary(_icd.B1CP_W[PRN - 1], _icd.B1CP_P[PRN - 1])
+    out = np.zeros(2 * P.size, dtype=np.int64)
+    out[0::2] = -P
+    out[1::2] = P
+    return out
+
+
+def generatePilotBOC61(PRN):
+    """BDS/B1C/include/generatePilotBOC61.m:103-110: twelve entries (-1)^ii * chip per chip."""
+    P = _weil_primary(_icd.B1CP_W[PRN - 1], _icd.B1CP_P[PRN - 1])
+    sign = np.array([(-1) ** ii for ii in range(1, 13)], dtype=np.int64)
+    return (P[:, None] * sign[None, :]).reshape(-1)
+
+
+def _e1_primary(hexrow):
+    bits = bin(int(hexrow, 16))[2:].zfill(4092)
+    return 1 - 2 * np.array([int(c) for c in bits], dtype=np.int64)        # generateE1Bcode.m:55
+
+
+def generateE1Bcode(PRN):
+    """GAL/GAL_E1C/include/generateE1Bcode.m:44-64 with the memory code of E1b.dat: BOC(1,1) sub-chips [c -c]."""
+    c = _e1_primary(_icd.E1B_HEX[PRN - 1])
+    out = np.zeros(2 * c.size, dtype=np.int64)
+    out[0::2] = c
+    out[1::2] = -c
+    return out
+
+
+def generateE1Ccode(PRN):
+    c = _e1_primary(_icd.E1C_HEX[PRN - 1])
+    out = np.zeros(2 * c.size, dtype=np.int64)
+    out[0::2] = c
+    out[1::2] = -c
+    return out

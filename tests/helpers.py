@@ -237,3 +237,30 @@ def nav_prompt_row(bits: np.ndarray, start: int, n: int, amp: float, sigma: floa
     if start - 1 + m < n:
         row[start - 1 + m:] = np.repeat(1 - 2 * rng.integers(0, 2, size=(n - start - m) // 20 + 2), 20)[: n - (start - 1 + m)]
     return polarity * amp * row + sigma * rng.standard_normal(n)
+
+
+def oracle_signal_codes(signal: str, prns, cl: bool = False, boc61: bool = False) -> dict:
+    """The signal's real primary codes from the ORACLE's restatement of the reference's generators (np_oracle.generate*), in the
+    {PRN: (components...)} layout of the scene builders and the oracle's acquisition / tracking functions.  The engine under test
+    is given no codes at all: it generates its own on the device (csrc/codegen.cu), so a parity test on these records also proves
+    that the two generators agree."""
+    gen = {"GPS_L5C": (O.generateL5Icode, O.generateL5Qcode, None), "GAL_E5a": (O.generateE5aIcode, O.generateE5aQcode, O.generateE5aQ_secondary),
+           "GAL_E5b": (O.generateE5bIcode, O.generateE5bQcode, O.generateE5bQ_secondary), "BDS_B2a": (O.generateB2aDataCode, O.generateB2aPilotCode, None)}
+    out = {}
+    for prn in prns:
+        prn = int(prn)
+        if signal in gen:
+            d, p, sec = gen[signal]
+            out[prn] = (d(prn).astype(np.int8), p(prn).astype(np.int8), (sec(prn) if sec else np.ones(100)).astype(np.int8))
+        elif signal == "GAL_E1C":
+            out[prn] = (O.generateE1Bcode(prn)[0::2].astype(np.int8), O.generateE1Ccode(prn)[0::2].astype(np.int8))   # primary chips
+        elif signal == "BDS_B1I":
+            out[prn] = (O.generateCAcode53(prn).astype(np.int8),)
+        elif signal == "GPS_L2C":
+            out[prn] = (O.generateCMcode(prn).astype(np.int8),) + ((O.generateCLcode(prn).astype(np.int8),) if cl else ())
+        elif signal == "BDS_B1C":
+            out[prn] = (O.generateDataBOC11(prn).astype(np.int8), O.generatePilotBOC11(prn).astype(np.int8)) + \
+                       ((O.generatePilotBOC61(prn).astype(np.int8),) if boc61 else ())
+        else:
+            raise ValueError(signal)
+    return out

@@ -1,0 +1,99 @@
+"""Primary-code generators: the library's bit-packed registers (csrc/codegen.h, called through the C ABI without
+a GPU) against the oracle's statement-by-statement restatement of the reference's generate*code.m files, for every SV, plus the
+known answers of the signal ICDs that survive independent of both (Galileo OS SIS ICD: first 24 chips of E5a-I and E5a-Q code 1,
+E1-B code 1) and the structure every spreading code must have."""
+import os
+
+import numpy as np
+import pytest
+
+import np_oracle as O
+from cu_sdr_collection_b200.engine import generate_code
+
+REF = "/root/reference"
+
+
+def _hex24(c):
+    return "%06X" % int("".join("1" if x == -1 else "0" for x in c[:24]), 2)
+
+
+CASES = [("GPS_L5C", 0, O.generateL5Icode, range(1, 64)), ("GPS_L5C", 1, O.generateL5Qcode, range(1, 64)),
+         ("GAL_E5a", 0, O.generateE5aIcode, range(1, 51)), ("GAL_E5a", 1, O.generateE5aQcode, range(1, 51)),
+         ("GAL_E5a", 2, O.generateE5aQ_secondary, range(1, 51)),
+         ("GAL_E5b", 0, O.generateE5bIcode, range(1, 51)), ("GAL_E5b", 1, O.generateE5bQcode, range(1, 51)),
+         ("GAL_E5b", 2, O.generateE5bQ_secondary, range(1, 51)),
+         ("BDS_B2a", 0, O.generateB2aDataCode, range(1, 64)), ("BDS_B2a", 1, O.generateB2aPilotCode, range(1, 64)),
+         ("BDS_B1I", 0, O.generateCAcode53, range(1, 59)),
+         ("GPS_L2C", 0, O.generateCMcode, range(1, 64)),
+         ("BDS_B1C", 0, O.generateDataBOC11, range(1, 64)), ("BDS_B1C", 1, O.generatePilotBOC11, range(1, 64)),
+         ("BDS_B1C", 2, O.generatePilotBOC61, (1, 7, 63))]
+
+
+@pytest.mark.parametrize("signal,comp,oracle_fn,svs", CASES, ids=[f"{c[0]}-{c[1]}" for c in CASES])
+def test_library_generators_equal_the_oracle_restatement(signal, comp, oracle_fn, svs):
+    svs = list(svs)
+    if len(svs) > 12:                               # every SV is cheap in the library; the +-1-list oracle takes ~20 ms per code
+        svs = svs[:6] + svs[len(svs) // 2: len(svs) // 2 + 3] + svs[-3:]
+    for sv in svs:
+        got = generate_code(signal, sv, comp)
+        want = oracle_fn(sv)
+        assert got.shape == want.shape and np.array_equal(got, want), (signal, comp, sv)
+
+
+def test_l2c_cl_code_and_e1_memory_codes():
+    got = generate_code("GPS_L2C", 1, 1)
+    want = O.generateCLcode(1)
+    assert got.size == 1534500 and np.array_equal(got, want)
+    assert not got[0::2].any() and np.all(np.abs(got[1::2]) == 1)                      # [0 c 0 c ...]
+    cm = generate_code("GPS_L2C", 1, 0)
+    assert not cm[1::2].any() and np.all(np.abs(cm[0::2]) == 1)                        # [c 0 c 0 ...]
+    for prn in (1, 2, 50):
+        b, c = generate_code("GAL_E1C", prn, 0), generate_code("GAL_E1C", prn, 1)
+        assert np.array_equal(b, O.generateE1Bcode(prn)[0::2]) and np.array_equal(c, O.generateE1Ccode(prn)[0::2])
+
+
+def test_icd_known_answers():
+    """Galileo OS SIS ICD: E1-B code 1 starts F5D710..., E5a-I code 1 (start value 30305) starts 3CEA9D, E5a-Q code 1 (25652)
+    starts 515537 - first chip = most significant bit, logic 1 = chip -1."""
+    assert _hex24(generate_code("GAL_E1C", 1, 0)) == "F5D710"
+    assert _hex24(generate_code("GAL_E5a", 1, 0)) == "3CEA9D"
+    assert _hex24(generate_code("GAL_E5a", 1, 1)) == "515537"
+    # IS-GPS-200 C/A (the generator the library has had since round 1) through the same entry point: PRN 1 starts 1440 octal
+    # (generateCAcode.m:90 returns -(g1 .* g2): logic 1 is chip +1 there)
+    ca = generate_code("GPS_L1CA", 1, 0)
+    assert "".join("1" if x == 1 else "0" for x in ca[:10]) == "1100100000"
+
+
+@pytest.mark.parametrize("signal,comp,n,svs", [("GPS_L5C", 0, 10230, (1, 2, 3)), ("GAL_E5a", 1, 10230, (1, 2, 3)), ("GAL_E5b", 0, 10230, (1, 2, 3)),
+                                               ("BDS_B2a", 0, 10230, (1, 2, 3)), ("BDS_B1I", 0, 2046, (1, 2, 3)), ("GPS_L2C", 0, 20460, (1, 2, 3)),
+                                               ("BDS_B1C", 1, 20460, (1, 2, 3))])
+def test_code_structure(signal, comp, n, svs):
+    """Balance, sharp autocorrelation and low cross-correlation of the generated primary codes."""
+    codes = []
+    for sv in svs:
+        c = generate_code(signal, sv, comp).astype(np.float64)
+        assert c.size == n
+        if signal == "GPS_L2C":
+            c = c[0::2]
+        if signal == "BDS_B1C":
+            assert np.array_equal(c[0::2], -c[1::2])
+            c = c[1::2]
+        assert abs(c.sum()) <= 0.02 * c.size + 2, (signal, sv, c.sum())
+        codes.append(c)
+    L = codes[0].size
+    F = [np.fft.fft(c) for c in codes]
+    auto = np.fft.ifft(F[0] * np.conj(F[0])).real
+    assert abs(auto[0] - L) < 1e-6 and np.max(np.abs(auto[1:])) < 0.08 * L
+    cross = np.fft.ifft(F[0] * np.conj(F[1])).real
+    assert np.max(np.abs(cross)) < 0.08 * L
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
+def test_committed_tables_are_what_the_reference_embeds(tmp_path):
+    """tools/extract_icd_tables.py re-run against the mounted reference reproduces the committed tables."""
+    import subprocess, sys, shutil
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    keep = {f: open(os.path.join(root, f)).read() for f in ("oracle/icd_tables.py", "cu-sdr-collection_b200/csrc/icd_tables.inc")}
+    subprocess.check_call([sys.executable, os.path.join(root, "tools", "extract_icd_tables.py")], stdout=subprocess.DEVNULL)
+    for f, txt in keep.items():
+        assert open(os.path.join(root, f)).read() == txt, f + " is stale"

@@ -71,8 +71,8 @@ def test_acquire_device_equals_host_results_variant_a():
 
 def test_acquire_device_equals_host_results_other_variants():
     """No fine stage (GAL E5b) and the variants that finish on the host (BDS B1I)."""
-    from cu_sdr_collection_b200.codes import standin_codes, standin_varb_codes
-    codes = standin_codes("GAL_E5b")
+    from cu_sdr_collection_b200.codes import icd_codes
+    codes = icd_codes("GAL_E5b")
     sc = synth.default_scene_fam5("GAL_E5b", codes, fs=18e6, nsat=2, seed=5)
     for x in sc.sats:
         x.cn0 = 50
@@ -87,7 +87,7 @@ def test_acquire_device_equals_host_results_other_variants():
         assert np.array_equal(dev[k], host[k]), k
     assert np.count_nonzero(host["carrFreq"]) == 2
     eng.close()
-    codes = standin_varb_codes("BDS_B1I")
+    codes = icd_codes("BDS_B1I")
     sc = synth.default_scene_varb("BDS_B1I", codes, fs=18e6, nsat=2, seed=3)
     for x in sc.sats:
         x.cn0 = 48
@@ -212,3 +212,21 @@ def test_sharded_grid_over_nccl_is_bit_identical(world, tmp_path):
                           "--master-port", str(29500 + os.getpid() % 400), str(script)], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("ok") == world
+
+
+def test_device_code_generators_equal_host_and_oracle():
+    """codegen_kernel (one thread per SV, the reference's generate*code.m as bit-packed registers) == the same generators on the
+    host == the oracle's statement-by-statement restatement."""
+    from cu_sdr_collection_b200.engine import generate_code
+    for signal, comp, fn, svs in (("GPS_L5C", 0, O.generateL5Icode, (1, 32)), ("GPS_L5C", 1, O.generateL5Qcode, (7,)),
+                                  ("GAL_E5a", 0, O.generateE5aIcode, (1, 50)), ("GAL_E5a", 2, O.generateE5aQ_secondary, (3,)),
+                                  ("GAL_E5b", 1, O.generateE5bQcode, (2,)), ("BDS_B2a", 0, O.generateB2aDataCode, (1, 63)),
+                                  ("BDS_B2a", 1, O.generateB2aPilotCode, (20,)), ("BDS_B1I", 0, O.generateCAcode53, (1, 40, 58)),
+                                  ("GPS_L2C", 0, O.generateCMcode, (1, 32)), ("GPS_L2C", 1, O.generateCLcode, (5,)),
+                                  ("BDS_B1C", 0, O.generateDataBOC11, (1,)), ("BDS_B1C", 1, O.generatePilotBOC11, (63,)),
+                                  ("BDS_B1C", 2, O.generatePilotBOC61, (19,))):
+        for sv in svs:
+            dev = generate_code(signal, sv, comp, device=0)
+            assert np.array_equal(dev, generate_code(signal, sv, comp)), (signal, comp, sv)
+            assert np.array_equal(dev, fn(sv)), (signal, comp, sv)
+    assert np.array_equal(generate_code("GAL_E1C", 1, 0, device=0), O.generateE1Bcode(1)[0::2])

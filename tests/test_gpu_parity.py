@@ -9,8 +9,7 @@ import pytest
 
 import np_oracle as O
 from cu_sdr_collection_b200 import Engine, acquisition, init_settings, preRun, synth, tracking
-from cu_sdr_collection_b200.codes import standin_e1_codes
-from helpers import (ROOT, c_acquisition, c_tracking, first_illconditioned_epoch, orc_set_e1_codes, scene,
+from helpers import (ROOT, c_acquisition, c_tracking, first_illconditioned_epoch, oracle_signal_codes, orc_set_e1_codes, scene,
                      to_oracle_settings, track_rel_err, windowed_iq_compare)
 from cu_sdr_collection_b200.engine import GC_PARAM_TRACK_EXACT_SUMS
 
@@ -466,11 +465,12 @@ def test_b3i_acquisition_tracking_and_wrappers_vs_oracle(tmp_path):
 
 # ------------------------------------------------------------------------------- Galileo E1 (GAL/GAL_E1C)
 def _e1c_case(fs, nsat, seed, extra, band, ms, nch, cn0=48, **kw):
-    codes = standin_e1_codes()
-    sc = synth.default_scene_e1c(codes, fs=fs, nsat=nsat, seed=seed)
+    sc = synth.default_scene_e1c({}, fs=fs, nsat=nsat, seed=seed)
     for x in sc.sats:
         x.cn0 = cn0
     sv = sorted({x.prn for x in sc.sats} | set(extra))
+    # the real E1-B / E1-C memory codes, from the oracle's generators; the engine is given none and decodes its own on the device
+    codes = sc.codes = oracle_signal_codes("GAL_E1C", sv)
     s = init_settings("GAL_E1C", samplingFreq=fs, acqSatelliteList=sv, acqSearchBand=band, msToProcess=ms, numberOfChannels=nch, **kw)
     so = to_oracle_settings(s)
     so.pilotTRKflag = s.pilotTRKflag
@@ -488,7 +488,7 @@ def test_e1c_acquisition_vs_oracle(fs, band, generic, monkeypatch):
     codes, sc, s, so, sv = _e1c_case(fs, nsat=2, seed=4, extra=[7], band=band, ms=80, nch=2)
     N = O.samples_per_code(so)
     raw = synth.make_record(sc, N * 42 + 64)
-    eng = Engine(s, codes=codes)
+    eng = Engine(s)
     got = eng.acquire(sv, host_iq=raw)
     assert got["carrFreq"].shape == (50,) and eng.stats()["fft_len"] == 2 * N
     assert eng.stats()["acq_path"] == (0 if generic else 1)      # 32736, 144000 and 160000 all have fused plans
@@ -500,8 +500,11 @@ def test_e1c_acquisition_vs_oracle(fs, band, generic, monkeypatch):
         start = (4092 - sat.code_phase) * (fs / 1.023e6)
         assert abs((got["codePhase"][sat.prn - 1] - 1 - start + N / 2) % N - N / 2) <= 2
     assert got["carrFreq"][7 - 1] == 0
-    with pytest.raises(Exception, match="no code set"):
-        Engine(s, codes={sv[0]: codes[sv[0]]}).acquire(sv, host_iq=raw)
+    # gc_set_code is an override: codes handed over by the caller (here the same ones, for one SV) give the same results
+    eng2 = Engine(s, codes={sv[0]: codes[sv[0]]})
+    got2 = eng2.acquire(sv, host_iq=raw)
+    assert np.array_equal(got2["carrFreq"], got["carrFreq"]) and np.array_equal(got2["peakMetric"], got["peakMetric"])
+    eng2.close()
     eng.close()
 
 
@@ -522,7 +525,7 @@ def test_e1c_tracking_and_wrappers_vs_oracle(fs, nE, pilot, tmp_path):
     ch.append(dict(PRN=0, acquiredFreq=0.0, codePhase=0, status="-"))
     path = tmp_path / "e1.bin"
     raw.tofile(path)
-    eng = Engine(s, codes=codes)
+    eng = Engine(s)
     with open(path, "rb") as fid:
         tr, _ = tracking(fid, ch, s, engine=eng)
     rout, rvv, rvi, rdone = c_tracking(raw, s, [c["PRN"] for c in ch], [c["acquiredFreq"] for c in ch],
@@ -545,12 +548,11 @@ def test_e1c_tracking_and_wrappers_vs_oracle(fs, nE, pilot, tmp_path):
 
 # ------------------------------------------------------------- GPS L5C, GAL E5a, GAL E5b, BDS B2a (10230-chip data + pilot)
 def _fam5_case(signal, nsat, seed, extra, nonCoh, ms, nch, cn0=50, **kw):
-    from cu_sdr_collection_b200.codes import standin_codes
-    codes = standin_codes(signal)
-    sc = synth.default_scene_fam5(signal, codes, fs=18e6, nsat=nsat, seed=seed)
+    sc = synth.default_scene_fam5(signal, {}, fs=18e6, nsat=nsat, seed=seed)
     for x in sc.sats:
         x.cn0 = cn0
     sv = sorted({x.prn for x in sc.sats} | set(extra))
+    codes = sc.codes = oracle_signal_codes(signal, sv)          # real ICD codes (oracle generators); the engine generates its own
     s = init_settings(signal, acqSatelliteList=sv, acqNonCohTime=nonCoh, msToProcess=ms, numberOfChannels=nch, **kw)
     so = to_oracle_settings(s)
     return codes, sc, s, so, sv
@@ -573,7 +575,7 @@ def test_fam5_acquisition_vs_oracle(signal, path, monkeypatch):
     N = 18000
     raw = synth.make_record(sc, N * (max(O._FAM5_MINPER[signal], 5) + 2))
     longSignal = O.read_acq_signal_fam5(raw, so)
-    eng = Engine(s, codes=codes)
+    eng = Engine(s)
     got = acquisition(longSignal, s, engine=eng, verbose=False)
     st = eng.stats()
     assert st["fft_len"] == 36000 and st["acq_path"] == {"split": 1, "cluster": 2, "generic": 0}[path]
@@ -609,7 +611,7 @@ def test_fam5_tracking_and_wrappers_vs_oracle(signal, pilot, nE, exact, tmp_path
     assert [(c["PRN"], c["codeFreq"], c["status"]) for c in ch] == [(c["PRN"], c["codeFreq"], c["status"]) for c in ref_ch]
     path = tmp_path / "fam5.bin"
     raw.tofile(path)
-    eng = Engine(s, codes=codes)
+    eng = Engine(s)
     eng.set_param(GC_PARAM_TRACK_EXACT_SUMS, exact)
     with open(path, "rb") as fid:
         tr, _ = tracking(fid, ch, s, engine=eng)
@@ -696,12 +698,11 @@ def test_sample_formats_vs_oracle(fileType, dataType, tmp_path):
 
 # ------------------------------------------------------------- acquisition variant B: BDS B1I, GPS L2C
 def _varb_case(signal, fs, nsat, seed, extra, cn0, **kw):
-    from cu_sdr_collection_b200.codes import standin_varb_codes
-    codes = standin_varb_codes(signal)
-    sc = synth.default_scene_varb(signal, codes, fs=fs, nsat=nsat, seed=seed)
+    sc = synth.default_scene_varb(signal, {}, fs=fs, nsat=nsat, seed=seed)
     for x in sc.sats:
         x.cn0 = cn0
     sv = sorted({x.prn for x in sc.sats} | set(extra))
+    codes = sc.codes = oracle_signal_codes(signal, sv)          # real ICD codes (oracle generators); the engine generates its own
     s = init_settings(signal, samplingFreq=fs, acqSatelliteList=sv, **kw)
     so = to_oracle_settings(s)
     so.stepSize, so.acqStep = s.stepSize, s.acqStep
@@ -726,7 +727,7 @@ def test_varb_acquisition_vs_oracle(signal, fs):
         raw = synth.make_record(sc, N * 3)
         longSignal = (raw[0::2] + 1j * raw[1::2]).astype(np.complex128)
         ref = O.acquisition_l2c(longSignal, so, codes, workers=os.cpu_count() or 1)
-    eng = Engine(s, codes=codes)
+    eng = Engine(s)
     got = acquisition(longSignal, s, engine=eng, verbose=False)
     # 72000 = 90 x 800 (B1I at 18 Msps) and 320000 = 400 x 800 (L2C at 8 Msps) have fused plans (spectrum shift = row + residue shift)
     assert got["carrFreq"].shape == ref["carrFreq"].shape and eng.stats()["acq_path"] == (1 if fs in (18e6, 8e6) else 0)
@@ -757,7 +758,7 @@ def test_b1i_tracking_and_wrappers_vs_oracle(nE, exact, tmp_path):
     ch.append(dict(PRN=0, acquiredFreq=0.0, codePhase=0, status="-"))
     path = tmp_path / "b1i.bin"
     raw.tofile(path)
-    eng = Engine(s, codes=codes)
+    eng = Engine(s)
     eng.set_param(GC_PARAM_TRACK_EXACT_SUMS, exact)
     with open(path, "rb") as fid:
         tr, _ = tracking(fid, ch, s, engine=eng)
@@ -779,12 +780,11 @@ def test_b1i_tracking_and_wrappers_vs_oracle(nE, exact, tmp_path):
 def test_b1c_acquisition_vs_oracle(fs, pilot):
     """Variant C: one wipe-off + FFT of 20 ms, Doppler bins by circshift, (|data|*sqrt(11) + |pilot|*sqrt(29))/sqrt(40),
     2-D maximum over bins x code phases, 25 Hz fine search over one 10 ms period (FFT length 360000 at 18 Msps)."""
-    from cu_sdr_collection_b200.codes import standin_b1c_codes
-    codes = standin_b1c_codes()
-    sc = synth.default_scene_varb("BDS_B1C", codes, fs=fs, nsat=2, seed=3)
+    sc = synth.default_scene_varb("BDS_B1C", {}, fs=fs, nsat=2, seed=3)
     for x in sc.sats:
         x.cn0 = 46
     sv = sorted({x.prn for x in sc.sats} | {30})
+    codes = sc.codes = oracle_signal_codes("BDS_B1C", sv)       # the real Weil codes (oracle generators)
     s = init_settings("BDS_B1C", samplingFreq=fs, acqSatelliteList=sv, acqSearchBand=4500.0 if fs < 10e6 else 4000.0, pilotACQflag=pilot)
     so = to_oracle_settings(s)
     so.acqStep, so.pilotACQflag, so.acqCohT = s.acqStep, s.pilotACQflag, s.acqCohT
@@ -792,7 +792,7 @@ def test_b1c_acquisition_vs_oracle(fs, pilot):
     raw = synth.make_record(sc, N * 2)
     longSignal = (raw[0::2] + 1j * raw[1::2]).astype(np.complex128)
     ref = O.acquisition_b1c(longSignal, so, codes, workers=os.cpu_count() or 1)
-    eng = Engine(s, codes=codes)
+    eng = Engine(s)
     got = acquisition(longSignal, s, engine=eng, verbose=False)
     assert got["carrFreq"].shape == ref["carrFreq"].shape == (max(sv),) and eng.stats()["fft_len"] == 2 * N
     assert eng.stats()["acq_path"] == (1 if fs == 18e6 else 0)          # 360000 = 450 x 800 has a fused plan
@@ -819,7 +819,7 @@ def test_l2c_tracking_and_wrappers_vs_oracle(fs, nE, exact, tmp_path):
     ch.append(dict(PRN=0, acquiredFreq=0.0, codePhase=0, status="-"))
     path = tmp_path / "l2c.bin"
     raw.tofile(path)
-    eng = Engine(s, codes=codes)
+    eng = Engine(s)
     eng.set_param(GC_PARAM_TRACK_EXACT_SUMS, exact)
     with open(path, "rb") as fid:
         tr, _ = tracking(fid, ch, s, engine=eng)
@@ -839,10 +839,8 @@ def test_l2c_tracking_and_wrappers_vs_oracle(fs, nE, exact, tmp_path):
 
 def _l2c_pilot_case(fs, nE, cn0=45):
     """GPS L2C scene with the CL pilot time-multiplexed into the CM signal; settings with pilotTRKflag = 1."""
-    from cu_sdr_collection_b200.codes import standin_varb_codes, standin_l2c_cl_codes
-    sc = synth.default_scene_varb("GPS_L2C", standin_varb_codes("GPS_L2C"), fs=fs, nsat=2, seed=3)
-    codes = standin_l2c_cl_codes([x.prn for x in sc.sats] + [30])
-    sc.codes = codes
+    sc = synth.default_scene_varb("GPS_L2C", {}, fs=fs, nsat=2, seed=3)
+    codes = sc.codes = oracle_signal_codes("GPS_L2C", [x.prn for x in sc.sats] + [30], cl=True)   # real CM and CL sequences
     for x in sc.sats:
         x.cn0 = cn0
     sv = sorted({x.prn for x in sc.sats} | {30})
@@ -862,7 +860,7 @@ def test_l2c_cl_phase_search_vs_oracle():
     raw = synth.make_record(sc, N * 3)
     longSignal = (raw[0::2] + 1j * raw[1::2]).astype(np.complex128)
     ref = O.acquisition_l2c(longSignal, so, codes, workers=os.cpu_count() or 1)
-    eng = Engine(s, codes=codes)
+    eng = Engine(s)
     got = acquisition(longSignal, s, engine=eng, verbose=False)
     assert np.array_equal(got["carrFreq"], ref["carrFreq"]) and np.array_equal(got["codePhase"], ref["codePhase"])
     assert np.array_equal(got["CLCodePhase"], ref["CLCodePhase"]), (got["CLCodePhase"], ref["CLCodePhase"])
@@ -890,7 +888,7 @@ def test_l2c_cl_pilot_tracking_vs_oracle(fs, nE, exact, tmp_path):
     ch.append(dict(PRN=0, acquiredFreq=0.0, codePhase=0, status="-", CLCodePhase=0))
     path = tmp_path / "l2c.bin"
     raw.tofile(path)
-    eng = Engine(s, codes=codes)
+    eng = Engine(s)
     eng.set_param(GC_PARAM_TRACK_EXACT_SUMS, exact)
     with open(path, "rb") as fid:
         tr, _ = tracking(fid, ch, s, engine=eng)
@@ -917,12 +915,9 @@ def test_b1c_wb_tracking_vs_oracle(fs, nE, exact, tmp_path):
     """BDS B1C WB_tracking (pilotTRKflag 2): data BOC(1,1), pilot BOC(1,1) and pilot BOC(6,1) tables (int8, 18 sums), the
     BOC(6,1) index ceil(tcode*6)+1, composite pilot correlations, carrier (data + 3 pilot)/4, code error weighted by
     CalcWeighingFactor's factor, six composite Pilot rows."""
-    from cu_sdr_collection_b200.codes import standin_b1c_codes, boc61_from_boc11
     from cu_sdr_collection_b200.tracking import calc_weighing_factor
-    base = standin_b1c_codes()
-    sc = synth.default_scene_varb("BDS_B1C", base, fs=fs, nsat=2, seed=3)
-    codes = {x.prn: (base[x.prn][0], base[x.prn][1], boc61_from_boc11(base[x.prn][1])) for x in sc.sats}
-    sc.codes = codes
+    sc = synth.default_scene_varb("BDS_B1C", {}, fs=fs, nsat=2, seed=3)
+    codes = sc.codes = oracle_signal_codes("BDS_B1C", [x.prn for x in sc.sats], boc61=True)
     for x in sc.sats:
         x.cn0 = 46
     s = init_settings("BDS_B1C", samplingFreq=fs, acqSatelliteList=sorted(x.prn for x in sc.sats), msToProcess=10 * nE,
@@ -942,7 +937,7 @@ def test_b1c_wb_tracking_vs_oracle(fs, nE, exact, tmp_path):
     ch = preRun(acq, s)
     path = tmp_path / "b1c.bin"
     raw.tofile(path)
-    eng = Engine(s, codes=codes)
+    eng = Engine(s)
     eng.set_param(GC_PARAM_TRACK_EXACT_SUMS, exact)
     with open(path, "rb") as fid:
         tr, _ = tracking(fid, ch, s, engine=eng)
@@ -973,9 +968,8 @@ def test_b1c_nb_tracking_and_wrappers_vs_oracle(fs, nE, exact, tmp_path):
     """BDS B1C NB_tracking (pilotTRKflag 1): 10 ms epochs (180000 samples at 18 Msps, one sample window in shared memory
     next to the two BOC(1,1) tables), carrier-aided code NCO, quadrature pilot atan(-I/Q), 11/40 : 29/40 weights,
     (1 - spacing)-scaled code discriminators, Pilot rows, DataCNo / PLD block on the host."""
-    from cu_sdr_collection_b200.codes import standin_b1c_codes
-    codes = standin_b1c_codes()
-    sc = synth.default_scene_varb("BDS_B1C", codes, fs=fs, nsat=2, seed=3)
+    sc = synth.default_scene_varb("BDS_B1C", {}, fs=fs, nsat=2, seed=3)
+    codes = sc.codes = oracle_signal_codes("BDS_B1C", [x.prn for x in sc.sats])
     for x in sc.sats:
         x.cn0 = 46
     s = init_settings("BDS_B1C", samplingFreq=fs, acqSatelliteList=sorted(x.prn for x in sc.sats), msToProcess=10 * nE,
@@ -993,7 +987,7 @@ def test_b1c_nb_tracking_and_wrappers_vs_oracle(fs, nE, exact, tmp_path):
     assert ch[0]["codeFreq"] == s.codeFreqBasis + (ch[0]["acquiredFreq"] - s.IF) / s.carrFreqBasis * s.codeFreqBasis
     path = tmp_path / "b1c.bin"
     raw.tofile(path)
-    eng = Engine(s, codes=codes)
+    eng = Engine(s)
     eng.set_param(GC_PARAM_TRACK_EXACT_SUMS, exact)
     with open(path, "rb") as fid:
         tr, _ = tracking(fid, ch, s, engine=eng)
@@ -1120,7 +1114,6 @@ def test_packed_2bit_record_equals_unpacked_schar_record(tmp_path):
 def test_acquire_track_one_call_other_signals(signal):
     """gc_acquire_track for the carrier-aided signals (channel.codeFreq from cfg.carr_freq_basis, GPS_L5C/include/preRun.m:69-71)
     and for GLONASS (channels carry K): the one call returns exactly what acquisition(), preRun() and tracking() return in turn."""
-    from cu_sdr_collection_b200.codes import standin_codes
     from cu_sdr_collection_b200.engine import GC_SV_NONE
     nE, codes = 60, None
     if signal == "BDS_B3I":
@@ -1136,14 +1129,15 @@ def test_acquire_track_one_call_other_signals(signal):
         sv, N, per = sorted({x.prn for x in sc.sats} | {5, -6}), 12000, 50
         s = init_settings(signal, samplingFreq=12e6, acqSatelliteList=sv, acqNonCohTime=6, msToProcess=nE, numberOfChannels=4)
     else:
-        codes = standin_codes(signal)
-        sc = synth.default_scene_fam5(signal, codes, fs=18e6, nsat=2, seed=5)
+        sc = synth.default_scene_fam5(signal, {}, fs=18e6, nsat=2, seed=5)
         for x in sc.sats:
             x.cn0 = 50
         sv, N, per = sorted({x.prn for x in sc.sats} | {25}), 18000, 44
+        sc.codes = oracle_signal_codes(signal, sv)
+        codes = None                                          # the engine generates its own
         s = init_settings(signal, acqSatelliteList=sv, acqNonCohTime=3, msToProcess=nE, numberOfChannels=3, pilotTRKflag=1, CNo_VSMinterval=20)
     raw = synth.make_record(sc, N * (nE + per))
-    eng = Engine(s, codes=codes) if codes is not None else Engine(s)
+    eng = Engine(s) if codes is not None else Engine(s)
     eng.set_record(raw)
     acq2 = eng.acquire(sv)
     ch2 = preRun(acq2, s)

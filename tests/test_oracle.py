@@ -282,7 +282,7 @@ def test_e1c_oracles_agree_and_closed_loop():
     comes back: PRN set, code phase, Doppler on the 10 Hz grid, tracking in lock (prompt energy in I)."""
     from cu_sdr_collection_b200 import init_settings
     from helpers import oracle_codes, orc_set_e1_codes, to_oracle_settings
-    tabs = codes.standin_e1_codes()
+    tabs = codes.icd_codes("GAL_E1C")
     fs, N = 4.092e6, 16368
     sc = synth.default_scene_e1c(tabs, fs=fs, nsat=2, seed=4)
     for x in sc.sats:
@@ -344,7 +344,7 @@ def test_fam5_oracle_closed_loop(signal):
     tracking pulls the data component into I and the quadrature pilot into Pilot_Q_P."""
     from cu_sdr_collection_b200 import init_settings
     from helpers import to_oracle_settings
-    tabs = codes.standin_codes(signal)
+    tabs = codes.icd_codes(signal)
     fs, N, nE = 18e6, 18000, 400
     sc = synth.default_scene_fam5(signal, tabs, fs=fs, nsat=2, seed=5)
     for x in sc.sats:
@@ -391,7 +391,7 @@ def test_varb_oracle_closed_loop():
     assert varb_step(init_settings("BDS_B1I", stepSize=0.0)) == 125.0 and varb_step(init_settings("BDS_B1I", stepSize=250.0)) == 250.0
     assert varb_step(init_settings("BDS_B1I", stepSize=60.0)) == 50.0
     # B1I at the reference's 18 Msps: two 4 ms blocks of 72000 samples
-    tabs = codes.standin_varb_codes("BDS_B1I")
+    tabs = codes.icd_codes("BDS_B1I")
     sc = synth.default_scene_varb("BDS_B1I", tabs, fs=18e6, nsat=2, seed=3)
     for x in sc.sats:
         x.cn0 = 48
@@ -407,7 +407,7 @@ def test_varb_oracle_closed_loop():
         start = (2046 - sat.code_phase) * (18e6 / 2.046e6)
         assert abs((ref["codePhase"][sat.prn - 1] - 1 - start + 9000) % 18000 - 9000) <= 2
     # L2C at a reduced rate (one 40 ms block)
-    tabs = codes.standin_varb_codes("GPS_L2C")
+    tabs = codes.icd_codes("GPS_L2C")
     fs = 2.046e6
     sc = synth.default_scene_varb("GPS_L2C", tabs, fs=fs, nsat=2, seed=3)
     for x in sc.sats:
@@ -430,7 +430,7 @@ def test_b1c_oracle_closed_loop():
     """Variant C (BDS B1C) restatement: injected SVs come back with code phase and Doppler on the 25 Hz fine grid."""
     from cu_sdr_collection_b200 import init_settings
     from helpers import to_oracle_settings
-    tabs = codes.standin_b1c_codes()
+    tabs = codes.icd_codes("BDS_B1C")
     fs = 4.092e6
     sc = synth.default_scene_varb("BDS_B1C", tabs, fs=fs, nsat=2, seed=3)
     for x in sc.sats:
@@ -455,8 +455,8 @@ def test_l2c_cl_pilot_oracle_closed_loop():
     from cu_sdr_collection_b200 import init_settings
     from helpers import to_oracle_settings
     fs = 2.046e6
-    sc = synth.default_scene_varb("GPS_L2C", codes.standin_varb_codes("GPS_L2C"), fs=fs, nsat=1, seed=3)
-    tabs = codes.standin_l2c_cl_codes([x.prn for x in sc.sats])
+    sc = synth.default_scene_varb("GPS_L2C", codes.icd_codes("GPS_L2C"), fs=fs, nsat=1, seed=3)
+    tabs = codes.icd_codes("GPS_L2C", [x.prn for x in sc.sats], cl=True)
     sc.codes = tabs
     sat = sc.sats[0]
     sat.cn0 = 45
@@ -500,7 +500,7 @@ def test_b1c_wb_oracle_closed_loop():
     from cu_sdr_collection_b200 import init_settings
     from cu_sdr_collection_b200.tracking import calc_weighing_factor
     from helpers import to_oracle_settings
-    base = codes.standin_b1c_codes()
+    base = codes.icd_codes("BDS_B1C")
     fs = 4.092e6
     sc = synth.default_scene_varb("BDS_B1C", base, fs=fs, nsat=1, seed=3)
     sat = sc.sats[0]
