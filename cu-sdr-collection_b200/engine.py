@@ -445,6 +445,23 @@ class MultiEngine:
             self._check(self.lib.gc_multi_track(self._m, *args), "gc_multi_track")
         return out, vv, vi, done
 
+    def cno_pld(self, n_channels: int, n_epochs: int):
+        """As Engine.cno_pld: every GPU holds the rows of its own block of channels, in channel order."""
+        nv = n_epochs // int(self.settings.CNo_VSMinterval)
+        out = np.zeros((n_channels, 5, nv))
+        per = (n_channels + self.n_gpus - 1) // self.n_gpus
+        for g in range(self.n_gpus):
+            c0 = g * per
+            nc = min(per, n_channels - c0)
+            if nc <= 0:
+                break
+            part = np.zeros((nc, 5, nv))
+            rc = self.lib.gc_get_cno_pld(self.lib.gc_multi_handle(self._m, g), nc, nv, _dp(part))
+            if rc != 0:
+                raise GnssCorrError(f"gc_get_cno_pld failed ({rc}) on GPU {g}")
+            out[c0:c0 + nc] = part
+        return out
+
     def times(self):
         a, t = C.c_double(), C.c_double()
         self._check(self.lib.gc_multi_get_times(self._m, C.byref(a), C.byref(t)), "gc_multi_get_times")
