@@ -9,6 +9,7 @@
 #include <functional>
 #include <limits>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/gnsscorr.h"
@@ -158,6 +159,7 @@ struct gc_handle {
     int cnoPldCh = 0, cnoPldV = 0;
     DevBuf<int> navInt;
     double tau1code = 0, tau2code = 0, tau1carr = 0, tau2carr = 0;
+    std::unordered_map<const void*, std::vector<char>> upCache;   // upload_cached: last bytes sent to a buffer
 };
 
 namespace {
@@ -183,6 +185,12 @@ cudaError_t upload(DevBuf<T>& b, const std::vector<T>& v, cudaStream_t s)
     return cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
 }
 
+// upload that is skipped when the buffer already holds exactly these bytes (the per-call tables of an acquisition - list slots,
+// shift map, bin-1 frequencies ... - are the same from call to call for the same SV list; each skipped copy saves a staged
+// pageable H2D of a few microseconds in front of the first kernel)
+template <class T>
+cudaError_t upload_cached(gc_handle* h, DevBuf<T>& b, const std::vector<T>& v, cudaStream_t s);
+
 // w_L^(r*c) = exp(-2*pi*i*r*c/L) tables in float, computed in long double
 std::vector<float2> tw_table_2d(int rows, int cols, int L)   // [r][c] -> w_L^(r*c)
 {
@@ -202,6 +210,18 @@ void calcLoopCoef(double LBW, double zeta, double k, double* tau1, double* tau2)
     const double Wn = LBW * 8 * zeta / (4 * zeta * zeta + 1);
     *tau1 = k / (Wn * Wn);
     *tau2 = 2.0 * zeta / Wn;
+}
+
+template <class T>
+cudaError_t upload_cached(gc_handle* h, DevBuf<T>& b, const std::vector<T>& v, cudaStream_t s)
+{
+    std::vector<char>& last = h->upCache[(const void*)&b];
+    const size_t nb = v.size() * sizeof(T);
+    if (b.p && b.cap >= v.size() && last.size() == nb && (nb == 0 || memcmp(last.data(), v.data(), nb) == 0)) return cudaSuccess;
+    cudaError_t e = upload(b, v, s);
+    if (e == cudaSuccess) last.assign(reinterpret_cast<const char*>(v.data()), reinterpret_cast<const char*>(v.data()) + nb);
+    else last.clear();
+    return e;
 }
 
 // SV id -> (valid, result index, replica slot, carrier offset)
@@ -1034,7 +1054,7 @@ static int acquire_varc(gc_handle* h, long long winStart, long long longLen, int
         cudaEventRecord(h->ev[2], st);
         std::vector<int2> map(nBins);
         for (int k = 0; k < nBins; ++k) map[k] = make_int2(0, k);                          // circshift(IQfreqDom, k) (:203)
-        GC_CUDA(h, upload(h->vbMap, map, st));
+        GC_CUDA(h, upload_cached(h, h->vbMap, map, st));
         std::vector<int> slotRep(nSv);
         for (int s = 0; s < nSv; ++s) slotRep[s] = (svList[s] - 1) * 2;
         GC_CUDA(h, upload(h->prnList, slotRep, st));
@@ -1231,7 +1251,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return sv_freq_offset(h, svList[a]) < sv_freq_offset(h, svList[b]); });
     std::vector<int> slotReplica(nSv);                // device list slot -> replica spectrum
     for (int s = 0; s < nSv; ++s) slotReplica[s] = sv_replica(h, svList[order[s]]);
-    GC_CUDA(h, upload(h->prnList, slotReplica, st));
+    GC_CUDA(h, upload_cached(h, h->prnList, slotReplica, st));
     GC_CUDA(h, h->partMax.reserve((size_t)nSv * nBins * h->parts));
     GC_CUDA(h, h->partIdx.reserve((size_t)nSv * nBins * h->parts));
     GC_CUDA(h, h->peaks.reserve(nSv));
@@ -1268,7 +1288,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
             for (int s = groupStart[gi]; s < groupStart[gi + 1]; ++s) coarseFreqOf[s] = coarseFreq;
         }
         GC_CUDA(h, cudaMemcpyAsync(h->dphi.p, dphi.data(), dphi.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-        GC_CUDA(h, upload(h->slotGroup, slotGroup, st));
+        GC_CUDA(h, upload_cached(h, h->slotGroup, slotGroup, st));
         const int f0 = mark();
         for (int gi = 0; gi < nGroups; ++gi) {
             FwdColsParams fp{};
@@ -1307,11 +1327,11 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
             GC_CUDA(h, cudaMemcpyAsync(h->dphi.p, d0.data(), d0.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
             std::vector<int2> map(nBins);
             for (int k = 0; k < nBins; ++k) map[k] = make_int2(0, k * h->binShift);
-            GC_CUDA(h, upload(h->vbMap, map, st));
+            GC_CUDA(h, upload_cached(h, h->vbMap, map, st));
         } else {
             GC_CUDA(h, cudaMemcpyAsync(h->dphi.p, dphi.data(), dphi.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
         }
-        GC_CUDA(h, upload(h->slotGroup, slotGroup, st));
+        GC_CUDA(h, upload_cached(h, h->slotGroup, slotGroup, st));
         const int f0 = mark();
         const int fwdRowsPerGroup = shifted ? nonCoh : nKm;
         FwdColsParams fp{};
@@ -1367,7 +1387,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
             if (shifted) {
                 std::vector<int2> map(nBins);
                 for (int k = 0; k < nBins; ++k) map[k] = make_int2(0, k * h->binShift);
-                GC_CUDA(h, upload(h->vbMap, map, st));
+                GC_CUDA(h, upload_cached(h, h->vbMap, map, st));
             }
             const int fwdRows = shifted ? nonCoh : nKm;
             FwdColsParams fp{};
@@ -1526,10 +1546,10 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
                                                                                        : NH20[q % 20];
             }
         }
-        GC_CUDA(h, upload(h->slotFreq0, slotFreq0, st));
-        GC_CUDA(h, upload(h->slotChipRow, slotChipRow, st));
-        GC_CUDA(h, upload(h->slotSv, slotSv, st));
-        if (!slotSec.empty()) GC_CUDA(h, upload(h->slotSecondary, slotSec, st));
+        GC_CUDA(h, upload_cached(h, h->slotFreq0, slotFreq0, st));
+        GC_CUDA(h, upload_cached(h, h->slotChipRow, slotChipRow, st));
+        GC_CUDA(h, upload_cached(h, h->slotSv, slotSv, st));
+        if (!slotSec.empty()) GC_CUDA(h, upload_cached(h, h->slotSecondary, slotSec, st));
         const int maxEnt = nSv * nCodes;
         GC_CUDA(h, h->metricDev.reserve(nSv));
         GC_CUDA(h, h->nAcqDev.reserve(1));
@@ -1568,13 +1588,24 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
             slotResult[s] = sv_result_index(h, svList[order[s]]);
             slotFreq0[s] = (c.IF + sv_freq_offset(h, svList[order[s]])) + c.acq_search_band;
         }
-        GC_CUDA(h, upload(h->slotResult, slotResult, st));
-        if (h->noFine) GC_CUDA(h, upload(h->slotFreq0, slotFreq0, st));
+        GC_CUDA(h, upload_cached(h, h->slotResult, slotResult, st));
+        if (h->noFine) GC_CUDA(h, upload_cached(h, h->slotFreq0, slotFreq0, st));
         PackParams pk{};
         pk.peaks = h->peaks.p; pk.sigPower = h->sigPower.p; pk.slotFreq0 = h->slotFreq0.p; pk.slotResult = h->slotResult.p;
         pk.best = h->noFine ? nullptr : h->fineBest.p; pk.nSv = nSv; pk.nonCoh = nonCoh; pk.resultLen = h->resultLen; pk.noFine = h->noFine ? 1 : 0;
         pk.threshold = c.acq_threshold; pk.step = c.acq_search_step; pk.fineStep = h->fineStep; pk.out = dOut;
         GC_CUDA(h, launch_pack_results(pk, st)); ++launches;
+        // the results stay on the device: no D2H of the peak / fine-search arrays and no host assembly - one synchronise, the timings
+        const int fa_ = fa, fb_ = fb;
+        float fineMs = 0, coarseMs = 0;
+        GC_CUDA(h, cudaStreamSynchronize(st));
+        if (fa_ >= 0) cudaEventElapsedTime(&fineMs, h->ev[fa_], h->ev[fb_]);
+        drain_events();
+        cudaEventElapsedTime(&coarseMs, h->ev[e0], h->ev[1]);
+        h->stats.n_acquired = -1;                             // (in the device buffer: carrFreq != 0)
+        h->stats.acq_fwd_ms = fwdMs; h->stats.acq_corr_ms = coarseMs - fwdMs; h->stats.acq_fine_ms = fineMs; h->stats.acq_total_ms = coarseMs + fineMs;
+        h->stats.corr_rows_ms = rowsMs; h->stats.corr_cols_ms = colsMs; h->stats.corr_row_launches = nRowLaunches; h->stats.acq_launches = launches;
+        return GC_OK;
     }
     std::vector<PeakOut> peaks(nSv);
     std::vector<int> best(nSv, 0);
@@ -1859,11 +1890,11 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
         long long hd[96];
         cudaMemcpy(hd, dbg, sizeof(hd), cudaMemcpyDeviceToHost);
         cudaFree(dbg);
-        const char* names[7] = {"top", "mbar", "samples", "sync1", "cluster", "control", "sync2"};
+        const char* names[8] = {"top", "mbar", "samples", "sync1", "cluster", "control", "sync2", "xwait"};
         for (int w = 0; w < 4; ++w) {
             if (w == 2) continue;
             fprintf(stderr, "[gc_track timing] warp %d cycles/epoch:", w);
-            for (int i = 0; i < 7; ++i) fprintf(stderr, " %s=%.0f", names[i], (double)hd[w * 8 + i] / nEpochs);
+            for (int i = 0; i < 8; ++i) fprintf(stderr, " %s=%.0f", names[i], (double)hd[w * 8 + i] / nEpochs);
             fprintf(stderr, "  (cluster=%d)\n", cluster);
         }
         for (int r = 0; r < cluster && cluster > 1; ++r) {

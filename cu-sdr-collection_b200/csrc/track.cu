@@ -169,8 +169,8 @@ __device__ void plan_epoch(const TrackParams& p, double codeFreq, double remCode
     {   // per-chunk edge prediction (track_kernel, fast chunks): needs at most one table-entry edge per correlator in 8 samples and a
         // samples-per-entry count that fits 8.24 fixed point
         const double dt = step * (double)p.subChip;
-        ep.fast = (!ep.generic && 8.0 * dt <= 1.0 && dt >= 0.0078125 && p.pilot != 5) ? 1 : 0;
-        ep.rinv = ep.fast ? (uint32_t)(16777216.0 * y / (double)p.subChip) : 0u;     // y = 1/step to ~1e-12: far inside the margin
+        ep.fast = (!ep.generic && 8.0 * dt <= 1.0 && dt >= 0.0078125 && p.pilot != 5 && p.subChip <= 2) ? 1 : 0;
+        ep.rinv = ep.fast ? (uint32_t)(y * (p.subChip == 2 ? 8388608.0 : 16777216.0)) : 0u;   // y = 1/step to ~1e-12: far inside the margin
     }
     ep.mE = __dmul_rn(__dadd_rn(ep.aE, ep.cE), 0.5);
     ep.mP = __dmul_rn(__dadd_rn(ep.aP, ep.cP), 0.5);
@@ -743,6 +743,7 @@ track_kernel(TrackParams p)
             if (G > 1) {
                 mbar_wait(&s_xbar[e & 1], xphase[e & 1]);       // all G partial sets have landed here
                 xphase[e & 1] ^= 1u;
+                GC_TICK(7)
                 // every CTA adds the G partials in the same (pairwise) order -> identical sums everywhere
                 const double* sl = s_cl + (e & 1) * kMaxCluster * NS;
 #pragma unroll

@@ -1,3 +1,4 @@
 cd $GRAFT_REPO_ROOT
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"sig_power|fwd_cols|fwd_rows|inv_rows|inv_cols|peak_select|fine_|pack_results|finish_replica" -c 400 --csv --log-file gpurun_out/r02_launches_raw.csv python bench.py --steps 2 --warmup 3 --no-tracking --no-cpu-baseline > gpurun_out/b.log 2>&1
-tail -3 gpurun_out/b.log | cut -c1-300
+GC_TRACK_DEBUG=1 python tools/prof_track.py 12 3000 1 2>&1 | grep -v "rank [1-6]"
+python tools/acq_bench.py 2>&1 | tail -4
+python bench.py --steps 10 --warmup 3 --no-tracking --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['ms_per_step'],'cold',d['e2e_cold']['ms'])"
