@@ -337,6 +337,9 @@ def main():
     multi_abi = None
     if world > 1:
         barrier()
+        # the other ranks wait on the HOST (gloo) while rank 0 drives every GPU: an NCCL barrier would park a spinning kernel of
+        # another process on the GPUs being measured and the two contexts would time-slice
+        cpu_group = dist.new_group(backend="gloo")
         if rank == 0:
             me = MultiEngine(settings, n_gpus=world)
             for _ in range(2):
@@ -349,6 +352,7 @@ def main():
             multi_abi = {"value": CELLS / mt, "unit": "cells/s", "ms_per_step": mt * 1e3,
                          "call": f"gc_multi_acquire_host on {world} GPUs from one process (host longSignal -> merged acqResults)"}
             me.close()
+        dist.barrier(group=cpu_group)
         barrier()
 
     # ---- tracking: 12 channels x 60000 ms (configs[2]), channels dealt over the ranks in blocks ---------------------------

@@ -2,6 +2,8 @@
 // tracking kernels.  Declared in include/gnsscorr.h, which cites the reference interface each
 // entry point replaces.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -28,6 +30,10 @@ thread_local std::string g_create_error;
 
 double m_round(double x) { return x >= 0 ? std::floor(x + 0.5) : -std::floor(-x + 0.5); }
 
+// bumped by every (re)allocation of a DevBuf: a captured acquisition graph holds raw device pointers and is only replayed while
+// this count is what it was when the graph was captured
+std::atomic<unsigned long long> g_allocGen{0};
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;
@@ -37,6 +43,7 @@ struct DevBuf {
         if (n <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
+        g_allocGen.fetch_add(1, std::memory_order_relaxed);
         cudaError_t e = cudaMalloc(&p, n * sizeof(T));
         if (e == cudaSuccess) cap = n;
         return e;
@@ -49,6 +56,39 @@ constexpr int kEvents = 160;
 // Cap of the inverse work buffer W (of the 180 GB of HBM).  The spectra X are re-read once per chunk, so fewer, larger chunks
 // save traffic: the headline grid (4.9 GB for 32 PRN) runs as one chunk (2.36 -> 2.29 ms), GAL E5b 27.3 -> 24.4 ms.
 constexpr double kWorkBytes = 6.0e9;
+
+// GC_HOST_TIMING=1: host wall-clock laps of gc_create / gc_acquire on stderr (where does a one-shot call spend its time)
+struct HostLaps {
+    bool on;
+    const char* tag;
+    std::chrono::steady_clock::time_point t0, last;
+    explicit HostLaps(const char* tag_) : on(getenv("GC_HOST_TIMING") != nullptr), tag(tag_)
+    {
+        if (on) t0 = last = std::chrono::steady_clock::now();
+    }
+    void lap(const char* what)
+    {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[gc host timing] %s: %-28s %9.3f ms  (+%.3f)\n", tag, what,
+                std::chrono::duration<double, std::milli>(now - t0).count(), std::chrono::duration<double, std::milli>(now - last).count());
+        last = now;
+    }
+};
+
+// what one enqueue of the variant A kernels recorded: which events bracket which stage, how many kernels
+struct AcqEnq {
+    int launches = 0, nRowLaunches = 0, e0 = -1, e1 = -1, fa = -1, fb = -1;
+    std::vector<std::pair<int, int>> rowEv, colEv, fwdEv;
+};
+// the kernels and result copies of one variant A acquisition as a CUDA graph: captured the second time the same call (window,
+// SV list, record, result buffer, device buffers) comes in, replayed from the third
+struct AcqGraph {
+    std::vector<char> key;
+    int hits = 0;
+    cudaGraphExec_t exec = nullptr;
+    AcqEnq info;
+};
 
 }  // namespace
 
@@ -160,6 +200,10 @@ struct gc_handle {
     DevBuf<int> navInt;
     double tau1code = 0, tau2code = 0, tau1carr = 0, tau2carr = 0;
     std::unordered_map<const void*, std::vector<char>> upCache;   // upload_cached: last bytes sent to a buffer
+    AcqGraph graph;              // variant A on a fused plan: the whole enqueue as one graph launch
+    bool graphOff = false;       // GC_ACQ_GRAPH=0, or a capture failed
+    char* pin = nullptr;         // pinned host staging of the per-call result copies (peaks, sigPower, fine bins, acquired count)
+    size_t pinBytes = 0;
 };
 
 namespace {
@@ -256,6 +300,7 @@ bool sv_has_code(const gc_handle* h, int sv)
 int build_replicas(gc_handle* h)
 {
     const int N = h->N, L = h->L, nRep = h->nReplicas, codeLen = h->cfg.code_length;
+    HostLaps laps("build_replicas");
     std::vector<int8_t> tab((size_t)nRep * N);
     std::vector<int16_t> idx40((size_t)h->nFinePeriods * N);
     if (h->e1c) {                                            // makeE1BTable.m / makeE1CTable.m; GAL_E1C acquisition.m:160-172, 209-214
@@ -293,6 +338,7 @@ int build_replicas(gc_handle* h)
             make_ca_table(prn, h->cfg.sampling_freq, h->cfg.code_freq_basis, codeLen, N, tab.data() + (size_t)(prn - 1) * N);
         gps_fine_index(h->cfg.sampling_freq, h->cfg.code_freq_basis, codeLen, 40LL * N, idx40.data());
     }
+    laps.lap("sampled code tables (host)");
     GC_CUDA(h, upload(h->codeTab, tab, h->stream));
     GC_CUDA(h, upload(h->chipIdx, idx40, h->stream));
     {   // chips of every SV / component for the fine search: row = result index * 2 + component (GLONASS: row 0)
@@ -353,6 +399,7 @@ int gc_create(gc_handle** out, const gc_config* cfg)
 {
     if (!out || !cfg) return fail(nullptr, GC_ERR_ARG, "gc_create: null argument");
     *out = nullptr;
+    HostLaps laps("gc_create");
     if (cfg->abi_version != GC_ABI_VERSION) return fail(nullptr, GC_ERR_ARG, "gc_create: abi_version mismatch");
     if (cfg->signal < GC_SIG_GPS_L1CA || cfg->signal > GC_SIG_BDS_B1C)
         return fail(nullptr, GC_ERR_UNSUPPORTED, "gc_create: signal not implemented (GPS L1CA/L5C/L2C, GLONASS G1/G2, BDS B1I/B1C/B3I/B2a, GAL E1C/E5a/E5b are)");
@@ -370,11 +417,13 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     if (ce != cudaSuccess || ndev == 0)
         return fail(nullptr, GC_ERR_CUDA, std::string("gc_create: no CUDA device (") + cudaGetErrorString(ce) + ") - this engine has no CPU fallback");
     if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, GC_ERR_ARG, "gc_create: bad device ordinal");
-    cudaDeviceProp prop{};
-    cudaGetDeviceProperties(&prop, cfg->device);
-    if (prop.major != 10)
-        return fail(nullptr, GC_ERR_CUDA, "gc_create: kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+    int ccMajor = 0, ccMinor = 0;                              // (cudaGetDeviceProperties costs 15-30 ms of a one-shot call)
+    cudaDeviceGetAttribute(&ccMajor, cudaDevAttrComputeCapabilityMajor, cfg->device);
+    cudaDeviceGetAttribute(&ccMinor, cudaDevAttrComputeCapabilityMinor, cfg->device);
+    if (ccMajor != 10)
+        return fail(nullptr, GC_ERR_CUDA, "gc_create: kernels are built for sm_100a only; device is sm_" + std::to_string(ccMajor) + std::to_string(ccMinor));
 
+    laps.lap("device query");
     gc_handle* h = new gc_handle();
     h->cfg = *cfg;
     h->fmt = cfg->file_type == GC_FILE_PACKED2 ? 4 : (cfg->sample_bytes == 2 ? 1 : 0) | (cfg->file_type == 1 ? 2 : 0);
@@ -388,6 +437,7 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     h->varC = (cfg->signal == GC_SIG_BDS_B1C);
     h->hostCodes = h->e1c || h->fam5 || h->varB || h->varC;
     { const char* e = getenv("GC_TRACK_EXACT_SUMS"); h->trackExact = e && atoi(e) != 0; }
+    { const char* e = getenv("GC_ACQ_GRAPH"); h->graphOff = e && atoi(e) == 0; }
     h->sub = h->e1c ? 2 : 1;
     h->nRep = (h->e1c || h->fam5) ? 2 : 1;                   // data + pilot replicas (B1C: set below from pilotACQflag) (GAL_E1C acquisition.m:186-192, GPS_L5C :171-175)
     h->fineStep = h->e1c ? 10.0 : 25.0;                      // GAL_E1C acquisition.m:138
@@ -418,6 +468,7 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     for (int i = 0; i < 2; ++i)
         if (cudaEventCreateWithFlags(&h->evRows[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->evCols[i], cudaEventDisableTiming) != cudaSuccess) { h->err = "cudaEventCreate failed"; return bail(GC_ERR_CUDA); }
 
+    laps.lap("streams, events");
     // acquisition.m:116-124,138-140
     h->N = (int)m_round(cfg->sampling_freq / (cfg->code_freq_basis / (double)cfg->code_length));
     h->L = 2 * h->N;
@@ -515,13 +566,16 @@ int gc_create(gc_handle** out, const gc_config* cfg)
             h->plan.tw = h->twGen.p + h->L;   // row 1 of the [2][L] table = w_L^t
             h->parts = 8;
         }
+        laps.lap("plan, twiddles");
         calcLoopCoef(cfg->dll_noise_bandwidth, cfg->dll_damping_ratio, 1.0, &h->tau1code, &h->tau2code);    // tracking.m:100
         calcLoopCoef(cfg->pll_noise_bandwidth, cfg->pll_damping_ratio, 0.25, &h->tau1carr, &h->tau2carr);   // tracking.m:109
         if (!h->hostCodes) {                                 // caller-supplied codes: replicas are built by the first gc_acquire
             int rc = build_replicas(h);
             if (rc != GC_OK) return rc;
         }
+        laps.lap("replicas enqueued");
         GC_CUDA(h, cudaStreamSynchronize(h->stream));
+        laps.lap("replicas done");
         return GC_OK;
     };
     int rc = setup();
@@ -533,6 +587,7 @@ int gc_create(gc_handle** out, const gc_config* cfg)
 void gc_destroy(gc_handle* h)
 {
     if (!h) return;
+    HostLaps laps("gc_destroy");
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->recOwned.release();
@@ -544,10 +599,13 @@ void gc_destroy(gc_handle* h)
     h->peaks.release(); h->sigPower.release(); h->fineSums.release(); h->fineResult.release(); h->fineProd.release();
     h->slotResult.release(); h->vcSlot.release(); h->vbRows.release(); h->vbPeak.release(); h->vbIdx.release(); h->vbSeg.release();
     h->chans.release(); h->trackCodes.release(); h->trackPilot.release(); h->trackOut.release(); h->epochsDone.release();
+    if (h->graph.exec) cudaGraphExecDestroy(h->graph.exec);
+    if (h->pin) cudaFreeHost(h->pin);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) { if (h->evRows[i]) cudaEventDestroy(h->evRows[i]); if (h->evCols[i]) cudaEventDestroy(h->evCols[i]); }
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);
+    laps.lap("buffers, events, streams freed");
     delete h;
 }
 
@@ -592,19 +650,25 @@ int gc_set_code(gc_handle* h, int32_t sv, int32_t component, const int8_t* chips
     return GC_OK;
 }
 
-int gc_set_record_host(gc_handle* h, const void* bytes, size_t nbytes)
+// sync = false: the copy stays in flight on the handle's stream (gc_acquire_host: the search that follows is stream ordered
+// behind it and synchronises before it returns, so the caller's buffer is free again when the call is)
+static int set_record_host(gc_handle* h, const void* bytes, size_t nbytes, bool sync)
 {
     if (!h || !bytes || nbytes == 0) return fail(h, GC_ERR_ARG, "gc_set_record_host: bad argument");
     cudaSetDevice(h->cfg.device);
     const size_t cap = ((nbytes + 15) & ~(size_t)15) + 256;
+    const bool grown = cap > h->recOwned.cap;
     GC_CUDA(h, h->recOwned.reserve(cap));
     GC_CUDA(h, cudaMemcpyAsync(h->recOwned.p, bytes, nbytes, cudaMemcpyHostToDevice, h->stream));
-    GC_CUDA(h, cudaMemsetAsync(h->recOwned.p + nbytes, 0, cap - nbytes, h->stream));
-    GC_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (grown || nbytes != h->recBytes || h->rec != h->recOwned.p)     // (the zero tail of an unchanged layout is still there)
+        GC_CUDA(h, cudaMemsetAsync(h->recOwned.p + nbytes, 0, cap - nbytes, h->stream));
+    if (sync) GC_CUDA(h, cudaStreamSynchronize(h->stream));
     h->rec = h->recOwned.p;
     h->recBytes = nbytes;
     return GC_OK;
 }
+
+int gc_set_record_host(gc_handle* h, const void* bytes, size_t nbytes) { return set_record_host(h, bytes, nbytes, true); }
 
 int gc_set_record_device(gc_handle* h, const void* dptr, size_t nbytes)
 {
@@ -1179,6 +1243,289 @@ static int acquire_varc(gc_handle* h, long long winStart, long long longLen, int
     return GC_OK;
 }
 
+// Variant A on a fused plan with the split correlation stage - the default path of every variant A signal (GPS L1CA, GLONASS,
+// B3I, E1, L5C, E5a, E5b, B2a).  All host tables and buffer reservations first, then ONE enqueue of the kernels and the small
+// result copies: issued directly the first time a call comes in, captured into a CUDA graph the second time the same call
+// (window, SV list, record, result buffer, device buffers) arrives, one cudaGraphLaunch from the third on.  The ~12 launches,
+// their event records and the four result copies cost more host time than the grid of a sharded search takes on the device.
+// Several carrier grids (GLONASS: one per frequency number) are transformed and searched in ONE pass each.
+static int acquire_plain(gc_handle* h, long long winStart, int32_t nSv, const int32_t* svList, const std::vector<int>& order,
+                         const std::vector<int>& groupStart /* nGroups + 1 entries */, const std::vector<int>& slotGroup,
+                         double* carrFreq, double* codePhase, double* peakMetric, int32_t* coarseBin, int32_t* coarseCodePhase,
+                         double* dOut)
+{
+    HostLaps laps("gc_acquire");
+    const gc_config& c = h->cfg;
+    const int N = h->N, L = h->L, nBins = h->nBins, nonCoh = h->nonCoh, nKm = nBins * nonCoh;
+    const int nGroups = (int)groupStart.size() - 1;
+    const int codeLen = c.code_length;
+    cudaStream_t st = h->stream;
+
+    // ---- host tables and buffers (nothing here is part of the graph) -------------------------------------------------------
+    std::vector<std::vector<double>> coarseFreqOf(nSv);   // per list slot: the bin frequencies it was searched on
+    std::vector<uint64_t> dphi((size_t)nGroups * nBins);
+    for (int gi = 0; gi < nGroups; ++gi) {
+        const double off = sv_freq_offset(h, svList[order[groupStart[gi]]]);
+        std::vector<double> coarseFreq(nBins);
+        for (int k = 0; k < nBins; ++k) {
+            coarseFreq[k] = (c.IF + off) + c.acq_search_band - c.acq_search_step * k;   // :169 (GLO :181-182)
+            dphi[(size_t)gi * nBins + k] = turns_to_fix(coarseFreq[k] * h->ts);
+        }
+        for (int s = groupStart[gi]; s < groupStart[gi + 1]; ++s) coarseFreqOf[s] = coarseFreq;
+    }
+    const bool shifted = h->binShift > 0;                    // only bin 0 of every grid is transformed, the other bins are shifts of it
+    const int fwdRowsPerGroup = shifted ? nonCoh : nKm;
+    GC_CUDA(h, h->X.reserve((size_t)nGroups * nKm * L));
+    if (shifted) {
+        std::vector<uint64_t> d0(nGroups);
+        for (int gi = 0; gi < nGroups; ++gi) d0[gi] = dphi[(size_t)gi * nBins];
+        GC_CUDA(h, upload_cached(h, h->dphi, d0, st));
+        std::vector<int2> map(nBins);
+        for (int k = 0; k < nBins; ++k) map[k] = make_int2(0, k * h->binShift);
+        GC_CUDA(h, upload_cached(h, h->vbMap, map, st));
+    } else {
+        GC_CUDA(h, upload_cached(h, h->dphi, dphi, st));
+    }
+    GC_CUDA(h, upload_cached(h, h->slotGroup, slotGroup, st));
+    int chunk = (int)std::max<long long>(1, (long long)(kWorkBytes / ((double)nKm * h->nRep * L * sizeof(float2))));
+    chunk = std::min(chunk, (int)nSv);
+    const int nChunks = (nSv + chunk - 1) / chunk;
+    GC_CUDA(h, h->W.reserve((size_t)chunk * nKm * h->nRep * L));
+    GC_CUDA(h, h->partMax.reserve((size_t)nSv * nBins * h->parts));
+    GC_CUDA(h, h->partIdx.reserve((size_t)nSv * nBins * h->parts));
+    GC_CUDA(h, h->peaks.reserve(nSv));
+    GC_CUDA(h, h->sigPower.reserve(1));
+    const int nCodes = h->fineTwoCodes ? 2 : 1;
+    const int nPeriods = h->nFinePeriods;                                            // :146-148 (B3I :131-133)
+    const int tabLen = codeLen * h->sub;                                             // chips, or BOC sub-chips, per code period
+    const int maxEnt = nSv * nCodes;
+    std::vector<double> slotFreq0(nSv);
+    for (int s = 0; s < nSv; ++s) slotFreq0[s] = (c.IF + sv_freq_offset(h, svList[order[s]])) + c.acq_search_band;   // coarseFreqBin(1), :169 (GLO :181-182)
+    bool haveSecondary = false;
+    if (!h->noFine) {
+        std::vector<int> slotChipRow(nSv), slotSv(nSv);
+        std::vector<int8_t> slotSec;
+        if (h->fineCombine == 4) slotSec.resize((size_t)nSv * nPeriods);
+        for (int s = 0; s < nSv; ++s) {
+            const int sv = svList[order[s]];
+            slotChipRow[s] = h->glo ? 0 : sv_result_index(h, sv) * 2;
+            slotSv[s] = sv;
+            if (h->fineCombine == 4) {
+                static const int8_t NH20[20] = {1, 1, 1, 1, 1, -1, 1, 1, -1, -1, 1, -1, 1, -1, 1, 1, -1, -1, -1, 1};   // GPS_L5C acquisition.m:134
+                for (int q = 0; q < nPeriods; ++q)
+                    slotSec[(size_t)s * nPeriods + q] = (c.signal == GC_SIG_GAL_E5A) ? h->hostCode[2][sv - 1][q]   // generateE5aQ_secondary
+                                                                                       : NH20[q % 20];
+            }
+        }
+        haveSecondary = !slotSec.empty();
+        GC_CUDA(h, upload_cached(h, h->slotFreq0, slotFreq0, st));
+        GC_CUDA(h, upload_cached(h, h->slotChipRow, slotChipRow, st));
+        GC_CUDA(h, upload_cached(h, h->slotSv, slotSv, st));
+        if (haveSecondary) GC_CUDA(h, upload_cached(h, h->slotSecondary, slotSec, st));
+        GC_CUDA(h, h->metricDev.reserve(nSv));
+        GC_CUDA(h, h->nAcqDev.reserve(1));
+        GC_CUDA(h, h->acqSlot.reserve(nSv));
+        GC_CUDA(h, h->fineChipRow.reserve(maxEnt));
+        GC_CUDA(h, h->fineCodePhase.reserve(maxEnt));
+        GC_CUDA(h, h->fdphi.reserve((size_t)maxEnt * h->nFine));
+        GC_CUDA(h, h->fineSv.reserve(nSv));
+        GC_CUDA(h, h->fineSecondary.reserve((size_t)nSv * nPeriods));
+        GC_CUDA(h, h->fineProd.reserve((size_t)maxEnt * nPeriods * N));
+        GC_CUDA(h, h->fineSums.reserve((size_t)maxEnt * h->nFine * nPeriods * 2));
+        GC_CUDA(h, h->fineResult.reserve((size_t)nSv * h->nFine));
+        GC_CUDA(h, h->fineBest.reserve(nSv));
+    }
+    if (dOut) {                                                   // acqResults assembled on the device for the collective that follows
+        std::vector<int> slotResult(nSv);
+        for (int s = 0; s < nSv; ++s) slotResult[s] = sv_result_index(h, svList[order[s]]);
+        GC_CUDA(h, upload_cached(h, h->slotResult, slotResult, st));
+        if (h->noFine) GC_CUDA(h, upload_cached(h, h->slotFreq0, slotFreq0, st));
+    }
+    // pinned staging of the result copies: [PeakOut peaks[nSv] | double sigPower | int best[nSv] | int nAcq]
+    const size_t offSig = (size_t)nSv * sizeof(PeakOut), offBest = offSig + sizeof(double), offN = offBest + (size_t)nSv * sizeof(int);
+    const size_t needPin = offN + sizeof(int);
+    if (needPin > h->pinBytes) {
+        if (h->pin) cudaFreeHost(h->pin);
+        h->pin = nullptr; h->pinBytes = 0;
+        GC_CUDA(h, cudaHostAlloc((void**)&h->pin, needPin + 256, cudaHostAllocDefault));
+        h->pinBytes = needPin + 256;
+    }
+    PeakOut* pinPeaks = reinterpret_cast<PeakOut*>(h->pin);
+    double* pinSig = reinterpret_cast<double*>(h->pin + offSig);
+    int* pinBest = reinterpret_cast<int*>(h->pin + offBest);
+    int* pinN = reinterpret_cast<int*>(h->pin + offN);
+    *pinN = -1;
+    laps.lap("host tables, buffers");
+
+    // ---- the enqueue ---------------------------------------------------------------------------------------------------------
+    const bool perChunkEvents = 2 * nChunks + 8 <= kEvents;
+    auto enqueue = [&](AcqEnq& q, bool capturing) -> int {
+        int evn = 0;
+        auto mark = [&]() {
+            if (capturing) cudaEventRecordWithFlags(h->ev[evn], st, cudaEventRecordExternal);
+            else cudaEventRecord(h->ev[evn], st);
+            return evn++;
+        };
+        q = AcqEnq{};
+        q.e0 = mark();
+        GC_CUDA(h, launch_sig_power(rec_of(h), winStart, N, h->sigPower.p, st)); ++q.launches;   // :151
+        int prev = mark();
+        FwdColsParams fp{};
+        fp.rec = rec_of(h); fp.winStart = winStart; fp.N = N; fp.nonCoh = nonCoh; fp.swapIQ = (h->glo && h->fmt != 2 && h->fmt != 3) ? 1 : 0;
+        fp.dphi = h->dphi.p; fp.out = h->X.p; fp.tw = h->twFused.p;          // row (grid, bin, block): the phase table is indexed grid*nBins + bin
+        GC_CUDA(h, launch_fwd_cols(L, fp, nGroups * fwdRowsPerGroup, false, st)); ++q.launches;
+        RowsParams rp{};
+        rp.X = h->X.p; rp.nRows = (long long)nGroups * fwdRowsPerGroup * h->fp.C;
+        GC_CUDA(h, launch_fwd_rows(L, rp, st)); ++q.launches;
+        { const int m = mark(); q.fwdEv.push_back({prev, m}); prev = m; }
+        for (int s0 = 0; s0 < nSv; s0 += chunk) {
+            const int nc = std::min(chunk, (int)nSv - s0);
+            RowsParams ip{};
+            ip.X = h->X.p; ip.Cc = h->Cc.p; ip.W = h->W.p; ip.tw = h->twFused.p;
+            ip.nonCoh = nonCoh; ip.nBins = nBins; ip.prnPerCta = 1; ip.mPerCta = 5;   // 5 warps, 96 registers, 20 warps/SM
+            ip.nRep = h->nRep; ip.repStride = 1;
+            if (nonCoh * h->nRep < 5) { ip.prnPerCta = 5; ip.mPerCta = 1; }           // few transforms per cell (Galileo E1: 2): fill the CTA with SVs
+            ip.nPrnChunk = nc; ip.prnSlot0 = s0; ip.prnList = h->prnList.p;
+            ip.slotGroup = h->slotGroup.p; ip.groupRows = fwdRowsPerGroup;
+            if (shifted) ip.binMap = h->vbMap.p;
+            GC_CUDA(h, launch_inv_rows(L, ip, st)); ++q.launches; ++q.nRowLaunches;
+            if (perChunkEvents) { const int m = mark(); q.rowEv.push_back({prev, m}); prev = m; }
+            InvColsParams cp{};
+            cp.W = h->W.p; cp.nBins = nBins; cp.nonCoh = nonCoh * h->nRep; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
+            cp.partMax = h->partMax.p; cp.partIdx = h->partIdx.p;
+            GC_CUDA(h, launch_inv_cols(L, cp, st)); ++q.launches;
+            if (perChunkEvents) { const int m = mark(); q.colEv.push_back({prev, m}); prev = m; }
+        }
+        GC_CUDA(h, launch_peak_select(h->partMax.p, h->partIdx.p, nSv, nBins, h->parts, h->peaks.p, st)); ++q.launches;
+        q.e1 = mark();
+        // threshold (:200-206) and fine search (:211-253) follow on the device without a host round trip: fine_setup_kernel
+        // decides which list slots are above the threshold and prepares their fine-search entries, the fine kernels are
+        // launched for the worst case (every slot acquired) and idle blocks leave at once
+        if (!h->noFine) {
+            FineSetup fs{};
+            fs.peaks = h->peaks.p; fs.sigPower = h->sigPower.p; fs.nSv = nSv; fs.nonCoh = nonCoh; fs.nFine = h->nFine; fs.nCodes = nCodes;
+            fs.nPeriods = nPeriods; fs.pilotComp = h->nRep - 1; fs.threshold = c.acq_threshold; fs.step = c.acq_search_step;
+            fs.fineStep = h->fineStep; fs.ts = h->ts; fs.slotFreq0 = h->slotFreq0.p; fs.slotChipRow = h->slotChipRow.p; fs.slotSv = h->slotSv.p;
+            fs.slotSecondary = haveSecondary ? h->slotSecondary.p : nullptr;
+            fs.metric = h->metricDev.p; fs.nAcq = h->nAcqDev.p; fs.acqSlot = h->acqSlot.p; fs.chipRow = h->fineChipRow.p;
+            fs.codePhase = h->fineCodePhase.p; fs.dphi = h->fdphi.p; fs.svId = h->fineSv.p; fs.secondary = h->fineSecondary.p;
+            q.fa = q.e1;
+            GC_CUDA(h, launch_fine_setup(fs, st)); ++q.launches;
+            FineParams fpp{};
+            fpp.rec = rec_of(h); fpp.winStart = winStart; fpp.N = N; fpp.nPeriods = nPeriods; fpp.nFine = h->nFine; fpp.codeLen = tabLen;
+            fpp.swapIQ = (h->glo && h->fmt != 2 && h->fmt != 3) ? 1 : 0; fpp.combine = h->fineCombine; fpp.chipIdx = h->chipIdx.p; fpp.svId = h->fineSv.p;
+            fpp.chips = h->chips.p; fpp.chipRow = h->fineChipRow.p; fpp.codePhase = h->fineCodePhase.p; fpp.dphi = h->fdphi.p; fpp.prod = h->fineProd.p;
+            fpp.sums = h->fineSums.p; fpp.best = h->fineBest.p; fpp.fineResult = h->fineResult.p;
+            fpp.nAcqDev = h->nAcqDev.p; fpp.nCodes = nCodes; fpp.secondary = h->fineSecondary.p;
+            GC_CUDA(h, launch_fine(fpp, maxEnt, nSv, st)); q.launches += 3;
+            q.fb = mark();
+        }
+        if (dOut) {
+            PackParams pk{};
+            pk.peaks = h->peaks.p; pk.sigPower = h->sigPower.p; pk.slotFreq0 = h->slotFreq0.p; pk.slotResult = h->slotResult.p;
+            pk.best = h->noFine ? nullptr : h->fineBest.p; pk.nSv = nSv; pk.nonCoh = nonCoh; pk.resultLen = h->resultLen; pk.noFine = h->noFine ? 1 : 0;
+            pk.threshold = c.acq_threshold; pk.step = c.acq_search_step; pk.fineStep = h->fineStep; pk.out = dOut;
+            GC_CUDA(h, launch_pack_results(pk, st)); ++q.launches;
+        } else {
+            GC_CUDA(h, cudaMemcpyAsync(pinPeaks, h->peaks.p, nSv * sizeof(PeakOut), cudaMemcpyDeviceToHost, st));
+            GC_CUDA(h, cudaMemcpyAsync(pinSig, h->sigPower.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+            if (!h->noFine) {
+                GC_CUDA(h, cudaMemcpyAsync(pinBest, h->fineBest.p, nSv * sizeof(int), cudaMemcpyDeviceToHost, st));
+                GC_CUDA(h, cudaMemcpyAsync(pinN, h->nAcqDev.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            }
+        }
+        return GC_OK;
+    };
+
+    // ---- direct, capture or replay ----------------------------------------------------------------------------------------------
+    std::vector<char> key;
+    auto put = [&](const void* p_, size_t n_) { const char* b = static_cast<const char*>(p_); key.insert(key.end(), b, b + n_); };
+    {
+        const unsigned long long gen = g_allocGen.load(std::memory_order_relaxed);
+        const void* recp = h->rec; const void* pinp = h->pin;
+        put(&winStart, sizeof winStart); put(&nSv, sizeof nSv); put(svList, sizeof(int32_t) * nSv); put(&recp, sizeof recp);
+        put(&h->recBytes, sizeof h->recBytes); put(&dOut, sizeof dOut); put(&gen, sizeof gen); put(&pinp, sizeof pinp);
+    }
+    AcqGraph& g = h->graph;
+    AcqEnq info;
+    int mode = 0;                                             // 0 direct, 1 capture, 2 replay
+    if (!h->graphOff) {
+        if (g.key == key) mode = g.exec ? 2 : (g.hits >= 1 ? 1 : 0);
+        else {
+            if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+            g.key = key; g.hits = 0;
+        }
+    }
+    if (mode == 1) {
+        cudaGraph_t graph = nullptr;
+        int rc = GC_OK;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) { h->graphOff = true; mode = 0; cudaGetLastError(); }
+        else {
+            rc = enqueue(info, true);
+            const cudaError_t ee = cudaStreamEndCapture(st, &graph);
+            if (rc == GC_OK && ee == cudaSuccess && graph && cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess) {
+                g.info = info;
+                mode = 2;
+            } else {                                          // never again on this handle; run this call directly
+                h->graphOff = true; g.exec = nullptr; mode = 0;
+                cudaGetLastError();
+            }
+            if (graph) cudaGraphDestroy(graph);
+        }
+        laps.lap("graph capture + instantiate");
+    }
+    if (mode == 2) {
+        info = g.info;
+        GC_CUDA(h, cudaGraphLaunch(g.exec, st));
+    } else {
+        const int rc = enqueue(info, false);
+        if (rc != GC_OK) return rc;
+        ++g.hits;
+    }
+    laps.lap(mode == 2 ? "graph launch" : "direct enqueue");
+    GC_CUDA(h, cudaStreamSynchronize(st));
+    laps.lap("synchronize");
+
+    // ---- timings and the host side of the results ---------------------------------------------------------------------------------
+    float rowsMs = 0, colsMs = 0, fwdMs = 0, fineMs = 0, coarseMs = 0, ms = 0;
+    for (auto& pr : info.rowEv) if (cudaEventElapsedTime(&ms, h->ev[pr.first], h->ev[pr.second]) == cudaSuccess) rowsMs += ms;
+    for (auto& pr : info.colEv) if (cudaEventElapsedTime(&ms, h->ev[pr.first], h->ev[pr.second]) == cudaSuccess) colsMs += ms;
+    for (auto& pr : info.fwdEv) if (cudaEventElapsedTime(&ms, h->ev[pr.first], h->ev[pr.second]) == cudaSuccess) fwdMs += ms;
+    if (info.fa >= 0 && cudaEventElapsedTime(&ms, h->ev[info.fa], h->ev[info.fb]) == cudaSuccess) fineMs = ms;
+    if (cudaEventElapsedTime(&ms, h->ev[info.e0], h->ev[info.e1]) == cudaSuccess) coarseMs = ms;
+    cudaGetLastError();
+    h->stats.acq_fwd_ms = fwdMs; h->stats.acq_corr_ms = coarseMs - fwdMs; h->stats.acq_fine_ms = fineMs; h->stats.acq_total_ms = coarseMs + fineMs;
+    h->stats.corr_rows_ms = rowsMs; h->stats.corr_cols_ms = colsMs; h->stats.corr_row_launches = info.nRowLaunches; h->stats.acq_launches = info.launches;
+    if (dOut) {
+        h->stats.n_acquired = -1;                             // (in the device buffer: carrFreq != 0)
+        return GC_OK;
+    }
+    const double sigPower = *pinSig;
+    std::vector<int> acq;   // list slots above the threshold, in list order (what fine_setup_kernel found too)
+    for (int s = 0; s < nSv; ++s) {
+        const int ri = sv_result_index(h, svList[order[s]]);
+        peakMetric[ri] = pinPeaks[s].peak / sigPower / nonCoh;                       // :200
+        if (coarseBin) coarseBin[ri] = pinPeaks[s].bin;
+        if (coarseCodePhase) coarseCodePhase[ri] = pinPeaks[s].codePhase;
+        if (peakMetric[ri] > c.acq_threshold) acq.push_back(s);                      // :206
+    }
+    const int nAcq = (int)acq.size();
+    h->stats.n_acquired = nAcq;
+    if (!h->noFine && *pinN != nAcq) return fail(h, GC_ERR_CUDA, "gc_acquire: device and host disagree on the acquired set");
+    for (int a = 0; a < nAcq; ++a) {
+        const int s = acq[a];
+        const int ri = sv_result_index(h, svList[order[s]]);
+        const double coarse = coarseFreqOf[s][pinPeaks[s].bin - 1];
+        carrFreq[ri] = h->noFine ? coarse                                            // GAL_E5b acquisition.m:203-205
+                                 : coarse + c.acq_search_step / 2 - h->fineStep * pinBest[a];   // :227, :254
+        codePhase[ri] = pinPeaks[s].codePhase;                                       // :256
+        if (!h->noFine && carrFreq[ri] == 0) carrFreq[ri] = 1;                       // :258
+    }
+    laps.lap("results");
+    return GC_OK;
+}
+
+
 static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int32_t* svList,
                         double* carrFreq, double* codePhase, double* peakMetric,
                         int32_t* coarseBin, int32_t* coarseCodePhase, long long longLen = 0 /* length(longSignal), B1C only */,
@@ -1265,10 +1612,12 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
     }
     const int nGroups = (int)groupStart.size();
     groupStart.push_back(nSv);
-    // several carrier grids (GLONASS: one per frequency number) are transformed and searched in ONE pass each instead of grid by grid
-    const bool batchGroups = h->fused && !h->cluster && !h->queue && !h->overlap && nGroups > 1 && !getenv("GC_ACQ_CHUNK_BINS") &&
-                             (double)nGroups * nKm * L * sizeof(float2) <= kWorkBytes;
-    GC_CUDA(h, h->X.reserve((size_t)((h->cluster || batchGroups) ? nGroups : 1) * nKm * L));
+    // the default path: split correlation stage on a fused plan, every carrier grid in one pass, one enqueue (graph) - acquire_plain
+    const bool plain = h->fused && !h->cluster && !h->queue && !h->overlap && !getenv("GC_ACQ_CHUNK_BINS") && !getenv("GC_ACQ_CHUNK_PRNS") &&
+                       !getenv("GC_ROWS_VARIANT") && !getenv("GC_ACQ_LEGACY") && (double)nGroups * nKm * L * sizeof(float2) <= kWorkBytes;
+    if (plain)
+        return acquire_plain(h, winStart, nSv, svList, order, groupStart, slotGroup, carrFreq, codePhase, peakMetric, coarseBin, coarseCodePhase, dOut);
+    GC_CUDA(h, h->X.reserve((size_t)(h->cluster ? nGroups : 1) * nKm * L));
     GC_CUDA(h, h->dphi.reserve((size_t)nGroups * nBins));
     std::vector<std::vector<double>> coarseFreqOf(nSv);   // per list slot: the bin frequencies it was searched on
 
@@ -1309,65 +1658,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         GC_CUDA(h, launch_corr_cluster(L, cp, st)); ++launches;
         rowEv.push_back({f1, mark()}); ++nRowLaunches;
     }
-    if (batchGroups) {
-        std::vector<uint64_t> dphi((size_t)nGroups * nBins);
-        for (int gi = 0; gi < nGroups; ++gi) {
-            const double off = sv_freq_offset(h, svList[order[groupStart[gi]]]);
-            std::vector<double> coarseFreq(nBins);
-            for (int k = 0; k < nBins; ++k) {
-                coarseFreq[k] = (c.IF + off) + c.acq_search_band - c.acq_search_step * k;   // :169 (GLO :181-182)
-                dphi[(size_t)gi * nBins + k] = turns_to_fix(coarseFreq[k] * h->ts);
-            }
-            for (int s = groupStart[gi]; s < groupStart[gi + 1]; ++s) coarseFreqOf[s] = coarseFreq;
-        }
-        const bool shifted = h->binShift > 0;                // only bin 0 of every grid is transformed, the other bins are shifts of it
-        if (shifted) {
-            std::vector<uint64_t> d0(nGroups);
-            for (int gi = 0; gi < nGroups; ++gi) d0[gi] = dphi[(size_t)gi * nBins];
-            GC_CUDA(h, cudaMemcpyAsync(h->dphi.p, d0.data(), d0.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-            std::vector<int2> map(nBins);
-            for (int k = 0; k < nBins; ++k) map[k] = make_int2(0, k * h->binShift);
-            GC_CUDA(h, upload_cached(h, h->vbMap, map, st));
-        } else {
-            GC_CUDA(h, cudaMemcpyAsync(h->dphi.p, dphi.data(), dphi.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-        }
-        GC_CUDA(h, upload_cached(h, h->slotGroup, slotGroup, st));
-        const int f0 = mark();
-        const int fwdRowsPerGroup = shifted ? nonCoh : nKm;
-        FwdColsParams fp{};
-        fp.rec = rec_of(h); fp.winStart = winStart; fp.N = N; fp.nonCoh = nonCoh; fp.swapIQ = (h->glo && h->fmt != 2 && h->fmt != 3) ? 1 : 0;
-        fp.dphi = h->dphi.p; fp.out = h->X.p; fp.tw = h->twFused.p;          // row (grid, bin, block): the phase table is indexed grid*nBins + bin
-        GC_CUDA(h, launch_fwd_cols(L, fp, nGroups * fwdRowsPerGroup, false, st)); ++launches;
-        RowsParams rp{};
-        rp.X = h->X.p; rp.nRows = (long long)nGroups * fwdRowsPerGroup * h->fp.C;
-        GC_CUDA(h, launch_fwd_rows(L, rp, st)); ++launches;
-        fwdEv.push_back({f0, mark()});
-        int chunk = (int)std::max<long long>(1, (long long)(kWorkBytes / ((double)nKm * h->nRep * L * sizeof(float2))));
-        chunk = std::min(chunk, (int)nSv);
-        GC_CUDA(h, h->W.reserve((size_t)chunk * nKm * h->nRep * L));
-        for (int s0 = 0; s0 < nSv; s0 += chunk) {
-            const int nc = std::min(chunk, (int)nSv - s0);
-            RowsParams ip{};
-            ip.X = h->X.p; ip.Cc = h->Cc.p; ip.W = h->W.p; ip.tw = h->twFused.p;
-            ip.nonCoh = nonCoh; ip.nBins = nBins; ip.prnPerCta = 1; ip.mPerCta = 5;
-            ip.nRep = h->nRep; ip.repStride = 1;
-            if (nonCoh * h->nRep < 5) { ip.prnPerCta = 5; ip.mPerCta = 1; }
-            ip.nPrnChunk = nc; ip.prnSlot0 = s0; ip.prnList = h->prnList.p;
-            ip.slotGroup = h->slotGroup.p; ip.groupRows = fwdRowsPerGroup;
-            if (shifted) ip.binMap = h->vbMap.p;
-            if (evn > kEvents - 12) drain_events();
-            const int a = mark();
-            GC_CUDA(h, launch_inv_rows(L, ip, st)); ++launches;
-            const int b = mark();
-            InvColsParams cp{};
-            cp.W = h->W.p; cp.nBins = nBins; cp.nonCoh = nonCoh * h->nRep; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
-            cp.partMax = h->partMax.p; cp.partIdx = h->partIdx.p;
-            GC_CUDA(h, launch_inv_cols(L, cp, st)); ++launches;
-            const int d = mark();
-            rowEv.push_back({a, b}); colEv.push_back({b, d}); ++nRowLaunches;
-        }
-    }
-    for (int g0 = 0; g0 < nSv && !h->cluster && !batchGroups;) {
+    for (int g0 = 0; g0 < nSv && !h->cluster;) {
         int g1 = g0 + 1;
         const double off = sv_freq_offset(h, svList[order[g0]]);
         while (g1 < nSv && sv_freq_offset(h, svList[order[g1]]) == off) ++g1;
@@ -1681,9 +1972,11 @@ int gc_acquire_host(gc_handle* h, const int8_t* iq, size_t nSamples, int32_t nSv
                     int32_t* coarseBin, int32_t* coarseCodePhase)
 {
     if (!h || !iq) return fail(h, GC_ERR_ARG, "gc_acquire_host: bad argument");
-    int rc = gc_set_record_host(h, iq, (size_t)rec_of(h).bytes_of((long long)nSamples));
+    int rc = set_record_host(h, iq, (size_t)rec_of(h).bytes_of((long long)nSamples), false);
     if (rc != GC_OK) return rc;
-    return acquire_impl(h, 0, nSv, svList, carrFreq, codePhase, peakMetric, coarseBin, coarseCodePhase, (long long)nSamples);
+    rc = acquire_impl(h, 0, nSv, svList, carrFreq, codePhase, peakMetric, coarseBin, coarseCodePhase, (long long)nSamples);
+    if (rc != GC_OK) cudaStreamSynchronize(h->stream);        // (an early return may have left the copy of `iq` in flight)
+    return rc;
 }
 
 int gc_track_nfields(const gc_handle* h)
