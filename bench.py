@@ -251,9 +251,15 @@ def main():
     res_buf = torch.zeros(4 * N_PRN, dtype=torch.float64, device=dev)
 
     def sharded_step():
-        """This rank's share of the grid, acqResults left on the device, ONE all-gather, merged acqResults on the host."""
-        eng.acquire_device(my_sv, res_buf)
-        return shard.merge_device_results(shard.all_gather_device(res_buf), N_PRN)
+        """This rank's share of the grid, acqResults left on the device, ONE all-gather, merged acqResults on the host.  The search
+        is enqueued without a host synchronisation (gc_acquire_device_async: one graph launch) and the all-gather is ordered behind
+        the engine's stream on the device; the only host wait of a step is the 1 KB D2H of the merged vectors."""
+        if world == 1:                           # nothing to gather: the synchronous call (measured 2 % faster than queueing torch's copy behind it)
+            eng.acquire_device(my_sv, res_buf)
+            return shard.merge_device_results(res_buf, N_PRN)
+        with torch.cuda.stream(ext):
+            eng.acquire_device_async(my_sv, res_buf)
+            return shard.merge_device_results(shard.all_gather_device(res_buf), N_PRN)
 
     sampler = ClockSampler(local)
     # ---- acquisition, device-timed with inputs resident in HBM ------------------------------
@@ -270,7 +276,7 @@ def main():
         flush_l2()
         ev[i][0].record(ext)
         acq = sharded_step()
-        ev[i][1].record()                        # after the all-gather and the 1 KB D2H on torch's stream
+        ev[i][1].record(ext)                     # after the all-gather and the 1 KB D2H, which are ordered on the engine's stream
         st = eng.stats()
         rows_ms += st["corr_rows_ms"]; cols_ms += st["corr_cols_ms"]; launches += st["acq_launches"]
     barrier()
@@ -604,7 +610,7 @@ def main():
                        "record": f"synthetic 60 s IF record, {rec.numel()} B resident in the HBM of every rank (same seed 20260101: the same bytes "
                                  f"everywhere; generated in {t_gen:.1f} s, untimed)",
                        "l2": "flushed between timed steps (256 MiB memset); per-step working set > 126 MB L2",
-                       "timing": "CUDA events per step from the engine's stream (start) to after the all-gather + 1 KB D2H (end), max over ranks",
+                       "timing": "CUDA events per step on the engine's stream: start, then the search (one graph launch), the all-gather ordered behind it and the 1 KB D2H, end; max over ranks",
                        "parallelism": f"{world} rank(s) x {len(my_sv)} PRN x 29 bins, acqResults left on the device (gc_acquire_device), "
                                       "1 NCCL all-gather of 4 x 32 doubles per rank, merge = sum"},
             "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": 2 * n_acq_samples,

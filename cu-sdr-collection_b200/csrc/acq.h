@@ -11,6 +11,7 @@ struct FusedPlanInfo {
     int L, C, RA, RB, R;
     int pfa;                  // 1: gcd(C, R) = 1, no twiddle between the passes; 0: [C][R] twiddle table needed
     int parts;                // column tiles per (SV, bin) in the partial-maximum arrays
+    int C1, C2;               // two-level column pass C = C1 x C2 (0: the column is one register codelet)
 };
 bool fused_plan_info(int L, FusedPlanInfo* out);   // false: no fused plan for this length
 
@@ -57,6 +58,7 @@ struct InvColsParams {
     int weighted;             // 1: magnitudes of even / odd transforms are weighted w0 / w1 and the sum scaled by wScale
     float w0, w1, wScale;     // (BDS B1C: (|data|*sqrt(11) + |pilot|*sqrt(29)) / sqrt(40), acquisition.m:213-214)
     float* magOut;            // optional [nPrnChunk][nBins][L]: the summed magnitudes in natural lag order (corrVec of variant B)
+    const float2* colTw;      // two-level column pass: [C1][C2] w_C^(-ta*beta) (gc_handle::twCols)
 };
 
 // correlation stage as one persistent kernel with an ordered work queue (acq_fused.cu, experimental: GC_ACQ_PATH=queue)

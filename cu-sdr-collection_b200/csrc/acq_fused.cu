@@ -344,7 +344,11 @@ fwd_cols_big_kernel(FwdColsParams p)
 }
 
 // inverse column pass + |.| + sum over blocks/replicas + max: grid (ceil(R/TC), nBins, nPrnChunk)
-template <class P>
+// SINGLE: one transform per cell (variant B: GPS L2C, BDS B1I; nothing to accumulate, so no accumulator array stays live across the
+// loads of the next pass and the maximum is taken as the outputs appear); MAGOUT: the magnitudes are also written in natural lag
+// order (corrVec of variant B's winner rows).  The w_C^(-ta*beta) table comes from global memory (InvColsParams::colTw, float64
+// on the host) instead of one sincospif per entry and CTA.
+template <class P, bool SINGLE, bool MAGOUT>
 __global__ void __launch_bounds__(BigGeo<P>::NT, BigGeo<P>::kMinCtas)
 inv_cols_big_kernel(InvColsParams p)
 {
@@ -352,47 +356,79 @@ inv_cols_big_kernel(InvColsParams p)
     constexpr int C = P::C, C1 = P::C1, C2 = P::C2, R = P::R, L = P::L, TC = G::TC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* Y = reinterpret_cast<float2*>(smem_raw);            // [ta][beta][col]
-    float2* TW = Y + C * TC;                                     // [ta][beta] = w_C^(-ta*beta): one sincospif per entry and CTA
-    for (int i = threadIdx.x; i < C; i += G::NT) TW[i] = unit_root((i / C2) * (i % C2), C, true);
-    __syncthreads();
+    float2* TW = Y + C * TC;                                     // [ta][beta] = w_C^(-ta*beta)
+    for (int i = threadIdx.x; i < C; i += G::NT) TW[i] = __ldg(p.colTw + i);
     const int col = threadIdx.x % TC, q = threadIdx.x / TC;
     const int pp = blockIdx.x * TC + col;
     const bool in = pp < R;
     const int k = blockIdx.y, pi = blockIdx.z;
-    float acc[C2];
-#pragma unroll
-    for (int i = 0; i < C2; ++i) acc[i] = 0.f;
     const float2* base = p.W + ((size_t)(pi * p.nBins + k) * p.nonCoh) * L + pp;
-    for (int m = 0; m < p.nonCoh; ++m) {
-        if (q < C2 && in) {                                     // phase 1: q = beta, input k1 = C2*alpha + beta
-            float2 x[C1];
+    const bool weighted = !SINGLE && p.weighted;
+    float best = -1.f;
+    int btb = 0x7fffffff;                                        // output tb of this thread's maximum (lag index grows with tb)
+    float acc[SINGLE ? 1 : C2];
+    if (!SINGLE) {
 #pragma unroll
-            for (int a = 0; a < C1; ++a) x[a] = __ldcs(base + (size_t)m * L + (size_t)(C2 * a + q) * R);
+        for (int i = 0; i < C2; ++i) acc[i] = 0.f;
+    }
+    float* mag = MAGOUT ? p.magOut + (size_t)(pi * p.nBins + k) * L + P::index(q, in ? P::row_index(pp) : 0) : nullptr;
+    const int nPass = SINGLE ? 1 : p.nonCoh;
+    const bool ph1 = q < C2 && in, ph2 = q < C1 && in;          // (every __syncthreads below is reached by the whole CTA)
+    if (!SINGLE) __syncthreads();                                // the twiddle table
+    for (int m = 0; m < nPass; ++m) {
+        if constexpr (SINGLE) {                                  // one short pass per CTA: the loads go out before the table barrier
+            float2 x[C1];
+            if (ph1) {                                          // phase 1: q = beta, input k1 = C2*alpha + beta
+                const float2* src = base + (size_t)q * R;
+#pragma unroll
+                for (int a = 0; a < C1; ++a) x[a] = __ldcs(src + (size_t)(C2 * a) * R);
+            }
+            __syncthreads();
+            if (ph1)
+                codelet::dft<C1, true>(x, [&](int ta, float re, float im) {
+                    Y[(ta * C2 + q) * TC + col] = cmul(make_float2(re, im), TW[ta * C2 + q]);
+                });
+        } else if (ph1) {
+            float2 x[C1];
+            const float2* src = base + (size_t)m * L + (size_t)q * R;
+#pragma unroll
+            for (int a = 0; a < C1; ++a) x[a] = __ldcs(src + (size_t)(C2 * a) * R);
             codelet::dft<C1, true>(x, [&](int ta, float re, float im) {
                 Y[(ta * C2 + q) * TC + col] = cmul(make_float2(re, im), TW[ta * C2 + q]);
             });
         }
         __syncthreads();
-        if (q < C1 && in) {                                     // phase 2: q = ta, outputs t1 = ta + C1*tb
+        if (ph2) {                                              // phase 2: q = ta, outputs t1 = ta + C1*tb
             float2 y[C2];
 #pragma unroll
             for (int b = 0; b < C2; ++b) y[b] = Y[(q * C2 + b) * TC + col];
-            const float wm = p.weighted ? ((m & 1) ? p.w1 : p.w0) : 1.f;
-            codelet::dft<C2, true>(y, [&](int tb, float re, float im) { acc[tb] = fmaf(wm, cabs_fast(re, im), acc[tb]); });
+            if (SINGLE) {
+                codelet::dft<C2, true>(y, [&](int tb, float re, float im) {
+                    const float v = cabs_fast(re, im);
+                    if (MAGOUT) mag[(size_t)(C1 * tb) * R] = v;
+                    const bool take = v > best || (v == best && tb < btb);
+                    best = take ? v : best; btb = take ? tb : btb;
+                });
+            } else {
+                const float wm = weighted ? ((m & 1) ? p.w1 : p.w0) : 1.f;
+                codelet::dft<C2, true>(y, [&](int tb, float re, float im) { acc[tb] = fmaf(wm, cabs_fast(re, im), acc[tb]); });
+            }
         }
-        __syncthreads();
+        if (m + 1 < nPass) __syncthreads();
     }
-    float best = -1.f;
     int bidx = 0x7fffffff;
-    if (q < C1 && in) {
-        const int rest = P::row_index(pp);
+    if (ph2) {
+        if (!SINGLE) {
 #pragma unroll
-        for (int tb = 0; tb < C2; ++tb) {
-            const int idx = P::index(q + C1 * tb, rest);
-            if (p.weighted) acc[tb] *= p.wScale;
-            if (p.magOut) p.magOut[(size_t)(pi * p.nBins + k) * L + idx] = acc[tb];
-            if (acc[tb] > best || (acc[tb] == best && idx < bidx)) { best = acc[tb]; bidx = idx; }
+            for (int tb = 0; tb < C2; ++tb) {
+                if (weighted) acc[tb] *= p.wScale;
+                if (MAGOUT) mag[(size_t)(C1 * tb) * R] = acc[tb];
+                best = fmaxf(best, acc[tb]);
+            }
+#pragma unroll
+            for (int tb = C2 - 1; tb >= 0; --tb) btb = (acc[tb] == best) ? tb : btb;      // first (smallest) lag holding the maximum
         }
+        bidx = P::index(q + C1 * btb, P::row_index(pp));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -651,10 +687,16 @@ struct Launch {
         if constexpr (P::kBig) {
             using G = BigGeo<P>;
             dim3 grid((P::R + G::TC - 1) / G::TC, p.nBins, p.nPrnChunk);
-            cudaError_t e = cudaFuncSetAttribute(inv_cols_big_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::kSmemInv);
-            if (e != cudaSuccess) return e;
-            inv_cols_big_kernel<P><<<grid, G::NT, G::kSmemInv, s>>>(p);
-            return cudaGetLastError();
+            if (!p.colTw) return cudaErrorInvalidValue;
+            auto go = [&](auto kern) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::kSmemInv);
+                if (e != cudaSuccess) return e;
+                kern<<<grid, G::NT, G::kSmemInv, s>>>(p);
+                return cudaGetLastError();
+            };
+            const bool single = p.nonCoh == 1;
+            if (p.magOut) return single ? go(inv_cols_big_kernel<P, true, true>) : go(inv_cols_big_kernel<P, false, true>);
+            return single ? go(inv_cols_big_kernel<P, true, false>) : go(inv_cols_big_kernel<P, false, false>);
         } else {
             dim3 grid((P::R + 127) / 128, p.nBins, p.nPrnChunk);
             inv_cols_kernel<P><<<grid, 128, 0, s>>>(p);
@@ -667,6 +709,7 @@ template <class P>
 void fill_info(FusedPlanInfo* o)
 {
     o->L = P::L; o->C = P::C; o->RA = P::RA; o->RB = P::RB; o->R = P::R; o->pfa = P::kPfa ? 1 : 0;
+    o->C1 = P::C1; o->C2 = P::C2;
     if constexpr (P::kBig) o->parts = (P::R + BigGeo<P>::TC - 1) / BigGeo<P>::TC;
     else o->parts = (P::R + 127) / 128;
 }

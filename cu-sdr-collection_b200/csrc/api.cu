@@ -166,6 +166,7 @@ struct gc_handle {
     bool cluster = false;        // correlation stage as one cluster kernel (acq_cluster.cu); else inv_rows + inv_cols
     FusedPlanInfo fp{};
     DevBuf<float2> twFused;      // [C][R] twiddles of fused plans with a Cooley-Tukey column/row link
+    DevBuf<float2> twCols;       // [C1][C2] w_C^(-ta*beta) of the two-level inverse column pass (long transforms)
 
     // resident record
     const int8_t* rec = nullptr;
@@ -202,6 +203,8 @@ struct gc_handle {
     std::unordered_map<const void*, std::vector<char>> upCache;   // upload_cached: last bytes sent to a buffer
     AcqGraph graph;              // variant A on a fused plan: the whole enqueue as one graph launch
     bool graphOff = false;       // GC_ACQ_GRAPH=0, or a capture failed
+    AcqEnq pendingInfo;          // events of the last variant A enqueue whose timings have not been read yet (gc_acquire_device_async)
+    bool statsPending = false;
     char* pin = nullptr;         // pinned host staging of the per-call result copies (peaks, sigPower, fine bins, acquired count)
     size_t pinBytes = 0;
 };
@@ -540,6 +543,17 @@ int gc_create(gc_handle** out, const gc_config* cfg)
                     }
                 GC_CUDA(h, upload(h->twFused, tw, h->stream));
             }
+            if (h->fp.C1 > 0) {   // inverse two-level column pass: w_C^(+ta*beta), ta < C1, beta < C2 (inv_cols_big_kernel)
+                const FusedPlanInfo& f = h->fp;
+                std::vector<float2> tw((size_t)f.C);
+                const long double two_pi = 6.283185307179586476925286766559005768L;
+                for (int ta = 0; ta < f.C1; ++ta)
+                    for (int be = 0; be < f.C2; ++be) {
+                        const long double a = two_pi * (long double)((ta * be) % f.C) / (long double)f.C;
+                        tw[(size_t)ta * f.C2 + be] = make_float2((float)cosl(a), (float)sinl(a));
+                    }
+                GC_CUDA(h, upload(h->twCols, tw, h->stream));
+            }
         } else {
             // fewest passes over the radices that have a kernel: register codelets (8 .. 50) and small primes / 4
             h->plan.L = h->L; h->plan.nf = 0;
@@ -592,7 +606,7 @@ void gc_destroy(gc_handle* h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->recOwned.release();
     h->twGen.release(); h->X.release(); h->T1.release(); h->T2.release(); h->T3.release();
-    h->chipIdx.release(); h->twFused.release();
+    h->chipIdx.release(); h->twFused.release(); h->twCols.release();
     h->Cc.release(); h->W.release(); h->dphi.release(); h->fdphi.release(); h->codeTab.release(); h->chips.release(); h->fineSecondary.release(); h->slotSecondary.release();
     h->slotFreq0.release(); h->metricDev.release(); h->slotChipRow.release(); h->slotSv.release(); h->nAcqDev.release(); h->acqSlot.release(); h->fineChipRow.release();
     h->prnList.release(); h->slotGroup.release(); h->partIdx.release(); h->fineCodePhase.release(); h->fineBest.release(); h->fineSv.release(); h->partMax.release();
@@ -874,7 +888,7 @@ static int acquire_varb(gc_handle* h, long long winStart, int32_t nSv, const int
             ip.nPrnChunk = nc; ip.prnSlot0 = s0; ip.prnList = h->prnList.p;
             GC_CUDA(h, launch_inv_rows(Lb, ip, st)); ++launches;
             InvColsParams cp{};
-            cp.W = h->W.p; cp.nBins = nB; cp.nonCoh = 1; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
+            cp.W = h->W.p; cp.colTw = h->twCols.p; cp.nBins = nB; cp.nonCoh = 1; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
             cp.partMax = h->partMax.p; cp.partIdx = h->partIdx.p; cp.magOut = magOut;
             GC_CUDA(h, launch_inv_cols(Lb, cp, st)); ++launches;
             return GC_OK;
@@ -1137,7 +1151,7 @@ static int acquire_varc(gc_handle* h, long long winStart, long long longLen, int
             ip.nPrnChunk = nc; ip.prnSlot0 = s0; ip.prnList = h->prnList.p;
             GC_CUDA(h, launch_inv_rows(Lc, ip, st)); ++launches;
             InvColsParams cp{};
-            cp.W = h->W.p; cp.nBins = nBins; cp.nonCoh = nRep; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
+            cp.W = h->W.p; cp.colTw = h->twCols.p; cp.nBins = nBins; cp.nonCoh = nRep; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
             cp.partMax = h->partMax.p; cp.partIdx = h->partIdx.p;
             if (nRep == 2) { cp.weighted = 1; cp.w0 = 3.3166247903554f; cp.w1 = 5.385164807134504f; cp.wScale = 1.0f / 6.324555320336759f; }
             GC_CUDA(h, launch_inv_cols(Lc, cp, st)); ++launches;
@@ -1243,6 +1257,23 @@ static int acquire_varc(gc_handle* h, long long winStart, long long longLen, int
     return GC_OK;
 }
 
+// device-side timings of the last variant A enqueue from its events (after the stream has been synchronised)
+static void resolve_acq_stats(gc_handle* h)
+{
+    if (!h->statsPending) return;
+    h->statsPending = false;
+    const AcqEnq& info = h->pendingInfo;
+    float rowsMs = 0, colsMs = 0, fwdMs = 0, fineMs = 0, coarseMs = 0, ms = 0;
+    for (auto& pr : info.rowEv) if (cudaEventElapsedTime(&ms, h->ev[pr.first], h->ev[pr.second]) == cudaSuccess) rowsMs += ms;
+    for (auto& pr : info.colEv) if (cudaEventElapsedTime(&ms, h->ev[pr.first], h->ev[pr.second]) == cudaSuccess) colsMs += ms;
+    for (auto& pr : info.fwdEv) if (cudaEventElapsedTime(&ms, h->ev[pr.first], h->ev[pr.second]) == cudaSuccess) fwdMs += ms;
+    if (info.fa >= 0 && cudaEventElapsedTime(&ms, h->ev[info.fa], h->ev[info.fb]) == cudaSuccess) fineMs = ms;
+    if (info.e0 >= 0 && cudaEventElapsedTime(&ms, h->ev[info.e0], h->ev[info.e1]) == cudaSuccess) coarseMs = ms;
+    cudaGetLastError();
+    h->stats.acq_fwd_ms = fwdMs; h->stats.acq_corr_ms = coarseMs - fwdMs; h->stats.acq_fine_ms = fineMs; h->stats.acq_total_ms = coarseMs + fineMs;
+    h->stats.corr_rows_ms = rowsMs; h->stats.corr_cols_ms = colsMs; h->stats.corr_row_launches = info.nRowLaunches; h->stats.acq_launches = info.launches;
+}
+
 // Variant A on a fused plan with the split correlation stage - the default path of every variant A signal (GPS L1CA, GLONASS,
 // B3I, E1, L5C, E5a, E5b, B2a).  All host tables and buffer reservations first, then ONE enqueue of the kernels and the small
 // result copies: issued directly the first time a call comes in, captured into a CUDA graph the second time the same call
@@ -1252,7 +1283,7 @@ static int acquire_varc(gc_handle* h, long long winStart, long long longLen, int
 static int acquire_plain(gc_handle* h, long long winStart, int32_t nSv, const int32_t* svList, const std::vector<int>& order,
                          const std::vector<int>& groupStart /* nGroups + 1 entries */, const std::vector<int>& slotGroup,
                          double* carrFreq, double* codePhase, double* peakMetric, int32_t* coarseBin, int32_t* coarseCodePhase,
-                         double* dOut)
+                         double* dOut, bool async)
 {
     HostLaps laps("gc_acquire");
     const gc_config& c = h->cfg;
@@ -1391,7 +1422,7 @@ static int acquire_plain(gc_handle* h, long long winStart, int32_t nSv, const in
             GC_CUDA(h, launch_inv_rows(L, ip, st)); ++q.launches; ++q.nRowLaunches;
             if (perChunkEvents) { const int m = mark(); q.rowEv.push_back({prev, m}); prev = m; }
             InvColsParams cp{};
-            cp.W = h->W.p; cp.nBins = nBins; cp.nonCoh = nonCoh * h->nRep; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
+            cp.W = h->W.p; cp.colTw = h->twCols.p; cp.nBins = nBins; cp.nonCoh = nonCoh * h->nRep; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
             cp.partMax = h->partMax.p; cp.partIdx = h->partIdx.p;
             GC_CUDA(h, launch_inv_cols(L, cp, st)); ++q.launches;
             if (perChunkEvents) { const int m = mark(); q.colEv.push_back({prev, m}); prev = m; }
@@ -1483,19 +1514,15 @@ static int acquire_plain(gc_handle* h, long long winStart, int32_t nSv, const in
         ++g.hits;
     }
     laps.lap(mode == 2 ? "graph launch" : "direct enqueue");
+    h->pendingInfo = info;
+    h->statsPending = true;
+    if (dOut && async) {                                      // gc_acquire_device_async: the caller orders its work behind the handle's stream
+        h->stats.n_acquired = -1;
+        return GC_OK;
+    }
     GC_CUDA(h, cudaStreamSynchronize(st));
     laps.lap("synchronize");
-
-    // ---- timings and the host side of the results ---------------------------------------------------------------------------------
-    float rowsMs = 0, colsMs = 0, fwdMs = 0, fineMs = 0, coarseMs = 0, ms = 0;
-    for (auto& pr : info.rowEv) if (cudaEventElapsedTime(&ms, h->ev[pr.first], h->ev[pr.second]) == cudaSuccess) rowsMs += ms;
-    for (auto& pr : info.colEv) if (cudaEventElapsedTime(&ms, h->ev[pr.first], h->ev[pr.second]) == cudaSuccess) colsMs += ms;
-    for (auto& pr : info.fwdEv) if (cudaEventElapsedTime(&ms, h->ev[pr.first], h->ev[pr.second]) == cudaSuccess) fwdMs += ms;
-    if (info.fa >= 0 && cudaEventElapsedTime(&ms, h->ev[info.fa], h->ev[info.fb]) == cudaSuccess) fineMs = ms;
-    if (cudaEventElapsedTime(&ms, h->ev[info.e0], h->ev[info.e1]) == cudaSuccess) coarseMs = ms;
-    cudaGetLastError();
-    h->stats.acq_fwd_ms = fwdMs; h->stats.acq_corr_ms = coarseMs - fwdMs; h->stats.acq_fine_ms = fineMs; h->stats.acq_total_ms = coarseMs + fineMs;
-    h->stats.corr_rows_ms = rowsMs; h->stats.corr_cols_ms = colsMs; h->stats.corr_row_launches = info.nRowLaunches; h->stats.acq_launches = info.launches;
+    resolve_acq_stats(h);
     if (dOut) {
         h->stats.n_acquired = -1;                             // (in the device buffer: carrFreq != 0)
         return GC_OK;
@@ -1529,7 +1556,7 @@ static int acquire_plain(gc_handle* h, long long winStart, int32_t nSv, const in
 static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int32_t* svList,
                         double* carrFreq, double* codePhase, double* peakMetric,
                         int32_t* coarseBin, int32_t* coarseCodePhase, long long longLen = 0 /* length(longSignal), B1C only */,
-                        double* dOut = nullptr /* gc_acquire_device: [4][resultLen] on the device */)
+                        double* dOut = nullptr /* gc_acquire_device: [4][resultLen] on the device */, bool async = false)
 {
     const gc_config& c = h->cfg;
     const int N = h->N, L = h->L, nBins = h->nBins, nonCoh = h->nonCoh, nKm = nBins * nonCoh;
@@ -1616,7 +1643,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
     const bool plain = h->fused && !h->cluster && !h->queue && !h->overlap && !getenv("GC_ACQ_CHUNK_BINS") && !getenv("GC_ACQ_CHUNK_PRNS") &&
                        !getenv("GC_ROWS_VARIANT") && !getenv("GC_ACQ_LEGACY") && (double)nGroups * nKm * L * sizeof(float2) <= kWorkBytes;
     if (plain)
-        return acquire_plain(h, winStart, nSv, svList, order, groupStart, slotGroup, carrFreq, codePhase, peakMetric, coarseBin, coarseCodePhase, dOut);
+        return acquire_plain(h, winStart, nSv, svList, order, groupStart, slotGroup, carrFreq, codePhase, peakMetric, coarseBin, coarseCodePhase, dOut, async);
     GC_CUDA(h, h->X.reserve((size_t)(h->cluster ? nGroups : 1) * nKm * L));
     GC_CUDA(h, h->dphi.reserve((size_t)nGroups * nBins));
     std::vector<std::vector<double>> coarseFreqOf(nSv);   // per list slot: the bin frequencies it was searched on
@@ -1753,7 +1780,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
                 GC_CUDA(h, launch_inv_rows(L, ip, st)); ++launches;
                 const int b = mark();
                 InvColsParams cp{};
-                cp.W = Wc; cp.nBins = nb; cp.bin0 = b0; cp.nBinsTotal = nBins; cp.nonCoh = nonCoh * h->nRep; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
+                cp.W = Wc; cp.colTw = h->twCols.p; cp.nBins = nb; cp.bin0 = b0; cp.nBinsTotal = nBins; cp.nonCoh = nonCoh * h->nRep; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
                 cp.partMax = h->partMax.p; cp.partIdx = h->partIdx.p;
                 if (overlap) {
                     GC_CUDA(h, cudaEventRecord(h->evRows[ci & 1], st));
@@ -1965,6 +1992,14 @@ int gc_acquire_device(gc_handle* h, int32_t nSv, const int32_t* svList, double* 
     if (!dResults) return fail(h, GC_ERR_ARG, "gc_acquire_device: null result buffer");
     std::vector<double> cf(h->resultLen), cp(h->resultLen), pm(h->resultLen);
     return acquire_impl(h, skip_samples(h), nSv, svList, cf.data(), cp.data(), pm.data(), nullptr, nullptr, 0, dResults);
+}
+
+int gc_acquire_device_async(gc_handle* h, int32_t nSv, const int32_t* svList, double* dResults)
+{
+    if (!h) return GC_ERR_ARG;
+    if (!dResults) return fail(h, GC_ERR_ARG, "gc_acquire_device_async: null result buffer");
+    std::vector<double> cf(h->resultLen), cp(h->resultLen), pm(h->resultLen);
+    return acquire_impl(h, skip_samples(h), nSv, svList, cf.data(), cp.data(), pm.data(), nullptr, nullptr, 0, dResults, true);
 }
 
 int gc_acquire_host(gc_handle* h, const int8_t* iq, size_t nSamples, int32_t nSv, const int32_t* svList,
@@ -2358,6 +2393,12 @@ void* gc_get_stream(const gc_handle* h) { return h ? (void*)h->stream : nullptr;
 int gc_get_stats(const gc_handle* h, gc_stats* out)
 {
     if (!h || !out) return GC_ERR_ARG;
+    if (h->statsPending) {                                    // an asynchronous acquisition: its events are read once its stream has drained
+        gc_handle* hm = const_cast<gc_handle*>(h);
+        cudaSetDevice(hm->cfg.device);
+        cudaStreamSynchronize(hm->stream);
+        resolve_acq_stats(hm);
+    }
     *out = h->stats;
     return GC_OK;
 }

@@ -58,7 +58,7 @@ EXPORTS = ["gc_abi_version", "gc_build_arch", "gc_acq_result_len", "gc_create", 
            "gc_last_error", "gc_set_code", "gc_set_record_host", "gc_set_record_device", "gc_acquire",
            "gc_acquire_host", "gc_track_nfields", "gc_track", "gc_track_file", "gc_get_stats", "gc_get_stream",
            "gc_set_param", "gc_get_cl_code_phase", "gc_set_cl_code_phase", "gc_nav_sync", "gc_acquire_track",
-           "gc_acquire_device", "gc_get_cno_pld", "gc_code_entries", "gc_generate_code", "gc_generate_code_device", "gc_multi_create", "gc_multi_destroy", "gc_multi_last_error", "gc_multi_n_gpus",
+           "gc_acquire_device", "gc_acquire_device_async", "gc_get_cno_pld", "gc_code_entries", "gc_generate_code", "gc_generate_code_device", "gc_multi_create", "gc_multi_destroy", "gc_multi_last_error", "gc_multi_n_gpus",
            "gc_multi_handle", "gc_multi_set_code", "gc_multi_set_param", "gc_multi_set_cl_code_phase",
            "gc_multi_get_cl_code_phase", "gc_multi_set_record_host", "gc_multi_acquire", "gc_multi_acquire_host",
            "gc_multi_track", "gc_multi_track_file", "gc_multi_get_times"]
@@ -102,6 +102,7 @@ def load_lib():
     lib.gc_get_stream.argtypes = [vp]
     lib.gc_get_stream.restype = C.c_void_p
     lib.gc_acquire_device.argtypes = [vp, C.c_int32, i32p, vp]
+    lib.gc_acquire_device_async.argtypes = [vp, C.c_int32, i32p, vp]
     lib.gc_get_cno_pld.argtypes = [vp, C.c_int32, C.c_int32, dp]
     lib.gc_code_entries.argtypes = [C.c_int32, C.c_int32]
     lib.gc_generate_code.argtypes = [C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32]
@@ -265,6 +266,16 @@ class Engine:
         n = self.lib.gc_acq_result_len(signal_id(self.settings))
         assert d_results.is_cuda and d_results.is_contiguous() and d_results.numel() == 4 * n and d_results.element_size() == 8
         self._check(self.lib.gc_acquire_device(self._h, sv.size, _ip(sv), d_results.data_ptr()), "gc_acquire_device")
+        return d_results
+
+    def acquire_device_async(self, sv_list, d_results):
+        """gc_acquire_device_async: as ``acquire_device`` but the call returns once the search is enqueued; ``d_results`` is
+        complete in stream order on the engine's stream (``stream_ptr``), so a collective enqueued behind that stream follows
+        without a host round trip."""
+        sv = np.asarray(list(sv_list), dtype=np.int32)
+        n = self.lib.gc_acq_result_len(signal_id(self.settings))
+        assert d_results.is_cuda and d_results.is_contiguous() and d_results.numel() == 4 * n and d_results.element_size() == 8
+        self._check(self.lib.gc_acquire_device_async(self._h, sv.size, _ip(sv), d_results.data_ptr()), "gc_acquire_device_async")
         return d_results
 
     # ---- tracking -----------------------------------------------------------------------

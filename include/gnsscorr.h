@@ -224,6 +224,12 @@ int gc_acquire(gc_handle* h, int32_t nSv, const int32_t* svList,
  * [peakMetric | codePhase | carrFreq | coarseBin], each indexed like the host arrays of gc_acquire; written on the handle's
  * stream and complete when the call returns.  Bit-identical to what gc_acquire returns on the host (same expressions). */
 int gc_acquire_device(gc_handle* h, int32_t nSv, const int32_t* svList, double* dResults);
+/* The same without the final synchronisation: returns as soon as the search is enqueued (one cudaGraphLaunch once the call has
+ * been seen twice); dResults is complete in STREAM ORDER on gc_get_stream(h), so a collective enqueued behind that stream (or a
+ * stream that waits on it) needs no host round trip between the search and the gather.  svList is copied before the call
+ * returns.  gc_get_stats synchronises the stream when it is asked for the timings of such a call.  Signals whose acquisition
+ * finishes on the host (variants B and C: BDS B1I, GPS L2C, BDS B1C) behave like gc_acquire_device. */
+int gc_acquire_device_async(gc_handle* h, int32_t nSv, const int32_t* svList, double* dResults);
 
 /* Same, but with longSignal supplied from HOST memory in the record's own sample format - int8 I,Q pairs for
  * fileType 2 / 'schar' (what the MEX gateway passes after checking the complex-double longSignal is integer valued),

@@ -69,6 +69,46 @@ def test_acquire_device_equals_host_results_variant_a():
     geng.close()
 
 
+def test_graph_replay_and_async_results_equal_the_first_call():
+    """The variant A enqueue runs directly on the first call, is captured into a CUDA graph on the second identical call and
+    replayed from the third; gc_acquire_device_async returns before the search has finished (results in stream order).  Every
+    form must return the first call's numbers bit for bit, also after a different SV list was searched in between, and the stats
+    must keep reporting kernel times."""
+    import torch
+    sc, s, sv, raw = _l1ca_case()
+    eng = Engine(s)
+    eng.set_record(raw)
+    first = eng.acquire(sv)
+    for _ in range(4):                                        # capture, then replays
+        again = eng.acquire(sv)
+        for k in ("peakMetric", "codePhase", "carrFreq", "coarseBin", "coarseCodePhase"):
+            assert np.array_equal(again[k], first[k]), k
+        st = eng.stats()
+        assert st["acq_total_ms"] > 0 and st["corr_rows_ms"] > 0 and st["acq_launches"] >= 9
+    other = eng.acquire(sv[:4])                               # another list resets the cached graph ...
+    idx = np.array(sv[:4]) - 1
+    assert np.array_equal(other["peakMetric"][idx], first["peakMetric"][idx]) and np.count_nonzero(other["peakMetric"]) == 4
+    n = 32
+    buf = torch.full((4 * n,), -1.0, dtype=torch.float64, device="cuda")
+    ext = torch.cuda.ExternalStream(eng.stream_ptr)
+    for _ in range(4):                                        # ... and the asynchronous form goes direct -> captured -> replayed too
+        buf.fill_(-1.0)
+        torch.cuda.synchronize()
+        eng.acquire_device_async(sv, buf)
+        with torch.cuda.stream(ext):
+            a = buf.clone()                                   # ordered behind the search on the engine's stream
+        ext.synchronize()
+        a = a.cpu().numpy()
+        assert np.array_equal(a[:n], first["peakMetric"]) and np.array_equal(a[n:2 * n], first["codePhase"])
+        assert np.array_equal(a[2 * n:3 * n], first["carrFreq"]) and np.array_equal(a[3 * n:].astype(np.int32), first["coarseBin"])
+        assert eng.stats()["acq_total_ms"] > 0
+    host = eng.acquire(sv, host_iq=raw[: 2 * 16368 * 46])     # gc_acquire_host: copy and search without a synchronisation between
+    host2 = eng.acquire(sv, host_iq=raw[: 2 * 16368 * 46])
+    for k in ("peakMetric", "codePhase", "carrFreq"):
+        assert np.array_equal(host[k], first[k]) and np.array_equal(host2[k], first[k]), k
+    eng.close()
+
+
 def test_acquire_device_equals_host_results_other_variants():
     """No fine stage (GAL E5b) and the variants that finish on the host (BDS B1I)."""
     from cu_sdr_collection_b200.codes import icd_codes

@@ -227,6 +227,44 @@ def test_golden_fixture_through_cuda():
     eng.close()
 
 
+@pytest.mark.parametrize("signal", __import__("golden_cases").SIGNALS)
+def test_golden_signal_fixture_through_cuda(signal, tmp_path):
+    """The committed per-folder fixtures (tests/golden/<signal>_case.npz, frozen oracle outputs) against the CUDA path through
+    the reference-facing wrappers: acquisition indices exact and peakMetric to 1e-6 (variant B: 1e-5), tracking absoluteSample
+    exact, correlator sums to 1e-6 of |P|, NCO rows to 1e-4 Hz / 1e-6 chips."""
+    import golden_cases as G
+    case = G.build(signal)
+    g = np.load(G.fixture_path(signal))
+    assert bytes(g["sha256"]).hex() == case.digest()
+    s = case.s
+    eng = Engine(s)
+    got = acquisition(case.long_signal, s, engine=eng, verbose=False)
+    n = min(got["carrFreq"].size, g["acq_carrFreq"].size)
+    assert np.array_equal(got["carrFreq"][:n], g["acq_carrFreq"][:n]) and np.array_equal(got["codePhase"][:n], g["acq_codePhase"][:n])
+    nz = g["acq_peakMetric"][:n] != 0
+    rel = np.abs(got["peakMetric"][:n][nz] - g["acq_peakMetric"][:n][nz]) / g["acq_peakMetric"][:n][nz]
+    assert rel.max() < (VARB_METRIC_TOL if signal in ("BDS_B1I", "GPS_L2C") else METRIC_TOL), rel.max()
+    if case.ch is not None:
+        path = tmp_path / "rec.bin"
+        case.raw_trk.tofile(path)
+        with open(path, "rb") as fid:
+            tr, _ = tracking(fid, case.ch, s, engine=eng)
+        live = [i for i in range(len(tr)) if f"trk{i}_I_P" in g.files]
+        assert live and all(tr[i]["status"] == "T" and tr[i]["epochsDone"] == case.nE for i in live)
+        for i in live:
+            ref = {k: g[f"trk{i}_{k}"] for k in G.TRK_KEYS}
+            if signal == "GPS_L2C":                           # fractional sample positions (GPS_L2C tracking.m:223)
+                assert np.max(np.abs(tr[i]["absoluteSample"] - ref["absoluteSample"])) < 1e-5
+            else:
+                assert np.array_equal(tr[i]["absoluteSample"], ref["absoluteSample"])
+            scale = np.hypot(ref["I_P"], ref["Q_P"])
+            for name in ("I_P", "Q_P", "I_E", "I_L", "Q_E", "Q_L"):
+                assert np.max(np.abs(tr[i][name] - ref[name]) / scale) < IQ_TOL, (signal, i, name)
+            assert np.max(np.abs(tr[i]["carrFreq"] - ref["carrFreq"])) < 1e-4 and np.max(np.abs(tr[i]["codeFreq"] - ref["codeFreq"])) < 1e-4
+            assert np.max(np.abs(tr[i]["remCodePhase"] - ref["remCodePhase"])) < 1e-6
+    eng.close()
+
+
 @pytest.mark.parametrize("cluster", [1, 2, 4, 8])
 def test_tracking_cluster_variants_agree(cluster, monkeypatch):
     """A channel spread over a thread-block cluster of 1/2/4/8 CTAs gives the same results."""
