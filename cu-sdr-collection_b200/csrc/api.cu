@@ -879,20 +879,31 @@ static int acquire_varb(gc_handle* h, long long winStart, int32_t nSv, const int
         int chunk = (int)std::max<long long>(1, (long long)(kWorkBytes / ((double)nRows * Lb * sizeof(float2))));
         chunk = std::min(chunk, (int)nSv);
         GC_CUDA(h, h->W.reserve(std::max((size_t)chunk * nRows, (size_t)nSv) * Lb));   // (the winner pass holds one row per SV)
-        auto correlate = [&](int s0, int nc, int nB, const int2* bm, int bmStride, float* magOut) -> int {
+        auto correlate = [&](int s0, int nc, int nB, const int2* bm, int bmStride, float* magOut, int b0 = 0, int nBTotal = 0) -> int {
             RowsParams ip{};
             ip.X = h->X.p; ip.Cc = h->Cc.p; ip.W = h->W.p; ip.tw = h->twFused.p;
-            ip.nonCoh = 1; ip.nBins = nB; ip.nRep = 1; ip.repStride = 1;
+            ip.nonCoh = 1; ip.nBins = nB; ip.bin0 = b0; ip.nRep = 1; ip.repStride = 1;
             ip.prnPerCta = 1; ip.mPerCta = 1; ip.binPerCta = 5; ip.binMap = bm; ip.binMapSlotStride = bmStride;
             if (nB == 1) { ip.prnPerCta = 5; ip.binPerCta = 1; }       // one row per SV: fill the CTA with SVs instead of bins
             ip.nPrnChunk = nc; ip.prnSlot0 = s0; ip.prnList = h->prnList.p;
             GC_CUDA(h, launch_inv_rows(Lb, ip, st)); ++launches;
             InvColsParams cp{};
-            cp.W = h->W.p; cp.colTw = h->twCols.p; cp.nBins = nB; cp.nonCoh = 1; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
+            cp.W = h->W.p; cp.colTw = h->twCols.p; cp.nBins = nB; cp.bin0 = b0; cp.nBinsTotal = nBTotal; cp.nonCoh = 1; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
             cp.partMax = h->partMax.p; cp.partIdx = h->partIdx.p; cp.magOut = magOut;
             GC_CUDA(h, launch_inv_cols(Lb, cp, st)); ++launches;
             return GC_OK;
         };
+        // GC_BIG_L2_MB = n: rows of one SV in groups whose work buffer is about n MB, so that the column pass reads what the row
+        // pass wrote from the 126 MB L2 instead of HBM (every element of W is written once and read once here)
+        const int l2mb = getenv("GC_BIG_L2_MB") ? atoi(getenv("GC_BIG_L2_MB")) : 0;
+        if (l2mb > 0) {
+            const int binChunk = std::max(5, (int)((double)l2mb * 1e6 / ((double)Lb * sizeof(float2))) / 5 * 5);
+            for (int s0 = 0; s0 < nSv; ++s0)
+                for (int b0 = 0; b0 < nRows; b0 += binChunk) {
+                    const int rc = correlate(s0, 1, std::min(binChunk, nRows - b0), h->vbMap.p, 0, nullptr, b0, nRows);
+                    if (rc != GC_OK) return rc;
+                }
+        } else
         for (int s0 = 0; s0 < nSv; s0 += chunk) {
             const int rc = correlate(s0, std::min(chunk, (int)nSv - s0), nRows, h->vbMap.p, 0, nullptr);
             if (rc != GC_OK) return rc;
@@ -1142,16 +1153,20 @@ static int acquire_varc(gc_handle* h, long long winStart, long long longLen, int
         int chunk = (int)std::max<long long>(1, (long long)(kWorkBytes / ((double)nBins * nRep * Lc * sizeof(float2))));
         chunk = std::min(chunk, (int)nSv);
         GC_CUDA(h, h->W.reserve((size_t)chunk * nBins * nRep * Lc));
-        for (int s0 = 0; s0 < nSv; s0 += chunk) {
-            const int nc = std::min(chunk, (int)nSv - s0);
+        const int l2mb = getenv("GC_BIG_L2_MB") ? atoi(getenv("GC_BIG_L2_MB")) : 0;     // (see acquire_varb)
+        const int binChunk = l2mb > 0 ? std::max(5, (int)((double)l2mb * 1e6 / ((double)nRep * Lc * sizeof(float2))) / 5 * 5) : nBins;
+        if (l2mb > 0) chunk = 1;
+        for (int s0 = 0; s0 < nSv; s0 += chunk)
+        for (int b0 = 0; b0 < nBins; b0 += binChunk) {
+            const int nc = std::min(chunk, (int)nSv - s0), nb = std::min(binChunk, nBins - b0);
             RowsParams ip{};
             ip.X = h->X.p; ip.Cc = h->Cc.p; ip.W = h->W.p; ip.tw = h->twFused.p;
-            ip.nonCoh = 1; ip.nBins = nBins; ip.nRep = nRep; ip.repStride = 1;
+            ip.nonCoh = 1; ip.nBins = nb; ip.bin0 = b0; ip.nRep = nRep; ip.repStride = 1;
             ip.prnPerCta = 1; ip.mPerCta = 1; ip.binPerCta = 5; ip.binMap = h->vbMap.p;
             ip.nPrnChunk = nc; ip.prnSlot0 = s0; ip.prnList = h->prnList.p;
             GC_CUDA(h, launch_inv_rows(Lc, ip, st)); ++launches;
             InvColsParams cp{};
-            cp.W = h->W.p; cp.colTw = h->twCols.p; cp.nBins = nBins; cp.nonCoh = nRep; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
+            cp.W = h->W.p; cp.colTw = h->twCols.p; cp.nBins = nb; cp.bin0 = b0; cp.nBinsTotal = nBins; cp.nonCoh = nRep; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
             cp.partMax = h->partMax.p; cp.partIdx = h->partIdx.p;
             if (nRep == 2) { cp.weighted = 1; cp.w0 = 3.3166247903554f; cp.w1 = 5.385164807134504f; cp.wScale = 1.0f / 6.324555320336759f; }
             GC_CUDA(h, launch_inv_cols(Lc, cp, st)); ++launches;
