@@ -138,7 +138,7 @@ def build(signal: str) -> Case:
                 acq["codePhase"][sat.prn - 1] = int(round(start)) % N + 1
                 acq["peakMetric"][sat.prn - 1] = 10.0 - i
             ch = preRun(acq, s)
-        return Case(signal=signal, s=s, so=so, sv=sv, raw_acq=raw_acq, raw_trk=raw, long_signal=O.read_acq_signal_fam5(raw_acq, so),
+        return Case(signal=signal, s=s, so=so, sv=sv, codes=codes, raw_acq=raw_acq, raw_trk=raw, long_signal=O.read_acq_signal_fam5(raw_acq, so),
                     acq_oracle=lambda: O.acquisition_fam5(O.read_acq_signal_fam5(raw_acq, so), so, codes, workers=nw), ch=ch,
                     trk_oracle=lambda: O.tracking_fam5(raw, O.preRun_fam5(acq, so), so, codes), nE=nE)
     if signal in ("BDS_B1I", "GPS_L2C"):
@@ -166,7 +166,7 @@ def build(signal: str) -> Case:
             acq_oracle = lambda: O.acquisition_l2c(long_signal, so, codes, workers=nw)
             ch = _handoff(sc, s, N, 20460, 1.023e6, 12.5, base=0)
             trk_oracle = lambda: O.tracking_l2c(raw, ch, so, codes)
-        return Case(signal=signal, s=s, so=so, sv=sv, raw_acq=raw_acq, raw_trk=raw, long_signal=long_signal, acq_oracle=acq_oracle, ch=ch,
+        return Case(signal=signal, s=s, so=so, sv=sv, codes=codes, raw_acq=raw_acq, raw_trk=raw, long_signal=long_signal, acq_oracle=acq_oracle, ch=ch,
                     trk_oracle=trk_oracle, nE=nE)
     if signal == "BDS_B1C":
         fs, nE = 4.092e6, 12
@@ -188,7 +188,7 @@ def build(signal: str) -> Case:
             acq["codePhase"][sat.prn - 1] = int(round(start)) % N + 1
             acq["peakMetric"][sat.prn - 1] = 20.0 - i
         ch = preRun(acq, s)
-        return Case(signal=signal, s=s, so=so, sv=sv, raw_acq=raw_acq, raw_trk=raw, long_signal=long_signal,
+        return Case(signal=signal, s=s, so=so, sv=sv, codes=codes, raw_acq=raw_acq, raw_trk=raw, long_signal=long_signal,
                     acq_oracle=lambda: O.acquisition_b1c(long_signal, so, codes, workers=nw), ch=ch,
                     trk_oracle=lambda: O.tracking_b1c_nb(raw, ch, so, codes), nE=nE)
     raise ValueError(signal)

@@ -264,3 +264,37 @@ def oracle_signal_codes(signal: str, prns, cl: bool = False, boc61: bool = False
         else:
             raise ValueError(signal)
     return out
+
+
+def c_acquisition_variant(case) -> dict:
+    """The SECOND witness (oracle/gnss_oracle_acq2.c, written from the reference's .m files) of the acquisition variants the first C
+    oracle does not cover, run on a tests/golden_cases.py case: GPS L5C / GAL E5a / GAL E5b / BDS B2a (two-replica variant A),
+    BDS B1I / GPS L2C (variant B), BDS B1C (variant C).  Returns the acqResults vectors in the NumPy oracle's layout."""
+    s, sig, sv, codes = case.so, case.signal, list(case.sv), case.codes
+    cs = orc_settings(s)
+    prn = np.asarray(sv, dtype=np.int32)
+    raw = np.ascontiguousarray(case.raw_acq, dtype=np.int8)
+    n_avail = raw.size // 2
+
+    def stack(comp, n):
+        return np.ascontiguousarray(np.stack([np.asarray(codes[p][comp], dtype=np.int8)[:n] for p in sv]))
+    nres = {"GPS_L5C": 32, "GAL_E5a": 50, "GAL_E5b": 50, "BDS_B2a": max(sv), "BDS_B1I": 58, "GPS_L2C": 32, "BDS_B1C": max(sv)}[sig]
+    cf, cp, pm = np.zeros(nres), np.zeros(nres), np.zeros(nres)
+    cb, ccp = np.zeros(nres, dtype=np.int32), np.zeros(nres, dtype=np.int32)
+    out = (P(cf), P(cp), P(pm), P(cb), P(ccp))
+    if sig in ("GPS_L5C", "GAL_E5a", "GAL_E5b", "BDS_B2a"):
+        d, p = stack(0, 10230), stack(1, 10230)
+        sec = np.ascontiguousarray(np.stack([np.asarray(codes[q][2], dtype=np.int8)[:100] for q in sv]))
+        rc = orc().orc_acquisition_fam5(P(raw), C.c_size_t(n_avail), C.byref(cs), {"GPS_L5C": 4, "GAL_E5a": 5, "GAL_E5b": 6, "BDS_B2a": 7}[sig],
+                                        P(prn), int(prn.size), P(d), P(p), P(sec), int(nres), *out)
+    elif sig in ("BDS_B1I", "GPS_L2C"):
+        l2c = sig == "GPS_L2C"
+        c0 = stack(0, 20460 if l2c else 2046)
+        step = float(s.acqStep) if l2c else float(getattr(s, "stepSize", 0) or 0)
+        rc = orc().orc_acquisition_varb(P(raw), C.c_size_t(n_avail), C.byref(cs), int(l2c), C.c_double(step), P(prn), int(prn.size), P(c0), *out)
+    else:
+        d, p = stack(0, 20460), stack(1, 20460)
+        rc = orc().orc_acquisition_b1c(P(raw), C.c_size_t(n_avail), C.byref(cs), C.c_double(float(s.acqStep)), int(s.acqCohT), int(s.pilotACQflag),
+                                       P(prn), int(prn.size), P(d), P(p), int(nres), *out)
+    assert rc == 0, rc
+    return dict(carrFreq=cf, codePhase=cp, peakMetric=pm, coarseBin=cb, coarseCodePhase=ccp)

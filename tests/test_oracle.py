@@ -596,3 +596,25 @@ def test_golden_signal_fixture_vs_oracle(signal):
         else:
             scale = np.maximum(np.hypot(g[k.rsplit("_", 2)[0] + "_I_P"], g[k.rsplit("_", 2)[0] + "_Q_P"]), 1.0) if k[-3:-1] in ("_I", "_Q") else 1.0
             assert np.all(np.abs(out[k] - g[k]) <= 1e-9 * scale + 1e-9 * np.abs(g[k])), k
+
+
+@pytest.mark.parametrize("signal", ["GPS_L5C", "GAL_E5a", "GAL_E5b", "BDS_B2a", "BDS_B1I", "GPS_L2C", "BDS_B1C"])
+def test_two_restatements_agree_on_the_acquisition_variants(signal):
+    """Two independent witnesses per folder: the NumPy restatement (oracle/np_oracle.py) and the C one written from the reference's
+    .m files (oracle/gnss_oracle_acq2.c: own sampled tables, own FFT, own search loops) on the seeded record of the folder's golden
+    case - acquired set, code phase, coarse bin and carrFreq exactly, peakMetric to 1e-8.  With the first C oracle (GPS L1CA,
+    GLONASS, BDS B3I, GAL E1) every one of the twelve folders now has both."""
+    import golden_cases as G
+    from helpers import c_acquisition_variant
+    case = G.build(signal)
+    a = case.acq_oracle()
+    c = c_acquisition_variant(case)
+    n = c["carrFreq"].size
+    assert a["carrFreq"].size >= n or signal in ("BDS_B2a", "BDS_B1C")
+    m = min(n, a["carrFreq"].size)
+    assert np.array_equal(a["carrFreq"][:m], c["carrFreq"][:m]), (a["carrFreq"][:m], c["carrFreq"][:m])
+    assert np.array_equal(a["codePhase"][:m], c["codePhase"][:m])
+    idx = np.array(case.sv) - 1
+    assert np.array_equal(np.asarray(a["coarseBin"])[idx], c["coarseBin"][idx])
+    assert np.allclose(a["peakMetric"][idx], c["peakMetric"][idx], rtol=1e-8, atol=0), (a["peakMetric"][idx], c["peakMetric"][idx])
+    assert np.count_nonzero(c["carrFreq"]) >= 2
