@@ -267,7 +267,7 @@ def oracle_signal_codes(signal: str, prns, cl: bool = False, boc61: bool = False
 
 
 def c_acquisition_variant(case) -> dict:
-    """The SECOND witness (oracle/gnss_oracle_acq2.c, written from the reference's .m files) of the acquisition variants the first C
+    """The SECOND witness (oracle/gnss_oracle_ext.c, written from the reference's .m files) of the acquisition variants the first C
     oracle does not cover, run on a tests/golden_cases.py case: GPS L5C / GAL E5a / GAL E5b / BDS B2a (two-replica variant A),
     BDS B1I / GPS L2C (variant B), BDS B1C (variant C).  Returns the acqResults vectors in the NumPy oracle's layout."""
     s, sig, sv, codes = case.so, case.signal, list(case.sv), case.codes
@@ -298,3 +298,101 @@ def c_acquisition_variant(case) -> dict:
                                        P(prn), int(prn.size), P(d), P(p), int(nres), *out)
     assert rc == 0, rc
     return dict(carrFreq=cf, codePhase=cp, peakMetric=pm, coarseBin=cb, coarseCodePhase=ccp)
+
+
+def c_tracking_variant(case) -> list:
+    """The SECOND witness (oracle/gnss_oracle_ext.c) of the trackers the first C oracle does not cover, on a golden case with a
+    channel hand-off: GPS L5C / GAL E5a / GAL E5b / BDS B2a (quadrature pilot, carrier-aided code NCO) and BDS B1I.  Returns one
+    dict of rows per channel (None for a channel that is off)."""
+    s, sig, codes, ch = case.so, case.signal, case.codes, case.ch
+    cs = orc_settings(s)
+    n_ch = len(ch)
+    prn = np.asarray([c["PRN"] for c in ch], dtype=np.int32)
+    af = np.asarray([c["acquiredFreq"] for c in ch], dtype=np.float64)
+    cp = np.asarray([float(c["codePhase"]) for c in ch], dtype=np.float64)
+    raw = np.ascontiguousarray(case.raw_trk, dtype=np.int8)
+    n_e = case.nE
+    L = int(s.codeLength)
+    live = [p for p in prn if p]
+    data = np.zeros((n_ch, L), dtype=np.int8)
+    pilot = np.zeros((n_ch, L), dtype=np.int8)
+    for i, p in enumerate(prn):
+        if p:
+            data[i] = np.asarray(codes[int(p)][0], dtype=np.int8)[:L]
+            if sig != "BDS_B1I":
+                pilot[i] = np.asarray(codes[int(p)][1], dtype=np.int8)[:L]
+    quad = int(sig != "BDS_B1I" and int(getattr(s, "pilotTRKflag", 0)) == 1)
+    cf0 = None if sig == "BDS_B1I" else np.asarray([c.get("codeFreq", s.codeFreqBasis) for c in ch], dtype=np.float64)
+    out = np.zeros((n_ch, 17, n_e))
+    done = np.zeros(n_ch, dtype=np.int32)
+    rc = orc().orc_tracking_codes(P(raw), C.c_size_t(raw.size), C.byref(cs), n_ch, P(prn), P(af), P(cp), P(cf0) if cf0 is not None else None,
+                                  P(data), P(pilot) if quad else None, quad, n_e, P(out), P(done))
+    assert rc == 0 and live, rc
+    names = ["absoluteSample", "codeFreq", "carrFreq", "I_P", "I_E", "I_L", "Q_E", "Q_P", "Q_L", "dllDiscr", "dllDiscrFilt", "pllDiscr",
+             "pllDiscrFilt", "remCodePhase", "remCarrPhase", "Pilot_I_P", "Pilot_Q_P"]
+    return [dict({k: out[i, j] for j, k in enumerate(names)}, epochsDone=int(done[i])) if prn[i] else None for i in range(n_ch)]
+
+
+_TRK_NAMES = ["absoluteSample", "codeFreq", "carrFreq", "I_P", "I_E", "I_L", "Q_E", "Q_P", "Q_L", "dllDiscr", "dllDiscrFilt", "pllDiscr",
+              "pllDiscrFilt", "remCodePhase", "remCarrPhase", "Pilot_I_P", "Pilot_Q_P", "Pilot_I_E", "Pilot_I_L", "Pilot_Q_E", "Pilot_Q_L"]
+
+
+def c_tracking_l2c(raw, so, ch, codes, n_epochs, cl_phase=None) -> list:
+    """Second witness of GPS_L2C/include/tracking.m (oracle/gnss_oracle_ext.c); codes[PRN] = (CM,) or (CM, CL); cl_phase = the
+    channels' CLCodePhase when the CL pilot is tracked."""
+    cs = orc_settings(so)
+    n_ch = len(ch)
+    prn = np.asarray([c["PRN"] for c in ch], dtype=np.int32)
+    af = np.asarray([c["acquiredFreq"] for c in ch], dtype=np.float64)
+    cp = np.asarray([float(c["codePhase"]) for c in ch], dtype=np.float64)
+    raw = np.ascontiguousarray(raw, dtype=np.int8)
+    L2 = 2 * int(so.codeLength)
+    cm = np.zeros((n_ch, L2), dtype=np.int8)
+    cl = None
+    cl_len = 767250
+    if cl_phase is not None:
+        cl = np.zeros((n_ch, 2 * cl_len), dtype=np.int8)
+    for i, p in enumerate(prn):
+        if p:
+            cm[i] = np.asarray(codes[int(p)][0], dtype=np.int8)
+            if cl is not None:
+                cl[i] = np.asarray(codes[int(p)][1], dtype=np.int8)
+    clp = np.asarray(cl_phase if cl_phase is not None else [0] * n_ch, dtype=np.int32)
+    out = np.zeros((n_ch, 21, n_epochs))
+    done = np.zeros(n_ch, dtype=np.int32)
+    rc = orc().orc_tracking_l2c(P(raw), C.c_size_t(raw.size), C.byref(cs), n_ch, P(prn), P(af), P(cp), P(cm), P(cl) if cl is not None else None,
+                                P(clp), C.c_long(cl_len), n_epochs, P(out), P(done))
+    assert rc == 0, rc
+    return [dict({k: out[i, j] for j, k in enumerate(_TRK_NAMES)}, epochsDone=int(done[i])) if prn[i] else None for i in range(n_ch)]
+
+
+def c_tracking_b1c_nb(raw, so, ch, codes, n_epochs, factor=None) -> list:
+    """Second witness of BDS/B1C/include/NB_tracking.m (oracle/gnss_oracle_ext.c); codes[PRN] = (data BOC(1,1), pilot BOC(1,1)).
+    With ``factor`` (CalcWeighingFactor's result): WB_tracking.m, codes[PRN][2] = the pilot BOC(6,1) sequence, 21 rows."""
+    cs = orc_settings(so)
+    n_ch = len(ch)
+    prn = np.asarray([c["PRN"] for c in ch], dtype=np.int32)
+    af = np.asarray([c["acquiredFreq"] for c in ch], dtype=np.float64)
+    cp = np.asarray([float(c["codePhase"]) for c in ch], dtype=np.float64)
+    cf0 = np.asarray([c.get("codeFreq", so.codeFreqBasis) for c in ch], dtype=np.float64)
+    raw = np.ascontiguousarray(raw, dtype=np.int8)
+    L2 = 2 * int(so.codeLength)
+    d, pl = np.zeros((n_ch, L2), dtype=np.int8), np.zeros((n_ch, L2), dtype=np.int8)
+    for i, p in enumerate(prn):
+        if p:
+            d[i] = np.asarray(codes[int(p)][0], dtype=np.int8)
+            pl[i] = np.asarray(codes[int(p)][1], dtype=np.int8)
+    done = np.zeros(n_ch, dtype=np.int32)
+    if factor is None:
+        out = np.zeros((n_ch, 17, n_epochs))
+        rc = orc().orc_tracking_b1c_nb(P(raw), C.c_size_t(raw.size), C.byref(cs), n_ch, P(prn), P(af), P(cp), P(cf0), P(d), P(pl), n_epochs, P(out), P(done))
+    else:
+        p61 = np.zeros((n_ch, 12 * int(so.codeLength)), dtype=np.int8)
+        for i, p in enumerate(prn):
+            if p:
+                p61[i] = np.asarray(codes[int(p)][2], dtype=np.int8)
+        out = np.zeros((n_ch, 21, n_epochs))
+        rc = orc().orc_tracking_b1c_wb(P(raw), C.c_size_t(raw.size), C.byref(cs), n_ch, P(prn), P(af), P(cp), P(cf0), P(d), P(pl), P(p61),
+                                       C.c_double(float(factor)), n_epochs, P(out), P(done))
+    assert rc == 0, rc
+    return [dict({k: out[i, j] for j, k in enumerate(_TRK_NAMES[:out.shape[1]])}, epochsDone=int(done[i])) if prn[i] else None for i in range(n_ch)]

@@ -601,7 +601,7 @@ def test_golden_signal_fixture_vs_oracle(signal):
 @pytest.mark.parametrize("signal", ["GPS_L5C", "GAL_E5a", "GAL_E5b", "BDS_B2a", "BDS_B1I", "GPS_L2C", "BDS_B1C"])
 def test_two_restatements_agree_on_the_acquisition_variants(signal):
     """Two independent witnesses per folder: the NumPy restatement (oracle/np_oracle.py) and the C one written from the reference's
-    .m files (oracle/gnss_oracle_acq2.c: own sampled tables, own FFT, own search loops) on the seeded record of the folder's golden
+    .m files (oracle/gnss_oracle_ext.c: own sampled tables, own FFT, own search loops) on the seeded record of the folder's golden
     case - acquired set, code phase, coarse bin and carrFreq exactly, peakMetric to 1e-8.  With the first C oracle (GPS L1CA,
     GLONASS, BDS B3I, GAL E1) every one of the twelve folders now has both."""
     import golden_cases as G
@@ -618,3 +618,108 @@ def test_two_restatements_agree_on_the_acquisition_variants(signal):
     assert np.array_equal(np.asarray(a["coarseBin"])[idx], c["coarseBin"][idx])
     assert np.allclose(a["peakMetric"][idx], c["peakMetric"][idx], rtol=1e-8, atol=0), (a["peakMetric"][idx], c["peakMetric"][idx])
     assert np.count_nonzero(c["carrFreq"]) >= 2
+
+
+@pytest.mark.parametrize("signal", ["GPS_L5C", "BDS_B2a", "BDS_B1I"])
+def test_two_restatements_agree_on_the_tracking_variants(signal):
+    """tracking() of the folders whose loop is B3I's with other codes (GPS L5C and its twins with the quadrature pilot, BDS B1I):
+    the NumPy restatement against the C one written from the reference's .m files, on the folder's golden case - block boundaries
+    exactly, every recorded row to 1e-9 (of |P| for the correlator sums; the two sum the samples in different orders)."""
+    import golden_cases as G
+    from helpers import c_tracking_variant
+    case = G.build(signal)
+    ref = case.trk_oracle()
+    got = c_tracking_variant(case)
+    n_live = 0
+    for r, g in zip(ref, got):
+        if g is None:
+            assert r["status"] == "-"
+            continue
+        n_live += 1
+        assert g["epochsDone"] == case.nE and r["status"] == "T"
+        assert np.array_equal(r["absoluteSample"], g["absoluteSample"])
+        scale = np.hypot(r["I_P"], r["Q_P"])
+        keys = ["I_P", "Q_P", "I_E", "I_L", "Q_E", "Q_L"] + (["Pilot_I_P", "Pilot_Q_P"] if "Pilot_I_P" in r else [])
+        for k in keys:
+            assert np.max(np.abs(r[k] - g[k]) / scale) < 1e-9, k
+        for k in ("codeFreq", "carrFreq", "remCodePhase", "remCarrPhase", "dllDiscr", "dllDiscrFilt", "pllDiscr", "pllDiscrFilt"):
+            assert np.allclose(r[k], g[k], rtol=1e-9, atol=1e-9), k
+    assert n_live >= 2
+
+
+def _rows_agree(ref, got, n_e, keys, l2c=False):
+    n_live = 0
+    for r, g in zip(ref, got):
+        if g is None:
+            assert r["status"] == "-"
+            continue
+        n_live += 1
+        assert g["epochsDone"] == n_e and r["status"] == "T"
+        if l2c:                                               # fractional sample positions (GPS_L2C tracking.m:223)
+            assert np.max(np.abs(r["absoluteSample"] - g["absoluteSample"])) < 1e-6
+        else:
+            assert np.array_equal(r["absoluteSample"], g["absoluteSample"])
+        scale = np.maximum(np.hypot(r["I_P"], r["Q_P"]), np.hypot(r.get("Pilot_I_P", 0.0), r.get("Pilot_Q_P", 0.0)))
+        for k in keys:
+            assert np.max(np.abs(r[k] - g[k]) / scale) < 1e-9, k
+        for k in ("codeFreq", "carrFreq", "remCodePhase", "remCarrPhase", "dllDiscr", "dllDiscrFilt", "pllDiscr", "pllDiscrFilt"):
+            assert np.allclose(r[k], g[k], rtol=1e-9, atol=1e-9), k
+    return n_live
+
+
+def test_two_restatements_agree_on_l2c_and_b1c_tracking():
+    """GPS L2C tracking (CM only, and with the CL pilot rolling through its 75 segments) and BDS B1C NB_tracking: the NumPy
+    restatement against the C one written from the reference's .m files (oracle/gnss_oracle_ext.c) - every recorded row to 1e-9."""
+    import golden_cases as G
+    from cu_sdr_collection_b200 import init_settings
+    from helpers import c_tracking_b1c_nb, c_tracking_l2c, oracle_signal_codes, to_oracle_settings
+    iq = ["I_P", "Q_P", "I_E", "I_L", "Q_E", "Q_L"]
+    case = G.build("GPS_L2C")                                  # pilotTRKflag 0
+    assert _rows_agree(case.trk_oracle(), c_tracking_l2c(case.raw_trk, case.so, case.ch, case.codes, case.nE), case.nE, iq, l2c=True) == 2
+    case = G.build("BDS_B1C")
+    got = c_tracking_b1c_nb(case.raw_trk, case.so, case.ch, case.codes, case.nE)
+    assert _rows_agree(case.trk_oracle(), got, case.nE, iq + ["Pilot_I_P", "Pilot_Q_P"]) == 2
+    # CL pilot: a scene with the CL code time-multiplexed in, channels started on different CL segments
+    fs, n_e = 2.046e6, 8
+    sc = synth.default_scene_varb("GPS_L2C", {}, fs=fs, nsat=2, seed=3)
+    codes = sc.codes = oracle_signal_codes("GPS_L2C", [x.prn for x in sc.sats], cl=True)
+    for x in sc.sats:
+        x.cn0 = 45
+    s = init_settings("GPS_L2C", samplingFreq=fs, acqSatelliteList=sorted(x.prn for x in sc.sats), acqSearchBand=9.0, pilotTRKflag=1,
+                      msToProcess=20 * n_e, numberOfChannels=2, CNo_VSMinterval=4)
+    so = to_oracle_settings(s)
+    so.stepSize, so.acqStep, so.acqCohT, so.pilotTRKflag = s.stepSize, s.acqStep, s.acqCohT, 1
+    N = O.samples_per_code(so)
+    raw = synth.make_record(sc, N * (n_e + 2))
+    ch = []
+    for i, sat in enumerate(sc.sats):
+        start = (20460 - sat.code_phase) * (fs / 1.023e6)
+        ch.append(dict(PRN=sat.prn, acquiredFreq=round((s.IF + sat.doppler) / 12.5) * 12.5, codePhase=int(round(start)) % N, status="T",
+                       CLCodePhase=(1, 73)[i]))             # the second channel wraps 75 -> 1 inside the run
+    ref = O.tracking_l2c(raw, ch, so, codes)
+    got = c_tracking_l2c(raw, so, ch, codes, n_e, cl_phase=[c["CLCodePhase"] for c in ch])
+    pil = ["Pilot_I_P", "Pilot_Q_P", "Pilot_I_E", "Pilot_I_L", "Pilot_Q_E", "Pilot_Q_L"]
+    assert _rows_agree(ref, got, n_e, iq + pil, l2c=True) == 2
+    # BDS B1C WB_tracking: BOC(6,1) pilot component, composite pilot, code error weighted by CalcWeighingFactor's factor
+    from cu_sdr_collection_b200 import preRun
+    fs, n_e = 4.092e6, 10
+    sc = synth.default_scene_varb("BDS_B1C", {}, fs=fs, nsat=2, seed=3)
+    codes = sc.codes = oracle_signal_codes("BDS_B1C", [x.prn for x in sc.sats], boc61=True)
+    for x in sc.sats:
+        x.cn0 = 46
+    s = init_settings("BDS_B1C", samplingFreq=fs, acqSatelliteList=sorted(x.prn for x in sc.sats), msToProcess=10 * n_e, numberOfChannels=2,
+                      CNo_VSMinterval=2, pilotTRKflag=2)
+    so = to_oracle_settings(s)
+    so.FEBW = s.FEBW
+    factor = O.CalcWeighingFactor(so)
+    N = O.samples_per_code(so)
+    raw = synth.make_record(sc, N * (n_e + 2))
+    acq = dict(carrFreq=np.zeros(63), codePhase=np.zeros(63), peakMetric=np.zeros(63))
+    for i, sat in enumerate(sc.sats):
+        acq["carrFreq"][sat.prn - 1] = round((s.IF + sat.doppler) / 25.0) * 25.0
+        acq["codePhase"][sat.prn - 1] = int(round((20460 - sat.code_phase) * (fs / 2.046e6))) % N + 1
+        acq["peakMetric"][sat.prn - 1] = 20.0 - i
+    ch = preRun(acq, s)
+    ref = O.tracking_b1c_wb(raw, ch, so, codes, factor)
+    got = c_tracking_b1c_nb(raw, so, ch, codes, n_e, factor=factor)
+    assert _rows_agree(ref, got, n_e, iq + pil) == 2
