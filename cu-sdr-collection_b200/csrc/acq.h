@@ -59,6 +59,7 @@ struct InvColsParams {
     float w0, w1, wScale;     // (BDS B1C: (|data|*sqrt(11) + |pilot|*sqrt(29)) / sqrt(40), acquisition.m:213-214)
     float* magOut;            // optional [nPrnChunk][nBins][L]: the summed magnitudes in natural lag order (corrVec of variant B)
     const float2* colTw;      // two-level column pass: [C1][C2] w_C^(-ta*beta) (gc_handle::twCols)
+    int persist;              // > 0: that many CTAs walk all (tile, bin, SV) items (register-codelet columns only)
 };
 
 // correlation stage as one persistent kernel with an ordered work queue (acq_fused.cu, experimental: GC_ACQ_PATH=queue)

@@ -207,13 +207,19 @@ __global__ void finish_replica_kernel(float2* Cc, size_t n, float scale)
 
 // ------------------------------------------------------------------ column pass (inverse) + |.| + sum + max
 // grid (ceil(R/128), nBins, nPrnChunk), block 128: thread = row position (ta, tb) of one (PRN, bin).
+// p.persist: a fixed number of CTAs walks the (tile, bin, SV) items - used when the pass runs on a high-priority stream next to
+// the row pass of the following chunk (GC_ACQ_OVERLAP), so that it takes one CTA slot per SM instead of every slot that frees up.
 template <class P>
 __global__ void __launch_bounds__(128)
 inv_cols_kernel(InvColsParams p)
 {
     constexpr int C = P::C, R = P::R, L = P::L;
-    const int pp = blockIdx.x * 128 + threadIdx.x;
-    const int k = blockIdx.y, pi = blockIdx.z;
+    constexpr int kTiles = (R + 127) / 128;
+    const long long nItems = p.persist ? (long long)kTiles * p.nBins * p.nPrnChunk : 1;
+    for (long long item = p.persist ? blockIdx.x : 0; item < nItems; item += gridDim.x) {
+    const int bx = p.persist ? (int)(item % kTiles) : blockIdx.x;
+    const int pp = bx * 128 + threadIdx.x;
+    const int k = p.persist ? (int)((item / kTiles) % p.nBins) : blockIdx.y, pi = p.persist ? (int)(item / ((long long)kTiles * p.nBins)) : blockIdx.z;
     float acc[C];
 #pragma unroll
     for (int i = 0; i < C; ++i) acc[i] = 0.f;
@@ -257,9 +263,11 @@ inv_cols_kernel(InvColsParams p)
     if (threadIdx.x == 0) {
         for (int w = 1; w < 4; ++w)
             if (s_b[w] > best || (s_b[w] == best && s_i[w] < bidx)) { best = s_b[w]; bidx = s_i[w]; }
-        const size_t o = ((size_t)(p.prnSlot0 + pi) * (p.nBinsTotal ? p.nBinsTotal : p.nBins) + p.bin0 + k) * gridDim.x + blockIdx.x;
+        const size_t o = ((size_t)(p.prnSlot0 + pi) * (p.nBinsTotal ? p.nBinsTotal : p.nBins) + p.bin0 + k) * kTiles + bx;
         p.partMax[o] = best;
         p.partIdx[o] = bidx;
+    }
+    if (p.persist) __syncthreads();                              // s_b / s_i are reused by the next item
     }
 }
 
@@ -699,6 +707,7 @@ struct Launch {
             return single ? go(inv_cols_big_kernel<P, true, false>) : go(inv_cols_big_kernel<P, false, false>);
         } else {
             dim3 grid((P::R + 127) / 128, p.nBins, p.nPrnChunk);
+            if (p.persist > 0) grid = dim3((unsigned)p.persist, 1, 1);
             inv_cols_kernel<P><<<grid, 128, 0, s>>>(p);
             return cudaGetLastError();
         }

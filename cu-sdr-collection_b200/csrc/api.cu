@@ -158,8 +158,9 @@ struct gc_handle {
     int N = 0, L = 0, nBins = 0, nFine = 0, nonCoh = 0;
     double ts = 0;
     bool fused = false;
-    int binShift = 0;            // variant A: acqSearchStep * L / fs when that is a whole number of FFT bins (else 0): the spectra of
-                                 // Doppler bin k are those of bin 0 shifted by k * binShift, so only bin 0 is transformed
+    int binShift = 0;            // variant A: binQ * acqSearchStep * L / fs when that is a whole number of FFT bins for a small binQ (else
+    int binQ = 1;                // 0): the spectra of Doppler bin k are those of bin k mod binQ shifted by (k div binQ) * binShift, so only
+                                 // the first binQ bins are transformed (binQ = 1: only bin 0)
     bool overlap = false;        // split correlation stage pipelined over two streams (GC_ACQ_OVERLAP)
     bool queue = false;          // correlation stage as one persistent kernel with an ordered work queue (GC_ACQ_PATH=queue)
     DevBuf<int> qctrl;
@@ -467,7 +468,12 @@ int gc_create(gc_handle** out, const gc_config* cfg)
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(GC_ERR_CUDA); }
     for (auto& e : h->ev)
         if (cudaEventCreate(&e) != cudaSuccess) { h->err = "cudaEventCreate failed"; return bail(GC_ERR_CUDA); }
-    if (cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(GC_ERR_CUDA); }
+    {   // the second stream carries the column passes of the overlapped pipeline (GC_ACQ_OVERLAP): highest priority, so that its few
+        // persistent CTAs are placed as soon as a slot frees up next to the row pass of the following chunk
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, hi) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(GC_ERR_CUDA); }
+    }
     for (int i = 0; i < 2; ++i)
         if (cudaEventCreateWithFlags(&h->evRows[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->evCols[i], cudaEventDisableTiming) != cudaSuccess) { h->err = "cudaEventCreate failed"; return bail(GC_ERR_CUDA); }
 
@@ -520,9 +526,15 @@ int gc_create(gc_handle** out, const gc_config* cfg)
         h->queue = h->fused && e && strcmp(e, "queue") == 0 && h->fp.C <= 50 && !h->varB && !h->varC;
     }
     if (h->fused && !h->cluster && !h->queue && !h->varB && !h->varC && !getenv("GC_ACQ_NO_SHIFT")) {
+        // acqSearchStep in FFT bins.  A whole number (500 Hz at 16.368, 18 and 12 Msps: 1): every bin is bin 0 shifted.  A fraction
+        // with a small denominator q (GAL E5b: 60 Hz = 0.12 bins, q = 25; GAL E1: 150 Hz = 1.2 bins, q = 5): bin k is bin k mod q
+        // shifted by (k div q) * (q * step) bins, so q spectra per block serve the whole grid (GC_ACQ_NO_SHIFT_Q=1: whole steps only)
         const double sh = cfg->acq_search_step * (double)h->L / cfg->sampling_freq;
-        const double shr = m_round(sh);
-        if (shr >= 1 && std::fabs(sh - shr) < 1e-9 && shr * (h->nBins - 1) < h->L) h->binShift = (int)shr;
+        const int qMax = getenv("GC_ACQ_NO_SHIFT_Q") ? 1 : std::min(h->nBins, 32);
+        for (int q = 1; q <= qMax; ++q) {
+            const double shq = sh * q, shr = m_round(shq);
+            if (shr >= 1 && std::fabs(shq - shr) < 1e-9 * q && shr * ((h->nBins - 1) / q + 1) < h->L) { h->binShift = (int)shr; h->binQ = q; break; }
+        }
     }
     h->stats.acq_path = h->cluster ? 2 : h->queue ? 3 : h->fused ? 1 : 0;   // 2 = fused plan + cluster correlation kernel, 1 = fused plan, split
                                                              // correlation stage, 0 = generic mixed-radix passes
@@ -1319,15 +1331,17 @@ static int acquire_plain(gc_handle* h, long long winStart, int32_t nSv, const in
         }
         for (int s = groupStart[gi]; s < groupStart[gi + 1]; ++s) coarseFreqOf[s] = coarseFreq;
     }
-    const bool shifted = h->binShift > 0;                    // only bin 0 of every grid is transformed, the other bins are shifts of it
-    const int fwdRowsPerGroup = shifted ? nonCoh : nKm;
-    GC_CUDA(h, h->X.reserve((size_t)nGroups * nKm * L));
+    const bool shifted = h->binShift > 0;                    // only the first binQ bins of every grid are transformed, the others are shifts of them
+    const int nq = shifted ? std::min(h->binQ, nBins) : nBins;
+    const int fwdRowsPerGroup = nq * nonCoh;
+    GC_CUDA(h, h->X.reserve((size_t)nGroups * fwdRowsPerGroup * L));
     if (shifted) {
-        std::vector<uint64_t> d0(nGroups);
-        for (int gi = 0; gi < nGroups; ++gi) d0[gi] = dphi[(size_t)gi * nBins];
+        std::vector<uint64_t> d0((size_t)nGroups * nq);
+        for (int gi = 0; gi < nGroups; ++gi)
+            for (int b = 0; b < nq; ++b) d0[(size_t)gi * nq + b] = dphi[(size_t)gi * nBins + b];
         GC_CUDA(h, upload_cached(h, h->dphi, d0, st));
         std::vector<int2> map(nBins);
-        for (int k = 0; k < nBins; ++k) map[k] = make_int2(0, k * h->binShift);
+        for (int k = 0; k < nBins; ++k) map[k] = make_int2(k % nq, (k / nq) * h->binShift);
         GC_CUDA(h, upload_cached(h, h->vbMap, map, st));
     } else {
         GC_CUDA(h, upload_cached(h, h->dphi, dphi, st));
@@ -1716,7 +1730,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         GC_CUDA(h, cudaMemcpyAsync(h->dphi.p, dphi.data(), nBins * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
         const int f0 = mark();
         if (h->fused) {
-            const bool shifted = h->binShift > 0;            // only bin 0 is transformed (dphi[0]); bin k = its spectrum shifted by k * binShift
+            const bool shifted = h->binShift > 0 && h->binQ == 1;   // only bin 0 is transformed (dphi[0]); bin k = its spectrum shifted by k * binShift
             if (shifted) {
                 std::vector<int2> map(nBins);
                 for (int k = 0; k < nBins; ++k) map[k] = make_int2(0, k * h->binShift);
@@ -1798,6 +1812,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
                 cp.W = Wc; cp.colTw = h->twCols.p; cp.nBins = nb; cp.bin0 = b0; cp.nBinsTotal = nBins; cp.nonCoh = nonCoh * h->nRep; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
                 cp.partMax = h->partMax.p; cp.partIdx = h->partIdx.p;
                 if (overlap) {
+                    if (const char* e = getenv("GC_COLS_PERSIST")) cp.persist = std::max(0, atoi(e)) * 148;   // CTAs per SM of the persistent column pass
                     GC_CUDA(h, cudaEventRecord(h->evRows[ci & 1], st));
                     GC_CUDA(h, cudaStreamWaitEvent(h->stream2, h->evRows[ci & 1], 0));
                     GC_CUDA(h, launch_inv_cols(L, cp, h->stream2)); ++launches;
