@@ -17,10 +17,11 @@ pytestmark = pytest.mark.gpu
 
 IQ_TOL = 1e-6        # north_star: floating-point I_P/Q_P within 1e-6 relative
 METRIC_TOL = 1e-6
-# Variant B (BDS B1I, GPS L2C): peakMetric = peak / SECOND peak of one fp32 correlation row.  The second peak is a noise-floor
-# value (~1/30 of the row's largest spectral products at these SNRs), so the fp32 transform's error - 1e-7 of the LARGE values -
-# is a few 1e-6 of it; the measured worst case is printed by the test and recorded in DESIGN.md.  Indices stay exact.
-VARB_METRIC_TOL = 1e-5
+# Variant B (BDS B1I, GPS L2C): peakMetric = peak / SECOND peak of one fp32 correlation row.  Round 1 gated it at 1e-5 on the argument
+# that the second peak is a noise-floor value; measured, the worst relative error over the variant B cases is 2.3e-7
+# (gpurun_out/r02_gputests.log: B1I 18 Msps 1.6e-7, L2C 2.046 Msps 2.3e-7, L2C 8 Msps 1.1e-7, B1I 4.092 Msps 1.0e-7), so the survey's
+# 1e-6 gate applies here like everywhere else.  Each test prints its measured worst case.
+VARB_METRIC_TOL = 1e-6
 # The 60000-epoch closed-loop comparison needs correlator sums that follow the float64 reference far below 1e-6: whenever the code
 # phase of a block start passes a sample-grid alignment, ~1000 samples of that block lie within 1e-6 chips of a chip edge at once,
 # and a loop state that is off by 1e-10 chips (fp32 sums) flips one of them about once per channel-minute, after which the two
