@@ -2292,8 +2292,12 @@ int gc_track(gc_handle* h, int32_t nCh, const int32_t* sv, const double* acqFreq
 
 int gc_get_cno_pld(const gc_handle* h, int32_t nCh, int32_t nIntervals, double* out)
 {
-    if (!h || !out) return GC_ERR_ARG;
-    if (h->cnoPldCh == 0 || nCh != h->cnoPldCh || nIntervals != h->cnoPldV) return GC_ERR_ARG;   // no B2a / B1C gc_track of that shape before
+    if (!h) return GC_ERR_ARG;
+    if (nIntervals == 0) return GC_OK;                         // a run shorter than one CNoInterval: zeros(1, 0) in the reference (NB_tracking.m:88-92)
+    gc_handle* hm = const_cast<gc_handle*>(h);
+    if (!out) return fail(hm, GC_ERR_ARG, "gc_get_cno_pld: null output");
+    if (h->cnoPldCh == 0 || nCh != h->cnoPldCh || nIntervals != h->cnoPldV)
+        return fail(hm, GC_ERR_ARG, "gc_get_cno_pld: no BDS B2a / B1C gc_track of that shape (channels, intervals) before this call");
     std::copy(h->cnoPld.begin(), h->cnoPld.end(), out);
     return GC_OK;
 }

@@ -6,27 +6,30 @@
 // Its start is known as soon as epoch e begins (start + blksize); only its length changes by a
 // sample or so, so a fixed-size window is fetched.
 //
-// Numerics (targets: I/Q sums within 1e-6 relative of the float64 reference, every recorded
-// state variable computed in float64 exactly as the reference does):
-//   * code phase: t(k) is evaluated per sample in float64 with the reference's own operation
-//     order (MATLAB colon vector a:d:b built from both ends, then ceil) because one chip flip
-//     changes a sum by ~1e-3 relative.  ceil() is a round-up add of 2^52 (FP64 pipe) instead of a
-//     float->int conversion (quarter-rate XU pipe);
-//   * carrier: phase kept as a 64-bit fixed-point fraction of a turn; one sincospif per 8-sample
-//     chunk, the 8 in-chunk rotations e^{-i*j*dphi} are per-epoch constants;
-//   * sums: fp32 inside a thread (8 samples per chunk, 4 chunks), float64 across threads.
+// Numerics (targets: I/Q sums within 1e-6 relative of the float64 reference over a minute-long closed loop - which in practice needs
+// them at ~1e-13, DESIGN.md section 2 - and every recorded state variable computed in float64 as the reference does):
+//   * code phase: t(k) in float64 with the reference's own operation order (MATLAB colon vector a:d:b built from both ends, then
+//     ceil) because one chip flip changes a sum by ~1e-3 relative.  ceil() is a round-up add of 1.5*2^52 (FP64 pipe) instead of a
+//     float->int conversion; where a table entry spans >= 8 samples the per-sample evaluation is replaced by a per-chunk edge
+//     prediction that falls back to it whenever a sample is within 2^-24 samples of an edge;
+//   * carrier: phase kept as a 64-bit fixed-point fraction of a turn; per 8-sample chunk one float64 phasor from a 1024-entry
+//     table + Taylor remainder (~2e-16), the 8 in-chunk rotations e^{-i*j*dphi} are per-epoch float64 constants;
+//   * samples, wipe-off, replica entries and sums: float64 throughout (byte -> double by PRMT, entries as double high words);
+//   * discriminators atan(Q/I), sqrt, divide: float64 as the reference evaluates them (GC_PARAM_TRACK_FAST_DISC selects fp32 forms,
+//     1e-7 relative, for callers that want the last 1.5 %); recorded pllDiscr / dllDiscr rows follow the oracle to ~1e-13;
+//   * remCarrPhase is the fixed-point phase in radians with the sign of carrFreq: the reference's rem(trigarg, 2*pi) recurrence to
+//     ~4e-8 rad after 60000 epochs, and modulo 2*pi where carrFreq changes sign on a baseband record.
 //
 // With few channels (BASELINE: 12) one CTA per channel leaves most of the chip idle and every
 // epoch is a dependent step, so a channel can instead be spread over a thread-block cluster of
-// G = 2/4/8 CTAs: each CTA stages and correlates 1/G of the block, pushes its six partial sums
-// into every peer's shared memory (DSMEM), one cluster barrier, and then every CTA closes the
+// G = 2/4/8 CTAs: each CTA stages and correlates 1/G of the block, pushes its partial sums
+// into every peer's shared memory (DSMEM, st.async + mbarrier complete_tx), and then every CTA closes the
 // loops redundantly from the same numbers (bit-identical state everywhere, no broadcast step).
 //
 // The per-epoch scalar work is split so that little of it sits on the critical path:
-//   warp 0 lane 0 : PLL (atan) and the 15 recorded values          after the sums are reduced
-//   warp 1 lane 0 : DLL and the geometry of the next block         concurrently with warp 0
-// Quotients and square roots of the discriminators use an fp32 seed plus one float64 Newton step
-// (~1e-14 relative); everything that feeds a ceil() (codePhaseStep, blksize) is exact IEEE.
+//   carrier-loop thread : PLL (float64 atan), the next block's carrier constants, the recorded values    after the sums are reduced
+//   code-loop thread    : DLL and the geometry of the next block                                          concurrently
+// Everything that feeds a ceil() (codePhaseStep, blksize) is exact IEEE.
 #include <type_traits>
 
 #include "common.cuh"
@@ -784,8 +787,8 @@ track_kernel(TrackParams p)
             double* sg = s_stage + (e % kStage);
             if (tid == kPllTid) {
                 // PLL (tracking.m:305-317)
-                // The discriminator is evaluated in fp32: its inputs are sums of fp32 products, so float64
-                // would not make it more accurate, and a float64 atan is ~1000 dependent cycles per epoch.
+                // float64 atan / divide as the reference evaluates it (p.exactDisc, the default); GC_PARAM_TRACK_FAST_DISC selects the
+                // fp32 form (~1e-7 relative in the recorded pllDiscr row and, through the filter, in carrFreq)
                 double carrError = p.exactDisc ? atan(__ddiv_rn(Q_P, I_P)) / kTwoPi
                                                : (double)atanf((float)Q_P / (float)I_P) * 0.15915494309189535;
                 if (PILOT) {                                     // GAL_E1C tracking.m:297-300

@@ -689,6 +689,24 @@ def test_fam5_tracking_and_wrappers_vs_oracle(signal, pilot, nE, exact, tmp_path
 
 
 # ------------------------------------------------------------- sample formats: int16 and real records
+def test_run_shorter_than_one_cno_interval_gives_empty_cno_rows(tmp_path):
+    """BDS B2a with msToProcess < CNoInterval: the reference's DataCNo / DataPLD ... are zeros(1, 0) (BDS/B2a/include/tracking.m:79-83);
+    the wrapper must return empty rows instead of failing on a zero-interval gc_get_cno_pld."""
+    codes, sc, s, so, sv = _fam5_case("BDS_B2a", nsat=1, seed=5, extra=[], nonCoh=3, ms=10, nch=1, pilotTRKflag=1, CNo_VSMinterval=20)
+    raw = synth.make_record(sc, 18000 * 14)
+    sat = sc.sats[0]
+    acq = dict(carrFreq=np.zeros(63), codePhase=np.zeros(63), peakMetric=np.zeros(63))
+    acq["carrFreq"][sat.prn - 1] = round((s.IF + sat.doppler) / 25.0) * 25.0
+    acq["codePhase"][sat.prn - 1] = int(round((10230 - sat.code_phase) * (18e6 / 10.23e6))) % 18000 + 1
+    acq["peakMetric"][sat.prn - 1] = 10.0
+    ch = preRun(acq, s)
+    path = tmp_path / "b2a.bin"
+    raw.tofile(path)
+    with open(path, "rb") as fid:
+        tr, _ = tracking(fid, ch, s)
+    assert tr[0]["status"] == "T" and tr[0]["epochsDone"] == 10 and tr[0]["DataCNo"].shape == (0,) and tr[0]["DataPLD"].shape == (0,)
+
+
 @pytest.mark.parametrize("fileType,dataType", [(2, "int16"), (1, "schar"), (1, "int16")])
 def test_sample_formats_vs_oracle(fileType, dataType, tmp_path):
     """GPS L1CA acquisition + tracking on int16 and on real (fileType 1) records - the dataAdaptCoeff / int16 branches of

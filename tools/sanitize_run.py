@@ -115,3 +115,55 @@ rows = [dict(I_P=1000.0 * (1 - 2 * rng.integers(0, 2, size=700)).repeat(20).asty
 print("nav", nav_sync(rows, s, eng)[0])
 eng.close()
 print("sanitize run (extended) ok")
+
+# ---- round 2: the graph enqueue (direct -> captured -> replayed), the asynchronous device-result call, the fractional-step
+#      shifted spectra (GAL E5b), the quadrature-pilot tracker with the C/N0 + lock-detector kernel (BDS B2a) and the on-device
+#      code generators (every code below is generated by the library) ------------------------------------------------------------
+import torch
+fs = 16.368e6
+sc = synth.default_scene(fs=fs, nsat=2, seed=5)
+for s_ in sc.sats:
+    s_.cn0 = 48
+sv = sorted({x.prn for x in sc.sats} | {1})
+s = init_settings(samplingFreq=fs, acqSatelliteList=sv, acqNonCohTime=2)
+raw = synth.make_record(sc, 16368 * 46)
+eng = Engine(s)
+eng.set_record(raw)
+first = eng.acquire(sv)
+for _ in range(3):
+    again = eng.acquire(sv)
+    assert np.array_equal(again["peakMetric"], first["peakMetric"])
+buf = torch.zeros(128, dtype=torch.float64, device="cuda")
+for _ in range(3):
+    eng.acquire_device_async(sv, buf)
+    torch.cuda.synchronize()
+assert np.array_equal(buf.cpu().numpy()[:32], first["peakMetric"])
+print("graph + async", eng.stats()["acq_launches"])
+eng.close()
+
+from cu_sdr_collection_b200.codes import icd_codes
+cd = icd_codes("GAL_E5b")
+sc = synth.default_scene_fam5("GAL_E5b", cd, fs=18e6, nsat=1, seed=5)
+sc.sats[0].cn0 = 50
+sv = [sc.sats[0].prn, 25]
+s = init_settings("GAL_E5b", acqSatelliteList=sv, acqNonCohTime=2, acqSearchBand=900.0, acqSearchStep=60.0)   # 31 bins, 25 spectra per block
+raw = synth.make_record(sc, 18000 * 104)
+eng = Engine(s)
+eng.set_record(raw)
+print("E5b", eng.acquire(sv)["carrFreq"][sv[0] - 1], eng.stats()["acq_path"])
+eng.close()
+
+cd = icd_codes("BDS_B2a")
+sc = synth.default_scene_fam5("BDS_B2a", cd, fs=18e6, nsat=1, seed=5)
+sat = sc.sats[0]
+sat.cn0 = 50
+s = init_settings("BDS_B2a", acqSatelliteList=[sat.prn], acqNonCohTime=2, msToProcess=80, numberOfChannels=1, pilotTRKflag=1, CNo_VSMinterval=20)
+raw = synth.make_record(sc, 18000 * 90)
+eng = Engine(s)
+eng.set_record(raw)
+acq = eng.acquire([sat.prn])
+ch = preRun(acq, s)
+tr, _ = tracking(None, ch, s, engine=eng)
+print("B2a acquire + pilot track + CNo/PLD", acq["carrFreq"][sat.prn - 1], tr[0]["epochsDone"], tr[0]["DataCNo"][-1])
+eng.close()
+print("sanitize run (round 2) ok")
