@@ -263,20 +263,27 @@ cudaError_t launch_peak_select(const float* partMax, const int* partIdx, int nPr
 __global__ void __launch_bounds__(128)
 fine_setup_kernel(FineSetup p)
 {
-    __shared__ int s_n;
-    if (threadIdx.x == 0) {
-        int n = 0;
-        const double sp = *p.sigPower;
-        for (int s = 0; s < p.nSv; ++s) {
-            const double m = __ddiv_rn(__ddiv_rn(p.peaks[s].peak, sp), (double)p.nonCoh);     // :200
-            p.metric[s] = m;
-            if (m > p.threshold) p.acqSlot[n++] = s;                                          // :206
-        }
-        *p.nAcq = n;
-        s_n = n;
+    // one thread per list slot (at most 63: two warps); the list of acquired slots in list order from the warps' ballots
+    __shared__ unsigned s_mask[4];
+    const int slot = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    bool above = false;
+    if (slot < p.nSv) {
+        const double m = __ddiv_rn(__ddiv_rn(p.peaks[slot].peak, *p.sigPower), (double)p.nonCoh);     // :200
+        p.metric[slot] = m;
+        above = m > p.threshold;                                                                        // :206
     }
+    const unsigned mask = __ballot_sync(0xffffffffu, above);
+    if (lane == 0) s_mask[warp] = mask;
     __syncthreads();
-    const int nAcq = s_n;
+    {
+        int before = __popc(mask & ((1u << lane) - 1u));
+        for (int w = 0; w < warp; ++w) before += __popc(s_mask[w]);
+        if (above) p.acqSlot[before] = slot;
+    }
+    int nAcq = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) nAcq += __popc(s_mask[w]);
+    if (threadIdx.x == 0) *p.nAcq = nAcq;
+    __syncthreads();                                             // acqSlot is read back below
     for (int e = threadIdx.x; e < nAcq * p.nCodes; e += blockDim.x) {
         const int a = e % nAcq, comp = p.nCodes == 2 ? e / nAcq : p.pilotComp;
         const int s = p.acqSlot[a];
@@ -308,26 +315,33 @@ cudaError_t launch_fine_setup(const FineSetup& p, cudaStream_t s)
 __global__ void pack_results_kernel(PackParams p)
 {
     for (int i = threadIdx.x; i < 4 * p.resultLen; i += blockDim.x) p.out[i] = 0.0;
-    __syncthreads();
-    if (threadIdx.x != 0) return;
-    const double sp = *p.sigPower;
-    int a = 0;
-    for (int s = 0; s < p.nSv; ++s) {
-        const int ri = p.slotResult[s];
-        const double m = __ddiv_rn(__ddiv_rn(p.peaks[s].peak, sp), (double)p.nonCoh);                 // :200
-        p.out[ri] = m;
-        p.out[3 * p.resultLen + ri] = (double)p.peaks[s].bin;
-        if (m > p.threshold) {                                                                        // :206
-            const double coarse = __dsub_rn(p.slotFreq0[s], __dmul_rn(p.step, (double)(p.peaks[s].bin - 1)));   // :169
-            double f = coarse;
-            if (!p.noFine) {
-                f = __dsub_rn(__dadd_rn(coarse, __ddiv_rn(p.step, 2.0)), __dmul_rn(p.fineStep, (double)p.best[a]));   // :227, :254
-                if (f == 0.0) f = 1.0;                                                                // :258
-            }
-            p.out[2 * p.resultLen + ri] = f;
-            p.out[p.resultLen + ri] = (double)p.peaks[s].codePhase;                                   // :256
-            ++a;
+    // one thread per list slot; a = the slot's position among the acquired ones (the order fine_setup_kernel numbered them in)
+    __shared__ unsigned s_mask[4];
+    const int s = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    bool above = false;
+    double m = 0.0;
+    if (s < p.nSv) {
+        m = __ddiv_rn(__ddiv_rn(p.peaks[s].peak, *p.sigPower), (double)p.nonCoh);                     // :200
+        above = m > p.threshold;                                                                      // :206
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, above);
+    if (lane == 0) s_mask[warp] = mask;
+    __syncthreads();                                             // (also orders the zero fill above before the entries below)
+    if (s >= p.nSv) return;
+    int a = __popc(mask & ((1u << lane) - 1u));
+    for (int w = 0; w < warp; ++w) a += __popc(s_mask[w]);
+    const int ri = p.slotResult[s];
+    p.out[ri] = m;
+    p.out[3 * p.resultLen + ri] = (double)p.peaks[s].bin;
+    if (above) {
+        const double coarse = __dsub_rn(p.slotFreq0[s], __dmul_rn(p.step, (double)(p.peaks[s].bin - 1)));   // :169
+        double f = coarse;
+        if (!p.noFine) {
+            f = __dsub_rn(__dadd_rn(coarse, __ddiv_rn(p.step, 2.0)), __dmul_rn(p.fineStep, (double)p.best[a]));   // :227, :254
+            if (f == 0.0) f = 1.0;                                                                    // :258
         }
+        p.out[2 * p.resultLen + ri] = f;
+        p.out[p.resultLen + ri] = (double)p.peaks[s].codePhase;                                       // :256
     }
 }
 
