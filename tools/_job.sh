@@ -1,4 +1,4 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 120 python tools/fine_diag.py 2>&1 | grep variant
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_multi.py -x -q -m gpu --timeout 240 --timeout-method thread -k "acq or golden or one_call or device or graph or multi" > gpurun_out/s2_pytest_acq.txt 2>&1; echo "pytest acq rc $?"; tail -3 gpurun_out/s2_pytest_acq.txt
+timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:inv_rows|inv_cols_big' -c 4 -o gpurun_out/r02b_b1c -f python tools/big_bench.py B1C > gpurun_out/r02b_ncu_b1c.log 2>&1; echo "b1c capture rc $?"
+ls -la gpurun_out/r02b_b1c.ncu-rep
