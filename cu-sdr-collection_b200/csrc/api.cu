@@ -2,7 +2,6 @@
 // tracking kernels.  Declared in include/gnsscorr.h, which cites the reference interface each
 // entry point replaces.
 #include <algorithm>
-#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -30,10 +29,6 @@ thread_local std::string g_create_error;
 
 double m_round(double x) { return x >= 0 ? std::floor(x + 0.5) : -std::floor(-x + 0.5); }
 
-// bumped by every (re)allocation of a DevBuf: a captured acquisition graph holds raw device pointers and is only replayed while
-// this count is what it was when the graph was captured
-std::atomic<unsigned long long> g_allocGen{0};
-
 template <class T>
 struct DevBuf {
     T* p = nullptr;
@@ -43,7 +38,6 @@ struct DevBuf {
         if (n <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
-        g_allocGen.fetch_add(1, std::memory_order_relaxed);
         cudaError_t e = cudaMalloc(&p, n * sizeof(T));
         if (e == cudaSuccess) cap = n;
         return e;
@@ -1501,10 +1495,16 @@ static int acquire_plain(gc_handle* h, long long winStart, int32_t nSv, const in
     std::vector<char> key;
     auto put = [&](const void* p_, size_t n_) { const char* b = static_cast<const char*>(p_); key.insert(key.end(), b, b + n_); };
     {
-        const unsigned long long gen = g_allocGen.load(std::memory_order_relaxed);
-        const void* recp = h->rec; const void* pinp = h->pin;
-        put(&winStart, sizeof winStart); put(&nSv, sizeof nSv); put(svList, sizeof(int32_t) * nSv); put(&recp, sizeof recp);
-        put(&h->recBytes, sizeof h->recBytes); put(&dOut, sizeof dOut); put(&gen, sizeof gen); put(&pinp, sizeof pinp);
+        // everything the enqueue bakes into kernel arguments: the call's own parameters and EVERY device pointer it passes (a buffer
+        // that was reallocated since the capture changes the key, so a stale graph is never replayed; other handles' allocations do
+        // not disturb it)
+        const void* ptrs[] = {h->rec, dOut, h->pin, h->sigPower.p, h->dphi.p, h->X.p, h->twFused.p, h->Cc.p, h->W.p, h->prnList.p, h->slotGroup.p,
+                              h->vbMap.p, h->partMax.p, h->partIdx.p, h->peaks.p, h->slotFreq0.p, h->slotChipRow.p, h->slotSv.p,
+                              h->slotSecondary.p, h->metricDev.p, h->nAcqDev.p, h->acqSlot.p, h->fineChipRow.p, h->fineCodePhase.p, h->fdphi.p,
+                              h->fineSv.p, h->fineSecondary.p, h->chipIdx.p, h->chips.p, h->fineProd.p, h->fineSums.p, h->fineBest.p,
+                              h->fineResult.p, h->slotResult.p};
+        put(&winStart, sizeof winStart); put(&nSv, sizeof nSv); put(svList, sizeof(int32_t) * nSv);
+        put(&h->recBytes, sizeof h->recBytes); put(ptrs, sizeof ptrs);
     }
     AcqGraph& g = h->graph;
     AcqEnq info;
