@@ -37,6 +37,8 @@ struct RowsParams {
     int nRep, repStride;      // inverse: replicas summed per SV (1, or 2 = data + pilot) and their distance in Cc; the
                               // work buffer then holds nonCoh*nRep transforms per (SV, bin), replica index fastest
     int prnPerCta, mPerCta;   // warps of an inverse CTA = binPerCta x prnPerCta x mPerCta (same row j1)
+    int zLoop;                // consecutive grid-z positions (block groups of mPerCta, then bins) a warp walks; 0 / 1 = one row per warp
+    int mGroups, zTotal;      // filled by the launcher: ceil(nonCoh*nRep / mPerCta), bin groups x mGroups
     const int* slotGroup;     // optional [nSv]: carrier grid of each list slot (GLONASS frequency numbers): the spectra of grid g start
     int groupRows;            // groupRows rows into X (nBins x nonCoh); nullptr = one grid
     int bin0;                 // first bin of this launch: nBins counts the bins of the launch (and of the W layout), the spectra

@@ -117,21 +117,32 @@ fwd_rows_kernel(RowsParams p)
 // in : element (ka, kb) at kb*RA + ka       out: element (ta, tb) at ta*RB + tb
 // grid: x = j1 (C rows), y = PRN group, z = bin * mGroups + block group, so that CTAs scheduled
 // together share one X slice (L1/L2 hits) while the replica spectra stay L2 resident.
-template <class P, int WARPS, int MINB>
+// LOOP: a warp walks zLoop consecutive z positions (block groups, then bins) of its (SV, row): the CTA launch and the
+// first-touch latencies of a 3 us row are paid once per zLoop rows and the replica row stays in L1 between them.  Nothing
+// thread-dependent is carried from one row to the next (the thread index is re-read behind an opaque barrier, so the index
+// arithmetic is redone per row and its registers are free during the codelets).
+template <class P, int WARPS, int MINB, bool LOOP>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 inv_rows_kernel(RowsParams p)
 {
     constexpr int C = P::C, RA = P::RA, RB = P::RB, R = P::R;
     constexpr int kPitchI = RB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float2* s_x = reinterpret_cast<float2*>(smem_raw) + warp * (RA * kPitchI);
+#pragma unroll 1
+    for (int it = 0; it < (LOOP ? p.zLoop : 1); ++it) {
+    int tid = threadIdx.x;
+    if (LOOP) asm volatile("" : "+r"(tid));
     const int k1 = blockIdx.x, pg = blockIdx.y;
+    const int vz = LOOP ? blockIdx.z * p.zLoop + it : blockIdx.z;
+    if (LOOP && vz >= p.zTotal) break;
     const int M = p.nonCoh * p.nRep;                             // transforms per (SV, bin): blocks x replicas
-    const int mGroups = (M + p.mPerCta - 1) / p.mPerCta;
-    // (a warp does this index arithmetic once per 1100-instruction row: the run-time divisions are kept to the cases that need them)
-    int k = blockIdx.z / mGroups;
-    const int mg = blockIdx.z - k * mGroups;
+    const int mGroups = p.mGroups;                               // ceil(M / mPerCta), from the launcher
+    const int kz = vz / mGroups;
+    const int mg = vz - kz * mGroups;
+    const int lane = tid & 31, warp = tid >> 5;
+    float2* s_x = reinterpret_cast<float2*>(smem_raw) + warp * (RA * kPitchI);
+    // (a warp does this index arithmetic once per row: the run-time divisions are kept to the cases that need them)
+    int k = kz;
     int wl = warp;
     if (p.binPerCta > 1) {                                       // several bins per CTA (variants B / C)
         const int wpb = p.prnPerCta * p.mPerCta;                 // warps per bin
@@ -142,7 +153,7 @@ inv_rows_kernel(RowsParams p)
     const int pq = (p.mPerCta == 1) ? wl : wl / p.mPerCta;
     const int pi = pg * p.prnPerCta + pq;                       // list slot within this launch's chunk
     const int mv = mg * p.mPerCta + (wl - pq * p.mPerCta);
-    if (pi >= p.nPrnChunk || mv >= M || k >= p.nBins) return;
+    if (pi >= p.nPrnChunk || mv >= M || k >= p.nBins) continue;
     const int m = (p.nRep == 1) ? mv : mv / p.nRep, r = mv - m * p.nRep;   // block, replica (data / pilot, GPS_L5C acquisition.m:171-175)
     // circshift(IQfreqDom, s) (BDS/B1I acquisition.m:88, GPS_L2C :73, B1C :203): product element j takes spectrum element j - s.
     // With j = j1 + C*j2 (row j1, in-row frequency j2 held by its residues mod RA and mod RB) that is row (j1 - s) mod C
@@ -192,6 +203,8 @@ inv_rows_kernel(RowsParams p)
             if (!P::kPfa) t = cmul_conj(t, __ldg(tw + ta * RB));  // conj(w_L^(j1*tau2))
             __stcs(dst + ta * RB + lane, t);
         });
+    }
+    if (LOOP) __syncwarp();                                      // the next row overwrites s_x
     }
 }
 
@@ -655,23 +668,28 @@ struct Launch {
         fwd_rows_kernel<P><<<grid, kRowWarps * 32, smem, s>>>(p);
         return cudaGetLastError();
     }
-    template <int WARPS, int MINB>
+    template <int WARPS, int MINB, bool LOOP>
     static cudaError_t inv_rows_t(const RowsParams& p, cudaStream_t s)
     {
         const int smem = (int)(sizeof(float2) * WARPS * P::RA * P::RB);
-        cudaError_t e = cudaFuncSetAttribute(inv_rows_kernel<P, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(inv_rows_kernel<P, WARPS, MINB, LOOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        const int mGroups = (p.nonCoh * p.nRep + p.mPerCta - 1) / p.mPerCta;
         const int pGroups = (p.nPrnChunk + p.prnPerCta - 1) / p.prnPerCta;
         const int bpc = p.binPerCta > 1 ? p.binPerCta : 1;
-        dim3 grid(P::C, pGroups, ((p.nBins + bpc - 1) / bpc) * mGroups);
-        inv_rows_kernel<P, WARPS, MINB><<<grid, WARPS * 32, smem, s>>>(p);
+        RowsParams q = p;
+        q.mGroups = (p.nonCoh * p.nRep + p.mPerCta - 1) / p.mPerCta;
+        q.zTotal = ((p.nBins + bpc - 1) / bpc) * q.mGroups;
+        q.zLoop = LOOP ? p.zLoop : 1;
+        dim3 grid(P::C, pGroups, (q.zTotal + q.zLoop - 1) / q.zLoop);
+        inv_rows_kernel<P, WARPS, MINB, LOOP><<<grid, WARPS * 32, smem, s>>>(q);
         return cudaGetLastError();
     }
     // p.prnPerCta * p.mPerCta warps per CTA: 5 (96 registers, 20 warps/SM) or 8 (128 registers, 16 warps/SM)
     static cudaError_t inv_rows(const RowsParams& p, cudaStream_t s)
     {
-        return ((p.binPerCta > 1 ? p.binPerCta : 1) * p.prnPerCta * p.mPerCta == 8) ? inv_rows_t<8, 2>(p, s) : inv_rows_t<5, 4>(p, s);
+        const bool eight = (p.binPerCta > 1 ? p.binPerCta : 1) * p.prnPerCta * p.mPerCta == 8;
+        if (p.zLoop > 1) return eight ? inv_rows_t<8, 2, true>(p, s) : inv_rows_t<5, 4, true>(p, s);
+        return eight ? inv_rows_t<8, 2, false>(p, s) : inv_rows_t<5, 4, false>(p, s);
     }
     static cudaError_t corr_queue(const QueueParams& p, cudaStream_t s)
     {

@@ -27,6 +27,17 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// grid-z positions a row warp walks in one CTA (RowsParams::zLoop); GC_ROWS_ZLOOP overrides (experiments)
+int rows_zloop(int L)
+{
+    static const int env = [] { const char* e = getenv("GC_ROWS_ZLOOP"); return e ? atoi(e) : 0; }();
+    if (env > 0) return env;
+    // measured (tools/acq_bench.py, tools/big_bench.py): 8 rows per warp gain 2 - 9 % on the 25-point row plans (E1 20 Msps
+    // 5.16 -> 4.67 ms, B1C 47.0 -> 45.3 ms); the 31-point codelet of the 32736 plan has no register to spare for the loop
+    // (48 bytes of spills) and ends where it started, so it keeps one row per warp
+    return L == 32736 ? 1 : 8;
+}
+
 double m_round(double x) { return x >= 0 ? std::floor(x + 0.5) : -std::floor(-x + 0.5); }
 
 template <class T>
@@ -892,6 +903,7 @@ static int acquire_varb(gc_handle* h, long long winStart, int32_t nSv, const int
             ip.prnPerCta = 1; ip.mPerCta = 1; ip.binPerCta = 5; ip.binMap = bm; ip.binMapSlotStride = bmStride;
             if (nB == 1) { ip.prnPerCta = 5; ip.binPerCta = 1; }       // one row per SV: fill the CTA with SVs instead of bins
             ip.nPrnChunk = nc; ip.prnSlot0 = s0; ip.prnList = h->prnList.p;
+            ip.zLoop = rows_zloop(Lb);
             GC_CUDA(h, launch_inv_rows(Lb, ip, st)); ++launches;
             InvColsParams cp{};
             cp.W = h->W.p; cp.colTw = h->twCols.p; cp.nBins = nB; cp.bin0 = b0; cp.nBinsTotal = nBTotal; cp.nonCoh = 1; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
@@ -1170,6 +1182,7 @@ static int acquire_varc(gc_handle* h, long long winStart, long long longLen, int
             ip.nonCoh = 1; ip.nBins = nb; ip.bin0 = b0; ip.nRep = nRep; ip.repStride = 1;
             ip.prnPerCta = 1; ip.mPerCta = 1; ip.binPerCta = 5; ip.binMap = h->vbMap.p;
             ip.nPrnChunk = nc; ip.prnSlot0 = s0; ip.prnList = h->prnList.p;
+            ip.zLoop = rows_zloop(Lc);
             GC_CUDA(h, launch_inv_rows(Lc, ip, st)); ++launches;
             InvColsParams cp{};
             cp.W = h->W.p; cp.colTw = h->twCols.p; cp.nBins = nb; cp.bin0 = b0; cp.nBinsTotal = nBins; cp.nonCoh = nRep; cp.nPrnChunk = nc; cp.prnSlot0 = s0;
@@ -1439,6 +1452,11 @@ static int acquire_plain(gc_handle* h, long long winStart, int32_t nSv, const in
             ip.nonCoh = nonCoh; ip.nBins = nBins; ip.prnPerCta = 1; ip.mPerCta = 5;   // 5 warps, 96 registers, 20 warps/SM
             ip.nRep = h->nRep; ip.repStride = 1;
             if (nonCoh * h->nRep < 5) { ip.prnPerCta = 5; ip.mPerCta = 1; }           // few transforms per cell (Galileo E1: 2): fill the CTA with SVs
+            if (const char* e = getenv("GC_ROWS_VARIANT")) {   // "PxM" warps per CTA = P PRNs x M blocks
+                int P = 0, M = 0;
+                if (sscanf(e, "%dx%d", &P, &M) == 2 && (P * M == 5 || P * M == 8)) { ip.prnPerCta = P; ip.mPerCta = M; }
+            }
+            ip.zLoop = rows_zloop(L);
             ip.nPrnChunk = nc; ip.prnSlot0 = s0; ip.prnList = h->prnList.p;
             ip.slotGroup = h->slotGroup.p; ip.groupRows = fwdRowsPerGroup;
             if (shifted) ip.binMap = h->vbMap.p;
@@ -1801,6 +1819,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
                     int P = 0, M = 0;
                     if (sscanf(e, "%dx%d", &P, &M) == 2 && (P * M == 5 || P * M == 8)) { ip.prnPerCta = P; ip.mPerCta = M; }
                 }
+                ip.zLoop = rows_zloop(L);
                 ip.nPrnChunk = nc; ip.prnSlot0 = s0; ip.prnList = h->prnList.p;
                 if (shifted) ip.binMap = h->vbMap.p;
                 if (evn > kEvents - 12) drain_events();

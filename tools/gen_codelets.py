@@ -17,7 +17,7 @@ intermediate is a fresh ``const float2``); all index maps are resolved at genera
 
   * odd primes P: direct DFT with the (x_j + x_{P-j}, x_j - x_{P-j}) symmetry:
     A_k = x_0 + sum_j cos(2 pi jk/P) s_j,  B_k = sum_j sin(2 pi jk/P) d_j,  X_k = A_k -/+ i B_k
-  * powers of two: radix-2 decimation in time (a +/- w*b as two FFMA2 chains; w = 1, -i free)
+  * powers of two: radix-2 decimation in time (a +/- w*b as three FFMA2: u = b*(1 + i*t), a +/- m*u; w = 1, -i free)
   * composites: coprime factors by the Good-Thomas prime-factor mapping (no twiddles), repeated
     factors (9 = 3x3, 25 = 5x5) by Cooley-Tukey with literal twiddles.
 
@@ -96,16 +96,17 @@ def prime_block(P, vals, inv):
         acc = new(f"f2add({acc}, {s[j]})")
     out[0] = acc
     for k in range(1, h + 1):
+        # A + iB as ONE chain (the sine terms enter as i*d_j through the operand swizzle), A - iB = 2A - (A + iB):
+        # 2h + 1 packed operations per output pair instead of 2h + 2
         a = vals[0]
-        b = None
         for j in range(1, h + 1):
             q = (j * k) % P
-            c = math.cos(2 * math.pi * q / P)
-            sn = math.sin(2 * math.pi * q / P)
-            a = new(f"f2fma({s[j]}, {lit(c)}, {a})")
-            b = new(f"f2scale({d[j]}, {lit(sn)})") if b is None else new(f"f2fma({d[j]}, {lit(sn)}, {b})")
-        lo = new(f"f2subi({a}, {b})")        # A - iB: forward X_k, inverse X_{P-k}
-        hi = new(f"f2addi({a}, {b})")
+            a = new(f"f2fma({s[j]}, {lit(math.cos(2 * math.pi * q / P))}, {a})")
+        hi = a
+        for j in range(1, h + 1):
+            q = (j * k) % P
+            hi = new(f"f2fma(f2rot({d[j]}), {lit(math.sin(2 * math.pi * q / P))}, {hi})")
+        lo = new(f"f2fma({a}, 2.0f, f2neg({hi}))")        # A - iB: forward X_k, inverse X_{P-k}
         if inv:
             lo, hi = hi, lo
         out[k] = lo
@@ -144,10 +145,19 @@ def pow2_block(N, vals, inv):
                         nxt[g + j] = new(f"f2subi({a}, {b})")
                         nxt[g + j + half] = new(f"f2addi({a}, {b})")
                 else:
+                    # a +/- w*b in THREE packed operations instead of four: the twiddle is factored as
+                    # w = wr * (1 + i*t) or w = wi * (r + i) with the ratio of the smaller to the larger part
+                    # (|ratio| <= 1), u = b + i*t*b (or r*b + i*b) is one FFMA2 shared by both outputs
                     ang = sgn * 2 * math.pi * num / den
                     wr, wi = math.cos(ang), math.sin(ang)
-                    nxt[g + j] = new(f"f2bfly({a}, {b}, {lit(wr)}, {lit(wi)})")
-                    nxt[g + j + half] = new(f"f2bfly({a}, {b}, {lit(-wr)}, {lit(-wi)})")
+                    if abs(wr) >= abs(wi):
+                        u = new(f"f2fma(f2rot({b}), {lit(wi / wr)}, {b})")
+                        m = wr
+                    else:
+                        u = new(f"f2fma({b}, {lit(wr / wi)}, f2rot({b}))")
+                        m = wi
+                    nxt[g + j] = new(f"f2fma({u}, {lit(m)}, {a})")
+                    nxt[g + j + half] = new(f"f2fma({u}, {lit(-m)}, {a})")
         cur = nxt
         half *= 2
     return cur
@@ -207,6 +217,7 @@ __device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return __fadd2_rn(
 __device__ __forceinline__ float2 f2addi(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.y, b.x)); }   // a + i*b
 __device__ __forceinline__ float2 f2subi(float2 a, float2 b) { return __fadd2_rn(a, make_float2(b.y, -b.x)); }   // a - i*b
 __device__ __forceinline__ float2 f2rot(float2 a) { return make_float2(-a.y, a.x); }                              // i*a
+__device__ __forceinline__ float2 f2neg(float2 a) { return make_float2(-a.x, -a.y); }
 __device__ __forceinline__ float2 f2scale(float2 a, float c) { return __fmul2_rn(a, make_float2(c, c)); }
 __device__ __forceinline__ float2 f2fma(float2 a, float c, float2 b) { return __ffma2_rn(a, make_float2(c, c), b); }   // a*c + b
 // t * (wr + i*wi)
