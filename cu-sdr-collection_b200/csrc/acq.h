@@ -175,6 +175,7 @@ struct FineParams {
     double* sums;             // [nAcq][nFine][nPeriods][2]  sumPerCode (:235-238)
     int* best;                // [nAcq] arg-max fine bin, 0-based (:253)
     double* fineResult;       // [nAcq][nFine]
+    int moments;              // 1: per-code sums through moments around the centre bin (fine_sum_moments_kernel)
 };
 cudaError_t launch_fine(const FineParams& p, int maxEntries, int maxAcq, cudaStream_t s);
 

@@ -32,10 +32,20 @@ int rows_zloop(int L)
 {
     static const int env = [] { const char* e = getenv("GC_ROWS_ZLOOP"); return e ? atoi(e) : 0; }();
     if (env > 0) return env;
-    // measured (tools/acq_bench.py, tools/big_bench.py): 8 rows per warp gain 2 - 9 % on the 25-point row plans (E1 20 Msps
-    // 5.16 -> 4.67 ms, B1C 47.0 -> 45.3 ms); the 31-point codelet of the 32736 plan has no register to spare for the loop
-    // (48 bytes of spills) and ends where it started, so it keeps one row per warp
-    return L == 32736 ? 1 : 8;
+    // measured (tools/acq_bench.py, tools/big_bench.py; profiles/r02c_rows_experiments.md): 16 rows per warp on the headline plan
+    // (rows 1.231 -> 1.194 ms), 8 on the 25-point row plans (E1 20 Msps 5.16 -> 4.67 ms, B1C 47.0 -> 45.3 ms)
+    return L == 32736 ? 16 : 8;
+}
+
+// fine search: the per-code sums go through moments around the centre bin (fine_sum_moments_kernel) where its third-order
+// expansion over a 256-sample run is exact to ~1e-8 of a term: |2 pi (f_j - f_centre) ts| * 128 <= 0.025; GC_FINE_MOMENTS=0
+// selects the bin-by-bin kernel
+int fine_moments(int nFine, double fineStep, double ts)
+{
+    static const int env = [] { const char* e = getenv("GC_FINE_MOMENTS"); return e ? atoi(e) : 1; }();
+    if (!env || nFine > 128) return 0;
+    const double tmax = 6.283185307179586 * fineStep * (nFine - nFine / 2) * ts * 128.0;
+    return tmax <= 0.025 ? 1 : 0;
 }
 
 double m_round(double x) { return x >= 0 ? std::floor(x + 0.5) : -std::floor(-x + 0.5); }
@@ -1489,6 +1499,7 @@ static int acquire_plain(gc_handle* h, long long winStart, int32_t nSv, const in
             fpp.chips = h->chips.p; fpp.chipRow = h->fineChipRow.p; fpp.codePhase = h->fineCodePhase.p; fpp.dphi = h->fdphi.p; fpp.prod = h->fineProd.p;
             fpp.sums = h->fineSums.p; fpp.best = h->fineBest.p; fpp.fineResult = h->fineResult.p;
             fpp.nAcqDev = h->nAcqDev.p; fpp.nCodes = nCodes; fpp.secondary = h->fineSecondary.p;
+            fpp.moments = fine_moments(h->nFine, h->fineStep, h->ts);
             GC_CUDA(h, launch_fine(fpp, maxEnt, nSv, st)); q.launches += 3;
             q.fb = mark();
         }
@@ -1945,6 +1956,7 @@ static int acquire_impl(gc_handle* h, long long winStart, int32_t nSv, const int
         fp.chips = h->chips.p; fp.chipRow = h->fineChipRow.p; fp.codePhase = h->fineCodePhase.p; fp.dphi = h->fdphi.p; fp.prod = h->fineProd.p;
         fp.sums = h->fineSums.p; fp.best = h->fineBest.p; fp.fineResult = h->fineResult.p;
         fp.nAcqDev = h->nAcqDev.p; fp.nCodes = nCodes; fp.secondary = h->fineSecondary.p;
+        fp.moments = fine_moments(h->nFine, h->fineStep, h->ts);
         GC_CUDA(h, launch_fine(fp, maxEnt, nSv, st)); launches += 3;
         fb = mark();
     }
