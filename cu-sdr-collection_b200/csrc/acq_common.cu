@@ -175,29 +175,38 @@ fine_sum_moments_kernel(FineParams p)
     float rs, rc;
     fix_sincos(dc * 32ull, &rs, &rc);                            // the centre carrier over 32 samples
     const int nRuns = (p.N + kFineRun - 1) / kFineRun;
+    short2 nxt[kFineRun / 32];                                   // the next run's samples are in flight while this one is summed
+#pragma unroll
+    for (int i = 0; i < kFineRun / 32; ++i) {
+        const int n = warp * kFineRun + lane + 32 * i;
+        nxt[i] = (warp < nRuns && n < p.N) ? x[n] : make_short2(0, 0);
+    }
     for (int b = warp; b < nRuns; b += 8) {
         const int n0 = b * kFineRun;
         const uint64_t g0 = (uint64_t)c * p.N + n0;             // finePhasePoints index of the run's first sample (:148)
+        short2 cur[kFineRun / 32];
+#pragma unroll
+        for (int i = 0; i < kFineRun / 32; ++i) {
+            cur[i] = nxt[i];
+            const int n = n0 + 8 * kFineRun + lane + 32 * i;
+            nxt[i] = (b + 8 < nRuns && n < p.N) ? x[n] : make_short2(0, 0);
+        }
         float ws, wc;
         fix_sincos(dc * (g0 + lane), &ws, &wc);                  // exp(-1i*f*finePhasePoints) of the centre bin, :230
         float m[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) m[i] = 0.f;
 #pragma unroll
-        for (int i = 0; i < kFineRun / 32; ++i) {
-            const int n = n0 + lane + 32 * i;
-            if (n < p.N) {
-                const short2 v = x[n];
-                const float I = (float)v.x, Q = (float)v.y;
-                const float zr = fmaf(wc, I, ws * Q), zi = fmaf(wc, Q, -ws * I);
-                const float r = (float)(lane + 32 * i - kFineRun / 2);
-                m[0] += zr; m[1] += zi;
-                float tr = zr * r, ti = zi * r;
-                m[2] += tr; m[3] += ti;
-                tr *= r; ti *= r;
-                m[4] += tr; m[5] += ti;
-                m[6] = fmaf(tr, r, m[6]); m[7] = fmaf(ti, r, m[7]);
-            }
+        for (int i = 0; i < kFineRun / 32; ++i) {                // (samples past the end of the code period were loaded as zero)
+            const float I = (float)cur[i].x, Q = (float)cur[i].y;
+            const float zr = fmaf(wc, I, ws * Q), zi = fmaf(wc, Q, -ws * I);
+            const float r = (float)(lane + 32 * i - kFineRun / 2);
+            m[0] += zr; m[1] += zi;
+            float tr = zr * r, ti = zi * r;
+            m[2] += tr; m[3] += ti;
+            tr *= r; ti *= r;
+            m[4] += tr; m[5] += ti;
+            m[6] = fmaf(tr, r, m[6]); m[7] = fmaf(ti, r, m[7]);
             const float nc = fmaf(wc, rc, -ws * rs);             // advance the phase by 32 samples (7 roundings per run)
             ws = fmaf(wc, rs, ws * rc);
             wc = nc;
@@ -238,96 +247,105 @@ fine_sum_moments_kernel(FineParams p)
 // maximum over the 20 start offsets of |sum of 20 consecutive per-code sums| (GLONASS: the two
 // 10 ms meander halves enter with opposite sign).  B3I (BDS/B3I/include/acquisition.m:193-211):
 // GEO PRNs (1-5, 59-63) carry 2 ms bits, the others the 20-bit Neumann-Hoffman code.
-__global__ void fine_select_kernel(FineParams p)
+// One (bin, alignment) pair per thread, each evaluated with the reference's own summation order; the maximum over the
+// alignments of a bin is order independent (non-negative doubles compare like their bit patterns: atomicMax in shared memory).
+__device__ __forceinline__ int fine_alignments(const FineParams& p, int prn)
+{
+    switch (p.combine) {
+        case 2: return ((prn >= 1 && prn <= 5) || (prn >= 59 && prn <= 63)) ? 2 : 20;
+        case 3: return 25;
+        case 4: return p.nPeriods;
+        case 5: return 1;
+        default: return p.nPeriods / 2;
+    }
+}
+
+__device__ double fine_power(const FineParams& p, int a, int nAcq, int j, int c, int prn)
+{
+    const double* s = p.sums + ((size_t)a * p.nFine + j) * p.nPeriods * 2;
+    const int half = p.nPeriods / 2;
+    if (p.combine == 4) {
+        // secondary code of the pilot, every circular alignment (GPS_L5C acquisition.m:214-219: the code is rotated
+        // by one element per step, after step c it holds sec(q - c))
+        const int8_t* sec = p.secondary + (size_t)a * p.nPeriods;
+        double r = 0, i = 0;
+        for (int q = 0; q < p.nPeriods; ++q) {
+            const double sc = (double)sec[(q - c + p.nPeriods) % p.nPeriods];
+            r += s[2 * q] * sc; i += s[2 * q + 1] * sc;
+        }
+        return hypot(r, i);
+    }
+    if (p.combine == 5) {
+        const double* s2 = p.sums + ((size_t)(a + nAcq) * p.nFine + j) * p.nPeriods * 2;
+        double t1 = 0, t2 = 0;
+        for (int q = 0; q < p.nPeriods; ++q) { t1 += hypot(s[2 * q], s[2 * q + 1]); t2 += hypot(s2[2 * q], s2[2 * q + 1]); }
+        return t1 + t2;
+    }
+    if (p.combine == 3 || (p.combine == 2 && fine_alignments(p, prn) == 20)) {
+        // Galileo E1: 25 code periods against the 25-chip pilot secondary code '380AD90', aligned and at the 24 other edges
+        // (GAL_E1C/include/acquisition.m:135, 236-252); B3I MEO / IGSO: the 20-bit Neumann-Hoffman code the same way
+        // (BDS/B3I/include/acquisition.m:127, 199-210).  code2ndShift = circshift(code', c)': element q takes code[(q - c) mod n]
+        const double SEC[25] = {1, 1, -1, -1, -1, 1, 1, 1, 1, 1, 1, 1, -1, 1, -1, 1, -1, -1, 1, -1, -1, 1, 1, -1, 1};
+        const double NH[20] = {1, 1, 1, 1, 1, -1, 1, 1, -1, -1, 1, -1, 1, -1, 1, 1, -1, -1, -1, 1};
+        const int n = p.combine == 3 ? 25 : 20;
+        const double* code = p.combine == 3 ? SEC : NH;
+        if (c == 0) {
+            double r = 0, i = 0;
+            for (int q = 0; q < n; ++q) { r += s[2 * q] * code[q]; i += s[2 * q + 1] * code[q]; }
+            return hypot(r, i);
+        }
+        double r1 = 0, i1 = 0, r2 = 0, i2 = 0;
+        for (int q = 0; q < n; ++q) {
+            const double sc = code[(q - c + n) % n];
+            if (q < c) { r1 += s[2 * q] * sc; i1 += s[2 * q + 1] * sc; }
+            else { r2 += s[2 * q] * sc; i2 += s[2 * q + 1] * sc; }
+        }
+        return hypot(r1, i1) + hypot(r2, i2);
+    }
+    if (p.combine == 2) {                                                        // B3I GEO: 2 ms bits (:193-198)
+        if (c == 0) {
+            double c1 = 0;
+            for (int q = 0; q < 20; q += 2) c1 += hypot(s[2 * q] + s[2 * q + 2], s[2 * q + 1] + s[2 * q + 3]);
+            return c1;
+        }
+        double c2 = hypot(s[0], s[1]) + hypot(s[38], s[39]);
+        for (int q = 1; q < 19; q += 2) c2 += hypot(s[2 * q] + s[2 * q + 2], s[2 * q + 1] + s[2 * q + 3]);
+        return c2;
+    }
+    double r = 0, i = 0;
+    if (p.combine == 0) {
+        for (int q = c; q < c + half; ++q) { r += s[2 * q]; i += s[2 * q + 1]; }
+    } else {                                             // 10 ms meander halves of opposite sign (GLO :246-252)
+        for (int q = c; q < c + half / 2; ++q) { r += s[2 * q]; i += s[2 * q + 1]; }
+        for (int q = c + half / 2; q < c + half; ++q) { r -= s[2 * q]; i -= s[2 * q + 1]; }
+    }
+    return sqrt(r * r + i * i);
+}
+
+__global__ void __launch_bounds__(256)
+fine_select_kernel(FineParams p)
 {
     const int a = blockIdx.x;
     const int nAcq = *p.nAcqDev;
     if (a >= nAcq) return;
-    const int half = p.nPeriods / 2;
-    const double NH[20] = {1, 1, 1, 1, 1, -1, 1, 1, -1, -1, 1, -1, 1, -1, 1, 1, -1, -1, -1, 1};   // :127
-    for (int j = threadIdx.x; j < p.nFine; j += blockDim.x) {
-        const double* s = p.sums + ((size_t)a * p.nFine + j) * p.nPeriods * 2;
-        double maxPower = 0;
-        if (p.combine == 4) {
-            // secondary code of the pilot, every circular alignment (GPS_L5C acquisition.m:214-219: the code is rotated
-            // by one element per step, after step c it holds sec(q - c))
-            const int8_t* sec = p.secondary + (size_t)a * p.nPeriods;
-            for (int c = 0; c < p.nPeriods; ++c) {
-                double r = 0, i = 0;
-                for (int q = 0; q < p.nPeriods; ++q) {
-                    const double sc = (double)sec[(q - c + p.nPeriods) % p.nPeriods];
-                    r += s[2 * q] * sc; i += s[2 * q + 1] * sc;
-                }
-                const double pw = hypot(r, i);
-                if (pw > maxPower) maxPower = pw;
-            }
-        } else if (p.combine == 5) {
-            const double* s2 = p.sums + ((size_t)(a + nAcq) * p.nFine + j) * p.nPeriods * 2;
-            double t1 = 0, t2 = 0;
-            for (int q = 0; q < p.nPeriods; ++q) { t1 += hypot(s[2 * q], s[2 * q + 1]); t2 += hypot(s2[2 * q], s2[2 * q + 1]); }
-            maxPower = t1 + t2;
-        } else if (p.combine == 3) {
-            // Galileo E1: 25 code periods against the 25-chip pilot secondary code '380AD90', aligned and at
-            // the 24 other edges (GAL_E1C/include/acquisition.m:135, 236-252)
-            const double SEC[25] = {1, 1, -1, -1, -1, 1, 1, 1, 1, 1, 1, 1, -1, 1, -1, 1, -1, -1, 1, -1, -1, 1, 1, -1, 1};
-            double r = 0, i = 0;
-            for (int q = 0; q < 25; ++q) { r += s[2 * q] * SEC[q]; i += s[2 * q + 1] * SEC[q]; }
-            maxPower = hypot(r, i);
-            for (int c = 1; c <= 24; ++c) {
-                // code2ndShift = circshift(secondaryCode', c)': element q takes SEC[(q - c) mod 25]
-                double r1 = 0, i1 = 0, r2 = 0, i2 = 0;
-                for (int q = 0; q < 25; ++q) {
-                    const double sc = SEC[(q - c + 25) % 25];
-                    if (q < c) { r1 += s[2 * q] * sc; i1 += s[2 * q + 1] * sc; }
-                    else { r2 += s[2 * q] * sc; i2 += s[2 * q + 1] * sc; }
-                }
-                const double pw = hypot(r1, i1) + hypot(r2, i2);
-                if (pw > maxPower) maxPower = pw;
-            }
-        } else if (p.combine == 2) {
-            const int prn = p.svId[a];
-            if ((prn >= 1 && prn <= 5) || (prn >= 59 && prn <= 63)) {               // :193-198
-                double c1 = 0, c2 = 0;
-                for (int q = 0; q < 20; q += 2) c1 += hypot(s[2 * q] + s[2 * q + 2], s[2 * q + 1] + s[2 * q + 3]);
-                c2 = hypot(s[0], s[1]) + hypot(s[38], s[39]);
-                for (int q = 1; q < 19; q += 2) c2 += hypot(s[2 * q] + s[2 * q + 2], s[2 * q + 1] + s[2 * q + 3]);
-                maxPower = c1 > c2 ? c1 : c2;
-            } else {                                                                 // :199-210
-                double r = 0, i = 0;
-                for (int q = 0; q < 20; ++q) { r += s[2 * q] * NH[q]; i += s[2 * q + 1] * NH[q]; }
-                maxPower = hypot(r, i);
-                for (int c = 1; c <= 19; ++c) {
-                    // NHcodeShift = circshift(NHcode', c)': element q takes NH[(q - c) mod 20]
-                    double r1 = 0, i1 = 0, r2 = 0, i2 = 0;
-                    for (int q = 0; q < 20; ++q) {
-                        const double nh = NH[(q - c + 20) % 20];
-                        if (q < c) { r1 += s[2 * q] * nh; i1 += s[2 * q + 1] * nh; }
-                        else { r2 += s[2 * q] * nh; i2 += s[2 * q + 1] * nh; }
-                    }
-                    const double pw = hypot(r1, i1) + hypot(r2, i2);
-                    if (pw > maxPower) maxPower = pw;
-                }
-            }
-        } else {
-            for (int c = 0; c < half; ++c) {
-                double r = 0, i = 0;
-                if (p.combine == 0) {
-                    for (int q = c; q < c + half; ++q) { r += s[2 * q]; i += s[2 * q + 1]; }
-                } else {                                             // 10 ms meander halves of opposite sign (GLO :246-252)
-                    for (int q = c; q < c + half / 2; ++q) { r += s[2 * q]; i += s[2 * q + 1]; }
-                    for (int q = c + half / 2; q < c + half; ++q) { r -= s[2 * q]; i -= s[2 * q + 1]; }
-                }
-                const double pw = sqrt(r * r + i * i);
-                if (pw > maxPower) maxPower = pw;
-            }
-        }
-        p.fineResult[a * p.nFine + j] = maxPower;
+    extern __shared__ unsigned long long s_best[];               // [nFine] bit pattern of the bin's maximum (>= 0)
+    for (int j = threadIdx.x; j < p.nFine; j += blockDim.x) s_best[j] = 0ull;
+    __syncthreads();
+    const int prn = p.combine == 2 ? p.svId[a] : 0;
+    const int nC = fine_alignments(p, prn);
+    for (int w = threadIdx.x; w < p.nFine * nC; w += blockDim.x) {
+        const int j = w / nC, c = w - j * nC;
+        const double pw = fine_power(p, a, nAcq, j, c, prn);
+        if (pw > 0) atomicMax(&s_best[j], (unsigned long long)__double_as_longlong(pw));
     }
     __syncthreads();
+    for (int j = threadIdx.x; j < p.nFine; j += blockDim.x) p.fineResult[a * p.nFine + j] = __longlong_as_double((long long)s_best[j]);
     if (threadIdx.x == 0) {
-        int best = 0; double bv = p.fineResult[a * p.nFine];
-        for (int j = 1; j < p.nFine; ++j)
-            if (p.fineResult[a * p.nFine + j] > bv) { bv = p.fineResult[a * p.nFine + j]; best = j; }
+        int best = 0; double bv = __longlong_as_double((long long)s_best[0]);
+        for (int j = 1; j < p.nFine; ++j) {
+            const double v = __longlong_as_double((long long)s_best[j]);
+            if (v > bv) { bv = v; best = j; }
+        }
         p.best[a] = best;
     }
 }
@@ -451,7 +469,7 @@ cudaError_t launch_fine(const FineParams& p, int nEntries, int nAcq, cudaStream_
         dim3 g2(p.nPeriods, nEntries, (p.nFine + kFineBins - 1) / kFineBins);
         fine_sum_kernel<<<g2, 256, 0, s>>>(p);
     }
-    fine_select_kernel<<<nAcq, 64, 0, s>>>(p);
+    fine_select_kernel<<<nAcq, 256, sizeof(unsigned long long) * p.nFine, s>>>(p);
     return cudaGetLastError();
 }
 

@@ -1,9 +1,5 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu --timeout 300 --timeout-method thread > gpurun_out/s3_pytest_gpu.txt 2>&1; echo "pytest rc $?"; tail -3 gpurun_out/s3_pytest_gpu.txt
-timeout 600 python bench.py > gpurun_out/s3_bench_n1.json 2> gpurun_out/s3_bench_n1.err; echo "bench rc $?"
-python -c "
-import json; d=json.load(open('gpurun_out/s3_bench_n1.json'))
-print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['ms_per_step'],'cold',d['e2e_cold']['ms'],'launches',d['gpu_launches'],'frac',d['roofline']['frac'],'rows ms',d['roofline']['launch_ms'])
-print('trk',d['tracking_value'],'batch',d['tracking_batch_value'],'e1c',d['gal_e1c_value'],'allc',d['all_constellation_ms'], 'parity', d['parity'])
-"
+run() { echo "== $*"; env "$@" timeout 120 python tools/acq_bench.py 2>&1 | grep "path\|checksum" | tail -2 | cut -c1-150; }
+run GC_X=1
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_multi.py -x -q -m gpu --timeout 240 --timeout-method thread -k "acq or golden or one_call or device or graph or multi" > gpurun_out/s3_pytest_acq.txt 2>&1; echo "pytest acq rc $?"; tail -3 gpurun_out/s3_pytest_acq.txt
