@@ -595,9 +595,9 @@ def main():
         pk, pk_src = peaks()
         achieved = cells_per_launch * BYTES_PER_CELL / (rows_launch_ms * 1e-3) / 1e9
         step_ach = CELLS * BYTES_PER_CELL / (step_ms * 1e-3) / 1e9
-        prof = os.path.join(ROOT, "profiles", "r02_traffic.json")   # ncu --set full capture of the dominant kernel
+        prof = os.path.join(ROOT, "profiles", "r02c_traffic.json")  # ncu --set full capture of the dominant kernel
         if not os.path.exists(prof):
-            prof = os.path.join(ROOT, "profiles", "r01_traffic.json")
+            prof = os.path.join(ROOT, "profiles", "r02_traffic.json")
         traffic = None
         if os.path.exists(prof):                                    # per launch like `achieved`: bytes per cell x cells of one launch
             tj = json.load(open(prof))
@@ -625,12 +625,12 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
                          "kernel": "inv_rows_kernel (spectrum multiply + inverse 31x32 row DFTs of the 33x32x31 prime-factor "
-                                   "transform, packed fp32x2 codelets)",
+                                   "transform - Rader 31-point and three-operation radix-2 codelets in packed fp32x2 - 16 rows per warp)",
                          "launch_ms": rows_launch_ms, "cells_per_launch": cells_per_launch, "peak_source": pk_src,
                          "whole_step_achieved": step_ach, "whole_step_frac": step_ach / (pk["hbm_gbs"] * world),
                          "kernel_share_of_step": {"inv_rows": rows_ms / args.steps / step_ms, "inv_cols": cols_ms / args.steps / step_ms},
-                         "note": "FFT stages carry about 69 flop per algorithmic byte; the rows kernel is bound by FP32 issue and "
-                                 "L2 throughput, the column kernel by the HBM read of the work buffer"},
+                         "note": "FFT stages carry about 60 flop per algorithmic byte; the rows kernel is bound by the FP32 pipe (68 % active, "
+                                 "math-pipe throttle the top stall; profiles/r02c_ncu_acq.md), the column kernel by the HBM read of the work buffer"},
             "cpu_baseline": cpu_acq,
             "parity": parity,
             "clocks": clocks,

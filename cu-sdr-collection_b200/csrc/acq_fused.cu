@@ -680,6 +680,13 @@ struct Launch {
         q.mGroups = (p.nonCoh * p.nRep + p.mPerCta - 1) / p.mPerCta;
         q.zTotal = ((p.nBins + bpc - 1) / bpc) * q.mGroups;
         q.zLoop = LOOP ? p.zLoop : 1;
+        if (LOOP) {
+            // never fewer than ~12 waves of CTAs: a small share of the grid (a few SVs per GPU of a multi-GPU run, GLONASS's
+            // small grids) keeps short CTAs so that its last wave stays a small part of the launch
+            const long long ctas1 = (long long)P::C * pGroups * q.zTotal;
+            const long long cap = ctas1 / (148LL * MINB * 12);
+            if (q.zLoop > cap) q.zLoop = (int)(cap > 1 ? cap : 1);
+        }
         dim3 grid(P::C, pGroups, (q.zTotal + q.zLoop - 1) / q.zLoop);
         inv_rows_kernel<P, WARPS, MINB, LOOP><<<grid, WARPS * 32, smem, s>>>(q);
         return cudaGetLastError();
