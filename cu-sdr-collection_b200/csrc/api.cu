@@ -1462,10 +1462,6 @@ static int acquire_plain(gc_handle* h, long long winStart, int32_t nSv, const in
             ip.nonCoh = nonCoh; ip.nBins = nBins; ip.prnPerCta = 1; ip.mPerCta = 5;   // 5 warps, 96 registers, 20 warps/SM
             ip.nRep = h->nRep; ip.repStride = 1;
             if (nonCoh * h->nRep < 5) { ip.prnPerCta = 5; ip.mPerCta = 1; }           // few transforms per cell (Galileo E1: 2): fill the CTA with SVs
-            if (const char* e = getenv("GC_ROWS_VARIANT")) {   // "PxM" warps per CTA = P PRNs x M blocks
-                int P = 0, M = 0;
-                if (sscanf(e, "%dx%d", &P, &M) == 2 && (P * M == 5 || P * M == 8)) { ip.prnPerCta = P; ip.mPerCta = M; }
-            }
             ip.zLoop = rows_zloop(L);
             ip.nPrnChunk = nc; ip.prnSlot0 = s0; ip.prnList = h->prnList.p;
             ip.slotGroup = h->slotGroup.p; ip.groupRows = fwdRowsPerGroup;
