@@ -1,6 +1,10 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-big() { echo "== big $*"; env "$@" timeout 200 python tools/big_bench.py L2C B1C E1C20 E1C18 B1I 2>&1 | grep "fft\|rror" | cut -c1-120; }
-big GC_COLS_BIG_PIPE=1
-big GC_COLS_BIG_PIPE=0
-timeout 500 python -m pytest tests/test_gpu_parity.py -x -q -m gpu --timeout 200 --timeout-method thread -k "b1c or l2c or e1c or varb or b1i or golden" > gpurun_out/s3_pytest_big.txt 2>&1; echo "pytest big rc $?"; tail -3 gpurun_out/s3_pytest_big.txt
+timeout 900 python -m pytest tests -x -q -m gpu --timeout 300 --timeout-method thread > gpurun_out/s3_pytest_gpu.txt 2>&1; echo "pytest rc $?"; tail -2 gpurun_out/s3_pytest_gpu.txt
+timeout 600 python bench.py > gpurun_out/s3_bench_n1.json 2> gpurun_out/s3_bench_n1.err; echo "bench rc $?"
+python -c "
+import json; d=json.load(open('gpurun_out/s3_bench_n1.json'))
+print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['ms_per_step'],'cold',d['e2e_cold']['ms'],'launches',d['gpu_launches'],'frac',d['roofline']['frac'],'rows ms',d['roofline']['launch_ms'])
+print('trk',d['tracking_value'],'batch',d['tracking_batch_value'],'e1c',d['gal_e1c_value'],'allc',d['all_constellation_ms'], 'parity', d['parity']['acquisition'])
+"
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
