@@ -52,6 +52,31 @@ def test_generated_codelets_match_direct_dft(tmp_path):
         "fft_codelets.cuh is stale: regenerate with tools/gen_codelets.py"
 
 
+def test_codelet_operation_counts():
+    """The packed-operation counts DESIGN.md quotes for the row pass are properties of the generated header: 194 for the
+    32-point codelet (three-operation butterflies), Rader's 31-point form below the direct symmetric one (510), 186 for the
+    30-point prime-factor codelet inside it, and every length at (or one trivial multiplication below) the generator's model."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_codelets", os.path.join(ROOT, "tools", "gen_codelets.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    src = open(os.path.join(ROOT, "cu-sdr-collection_b200", "csrc", "fft_codelets.cuh")).read()
+
+    def emitted(n):
+        body = re.search(r"void dft%d_inv\(.*?\n\{\n(.*?)\n\}\n" % n, src, re.S).group(1)
+        ops = 0
+        for line in body.split("\n"):
+            m = re.match(r"\s*const float2 v\d+ = (f2\w+)\(", line)
+            if m:
+                ops += 2 if m.group(1) == "f2cmulc" else 1
+        return ops
+
+    assert emitted(32) == 194 and emitted(30) == 186
+    assert emitted(31) <= 432 < gen.packed_ops_direct(31) == 510
+    for n in (4, 8, 9, 10, 16, 18, 20, 25, 30, 31, 32, 33, 40, 45, 50):
+        assert gen.packed_ops(n) - 1 <= emitted(n) <= gen.packed_ops(n), n
+
+
 def test_no_gpu_means_loud_failure_not_fallback():
     import torch
     if torch.cuda.is_available():
