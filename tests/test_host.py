@@ -77,6 +77,37 @@ def test_codelet_operation_counts():
         assert gen.packed_ops(n) - 1 <= emitted(n) <= gen.packed_ops(n), n
 
 
+def test_fine_search_moment_expansion_bound():
+    """fine_sum_moments_kernel (csrc/acq_common.cu) replaces the 21 per-bin carrier wipe-offs of acquisition.m:230-238 by one
+    wipe-off at the centre bin and four moments per run of 256 samples.  The same arithmetic in NumPy (float32 moments, the
+    kernel's operation order) against the direct float64 sums, at the reference's defaults (16.368 Msps, fine bins 25 Hz apart
+    over +-250 Hz): the difference stays below 1e-6 of the sum's scale - the fine-bin arg-max cannot move."""
+    rng = np.random.default_rng(7)
+    fs, N, run = 16.368e6, 16368, 256
+    c = 3                                                        # fourth code period: finePhasePoints index c*N + n
+    z = (rng.integers(-128, 128, N) + 1j * rng.integers(-128, 128, N))
+    f_c = 4.092e6 + 1234.0
+    z = z * np.exp(2j * np.pi * (f_c + 60.0) / fs * (c * N + np.arange(N)))     # a tone near the centre bin, as after x.*code
+    g = c * N + np.arange(N, dtype=np.float64)
+    worst = 0.0
+    scale = np.abs(np.sum(z * np.exp(-2j * np.pi * (f_c + 60.0) / fs * g)))
+    zc = (z * np.exp(-2j * np.pi * f_c / fs * g)).astype(np.complex64)            # the centre-bin wipe-off, once
+    for j in range(-10, 11):
+        d = 25.0 * j / fs                                        # turns per sample between bin j and the centre bin
+        direct = np.sum(z * np.exp(-2j * np.pi * (f_c / fs + d) * g))
+        t = np.float32(2 * np.pi * d)
+        acc = 0j
+        for n0 in range(0, N, run):
+            seg = zc[n0:n0 + run]
+            r = (np.arange(len(seg)) - run // 2).astype(np.float32)
+            m0 = seg.sum(dtype=np.complex64); m1 = (seg * r).sum(dtype=np.complex64)
+            m2 = (seg * r * r).sum(dtype=np.complex64); m3 = (seg * r * r * r).sum(dtype=np.complex64)
+            poly = m0 - 1j * t * m1 - np.float32(0.5) * t * t * m2 + 1j * (t * t * t / np.float32(6)) * m3
+            acc += complex(poly) * np.exp(-2j * np.pi * d * (c * N + n0 + run // 2))
+        worst = max(worst, abs(acc - direct) / scale)
+    assert worst < 1e-6, worst
+
+
 def test_no_gpu_means_loud_failure_not_fallback():
     import torch
     if torch.cuda.is_available():
