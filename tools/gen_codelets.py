@@ -17,8 +17,11 @@ intermediate is a fresh ``const float2``); all index maps are resolved at genera
 
   * odd primes P: direct DFT with the (x_j + x_{P-j}, x_j - x_{P-j}) symmetry:
     A_k = x_0 + sum_j cos(2 pi jk/P) s_j,  B_k = sum_j sin(2 pi jk/P) d_j,  X_k = A_k -/+ i B_k
-  * primes where it is cheaper (31: 432 packed operations against 510): Rader's cyclic convolution of length P - 1 through
+  * primes where it is cheaper (31: 417 packed operations against 510): Rader's cyclic convolution of length P - 1 through
     two (P-1)-point codelets and literal spectrum values
+  * a multiplication by a literal complex constant (Cooley-Tukey twiddles, Rader's spectrum values) stays "lazy" until its
+    consumer is known: where the product feeds a sum / difference pair it is accumulated straight into the sum and the
+    difference is 2a - s (five operations instead of six for two products, three instead of four for one)
   * powers of two: radix-2 decimation in time (a +/- w*b as three FFMA2: u = b*(1 + i*t), a +/- m*u; w = 1, -i free)
   * composites: coprime factors by the Good-Thomas prime-factor mapping (no twiddles), repeated
     factors (9 = 3x3, 25 = 5x5) by Cooley-Tukey with literal twiddles.
@@ -77,21 +80,60 @@ def split(n):
     return p, n // p, False
 
 
+class Lazy:
+    """v * (wr + i*wi) not yet emitted: a product that feeds a sum / difference pair is fused into it (pair_sd)."""
+
+    def __init__(self, v, wr, wi):
+        self.v, self.wr, self.wi, self.name = v, wr, wi, None
+
+
+def force(x):
+    if isinstance(x, Lazy):
+        if x.name is None:
+            x.name = new(f"f2cmulc({x.v}, {lit(x.wr)}, {lit(x.wi)})")
+        return x.name
+    return x
+
+
 def cmul_const(v, wr, wi):
-    """v * (wr + i*wi) with literal wr, wi."""
+    """v * (wr + i*wi) with literal wr, wi (general constants stay lazy until their consumer is known)."""
+    v = force(v)
     if abs(wi) < 1e-15:
         if abs(wr - 1) < 1e-15:
             return v
         return new(f"f2scale({v}, {lit(wr)})")
     if abs(wr) < 1e-15:
         return new(f"f2scale(f2rot({v}), {lit(wi)})")
-    return new(f"f2cmulc({v}, {lit(wr)}, {lit(wi)})")
+    return Lazy(v, wr, wi)
+
+
+def pair_sd(a, b):
+    """(a + b, a - b).  A literal product among the operands is accumulated straight into the sum (two FFMA2) and the difference
+    taken as 2a - s (or s - 2b): five operations instead of six for two products, three instead of four for one."""
+    la, lb = isinstance(a, Lazy) and a.name is None, isinstance(b, Lazy) and b.name is None
+    if lb:
+        pa = force(a)
+        t = new(f"f2fma({b.v}, {lit(b.wr)}, {pa})")
+        sm = new(f"f2fma(f2rot({b.v}), {lit(b.wi)}, {t})")
+        return sm, new(f"f2fma({pa}, 2.0f, f2neg({sm}))")
+    if la:
+        pb = force(b)
+        t = new(f"f2fma({a.v}, {lit(a.wr)}, {pb})")
+        sm = new(f"f2fma(f2rot({a.v}), {lit(a.wi)}, {t})")
+        return sm, new(f"f2fma({pb}, -2.0f, {sm})")
+    a, b = force(a), force(b)
+    return new(f"f2add({a}, {b})"), new(f"f2sub({a}, {b})")
 
 
 def prime_block(P, vals, inv):
     h = (P - 1) // 2
-    s = [None] + [new(f"f2add({vals[j]}, {vals[P - j]})") for j in range(1, h + 1)]
-    d = [None] + [new(f"f2sub({vals[j]}, {vals[P - j]})") for j in range(1, h + 1)]
+    vals = list(vals)
+    vals[0] = force(vals[0])
+    s, d = [None], [None]
+    for j in range(1, h + 1):
+        sj, dj = pair_sd(vals[j], vals[P - j])
+        s.append(sj)
+        d.append(dj)
     out = [None] * P
     acc = vals[0]
     for j in range(1, h + 1):
@@ -162,9 +204,10 @@ def rader_block(P, vals, inv):
     g = primitive_root(P)
     gi = pow(g, -1, P)
     sgn = 1.0 if inv else -1.0
-    a = [vals[pow(g, q, P)] for q in range(n)]
     b = [cmath.exp(sgn * 2j * math.pi * pow(gi, r, P) / P) for r in range(n)]
     Bf = [sum(b[r] * cmath.exp(-2j * math.pi * k * r / n) for r in range(n)) / n for k in range(n)]
+    vals = [force(v) for v in vals]
+    a = [vals[pow(g, q, P)] for q in range(n)]
     A = dft(n, a, False)
     out = [None] * P
     out[0] = new(f"f2add({vals[0]}, {A[0]})")
@@ -199,9 +242,10 @@ def pow2_block(N, vals, inv):
                 a, b = cur[g + j], cur[g + j + half]
                 num, den = j, 2 * half                     # w = exp(sgn * 2 pi i * j / (2*half))
                 if num == 0:
-                    nxt[g + j] = new(f"f2add({a}, {b})")
-                    nxt[g + j + half] = new(f"f2sub({a}, {b})")
-                elif 4 * num == den:                       # w = -i (fwd) / +i (inv)
+                    nxt[g + j], nxt[g + j + half] = pair_sd(a, b)
+                    continue
+                a, b = force(a), force(b)
+                if 4 * num == den:                       # w = -i (fwd) / +i (inv)
                     if inv:
                         nxt[g + j] = new(f"f2addi({a}, {b})")
                         nxt[g + j + half] = new(f"f2subi({a}, {b})")
@@ -230,7 +274,7 @@ def pow2_block(N, vals, inv):
 def dft(N, vals, inv):
     """DFT-N of the SSA values vals[0..N-1]; returns the outputs in natural order."""
     if N == 1:
-        return list(vals)
+        return [force(v) for v in vals]
     if is_pow2(N):
         return pow2_block(N, vals, inv)
     if is_prime(N):
@@ -268,7 +312,7 @@ def gen_codelet(N):
         nm = f"dft{N}_{'inv' if inv else 'fwd'}"
         w(f"template <class F> __device__ __forceinline__ void {nm}(float2 (&x)[{N}], F&& emit)")
         w("{")
-        res = dft(N, [f"x[{i}]" for i in range(N)], inv)
+        res = [force(r) for r in dft(N, [f"x[{i}]" for i in range(N)], inv)]
         for k in range(N):
             w(f"    emit({k}, {res[k]}.x, {res[k]}.y);")
         w("}")
