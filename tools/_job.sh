@@ -1,2 +1,2 @@
 cd $GRAFT_REPO_ROOT
-timeout 60 python tools/acq_bench.py 2>&1 | grep "path\|checksum\|acquired" | tail -3 | cut -c1-200
+timeout 30 python tools/mini_parity.py 2>&1 | tail -2
