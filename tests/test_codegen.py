@@ -97,3 +97,77 @@ def test_committed_tables_are_what_the_reference_embeds(tmp_path):
     subprocess.check_call([sys.executable, os.path.join(root, "tools", "extract_icd_tables.py")], stdout=subprocess.DEVNULL)
     for f, txt in keep.items():
         assert open(os.path.join(root, f)).read() == txt, f + " is stale"
+
+
+# ---- GPS ICD known answers that survive independent of the reference and of both restatements --------------------------------
+# IS-GPS-200 Table 3-IIa (L2 CM / L2 CL): initial shift-register state and END state (the state that outputs the last chip, i.e.
+# after 10229 / 767249 shifts) in octal, PRN 1..3.  IS-GPS-705 Table 3-Ia/Ib (L5): XB code advance and the XB register state it
+# leads to ("initial XB code state", stage 1 leftmost), PRN 1..3.
+L2CM_ICD = {1: (0o742417664, 0o552566002), 2: (0o756014035, 0o034445034), 3: (0o002747144, 0o723443711)}
+L2CL_ICD = {1: (0o624145772, 0o267724236), 2: (0o506610362, 0o167516066), 3: (0o220360016, 0o771756405)}
+L5I_ICD = {1: (266, "0101011100100"), 2: (365, "1100000110101"), 3: (804, "0100000001000")}
+L5Q_ICD = {1: (1701, "1001011001100"), 2: (323, "0100011110110"), 3: (5292, "1111000100011")}
+
+
+def _l2c_register(state, n):
+    """The 27-stage modular register of IS-GPS-200 Figure 3-12 as an integer (bit 0 = output stage): the output chip is fed
+    back into stages 4, 7, 9, 12, 15, 17, 19, 22, 23, 24, 25 counted from the input end (polynomial 1112225171 octal).  Returns the
+    n output bits and the state after n - 1 shifts."""
+    mask = sum(1 << (27 - p) for p in (4, 7, 9, 12, 15, 17, 19, 22, 23, 24, 25))
+    out = np.empty(n, dtype=np.int8)
+    last = state
+    for i in range(n):
+        last = state
+        b = state & 1
+        out[i] = b
+        state = (state >> 1) | (b << 26)
+        if b:
+            state ^= mask
+    return out, last
+
+
+def test_l2c_registers_reach_the_icd_end_states_and_match_the_generators():
+    for prn, (init, end) in L2CM_ICD.items():
+        bits, last = _l2c_register(init, 10230)
+        assert last == end, (prn, oct(last))
+        chips = 1 - 2 * bits.astype(np.int64)                                        # logic 1 = chip -1
+        assert np.array_equal(generate_code("GPS_L2C", prn, 0)[0::2], chips)         # the library (bit-packed register)
+        assert np.array_equal(O.generateCMcode(prn)[0::2], chips)                    # the oracle (generateCMcode.m restated)
+    for prn, (init, end) in L2CL_ICD.items():
+        bits, last = _l2c_register(init, 767250)
+        assert last == end, (prn, oct(last))
+        if prn == 1:
+            assert np.array_equal(generate_code("GPS_L2C", prn, 1)[1::2], 1 - 2 * bits.astype(np.int64))
+
+
+def _l5_xb_state(advance):
+    """XB register of IS-GPS-705 (1 + x + x^3 + x^4 + x^6 + x^7 + x^8 + x^12 + x^13, all ones at the start) after `advance` shifts,
+    stage 1 leftmost."""
+    reg = [1] * 13
+    for _ in range(advance):
+        fb = reg[0] ^ reg[2] ^ reg[3] ^ reg[5] ^ reg[6] ^ reg[7] ^ reg[11] ^ reg[12]
+        reg = [fb] + reg[:-1]
+    return reg
+
+
+def _l5_code(advance, n=10230):
+    """XA (1 + x^9 + x^10 + x^12 + x^13, short-cycled: the state 1111111111101 is followed by all ones) xor XB advanced."""
+    xa, xb = [1] * 13, _l5_xb_state(advance)
+    out = np.empty(n, dtype=np.int64)
+    for i in range(n):
+        out[i] = xa[12] ^ xb[12]
+        if xa == [1] * 11 + [0, 1]:
+            xa = [1] * 13
+        else:
+            xa = [xa[8] ^ xa[9] ^ xa[11] ^ xa[12]] + xa[:-1]
+        xb = [xb[0] ^ xb[2] ^ xb[3] ^ xb[5] ^ xb[6] ^ xb[7] ^ xb[11] ^ xb[12]] + xb[:-1]
+    return 1 - 2 * out
+
+
+def test_l5_xb_advances_reach_the_icd_states_and_match_the_generators():
+    for comp, table in ((0, L5I_ICD), (1, L5Q_ICD)):
+        for prn, (advance, state) in table.items():
+            assert "".join(str(b) for b in _l5_xb_state(advance)) == state, (comp, prn)
+            want = _l5_code(advance)
+            assert np.array_equal(generate_code("GPS_L5C", prn, comp), want)
+            assert np.array_equal((O.generateL5Icode if comp == 0 else O.generateL5Qcode)(prn), want)
