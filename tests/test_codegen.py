@@ -58,6 +58,13 @@ def test_icd_known_answers():
     assert _hex24(generate_code("GAL_E1C", 1, 0)) == "F5D710"
     assert _hex24(generate_code("GAL_E5a", 1, 0)) == "3CEA9D"
     assert _hex24(generate_code("GAL_E5a", 1, 1)) == "515537"
+    # E5a-I codes 2 and 3 (start values 14234, 27213) start 9D8CF1, 45D1C8
+    assert _hex24(generate_code("GAL_E5a", 2, 0)) == "9D8CF1" and _hex24(generate_code("GAL_E5a", 3, 0)) == "45D1C8"
+    # E5b: base register 1 starts all ones, so the first 14 chips of a code are the complement of the ICD's 14-bit start value of
+    # base register 2 - 07220 (octal) for E5b-I code 1, 03331 for E5b-Q code 1
+    for comp, start in ((0, 0o07220), (1, 0o03331)):
+        first14 = "".join("1" if x == -1 else "0" for x in generate_code("GAL_E5b", 1, comp)[:14])
+        assert int(first14, 2) == (~start) & 0x3FFF, (comp, first14)
     # IS-GPS-200 C/A (the generator the library has had since round 1) through the same entry point: PRN 1 starts 1440 octal
     # (generateCAcode.m:90 returns -(g1 .* g2): logic 1 is chip +1 there)
     ca = generate_code("GPS_L1CA", 1, 0)
