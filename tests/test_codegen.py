@@ -178,3 +178,107 @@ def test_l5_xb_advances_reach_the_icd_states_and_match_the_generators():
             want = _l5_code(advance)
             assert np.array_equal(generate_code("GPS_L5C", prn, comp), want)
             assert np.array_equal((O.generateL5Icode if comp == 0 else O.generateL5Qcode)(prn), want)
+
+
+def _b1i_icd(tap_a, tap_b, n=2046):
+    """BDS-SIS-ICD (B1I): G1 = 1 + X + X^7 + X^8 + X^9 + X^10 + X^11, G2 = 1 + X + X^2 + X^3 + X^4 + X^5 + X^8 + X^9 + X^11, both
+    registers start 01010101010, the G2 output is the xor of two phase-selector stages; logic values."""
+    g1 = [0, 1] * 5 + [0]
+    g2 = list(g1)
+    out = np.empty(n, dtype=np.int64)
+    for i in range(n):
+        out[i] = g1[10] ^ g2[tap_a - 1] ^ g2[tap_b - 1]
+        f1 = g1[0] ^ g1[6] ^ g1[7] ^ g1[8] ^ g1[9] ^ g1[10]
+        f2 = g2[0] ^ g2[1] ^ g2[2] ^ g2[3] ^ g2[4] ^ g2[7] ^ g2[8] ^ g2[10]
+        g1 = [f1] + g1[:-1]
+        g2 = [f2] + g2[:-1]
+    return out
+
+
+def test_b1i_codes_follow_the_icd_registers():
+    """An integer restatement of the ICD's two 11-stage registers with the ICD's phase assignment of PRN 1 - 10 (1+3, 1+4, 1+5,
+    1+6, 1+8, 1+9, 1+10, 1+11, 2+7, 3+4) against the library and the oracle.  generateCAcode53.m:103 ends with
+    CAcode = -(g1 .* g2): in the reference (and therefore here) logic 1 is chip +1 for this signal."""
+    taps = {1: (1, 3), 2: (1, 4), 3: (1, 5), 4: (1, 6), 5: (1, 8), 6: (1, 9), 7: (1, 10), 8: (1, 11), 9: (2, 7), 10: (3, 4)}
+    for prn, (a, b) in taps.items():
+        want = 2 * _b1i_icd(a, b) - 1
+        assert np.array_equal(generate_code("BDS_B1I", prn, 0), want), prn
+        assert np.array_equal(O.generateCAcode53(prn), want), prn
+
+
+def _b3i_icd(g2_init, n=10230):
+    """BDS-SIS-ICD (B3I): G1 = 1 + X + X^3 + X^4 + X^13 (all ones at the start, short-cycled: the state 1111111111100 is followed by
+    all ones), G2 = 1 + X + X^5 + X^6 + X^7 + X^9 + X^10 + X^12 + X^13 started from the PRN's 13-bit phase; logic values."""
+    g1, g2 = [1] * 13, [int(c) for c in g2_init]
+    out = np.empty(n, dtype=np.int64)
+    for i in range(n):
+        out[i] = g1[12] ^ g2[12]
+        g1 = [1] * 13 if g1 == [1] * 11 + [0, 0] else [g1[0] ^ g1[2] ^ g1[3] ^ g1[12]] + g1[:-1]
+        g2 = [g2[0] ^ g2[4] ^ g2[5] ^ g2[6] ^ g2[8] ^ g2[9] ^ g2[11] ^ g2[12]] + g2[:-1]
+    return out
+
+
+def test_b3i_codes_follow_the_icd_registers():
+    """The ICD's G2 initial phases of PRN 1 - 10 through an integer restatement of its two 13-stage registers, against the
+    library's and the oracle's generators (logic 1 = chip -1)."""
+    phases = {1: "1010111111111", 2: "1111000101011", 3: "1011110001010", 4: "1111111111011", 5: "1100100011111",
+              6: "1001001100100", 7: "1111111010010", 8: "1110111111101", 9: "1010000000010", 10: "0010000011011"}
+    for prn, init in phases.items():
+        want = 1 - 2 * _b3i_icd(init)
+        assert np.array_equal(generate_code("BDS_B3I", prn, 0), want), prn
+        assert np.array_equal(O.generateB3Icode(prn), want), prn
+
+
+def _b2a_icd(g2_init, taps1, taps2, n=10230):
+    """BDS-SIS-ICD (B2a): register 1 starts all ones and is reset after 8190 chips, register 2 starts from the PRN's 13-bit
+    value; the code is the xor of the two last stages; logic values."""
+    g1, g2 = [1] * 13, [int(c) for c in g2_init]
+    out = np.empty(n, dtype=np.int64)
+    for i in range(n):
+        out[i] = g1[12] ^ g2[12]
+        if i == 8189:
+            g1 = [1] * 13
+        else:
+            f = 0
+            for p in taps1:
+                f ^= g1[p - 1]
+            g1 = [f] + g1[:-1]
+        f = 0
+        for p in taps2:
+            f ^= g2[p - 1]
+        g2 = [f] + g2[:-1]
+    return out
+
+
+def test_b2a_and_glonass_codes_follow_the_icd_registers():
+    """B2a data (g1 = 1 + x + x^5 + x^11 + x^13, g2 = 1 + x^3 + x^5 + x^9 + x^11 + x^12 + x^13) and pilot (g1 = 1 + x^3 + x^6 + x^7 +
+    x^13, g2 = 1 + x + x^5 + x^7 + x^8 + x^12 + x^13) codes of PRN 1 - 5 from the ICD's register-2 initial values, and the GLONASS
+    ST code (1 + x^5 + x^9, nine ones at the start, taken from stage 7) - integer restatements of the ICD figures against the
+    library's and the oracle's generators (logic 1 = chip -1)."""
+    init = {1: "1000000100101", 2: "1000000110100", 3: "1000010101101", 4: "1000101001111", 5: "1000101010101"}
+    for prn, v in init.items():
+        d = 1 - 2 * _b2a_icd(v, (1, 5, 11, 13), (3, 5, 9, 11, 12, 13))
+        p = 1 - 2 * _b2a_icd(v, (3, 6, 7, 13), (1, 5, 7, 8, 12, 13))
+        assert np.array_equal(generate_code("BDS_B2a", prn, 0), d) and np.array_equal(O.generateB2aDataCode(prn), d), prn
+        assert np.array_equal(generate_code("BDS_B2a", prn, 1), p) and np.array_equal(O.generateB2aPilotCode(prn), p), prn
+    reg, st = [1] * 9, []
+    for _ in range(511):
+        st.append(reg[6])
+        reg = [reg[4] ^ reg[8]] + reg[:-1]
+    assert np.array_equal(generate_code("GLO_GL1", 0, 0), 1 - 2 * np.array(st))
+
+
+def test_b1c_primary_codes_follow_the_icd_weil_construction():
+    """BDS-SIS-ICD (B1C): Legendre sequence of length 10243 (L(k) = 1 for the quadratic residues - taken here from the set of squares,
+    not from Euler's criterion as the oracle does), Weil code L(k) xor L(k + w), truncated to 10230 chips from position p; the ICD's
+    (w, p) of PRN 1 and 2: data (2678, 699), (4802, 694), pilot (796, 7575), (156, 2369).  generateDataBOC11.m:86-89 writes the chip
+    1 - 2*W as the sub-chip pair [-c, c]."""
+    N = 10243
+    L = np.zeros(N, dtype=np.int64)
+    L[(np.arange(1, N, dtype=np.int64) ** 2) % N] = 1
+    for comp, params in ((0, {1: (2678, 699), 2: (4802, 694)}), (1, {1: (796, 7575), 2: (156, 2369)})):
+        for prn, (w, p) in params.items():
+            k = (np.arange(10230) + p - 1) % N
+            c = 1 - 2 * (L[k] ^ L[(k + w) % N])
+            got = generate_code("BDS_B1C", prn, comp)
+            assert np.array_equal(got[0::2], -c) and np.array_equal(got[1::2], c), (comp, prn)
